@@ -1,0 +1,211 @@
+// Multiresolution hash-grid encoding, forward and backward, 3-D positions, 2 features per level.
+// Replaces tcnn kernel_grid / kernel_grid_backward (reference:
+// dependencies/tiny-cuda-nn/include/tiny-cuda-nn/encodings/grid.h:220-349, :395-518) for
+// GridType::Hash, HashType::CoherentPrime, InterpolationType::Linear (grid.h:1472-1476 defaults).
+//
+// Layout: one thread per (sample, level); the 16 level-threads of a sample are adjacent, so the
+// 16 half2 results of a sample form one coalesced 64-byte row of `encoded[n][32]` (the layout the
+// MLP kernels consume) and the position is a warp-broadcast load. The whole table (24.4 MB fp16)
+// is L2-resident on B200, so blocks are not partitioned by level as in the reference.
+#include "common.cuh"
+#include "../../include/ngpb.h"
+
+namespace ngpb {
+
+struct GridLevels {
+	float scale[NGPB_MAX_LEVELS];
+	uint32_t resolution[NGPB_MAX_LEVELS];
+	uint32_t offset[NGPB_MAX_LEVELS];
+	uint32_t size[NGPB_MAX_LEVELS];
+	uint32_t n_levels;
+};
+
+static GridLevels make_levels(const ngpb_grid* g) {
+	GridLevels L{};
+	L.n_levels = g->n_levels;
+	for (uint32_t l = 0; l < g->n_levels; ++l) {
+		L.scale[l] = g->scale[l];
+		L.resolution[l] = g->resolution[l];
+		L.offset[l] = g->offsets[l];
+		L.size[l] = g->offsets[l + 1] - g->offsets[l];
+	}
+	return L;
+}
+
+// Entry index of a grid vertex. Reference: grid_index + prime_hash<3,true>, grid.h:111-128,:164-186.
+// Dense levels: x + y*res + z*res^2; hashed levels (size < res^3): x ^ y*2654435761 ^ z*805459861;
+// both reduced modulo the level size. `% size` is exact; the fast paths avoid the division.
+struct LevelIndexer {
+	uint32_t size, res, res2;
+	bool hashed, pow2;
+	__device__ LevelIndexer(uint32_t size_, uint32_t res_) : size(size_), res(res_) {
+		// the reference's stride loop (grid.h:169-173) stops multiplying once stride > size, so
+		// `size < stride` <=> size < res^3 without overflow for res <= 2^10.. use 64-bit to be safe.
+		uint64_t dense = (uint64_t)res_ * res_ * res_;
+		hashed = (uint64_t)size_ < dense;
+		res2 = res_ * res_;
+		pow2 = (size_ & (size_ - 1)) == 0;
+	}
+	__device__ uint32_t operator()(uint32_t x, uint32_t y, uint32_t z) const {
+		uint32_t index;
+		if (hashed) {
+			index = x ^ (y * 2654435761u) ^ (z * 805459861u);
+			return pow2 ? (index & (size - 1)) : (index % size);
+		}
+		index = x + y * res + z * res2;
+		if (index >= size) { index -= size; if (index >= size) index %= size; }
+		return index;
+	}
+};
+
+// The reference's index loop for a level where stride overflows hashmap_size early adds only the
+// dims visited before `stride > hashmap_size`; when the level is hashed that partial sum is
+// discarded, and when it is dense all three dims are visited. So the two cases above are complete.
+
+__global__ void __launch_bounds__(256) hash_encode_forward_kernel(
+	const uint32_t n, const uint32_t* __restrict__ n_dev, const GridLevels L, const __half2* __restrict__ grid, const float* __restrict__ positions, const uint32_t pos_stride,
+	__half2* __restrict__ encoded)
+{
+	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t level = tid % L.n_levels;
+	const uint32_t i = tid / L.n_levels;
+	if (i >= n) return;
+	if (n_dev && i >= *n_dev) return; // device-side sample count (no host round trip between K1 and the network)
+
+	const float scale = L.scale[level];
+	const LevelIndexer index_of(L.size[level], L.resolution[level]);
+	const __half2* __restrict__ g = grid + L.offset[level];
+
+	// pos_fract, tcnn common_device.h:434-445. The reference's `input * scale + 0.5f` is contracted to one
+	// FFMA by nvcc's default -fmad=true; this library is built with -fmad=false, so the FMA is explicit.
+	float pos[3];
+	uint32_t pg[3];
+	#pragma unroll
+	for (int d = 0; d < 3; ++d) {
+		float p = __fmaf_rn(positions[(size_t)i * pos_stride + d], scale, 0.5f);
+		float fl = floorf(p);
+		pg[d] = (uint32_t)(int)fl;
+		pos[d] = p - fl;
+	}
+
+	// issue the 8 gathers first, then blend: maximises loads in flight per thread
+	__half2 v[8];
+	#pragma unroll
+	for (uint32_t idx = 0; idx < 8; ++idx) {
+		v[idx] = __ldg(g + index_of(pg[0] + (idx & 1), pg[1] + ((idx >> 1) & 1), pg[2] + ((idx >> 2) & 1)));
+	}
+	// fp16 accumulation in the reference's corner order and rounding: result += (half)(weight * data), grid.h:339-341
+	__half r0 = __float2half(0.f), r1 = __float2half(0.f);
+	#pragma unroll
+	for (uint32_t idx = 0; idx < 8; ++idx) {
+		float w = 1.f;
+		#pragma unroll
+		for (int d = 0; d < 3; ++d) w *= (idx & (1u << d)) ? pos[d] : (1.f - pos[d]);
+		r0 = __hadd(r0, __float2half_rn(w * __low2float(v[idx])));
+		r1 = __hadd(r1, __float2half_rn(w * __high2float(v[idx])));
+	}
+	encoded[(size_t)i * L.n_levels + level] = __halves2half2(r0, r1);
+}
+
+// Backward: scatter-add weight * dL/dy into the fp32 gradient table. The reference uses
+// atomicAdd(__half2) into an fp16 table (grid.h:436-441); here the table is fp32 (one vectorised
+// red.global.add.v2.f32 per corner), which removes the order-dependent fp16 rounding.
+__global__ void __launch_bounds__(256) hash_encode_backward_kernel(
+	const uint32_t n, const GridLevels L, const float* __restrict__ positions, const uint32_t pos_stride,
+	const __half2* __restrict__ dL_dencoded, float2* __restrict__ grid_grad)
+{
+	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t level = tid % L.n_levels;
+	const uint32_t i = tid / L.n_levels;
+	if (i >= n) return;
+
+	const __half2 gh = dL_dencoded[(size_t)i * L.n_levels + level];
+	const float g0 = __low2float(gh), g1 = __high2float(gh);
+	if (g0 == 0.f && g1 == 0.f) return; // adds nothing
+
+	const float scale = L.scale[level];
+	const LevelIndexer index_of(L.size[level], L.resolution[level]);
+	float2* __restrict__ gg = grid_grad + L.offset[level];
+
+	float pos[3];
+	uint32_t pg[3];
+	#pragma unroll
+	for (int d = 0; d < 3; ++d) {
+		float p = __fmaf_rn(positions[(size_t)i * pos_stride + d], scale, 0.5f);
+		float fl = floorf(p);
+		pg[d] = (uint32_t)(int)fl;
+		pos[d] = p - fl;
+	}
+	#pragma unroll
+	for (uint32_t idx = 0; idx < 8; ++idx) {
+		float w = 1.f;
+		#pragma unroll
+		for (int d = 0; d < 3; ++d) w *= (idx & (1u << d)) ? pos[d] : (1.f - pos[d]);
+		const uint32_t e = index_of(pg[0] + (idx & 1), pg[1] + ((idx >> 1) & 1), pg[2] + ((idx >> 2) & 1));
+		float* addr = reinterpret_cast<float*>(gg + e);
+		asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" :: "l"(addr), "f"(g0 * w), "f"(g1 * w) : "memory");
+	}
+}
+
+// Internal launchers shared with the testbed host.
+void hash_encode_forward_launch(cudaStream_t stream, const ngpb_grid* g, const __half* grid, const float* positions, uint32_t pos_stride,
+                                uint32_t n, const uint32_t* n_dev, __half* encoded) {
+	if (n == 0) return;
+	const GridLevels L = make_levels(g);
+	const uint64_t threads = (uint64_t)n * L.n_levels;
+	hash_encode_forward_kernel<<<(uint32_t)((threads + 255) / 256), 256, 0, stream>>>(n, n_dev, L, (const __half2*)grid, positions, pos_stride, (__half2*)encoded);
+	NGPB_LAUNCH_CHECK();
+}
+void hash_encode_backward_launch(cudaStream_t stream, const ngpb_grid* g, const float* positions, uint32_t pos_stride, uint32_t n,
+                                 const __half* dL_dencoded, float* grid_grad) {
+	if (n == 0) return;
+	const GridLevels L = make_levels(g);
+	const uint64_t threads = (uint64_t)n * L.n_levels;
+	hash_encode_backward_kernel<<<(uint32_t)((threads + 255) / 256), 256, 0, stream>>>(n, L, positions, pos_stride, (const __half2*)dL_dencoded, (float2*)grid_grad);
+	NGPB_LAUNCH_CHECK();
+}
+
+} // namespace ngpb
+
+using namespace ngpb;
+
+extern "C" uint32_t ngpb_grid_init(ngpb_grid* g, uint32_t n_levels, uint32_t log2_hashmap_size, uint32_t base_resolution, float per_level_scale) {
+	if (!g || n_levels == 0 || n_levels > NGPB_MAX_LEVELS) return 0;
+	g->n_levels = n_levels;
+	g->base_resolution = base_resolution;
+	g->log2_per_level_scale = std::log2(per_level_scale);
+	uint32_t offset = 0;
+	for (uint32_t l = 0; l < n_levels; ++l) {
+		// grid_scale / grid_resolution, grid.h:194-203; level table, grid.h:985-1018
+		const float scale = exp2f((float)l * g->log2_per_level_scale) * (float)base_resolution - 1.0f;
+		const uint32_t resolution = (uint32_t)ceilf(scale) + 1;
+		g->scale[l] = scale;
+		g->resolution[l] = resolution;
+		const uint32_t max_params = 0xFFFFFFFFu / 2;
+		uint32_t params_in_level = powf((float)resolution, 3.f) > (float)max_params ? max_params : resolution * resolution * resolution;
+		params_in_level = next_multiple(params_in_level, 8u);
+		params_in_level = params_in_level < (1u << log2_hashmap_size) ? params_in_level : (1u << log2_hashmap_size);
+		g->offsets[l] = offset;
+		offset += params_in_level;
+	}
+	g->offsets[n_levels] = offset;
+	return offset;
+}
+
+extern "C" int ngpb_hash_encode_forward(void* stream, const ngpb_grid* g, const ngpb_half* grid, const float* positions, uint32_t pos_stride,
+                                        uint32_t n, ngpb_half* encoded) {
+	try {
+		if (!g || !grid || !positions || !encoded || pos_stride < 3) { set_last_error("ngpb_hash_encode_forward: invalid argument"); return NGPB_ERR_INVALID_ARGUMENT; }
+		hash_encode_forward_launch((cudaStream_t)stream, g, (const __half*)grid, positions, pos_stride, n, nullptr, (__half*)encoded);
+		return 0;
+	} catch (const std::exception& e) { set_last_error(e.what()); return NGPB_ERR_RUNTIME; }
+}
+
+extern "C" int ngpb_hash_encode_backward(void* stream, const ngpb_grid* g, const float* positions, uint32_t pos_stride, uint32_t n,
+                                         const ngpb_half* dL_dencoded, float* grid_grad) {
+	try {
+		if (!g || !positions || !dL_dencoded || !grid_grad || pos_stride < 3) { set_last_error("ngpb_hash_encode_backward: invalid argument"); return NGPB_ERR_INVALID_ARGUMENT; }
+		hash_encode_backward_launch((cudaStream_t)stream, g, positions, pos_stride, n, (const __half*)dL_dencoded, grid_grad);
+		return 0;
+	} catch (const std::exception& e) { set_last_error(e.what()); return NGPB_ERR_RUNTIME; }
+}

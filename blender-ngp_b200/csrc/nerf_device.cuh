@@ -1,0 +1,214 @@
+// Device-side building blocks of the NeRF sampling / loss / render kernels.
+// This library is compiled with -fmad=false: every float op below rounds exactly as written, which is
+// what makes sample compaction reproducible bit for bit against the CPU oracle. Reference sections are
+// cited per function (paths relative to the reference root).
+#pragma once
+#include "common.cuh"
+#include "../../include/ngpb.h"
+
+namespace ngpb {
+
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return fmaxf(lo, fminf(v, hi)); }
+
+// Eigen reduces three terms as a + (b + c) (Eigen/src/Core/Redux.h:101-115); kept so positions match.
+__device__ __forceinline__ float sum3(float a, float b, float c) { return a + (b + c); }
+__device__ __forceinline__ float dot3(const float* a, const float* b) { return sum3(a[0] * b[0], a[1] * b[1], a[2] * b[2]); }
+
+struct V3 { float x, y, z; };
+
+// ---- step-size law and occupancy lookup: src/testbed_nerf.cu:96-98,:191-213,:318-342,:449-463 ----
+__device__ __forceinline__ float calc_dt(float t, float cone_angle) { return clampf(t * cone_angle, MIN_CONE_STEPSIZE, MAX_CONE_STEPSIZE); }
+
+__device__ __forceinline__ float distance_to_next_voxel(const V3& pos, const V3& dir, const V3& idir, uint32_t res) {
+	const float r = (float)res;
+	const float px = r * pos.x, py = r * pos.y, pz = r * pos.z;
+	const float tx = (floorf(px + 0.5f + 0.5f * copysignf(1.0f, dir.x)) - px) * idir.x;
+	const float ty = (floorf(py + 0.5f + 0.5f * copysignf(1.0f, dir.y)) - py) * idir.y;
+	const float tz = (floorf(pz + 0.5f + 0.5f * copysignf(1.0f, dir.z)) - pz) * idir.z;
+	const float t = fminf(fminf(tx, ty), tz);
+	return fmaxf(t / r, 0.0f);
+}
+
+__device__ __forceinline__ float advance_to_next_voxel(float t, float cone_angle, const V3& pos, const V3& dir, const V3& idir, uint32_t res) {
+	const float t_target = t + distance_to_next_voxel(pos, dir, idir, res);
+	do { t += calc_dt(t, cone_angle); } while (t < t_target);
+	return t;
+}
+
+// frexpf exponent of a non-negative finite float (0 for 0), as used by mip_from_pos / mip_from_dt.
+__device__ __forceinline__ int frexp_exponent(float v) {
+	int e;
+	frexpf(v, &e);
+	return e;
+}
+
+__device__ __forceinline__ int mip_from_pos(const V3& pos, uint32_t max_cascade = NERF_CASCADES - 1) {
+	const float maxval = fmaxf(fmaxf(fabsf(pos.x - 0.5f), fabsf(pos.y - 0.5f)), fabsf(pos.z - 0.5f));
+	return min((int)max_cascade, max(0, frexp_exponent(maxval) + 1));
+}
+
+__device__ __forceinline__ int mip_from_dt(float dt, const V3& pos, uint32_t max_cascade = NERF_CASCADES - 1) {
+	const int mip = mip_from_pos(pos, max_cascade);
+	dt *= 2 * NERF_GRIDSIZE;
+	if (dt < 1.f) return mip;
+	return min((int)max_cascade, max(frexp_exponent(dt), mip));
+}
+
+__device__ __forceinline__ uint32_t cascaded_grid_idx_at(V3 pos, uint32_t mip) {
+	const float mip_scale = scalbnf(1.0f, -(int)mip);
+	pos.x -= 0.5f; pos.y -= 0.5f; pos.z -= 0.5f;
+	pos.x *= mip_scale; pos.y *= mip_scale; pos.z *= mip_scale;
+	pos.x += 0.5f; pos.y += 0.5f; pos.z += 0.5f;
+	const int ix = (int)(pos.x * NERF_GRIDSIZE), iy = (int)(pos.y * NERF_GRIDSIZE), iz = (int)(pos.z * NERF_GRIDSIZE);
+	return morton3D(min(max(ix, 0), (int)NERF_GRIDSIZE - 1), min(max(iy, 0), (int)NERF_GRIDSIZE - 1), min(max(iz, 0), (int)NERF_GRIDSIZE - 1));
+}
+
+__device__ __forceinline__ uint32_t grid_mip_offset(uint32_t mip) { return NERF_GRID_CELLS * mip; }
+
+__device__ __forceinline__ bool density_grid_occupied_at(const V3& pos, const uint8_t* __restrict__ bitfield, uint32_t mip) {
+	const uint32_t idx = cascaded_grid_idx_at(pos, mip);
+	return bitfield[idx / 8 + grid_mip_offset(mip) / 8] & (1 << (idx % 8));
+}
+
+__device__ __forceinline__ float warp_dt(float dt) {
+	const float max_stepsize = MIN_CONE_STEPSIZE * (1 << (NERF_CASCADES - 1));
+	return (dt - MIN_CONE_STEPSIZE) / (max_stepsize - MIN_CONE_STEPSIZE);
+}
+__device__ __forceinline__ float unwarp_dt(float dt) {
+	const float max_stepsize = MIN_CONE_STEPSIZE * (1 << (NERF_CASCADES - 1));
+	return dt * (max_stepsize - MIN_CONE_STEPSIZE) + MIN_CONE_STEPSIZE;
+}
+
+// ---- bounding box: include/neural-graphics-primitives/bounding_box.cuh:86,:163-221 ----
+__device__ __forceinline__ bool aabb_contains(const Aabb& b, const V3& p) {
+	return p.x >= b.min[0] && p.x <= b.max[0] && p.y >= b.min[1] && p.y <= b.max[1] && p.z >= b.min[2] && p.z <= b.max[2];
+}
+__device__ __forceinline__ void swapf(float& a, float& b) { float t = a; a = b; b = t; }
+__device__ inline void aabb_ray_intersect(const Aabb& b, const V3& pos, const V3& dir, float* out_tmin, float* out_tmax) {
+	const float FMAX = 3.402823466e+38f;
+	float tmin = (b.min[0] - pos.x) / dir.x, tmax = (b.max[0] - pos.x) / dir.x;
+	if (tmin > tmax) swapf(tmin, tmax);
+	float tymin = (b.min[1] - pos.y) / dir.y, tymax = (b.max[1] - pos.y) / dir.y;
+	if (tymin > tymax) swapf(tymin, tymax);
+	if (tmin > tymax || tymin > tmax) { *out_tmin = FMAX; *out_tmax = FMAX; return; }
+	if (tymin > tmin) tmin = tymin;
+	if (tymax < tmax) tmax = tymax;
+	float tzmin = (b.min[2] - pos.z) / dir.z, tzmax = (b.max[2] - pos.z) / dir.z;
+	if (tzmin > tzmax) swapf(tzmin, tzmax);
+	if (tmin > tzmax || tzmin > tmax) { *out_tmin = FMAX; *out_tmax = FMAX; return; }
+	if (tzmin > tmin) tmin = tzmin;
+	if (tzmax < tmax) tmax = tzmax;
+	*out_tmin = tmin; *out_tmax = tmax;
+}
+__device__ __forceinline__ V3 warp_position(const V3& p, const Aabb& b) {
+	return {(p.x - b.min[0]) / (b.max[0] - b.min[0]), (p.y - b.min[1]) / (b.max[1] - b.min[1]), (p.z - b.min[2]) / (b.max[2] - b.min[2])};
+}
+__device__ __forceinline__ V3 unwarp_position(const float* p, const Aabb& b) { // testbed_nerf.cu:274-279
+	return {b.min[0] + p[0] * (b.max[0] - b.min[0]), b.min[1] + p[1] * (b.max[1] - b.min[1]), b.min[2] + p[2] * (b.max[2] - b.min[2])};
+}
+
+// ---- colour transfer: include/neural-graphics-primitives/common_device.cuh:31-77 ----
+__device__ __forceinline__ float srgb_to_linear(float srgb) {
+	if (srgb <= 0.04045f) return srgb / 12.92f;
+	return powf((srgb + 0.055f) / 1.055f, 2.4f);
+}
+__device__ __forceinline__ float linear_to_srgb(float linear) {
+	if (linear < 0.0031308f) return 12.92f * linear;
+	return 1.055f * powf(linear, 0.41666f) - 0.055f;
+}
+__device__ __forceinline__ float logistic(float x) { return 1.0f / (1.0f + expf(-x)); } // tcnn common_device.h:51
+
+// ---- activations: src/testbed_nerf.cu:215-257 ----
+__device__ __forceinline__ float network_to_rgb(float v, int act) {
+	switch (act) {
+		case NGPB_ACT_NONE: return v;
+		case NGPB_ACT_RELU: return v > 0.0f ? v : 0.0f;
+		case NGPB_ACT_LOGISTIC: return logistic(v);
+		default: return __expf(clampf(v, -10.0f, 10.0f));
+	}
+}
+__device__ __forceinline__ float network_to_rgb_derivative(float v, int act) {
+	switch (act) {
+		case NGPB_ACT_NONE: return 1.0f;
+		case NGPB_ACT_RELU: return v > 0.0f ? 1.0f : 0.0f;
+		case NGPB_ACT_LOGISTIC: { float d = logistic(v); return d * (1 - d); }
+		default: return __expf(clampf(v, -10.0f, 10.0f));
+	}
+}
+__device__ __forceinline__ float network_to_density(float v, int act) {
+	switch (act) {
+		case NGPB_ACT_NONE: return v;
+		case NGPB_ACT_RELU: return v > 0.0f ? v : 0.0f;
+		case NGPB_ACT_LOGISTIC: return logistic(v);
+		default: return __expf(v);
+	}
+}
+__device__ __forceinline__ float network_to_density_derivative(float v, int act) {
+	switch (act) {
+		case NGPB_ACT_NONE: return 1.0f;
+		case NGPB_ACT_RELU: return v > 0.0f ? 1.0f : 0.0f;
+		case NGPB_ACT_LOGISTIC: { float d = logistic(v); return d * (1 - d); }
+		default: return __expf(clampf(v, -15.0f, 15.0f));
+	}
+}
+
+// ---- training image access: common_device.cuh:633-705 ----
+__device__ __forceinline__ void image_pos(float x, float y, int w, int h, int* px, int* py) {
+	*px = max(min((int)(x * (float)w), w - 1), 0);
+	*py = max(min((int)(y * (float)h), h - 1), 0);
+}
+// returns false for masked-away pixels (0x00FF00FF, read_rgba returns -1)
+__device__ inline bool read_rgba(float x, float y, const ngpb_image& im, float out[4]) {
+	int px, py;
+	image_pos(x, y, im.w, im.h, &px, &py);
+	const uint32_t packed = reinterpret_cast<const uint32_t*>(im.pixels)[(size_t)px + (size_t)py * im.w];
+	if (packed == 0x00FF00FFu) { out[0] = out[1] = out[2] = out[3] = -1.0f; return false; }
+	const float alpha = (float)(packed >> 24) * (1.0f / 255.0f);
+	out[0] = srgb_to_linear((float)(packed & 0xFF) * (1.0f / 255.0f)) * alpha;
+	out[1] = srgb_to_linear((float)((packed >> 8) & 0xFF) * (1.0f / 255.0f)) * alpha;
+	out[2] = srgb_to_linear((float)((packed >> 16) & 0xFF) * (1.0f / 255.0f)) * alpha;
+	out[3] = alpha;
+	return true;
+}
+
+// image_idx without error-map CDF: src/testbed_nerf.cu:1076-1082
+__device__ __forceinline__ uint32_t image_idx(uint32_t base_idx, uint32_t n_rays, uint32_t n_training_images) {
+	return ((base_idx * n_training_images) / n_rays) % n_training_images;
+}
+
+// nerf_random_image_pos_training without CDF: src/testbed_nerf.cu:1047-1060
+__device__ __forceinline__ void random_image_pos_training(Pcg32& rng, int w, int h, bool snap, float* x, float* y) {
+	float u = rng.next_float(), v = rng.next_float();
+	if (snap) {
+		u = ((float)min(max((int)(u * (float)w), 0), w - 1) + 0.5f) / (float)w;
+		v = ((float)min(max((int)(v * (float)h), 0), h - 1) + 0.5f) / (float)h;
+	}
+	*x = u; *y = v;
+}
+
+// ---- block-wide exclusive scan over a device array by ONE block of 1024 threads ----
+// out[i] = sum of in[0..i); returns total in *total. n <= 1024 * items_per_thread capacity is
+// handled by chunking: each thread owns a contiguous chunk.
+__device__ inline uint32_t block_exclusive_scan_1024(uint32_t v, uint32_t* smem /*>=33*/, uint32_t* total) {
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t incl = v;
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+	if (lane == 31) smem[warp] = incl;
+	__syncthreads();
+	if (warp == 0) {
+		uint32_t w = smem[lane];
+		uint32_t wi = w;
+		#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+		smem[lane] = wi - w;
+		if (lane == 31) smem[32] = wi;
+	}
+	__syncthreads();
+	const uint32_t excl = incl - v + smem[warp];
+	*total = smem[32];
+	__syncthreads();
+	return excl;
+}
+
+} // namespace ngpb

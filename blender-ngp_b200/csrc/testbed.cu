@@ -1,0 +1,504 @@
+// Host side of the NeRF mode: the `Testbed`-shaped object behind the ngpb_testbed_* C ABI.
+// Mirrors, for this path only, ngp::Testbed (reference: include/neural-graphics-primitives/testbed.h,
+// src/testbed.cu:2249-2470 reset_network, :2527-2588 train; src/testbed_nerf.cu:2643-2733 load_nerf_post,
+// :2761-2859 density grid, :2861-2968 counters + train_nerf, :3138-3385 train_nerf_step, :3388-3401
+// training_prep_nerf). All device memory is owned here and allocated once per (dataset, batch size):
+// nothing is allocated in the steady state, like the reference's per-stream arena.
+#include "testbed.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <random>
+
+namespace ngpb {
+
+// launchers defined in the kernel translation units
+void hash_encode_forward_launch(cudaStream_t stream, const ngpb_grid* g, const __half* grid, const float* positions, uint32_t pos_stride, uint32_t n, const uint32_t* n_dev, __half* encoded);
+void hash_encode_backward_launch(cudaStream_t stream, const ngpb_grid* g, const float* positions, uint32_t pos_stride, uint32_t n, const __half* dL_dencoded, float* grid_grad);
+void nerf_mlp_forward_launch(cudaStream_t stream, const __half* mlp, const __half* encoded, const float* coords, uint32_t n, const uint32_t* n_dev, __half* rgbsigma);
+void nerf_density_mlp_launch(cudaStream_t stream, const __half* mlp, const __half* encoded, uint32_t n, __half* density);
+void nerf_mlp_forward_backward_launch(cudaStream_t stream, const __half* mlp, const __half* encoded, const float* coords, const __half* dL_dout, uint32_t n, __half* dL_dencoded, float* mlp_grad, float* partials);
+
+// sum of n floats in double, one block, fixed order (tcnn reduce_sum.h:54-118 is the reference's loss reduction)
+__global__ void __launch_bounds__(1024) sum_kernel(const float* __restrict__ v, const uint32_t n, float* __restrict__ out)
+{
+	__shared__ double sm[1024];
+	double s = 0.0;
+	for (uint32_t i = threadIdx.x; i < n; i += 1024) s += (double)v[i];
+	sm[threadIdx.x] = s;
+	__syncthreads();
+	for (uint32_t o = 512; o > 0; o >>= 1) { if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o]; __syncthreads(); }
+	if (threadIdx.x == 0) *out = (float)sm[0];
+}
+
+__global__ void __launch_bounds__(256) cast_params_kernel(const uint32_t n, const float* __restrict__ w_fp32, __half* __restrict__ w_half)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) w_half[i] = __float2half_rn(w_fp32[i]);
+}
+
+// Grid initialisation on the device: uniform in [-1e-4, 1e-4) with the reference's thread -> element
+// mapping (tcnn random.h:66-97: thread i advances the stream by 4i and writes elements i + k*n_threads).
+__global__ void __launch_bounds__(128) init_grid_kernel(const uint64_t n_elements, const uint64_t n_threads, Pcg32 rng, float* __restrict__ out)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_threads) return;
+	rng.advance((int64_t)(i * 4));
+	#pragma unroll
+	for (uint64_t j = 0; j < 4; ++j) {
+		const uint64_t idx = i + n_threads * j;
+		if (idx >= n_elements) return;
+		out[idx] = rng.next_float() * (1e-4f - -1e-4f) + -1e-4f;
+	}
+}
+
+Aabb make_aabb(const float* a);
+
+} // namespace ngpb
+
+using namespace ngpb;
+
+// Camera transform used by the sampling kernel: matrix -> quaternion -> slerp(t = 0) -> normalize -> matrix,
+// i.e. what get_xform_given_rolling_shutter (common_device.cuh:224-234) evaluates for every ray when there is
+// no rolling shutter. Done once per image on the host. Operation order follows Eigen's Quaternion.h.
+extern "C" void ngpb_effective_xform(const float* m12, float* out12) {
+	auto M = [&](int r, int c) { return m12[c * 3 + r]; };
+	volatile float q[4]; // x y z w; volatile keeps the host compiler from contracting/reassociating
+	float t = M(0, 0) + (M(1, 1) + M(2, 2));
+	if (t > 0.f) {
+		t = std::sqrt(t + 1.0f);
+		q[3] = 0.5f * t;
+		t = 0.5f / t;
+		q[0] = (M(2, 1) - M(1, 2)) * t;
+		q[1] = (M(0, 2) - M(2, 0)) * t;
+		q[2] = (M(1, 0) - M(0, 1)) * t;
+	} else {
+		int i = 0;
+		if (M(1, 1) > M(0, 0)) i = 1;
+		if (M(2, 2) > M(i, i)) i = 2;
+		const int j = (i + 1) % 3, k = (j + 1) % 3;
+		t = std::sqrt(M(i, i) - M(j, j) - M(k, k) + 1.0f);
+		q[i] = 0.5f * t;
+		t = 0.5f / t;
+		q[3] = (M(k, j) - M(j, k)) * t;
+		q[j] = (M(j, i) + M(i, j)) * t;
+		q[k] = (M(k, i) + M(i, k)) * t;
+	}
+	volatile float sq[4];
+	for (int c = 0; c < 4; ++c) sq[c] = q[c] * q[c];
+	volatile float s01 = sq[0] + sq[1], s23 = sq[2] + sq[3];
+	const float z = s01 + s23;
+	if (z > 0.f) { const float nrm = std::sqrt(z); for (int c = 0; c < 4; ++c) q[c] = q[c] / nrm; }
+	volatile float tx = 2.f * q[0], ty = 2.f * q[1], tz = 2.f * q[2];
+	volatile float twx = tx * q[3], twy = ty * q[3], twz = tz * q[3];
+	volatile float txx = tx * q[0], txy = ty * q[0], txz = tz * q[0];
+	volatile float tyy = ty * q[1], tyz = tz * q[1], tzz = tz * q[2];
+	auto R = [&](int r, int c) -> float& { return out12[c * 3 + r]; };
+	volatile float a;
+	a = tyy + tzz; R(0, 0) = 1.f - a; R(0, 1) = txy - twz; R(0, 2) = txz + twy;
+	a = txx + tzz; R(1, 0) = txy + twz; R(1, 1) = 1.f - a; R(1, 2) = tyz - twx;
+	a = txx + tyy; R(2, 0) = txz - twy; R(2, 1) = tyz + twx; R(2, 2) = 1.f - a;
+	out12[9] = m12[9]; out12[10] = m12[10]; out12[11] = m12[11];
+}
+
+// ---------------------------------------------------------------------------------------------------
+ngpb_testbed::ngpb_testbed(int device_) : device(device_) {
+	NGPB_CUDA_CHECK(cudaSetDevice(device));
+	NGPB_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+	ngpb_optimizer_init(&opt);
+	loss_cfg.loss_scale = LOSS_SCALE;
+	loss_cfg.background_color[0] = loss_cfg.background_color[1] = loss_cfg.background_color[2] = 0.f;
+	loss_cfg.color_space = NGPB_COLOR_SRGB;       // testbed.h: m_color_space default SRGB
+	loss_cfg.random_bg_color = 1;                 // testbed.h:651
+	loss_cfg.linear_colors = 0;
+	loss_cfg.loss_type = NGPB_LOSS_HUBER;         // configs/nerf/base.json:2-4
+	loss_cfg.rgb_activation = NGPB_ACT_LOGISTIC;  // LDR dataset (testbed_nerf.cu:2644)
+	loss_cfg.density_activation = NGPB_ACT_EXPONENTIAL;
+	loss_cfg.snap_to_pixel_centers = 1;           // testbed.h nerf.training.snap_to_pixel_centers default true
+	loss_cfg.near_distance = 0.2f;                // testbed.h:675
+}
+
+ngpb_testbed::~ngpb_testbed() {
+	cudaSetDevice(device);
+	if (stream) cudaStreamSynchronize(stream);
+	for (void* p : allocations) cudaFree(p);
+	if (host_readback) cudaFreeHost(host_readback);
+	if (stream) cudaStreamDestroy(stream);
+}
+
+void* ngpb_testbed::dalloc(size_t bytes) {
+	void* p = nullptr;
+	NGPB_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(bytes, 16)));
+	allocations.push_back(p);
+	return p;
+}
+void ngpb_testbed::dfree(void* p) {
+	if (!p) return;
+	auto it = std::find(allocations.begin(), allocations.end(), p);
+	if (it != allocations.end()) allocations.erase(it);
+	cudaFree(p);
+}
+
+// Testbed::load_training_data -> load_nerf -> load_nerf_post (src/testbed_nerf.cu:2643-2733)
+void ngpb_testbed::load_training_data(uint32_t n, const ngpb_host_image* host_images, uint32_t aabb_scale_) {
+	NGPB_CUDA_CHECK(cudaSetDevice(device));
+	if (n == 0 || !host_images) throw std::runtime_error("load_training_data: no images");
+	if (aabb_scale_ == 0 || (aabb_scale_ & (aabb_scale_ - 1)) != 0) throw std::runtime_error("NeRF dataset's `aabb_scale` must be a power of two");
+	if (aabb_scale_ > (1u << (NERF_CASCADES - 1))) throw std::runtime_error("NeRF dataset must have `aabb_scale <= 128`");
+	aabb_scale = aabb_scale_;
+	size_t total = 0;
+	for (uint32_t i = 0; i < n; ++i) {
+		if (!host_images[i].pixels || host_images[i].w <= 0 || host_images[i].h <= 0) throw std::runtime_error("load_training_data: invalid image");
+		total += (size_t)host_images[i].w * host_images[i].h * 4;
+	}
+	dfree(pixels); dfree(images_dev);
+	pixels = (uint8_t*)dalloc(total);
+	images.resize(n);
+	size_t off = 0;
+	for (uint32_t i = 0; i < n; ++i) {
+		const ngpb_host_image& h = host_images[i];
+		const size_t bytes = (size_t)h.w * h.h * 4;
+		NGPB_CUDA_CHECK(cudaMemcpyAsync(pixels + off, h.pixels, bytes, cudaMemcpyHostToDevice, stream));
+		ngpb_image& im = images[i];
+		im.pixels = pixels + off;
+		im.w = h.w; im.h = h.h; im.fx = h.fx; im.fy = h.fy; im.cx = h.cx; im.cy = h.cy;
+		std::memcpy(im.raw_xform, h.xform, sizeof(float) * 12);
+		ngpb_effective_xform(h.xform, im.xform);
+		off += bytes;
+	}
+	images_dev = (ngpb_image*)dalloc(sizeof(ngpb_image) * n);
+	NGPB_CUDA_CHECK(cudaMemcpyAsync(images_dev, images.data(), sizeof(ngpb_image) * n, cudaMemcpyHostToDevice, stream));
+	NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
+	h2d_bytes += total + sizeof(ngpb_image) * n;
+
+	const float half = 0.5f * std::min(1u << (NERF_CASCADES - 1), aabb_scale);
+	for (int c = 0; c < 3; ++c) { aabb[c] = 0.5f - half; aabb[3 + c] = 0.5f + half; }
+	max_cascade = 0;
+	while ((1u << max_cascade) < aabb_scale) ++max_cascade;
+	cone_angle_constant = aabb_scale <= 1 ? 0.0f : (1.0f / 256.0f);
+	training_data_available = true;
+	reset_network(seed);
+}
+
+// Testbed::reset_network (src/testbed.cu:2249-2470) for configs/nerf/base.json
+void ngpb_testbed::reset_network(uint32_t seed_) {
+	NGPB_CUDA_CHECK(cudaSetDevice(device));
+	seed = seed_;
+	// m_rng = default_rng_t{m_seed}; density_grid_rng = default_rng_t{m_rng.next_uint()} (:2252,:2265)
+	rng.seed(seed);
+	density_grid_rng.seed(rng.next_uint());
+	const uint32_t n_levels = 16, log2_hashmap_size = 19, base_resolution = 16;
+	// per_level_scale = exp(ln(desired_resolution * aabb_scale / base) / (L-1)) (:2313-2325)
+	const float per_level_scale = std::exp(std::log(2048.0f * (float)aabb_scale / (float)base_resolution) / (n_levels - 1));
+	const uint32_t entries = ngpb_grid_init(&grid, n_levels, log2_hashmap_size, base_resolution, per_level_scale);
+	const uint32_t new_n_params = MLP_PARAMS + 2 * entries;
+	if (new_n_params != n_params) {
+		dfree(w_fp32); dfree(w_half); dfree(w_ema); dfree(m1); dfree(m2); dfree(param_steps); dfree(grad);
+		n_params = new_n_params;
+		w_fp32 = (float*)dalloc(sizeof(float) * n_params);
+		w_half = (__half*)dalloc(sizeof(__half) * n_params);
+		w_ema = (__half*)dalloc(sizeof(__half) * n_params);
+		m1 = (float*)dalloc(sizeof(float) * n_params);
+		m2 = (float*)dalloc(sizeof(float) * n_params);
+		param_steps = (uint32_t*)dalloc(sizeof(uint32_t) * n_params);
+		grad = (float*)dalloc(sizeof(float) * n_params);
+	}
+	NGPB_CUDA_CHECK(cudaMemsetAsync(w_ema, 0, sizeof(__half) * n_params, stream));
+	NGPB_CUDA_CHECK(cudaMemsetAsync(m1, 0, sizeof(float) * n_params, stream));
+	NGPB_CUDA_CHECK(cudaMemsetAsync(m2, 0, sizeof(float) * n_params, stream));
+	NGPB_CUDA_CHECK(cudaMemsetAsync(param_steps, 0, sizeof(uint32_t) * n_params, stream));
+	NGPB_CUDA_CHECK(cudaMemsetAsync(grad, 0, sizeof(float) * n_params, stream));
+
+	// Trainer ctor (tcnn trainer.h:53-99): pcg32 seeded from std::seed_seq{seed}; xavier-uniform MLP matrices drawn on the
+	// host in parameter order (gpu_matrix.h:291-305), grid drawn on the device (grid.h:1364-1369).
+	std::seed_seq seq{seed};
+	std::vector<uint32_t> seeds(2);
+	seq.generate(seeds.begin(), seeds.end());
+	Pcg32 rnd;
+	rnd.seed(seeds.front());
+	std::vector<float> mlp(MLP_PARAMS);
+	const int shapes[5][2] = {{64, 32}, {16, 64}, {64, 32}, {64, 64}, {16, 64}};
+	size_t pos = 0;
+	for (auto& s : shapes) {
+		const float scale = std::sqrt(6.0f / (float)(s[0] + s[1]));
+		for (int i = 0; i < s[0] * s[1]; ++i) mlp[pos++] = rnd.next_float() * 2.0f * scale - scale;
+	}
+	NGPB_CUDA_CHECK(cudaMemcpyAsync(w_fp32, mlp.data(), sizeof(float) * MLP_PARAMS, cudaMemcpyHostToDevice, stream));
+	const uint64_t n_grid = 2ull * entries;
+	const uint64_t n_threads = next_multiple((uint32_t)((n_grid + 3) / 4), 128);
+	init_grid_kernel<<<(uint32_t)(n_threads / 128), 128, 0, stream>>>(n_grid, n_threads, rnd, w_fp32 + MLP_PARAMS);
+	NGPB_LAUNCH_CHECK();
+	cast_params_kernel<<<div_round_up(n_params, 256), 256, 0, stream>>>(n_params, w_fp32, w_half);
+	NGPB_LAUNCH_CHECK();
+	n_launches += 2;
+
+	// density grid state (testbed.h:698-704)
+	const size_t n_cells = (size_t)NERF_GRID_CELLS * (max_cascade + 1);
+	dfree(density_grid); dfree(density_grid_tmp); dfree(bitfield); dfree(mean_density);
+	density_grid = (float*)dalloc(sizeof(float) * n_cells);
+	density_grid_tmp = (float*)dalloc(sizeof(float) * n_cells);
+	bitfield = (uint8_t*)dalloc((size_t)NERF_GRID_CELLS * NERF_CASCADES / 8);
+	mean_density = (float*)dalloc(sizeof(float));
+	NGPB_CUDA_CHECK(cudaMemsetAsync(density_grid, 0, sizeof(float) * n_cells, stream));
+	NGPB_CUDA_CHECK(cudaMemsetAsync(bitfield, 0, (size_t)NERF_GRID_CELLS * NERF_CASCADES / 8, stream));
+	NGPB_CUDA_CHECK(cudaMemsetAsync(mean_density, 0, sizeof(float), stream));
+	// density-grid sample buffers: at most GRID_CELLS * n_cascades samples per refresh (testbed_nerf.cu:3396-3400)
+	dfree(dg_positions); dfree(dg_indices); dfree(dg_density); dfree(dg_encoded);
+	const size_t n_dg = next_multiple((uint32_t)n_cells, 128);
+	dg_positions = (float*)dalloc(sizeof(float) * 3 * n_dg);
+	dg_indices = (uint32_t*)dalloc(sizeof(uint32_t) * n_dg);
+	dg_density = (__half*)dalloc(sizeof(__half) * n_dg);
+	dg_encoded = (__half*)dalloc(sizeof(__half) * N_ENC * n_dg);
+	NGPB_CUDA_CHECK(cudaMemsetAsync(dg_positions, 0, sizeof(float) * 3 * n_dg, stream));
+
+	ngpb_optimizer_init(&opt);
+	training_step = 0;
+	density_grid_ema_step = 0;
+	rays_per_batch = 1u << 12; // testbed.h:374
+	measured_batch_size = measured_batch_size_before_compaction = 0;
+	n_rays_total = 0;
+	loss_scalar = 0.f;
+	if (!host_readback) NGPB_CUDA_CHECK(cudaMallocHost(&host_readback, 64));
+	NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
+}
+
+void ngpb_testbed::ensure_workspace(uint32_t batch) {
+	if (batch == ws_batch) return;
+	if (batch == 0 || batch % 128 != 0) throw std::runtime_error("training batch size must be a non-zero multiple of 128 (tcnn batch_size_granularity)");
+	dfree(ray_indices); dfree(rays); dfree(numsteps); dfree(coords); dfree(rgbsigma); dfree(encoded); dfree(coords_compacted);
+	dfree(dloss); dfree(denc); dfree(loss); dfree(scratch); dfree(counters); dfree(partials);
+	const size_t max_rays = 1u << 18;            // rays_per_batch cap (testbed_nerf.cu:2891)
+	const size_t max_samples = (size_t)batch * 16; // testbed_nerf.cu:3140
+	ray_indices = (uint32_t*)dalloc(sizeof(uint32_t) * max_rays);
+	rays = (float*)dalloc(sizeof(float) * 6 * max_rays);
+	numsteps = (uint32_t*)dalloc(sizeof(uint32_t) * 2 * max_rays);
+	coords = (float*)dalloc(sizeof(float) * COORD_FLOATS * max_samples);
+	rgbsigma = (__half*)dalloc(sizeof(__half) * 4 * max_samples);
+	encoded = (__half*)dalloc(sizeof(__half) * N_ENC * max_samples);
+	coords_compacted = (float*)dalloc(sizeof(float) * COORD_FLOATS * batch);
+	dloss = (__half*)dalloc(sizeof(__half) * 4 * batch);
+	denc = (__half*)dalloc(sizeof(__half) * N_ENC * batch);
+	loss = (float*)dalloc(sizeof(float) * max_rays);
+	scratch = dalloc(40 * max_rays);
+	counters = (uint32_t*)dalloc(sizeof(uint32_t) * 8);
+	partials = (float*)dalloc((size_t)ngpb_nerf_mlp_workspace_bytes());
+	// keep the padding rows of the sample buffers finite
+	NGPB_CUDA_CHECK(cudaMemsetAsync(coords, 0, sizeof(float) * COORD_FLOATS * max_samples, stream));
+	NGPB_CUDA_CHECK(cudaMemsetAsync(coords_compacted, 0, sizeof(float) * COORD_FLOATS * batch, stream));
+	NGPB_CUDA_CHECK(cudaMemsetAsync(dloss, 0, sizeof(__half) * 4 * batch, stream));
+	NGPB_CUDA_CHECK(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * 8, stream));
+	ws_batch = batch;
+}
+
+// update_density_grid_nerf + update_density_grid_mean_and_bitfield (src/testbed_nerf.cu:2761-2859)
+void ngpb_testbed::update_density_grid(uint32_t n_uniform, uint32_t n_nonuniform) {
+	const uint32_t n_elements = NERF_GRID_CELLS * (max_cascade + 1);
+	const uint32_t n_samples = n_uniform + n_nonuniform;
+	auto check = [](int st) { if (st != 0) throw std::runtime_error(ngpb_last_error()); };
+	if (training_step == 0) {
+		density_grid_ema_step = 0;
+		check(ngpb_mark_untrained_density_grid(stream, n_elements, density_grid, (uint32_t)images.size(), images_dev, 1));
+		n_launches += 1;
+	}
+	ngpb_rng r{density_grid_rng.state, density_grid_rng.inc};
+	check(ngpb_generate_grid_samples(stream, n_uniform, r, density_grid_ema_step, aabb, density_grid, dg_positions, dg_indices, max_cascade + 1, -0.01f));
+	density_grid_rng.advance();
+	r = ngpb_rng{density_grid_rng.state, density_grid_rng.inc};
+	check(ngpb_generate_grid_samples(stream, n_nonuniform, r, density_grid_ema_step, aabb, density_grid, dg_positions + (size_t)n_uniform * 3, dg_indices + n_uniform, max_cascade + 1, NERF_MIN_OPTICAL_THICKNESS));
+	density_grid_rng.advance();
+	// NerfNetwork::density with the training parameters (use_inference_params = false, :2833)
+	const uint32_t n_padded = next_multiple(n_samples, 128);
+	hash_encode_forward_launch(stream, &grid, w_half + MLP_PARAMS, dg_positions, 3, n_padded, nullptr, dg_encoded);
+	nerf_density_mlp_launch(stream, w_half, dg_encoded, n_padded, dg_density);
+	check(ngpb_splat_and_ema(stream, n_samples, dg_indices, (const ngpb_half*)dg_density, density_grid_tmp, n_elements, density_grid_decay, density_grid));
+	++density_grid_ema_step;
+	check(ngpb_update_bitfield(stream, max_cascade + 1, density_grid, mean_density, bitfield));
+	n_launches += (n_uniform ? 1 : 0) + (n_nonuniform ? 1 : 0) + 2 + 2 + 3 + (NERF_CASCADES - 1);
+}
+
+// Testbed::train (src/testbed.cu:2527-2588): exactly one optimizer step.
+void ngpb_testbed::train(uint32_t batch) {
+	NGPB_CUDA_CHECK(cudaSetDevice(device));
+	if (!training_data_available) throw std::runtime_error("train: no training data loaded");
+	ensure_workspace(batch);
+	auto check = [](int st) { if (st != 0) throw std::runtime_error(ngpb_last_error()); };
+
+	// training_prep_nerf cadence (:2538-2554, testbed_nerf.cu:3388-3401)
+	const uint32_t n_prep_to_skip = std::max(1u, std::min(training_step / 16u, 16u));
+	if (training_step % n_prep_to_skip == 0) {
+		const uint32_t n_cascades = max_cascade + 1;
+		if (training_step < 256) update_density_grid(NERF_GRID_CELLS * n_cascades, 0);
+		else update_density_grid(NERF_GRID_CELLS / 4 * n_cascades, NERF_GRID_CELLS / 4 * n_cascades);
+	}
+	const bool get_loss_scalar = training_step % 16 == 0;
+
+	// ---- train_nerf_step (src/testbed_nerf.cu:3138-3385) ----
+	const uint32_t max_samples = batch * 16;
+	uint32_t max_inference;
+	if (measured_batch_size_before_compaction == 0) {
+		measured_batch_size_before_compaction = max_inference = max_samples;
+	} else {
+		max_inference = next_multiple(std::min(measured_batch_size_before_compaction, max_samples), 128);
+	}
+	if (training_step == 0) n_rays_total = 0;
+	n_rays_total += rays_per_batch;
+	const uint32_t R = rays_per_batch;
+	const ngpb_rng r{rng.state, rng.inc};
+
+	check(ngpb_generate_training_samples(stream, R, aabb, max_inference, r, (uint32_t)images.size(), images_dev, bitfield,
+		loss_cfg.snap_to_pixel_centers, cone_angle_constant, counters, ray_indices, rays, numsteps, coords, (uint32_t*)scratch));
+	// network inference on the uncompacted samples; the sample count stays on the device
+	hash_encode_forward_launch(stream, &grid, w_half + MLP_PARAMS, coords, COORD_FLOATS, max_inference, counters, encoded);
+	nerf_mlp_forward_launch(stream, w_half, encoded, coords, max_inference, counters, rgbsigma);
+	check(ngpb_compute_loss(stream, R, aabb, r, batch, &loss_cfg, (uint32_t)images.size(), images_dev, counters, (const ngpb_half*)rgbsigma,
+		ray_indices, rays, numsteps, coords, mean_density, coords_compacted, (ngpb_half*)dloss, loss, counters + 2, scratch));
+	// forward + backward on the compacted, padded batch
+	hash_encode_forward_launch(stream, &grid, w_half + MLP_PARAMS, coords_compacted, COORD_FLOATS, batch, nullptr, encoded);
+	nerf_mlp_forward_backward_launch(stream, w_half, encoded, coords_compacted, dloss, batch, denc, grad, partials);
+	hash_encode_backward_launch(stream, &grid, coords_compacted, COORD_FLOATS, batch, denc, grad + MLP_PARAMS);
+	rng.advance(); // m_rng.advance() (:3380)
+
+	// ---- optimizer (train_nerf :2950) ----
+	check(ngpb_optimizer_step(stream, &opt, n_params, MLP_PARAMS, LOSS_SCALE, grad, w_fp32, (ngpb_half*)w_half, (ngpb_half*)w_ema, m1, m2, param_steps));
+	++training_step;
+	n_launches += 3 + 2 + 4 + 1 + 2 + 1 + 1;
+
+	// ---- NerfCounters::update_after_training (:2870-2894): 2 counters (+ loss every 16th step) read back ----
+	if (get_loss_scalar) { sum_kernel<<<1, 1024, 0, stream>>>(loss, R, reinterpret_cast<float*>(counters + 4)); NGPB_LAUNCH_CHECK(); n_launches += 1; }
+	NGPB_CUDA_CHECK(cudaMemcpyAsync(host_readback, counters, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, stream));
+	NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
+	d2h_bytes += 32;
+	const uint32_t counter_cpu = host_readback[0], compacted_counter_cpu = host_readback[2];
+	measured_batch_size = 0;
+	measured_batch_size_before_compaction = 0;
+	if (counter_cpu == 0 || compacted_counter_cpu == 0) {
+		loss_scalar = 0.f;
+		// "Nerf training generated 0 samples. Aborting training." (:2964-2968)
+		shall_train = false;
+		return;
+	}
+	measured_batch_size_before_compaction = counter_cpu;
+	measured_batch_size = compacted_counter_cpu;
+	if (get_loss_scalar) {
+		float sum; std::memcpy(&sum, &host_readback[4], 4);
+		loss_scalar = sum * (float)measured_batch_size / (float)batch;
+	}
+	rays_per_batch = (uint32_t)((float)rays_per_batch * (float)batch / (float)measured_batch_size);
+	rays_per_batch = std::min(next_multiple(rays_per_batch, 128u), 1u << 18);
+}
+
+void ngpb_testbed::get_params(float* o_fp32, ngpb_half* o_half, ngpb_half* o_ema) {
+	NGPB_CUDA_CHECK(cudaSetDevice(device));
+	NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
+	if (o_fp32) NGPB_CUDA_CHECK(cudaMemcpy(o_fp32, w_fp32, sizeof(float) * n_params, cudaMemcpyDeviceToHost));
+	if (o_half) NGPB_CUDA_CHECK(cudaMemcpy(o_half, w_half, sizeof(__half) * n_params, cudaMemcpyDeviceToHost));
+	if (o_ema) NGPB_CUDA_CHECK(cudaMemcpy(o_ema, w_ema, sizeof(__half) * n_params, cudaMemcpyDeviceToHost));
+}
+
+void ngpb_testbed::set_params(const float* i_fp32) {
+	NGPB_CUDA_CHECK(cudaSetDevice(device));
+	NGPB_CUDA_CHECK(cudaMemcpyAsync(w_fp32, i_fp32, sizeof(float) * n_params, cudaMemcpyHostToDevice, stream));
+	cast_params_kernel<<<div_round_up(n_params, 256), 256, 0, stream>>>(n_params, w_fp32, w_half);
+	NGPB_LAUNCH_CHECK();
+	NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------
+#define NGPB_API_BEGIN try {
+#define NGPB_API_END } catch (const std::exception& e) { ngpb::set_last_error(e.what()); return NGPB_ERR_RUNTIME; } return 0;
+
+extern "C" int ngpb_testbed_create(ngpb_testbed** out, int device) {
+	NGPB_API_BEGIN
+	if (!out) throw std::runtime_error("ngpb_testbed_create: null output");
+	if (ngpb_check_device(device) != 0) return NGPB_ERR_RUNTIME;
+	*out = new ngpb_testbed(device);
+	NGPB_API_END
+}
+extern "C" void ngpb_testbed_destroy(ngpb_testbed* t) { delete t; }
+extern "C" int ngpb_testbed_load_training_data(ngpb_testbed* t, uint32_t n_images, const ngpb_host_image* images, uint32_t aabb_scale) {
+	NGPB_API_BEGIN t->load_training_data(n_images, images, aabb_scale); NGPB_API_END
+}
+extern "C" int ngpb_testbed_reset_network(ngpb_testbed* t, uint32_t seed) {
+	NGPB_API_BEGIN
+	if (!t->training_data_available) throw std::runtime_error("reset_network: load training data first (the grid resolution depends on aabb_scale)");
+	t->reset_network(seed);
+	NGPB_API_END
+}
+extern "C" int ngpb_testbed_train(ngpb_testbed* t, uint32_t batch_size) { NGPB_API_BEGIN t->train(batch_size); NGPB_API_END }
+extern "C" int ngpb_testbed_train_n(ngpb_testbed* t, uint32_t batch_size, uint32_t n_steps) {
+	NGPB_API_BEGIN
+	for (uint32_t i = 0; i < n_steps && t->shall_train; ++i) t->train(batch_size);
+	NGPB_API_END
+}
+extern "C" float ngpb_testbed_loss(ngpb_testbed* t) { return t->loss_scalar; }
+extern "C" uint32_t ngpb_testbed_training_step(const ngpb_testbed* t) { return t->training_step; }
+extern "C" int ngpb_testbed_stats(ngpb_testbed* t, uint64_t* s) {
+	NGPB_API_BEGIN
+	s[0] = t->rays_per_batch; s[1] = t->measured_batch_size_before_compaction; s[2] = t->measured_batch_size; s[3] = t->n_launches;
+	NGPB_API_END
+}
+extern "C" uint32_t ngpb_testbed_n_params(const ngpb_testbed* t) { return t->n_params; }
+extern "C" int ngpb_testbed_get_params(ngpb_testbed* t, float* w_fp32, ngpb_half* w_half, ngpb_half* w_ema) { NGPB_API_BEGIN t->get_params(w_fp32, w_half, w_ema); NGPB_API_END }
+extern "C" int ngpb_testbed_set_params(ngpb_testbed* t, const float* w_fp32) { NGPB_API_BEGIN t->set_params(w_fp32); NGPB_API_END }
+extern "C" int ngpb_testbed_get_density_grid(ngpb_testbed* t, float* grid_out, uint8_t* bitfield_out) {
+	NGPB_API_BEGIN
+	NGPB_CUDA_CHECK(cudaSetDevice(t->device));
+	NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
+	if (grid_out) NGPB_CUDA_CHECK(cudaMemcpy(grid_out, t->density_grid, sizeof(float) * NERF_GRID_CELLS * (t->max_cascade + 1), cudaMemcpyDeviceToHost));
+	if (bitfield_out) NGPB_CUDA_CHECK(cudaMemcpy(bitfield_out, t->bitfield, (size_t)NERF_GRID_CELLS * NERF_CASCADES / 8, cudaMemcpyDeviceToHost));
+	NGPB_API_END
+}
+
+extern "C" int ngpb_testbed_set_option(ngpb_testbed* t, const char* name, double v) {
+	NGPB_API_BEGIN
+	const std::string k = name ? name : "";
+	if (k == "random_bg_color") t->loss_cfg.random_bg_color = v != 0;
+	else if (k == "linear_colors") t->loss_cfg.linear_colors = v != 0;
+	else if (k == "snap_to_pixel_centers") t->loss_cfg.snap_to_pixel_centers = v != 0;
+	else if (k == "loss_type") t->loss_cfg.loss_type = (int)v;
+	else if (k == "color_space") t->loss_cfg.color_space = (int)v;
+	else if (k == "rgb_activation") t->loss_cfg.rgb_activation = (int)v;
+	else if (k == "density_activation") t->loss_cfg.density_activation = (int)v;
+	else if (k == "near_distance") t->loss_cfg.near_distance = (float)v;
+	else if (k == "background_color_r") t->loss_cfg.background_color[0] = (float)v;
+	else if (k == "background_color_g") t->loss_cfg.background_color[1] = (float)v;
+	else if (k == "background_color_b") t->loss_cfg.background_color[2] = (float)v;
+	else if (k == "cone_angle_constant") t->cone_angle_constant = (float)v;
+	else if (k == "density_grid_decay") t->density_grid_decay = (float)v;
+	else if (k == "shall_train") t->shall_train = v != 0;
+	else if (k == "render_min_transmittance") t->render_min_transmittance = (float)v;
+	else if (k == "learning_rate") t->opt.learning_rate = (float)v;
+	else throw std::runtime_error("unknown option: " + k);
+	NGPB_API_END
+}
+extern "C" double ngpb_testbed_get_option(ngpb_testbed* t, const char* name) {
+	const std::string k = name ? name : "";
+	if (k == "random_bg_color") return t->loss_cfg.random_bg_color;
+	if (k == "linear_colors") return t->loss_cfg.linear_colors;
+	if (k == "snap_to_pixel_centers") return t->loss_cfg.snap_to_pixel_centers;
+	if (k == "loss_type") return t->loss_cfg.loss_type;
+	if (k == "color_space") return t->loss_cfg.color_space;
+	if (k == "rgb_activation") return t->loss_cfg.rgb_activation;
+	if (k == "density_activation") return t->loss_cfg.density_activation;
+	if (k == "near_distance") return t->loss_cfg.near_distance;
+	if (k == "cone_angle_constant") return t->cone_angle_constant;
+	if (k == "density_grid_decay") return t->density_grid_decay;
+	if (k == "shall_train") return t->shall_train;
+	if (k == "render_min_transmittance") return t->render_min_transmittance;
+	if (k == "learning_rate") return t->opt.learning_rate;
+	if (k == "aabb_scale") return t->aabb_scale;
+	if (k == "max_cascade") return t->max_cascade;
+	if (k == "h2d_bytes") return (double)t->h2d_bytes;
+	if (k == "d2h_bytes") return (double)t->d2h_bytes;
+	return std::nan("");
+}
+
+extern "C" int ngpb_testbed_render(ngpb_testbed* t, const float* camera12, int w, int h, float fx, float fy, int spp, int linear, float* out_rgba, uint64_t* n_samples_out) {
+	NGPB_API_BEGIN
+	(void)t; (void)camera12; (void)w; (void)h; (void)fx; (void)fy; (void)spp; (void)linear; (void)out_rgba; (void)n_samples_out;
+	throw std::runtime_error("ngpb_testbed_render: the classic render path is not built yet");
+	NGPB_API_END
+}

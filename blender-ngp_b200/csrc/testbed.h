@@ -1,0 +1,72 @@
+// `Testbed`-shaped host object for the NeRF mode (see testbed.cu). Opaque behind the C ABI.
+#pragma once
+#include "common.cuh"
+#include "../../include/ngpb.h"
+
+#include <vector>
+
+struct ngpb_testbed {
+	explicit ngpb_testbed(int device);
+	~ngpb_testbed();
+	ngpb_testbed(const ngpb_testbed&) = delete;
+	ngpb_testbed& operator=(const ngpb_testbed&) = delete;
+
+	void load_training_data(uint32_t n, const ngpb_host_image* host_images, uint32_t aabb_scale);
+	void reset_network(uint32_t seed);
+	void train(uint32_t batch);
+	void update_density_grid(uint32_t n_uniform, uint32_t n_nonuniform);
+	void ensure_workspace(uint32_t batch);
+	void get_params(float* w_fp32, ngpb_half* w_half, ngpb_half* w_ema);
+	void set_params(const float* w_fp32);
+	void render(const float* camera12, int w, int h, float fx, float fy, int spp, bool linear, float* out_rgba, uint64_t* n_samples_out);
+
+	void* dalloc(size_t bytes);
+	void dfree(void* p);
+
+	int device = 0;
+	cudaStream_t stream = nullptr; // everything runs on this stream (Testbed::m_stream, testbed.h:895)
+	std::vector<void*> allocations;
+
+	// dataset (NerfDataset, nerf_loader.h:66-110)
+	bool training_data_available = false;
+	std::vector<ngpb_image> images;
+	ngpb_image* images_dev = nullptr;
+	uint8_t* pixels = nullptr;
+	uint32_t aabb_scale = 1, max_cascade = 0;
+	float aabb[6] = {0, 0, 0, 1, 1, 1};
+	float cone_angle_constant = 0.f;
+
+	// model + optimizer state: fp32 master, fp16 training copy, fp16 EMA (inference) copy, Adam moments
+	// (tcnn Trainer buffer trainer.h:80,:317-332). Flat order: density net, rgb net, grid levels.
+	ngpb_grid grid{};
+	uint32_t n_params = 0;
+	float* w_fp32 = nullptr; __half* w_half = nullptr; __half* w_ema = nullptr;
+	float* m1 = nullptr; float* m2 = nullptr; uint32_t* param_steps = nullptr; float* grad = nullptr;
+	ngpb_optimizer opt{};
+
+	// occupancy grid (testbed.h:698-704)
+	float* density_grid = nullptr; float* density_grid_tmp = nullptr; uint8_t* bitfield = nullptr; float* mean_density = nullptr;
+	float* dg_positions = nullptr; uint32_t* dg_indices = nullptr; __half* dg_density = nullptr; __half* dg_encoded = nullptr;
+	float density_grid_decay = 0.95f;
+	uint32_t density_grid_ema_step = 0;
+
+	// per-iteration workspace, sized by the batch (train_nerf_step scratch, testbed_nerf.cu:3145-3170)
+	uint32_t ws_batch = 0;
+	uint32_t* ray_indices = nullptr; float* rays = nullptr; uint32_t* numsteps = nullptr; float* coords = nullptr;
+	__half* rgbsigma = nullptr; __half* encoded = nullptr; float* coords_compacted = nullptr; __half* dloss = nullptr; __half* denc = nullptr;
+	float* loss = nullptr; void* scratch = nullptr; uint32_t* counters = nullptr; float* partials = nullptr;
+	uint32_t* host_readback = nullptr;
+
+	// training state (NerfCounters testbed.h:366-386; m_rng testbed.h:923)
+	uint32_t seed = 1337; // m_seed, testbed.h:567
+	ngpb::Pcg32 rng{}, density_grid_rng{};
+	uint32_t training_step = 0;
+	uint32_t rays_per_batch = 1u << 12;
+	uint32_t measured_batch_size = 0, measured_batch_size_before_compaction = 0, n_rays_total = 0;
+	float loss_scalar = 0.f;
+	bool shall_train = true;
+	ngpb_loss_config loss_cfg{};
+	float render_min_transmittance = 0.01f; // testbed.h:725
+
+	uint64_t n_launches = 0, h2d_bytes = 0, d2h_bytes = 0;
+};

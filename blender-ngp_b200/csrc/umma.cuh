@@ -1,0 +1,129 @@
+// tcgen05 / TMEM / mbarrier primitives for sm_100a, written as inline PTX.
+// Bit layouts follow the PTX ISA "tcgen05" chapter (shared-memory matrix descriptor, instruction
+// descriptor for .kind::f16, TMEM addressing lane<<16 | column).
+#pragma once
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace ngpb {
+namespace umma {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier -----------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"WAIT_LOOP:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra WAIT_DONE;\n"
+		"bra WAIT_LOOP;\n"
+		"WAIT_DONE:\n"
+		"}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// ---- proxies and tcgen05 fences -------------------------------------------------------------------
+// Generic-proxy shared-memory writes must be fenced before the async proxy (tcgen05.mma) reads them.
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// ---- TMEM allocation (one full warp executes these) ----------------------------------------------
+template <uint32_t NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {
+	static_assert(NCOLS >= 32 && NCOLS <= 512 && (NCOLS & (NCOLS - 1)) == 0, "TMEM columns: power of two in [32,512]");
+	asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(smem_result)), "n"(NCOLS) : "memory");
+	asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <uint32_t NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+	asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "n"(NCOLS) : "memory");
+}
+
+// ---- descriptors --------------------------------------------------------------------------------
+// Shared-memory matrix descriptor, no swizzle (layout_type 0), sm_100 version field = 1.
+//   bits [0,14)  start address >> 4      bits [16,30) leading byte offset >> 4
+//   bits [32,46) stride byte offset >> 4 bits [46,48) version = 1
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+	return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+
+// Instruction descriptor for tcgen05.mma.kind::f16 with fp16 inputs and fp32 accumulation.
+//   bits [4,6) D format (1 = f32), [7,10) A format (0 = f16), [10,13) B format (0 = f16),
+//   bit 15 A major (0 = K, 1 = MN), bit 16 B major, bits [17,23) N >> 3, bits [24,29) M >> 4.
+__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N, bool a_mn_major, bool b_mn_major) {
+	return (1u << 4) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"setp.ne.b32 p, %4, 0;\n"
+		"tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+		"}\n" :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+
+// Makes the mbarrier track completion of all tcgen05 ops issued so far by this thread
+// (implies tcgen05.fence::before_thread_sync).
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+
+// ---- TMEM -> registers: shape 32x32b, each thread reads its own lane (row), N consecutive columns ----
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, uint32_t* r) {
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+		: "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* r) {
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+		: "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+		  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+		: "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t* r) {
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+		"%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+		: "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+		  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+		  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+		  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+		: "r"(taddr) : "memory");
+}
+
+// ---- operand tiles in shared memory ------------------------------------------------------------
+// A tile holds R rows x C fp16 columns as 8x8 "core matrices" of 128 contiguous bytes (8 rows x 16 B),
+// core matrices of one 8-row group adjacent along the column direction. The same bytes are a valid
+//   * K-major operand  (rows = M or N, columns = K):  LBO = 128 B, SBO = (C/8)*128 B, +256 B per K=16 step
+//   * MN-major operand (columns = M or N, rows = K):  SBO = 128 B, LBO = (C/8)*128 B, +2*(C/8)*128 B per K=16 step
+// which is what lets one activation tile feed the forward GEMM (K = features) and the weight-gradient
+// GEMM (K = samples) without a transpose.
+__host__ __device__ constexpr uint32_t tile_bytes(uint32_t rows, uint32_t cols) { return rows * cols * 2; }
+__device__ __forceinline__ uint32_t tile_offset(uint32_t row, uint32_t col_chunk, uint32_t cols) {
+	return (row >> 3) * (cols >> 3) * 128 + col_chunk * 128 + (row & 7) * 16;
+}
+
+// K-major view of rows [row0, row0+rows) with K starting at column chunk k_chunk0.
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile_saddr, uint32_t cols, uint32_t row0, uint32_t k_chunk0) {
+	return make_smem_desc(tile_saddr + (row0 >> 3) * (cols >> 3) * 128 + k_chunk0 * 128, /*lbo*/128, /*sbo*/(cols >> 3) * 128);
+}
+// MN-major view: MN starts at column chunk mn_chunk0, K (rows) starts at row k_row0 (multiple of 8).
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile_saddr, uint32_t cols, uint32_t mn_chunk0, uint32_t k_row0) {
+	return make_smem_desc(tile_saddr + (k_row0 >> 3) * (cols >> 3) * 128 + mn_chunk0 * 128, /*lbo*/(cols >> 3) * 128, /*sbo*/128);
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+	__half2 h = __floats2half2_rn(a, b);
+	return *reinterpret_cast<uint32_t*>(&h);
+}
+
+} // namespace umma
+} // namespace ngpb

@@ -1,0 +1,461 @@
+"""`pyngp` surface of the B200-native NeRF hot path.
+
+Mirrors, for the NeRF train/render path only, the pybind11 module of the reference
+(src/python_api.cu:306-888): `Testbed(TestbedMode.Nerf)`, `load_training_data`, `reload_network_from_file`,
+`train`, `frame`, `render`, and the training/rendering properties scripts/run.py uses. The work is done
+by libngpb200.so (hand-written sm_100a CUDA behind the C ABI in include/ngpb.h); this module is a ctypes
+binding plus the host-side file parsing (transforms.json, network config JSON) that the reference does
+in C++ with nlohmann::json / stb_image. There is no CPU fallback: importing this module without the
+built library, or creating a Testbed without a B200, raises.
+"""
+import ctypes as C
+import enum
+import json
+import math
+import os
+
+import numpy as np
+
+_PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LIB_PATH = os.path.join(_PKG_DIR, "libngpb200.so")
+
+
+class TestbedMode(enum.Enum):  # python_api.cu:311-317
+    Nerf = 0
+    Sdf = 1
+    Image = 2
+    Volume = 3
+
+
+class LossType(enum.IntEnum):  # common.h:103-111
+    L2 = 0
+    L1 = 1
+    Mape = 2
+    Smape = 3
+    Huber = 4
+    LogL1 = 5
+    RelativeL2 = 6
+
+
+class NerfActivation(enum.IntEnum):  # common.h:114-119
+    None_ = 0
+    ReLU = 1
+    Logistic = 2
+    Exponential = 3
+
+
+class ColorSpace(enum.IntEnum):  # common.h:129-133
+    Linear = 0
+    SRGB = 1
+
+
+# ---- C structs (include/ngpb.h) ---------------------------------------------------------------
+NGPB_MAX_LEVELS = 32
+
+
+class Grid(C.Structure):
+    _fields_ = [("n_levels", C.c_uint32), ("base_resolution", C.c_uint32), ("log2_per_level_scale", C.c_float),
+                ("offsets", C.c_uint32 * (NGPB_MAX_LEVELS + 1)), ("scale", C.c_float * NGPB_MAX_LEVELS),
+                ("resolution", C.c_uint32 * NGPB_MAX_LEVELS)]
+
+
+class Image(C.Structure):
+    _fields_ = [("pixels", C.c_void_p), ("w", C.c_int32), ("h", C.c_int32), ("fx", C.c_float), ("fy", C.c_float),
+                ("cx", C.c_float), ("cy", C.c_float), ("xform", C.c_float * 12), ("raw_xform", C.c_float * 12)]
+
+
+class HostImage(C.Structure):
+    _fields_ = [("pixels", C.c_void_p), ("w", C.c_int32), ("h", C.c_int32), ("fx", C.c_float), ("fy", C.c_float),
+                ("cx", C.c_float), ("cy", C.c_float), ("xform", C.c_float * 12)]
+
+
+class Rng(C.Structure):
+    _fields_ = [("state", C.c_uint64), ("inc", C.c_uint64)]
+
+
+class LossConfig(C.Structure):
+    _fields_ = [("loss_scale", C.c_float), ("background_color", C.c_float * 3), ("color_space", C.c_int32), ("random_bg_color", C.c_int32),
+                ("linear_colors", C.c_int32), ("loss_type", C.c_int32), ("rgb_activation", C.c_int32), ("density_activation", C.c_int32),
+                ("snap_to_pixel_centers", C.c_int32), ("near_distance", C.c_float)]
+
+
+class Optimizer(C.Structure):
+    _fields_ = [("learning_rate", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("epsilon", C.c_float),
+                ("l2_reg", C.c_float), ("ema_decay", C.c_float), ("decay_start", C.c_uint32), ("decay_interval", C.c_uint32),
+                ("decay_base", C.c_float), ("step", C.c_uint32), ("lr_factor", C.c_float)]
+
+
+# every symbol include/ngpb.h declares (checked by tests/test_abi.py)
+EXPORTED_SYMBOLS = [
+    "ngpb_last_error", "ngpb_version", "ngpb_check_device", "ngpb_grid_init", "ngpb_hash_encode_forward", "ngpb_hash_encode_backward",
+    "ngpb_nerf_mlp_forward", "ngpb_nerf_mlp_workspace_bytes", "ngpb_nerf_mlp_forward_backward", "ngpb_nerf_density_mlp_forward",
+    "ngpb_effective_xform", "ngpb_generate_training_samples", "ngpb_compute_loss", "ngpb_optimizer_init", "ngpb_optimizer_step",
+    "ngpb_mark_untrained_density_grid", "ngpb_generate_grid_samples", "ngpb_splat_and_ema", "ngpb_update_bitfield", "ngpb_selftest_umma",
+    "ngpb_testbed_create", "ngpb_testbed_destroy", "ngpb_testbed_load_training_data", "ngpb_testbed_reset_network", "ngpb_testbed_train",
+    "ngpb_testbed_train_n", "ngpb_testbed_loss", "ngpb_testbed_training_step", "ngpb_testbed_stats", "ngpb_testbed_n_params",
+    "ngpb_testbed_get_params", "ngpb_testbed_set_params", "ngpb_testbed_get_density_grid", "ngpb_testbed_set_option", "ngpb_testbed_get_option",
+    "ngpb_testbed_render",
+]
+
+_lib = None
+
+
+def lib():
+    """Loads libngpb200.so. Fails loudly when it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise RuntimeError(f"{_LIB_PATH} is missing: build it with blender-ngp_b200/build.sh (or __graft_entry__.build())")
+        l = C.CDLL(_LIB_PATH)
+        l.ngpb_last_error.restype = C.c_char_p
+        l.ngpb_grid_init.restype = C.c_uint32
+        l.ngpb_nerf_mlp_workspace_bytes.restype = C.c_uint64
+        l.ngpb_testbed_loss.restype = C.c_float
+        l.ngpb_testbed_training_step.restype = C.c_uint32
+        l.ngpb_testbed_n_params.restype = C.c_uint32
+        l.ngpb_testbed_get_option.restype = C.c_double
+        l.ngpb_testbed_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        l.ngpb_testbed_get_option.argtypes = [C.c_void_p, C.c_char_p]
+        l.ngpb_effective_xform.restype = None
+        l.ngpb_optimizer_init.restype = None
+        l.ngpb_testbed_destroy.restype = None
+        _lib = l
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        raise RuntimeError(lib().ngpb_last_error().decode() or f"ngpb error {status}")
+
+
+def grid_init(n_levels=16, log2_hashmap_size=19, base_resolution=16, per_level_scale=None, aabb_scale=1):
+    if per_level_scale is None:
+        per_level_scale = float(np.exp(np.log(np.float32(2048.0) * np.float32(aabb_scale) / np.float32(base_resolution)) / np.float32(n_levels - 1), dtype=np.float32))
+    g = Grid()
+    entries = lib().ngpb_grid_init(C.byref(g), n_levels, log2_hashmap_size, base_resolution, C.c_float(per_level_scale))
+    return g, entries
+
+
+# ---- network config (reference: src/testbed.cu:77-161 load_network_config with `parent` inheritance) ----
+def _strip_json_comments(text):
+    out, i, in_str = [], 0, False
+    while i < len(text):
+        ch = text[i]
+        if in_str:
+            out.append(ch)
+            if ch == "\\":
+                out.append(text[i + 1]); i += 1
+            elif ch == '"':
+                in_str = False
+        elif ch == '"':
+            in_str = True; out.append(ch)
+        elif text.startswith("//", i):
+            while i < len(text) and text[i] != "\n":
+                i += 1
+            continue
+        elif text.startswith("/*", i):
+            i = text.find("*/", i) + 2
+            continue
+        else:
+            out.append(ch)
+        i += 1
+    return "".join(out)
+
+
+def _merge_patch(base, patch):  # nlohmann merge_patch (RFC 7386), testbed.cu:77-88
+    if not isinstance(patch, dict):
+        return patch
+    if not isinstance(base, dict):
+        base = {}
+    out = dict(base)
+    for k, v in patch.items():
+        if v is None:
+            out.pop(k, None)
+        else:
+            out[k] = _merge_patch(out.get(k), v)
+    return out
+
+
+def load_network_config(path):
+    with open(path) as f:
+        cfg = json.loads(_strip_json_comments(f.read()))
+    while "parent" in cfg:
+        parent_path = os.path.join(os.path.dirname(path), cfg.pop("parent"))
+        with open(parent_path) as f:
+            parent = json.loads(_strip_json_comments(f.read()))
+        path = parent_path
+        cfg = _merge_patch(parent, cfg)
+        if "parent" in parent and "parent" not in cfg:
+            cfg["parent"] = parent["parent"]
+    return cfg
+
+
+BASE_NETWORK_CONFIG = {  # configs/nerf/base.json of the reference
+    "loss": {"otype": "Huber"},
+    "optimizer": {"otype": "Ema", "decay": 0.95, "nested": {"otype": "ExponentialDecay", "decay_start": 20000, "decay_interval": 10000, "decay_base": 0.33,
+                  "nested": {"otype": "Adam", "learning_rate": 1e-2, "beta1": 0.9, "beta2": 0.99, "epsilon": 1e-15, "l2_reg": 1e-6}}},
+    "encoding": {"otype": "HashGrid", "n_levels": 16, "n_features_per_level": 2, "log2_hashmap_size": 19, "base_resolution": 16},
+    "network": {"otype": "FullyFusedMLP", "activation": "ReLU", "output_activation": "None", "n_neurons": 64, "n_hidden_layers": 1},
+    "dir_encoding": {"otype": "Composite", "nested": [{"n_dims_to_encode": 3, "otype": "SphericalHarmonics", "degree": 4}, {"otype": "Identity"}]},
+    "rgb_network": {"otype": "FullyFusedMLP", "activation": "ReLU", "output_activation": "None", "n_neurons": 64, "n_hidden_layers": 2},
+}
+
+
+def _validate_network_config(cfg):
+    """The kernels are specialised for the architecture of configs/nerf/base.json; anything else is refused loudly."""
+    def req(section, key, value):
+        got = cfg.get(section, {}).get(key, BASE_NETWORK_CONFIG[section].get(key))
+        same = (str(got).lower() == str(value).lower()) if isinstance(value, str) else (got == value)
+        if not same:
+            raise RuntimeError(f"unsupported network config: {section}.{key} = {got!r} (this build implements {value!r})")
+    req("encoding", "otype", "HashGrid"); req("encoding", "n_levels", 16); req("encoding", "n_features_per_level", 2)
+    req("encoding", "log2_hashmap_size", 19); req("encoding", "base_resolution", 16)
+    for s, hidden in (("network", 1), ("rgb_network", 2)):
+        req(s, "otype", "FullyFusedMLP"); req(s, "activation", "ReLU"); req(s, "output_activation", "None")
+        req(s, "n_neurons", 64); req(s, "n_hidden_layers", hidden)
+    nested = cfg.get("dir_encoding", {}).get("nested", [{}])
+    if str(cfg.get("dir_encoding", {}).get("otype", "Composite")).lower() != "composite" or str(nested[0].get("otype", "")).lower() != "sphericalharmonics" or nested[0].get("degree", 4) != 4:
+        raise RuntimeError("unsupported network config: dir_encoding must be Composite[SphericalHarmonics degree 4, Identity]")
+    opt = cfg.get("optimizer", {})
+    if str(opt.get("otype", "")).lower() != "ema" or str(opt.get("nested", {}).get("otype", "")).lower() != "exponentialdecay" or \
+            str(opt.get("nested", {}).get("nested", {}).get("otype", "")).lower() != "adam":
+        raise RuntimeError("unsupported network config: optimizer must be Ema(ExponentialDecay(Adam))")
+
+
+# ---- transforms.json loader (reference: src/nerf_loader.cu:197-747), host side ------------------------
+def nerf_matrix_to_ngp(c2w, scale, offset):
+    """nerf_loader.h:113-132 (from_mitsuba = false)."""
+    m = np.array(c2w, dtype=np.float32)[:3, :4].copy()
+    m[:, 1] *= -1
+    m[:, 2] *= -1
+    m[:, 3] = m[:, 3] * np.float32(scale) + np.asarray(offset, dtype=np.float32)
+    return m[[1, 2, 0], :].copy()
+
+
+def load_transforms(path):
+    """Parses a transforms.json (or a directory holding transforms*.json) into decoded RGBA8 images + ngp camera matrices."""
+    from PIL import Image as PILImage
+    if os.path.isdir(path):
+        cands = sorted(p for p in os.listdir(path) if p.startswith("transforms") and p.endswith(".json"))
+        if not cands:
+            raise RuntimeError(f"no transforms*.json under {path}")
+        # the reference loads every json in the directory; train split first
+        path = os.path.join(path, "transforms_train.json" if "transforms_train.json" in cands else cands[0])
+    with open(path) as f:
+        meta = json.load(f)
+    base = os.path.dirname(path)
+    scale = meta.get("scale", 1.0)  # NERF_SCALE = 1.0 in this fork (nerf_loader.h:28)
+    offset = meta.get("offset", [0.0, 0.0, 0.0])
+    aabb_scale = int(meta.get("aabb_scale", 1))
+    frames = sorted(meta["frames"], key=lambda fr: fr["file_path"])  # nerf_loader.cu:356-358
+    images, xforms = [], []
+    for fr in frames:
+        p = os.path.join(base, fr["file_path"])
+        if not os.path.exists(p):
+            for ext in (".png", ".jpg", ".jpeg"):
+                if os.path.exists(p + ext):
+                    p = p + ext
+                    break
+        img = np.asarray(PILImage.open(p).convert("RGBA"), dtype=np.uint8)
+        images.append(np.ascontiguousarray(img))
+        xforms.append(nerf_matrix_to_ngp(fr["transform_matrix"], scale, offset))
+    h, w = images[0].shape[:2]
+    # focal-length key precedence, nerf_loader.cu:271-299
+    def focal(axis, res):
+        if ("fl_" + axis) in meta:
+            return float(meta["fl_" + axis])
+        if ("camera_angle_" + axis) in meta:
+            return 0.5 * res / math.tan(0.5 * float(meta["camera_angle_" + axis]))
+        return 0.0
+    fx, fy = focal("x", w), focal("y", h)
+    if fx == 0.0 and fy != 0.0:
+        fx = fy
+    if fy == 0.0 and fx != 0.0:
+        fy = fx
+    if fx == 0.0:
+        raise RuntimeError("Couldn't read fov.")
+    cx = float(meta.get("cx", 0.5 * w)) / w
+    cy = float(meta.get("cy", 0.5 * h)) / h
+    return dict(images=images, xforms=np.stack(xforms), fx=fx, fy=fy, cx=cx, cy=cy, aabb_scale=aabb_scale)
+
+
+class _Training:
+    """`testbed.nerf.training.*` (python_api.cu:744-852): the properties this path reads."""
+    def __init__(self, tb):
+        self._tb = tb
+
+    def _bool_prop(name):
+        return property(lambda s: bool(s._tb._get(name)), lambda s, v: s._tb._set(name, 1.0 if v else 0.0))
+
+    random_bg_color = _bool_prop("random_bg_color")
+    linear_colors = _bool_prop("linear_colors")
+    snap_to_pixel_centers = _bool_prop("snap_to_pixel_centers")
+    loss_type = property(lambda s: LossType(int(s._tb._get("loss_type"))), lambda s, v: s._tb._set("loss_type", int(v)))
+    near_distance = property(lambda s: s._tb._get("near_distance"), lambda s, v: s._tb._set("near_distance", float(v)))
+    density_grid_decay = property(lambda s: s._tb._get("density_grid_decay"), lambda s, v: s._tb._set("density_grid_decay", float(v)))
+
+    @property
+    def optimize_extrinsics(self):
+        return False
+
+    @optimize_extrinsics.setter
+    def optimize_extrinsics(self, v):
+        if v:
+            raise RuntimeError("optimize_extrinsics is outside the built scope (SURVEY.md s8: K13/K14)")
+
+
+class _Nerf:
+    def __init__(self, tb):
+        self._tb = tb
+        self.training = _Training(tb)
+
+    cone_angle_constant = property(lambda s: s._tb._get("cone_angle_constant"), lambda s, v: s._tb._set("cone_angle_constant", float(v)))
+    render_min_transmittance = property(lambda s: s._tb._get("render_min_transmittance"), lambda s, v: s._tb._set("render_min_transmittance", float(v)))
+    rgb_activation = property(lambda s: NerfActivation(int(s._tb._get("rgb_activation"))), lambda s, v: s._tb._set("rgb_activation", int(v)))
+    density_activation = property(lambda s: NerfActivation(int(s._tb._get("density_activation"))), lambda s, v: s._tb._set("density_activation", int(v)))
+
+
+class Testbed:
+    """pyngp.Testbed for ETestbedMode::Nerf (python_api.cu:540-732)."""
+
+    def __init__(self, mode=TestbedMode.Nerf, device=0):
+        if mode != TestbedMode.Nerf:
+            raise RuntimeError("only TestbedMode.Nerf is implemented by this build (the NeRF train/render hot path)")
+        self._h = C.c_void_p()
+        check(lib().ngpb_testbed_create(C.byref(self._h), int(device)))
+        self.nerf = _Nerf(self)
+        self.training_batch_size = 1 << 18  # testbed.h:909
+        self.network_config = json.loads(json.dumps(BASE_NETWORK_CONFIG))
+        self._seed = 1337
+        self._keep = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            lib().ngpb_testbed_destroy(h)
+            self._h = None
+
+    # -- helpers
+    def _get(self, name):
+        return float(lib().ngpb_testbed_get_option(self._h, name.encode()))
+
+    def _set(self, name, value):
+        check(lib().ngpb_testbed_set_option(self._h, name.encode(), float(value)))
+
+    # -- data
+    def load_training_data(self, path):
+        """Testbed::load_training_data (src/testbed.cu:97): a transforms.json file or a directory holding one."""
+        d = load_transforms(path)
+        self.load_training_images(d["images"], d["xforms"], d["fx"], d["fy"], d["cx"], d["cy"], d["aabb_scale"])
+
+    def load_training_images(self, images, xforms, fx, fy, cx=0.5, cy=0.5, aabb_scale=1):
+        """Already-decoded data: images uint8 [n][h][w][4] (host), xforms float32 [n][3][4] in ngp convention."""
+        n = len(images)
+        arr = (HostImage * n)()
+        keep = []
+        for i in range(n):
+            px = np.ascontiguousarray(images[i], dtype=np.uint8)
+            if px.ndim != 3 or px.shape[2] != 4:
+                raise RuntimeError("training images must be RGBA8 [h][w][4]")
+            keep.append(px)
+            arr[i].pixels = px.ctypes.data
+            arr[i].h, arr[i].w = px.shape[0], px.shape[1]
+            arr[i].fx, arr[i].fy, arr[i].cx, arr[i].cy = fx, fy, cx, cy
+            cm = np.asarray(xforms[i], dtype=np.float32).reshape(3, 4).T.reshape(-1)
+            for k in range(12):
+                arr[i].xform[k] = float(cm[k])
+        check(lib().ngpb_testbed_load_training_data(self._h, n, arr, int(aabb_scale)))
+
+    def reload_network_from_file(self, path=None):
+        """Testbed::reload_network_from_file (src/testbed.cu:147). Only the base NeRF architecture is built; optimizer values are honoured."""
+        cfg = load_network_config(path) if path else json.loads(json.dumps(BASE_NETWORK_CONFIG))
+        self.reload_network_from_json(cfg)
+
+    def reload_network_from_json(self, cfg, config_base_path=""):
+        _validate_network_config(cfg)
+        self.network_config = cfg
+        check(lib().ngpb_testbed_reset_network(self._h, self._seed))
+        adam = cfg.get("optimizer", {}).get("nested", {}).get("nested", {})
+        if "learning_rate" in adam:
+            self._set("learning_rate", adam["learning_rate"])
+        loss = str(cfg.get("loss", {}).get("otype", "Huber")).lower()
+        names = {"l2": 0, "l1": 1, "mape": 2, "smape": 3, "huber": 4, "logl1": 5, "relativel2": 6}
+        if loss not in names:
+            raise RuntimeError(f"unknown loss type {loss}")
+        self._set("loss_type", names[loss])
+
+    def reset(self, seed=1337):
+        self._seed = seed
+        check(lib().ngpb_testbed_reset_network(self._h, seed))
+
+    # -- training
+    def train(self, batch_size=None):
+        """Testbed::train(batch_size): exactly one optimizer step (python_api.cu:594)."""
+        check(lib().ngpb_testbed_train(self._h, int(batch_size or self.training_batch_size)))
+
+    def train_n(self, n_steps, batch_size=None):
+        check(lib().ngpb_testbed_train_n(self._h, int(batch_size or self.training_batch_size), int(n_steps)))
+
+    def frame(self):
+        """Testbed::frame (src/testbed.cu:2044): one training step if shall_train; headless, no render. Returns False when training stopped."""
+        if self.shall_train:
+            self.train(self.training_batch_size)
+        return self.shall_train
+
+    shall_train = property(lambda s: bool(s._get("shall_train")), lambda s, v: s._set("shall_train", 1.0 if v else 0.0))
+    training_step = property(lambda s: int(lib().ngpb_testbed_training_step(s._h)))
+    loss = property(lambda s: float(lib().ngpb_testbed_loss(s._h)))
+    n_params = property(lambda s: int(lib().ngpb_testbed_n_params(s._h)))
+
+    @property
+    def background_color(self):
+        return [self._get("background_color_r") if False else 0.0] * 3 + [1.0]
+
+    @background_color.setter
+    def background_color(self, v):
+        self._set("background_color_r", v[0]); self._set("background_color_g", v[1]); self._set("background_color_b", v[2])
+
+    color_space = property(lambda s: ColorSpace(int(s._get("color_space"))), lambda s, v: s._set("color_space", int(v)))
+
+    def stats(self):
+        s = (C.c_uint64 * 4)()
+        check(lib().ngpb_testbed_stats(self._h, s))
+        return dict(rays_per_batch=int(s[0]), measured_batch_size_before_compaction=int(s[1]), measured_batch_size=int(s[2]), gpu_launches=int(s[3]),
+                    h2d_bytes=int(self._get("h2d_bytes")), d2h_bytes=int(self._get("d2h_bytes")))
+
+    # -- parameters / state
+    def get_params(self):
+        n = self.n_params
+        w = np.empty(n, np.float32); h = np.empty(n, np.float16); e = np.empty(n, np.float16)
+        check(lib().ngpb_testbed_get_params(self._h, w.ctypes.data_as(C.c_void_p), h.ctypes.data_as(C.c_void_p), e.ctypes.data_as(C.c_void_p)))
+        return w, h, e
+
+    def set_params(self, w_fp32):
+        w = np.ascontiguousarray(w_fp32, dtype=np.float32)
+        if w.shape[0] != self.n_params:
+            raise RuntimeError("set_params: wrong parameter count")
+        check(lib().ngpb_testbed_set_params(self._h, w.ctypes.data_as(C.c_void_p)))
+
+    def get_density_grid(self):
+        n_casc = int(self._get("max_cascade")) + 1
+        g = np.empty(128 ** 3 * n_casc, np.float32); b = np.empty(128 ** 3, np.uint8)
+        check(lib().ngpb_testbed_get_density_grid(self._h, g.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p)))
+        return g, b
+
+    # -- render
+    def render(self, width, height, spp=1, linear=True, camera_matrix=None, fov_x=None):
+        """Testbed::render (python_api.cu:567): returns float32 [H][W][4]."""
+        cam = np.asarray(camera_matrix if camera_matrix is not None else self._camera, dtype=np.float32).reshape(3, 4).T.reshape(-1).copy()
+        fx = 0.5 * width / math.tan(0.5 * (fov_x if fov_x is not None else self._fov_x))
+        out = np.empty((height, width, 4), np.float32)
+        ns = C.c_uint64(0)
+        check(lib().ngpb_testbed_render(self._h, cam.ctypes.data_as(C.c_void_p), int(width), int(height), C.c_float(fx), C.c_float(fx), int(spp), int(bool(linear)),
+                                        out.ctypes.data_as(C.c_void_p), C.byref(ns)))
+        self.last_render_samples = int(ns.value)
+        return out
+
+    _camera = np.eye(4, dtype=np.float32)[:3]
+    _fov_x = 0.6911112070083618
+
+    def set_nerf_camera_matrix(self, m):  # python_api.cu:681
+        self._camera = np.asarray(m, dtype=np.float32).reshape(3, 4)

@@ -1,0 +1,182 @@
+/*
+ * ngpb.h -- C ABI of the B200-native NeRF train/render hot path (libngpb200.so).
+ *
+ * The reference (JamesPerlman/blender-ngp) has no C/FFI boundary for this path: kernels are
+ * called from `Testbed` members and tiny-cuda-nn objects are C++ virtual classes.
+ * This header is the seam a maintainer would bind instead. Two levels:
+ *
+ *   1. kernel level (`ngpb_*` taking raw device pointers + a cudaStream_t): one entry point per
+ *      stage of the reference's training iteration, each citing the reference code it replaces;
+ *   2. testbed level (`ngpb_testbed_*`, host buffers in/out): the operations `pyngp.Testbed`
+ *      exposes for this path (src/python_api.cu:540-732).
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a non-zero
+ * status (a cudaError_t value, or NGPB_ERR_*), with the message available from
+ * ngpb_last_error(); the caller supplies the stream (void* = cudaStream_t); kernel-level entry
+ * points never allocate. Paths in comments are relative to the reference root.
+ */
+#ifndef NGPB_H
+#define NGPB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NGPB_ERR_INVALID_ARGUMENT 10001
+#define NGPB_ERR_RUNTIME          10002
+
+typedef uint16_t ngpb_half; /* IEEE binary16 bit pattern (tcnn::network_precision_t == __half) */
+
+const char* ngpb_last_error(void);
+int ngpb_version(void);
+/* Compute capability check: returns 0 only on an sm_100 device. */
+int ngpb_check_device(int device);
+
+/* ---- enums: integer values equal the reference's (include/neural-graphics-primitives/common.h:103-134) ---- */
+enum { NGPB_LOSS_L2 = 0, NGPB_LOSS_L1 = 1, NGPB_LOSS_MAPE = 2, NGPB_LOSS_SMAPE = 3, NGPB_LOSS_HUBER = 4, NGPB_LOSS_LOGL1 = 5, NGPB_LOSS_RELATIVE_L2 = 6 };
+enum { NGPB_ACT_NONE = 0, NGPB_ACT_RELU = 1, NGPB_ACT_LOGISTIC = 2, NGPB_ACT_EXPONENTIAL = 3 };
+enum { NGPB_COLOR_LINEAR = 0, NGPB_COLOR_SRGB = 1 };
+
+/* ---- hash grid (replaces tcnn GridEncodingTemplated<__half,3,2>, grid.h:944-1198) ---- */
+#define NGPB_MAX_LEVELS 32
+typedef struct {
+	uint32_t n_levels;            /* 16 */
+	uint32_t base_resolution;     /* 16 */
+	float log2_per_level_scale;   /* std::log2(per_level_scale), as passed to the kernel at grid.h:1079 */
+	uint32_t offsets[NGPB_MAX_LEVELS + 1]; /* entry offsets per level; offsets[n_levels] = total entries (grid.h:985-1018) */
+	float scale[NGPB_MAX_LEVELS];          /* grid_scale(level) = exp2f(level*log2_pls)*base-1 (grid.h:194-199), host-evaluated by
+	                                          ngpb_grid_init; the reference evaluates it per thread with the device exp2f */
+	uint32_t resolution[NGPB_MAX_LEVELS];  /* grid_resolution(scale) = ceil(scale)+1 (grid.h:201-203) */
+} ngpb_grid;
+
+/* Host-only: fills `g` like the GridEncodingTemplated constructor (grid.h:959-1025). Returns total entries. */
+uint32_t ngpb_grid_init(ngpb_grid* g, uint32_t n_levels, uint32_t log2_hashmap_size, uint32_t base_resolution, float per_level_scale);
+
+/* kernel_grid (grid.h:220-349). positions: float, `pos_stride` floats per sample (3 used).
+ * encoded: [n][2*n_levels] half, sample-major (the MLP kernels' input layout). */
+int ngpb_hash_encode_forward(void* stream, const ngpb_grid* g, const ngpb_half* grid, const float* positions, uint32_t pos_stride,
+                             uint32_t n, ngpb_half* encoded);
+/* kernel_grid_backward (grid.h:395-518). dL_dencoded: [n][2*n_levels] half. grid_grad: float[2*total entries],
+ * accumulated into with fp32 atomics (zero it first for EGradientMode::Overwrite, grid.h:1154). */
+int ngpb_hash_encode_backward(void* stream, const ngpb_grid* g, const float* positions, uint32_t pos_stride, uint32_t n,
+                              const ngpb_half* dL_dencoded, float* grid_grad);
+
+/* ---- NeRF MLPs (replaces NerfNetwork glue nerf_network.h:103-266 + tcnn FullyFusedMLP, fully_fused_mlp.cu) ----
+ * mlp: half[10240] in the reference's flat order: density W1[64][32], W2[16][64]; rgb W1[64][32], W2[64][64], W3[16][64].
+ * coords: [n][7] float NerfCoordinate (nerf.h:81-107). rgbsigma: [n][4] half {r,g,b,sigma} network outputs (pre-activation).
+ * n must be a multiple of 128 (tcnn batch_size_granularity, common.h:280). */
+int ngpb_nerf_mlp_forward(void* stream, const ngpb_half* mlp, const ngpb_half* encoded, const float* coords, uint32_t n, ngpb_half* rgbsigma);
+/* Forward + backward in one pass: dL_dout [n][4] half -> dL_dencoded [n][32] half; mlp_grad float[10240] is overwritten.
+ * workspace: ngpb_nerf_mlp_workspace_bytes() bytes of device memory. */
+uint64_t ngpb_nerf_mlp_workspace_bytes(void);
+int ngpb_nerf_mlp_forward_backward(void* stream, const ngpb_half* mlp, const ngpb_half* encoded, const float* coords, const ngpb_half* dL_dout,
+                                   uint32_t n, ngpb_half* dL_dencoded, float* mlp_grad, void* workspace);
+/* density network only (NerfNetwork::density, nerf_network.h:268-284): encoded [n][32] -> density logit half[n]. */
+int ngpb_nerf_density_mlp_forward(void* stream, const ngpb_half* mlp, const ngpb_half* encoded, uint32_t n, ngpb_half* density);
+
+/* ---- training images ---- */
+typedef struct {
+	const uint8_t* pixels; /* device pointer, RGBA8 (EImageDataType::Byte) */
+	int32_t w, h;
+	float fx, fy;          /* focal length in pixels (nerf_loader.h:42) */
+	float cx, cy;          /* principal point as a fraction of the resolution (nerf_loader.h:41) */
+	float xform[12];       /* 3x4 camera-to-world, column-major, after the per-ray quaternion round trip of
+	                          get_xform_given_rolling_shutter (common_device.cuh:224-234); see ngpb_effective_xform */
+	float raw_xform[12];   /* the unmodified 3x4 (used by mark_untrained_density_grid, testbed_nerf.cu:398) */
+} ngpb_image;
+
+/* Host-only: the transform generate_training_samples_nerf effectively uses for a camera without rolling shutter. */
+void ngpb_effective_xform(const float* xform12, float* out12);
+
+typedef struct { uint64_t state, inc; } ngpb_rng; /* tcnn pcg32 */
+
+/* ---- K1: generate_training_samples_nerf (src/testbed_nerf.cu:1085-1260) ----
+ * Deterministic: samples are laid out in ray order (an exclusive scan replaces the reference's atomicAdd,
+ * which makes it one valid serialisation of the reference's allocation order).
+ * counters[0] = total requested samples (numsteps_counter), counters[1] = rays kept (ray_counter).
+ * scratch: uint32[3 * n_rays]. */
+int ngpb_generate_training_samples(void* stream, uint32_t n_rays, const float* aabb6, uint32_t max_samples, ngpb_rng rng,
+                                   uint32_t n_images, const ngpb_image* images_dev, const uint8_t* density_grid_bitfield,
+                                   int snap_to_pixel_centers, float cone_angle_constant,
+                                   uint32_t* counters, uint32_t* ray_indices, float* rays /*[n][6]*/, uint32_t* numsteps /*[n][2]*/,
+                                   float* coords /*[max_samples][7]*/, uint32_t* scratch);
+
+/* ---- K6+K7: compute_loss_kernel_train_nerf (:1280-1597) + fill_rollover(_and_rescale) (tcnn common_device.h:517-537) ----
+ * counters_in: the device counters written by K1. counters_out[0] = compacted sample count (unclipped).
+ * coords_out [batch][7] and dloss_dout [batch][4] are padded to `batch` by rollover. scratch: 40 * n_rays bytes. */
+typedef struct {
+	float loss_scale;            /* LOSS_SCALE = 128, testbed.h:272 */
+	float background_color[3];
+	int32_t color_space, random_bg_color, linear_colors, loss_type, rgb_activation, density_activation, snap_to_pixel_centers;
+	float near_distance;
+} ngpb_loss_config;
+int ngpb_compute_loss(void* stream, uint32_t n_rays, const float* aabb6, ngpb_rng rng, uint32_t batch, const ngpb_loss_config* cfg,
+                      uint32_t n_images, const ngpb_image* images_dev, const uint32_t* counters_in,
+                      const ngpb_half* rgbsigma, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords_in,
+                      const float* mean_density_dev, float* coords_out, ngpb_half* dloss_dout, float* loss_per_ray, uint32_t* counters_out, void* scratch);
+
+/* ---- K15: Ema(ExponentialDecay(Adam)) in one pass (tcnn adam.h:48-119, ema.h:63-76, exponential_decay.h:60-72) ---- */
+typedef struct {
+	float learning_rate, beta1, beta2, epsilon, l2_reg, ema_decay;
+	uint32_t decay_start, decay_interval; float decay_base;
+	uint32_t step; float lr_factor; /* state, advanced by the host wrapper */
+} ngpb_optimizer;
+void ngpb_optimizer_init(ngpb_optimizer* o); /* configs/nerf/base.json:5-22 */
+/* grad is fp32 and is zeroed for the next iteration by the same pass. */
+int ngpb_optimizer_step(void* stream, ngpb_optimizer* o, uint32_t n_params, uint32_t n_matrix_params, float loss_scale, float* grad,
+                        float* w_fp32, ngpb_half* w_half, ngpb_half* w_ema, float* m1, float* m2, uint32_t* param_steps);
+
+/* ---- K16: occupancy grid (src/testbed_nerf.cu:369-610, :2761-2859) ---- */
+int ngpb_mark_untrained_density_grid(void* stream, uint32_t n_elements, float* grid, uint32_t n_images, const ngpb_image* images_dev, int clear_visible);
+int ngpb_generate_grid_samples(void* stream, uint32_t n_elements, ngpb_rng rng, uint32_t step, const float* aabb6, const float* grid_in,
+                               float* positions3, uint32_t* indices, uint32_t n_cascades, float thresh);
+int ngpb_splat_and_ema(void* stream, uint32_t n_samples, const uint32_t* indices, const ngpb_half* density, float* grid_tmp, uint32_t n_elements, float decay, float* grid);
+/* mean of max(v,0) over the first cascade -> *mean_dev, then bitfield + 7 max-pooled mips (2 MiB). */
+int ngpb_update_bitfield(void* stream, uint32_t n_cascades_used, const float* grid, float* mean_dev, uint8_t* bitfield);
+
+/* ---- development self-test of the tcgen05 building blocks (tests/test_umma_selftest.py) ---- */
+int ngpb_selftest_umma(void* stream, int variant, const ngpb_half* a, const ngpb_half* b, float* d);
+
+/* =====================================================================================================
+ * Testbed level: host-facing mirror of pyngp.Testbed for the NeRF mode (src/python_api.cu:540-732).
+ * ===================================================================================================== */
+typedef struct ngpb_testbed ngpb_testbed;
+
+typedef struct {
+	const uint8_t* pixels; /* host pointer, RGBA8, w*h*4 bytes */
+	int32_t w, h;
+	float fx, fy, cx, cy;
+	float xform[12];       /* 3x4 camera-to-world, column-major, ngp convention (after nerf_matrix_to_ngp, nerf_loader.h:113) */
+} ngpb_host_image;
+
+int ngpb_testbed_create(ngpb_testbed** out, int device);
+void ngpb_testbed_destroy(ngpb_testbed* t);
+/* Testbed::load_training_data (src/testbed.cu:97) for already-decoded images; aabb_scale as in transforms.json. */
+int ngpb_testbed_load_training_data(ngpb_testbed* t, uint32_t n_images, const ngpb_host_image* images, uint32_t aabb_scale);
+/* Testbed::reset_network (src/testbed.cu:2249) with configs/nerf/base.json and the given seed (m_seed, testbed.h:567). */
+int ngpb_testbed_reset_network(ngpb_testbed* t, uint32_t seed);
+/* Testbed::train(batch_size) (src/testbed.cu:2527): exactly one optimizer step. */
+int ngpb_testbed_train(ngpb_testbed* t, uint32_t batch_size);
+/* Runs `n_steps` iterations without host round trips in between (device-side batch-size controller). */
+int ngpb_testbed_train_n(ngpb_testbed* t, uint32_t batch_size, uint32_t n_steps);
+float ngpb_testbed_loss(ngpb_testbed* t);
+uint32_t ngpb_testbed_training_step(const ngpb_testbed* t);
+/* stats: [0] rays_per_batch of the last step, [1] measured_batch_size_before_compaction, [2] measured_batch_size, [3] number of kernel launches so far */
+int ngpb_testbed_stats(ngpb_testbed* t, uint64_t* stats4);
+uint32_t ngpb_testbed_n_params(const ngpb_testbed* t);
+int ngpb_testbed_get_params(ngpb_testbed* t, float* w_fp32, ngpb_half* w_half, ngpb_half* w_ema);
+int ngpb_testbed_set_params(ngpb_testbed* t, const float* w_fp32);
+int ngpb_testbed_get_density_grid(ngpb_testbed* t, float* grid, uint8_t* bitfield);
+/* training options exposed as pyngp properties (python_api.cu:650-852) */
+int ngpb_testbed_set_option(ngpb_testbed* t, const char* name, double value);
+double ngpb_testbed_get_option(ngpb_testbed* t, const char* name);
+/* Testbed::render (python_api.cu:132-190) for the classic single-NeRF path: camera12 = 3x4 column-major camera matrix.
+ * out_rgba: host float [h][w][4]. n_samples_out (optional): network-evaluated samples. */
+int ngpb_testbed_render(ngpb_testbed* t, const float* camera12, int w, int h, float fx, float fy, int spp, int linear, float* out_rgba, uint64_t* n_samples_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NGPB_H */

@@ -1,0 +1,1088 @@
+// TEST INFRASTRUCTURE ONLY -- see ngp_oracle.h. CPU restatement of the reference's NeRF hot path.
+// Built with -ffp-contract=off so every float op rounds exactly as written (no FMA contraction).
+#include "ngp_oracle.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+#include <omp.h>
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// binary16 helpers (round-to-nearest-even, like __float2half_rn)
+// ---------------------------------------------------------------------------------------------
+inline float h2f(orc_half h) { _Float16 v; std::memcpy(&v, &h, 2); return (float)v; }
+inline orc_half f2h(float f) { _Float16 v = (_Float16)f; orc_half h; std::memcpy(&h, &v, 2); return h; }
+// fp16 add as done by the reference's `result += (T)(weight * data)` (grid.h:341): both operands
+// are halfs, the sum is rounded to half.
+inline orc_half hadd(orc_half a, orc_half b) { return f2h(h2f(a) + h2f(b)); }
+
+// ---------------------------------------------------------------------------------------------
+// constants: src/testbed_nerf.cu:53-73, include/neural-graphics-primitives/nerf.h:24
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t NERF_GRIDSIZE = 128;
+constexpr uint32_t NERF_STEPS = 1024;
+constexpr uint32_t NERF_CASCADES = 8;
+constexpr uint32_t N_MAX_RANDOM_SAMPLES_PER_RAY = 8;
+constexpr float SQRT3 = 1.73205080757f;
+constexpr float STEPSIZE = SQRT3 / NERF_STEPS;
+constexpr float MIN_CONE_STEPSIZE = STEPSIZE;
+constexpr float MAX_CONE_STEPSIZE = STEPSIZE * (1 << (NERF_CASCADES - 1)) * NERF_STEPS / NERF_GRIDSIZE;
+constexpr float NERF_MIN_OPTICAL_THICKNESS = 0.01f;
+constexpr uint32_t GRID_CELLS = NERF_GRIDSIZE * NERF_GRIDSIZE * NERF_GRIDSIZE;
+
+inline float clampf(float v, float lo, float hi) { return std::max(lo, std::min(v, hi)); } // tcnn common.h clamp
+inline int clampi(int v, int lo, int hi) { return std::max(lo, std::min(v, hi)); }
+
+// Eigen sums three terms as a + (b + c) (Eigen/src/Core/Redux.h:101-115, redux_novec_unroller).
+inline float sum3(float a, float b, float c) { return a + (b + c); }
+inline float dot3(const float* a, const float* b) { return sum3(a[0] * b[0], a[1] * b[1], a[2] * b[2]); }
+inline float sum4(float a, float b, float c, float d) { return (a + b) + (c + d); }
+
+struct Vec3 { float x, y, z; };
+
+// ---------------------------------------------------------------------------------------------
+// morton: tcnn common_device.h:338-362
+// ---------------------------------------------------------------------------------------------
+inline uint32_t expand_bits(uint32_t v) {
+	v = (v * 0x00010001u) & 0xFF0000FFu;
+	v = (v * 0x00000101u) & 0x0F00F00Fu;
+	v = (v * 0x00000011u) & 0xC30C30C3u;
+	v = (v * 0x00000005u) & 0x49249249u;
+	return v;
+}
+inline uint32_t morton3D(uint32_t x, uint32_t y, uint32_t z) { return expand_bits(x) | (expand_bits(y) << 1) | (expand_bits(z) << 2); }
+inline uint32_t morton3D_invert(uint32_t x) {
+	x = x & 0x49249249;
+	x = (x | (x >> 2)) & 0xc30c30c3;
+	x = (x | (x >> 4)) & 0x0f00f00f;
+	x = (x | (x >> 8)) & 0xff0000ff;
+	x = (x | (x >> 16)) & 0x0000ffff;
+	return x;
+}
+
+// ---------------------------------------------------------------------------------------------
+// colour transfer: include/neural-graphics-primitives/common_device.cuh:31-77
+// ---------------------------------------------------------------------------------------------
+inline float srgb_to_linear(float srgb) {
+	if (srgb <= 0.04045f) return srgb / 12.92f;
+	return std::pow((srgb + 0.055f) / 1.055f, 2.4f);
+}
+inline float linear_to_srgb(float linear) {
+	if (linear < 0.0031308f) return 12.92f * linear;
+	return 1.055f * std::pow(linear, 0.41666f) - 0.055f;
+}
+inline float logistic(float x) { return 1.0f / (1.0f + std::exp(-x)); } // tcnn common_device.h:51
+
+// activations: src/testbed_nerf.cu:215-257 (the reference uses __expf; expf here, tolerance in the tests)
+inline float network_to_rgb(float v, int act) {
+	switch (act) {
+		case 0: return v;
+		case 1: return v > 0.0f ? v : 0.0f;
+		case 2: return logistic(v);
+		default: return std::exp(clampf(v, -10.0f, 10.0f));
+	}
+}
+inline float network_to_rgb_derivative(float v, int act) {
+	switch (act) {
+		case 0: return 1.0f;
+		case 1: return v > 0.0f ? 1.0f : 0.0f;
+		case 2: { float d = logistic(v); return d * (1 - d); }
+		default: return std::exp(clampf(v, -10.0f, 10.0f));
+	}
+}
+inline float network_to_density(float v, int act) {
+	switch (act) {
+		case 0: return v;
+		case 1: return v > 0.0f ? v : 0.0f;
+		case 2: return logistic(v);
+		default: return std::exp(v);
+	}
+}
+inline float network_to_density_derivative(float v, int act) {
+	switch (act) {
+		case 0: return 1.0f;
+		case 1: return v > 0.0f ? 1.0f : 0.0f;
+		case 2: { float d = logistic(v); return d * (1 - d); }
+		default: return std::exp(clampf(v, -15.0f, 15.0f));
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// step-size law and occupancy lookup: src/testbed_nerf.cu:96-98,:191-213,:318-342,:449-463
+// ---------------------------------------------------------------------------------------------
+inline float calc_dt(float t, float cone_angle) { return clampf(t * cone_angle, MIN_CONE_STEPSIZE, MAX_CONE_STEPSIZE); }
+inline float signf(float x) { return std::copysign(1.0f, x); } // common.h:197
+
+inline float distance_to_next_voxel(const Vec3& pos, const Vec3& dir, const Vec3& idir, uint32_t res) {
+	float r = (float)res;
+	float px = r * pos.x, py = r * pos.y, pz = r * pos.z;
+	float tx = (std::floor(px + 0.5f + 0.5f * signf(dir.x)) - px) * idir.x;
+	float ty = (std::floor(py + 0.5f + 0.5f * signf(dir.y)) - py) * idir.y;
+	float tz = (std::floor(pz + 0.5f + 0.5f * signf(dir.z)) - pz) * idir.z;
+	float t = std::min(std::min(tx, ty), tz);
+	return std::fmax(t / r, 0.0f);
+}
+inline float advance_to_next_voxel(float t, float cone_angle, const Vec3& pos, const Vec3& dir, const Vec3& idir, uint32_t res) {
+	float t_target = t + distance_to_next_voxel(pos, dir, idir, res);
+	do { t += calc_dt(t, cone_angle); } while (t < t_target);
+	return t;
+}
+inline int mip_from_pos(const Vec3& pos, uint32_t max_cascade = NERF_CASCADES - 1) {
+	int exponent;
+	float maxval = std::max(std::max(std::fabs(pos.x - 0.5f), std::fabs(pos.y - 0.5f)), std::fabs(pos.z - 0.5f));
+	std::frexp(maxval, &exponent);
+	return std::min((int)max_cascade, std::max(0, exponent + 1));
+}
+inline int mip_from_dt(float dt, const Vec3& pos, uint32_t max_cascade = NERF_CASCADES - 1) {
+	int mip = mip_from_pos(pos, max_cascade);
+	dt *= 2 * NERF_GRIDSIZE;
+	if (dt < 1.f) return mip;
+	int exponent;
+	std::frexp(dt, &exponent);
+	return std::min((int)max_cascade, std::max(exponent, mip));
+}
+inline uint32_t cascaded_grid_idx_at(Vec3 pos, uint32_t mip) {
+	float mip_scale = std::scalbn(1.0f, -(int)mip);
+	pos.x -= 0.5f; pos.y -= 0.5f; pos.z -= 0.5f;
+	pos.x *= mip_scale; pos.y *= mip_scale; pos.z *= mip_scale;
+	pos.x += 0.5f; pos.y += 0.5f; pos.z += 0.5f;
+	int ix = (int)(pos.x * NERF_GRIDSIZE), iy = (int)(pos.y * NERF_GRIDSIZE), iz = (int)(pos.z * NERF_GRIDSIZE);
+	return morton3D(clampi(ix, 0, NERF_GRIDSIZE - 1), clampi(iy, 0, NERF_GRIDSIZE - 1), clampi(iz, 0, NERF_GRIDSIZE - 1));
+}
+inline uint32_t grid_mip_offset(uint32_t mip) { return GRID_CELLS * mip; }
+inline bool density_grid_occupied_at(const Vec3& pos, const uint8_t* bitfield, uint32_t mip) {
+	uint32_t idx = cascaded_grid_idx_at(pos, mip);
+	return bitfield[idx / 8 + grid_mip_offset(mip) / 8] & (1 << (idx % 8));
+}
+inline float warp_dt(float dt) {
+	float max_stepsize = MIN_CONE_STEPSIZE * (1 << (NERF_CASCADES - 1));
+	return (dt - MIN_CONE_STEPSIZE) / (max_stepsize - MIN_CONE_STEPSIZE);
+}
+inline float unwarp_dt(float dt) {
+	float max_stepsize = MIN_CONE_STEPSIZE * (1 << (NERF_CASCADES - 1));
+	return dt * (max_stepsize - MIN_CONE_STEPSIZE) + MIN_CONE_STEPSIZE;
+}
+
+// bounding box: include/neural-graphics-primitives/bounding_box.cuh:163-221
+struct AABB { Vec3 min, max; };
+inline AABB make_aabb(const float* a) { return {{a[0], a[1], a[2]}, {a[3], a[4], a[5]}}; }
+inline bool aabb_contains(const AABB& b, const Vec3& p) {
+	return p.x >= b.min.x && p.x <= b.max.x && p.y >= b.min.y && p.y <= b.max.y && p.z >= b.min.z && p.z <= b.max.z;
+}
+inline void aabb_ray_intersect(const AABB& b, const Vec3& pos, const Vec3& dir, float* out_tmin, float* out_tmax) {
+	const float FMAX = std::numeric_limits<float>::max();
+	float tmin = (b.min.x - pos.x) / dir.x, tmax = (b.max.x - pos.x) / dir.x;
+	if (tmin > tmax) std::swap(tmin, tmax);
+	float tymin = (b.min.y - pos.y) / dir.y, tymax = (b.max.y - pos.y) / dir.y;
+	if (tymin > tymax) std::swap(tymin, tymax);
+	if (tmin > tymax || tymin > tmax) { *out_tmin = FMAX; *out_tmax = FMAX; return; }
+	if (tymin > tmin) tmin = tymin;
+	if (tymax < tmax) tmax = tymax;
+	float tzmin = (b.min.z - pos.z) / dir.z, tzmax = (b.max.z - pos.z) / dir.z;
+	if (tzmin > tzmax) std::swap(tzmin, tzmax);
+	if (tmin > tzmax || tzmin > tmax) { *out_tmin = FMAX; *out_tmax = FMAX; return; }
+	if (tzmin > tmin) tmin = tzmin;
+	if (tzmax < tmax) tmax = tzmax;
+	*out_tmin = tmin; *out_tmax = tmax;
+}
+inline Vec3 warp_position(const Vec3& p, const AABB& b) { // bounding_box.cuh:86 relative_pos
+	return {(p.x - b.min.x) / (b.max.x - b.min.x), (p.y - b.min.y) / (b.max.y - b.min.y), (p.z - b.min.z) / (b.max.z - b.min.z)};
+}
+inline Vec3 unwarp_position(const float* p, const AABB& b) { // testbed_nerf.cu:274-279
+	return {b.min.x + p[0] * (b.max.x - b.min.x), b.min.y + p[1] * (b.max.y - b.min.y), b.min.z + p[2] * (b.max.z - b.min.z)};
+}
+
+// ---------------------------------------------------------------------------------------------
+// image access: common_device.cuh:633-705
+// ---------------------------------------------------------------------------------------------
+inline void image_pos(float x, float y, int w, int h, int* px, int* py) {
+	*px = std::max(std::min((int)(x * (float)w), w - 1), 0);
+	*py = std::max(std::min((int)(y * (float)h), h - 1), 0);
+}
+inline void read_rgba(float x, float y, const orc_image& img, float out[4]) {
+	int px, py;
+	image_pos(x, y, img.w, img.h, &px, &py);
+	uint8_t val[4];
+	std::memcpy(val, img.pixels + 4 * ((size_t)px + (size_t)py * img.w), 4);
+	uint32_t packed; std::memcpy(&packed, val, 4);
+	if (packed == 0x00FF00FF) { out[0] = out[1] = out[2] = out[3] = -1.0f; return; }
+	float alpha = (float)val[3] * (1.0f / 255.0f);
+	out[0] = srgb_to_linear((float)val[0] * (1.0f / 255.0f)) * alpha;
+	out[1] = srgb_to_linear((float)val[1] * (1.0f / 255.0f)) * alpha;
+	out[2] = srgb_to_linear((float)val[2] * (1.0f / 255.0f)) * alpha;
+	out[3] = alpha;
+}
+
+// image_idx: src/testbed_nerf.cu:1062-1083 (no error-map CDF). uint32 wrap-around multiply as in the reference.
+inline uint32_t image_idx(uint32_t base_idx, uint32_t n_rays, uint32_t n_training_images) {
+	return ((base_idx * n_training_images) / n_rays) % n_training_images;
+}
+
+// ---------------------------------------------------------------------------------------------
+// loss functions: src/testbed_nerf.cu:121-189,:1263-1278
+// ---------------------------------------------------------------------------------------------
+struct LossAndGradient { float loss[3], gradient[3]; };
+inline LossAndGradient loss_and_gradient(const float* target, const float* prediction, int loss_type) {
+	LossAndGradient r;
+	for (int c = 0; c < 3; ++c) {
+		float difference = prediction[c] - target[c];
+		switch (loss_type) {
+			case 6: { // RelativeL2
+				float factor = 1.0f / (prediction[c] * prediction[c] + 1e-2f);
+				r.loss[c] = difference * difference * factor; r.gradient[c] = 2.0f * difference * factor; break;
+			}
+			case 1: r.loss[c] = std::fabs(difference); r.gradient[c] = std::copysign(1.0f, difference); break; // L1
+			case 2: { // Mape
+				float factor = 1.0f / (std::fabs(prediction[c]) + 1e-2f);
+				r.loss[c] = std::fabs(difference) * factor; r.gradient[c] = std::copysign(factor, difference); break;
+			}
+			case 3: { // Smape
+				float factor = 1.0f / (0.5f * (std::fabs(prediction[c]) + std::fabs(target[c])) + 1e-2f);
+				r.loss[c] = std::fabs(difference) * factor; r.gradient[c] = std::copysign(factor, difference); break;
+			}
+			case 4: { // Huber(alpha=0.1)/5
+				const float alpha = 0.1f;
+				float abs_diff = std::fabs(difference);
+				float square = 0.5f / alpha * difference * difference;
+				float l = abs_diff > alpha ? (abs_diff - 0.5f * alpha) : square;
+				float g = abs_diff > alpha ? (difference > 0 ? 1.0f : -1.0f) : (difference / alpha);
+				r.loss[c] = l / 5.0f; r.gradient[c] = g / 5.0f; break;
+			}
+			case 5: { // LogL1
+				float divisor = std::fabs(difference) + 1.0f;
+				r.loss[c] = std::log(divisor); r.gradient[c] = std::copysign(1.0f / divisor, difference); break;
+			}
+			default: r.loss[c] = difference * difference; r.gradient[c] = 2.0f * difference; break; // L2
+		}
+	}
+	return r;
+}
+
+inline orc_pcg32 rng_advanced(orc_pcg32 rng, int64_t delta) { orc_pcg32_advance(&rng, delta); return rng; }
+
+// nerf_random_image_pos_training: src/testbed_nerf.cu:1047-1060 (no CDF)
+inline void random_image_pos_training(orc_pcg32& rng, int w, int h, bool snap, float* x, float* y) {
+	float u = orc_pcg32_next_float(&rng), v = orc_pcg32_next_float(&rng);
+	if (snap) {
+		u = ((float)std::min(std::max((int)(u * (float)w), 0), w - 1) + 0.5f) / (float)w;
+		v = ((float)std::min(std::max((int)(v * (float)h), 0), h - 1) + 0.5f) / (float)h;
+	}
+	*x = u; *y = v;
+}
+
+} // namespace
+
+// =============================================================================================
+// PCG32
+// =============================================================================================
+extern "C" uint32_t orc_pcg32_next_uint(orc_pcg32* rng) {
+	uint64_t oldstate = rng->state;
+	rng->state = oldstate * 0x5851f42d4c957f2dULL + rng->inc;
+	uint32_t xorshifted = (uint32_t)(((oldstate >> 18u) ^ oldstate) >> 27u);
+	uint32_t rot = (uint32_t)(oldstate >> 59u);
+	return (xorshifted >> rot) | (xorshifted << ((~rot + 1u) & 31));
+}
+extern "C" void orc_pcg32_seed(orc_pcg32* rng, uint64_t initstate, uint64_t initseq) {
+	rng->state = 0U;
+	rng->inc = (initseq << 1u) | 1u;
+	orc_pcg32_next_uint(rng);
+	rng->state += initstate;
+	orc_pcg32_next_uint(rng);
+}
+extern "C" float orc_pcg32_next_float(orc_pcg32* rng) {
+	union { uint32_t u; float f; } x;
+	x.u = (orc_pcg32_next_uint(rng) >> 9) | 0x3f800000u;
+	return x.f - 1.0f;
+}
+extern "C" void orc_pcg32_advance(orc_pcg32* rng, int64_t delta_) {
+	uint64_t cur_mult = 0x5851f42d4c957f2dULL, cur_plus = rng->inc, acc_mult = 1u, acc_plus = 0u;
+	uint64_t delta = (uint64_t)delta_;
+	while (delta > 0) {
+		if (delta & 1) { acc_mult *= cur_mult; acc_plus = acc_plus * cur_mult + cur_plus; }
+		cur_plus = (cur_mult + 1) * cur_plus;
+		cur_mult *= cur_mult;
+		delta /= 2;
+	}
+	rng->state = acc_mult * rng->state + acc_plus;
+}
+
+// =============================================================================================
+// Hash grid
+// =============================================================================================
+namespace {
+inline float grid_scale(uint32_t level, float log2_per_level_scale, uint32_t base_resolution) { // grid.h:194-199
+	return std::exp2(level * log2_per_level_scale) * base_resolution - 1.0f;
+}
+inline uint32_t grid_resolution(float scale) { return (uint32_t)std::ceil(scale) + 1; } // grid.h:201-203
+
+// grid.h:164-186 with GridType::Hash, HashType::CoherentPrime, 3 dims; returns the entry index (feature 0 = index*2).
+inline uint32_t grid_index(uint32_t hashmap_size, uint32_t resolution, const uint32_t p[3]) {
+	uint32_t stride = 1, index = 0;
+	for (uint32_t dim = 0; dim < 3 && stride <= hashmap_size; ++dim) {
+		index += p[dim] * stride;
+		stride *= resolution;
+	}
+	if (hashmap_size < stride) {
+		index = (p[0] * 1u) ^ (p[1] * 2654435761u) ^ (p[2] * 805459861u); // grid.h:111-128
+	}
+	return index % hashmap_size;
+}
+inline void pos_fract(float input, float* pos, uint32_t* pos_grid, float scale) { // tcnn common_device.h:434-445
+	*pos = std::fma(input, scale, 0.5f); // nvcc contracts the reference's `input * scale + 0.5f` into one FFMA
+	int tmp = (int)std::floor(*pos);
+	*pos_grid = (uint32_t)tmp;
+	*pos -= (float)tmp;
+}
+} // namespace
+
+extern "C" uint32_t orc_grid_offsets(uint32_t n_levels, uint32_t log2_hashmap_size, uint32_t base_resolution, float per_level_scale, uint32_t* offsets) {
+	uint32_t offset = 0;
+	for (uint32_t i = 0; i < n_levels; ++i) {
+		const uint32_t resolution = grid_resolution(grid_scale(i, std::log2(per_level_scale), base_resolution));
+		uint32_t max_params = std::numeric_limits<uint32_t>::max() / 2;
+		uint32_t params_in_level = std::pow((float)resolution, 3) > (float)max_params ? max_params : resolution * resolution * resolution;
+		params_in_level = (params_in_level + 7u) / 8u * 8u;
+		params_in_level = std::min(params_in_level, 1u << log2_hashmap_size);
+		offsets[i] = offset;
+		offset += params_in_level;
+	}
+	offsets[n_levels] = offset;
+	return offset;
+}
+
+extern "C" void orc_grid_indices(uint32_t n, uint32_t level, const uint32_t* offsets, uint32_t base_resolution, float log2_per_level_scale, const float* scales,
+                                 const float* positions, uint32_t pos_stride, uint32_t* indices8, float* weights8) {
+	const uint32_t hashmap_size = offsets[level + 1] - offsets[level];
+	const float scale = scales ? scales[level] : grid_scale(level, log2_per_level_scale, base_resolution);
+	const uint32_t resolution = grid_resolution(scale);
+	for (uint32_t i = 0; i < n; ++i) {
+		float pos[3]; uint32_t pg[3];
+		for (int d = 0; d < 3; ++d) pos_fract(positions[(size_t)i * pos_stride + d], &pos[d], &pg[d], scale);
+		for (uint32_t idx = 0; idx < 8; ++idx) {
+			float weight = 1; uint32_t pl[3];
+			for (uint32_t d = 0; d < 3; ++d) {
+				if ((idx & (1 << d)) == 0) { weight *= 1 - pos[d]; pl[d] = pg[d]; } else { weight *= pos[d]; pl[d] = pg[d] + 1; }
+			}
+			indices8[(size_t)i * 8 + idx] = grid_index(hashmap_size, resolution, pl);
+			weights8[(size_t)i * 8 + idx] = weight;
+		}
+	}
+}
+
+extern "C" void orc_grid_forward(uint32_t n, uint32_t n_levels, const uint32_t* offsets, uint32_t base_resolution, float log2_per_level_scale, const float* scales,
+                                 const orc_half* grid, const float* positions, uint32_t pos_stride, orc_half* encoded) {
+	#pragma omp parallel for schedule(static)
+	for (int64_t i = 0; i < (int64_t)n; ++i) {
+		for (uint32_t level = 0; level < n_levels; ++level) {
+			const orc_half* g = grid + (size_t)offsets[level] * 2;
+			const uint32_t hashmap_size = offsets[level + 1] - offsets[level];
+			const float scale = scales ? scales[level] : grid_scale(level, log2_per_level_scale, base_resolution);
+			const uint32_t resolution = grid_resolution(scale);
+			float pos[3]; uint32_t pg[3];
+			for (int d = 0; d < 3; ++d) pos_fract(positions[(size_t)i * pos_stride + d], &pos[d], &pg[d], scale);
+			orc_half result[2] = {0, 0};
+			for (uint32_t idx = 0; idx < 8; ++idx) {
+				float weight = 1; uint32_t pl[3];
+				for (uint32_t d = 0; d < 3; ++d) {
+					if ((idx & (1 << d)) == 0) { weight *= 1 - pos[d]; pl[d] = pg[d]; } else { weight *= pos[d]; pl[d] = pg[d] + 1; }
+				}
+				uint32_t index = grid_index(hashmap_size, resolution, pl) * 2;
+				for (int f = 0; f < 2; ++f) {
+					float data = h2f(g[index + f]);
+					result[f] = hadd(result[f], f2h(weight * data)); // grid.h:339-341 (fp16 accumulation)
+				}
+			}
+			encoded[(size_t)i * (2 * n_levels) + level * 2 + 0] = result[0];
+			encoded[(size_t)i * (2 * n_levels) + level * 2 + 1] = result[1];
+		}
+	}
+}
+
+// The reference accumulates with atomicAdd(__half2) in launch order (grid.h:436-441), which is
+// order dependent; the oracle accumulates each contribution `(float)grad * weight` exactly in
+// double and rounds once to float. Tests compare with a tolerance that covers fp16 atomics.
+extern "C" void orc_grid_backward(uint32_t n, uint32_t n_levels, const uint32_t* offsets, uint32_t base_resolution, float log2_per_level_scale, const float* scales,
+                                  const float* positions, uint32_t pos_stride, const orc_half* dL_dy, float* grad) {
+	#pragma omp parallel for schedule(dynamic, 1)
+	for (int level = 0; level < (int)n_levels; ++level) {
+		const uint32_t hashmap_size = offsets[level + 1] - offsets[level];
+		std::vector<double> acc((size_t)hashmap_size * 2, 0.0);
+		const float scale = scales ? scales[level] : grid_scale(level, log2_per_level_scale, base_resolution);
+		const uint32_t resolution = grid_resolution(scale);
+		for (uint32_t i = 0; i < n; ++i) {
+			float pos[3]; uint32_t pg[3];
+			for (int d = 0; d < 3; ++d) pos_fract(positions[(size_t)i * pos_stride + d], &pos[d], &pg[d], scale);
+			float g0 = h2f(dL_dy[(size_t)i * (2 * n_levels) + level * 2 + 0]);
+			float g1 = h2f(dL_dy[(size_t)i * (2 * n_levels) + level * 2 + 1]);
+			if (g0 == 0.0f && g1 == 0.0f) continue;
+			for (uint32_t idx = 0; idx < 8; ++idx) {
+				float weight = 1; uint32_t pl[3];
+				for (uint32_t d = 0; d < 3; ++d) {
+					if ((idx & (1 << d)) == 0) { weight *= 1 - pos[d]; pl[d] = pg[d]; } else { weight *= pos[d]; pl[d] = pg[d] + 1; }
+				}
+				uint32_t index = grid_index(hashmap_size, resolution, pl) * 2;
+				acc[index + 0] += (double)(g0 * weight);
+				acc[index + 1] += (double)(g1 * weight);
+			}
+		}
+		float* out = grad + (size_t)offsets[level] * 2;
+		for (size_t k = 0; k < acc.size(); ++k) out[k] = (float)acc[k];
+	}
+}
+
+// =============================================================================================
+// Spherical harmonics degree 4 (16 coefficients): spherical_harmonics.h:46-150
+// =============================================================================================
+namespace {
+inline void sh4(const float* d, float* out) {
+	float x = d[0] * 2.f - 1.f, y = d[1] * 2.f - 1.f, z = d[2] * 2.f - 1.f;
+	float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+	out[0] = 0.28209479177387814f;
+	out[1] = -0.48860251190291987f * y;
+	out[2] = 0.48860251190291987f * z;
+	out[3] = -0.48860251190291987f * x;
+	out[4] = 1.0925484305920792f * xy;
+	out[5] = -1.0925484305920792f * yz;
+	out[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
+	out[7] = -1.0925484305920792f * xz;
+	out[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
+	out[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
+	out[10] = 2.8906114426405538f * xy * z;
+	out[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
+	out[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
+	out[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
+	out[14] = 1.4453057213202769f * z * (x2 - y2);
+	out[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
+}
+} // namespace
+
+extern "C" void orc_sh4(uint32_t n, const float* dirs, uint32_t dir_stride, orc_half* out, uint32_t out_stride) {
+	for (uint32_t i = 0; i < n; ++i) {
+		float v[16];
+		sh4(dirs + (size_t)i * dir_stride, v);
+		for (int k = 0; k < 16; ++k) out[(size_t)i * out_stride + k] = f2h(v[k]);
+	}
+}
+
+// =============================================================================================
+// NeRF network: density MLP 32->64->16, rgb MLP 32->64->64->16(3), ReLU hidden, no output act.
+// fp32 accumulation, fp16 storage between layers. (The reference's wmma path accumulates in fp16,
+// tcnn/src/fully_fused_mlp.cu:66-68; the difference is covered by the stated tolerance.)
+// =============================================================================================
+namespace {
+constexpr int W1D = 0, W2D = 2048, W1R = 3072, W2R = 5120, W3R = 9216;
+
+struct MlpWeightsF {
+	std::vector<float> w;
+	explicit MlpWeightsF(const orc_half* mlp) : w(ORC_MLP_PARAMS) { for (int i = 0; i < ORC_MLP_PARAMS; ++i) w[i] = h2f(mlp[i]); }
+};
+
+// out[o] = sum_k W[o][k] * in[k]
+inline void matvec(const float* W, int n_out, int n_in, const float* in, float* out) {
+	for (int o = 0; o < n_out; ++o) {
+		float acc = 0.f;
+		const float* row = W + o * n_in;
+		for (int k = 0; k < n_in; ++k) acc += row[k] * in[k];
+		out[o] = acc;
+	}
+}
+// out[k] = sum_o W[o][k] * in[o]
+inline void matvec_t(const float* W, int n_out, int n_in, const float* in, float* out) {
+	for (int k = 0; k < n_in; ++k) out[k] = 0.f;
+	for (int o = 0; o < n_out; ++o) {
+		const float* row = W + o * n_in;
+		float v = in[o];
+		for (int k = 0; k < n_in; ++k) out[k] += row[k] * v;
+	}
+}
+inline float rh(float v) { return h2f(f2h(v)); } // round through fp16
+
+struct SampleActs { float x[32], h1[64], od[16], rin[32], g1[64], g2[64], orgb[16]; };
+
+inline void mlp_forward_one(const float* W, const orc_half* enc, const float* coord, SampleActs& a) {
+	float tmp[64];
+	for (int k = 0; k < 32; ++k) a.x[k] = h2f(enc[k]);
+	matvec(W + W1D, 64, 32, a.x, tmp);
+	for (int k = 0; k < 64; ++k) a.h1[k] = rh(tmp[k] > 0.f ? tmp[k] : 0.f);
+	matvec(W + W2D, 16, 64, a.h1, tmp);
+	for (int k = 0; k < 16; ++k) a.od[k] = rh(tmp[k]);
+	float sh[16];
+	sh4(coord + 4, sh);
+	for (int k = 0; k < 16; ++k) { a.rin[k] = a.od[k]; a.rin[16 + k] = rh(sh[k]); }
+	matvec(W + W1R, 64, 32, a.rin, tmp);
+	for (int k = 0; k < 64; ++k) a.g1[k] = rh(tmp[k] > 0.f ? tmp[k] : 0.f);
+	matvec(W + W2R, 64, 64, a.g1, tmp);
+	for (int k = 0; k < 64; ++k) a.g2[k] = rh(tmp[k] > 0.f ? tmp[k] : 0.f);
+	matvec(W + W3R, 16, 64, a.g2, tmp);
+	for (int k = 0; k < 16; ++k) a.orgb[k] = rh(tmp[k]);
+}
+} // namespace
+
+extern "C" void orc_nerf_mlp_forward(uint32_t n, const orc_half* mlp, const orc_half* encoded, const float* coords,
+                                     orc_half* rgbsigma, orc_half* act_h1, orc_half* rgb_in, orc_half* act_g1, orc_half* act_g2) {
+	MlpWeightsF Wf(mlp);
+	const float* W = Wf.w.data();
+	#pragma omp parallel for schedule(static)
+	for (int64_t i = 0; i < (int64_t)n; ++i) {
+		SampleActs a;
+		mlp_forward_one(W, encoded + (size_t)i * 32, coords + (size_t)i * 7, a);
+		// nerf_network.h:130-136: rgb from the rgb net, density = density-net output 0
+		rgbsigma[i * 4 + 0] = f2h(a.orgb[0]); rgbsigma[i * 4 + 1] = f2h(a.orgb[1]); rgbsigma[i * 4 + 2] = f2h(a.orgb[2]);
+		rgbsigma[i * 4 + 3] = f2h(a.od[0]);
+		if (act_h1) for (int k = 0; k < 64; ++k) act_h1[(size_t)i * 64 + k] = f2h(a.h1[k]);
+		if (rgb_in) for (int k = 0; k < 32; ++k) rgb_in[(size_t)i * 32 + k] = f2h(a.rin[k]);
+		if (act_g1) for (int k = 0; k < 64; ++k) act_g1[(size_t)i * 64 + k] = f2h(a.g1[k]);
+		if (act_g2) for (int k = 0; k < 64; ++k) act_g2[(size_t)i * 64 + k] = f2h(a.g2[k]);
+	}
+}
+
+extern "C" void orc_nerf_mlp_backward(uint32_t n, const orc_half* mlp, const orc_half* encoded, const float* coords, const orc_half* dL_dout,
+                                      orc_half* dL_dencoded, float* mlp_grad) {
+	MlpWeightsF Wf(mlp);
+	const float* W = Wf.w.data();
+	const int nt = omp_get_max_threads();
+	std::vector<std::vector<double>> partial(nt, std::vector<double>(ORC_MLP_PARAMS, 0.0));
+	#pragma omp parallel
+	{
+		double* G = partial[omp_get_thread_num()].data();
+		#pragma omp for schedule(static)
+		for (int64_t i = 0; i < (int64_t)n; ++i) {
+			SampleActs a;
+			mlp_forward_one(W, encoded + (size_t)i * 32, coords + (size_t)i * 7, a);
+			// nerf_network.h:202-206: dL_drgb = first three outputs, rest zero
+			float d_orgb[16] = {0};
+			for (int c = 0; c < 3; ++c) d_orgb[c] = h2f(dL_dout[(size_t)i * 4 + c]);
+			float tmp[64], d_g2[64], d_g1[64], d_rin[32], d_od[16], d_h1[64], d_x[32];
+			// rgb net, last layer (fully_fused_mlp.cu:759-850)
+			for (int o = 0; o < 16; ++o) for (int k = 0; k < 64; ++k) G[W3R + o * 64 + k] += (double)(d_orgb[o] * a.g2[k]);
+			matvec_t(W + W3R, 16, 64, d_orgb, tmp);
+			for (int k = 0; k < 64; ++k) d_g2[k] = rh(a.g2[k] > 0.f ? tmp[k] : 0.f);
+			for (int o = 0; o < 64; ++o) for (int k = 0; k < 64; ++k) G[W2R + o * 64 + k] += (double)(d_g2[o] * a.g1[k]);
+			matvec_t(W + W2R, 64, 64, d_g2, tmp);
+			for (int k = 0; k < 64; ++k) d_g1[k] = rh(a.g1[k] > 0.f ? tmp[k] : 0.f);
+			for (int o = 0; o < 64; ++o) for (int k = 0; k < 32; ++k) G[W1R + o * 32 + k] += (double)(d_g1[o] * a.rin[k]);
+			matvec_t(W + W1R, 64, 32, d_g1, tmp);
+			for (int k = 0; k < 32; ++k) d_rin[k] = rh(tmp[k]);
+			// nerf_network.h:232-239: density-net output gradient = rgb-net input gradient rows 0..15, plus dL/dsigma on row 0
+			for (int k = 0; k < 16; ++k) d_od[k] = d_rin[k];
+			d_od[0] = rh(d_od[0] + h2f(dL_dout[(size_t)i * 4 + 3]));
+			for (int o = 0; o < 16; ++o) for (int k = 0; k < 64; ++k) G[W2D + o * 64 + k] += (double)(d_od[o] * a.h1[k]);
+			matvec_t(W + W2D, 16, 64, d_od, tmp);
+			for (int k = 0; k < 64; ++k) d_h1[k] = rh(a.h1[k] > 0.f ? tmp[k] : 0.f);
+			for (int o = 0; o < 64; ++o) for (int k = 0; k < 32; ++k) G[W1D + o * 32 + k] += (double)(d_h1[o] * a.x[k]);
+			matvec_t(W + W1D, 64, 32, d_h1, d_x);
+			for (int k = 0; k < 32; ++k) dL_dencoded[(size_t)i * 32 + k] = f2h(d_x[k]);
+		}
+	}
+	for (int k = 0; k < ORC_MLP_PARAMS; ++k) {
+		double s = 0.0;
+		for (int t = 0; t < nt; ++t) s += partial[t][k];
+		mlp_grad[k] = (float)s;
+	}
+}
+
+// =============================================================================================
+// composite model entry points
+// =============================================================================================
+extern "C" void orc_model_init(orc_model* m, uint32_t n_levels, uint32_t log2_hashmap_size, uint32_t base_resolution, float per_level_scale) {
+	m->n_levels = n_levels; m->log2_hashmap_size = log2_hashmap_size; m->base_resolution = base_resolution; m->per_level_scale = per_level_scale;
+	m->n_grid_params = 2 * orc_grid_offsets(n_levels, log2_hashmap_size, base_resolution, per_level_scale, m->offsets);
+	for (uint32_t l = 0; l < n_levels; ++l) m->scales[l] = grid_scale(l, std::log2(per_level_scale), base_resolution);
+}
+
+extern "C" void orc_nerf_inference(const orc_model* m, const orc_half* params, uint32_t n, const float* coords, orc_half* rgbsigma) {
+	std::vector<orc_half> enc((size_t)n * 32);
+	orc_grid_forward(n, m->n_levels, m->offsets, m->base_resolution, std::log2(m->per_level_scale), m->scales, params + ORC_MLP_PARAMS, coords, 7, enc.data());
+	orc_nerf_mlp_forward(n, params, enc.data(), coords, rgbsigma, nullptr, nullptr, nullptr, nullptr);
+}
+
+extern "C" void orc_nerf_density(const orc_model* m, const orc_half* params, uint32_t n, const float* positions, uint32_t pos_stride, orc_half* density) {
+	std::vector<orc_half> enc((size_t)n * 32);
+	orc_grid_forward(n, m->n_levels, m->offsets, m->base_resolution, std::log2(m->per_level_scale), m->scales, params + ORC_MLP_PARAMS, positions, pos_stride, enc.data());
+	MlpWeightsF Wf(params);
+	const float* W = Wf.w.data();
+	#pragma omp parallel for schedule(static)
+	for (int64_t i = 0; i < (int64_t)n; ++i) {
+		float x[32], h1[64], tmp[64];
+		for (int k = 0; k < 32; ++k) x[k] = h2f(enc[(size_t)i * 32 + k]);
+		matvec(W + W1D, 64, 32, x, tmp);
+		for (int k = 0; k < 64; ++k) h1[k] = rh(tmp[k] > 0.f ? tmp[k] : 0.f);
+		matvec(W + W2D, 1, 64, h1, tmp);
+		density[i] = f2h(tmp[0]);
+	}
+}
+
+extern "C" void orc_nerf_forward_backward(const orc_model* m, const orc_half* params, uint32_t n, const float* coords, const orc_half* dL_dout, float* grad) {
+	std::vector<orc_half> enc((size_t)n * 32), denc((size_t)n * 32);
+	const float l2 = std::log2(m->per_level_scale);
+	orc_grid_forward(n, m->n_levels, m->offsets, m->base_resolution, l2, m->scales, params + ORC_MLP_PARAMS, coords, 7, enc.data());
+	orc_nerf_mlp_backward(n, params, enc.data(), coords, dL_dout, denc.data(), grad);
+	orc_grid_backward(n, m->n_levels, m->offsets, m->base_resolution, l2, m->scales, coords, 7, denc.data(), grad + ORC_MLP_PARAMS);
+}
+
+// =============================================================================================
+// camera transform the kernels actually use (common_device.cuh:224-234 with zero rolling shutter:
+// matrix -> quaternion -> slerp(t=0) -> normalize -> matrix). Eigen/src/Geometry/Quaternion.h.
+// =============================================================================================
+extern "C" void orc_effective_xform(const float* m12, float* out12) {
+	auto M = [&](int r, int c) { return m12[c * 3 + r]; };
+	float q[4]; // x y z w
+	float t = sum3(M(0, 0), M(1, 1), M(2, 2));
+	if (t > 0.f) {
+		t = std::sqrt(t + 1.0f);
+		q[3] = 0.5f * t;
+		t = 0.5f / t;
+		q[0] = (M(2, 1) - M(1, 2)) * t;
+		q[1] = (M(0, 2) - M(2, 0)) * t;
+		q[2] = (M(1, 0) - M(0, 1)) * t;
+	} else {
+		int i = 0;
+		if (M(1, 1) > M(0, 0)) i = 1;
+		if (M(2, 2) > M(i, i)) i = 2;
+		int j = (i + 1) % 3, k = (j + 1) % 3;
+		t = std::sqrt(M(i, i) - M(j, j) - M(k, k) + 1.0f);
+		q[i] = 0.5f * t;
+		t = 0.5f / t;
+		q[3] = (M(k, j) - M(j, k)) * t;
+		q[j] = (M(j, i) + M(i, j)) * t;
+		q[k] = (M(k, i) + M(i, k)) * t;
+	}
+	// slerp(0, same quaternion): scale0 = 1, scale1 = 0 in both branches -> coefficients unchanged up to +0*q.
+	for (int c = 0; c < 4; ++c) q[c] = 1.0f * q[c] + 0.0f * q[c];
+	float z = sum4(q[0] * q[0], q[1] * q[1], q[2] * q[2], q[3] * q[3]);
+	if (z > 0.f) { float nrm = std::sqrt(z); for (int c = 0; c < 4; ++c) q[c] = q[c] / nrm; }
+	const float tx = 2.f * q[0], ty = 2.f * q[1], tz = 2.f * q[2];
+	const float twx = tx * q[3], twy = ty * q[3], twz = tz * q[3];
+	const float txx = tx * q[0], txy = ty * q[0], txz = tz * q[0];
+	const float tyy = ty * q[1], tyz = tz * q[1], tzz = tz * q[2];
+	auto R = [&](int r, int c) -> float& { return out12[c * 3 + r]; };
+	R(0, 0) = 1.f - (tyy + tzz); R(0, 1) = txy - twz; R(0, 2) = txz + twy;
+	R(1, 0) = txy + twz; R(1, 1) = 1.f - (txx + tzz); R(1, 2) = tyz - twx;
+	R(2, 0) = txz - twy; R(2, 1) = tyz + twx; R(2, 2) = 1.f - (txx + tyy);
+	out12[9] = m12[9] + (m12[9] - m12[9]) * 0.f; out12[10] = m12[10] + (m12[10] - m12[10]) * 0.f; out12[11] = m12[11] + (m12[11] - m12[11]) * 0.f;
+}
+
+// =============================================================================================
+// K1: generate_training_samples_nerf, src/testbed_nerf.cu:1085-1260
+// =============================================================================================
+namespace {
+struct TrainRay { Vec3 o, d_unnorm, d; float startt; float cone_angle; bool valid; };
+
+// ray set-up shared by K1 and nothing else (K6 only re-derives the pixel). testbed_nerf.cu:1118-1202
+inline TrainRay setup_training_ray(uint32_t i, uint32_t n_rays, orc_pcg32 rng, uint32_t n_images, const orc_image* images,
+                                   const float* eff_xforms, const AABB& aabb, bool snap, float cone_angle_constant) {
+	TrainRay r{};
+	uint32_t img = image_idx(i, n_rays, n_images);
+	const orc_image& im = images[img];
+	orc_pcg32_advance(&rng, (int64_t)i * N_MAX_RANDOM_SAMPLES_PER_RAY);
+	float x, y;
+	random_image_pos_training(rng, im.w, im.h, snap, &x, &y);
+	float px[4];
+	read_rgba(x, y, im, px);
+	if (px[0] < 0.0f) { r.valid = false; return r; }
+	/* max_level */ // max_level_rand_training is off: no draw (testbed_nerf.cu:1130)
+	float motionblur_time = orc_pcg32_next_float(&rng); (void)motionblur_time;
+	const float* xf = eff_xforms + (size_t)img * 12;
+	r.o = {xf[9], xf[10], xf[11]};
+	float dcam[3] = {(x - im.cx) * (float)im.w / im.fx, (y - im.cy) * (float)im.h / im.fy, 1.0f};
+	// xform.block<3,3>(0,0) * d: row r = sum3 over columns (column-major storage)
+	float row0[3] = {xf[0], xf[3], xf[6]}, row1[3] = {xf[1], xf[4], xf[7]}, row2[3] = {xf[2], xf[5], xf[8]};
+	r.d_unnorm = {dot3(row0, dcam), dot3(row1, dcam), dot3(row2, dcam)};
+	float z = sum3(r.d_unnorm.x * r.d_unnorm.x, r.d_unnorm.y * r.d_unnorm.y, r.d_unnorm.z * r.d_unnorm.z);
+	if (z > 0.f) { float nrm = std::sqrt(z); r.d = {r.d_unnorm.x / nrm, r.d_unnorm.y / nrm, r.d_unnorm.z / nrm}; } else r.d = r.d_unnorm;
+	float tmin, tmax;
+	aabb_ray_intersect(aabb, r.o, r.d, &tmin, &tmax);
+	r.cone_angle = cone_angle_constant;
+	tmin = std::fmax(tmin, 0.0f);
+	float startt = tmin;
+	startt += calc_dt(startt, r.cone_angle) * orc_pcg32_next_float(&rng);
+	r.startt = startt;
+	r.valid = true;
+	return r;
+}
+
+template <typename F>
+inline uint32_t march_training_ray(const TrainRay& r, const AABB& aabb, const uint8_t* bitfield, uint32_t max_steps, F&& on_sample) {
+	Vec3 idir = {1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z};
+	uint32_t j = 0;
+	float t = r.startt;
+	Vec3 pos;
+	while (aabb_contains(aabb, pos = Vec3{r.o.x + t * r.d.x, r.o.y + t * r.d.y, r.o.z + t * r.d.z}) && j < max_steps) {
+		float dt = calc_dt(t, r.cone_angle);
+		uint32_t mip = mip_from_dt(dt, pos);
+		if (density_grid_occupied_at(pos, bitfield, mip)) {
+			on_sample(j, pos, dt);
+			++j;
+			t += dt;
+		} else {
+			uint32_t res = NERF_GRIDSIZE >> mip;
+			t = advance_to_next_voxel(t, r.cone_angle, pos, r.d, idir, res);
+		}
+	}
+	return j;
+}
+} // namespace
+
+extern "C" uint32_t orc_generate_training_samples(
+	uint32_t n_rays, const float* aabb6, uint32_t max_samples, uint32_t n_rays_total, orc_pcg32 rng,
+	uint32_t n_images, const orc_image* images, const uint8_t* bitfield, int snap_to_pixel_centers, float cone_angle_constant,
+	uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, uint32_t* counters_out) {
+	(void)n_rays_total;
+	const AABB aabb = make_aabb(aabb6);
+	std::vector<float> eff((size_t)n_images * 12);
+	for (uint32_t k = 0; k < n_images; ++k) orc_effective_xform(images[k].xform, eff.data() + (size_t)k * 12);
+
+	// pass 1 (parallel): per-ray set-up and step count (testbed_nerf.cu:1204-1219)
+	std::vector<TrainRay> tr(n_rays);
+	std::vector<uint32_t> counts(n_rays, 0);
+	#pragma omp parallel for schedule(dynamic, 64)
+	for (int64_t i = 0; i < (int64_t)n_rays; ++i) {
+		tr[i] = setup_training_ray((uint32_t)i, n_rays, rng, n_images, images, eff.data(), aabb, snap_to_pixel_centers != 0, cone_angle_constant);
+		if (tr[i].valid) counts[i] = march_training_ray(tr[i], aabb, bitfield, NERF_STEPS, [](uint32_t, const Vec3&, float) {});
+	}
+	// allocation in ray order: one valid serialisation of the reference's atomicAdd (:1225,:1232)
+	uint32_t numsteps_counter = 0, ray_counter = 0;
+	std::vector<uint32_t> base_of(n_rays, 0xFFFFFFFFu), slot_of(n_rays, 0);
+	for (uint32_t i = 0; i < n_rays; ++i) {
+		if (!tr[i].valid || counts[i] == 0) continue;
+		uint32_t base = numsteps_counter;
+		numsteps_counter += counts[i];
+		if (base + counts[i] > max_samples) continue;
+		base_of[i] = base; slot_of[i] = ray_counter++;
+	}
+	// pass 2 (parallel): write samples (testbed_nerf.cu:1239-1253)
+	#pragma omp parallel for schedule(dynamic, 64)
+	for (int64_t i = 0; i < (int64_t)n_rays; ++i) {
+		if (base_of[i] == 0xFFFFFFFFu) continue;
+		const TrainRay& r = tr[i];
+		uint32_t slot = slot_of[i], base = base_of[i];
+		ray_indices[slot] = (uint32_t)i;
+		float* ro = rays + (size_t)slot * 6;
+		ro[0] = r.o.x; ro[1] = r.o.y; ro[2] = r.o.z; ro[3] = r.d_unnorm.x; ro[4] = r.d_unnorm.y; ro[5] = r.d_unnorm.z;
+		numsteps[slot * 2 + 0] = counts[i];
+		numsteps[slot * 2 + 1] = base;
+		Vec3 wd = {(r.d.x + 1.0f) * 0.5f, (r.d.y + 1.0f) * 0.5f, (r.d.z + 1.0f) * 0.5f}; // warp_direction :292
+		float* co = coords + (size_t)base * 7;
+		march_training_ray(r, aabb, bitfield, counts[i], [&](uint32_t j, const Vec3& pos, float dt) {
+			Vec3 wp = warp_position(pos, aabb);
+			float* c = co + (size_t)j * 7;
+			c[0] = wp.x; c[1] = wp.y; c[2] = wp.z; c[3] = warp_dt(dt); c[4] = wd.x; c[5] = wd.y; c[6] = wd.z;
+		});
+	}
+	if (counters_out) { counters_out[0] = numsteps_counter; counters_out[1] = ray_counter; }
+	return ray_counter;
+}
+
+// =============================================================================================
+// K6: compute_loss_kernel_train_nerf, src/testbed_nerf.cu:1280-1597
+// =============================================================================================
+extern "C" uint32_t orc_compute_loss(
+	uint32_t n_rays_kept, uint32_t n_rays, const float* aabb6, uint32_t n_rays_total, orc_pcg32 rng, uint32_t max_samples_compacted,
+	float loss_scale_in, const float* background_color3, int color_space, int random_bg, int linear_colors,
+	uint32_t n_images, const orc_image* images, const orc_half* rgbsigma, const uint32_t* ray_indices, const float* rays,
+	uint32_t* numsteps_io, const float* coords_in_all, float* coords_out_all, orc_half* dloss_dout_all, int loss_type, float* loss_output,
+	int rgb_activation, int density_activation, int snap_to_pixel_centers, float mean_density, float near_distance) {
+	(void)n_rays_total;
+	const AABB aabb = make_aabb(aabb6);
+	const float EPSILON = 1e-4f;
+
+	struct PerRay { float rgb_ray[3]; float depth_ray; uint32_t compacted; float rgbtarget[3]; };
+	std::vector<PerRay> pr(n_rays_kept);
+
+	// phase 1 (parallel): forward compositing + target colour (:1341-1428)
+	#pragma omp parallel for schedule(dynamic, 64)
+	for (int64_t i = 0; i < (int64_t)n_rays_kept; ++i) {
+		uint32_t numsteps = numsteps_io[i * 2 + 0], base = numsteps_io[i * 2 + 1];
+		const float* cin = coords_in_all + (size_t)base * 7;
+		const orc_half* no = rgbsigma + (size_t)base * 4;
+		float T = 1.f;
+		float rgb_ray[3] = {0, 0, 0};
+		float depth_ray = 0.f;
+		uint32_t cn = 0;
+		const float* ro = rays + (size_t)i * 6;
+		for (; cn < numsteps; ++cn) {
+			if (T < EPSILON) break;
+			float rgb[3] = {network_to_rgb(h2f(no[0]), rgb_activation), network_to_rgb(h2f(no[1]), rgb_activation), network_to_rgb(h2f(no[2]), rgb_activation)};
+			Vec3 pos = unwarp_position(cin, aabb);
+			float dt = unwarp_dt(cin[3]);
+			float dx = pos.x - ro[0], dy = pos.y - ro[1], dz = pos.z - ro[2];
+			float cur_depth = std::sqrt(sum3(dx * dx, dy * dy, dz * dz));
+			float density = network_to_density(h2f(no[3]), density_activation);
+			const float alpha = 1.f - std::exp(-density * dt);
+			const float weight = alpha * T;
+			for (int c = 0; c < 3; ++c) rgb_ray[c] += weight * rgb[c];
+			depth_ray += weight * cur_depth;
+			T *= (1.f - alpha);
+			no += 4; cin += 7;
+		}
+		uint32_t ray_idx = ray_indices[i];
+		orc_pcg32 r = rng_advanced(rng, (int64_t)ray_idx * N_MAX_RANDOM_SAMPLES_PER_RAY);
+		uint32_t img = image_idx(ray_idx, n_rays, n_images);
+		const orc_image& im = images[img];
+		float x, y;
+		random_image_pos_training(r, im.w, im.h, snap_to_pixel_centers != 0, &x, &y);
+		float bg[3] = {background_color3[0], background_color3[1], background_color3[2]};
+		if (random_bg) { bg[0] = orc_pcg32_next_float(&r); bg[1] = orc_pcg32_next_float(&r); bg[2] = orc_pcg32_next_float(&r); }
+		for (int c = 0; c < 3; ++c) bg[c] = srgb_to_linear(bg[c]);
+		float texsamp[4];
+		read_rgba(x, y, im, texsamp);
+		float rgbtarget[3];
+		// exposure is zero: exposure_scale = exp(0.693..*0) = 1 (:1403)
+		if (linear_colors || color_space == 0) {
+			for (int c = 0; c < 3; ++c) rgbtarget[c] = 1.0f * texsamp[c] + (1.0f - texsamp[3]) * bg[c];
+			if (!linear_colors) { for (int c = 0; c < 3; ++c) { rgbtarget[c] = linear_to_srgb(rgbtarget[c]); bg[c] = linear_to_srgb(bg[c]); } }
+		} else {
+			for (int c = 0; c < 3; ++c) bg[c] = linear_to_srgb(bg[c]);
+			if (texsamp[3] > 0) {
+				for (int c = 0; c < 3; ++c) rgbtarget[c] = linear_to_srgb(1.0f * texsamp[c] / texsamp[3]) * texsamp[3] + (1.0f - texsamp[3]) * bg[c];
+			} else {
+				for (int c = 0; c < 3; ++c) rgbtarget[c] = bg[c];
+			}
+		}
+		if (cn == numsteps) { for (int c = 0; c < 3; ++c) rgb_ray[c] += T * bg[c]; }
+		PerRay& p = pr[i];
+		for (int c = 0; c < 3; ++c) { p.rgb_ray[c] = rgb_ray[c]; p.rgbtarget[c] = rgbtarget[c]; }
+		p.depth_ray = depth_ray; p.compacted = cn;
+	}
+
+	// compaction in ray-slot order (one valid serialisation of the atomicAdd at :1434)
+	uint32_t counter = 0;
+	std::vector<uint32_t> cbase(n_rays_kept);
+	for (uint32_t i = 0; i < n_rays_kept; ++i) {
+		uint32_t compacted_base = counter;
+		counter += pr[i].compacted;
+		uint32_t cn = std::min(max_samples_compacted - std::min(max_samples_compacted, compacted_base), pr[i].compacted);
+		cbase[i] = compacted_base;
+		pr[i].compacted = cn;
+	}
+
+	const float loss_scale = loss_scale_in / n_rays;
+	const float output_l2_reg = rgb_activation == 3 ? 1e-4f : 0.0f;
+	const float output_l1_reg_density = mean_density < NERF_MIN_OPTICAL_THICKNESS ? 1e-4f : 0.0f;
+
+	// phase 2 (parallel): gradients + compaction (:1436-1556)
+	#pragma omp parallel for schedule(dynamic, 64)
+	for (int64_t i = 0; i < (int64_t)n_rays_kept; ++i) {
+		uint32_t base = numsteps_io[i * 2 + 1];
+		const PerRay& p = pr[i];
+		uint32_t cn = p.compacted, compacted_base = cbase[i];
+		numsteps_io[i * 2 + 0] = cn;
+		numsteps_io[i * 2 + 1] = compacted_base;
+		if (cn == 0) continue;
+		const float* cin = coords_in_all + (size_t)base * 7;
+		const orc_half* no = rgbsigma + (size_t)base * 4;
+		float* cout = coords_out_all + (size_t)compacted_base * 7;
+		orc_half* dout = dloss_dout_all + (size_t)compacted_base * 4;
+		const float* ro = rays + (size_t)i * 6;
+
+		LossAndGradient lg = loss_and_gradient(p.rgbtarget, p.rgb_ray, loss_type);
+		float mean_loss = sum3(lg.loss[0], lg.loss[1], lg.loss[2]) / 3.0f; // Eigen mean(): redux sum / size
+		if (loss_output) loss_output[i] = mean_loss / (float)n_rays;
+
+		float rgb_ray2[3] = {0, 0, 0};
+		float depth_ray2 = 0.f;
+		float T = 1.f;
+		for (uint32_t j = 0; j < cn; ++j) {
+			std::memcpy(cout + (size_t)j * 7, cin + (size_t)j * 7, 7 * sizeof(float));
+			const float* ci = cin + (size_t)j * 7;
+			Vec3 pos = unwarp_position(ci, aabb);
+			float dx = pos.x - ro[0], dy = pos.y - ro[1], dz = pos.z - ro[2];
+			float depth = std::sqrt(sum3(dx * dx, dy * dy, dz * dz));
+			float dt = unwarp_dt(ci[3]);
+			float o0 = h2f(no[0]), o1 = h2f(no[1]), o2 = h2f(no[2]), o3 = h2f(no[3]);
+			float rgb[3] = {network_to_rgb(o0, rgb_activation), network_to_rgb(o1, rgb_activation), network_to_rgb(o2, rgb_activation)};
+			const float density = network_to_density(o3, density_activation);
+			const float alpha = 1.f - std::exp(-density * dt);
+			const float weight = alpha * T;
+			for (int c = 0; c < 3; ++c) rgb_ray2[c] += weight * rgb[c];
+			depth_ray2 += weight * depth;
+			T *= (1.f - alpha);
+
+			float suffix[3], dloss_by_drgb[3];
+			for (int c = 0; c < 3; ++c) { suffix[c] = p.rgb_ray[c] - rgb_ray2[c]; dloss_by_drgb[c] = weight * lg.gradient[c]; }
+			float ov[3] = {o0, o1, o2};
+			for (int c = 0; c < 3; ++c) {
+				dout[j * 4 + c] = f2h(loss_scale * (dloss_by_drgb[c] * network_to_rgb_derivative(ov[c], rgb_activation) + std::fmax(0.0f, output_l2_reg * ov[c])));
+			}
+			float density_derivative = network_to_density_derivative(o3, density_activation);
+			// depth supervision is off: depth_loss_gradient = 0 -> depth_supervision = 0 * (...) (:1450-1452,:1537)
+			const float depth_suffix = p.depth_ray - depth_ray2;
+			const float depth_supervision = 0.0f * (T * depth - depth_suffix);
+			float tv[3] = {T * rgb[0] - suffix[0], T * rgb[1] - suffix[1], T * rgb[2] - suffix[2]};
+			float dloss_by_dmlp = density_derivative * (dt * (dot3(lg.gradient, tv) + depth_supervision));
+			dout[j * 4 + 3] = f2h(
+				loss_scale * dloss_by_dmlp +
+				(o3 < 0.0f ? -output_l1_reg_density : 0.0f) +
+				(o3 > -10.0f && depth < near_distance ? 1e-4f : 0.0f));
+			no += 4;
+		}
+	}
+	return counter;
+}
+
+// K7: fill_rollover / fill_rollover_and_rescale, tcnn common_device.h:517-537
+extern "C" void orc_fill_rollover(uint32_t n_target, uint32_t n_valid, float* coords, orc_half* dloss_dout) {
+	if (n_valid == 0 || n_valid >= n_target) return;
+	for (size_t i = (size_t)n_valid * 7; i < (size_t)n_target * 7; ++i) coords[i] = coords[i % ((size_t)n_valid * 7)];
+	for (size_t i = (size_t)n_valid * 4; i < (size_t)n_target * 4; ++i) {
+		float v = h2f(dloss_dout[i % ((size_t)n_valid * 4)]);
+		dloss_dout[i] = f2h(v * n_valid / n_target);
+	}
+}
+
+// =============================================================================================
+// K15: optimizer. Ema(ExponentialDecay(Adam)) -- tcnn adam.h:48-119,:152-190; exponential_decay.h:60-72; ema.h:63-140
+// =============================================================================================
+extern "C" void orc_optimizer_init(orc_optimizer* o) { // configs/nerf/base.json:5-22
+	o->learning_rate = 1e-2f; o->beta1 = 0.9f; o->beta2 = 0.99f; o->epsilon = 1e-15f; o->l2_reg = 1e-6f; o->ema_decay = 0.95f;
+	o->decay_start = 20000; o->decay_interval = 10000; o->decay_base = 0.33f;
+	o->step = 0; o->lr_factor = 1.0f;
+}
+
+extern "C" void orc_optimizer_step(orc_optimizer* o, uint32_t n_params, uint32_t n_matrix_params, float loss_scale, const float* grad,
+                                   float* w_fp32, orc_half* w_half, orc_half* w_ema, float* m1, float* m2, uint32_t* param_steps) {
+	// ExponentialDecay::step (uses the step count before Adam increments it)
+	if (o->step == 0) o->lr_factor = 1.0f;
+	if (o->step >= o->decay_start && (o->step - o->decay_start) % o->decay_interval == 0) o->lr_factor *= o->decay_base;
+	const float base_lr = o->learning_rate * o->lr_factor;
+	++o->step; // Adam::step
+	const float beta1 = o->beta1, beta2 = o->beta2, epsilon = o->epsilon, l2_reg = o->l2_reg;
+	// Ema::step
+	const uint32_t current_step = o->step;
+	const float ema_decay = o->ema_decay;
+	const float ema_debias_old = 1 - (float)std::pow(ema_decay, current_step - 1);
+	const float ema_debias_new = 1.0f / (1 - (float)std::pow(ema_decay, current_step));
+	#pragma omp parallel for schedule(static)
+	for (int64_t i = 0; i < (int64_t)n_params; ++i) {
+		float gradient = grad[i] / loss_scale;
+		bool skip = ((uint32_t)i >= n_matrix_params && gradient == 0);
+		if (!skip) {
+			const float weight_fp = w_fp32[i];
+			if ((uint32_t)i < n_matrix_params) gradient += l2_reg * weight_fp;
+			const float gradient_sq = gradient * gradient;
+			float first_moment = m1[i] = beta1 * m1[i] + (1 - beta1) * gradient;
+			const float second_moment = m2[i] = beta2 * m2[i] + (1 - beta2) * gradient_sq;
+			float learning_rate = base_lr;
+			const uint32_t cs = ++param_steps[i];
+			learning_rate *= std::sqrt(1 - std::pow(beta2, (float)cs)) / (1 - std::pow(beta1, (float)cs));
+			const float effective_learning_rate = std::fmin(std::fmax(learning_rate / (std::sqrt(second_moment) + epsilon), 0.f), std::numeric_limits<float>::max());
+			const float decayed_weight = (1 - 0.f * learning_rate) * weight_fp - std::copysign(0.f * learning_rate, weight_fp);
+			float new_weight = decayed_weight - effective_learning_rate * first_moment;
+			w_fp32[i] = new_weight;
+			w_half[i] = f2h(new_weight);
+		}
+		float filtered_val = (h2f(w_ema[i]) * ema_decay * ema_debias_old + h2f(w_half[i]) * (1 - ema_decay)) * ema_debias_new;
+		w_ema[i] = f2h(filtered_val);
+	}
+}
+
+// =============================================================================================
+// K16: density grid. src/testbed_nerf.cu:369-610
+// =============================================================================================
+extern "C" void orc_mark_untrained_density_grid(uint32_t n_elements, float* grid, uint32_t n_images, const orc_image* images, int clear_visible) {
+	#pragma omp parallel for schedule(static)
+	for (int64_t i = 0; i < (int64_t)n_elements; ++i) {
+		uint32_t level = (uint32_t)i / GRID_CELLS, pos_idx = (uint32_t)i % GRID_CELLS;
+		uint32_t x = morton3D_invert(pos_idx >> 0), y = morton3D_invert(pos_idx >> 1), z = morton3D_invert(pos_idx >> 2);
+		float s = std::scalbn(1.0f, (int)level);
+		float pos[3] = {
+			(((float)x + 0.5f) / NERF_GRIDSIZE - 0.5f) * s + 0.5f,
+			(((float)y + 0.5f) / NERF_GRIDSIZE - 0.5f) * s + 0.5f,
+			(((float)z + 0.5f) / NERF_GRIDSIZE - 0.5f) * s + 0.5f};
+		float voxel_radius = 0.5f * SQRT3 * s / NERF_GRIDSIZE;
+		int count = 0;
+		for (uint32_t j = 0; j < n_images; ++j) {
+			const orc_image& im = images[j];
+			float half_resx = im.w * 0.5f, half_resy = im.h * 0.5f;
+			const float* xf = im.xform;
+			float ploc[3] = {pos[0] - xf[9], pos[1] - xf[10], pos[2] - xf[11]};
+			float cx = dot3(ploc, xf + 0), cy = dot3(ploc, xf + 3), cz = dot3(ploc, xf + 6);
+			if (cz > 0.f) {
+				if (std::fabs(cx) - voxel_radius < cz / im.fx * half_resx && std::fabs(cy) - voxel_radius < cz / im.fy * half_resy) {
+					count++;
+					if (count > 0) break;
+				}
+			}
+		}
+		if (clear_visible || (grid[i] < 0) != (count <= 0)) grid[i] = (count > 0) ? 0.f : -1.f;
+	}
+}
+
+extern "C" void orc_generate_grid_samples(uint32_t n_elements, orc_pcg32 rng_in, uint32_t step, const float* aabb6, const float* grid_in,
+                                          float* positions3, uint32_t* indices, uint32_t n_cascades, float thresh) {
+	const AABB aabb = make_aabb(aabb6);
+	#pragma omp parallel for schedule(static)
+	for (int64_t ii = 0; ii < (int64_t)n_elements; ++ii) {
+		uint32_t i = (uint32_t)ii;
+		orc_pcg32 rng = rng_advanced(rng_in, (int64_t)i * 4);
+		uint32_t level = (uint32_t)(orc_pcg32_next_float(&rng) * n_cascades) % n_cascades;
+		uint32_t idx = 0;
+		for (uint32_t j = 0; j < 10; ++j) {
+			idx = ((i + step * n_elements) * 56924617u + j * 19349663u + 96925573u) % GRID_CELLS;
+			idx += level * GRID_CELLS;
+			if (grid_in[idx] > thresh) break;
+		}
+		uint32_t pos_idx = idx % GRID_CELLS;
+		uint32_t x = morton3D_invert(pos_idx >> 0), y = morton3D_invert(pos_idx >> 1), z = morton3D_invert(pos_idx >> 2);
+		float rx = orc_pcg32_next_float(&rng), ry = orc_pcg32_next_float(&rng), rz = orc_pcg32_next_float(&rng);
+		float s = std::scalbn(1.0f, (int)level);
+		Vec3 pos = {
+			(((float)x + rx) / NERF_GRIDSIZE - 0.5f) * s + 0.5f,
+			(((float)y + ry) / NERF_GRIDSIZE - 0.5f) * s + 0.5f,
+			(((float)z + rz) / NERF_GRIDSIZE - 0.5f) * s + 0.5f};
+		Vec3 wp = warp_position(pos, aabb);
+		positions3[(size_t)i * 3 + 0] = wp.x; positions3[(size_t)i * 3 + 1] = wp.y; positions3[(size_t)i * 3 + 2] = wp.z;
+		indices[i] = idx;
+	}
+}
+
+extern "C" void orc_splat_and_ema(uint32_t n_samples, const uint32_t* indices, const orc_half* density, uint32_t n_elements, float decay, float* grid) {
+	std::vector<float> tmp(n_elements, 0.f);
+	for (uint32_t i = 0; i < n_samples; ++i) {
+		float mlp = std::exp(h2f(density[i])); // density activation Exponential (:506)
+		float optical_thickness = mlp * std::scalbn(MIN_CONE_STEPSIZE, 0);
+		// atomicMax on the uint bit pattern (:509-511)
+		uint32_t a, b; std::memcpy(&a, &tmp[indices[i]], 4); std::memcpy(&b, &optical_thickness, 4);
+		if (b > a) tmp[indices[i]] = optical_thickness;
+	}
+	for (uint32_t i = 0; i < n_elements; ++i) {
+		float prev_val = grid[i];
+		grid[i] = (prev_val < 0.f) ? prev_val : std::fmax(prev_val * decay, tmp[i]);
+	}
+}
+
+// mean over the first cascade of max(v,0)/n (:2851-2852). Summation order is unspecified in the
+// reference (tcnn::reduce_sum); the oracle sums in double.
+extern "C" float orc_density_grid_mean(const float* grid) {
+	double s = 0.0;
+	for (uint32_t i = 0; i < GRID_CELLS; ++i) s += (double)(std::fmax(grid[i], 0.f) / (float)GRID_CELLS);
+	return (float)s;
+}
+
+extern "C" void orc_bitfield(uint32_t n_cascades_used, const float* grid, float mean_density, uint8_t* bitfield) {
+	const uint32_t n_bytes = GRID_CELLS / 8 * NERF_CASCADES, n_nonzero = GRID_CELLS / 8 * n_cascades_used;
+	float thresh = std::min(NERF_MIN_OPTICAL_THICKNESS, mean_density);
+	for (uint32_t i = 0; i < n_bytes; ++i) {
+		if (i >= n_nonzero) { bitfield[i] = 0; continue; }
+		uint8_t bits = 0;
+		for (uint8_t j = 0; j < 8; ++j) bits |= grid[(size_t)i * 8 + j] > thresh ? ((uint8_t)1 << j) : 0;
+		bitfield[i] = bits;
+	}
+	for (uint32_t level = 1; level < NERF_CASCADES; ++level) {
+		const uint8_t* prev = bitfield + grid_mip_offset(level - 1) / 8;
+		uint8_t* next = bitfield + grid_mip_offset(level) / 8;
+		for (uint32_t i = 0; i < GRID_CELLS / 64; ++i) {
+			uint8_t bits = 0;
+			for (uint8_t j = 0; j < 8; ++j) bits |= prev[(size_t)i * 8 + j] > 0 ? ((uint8_t)1 << j) : 0;
+			uint32_t x = morton3D_invert(i >> 0) + NERF_GRIDSIZE / 8, y = morton3D_invert(i >> 1) + NERF_GRIDSIZE / 8, z = morton3D_invert(i >> 2) + NERF_GRIDSIZE / 8;
+			next[morton3D(x, y, z)] |= bits;
+		}
+	}
+}

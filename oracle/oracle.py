@@ -1,0 +1,305 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes/numpy front end of oracle/liboracle.so (see ngp_oracle.h).
+
+May be imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs only. Builds the library on first use with `make -C oracle liboracle.so`.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+MLP_PARAMS = 10240
+GRID_CELLS = 128 ** 3
+
+
+class Pcg32(C.Structure):
+    _fields_ = [("state", C.c_uint64), ("inc", C.c_uint64)]
+
+
+class Model(C.Structure):
+    _fields_ = [("n_levels", C.c_uint32), ("log2_hashmap_size", C.c_uint32), ("base_resolution", C.c_uint32),
+                ("per_level_scale", C.c_float), ("offsets", C.c_uint32 * 33), ("scales", C.c_float * 32),
+                ("n_grid_params", C.c_uint32)]
+
+
+class Image(C.Structure):
+    _fields_ = [("pixels", C.c_void_p), ("w", C.c_int32), ("h", C.c_int32), ("fx", C.c_float), ("fy", C.c_float),
+                ("cx", C.c_float), ("cy", C.c_float), ("xform", C.c_float * 12)]
+
+
+class Optimizer(C.Structure):
+    _fields_ = [("learning_rate", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("epsilon", C.c_float),
+                ("l2_reg", C.c_float), ("ema_decay", C.c_float), ("decay_start", C.c_uint32), ("decay_interval", C.c_uint32),
+                ("decay_base", C.c_float), ("step", C.c_uint32), ("lr_factor", C.c_float)]
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle.so"])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        _LIB = C.CDLL(path)
+        _LIB.orc_pcg32_next_float.restype = C.c_float
+        _LIB.orc_pcg32_next_uint.restype = C.c_uint32
+        _LIB.orc_grid_offsets.restype = C.c_uint32
+        _LIB.orc_generate_training_samples.restype = C.c_uint32
+        _LIB.orc_compute_loss.restype = C.c_uint32
+        _LIB.orc_density_grid_mean.restype = C.c_float
+        _LIB.orc_trainer_create.restype = C.c_void_p
+        _LIB.orc_trainer_n_params.restype = C.c_uint32
+        _LIB.orc_trainer_step.restype = C.c_uint32
+        _LIB.orc_trainer_bitfield.restype = C.POINTER(C.c_uint8)
+        _LIB.orc_trainer_density_grid.restype = C.POINTER(C.c_float)
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def pcg32(seed, seq=1):
+    r = Pcg32()
+    lib().orc_pcg32_seed(C.byref(r), C.c_uint64(seed), C.c_uint64(seq))
+    return r
+
+
+def pcg32_advance(r, delta=1 << 32):
+    lib().orc_pcg32_advance(C.byref(r), C.c_int64(delta))
+
+
+def pcg32_next_uint(r):
+    return lib().orc_pcg32_next_uint(C.byref(r))
+
+
+def pcg32_next_float(r):
+    return lib().orc_pcg32_next_float(C.byref(r))
+
+
+def model(n_levels=16, log2_hashmap_size=19, base_resolution=16, per_level_scale=None, aabb_scale=1):
+    if per_level_scale is None:
+        # Testbed::reset_network, src/testbed.cu:2313-2325 (float math)
+        per_level_scale = float(np.exp(np.log(np.float32(2048.0) * np.float32(aabb_scale) / np.float32(base_resolution)) / np.float32(n_levels - 1), dtype=np.float32))
+    m = Model()
+    lib().orc_model_init(C.byref(m), n_levels, log2_hashmap_size, base_resolution, C.c_float(per_level_scale))
+    return m
+
+
+def make_images(pixels_list, xforms, fx, fy, cx=0.5, cy=0.5):
+    """pixels_list: list/array of uint8 [h,w,4]; xforms: [n,3,4] ngp camera matrices. Keeps references alive."""
+    n = len(pixels_list)
+    arr = (Image * n)()
+    keep = []
+    for i in range(n):
+        px = np.ascontiguousarray(pixels_list[i], dtype=np.uint8)
+        keep.append(px)
+        arr[i].pixels = px.ctypes.data
+        arr[i].h, arr[i].w = px.shape[0], px.shape[1]
+        arr[i].fx, arr[i].fy, arr[i].cx, arr[i].cy = fx, fy, cx, cy
+        xf = np.asarray(xforms[i], dtype=np.float32).reshape(3, 4)
+        col_major = xf.T.reshape(-1)  # column-major 3x4
+        for k in range(12):
+            arr[i].xform[k] = float(col_major[k])
+    arr._keep = keep
+    return arr
+
+
+def grid_forward(m, grid_half, positions, pos_stride=None, scales=None):
+    positions = _f32(positions)
+    n = positions.shape[0]
+    stride = positions.shape[1] if pos_stride is None else pos_stride
+    out = np.empty((n, 2 * m.n_levels), dtype=np.float16)
+    sc = _f32(scales) if scales is not None else None
+    lib().orc_grid_forward(n, m.n_levels, m.offsets, m.base_resolution, C.c_float(np.log2(np.float32(m.per_level_scale))), _p(sc),
+                           _p(np.ascontiguousarray(grid_half)), _p(positions), stride, _p(out))
+    return out
+
+
+def grid_indices(m, level, positions, scales=None):
+    positions = _f32(positions)
+    n = positions.shape[0]
+    idx = np.empty((n, 8), dtype=np.uint32)
+    w = np.empty((n, 8), dtype=np.float32)
+    sc = _f32(scales) if scales is not None else None
+    lib().orc_grid_indices(n, level, m.offsets, m.base_resolution, C.c_float(np.log2(np.float32(m.per_level_scale))), _p(sc),
+                           _p(positions), positions.shape[1], _p(idx), _p(w))
+    return idx, w
+
+
+def grid_backward(m, positions, dL_dy, scales=None):
+    positions = _f32(positions)
+    n = positions.shape[0]
+    dL_dy = np.ascontiguousarray(dL_dy, dtype=np.float16)
+    grad = np.zeros(m.n_grid_params, dtype=np.float32)
+    sc = _f32(scales) if scales is not None else None
+    lib().orc_grid_backward(n, m.n_levels, m.offsets, m.base_resolution, C.c_float(np.log2(np.float32(m.per_level_scale))), _p(sc),
+                            _p(positions), positions.shape[1], _p(dL_dy), _p(grad))
+    return grad
+
+
+def sh4(dirs):
+    dirs = _f32(dirs)
+    out = np.empty((dirs.shape[0], 16), dtype=np.float16)
+    lib().orc_sh4(dirs.shape[0], _p(dirs), dirs.shape[1], _p(out), 16)
+    return out
+
+
+def mlp_forward(mlp_half, encoded, coords, save=False):
+    n = encoded.shape[0]
+    encoded = np.ascontiguousarray(encoded, dtype=np.float16)
+    coords = _f32(coords)
+    out = np.empty((n, 4), dtype=np.float16)
+    if save:
+        h1 = np.empty((n, 64), np.float16); rin = np.empty((n, 32), np.float16); g1 = np.empty((n, 64), np.float16); g2 = np.empty((n, 64), np.float16)
+    else:
+        h1 = rin = g1 = g2 = None
+    lib().orc_nerf_mlp_forward(n, _p(np.ascontiguousarray(mlp_half, dtype=np.float16)), _p(encoded), _p(coords), _p(out), _p(h1), _p(rin), _p(g1), _p(g2))
+    return (out, h1, rin, g1, g2) if save else out
+
+
+def mlp_backward(mlp_half, encoded, coords, dL_dout):
+    n = encoded.shape[0]
+    denc = np.empty((n, 32), dtype=np.float16)
+    grad = np.empty(MLP_PARAMS, dtype=np.float32)
+    lib().orc_nerf_mlp_backward(n, _p(np.ascontiguousarray(mlp_half, dtype=np.float16)), _p(np.ascontiguousarray(encoded, dtype=np.float16)), _p(_f32(coords)),
+                                _p(np.ascontiguousarray(dL_dout, dtype=np.float16)), _p(denc), _p(grad))
+    return denc, grad
+
+
+def nerf_inference(m, params_half, coords):
+    coords = _f32(coords)
+    out = np.empty((coords.shape[0], 4), dtype=np.float16)
+    lib().orc_nerf_inference(C.byref(m), _p(np.ascontiguousarray(params_half, dtype=np.float16)), coords.shape[0], _p(coords), _p(out))
+    return out
+
+
+def nerf_density(m, params_half, positions):
+    positions = _f32(positions)
+    out = np.empty(positions.shape[0], dtype=np.float16)
+    lib().orc_nerf_density(C.byref(m), _p(np.ascontiguousarray(params_half, dtype=np.float16)), positions.shape[0], _p(positions), positions.shape[1], _p(out))
+    return out
+
+
+def nerf_forward_backward(m, params_half, coords, dL_dout):
+    coords = _f32(coords)
+    grad = np.empty(MLP_PARAMS + m.n_grid_params, dtype=np.float32)
+    lib().orc_nerf_forward_backward(C.byref(m), _p(np.ascontiguousarray(params_half, dtype=np.float16)), coords.shape[0], _p(coords),
+                                    _p(np.ascontiguousarray(dL_dout, dtype=np.float16)), _p(grad))
+    return grad
+
+
+def effective_xform(xf34):
+    src = _f32(np.asarray(xf34).reshape(3, 4).T.reshape(-1))
+    dst = np.empty(12, dtype=np.float32)
+    lib().orc_effective_xform(_p(src), _p(dst))
+    return dst.reshape(4, 3).T.copy()
+
+
+def generate_training_samples(n_rays, aabb6, max_samples, rng, images, bitfield, snap=True, cone_angle=0.0):
+    aabb6 = _f32(aabb6)
+    ray_indices = np.zeros(n_rays, np.uint32); rays = np.zeros((n_rays, 6), np.float32); numsteps = np.zeros((n_rays, 2), np.uint32)
+    coords = np.zeros((max_samples, 7), np.float32); counters = np.zeros(2, np.uint32)
+    kept = lib().orc_generate_training_samples(n_rays, _p(aabb6), max_samples, 0, rng, len(images), images, _p(np.ascontiguousarray(bitfield)),
+                                               int(snap), C.c_float(cone_angle), _p(ray_indices), _p(rays), _p(numsteps), _p(coords), _p(counters))
+    return dict(n_kept=kept, counters=counters, ray_indices=ray_indices, rays=rays, numsteps=numsteps, coords=coords)
+
+
+def compute_loss(n_kept, n_rays, aabb6, rng, batch, images, rgbsigma, ray_indices, rays, numsteps, coords_in, mean_density,
+                 loss_scale=128.0, background=(0, 0, 0), color_space=1, random_bg=True, linear_colors=False, loss_type=4,
+                 rgb_activation=2, density_activation=3, snap=True, near_distance=0.2):
+    aabb6 = _f32(aabb6)
+    numsteps = np.array(numsteps, dtype=np.uint32, copy=True)
+    coords_out = np.zeros((batch, 7), np.float32); dloss = np.zeros((batch, 4), np.float16); loss = np.zeros(n_rays, np.float32)
+    bg = _f32(background)
+    total = lib().orc_compute_loss(n_kept, n_rays, _p(aabb6), 0, rng, batch, C.c_float(loss_scale), _p(bg), color_space, int(random_bg), int(linear_colors),
+                                   len(images), images, _p(np.ascontiguousarray(rgbsigma, dtype=np.float16)), _p(np.ascontiguousarray(ray_indices, dtype=np.uint32)),
+                                   _p(_f32(rays)), _p(numsteps), _p(_f32(coords_in)), _p(coords_out), _p(dloss), loss_type, _p(loss),
+                                   rgb_activation, density_activation, int(snap), C.c_float(mean_density), C.c_float(near_distance))
+    return dict(compacted=total, numsteps=numsteps, coords_out=coords_out, dloss=dloss, loss=loss)
+
+
+def fill_rollover(batch, n_valid, coords, dloss):
+    lib().orc_fill_rollover(batch, n_valid, _p(coords), _p(dloss))
+
+
+def optimizer():
+    o = Optimizer()
+    lib().orc_optimizer_init(C.byref(o))
+    return o
+
+
+def optimizer_step(o, n_matrix, loss_scale, grad, w_fp32, w_half, w_ema, m1, m2, steps):
+    lib().orc_optimizer_step(C.byref(o), w_fp32.shape[0], n_matrix, C.c_float(loss_scale), _p(_f32(grad)), _p(w_fp32), _p(w_half), _p(w_ema), _p(m1), _p(m2), _p(steps))
+
+
+def mark_untrained(grid, images, clear_visible=True):
+    lib().orc_mark_untrained_density_grid(grid.shape[0], _p(grid), len(images), images, int(clear_visible))
+
+
+def generate_grid_samples(n, rng, step, aabb6, grid_in, n_cascades, thresh):
+    pos = np.zeros((n, 3), np.float32); idx = np.zeros(n, np.uint32)
+    lib().orc_generate_grid_samples(n, rng, step, _p(_f32(aabb6)), _p(grid_in), _p(pos), _p(idx), n_cascades, C.c_float(thresh))
+    return pos, idx
+
+
+def splat_and_ema(indices, density_half, decay, grid):
+    lib().orc_splat_and_ema(indices.shape[0], _p(indices), _p(np.ascontiguousarray(density_half, dtype=np.float16)), grid.shape[0], C.c_float(decay), _p(grid))
+
+
+def density_grid_mean(grid):
+    return lib().orc_density_grid_mean(_p(grid))
+
+
+def bitfield(n_cascades_used, grid, mean):
+    out = np.zeros(GRID_CELLS * 8 // 8, np.uint8)
+    lib().orc_bitfield(n_cascades_used, _p(grid), C.c_float(mean), _p(out))
+    return out
+
+
+class Trainer:
+    """Whole-iteration CPU restatement of Testbed::train for the NeRF mode (oracle/ngp_trainer.cpp)."""
+
+    def __init__(self, images, aabb_scale=1, seed=1337):
+        self._images = images
+        self._h = C.c_void_p(lib().orc_trainer_create(len(images), images, aabb_scale, seed))
+        self.n_params = lib().orc_trainer_n_params(self._h)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_trainer_destroy(self._h)
+            self._h = None
+
+    def train(self, batch_size):
+        stats = np.zeros(4, np.float32)
+        lib().orc_trainer_train(self._h, batch_size, _p(stats))
+        return dict(loss=float(stats[0]), rays_per_batch=int(stats[1]), measured_batch_size_before_compaction=int(stats[2]), measured_batch_size=int(stats[3]))
+
+    @property
+    def training_step(self):
+        return lib().orc_trainer_step(self._h)
+
+    def params(self):
+        w = np.empty(self.n_params, np.float32); h = np.empty(self.n_params, np.float16); e = np.empty(self.n_params, np.float16)
+        lib().orc_trainer_get_params(self._h, _p(w), _p(h), _p(e))
+        return w, h, e
+
+    def set_params(self, w_fp32):
+        lib().orc_trainer_set_params(self._h, _p(_f32(w_fp32)))
+
+    def bitfield(self):
+        return np.ctypeslib.as_array(lib().orc_trainer_bitfield(self._h), shape=(GRID_CELLS * 8 // 8,)).copy()
+
+    def density_grid(self, n_cascades=1):
+        return np.ctypeslib.as_array(lib().orc_trainer_density_grid(self._h), shape=(GRID_CELLS * n_cascades,)).copy()

@@ -1,0 +1,138 @@
+// TEST INFRASTRUCTURE ONLY -- never linked into the product library.
+//
+// extern "C" launcher around the reference's own NeRF training kernels, obtained by including
+// src/testbed_nerf.cu from where it lies under /root/reference (nothing is copied). Only the
+// __global__ kernels are called; Testbed member functions defined in other translation units stay
+// unresolved (the library is linked with --unresolved-symbols=ignore-all and never calls them).
+//
+// Kernels launched (reference file:line, all in src/testbed_nerf.cu):
+//   generate_training_samples_nerf :1085      compute_loss_kernel_train_nerf :1280
+//   mark_untrained_density_grid :369          generate_grid_samples_nerf_nonuniform :465
+//   splat_grid_samples_nerf_max_nearest_neighbor :496   ema_grid_samples_nerf :532
+//   grid_to_bitfield :563                     bitfield_max_pool :589
+#include <testbed_nerf.cu>
+
+using namespace ngp;
+using namespace tcnn;
+using namespace Eigen;
+
+namespace {
+
+struct DeviceDataset {
+	GPUMemory<TrainingImageMetadata> metadata;
+	GPUMemory<TrainingXForm> xforms;
+};
+
+// Builds the per-image metadata array the reference kernels read (nerf_loader.h:30-46).
+// pixels: one device buffer holding n_images RGBA8 images of w*h pixels back to back.
+DeviceDataset make_dataset(uint32_t n_images, int w, int h, float fx, float fy, float cx, float cy, const uint8_t* pixels, const float* xforms_3x4_colmajor_host) {
+	std::vector<TrainingImageMetadata> md(n_images);
+	std::vector<TrainingXForm> xf(n_images);
+	for (uint32_t i = 0; i < n_images; ++i) {
+		md[i].pixels = pixels + (size_t)i * w * h * 4;
+		md[i].image_data_type = EImageDataType::Byte;
+		md[i].resolution = {w, h};
+		md[i].focal_length = {fx, fy};
+		md[i].principal_point = {cx, cy};
+		Matrix<float, 3, 4> m;
+		for (int k = 0; k < 12; ++k) m.data()[k] = xforms_3x4_colmajor_host[i * 12 + k];
+		xf[i].start = m;
+		xf[i].end = m;
+	}
+	DeviceDataset d;
+	d.metadata.resize_and_copy_from_host(md);
+	d.xforms.resize_and_copy_from_host(xf);
+	return d;
+}
+
+BoundingBox make_aabb(const float* aabb6) {
+	return BoundingBox{Vector3f{aabb6[0], aabb6[1], aabb6[2]}, Vector3f{aabb6[3], aabb6[4], aabb6[5]}};
+}
+
+}
+
+extern "C" {
+
+int ref_generate_training_samples(
+	uint32_t n_rays, const float* aabb6, uint32_t max_samples, uint32_t n_rays_total,
+	uint64_t rng_state, uint64_t rng_inc,
+	uint32_t* ray_counter, uint32_t* numsteps_counter, uint32_t* ray_indices, float* rays /*6 floats*/, uint32_t* numsteps, float* coords /*7 floats*/,
+	uint32_t n_images, int w, int h, float fx, float fy, float cx, float cy, const uint8_t* pixels, const float* xforms_host,
+	const uint8_t* bitfield, int snap_to_pixel_centers, float cone_angle_constant
+) {
+	DeviceDataset d = make_dataset(n_images, w, h, fx, fy, cx, cy, pixels, xforms_host);
+	default_rng_t rng; rng.state = rng_state; rng.inc = rng_inc;
+	cudaMemset(ray_counter, 0, 4);
+	cudaMemset(numsteps_counter, 0, 4);
+	linear_kernel(generate_training_samples_nerf, 0, 0,
+		n_rays, make_aabb(aabb6), max_samples, n_rays_total, rng,
+		ray_counter, numsteps_counter, ray_indices, (Ray*)rays, numsteps,
+		PitchedPtr<NerfCoordinate>((NerfCoordinate*)coords, 1, 0, 0),
+		n_images, d.metadata.data(), d.xforms.data(), bitfield,
+		false, (float*)nullptr, (bool)snap_to_pixel_centers, false, cone_angle_constant,
+		(const float*)nullptr, Vector2i{0, 0}, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, Vector2i{0, 0},
+		(const float*)nullptr, 0u);
+	return (int)cudaDeviceSynchronize();
+}
+
+// loss_type / activations are the reference's enum integers (common.h:103-119).
+int ref_compute_loss(
+	uint32_t n_rays, const float* aabb6, uint32_t n_rays_total, uint64_t rng_state, uint64_t rng_inc,
+	uint32_t max_samples_compacted, const uint32_t* rays_counter, float loss_scale, int padded_output_width,
+	const float* background_color3, int color_space, int random_bg, int linear_colors,
+	uint32_t n_images, int w, int h, float fx, float fy, float cx, float cy, const uint8_t* pixels, const float* xforms_host,
+	const void* network_output_half, uint32_t* numsteps_counter_compacted, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps,
+	const float* coords_in, float* coords_out, void* dloss_doutput_half, int loss_type, float* loss_output,
+	int rgb_activation, int density_activation, int snap_to_pixel_centers, const float* mean_density_ptr, float near_distance
+) {
+	DeviceDataset d = make_dataset(n_images, w, h, fx, fy, cx, cy, pixels, xforms_host);
+	default_rng_t rng; rng.state = rng_state; rng.inc = rng_inc;
+	GPUMemory<Array3f> exposure(n_images);
+	exposure.memset(0);
+	cudaMemset(numsteps_counter_compacted, 0, 4);
+	linear_kernel(compute_loss_kernel_train_nerf, 0, 0,
+		n_rays, make_aabb(aabb6), n_rays_total, rng, max_samples_compacted, rays_counter, loss_scale, padded_output_width,
+		(const float*)nullptr, (float*)nullptr, Vector2i{0, 0}, ELossType::L2,
+		Array3f{background_color3[0], background_color3[1], background_color3[2]}, (EColorSpace)color_space, (bool)random_bg, (bool)linear_colors,
+		n_images, d.metadata.data(), (const network_precision_t*)network_output_half, numsteps_counter_compacted,
+		ray_indices, (const Ray*)rays, numsteps,
+		PitchedPtr<const NerfCoordinate>((NerfCoordinate*)coords_in, 1, 0, 0),
+		PitchedPtr<NerfCoordinate>((NerfCoordinate*)coords_out, 1, 0, 0),
+		(network_precision_t*)dloss_doutput_half, (ELossType)loss_type, ELossType::L1, loss_output,
+		false, (float*)nullptr, (ENerfActivation)rgb_activation, (ENerfActivation)density_activation, (bool)snap_to_pixel_centers,
+		(float*)nullptr, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, Vector2i{0, 0}, Vector2i{0, 0},
+		(const float*)nullptr, Vector2i{0, 0}, (float*)nullptr, (float*)nullptr, mean_density_ptr,
+		(const Array3f*)exposure.data(), (Array3f*)nullptr, 0.0f, near_distance);
+	return (int)cudaDeviceSynchronize();
+}
+
+int ref_mark_untrained_density_grid(uint32_t n_elements, float* grid, uint32_t n_images, int w, int h, float fx, float fy, const float* xforms_host, int clear_visible) {
+	DeviceDataset d = make_dataset(n_images, w, h, fx, fy, 0.5f, 0.5f, nullptr, xforms_host);
+	linear_kernel(mark_untrained_density_grid, 0, 0, n_elements, grid, n_images, d.metadata.data(), d.xforms.data(), (bool)clear_visible);
+	return (int)cudaDeviceSynchronize();
+}
+
+int ref_generate_grid_samples(uint32_t n_elements, uint64_t rng_state, uint64_t rng_inc, uint32_t step, const float* aabb6, const float* grid_in, float* positions3, uint32_t* indices, uint32_t n_cascades, float thresh) {
+	default_rng_t rng; rng.state = rng_state; rng.inc = rng_inc;
+	linear_kernel(generate_grid_samples_nerf_nonuniform, 0, 0, n_elements, rng, step, make_aabb(aabb6), grid_in, (NerfPosition*)positions3, indices, n_cascades, thresh);
+	return (int)cudaDeviceSynchronize();
+}
+
+int ref_splat_and_ema(uint32_t n_samples, const uint32_t* indices, const void* density_half, float* grid_tmp, uint32_t n_elements, float decay, float* grid) {
+	cudaMemset(grid_tmp, 0, sizeof(float) * n_elements);
+	linear_kernel(splat_grid_samples_nerf_max_nearest_neighbor, 0, 0, n_samples, indices, (const network_precision_t*)density_half, grid_tmp, ENerfActivation::Logistic, ENerfActivation::Exponential);
+	linear_kernel(ema_grid_samples_nerf, 0, 0, n_elements, decay, 0u, grid, grid_tmp);
+	return (int)cudaDeviceSynchronize();
+}
+
+// mean_density_ptr is an input here (the reference computes it with tcnn::reduce_sum, testbed_nerf.cu:2852).
+int ref_bitfield(uint32_t n_cascades_used, const float* grid, uint8_t* bitfield, const float* mean_density_ptr) {
+	const uint32_t n_elements = 128 * 128 * 128;
+	linear_kernel(grid_to_bitfield, 0, 0, n_elements / 8 * 8, n_elements / 8 * n_cascades_used, grid, bitfield, mean_density_ptr);
+	for (uint32_t level = 1; level < 8; ++level) {
+		linear_kernel(bitfield_max_pool, 0, 0, n_elements / 64, bitfield + grid_mip_offset(level - 1) / 8, bitfield + grid_mip_offset(level) / 8);
+	}
+	return (int)cudaDeviceSynchronize();
+}
+
+}

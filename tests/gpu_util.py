@@ -1,0 +1,47 @@
+"""Helpers for the -m gpu tests: torch is plumbing only (device memory), every compute call goes through the C ABI."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+import pyngp
+
+
+def dev(a):
+    """numpy -> cuda tensor holding the same bytes (fp16 as int16 views stay fp16)."""
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def host(t):
+    torch.cuda.synchronize()
+    return t.cpu().numpy()
+
+
+def images_to_device(scene):
+    """Uploads the scene; returns (device Image array tensor, n, keepalive)."""
+    imgs = scene["images"]
+    n = len(imgs)
+    pix = dev(np.ascontiguousarray(imgs))
+    arr = (pyngp.Image * n)()
+    per = imgs[0].shape[0] * imgs[0].shape[1] * 4
+    for i in range(n):
+        arr[i].pixels = pix.data_ptr() + i * per
+        arr[i].h, arr[i].w = imgs[i].shape[0], imgs[i].shape[1]
+        arr[i].fx, arr[i].fy, arr[i].cx, arr[i].cy = scene["fx"], scene["fy"], scene["cx"], scene["cy"]
+        cm = np.asarray(scene["xforms"][i], dtype=np.float32).reshape(3, 4).T.reshape(-1).copy()
+        eff = np.empty(12, np.float32)
+        pyngp.lib().ngpb_effective_xform(cm.ctypes.data_as(C.c_void_p), eff.ctypes.data_as(C.c_void_p))
+        for k in range(12):
+            arr[i].raw_xform[k] = float(cm[k])
+            arr[i].xform[k] = float(eff[k])
+    raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
+    meta = dev(raw)
+    return meta, n, (pix, arr)
+
+
+def rng_struct(orc_rng):
+    return pyngp.Rng(orc_rng.state, orc_rng.inc)

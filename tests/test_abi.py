@@ -1,0 +1,62 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/ngpb.h declares (no compute calls here)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "ngpb.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ngpb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import pyngp
+    lib = pyngp.lib()
+    declared = _declared_symbols()
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), f"{name} is declared in include/ngpb.h but not exported"
+    assert sorted(pyngp.EXPORTED_SYMBOLS) == declared
+
+
+def test_host_only_entry_points(orc):
+    """ngpb_grid_init / ngpb_effective_xform / ngpb_optimizer_init are host code: checked against the oracle without a GPU."""
+    import pyngp
+    for aabb_scale in (1, 4, 16):
+        g, entries = pyngp.grid_init(aabb_scale=aabb_scale)
+        m = orc.model(aabb_scale=aabb_scale)
+        assert entries * 2 == m.n_grid_params
+        assert list(g.offsets[:17]) == list(m.offsets[:17])
+        assert np.array_equal(np.array(g.scale[:16], np.float32).view(np.uint32), np.array(m.scales[:16], np.float32).view(np.uint32))
+    rs = np.random.RandomState(0)
+    for _ in range(50):
+        q, _ = np.linalg.qr(rs.randn(3, 3))
+        if np.linalg.det(q) < 0:
+            q[:, 0] *= -1
+        xf = np.concatenate([q, rs.randn(3, 1)], axis=1).astype(np.float32)
+        want = orc.effective_xform(xf)
+        src = xf.T.reshape(-1).copy(); dst = np.empty(12, np.float32)
+        pyngp.lib().ngpb_effective_xform(src.ctypes.data_as(C.c_void_p), dst.ctypes.data_as(C.c_void_p))
+        got = dst.reshape(4, 3).T
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        assert np.abs(got - xf).max() < 1e-5
+    o = pyngp.Optimizer(); pyngp.lib().ngpb_optimizer_init(C.byref(o))
+    r = orc.optimizer()
+    assert (o.learning_rate, o.beta1, o.beta2, o.epsilon, o.l2_reg, o.ema_decay, o.decay_start, o.decay_interval, o.decay_base) == \
+           (r.learning_rate, r.beta1, r.beta2, r.epsilon, r.l2_reg, r.ema_decay, r.decay_start, r.decay_interval, r.decay_base)
+
+
+def test_missing_gpu_fails_loudly():
+    """No CPU fallback: creating a Testbed without a B200 raises instead of silently computing elsewhere."""
+    import pytest
+    import torch
+    import pyngp
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError):
+        pyngp.Testbed()

@@ -1,0 +1,206 @@
+"""The CPU oracle against known answers: PCG32 reference output, the level table SURVEY.md s8 derives from the
+reference, analytic gradients, internal invariants of K1/K6, and the reference golden vectors under tests/golden/."""
+import os
+
+import numpy as np
+import pytest
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_pcg32_known_answer(orc):
+    # pcg32 demo, pcg32_srandom(42, 54): the published first outputs of the minimal C implementation
+    r = orc.pcg32(42, 54)
+    assert [orc.pcg32_next_uint(r) for _ in range(6)] == [0xa15c02b7, 0x7b47f409, 0xba1d3330, 0x83d2f293, 0xbfa4784b, 0xcbed606e]
+    # advance(k) == k draws
+    a = orc.pcg32(1337); b = orc.pcg32(1337)
+    for _ in range(1000):
+        orc.pcg32_next_uint(a)
+    orc.pcg32_advance(b, 1000)
+    assert a.state == b.state
+    f = orc.pcg32_next_float(a)
+    assert 0.0 <= f < 1.0
+
+
+def test_level_table_matches_reference_derivation(orc):
+    """lego config (aabb_scale 1): resolutions and entry counts computed from grid.h:985-1018."""
+    m = orc.model(aabb_scale=1)
+    sizes = [m.offsets[i + 1] - m.offsets[i] for i in range(16)]
+    assert sizes[:5] == [4096, 12168, 29792, 79512, 205384]
+    assert sizes[5:] == [524288] * 11
+    assert m.offsets[16] == 6098120 and m.n_grid_params == 12196240
+    res = [int(np.ceil(m.scales[i])) + 1 for i in range(16)]
+    assert res == [16, 23, 31, 43, 59, 81, 112, 154, 213, 295, 407, 562, 777, 1073, 1483, 2048]
+    fox = orc.model(aabb_scale=4)
+    assert fox.n_grid_params == 13074912  # fox, pls 1.515717
+
+
+def test_grid_forward_is_interpolation_and_backward_is_its_adjoint(orc):
+    m = orc.model()
+    rs = np.random.RandomState(0)
+    table = (rs.randn(m.n_grid_params) * 0.5).astype(np.float16)
+    pos = rs.rand(2000, 3).astype(np.float32)
+    enc = orc.grid_forward(m, table, pos).astype(np.float64)
+    # weights of the 8 corners sum to one and reproduce the forward value (up to the fp16 accumulation of grid.h:341)
+    for level in (0, 4, 9, 15):
+        idx, w = orc.grid_indices(m, level, pos)
+        assert np.allclose(w.sum(1), 1.0, atol=1e-5)
+        assert idx.max() < m.offsets[level + 1] - m.offsets[level]
+        t = table[2 * m.offsets[level]: 2 * m.offsets[level + 1]].astype(np.float64).reshape(-1, 2)
+        manual = (t[idx] * w[..., None]).sum(1)
+        assert np.abs(manual - enc[:, 2 * level: 2 * level + 2]).max() < 4e-3
+    # adjoint: <dy, J t> == <J^T dy, t> for the linear map t -> enc (exact weights, fp16 data)
+    dy = (rs.randn(2000, 32) * 0.1).astype(np.float16)
+    grad = orc.grid_backward(m, pos, dy).astype(np.float64)
+    lhs = (dy.astype(np.float64) * enc).sum()
+    rhs = (grad * table.astype(np.float64)).sum()
+    assert abs(lhs - rhs) < 2e-3 * abs(lhs)
+
+
+def test_mlp_backward_matches_finite_differences(orc):
+    rs = np.random.RandomState(1)
+    shapes = [(64, 32), (16, 64), (64, 32), (64, 64), (16, 64)]
+    w = np.concatenate([(rs.rand(o * i) * 2 - 1) * np.sqrt(6.0 / (o + i)) for o, i in shapes]).astype(np.float16)
+    n = 256
+    enc = (rs.randn(n, 32) * 0.5).astype(np.float16)
+    coords = rs.rand(n, 7).astype(np.float32)
+    dout = (rs.randn(n, 4)).astype(np.float16)
+    denc, grad = orc.mlp_backward(w, enc, coords, dout)
+
+    def objective(weights):
+        out = orc.mlp_forward(weights, enc, coords).astype(np.float64)
+        return (out * dout.astype(np.float64)).sum()
+    # central differences on a few weights of every matrix; fp16 storage limits the step, so compare loosely
+    base = 0
+    for o, i in shapes:
+        for k in rs.choice(o * i, 6, replace=False):
+            idx = base + k
+            if base == 9216 and k >= 3 * 64:
+                continue  # padded rgb outputs carry no gradient
+            step = max(abs(float(w[idx])) * 0.05, 0.01)
+            wp, wm = w.copy(), w.copy()
+            wp[idx] = np.float16(float(w[idx]) + step); wm[idx] = np.float16(float(w[idx]) - step)
+            fd = (objective(wp) - objective(wm)) / (float(wp[idx]) - float(wm[idx]))
+            assert abs(fd - grad[idx]) < 0.08 * max(1.0, abs(grad[idx]), abs(fd)) + 0.6, (idx, fd, grad[idx])
+        base += o * i
+    assert np.all(grad[9216 + 3 * 64:] == 0)
+    assert denc.shape == (n, 32) and np.isfinite(denc.astype(np.float32)).all()
+
+
+def test_generate_training_samples_invariants(orc, small_scene):
+    from conftest import scene_occupancy_bitfield
+    grid, bits = scene_occupancy_bitfield(orc)
+    imgs = orc.make_images(small_scene["images"], small_scene["xforms"], small_scene["fx"], small_scene["fy"])
+    rng = orc.pcg32(1337)
+    n_rays = 4096
+    out = orc.generate_training_samples(n_rays, [0, 0, 0, 1, 1, 1], 1 << 17, rng, imgs, bits)
+    k = out["n_kept"]
+    ns = out["numsteps"][:k]
+    assert k > 0 and np.all(ns[:, 0] > 0) and np.all(ns[:, 0] <= 1024)
+    assert np.array_equal(ns[:, 1], np.concatenate([[0], np.cumsum(ns[:-1, 0])]))  # exclusive prefix in ray order
+    assert ns[:, 0].sum() == out["counters"][0]
+    assert np.all(np.diff(out["ray_indices"][:k].astype(np.int64)) > 0)            # slots in increasing ray index
+    c = out["coords"][: out["counters"][0]]
+    assert np.all((c[:, :3] >= 0) & (c[:, :3] <= 1))
+    assert np.all(c[:, 3] == 0)  # warp_dt(MIN_CONE_STEPSIZE) with cone_angle 0
+    # every sample lies in an occupied cell of cascade 0
+    cell = np.clip((c[:, :3] * 128).astype(np.int64), 0, 127)
+
+    def expand(v):
+        v = (v * 0x00010001) & 0xFF0000FF; v = (v * 0x00000101) & 0x0F00F00F; v = (v * 0x00000011) & 0xC30C30C3; v = (v * 0x00000005) & 0x49249249
+        return v
+    mort = expand(cell[:, 0]) | (expand(cell[:, 1]) << 1) | (expand(cell[:, 2]) << 2)
+    assert np.all(grid[mort] > 0)
+    # determinism
+    out2 = orc.generate_training_samples(n_rays, [0, 0, 0, 1, 1, 1], 1 << 17, rng, imgs, bits)
+    assert np.array_equal(out["coords"], out2["coords"])
+
+
+def test_compute_loss_invariants(orc, small_scene):
+    from conftest import scene_occupancy_bitfield
+    _, bits = scene_occupancy_bitfield(orc)
+    imgs = orc.make_images(small_scene["images"], small_scene["xforms"], small_scene["fx"], small_scene["fy"])
+    rng = orc.pcg32(5)
+    n_rays, batch = 1024, 4096
+    k1 = orc.generate_training_samples(n_rays, [0, 0, 0, 1, 1, 1], 1 << 16, rng, imgs, bits)
+    n_s = int(k1["counters"][0])
+    rs = np.random.RandomState(0)
+    rgbsigma = np.zeros((1 << 16, 4), np.float16)
+    rgbsigma[:n_s] = rs.randn(n_s, 4).astype(np.float16)
+    rgbsigma[:n_s, 3] += 3  # dense medium: early termination compacts strongly
+    out = orc.compute_loss(k1["n_kept"], n_rays, [0, 0, 0, 1, 1, 1], rng, batch, imgs, rgbsigma, k1["ray_indices"], k1["rays"], k1["numsteps"], k1["coords"], 0.005)
+    k = k1["n_kept"]
+    cn = out["numsteps"][:k]
+    assert np.all(cn[:, 0] <= k1["numsteps"][:k, 0])
+    assert out["compacted"] < n_s  # terminated rays dropped their tails
+    assert cn[:, 0].sum() == min(out["compacted"], batch) or out["compacted"] > batch
+    # compacted coordinates are the prefix of each ray's samples
+    for i in (0, k // 2, k - 1):
+        b0, c0 = k1["numsteps"][i, 1], cn[i]
+        if c0[0]:
+            assert np.array_equal(out["coords_out"][c0[1]: c0[1] + c0[0]], k1["coords"][b0: b0 + c0[0]])
+    assert np.isfinite(out["dloss"].astype(np.float32)).all() and np.abs(out["dloss"].astype(np.float32)).max() > 0
+    assert np.all(out["loss"] >= 0) and out["loss"].sum() > 0
+
+
+def test_trainer_loss_decreases(orc, small_scene):
+    """Whole-iteration restatement: a few steps at a small batch reduce the loss and adapt rays_per_batch (testbed_nerf.cu:2890)."""
+    imgs = orc.make_images(small_scene["images"], small_scene["xforms"], small_scene["fx"], small_scene["fy"])
+    t = orc.Trainer(imgs, aabb_scale=1, seed=1337)
+    assert t.n_params == 12206480
+    stats = [t.train(1 << 12) for _ in range(17)]
+    assert stats[0]["rays_per_batch"] == 4096
+    assert stats[1]["rays_per_batch"] != 4096 and stats[1]["rays_per_batch"] % 128 == 0
+    assert 0 < stats[16]["loss"] < stats[0]["loss"]
+    assert t.training_step == 17
+    w, h, e = t.params()
+    assert np.isfinite(w).all()
+
+
+def _golden(name):
+    p = os.path.join(GOLDEN, name)
+    if not os.path.exists(p):
+        pytest.skip(f"{name} not generated yet (oracle/gen_golden.py on the GPU box)")
+    return np.load(p)
+
+
+def test_golden_grid_forward(orc):
+    """Reference kernel_grid<__half,3,2> output (tcnn grid.h:220), run on a B200 from the reference's own sources."""
+    g = _golden("ref_grid.npz")
+    m = orc.model(aabb_scale=int(g["aabb_scale"]))
+    got = orc.grid_forward(m, g["table"], g["positions"], scales=g["device_scales"])
+    want = g["encoded_soa"].T  # reference layout is [feature][sample]
+    assert np.array_equal(got.view(np.uint16), np.ascontiguousarray(want).view(np.uint16))
+
+
+def test_golden_grid_backward(orc):
+    g = _golden("ref_grid.npz")
+    m = orc.model(aabb_scale=int(g["aabb_scale"]))
+    got = orc.grid_backward(m, g["positions"], np.ascontiguousarray(g["dy_soa"].T), scales=g["device_scales"])
+    want = g["grad"].astype(np.float32)
+    # the reference accumulates with fp16 atomics (grid.h:436-441): tolerance = fp16 rounding of the running sums
+    assert np.abs(got - want).max() <= 2e-2 * np.abs(want).max()
+    assert np.array_equal(got != 0, want != 0) or (np.abs(got[(got != 0) != (want != 0)]).max() < 1e-6)
+
+
+def test_golden_sh(orc):
+    g = _golden("ref_grid.npz")
+    got = orc.sh4(g["dirs"])
+    assert np.array_equal(got.view(np.uint16), g["sh"].view(np.uint16))
+
+
+def test_golden_training_samples(orc):
+    """Reference generate_training_samples_nerf (src/testbed_nerf.cu:1085) built with -fmad=false: identical sample set."""
+    g = _golden("ref_k1_nofma.npz")
+    imgs = orc.make_images(g["images"], g["xforms"], float(g["fx"]), float(g["fy"]))
+    rng = orc.Pcg32(int(g["rng_state"]), int(g["rng_inc"]))
+    out = orc.generate_training_samples(int(g["n_rays"]), g["aabb"], int(g["max_samples"]), rng, imgs, g["bitfield"])
+    # the reference's slot order is atomic-order dependent: canonicalise by ray index
+    order = np.argsort(g["ray_indices"][: int(g["ray_counter"])])
+    assert int(g["ray_counter"]) == out["n_kept"] and int(g["numsteps_counter"]) == out["counters"][0]
+    assert np.array_equal(g["ray_indices"][order], out["ray_indices"][: out["n_kept"]])
+    assert np.array_equal(g["numsteps"][order, 0], out["numsteps"][: out["n_kept"], 0])
+    for j in order[:: max(1, len(order) // 200)]:
+        i = int(np.searchsorted(out["ray_indices"][: out["n_kept"]], g["ray_indices"][j]))
+        n, b_ref, b = int(g["numsteps"][j, 0]), int(g["numsteps"][j, 1]), int(out["numsteps"][i, 1])
+        assert np.array_equal(g["coords"][b_ref: b_ref + n].view(np.uint32), out["coords"][b: b + n].view(np.uint32))
