@@ -48,3 +48,11 @@ def scene_occupancy_bitfield(orc, margin=1):
         m = (cx >= lo[0]) & (cx <= hi[0]) & (cy >= lo[1]) & (cy <= hi[1]) & (cz >= lo[2]) & (cz <= hi[2])
         grid[m] = 1.0
     return grid, orc.bitfield(1, grid, 0.5)
+
+
+@pytest.fixture(autouse=True)
+def _release_device_temporaries(request):
+    yield
+    if request.node.get_closest_marker("gpu") is not None:
+        import gpu_util
+        gpu_util.release()

@@ -7,9 +7,21 @@ import torch
 import pyngp
 
 
+_keepalive = []
+
+
 def dev(a):
-    """numpy -> cuda tensor holding the same bytes (fp16 as int16 views stay fp16)."""
-    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    """numpy -> cuda tensor holding the same bytes (fp16 as int16 views stay fp16). The tensor is kept alive until the
+    end of the test (release()), so `ptr(dev(x))` is safe: a dropped temporary would hand its block back to torch's
+    caching allocator, and the next dev() in the same argument list would overwrite it before the kernel runs."""
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    _keepalive.append(t)
+    return t
+
+
+def release():
+    torch.cuda.synchronize()
+    _keepalive.clear()
 
 
 def ptr(t):

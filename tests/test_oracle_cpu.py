@@ -148,11 +148,14 @@ def test_trainer_loss_decreases(orc, small_scene):
     imgs = orc.make_images(small_scene["images"], small_scene["xforms"], small_scene["fx"], small_scene["fy"])
     t = orc.Trainer(imgs, aabb_scale=1, seed=1337)
     assert t.n_params == 12206480
-    stats = [t.train(1 << 12) for _ in range(17)]
+    stats = [t.train(1 << 12) for _ in range(33)]
     assert stats[0]["rays_per_batch"] == 4096
     assert stats[1]["rays_per_batch"] != 4096 and stats[1]["rays_per_batch"] % 128 == 0
-    assert 0 < stats[16]["loss"] < stats[0]["loss"]
-    assert t.training_step == 17
+    # the loss scalar is refreshed every 16th step and is weighted by measured/batch and by the fraction of rays that fit
+    # the batch (testbed_nerf.cu:2885-2888), so compare two steps in the same regime (rays_per_batch settled at 128)
+    assert stats[16]["rays_per_batch"] == stats[32]["rays_per_batch"] == 128
+    assert 0 < stats[32]["loss"] < stats[16]["loss"]
+    assert t.training_step == 33
     w, h, e = t.params()
     assert np.isfinite(w).all()
 
