@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- NeRF training throughput of the B200-native hot path (BASELINE.json: "NeRF train iters/sec").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]                # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]  # the CPU restatement of the reference, host cores
+
+Workload (BASELINE.json configs[1]): Lego-shaped synthetic scene, 100 cameras x 800x800 RGBA8, configs/nerf/base.json
+(hash grid 16x2 / T=2^19, 64-wide density + rgb MLPs), target batch 2^18 compacted samples per iteration, random-init
+weights, seed 1337. One "step" = one `Testbed.train(batch)` = one optimizer step incl. ray generation, marching,
+inference on the uncompacted samples, compositing/loss/compaction, forward+backward, Adam/EMA, and the occupancy-grid
+refresh at the reference's cadence. `value` is device-timed (CUDA events on the testbed's stream) with the dataset
+resident in HBM; `e2e` goes through the public `pyngp.Testbed` calls with the dataset starting in pinned HOST memory
+(its upload is inside the timed region) and the loss read back to the host every step.
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "blender-ngp_b200"))
+
+METRIC = "nerf_train_iters_per_sec"
+UNIT = "it/s (batch 2^18 compacted samples per iteration)"
+BATCH = 1 << 18
+N_IMAGES, RES = 100, 800
+
+# Algorithmic bytes / flops per unit (restated in DESIGN.md s4)
+HASH_FWD_BYTES = 12 + 16 * 8 * 4 + 16 * 2 * 2      # 588 B/sample: position + 128 gathers x 4 B + 32 fp16 features out
+HASH_BWD_BYTES = 12 + 64 + 16 * 8 * 2 * 4           # 1100 B/sample: position + dL/dy + 128 x (2 x fp32) scatter-adds
+MLP_FWD_FLOPS = 20480                               # padded widths as executed
+MLP_TRAIN_FLOPS = 61440
+OPT_BYTES_FIXED = 4 + 4 + 2 + 2 + 2                 # grad read + grad zero-write (touched) + fp16 w read + EMA read/write, per param
+STAGE_ALGO = {  # stage -> (bound, per-unit quantity, unit of `achieved`)
+    "encode_inference": ("hbm", HASH_FWD_BYTES, "GB/s"),
+    "encode_train": ("hbm", HASH_FWD_BYTES, "GB/s"),
+    "encode_backward": ("hbm", HASH_BWD_BYTES, "GB/s"),
+    "mlp_inference": ("tensor", MLP_FWD_FLOPS, "TFLOP/s"),
+    "mlp_train": ("tensor", MLP_TRAIN_FLOPS, "TFLOP/s"),
+    "optimizer": ("hbm", 10, "GB/s"),
+}
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=200)
+    p.add_argument("--warmup", type=int, default=10)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--preroll", type=int, default=512, help="untimed training steps before warm-up, so the timed steps run in the steady regime "
+                   "(occupancy grid has culled empty space, refresh every 16 steps; the first 256 steps refresh 2M cells every step)")
+    p.add_argument("--batch", type=int, default=BATCH)
+    p.add_argument("--n-images", type=int, default=N_IMAGES)
+    p.add_argument("--res", type=int, default=RES)
+    p.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline leg")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(hbm=float(d["hbm_gbs"]), tensor_burst=float(d["bf16_tflops"]), tensor_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), src="measured")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms during the timed region (B200_PROFILING.md's clocks line)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 8:
+                continue
+            try:
+                sm.append(float(c[1])); smax.append(float(c[2])); power.append(float(c[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), power_w_max=float(max(power)), samples=len(sm), reasons=sorted(reasons))
+        return out
+
+
+def make_scene(n_images, res, device):
+    import synthetic
+    return synthetic.make_lego_scene(n_images, res, device=device, seed=0, as_numpy=False)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle's whole-iteration restatement (oracle/ngp_trainer.cpp) on the host cores
+# ---------------------------------------------------------------------------------------------------------
+def cpu_baseline(images_np, xforms, fx, fy, seconds, steps_cap=10 ** 9, warmup=1, batch_cpu=1 << 14):
+    """Times the CPU restatement of Testbed::train at a reduced batch in the steady-state regime (step counter 257: occupancy
+    refresh every 16 steps; occupancy grid set from the scene geometry), and scales samples/s to the metric's batch."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle as orc
+    from conftest import scene_occupancy_bitfield
+    imgs = orc.make_images(images_np, xforms, fx, fy)
+    grid, _ = scene_occupancy_bitfield(orc)
+    t = orc.Trainer(imgs, aabb_scale=1, seed=1337)
+    t.set_state(257, 0, grid)
+    for _ in range(warmup + 2):  # lets rays_per_batch settle (it adapts in two steps)
+        t.train(batch_cpu)
+    n, t0 = 0, time.perf_counter()
+    per_step = []
+    while n < steps_cap:
+        s0 = time.perf_counter()
+        t.train(batch_cpu)
+        per_step.append(time.perf_counter() - s0)
+        n += 1
+        if time.perf_counter() - t0 > seconds:
+            break
+    dt = time.perf_counter() - t0
+    it_s_cpu_batch = n / dt
+    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+    return dict(value=it_s_cpu_batch * batch_cpu / BATCH, unit=UNIT, cores=cores, kind="port",
+                sample=f"{n} training iterations at batch 2^{int(np.log2(batch_cpu))} ({it_s_cpu_batch:.2f} it/s), OpenMP over {cores} host threads, "
+                       f"steady-state regime (step counter 257, occupancy grid from scene geometry); value = it/s x 2^{int(np.log2(batch_cpu))}/2^18",
+                ms_per_step_cpu_batch=1e3 * float(np.mean(per_step))), per_step
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    try:
+        import torch
+        dev = "cuda" if torch.cuda.is_available() else "cpu"
+    except Exception:
+        dev = "cpu"
+    n_images = args.n_images if dev == "cuda" else min(args.n_images, 8)  # scene synthesis on the CPU costs ~4 s per 800x800 image
+    scene = make_scene(n_images, args.res, dev)
+    images_np = scene["images"].cpu().numpy()
+    steps = max(1, args.steps)
+    # each step is a bounded sample of the workload: one iteration at batch 2^14 (1/16 of the metric's batch)
+    cb, per_step = cpu_baseline(images_np, scene["xforms"], scene["fx"], scene["fy"], seconds=1e9, steps_cap=steps, warmup=args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": cb["ms_per_step_cpu_batch"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16 storage / fp32 accumulate",
+        "data": "synthetic",
+        "config": {"workload": f"NeRF Lego-shaped synthetic scene ({n_images} cams {args.res}x{args.res}), configs/nerf/base.json, CPU restatement of the reference "
+                               "(the reference has no CPU path of its own, SURVEY.md s8d); bounded sample per step: one iteration at batch 2^14",
+                   "batch": 1 << 14, "metric_batch": BATCH},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import pyngp
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback for the product path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    K, W = max(1, args.steps), max(3, args.warmup)
+    scene = make_scene(args.n_images, args.res, f"cuda:{local_rank}")
+    images_dev = scene["images"]
+    host_images = torch.empty(images_dev.shape, dtype=torch.uint8, pin_memory=True)
+    host_images.copy_(images_dev)
+    del images_dev
+    torch.cuda.synchronize()
+    images_np = host_images.numpy()
+    dataset_bytes = int(images_np.nbytes)
+
+    def new_testbed():
+        tb = pyngp.Testbed(device=local_rank)
+        if world > 1:
+            tb.init_data_parallel(rank, world)
+        return tb
+
+    # ---- device-timed arm: dataset resident in HBM ----
+    tb = new_testbed()
+    tb.load_training_images(list(images_np), scene["xforms"], scene["fx"], scene["fy"])
+    tb.train_n(args.preroll, args.batch)
+    tb.train_n(W, args.batch)
+    stream = torch.cuda.ExternalStream(tb.stream, device=torch.device("cuda", local_rank))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = tb.stats()["gpu_launches"]
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    cuda_profiler = os.environ.get("NGPB_BENCH_CUDA_PROFILER") == "1"  # ncu --profile-from-start off: capture the timed region only
+    if cuda_profiler:
+        torch.cuda.profiler.start()
+    ev0.record(stream)
+    tb.train_n(K, args.batch)
+    ev1.record(stream)
+    barrier()
+    if cuda_profiler:
+        torch.cuda.profiler.stop()
+    clk = clocks.stop()
+    ms = ev0.elapsed_time(ev1)
+    st = tb.stats()
+    launches = st["gpu_launches"] - launches0
+    loss = tb.loss
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / K
+    # whole-job aggregate: every rank processes `batch` compacted samples per step on its own ray shard
+    value = world * (args.batch / BATCH) * 1e3 / ms_per_step
+
+    # ---- per-stage device times for the roofline (separate pass with event brackets around every stage) ----
+    tb.profile_stages(True)
+    tb.stage_times(reset=True)
+    n_prof = min(K, 64)
+    tb.train_n(n_prof, args.batch)
+    stages = tb.stage_times(reset=True)
+    tb.profile_stages(False)
+    pk = peaks()
+    stage_report = {}
+    total_stage_ms = sum(v[0] for v in stages.values()) or 1.0
+    for name, (sms, calls, units) in stages.items():
+        if calls == 0:
+            continue
+        rep = dict(ms_per_call=sms / calls, calls_per_step=calls / n_prof, share=sms / total_stage_ms, units_per_call=units / calls)
+        if name in STAGE_ALGO and sms > 0:
+            bound, per_unit, unit = STAGE_ALGO[name]
+            achieved = units * per_unit / (sms * 1e-3) / (1e9 if bound == "hbm" else 1e12)
+            peak = pk["hbm"] if bound == "hbm" else pk["tensor_sustained"]
+            rep.update(bound=bound, achieved=achieved, peak=peak, unit=unit, frac=achieved / peak)
+        stage_report[name] = rep
+    # dominant kernel = the stage with the largest share of the step among those with a roofline model
+    dom = max((n for n in stage_report if "frac" in stage_report[n]), key=lambda n: stage_report[n]["share"])
+    d = stage_report[dom]
+    roofline = dict(kernel=dom, bound=d["bound"], achieved=d["achieved"], peak=d["peak"], unit=d["unit"], frac=d["frac"], traffic=None,
+                    peak_source=f"MEASURED_PEAKS.json ({pk['src']}; {'hbm_gbs' if d['bound'] == 'hbm' else 'bf16_tflops_sustained'})",
+                    share_of_step=d["share"], per_stage=stage_report)
+    del tb
+
+    # ---- e2e arm: public pyngp surface, dataset starts in pinned host memory, loss read back every step ----
+    tb = new_testbed()
+    barrier()
+    t0 = time.perf_counter()
+    tb.load_training_images(list(images_np), scene["xforms"], scene["fx"], scene["fy"])  # H2D of the whole dataset, inside the timed region
+    t_load = time.perf_counter() - t0
+    tb.train_n(args.preroll, args.batch)  # untimed pre-roll to the same regime as above
+    for _ in range(W):
+        tb.train(args.batch); _ = tb.loss
+    s0 = tb.stats()
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(K):
+        tb.train(args.batch)      # one optimizer step through the public call; syncs and reads the counters (+ loss every 16th step) back
+        _ = tb.loss               # host-side read of the step's result
+    torch.cuda.synchronize()
+    t_steps = time.perf_counter() - t1
+    s1 = tb.stats()
+    e2e_s = t_load + t_steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = dict(value=world * (args.batch / BATCH) * K / e2e_s, unit=UNIT,
+               h2d_bytes_per_step=(dataset_bytes + 0.0) / K, d2h_bytes_per_step=(s1["d2h_bytes"] - s0["d2h_bytes"]) / K,
+               dataset_upload_ms=1e3 * t_load, ms_per_step_host=1e3 * t_steps / K)
+    del tb
+
+    cb = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb, _ = cpu_baseline(images_np, scene["xforms"], scene["fx"], scene["fy"], seconds=args.cpu_seconds)
+        cb = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16 storage / fp32 accumulate (tcgen05 kind::f16)",
+            "data": "synthetic",
+            "config": {"workload": f"NeRF Lego-shaped synthetic scene ({args.n_images} cams {args.res}x{args.res} RGBA8), configs/nerf/base.json, "
+                                   f"batch 2^{int(np.log2(args.batch))} compacted samples/iteration/GPU, seed 1337",
+                       "batch": args.batch, "rays_per_batch": st["rays_per_batch"], "samples_before_compaction": st["measured_batch_size_before_compaction"],
+                       "samples_per_sec": value * BATCH, "pre_trained_steps": args.preroll + W, "final_loss": loss,
+                       "parallelism": "single GPU" if world == 1 else f"dp{world}: ray-sharded replicas, NCCL gradient all-reduce",
+                       "l2": "no flush: the per-iteration working set (256 MB images + 293 MB parameter/optimizer state + ~150 MB sample buffers) exceeds the 126 MB L2"},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roofline,
+        }
+        if cb is not None:
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -192,6 +192,30 @@ extern "C" uint32_t ngpb_grid_init(ngpb_grid* g, uint32_t n_levels, uint32_t log
 	return offset;
 }
 
+// grid_scale as the reference's kernels evaluate it: per thread, with the device's exp2f (grid.h:194-199, called at :241).
+__global__ void grid_scales_kernel(const uint32_t n_levels, const float log2_per_level_scale, const uint32_t base_resolution, float* __restrict__ out)
+{
+	const uint32_t l = threadIdx.x;
+	if (l < n_levels) out[l] = exp2f((float)l * log2_per_level_scale) * (float)base_resolution - 1.0f;
+}
+
+extern "C" int ngpb_grid_device_scales(void* stream_, ngpb_grid* g) {
+	try {
+		if (!g || g->n_levels == 0 || g->n_levels > NGPB_MAX_LEVELS) { set_last_error("ngpb_grid_device_scales: invalid argument"); return NGPB_ERR_INVALID_ARGUMENT; }
+		cudaStream_t stream = (cudaStream_t)stream_;
+		float* d = nullptr;
+		NGPB_CUDA_CHECK(cudaMalloc(&d, sizeof(float) * NGPB_MAX_LEVELS));
+		grid_scales_kernel<<<1, NGPB_MAX_LEVELS, 0, stream>>>(g->n_levels, g->log2_per_level_scale, g->base_resolution, d);
+		cudaError_t e = cudaGetLastError();
+		if (e == cudaSuccess) e = cudaMemcpyAsync(g->scale, d, sizeof(float) * g->n_levels, cudaMemcpyDeviceToHost, stream);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+		cudaFree(d);
+		NGPB_CUDA_CHECK(e);
+		for (uint32_t l = 0; l < g->n_levels; ++l) g->resolution[l] = (uint32_t)ceilf(g->scale[l]) + 1;
+		return 0;
+	} catch (const std::exception& e) { set_last_error(e.what()); return NGPB_ERR_RUNTIME; }
+}
+
 extern "C" int ngpb_hash_encode_forward(void* stream, const ngpb_grid* g, const ngpb_half* grid, const float* positions, uint32_t pos_stride,
                                         uint32_t n, ngpb_half* encoded) {
 	try {

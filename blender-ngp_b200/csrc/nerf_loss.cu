@@ -2,9 +2,11 @@
 // Replaces compute_loss_kernel_train_nerf (reference: src/testbed_nerf.cu:1280-1597) and
 // fill_rollover / fill_rollover_and_rescale (tcnn common_device.h:517-537).
 //
-// Same three-stage shape as K1 so that compaction is deterministic: (A) per-ray forward compositing
-// with early termination, (B) exclusive scan of the per-ray compacted step counts in ray-slot order
-// (one valid serialisation of the atomicAdd at :1434), (C) per-ray gradient pass that writes the
+// Same three-stage shape as K1 so that compaction is deterministic: (A) forward compositing with early
+// termination, one WARP per ray and one lane per sample (the reference walks each ray serially in one
+// thread, so its run time is set by the longest ray), (B) exclusive scan of the compacted step counts
+// in ray-slot order (one valid serialisation of the atomicAdd at :1434; block-local in (A), the
+// per-block totals by one small block), (C) gradient pass, again a warp per ray, that writes the
 // compacted coordinates and dL/dout, (D) roll-over padding to the fixed batch size.
 // Not built (out of scope for the lego/fox configs): envmap, exposure gradients,
 // depth supervision, error-map accumulation, max_level_rand_training.
@@ -59,7 +61,7 @@ __device__ inline LossAndGradient loss_and_gradient(const float* target, const f
 	return r;
 }
 
-struct __align__(16) RayState { float rgb_ray[3]; float depth_ray; float rgbtarget[3]; uint32_t compacted; };
+struct __align__(16) RayState { float rgb_ray[3]; float pad; float rgbtarget[3]; uint32_t compacted; };
 
 __device__ __forceinline__ void load_rgbsigma(const __half* p, float o[4]) {
 	const uint2 raw = *reinterpret_cast<const uint2*>(p);
@@ -67,183 +69,254 @@ __device__ __forceinline__ void load_rgbsigma(const __half* p, float o[4]) {
 	o[0] = __low2float(a); o[1] = __high2float(a); o[2] = __low2float(b); o[3] = __high2float(b);
 }
 
-// (A) forward compositing, :1341-1428
-__global__ void __launch_bounds__(128) loss_composite_kernel(
-	const LossParams P, const ngpb_image* __restrict__ images, const uint32_t* __restrict__ counters_in,
-	const __half* __restrict__ rgbsigma, const uint32_t* __restrict__ ray_indices, const float* __restrict__ rays, const uint32_t* __restrict__ numsteps_in,
-	const float* __restrict__ coords_in, RayState* __restrict__ state, uint32_t* __restrict__ compacted_counts)
-{
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= P.n_rays) return;
-	if (i >= counters_in[1]) { compacted_counts[i] = 0; return; }
-	const uint32_t numsteps = numsteps_in[i * 2 + 0], base = numsteps_in[i * 2 + 1];
-	const float* cin = coords_in + (size_t)base * COORD_FLOATS;
-	const __half* no = rgbsigma + (size_t)base * 4;
-	const float EPSILON = 1e-4f;
-	float T = 1.f;
-	float rgb_ray[3] = {0.f, 0.f, 0.f};
-	float depth_ray = 0.f;
-	uint32_t cn = 0;
-	const float ro[3] = {rays[(size_t)i * 6 + 0], rays[(size_t)i * 6 + 1], rays[(size_t)i * 6 + 2]};
-	for (; cn < numsteps; ++cn) {
-		if (T < EPSILON) break;
-		float o[4];
-		load_rgbsigma(no, o);
-		const float rgb[3] = {network_to_rgb(o[0], P.cfg.rgb_activation), network_to_rgb(o[1], P.cfg.rgb_activation), network_to_rgb(o[2], P.cfg.rgb_activation)};
-		const V3 pos = unwarp_position(cin, P.aabb);
-		const float dt = unwarp_dt(cin[3]);
-		const float dx = pos.x - ro[0], dy = pos.y - ro[1], dz = pos.z - ro[2];
-		const float cur_depth = sqrtf(sum3(dx * dx, dy * dy, dz * dz));
-		const float density = network_to_density(o[3], P.cfg.density_activation);
-		const float alpha = 1.f - __expf(-density * dt);
-		const float weight = alpha * T;
+// ---- warp-cooperative ray walk --------------------------------------------------------------------
+// One warp per ray, one lane per sample, 32 samples per round. The reference walks a ray's samples serially in one
+// thread (:1341-1373); here the per-sample math (activations, exp) runs in parallel across the lanes and only the
+// transmittance product is serial: lane l multiplies a_0 .. a_{l-1} in the reference's left-to-right order, so T
+// before every sample -- and with it the early-termination index -- carries the same rounding as the serial loop.
+constexpr uint32_t LOSS_RAYS_PER_BLOCK = 32; // 1024 threads
+constexpr float T_EPSILON = 1e-4f;
+
+struct SampleEval { float rgb[3]; float alpha, one_minus_alpha, dt; float o[4]; };
+
+__device__ __forceinline__ SampleEval eval_sample(const __half* __restrict__ rgbsigma, const float* __restrict__ coords_in, size_t idx, const ngpb_loss_config& cfg, bool valid) {
+	SampleEval e;
+	if (valid) {
+		load_rgbsigma(rgbsigma + idx * 4, e.o);
+		e.dt = unwarp_dt(coords_in[idx * COORD_FLOATS + 3]);
 		#pragma unroll
-		for (int c = 0; c < 3; ++c) rgb_ray[c] += weight * rgb[c];
-		depth_ray += weight * cur_depth;
-		T *= (1.f - alpha);
-		no += 4; cin += COORD_FLOATS;
-	}
-	// same RNG stream as K1 to recover the pixel, then the random background (:1378-1392)
-	const uint32_t ray_idx = ray_indices[i];
-	Pcg32 rng = P.rng;
-	rng.advance((int64_t)ray_idx * N_MAX_RANDOM_SAMPLES_PER_RAY);
-	const uint32_t img = image_idx(ray_idx, P.n_rays, P.n_images);
-	const ngpb_image& im = images[img];
-	float x, y;
-	random_image_pos_training(rng, im.w, im.h, P.cfg.snap_to_pixel_centers != 0, &x, &y);
-	float bg[3] = {P.cfg.background_color[0], P.cfg.background_color[1], P.cfg.background_color[2]};
-	if (P.cfg.random_bg_color) { bg[0] = rng.next_float(); bg[1] = rng.next_float(); bg[2] = rng.next_float(); }
-	#pragma unroll
-	for (int c = 0; c < 3; ++c) bg[c] = srgb_to_linear(bg[c]);
-	float texsamp[4];
-	read_rgba(x, y, im, texsamp);
-	float rgbtarget[3];
-	if (P.cfg.linear_colors || P.cfg.color_space == NGPB_COLOR_LINEAR) {
-		#pragma unroll
-		for (int c = 0; c < 3; ++c) rgbtarget[c] = 1.0f * texsamp[c] + (1.0f - texsamp[3]) * bg[c];
-		if (!P.cfg.linear_colors) {
-			#pragma unroll
-			for (int c = 0; c < 3; ++c) { rgbtarget[c] = linear_to_srgb(rgbtarget[c]); bg[c] = linear_to_srgb(bg[c]); }
-		}
+		for (int c = 0; c < 3; ++c) e.rgb[c] = network_to_rgb(e.o[c], cfg.rgb_activation);
+		const float density = network_to_density(e.o[3], cfg.density_activation);
+		e.alpha = 1.f - __expf(-density * e.dt);
+		e.one_minus_alpha = 1.f - e.alpha;
 	} else {
+		e.o[0] = e.o[1] = e.o[2] = e.o[3] = 0.f; e.dt = 0.f;
+		e.rgb[0] = e.rgb[1] = e.rgb[2] = 0.f; e.alpha = 0.f; e.one_minus_alpha = 1.f; // neutral: multiplying by 1.0f is exact
+	}
+	return e;
+}
+
+// T before this lane's sample, given T before lane 0's sample; products taken in sample order.
+__device__ __forceinline__ float sequential_prefix_product(float T_in, float one_minus_alpha, uint32_t lane) {
+	float T = T_in;
+	#pragma unroll
+	for (uint32_t k = 0; k < 31; ++k) {
+		const float v = __shfl_sync(0xffffffffu, one_minus_alpha, k);
+		if (k < lane) T *= v;
+	}
+	return T;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+	#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+__device__ __forceinline__ float warp_inclusive_sum(float v, uint32_t lane) {
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= (uint32_t)o) v += t; }
+	return v;
+}
+
+// Block-wide exclusive scan of one value per warp (32 warps); returns the exclusive prefix for this warp and the block total.
+__device__ __forceinline__ uint32_t block_scan_warps(uint32_t v_warp, uint32_t* smem /*[33]*/, uint32_t* total) {
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (lane == 0) smem[warp] = v_warp;
+	__syncthreads();
+	if (warp == 0) {
+		const uint32_t w = smem[lane];
+		uint32_t wi = w;
 		#pragma unroll
-		for (int c = 0; c < 3; ++c) bg[c] = linear_to_srgb(bg[c]);
-		if (texsamp[3] > 0) {
+		for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= (uint32_t)o) wi += t; }
+		smem[lane] = wi - w;
+		if (lane == 31) smem[32] = wi;
+	}
+	__syncthreads();
+	*total = smem[32];
+	return smem[warp];
+}
+
+// (A) forward compositing, :1341-1428. Writes the per-ray state, the ray's compacted step count, its exclusive prefix inside
+// the block (local_bases) and the block's total (block_sums).
+__global__ void __launch_bounds__(1024) loss_composite_kernel(
+	const LossParams P, const ngpb_image* __restrict__ images, const uint32_t* __restrict__ counters_in,
+	const __half* __restrict__ rgbsigma, const uint32_t* __restrict__ ray_indices, const uint32_t* __restrict__ numsteps_in,
+	const float* __restrict__ coords_in, RayState* __restrict__ state, uint32_t* __restrict__ compacted_counts, uint32_t* __restrict__ local_bases,
+	uint32_t* __restrict__ block_sums)
+{
+	__shared__ uint32_t scan_smem[33];
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t i = blockIdx.x * LOSS_RAYS_PER_BLOCK + warp;
+	const bool active = i < P.n_rays && i < counters_in[1];
+	uint32_t cn = 0;
+	if (active) {
+		const uint32_t numsteps = numsteps_in[i * 2 + 0], base = numsteps_in[i * 2 + 1];
+		float T_in = 1.f;
+		float rgb_ray[3] = {0.f, 0.f, 0.f};
+		bool stopped = false;
+		for (uint32_t r0 = 0; r0 < numsteps && !stopped; r0 += 32) {
+			const uint32_t j = r0 + lane;
+			const bool valid = j < numsteps;
+			const SampleEval e = eval_sample(rgbsigma, coords_in, (size_t)base + j, P.cfg, valid);
+			const float T = sequential_prefix_product(T_in, e.one_minus_alpha, lane);
+			// the serial loop tests `T < EPSILON` before it touches a sample (:1352): the walk ends at the first such sample
+			const uint32_t stop_mask = __ballot_sync(0xffffffffu, valid && T < T_EPSILON);
+			const uint32_t first_stop = stop_mask ? (uint32_t)__ffs(stop_mask) - 1 : 32u;
+			const bool counted = valid && lane < first_stop;
+			const float weight = counted ? e.alpha * T : 0.f;
 			#pragma unroll
-			for (int c = 0; c < 3; ++c) rgbtarget[c] = linear_to_srgb(1.0f * texsamp[c] / texsamp[3]) * texsamp[3] + (1.0f - texsamp[3]) * bg[c];
+			for (int c = 0; c < 3; ++c) rgb_ray[c] += warp_sum(weight * e.rgb[c]);
+			cn += __popc(__ballot_sync(0xffffffffu, counted));
+			stopped = stop_mask != 0;
+			T_in = __shfl_sync(0xffffffffu, T * e.one_minus_alpha, 31);
+		}
+		// same RNG stream as K1 to recover the pixel, then the random background (:1378-1392)
+		const uint32_t ray_idx = ray_indices[i];
+		Pcg32 rng = P.rng;
+		rng.advance((int64_t)ray_idx * N_MAX_RANDOM_SAMPLES_PER_RAY);
+		const uint32_t img = image_idx(ray_idx, P.n_rays, P.n_images);
+		const ngpb_image& im = images[img];
+		float x, y;
+		random_image_pos_training(rng, im.w, im.h, P.cfg.snap_to_pixel_centers != 0, &x, &y);
+		float bg[3] = {P.cfg.background_color[0], P.cfg.background_color[1], P.cfg.background_color[2]};
+		if (P.cfg.random_bg_color) { bg[0] = rng.next_float(); bg[1] = rng.next_float(); bg[2] = rng.next_float(); }
+		#pragma unroll
+		for (int c = 0; c < 3; ++c) bg[c] = srgb_to_linear(bg[c]);
+		float texsamp[4];
+		read_rgba(x, y, im, texsamp);
+		float rgbtarget[3];
+		if (P.cfg.linear_colors || P.cfg.color_space == NGPB_COLOR_LINEAR) {
+			#pragma unroll
+			for (int c = 0; c < 3; ++c) rgbtarget[c] = 1.0f * texsamp[c] + (1.0f - texsamp[3]) * bg[c];
+			if (!P.cfg.linear_colors) {
+				#pragma unroll
+				for (int c = 0; c < 3; ++c) { rgbtarget[c] = linear_to_srgb(rgbtarget[c]); bg[c] = linear_to_srgb(bg[c]); }
+			}
 		} else {
 			#pragma unroll
-			for (int c = 0; c < 3; ++c) rgbtarget[c] = bg[c];
+			for (int c = 0; c < 3; ++c) bg[c] = linear_to_srgb(bg[c]);
+			if (texsamp[3] > 0) {
+				#pragma unroll
+				for (int c = 0; c < 3; ++c) rgbtarget[c] = linear_to_srgb(1.0f * texsamp[c] / texsamp[3]) * texsamp[3] + (1.0f - texsamp[3]) * bg[c];
+			} else {
+				#pragma unroll
+				for (int c = 0; c < 3; ++c) rgbtarget[c] = bg[c];
+			}
+		}
+		if (cn == numsteps) { // the ray reached the end of its samples: composite the background behind it (:1424-1427)
+			#pragma unroll
+			for (int c = 0; c < 3; ++c) rgb_ray[c] += T_in * bg[c];
+		}
+		if (lane == 0) {
+			RayState s;
+			#pragma unroll
+			for (int c = 0; c < 3; ++c) { s.rgb_ray[c] = rgb_ray[c]; s.rgbtarget[c] = rgbtarget[c]; }
+			s.pad = 0.f;
+			s.compacted = cn;
+			state[i] = s;
 		}
 	}
-	if (cn == numsteps) {
-		#pragma unroll
-		for (int c = 0; c < 3; ++c) rgb_ray[c] += T * bg[c];
-	}
-	RayState s;
-	#pragma unroll
-	for (int c = 0; c < 3; ++c) { s.rgb_ray[c] = rgb_ray[c]; s.rgbtarget[c] = rgbtarget[c]; }
-	s.depth_ray = depth_ray;
-	s.compacted = cn;
-	state[i] = s;
-	compacted_counts[i] = cn;
+	uint32_t total;
+	const uint32_t local = block_scan_warps(cn, scan_smem, &total);
+	if (lane == 0 && i < P.n_rays) { compacted_counts[i] = cn; local_bases[i] = local; }
+	if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
 }
 
-// (B) one block: exclusive scan of compacted counts + clipping to the batch (:1434-1437)
-__global__ void __launch_bounds__(1024) loss_scan_kernel(const uint32_t n_rays, const uint32_t batch, uint32_t* __restrict__ compacted_counts,
-                                                         uint32_t* __restrict__ compacted_bases, uint32_t* __restrict__ counters_out)
+// (B) one block: exclusive scan of the per-block totals (one valid serialisation of the atomicAdd at :1434).
+__global__ void __launch_bounds__(1024) loss_scan_kernel(const uint32_t n_blocks, uint32_t* __restrict__ block_sums, uint32_t* __restrict__ counters_out)
 {
 	__shared__ uint32_t smem[33];
-	const uint32_t per_thread = (n_rays + 1023) / 1024;
-	const uint32_t begin = min(threadIdx.x * per_thread, n_rays), end = min(begin + per_thread, n_rays);
-	uint32_t sum = 0;
-	for (uint32_t i = begin; i < end; ++i) sum += compacted_counts[i];
-	uint32_t total;
-	uint32_t base = block_exclusive_scan_1024(sum, smem, &total);
-	for (uint32_t i = begin; i < end; ++i) {
-		const uint32_t c = compacted_counts[i];
-		compacted_bases[i] = base;
-		compacted_counts[i] = min(batch - min(batch, base), c);
-		base += c;
+	uint32_t carry = 0;
+	for (uint32_t t0 = 0; t0 < n_blocks; t0 += 1024) {
+		const uint32_t b = t0 + threadIdx.x;
+		const uint32_t v = b < n_blocks ? block_sums[b] : 0u;
+		uint32_t total;
+		const uint32_t excl = block_exclusive_scan_1024(v, smem, &total);
+		if (b < n_blocks) block_sums[b] = carry + excl;
+		carry += total;
 	}
-	if (threadIdx.x == 0) counters_out[0] = total;
+	if (threadIdx.x == 0) counters_out[0] = carry;
 }
 
-// (C) gradient pass, :1436-1556
-__global__ void __launch_bounds__(128) loss_gradient_kernel(
+// (C) gradient pass, :1436-1556: same walk over the first `cn` samples of the ray, now with the ray's colour known.
+__global__ void __launch_bounds__(1024) loss_gradient_kernel(
 	const LossParams P, const uint32_t* __restrict__ counters_in, const float* __restrict__ mean_density_ptr,
 	const __half* __restrict__ rgbsigma, const float* __restrict__ rays, uint32_t* __restrict__ numsteps_io, const float* __restrict__ coords_in,
-	const RayState* __restrict__ state, const uint32_t* __restrict__ compacted_counts, const uint32_t* __restrict__ compacted_bases,
+	const RayState* __restrict__ state, const uint32_t* __restrict__ compacted_counts, const uint32_t* __restrict__ local_bases, const uint32_t* __restrict__ block_prefix,
 	float* __restrict__ coords_out, __half* __restrict__ dloss_dout, float* __restrict__ loss_output)
 {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t i = blockIdx.x * LOSS_RAYS_PER_BLOCK + warp;
 	if (i >= P.n_rays) return;
-	if (i >= counters_in[1]) { if (loss_output) loss_output[i] = 0.f; return; }
+	if (i >= counters_in[1]) { if (loss_output && lane == 0) loss_output[i] = 0.f; return; }
 	const uint32_t base = numsteps_io[i * 2 + 1];
-	const uint32_t cn = compacted_counts[i], compacted_base = compacted_bases[i];
-	numsteps_io[i * 2 + 0] = cn;
-	numsteps_io[i * 2 + 1] = compacted_base;
-	if (cn == 0) { if (loss_output) loss_output[i] = 0.f; return; }
+	// clip to the batch (:1436-1437)
+	const uint32_t compacted_base = block_prefix[blockIdx.x] + local_bases[i];
+	const uint32_t cn = min(P.batch - min(P.batch, compacted_base), compacted_counts[i]);
+	__syncwarp();
+	if (lane == 0) { numsteps_io[i * 2 + 0] = cn; numsteps_io[i * 2 + 1] = compacted_base; }
+	if (cn == 0) { if (loss_output && lane == 0) loss_output[i] = 0.f; return; }
 	const RayState s = state[i];
-	const float* cin = coords_in + (size_t)base * COORD_FLOATS;
-	const __half* no = rgbsigma + (size_t)base * 4;
-	float* cout = coords_out + (size_t)compacted_base * COORD_FLOATS;
-	__half* dout = dloss_dout + (size_t)compacted_base * 4;
 	const float ro[3] = {rays[(size_t)i * 6 + 0], rays[(size_t)i * 6 + 1], rays[(size_t)i * 6 + 2]};
 
 	const LossAndGradient lg = loss_and_gradient(s.rgbtarget, s.rgb_ray, P.cfg.loss_type);
 	const float mean_loss = sum3(lg.loss[0], lg.loss[1], lg.loss[2]) / 3.0f;
-	if (loss_output) loss_output[i] = mean_loss / (float)P.n_rays;
+	if (loss_output && lane == 0) loss_output[i] = mean_loss / (float)P.n_rays;
 
 	const float loss_scale = P.cfg.loss_scale / P.n_rays;
 	const float output_l2_reg = P.cfg.rgb_activation == NGPB_ACT_EXPONENTIAL ? 1e-4f : 0.0f;
 	const float output_l1_reg_density = *mean_density_ptr < NERF_MIN_OPTICAL_THICKNESS ? 1e-4f : 0.0f;
 
-	float rgb_ray2[3] = {0.f, 0.f, 0.f};
-	float depth_ray2 = 0.f;
-	float T = 1.f;
-	for (uint32_t j = 0; j < cn; ++j) {
-		const float* ci = cin + (size_t)j * COORD_FLOATS;
-		float cv[COORD_FLOATS];
-		#pragma unroll
-		for (int k = 0; k < (int)COORD_FLOATS; ++k) { cv[k] = ci[k]; cout[(size_t)j * COORD_FLOATS + k] = cv[k]; }
-		const V3 pos = unwarp_position(cv, P.aabb);
-		const float dx = pos.x - ro[0], dy = pos.y - ro[1], dz = pos.z - ro[2];
-		const float depth = sqrtf(sum3(dx * dx, dy * dy, dz * dz));
-		const float dt = unwarp_dt(cv[3]);
-		float o[4];
-		load_rgbsigma(no, o);
-		const float rgb[3] = {network_to_rgb(o[0], P.cfg.rgb_activation), network_to_rgb(o[1], P.cfg.rgb_activation), network_to_rgb(o[2], P.cfg.rgb_activation)};
-		const float density = network_to_density(o[3], P.cfg.density_activation);
-		const float alpha = 1.f - __expf(-density * dt);
-		const float weight = alpha * T;
-		#pragma unroll
-		for (int c = 0; c < 3; ++c) rgb_ray2[c] += weight * rgb[c];
-		depth_ray2 += weight * depth;
-		T *= (1.f - alpha);
+	// compacted coordinates: a contiguous copy of the ray's first cn records, done by the whole warp
+	{
+		const float* src = coords_in + (size_t)base * COORD_FLOATS;
+		float* dst = coords_out + (size_t)compacted_base * COORD_FLOATS;
+		for (uint32_t k = lane; k < cn * COORD_FLOATS; k += 32) dst[k] = src[k];
+	}
 
-		float suffix[3], tv[3], g[4];
+	float T_in = 1.f;
+	float prefix_rgb[3] = {0.f, 0.f, 0.f}; // rgb_ray2 after the previous round
+	for (uint32_t r0 = 0; r0 < cn; r0 += 32) {
+		const uint32_t j = r0 + lane;
+		const bool valid = j < cn;
+		const size_t idx = (size_t)base + j;
+		const SampleEval e = eval_sample(rgbsigma, coords_in, idx, P.cfg, valid);
+		const float T_before = sequential_prefix_product(T_in, e.one_minus_alpha, lane);
+		const float weight = valid ? e.alpha * T_before : 0.f;
+		const float T = T_before * e.one_minus_alpha; // transmittance after this sample (:1520)
+		float rgb_ray2[3];
 		#pragma unroll
-		for (int c = 0; c < 3; ++c) {
-			suffix[c] = s.rgb_ray[c] - rgb_ray2[c];
-			const float dloss_by_drgb = weight * lg.gradient[c];
-			g[c] = loss_scale * (dloss_by_drgb * network_to_rgb_derivative(o[c], P.cfg.rgb_activation) + fmaxf(0.0f, output_l2_reg * o[c]));
-			tv[c] = T * rgb[c] - suffix[c];
+		for (int c = 0; c < 3; ++c) rgb_ray2[c] = prefix_rgb[c] + warp_inclusive_sum(weight * e.rgb[c], lane);
+		if (valid) {
+			const float* ci = coords_in + idx * COORD_FLOATS;
+			const float cpos[3] = {ci[0], ci[1], ci[2]};
+			const V3 pos = unwarp_position(cpos, P.aabb);
+			const float dx = pos.x - ro[0], dy = pos.y - ro[1], dz = pos.z - ro[2];
+			const float depth = sqrtf(sum3(dx * dx, dy * dy, dz * dz));
+			float tv[3], g[4];
+			#pragma unroll
+			for (int c = 0; c < 3; ++c) {
+				const float suffix = s.rgb_ray[c] - rgb_ray2[c];
+				const float dloss_by_drgb = weight * lg.gradient[c];
+				g[c] = loss_scale * (dloss_by_drgb * network_to_rgb_derivative(e.o[c], P.cfg.rgb_activation) + fmaxf(0.0f, output_l2_reg * e.o[c]));
+				tv[c] = T * e.rgb[c] - suffix;
+			}
+			const float density_derivative = network_to_density_derivative(e.o[3], P.cfg.density_activation);
+			// depth supervision is off (:1450-1452): its term is identically zero
+			const float dloss_by_dmlp = density_derivative * (e.dt * dot3(lg.gradient, tv));
+			g[3] = loss_scale * dloss_by_dmlp +
+				(e.o[3] < 0.0f ? -output_l1_reg_density : 0.0f) +
+				(e.o[3] > -10.0f && depth < P.cfg.near_distance ? 1e-4f : 0.0f);
+			const __half2 h01 = __halves2half2(__float2half_rn(g[0]), __float2half_rn(g[1]));
+			const __half2 h23 = __halves2half2(__float2half_rn(g[2]), __float2half_rn(g[3]));
+			uint2 packed;
+			packed.x = *reinterpret_cast<const uint32_t*>(&h01);
+			packed.y = *reinterpret_cast<const uint32_t*>(&h23);
+			*reinterpret_cast<uint2*>(dloss_dout + ((size_t)compacted_base + j) * 4) = packed;
 		}
-		const float density_derivative = network_to_density_derivative(o[3], P.cfg.density_activation);
-		const float depth_suffix = s.depth_ray - depth_ray2;
-		const float depth_supervision = 0.0f * (T * depth - depth_suffix); // depth supervision off (:1450-1452)
-		const float dloss_by_dmlp = density_derivative * (dt * (dot3(lg.gradient, tv) + depth_supervision));
-		g[3] = loss_scale * dloss_by_dmlp +
-			(o[3] < 0.0f ? -output_l1_reg_density : 0.0f) +
-			(o[3] > -10.0f && depth < P.cfg.near_distance ? 1e-4f : 0.0f);
-		const __half2 h01 = __halves2half2(__float2half_rn(g[0]), __float2half_rn(g[1]));
-		const __half2 h23 = __halves2half2(__float2half_rn(g[2]), __float2half_rn(g[3]));
-		uint2 packed;
-		packed.x = *reinterpret_cast<const uint32_t*>(&h01);
-		packed.y = *reinterpret_cast<const uint32_t*>(&h23);
-		*reinterpret_cast<uint2*>(dout + (size_t)j * 4) = packed;
-		no += 4;
+		#pragma unroll
+		for (int c = 0; c < 3; ++c) prefix_rgb[c] = __shfl_sync(0xffffffffu, rgb_ray2[c], 31);
+		T_in = __shfl_sync(0xffffffffu, T, 31);
 	}
 }
 
@@ -272,6 +345,10 @@ Aabb make_aabb(const float* a);
 
 using namespace ngpb;
 
+extern "C" uint64_t ngpb_compute_loss_scratch_bytes(uint32_t n_rays) {
+	return (uint64_t)n_rays * (sizeof(RayState) + 8) + (uint64_t)div_round_up(n_rays, LOSS_RAYS_PER_BLOCK) * 4 + 64;
+}
+
 extern "C" int ngpb_compute_loss(void* stream_, uint32_t n_rays, const float* aabb6, ngpb_rng rng_, uint32_t batch, const ngpb_loss_config* cfg,
                                  uint32_t n_images, const ngpb_image* images_dev, const uint32_t* counters_in,
                                  const ngpb_half* rgbsigma, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords_in,
@@ -289,16 +366,17 @@ extern "C" int ngpb_compute_loss(void* stream_, uint32_t n_rays, const float* aa
 		P.aabb = make_aabb(aabb6);
 		P.rng.state = rng_.state; P.rng.inc = rng_.inc;
 		P.cfg = *cfg;
-		// scratch layout: RayState[n_rays] (32 B each) | uint32 counts[n_rays] | uint32 bases[n_rays]
+		// scratch layout: RayState[n_rays] (32 B each) | uint32 counts[n_rays] | uint32 local_bases[n_rays] | uint32 block_sums[n_blocks]
 		RayState* state = reinterpret_cast<RayState*>(scratch);
 		uint32_t* counts = reinterpret_cast<uint32_t*>(state + n_rays);
-		uint32_t* bases = counts + n_rays;
-		const uint32_t blocks = div_round_up(n_rays, 128);
-		loss_composite_kernel<<<blocks, 128, 0, stream>>>(P, images_dev, counters_in, (const __half*)rgbsigma, ray_indices, rays, numsteps, coords_in, state, counts);
+		uint32_t* local_bases = counts + n_rays;
+		uint32_t* block_sums = local_bases + n_rays;
+		const uint32_t blocks = div_round_up(n_rays, LOSS_RAYS_PER_BLOCK);
+		loss_composite_kernel<<<blocks, 1024, 0, stream>>>(P, images_dev, counters_in, (const __half*)rgbsigma, ray_indices, numsteps, coords_in, state, counts, local_bases, block_sums);
 		NGPB_LAUNCH_CHECK();
-		loss_scan_kernel<<<1, 1024, 0, stream>>>(n_rays, batch, counts, bases, counters_out);
+		loss_scan_kernel<<<1, 1024, 0, stream>>>(blocks, block_sums, counters_out);
 		NGPB_LAUNCH_CHECK();
-		loss_gradient_kernel<<<blocks, 128, 0, stream>>>(P, counters_in, mean_density_dev, (const __half*)rgbsigma, rays, numsteps, coords_in, state, counts, bases,
+		loss_gradient_kernel<<<blocks, 1024, 0, stream>>>(P, counters_in, mean_density_dev, (const __half*)rgbsigma, rays, numsteps, coords_in, state, counts, local_bases, block_sums,
 			coords_out, (__half*)dloss_dout, loss_per_ray);
 		NGPB_LAUNCH_CHECK();
 		rollover_kernel<<<div_round_up(batch, 256), 256, 0, stream>>>(batch, counters_out, coords_out, (__half*)dloss_dout);

@@ -123,8 +123,33 @@ ngpb_testbed::~ngpb_testbed() {
 	cudaSetDevice(device);
 	if (stream) cudaStreamSynchronize(stream);
 	for (void* p : allocations) cudaFree(p);
+	for (auto& e : stage_ev) { if (e[0]) cudaEventDestroy(e[0]); if (e[1]) cudaEventDestroy(e[1]); }
 	if (host_readback) cudaFreeHost(host_readback);
 	if (stream) cudaStreamDestroy(stream);
+}
+
+void ngpb_testbed::stage_begin(int s) {
+	if (!profile_stages) return;
+	if (!stage_ev[s][0]) { NGPB_CUDA_CHECK(cudaEventCreate(&stage_ev[s][0])); NGPB_CUDA_CHECK(cudaEventCreate(&stage_ev[s][1])); }
+	if (stage_used[s]) stage_collect(); // a stage that runs twice before a collect: fold the first interval in now
+	NGPB_CUDA_CHECK(cudaEventRecord(stage_ev[s][0], stream));
+}
+void ngpb_testbed::stage_end(int s, uint64_t units) {
+	if (!profile_stages) return;
+	NGPB_CUDA_CHECK(cudaEventRecord(stage_ev[s][1], stream));
+	stage_used[s] = true;
+	stage_calls[s] += 1;
+	stage_units[s] += units;
+}
+void ngpb_testbed::stage_collect() {
+	for (int s = 0; s < NGPB_N_STAGES; ++s) {
+		if (!stage_used[s]) continue;
+		NGPB_CUDA_CHECK(cudaEventSynchronize(stage_ev[s][1]));
+		float ms = 0.f;
+		NGPB_CUDA_CHECK(cudaEventElapsedTime(&ms, stage_ev[s][0], stage_ev[s][1]));
+		stage_ms[s] += ms;
+		stage_used[s] = false;
+	}
 }
 
 void* ngpb_testbed::dalloc(size_t bytes) {
@@ -192,6 +217,7 @@ void ngpb_testbed::reset_network(uint32_t seed_) {
 	// per_level_scale = exp(ln(desired_resolution * aabb_scale / base) / (L-1)) (:2313-2325)
 	const float per_level_scale = std::exp(std::log(2048.0f * (float)aabb_scale / (float)base_resolution) / (n_levels - 1));
 	const uint32_t entries = ngpb_grid_init(&grid, n_levels, log2_hashmap_size, base_resolution, per_level_scale);
+	if (ngpb_grid_device_scales(stream, &grid) != 0) throw std::runtime_error(ngpb_last_error());
 	const uint32_t new_n_params = MLP_PARAMS + 2 * entries;
 	if (new_n_params != n_params) {
 		dfree(w_fp32); dfree(w_half); dfree(w_ema); dfree(m1); dfree(m2); dfree(param_steps); dfree(grad);
@@ -280,7 +306,7 @@ void ngpb_testbed::ensure_workspace(uint32_t batch) {
 	dloss = (__half*)dalloc(sizeof(__half) * 4 * batch);
 	denc = (__half*)dalloc(sizeof(__half) * N_ENC * batch);
 	loss = (float*)dalloc(sizeof(float) * max_rays);
-	scratch = dalloc(40 * max_rays);
+	scratch = dalloc((size_t)std::max(ngpb_generate_training_samples_scratch_bytes((uint32_t)max_rays), ngpb_compute_loss_scratch_bytes((uint32_t)max_rays)));
 	counters = (uint32_t*)dalloc(sizeof(uint32_t) * 8);
 	partials = (float*)dalloc((size_t)ngpb_nerf_mlp_workspace_bytes());
 	// keep the padding rows of the sample buffers finite
@@ -328,8 +354,10 @@ void ngpb_testbed::train(uint32_t batch) {
 	const uint32_t n_prep_to_skip = std::max(1u, std::min(training_step / 16u, 16u));
 	if (training_step % n_prep_to_skip == 0) {
 		const uint32_t n_cascades = max_cascade + 1;
+		stage_begin(NGPB_STAGE_DENSITY_GRID);
 		if (training_step < 256) update_density_grid(NERF_GRID_CELLS * n_cascades, 0);
 		else update_density_grid(NERF_GRID_CELLS / 4 * n_cascades, NERF_GRID_CELLS / 4 * n_cascades);
+		stage_end(NGPB_STAGE_DENSITY_GRID, training_step < 256 ? NERF_GRID_CELLS * n_cascades : NERF_GRID_CELLS / 2 * n_cascades);
 	}
 	const bool get_loss_scalar = training_step % 16 == 0;
 
@@ -346,21 +374,39 @@ void ngpb_testbed::train(uint32_t batch) {
 	const uint32_t R = rays_per_batch;
 	const ngpb_rng r{rng.state, rng.inc};
 
+	// the uncompacted sample count of this step stays on the device; for the per-stage accounting the previous step's is used
+	const uint64_t n_uncompacted_est = std::min(measured_batch_size_before_compaction, max_inference);
+	stage_begin(NGPB_STAGE_SAMPLING);
 	check(ngpb_generate_training_samples(stream, R, aabb, max_inference, r, (uint32_t)images.size(), images_dev, bitfield,
-		loss_cfg.snap_to_pixel_centers, cone_angle_constant, counters, ray_indices, rays, numsteps, coords, (uint32_t*)scratch));
+		loss_cfg.snap_to_pixel_centers, cone_angle_constant, counters, ray_indices, rays, numsteps, coords, scratch));
+	stage_end(NGPB_STAGE_SAMPLING, R);
 	// network inference on the uncompacted samples; the sample count stays on the device
+	stage_begin(NGPB_STAGE_ENCODE_INFERENCE);
 	hash_encode_forward_launch(stream, &grid, w_half + MLP_PARAMS, coords, COORD_FLOATS, max_inference, counters, encoded);
+	stage_end(NGPB_STAGE_ENCODE_INFERENCE, n_uncompacted_est);
+	stage_begin(NGPB_STAGE_MLP_INFERENCE);
 	nerf_mlp_forward_launch(stream, w_half, encoded, coords, max_inference, counters, rgbsigma);
+	stage_end(NGPB_STAGE_MLP_INFERENCE, n_uncompacted_est);
+	stage_begin(NGPB_STAGE_LOSS);
 	check(ngpb_compute_loss(stream, R, aabb, r, batch, &loss_cfg, (uint32_t)images.size(), images_dev, counters, (const ngpb_half*)rgbsigma,
 		ray_indices, rays, numsteps, coords, mean_density, coords_compacted, (ngpb_half*)dloss, loss, counters + 2, scratch));
+	stage_end(NGPB_STAGE_LOSS, R);
 	// forward + backward on the compacted, padded batch
+	stage_begin(NGPB_STAGE_ENCODE_TRAIN);
 	hash_encode_forward_launch(stream, &grid, w_half + MLP_PARAMS, coords_compacted, COORD_FLOATS, batch, nullptr, encoded);
+	stage_end(NGPB_STAGE_ENCODE_TRAIN, batch);
+	stage_begin(NGPB_STAGE_MLP_TRAIN);
 	nerf_mlp_forward_backward_launch(stream, w_half, encoded, coords_compacted, dloss, batch, denc, grad, partials);
+	stage_end(NGPB_STAGE_MLP_TRAIN, batch);
+	stage_begin(NGPB_STAGE_ENCODE_BACKWARD);
 	hash_encode_backward_launch(stream, &grid, coords_compacted, COORD_FLOATS, batch, denc, grad + MLP_PARAMS);
+	stage_end(NGPB_STAGE_ENCODE_BACKWARD, batch);
 	rng.advance(); // m_rng.advance() (:3380)
 
 	// ---- optimizer (train_nerf :2950) ----
+	stage_begin(NGPB_STAGE_OPTIMIZER);
 	check(ngpb_optimizer_step(stream, &opt, n_params, MLP_PARAMS, LOSS_SCALE, grad, w_fp32, (ngpb_half*)w_half, (ngpb_half*)w_ema, m1, m2, param_steps));
+	stage_end(NGPB_STAGE_OPTIMIZER, n_params);
 	++training_step;
 	n_launches += 3 + 2 + 4 + 1 + 2 + 1 + 1;
 
@@ -368,6 +414,7 @@ void ngpb_testbed::train(uint32_t batch) {
 	if (get_loss_scalar) { sum_kernel<<<1, 1024, 0, stream>>>(loss, R, reinterpret_cast<float*>(counters + 4)); NGPB_LAUNCH_CHECK(); n_launches += 1; }
 	NGPB_CUDA_CHECK(cudaMemcpyAsync(host_readback, counters, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, stream));
 	NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
+	if (profile_stages) stage_collect();
 	d2h_bytes += 32;
 	const uint32_t counter_cpu = host_readback[0], compacted_counter_cpu = host_readback[2];
 	measured_batch_size = 0;
@@ -452,6 +499,21 @@ extern "C" int ngpb_testbed_get_density_grid(ngpb_testbed* t, float* grid_out, u
 	NGPB_API_END
 }
 
+extern "C" void* ngpb_testbed_stream(ngpb_testbed* t) { return t ? (void*)t->stream : nullptr; }
+extern "C" int ngpb_testbed_stage_times(ngpb_testbed* t, double* ms, uint64_t* calls, uint64_t* units, int reset) {
+	NGPB_API_BEGIN
+	NGPB_CUDA_CHECK(cudaSetDevice(t->device));
+	NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
+	t->stage_collect();
+	for (int s = 0; s < NGPB_N_STAGES; ++s) {
+		if (ms) ms[s] = t->stage_ms[s];
+		if (calls) calls[s] = t->stage_calls[s];
+		if (units) units[s] = t->stage_units[s];
+		if (reset) { t->stage_ms[s] = 0.0; t->stage_calls[s] = 0; t->stage_units[s] = 0; }
+	}
+	NGPB_API_END
+}
+
 extern "C" int ngpb_testbed_set_option(ngpb_testbed* t, const char* name, double v) {
 	NGPB_API_BEGIN
 	const std::string k = name ? name : "";
@@ -471,6 +533,7 @@ extern "C" int ngpb_testbed_set_option(ngpb_testbed* t, const char* name, double
 	else if (k == "shall_train") t->shall_train = v != 0;
 	else if (k == "render_min_transmittance") t->render_min_transmittance = (float)v;
 	else if (k == "learning_rate") t->opt.learning_rate = (float)v;
+	else if (k == "profile_stages") t->profile_stages = v != 0;
 	else throw std::runtime_error("unknown option: " + k);
 	NGPB_API_END
 }

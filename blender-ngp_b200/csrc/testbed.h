@@ -69,4 +69,16 @@ struct ngpb_testbed {
 	float render_min_transmittance = 0.01f; // testbed.h:725
 
 	uint64_t n_launches = 0, h2d_bytes = 0, d2h_bytes = 0;
+
+	// Optional per-stage device timing (CUDA events on `stream`), read by bench.py for the roofline of each kernel.
+	// Off by default: when on, two event records bracket every stage of train().
+	bool profile_stages = false;
+	cudaEvent_t stage_ev[NGPB_N_STAGES][2] = {};
+	bool stage_used[NGPB_N_STAGES] = {};
+	double stage_ms[NGPB_N_STAGES] = {};
+	uint64_t stage_calls[NGPB_N_STAGES] = {};
+	uint64_t stage_units[NGPB_N_STAGES] = {}; // samples (or rays / params) the stage processed, summed over calls
+	void stage_begin(int s);
+	void stage_end(int s, uint64_t units);
+	void stage_collect(); // after a stream synchronize
 };

@@ -94,7 +94,7 @@ EXPORTED_SYMBOLS = [
     "ngpb_testbed_create", "ngpb_testbed_destroy", "ngpb_testbed_load_training_data", "ngpb_testbed_reset_network", "ngpb_testbed_train",
     "ngpb_testbed_train_n", "ngpb_testbed_loss", "ngpb_testbed_training_step", "ngpb_testbed_stats", "ngpb_testbed_n_params",
     "ngpb_testbed_get_params", "ngpb_testbed_set_params", "ngpb_testbed_get_density_grid", "ngpb_testbed_set_option", "ngpb_testbed_get_option",
-    "ngpb_testbed_render",
+    "ngpb_testbed_render", "ngpb_testbed_stream", "ngpb_testbed_stage_times", "ngpb_grid_device_scales", "ngpb_generate_training_samples_scratch_bytes", "ngpb_compute_loss_scratch_bytes",
 ]
 
 _lib = None
@@ -110,6 +110,8 @@ def lib():
         l.ngpb_last_error.restype = C.c_char_p
         l.ngpb_grid_init.restype = C.c_uint32
         l.ngpb_nerf_mlp_workspace_bytes.restype = C.c_uint64
+        l.ngpb_generate_training_samples_scratch_bytes.restype = C.c_uint64
+        l.ngpb_compute_loss_scratch_bytes.restype = C.c_uint64
         l.ngpb_testbed_loss.restype = C.c_float
         l.ngpb_testbed_training_step.restype = C.c_uint32
         l.ngpb_testbed_n_params.restype = C.c_uint32
@@ -119,6 +121,8 @@ def lib():
         l.ngpb_effective_xform.restype = None
         l.ngpb_optimizer_init.restype = None
         l.ngpb_testbed_destroy.restype = None
+        l.ngpb_testbed_stream.restype = C.c_void_p
+        l.ngpb_testbed_stream.argtypes = [C.c_void_p]
         _lib = l
     return _lib
 
@@ -128,11 +132,14 @@ def check(status):
         raise RuntimeError(lib().ngpb_last_error().decode() or f"ngpb error {status}")
 
 
-def grid_init(n_levels=16, log2_hashmap_size=19, base_resolution=16, per_level_scale=None, aabb_scale=1):
+def grid_init(n_levels=16, log2_hashmap_size=19, base_resolution=16, per_level_scale=None, aabb_scale=1, device_scales=False):
+    """ngpb_grid for the given hash-grid config; device_scales=True replaces the level scales by the device-evaluated ones (needs a GPU)."""
     if per_level_scale is None:
         per_level_scale = float(np.exp(np.log(np.float32(2048.0) * np.float32(aabb_scale) / np.float32(base_resolution)) / np.float32(n_levels - 1), dtype=np.float32))
     g = Grid()
     entries = lib().ngpb_grid_init(C.byref(g), n_levels, log2_hashmap_size, base_resolution, C.c_float(per_level_scale))
+    if device_scales:
+        check(lib().ngpb_grid_device_scales(None, C.byref(g)))
     return g, entries
 
 
@@ -422,6 +429,24 @@ class Testbed:
         check(lib().ngpb_testbed_stats(self._h, s))
         return dict(rays_per_batch=int(s[0]), measured_batch_size_before_compaction=int(s[1]), measured_batch_size=int(s[2]), gpu_launches=int(s[3]),
                     h2d_bytes=int(self._get("h2d_bytes")), d2h_bytes=int(self._get("d2h_bytes")))
+
+    STAGES = ["sampling", "encode_inference", "mlp_inference", "loss", "encode_train", "mlp_train", "encode_backward", "optimizer",
+              "density_grid", "allreduce"]
+
+    def profile_stages(self, on=True):
+        self._set("profile_stages", 1.0 if on else 0.0)
+
+    def stage_times(self, reset=False):
+        """Per-stage device time (CUDA events on the testbed's stream): {stage: (ms, calls, units)} accumulated since the last reset."""
+        n = len(self.STAGES)
+        ms = (C.c_double * n)(); calls = (C.c_uint64 * n)(); units = (C.c_uint64 * n)()
+        check(lib().ngpb_testbed_stage_times(self._h, ms, calls, units, int(reset)))
+        return {name: (float(ms[i]), int(calls[i]), int(units[i])) for i, name in enumerate(self.STAGES)}
+
+    @property
+    def stream(self):
+        """cudaStream_t (as int) every kernel of this testbed runs on."""
+        return int(lib().ngpb_testbed_stream(self._h) or 0)
 
     # -- parameters / state
     def get_params(self):

@@ -54,6 +54,11 @@ typedef struct {
 /* Host-only: fills `g` like the GridEncodingTemplated constructor (grid.h:959-1025). Returns total entries. */
 uint32_t ngpb_grid_init(ngpb_grid* g, uint32_t n_levels, uint32_t log2_hashmap_size, uint32_t base_resolution, float per_level_scale);
 
+/* Replaces g->scale[] / g->resolution[] by the values the DEVICE's exp2f gives, which is what the reference's kernels use (they call
+ * grid_scale per thread, grid.h:241); glibc's exp2f differs by one ulp on some levels. The level offsets stay host-derived, as in
+ * the reference's constructor. Needs a GPU; synchronises the stream. */
+int ngpb_grid_device_scales(void* stream, ngpb_grid* g);
+
 /* kernel_grid (grid.h:220-349). positions: float, `pos_stride` floats per sample (3 used).
  * encoded: [n][2*n_levels] half, sample-major (the MLP kernels' input layout). */
 int ngpb_hash_encode_forward(void* stream, const ngpb_grid* g, const ngpb_half* grid, const float* positions, uint32_t pos_stride,
@@ -96,16 +101,19 @@ typedef struct { uint64_t state, inc; } ngpb_rng; /* tcnn pcg32 */
  * Deterministic: samples are laid out in ray order (an exclusive scan replaces the reference's atomicAdd,
  * which makes it one valid serialisation of the reference's allocation order).
  * counters[0] = total requested samples (numsteps_counter), counters[1] = rays kept (ray_counter).
- * scratch: uint32[3 * n_rays]. */
+ * scratch: ngpb_generate_training_samples_scratch_bytes(n_rays) bytes (per-ray counts, prefixes and march records). */
+uint64_t ngpb_generate_training_samples_scratch_bytes(uint32_t n_rays);
 int ngpb_generate_training_samples(void* stream, uint32_t n_rays, const float* aabb6, uint32_t max_samples, ngpb_rng rng,
                                    uint32_t n_images, const ngpb_image* images_dev, const uint8_t* density_grid_bitfield,
                                    int snap_to_pixel_centers, float cone_angle_constant,
                                    uint32_t* counters, uint32_t* ray_indices, float* rays /*[n][6]*/, uint32_t* numsteps /*[n][2]*/,
-                                   float* coords /*[max_samples][7]*/, uint32_t* scratch);
+                                   float* coords /*[max_samples][7]*/, void* scratch);
 
 /* ---- K6+K7: compute_loss_kernel_train_nerf (:1280-1597) + fill_rollover(_and_rescale) (tcnn common_device.h:517-537) ----
  * counters_in: the device counters written by K1. counters_out[0] = compacted sample count (unclipped).
- * coords_out [batch][7] and dloss_dout [batch][4] are padded to `batch` by rollover. scratch: 40 * n_rays bytes. */
+ * coords_out [batch][7] and dloss_dout [batch][4] are padded to `batch` by rollover.
+ * scratch: ngpb_compute_loss_scratch_bytes(n_rays) bytes. */
+uint64_t ngpb_compute_loss_scratch_bytes(uint32_t n_rays);
 typedef struct {
 	float loss_scale;            /* LOSS_SCALE = 128, testbed.h:272 */
 	float background_color[3];
@@ -169,6 +177,23 @@ uint32_t ngpb_testbed_n_params(const ngpb_testbed* t);
 int ngpb_testbed_get_params(ngpb_testbed* t, float* w_fp32, ngpb_half* w_half, ngpb_half* w_ema);
 int ngpb_testbed_set_params(ngpb_testbed* t, const float* w_fp32);
 int ngpb_testbed_get_density_grid(ngpb_testbed* t, float* grid, uint8_t* bitfield);
+/* The stream every testbed kernel is launched on (Testbed::m_stream, testbed.h:895), as a cudaStream_t. */
+void* ngpb_testbed_stream(ngpb_testbed* t);
+/* Per-stage device time of train(), measured with CUDA events on that stream while the option "profile_stages" is 1.
+ * Stage indices: */
+enum { NGPB_STAGE_SAMPLING = 0,      /* K1  generate_training_samples                        units: rays      */
+       NGPB_STAGE_ENCODE_INFERENCE,  /* K2  hash encode of the uncompacted samples            units: samples   */
+       NGPB_STAGE_MLP_INFERENCE,     /* K3  MLP forward of the uncompacted samples            units: samples   */
+       NGPB_STAGE_LOSS,              /* K6+K7 compositing, loss, compaction, roll-over        units: rays      */
+       NGPB_STAGE_ENCODE_TRAIN,      /* K2  hash encode of the compacted batch                units: samples   */
+       NGPB_STAGE_MLP_TRAIN,         /* K8-K11 MLP forward + backward + weight gradients      units: samples   */
+       NGPB_STAGE_ENCODE_BACKWARD,   /* K12 hash-grid scatter-add                             units: samples   */
+       NGPB_STAGE_OPTIMIZER,         /* K15 Adam + EMA + gradient reset                       units: params    */
+       NGPB_STAGE_DENSITY_GRID,      /* K16 occupancy-grid refresh                            units: samples   */
+       NGPB_STAGE_ALLREDUCE,         /* gradient all-reduce (multi-GPU only)                  units: bytes     */
+       NGPB_N_STAGES };
+/* ms[NGPB_N_STAGES], calls[NGPB_N_STAGES], units[NGPB_N_STAGES]: accumulated since the last reset (reset != 0 clears). */
+int ngpb_testbed_stage_times(ngpb_testbed* t, double* ms, uint64_t* calls, uint64_t* units, int reset);
 /* training options exposed as pyngp properties (python_api.cu:650-852) */
 int ngpb_testbed_set_option(ngpb_testbed* t, const char* name, double value);
 double ngpb_testbed_get_option(ngpb_testbed* t, const char* name);

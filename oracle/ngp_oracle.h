@@ -135,6 +135,10 @@ const float* orc_trainer_density_grid(const orc_trainer* t);
 // One Testbed::train(batch) call. stats_out: [0]=loss, [1]=rays_per_batch used, [2]=measured batch (uncompacted), [3]=measured compacted.
 void orc_trainer_train(orc_trainer* t, uint32_t batch_size, float* stats_out);
 uint32_t orc_trainer_step(const orc_trainer* t);
+/* bench.py's CPU baseline only: puts the trainer into a given regime without running the preceding steps -- sets the step
+ * counter (which fixes the occupancy-refresh cadence, src/testbed.cu:2538), the ray count, and replaces the occupancy grid
+ * (mean + bitfield recomputed as update_density_grid_mean_and_bitfield does, src/testbed_nerf.cu:2844-2859). */
+void orc_trainer_set_state(orc_trainer* t, uint32_t training_step, uint32_t rays_per_batch, const float* density_grid);
 
 // ---- K17 classic render (src/testbed_nerf.cu:612-989,:1748-1978,:2047-2267): one pixel at a time ----
 // camera12: 3x4 column-major camera matrix. out_rgba: [h][w][4] float (linear, premultiplied, before tonemap).

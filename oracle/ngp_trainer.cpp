@@ -114,6 +114,17 @@ extern "C" void orc_trainer_set_params(orc_trainer* t, const float* w_fp32) {
 	for (size_t i = 0; i < t->n_params; ++i) t->w_half[i] = f2h(t->w_fp32[i]);
 }
 
+extern "C" void orc_trainer_set_state(orc_trainer* t, uint32_t training_step, uint32_t rays_per_batch, const float* density_grid) {
+	t->training_step = training_step;
+	t->density_grid_ema_step = training_step;
+	if (rays_per_batch) t->rays_per_batch = rays_per_batch;
+	if (density_grid) {
+		std::memcpy(t->density_grid.data(), density_grid, t->density_grid.size() * sizeof(float));
+		t->mean_density = orc_density_grid_mean(t->density_grid.data());
+		orc_bitfield(t->max_cascade + 1, t->density_grid.data(), t->mean_density, t->bitfield.data());
+	}
+}
+
 // update_density_grid_nerf + update_density_grid_mean_and_bitfield: src/testbed_nerf.cu:2761-2859
 static void update_density_grid(orc_trainer* t, uint32_t n_uniform, uint32_t n_nonuniform) {
 	const uint32_t n_elements = GRID_CELLS * (t->max_cascade + 1);

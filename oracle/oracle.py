@@ -290,6 +290,10 @@ class Trainer:
     def training_step(self):
         return lib().orc_trainer_step(self._h)
 
+    def set_state(self, training_step, rays_per_batch=0, density_grid=None):
+        g = _f32(density_grid) if density_grid is not None else None
+        lib().orc_trainer_set_state(self._h, int(training_step), int(rays_per_batch), _p(g))
+
     def params(self):
         w = np.empty(self.n_params, np.float32); h = np.empty(self.n_params, np.float16); e = np.empty(self.n_params, np.float16)
         lib().orc_trainer_get_params(self._h, _p(w), _p(h), _p(e))

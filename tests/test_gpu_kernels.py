@@ -54,7 +54,9 @@ def test_umma_selftest(L, variant):
 def _grid_inputs(orc, n, seed, aabb_scale=1):
     import pyngp
     m = orc.model(aabb_scale=aabb_scale)
-    g, entries = pyngp.grid_init(aabb_scale=aabb_scale)
+    g, entries = pyngp.grid_init(aabb_scale=aabb_scale, device_scales=True)
+    for l in range(16):
+        m.scales[l] = g.scale[l]  # the oracle follows the device-evaluated level scales (ngpb_grid_device_scales)
     assert entries * 2 == m.n_grid_params
     rs = np.random.RandomState(seed)
     table = (rs.randn(m.n_grid_params) * 0.5).astype(np.float16)
@@ -69,12 +71,37 @@ def test_hash_encode_forward_bit_exact(L, orc, aabb_scale, n):
     import pyngp
     from gpu_util import dev, ptr, host
     m, g, table, pos = _grid_inputs(orc, n, 7, aabb_scale)
-    want = orc.grid_forward(m, table, pos)
+    want = orc.grid_forward(m, table, pos, scales=np.array(m.scales[:16], np.float32))
     d_table, d_pos = dev(table), dev(pos)
     d_out = torch.zeros((n, 32), dtype=torch.float16, device="cuda")
     pyngp.check(L.ngpb_hash_encode_forward(None, C.byref(g), ptr(d_table), ptr(d_pos), 7, n, ptr(d_out)))
     got = host(d_out)
     assert np.array_equal(got.view(np.uint16), want.view(np.uint16)), f"max abs diff {np.abs(got.astype(np.float32) - want.astype(np.float32)).max()}"
+
+
+def test_hash_encode_matches_reference_golden(L, orc):
+    """The CUDA kernels against the REFERENCE's own kernel_grid / kernel_grid_backward outputs (tests/golden/ref_grid.npz, produced on a
+    B200 from the reference sources by oracle/gen_golden.py): forward bit-exact, backward within the reference's fp16-atomic rounding."""
+    import os
+    import pyngp
+    from gpu_util import dev, ptr, host
+    from golden_inputs import grid_inputs, N_GRID, N_GRID_BWD
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_grid.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden vectors not generated")
+    gold = np.load(path)
+    g, entries = pyngp.grid_init(aabb_scale=int(gold["aabb_scale"]), device_scales=True)
+    assert np.array_equal(np.array(g.scale[:16], np.float32).view(np.uint32), gold["device_scales"].view(np.uint32))
+    table, positions, dy, _ = grid_inputs(entries * 2)
+    d_out = torch.zeros((N_GRID, 32), dtype=torch.float16, device="cuda")
+    pyngp.check(L.ngpb_hash_encode_forward(None, C.byref(g), ptr(dev(table)), ptr(dev(positions)), 3, N_GRID, ptr(d_out)))
+    assert np.array_equal(host(d_out).view(np.uint16), np.ascontiguousarray(gold["encoded_soa"].T).view(np.uint16))
+    d_grad = torch.zeros(entries * 2, dtype=torch.float32, device="cuda")
+    pyngp.check(L.ngpb_hash_encode_backward(None, C.byref(g), ptr(dev(positions)), 3, N_GRID_BWD, ptr(dev(np.ascontiguousarray(dy[:, :N_GRID_BWD].T))), ptr(d_grad)))
+    want = np.zeros(entries * 2, np.float32)
+    want[gold["grad_idx"]] = gold["grad_val"].astype(np.float32)
+    got = host(d_grad)
+    assert np.abs(got - want).max() <= 2e-2 * np.abs(want).max()
 
 
 def test_hash_encode_forward_empty_and_errors(L, orc):
@@ -97,7 +124,7 @@ def test_hash_encode_backward(L, orc):
     rs = np.random.RandomState(5)
     dy = (rs.randn(n, 32) * 0.01).astype(np.float16)
     dy[::7] = 0  # zero-gradient samples are skipped
-    want = orc.grid_backward(m, pos, dy)
+    want = orc.grid_backward(m, pos, dy, scales=np.array(m.scales[:16], np.float32))
     d_pos, d_dy = dev(pos), dev(dy)
     d_grad = torch.zeros(m.n_grid_params, dtype=torch.float32, device="cuda")
     pyngp.check(L.ngpb_hash_encode_backward(None, C.byref(g), ptr(d_pos), 7, n, ptr(d_dy), ptr(d_grad)))
@@ -205,7 +232,7 @@ def _run_k1(L, scene, bitfield, n_rays, max_samples, rng, snap=True):
     rays = torch.zeros((n_rays, 6), dtype=torch.float32, device="cuda")
     numsteps = torch.zeros((n_rays, 2), dtype=torch.int32, device="cuda")
     coords = torch.zeros((max_samples, 7), dtype=torch.float32, device="cuda")
-    scratch = torch.zeros(3 * n_rays + 16, dtype=torch.int32, device="cuda")
+    scratch = torch.zeros(int(L.ngpb_generate_training_samples_scratch_bytes(n_rays)), dtype=torch.uint8, device="cuda")
     pyngp.check(L.ngpb_generate_training_samples(None, n_rays, aabb.ctypes.data_as(C.c_void_p), max_samples, rng_struct(rng), n_img, ptr(meta), ptr(d_bits),
                                                  int(snap), C.c_float(0.0), ptr(counters), ptr(ray_indices), ptr(rays), ptr(numsteps), ptr(coords), ptr(scratch)))
     return dict(counters=host(counters).view(np.uint32), ray_indices=host(ray_indices).view(np.uint32), rays=host(rays),
@@ -281,7 +308,7 @@ def test_compute_loss(L, orc, small_scene, batch):
     dloss = torch.zeros((batch, 4), dtype=torch.float16, device="cuda")
     loss = torch.zeros(n_rays, dtype=torch.float32, device="cuda")
     counters_out = torch.zeros(4, dtype=torch.int32, device="cuda")
-    scratch = torch.zeros(40 * n_rays + 64, dtype=torch.uint8, device="cuda")
+    scratch = torch.zeros(int(L.ngpb_compute_loss_scratch_bytes(n_rays)), dtype=torch.uint8, device="cuda")
     pyngp.check(L.ngpb_compute_loss(None, n_rays, aabb.ctypes.data_as(C.c_void_p), rng_struct(rng), batch, C.byref(cfg), d["n_img"], ptr(d["meta"]), ptr(d["counters"]),
                                     ptr(d_rgbsigma), ptr(d["ray_indices"]), ptr(d["rays"]), ptr(d["numsteps"]), ptr(d["coords"]), ptr(d_mean),
                                     ptr(coords_out), ptr(dloss), ptr(loss), ptr(counters_out), ptr(scratch)))
