@@ -153,6 +153,7 @@ void hash_encode_forward_launch(cudaStream_t stream, const ngpb_grid* g, const _
 	if (n == 0) return;
 	const GridLevels L = make_levels(g);
 	const uint64_t threads = (uint64_t)n * L.n_levels;
+	NGPB_STEP_KERNEL(hash_encode_forward_kernel);
 	hash_encode_forward_kernel<<<(uint32_t)((threads + 255) / 256), 256, 0, stream>>>(n, n_dev, L, (const __half2*)grid, positions, pos_stride, (__half2*)encoded);
 	NGPB_LAUNCH_CHECK();
 }
@@ -161,6 +162,7 @@ void hash_encode_backward_launch(cudaStream_t stream, const ngpb_grid* g, const 
 	if (n == 0) return;
 	const GridLevels L = make_levels(g);
 	const uint64_t threads = (uint64_t)n * L.n_levels;
+	NGPB_STEP_KERNEL(hash_encode_backward_kernel);
 	hash_encode_backward_kernel<<<(uint32_t)((threads + 255) / 256), 256, 0, stream>>>(n, L, positions, pos_stride, (const __half2*)dL_dencoded, (float2*)grid_grad);
 	NGPB_LAUNCH_CHECK();
 }

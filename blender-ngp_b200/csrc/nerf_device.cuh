@@ -26,7 +26,8 @@ __device__ __forceinline__ float distance_to_next_voxel(const V3& pos, const V3&
 	const float ty = (floorf(py + 0.5f + 0.5f * copysignf(1.0f, dir.y)) - py) * idir.y;
 	const float tz = (floorf(pz + 0.5f + 0.5f * copysignf(1.0f, dir.z)) - pz) * idir.z;
 	const float t = fminf(fminf(tx, ty), tz);
-	return fmaxf(t / r, 0.0f);
+	// res is a power of two (NERF_GRIDSIZE >> mip), so t / res and t * (1 / res) are the same real number before rounding
+	return fmaxf(t * __uint_as_float((127u - (uint32_t)(31 - __clz((int)res))) << 23), 0.0f);
 }
 
 __device__ __forceinline__ float advance_to_next_voxel(float t, float cone_angle, const V3& pos, const V3& dir, const V3& idir, uint32_t res) {
@@ -35,12 +36,16 @@ __device__ __forceinline__ float advance_to_next_voxel(float t, float cone_angle
 	return t;
 }
 
-// frexpf exponent of a non-negative finite float (0 for 0), as used by mip_from_pos / mip_from_dt.
+// frexpf exponent of a non-negative finite float, as used by mip_from_pos / mip_from_dt: v = m * 2^e with m in [0.5, 1);
+// frexpf(0) reports exponent 0. Read from the bit pattern instead of calling the library routine. Subnormal inputs (|v| < 2^-126)
+// report -126 instead of their true, smaller exponent: every caller clamps the result from below at 0, so it is indistinguishable.
 __device__ __forceinline__ int frexp_exponent(float v) {
-	int e;
-	frexpf(v, &e);
-	return e;
+	const uint32_t b = __float_as_uint(v) & 0x7FFFFFFFu;
+	return b == 0u ? 0 : (int)(b >> 23) - 126;
 }
+
+// 2^-mip for mip in [0, 126], exact (what scalbnf(1.0f, -mip) returns)
+__device__ __forceinline__ float exp2_neg(uint32_t mip) { return __uint_as_float((127u - mip) << 23); }
 
 __device__ __forceinline__ int mip_from_pos(const V3& pos, uint32_t max_cascade = NERF_CASCADES - 1) {
 	const float maxval = fmaxf(fmaxf(fabsf(pos.x - 0.5f), fabsf(pos.y - 0.5f)), fabsf(pos.z - 0.5f));
@@ -55,7 +60,7 @@ __device__ __forceinline__ int mip_from_dt(float dt, const V3& pos, uint32_t max
 }
 
 __device__ __forceinline__ uint32_t cascaded_grid_idx_at(V3 pos, uint32_t mip) {
-	const float mip_scale = scalbnf(1.0f, -(int)mip);
+	const float mip_scale = exp2_neg(mip);
 	pos.x -= 0.5f; pos.y -= 0.5f; pos.z -= 0.5f;
 	pos.x *= mip_scale; pos.y *= mip_scale; pos.z *= mip_scale;
 	pos.x += 0.5f; pos.y += 0.5f; pos.z += 0.5f;

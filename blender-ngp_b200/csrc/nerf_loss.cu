@@ -372,6 +372,7 @@ extern "C" int ngpb_compute_loss(void* stream_, uint32_t n_rays, const float* aa
 		uint32_t* local_bases = counts + n_rays;
 		uint32_t* block_sums = local_bases + n_rays;
 		const uint32_t blocks = div_round_up(n_rays, LOSS_RAYS_PER_BLOCK);
+		NGPB_STEP_KERNEL(loss_composite_kernel); NGPB_STEP_KERNEL(loss_scan_kernel); NGPB_STEP_KERNEL(loss_gradient_kernel); NGPB_STEP_KERNEL(rollover_kernel);
 		loss_composite_kernel<<<blocks, 1024, 0, stream>>>(P, images_dev, counters_in, (const __half*)rgbsigma, ray_indices, numsteps, coords_in, state, counts, local_bases, block_sums);
 		NGPB_LAUNCH_CHECK();
 		loss_scan_kernel<<<1, 1024, 0, stream>>>(blocks, block_sums, counters_out);

@@ -426,6 +426,8 @@ static void launch_mlp(cudaStream_t stream, const MlpArgs& a, uint32_t grid, uin
 	static bool configured = false;
 	if (!configured) {
 		NGPB_CUDA_CHECK(cudaFuncSetAttribute(nerf_mlp_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+		// the training kernel overlaps the sampling stream (see common.cuh); the inference kernels run alone and want 4 CTAs x 53 KB
+		if (MODE == MODE_TRAIN) NGPB_CUDA_CHECK(cudaFuncSetAttribute(nerf_mlp_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, kSmemCarveoutPercent));
 		configured = true;
 	}
 	nerf_mlp_kernel<MODE><<<grid, 128, smem_bytes, stream>>>(a);
@@ -449,6 +451,7 @@ void nerf_mlp_forward_backward_launch(cudaStream_t stream, const __half* mlp, co
 	const uint32_t tiles = n / TILE;
 	const uint32_t grid = std::min(tiles, TRAIN_GRID);
 	launch_mlp<MODE_TRAIN>(stream, a, grid, SMEM_TRAIN);
+	NGPB_STEP_KERNEL(reduce_partials_kernel);
 	reduce_partials_kernel<<<div_round_up(MLP_PARAMS, 256), 256, 0, stream>>>(partials, grid, mlp_grad);
 	NGPB_LAUNCH_CHECK();
 }

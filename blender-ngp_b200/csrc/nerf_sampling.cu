@@ -282,6 +282,7 @@ extern "C" int ngpb_generate_training_samples(void* stream_, uint32_t n_rays, co
 		const uint32_t blocks = div_round_up(n_rays, K1_BLOCK);
 		uint2* block_sums = reinterpret_cast<uint2*>(local_slots + next_multiple(n_rays, 2));
 		MarchWord* words = reinterpret_cast<MarchWord*>(block_sums + blocks);
+		NGPB_STEP_KERNEL(count_training_samples_kernel); NGPB_STEP_KERNEL(scan_training_samples_kernel); NGPB_STEP_KERNEL(write_training_samples_kernel);
 		count_training_samples_kernel<<<blocks, K1_BLOCK, 0, stream>>>(n_rays, aabb, rng, n_images, images_dev, bitfield, snap_to_pixel_centers != 0, cone_angle_constant,
 			counts, n_words, words, local_bases, local_slots, block_sums);
 		NGPB_LAUNCH_CHECK();

@@ -76,6 +76,7 @@ extern "C" int ngpb_optimizer_step(void* stream, ngpb_optimizer* o, uint32_t n_p
 		P.ema_debias_old = 1 - (float)std::pow(o->ema_decay, o->step - 1);
 		P.ema_debias_new = 1.0f / (1 - (float)std::pow(o->ema_decay, o->step));
 		if (n_params == 0) return 0;
+		NGPB_STEP_KERNEL(adam_ema_kernel);
 		adam_ema_kernel<<<div_round_up(n_params, 256), 256, 0, (cudaStream_t)stream>>>(P, grad, w_fp32, (__half*)w_half, (__half*)w_ema, m1, m2, param_steps);
 		NGPB_LAUNCH_CHECK();
 		return 0;

@@ -106,6 +106,14 @@ extern "C" void ngpb_effective_xform(const float* m12, float* out12) {
 ngpb_testbed::ngpb_testbed(int device_) : device(device_) {
 	NGPB_CUDA_CHECK(cudaSetDevice(device));
 	NGPB_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+	// higher priority: when the sampling kernels are launched behind a kernel that fills the machine, their (few, long-running)
+	// blocks are placed as soon as the running kernel's blocks retire instead of after its whole grid
+	int prio_low = 0, prio_high = 0;
+	NGPB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
+	NGPB_CUDA_CHECK(cudaStreamCreateWithPriority(&sampling_stream, cudaStreamNonBlocking, prio_high));
+	NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&prefetch_done, cudaEventDisableTiming));
+	NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&loss_ready, cudaEventDisableTiming));
+	NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&counters_ready, cudaEventDisableTiming));
 	ngpb_optimizer_init(&opt);
 	loss_cfg.loss_scale = LOSS_SCALE;
 	loss_cfg.background_color[0] = loss_cfg.background_color[1] = loss_cfg.background_color[2] = 0.f;
@@ -121,22 +129,27 @@ ngpb_testbed::ngpb_testbed(int device_) : device(device_) {
 
 ngpb_testbed::~ngpb_testbed() {
 	cudaSetDevice(device);
+	if (sampling_stream) cudaStreamSynchronize(sampling_stream);
 	if (stream) cudaStreamSynchronize(stream);
+	if (prefetch_done) cudaEventDestroy(prefetch_done);
+	if (loss_ready) cudaEventDestroy(loss_ready);
+	if (counters_ready) cudaEventDestroy(counters_ready);
+	if (sampling_stream) cudaStreamDestroy(sampling_stream);
 	for (void* p : allocations) cudaFree(p);
 	for (auto& e : stage_ev) { if (e[0]) cudaEventDestroy(e[0]); if (e[1]) cudaEventDestroy(e[1]); }
 	if (host_readback) cudaFreeHost(host_readback);
 	if (stream) cudaStreamDestroy(stream);
 }
 
-void ngpb_testbed::stage_begin(int s) {
+void ngpb_testbed::stage_begin(int s, cudaStream_t st) {
 	if (!profile_stages) return;
 	if (!stage_ev[s][0]) { NGPB_CUDA_CHECK(cudaEventCreate(&stage_ev[s][0])); NGPB_CUDA_CHECK(cudaEventCreate(&stage_ev[s][1])); }
 	if (stage_used[s]) stage_collect(); // a stage that runs twice before a collect: fold the first interval in now
-	NGPB_CUDA_CHECK(cudaEventRecord(stage_ev[s][0], stream));
+	NGPB_CUDA_CHECK(cudaEventRecord(stage_ev[s][0], st));
 }
-void ngpb_testbed::stage_end(int s, uint64_t units) {
+void ngpb_testbed::stage_end(int s, uint64_t units, cudaStream_t st) {
 	if (!profile_stages) return;
-	NGPB_CUDA_CHECK(cudaEventRecord(stage_ev[s][1], stream));
+	NGPB_CUDA_CHECK(cudaEventRecord(stage_ev[s][1], st));
 	stage_used[s] = true;
 	stage_calls[s] += 1;
 	stage_units[s] += units;
@@ -177,8 +190,15 @@ void ngpb_testbed::load_training_data(uint32_t n, const ngpb_host_image* host_im
 		if (!host_images[i].pixels || host_images[i].w <= 0 || host_images[i].h <= 0) throw std::runtime_error("load_training_data: invalid image");
 		total += (size_t)host_images[i].w * host_images[i].h * 4;
 	}
-	dfree(pixels); dfree(images_dev);
-	pixels = (uint8_t*)dalloc(total);
+	drop_prefetch();
+	NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
+	// a reload of a same-sized dataset reuses the device buffers (no allocation in the steady state, like the reference's arena)
+	if (total != pixels_bytes || n != images.size()) {
+		dfree(pixels); dfree(images_dev);
+		pixels = (uint8_t*)dalloc(total);
+		images_dev = (ngpb_image*)dalloc(sizeof(ngpb_image) * n);
+		pixels_bytes = total;
+	}
 	images.resize(n);
 	size_t off = 0;
 	for (uint32_t i = 0; i < n; ++i) {
@@ -192,7 +212,6 @@ void ngpb_testbed::load_training_data(uint32_t n, const ngpb_host_image* host_im
 		ngpb_effective_xform(h.xform, im.xform);
 		off += bytes;
 	}
-	images_dev = (ngpb_image*)dalloc(sizeof(ngpb_image) * n);
 	NGPB_CUDA_CHECK(cudaMemcpyAsync(images_dev, images.data(), sizeof(ngpb_image) * n, cudaMemcpyHostToDevice, stream));
 	NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
 	h2d_bytes += total + sizeof(ngpb_image) * n;
@@ -209,6 +228,8 @@ void ngpb_testbed::load_training_data(uint32_t n, const ngpb_host_image* host_im
 // Testbed::reset_network (src/testbed.cu:2249-2470) for configs/nerf/base.json
 void ngpb_testbed::reset_network(uint32_t seed_) {
 	NGPB_CUDA_CHECK(cudaSetDevice(device));
+	drop_prefetch();
+	loss_pending = false;
 	seed = seed_;
 	// m_rng = default_rng_t{m_seed}; density_grid_rng = default_rng_t{m_rng.next_uint()} (:2252,:2265)
 	rng.seed(seed);
@@ -261,21 +282,27 @@ void ngpb_testbed::reset_network(uint32_t seed_) {
 
 	// density grid state (testbed.h:698-704)
 	const size_t n_cells = (size_t)NERF_GRID_CELLS * (max_cascade + 1);
-	dfree(density_grid); dfree(density_grid_tmp); dfree(bitfield); dfree(mean_density);
-	density_grid = (float*)dalloc(sizeof(float) * n_cells);
-	density_grid_tmp = (float*)dalloc(sizeof(float) * n_cells);
-	bitfield = (uint8_t*)dalloc((size_t)NERF_GRID_CELLS * NERF_CASCADES / 8);
-	mean_density = (float*)dalloc(sizeof(float));
+	const bool realloc_grid = n_cells != density_grid_cells;
+	if (realloc_grid) {
+		dfree(density_grid); dfree(density_grid_tmp); dfree(bitfield); dfree(mean_density);
+		density_grid = (float*)dalloc(sizeof(float) * n_cells);
+		density_grid_tmp = (float*)dalloc(sizeof(float) * n_cells);
+		bitfield = (uint8_t*)dalloc((size_t)NERF_GRID_CELLS * NERF_CASCADES / 8);
+		mean_density = (float*)dalloc(sizeof(float));
+	}
 	NGPB_CUDA_CHECK(cudaMemsetAsync(density_grid, 0, sizeof(float) * n_cells, stream));
 	NGPB_CUDA_CHECK(cudaMemsetAsync(bitfield, 0, (size_t)NERF_GRID_CELLS * NERF_CASCADES / 8, stream));
 	NGPB_CUDA_CHECK(cudaMemsetAsync(mean_density, 0, sizeof(float), stream));
 	// density-grid sample buffers: at most GRID_CELLS * n_cascades samples per refresh (testbed_nerf.cu:3396-3400)
-	dfree(dg_positions); dfree(dg_indices); dfree(dg_density); dfree(dg_encoded);
 	const size_t n_dg = next_multiple((uint32_t)n_cells, 128);
-	dg_positions = (float*)dalloc(sizeof(float) * 3 * n_dg);
-	dg_indices = (uint32_t*)dalloc(sizeof(uint32_t) * n_dg);
-	dg_density = (__half*)dalloc(sizeof(__half) * n_dg);
-	dg_encoded = (__half*)dalloc(sizeof(__half) * N_ENC * n_dg);
+	if (realloc_grid) {
+		dfree(dg_positions); dfree(dg_indices); dfree(dg_density); dfree(dg_encoded);
+		dg_positions = (float*)dalloc(sizeof(float) * 3 * n_dg);
+		dg_indices = (uint32_t*)dalloc(sizeof(uint32_t) * n_dg);
+		dg_density = (__half*)dalloc(sizeof(__half) * n_dg);
+		dg_encoded = (__half*)dalloc(sizeof(__half) * N_ENC * n_dg);
+		density_grid_cells = n_cells;
+	}
 	NGPB_CUDA_CHECK(cudaMemsetAsync(dg_positions, 0, sizeof(float) * 3 * n_dg, stream));
 
 	ngpb_optimizer_init(&opt);
@@ -286,11 +313,14 @@ void ngpb_testbed::reset_network(uint32_t seed_) {
 	n_rays_total = 0;
 	loss_scalar = 0.f;
 	if (!host_readback) NGPB_CUDA_CHECK(cudaMallocHost(&host_readback, 64));
+	host_readback[8] = 0;
 	NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
 }
 
 void ngpb_testbed::ensure_workspace(uint32_t batch) {
 	if (batch == ws_batch) return;
+	drop_prefetch();
+	NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
 	if (batch == 0 || batch % 128 != 0) throw std::runtime_error("training batch size must be a non-zero multiple of 128 (tcnn batch_size_granularity)");
 	dfree(ray_indices); dfree(rays); dfree(numsteps); dfree(coords); dfree(rgbsigma); dfree(encoded); dfree(coords_compacted);
 	dfree(dloss); dfree(denc); dfree(loss); dfree(scratch); dfree(counters); dfree(partials);
@@ -343,21 +373,53 @@ void ngpb_testbed::update_density_grid(uint32_t n_uniform, uint32_t n_nonuniform
 	n_launches += (n_uniform ? 1 : 0) + (n_nonuniform ? 1 : 0) + 2 + 2 + 3 + (NERF_CASCADES - 1);
 }
 
+// Launches K1 for the step described by `p` on stream `st`.
+void ngpb_testbed::launch_sampling(cudaStream_t st, const SamplingRequest& p) {
+	stage_begin(NGPB_STAGE_SAMPLING, st);
+	if (ngpb_generate_training_samples(st, p.n_rays, aabb, p.max_inference, p.rng, (uint32_t)images.size(), images_dev, bitfield,
+		p.snap, p.cone_angle, counters, ray_indices, rays, numsteps, coords, scratch) != 0) throw std::runtime_error(ngpb_last_error());
+	stage_end(NGPB_STAGE_SAMPLING, p.n_rays, st);
+	n_launches += 3;
+}
+
+void ngpb_testbed::drop_prefetch() {
+	if (!prefetch_valid) return;
+	NGPB_CUDA_CHECK(cudaStreamSynchronize(sampling_stream)); // its outputs are about to be overwritten or freed
+	prefetch_valid = false;
+}
+
+void ngpb_testbed::collect_loss_scalar() {
+	if (!loss_pending) return;
+	NGPB_CUDA_CHECK(cudaEventSynchronize(loss_ready));
+	float sum; std::memcpy(&sum, &host_readback[8], 4);
+	loss_scalar = sum * loss_pending_scale;
+	loss_pending = false;
+}
+
 // Testbed::train (src/testbed.cu:2527-2588): exactly one optimizer step.
-void ngpb_testbed::train(uint32_t batch) {
+//
+// Stream schedule. The reference runs every stage back to back on one stream and reads two counters back at the end of the step
+// (NerfCounters::update_after_training, testbed_nerf.cu:2870-2894) to size the next step's ray batch. Here the read-back sits right
+// after the loss kernels, which is where the counters are final, and ray generation + marching for the NEXT step (K1: it depends on
+// the occupancy grid, the RNG and the ray count, not on the weights) is launched on a second stream at that point, so that this
+// latency-bound kernel overlaps the bandwidth-bound second half of the step (forward/backward on the compacted batch, optimizer).
+// Steps that refresh the occupancy grid first are not prefetched. Results are identical to the serial schedule.
+void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 	NGPB_CUDA_CHECK(cudaSetDevice(device));
 	if (!training_data_available) throw std::runtime_error("train: no training data loaded");
+	if (batch != ws_batch) drop_prefetch();
 	ensure_workspace(batch);
 	auto check = [](int st) { if (st != 0) throw std::runtime_error(ngpb_last_error()); };
 
 	// training_prep_nerf cadence (:2538-2554, testbed_nerf.cu:3388-3401)
 	const uint32_t n_prep_to_skip = std::max(1u, std::min(training_step / 16u, 16u));
 	if (training_step % n_prep_to_skip == 0) {
+		drop_prefetch();
 		const uint32_t n_cascades = max_cascade + 1;
-		stage_begin(NGPB_STAGE_DENSITY_GRID);
+		stage_begin(NGPB_STAGE_DENSITY_GRID, stream);
 		if (training_step < 256) update_density_grid(NERF_GRID_CELLS * n_cascades, 0);
 		else update_density_grid(NERF_GRID_CELLS / 4 * n_cascades, NERF_GRID_CELLS / 4 * n_cascades);
-		stage_end(NGPB_STAGE_DENSITY_GRID, training_step < 256 ? NERF_GRID_CELLS * n_cascades : NERF_GRID_CELLS / 2 * n_cascades);
+		stage_end(NGPB_STAGE_DENSITY_GRID, training_step < 256 ? NERF_GRID_CELLS * n_cascades : NERF_GRID_CELLS / 2 * n_cascades, stream);
 	}
 	const bool get_loss_scalar = training_step % 16 == 0;
 
@@ -372,67 +434,102 @@ void ngpb_testbed::train(uint32_t batch) {
 	if (training_step == 0) n_rays_total = 0;
 	n_rays_total += rays_per_batch;
 	const uint32_t R = rays_per_batch;
-	const ngpb_rng r{rng.state, rng.inc};
+	const SamplingRequest req{training_step, R, max_inference, ngpb_rng{rng.state, rng.inc}, loss_cfg.snap_to_pixel_centers, cone_angle_constant};
+	const ngpb_rng r = req.rng;
 
 	// the uncompacted sample count of this step stays on the device; for the per-stage accounting the previous step's is used
 	const uint64_t n_uncompacted_est = std::min(measured_batch_size_before_compaction, max_inference);
-	stage_begin(NGPB_STAGE_SAMPLING);
-	check(ngpb_generate_training_samples(stream, R, aabb, max_inference, r, (uint32_t)images.size(), images_dev, bitfield,
-		loss_cfg.snap_to_pixel_centers, cone_angle_constant, counters, ray_indices, rays, numsteps, coords, scratch));
-	stage_end(NGPB_STAGE_SAMPLING, R);
+	if (prefetch_valid && prefetch == req) {
+		NGPB_CUDA_CHECK(cudaStreamWaitEvent(stream, prefetch_done, 0)); // K1 of this step already ran (or is running) on the sampling stream
+		prefetch_valid = false;
+	} else {
+		drop_prefetch();
+		launch_sampling(stream, req);
+	}
 	// network inference on the uncompacted samples; the sample count stays on the device
-	stage_begin(NGPB_STAGE_ENCODE_INFERENCE);
+	stage_begin(NGPB_STAGE_ENCODE_INFERENCE, stream);
 	hash_encode_forward_launch(stream, &grid, w_half + MLP_PARAMS, coords, COORD_FLOATS, max_inference, counters, encoded);
-	stage_end(NGPB_STAGE_ENCODE_INFERENCE, n_uncompacted_est);
-	stage_begin(NGPB_STAGE_MLP_INFERENCE);
+	stage_end(NGPB_STAGE_ENCODE_INFERENCE, n_uncompacted_est, stream);
+	stage_begin(NGPB_STAGE_MLP_INFERENCE, stream);
 	nerf_mlp_forward_launch(stream, w_half, encoded, coords, max_inference, counters, rgbsigma);
-	stage_end(NGPB_STAGE_MLP_INFERENCE, n_uncompacted_est);
-	stage_begin(NGPB_STAGE_LOSS);
+	stage_end(NGPB_STAGE_MLP_INFERENCE, n_uncompacted_est, stream);
+	stage_begin(NGPB_STAGE_LOSS, stream);
 	check(ngpb_compute_loss(stream, R, aabb, r, batch, &loss_cfg, (uint32_t)images.size(), images_dev, counters, (const ngpb_half*)rgbsigma,
 		ray_indices, rays, numsteps, coords, mean_density, coords_compacted, (ngpb_half*)dloss, loss, counters + 2, scratch));
-	stage_end(NGPB_STAGE_LOSS, R);
+	stage_end(NGPB_STAGE_LOSS, R, stream);
+	n_launches += 2 + 4;
+
+	// ---- the two counters of NerfCounters::update_after_training (:2870-2894) are final here: start their read-back ----
+	collect_loss_scalar(); // (frees the read-back slot of an earlier step's loss)
+	NGPB_CUDA_CHECK(cudaMemcpyAsync(host_readback, counters, sizeof(uint32_t) * 4, cudaMemcpyDeviceToHost, stream));
+	NGPB_CUDA_CHECK(cudaEventRecord(counters_ready, stream));
+	d2h_bytes += 16;
+
+	// ---- second half of the step, enqueued without waiting for the read-back (nothing in it depends on the host) ----
 	// forward + backward on the compacted, padded batch
-	stage_begin(NGPB_STAGE_ENCODE_TRAIN);
+	stage_begin(NGPB_STAGE_ENCODE_TRAIN, stream);
 	hash_encode_forward_launch(stream, &grid, w_half + MLP_PARAMS, coords_compacted, COORD_FLOATS, batch, nullptr, encoded);
-	stage_end(NGPB_STAGE_ENCODE_TRAIN, batch);
-	stage_begin(NGPB_STAGE_MLP_TRAIN);
+	stage_end(NGPB_STAGE_ENCODE_TRAIN, batch, stream);
+	stage_begin(NGPB_STAGE_MLP_TRAIN, stream);
 	nerf_mlp_forward_backward_launch(stream, w_half, encoded, coords_compacted, dloss, batch, denc, grad, partials);
-	stage_end(NGPB_STAGE_MLP_TRAIN, batch);
-	stage_begin(NGPB_STAGE_ENCODE_BACKWARD);
+	stage_end(NGPB_STAGE_MLP_TRAIN, batch, stream);
+	stage_begin(NGPB_STAGE_ENCODE_BACKWARD, stream);
 	hash_encode_backward_launch(stream, &grid, coords_compacted, COORD_FLOATS, batch, denc, grad + MLP_PARAMS);
-	stage_end(NGPB_STAGE_ENCODE_BACKWARD, batch);
+	stage_end(NGPB_STAGE_ENCODE_BACKWARD, batch, stream);
+	// optimizer (train_nerf :2950)
+	stage_begin(NGPB_STAGE_OPTIMIZER, stream);
+	check(ngpb_optimizer_step(stream, &opt, n_params, MLP_PARAMS, LOSS_SCALE, grad, w_fp32, (ngpb_half*)w_half, (ngpb_half*)w_ema, m1, m2, param_steps));
+	stage_end(NGPB_STAGE_OPTIMIZER, n_params, stream);
+	n_launches += 1 + 2 + 1 + 1;
+	// loss scalar every 16th step (:2885-2888): reduced on the device, read back without stalling the stream
+	if (get_loss_scalar) {
+		NGPB_STEP_KERNEL(sum_kernel);
+		sum_kernel<<<1, 1024, 0, stream>>>(loss, R, reinterpret_cast<float*>(counters + 4));
+		NGPB_LAUNCH_CHECK();
+		n_launches += 1;
+		NGPB_CUDA_CHECK(cudaMemcpyAsync(host_readback + 8, counters + 4, sizeof(float), cudaMemcpyDeviceToHost, stream));
+		NGPB_CUDA_CHECK(cudaEventRecord(loss_ready, stream));
+		d2h_bytes += 4;
+	}
+	++training_step;
 	rng.advance(); // m_rng.advance() (:3380)
 
-	// ---- optimizer (train_nerf :2950) ----
-	stage_begin(NGPB_STAGE_OPTIMIZER);
-	check(ngpb_optimizer_step(stream, &opt, n_params, MLP_PARAMS, LOSS_SCALE, grad, w_fp32, (ngpb_half*)w_half, (ngpb_half*)w_ema, m1, m2, param_steps));
-	stage_end(NGPB_STAGE_OPTIMIZER, n_params);
-	++training_step;
-	n_launches += 3 + 2 + 4 + 1 + 2 + 1 + 1;
-
-	// ---- NerfCounters::update_after_training (:2870-2894): 2 counters (+ loss every 16th step) read back ----
-	if (get_loss_scalar) { sum_kernel<<<1, 1024, 0, stream>>>(loss, R, reinterpret_cast<float*>(counters + 4)); NGPB_LAUNCH_CHECK(); n_launches += 1; }
-	NGPB_CUDA_CHECK(cudaMemcpyAsync(host_readback, counters, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, stream));
-	NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
-	if (profile_stages) stage_collect();
-	d2h_bytes += 32;
+	// ---- batch-size controller (:2870-2894) ----
+	NGPB_CUDA_CHECK(cudaEventSynchronize(counters_ready));
 	const uint32_t counter_cpu = host_readback[0], compacted_counter_cpu = host_readback[2];
 	measured_batch_size = 0;
 	measured_batch_size_before_compaction = 0;
 	if (counter_cpu == 0 || compacted_counter_cpu == 0) {
-		loss_scalar = 0.f;
 		// "Nerf training generated 0 samples. Aborting training." (:2964-2968)
+		NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
+		loss_scalar = 0.f;
+		loss_pending = false;
 		shall_train = false;
+		if (profile_stages) stage_collect();
 		return;
 	}
 	measured_batch_size_before_compaction = counter_cpu;
 	measured_batch_size = compacted_counter_cpu;
-	if (get_loss_scalar) {
-		float sum; std::memcpy(&sum, &host_readback[4], 4);
-		loss_scalar = sum * (float)measured_batch_size / (float)batch;
-	}
+	if (get_loss_scalar) { loss_pending = true; loss_pending_scale = (float)measured_batch_size / (float)batch; }
 	rays_per_batch = (uint32_t)((float)rays_per_batch * (float)batch / (float)measured_batch_size);
 	rays_per_batch = std::min(next_multiple(rays_per_batch, 128u), 1u << 18);
+
+	// ---- K1 of the next step, on the sampling stream, unless that step starts with an occupancy-grid refresh ----
+	{
+		const uint32_t next_skip = std::max(1u, std::min(training_step / 16u, 16u));
+		if (overlap_sampling && training_step % next_skip != 0) {
+			prefetch = SamplingRequest{training_step, rays_per_batch, next_multiple(std::min(measured_batch_size_before_compaction, max_samples), 128),
+				ngpb_rng{rng.state, rng.inc}, loss_cfg.snap_to_pixel_centers, cone_angle_constant};
+			launch_sampling(sampling_stream, prefetch);
+			NGPB_CUDA_CHECK(cudaEventRecord(prefetch_done, sampling_stream));
+			prefetch_valid = true;
+		}
+	}
+	if (sync_at_end) {
+		NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
+		collect_loss_scalar();
+		if (profile_stages) stage_collect();
+	}
 }
 
 void ngpb_testbed::get_params(float* o_fp32, ngpb_half* o_half, ngpb_half* o_ema) {
@@ -474,13 +571,17 @@ extern "C" int ngpb_testbed_reset_network(ngpb_testbed* t, uint32_t seed) {
 	t->reset_network(seed);
 	NGPB_API_END
 }
-extern "C" int ngpb_testbed_train(ngpb_testbed* t, uint32_t batch_size) { NGPB_API_BEGIN t->train(batch_size); NGPB_API_END }
+extern "C" int ngpb_testbed_train(ngpb_testbed* t, uint32_t batch_size) { NGPB_API_BEGIN t->train(batch_size, true); NGPB_API_END }
 extern "C" int ngpb_testbed_train_n(ngpb_testbed* t, uint32_t batch_size, uint32_t n_steps) {
 	NGPB_API_BEGIN
-	for (uint32_t i = 0; i < n_steps && t->shall_train; ++i) t->train(batch_size);
+	// steps run back to back: the only host wait inside a step is the counter read-back that sizes the next ray batch
+	for (uint32_t i = 0; i < n_steps && t->shall_train; ++i) t->train(batch_size, i + 1 == n_steps);
 	NGPB_API_END
 }
-extern "C" float ngpb_testbed_loss(ngpb_testbed* t) { return t->loss_scalar; }
+extern "C" float ngpb_testbed_loss(ngpb_testbed* t) {
+	try { cudaSetDevice(t->device); t->collect_loss_scalar(); } catch (...) {}
+	return t->loss_scalar;
+}
 extern "C" uint32_t ngpb_testbed_training_step(const ngpb_testbed* t) { return t->training_step; }
 extern "C" int ngpb_testbed_stats(ngpb_testbed* t, uint64_t* s) {
 	NGPB_API_BEGIN
@@ -534,6 +635,7 @@ extern "C" int ngpb_testbed_set_option(ngpb_testbed* t, const char* name, double
 	else if (k == "render_min_transmittance") t->render_min_transmittance = (float)v;
 	else if (k == "learning_rate") t->opt.learning_rate = (float)v;
 	else if (k == "profile_stages") t->profile_stages = v != 0;
+	else if (k == "overlap_sampling") { t->drop_prefetch(); t->overlap_sampling = v != 0; }
 	else throw std::runtime_error("unknown option: " + k);
 	NGPB_API_END
 }

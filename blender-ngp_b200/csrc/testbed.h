@@ -13,12 +13,29 @@ struct ngpb_testbed {
 
 	void load_training_data(uint32_t n, const ngpb_host_image* host_images, uint32_t aabb_scale);
 	void reset_network(uint32_t seed);
-	void train(uint32_t batch);
+	void train(uint32_t batch, bool sync_at_end = true);
 	void update_density_grid(uint32_t n_uniform, uint32_t n_nonuniform);
 	void ensure_workspace(uint32_t batch);
 	void get_params(float* w_fp32, ngpb_half* w_half, ngpb_half* w_ema);
 	void set_params(const float* w_fp32);
 	void render(const float* camera12, int w, int h, float fx, float fy, int spp, bool linear, float* out_rgba, uint64_t* n_samples_out);
+
+	// K1 of the next step, prefetched on a second stream (see train())
+	struct SamplingRequest {
+		uint32_t step, n_rays, max_inference; ngpb_rng rng; int snap; float cone_angle;
+		bool operator==(const SamplingRequest& o) const {
+			return step == o.step && n_rays == o.n_rays && max_inference == o.max_inference && rng.state == o.rng.state && rng.inc == o.rng.inc && snap == o.snap && cone_angle == o.cone_angle;
+		}
+	};
+	void launch_sampling(cudaStream_t st, const SamplingRequest& p);
+	void drop_prefetch();
+	void collect_loss_scalar();
+	cudaStream_t sampling_stream = nullptr;
+	cudaEvent_t prefetch_done = nullptr, loss_ready = nullptr, counters_ready = nullptr;
+	SamplingRequest prefetch{};
+	bool prefetch_valid = false, overlap_sampling = true;
+	bool loss_pending = false;
+	float loss_pending_scale = 0.f;
 
 	void* dalloc(size_t bytes);
 	void dfree(void* p);
@@ -32,6 +49,7 @@ struct ngpb_testbed {
 	std::vector<ngpb_image> images;
 	ngpb_image* images_dev = nullptr;
 	uint8_t* pixels = nullptr;
+	size_t pixels_bytes = 0, density_grid_cells = 0;
 	uint32_t aabb_scale = 1, max_cascade = 0;
 	float aabb[6] = {0, 0, 0, 1, 1, 1};
 	float cone_angle_constant = 0.f;
@@ -78,7 +96,7 @@ struct ngpb_testbed {
 	double stage_ms[NGPB_N_STAGES] = {};
 	uint64_t stage_calls[NGPB_N_STAGES] = {};
 	uint64_t stage_units[NGPB_N_STAGES] = {}; // samples (or rays / params) the stage processed, summed over calls
-	void stage_begin(int s);
-	void stage_end(int s, uint64_t units);
+	void stage_begin(int s, cudaStream_t st);
+	void stage_end(int s, uint64_t units, cudaStream_t st);
 	void stage_collect(); // after a stream synchronize
 };

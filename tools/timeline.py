@@ -1,0 +1,37 @@
+"""Kernel timeline of a few training steps through CUPTI (torch.profiler), since nsys is not in the image.
+usage: python tools/timeline.py [n_steps] [out.json]  -> prints per-kernel start/duration/stream for the last steps."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "blender-ngp_b200"))
+import pyngp
+import synthetic
+
+n_steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+mode = sys.argv[2] if len(sys.argv) > 2 else "train_n"
+scene = synthetic.make_lego_scene(100, 800, device="cuda", as_numpy=True)
+tb = pyngp.Testbed()
+tb.load_training_images(list(scene["images"]), scene["xforms"], scene["fx"], scene["fy"])
+tb.train_n(530)
+torch.cuda.synchronize()
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    if mode == "train_n":
+        tb.train_n(n_steps)
+    else:
+        for _ in range(n_steps):
+            tb.train(); _ = tb.loss
+    torch.cuda.synchronize()
+path = os.path.join(ROOT, "gpurun_out", "timeline.json")
+prof.export_chrome_trace(path)
+ev = json.load(open(path))["traceEvents"]
+k = [e for e in ev if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
+k.sort(key=lambda e: e["ts"])
+t0 = k[0]["ts"]
+for e in k:
+    print(f'{e["ts"] - t0:10.1f} {e["dur"]:8.1f} us  stream {e["args"].get("stream")}  {e["name"][:60]}')
