@@ -117,7 +117,7 @@ ngpb_testbed::ngpb_testbed(int device_) : device(device_) {
 	ngpb_optimizer_init(&opt);
 	loss_cfg.loss_scale = LOSS_SCALE;
 	loss_cfg.background_color[0] = loss_cfg.background_color[1] = loss_cfg.background_color[2] = 0.f;
-	loss_cfg.color_space = NGPB_COLOR_SRGB;       // testbed.h: m_color_space default SRGB
+	loss_cfg.color_space = NGPB_COLOR_LINEAR;     // m_color_space default, testbed.h:846
 	loss_cfg.random_bg_color = 1;                 // testbed.h:651
 	loss_cfg.linear_colors = 0;
 	loss_cfg.loss_type = NGPB_LOSS_HUBER;         // configs/nerf/base.json:2-4
@@ -635,6 +635,11 @@ extern "C" int ngpb_testbed_set_option(ngpb_testbed* t, const char* name, double
 	else if (k == "render_min_transmittance") t->render_min_transmittance = (float)v;
 	else if (k == "learning_rate") t->opt.learning_rate = (float)v;
 	else if (k == "profile_stages") t->profile_stages = v != 0;
+	else if (k == "render_snap_to_pixel_centers") t->render_snap_to_pixel_centers = v != 0;
+	else if (k == "render_near_distance") t->render_near_distance = (float)v;
+	else if (k == "exposure") t->exposure = (float)v;
+	else if (k == "background_color_a") t->background_alpha = (float)v;
+	else if (k == "render_with_training_params") t->render_with_training_params = v != 0;
 	else if (k == "overlap_sampling") { t->drop_prefetch(); t->overlap_sampling = v != 0; }
 	else throw std::runtime_error("unknown option: " + k);
 	NGPB_API_END
@@ -654,6 +659,13 @@ extern "C" double ngpb_testbed_get_option(ngpb_testbed* t, const char* name) {
 	if (k == "shall_train") return t->shall_train;
 	if (k == "render_min_transmittance") return t->render_min_transmittance;
 	if (k == "learning_rate") return t->opt.learning_rate;
+	if (k == "render_snap_to_pixel_centers") return t->render_snap_to_pixel_centers;
+	if (k == "render_near_distance") return t->render_near_distance;
+	if (k == "exposure") return t->exposure;
+	if (k == "background_color_r") return t->loss_cfg.background_color[0];
+	if (k == "background_color_g") return t->loss_cfg.background_color[1];
+	if (k == "background_color_b") return t->loss_cfg.background_color[2];
+	if (k == "background_color_a") return t->background_alpha;
 	if (k == "aabb_scale") return t->aabb_scale;
 	if (k == "max_cascade") return t->max_cascade;
 	if (k == "h2d_bytes") return (double)t->h2d_bytes;
@@ -661,9 +673,54 @@ extern "C" double ngpb_testbed_get_option(ngpb_testbed* t, const char* name) {
 	return std::nan("");
 }
 
+// Testbed::render_to_cpu (src/python_api.cu:132-190) -> render_frame (src/testbed.cu:2695) -> render_nerf (src/testbed_nerf.cu:2354) for a static camera.
+void ngpb_testbed::render(const float* camera12, int w, int h, float fx, float fy, int spp, bool linear, float* out_rgba, uint64_t* n_samples_out) {
+	NGPB_CUDA_CHECK(cudaSetDevice(device));
+	if (!camera12 || !out_rgba || w <= 0 || h <= 0 || spp <= 0) throw std::runtime_error("render: invalid argument");
+	if (n_params == 0) throw std::runtime_error("render: no network (load training data or a snapshot first)");
+	const uint32_t n_pixels = (uint32_t)w * (uint32_t)h;
+	const size_t need = (size_t)ngpb_render_workspace_bytes(n_pixels);
+	if (need > render_ws_bytes) {
+		NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
+		dfree(render_ws);
+		render_ws = dalloc(need);
+		render_ws_bytes = need;
+	}
+	ngpb_render_config c{};
+	c.width = w; c.height = h; c.fx = fx; c.fy = fy;
+	c.screen_center[0] = c.screen_center[1] = 0.5f;
+	std::memcpy(c.camera, camera12, sizeof(float) * 12);
+	c.spp = spp; c.snap_to_pixel_centers = render_snap_to_pixel_centers;
+	std::memcpy(c.aabb, aabb, sizeof(aabb));
+	std::memcpy(c.render_aabb, aabb, sizeof(aabb)); // m_render_aabb = m_aabb (testbed_nerf.cu:2717)
+	c.cone_angle_constant = cone_angle_constant; c.min_transmittance = render_min_transmittance; c.near_distance = render_near_distance;
+	c.rgb_activation = loss_cfg.rgb_activation; c.density_activation = loss_cfg.density_activation; c.train_in_linear_colors = loss_cfg.linear_colors;
+	c.color_space = loss_cfg.color_space; c.output_srgb = linear ? 0 : 1;
+	c.exposure = exposure;
+	for (int k = 0; k < 3; ++k) c.background_color[k] = loss_cfg.background_color[k];
+	c.background_color[3] = background_alpha;
+	// the prefetched sampling kernels of the next training step share no buffer with the render path; the main stream orders the rest
+	cudaEvent_t e0, e1;
+	NGPB_CUDA_CHECK(cudaEventCreate(&e0)); NGPB_CUDA_CHECK(cudaEventCreate(&e1));
+	NGPB_CUDA_CHECK(cudaEventRecord(e0, stream));
+	uint32_t launches = 0;
+	// Network::inference_mixed_precision defaults to the inference (EMA) parameters (testbed_nerf.cu:2223)
+	const int st = ngpb_render_nerf(stream, &c, &grid, (const ngpb_half*)(render_with_training_params ? w_half : w_ema), bitfield, render_ws, out_rgba, n_samples_out, &launches);
+	NGPB_CUDA_CHECK(cudaEventRecord(e1, stream));
+	NGPB_CUDA_CHECK(cudaEventSynchronize(e1));
+	float ms = 0.f;
+	cudaEventElapsedTime(&ms, e0, e1);
+	last_render_ms = ms;
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
+	if (st != 0) throw std::runtime_error(ngpb_last_error());
+	n_launches += launches;
+	d2h_bytes += (uint64_t)n_pixels * 16;
+}
+
+extern "C" double ngpb_testbed_last_render_ms(const ngpb_testbed* t) { return t ? t->last_render_ms : 0.0; }
+
 extern "C" int ngpb_testbed_render(ngpb_testbed* t, const float* camera12, int w, int h, float fx, float fy, int spp, int linear, float* out_rgba, uint64_t* n_samples_out) {
 	NGPB_API_BEGIN
-	(void)t; (void)camera12; (void)w; (void)h; (void)fx; (void)fy; (void)spp; (void)linear; (void)out_rgba; (void)n_samples_out;
-	throw std::runtime_error("ngpb_testbed_render: the classic render path is not built yet");
+	t->render(camera12, w, h, fx, fy, spp, linear != 0, out_rgba, n_samples_out);
 	NGPB_API_END
 }

@@ -85,6 +85,12 @@ struct ngpb_testbed {
 	bool shall_train = true;
 	ngpb_loss_config loss_cfg{};
 	float render_min_transmittance = 0.01f; // testbed.h:725
+	// render state (testbed.h:547,:853,:875,:889)
+	int render_snap_to_pixel_centers = 0;
+	float render_near_distance = 0.f, exposure = 0.f, background_alpha = 1.0f;
+	bool render_with_training_params = false;
+	void* render_ws = nullptr; size_t render_ws_bytes = 0;
+	double last_render_ms = 0.0;
 
 	uint64_t n_launches = 0, h2d_bytes = 0, d2h_bytes = 0;
 

@@ -85,6 +85,14 @@ class Optimizer(C.Structure):
                 ("decay_base", C.c_float), ("step", C.c_uint32), ("lr_factor", C.c_float)]
 
 
+class RenderConfig(C.Structure):  # ngpb_render_config
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("fx", C.c_float), ("fy", C.c_float), ("screen_center", C.c_float * 2), ("camera", C.c_float * 12),
+                ("spp", C.c_int32), ("snap_to_pixel_centers", C.c_int32), ("aabb", C.c_float * 6), ("render_aabb", C.c_float * 6),
+                ("cone_angle_constant", C.c_float), ("min_transmittance", C.c_float), ("near_distance", C.c_float),
+                ("rgb_activation", C.c_int32), ("density_activation", C.c_int32), ("train_in_linear_colors", C.c_int32),
+                ("color_space", C.c_int32), ("output_srgb", C.c_int32), ("exposure", C.c_float), ("background_color", C.c_float * 4)]
+
+
 # every symbol include/ngpb.h declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = [
     "ngpb_last_error", "ngpb_version", "ngpb_check_device", "ngpb_grid_init", "ngpb_hash_encode_forward", "ngpb_hash_encode_backward",
@@ -94,7 +102,7 @@ EXPORTED_SYMBOLS = [
     "ngpb_testbed_create", "ngpb_testbed_destroy", "ngpb_testbed_load_training_data", "ngpb_testbed_reset_network", "ngpb_testbed_train",
     "ngpb_testbed_train_n", "ngpb_testbed_loss", "ngpb_testbed_training_step", "ngpb_testbed_stats", "ngpb_testbed_n_params",
     "ngpb_testbed_get_params", "ngpb_testbed_set_params", "ngpb_testbed_get_density_grid", "ngpb_testbed_set_option", "ngpb_testbed_get_option",
-    "ngpb_testbed_render", "ngpb_testbed_stream", "ngpb_testbed_stage_times", "ngpb_grid_device_scales", "ngpb_generate_training_samples_scratch_bytes", "ngpb_compute_loss_scratch_bytes",
+    "ngpb_testbed_render", "ngpb_testbed_stream", "ngpb_testbed_stage_times", "ngpb_grid_device_scales", "ngpb_render_workspace_bytes", "ngpb_render_nerf", "ngpb_testbed_last_render_ms", "ngpb_generate_training_samples_scratch_bytes", "ngpb_compute_loss_scratch_bytes",
 ]
 
 _lib = None
@@ -112,6 +120,9 @@ def lib():
         l.ngpb_nerf_mlp_workspace_bytes.restype = C.c_uint64
         l.ngpb_generate_training_samples_scratch_bytes.restype = C.c_uint64
         l.ngpb_compute_loss_scratch_bytes.restype = C.c_uint64
+        l.ngpb_render_workspace_bytes.restype = C.c_uint64
+        l.ngpb_testbed_last_render_ms.restype = C.c_double
+        l.ngpb_testbed_last_render_ms.argtypes = [C.c_void_p]
         l.ngpb_testbed_loss.restype = C.c_float
         l.ngpb_testbed_training_step.restype = C.c_uint32
         l.ngpb_testbed_n_params.restype = C.c_uint32
@@ -283,7 +294,7 @@ def load_transforms(path):
         raise RuntimeError("Couldn't read fov.")
     cx = float(meta.get("cx", 0.5 * w)) / w
     cy = float(meta.get("cy", 0.5 * h)) / h
-    return dict(images=images, xforms=np.stack(xforms), fx=fx, fy=fy, cx=cx, cy=cy, aabb_scale=aabb_scale)
+    return dict(images=images, xforms=np.stack(xforms), fx=fx, fy=fy, cx=cx, cy=cy, aabb_scale=aabb_scale, scale=scale, offset=offset)
 
 
 class _Training:
@@ -353,6 +364,7 @@ class Testbed:
     def load_training_data(self, path):
         """Testbed::load_training_data (src/testbed.cu:97): a transforms.json file or a directory holding one."""
         d = load_transforms(path)
+        self._dataset_scale, self._dataset_offset = d["scale"], tuple(d["offset"])
         self.load_training_images(d["images"], d["xforms"], d["fx"], d["fy"], d["cx"], d["cy"], d["aabb_scale"])
 
     def load_training_images(self, images, xforms, fx, fy, cx=0.5, cy=0.5, aabb_scale=1):
@@ -415,12 +427,13 @@ class Testbed:
     n_params = property(lambda s: int(lib().ngpb_testbed_n_params(s._h)))
 
     @property
-    def background_color(self):
-        return [self._get("background_color_r") if False else 0.0] * 3 + [1.0]
+    def background_color(self):  # m_background_color, RGBA (testbed.h:875)
+        return [self._get("background_color_" + c) for c in "rgba"]
 
     @background_color.setter
     def background_color(self, v):
-        self._set("background_color_r", v[0]); self._set("background_color_g", v[1]); self._set("background_color_b", v[2])
+        for c, x in zip("rgba", v):
+            self._set("background_color_" + c, float(x))
 
     color_space = property(lambda s: ColorSpace(int(s._get("color_space"))), lambda s, v: s._set("color_space", int(v)))
 
@@ -468,19 +481,43 @@ class Testbed:
         return g, b
 
     # -- render
-    def render(self, width, height, spp=1, linear=True, camera_matrix=None, fov_x=None):
-        """Testbed::render (python_api.cu:567): returns float32 [H][W][4]."""
-        cam = np.asarray(camera_matrix if camera_matrix is not None else self._camera, dtype=np.float32).reshape(3, 4).T.reshape(-1).copy()
-        fx = 0.5 * width / math.tan(0.5 * (fov_x if fov_x is not None else self._fov_x))
+    def render(self, width, height, spp=1, linear=True, start_t=-1.0, end_t=-1.0, fps=30.0, shutter_fraction=1.0):
+        """Testbed::render (python_api.cu:567 -> render_to_cpu :132): float32 [H][W][4], RGBA after accumulation over `spp` samples and
+        tone mapping; `linear=False` converts to sRGB. Static camera only (camera paths / motion blur are outside the built scope)."""
+        if start_t >= 0.0:
+            raise RuntimeError("camera-path rendering (start_t >= 0) is outside the built scope")
+        cam = np.asarray(self.camera_matrix, dtype=np.float32).reshape(3, 4).T.reshape(-1).copy()
+        # Testbed::calc_focal_length (src/testbed.cu:2589): relative focal length x resolution[fov_axis] x zoom, same for x and y
+        rel = self._relative_focal_length
+        res_axis = (width, height)[self.fov_axis]
+        fx, fy = rel[0] * res_axis, rel[1] * res_axis
         out = np.empty((height, width, 4), np.float32)
         ns = C.c_uint64(0)
-        check(lib().ngpb_testbed_render(self._h, cam.ctypes.data_as(C.c_void_p), int(width), int(height), C.c_float(fx), C.c_float(fx), int(spp), int(bool(linear)),
+        check(lib().ngpb_testbed_render(self._h, cam.ctypes.data_as(C.c_void_p), int(width), int(height), C.c_float(fx), C.c_float(fy), int(spp), int(bool(linear)),
                                         out.ctypes.data_as(C.c_void_p), C.byref(ns)))
         self.last_render_samples = int(ns.value)
+        self.last_render_ms = float(lib().ngpb_testbed_last_render_ms(self._h))
         return out
 
-    _camera = np.eye(4, dtype=np.float32)[:3]
-    _fov_x = 0.6911112070083618
+    fov_axis = 1  # m_fov_axis (testbed.h:528)
+    _relative_focal_length = (1.0, 1.0)  # m_relative_focal_length (testbed.h:527)
+    camera_matrix = np.eye(4, dtype=np.float32)[:3]  # m_camera, 3x4, ngp convention
+    _dataset_scale, _dataset_offset = 1.0, (0.0, 0.0, 0.0)
 
-    def set_nerf_camera_matrix(self, m):  # python_api.cu:681
-        self._camera = np.asarray(m, dtype=np.float32).reshape(3, 4)
+    @property
+    def fov(self):  # degrees along fov_axis (Testbed::fov, src/testbed.cu:2153)
+        return math.degrees(2.0 * math.atan(0.5 / self._relative_focal_length[self.fov_axis]))
+
+    @fov.setter
+    def fov(self, deg):  # Testbed::set_fov (:2157)
+        f = 0.5 / math.tan(0.5 * math.radians(deg))
+        self._relative_focal_length = (f, f)
+
+    snap_to_pixel_centers = property(lambda s: bool(s._get("render_snap_to_pixel_centers")), lambda s, v: s._set("render_snap_to_pixel_centers", 1.0 if v else 0.0))
+    exposure = property(lambda s: s._get("exposure"), lambda s, v: s._set("exposure", float(v)))
+    render_near_distance = property(lambda s: s._get("render_near_distance"), lambda s, v: s._set("render_near_distance", float(v)))
+
+    def set_nerf_camera_matrix(self, m):
+        """python_api.cu:681 -> Testbed::set_nerf_camera_matrix: a NeRF-convention camera-to-world matrix, converted with the dataset's
+        scale / offset (NerfDataset::nerf_matrix_to_ngp, nerf_loader.h:113-132)."""
+        self.camera_matrix = nerf_matrix_to_ngp(np.asarray(m, dtype=np.float32), self._dataset_scale, self._dataset_offset)

@@ -144,6 +144,30 @@ int ngpb_splat_and_ema(void* stream, uint32_t n_samples, const uint32_t* indices
 /* mean of max(v,0) over the first cascade -> *mean_dev, then bitfield + 7 max-pooled mips (2 MiB). */
 int ngpb_update_bitfield(void* stream, uint32_t n_cascades_used, const float* grid, float* mean_dev, uint8_t* bitfield);
 
+/* ---- K17: classic single-NeRF render (Testbed::render_nerf, src/testbed_nerf.cu:2354-2499; NerfTracer :2047-2267), ERenderMode::Shade,
+ * perspective camera, followed by CudaRenderBuffer::accumulate + tonemap (src/render_buffer.cu:606-660). ---- */
+#define NGPB_RENDER_FIRST_PASS_STEPS 4   /* march steps per live ray in the first pass; later passes take more as rays die */
+#define NGPB_RENDER_MAX_PASS_STEPS 32
+typedef struct {
+	int32_t width, height;
+	float fx, fy;               /* focal length in pixels (Testbed::calc_focal_length, src/testbed.cu:2589) */
+	float screen_center[2];     /* Testbed::render_screen_center(), (0.5, 0.5) by default */
+	float camera[12];           /* 3x4 camera-to-world, column-major, ngp convention */
+	int32_t spp, snap_to_pixel_centers;
+	float aabb[6], render_aabb[6];
+	float cone_angle_constant, min_transmittance, near_distance;
+	int32_t rgb_activation, density_activation, train_in_linear_colors;
+	int32_t color_space;        /* m_color_space: the space the accumulation buffer averages in */
+	int32_t output_srgb;        /* !linear argument of Testbed::render */
+	float exposure, background_color[4];
+} ngpb_render_config;
+uint64_t ngpb_render_workspace_bytes(uint32_t n_pixels);
+/* params: half[10240 + grid] (inference = EMA weights for Testbed::render); bitfield: occupancy bits incl. mips; workspace: device memory of
+ * ngpb_render_workspace_bytes(width*height). out_rgba_host: float [height][width][4] (host). n_samples_out: samples that went through the
+ * network for live rays; n_launches_out: kernels launched. Synchronises the stream (the live-ray count is read back once per pass). */
+int ngpb_render_nerf(void* stream, const ngpb_render_config* cfg, const ngpb_grid* g, const ngpb_half* params, const uint8_t* bitfield,
+                     void* workspace, float* out_rgba_host, uint64_t* n_samples_out, uint32_t* n_launches_out);
+
 /* ---- development self-test of the tcgen05 building blocks (tests/test_umma_selftest.py) ---- */
 int ngpb_selftest_umma(void* stream, int variant, const ngpb_half* a, const ngpb_half* b, float* d);
 
@@ -200,6 +224,8 @@ double ngpb_testbed_get_option(ngpb_testbed* t, const char* name);
 /* Testbed::render (python_api.cu:132-190) for the classic single-NeRF path: camera12 = 3x4 column-major camera matrix.
  * out_rgba: host float [h][w][4]. n_samples_out (optional): network-evaluated samples. */
 int ngpb_testbed_render(ngpb_testbed* t, const float* camera12, int w, int h, float fx, float fy, int spp, int linear, float* out_rgba, uint64_t* n_samples_out);
+/* Device milliseconds (CUDA events on the testbed's stream) of the last ngpb_testbed_render call, excluding the final device-to-host copy. */
+double ngpb_testbed_last_render_ms(const ngpb_testbed* t);
 
 #ifdef __cplusplus
 }

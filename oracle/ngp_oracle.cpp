@@ -1086,3 +1086,177 @@ extern "C" void orc_bitfield(uint32_t n_cascades_used, const float* grid, float 
 		}
 	}
 }
+
+// =============================================================================================
+// Classic single-NeRF render (Testbed::render_nerf, src/testbed_nerf.cu:2354-2499), ERenderMode::Shade,
+// perspective camera, no lens distortion / masks / envmap / depth of field:
+//   init_rays_with_payload_kernel_nerf :1809-1978 + pixel_to_ray common_device.cuh:260-317
+//   advance_pos_nerf :612-664, generate_next_nerf_network_inputs :705-766, composite_kernel_nerf :767-989,
+//   compact_kernel_nerf :1784-1807 (a finished ray is shaded only if its alpha exceeds 0.001), shade_kernel_nerf :1748-1782
+//   low-discrepancy jitter: random_val.cuh:159-322 (Burley's shuffled scrambled Sobol)
+//   CudaRenderBuffer::accumulate / tonemap: src/render_buffer.cu:235-266, :268-349, :540-567, :606-660
+// The reference's wavefront (compaction every 1-8 steps) only schedules the work: per ray the samples, their order and the
+// termination test are those of the serial loop below.
+// =============================================================================================
+namespace {
+inline uint32_t sobol(uint32_t index, uint32_t dim) {
+	static const uint32_t directions[2][32] = {
+		{0x80000000, 0x40000000, 0x20000000, 0x10000000, 0x08000000, 0x04000000, 0x02000000, 0x01000000,
+		 0x00800000, 0x00400000, 0x00200000, 0x00100000, 0x00080000, 0x00040000, 0x00020000, 0x00010000,
+		 0x00008000, 0x00004000, 0x00002000, 0x00001000, 0x00000800, 0x00000400, 0x00000200, 0x00000100,
+		 0x00000080, 0x00000040, 0x00000020, 0x00000010, 0x00000008, 0x00000004, 0x00000002, 0x00000001},
+		{0x80000000, 0xc0000000, 0xa0000000, 0xf0000000, 0x88000000, 0xcc000000, 0xaa000000, 0xff000000,
+		 0x80800000, 0xc0c00000, 0xa0a00000, 0xf0f00000, 0x88880000, 0xcccc0000, 0xaaaa0000, 0xffff0000,
+		 0x80008000, 0xc000c000, 0xa000a000, 0xf000f000, 0x88008800, 0xcc00cc00, 0xaa00aa00, 0xff00ff00,
+		 0x80808080, 0xc0c0c0c0, 0xa0a0a0a0, 0xf0f0f0f0, 0x88888888, 0xcccccccc, 0xaaaaaaaa, 0xffffffff}};
+	uint32_t X = 0;
+	for (uint32_t bit = 0; bit < 32; bit++) X ^= ((index >> bit) & 1) * directions[dim][bit];
+	return X;
+}
+inline uint32_t hash_combine(uint32_t seed, uint32_t v) { return seed ^ (v + (seed << 6) + (seed >> 2)); }
+inline uint32_t reverse_bits(uint32_t x) {
+	x = (((x & 0xaaaaaaaa) >> 1) | ((x & 0x55555555) << 1));
+	x = (((x & 0xcccccccc) >> 2) | ((x & 0x33333333) << 2));
+	x = (((x & 0xf0f0f0f0) >> 4) | ((x & 0x0f0f0f0f) << 4));
+	x = (((x & 0xff00ff00) >> 8) | ((x & 0x00ff00ff) << 8));
+	return ((x >> 16) | (x << 16));
+}
+inline uint32_t laine_karras_permutation(uint32_t x, uint32_t seed) {
+	x += seed; x ^= x * 0x6c50b47cu; x ^= x * 0xb82f1e52u; x ^= x * 0xc7afe638u; x ^= x * 0x8d22f6e6u;
+	return x;
+}
+inline uint32_t nested_uniform_scramble_base2(uint32_t x, uint32_t seed) { return reverse_bits(laine_karras_permutation(reverse_bits(x), seed)); }
+inline float ld_random_val(uint32_t index, uint32_t seed, uint32_t dim = 0) {
+	const float S = float(1.0 / (1ull << 32));
+	index = nested_uniform_scramble_base2(index, seed);
+	return (float)nested_uniform_scramble_base2(sobol(index, dim), hash_combine(seed, dim)) * S;
+}
+inline void ld_random_val_2d(uint32_t index, uint32_t seed, float* out) {
+	const float S = float(1.0 / (1ull << 32));
+	index = nested_uniform_scramble_base2(index, seed);
+	for (uint32_t i = 0; i < 2; ++i) out[i] = (float)nested_uniform_scramble_base2(sobol(index, i), hash_combine(seed, i)) * S;
+}
+inline float fractf(float x) { return x - std::floor(x); }
+inline void ld_random_pixel_offset(uint32_t spp, float* out) {
+	float a[2], b[2];
+	ld_random_val_2d(0, 0xdeadbeef, a);
+	ld_random_val_2d(spp, 0xdeadbeef, b);
+	for (int i = 0; i < 2; ++i) out[i] = fractf((0.5f - a[i]) + b[i]);
+}
+} // namespace
+
+extern "C" void orc_render_nerf(const orc_model* m, const orc_half* params, const uint8_t* bitfield, const orc_render_config* c, float* out_rgba, uint64_t* n_samples_out) {
+	const int W = c->width, H = c->height;
+	const AABB train_aabb = make_aabb(c->aabb), render_aabb = make_aabb(c->render_aabb);
+	std::vector<float> accumulate((size_t)W * H * 4, 0.f);
+	uint64_t n_samples_total = 0;
+	for (int s = 0; s < c->spp; ++s) {
+		std::vector<float> frame((size_t)W * H * 4, 0.f);
+		float offset[2];
+		ld_random_pixel_offset(c->snap_to_pixel_centers ? 0 : (uint32_t)s, offset);
+		uint64_t n_samples_spp = 0;
+		#pragma omp parallel for schedule(dynamic, 64) reduction(+ : n_samples_spp)
+		for (int64_t idx = 0; idx < (int64_t)W * H; ++idx) {
+			const int x = (int)(idx % W), y = (int)(idx / W);
+			// pixel_to_ray, perspective
+			const float uvx = ((float)x + offset[0]) / (float)W, uvy = ((float)y + offset[1]) / (float)H;
+			const float dcam[3] = {(uvx - c->screen_center[0]) * (float)W / c->fx, (uvy - c->screen_center[1]) * (float)H / c->fy, 1.0f};
+			const float* cm = c->camera;
+			const float row0[3] = {cm[0], cm[3], cm[6]}, row1[3] = {cm[1], cm[4], cm[7]}, row2[3] = {cm[2], cm[5], cm[8]};
+			Vec3 d = {dot3(row0, dcam), dot3(row1, dcam), dot3(row2, dcam)};
+			Vec3 o = {cm[9], cm[10], cm[11]};
+			o = {o.x + d.x * c->near_distance, o.y + d.y * c->near_distance, o.z + d.z * c->near_distance};
+			// init_rays_with_payload_kernel_nerf
+			const float z = sum3(d.x * d.x, d.y * d.y, d.z * d.z);
+			if (z > 0.f) { const float nrm = std::sqrt(z); d = {d.x / nrm, d.y / nrm, d.z / nrm}; }
+			float tmin, tmax;
+			aabb_ray_intersect(render_aabb, o, d, &tmin, &tmax);
+			float t = std::fmax(tmin, 0.0f) + 1e-6f;
+			if (!aabb_contains(render_aabb, Vec3{o.x + d.x * t, o.y + d.y * t, o.z + d.z * t})) continue;
+			// advance_pos_nerf
+			const Vec3 idir = {1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+			const float cone_angle = c->cone_angle_constant;
+			t += ld_random_val((uint32_t)s, (uint32_t)idx * 786433u) * calc_dt(t, cone_angle);
+			bool alive = true;
+			auto march_to_occupied = [&](Vec3& pos, float& dt) -> bool { // false: left the render box
+				while (true) {
+					pos = {o.x + d.x * t, o.y + d.y * t, o.z + d.z * t};
+					if (!aabb_contains(render_aabb, pos)) return false;
+					dt = calc_dt(t, cone_angle);
+					const uint32_t mip = (uint32_t)mip_from_dt(dt, pos);
+					if (density_grid_occupied_at(pos, bitfield, mip)) return true;
+					t = advance_to_next_voxel(t, cone_angle, pos, d, idir, NERF_GRIDSIZE >> mip);
+				}
+			};
+			{ Vec3 p; float dt; alive = march_to_occupied(p, dt); }
+			float rgba[4] = {0.f, 0.f, 0.f, 0.f};
+			const Vec3 wd = {(d.x + 1.0f) * 0.5f, (d.y + 1.0f) * 0.5f, (d.z + 1.0f) * 0.5f};
+			while (alive) {
+				// generate_next_nerf_network_inputs: up to 8 samples, then the network, then composite_kernel_nerf
+				float coords[8 * 7];
+				orc_half out[8 * 4];
+				uint32_t n = 0;
+				for (; n < 8; ++n) {
+					Vec3 pos; float dt;
+					if (!march_to_occupied(pos, dt)) break;
+					const Vec3 wp = warp_position(pos, train_aabb);
+					float* cc = coords + n * 7;
+					cc[0] = wp.x; cc[1] = wp.y; cc[2] = wp.z; cc[3] = warp_dt(dt); cc[4] = wd.x; cc[5] = wd.y; cc[6] = wd.z;
+					t += dt;
+				}
+				if (n) orc_nerf_inference(m, params, n, coords, out);
+				n_samples_spp += n;
+				uint32_t j = 0;
+				for (; j < n; ++j) {
+					const float T = 1.f - rgba[3];
+					const float dt = unwarp_dt(coords[j * 7 + 3]);
+					const float alpha = 1.f - std::exp(-network_to_density(h2f(out[j * 4 + 3]), c->density_activation) * dt);
+					const float weight = alpha * T;
+					for (int k = 0; k < 3; ++k) rgba[k] += network_to_rgb(h2f(out[j * 4 + k]), c->rgb_activation) * weight;
+					rgba[3] += weight;
+					if (rgba[3] > (1.0f - c->min_transmittance)) {
+						const float w = rgba[3];
+						for (int k = 0; k < 4; ++k) rgba[k] /= w;
+						break;
+					}
+				}
+				if (j < 8) alive = false; // terminated, or left the box before the chunk was full
+			}
+			if (rgba[3] > 0.001f) { // compact_kernel_nerf keeps only these; shade_kernel_nerf
+				float tmp[4] = {rgba[0], rgba[1], rgba[2], rgba[3]};
+				if (!c->train_in_linear_colors) for (int k = 0; k < 3; ++k) tmp[k] = srgb_to_linear(tmp[k]);
+				float* f = &frame[(size_t)idx * 4];
+				const float one_minus = 1.0f - tmp[3];
+				for (int k = 0; k < 4; ++k) f[k] = tmp[k] + f[k] * one_minus;
+			}
+		}
+		n_samples_total += n_samples_spp;
+		// accumulate_kernel
+		const float sample_count = (float)s;
+		for (size_t i = 0; i < (size_t)W * H; ++i) {
+			float color[4] = {frame[i * 4], frame[i * 4 + 1], frame[i * 4 + 2], frame[i * 4 + 3]};
+			float* tmp = &accumulate[i * 4];
+			if (c->color_space == 1) for (int k = 0; k < 3; ++k) color[k] = linear_to_srgb(color[k]);
+			for (int k = 0; k < 4; ++k) tmp[k] = (tmp[k] * sample_count + color[k]) / (sample_count + 1);
+		}
+	}
+	// tonemap_kernel (identity curve, no DLSS clamp)
+	float bg[4] = {c->background_color[0], c->background_color[1], c->background_color[2], c->background_color[3]};
+	if (c->color_space != 1) for (int k = 0; k < 3; ++k) bg[k] = srgb_to_linear(bg[k]);
+	const float exposure_scale = std::pow(2.0f, c->exposure);
+	for (size_t i = 0; i < (size_t)W * H; ++i) {
+		float color[4] = {accumulate[i * 4], accumulate[i * 4 + 1], accumulate[i * 4 + 2], accumulate[i * 4 + 3]};
+		const float weight = (1 - color[3]) * bg[3];
+		for (int k = 0; k < 3; ++k) color[k] += bg[k] * weight;
+		color[3] += weight;
+		for (int k = 0; k < 3; ++k) {
+			float v = color[k];
+			if (c->color_space == 1) v = srgb_to_linear(v);
+			v *= exposure_scale;
+			if (c->output_srgb) v = linear_to_srgb(v);
+			color[k] = v;
+		}
+		for (int k = 0; k < 4; ++k) out_rgba[i * 4 + k] = color[k];
+	}
+	if (n_samples_out) *n_samples_out = n_samples_total;
+}

@@ -147,6 +147,23 @@ uint64_t orc_render(const orc_model* m, const orc_half* params, const uint8_t* b
                     const float* camera12, int w, int h, float fx, float fy, float cx, float cy, float cone_angle_constant,
                     float min_transmittance, int rgb_activation, int density_activation, float* out_rgba, float* out_depth);
 
+// ---- classic render (Testbed::render_nerf, ERenderMode::Shade): see ngp_oracle.cpp for the reference sections ----
+typedef struct {
+	int32_t width, height;
+	float fx, fy;               // focal length in pixels (Testbed::calc_focal_length, src/testbed.cu:2589)
+	float screen_center[2];     // render_screen_center(), (0.5, 0.5) by default
+	float camera[12];           // 3x4 camera-to-world, column-major, ngp convention
+	int32_t spp, snap_to_pixel_centers;
+	float aabb[6], render_aabb[6];
+	float cone_angle_constant, min_transmittance, near_distance;
+	int32_t rgb_activation, density_activation, train_in_linear_colors;
+	int32_t color_space;        // m_color_space (0 linear, 1 sRGB): the space the accumulation buffer averages in
+	int32_t output_srgb;        // !linear argument of Testbed::render
+	float exposure, background_color[4];
+} orc_render_config;
+// out_rgba: float [height][width][4]. n_samples_out (nullable): network-evaluated samples.
+void orc_render_nerf(const orc_model* m, const orc_half* params, const uint8_t* bitfield, const orc_render_config* c, float* out_rgba, uint64_t* n_samples_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,7 +38,7 @@ struct orc_trainer {
 	uint32_t measured_batch_size_before_compaction = 0, measured_batch_size = 0, n_rays_total = 0;
 	// nerf.training defaults (testbed.h:640-676)
 	int snap_to_pixel_centers = 1, random_bg_color = 1, linear_colors = 0, loss_type = 4 /*Huber*/;
-	int rgb_activation = 2 /*Logistic*/, density_activation = 3 /*Exponential*/, color_space = 1 /*SRGB*/;
+	int rgb_activation = 2 /*Logistic*/, density_activation = 3 /*Exponential*/, color_space = 0 /*Linear: m_color_space default, testbed.h:846*/;
 	float near_distance = 0.2f, density_grid_decay = 0.95f;
 	float background_color[3] = {0.f, 0.f, 0.f};
 };

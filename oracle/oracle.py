@@ -268,6 +268,42 @@ def bitfield(n_cascades_used, grid, mean):
     return out
 
 
+class RenderConfig(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("fx", C.c_float), ("fy", C.c_float), ("screen_center", C.c_float * 2), ("camera", C.c_float * 12),
+                ("spp", C.c_int32), ("snap_to_pixel_centers", C.c_int32), ("aabb", C.c_float * 6), ("render_aabb", C.c_float * 6),
+                ("cone_angle_constant", C.c_float), ("min_transmittance", C.c_float), ("near_distance", C.c_float),
+                ("rgb_activation", C.c_int32), ("density_activation", C.c_int32), ("train_in_linear_colors", C.c_int32),
+                ("color_space", C.c_int32), ("output_srgb", C.c_int32), ("exposure", C.c_float), ("background_color", C.c_float * 4)]
+
+
+def render_config(width, height, fx, fy, camera34, spp=1, snap=False, aabb=(0, 0, 0, 1, 1, 1), cone_angle=0.0, min_transmittance=0.01, near_distance=0.0,
+                  rgb_activation=2, density_activation=3, linear_colors=False, color_space=0, output_srgb=False, exposure=0.0, background=(0, 0, 0, 1)):
+    """Defaults are the reference's Testbed defaults (testbed.h:547,:725,:846,:853,:875,:889)."""
+    c = RenderConfig()
+    c.width, c.height, c.fx, c.fy = width, height, fx, fy
+    c.screen_center[0] = c.screen_center[1] = 0.5
+    cm = np.asarray(camera34, dtype=np.float32).reshape(3, 4).T.reshape(-1)
+    for k in range(12):
+        c.camera[k] = float(cm[k])
+    c.spp, c.snap_to_pixel_centers = spp, int(snap)
+    for k in range(6):
+        c.aabb[k] = c.render_aabb[k] = float(aabb[k])
+    c.cone_angle_constant, c.min_transmittance, c.near_distance = cone_angle, min_transmittance, near_distance
+    c.rgb_activation, c.density_activation, c.train_in_linear_colors = rgb_activation, density_activation, int(linear_colors)
+    c.color_space, c.output_srgb, c.exposure = color_space, int(output_srgb), exposure
+    for k in range(4):
+        c.background_color[k] = float(background[k])
+    return c
+
+
+def render_nerf(m, params_half, bitfield, cfg):
+    """Classic render of one frame on the CPU: float32 [H][W][4] and the number of samples marched."""
+    out = np.zeros((cfg.height, cfg.width, 4), np.float32)
+    ns = C.c_uint64(0)
+    lib().orc_render_nerf(C.byref(m), _p(np.ascontiguousarray(params_half, dtype=np.float16)), _p(np.ascontiguousarray(bitfield)), C.byref(cfg), _p(out), C.byref(ns))
+    return out, int(ns.value)
+
+
 class Trainer:
     """Whole-iteration CPU restatement of Testbed::train for the NeRF mode (oracle/ngp_trainer.cpp)."""
 
