@@ -13,5 +13,5 @@ for f in common hash_grid nerf_mlp nerf_sampling nerf_loss optimizer density_gri
 	fi
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -shared -gencode arch=compute_100a,code=sm_100a -o libngpb200.so build/*.o -lcudart
+$NVCC -shared -gencode arch=compute_100a,code=sm_100a -o libngpb200.so build/*.o -lcudart -ldl
 echo "built $(pwd)/libngpb200.so"

@@ -16,6 +16,7 @@ namespace ngpb {
 
 struct LossParams {
 	uint32_t n_rays, batch, n_images;
+	uint32_t n_rays_global; // rays of the whole (all-shard) batch: pixel selection and loss normalisation use it (:1062-1083, :1493)
 	Aabb aabb;
 	Pcg32 rng;
 	ngpb_loss_config cfg;
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(1024) loss_composite_kernel(
 		const uint32_t ray_idx = ray_indices[i];
 		Pcg32 rng = P.rng;
 		rng.advance((int64_t)ray_idx * N_MAX_RANDOM_SAMPLES_PER_RAY);
-		const uint32_t img = image_idx(ray_idx, P.n_rays, P.n_images);
+		const uint32_t img = image_idx(ray_idx, P.n_rays_global, P.n_images);
 		const ngpb_image& im = images[img];
 		float x, y;
 		random_image_pos_training(rng, im.w, im.h, P.cfg.snap_to_pixel_centers != 0, &x, &y);
@@ -261,9 +262,9 @@ __global__ void __launch_bounds__(1024) loss_gradient_kernel(
 
 	const LossAndGradient lg = loss_and_gradient(s.rgbtarget, s.rgb_ray, P.cfg.loss_type);
 	const float mean_loss = sum3(lg.loss[0], lg.loss[1], lg.loss[2]) / 3.0f;
-	if (loss_output && lane == 0) loss_output[i] = mean_loss / (float)P.n_rays;
+	if (loss_output && lane == 0) loss_output[i] = mean_loss / (float)P.n_rays_global;
 
-	const float loss_scale = P.cfg.loss_scale / P.n_rays;
+	const float loss_scale = P.cfg.loss_scale / P.n_rays_global;
 	const float output_l2_reg = P.cfg.rgb_activation == NGPB_ACT_EXPONENTIAL ? 1e-4f : 0.0f;
 	const float output_l1_reg_density = *mean_density_ptr < NERF_MIN_OPTICAL_THICKNESS ? 1e-4f : 0.0f;
 
@@ -349,7 +350,15 @@ extern "C" uint64_t ngpb_compute_loss_scratch_bytes(uint32_t n_rays) {
 	return (uint64_t)n_rays * (sizeof(RayState) + 8) + (uint64_t)div_round_up(n_rays, LOSS_RAYS_PER_BLOCK) * 4 + 64;
 }
 
-extern "C" int ngpb_compute_loss(void* stream_, uint32_t n_rays, const float* aabb6, ngpb_rng rng_, uint32_t batch, const ngpb_loss_config* cfg,
+extern "C" int ngpb_compute_loss(void* stream, uint32_t n_rays, const float* aabb6, ngpb_rng rng, uint32_t batch, const ngpb_loss_config* cfg,
+                                 uint32_t n_images, const ngpb_image* images_dev, const uint32_t* counters_in,
+                                 const ngpb_half* rgbsigma, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords_in,
+                                 const float* mean_density_dev, float* coords_out, ngpb_half* dloss_dout, float* loss_per_ray, uint32_t* counters_out, void* scratch) {
+	return ngpb_compute_loss_sharded(stream, n_rays, n_rays, aabb6, rng, batch, cfg, n_images, images_dev, counters_in, rgbsigma, ray_indices, rays, numsteps, coords_in,
+		mean_density_dev, coords_out, dloss_dout, loss_per_ray, counters_out, scratch);
+}
+
+extern "C" int ngpb_compute_loss_sharded(void* stream_, uint32_t n_rays, uint32_t n_rays_global, const float* aabb6, ngpb_rng rng_, uint32_t batch, const ngpb_loss_config* cfg,
                                  uint32_t n_images, const ngpb_image* images_dev, const uint32_t* counters_in,
                                  const ngpb_half* rgbsigma, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords_in,
                                  const float* mean_density_dev, float* coords_out, ngpb_half* dloss_dout, float* loss_per_ray, uint32_t* counters_out, void* scratch) {
@@ -362,7 +371,7 @@ extern "C" int ngpb_compute_loss(void* stream_, uint32_t n_rays, const float* aa
 		cudaStream_t stream = (cudaStream_t)stream_;
 		if (n_rays == 0) { NGPB_CUDA_CHECK(cudaMemsetAsync(counters_out, 0, sizeof(uint32_t), stream)); return 0; }
 		LossParams P;
-		P.n_rays = n_rays; P.batch = batch; P.n_images = n_images;
+		P.n_rays = n_rays; P.batch = batch; P.n_images = n_images; P.n_rays_global = n_rays_global;
 		P.aabb = make_aabb(aabb6);
 		P.rng.state = rng_.state; P.rng.inc = rng_.inc;
 		P.cfg = *cfg;

@@ -122,7 +122,7 @@ constexpr uint32_t K1_BLOCK = 128;
 
 // Pass 1: one thread per ray. Sample count, march record, and the block-local exclusive prefixes of (count, count > 0).
 __global__ void __launch_bounds__(K1_BLOCK) count_training_samples_kernel(
-	const uint32_t n_rays, const Aabb aabb, const Pcg32 rng, const uint32_t n_images, const ngpb_image* __restrict__ images,
+	const uint32_t n_rays, const uint32_t ray_offset, const uint32_t n_rays_global, const Aabb aabb, const Pcg32 rng, const uint32_t n_images, const ngpb_image* __restrict__ images,
 	const uint8_t* __restrict__ bitfield, const bool snap, const float cone_angle_constant,
 	uint32_t* __restrict__ counts, uint32_t* __restrict__ n_words, MarchWord* __restrict__ words, uint32_t* __restrict__ local_bases, uint32_t* __restrict__ local_slots,
 	uint2* __restrict__ block_sums)
@@ -132,7 +132,8 @@ __global__ void __launch_bounds__(K1_BLOCK) count_training_samples_kernel(
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	uint32_t c = 0;
 	if (i < n_rays) {
-		const TrainRay r = setup_training_ray(i, n_rays, rng, n_images, images, aabb, snap, cone_angle_constant);
+		// everything about a ray derives from its GLOBAL index (:1118-1121, :1062-1083): a shard reproduces its slice of the full batch
+		const TrainRay r = setup_training_ray(ray_offset + i, n_rays_global, rng, n_images, images, aabb, snap, cone_angle_constant);
 		uint32_t nw = 0;
 		if (r.valid) c = march_and_record(r, aabb, bitfield, words + (size_t)i * MARCH_MAX_WORDS, &nw);
 		counts[i] = c;
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(1024) scan_training_samples_kernel(const uint3
 // ray's slot is the number of sample-bearing rays before it.
 constexpr uint32_t WRITE_RAYS_PER_BLOCK = 8;
 __global__ void __launch_bounds__(WRITE_RAYS_PER_BLOCK * 32) write_training_samples_kernel(
-	const uint32_t n_rays, const uint32_t max_samples, const Aabb aabb, const Pcg32 rng, const uint32_t n_images, const ngpb_image* __restrict__ images,
+	const uint32_t n_rays, const uint32_t ray_offset, const uint32_t n_rays_global, const uint32_t max_samples, const Aabb aabb, const Pcg32 rng, const uint32_t n_images, const ngpb_image* __restrict__ images,
 	const uint8_t* __restrict__ bitfield, const bool snap, const float cone_angle_constant,
 	const uint32_t* __restrict__ counts, const uint32_t* __restrict__ n_words, const MarchWord* __restrict__ words,
 	const uint32_t* __restrict__ local_bases, const uint32_t* __restrict__ local_slots, const uint2* __restrict__ block_prefix,
@@ -201,9 +202,9 @@ __global__ void __launch_bounds__(WRITE_RAYS_PER_BLOCK * 32) write_training_samp
 	if (threadIdx.x == 0 && n_kept_block) atomicAdd(&counters[1], n_kept_block);
 	if (!kept) return;
 
-	const TrainRay r = setup_training_ray(i, n_rays, rng, n_images, images, aabb, snap, cone_angle_constant); // same on every lane
+	const TrainRay r = setup_training_ray(ray_offset + i, n_rays_global, rng, n_images, images, aabb, snap, cone_angle_constant); // same on every lane
 	if (lane == 0) {
-		ray_indices[slot] = i;
+		ray_indices[slot] = ray_offset + i; // global ray index: K6 re-derives pixel and background from it
 		float* ro = rays + (size_t)slot * 6;
 		ro[0] = r.o.x; ro[1] = r.o.y; ro[2] = r.o.z; ro[3] = r.d_unnorm.x; ro[4] = r.d_unnorm.y; ro[5] = r.d_unnorm.z;
 		numsteps[slot * 2 + 0] = count;
@@ -260,13 +261,22 @@ extern "C" uint64_t ngpb_generate_training_samples_scratch_bytes(uint32_t n_rays
 	return (uint64_t)n_rays * 16 + 8 + (uint64_t)div_round_up(n_rays, K1_BLOCK) * sizeof(uint2) + (uint64_t)n_rays * MARCH_MAX_WORDS * sizeof(MarchWord) + 64;
 }
 
-extern "C" int ngpb_generate_training_samples(void* stream_, uint32_t n_rays, const float* aabb6, uint32_t max_samples, ngpb_rng rng_,
+extern "C" int ngpb_generate_training_samples(void* stream, uint32_t n_rays, const float* aabb6, uint32_t max_samples, ngpb_rng rng,
+                                              uint32_t n_images, const ngpb_image* images_dev, const uint8_t* bitfield,
+                                              int snap_to_pixel_centers, float cone_angle_constant,
+                                              uint32_t* counters, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, void* scratch) {
+	return ngpb_generate_training_samples_sharded(stream, n_rays, 0, n_rays, aabb6, max_samples, rng, n_images, images_dev, bitfield, snap_to_pixel_centers, cone_angle_constant,
+		counters, ray_indices, rays, numsteps, coords, scratch);
+}
+
+extern "C" int ngpb_generate_training_samples_sharded(void* stream_, uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, const float* aabb6, uint32_t max_samples, ngpb_rng rng_,
                                               uint32_t n_images, const ngpb_image* images_dev, const uint8_t* bitfield,
                                               int snap_to_pixel_centers, float cone_angle_constant,
                                               uint32_t* counters, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, void* scratch_) {
 	try {
 		uint32_t* scratch = reinterpret_cast<uint32_t*>(scratch_);
-		if (!aabb6 || !images_dev || !bitfield || !counters || !ray_indices || !rays || !numsteps || !coords || !scratch || n_images == 0) {
+		if (!aabb6 || !images_dev || !bitfield || !counters || !ray_indices || !rays || !numsteps || !coords || !scratch || n_images == 0 ||
+		    (uint64_t)ray_offset + n_rays > n_rays_global) {
 			set_last_error("ngpb_generate_training_samples: invalid argument");
 			return NGPB_ERR_INVALID_ARGUMENT;
 		}
@@ -283,12 +293,12 @@ extern "C" int ngpb_generate_training_samples(void* stream_, uint32_t n_rays, co
 		uint2* block_sums = reinterpret_cast<uint2*>(local_slots + next_multiple(n_rays, 2));
 		MarchWord* words = reinterpret_cast<MarchWord*>(block_sums + blocks);
 		NGPB_STEP_KERNEL(count_training_samples_kernel); NGPB_STEP_KERNEL(scan_training_samples_kernel); NGPB_STEP_KERNEL(write_training_samples_kernel);
-		count_training_samples_kernel<<<blocks, K1_BLOCK, 0, stream>>>(n_rays, aabb, rng, n_images, images_dev, bitfield, snap_to_pixel_centers != 0, cone_angle_constant,
+		count_training_samples_kernel<<<blocks, K1_BLOCK, 0, stream>>>(n_rays, ray_offset, n_rays_global, aabb, rng, n_images, images_dev, bitfield, snap_to_pixel_centers != 0, cone_angle_constant,
 			counts, n_words, words, local_bases, local_slots, block_sums);
 		NGPB_LAUNCH_CHECK();
 		scan_training_samples_kernel<<<1, 1024, 0, stream>>>(blocks, block_sums, counters);
 		NGPB_LAUNCH_CHECK();
-		write_training_samples_kernel<<<div_round_up(n_rays, WRITE_RAYS_PER_BLOCK), WRITE_RAYS_PER_BLOCK * 32, 0, stream>>>(n_rays, max_samples, aabb, rng, n_images, images_dev, bitfield,
+		write_training_samples_kernel<<<div_round_up(n_rays, WRITE_RAYS_PER_BLOCK), WRITE_RAYS_PER_BLOCK * 32, 0, stream>>>(n_rays, ray_offset, n_rays_global, max_samples, aabb, rng, n_images, images_dev, bitfield,
 			snap_to_pixel_centers != 0, cone_angle_constant, counts, n_words, words, local_bases, local_slots, block_sums, counters, ray_indices, rays, numsteps, coords);
 		NGPB_LAUNCH_CHECK();
 		return 0;

@@ -5,6 +5,7 @@
 // training_prep_nerf). All device memory is owned here and allocated once per (dataset, batch size):
 // nothing is allocated in the steady state, like the reference's per-stream arena.
 #include "testbed.h"
+#include "nccl_dl.h"
 
 #include <algorithm>
 #include <cmath>
@@ -131,6 +132,7 @@ ngpb_testbed::~ngpb_testbed() {
 	cudaSetDevice(device);
 	if (sampling_stream) cudaStreamSynchronize(sampling_stream);
 	if (stream) cudaStreamSynchronize(stream);
+	if (nccl_comm) { try { NcclApi::get().CommDestroy(nccl_comm); } catch (...) {} }
 	if (prefetch_done) cudaEventDestroy(prefetch_done);
 	if (loss_ready) cudaEventDestroy(loss_ready);
 	if (counters_ready) cudaEventDestroy(counters_ready);
@@ -337,13 +339,13 @@ void ngpb_testbed::ensure_workspace(uint32_t batch) {
 	denc = (__half*)dalloc(sizeof(__half) * N_ENC * batch);
 	loss = (float*)dalloc(sizeof(float) * max_rays);
 	scratch = dalloc((size_t)std::max(ngpb_generate_training_samples_scratch_bytes((uint32_t)max_rays), ngpb_compute_loss_scratch_bytes((uint32_t)max_rays)));
-	counters = (uint32_t*)dalloc(sizeof(uint32_t) * 8);
+	counters = (uint32_t*)dalloc(sizeof(uint32_t) * 16); // [0..1] K1, [2] K6, [4] loss sum, [8..10] all-reduced copies (data parallel)
 	partials = (float*)dalloc((size_t)ngpb_nerf_mlp_workspace_bytes());
 	// keep the padding rows of the sample buffers finite
 	NGPB_CUDA_CHECK(cudaMemsetAsync(coords, 0, sizeof(float) * COORD_FLOATS * max_samples, stream));
 	NGPB_CUDA_CHECK(cudaMemsetAsync(coords_compacted, 0, sizeof(float) * COORD_FLOATS * batch, stream));
 	NGPB_CUDA_CHECK(cudaMemsetAsync(dloss, 0, sizeof(__half) * 4 * batch, stream));
-	NGPB_CUDA_CHECK(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * 8, stream));
+	NGPB_CUDA_CHECK(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * 16, stream));
 	ws_batch = batch;
 }
 
@@ -373,11 +375,33 @@ void ngpb_testbed::update_density_grid(uint32_t n_uniform, uint32_t n_nonuniform
 	n_launches += (n_uniform ? 1 : 0) + (n_nonuniform ? 1 : 0) + 2 + 2 + 3 + (NERF_CASCADES - 1);
 }
 
+// Sample budget of the next step's K1 (the reference uses last step's uncompacted count, :3185-3190). With several ranks the count known
+// here is the average over the ranks, and a rank's own shard can need more: a 25 % margin keeps a shard from dropping rays.
+uint32_t ngpb_testbed::inference_budget(uint32_t measured_before_compaction) const {
+	return dp_world > 1 ? measured_before_compaction + measured_before_compaction / 4 + 1024 : measured_before_compaction;
+}
+
+void ngpb_testbed::init_data_parallel(int rank, int world, const void* unique_id128) {
+	NGPB_CUDA_CHECK(cudaSetDevice(device));
+	if (world < 1 || rank < 0 || rank >= world) throw std::runtime_error("init_data_parallel: invalid rank / world size");
+	drop_prefetch();
+	NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
+	if (nccl_comm) { NcclApi::get().CommDestroy(nccl_comm); nccl_comm = nullptr; }
+	dp_rank = rank; dp_world = world;
+	if (world == 1) return;
+	if (!unique_id128) throw std::runtime_error("init_data_parallel: the NCCL unique id is required for world > 1");
+	NcclApi& nccl = NcclApi::get();
+	NcclApi::UniqueId id;
+	std::memcpy(&id, unique_id128, sizeof(id));
+	nccl.check(nccl.CommInitRank(&nccl_comm, world, id, rank), "ncclCommInitRank");
+}
+
 // Launches K1 for the step described by `p` on stream `st`.
 void ngpb_testbed::launch_sampling(cudaStream_t st, const SamplingRequest& p) {
 	stage_begin(NGPB_STAGE_SAMPLING, st);
-	if (ngpb_generate_training_samples(st, p.n_rays, aabb, p.max_inference, p.rng, (uint32_t)images.size(), images_dev, bitfield,
-		p.snap, p.cone_angle, counters, ray_indices, rays, numsteps, coords, scratch) != 0) throw std::runtime_error(ngpb_last_error());
+	// this rank's shard: local rays [rank * n_rays, (rank + 1) * n_rays) of a global batch of world * n_rays rays
+	if (ngpb_generate_training_samples_sharded(st, p.n_rays, (uint32_t)dp_rank * p.n_rays, (uint32_t)dp_world * p.n_rays, aabb, p.max_inference, p.rng,
+		(uint32_t)images.size(), images_dev, bitfield, p.snap, p.cone_angle, counters, ray_indices, rays, numsteps, coords, scratch) != 0) throw std::runtime_error(ngpb_last_error());
 	stage_end(NGPB_STAGE_SAMPLING, p.n_rays, st);
 	n_launches += 3;
 }
@@ -429,7 +453,7 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 	if (measured_batch_size_before_compaction == 0) {
 		measured_batch_size_before_compaction = max_inference = max_samples;
 	} else {
-		max_inference = next_multiple(std::min(measured_batch_size_before_compaction, max_samples), 128);
+		max_inference = next_multiple(std::min(inference_budget(measured_batch_size_before_compaction), max_samples), 128);
 	}
 	if (training_step == 0) n_rays_total = 0;
 	n_rays_total += rays_per_batch;
@@ -454,14 +478,20 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 	nerf_mlp_forward_launch(stream, w_half, encoded, coords, max_inference, counters, rgbsigma);
 	stage_end(NGPB_STAGE_MLP_INFERENCE, n_uncompacted_est, stream);
 	stage_begin(NGPB_STAGE_LOSS, stream);
-	check(ngpb_compute_loss(stream, R, aabb, r, batch, &loss_cfg, (uint32_t)images.size(), images_dev, counters, (const ngpb_half*)rgbsigma,
+	check(ngpb_compute_loss_sharded(stream, R, (uint32_t)dp_world * R, aabb, r, batch, &loss_cfg, (uint32_t)images.size(), images_dev, counters, (const ngpb_half*)rgbsigma,
 		ray_indices, rays, numsteps, coords, mean_density, coords_compacted, (ngpb_half*)dloss, loss, counters + 2, scratch));
 	stage_end(NGPB_STAGE_LOSS, R, stream);
 	n_launches += 2 + 4;
+	if (dp_world > 1) {
+		// the controller needs the GLOBAL sample counts so that every rank derives the same next ray count: sum {uncompacted, kept rays,
+		// compacted} into counters[8..10] (the local values stay in [0..2] for the kernels of this step)
+		NcclApi& nccl = NcclApi::get();
+		nccl.check(nccl.AllReduce(counters, counters + 8, 3, NcclApi::Uint32, NcclApi::Sum, nccl_comm, stream), "ncclAllReduce(counters)");
+	}
 
 	// ---- the two counters of NerfCounters::update_after_training (:2870-2894) are final here: start their read-back ----
 	collect_loss_scalar(); // (frees the read-back slot of an earlier step's loss)
-	NGPB_CUDA_CHECK(cudaMemcpyAsync(host_readback, counters, sizeof(uint32_t) * 4, cudaMemcpyDeviceToHost, stream));
+	NGPB_CUDA_CHECK(cudaMemcpyAsync(host_readback, counters + (dp_world > 1 ? 8 : 0), sizeof(uint32_t) * 4, cudaMemcpyDeviceToHost, stream));
 	NGPB_CUDA_CHECK(cudaEventRecord(counters_ready, stream));
 	d2h_bytes += 16;
 
@@ -476,6 +506,14 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 	stage_begin(NGPB_STAGE_ENCODE_BACKWARD, stream);
 	hash_encode_backward_launch(stream, &grid, coords_compacted, COORD_FLOATS, batch, denc, grad + MLP_PARAMS);
 	stage_end(NGPB_STAGE_ENCODE_BACKWARD, batch, stream);
+	if (dp_world > 1) {
+		// the one exchange step of the path: sum of the shards' gradients = gradient of the global batch (the loss is normalised by the global
+		// ray count). fp32, in place, on the training stream; NCCL over NVLink / NVSwitch returns the same bits on every rank.
+		stage_begin(NGPB_STAGE_ALLREDUCE, stream);
+		NcclApi& nccl = NcclApi::get();
+		nccl.check(nccl.AllReduce(grad, grad, n_params, NcclApi::Float32, NcclApi::Sum, nccl_comm, stream), "ncclAllReduce(gradients)");
+		stage_end(NGPB_STAGE_ALLREDUCE, (uint64_t)n_params * 4, stream);
+	}
 	// optimizer (train_nerf :2950)
 	stage_begin(NGPB_STAGE_OPTIMIZER, stream);
 	check(ngpb_optimizer_step(stream, &opt, n_params, MLP_PARAMS, LOSS_SCALE, grad, w_fp32, (ngpb_half*)w_half, (ngpb_half*)w_ema, m1, m2, param_steps));
@@ -487,6 +525,10 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 		sum_kernel<<<1, 1024, 0, stream>>>(loss, R, reinterpret_cast<float*>(counters + 4));
 		NGPB_LAUNCH_CHECK();
 		n_launches += 1;
+		if (dp_world > 1) {
+			NcclApi& nccl = NcclApi::get();
+			nccl.check(nccl.AllReduce(counters + 4, counters + 4, 1, NcclApi::Float32, NcclApi::Sum, nccl_comm, stream), "ncclAllReduce(loss)");
+		}
 		NGPB_CUDA_CHECK(cudaMemcpyAsync(host_readback + 8, counters + 4, sizeof(float), cudaMemcpyDeviceToHost, stream));
 		NGPB_CUDA_CHECK(cudaEventRecord(loss_ready, stream));
 		d2h_bytes += 4;
@@ -508,8 +550,9 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 		if (profile_stages) stage_collect();
 		return;
 	}
-	measured_batch_size_before_compaction = counter_cpu;
-	measured_batch_size = compacted_counter_cpu;
+	// per-rank averages of the global counts: with one rank these are the reference's values; with several, every rank sees the same numbers
+	measured_batch_size_before_compaction = counter_cpu / (uint32_t)dp_world;
+	measured_batch_size = std::max(1u, compacted_counter_cpu / (uint32_t)dp_world);
 	if (get_loss_scalar) { loss_pending = true; loss_pending_scale = (float)measured_batch_size / (float)batch; }
 	rays_per_batch = (uint32_t)((float)rays_per_batch * (float)batch / (float)measured_batch_size);
 	rays_per_batch = std::min(next_multiple(rays_per_batch, 128u), 1u << 18);
@@ -518,7 +561,7 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 	{
 		const uint32_t next_skip = std::max(1u, std::min(training_step / 16u, 16u));
 		if (overlap_sampling && training_step % next_skip != 0) {
-			prefetch = SamplingRequest{training_step, rays_per_batch, next_multiple(std::min(measured_batch_size_before_compaction, max_samples), 128),
+			prefetch = SamplingRequest{training_step, rays_per_batch, next_multiple(std::min(inference_budget(measured_batch_size_before_compaction), max_samples), 128),
 				ngpb_rng{rng.state, rng.inc}, loss_cfg.snap_to_pixel_centers, cone_angle_constant};
 			launch_sampling(sampling_stream, prefetch);
 			NGPB_CUDA_CHECK(cudaEventRecord(prefetch_done, sampling_stream));
@@ -598,6 +641,19 @@ extern "C" int ngpb_testbed_get_density_grid(ngpb_testbed* t, float* grid_out, u
 	if (grid_out) NGPB_CUDA_CHECK(cudaMemcpy(grid_out, t->density_grid, sizeof(float) * NERF_GRID_CELLS * (t->max_cascade + 1), cudaMemcpyDeviceToHost));
 	if (bitfield_out) NGPB_CUDA_CHECK(cudaMemcpy(bitfield_out, t->bitfield, (size_t)NERF_GRID_CELLS * NERF_CASCADES / 8, cudaMemcpyDeviceToHost));
 	NGPB_API_END
+}
+
+extern "C" int ngpb_nccl_unique_id(void* out128) {
+	NGPB_API_BEGIN
+	if (!out128) throw std::runtime_error("ngpb_nccl_unique_id: null output");
+	NcclApi& nccl = NcclApi::get();
+	NcclApi::UniqueId id;
+	nccl.check(nccl.GetUniqueId(&id), "ncclGetUniqueId");
+	std::memcpy(out128, &id, sizeof(id));
+	NGPB_API_END
+}
+extern "C" int ngpb_testbed_init_data_parallel(ngpb_testbed* t, int rank, int world, const void* unique_id128) {
+	NGPB_API_BEGIN t->init_data_parallel(rank, world, unique_id128); NGPB_API_END
 }
 
 extern "C" void* ngpb_testbed_stream(ngpb_testbed* t) { return t ? (void*)t->stream : nullptr; }

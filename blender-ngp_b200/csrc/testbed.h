@@ -37,6 +37,13 @@ struct ngpb_testbed {
 	bool loss_pending = false;
 	float loss_pending_scale = 0.f;
 
+	// data parallelism: every rank holds a replica and marches its shard of the global ray batch; gradients (and the two
+	// batch-size counters) are summed over NCCL before the optimizer, so the replicas stay bit-identical.
+	int dp_rank = 0, dp_world = 1;
+	void* nccl_comm = nullptr;
+	void init_data_parallel(int rank, int world, const void* unique_id128);
+	uint32_t inference_budget(uint32_t measured_before_compaction) const;
+
 	void* dalloc(size_t bytes);
 	void dfree(void* p);
 

@@ -102,7 +102,7 @@ EXPORTED_SYMBOLS = [
     "ngpb_testbed_create", "ngpb_testbed_destroy", "ngpb_testbed_load_training_data", "ngpb_testbed_reset_network", "ngpb_testbed_train",
     "ngpb_testbed_train_n", "ngpb_testbed_loss", "ngpb_testbed_training_step", "ngpb_testbed_stats", "ngpb_testbed_n_params",
     "ngpb_testbed_get_params", "ngpb_testbed_set_params", "ngpb_testbed_get_density_grid", "ngpb_testbed_set_option", "ngpb_testbed_get_option",
-    "ngpb_testbed_render", "ngpb_testbed_stream", "ngpb_testbed_stage_times", "ngpb_grid_device_scales", "ngpb_render_workspace_bytes", "ngpb_render_nerf", "ngpb_testbed_last_render_ms", "ngpb_generate_training_samples_scratch_bytes", "ngpb_compute_loss_scratch_bytes",
+    "ngpb_testbed_render", "ngpb_testbed_stream", "ngpb_testbed_stage_times", "ngpb_grid_device_scales", "ngpb_generate_training_samples_sharded", "ngpb_compute_loss_sharded", "ngpb_nccl_unique_id", "ngpb_testbed_init_data_parallel", "ngpb_render_workspace_bytes", "ngpb_render_nerf", "ngpb_testbed_last_render_ms", "ngpb_generate_training_samples_scratch_bytes", "ngpb_compute_loss_scratch_bytes",
 ]
 
 _lib = None
@@ -442,6 +442,24 @@ class Testbed:
         check(lib().ngpb_testbed_stats(self._h, s))
         return dict(rays_per_batch=int(s[0]), measured_batch_size_before_compaction=int(s[1]), measured_batch_size=int(s[2]), gpu_launches=int(s[3]),
                     h2d_bytes=int(self._get("h2d_bytes")), d2h_bytes=int(self._get("d2h_bytes")))
+
+    def init_data_parallel(self, rank, world, group=None):
+        """Joins this Testbed to a data-parallel group of `world` processes (one per GPU). Needs torch.distributed to be initialised: it carries
+        the 128-byte NCCL unique id from rank 0 to the others; the gradient all-reduce itself runs inside libngpb200.so on its own communicator."""
+        if world == 1:
+            check(lib().ngpb_testbed_init_data_parallel(self._h, 0, 1, None))
+            return
+        import torch
+        import torch.distributed as dist
+        uid = C.create_string_buffer(128)
+        if rank == 0:
+            check(lib().ngpb_nccl_unique_id(uid))
+        t = torch.frombuffer(bytearray(uid.raw), dtype=torch.uint8).clone()
+        if dist.get_backend(group) == "nccl":
+            t = t.cuda()
+        dist.broadcast(t, src=0, group=group)
+        raw = bytes(t.cpu().numpy().tobytes())
+        check(lib().ngpb_testbed_init_data_parallel(self._h, int(rank), int(world), raw))
 
     STAGES = ["sampling", "encode_inference", "mlp_inference", "loss", "encode_train", "mlp_train", "encode_backward", "optimizer",
               "density_grid", "allreduce"]

@@ -109,6 +109,14 @@ int ngpb_generate_training_samples(void* stream, uint32_t n_rays, const float* a
                                    uint32_t* counters, uint32_t* ray_indices, float* rays /*[n][6]*/, uint32_t* numsteps /*[n][2]*/,
                                    float* coords /*[max_samples][7]*/, void* scratch);
 
+/* Ray-sharded form for data-parallel training: this call handles the global rays [ray_offset, ray_offset + n_rays) of a batch of
+ * n_rays_global rays. Pixel, image and RNG stream of a ray derive from its global index (:1062-1083, :1118-1121), so the shards of a batch
+ * together produce exactly the samples of the unsharded call; ray_indices holds global indices. */
+int ngpb_generate_training_samples_sharded(void* stream, uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, const float* aabb6, uint32_t max_samples, ngpb_rng rng,
+                                           uint32_t n_images, const ngpb_image* images_dev, const uint8_t* density_grid_bitfield,
+                                           int snap_to_pixel_centers, float cone_angle_constant,
+                                           uint32_t* counters, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, void* scratch);
+
 /* ---- K6+K7: compute_loss_kernel_train_nerf (:1280-1597) + fill_rollover(_and_rescale) (tcnn common_device.h:517-537) ----
  * counters_in: the device counters written by K1. counters_out[0] = compacted sample count (unclipped).
  * coords_out [batch][7] and dloss_dout [batch][4] are padded to `batch` by rollover.
@@ -124,6 +132,13 @@ int ngpb_compute_loss(void* stream, uint32_t n_rays, const float* aabb6, ngpb_rn
                       uint32_t n_images, const ngpb_image* images_dev, const uint32_t* counters_in,
                       const ngpb_half* rgbsigma, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords_in,
                       const float* mean_density_dev, float* coords_out, ngpb_half* dloss_dout, float* loss_per_ray, uint32_t* counters_out, void* scratch);
+
+/* Ray-sharded form: n_rays rays of this shard out of n_rays_global; the loss and its gradient are normalised by n_rays_global (:1493), so the
+ * sum of the shards' gradients is the gradient of the unsharded batch. */
+int ngpb_compute_loss_sharded(void* stream, uint32_t n_rays, uint32_t n_rays_global, const float* aabb6, ngpb_rng rng, uint32_t batch, const ngpb_loss_config* cfg,
+                              uint32_t n_images, const ngpb_image* images_dev, const uint32_t* counters_in,
+                              const ngpb_half* rgbsigma, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords_in,
+                              const float* mean_density_dev, float* coords_out, ngpb_half* dloss_dout, float* loss_per_ray, uint32_t* counters_out, void* scratch);
 
 /* ---- K15: Ema(ExponentialDecay(Adam)) in one pass (tcnn adam.h:48-119, ema.h:63-76, exponential_decay.h:60-72) ---- */
 typedef struct {
@@ -201,6 +216,16 @@ uint32_t ngpb_testbed_n_params(const ngpb_testbed* t);
 int ngpb_testbed_get_params(ngpb_testbed* t, float* w_fp32, ngpb_half* w_half, ngpb_half* w_ema);
 int ngpb_testbed_set_params(ngpb_testbed* t, const float* w_fp32);
 int ngpb_testbed_get_density_grid(ngpb_testbed* t, float* grid, uint8_t* bitfield);
+/* ---- data-parallel training over the GPUs of one box (the reference is single-GPU, README.md:239-241) ----
+ * One process per GPU. Every rank loads the same dataset and resets the network with the same seed (bit-identical replicas), then:
+ *   rank 0: ngpb_nccl_unique_id(id); broadcast the 128 bytes to all ranks by any means (bench.py uses torch.distributed);
+ *   all:    ngpb_testbed_init_data_parallel(t, rank, world, id).
+ * Afterwards each ngpb_testbed_train step marches this rank's shard of a global batch of world x rays_per_batch rays to `batch_size`
+ * compacted samples, all-reduces (sum) the fp32 gradients and the batch-size counters over NCCL, and applies the same optimizer step on
+ * every rank. NCCL is resolved with dlopen("libnccl.so.2") at the first call. */
+int ngpb_nccl_unique_id(void* out128);
+int ngpb_testbed_init_data_parallel(ngpb_testbed* t, int rank, int world, const void* unique_id128);
+
 /* The stream every testbed kernel is launched on (Testbed::m_stream, testbed.h:895), as a cudaStream_t. */
 void* ngpb_testbed_stream(ngpb_testbed* t);
 /* Per-stage device time of train(), measured with CUDA events on that stream while the option "profile_stages" is 1.

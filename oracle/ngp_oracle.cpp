@@ -735,6 +735,16 @@ extern "C" uint32_t orc_generate_training_samples(
 	uint32_t n_images, const orc_image* images, const uint8_t* bitfield, int snap_to_pixel_centers, float cone_angle_constant,
 	uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, uint32_t* counters_out) {
 	(void)n_rays_total;
+	return orc_generate_training_samples_sharded(n_rays, 0, n_rays, aabb6, max_samples, rng, n_images, images, bitfield, snap_to_pixel_centers, cone_angle_constant,
+		ray_indices, rays, numsteps, coords, counters_out);
+}
+
+// The rays [ray_offset, ray_offset + n_rays) of a batch of n_rays_global rays: pixel, image and RNG stream of a ray derive from its global
+// index (:1062-1083, :1118-1121), which is what makes ray-sharded data parallelism reproduce the unsharded batch.
+extern "C" uint32_t orc_generate_training_samples_sharded(
+	uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, const float* aabb6, uint32_t max_samples, orc_pcg32 rng,
+	uint32_t n_images, const orc_image* images, const uint8_t* bitfield, int snap_to_pixel_centers, float cone_angle_constant,
+	uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, uint32_t* counters_out) {
 	const AABB aabb = make_aabb(aabb6);
 	std::vector<float> eff((size_t)n_images * 12);
 	for (uint32_t k = 0; k < n_images; ++k) orc_effective_xform(images[k].xform, eff.data() + (size_t)k * 12);
@@ -744,7 +754,7 @@ extern "C" uint32_t orc_generate_training_samples(
 	std::vector<uint32_t> counts(n_rays, 0);
 	#pragma omp parallel for schedule(dynamic, 64)
 	for (int64_t i = 0; i < (int64_t)n_rays; ++i) {
-		tr[i] = setup_training_ray((uint32_t)i, n_rays, rng, n_images, images, eff.data(), aabb, snap_to_pixel_centers != 0, cone_angle_constant);
+		tr[i] = setup_training_ray(ray_offset + (uint32_t)i, n_rays_global, rng, n_images, images, eff.data(), aabb, snap_to_pixel_centers != 0, cone_angle_constant);
 		if (tr[i].valid) counts[i] = march_training_ray(tr[i], aabb, bitfield, NERF_STEPS, [](uint32_t, const Vec3&, float) {});
 	}
 	// allocation in ray order: one valid serialisation of the reference's atomicAdd (:1225,:1232)
@@ -763,7 +773,7 @@ extern "C" uint32_t orc_generate_training_samples(
 		if (base_of[i] == 0xFFFFFFFFu) continue;
 		const TrainRay& r = tr[i];
 		uint32_t slot = slot_of[i], base = base_of[i];
-		ray_indices[slot] = (uint32_t)i;
+		ray_indices[slot] = ray_offset + (uint32_t)i;
 		float* ro = rays + (size_t)slot * 6;
 		ro[0] = r.o.x; ro[1] = r.o.y; ro[2] = r.o.z; ro[3] = r.d_unnorm.x; ro[4] = r.d_unnorm.y; ro[5] = r.d_unnorm.z;
 		numsteps[slot * 2 + 0] = counts[i];

@@ -94,6 +94,12 @@ uint32_t orc_generate_training_samples(
 	uint32_t n_images, const orc_image* images, const uint8_t* bitfield, int snap_to_pixel_centers, float cone_angle_constant,
 	uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, uint32_t* counters_out);
 
+// Rays [ray_offset, ray_offset + n_rays) of a batch of n_rays_global rays (ray_indices holds global indices): the data-parallel shard.
+uint32_t orc_generate_training_samples_sharded(
+	uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, const float* aabb6, uint32_t max_samples, orc_pcg32 rng,
+	uint32_t n_images, const orc_image* images, const uint8_t* bitfield, int snap_to_pixel_centers, float cone_angle_constant,
+	uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, uint32_t* counters_out);
+
 // ---- K6: src/testbed_nerf.cu:1280-1597 (sequential in ray order) ----------------------------
 // Returns the compacted sample count (unclipped numsteps_counter_compacted).
 uint32_t orc_compute_loss(

@@ -207,8 +207,16 @@ def effective_xform(xf34):
     return dst.reshape(4, 3).T.copy()
 
 
-def generate_training_samples(n_rays, aabb6, max_samples, rng, images, bitfield, snap=True, cone_angle=0.0):
+def generate_training_samples(n_rays, aabb6, max_samples, rng, images, bitfield, snap=True, cone_angle=0.0, ray_offset=0, n_rays_global=None):
     aabb6 = _f32(aabb6)
+    if n_rays_global is not None:
+        ray_indices = np.zeros(n_rays, np.uint32); rays = np.zeros((n_rays, 6), np.float32); numsteps = np.zeros((n_rays, 2), np.uint32)
+        coords = np.zeros((max_samples, 7), np.float32); counters = np.zeros(2, np.uint32)
+        lib().orc_generate_training_samples_sharded.restype = C.c_uint32
+        kept = lib().orc_generate_training_samples_sharded(n_rays, int(ray_offset), int(n_rays_global), _p(aabb6), max_samples, rng, len(images), images,
+                                                           _p(np.ascontiguousarray(bitfield)), int(snap), C.c_float(cone_angle), _p(ray_indices), _p(rays), _p(numsteps),
+                                                           _p(coords), _p(counters))
+        return dict(n_kept=kept, counters=counters, ray_indices=ray_indices, rays=rays, numsteps=numsteps, coords=coords)
     ray_indices = np.zeros(n_rays, np.uint32); rays = np.zeros((n_rays, 6), np.float32); numsteps = np.zeros((n_rays, 2), np.uint32)
     coords = np.zeros((max_samples, 7), np.float32); counters = np.zeros(2, np.uint32)
     kept = lib().orc_generate_training_samples(n_rays, _p(aabb6), max_samples, 0, rng, len(images), images, _p(np.ascontiguousarray(bitfield)),

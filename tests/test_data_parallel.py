@@ -1,0 +1,79 @@
+"""Data-parallel host logic on CPU: two processes over torch.distributed's gloo backend (the GPU path uses NCCL, tests/test_gpu_kernels.py and
+bench.py --gpus N). Each rank marches its shard of a ray batch with the oracle; together the shards must be exactly the unsharded batch, and
+the all-reduced counters must drive every rank's batch-size controller to the same next ray count."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    sys.path[:0] = [os.path.join(ROOT, "blender-ngp_b200"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+    import oracle as orc
+    import synthetic
+    from conftest import scene_occupancy_bitfield
+    from pyngp import dp
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    scene = synthetic.make_lego_scene(8, 64, device="cpu", seed=0)
+    imgs = orc.make_images(scene["images"], scene["xforms"], scene["fx"], scene["fy"])
+    _, bits = scene_occupancy_bitfield(orc)
+    rng = orc.pcg32(1337)
+    rays_per_batch, batch = 1024, 1 << 14
+    offset, n_global = dp.shard(rank, world, rays_per_batch)
+    out = orc.generate_training_samples(rays_per_batch, [0, 0, 0, 1, 1, 1], 1 << 17, rng, imgs, bits, ray_offset=offset, n_rays_global=n_global)
+    k = out["n_kept"]
+    # all-reduce of the counters (what ncclAllReduce does on the GPU path)
+    counters = torch.tensor([int(out["counters"][0]), k, int(out["numsteps"][:k, 0].sum())], dtype=torch.int64)
+    dist.all_reduce(counters)
+    nxt = dp.next_rays_per_batch(rays_per_batch, batch, int(counters[2]), world)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, nxt)
+    assert len(set(gathered)) == 1, gathered  # every rank derives the same next ray count
+    np.savez(os.path.join(out_dir, f"shard{rank}.npz"), ray_indices=out["ray_indices"][:k], numsteps=out["numsteps"][:k], coords=out["coords"],
+             rays=out["rays"][:k], total=counters.numpy(), nxt=nxt)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_shards_tile_the_global_batch(tmp_path):
+    import torch.multiprocessing as mp
+    sys.path[:0] = [os.path.join(ROOT, "blender-ngp_b200"), os.path.join(ROOT, "oracle")]
+    import oracle as orc
+    import synthetic
+    from conftest import scene_occupancy_bitfield
+    world, port = 2, 29500 + os.getpid() % 2000
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    shards = [np.load(tmp_path / f"shard{r}.npz") for r in range(world)]
+    scene = synthetic.make_lego_scene(8, 64, device="cpu", seed=0)
+    imgs = orc.make_images(scene["images"], scene["xforms"], scene["fx"], scene["fy"])
+    _, bits = scene_occupancy_bitfield(orc)
+    full = orc.generate_training_samples(2048, [0, 0, 0, 1, 1, 1], 1 << 18, orc.pcg32(1337), imgs, bits)
+    k = full["n_kept"]
+    # union of the shards' rays == the unsharded batch, ray by ray and sample by sample
+    idx = np.concatenate([s["ray_indices"] for s in shards])
+    assert np.array_equal(idx, full["ray_indices"][:k])  # shard 0's rays come first: global order is preserved
+    assert int(shards[0]["total"][0]) == int(full["counters"][0]) and int(shards[0]["total"][1]) == k
+    pos = 0
+    for s in shards:
+        for j in range(len(s["ray_indices"])):
+            n, b = int(s["numsteps"][j, 0]), int(s["numsteps"][j, 1])
+            nf, bf = int(full["numsteps"][pos, 0]), int(full["numsteps"][pos, 1])
+            assert n == nf
+            assert np.array_equal(s["coords"][b: b + n].view(np.uint32), full["coords"][bf: bf + n].view(np.uint32))
+            assert np.array_equal(s["rays"][j].view(np.uint32), full["rays"][pos].view(np.uint32))
+            pos += 1
+    assert shards[0]["nxt"] == shards[1]["nxt"] and int(shards[0]["nxt"]) % 128 == 0
+
+
+def test_controller_matches_single_rank():
+    sys.path[:0] = [os.path.join(ROOT, "blender-ngp_b200")]
+    from pyngp import dp
+    # world = 1 reduces to the reference's update (testbed_nerf.cu:2890-2891)
+    assert dp.next_rays_per_batch(4096, 1 << 18, 65139, 1) == min(dp.next_multiple(int(np.float32(4096.0 * (1 << 18)) / np.float32(65139)), 128), 1 << 18)
+    assert dp.shard(3, 8, 1024) == (3072, 8192)
+    assert dp.next_rays_per_batch(1 << 18, 1 << 18, 10, 1) == 1 << 18  # capped

@@ -221,7 +221,7 @@ def test_mlp_forward_backward(L, orc):
 # ------------------------------------------------------------------------------------------------------
 # K1: ray generation + marching, bit-exact
 # ------------------------------------------------------------------------------------------------------
-def _run_k1(L, scene, bitfield, n_rays, max_samples, rng, snap=True):
+def _run_k1(L, scene, bitfield, n_rays, max_samples, rng, snap=True, ray_offset=0, n_rays_global=None):
     import pyngp
     from gpu_util import dev, ptr, host, images_to_device, rng_struct
     meta, n_img, keep = images_to_device(scene)
@@ -233,8 +233,13 @@ def _run_k1(L, scene, bitfield, n_rays, max_samples, rng, snap=True):
     numsteps = torch.zeros((n_rays, 2), dtype=torch.int32, device="cuda")
     coords = torch.zeros((max_samples, 7), dtype=torch.float32, device="cuda")
     scratch = torch.zeros(int(L.ngpb_generate_training_samples_scratch_bytes(n_rays)), dtype=torch.uint8, device="cuda")
-    pyngp.check(L.ngpb_generate_training_samples(None, n_rays, aabb.ctypes.data_as(C.c_void_p), max_samples, rng_struct(rng), n_img, ptr(meta), ptr(d_bits),
-                                                 int(snap), C.c_float(0.0), ptr(counters), ptr(ray_indices), ptr(rays), ptr(numsteps), ptr(coords), ptr(scratch)))
+    if n_rays_global is None:
+        pyngp.check(L.ngpb_generate_training_samples(None, n_rays, aabb.ctypes.data_as(C.c_void_p), max_samples, rng_struct(rng), n_img, ptr(meta), ptr(d_bits),
+                                                     int(snap), C.c_float(0.0), ptr(counters), ptr(ray_indices), ptr(rays), ptr(numsteps), ptr(coords), ptr(scratch)))
+    else:
+        pyngp.check(L.ngpb_generate_training_samples_sharded(None, n_rays, ray_offset, n_rays_global, aabb.ctypes.data_as(C.c_void_p), max_samples, rng_struct(rng), n_img,
+                                                             ptr(meta), ptr(d_bits), int(snap), C.c_float(0.0), ptr(counters), ptr(ray_indices), ptr(rays), ptr(numsteps),
+                                                             ptr(coords), ptr(scratch)))
     return dict(counters=host(counters).view(np.uint32), ray_indices=host(ray_indices).view(np.uint32), rays=host(rays),
                 numsteps=host(numsteps).view(np.uint32), coords=host(coords), dev=dict(meta=meta, n_img=n_img, keep=keep, bits=d_bits, counters=counters,
                 ray_indices=ray_indices, rays=rays, numsteps=numsteps, coords=coords))
@@ -274,6 +279,27 @@ def test_generate_training_samples_overflow_and_empty(L, orc, small_scene):
     empty = np.zeros_like(bits)
     got = _run_k1(L, small_scene, empty, 1024, 4096, rng)
     assert got["counters"][0] == 0 and got["counters"][1] == 0
+
+
+def test_sharded_sampling_tiles_the_batch(L, orc, small_scene):
+    """Data-parallel shards: two half-batches with ray offsets produce, ray for ray and bit for bit, the unsharded batch."""
+    from conftest import scene_occupancy_bitfield
+    _, bits = scene_occupancy_bitfield(orc)
+    rng = orc.pcg32(4321)
+    full = _run_k1(L, small_scene, bits, 4096, 1 << 18, rng)
+    k = int(full["counters"][1])
+    pos = 0
+    for r in range(2):
+        sh = _run_k1(L, small_scene, bits, 2048, 1 << 18, rng, ray_offset=r * 2048, n_rays_global=4096)
+        ks = int(sh["counters"][1])
+        assert np.array_equal(sh["ray_indices"][:ks], full["ray_indices"][pos: pos + ks])
+        assert np.array_equal(sh["numsteps"][:ks, 0], full["numsteps"][pos: pos + ks, 0])
+        assert np.array_equal(sh["rays"][:ks].view(np.uint32), full["rays"][pos: pos + ks].view(np.uint32))
+        b0 = int(full["numsteps"][pos, 1]); n = int(sh["counters"][0])
+        assert np.array_equal(sh["coords"][:n].view(np.uint32), full["coords"][b0: b0 + n].view(np.uint32))
+        pos += ks
+    assert pos == k
+    assert L.ngpb_generate_training_samples_sharded(None, 2048, 3000, 4096, None, 0, None, 0, None, None, 0, C.c_float(0), None, None, None, None, None, None) != 0
 
 
 # ------------------------------------------------------------------------------------------------------
