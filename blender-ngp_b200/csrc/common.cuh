@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 
@@ -29,11 +30,12 @@ constexpr uint32_t kNumSMs = 148;
 // so a kernel with a different requirement (the MLP training kernel needs 143 KB of shared memory) would otherwise wait for the
 // long-running ray-marching kernel that overlaps it on the second stream to drain first (measured: 130 us per step).
 constexpr int kSmemCarveoutPercent = 72; // 164 KB shared + ~64 KB L1
+inline int step_carveout() { static const int v = getenv("NGPB_CARVEOUT") ? atoi(getenv("NGPB_CARVEOUT")) : -1; return v; }
 #define NGPB_STEP_KERNEL(kernel)                                                                                           \
 	do {                                                                                                                   \
 		static bool _configured = false;                                                                                   \
 		if (!_configured) {                                                                                                \
-			NGPB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kSmemCarveoutPercent)); \
+			if (step_carveout() >= 0) NGPB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, step_carveout())); \
 			_configured = true;                                                                                            \
 		}                                                                                                                  \
 	} while (0)

@@ -3,11 +3,9 @@
 // dependencies/tiny-cuda-nn/include/tiny-cuda-nn/encodings/grid.h:220-349, :395-518) for
 // GridType::Hash, HashType::CoherentPrime, InterpolationType::Linear (grid.h:1472-1476 defaults).
 //
-// Layout: one thread per (sample, level); the 16 level-threads of a sample are adjacent, so the
-// 16 half2 results of a sample form one coalesced 64-byte row of `encoded[n][32]` (the layout the
-// MLP kernels consume) and the position is a warp-broadcast load. The whole table (24.4 MB fp16)
-// is L2-resident on B200, so blocks are not partitioned by level as in the reference.
+// Layout: see the note above hash_encode_forward_kernel. The whole table (24.4 MB fp16) is L2-resident on B200.
 #include "common.cuh"
+#include <cstdlib>
 #include "../../include/ngpb.h"
 
 namespace ngpb {
@@ -62,31 +60,50 @@ struct LevelIndexer {
 // dims visited before `stride > hashmap_size`; when the level is hashed that partial sum is
 // discarded, and when it is dense all three dims are visited. So the two cases above are complete.
 
+// Backward thread mapping: a block of 512 threads handles ENC_SAMPLES = 32 consecutive samples, warp w works on level w (and w+16, ...),
+// lane l on sample s0 + l: the level is warp-uniform (uniform constant loads) and dL/dy enters through shared memory.
+constexpr uint32_t ENC_SAMPLES = 32;
+constexpr uint32_t ENC_WARPS = 16;
+
+__device__ __forceinline__ void level_position(const float* __restrict__ positions, size_t i, uint32_t pos_stride, float scale, float pos[3], uint32_t pg[3]) {
+	// pos_fract, tcnn common_device.h:434-445. The reference's `input * scale + 0.5f` is contracted to one FFMA by nvcc's default
+	// -fmad=true; this library is built with -fmad=false, so the FMA is explicit.
+	#pragma unroll
+	for (int d = 0; d < 3; ++d) {
+		const float p = __fmaf_rn(positions[i * pos_stride + d], scale, 0.5f);
+		const float fl = floorf(p);
+		pg[d] = (uint32_t)(int)fl;
+		pos[d] = p - fl;
+	}
+}
+
+// Forward. One thread per (sample, level); the 16 level-threads of a sample are adjacent, so a warp holds two consecutive samples, the
+// position is a broadcast load and the 16 half2 results of a sample form one coalesced 64-byte row of `encoded[n][32]`. Consecutive warps
+// work on consecutive samples of a ray at the same time, which keeps the coarse and middle levels' lines hot in L1 (a level-per-warp
+// mapping was measured: 45 % L1 hit rate instead of 69 %, twice the L2 sectors, 1.6x slower).
+// The per-level constants come from a shared-memory copy of the table: indexing the kernel-parameter arrays with a per-thread level
+// compiles to divergent constant-bank loads, which serialise in the address-divergence unit (ncu: ADU pipe at 88 % of peak).
+struct LevelConst { float scale; uint32_t size, resolution, offset; };
+
 __global__ void __launch_bounds__(256) hash_encode_forward_kernel(
 	const uint32_t n, const uint32_t* __restrict__ n_dev, const GridLevels L, const __half2* __restrict__ grid, const float* __restrict__ positions, const uint32_t pos_stride,
 	__half2* __restrict__ encoded)
 {
+	__shared__ LevelConst lc[NGPB_MAX_LEVELS];
+	if (threadIdx.x < L.n_levels) lc[threadIdx.x] = LevelConst{L.scale[threadIdx.x], L.size[threadIdx.x], L.resolution[threadIdx.x], L.offset[threadIdx.x]};
+	__syncthreads();
 	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t level = tid % L.n_levels;
 	const uint32_t i = tid / L.n_levels;
 	if (i >= n) return;
 	if (n_dev && i >= *n_dev) return; // device-side sample count (no host round trip between K1 and the network)
 
-	const float scale = L.scale[level];
-	const LevelIndexer index_of(L.size[level], L.resolution[level]);
-	const __half2* __restrict__ g = grid + L.offset[level];
-
-	// pos_fract, tcnn common_device.h:434-445. The reference's `input * scale + 0.5f` is contracted to one
-	// FFMA by nvcc's default -fmad=true; this library is built with -fmad=false, so the FMA is explicit.
+	const LevelConst c = lc[level];
+	const LevelIndexer index_of(c.size, c.resolution);
+	const __half2* __restrict__ g = grid + c.offset;
 	float pos[3];
 	uint32_t pg[3];
-	#pragma unroll
-	for (int d = 0; d < 3; ++d) {
-		float p = __fmaf_rn(positions[(size_t)i * pos_stride + d], scale, 0.5f);
-		float fl = floorf(p);
-		pg[d] = (uint32_t)(int)fl;
-		pos[d] = p - fl;
-	}
+	level_position(positions, i, pos_stride, c.scale, pos, pg);
 
 	// issue the 8 gathers first, then blend: maximises loads in flight per thread
 	__half2 v[8];
@@ -107,43 +124,43 @@ __global__ void __launch_bounds__(256) hash_encode_forward_kernel(
 	encoded[(size_t)i * L.n_levels + level] = __halves2half2(r0, r1);
 }
 
-// Backward: scatter-add weight * dL/dy into the fp32 gradient table. The reference uses
-// atomicAdd(__half2) into an fp16 table (grid.h:436-441); here the table is fp32 (one vectorised
-// red.global.add.v2.f32 per corner), which removes the order-dependent fp16 rounding.
-__global__ void __launch_bounds__(256) hash_encode_backward_kernel(
+// Backward: scatter-add weight * dL/dy into the fp32 gradient table. The reference uses atomicAdd(__half2) into an fp16 table
+// (grid.h:436-441); here the table is fp32 (one vectorised red.global.add.v2.f32 per corner), which removes the order-dependent fp16
+// rounding. Same thread mapping as the forward kernel; dL/dy enters through shared memory (coalesced read of the block's 2 KB).
+__global__ void __launch_bounds__(ENC_SAMPLES * ENC_WARPS) hash_encode_backward_kernel(
 	const uint32_t n, const GridLevels L, const float* __restrict__ positions, const uint32_t pos_stride,
 	const __half2* __restrict__ dL_dencoded, float2* __restrict__ grid_grad)
 {
-	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-	const uint32_t level = tid % L.n_levels;
-	const uint32_t i = tid / L.n_levels;
+	__shared__ __half2 tile[ENC_SAMPLES][NGPB_MAX_LEVELS + 1];
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t s0 = blockIdx.x * ENC_SAMPLES;
+	if (s0 >= n) return;
+	const uint32_t n_here = min(ENC_SAMPLES, n - s0);
+	for (uint32_t k = threadIdx.x; k < n_here * L.n_levels; k += blockDim.x) {
+		tile[k / L.n_levels][k % L.n_levels] = dL_dencoded[(size_t)s0 * L.n_levels + k];
+	}
+	__syncthreads();
+	const uint32_t i = s0 + lane;
 	if (i >= n) return;
 
-	const __half2 gh = dL_dencoded[(size_t)i * L.n_levels + level];
-	const float g0 = __low2float(gh), g1 = __high2float(gh);
-	if (g0 == 0.f && g1 == 0.f) return; // adds nothing
-
-	const float scale = L.scale[level];
-	const LevelIndexer index_of(L.size[level], L.resolution[level]);
-	float2* __restrict__ gg = grid_grad + L.offset[level];
-
-	float pos[3];
-	uint32_t pg[3];
-	#pragma unroll
-	for (int d = 0; d < 3; ++d) {
-		float p = __fmaf_rn(positions[(size_t)i * pos_stride + d], scale, 0.5f);
-		float fl = floorf(p);
-		pg[d] = (uint32_t)(int)fl;
-		pos[d] = p - fl;
-	}
-	#pragma unroll
-	for (uint32_t idx = 0; idx < 8; ++idx) {
-		float w = 1.f;
+	for (uint32_t level = warp; level < L.n_levels; level += ENC_WARPS) {
+		const __half2 gh = tile[lane][level];
+		const float g0 = __low2float(gh), g1 = __high2float(gh);
+		if (g0 == 0.f && g1 == 0.f) continue; // adds nothing
+		const LevelIndexer index_of(L.size[level], L.resolution[level]);
+		float2* __restrict__ gg = grid_grad + L.offset[level];
+		float pos[3];
+		uint32_t pg[3];
+		level_position(positions, i, pos_stride, L.scale[level], pos, pg);
 		#pragma unroll
-		for (int d = 0; d < 3; ++d) w *= (idx & (1u << d)) ? pos[d] : (1.f - pos[d]);
-		const uint32_t e = index_of(pg[0] + (idx & 1), pg[1] + ((idx >> 1) & 1), pg[2] + ((idx >> 2) & 1));
-		float* addr = reinterpret_cast<float*>(gg + e);
-		asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" :: "l"(addr), "f"(g0 * w), "f"(g1 * w) : "memory");
+		for (uint32_t idx = 0; idx < 8; ++idx) {
+			float w = 1.f;
+			#pragma unroll
+			for (int d = 0; d < 3; ++d) w *= (idx & (1u << d)) ? pos[d] : (1.f - pos[d]);
+			const uint32_t e = index_of(pg[0] + (idx & 1), pg[1] + ((idx >> 1) & 1), pg[2] + ((idx >> 2) & 1));
+			float* addr = reinterpret_cast<float*>(gg + e);
+			asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" :: "l"(addr), "f"(g0 * w), "f"(g1 * w) : "memory");
+		}
 	}
 }
 
@@ -153,7 +170,7 @@ void hash_encode_forward_launch(cudaStream_t stream, const ngpb_grid* g, const _
 	if (n == 0) return;
 	const GridLevels L = make_levels(g);
 	const uint64_t threads = (uint64_t)n * L.n_levels;
-	NGPB_STEP_KERNEL(hash_encode_forward_kernel);
+	// no explicit shared-memory carve-out for this kernel: any non-default preference was measured 3x slower (L1 is what feeds the gathers)
 	hash_encode_forward_kernel<<<(uint32_t)((threads + 255) / 256), 256, 0, stream>>>(n, n_dev, L, (const __half2*)grid, positions, pos_stride, (__half2*)encoded);
 	NGPB_LAUNCH_CHECK();
 }
@@ -161,9 +178,7 @@ void hash_encode_backward_launch(cudaStream_t stream, const ngpb_grid* g, const 
                                  const __half* dL_dencoded, float* grid_grad) {
 	if (n == 0) return;
 	const GridLevels L = make_levels(g);
-	const uint64_t threads = (uint64_t)n * L.n_levels;
-	NGPB_STEP_KERNEL(hash_encode_backward_kernel);
-	hash_encode_backward_kernel<<<(uint32_t)((threads + 255) / 256), 256, 0, stream>>>(n, L, positions, pos_stride, (const __half2*)dL_dencoded, (float2*)grid_grad);
+	hash_encode_backward_kernel<<<div_round_up(n, ENC_SAMPLES), ENC_SAMPLES * ENC_WARPS, 0, stream>>>(n, L, positions, pos_stride, (const __half2*)dL_dencoded, (float2*)grid_grad);
 	NGPB_LAUNCH_CHECK();
 }
 

@@ -427,7 +427,7 @@ static void launch_mlp(cudaStream_t stream, const MlpArgs& a, uint32_t grid, uin
 	if (!configured) {
 		NGPB_CUDA_CHECK(cudaFuncSetAttribute(nerf_mlp_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
 		// the training kernel overlaps the sampling stream (see common.cuh); the inference kernels run alone and want 4 CTAs x 53 KB
-		if (MODE == MODE_TRAIN) NGPB_CUDA_CHECK(cudaFuncSetAttribute(nerf_mlp_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, kSmemCarveoutPercent));
+		if (MODE == MODE_TRAIN && step_carveout() >= 0) NGPB_CUDA_CHECK(cudaFuncSetAttribute(nerf_mlp_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, step_carveout()));
 		configured = true;
 	}
 	nerf_mlp_kernel<MODE><<<grid, 128, smem_bytes, stream>>>(a);

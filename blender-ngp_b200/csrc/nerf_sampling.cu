@@ -11,7 +11,7 @@
 
 namespace ngpb {
 
-struct TrainRay { V3 o, d_unnorm, d; float startt, cone_angle; bool valid; };
+struct TrainRay { V3 o, d_unnorm, d; float startt, cone_angle, tmax; bool valid; };
 
 // Ray set-up: testbed_nerf.cu:1118-1202 (perspective lens, no rolling shutter, no distortion map,
 // uniform pixel sampling). RNG draws in the reference's order: xy(2), motion-blur time(1), start jitter(1).
@@ -36,6 +36,7 @@ __device__ inline TrainRay setup_training_ray(uint32_t i, uint32_t n_rays, Pcg32
 	if (z > 0.f) { const float nrm = sqrtf(z); r.d = {r.d_unnorm.x / nrm, r.d_unnorm.y / nrm, r.d_unnorm.z / nrm}; } else r.d = r.d_unnorm;
 	float tmin, tmax;
 	aabb_ray_intersect(aabb, r.o, r.d, &tmin, &tmax);
+	r.tmax = tmax;
 	r.cone_angle = cone_angle_constant; // calc_cone_angle (:87-94)
 	tmin = fmaxf(tmin, 0.0f);
 	float startt = tmin;
@@ -46,57 +47,64 @@ __device__ inline TrainRay setup_training_ray(uint32_t i, uint32_t n_rays, Pcg32
 }
 
 // ---- marching ----------------------------------------------------------------------------------------
-// Reference: testbed_nerf.cu:1204-1219 (count pass) and :1239-1253 (write pass): the ray is marched twice.
-// Both branches of the march advance t the same way -- `t += calc_dt(t, cone_angle)`, once per sample in an occupied cell,
-// repeatedly until the cell's exit in an empty one (advance_to_next_voxel, :449-463) -- so the ray's t values form ONE chain
-// t_0, t_1, ... that does not depend on the occupancy grid; the grid only selects which t_k become samples. The march is
-// therefore done once: it records, per 32 chain steps, a bit mask of the emitted samples and the t at the first step
-// (MarchWord). The write pass is then parallel over the words of a ray: every lane replays 32 steps of the chain from its
-// word's t (the same float additions) and writes the samples whose bits are set.
-struct MarchWord { uint32_t mask; float t; };
-constexpr uint32_t MARCH_MAX_WORDS = 72;         // 2304 chain steps; a unit-cube ray takes <= 1025, aabb_scale 128 about 2100
-constexpr uint32_t MARCH_OVERFLOW = 0x80000000u; // flag in n_words: the chain outgrew the record, the write pass re-marches this ray
+// Reference: testbed_nerf.cu:1204-1219 (count pass) and :1239-1253 (write pass): one thread marches a whole ray, twice.
+//
+// Both branches of that march advance t the same way -- `t += calc_dt(t, cone_angle)`, once per sample in an occupied cell, repeatedly
+// until the cell's exit in an empty one (advance_to_next_voxel, :449-463). So the t values of a ray form ONE chain t_0, t_1, ... that does
+// not depend on the occupancy grid ("candidates"); the march only decides which candidates it VISITS (an empty visited candidate jumps to
+// the first later candidate with t >= its cell-exit time; an occupied one emits a sample and moves to the next candidate) and a visited
+// occupied candidate is a sample. That turns the serial march into a parallel one without changing a single result:
+//   1. chain kernel (thread per ray): set-up, then the chain alone (one FADD per step), storing t at every 32nd candidate ("word");
+//   2. word kernel (thread per word, ~22 per ray): marches its 32 candidates ASSUMING candidate 0 is visited, records the visited set, the
+//      emitted set and how the walk leaves the word (exit state);
+//   3. resolve kernel (thread per ray): walks the ray's words in order with the true entry; if the true entry candidate is in the word's
+//      visited set, the walk from there on is the recorded one (the march is deterministic from any visited candidate), otherwise -- only when
+//      a candidate sits within rounding of a cell boundary -- that word is re-marched from the true entry. Also applies the 1024-sample cap.
+//   4. scan + write kernels: as before, parallel over words, replaying each word's 32 chain steps with the same float additions.
+// The ray's critical path drops from ~200 dependent cell hops to ~7, and the kernel becomes throughput- instead of latency-bound.
+struct __align__(16) MarchWord {
+	float t;            // chain value at the word's first candidate
+	uint32_t visited;   // candidates the walk visits (word kernel: assuming candidate 0 is visited)
+	uint32_t emitted;   // samples; after the resolve kernel: the ray's true samples in this word
+	float tau;          // exit state: -inf = the next word's candidate 0 is visited; finite = pending jump target (next visited: first later
+	                    // candidate with t >= tau); NaN = the ray ended in this word (a visited candidate lay outside the box)
+};
+struct __align__(16) RayRec { float o[3]; float cone_angle; float d[3]; uint32_t n_words; float d_unnorm[3]; float pad; };
+constexpr uint32_t MARCH_MAX_WORDS = 72;         // 2304 candidates; a unit-cube ray has <= 1025, aabb_scale 128 about 2100
+constexpr uint32_t MARCH_OVERFLOW = 0x80000000u; // flag in n_words: the chain outgrew the record; this ray is marched serially instead
+constexpr float TAU_NEXT = -INFINITY;
 
-// Serial march of one ray. Returns the number of samples; fills words[0 .. *n_words) unless the chain overflows.
-__device__ inline uint32_t march_and_record(const TrainRay& r, const Aabb& aabb, const uint8_t* __restrict__ bitfield, MarchWord* __restrict__ words, uint32_t* n_words_out) {
-	const V3 idir = {1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z};
-	uint32_t j = 0, k = 0, mask = 0, n_words = 0;
-	bool overflow = false;
-	float t = r.startt, word_t = r.startt;
-	V3 pos;
-	// one chain step: t_{k+1} = t_k + calc_dt(t_k); closes the current word every 32 steps
-	#define NGPB_CHAIN_STEP()                                                             \
-		do {                                                                              \
-			t += calc_dt(t, r.cone_angle);                                                \
-			if ((++k & 31u) == 0) {                                                       \
-				if (n_words < MARCH_MAX_WORDS) { words[n_words].mask = mask; words[n_words].t = word_t; } else overflow = true; \
-				++n_words; mask = 0; word_t = t;                                          \
-			}                                                                             \
-		} while (0)
-	while (aabb_contains(aabb, pos = V3{r.o.x + t * r.d.x, r.o.y + t * r.d.y, r.o.z + t * r.d.z}) && j < NERF_STEPS) {
-		const float dt = calc_dt(t, r.cone_angle);
+__device__ __forceinline__ bool tau_is_end(float tau) { return tau != tau; }
+
+// Marches the 32 candidates of one word starting with candidate `entry` visited. t_word: chain value at candidate 0.
+__device__ inline void march_word(const V3& o, const V3& d, const V3& idir, float cone_angle, const Aabb& aabb, const uint8_t* __restrict__ bitfield,
+                                  float t_word, uint32_t entry, uint32_t* visited_out, uint32_t* emitted_out, float* tau_out) {
+	float t = t_word;
+	uint32_t c = 0, visited = 0, emitted = 0;
+	for (; c < entry; ++c) t += calc_dt(t, cone_angle);
+	float tau = TAU_NEXT;
+	while (c < 32) {
+		const V3 pos = V3{o.x + t * d.x, o.y + t * d.y, o.z + t * d.z};
+		if (!aabb_contains(aabb, pos)) { tau = __uint_as_float(0x7FC00000u); break; }
+		visited |= 1u << c;
+		const float dt = calc_dt(t, cone_angle);
 		const uint32_t mip = mip_from_dt(dt, pos);
 		if (density_grid_occupied_at(pos, bitfield, mip)) {
-			mask |= 1u << (k & 31u);
-			++j;
-			NGPB_CHAIN_STEP();
+			emitted |= 1u << c;
+			t += dt;
+			++c;
 		} else {
-			const uint32_t res = NERF_GRIDSIZE >> mip;
-			const float t_target = t + distance_to_next_voxel(pos, r.d, idir, res);
-			do { NGPB_CHAIN_STEP(); } while (t < t_target);
+			const float t_target = t + distance_to_next_voxel(pos, d, idir, NERF_GRIDSIZE >> mip);
+			do { t += calc_dt(t, cone_angle); ++c; } while (t < t_target && c < 32); // advance_to_next_voxel, cut at the word's end
+			if (t < t_target) { tau = t_target; break; } // the jump continues in a later word
 		}
 	}
-	#undef NGPB_CHAIN_STEP
-	if (mask) {
-		if (n_words < MARCH_MAX_WORDS) { words[n_words].mask = mask; words[n_words].t = word_t; } else overflow = true;
-		++n_words;
-	}
-	*n_words_out = overflow ? MARCH_OVERFLOW : n_words;
-	return j;
+	*visited_out = visited; *emitted_out = emitted; *tau_out = tau;
 }
 
-// Re-march that writes directly (the reference's second pass); only used for rays whose chain overflowed the record.
-__device__ inline void march_and_write(const TrainRay& r, const Aabb& aabb, const uint8_t* __restrict__ bitfield, uint32_t max_steps, float* __restrict__ coords_out) {
+// Serial march of a whole ray (the reference's loop), used only for rays whose chain does not fit MARCH_MAX_WORDS words.
+template <bool WRITE>
+__device__ inline uint32_t march_serial(const TrainRay& r, const Aabb& aabb, const uint8_t* __restrict__ bitfield, uint32_t max_steps, float* __restrict__ coords_out) {
 	const V3 idir = {1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z};
 	const V3 wd = {(r.d.x + 1.0f) * 0.5f, (r.d.y + 1.0f) * 0.5f, (r.d.z + 1.0f) * 0.5f}; // warp_direction (:292)
 	uint32_t j = 0;
@@ -106,38 +114,135 @@ __device__ inline void march_and_write(const TrainRay& r, const Aabb& aabb, cons
 		const float dt = calc_dt(t, r.cone_angle);
 		const uint32_t mip = mip_from_dt(dt, pos);
 		if (density_grid_occupied_at(pos, bitfield, mip)) {
-			const V3 wp = warp_position(pos, aabb);
-			float* c = coords_out + (size_t)j * COORD_FLOATS;
-			c[0] = wp.x; c[1] = wp.y; c[2] = wp.z; c[3] = warp_dt(dt); c[4] = wd.x; c[5] = wd.y; c[6] = wd.z;
+			if (WRITE) {
+				const V3 wp = warp_position(pos, aabb);
+				float* c = coords_out + (size_t)j * COORD_FLOATS;
+				c[0] = wp.x; c[1] = wp.y; c[2] = wp.z; c[3] = warp_dt(dt); c[4] = wd.x; c[5] = wd.y; c[6] = wd.z;
+			}
 			++j;
 			t += dt;
 		} else {
-			const uint32_t res = NERF_GRIDSIZE >> mip;
-			t = advance_to_next_voxel(t, r.cone_angle, pos, r.d, idir, res);
+			t = advance_to_next_voxel(t, r.cone_angle, pos, r.d, idir, NERF_GRIDSIZE >> mip);
 		}
 	}
+	return j;
 }
 
 constexpr uint32_t K1_BLOCK = 128;
 
-// Pass 1: one thread per ray. Sample count, march record, and the block-local exclusive prefixes of (count, count > 0).
-__global__ void __launch_bounds__(K1_BLOCK) count_training_samples_kernel(
+// Pass 1: one thread per ray. Set-up and the t chain; appends one work item per word to `items`.
+__global__ void __launch_bounds__(K1_BLOCK) chain_training_rays_kernel(
 	const uint32_t n_rays, const uint32_t ray_offset, const uint32_t n_rays_global, const Aabb aabb, const Pcg32 rng, const uint32_t n_images, const ngpb_image* __restrict__ images,
-	const uint8_t* __restrict__ bitfield, const bool snap, const float cone_angle_constant,
-	uint32_t* __restrict__ counts, uint32_t* __restrict__ n_words, MarchWord* __restrict__ words, uint32_t* __restrict__ local_bases, uint32_t* __restrict__ local_slots,
-	uint2* __restrict__ block_sums)
+	const bool snap, const float cone_angle_constant, RayRec* __restrict__ recs, MarchWord* __restrict__ words, uint32_t* __restrict__ items, uint32_t* __restrict__ n_items)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t lane = threadIdx.x & 31;
+	uint32_t n_words = 0;
+	bool overflow = false;
+	if (i < n_rays) {
+		// everything about a ray derives from its GLOBAL index (:1118-1121, :1062-1083): a shard reproduces its slice of the full batch
+		const TrainRay r = setup_training_ray(ray_offset + i, n_rays_global, rng, n_images, images, aabb, snap, cone_angle_constant);
+		if (r.valid && r.tmax < 3.0e38f) {
+			MarchWord* w = words + (size_t)i * MARCH_MAX_WORDS;
+			// every candidate beyond t_end is outside the box by a margin far above the rounding of o + t * d, so no visited candidate of the
+			// reference's march lies past the last stored word
+			const float t_end = r.tmax + 2.0f * calc_dt(fmaxf(r.tmax, 0.f), r.cone_angle) + 1e-4f;
+			float t = r.startt;
+			while (true) { // one word (32 chain steps) per iteration; the end test runs once per word, so up to 31 surplus candidates are harmless
+				if (n_words == MARCH_MAX_WORDS) { overflow = true; break; }
+				w[n_words++].t = t;
+				if (!(t <= t_end)) break;
+				#pragma unroll
+				for (int k = 0; k < 32; ++k) t += calc_dt(t, r.cone_angle);
+			}
+		}
+		RayRec rec;
+		rec.o[0] = r.o.x; rec.o[1] = r.o.y; rec.o[2] = r.o.z; rec.cone_angle = r.cone_angle;
+		rec.d[0] = r.d.x; rec.d[1] = r.d.y; rec.d[2] = r.d.z;
+		rec.d_unnorm[0] = r.d_unnorm.x; rec.d_unnorm[1] = r.d_unnorm.y; rec.d_unnorm[2] = r.d_unnorm.z; rec.pad = 0.f;
+		rec.n_words = overflow ? MARCH_OVERFLOW : n_words;
+		recs[i] = rec;
+	}
+	// one work item per word, appended in ray order within the warp (ONE atomic per warp)
+	const uint32_t mine = overflow ? 0u : n_words;
+	uint32_t incl = mine;
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { const uint32_t tt = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += tt; }
+	const uint32_t warp_total = __shfl_sync(0xffffffffu, incl, 31);
+	uint32_t base = 0;
+	if (lane == 31 && warp_total) base = atomicAdd(n_items, warp_total);
+	base = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
+	for (uint32_t w = 0; w < mine; ++w) items[base + w] = i * 128u + w;
+}
+
+// Pass 2: one thread per word: march the word's 32 candidates assuming candidate 0 is visited.
+__global__ void __launch_bounds__(128) march_words_kernel(const uint32_t* __restrict__ n_items, const uint32_t* __restrict__ items, const Aabb aabb, const uint8_t* __restrict__ bitfield,
+                                                          const RayRec* __restrict__ recs, MarchWord* __restrict__ words)
+{
+	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= *n_items) return;
+	const uint32_t item = items[k], i = item >> 7, w = item & 127u;
+	const RayRec rec = recs[i];
+	const V3 o = {rec.o[0], rec.o[1], rec.o[2]}, d = {rec.d[0], rec.d[1], rec.d[2]};
+	const V3 idir = {1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+	MarchWord* mw = words + (size_t)i * MARCH_MAX_WORDS + w;
+	uint32_t visited, emitted; float tau;
+	march_word(o, d, idir, rec.cone_angle, aabb, bitfield, mw->t, 0, &visited, &emitted, &tau);
+	mw->visited = visited; mw->emitted = emitted; mw->tau = tau;
+}
+
+// Pass 3: one thread per ray: resolve the words in order, then the block-local exclusive prefixes of (count, count > 0).
+__global__ void __launch_bounds__(K1_BLOCK) resolve_training_rays_kernel(
+	const uint32_t n_rays, const uint32_t ray_offset, const uint32_t n_rays_global, const Aabb aabb, const Pcg32 rng, const uint32_t n_images, const ngpb_image* __restrict__ images,
+	const uint8_t* __restrict__ bitfield, const bool snap, const float cone_angle_constant, const RayRec* __restrict__ recs, MarchWord* __restrict__ words,
+	uint32_t* __restrict__ counts, uint32_t* __restrict__ n_words_out, uint32_t* __restrict__ local_bases, uint32_t* __restrict__ local_slots, uint2* __restrict__ block_sums)
 {
 	__shared__ uint32_t warp_sums[2][K1_BLOCK / 32];
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	uint32_t c = 0;
 	if (i < n_rays) {
-		// everything about a ray derives from its GLOBAL index (:1118-1121, :1062-1083): a shard reproduces its slice of the full batch
-		const TrainRay r = setup_training_ray(ray_offset + i, n_rays_global, rng, n_images, images, aabb, snap, cone_angle_constant);
-		uint32_t nw = 0;
-		if (r.valid) c = march_and_record(r, aabb, bitfield, words + (size_t)i * MARCH_MAX_WORDS, &nw);
+		const RayRec rec = recs[i];
+		uint32_t nw = rec.n_words;
+		if (nw == MARCH_OVERFLOW) {
+			const TrainRay r = setup_training_ray(ray_offset + i, n_rays_global, rng, n_images, images, aabb, snap, cone_angle_constant);
+			c = march_serial<false>(r, aabb, bitfield, NERF_STEPS, nullptr);
+		} else if (nw) {
+			const V3 o = {rec.o[0], rec.o[1], rec.o[2]}, d = {rec.d[0], rec.d[1], rec.d[2]};
+			const V3 idir = {1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+			MarchWord* rw = words + (size_t)i * MARCH_MAX_WORDS;
+			float tau_in = TAU_NEXT;
+			uint32_t w = 0;
+			for (; w < nw; ++w) {
+				const MarchWord mw = rw[w];
+				// true entry: the first candidate of this word with t >= tau_in
+				uint32_t e = 0;
+				if (tau_in != TAU_NEXT) {
+					float t = mw.t;
+					while (e < 32 && t < tau_in) { t += calc_dt(t, rec.cone_angle); ++e; }
+					if (e == 32) { rw[w].emitted = 0; continue; } // the jump passes over the whole word
+				}
+				uint32_t emitted; float tau_out;
+				if ((mw.visited >> e) & 1u) { emitted = mw.emitted & (0xFFFFFFFFu << e); tau_out = mw.tau; }
+				else { uint32_t v; march_word(o, d, idir, rec.cone_angle, aabb, bitfield, mw.t, e, &v, &emitted, &tau_out); }
+				// the march stops once it holds NERF_STEPS samples (:1209)
+				const uint32_t n_here = __popc(emitted);
+				if (c + n_here >= NERF_STEPS) {
+					while (c + __popc(emitted) > NERF_STEPS) emitted &= ~(1u << (31 - __clz((int)emitted)));
+					c = NERF_STEPS;
+					rw[w].emitted = emitted;
+					++w;
+					break;
+				}
+				c += n_here;
+				rw[w].emitted = emitted;
+				if (tau_is_end(tau_out)) { ++w; break; }
+				tau_in = tau_out;
+			}
+			nw = w; // later words hold no samples
+		}
 		counts[i] = c;
-		n_words[i] = nw;
+		n_words_out[i] = nw;
 	}
 	// block-local exclusive scans in ray order
 	uint32_t incl_c = c, incl_z = c > 0 ? 1u : 0u;
@@ -158,8 +263,8 @@ __global__ void __launch_bounds__(K1_BLOCK) count_training_samples_kernel(
 	if (threadIdx.x == 0) block_sums[blockIdx.x] = make_uint2(tot_c, tot_z);
 }
 
-// Pass 2: one block. Exclusive scan of the per-block totals: sample bases (the reference's numsteps_counter atomicAdd, :1225)
-// and ray slots (the ray_counter atomicAdd, :1232). counters[0] = samples requested; counters[1] is zeroed and counted by pass 3.
+// Pass 4: one block. Exclusive scan of the per-block totals: sample bases (the reference's numsteps_counter atomicAdd, :1225)
+// and ray slots (the ray_counter atomicAdd, :1232). counters[0] = samples requested; counters[1] is zeroed and counted by pass 5.
 __global__ void __launch_bounds__(1024) scan_training_samples_kernel(const uint32_t n_blocks, uint2* __restrict__ block_sums, uint32_t* __restrict__ counters)
 {
 	__shared__ uint32_t smem[33];
@@ -176,14 +281,14 @@ __global__ void __launch_bounds__(1024) scan_training_samples_kernel(const uint3
 	if (threadIdx.x == 0) { counters[0] = carry_c; counters[1] = 0; }
 }
 
-// Pass 3: one warp per ray, one lane per march word. A ray is kept iff it has samples and base + count <= max_samples
+// Pass 5: one warp per ray, one lane per march word. A ray is kept iff it has samples and base + count <= max_samples
 // (:1221-1228); since bases grow with the ray index the kept rays are exactly the sample-bearing rays before the cut, so a kept
 // ray's slot is the number of sample-bearing rays before it.
 constexpr uint32_t WRITE_RAYS_PER_BLOCK = 8;
 __global__ void __launch_bounds__(WRITE_RAYS_PER_BLOCK * 32) write_training_samples_kernel(
 	const uint32_t n_rays, const uint32_t ray_offset, const uint32_t n_rays_global, const uint32_t max_samples, const Aabb aabb, const Pcg32 rng, const uint32_t n_images, const ngpb_image* __restrict__ images,
 	const uint8_t* __restrict__ bitfield, const bool snap, const float cone_angle_constant,
-	const uint32_t* __restrict__ counts, const uint32_t* __restrict__ n_words, const MarchWord* __restrict__ words,
+	const uint32_t* __restrict__ counts, const uint32_t* __restrict__ n_words, const RayRec* __restrict__ recs, const MarchWord* __restrict__ words,
 	const uint32_t* __restrict__ local_bases, const uint32_t* __restrict__ local_slots, const uint2* __restrict__ block_prefix,
 	uint32_t* __restrict__ counters, uint32_t* __restrict__ ray_indices, float* __restrict__ rays, uint32_t* __restrict__ numsteps, float* __restrict__ coords)
 {
@@ -202,40 +307,44 @@ __global__ void __launch_bounds__(WRITE_RAYS_PER_BLOCK * 32) write_training_samp
 	if (threadIdx.x == 0 && n_kept_block) atomicAdd(&counters[1], n_kept_block);
 	if (!kept) return;
 
-	const TrainRay r = setup_training_ray(ray_offset + i, n_rays_global, rng, n_images, images, aabb, snap, cone_angle_constant); // same on every lane
+	const RayRec rec = recs[i];
+	const V3 o = {rec.o[0], rec.o[1], rec.o[2]}, d = {rec.d[0], rec.d[1], rec.d[2]};
 	if (lane == 0) {
 		ray_indices[slot] = ray_offset + i; // global ray index: K6 re-derives pixel and background from it
 		float* ro = rays + (size_t)slot * 6;
-		ro[0] = r.o.x; ro[1] = r.o.y; ro[2] = r.o.z; ro[3] = r.d_unnorm.x; ro[4] = r.d_unnorm.y; ro[5] = r.d_unnorm.z;
+		ro[0] = o.x; ro[1] = o.y; ro[2] = o.z; ro[3] = rec.d_unnorm[0]; ro[4] = rec.d_unnorm[1]; ro[5] = rec.d_unnorm[2];
 		numsteps[slot * 2 + 0] = count;
 		numsteps[slot * 2 + 1] = base;
 	}
 	float* out = coords + (size_t)base * COORD_FLOATS;
 	const uint32_t nw = n_words[i];
 	if (nw & MARCH_OVERFLOW) {
-		if (lane == 0) march_and_write(r, aabb, bitfield, count, out);
+		if (lane == 0) {
+			const TrainRay r = setup_training_ray(ray_offset + i, n_rays_global, rng, n_images, images, aabb, snap, cone_angle_constant);
+			march_serial<true>(r, aabb, bitfield, count, out);
+		}
 		return;
 	}
-	const V3 wd = {(r.d.x + 1.0f) * 0.5f, (r.d.y + 1.0f) * 0.5f, (r.d.z + 1.0f) * 0.5f}; // warp_direction (:292)
+	const V3 wd = {(d.x + 1.0f) * 0.5f, (d.y + 1.0f) * 0.5f, (d.z + 1.0f) * 0.5f}; // warp_direction (:292)
 	const MarchWord* rw = words + (size_t)i * MARCH_MAX_WORDS;
 	uint32_t carry = 0;
 	for (uint32_t w0 = 0; w0 < nw; w0 += 32) {
 		const uint32_t w = w0 + lane;
-		MarchWord mw = {0u, 0.f};
+		MarchWord mw = {0.f, 0u, 0u, 0.f};
 		if (w < nw) mw = rw[w];
-		const uint32_t n_here = __popc(mw.mask);
+		const uint32_t n_here = __popc(mw.emitted);
 		uint32_t incl = n_here;
 		#pragma unroll
-		for (int o = 1; o < 32; o <<= 1) { const uint32_t tt = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += tt; }
+		for (int k = 1; k < 32; k <<= 1) { const uint32_t tt = __shfl_up_sync(0xffffffffu, incl, k); if (lane >= (uint32_t)k) incl += tt; }
 		uint32_t j = carry + incl - n_here;
 		carry += __shfl_sync(0xffffffffu, incl, 31);
 		float t = mw.t;
-		uint32_t m = mw.mask;
-		// replay this word's 32 chain steps; stop after the last set bit
+		uint32_t m = mw.emitted;
+		// replay this word's chain steps up to its last sample
 		while (m) {
-			const float dt = calc_dt(t, r.cone_angle);
+			const float dt = calc_dt(t, rec.cone_angle);
 			if (m & 1u) {
-				const V3 pos = V3{r.o.x + t * r.d.x, r.o.y + t * r.d.y, r.o.z + t * r.d.z};
+				const V3 pos = V3{o.x + t * d.x, o.y + t * d.y, o.z + t * d.z};
 				const V3 wp = warp_position(pos, aabb);
 				float* c = out + (size_t)j * COORD_FLOATS;
 				c[0] = wp.x; c[1] = wp.y; c[2] = wp.z; c[3] = warp_dt(dt); c[4] = wd.x; c[5] = wd.y; c[6] = wd.z;
@@ -257,9 +366,35 @@ Aabb make_aabb(const float* a) {
 
 using namespace ngpb;
 
-extern "C" uint64_t ngpb_generate_training_samples_scratch_bytes(uint32_t n_rays) {
-	return (uint64_t)n_rays * 16 + 8 + (uint64_t)div_round_up(n_rays, K1_BLOCK) * sizeof(uint2) + (uint64_t)n_rays * MARCH_MAX_WORDS * sizeof(MarchWord) + 64;
+namespace {
+struct K1Scratch {
+	uint32_t *counts, *n_words, *local_bases, *local_slots, *items, *n_items;
+	uint2* block_sums;
+	RayRec* recs;
+	MarchWord* words;
+	size_t bytes;
+};
+// Carves (base == nullptr: only sizes) the K1 scratch buffer for n_rays rays.
+K1Scratch k1_scratch(uint32_t n_rays, void* base) {
+	uint8_t* p = reinterpret_cast<uint8_t*>(base);
+	size_t off = 0;
+	auto take = [&](size_t bytes) { uint8_t* q = p ? p + off : nullptr; off += (bytes + 255) / 256 * 256; return q; };
+	K1Scratch s{};
+	s.counts = (uint32_t*)take((size_t)n_rays * 4);
+	s.n_words = (uint32_t*)take((size_t)n_rays * 4);
+	s.local_bases = (uint32_t*)take((size_t)n_rays * 4);
+	s.local_slots = (uint32_t*)take((size_t)n_rays * 4);
+	s.block_sums = (uint2*)take((size_t)div_round_up(n_rays, K1_BLOCK) * sizeof(uint2));
+	s.n_items = (uint32_t*)take(256);
+	s.recs = (RayRec*)take((size_t)n_rays * sizeof(RayRec));
+	s.items = (uint32_t*)take((size_t)n_rays * MARCH_MAX_WORDS * 4);
+	s.words = (MarchWord*)take((size_t)n_rays * MARCH_MAX_WORDS * sizeof(MarchWord));
+	s.bytes = off;
+	return s;
 }
+} // namespace
+
+extern "C" uint64_t ngpb_generate_training_samples_scratch_bytes(uint32_t n_rays) { return k1_scratch(n_rays, nullptr).bytes; }
 
 extern "C" int ngpb_generate_training_samples(void* stream, uint32_t n_rays, const float* aabb6, uint32_t max_samples, ngpb_rng rng,
                                               uint32_t n_images, const ngpb_image* images_dev, const uint8_t* bitfield,
@@ -274,7 +409,7 @@ extern "C" int ngpb_generate_training_samples_sharded(void* stream_, uint32_t n_
                                               int snap_to_pixel_centers, float cone_angle_constant,
                                               uint32_t* counters, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, void* scratch_) {
 	try {
-		uint32_t* scratch = reinterpret_cast<uint32_t*>(scratch_);
+		void* scratch = scratch_;
 		if (!aabb6 || !images_dev || !bitfield || !counters || !ray_indices || !rays || !numsteps || !coords || !scratch || n_images == 0 ||
 		    (uint64_t)ray_offset + n_rays > n_rays_global) {
 			set_last_error("ngpb_generate_training_samples: invalid argument");
@@ -284,22 +419,28 @@ extern "C" int ngpb_generate_training_samples_sharded(void* stream_, uint32_t n_
 		if (n_rays == 0) { NGPB_CUDA_CHECK(cudaMemsetAsync(counters, 0, 2 * sizeof(uint32_t), stream)); return 0; }
 		const Aabb aabb = make_aabb(aabb6);
 		Pcg32 rng; rng.state = rng_.state; rng.inc = rng_.inc;
-		// scratch layout: counts | n_words | local_bases | local_slots (uint32[n_rays] each) | block_sums (uint2[n_blocks]) | MarchWord[n_rays][MARCH_MAX_WORDS]
-		uint32_t* counts = scratch;
-		uint32_t* n_words = counts + n_rays;
-		uint32_t* local_bases = n_words + n_rays;
-		uint32_t* local_slots = local_bases + n_rays;
+		const K1Scratch sc = k1_scratch(n_rays, scratch);
+		uint32_t *counts = sc.counts, *n_words = sc.n_words, *local_bases = sc.local_bases, *local_slots = sc.local_slots;
+		uint2* block_sums = sc.block_sums;
+		MarchWord* words = sc.words;
 		const uint32_t blocks = div_round_up(n_rays, K1_BLOCK);
-		uint2* block_sums = reinterpret_cast<uint2*>(local_slots + next_multiple(n_rays, 2));
-		MarchWord* words = reinterpret_cast<MarchWord*>(block_sums + blocks);
-		NGPB_STEP_KERNEL(count_training_samples_kernel); NGPB_STEP_KERNEL(scan_training_samples_kernel); NGPB_STEP_KERNEL(write_training_samples_kernel);
-		count_training_samples_kernel<<<blocks, K1_BLOCK, 0, stream>>>(n_rays, ray_offset, n_rays_global, aabb, rng, n_images, images_dev, bitfield, snap_to_pixel_centers != 0, cone_angle_constant,
-			counts, n_words, words, local_bases, local_slots, block_sums);
+		const bool snap = snap_to_pixel_centers != 0;
+		NGPB_CUDA_CHECK(cudaMemsetAsync(sc.n_items, 0, 4, stream));
+		chain_training_rays_kernel<<<blocks, K1_BLOCK, 0, stream>>>(n_rays, ray_offset, n_rays_global, aabb, rng, n_images, images_dev, snap, cone_angle_constant,
+			sc.recs, words, sc.items, sc.n_items);
+		NGPB_LAUNCH_CHECK();
+		// one thread per word; the word count lives on the device, so the grid covers the worst case and surplus blocks exit at once.
+		// A ray of the unit cube has at most 33 words (1025 candidates); larger scenes up to MARCH_MAX_WORDS.
+		const uint64_t max_items = (uint64_t)n_rays * MARCH_MAX_WORDS;
+		march_words_kernel<<<(uint32_t)((max_items + 127) / 128), 128, 0, stream>>>(sc.n_items, sc.items, aabb, bitfield, sc.recs, words);
+		NGPB_LAUNCH_CHECK();
+		resolve_training_rays_kernel<<<blocks, K1_BLOCK, 0, stream>>>(n_rays, ray_offset, n_rays_global, aabb, rng, n_images, images_dev, bitfield, snap, cone_angle_constant,
+			sc.recs, words, counts, n_words, local_bases, local_slots, block_sums);
 		NGPB_LAUNCH_CHECK();
 		scan_training_samples_kernel<<<1, 1024, 0, stream>>>(blocks, block_sums, counters);
 		NGPB_LAUNCH_CHECK();
 		write_training_samples_kernel<<<div_round_up(n_rays, WRITE_RAYS_PER_BLOCK), WRITE_RAYS_PER_BLOCK * 32, 0, stream>>>(n_rays, ray_offset, n_rays_global, max_samples, aabb, rng, n_images, images_dev, bitfield,
-			snap_to_pixel_centers != 0, cone_angle_constant, counts, n_words, words, local_bases, local_slots, block_sums, counters, ray_indices, rays, numsteps, coords);
+			snap_to_pixel_centers != 0, cone_angle_constant, counts, n_words, sc.recs, words, local_bases, local_slots, block_sums, counters, ray_indices, rays, numsteps, coords);
 		NGPB_LAUNCH_CHECK();
 		return 0;
 	} catch (const std::exception& e) { set_last_error(e.what()); return NGPB_ERR_RUNTIME; }

@@ -9,6 +9,7 @@
 // Hash-grid entries whose gradient is exactly zero are skipped by Adam (adam.h:76-79) but still take
 // part in the EMA, exactly as in the reference.
 #include "common.cuh"
+#include <cmath>
 #include "../../include/ngpb.h"
 
 namespace ngpb {
@@ -16,37 +17,69 @@ namespace ngpb {
 struct AdamParams {
 	uint32_t n, n_matrix;
 	float loss_scale, base_lr, beta1, beta2, epsilon, l2_reg;
+	float log2_beta1, log2_beta2;
 	float ema_decay, ema_debias_old, ema_debias_new;
 };
 
+// One parameter. Returns the fp16 value the EMA filters (the updated weight, or the unchanged one when Adam skips the entry).
+__device__ __forceinline__ void adam_ema_one(const AdamParams& P, bool is_matrix, float& grad, float& w, float& m1, float& m2, uint32_t& steps, __half& wh, __half& ema) {
+	float gradient = grad / P.loss_scale;
+	if (is_matrix || gradient != 0.f) { // hash-grid entries with a zero gradient are skipped (adam.h:76-79)
+		grad = 0.f;
+		if (is_matrix) gradient += P.l2_reg * w; // L2 only on matrix params (adam.h:88-91)
+		const float gradient_sq = gradient * gradient;
+		m1 = P.beta1 * m1 + (1 - P.beta1) * gradient;
+		m2 = P.beta2 * m2 + (1 - P.beta2) * gradient_sq;
+		const float step = (float)(++steps); // per-parameter debiasing (adam.h:104)
+		// beta^step as exp2(step * log2(beta)): the reference calls powf here; the two agree to ~1e-6 relative, far inside the fp32
+		// resolution of the resulting weight change, and powf was two thirds of this kernel's instructions
+		const float learning_rate = P.base_lr * sqrtf(1 - exp2f(step * P.log2_beta2)) / (1 - exp2f(step * P.log2_beta1));
+		const float effective_learning_rate = fminf(fmaxf(learning_rate / (sqrtf(m2) + P.epsilon), 0.f), 3.402823466e+38f);
+		w = w - effective_learning_rate * m1; // weight decay terms are zero in nerf/base.json
+		wh = __float2half_rn(w);
+	}
+	ema = __float2half_rn((__half2float(ema) * P.ema_decay * P.ema_debias_old + __half2float(wh) * (1 - P.ema_decay)) * P.ema_debias_new);
+}
+
+// Four parameters per thread (128-bit accesses on the fp32 arrays, 64-bit on the fp16 ones); n4 = n / 4 full groups, the tail is scalar.
 __global__ void __launch_bounds__(256) adam_ema_kernel(const AdamParams P, float* __restrict__ grad, float* __restrict__ w_fp32, __half* __restrict__ w_half,
                                                        __half* __restrict__ w_ema, float* __restrict__ m1, float* __restrict__ m2, uint32_t* __restrict__ param_steps)
 {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= P.n) return;
-	float gradient = grad[i] / P.loss_scale;
-	__half wh = w_half[i];
-	const bool is_matrix = i < P.n_matrix;
-	if (is_matrix || gradient != 0.f) {
-		grad[i] = 0.f; // (a zero hash gradient is already zero)
-		const float weight_fp = w_fp32[i];
-		if (is_matrix) gradient += P.l2_reg * weight_fp; // L2 only on matrix params (adam.h:88-91)
-		const float gradient_sq = gradient * gradient;
-		const float first_moment = P.beta1 * m1[i] + (1 - P.beta1) * gradient;
-		const float second_moment = P.beta2 * m2[i] + (1 - P.beta2) * gradient_sq;
-		m1[i] = first_moment;
-		m2[i] = second_moment;
-		float learning_rate = P.base_lr;
-		const uint32_t current_step = ++param_steps[i]; // per-parameter debiasing (adam.h:104)
-		learning_rate *= sqrtf(1 - powf(P.beta2, (float)current_step)) / (1 - powf(P.beta1, (float)current_step));
-		const float effective_learning_rate = fminf(fmaxf(learning_rate / (sqrtf(second_moment) + P.epsilon), 0.f), 3.402823466e+38f);
-		const float new_weight = weight_fp - effective_learning_rate * first_moment; // weight decay terms are zero in nerf/base.json
-		w_fp32[i] = new_weight;
-		wh = __float2half_rn(new_weight);
-		w_half[i] = wh;
+	const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t n4 = P.n / 4;
+	if (q < n4) {
+		float4 g = reinterpret_cast<float4*>(grad)[q];
+		const uint2 whr = reinterpret_cast<const uint2*>(w_half)[q];
+		uint2 emr = reinterpret_cast<uint2*>(w_ema)[q];
+		__half wh[4], em[4];
+		*reinterpret_cast<uint2*>(wh) = whr; *reinterpret_cast<uint2*>(em) = emr;
+		float gv[4] = {g.x, g.y, g.z, g.w};
+		const uint32_t i0 = q * 4;
+		bool any = i0 < P.n_matrix;
+		#pragma unroll
+		for (int k = 0; k < 4; ++k) any |= gv[k] != 0.f;
+		if (any) { // at least one entry takes an Adam step: bring in the optimizer state of the group
+			float4 w = reinterpret_cast<float4*>(w_fp32)[q], a = reinterpret_cast<float4*>(m1)[q], b = reinterpret_cast<float4*>(m2)[q];
+			uint4 st = reinterpret_cast<uint4*>(param_steps)[q];
+			float wv[4] = {w.x, w.y, w.z, w.w}, av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+			uint32_t sv[4] = {st.x, st.y, st.z, st.w};
+			#pragma unroll
+			for (int k = 0; k < 4; ++k) adam_ema_one(P, i0 + k < P.n_matrix, gv[k], wv[k], av[k], bv[k], sv[k], wh[k], em[k]);
+			reinterpret_cast<float4*>(grad)[q] = make_float4(gv[0], gv[1], gv[2], gv[3]);
+			reinterpret_cast<float4*>(w_fp32)[q] = make_float4(wv[0], wv[1], wv[2], wv[3]);
+			reinterpret_cast<float4*>(m1)[q] = make_float4(av[0], av[1], av[2], av[3]);
+			reinterpret_cast<float4*>(m2)[q] = make_float4(bv[0], bv[1], bv[2], bv[3]);
+			reinterpret_cast<uint4*>(param_steps)[q] = make_uint4(sv[0], sv[1], sv[2], sv[3]);
+			reinterpret_cast<uint2*>(w_half)[q] = *reinterpret_cast<uint2*>(wh);
+		} else { // only the EMA moves
+			#pragma unroll
+			for (int k = 0; k < 4; ++k) em[k] = __float2half_rn((__half2float(em[k]) * P.ema_decay * P.ema_debias_old + __half2float(wh[k]) * (1 - P.ema_decay)) * P.ema_debias_new);
+		}
+		reinterpret_cast<uint2*>(w_ema)[q] = *reinterpret_cast<uint2*>(em);
+	} else {
+		const uint32_t i = n4 * 4 + (q - n4);
+		if (i < P.n) adam_ema_one(P, i < P.n_matrix, grad[i], w_fp32[i], m1[i], m2[i], param_steps[i], w_half[i], w_ema[i]);
 	}
-	const float filtered_val = (__half2float(w_ema[i]) * P.ema_decay * P.ema_debias_old + __half2float(wh) * (1 - P.ema_decay)) * P.ema_debias_new;
-	w_ema[i] = __float2half_rn(filtered_val);
 }
 
 } // namespace ngpb
@@ -70,6 +103,7 @@ extern "C" int ngpb_optimizer_step(void* stream, ngpb_optimizer* o, uint32_t n_p
 		P.n = n_params; P.n_matrix = n_matrix_params; P.loss_scale = loss_scale;
 		P.base_lr = o->learning_rate * o->lr_factor;
 		P.beta1 = o->beta1; P.beta2 = o->beta2; P.epsilon = o->epsilon; P.l2_reg = o->l2_reg;
+		P.log2_beta1 = (float)std::log2((double)o->beta1); P.log2_beta2 = (float)std::log2((double)o->beta2);
 		++o->step; // AdamOptimizer::step (adam.h:152)
 		// EmaOptimizer::step (ema.h:102-108)
 		P.ema_decay = o->ema_decay;
@@ -77,7 +111,7 @@ extern "C" int ngpb_optimizer_step(void* stream, ngpb_optimizer* o, uint32_t n_p
 		P.ema_debias_new = 1.0f / (1 - (float)std::pow(o->ema_decay, o->step));
 		if (n_params == 0) return 0;
 		NGPB_STEP_KERNEL(adam_ema_kernel);
-		adam_ema_kernel<<<div_round_up(n_params, 256), 256, 0, (cudaStream_t)stream>>>(P, grad, w_fp32, (__half*)w_half, (__half*)w_ema, m1, m2, param_steps);
+		adam_ema_kernel<<<div_round_up(n_params / 4 + n_params % 4, 256), 256, 0, (cudaStream_t)stream>>>(P, grad, w_fp32, (__half*)w_half, (__half*)w_ema, m1, m2, param_steps);
 		NGPB_LAUNCH_CHECK();
 		return 0;
 	} catch (const std::exception& e) { set_last_error(e.what()); return NGPB_ERR_RUNTIME; }

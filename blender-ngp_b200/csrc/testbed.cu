@@ -115,6 +115,7 @@ ngpb_testbed::ngpb_testbed(int device_) : device(device_) {
 	NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&prefetch_done, cudaEventDisableTiming));
 	NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&loss_ready, cudaEventDisableTiming));
 	NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&counters_ready, cudaEventDisableTiming));
+	NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&mlp_train_done, cudaEventDisableTiming));
 	ngpb_optimizer_init(&opt);
 	loss_cfg.loss_scale = LOSS_SCALE;
 	loss_cfg.background_color[0] = loss_cfg.background_color[1] = loss_cfg.background_color[2] = 0.f;
@@ -136,6 +137,7 @@ ngpb_testbed::~ngpb_testbed() {
 	if (prefetch_done) cudaEventDestroy(prefetch_done);
 	if (loss_ready) cudaEventDestroy(loss_ready);
 	if (counters_ready) cudaEventDestroy(counters_ready);
+	if (mlp_train_done) cudaEventDestroy(mlp_train_done);
 	if (sampling_stream) cudaStreamDestroy(sampling_stream);
 	for (void* p : allocations) cudaFree(p);
 	for (auto& e : stage_ev) { if (e[0]) cudaEventDestroy(e[0]); if (e[1]) cudaEventDestroy(e[1]); }
@@ -403,7 +405,7 @@ void ngpb_testbed::launch_sampling(cudaStream_t st, const SamplingRequest& p) {
 	if (ngpb_generate_training_samples_sharded(st, p.n_rays, (uint32_t)dp_rank * p.n_rays, (uint32_t)dp_world * p.n_rays, aabb, p.max_inference, p.rng,
 		(uint32_t)images.size(), images_dev, bitfield, p.snap, p.cone_angle, counters, ray_indices, rays, numsteps, coords, scratch) != 0) throw std::runtime_error(ngpb_last_error());
 	stage_end(NGPB_STAGE_SAMPLING, p.n_rays, st);
-	n_launches += 3;
+	n_launches += 5;
 }
 
 void ngpb_testbed::drop_prefetch() {
@@ -503,6 +505,7 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 	stage_begin(NGPB_STAGE_MLP_TRAIN, stream);
 	nerf_mlp_forward_backward_launch(stream, w_half, encoded, coords_compacted, dloss, batch, denc, grad, partials);
 	stage_end(NGPB_STAGE_MLP_TRAIN, batch, stream);
+	NGPB_CUDA_CHECK(cudaEventRecord(mlp_train_done, stream));
 	stage_begin(NGPB_STAGE_ENCODE_BACKWARD, stream);
 	hash_encode_backward_launch(stream, &grid, coords_compacted, COORD_FLOATS, batch, denc, grad + MLP_PARAMS);
 	stage_end(NGPB_STAGE_ENCODE_BACKWARD, batch, stream);
@@ -563,6 +566,8 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 		if (overlap_sampling && training_step % next_skip != 0) {
 			prefetch = SamplingRequest{training_step, rays_per_batch, next_multiple(std::min(inference_budget(measured_batch_size_before_compaction), max_samples), 128),
 				ngpb_rng{rng.state, rng.inc}, loss_cfg.snap_to_pixel_centers, cone_angle_constant};
+			static const bool after_mlp = getenv("NGPB_K1_AFTER_MLP") && atoi(getenv("NGPB_K1_AFTER_MLP")) != 0;
+			if (after_mlp) NGPB_CUDA_CHECK(cudaStreamWaitEvent(sampling_stream, mlp_train_done, 0));
 			launch_sampling(sampling_stream, prefetch);
 			NGPB_CUDA_CHECK(cudaEventRecord(prefetch_done, sampling_stream));
 			prefetch_valid = true;

@@ -31,7 +31,7 @@ struct ngpb_testbed {
 	void drop_prefetch();
 	void collect_loss_scalar();
 	cudaStream_t sampling_stream = nullptr;
-	cudaEvent_t prefetch_done = nullptr, loss_ready = nullptr, counters_ready = nullptr;
+	cudaEvent_t prefetch_done = nullptr, loss_ready = nullptr, counters_ready = nullptr, mlp_train_done = nullptr;
 	SamplingRequest prefetch{};
 	bool prefetch_valid = false, overlap_sampling = true;
 	bool loss_pending = false;
