@@ -64,6 +64,7 @@ struct LevelIndexer {
 // lane l on sample s0 + l: the level is warp-uniform (uniform constant loads) and dL/dy enters through shared memory.
 constexpr uint32_t ENC_SAMPLES = 32;
 constexpr uint32_t ENC_WARPS = 16;
+constexpr uint32_t COARSE_RES = 128; // levels up to this resolution aggregate their atomics per run of equal cells (cell coordinates fit 8 bits)
 
 __device__ __forceinline__ void level_position(const float* __restrict__ positions, size_t i, uint32_t pos_stride, float scale, float pos[3], uint32_t pg[3]) {
 	// pos_fract, tcnn common_device.h:434-445. The reference's `input * scale + 0.5f` is contracted to one FFMA by nvcc's default
@@ -141,25 +142,65 @@ __global__ void __launch_bounds__(ENC_SAMPLES * ENC_WARPS) hash_encode_backward_
 	}
 	__syncthreads();
 	const uint32_t i = s0 + lane;
-	if (i >= n) return;
+	const bool valid = i < n; // (no early exit: the coarse levels use warp-wide shuffles)
 
 	for (uint32_t level = warp; level < L.n_levels; level += ENC_WARPS) {
-		const __half2 gh = tile[lane][level];
+		const __half2 gh = valid ? tile[lane][level] : __floats2half2_rn(0.f, 0.f);
 		const float g0 = __low2float(gh), g1 = __high2float(gh);
-		if (g0 == 0.f && g1 == 0.f) continue; // adds nothing
-		const LevelIndexer index_of(L.size[level], L.resolution[level]);
+		const bool contributes = g0 != 0.f || g1 != 0.f; // a zero gradient adds nothing
+		const uint32_t res = L.resolution[level];
+		const LevelIndexer index_of(L.size[level], res);
 		float2* __restrict__ gg = grid_grad + L.offset[level];
-		float pos[3];
-		uint32_t pg[3];
-		level_position(positions, i, pos_stride, L.scale[level], pos, pg);
-		#pragma unroll
-		for (uint32_t idx = 0; idx < 8; ++idx) {
-			float w = 1.f;
+		float pos[3] = {0.f, 0.f, 0.f};
+		uint32_t pg[3] = {0u, 0u, 0u};
+		if (contributes) level_position(positions, i, pos_stride, L.scale[level], pos, pg);
+
+		if (res <= COARSE_RES) {
+			// Coarse level (warp-uniform branch): consecutive samples of a ray sit in the same cell, so most of the warp's 32 x 8 updates go
+			// to a handful of entries -- and the whole batch hammers a few thousand addresses. Sum the contributions of each run of lanes
+			// with equal cell over the run (segmented warp scan) and let the run's last lane issue the 8 atomics.
+			const uint32_t key = contributes ? (pg[0] | (pg[1] << 8) | (pg[2] << 16)) : (0xFF000000u | lane);
+			const uint32_t key_prev = __shfl_up_sync(0xffffffffu, key, 1), key_next = __shfl_down_sync(0xffffffffu, key, 1);
+			const bool head = lane == 0 || key != key_prev, last = lane == 31 || key != key_next;
+			uint32_t head_lane = head ? lane : 0u; // inclusive max-scan: the lane at which this lane's run starts
 			#pragma unroll
-			for (int d = 0; d < 3; ++d) w *= (idx & (1u << d)) ? pos[d] : (1.f - pos[d]);
-			const uint32_t e = index_of(pg[0] + (idx & 1), pg[1] + ((idx >> 1) & 1), pg[2] + ((idx >> 2) & 1));
-			float* addr = reinterpret_cast<float*>(gg + e);
-			asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" :: "l"(addr), "f"(g0 * w), "f"(g1 * w) : "memory");
+			for (int o = 1; o < 32; o <<= 1) { const uint32_t h = __shfl_up_sync(0xffffffffu, head_lane, o); if (lane >= (uint32_t)o) head_lane = max(head_lane, h); }
+			float acc[8][2];
+			#pragma unroll
+			for (uint32_t idx = 0; idx < 8; ++idx) {
+				float w = 1.f;
+				#pragma unroll
+				for (int d = 0; d < 3; ++d) w *= (idx & (1u << d)) ? pos[d] : (1.f - pos[d]);
+				acc[idx][0] = contributes ? g0 * w : 0.f;
+				acc[idx][1] = contributes ? g1 * w : 0.f;
+			}
+			#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				const bool take = lane >= (uint32_t)o && lane - (uint32_t)o >= head_lane;
+				#pragma unroll
+				for (uint32_t idx = 0; idx < 8; ++idx) {
+					const float a0 = __shfl_up_sync(0xffffffffu, acc[idx][0], o), a1 = __shfl_up_sync(0xffffffffu, acc[idx][1], o);
+					if (take) { acc[idx][0] += a0; acc[idx][1] += a1; }
+				}
+			}
+			if (last && contributes) {
+				#pragma unroll
+				for (uint32_t idx = 0; idx < 8; ++idx) {
+					const uint32_t e = index_of(pg[0] + (idx & 1), pg[1] + ((idx >> 1) & 1), pg[2] + ((idx >> 2) & 1));
+					float* addr = reinterpret_cast<float*>(gg + e);
+					asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" :: "l"(addr), "f"(acc[idx][0]), "f"(acc[idx][1]) : "memory");
+				}
+			}
+		} else if (contributes) {
+			#pragma unroll
+			for (uint32_t idx = 0; idx < 8; ++idx) {
+				float w = 1.f;
+				#pragma unroll
+				for (int d = 0; d < 3; ++d) w *= (idx & (1u << d)) ? pos[d] : (1.f - pos[d]);
+				const uint32_t e = index_of(pg[0] + (idx & 1), pg[1] + ((idx >> 1) & 1), pg[2] + ((idx >> 2) & 1));
+				float* addr = reinterpret_cast<float*>(gg + e);
+				asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" :: "l"(addr), "f"(g0 * w), "f"(g1 * w) : "memory");
+			}
 		}
 	}
 }
