@@ -34,17 +34,16 @@ N_IMAGES, RES = 100, 800
 
 # Algorithmic bytes / flops per unit (restated in DESIGN.md s4)
 HASH_FWD_BYTES = 12 + 16 * 8 * 4 + 16 * 2 * 2      # 588 B/sample: position + 128 gathers x 4 B + 32 fp16 features out
-HASH_BWD_BYTES = 12 + 64 + 16 * 8 * 2 * 4           # 1100 B/sample: position + dL/dy + 128 x (2 x fp32) scatter-adds
+HASH_BWD_BYTES = 12 + 64 + 16 * 8 * 2 * 4           # 1100 B/sample: position + dL/dy + 128 x (2 x fp32) scatter-adds (counted once, before aggregation)
 MLP_FWD_FLOPS = 20480                               # padded widths as executed
 MLP_TRAIN_FLOPS = 61440
-OPT_BYTES_FIXED = 4 + 4 + 2 + 2 + 2                 # grad read + grad zero-write (touched) + fp16 w read + EMA read/write, per param
 STAGE_ALGO = {  # stage -> (bound, per-unit quantity, unit of `achieved`)
     "encode_inference": ("hbm", HASH_FWD_BYTES, "GB/s"),
     "encode_train": ("hbm", HASH_FWD_BYTES, "GB/s"),
     "encode_backward": ("hbm", HASH_BWD_BYTES, "GB/s"),
     "mlp_inference": ("tensor", MLP_FWD_FLOPS, "TFLOP/s"),
     "mlp_train": ("tensor", MLP_TRAIN_FLOPS, "TFLOP/s"),
-    "optimizer": ("hbm", 10, "GB/s"),
+    "optimizer": ("hbm", 46, "GB/s"),  # per parameter: grad r+w 8, fp32 weight r+w 8, two moments r+w 16, step counter r+w 8, fp16 weight w 2, EMA r+w 4
 }
 
 
@@ -194,6 +193,7 @@ def main():
     import torch
     import torch.distributed as dist
     import pyngp
+    import synthetic
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -287,6 +287,25 @@ def main():
                     peak_source=f"MEASURED_PEAKS.json ({pk['src']}; {'hbm_gbs' if d['bound'] == 'hbm' else 'bf16_tflops_sustained'})",
                     share_of_step=d["share"], per_stage=stage_report)
 
+    # ---- render leg (second half of BASELINE.json's metric: "render Msamples/sec"): one 800x800 frame of the trained model, device-timed ----
+    render = None
+    try:
+        import math
+        cam = synthetic.nerf_matrix_to_ngp(synthetic.hemisphere_cameras(7, seed=3)[2])
+        tb.camera_matrix = cam
+        tb.fov_axis = 0
+        tb.fov = math.degrees(synthetic.CAMERA_ANGLE_X)
+        tb.render(args.res, args.res, 1, True)  # warm-up (workspace allocation)
+        ms_r, ns_r = [], []
+        for _ in range(5):
+            tb.render(args.res, args.res, 1, True)
+            ms_r.append(tb.last_render_ms); ns_r.append(tb.last_render_samples)
+        render = dict(metric="nerf_render_msamples_per_sec", value=float(np.median(ns_r)) / (float(np.median(ms_r)) * 1e-3) / 1e6, unit="Msamples/s",
+                      ms_per_frame=float(np.median(ms_r)), samples_per_frame=int(np.median(ns_r)), resolution=[args.res, args.res], spp=1,
+                      note="network-evaluated samples of live rays / device time of Testbed.render (CUDA events around the whole call, incl. the frame's device-to-host copy)")
+    except Exception as e:  # the render leg never invalidates the training number
+        render = dict(error=str(e))
+
     # ---- e2e arm: public pyngp surface, dataset starts in pinned host memory, loss read back every step ----
     # (same Testbed object: reloading a same-sized dataset re-uploads it and re-initialises the model without new allocations)
     tb._set("overlap_sampling", 1.0)
@@ -332,7 +351,7 @@ def main():
                        "samples_per_sec": value * BATCH, "pre_trained_steps": args.preroll + W, "final_loss": loss,
                        "parallelism": "single GPU" if world == 1 else f"dp{world}: ray-sharded replicas, NCCL gradient all-reduce",
                        "l2": "no flush: the per-iteration working set (256 MB images + 293 MB parameter/optimizer state + ~150 MB sample buffers) exceeds the 126 MB L2"},
-            "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roofline,
+            "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roofline, "render": render,
         }
         if cb is not None:
             line["cpu_baseline"] = cb

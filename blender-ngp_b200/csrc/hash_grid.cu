@@ -86,6 +86,31 @@ __device__ __forceinline__ void level_position(const float* __restrict__ positio
 // compiles to divergent constant-bank loads, which serialise in the address-divergence unit (ncu: ADU pipe at 88 % of peak).
 struct LevelConst { float scale; uint32_t size, resolution, offset; };
 
+// The 8 corner entry indices of a cell (grid_index + prime_hash, grid.h:111-128,:164-186), with the per-axis products shared between corners.
+__device__ __forceinline__ void corner_indices(const LevelConst& c, const uint32_t pg[3], uint32_t idx[8]) {
+	const uint64_t dense = (uint64_t)c.resolution * c.resolution * c.resolution;
+	const uint32_t x[2] = {pg[0], pg[0] + 1};
+	if ((uint64_t)c.size < dense) { // hashed level: x ^ y * 2654435761 ^ z * 805459861
+		const uint32_t y0 = pg[1] * 2654435761u, z0 = pg[2] * 805459861u;
+		const uint32_t y[2] = {y0, y0 + 2654435761u}, z[2] = {z0, z0 + 805459861u};
+		const bool pow2 = (c.size & (c.size - 1)) == 0;
+		#pragma unroll
+		for (uint32_t k = 0; k < 8; ++k) {
+			const uint32_t h = x[k & 1] ^ y[(k >> 1) & 1] ^ z[k >> 2];
+			idx[k] = pow2 ? (h & (c.size - 1)) : (h % c.size);
+		}
+	} else { // dense level: x + y * res + z * res^2, wrapped into the level (the +0.5 offset can index `res`, common_device.h:404-408)
+		const uint32_t y0 = pg[1] * c.resolution, z0 = pg[2] * c.resolution * c.resolution;
+		const uint32_t y[2] = {y0, y0 + c.resolution}, z[2] = {z0, z0 + c.resolution * c.resolution};
+		#pragma unroll
+		for (uint32_t k = 0; k < 8; ++k) {
+			uint32_t h = x[k & 1] + y[(k >> 1) & 1] + z[k >> 2];
+			if (h >= c.size) { h -= c.size; if (h >= c.size) h %= c.size; }
+			idx[k] = h;
+		}
+	}
+}
+
 __global__ void __launch_bounds__(256) hash_encode_forward_kernel(
 	const uint32_t n, const uint32_t* __restrict__ n_dev, const GridLevels L, const __half2* __restrict__ grid, const float* __restrict__ positions, const uint32_t pos_stride,
 	__half2* __restrict__ encoded)
@@ -94,35 +119,38 @@ __global__ void __launch_bounds__(256) hash_encode_forward_kernel(
 	if (threadIdx.x < L.n_levels) lc[threadIdx.x] = LevelConst{L.scale[threadIdx.x], L.size[threadIdx.x], L.resolution[threadIdx.x], L.offset[threadIdx.x]};
 	__syncthreads();
 	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-	const uint32_t level = tid % L.n_levels;
-	const uint32_t i = tid / L.n_levels;
+	uint32_t level, i;
+	if (L.n_levels == 16) { level = tid & 15u; i = tid >> 4; } else { level = tid % L.n_levels; i = tid / L.n_levels; }
 	if (i >= n) return;
 	if (n_dev && i >= *n_dev) return; // device-side sample count (no host round trip between K1 and the network)
 
 	const LevelConst c = lc[level];
-	const LevelIndexer index_of(c.size, c.resolution);
 	const __half2* __restrict__ g = grid + c.offset;
 	float pos[3];
 	uint32_t pg[3];
 	level_position(positions, i, pos_stride, c.scale, pos, pg);
+	uint32_t idx[8];
+	corner_indices(c, pg, idx);
 
 	// issue the 8 gathers first, then blend: maximises loads in flight per thread
 	__half2 v[8];
 	#pragma unroll
-	for (uint32_t idx = 0; idx < 8; ++idx) {
-		v[idx] = __ldg(g + index_of(pg[0] + (idx & 1), pg[1] + ((idx >> 1) & 1), pg[2] + ((idx >> 2) & 1)));
-	}
-	// fp16 accumulation in the reference's corner order and rounding: result += (half)(weight * data), grid.h:339-341
-	__half r0 = __float2half(0.f), r1 = __float2half(0.f);
+	for (uint32_t k = 0; k < 8; ++k) v[k] = __ldg(g + idx[k]);
+
+	// trilinear weights in the reference's multiplication order ((wx * wy) * wz, grid.h:326-337), products shared between corners
+	const float wx[2] = {1.f - pos[0], pos[0]}, wy[2] = {1.f - pos[1], pos[1]}, wz[2] = {1.f - pos[2], pos[2]};
+	float wxy[4];
 	#pragma unroll
-	for (uint32_t idx = 0; idx < 8; ++idx) {
-		float w = 1.f;
-		#pragma unroll
-		for (int d = 0; d < 3; ++d) w *= (idx & (1u << d)) ? pos[d] : (1.f - pos[d]);
-		r0 = __hadd(r0, __float2half_rn(w * __low2float(v[idx])));
-		r1 = __hadd(r1, __float2half_rn(w * __high2float(v[idx])));
+	for (uint32_t k = 0; k < 4; ++k) wxy[k] = wx[k & 1] * wy[k >> 1];
+	// fp16 accumulation in the reference's corner order and rounding: result += (half)(weight * data), grid.h:339-341 (both features at once)
+	__half2 r = __floats2half2_rn(0.f, 0.f);
+	#pragma unroll
+	for (uint32_t k = 0; k < 8; ++k) {
+		const float w = wxy[k & 3] * wz[k >> 2];
+		const float2 f = __half22float2(v[k]);
+		r = __hadd2(r, __floats2half2_rn(w * f.x, w * f.y));
 	}
-	encoded[(size_t)i * L.n_levels + level] = __halves2half2(r0, r1);
+	encoded[(size_t)i * L.n_levels + level] = r;
 }
 
 // Backward: scatter-add weight * dL/dy into the fp32 gradient table. The reference uses atomicAdd(__half2) into an fp16 table

@@ -62,7 +62,7 @@ __device__ inline LossAndGradient loss_and_gradient(const float* target, const f
 	return r;
 }
 
-struct __align__(16) RayState { float rgb_ray[3]; float pad; float rgbtarget[3]; uint32_t compacted; };
+struct __align__(16) RayState { float rgb_ray[3]; float pad; float rgbtarget[3]; uint32_t compacted; float bg[3]; float pad2; };
 
 __device__ __forceinline__ void load_rgbsigma(const __half* p, float o[4]) {
 	const uint2 raw = *reinterpret_cast<const uint2*>(p);
@@ -137,6 +137,54 @@ __device__ __forceinline__ uint32_t block_scan_warps(uint32_t v_warp, uint32_t* 
 	return smem[warp];
 }
 
+// (A0) target colour and background of every ray, one THREAD per ray (:1378-1420): the pixel is recovered from the same RNG stream as K1, the
+// random background comes from the next three draws. Kept out of the warp-per-ray kernels, where all 32 lanes would repeat it.
+__global__ void __launch_bounds__(128) loss_target_kernel(const LossParams P, const ngpb_image* __restrict__ images, const uint32_t* __restrict__ counters_in,
+                                                          const uint32_t* __restrict__ ray_indices, RayState* __restrict__ state)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= P.n_rays || i >= counters_in[1]) return;
+	{
+		// same RNG stream as K1 to recover the pixel, then the random background (:1378-1392)
+		const uint32_t ray_idx = ray_indices[i];
+		Pcg32 rng = P.rng;
+		rng.advance((int64_t)ray_idx * N_MAX_RANDOM_SAMPLES_PER_RAY);
+		const uint32_t img = image_idx(ray_idx, P.n_rays_global, P.n_images);
+		const ngpb_image& im = images[img];
+		float x, y;
+		random_image_pos_training(rng, im.w, im.h, P.cfg.snap_to_pixel_centers != 0, &x, &y);
+		float bg[3] = {P.cfg.background_color[0], P.cfg.background_color[1], P.cfg.background_color[2]};
+		if (P.cfg.random_bg_color) { bg[0] = rng.next_float(); bg[1] = rng.next_float(); bg[2] = rng.next_float(); }
+		#pragma unroll
+		for (int c = 0; c < 3; ++c) bg[c] = srgb_to_linear(bg[c]);
+		float texsamp[4];
+		read_rgba(x, y, im, texsamp);
+		float rgbtarget[3];
+		if (P.cfg.linear_colors || P.cfg.color_space == NGPB_COLOR_LINEAR) {
+			#pragma unroll
+			for (int c = 0; c < 3; ++c) rgbtarget[c] = 1.0f * texsamp[c] + (1.0f - texsamp[3]) * bg[c];
+			if (!P.cfg.linear_colors) {
+				#pragma unroll
+				for (int c = 0; c < 3; ++c) { rgbtarget[c] = linear_to_srgb(rgbtarget[c]); bg[c] = linear_to_srgb(bg[c]); }
+			}
+		} else {
+			#pragma unroll
+			for (int c = 0; c < 3; ++c) bg[c] = linear_to_srgb(bg[c]);
+			if (texsamp[3] > 0) {
+				#pragma unroll
+				for (int c = 0; c < 3; ++c) rgbtarget[c] = linear_to_srgb(1.0f * texsamp[c] / texsamp[3]) * texsamp[3] + (1.0f - texsamp[3]) * bg[c];
+			} else {
+				#pragma unroll
+				for (int c = 0; c < 3; ++c) rgbtarget[c] = bg[c];
+			}
+		}
+		RayState s{};
+		#pragma unroll
+		for (int c = 0; c < 3; ++c) { s.rgbtarget[c] = rgbtarget[c]; s.bg[c] = bg[c]; }
+		state[i] = s;
+	}
+}
+
 // (A) forward compositing, :1341-1428. Writes the per-ray state, the ray's compacted step count, its exclusive prefix inside
 // the block (local_bases) and the block's total (block_sums).
 __global__ void __launch_bounds__(1024) loss_composite_kernel(
@@ -171,39 +219,9 @@ __global__ void __launch_bounds__(1024) loss_composite_kernel(
 			stopped = stop_mask != 0;
 			T_in = __shfl_sync(0xffffffffu, T * e.one_minus_alpha, 31);
 		}
-		// same RNG stream as K1 to recover the pixel, then the random background (:1378-1392)
-		const uint32_t ray_idx = ray_indices[i];
-		Pcg32 rng = P.rng;
-		rng.advance((int64_t)ray_idx * N_MAX_RANDOM_SAMPLES_PER_RAY);
-		const uint32_t img = image_idx(ray_idx, P.n_rays_global, P.n_images);
-		const ngpb_image& im = images[img];
-		float x, y;
-		random_image_pos_training(rng, im.w, im.h, P.cfg.snap_to_pixel_centers != 0, &x, &y);
-		float bg[3] = {P.cfg.background_color[0], P.cfg.background_color[1], P.cfg.background_color[2]};
-		if (P.cfg.random_bg_color) { bg[0] = rng.next_float(); bg[1] = rng.next_float(); bg[2] = rng.next_float(); }
-		#pragma unroll
-		for (int c = 0; c < 3; ++c) bg[c] = srgb_to_linear(bg[c]);
-		float texsamp[4];
-		read_rgba(x, y, im, texsamp);
-		float rgbtarget[3];
-		if (P.cfg.linear_colors || P.cfg.color_space == NGPB_COLOR_LINEAR) {
-			#pragma unroll
-			for (int c = 0; c < 3; ++c) rgbtarget[c] = 1.0f * texsamp[c] + (1.0f - texsamp[3]) * bg[c];
-			if (!P.cfg.linear_colors) {
-				#pragma unroll
-				for (int c = 0; c < 3; ++c) { rgbtarget[c] = linear_to_srgb(rgbtarget[c]); bg[c] = linear_to_srgb(bg[c]); }
-			}
-		} else {
-			#pragma unroll
-			for (int c = 0; c < 3; ++c) bg[c] = linear_to_srgb(bg[c]);
-			if (texsamp[3] > 0) {
-				#pragma unroll
-				for (int c = 0; c < 3; ++c) rgbtarget[c] = linear_to_srgb(1.0f * texsamp[c] / texsamp[3]) * texsamp[3] + (1.0f - texsamp[3]) * bg[c];
-			} else {
-				#pragma unroll
-				for (int c = 0; c < 3; ++c) rgbtarget[c] = bg[c];
-			}
-		}
+		const RayState tgt = state[i]; // target colour and background, from loss_target_kernel
+		const float bg[3] = {tgt.bg[0], tgt.bg[1], tgt.bg[2]};
+		const float rgbtarget[3] = {tgt.rgbtarget[0], tgt.rgbtarget[1], tgt.rgbtarget[2]};
 		if (cn == numsteps) { // the ray reached the end of its samples: composite the background behind it (:1424-1427)
 			#pragma unroll
 			for (int c = 0; c < 3; ++c) rgb_ray[c] += T_in * bg[c];
@@ -212,7 +230,9 @@ __global__ void __launch_bounds__(1024) loss_composite_kernel(
 			RayState s;
 			#pragma unroll
 			for (int c = 0; c < 3; ++c) { s.rgb_ray[c] = rgb_ray[c]; s.rgbtarget[c] = rgbtarget[c]; }
-			s.pad = 0.f;
+			s.pad = 0.f; s.pad2 = 0.f;
+			#pragma unroll
+			for (int c = 0; c < 3; ++c) s.bg[c] = bg[c];
 			s.compacted = cn;
 			state[i] = s;
 		}
@@ -382,6 +402,9 @@ extern "C" int ngpb_compute_loss_sharded(void* stream_, uint32_t n_rays, uint32_
 		uint32_t* block_sums = local_bases + n_rays;
 		const uint32_t blocks = div_round_up(n_rays, LOSS_RAYS_PER_BLOCK);
 		NGPB_STEP_KERNEL(loss_composite_kernel); NGPB_STEP_KERNEL(loss_scan_kernel); NGPB_STEP_KERNEL(loss_gradient_kernel); NGPB_STEP_KERNEL(rollover_kernel);
+		NGPB_STEP_KERNEL(loss_target_kernel);
+		loss_target_kernel<<<div_round_up(n_rays, 128), 128, 0, stream>>>(P, images_dev, counters_in, ray_indices, state);
+		NGPB_LAUNCH_CHECK();
 		loss_composite_kernel<<<blocks, 1024, 0, stream>>>(P, images_dev, counters_in, (const __half*)rgbsigma, ray_indices, numsteps, coords_in, state, counts, local_bases, block_sums);
 		NGPB_LAUNCH_CHECK();
 		loss_scan_kernel<<<1, 1024, 0, stream>>>(blocks, block_sums, counters_out);

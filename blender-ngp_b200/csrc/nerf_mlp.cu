@@ -44,14 +44,17 @@ constexpr uint32_t S_X   = SW_END;            // [128][32]  hash-grid features
 constexpr uint32_t S_H1  = S_X + 8192;        // [128][64]  relu(density hidden)      (inference: reused for G1, G2)
 constexpr uint32_t S_RIN = S_H1 + 16384;      // [128][32]  rgb-net input = [density out 16 | SH 16]
 constexpr uint32_t S_INFER_END = S_RIN + 8192;
+// training-only tiles. Buffers whose lifetimes do not overlap share storage, which brings a CTA to 104 KB so that TWO fit on an SM and
+// their serial MMA -> epilogue chains overlap:  dG1 is written after G2's last use (the ReLU mask of dG2), dH1 after dG2's last use (the
+// GEMMs of the step that produces dG1), dOd after dOr's last use (the first backward step).
 constexpr uint32_t S_G1  = S_INFER_END;       // [128][64]
 constexpr uint32_t S_G2  = S_G1 + 16384;      // [128][64]
+constexpr uint32_t S_DG1 = S_G2;              //            aliases G2
 constexpr uint32_t S_DOR = S_G2 + 16384;      // [128][16]  dL/d(rgb-net out), cols 3..15 zero
+constexpr uint32_t S_DOD = S_DOR;             //            dL/d(density-net out), aliases dOr
 constexpr uint32_t S_DG2 = S_DOR + 4096;      // [128][64]
-constexpr uint32_t S_DG1 = S_DG2 + 16384;     // [128][64]
-constexpr uint32_t S_DOD = S_DG1 + 16384;     // [128][16]  dL/d(density-net out)
-constexpr uint32_t S_DH1 = S_DOD + 4096;      // [128][64]
-constexpr uint32_t S_TRAIN_END = S_DH1 + 16384;
+constexpr uint32_t S_DH1 = S_DG2;             //            aliases dG2
+constexpr uint32_t S_TRAIN_END = S_DG2 + 16384;
 constexpr uint32_t S_CTRL = 64;               // mbarrier + tmem address, placed after the tiles
 
 // ---- TMEM map (columns) ---------------------------------------------------------------------------
@@ -187,7 +190,7 @@ struct MlpArgs {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(128) nerf_mlp_kernel(const MlpArgs args)
+__global__ void __launch_bounds__(128, MODE == 2 ? 2 : 4) nerf_mlp_kernel(const MlpArgs args)
 {
 	extern __shared__ __align__(128) uint8_t smem[];
 	constexpr uint32_t TILES_END = MODE == MODE_TRAIN ? S_TRAIN_END : S_INFER_END;
@@ -418,7 +421,8 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
 
 constexpr uint32_t SMEM_INFER = S_INFER_END + S_CTRL;
 constexpr uint32_t SMEM_TRAIN = S_TRAIN_END + S_CTRL;
-constexpr uint32_t TRAIN_GRID = kNumSMs; // one CTA per SM (143 KB of shared memory each)
+constexpr uint32_t TRAIN_CTAS_PER_SM = 2;
+constexpr uint32_t TRAIN_GRID = kNumSMs * TRAIN_CTAS_PER_SM; // two CTAs per SM (104 KB of shared memory and 256 TMEM columns each)
 constexpr uint32_t INFER_CTAS_PER_SM = 4;
 
 template <int MODE>
