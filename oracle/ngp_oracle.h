@@ -144,6 +144,8 @@ uint32_t orc_trainer_step(const orc_trainer* t);
 /* bench.py's CPU baseline only: puts the trainer into a given regime without running the preceding steps -- sets the step
  * counter (which fixes the occupancy-refresh cadence, src/testbed.cu:2538), the ray count, and replaces the occupancy grid
  * (mean + bitfield recomputed as update_density_grid_mean_and_bitfield does, src/testbed_nerf.cu:2844-2859). */
+/* per-level grid scales as the device evaluates them (see orc_grid_forward's `scales`) */
+void orc_trainer_set_level_scales(orc_trainer* t, const float* scales);
 void orc_trainer_set_state(orc_trainer* t, uint32_t training_step, uint32_t rays_per_batch, const float* density_grid);
 
 // ---- K17 classic render (src/testbed_nerf.cu:612-989,:1748-1978,:2047-2267): one pixel at a time ----

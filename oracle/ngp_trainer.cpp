@@ -114,6 +114,10 @@ extern "C" void orc_trainer_set_params(orc_trainer* t, const float* w_fp32) {
 	for (size_t i = 0; i < t->n_params; ++i) t->w_half[i] = f2h(t->w_fp32[i]);
 }
 
+extern "C" void orc_trainer_set_level_scales(orc_trainer* t, const float* scales) {
+	for (uint32_t l = 0; l < t->model.n_levels; ++l) t->model.scales[l] = scales[l];
+}
+
 extern "C" void orc_trainer_set_state(orc_trainer* t, uint32_t training_step, uint32_t rays_per_batch, const float* density_grid) {
 	t->training_step = training_step;
 	t->density_grid_ema_step = training_step;

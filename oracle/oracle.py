@@ -334,6 +334,9 @@ class Trainer:
     def training_step(self):
         return lib().orc_trainer_step(self._h)
 
+    def set_level_scales(self, scales):
+        lib().orc_trainer_set_level_scales(self._h, _p(_f32(scales)))
+
     def set_state(self, training_step, rays_per_batch=0, density_grid=None):
         g = _f32(density_grid) if density_grid is not None else None
         lib().orc_trainer_set_state(self._h, int(training_step), int(rays_per_batch), _p(g))

@@ -519,3 +519,47 @@ def test_render_empty_grid_is_background(L, orc):
     assert ns.value == 0 and nl.value >= 3
     np.testing.assert_allclose(out[..., :3], np.broadcast_to(np.array([0.2, 0.4, 0.6], np.float32), (24, 32, 3)), atol=2e-5)  # the sRGB pair uses the exponent 0.41666, not 1/2.4 (common_device.cuh:52)
     assert np.all(out[..., 3] == 1.0)
+
+
+# ------------------------------------------------------------------------------------------------------
+# whole iteration through the Testbed surface vs the oracle's whole-iteration restatement
+# ------------------------------------------------------------------------------------------------------
+def test_training_iteration_matches_oracle(L, orc, small_scene):
+    """Testbed::train on the GPU against oracle/ngp_trainer.cpp from the same seed. Initial parameters are bit-identical (same PCG32 streams,
+    tcnn's thread -> element mapping). After that the two runs differ only through floating-point paths (tensor-core MLP vs CPU), which
+    flips occupancy cells sitting on the threshold, so counters agree statistically: ray-batch controller within 5 %, loss within 25 %."""
+    import pyngp
+    tb = pyngp.Testbed()
+    tb.load_training_images(small_scene["images"], small_scene["xforms"], small_scene["fx"], small_scene["fy"])
+    imgs = orc.make_images(small_scene["images"], small_scene["xforms"], small_scene["fx"], small_scene["fy"])
+    ot = orc.Trainer(imgs, aabb_scale=1, seed=1337)
+    g, _ = pyngp.grid_init(device_scales=True)
+    ot.set_level_scales(np.array(g.scale[:16], np.float32))
+    assert tb.n_params == ot.n_params
+    w_gpu, h_gpu, _ = tb.get_params()
+    w_cpu, h_cpu, _ = ot.params()
+    assert np.array_equal(w_gpu.view(np.uint32), w_cpu.view(np.uint32))  # identical initialisation
+    assert np.array_equal(h_gpu.view(np.uint16), h_cpu.view(np.uint16))
+    batch = 1 << 14
+    n_steps = 5
+    cpu = [ot.train(batch) for _ in range(n_steps)]
+    gpu = []
+    for _ in range(n_steps):
+        r_before = tb.stats()["rays_per_batch"]
+        tb.train(batch)
+        st = tb.stats()
+        gpu.append(dict(rays_per_batch=r_before, loss=tb.loss, before=st["measured_batch_size_before_compaction"], after=st["measured_batch_size"]))
+    assert gpu[0]["rays_per_batch"] == cpu[0]["rays_per_batch"] == 4096
+    for k in range(n_steps):
+        for a, b, what in ((gpu[k]["rays_per_batch"], cpu[k]["rays_per_batch"], "rays_per_batch"),
+                           (gpu[k]["before"], cpu[k]["measured_batch_size_before_compaction"], "samples before compaction"),
+                           (gpu[k]["after"], cpu[k]["measured_batch_size"], "compacted samples")):
+            assert abs(a - b) <= 0.05 * b + 256, f"step {k}: {what} {a} vs {b}"
+    assert abs(gpu[0]["loss"] - cpu[0]["loss"]) <= 0.25 * cpu[0]["loss"]
+    # the occupancy grids agree except for cells on the threshold
+    _, bits_gpu = tb.get_density_grid()
+    bits_cpu = ot.bitfield()
+    n_bits = 128 ** 3
+    flips = int(np.unpackbits(bits_gpu[: n_bits // 8] ^ bits_cpu[: n_bits // 8]).sum())
+    occupied = int(np.unpackbits(bits_cpu[: n_bits // 8]).sum())
+    assert occupied > 1000 and flips <= 0.05 * occupied, f"{flips} of {occupied} occupancy bits differ"
