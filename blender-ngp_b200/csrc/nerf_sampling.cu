@@ -327,6 +327,9 @@ __global__ void __launch_bounds__(WRITE_RAYS_PER_BLOCK * 32) write_training_samp
 	}
 	const V3 wd = {(d.x + 1.0f) * 0.5f, (d.y + 1.0f) * 0.5f, (d.z + 1.0f) * 0.5f}; // warp_direction (:292)
 	const MarchWord* rw = words + (size_t)i * MARCH_MAX_WORDS;
+	// One lane per SAMPLE (a lane per word leaves most lanes idle: a ray's ~15 samples sit in two or three of its ~22 words).
+	// Words are taken 32 at a time (lane = word): prefix counts give every sample its word; the lane then replays that word's chain up to
+	// the sample's candidate (the same float additions as the march).
 	uint32_t carry = 0;
 	for (uint32_t w0 = 0; w0 < nw; w0 += 32) {
 		const uint32_t w = w0 + lane;
@@ -336,23 +339,33 @@ __global__ void __launch_bounds__(WRITE_RAYS_PER_BLOCK * 32) write_training_samp
 		uint32_t incl = n_here;
 		#pragma unroll
 		for (int k = 1; k < 32; k <<= 1) { const uint32_t tt = __shfl_up_sync(0xffffffffu, incl, k); if (lane >= (uint32_t)k) incl += tt; }
-		uint32_t j = carry + incl - n_here;
-		carry += __shfl_sync(0xffffffffu, incl, 31);
-		float t = mw.t;
-		uint32_t m = mw.emitted;
-		// replay this word's chain steps up to its last sample
-		while (m) {
-			const float dt = calc_dt(t, rec.cone_angle);
-			if (m & 1u) {
+		const uint32_t excl = incl - n_here;
+		const uint32_t n_chunk = __shfl_sync(0xffffffffu, incl, 31);
+		for (uint32_t s0 = 0; s0 < n_chunk; s0 += 32) {
+			const uint32_t s = s0 + lane; // sample index within this chunk of words
+			// the last word whose exclusive prefix is <= s holds sample s
+			uint32_t lo = 0;
+			#pragma unroll
+			for (uint32_t step = 16; step > 0; step >>= 1) {
+				const uint32_t cand = lo + step;
+				const uint32_t v = __shfl_sync(0xffffffffu, excl, cand & 31);
+				if (v <= s) lo = cand;
+			}
+			const uint32_t mask = __shfl_sync(0xffffffffu, mw.emitted, lo);
+			const float t_word = __shfl_sync(0xffffffffu, mw.t, lo);
+			const uint32_t rank = s - __shfl_sync(0xffffffffu, excl, lo);
+			if (s < n_chunk) {
+				const uint32_t bit = __fns(mask, 0, (int)rank + 1); // position of the (rank+1)-th set bit
+				float t = t_word;
+				for (uint32_t k = 0; k < bit; ++k) t += calc_dt(t, rec.cone_angle);
+				const float dt = calc_dt(t, rec.cone_angle);
 				const V3 pos = V3{o.x + t * d.x, o.y + t * d.y, o.z + t * d.z};
 				const V3 wp = warp_position(pos, aabb);
-				float* c = out + (size_t)j * COORD_FLOATS;
+				float* c = out + (size_t)(carry + s) * COORD_FLOATS;
 				c[0] = wp.x; c[1] = wp.y; c[2] = wp.z; c[3] = warp_dt(dt); c[4] = wd.x; c[5] = wd.y; c[6] = wd.z;
-				++j;
 			}
-			t += dt;
-			m >>= 1;
 		}
+		carry += n_chunk;
 	}
 }
 
