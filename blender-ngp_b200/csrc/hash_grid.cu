@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256) hash_encode_forward_kernel(
 // rounding. Same thread mapping as the forward kernel; dL/dy enters through shared memory (coalesced read of the block's 2 KB).
 __global__ void __launch_bounds__(ENC_SAMPLES * ENC_WARPS) hash_encode_backward_kernel(
 	const uint32_t n, const GridLevels L, const float* __restrict__ positions, const uint32_t pos_stride,
-	const __half2* __restrict__ dL_dencoded, float2* __restrict__ grid_grad)
+	const __half2* __restrict__ dL_dencoded, float2* __restrict__ grid_grad, const uint32_t level_begin, const uint32_t level_end)
 {
 	__shared__ __half2 tile[ENC_SAMPLES][NGPB_MAX_LEVELS + 1];
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(ENC_SAMPLES * ENC_WARPS) hash_encode_backward_
 	const uint32_t i = s0 + lane;
 	const bool valid = i < n; // (no early exit: the coarse levels use warp-wide shuffles)
 
-	for (uint32_t level = warp; level < L.n_levels; level += ENC_WARPS) {
+	for (uint32_t level = level_begin + warp; level < level_end; level += ENC_WARPS) {
 		const __half2 gh = valid ? tile[lane][level] : __floats2half2_rn(0.f, 0.f);
 		const float g0 = __low2float(gh), g1 = __high2float(gh);
 		const bool contributes = g0 != 0.f || g1 != 0.f; // a zero gradient adds nothing
@@ -243,11 +243,12 @@ void hash_encode_forward_launch(cudaStream_t stream, const ngpb_grid* g, const _
 	hash_encode_forward_kernel<<<(uint32_t)((threads + 255) / 256), 256, 0, stream>>>(n, n_dev, L, (const __half2*)grid, positions, pos_stride, (__half2*)encoded);
 	NGPB_LAUNCH_CHECK();
 }
+// [level_begin, level_end): the levels to scatter (all of them: 0, n_levels); the data-parallel pipeline launches level groups separately
 void hash_encode_backward_launch(cudaStream_t stream, const ngpb_grid* g, const float* positions, uint32_t pos_stride, uint32_t n,
-                                 const __half* dL_dencoded, float* grid_grad) {
-	if (n == 0) return;
+                                 const __half* dL_dencoded, float* grid_grad, uint32_t level_begin, uint32_t level_end) {
+	if (n == 0 || level_begin >= level_end) return;
 	const GridLevels L = make_levels(g);
-	hash_encode_backward_kernel<<<div_round_up(n, ENC_SAMPLES), ENC_SAMPLES * ENC_WARPS, 0, stream>>>(n, L, positions, pos_stride, (const __half2*)dL_dencoded, (float2*)grid_grad);
+	hash_encode_backward_kernel<<<div_round_up(n, ENC_SAMPLES), ENC_SAMPLES * ENC_WARPS, 0, stream>>>(n, L, positions, pos_stride, (const __half2*)dL_dencoded, (float2*)grid_grad, level_begin, level_end);
 	NGPB_LAUNCH_CHECK();
 }
 
@@ -315,7 +316,7 @@ extern "C" int ngpb_hash_encode_backward(void* stream, const ngpb_grid* g, const
                                          const ngpb_half* dL_dencoded, float* grid_grad) {
 	try {
 		if (!g || !positions || !dL_dencoded || !grid_grad || pos_stride < 3) { set_last_error("ngpb_hash_encode_backward: invalid argument"); return NGPB_ERR_INVALID_ARGUMENT; }
-		hash_encode_backward_launch((cudaStream_t)stream, g, positions, pos_stride, n, (const __half*)dL_dencoded, grid_grad);
+		hash_encode_backward_launch((cudaStream_t)stream, g, positions, pos_stride, n, (const __half*)dL_dencoded, grid_grad, 0, g->n_levels);
 		return 0;
 	} catch (const std::exception& e) { set_last_error(e.what()); return NGPB_ERR_RUNTIME; }
 }

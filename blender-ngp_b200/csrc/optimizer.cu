@@ -10,6 +10,7 @@
 // part in the EMA, exactly as in the reference.
 #include "common.cuh"
 #include <cmath>
+#include <cstring>
 #include "../../include/ngpb.h"
 
 namespace ngpb {
@@ -92,27 +93,47 @@ extern "C" void ngpb_optimizer_init(ngpb_optimizer* o) { // configs/nerf/base.js
 	o->step = 0; o->lr_factor = 1.0f;
 }
 
+namespace ngpb {
+// Host part of one optimizer step: the learning-rate schedule and EMA debiasing factors (advances o->step). Returned as an opaque blob of
+// sizeof(AdamParams) so that the testbed can launch the parameter sweep in chunks (data-parallel pipeline, testbed.cu).
+void optimizer_prepare(ngpb_optimizer* o, float loss_scale, void* params_out) {
+	// ExponentialDecayOptimizer::step reads the step count before Adam increments it (exponential_decay.h:60-72)
+	if (o->step == 0) o->lr_factor = 1.0f;
+	if (o->step >= o->decay_start && o->decay_interval > 0 && (o->step - o->decay_start) % o->decay_interval == 0) o->lr_factor *= o->decay_base;
+	AdamParams P{};
+	P.loss_scale = loss_scale;
+	P.base_lr = o->learning_rate * o->lr_factor;
+	P.beta1 = o->beta1; P.beta2 = o->beta2; P.epsilon = o->epsilon; P.l2_reg = o->l2_reg;
+	P.log2_beta1 = (float)std::log2((double)o->beta1); P.log2_beta2 = (float)std::log2((double)o->beta2);
+	++o->step; // AdamOptimizer::step (adam.h:152)
+	// EmaOptimizer::step (ema.h:102-108)
+	P.ema_decay = o->ema_decay;
+	P.ema_debias_old = 1 - (float)std::pow(o->ema_decay, o->step - 1);
+	P.ema_debias_new = 1.0f / (1 - (float)std::pow(o->ema_decay, o->step));
+	std::memcpy(params_out, &P, sizeof(P));
+}
+size_t optimizer_params_bytes() { return sizeof(AdamParams); }
+// Sweeps parameters [first, first + count) (first and count multiples of 4 except for the last range).
+void optimizer_launch(cudaStream_t stream, const void* params, uint32_t first, uint32_t count, uint32_t n_matrix_params, float* grad, float* w_fp32, __half* w_half,
+                      __half* w_ema, float* m1, float* m2, uint32_t* param_steps) {
+	if (count == 0) return;
+	AdamParams P;
+	std::memcpy(&P, params, sizeof(P));
+	P.n = count;
+	P.n_matrix = n_matrix_params > first ? n_matrix_params - first : 0u;
+	NGPB_STEP_KERNEL(adam_ema_kernel);
+	adam_ema_kernel<<<div_round_up(count / 4 + count % 4, 256), 256, 0, stream>>>(P, grad + first, w_fp32 + first, w_half + first, w_ema + first, m1 + first, m2 + first, param_steps + first);
+	NGPB_LAUNCH_CHECK();
+}
+} // namespace ngpb
+
 extern "C" int ngpb_optimizer_step(void* stream, ngpb_optimizer* o, uint32_t n_params, uint32_t n_matrix_params, float loss_scale, float* grad,
                                    float* w_fp32, ngpb_half* w_half, ngpb_half* w_ema, float* m1, float* m2, uint32_t* param_steps) {
 	try {
 		if (!o || !grad || !w_fp32 || !w_half || !w_ema || !m1 || !m2 || !param_steps) { set_last_error("ngpb_optimizer_step: invalid argument"); return NGPB_ERR_INVALID_ARGUMENT; }
-		// ExponentialDecayOptimizer::step reads the step count before Adam increments it (exponential_decay.h:60-72)
-		if (o->step == 0) o->lr_factor = 1.0f;
-		if (o->step >= o->decay_start && o->decay_interval > 0 && (o->step - o->decay_start) % o->decay_interval == 0) o->lr_factor *= o->decay_base;
 		AdamParams P;
-		P.n = n_params; P.n_matrix = n_matrix_params; P.loss_scale = loss_scale;
-		P.base_lr = o->learning_rate * o->lr_factor;
-		P.beta1 = o->beta1; P.beta2 = o->beta2; P.epsilon = o->epsilon; P.l2_reg = o->l2_reg;
-		P.log2_beta1 = (float)std::log2((double)o->beta1); P.log2_beta2 = (float)std::log2((double)o->beta2);
-		++o->step; // AdamOptimizer::step (adam.h:152)
-		// EmaOptimizer::step (ema.h:102-108)
-		P.ema_decay = o->ema_decay;
-		P.ema_debias_old = 1 - (float)std::pow(o->ema_decay, o->step - 1);
-		P.ema_debias_new = 1.0f / (1 - (float)std::pow(o->ema_decay, o->step));
-		if (n_params == 0) return 0;
-		NGPB_STEP_KERNEL(adam_ema_kernel);
-		adam_ema_kernel<<<div_round_up(n_params / 4 + n_params % 4, 256), 256, 0, (cudaStream_t)stream>>>(P, grad, w_fp32, (__half*)w_half, (__half*)w_ema, m1, m2, param_steps);
-		NGPB_LAUNCH_CHECK();
+		optimizer_prepare(o, loss_scale, &P);
+		optimizer_launch((cudaStream_t)stream, &P, 0, n_params, n_matrix_params, grad, w_fp32, (__half*)w_half, (__half*)w_ema, m1, m2, param_steps);
 		return 0;
 	} catch (const std::exception& e) { set_last_error(e.what()); return NGPB_ERR_RUNTIME; }
 }

@@ -16,7 +16,12 @@ namespace ngpb {
 
 // launchers defined in the kernel translation units
 void hash_encode_forward_launch(cudaStream_t stream, const ngpb_grid* g, const __half* grid, const float* positions, uint32_t pos_stride, uint32_t n, const uint32_t* n_dev, __half* encoded);
-void hash_encode_backward_launch(cudaStream_t stream, const ngpb_grid* g, const float* positions, uint32_t pos_stride, uint32_t n, const __half* dL_dencoded, float* grid_grad);
+void hash_encode_backward_launch(cudaStream_t stream, const ngpb_grid* g, const float* positions, uint32_t pos_stride, uint32_t n, const __half* dL_dencoded, float* grid_grad,
+                                 uint32_t level_begin, uint32_t level_end);
+void optimizer_prepare(ngpb_optimizer* o, float loss_scale, void* params_out);
+size_t optimizer_params_bytes();
+void optimizer_launch(cudaStream_t stream, const void* params, uint32_t first, uint32_t count, uint32_t n_matrix_params, float* grad, float* w_fp32, __half* w_half,
+                      __half* w_ema, float* m1, float* m2, uint32_t* param_steps);
 void nerf_mlp_forward_launch(cudaStream_t stream, const __half* mlp, const __half* encoded, const float* coords, uint32_t n, const uint32_t* n_dev, __half* rgbsigma);
 void nerf_density_mlp_launch(cudaStream_t stream, const __half* mlp, const __half* encoded, uint32_t n, __half* density);
 void nerf_mlp_forward_backward_launch(cudaStream_t stream, const __half* mlp, const __half* encoded, const float* coords, const __half* dL_dout, uint32_t n, __half* dL_dencoded, float* mlp_grad, float* partials);
@@ -132,7 +137,11 @@ ngpb_testbed::ngpb_testbed(int device_) : device(device_) {
 ngpb_testbed::~ngpb_testbed() {
 	cudaSetDevice(device);
 	if (sampling_stream) cudaStreamSynchronize(sampling_stream);
+	if (comm_stream) cudaStreamSynchronize(comm_stream);
 	if (stream) cudaStreamSynchronize(stream);
+	for (auto& e : dp_scatter_done) if (e) cudaEventDestroy(e);
+	for (auto& e : dp_reduce_done) if (e) cudaEventDestroy(e);
+	if (comm_stream) cudaStreamDestroy(comm_stream);
 	if (nccl_comm) { try { NcclApi::get().CommDestroy(nccl_comm); } catch (...) {} }
 	if (prefetch_done) cudaEventDestroy(prefetch_done);
 	if (loss_ready) cudaEventDestroy(loss_ready);
@@ -396,6 +405,26 @@ void ngpb_testbed::init_data_parallel(int rank, int world, const void* unique_id
 	NcclApi::UniqueId id;
 	std::memcpy(&id, unique_id128, sizeof(id));
 	nccl.check(nccl.CommInitRank(&nccl_comm, world, id, rank), "ncclCommInitRank");
+	if (!comm_stream) {
+		int prio_low = 0, prio_high = 0;
+		NGPB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
+		NGPB_CUDA_CHECK(cudaStreamCreateWithPriority(&comm_stream, cudaStreamNonBlocking, prio_high));
+		for (auto& e : dp_scatter_done) NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		for (auto& e : dp_reduce_done) NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+	}
+}
+
+// Level boundaries of the DP_CHUNKS parameter ranges: roughly equal numbers of grid entries per range.
+void ngpb_testbed::dp_level_split(uint32_t* split) const {
+	const uint32_t total = grid.offsets[grid.n_levels];
+	split[0] = 0;
+	uint32_t level = 0;
+	for (uint32_t c = 1; c < DP_CHUNKS; ++c) {
+		const uint64_t target = (uint64_t)total * c / DP_CHUNKS;
+		while (level < grid.n_levels && grid.offsets[level + 1] <= target) ++level;
+		split[c] = std::max(level, split[c - 1]);
+	}
+	split[DP_CHUNKS] = grid.n_levels;
 }
 
 // Launches K1 for the step described by `p` on stream `st`.
@@ -506,21 +535,48 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 	nerf_mlp_forward_backward_launch(stream, w_half, encoded, coords_compacted, dloss, batch, denc, grad, partials);
 	stage_end(NGPB_STAGE_MLP_TRAIN, batch, stream);
 	NGPB_CUDA_CHECK(cudaEventRecord(mlp_train_done, stream));
-	stage_begin(NGPB_STAGE_ENCODE_BACKWARD, stream);
-	hash_encode_backward_launch(stream, &grid, coords_compacted, COORD_FLOATS, batch, denc, grad + MLP_PARAMS);
-	stage_end(NGPB_STAGE_ENCODE_BACKWARD, batch, stream);
-	if (dp_world > 1) {
-		// the one exchange step of the path: sum of the shards' gradients = gradient of the global batch (the loss is normalised by the global
-		// ray count). fp32, in place, on the training stream; NCCL over NVLink / NVSwitch returns the same bits on every rank.
-		stage_begin(NGPB_STAGE_ALLREDUCE, stream);
+	if (dp_world == 1) {
+		stage_begin(NGPB_STAGE_ENCODE_BACKWARD, stream);
+		hash_encode_backward_launch(stream, &grid, coords_compacted, COORD_FLOATS, batch, denc, grad + MLP_PARAMS, 0, grid.n_levels);
+		stage_end(NGPB_STAGE_ENCODE_BACKWARD, batch, stream);
+		// optimizer (train_nerf :2950)
+		stage_begin(NGPB_STAGE_OPTIMIZER, stream);
+		check(ngpb_optimizer_step(stream, &opt, n_params, MLP_PARAMS, LOSS_SCALE, grad, w_fp32, (ngpb_half*)w_half, (ngpb_half*)w_ema, m1, m2, param_steps));
+		stage_end(NGPB_STAGE_OPTIMIZER, n_params, stream);
+	} else {
+		// Data parallel: the one exchange step of the path. The sum of the shards' gradients is the gradient of the global batch (the loss is
+		// normalised by the global ray count); fp32, in place, NCCL over NVLink / NVSwitch returns the same bits on every rank.
+		// Pipelined over DP_CHUNKS contiguous parameter ranges (MLP + levels 0-6 | 7-9 | 10-12 | 13-15 for the base config): the scatter-add of
+		// a level group runs on the training stream, its all-reduce on the communication stream as soon as the group is complete, and the
+		// optimizer sweep of a range as soon as its all-reduce is: scatter(g+1), all-reduce(g) and Adam(g-1) overlap.
 		NcclApi& nccl = NcclApi::get();
-		nccl.check(nccl.AllReduce(grad, grad, n_params, NcclApi::Float32, NcclApi::Sum, nccl_comm, stream), "ncclAllReduce(gradients)");
-		stage_end(NGPB_STAGE_ALLREDUCE, (uint64_t)n_params * 4, stream);
+		uint8_t opt_params[256];
+		optimizer_prepare(&opt, LOSS_SCALE, opt_params);
+		uint32_t level_split[DP_CHUNKS + 1];
+		dp_level_split(level_split);
+		stage_begin(NGPB_STAGE_ENCODE_BACKWARD, stream);
+		stage_begin(NGPB_STAGE_ALLREDUCE, comm_stream);
+		for (uint32_t c = 0; c < DP_CHUNKS; ++c) {
+			hash_encode_backward_launch(stream, &grid, coords_compacted, COORD_FLOATS, batch, denc, grad + MLP_PARAMS, level_split[c], level_split[c + 1]);
+			NGPB_CUDA_CHECK(cudaEventRecord(dp_scatter_done[c], stream));
+			const uint32_t first = c == 0 ? 0u : MLP_PARAMS + 2 * grid.offsets[level_split[c]];
+			const uint32_t last = MLP_PARAMS + 2 * grid.offsets[level_split[c + 1]];
+			NGPB_CUDA_CHECK(cudaStreamWaitEvent(comm_stream, dp_scatter_done[c], 0));
+			if (last > first) nccl.check(nccl.AllReduce(grad + first, grad + first, last - first, NcclApi::Float32, NcclApi::Sum, nccl_comm, comm_stream), "ncclAllReduce(gradients)");
+			NGPB_CUDA_CHECK(cudaEventRecord(dp_reduce_done[c], comm_stream));
+		}
+		stage_end(NGPB_STAGE_ENCODE_BACKWARD, batch, stream);
+		stage_end(NGPB_STAGE_ALLREDUCE, (uint64_t)n_params * 4, comm_stream);
+		stage_begin(NGPB_STAGE_OPTIMIZER, stream);
+		for (uint32_t c = 0; c < DP_CHUNKS; ++c) {
+			const uint32_t first = c == 0 ? 0u : MLP_PARAMS + 2 * grid.offsets[level_split[c]];
+			const uint32_t last = MLP_PARAMS + 2 * grid.offsets[level_split[c + 1]];
+			NGPB_CUDA_CHECK(cudaStreamWaitEvent(stream, dp_reduce_done[c], 0));
+			optimizer_launch(stream, opt_params, first, last - first, MLP_PARAMS, grad, w_fp32, w_half, w_ema, m1, m2, param_steps);
+		}
+		stage_end(NGPB_STAGE_OPTIMIZER, n_params, stream);
+		n_launches += 2 * (DP_CHUNKS - 1);
 	}
-	// optimizer (train_nerf :2950)
-	stage_begin(NGPB_STAGE_OPTIMIZER, stream);
-	check(ngpb_optimizer_step(stream, &opt, n_params, MLP_PARAMS, LOSS_SCALE, grad, w_fp32, (ngpb_half*)w_half, (ngpb_half*)w_ema, m1, m2, param_steps));
-	stage_end(NGPB_STAGE_OPTIMIZER, n_params, stream);
 	n_launches += 1 + 2 + 1 + 1;
 	// loss scalar every 16th step (:2885-2888): reduced on the device, read back without stalling the stream
 	if (get_loss_scalar) {

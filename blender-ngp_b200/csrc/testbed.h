@@ -41,6 +41,10 @@ struct ngpb_testbed {
 	// batch-size counters) are summed over NCCL before the optimizer, so the replicas stay bit-identical.
 	int dp_rank = 0, dp_world = 1;
 	void* nccl_comm = nullptr;
+	static constexpr uint32_t DP_CHUNKS = 4;
+	cudaStream_t comm_stream = nullptr;
+	cudaEvent_t dp_scatter_done[DP_CHUNKS] = {}, dp_reduce_done[DP_CHUNKS] = {};
+	void dp_level_split(uint32_t* split) const;
 	void init_data_parallel(int rank, int world, const void* unique_id128);
 	uint32_t inference_budget(uint32_t measured_before_compaction) const;
 
