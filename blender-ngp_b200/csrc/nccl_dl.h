@@ -14,13 +14,15 @@ namespace ngpb {
 struct NcclApi {
 	typedef struct { char internal[128]; } UniqueId;
 	typedef void* Comm;
-	enum { Uint32 = 3, Float32 = 7 };
+	enum { Uint32 = 3, Float16 = 6, Float32 = 7 };
 	enum { Sum = 0 };
 
 	int (*GetUniqueId)(UniqueId*) = nullptr;
 	int (*CommInitRank)(Comm*, int, UniqueId, int) = nullptr;
 	int (*CommDestroy)(Comm) = nullptr;
 	int (*AllReduce)(const void*, void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
+	int (*ReduceScatter)(const void*, void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
+	int (*AllGather)(const void*, void*, size_t, int, Comm, cudaStream_t) = nullptr;
 	const char* (*GetErrorString)(int) = nullptr;
 	int (*GroupStart)() = nullptr;
 	int (*GroupEnd)() = nullptr;
@@ -44,6 +46,8 @@ private:
 		a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(sym("ncclCommInitRank"));
 		a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(sym("ncclCommDestroy"));
 		a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(sym("ncclAllReduce"));
+		a.ReduceScatter = reinterpret_cast<decltype(a.ReduceScatter)>(sym("ncclReduceScatter"));
+		a.AllGather = reinterpret_cast<decltype(a.AllGather)>(sym("ncclAllGather"));
 		a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(sym("ncclGetErrorString"));
 		a.GroupStart = reinterpret_cast<decltype(a.GroupStart)>(sym("ncclGroupStart"));
 		a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(sym("ncclGroupEnd"));

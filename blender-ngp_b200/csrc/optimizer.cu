@@ -20,6 +20,7 @@ struct AdamParams {
 	float loss_scale, base_lr, beta1, beta2, epsilon, l2_reg;
 	float log2_beta1, log2_beta2;
 	float ema_decay, ema_debias_old, ema_debias_new;
+	uint32_t do_ema; // 0: the EMA is swept separately (sharded data-parallel optimizer)
 };
 
 // One parameter. Returns the fp16 value the EMA filters (the updated weight, or the unchanged one when Adam skips the entry).
@@ -39,7 +40,7 @@ __device__ __forceinline__ void adam_ema_one(const AdamParams& P, bool is_matrix
 		w = w - effective_learning_rate * m1; // weight decay terms are zero in nerf/base.json
 		wh = __float2half_rn(w);
 	}
-	ema = __float2half_rn((__half2float(ema) * P.ema_decay * P.ema_debias_old + __half2float(wh) * (1 - P.ema_decay)) * P.ema_debias_new);
+	if (P.do_ema) ema = __float2half_rn((__half2float(ema) * P.ema_decay * P.ema_debias_old + __half2float(wh) * (1 - P.ema_decay)) * P.ema_debias_new);
 }
 
 // Four parameters per thread (128-bit accesses on the fp32 arrays, 64-bit on the fp16 ones); n4 = n / 4 full groups, the tail is scalar.
@@ -72,15 +73,33 @@ __global__ void __launch_bounds__(256) adam_ema_kernel(const AdamParams P, float
 			reinterpret_cast<float4*>(m2)[q] = make_float4(bv[0], bv[1], bv[2], bv[3]);
 			reinterpret_cast<uint4*>(param_steps)[q] = make_uint4(sv[0], sv[1], sv[2], sv[3]);
 			reinterpret_cast<uint2*>(w_half)[q] = *reinterpret_cast<uint2*>(wh);
-		} else { // only the EMA moves
+		} else if (P.do_ema) { // only the EMA moves
 			#pragma unroll
 			for (int k = 0; k < 4; ++k) em[k] = __float2half_rn((__half2float(em[k]) * P.ema_decay * P.ema_debias_old + __half2float(wh[k]) * (1 - P.ema_decay)) * P.ema_debias_new);
 		}
-		reinterpret_cast<uint2*>(w_ema)[q] = *reinterpret_cast<uint2*>(em);
+		if (P.do_ema) reinterpret_cast<uint2*>(w_ema)[q] = *reinterpret_cast<uint2*>(em);
 	} else {
 		const uint32_t i = n4 * 4 + (q - n4);
 		if (i < P.n) adam_ema_one(P, i < P.n_matrix, grad[i], w_fp32[i], m1[i], m2[i], param_steps[i], w_half[i], w_ema[i]);
 	}
+}
+
+// EMA of the fp16 weights alone (ema_step_half_precision, ema.h:63-76), 8 parameters per thread; n rounded up to a multiple of 8 by the caller's padding.
+__global__ void __launch_bounds__(256) ema_sweep_kernel(const AdamParams P, const uint32_t n8, const __half* __restrict__ w_half, __half* __restrict__ w_ema)
+{
+	const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= n8) return;
+	const uint4 wr = reinterpret_cast<const uint4*>(w_half)[q];
+	uint4 er = reinterpret_cast<uint4*>(w_ema)[q];
+	const __half2* w2 = reinterpret_cast<const __half2*>(&wr);
+	__half2* e2 = reinterpret_cast<__half2*>(&er);
+	#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		const float2 w = __half22float2(w2[k]), e = __half22float2(e2[k]);
+		e2[k] = __floats2half2_rn((e.x * P.ema_decay * P.ema_debias_old + w.x * (1 - P.ema_decay)) * P.ema_debias_new,
+		                          (e.y * P.ema_decay * P.ema_debias_old + w.y * (1 - P.ema_decay)) * P.ema_debias_new);
+	}
+	reinterpret_cast<uint4*>(w_ema)[q] = er;
 }
 
 } // namespace ngpb
@@ -110,7 +129,17 @@ void optimizer_prepare(ngpb_optimizer* o, float loss_scale, void* params_out) {
 	P.ema_decay = o->ema_decay;
 	P.ema_debias_old = 1 - (float)std::pow(o->ema_decay, o->step - 1);
 	P.ema_debias_new = 1.0f / (1 - (float)std::pow(o->ema_decay, o->step));
+	P.do_ema = 1;
 	std::memcpy(params_out, &P, sizeof(P));
+}
+void optimizer_disable_fused_ema(void* params) { AdamParams P; std::memcpy(&P, params, sizeof(P)); P.do_ema = 0; std::memcpy(params, &P, sizeof(P)); }
+// EMA over parameters [0, n_padded), n_padded a multiple of 8 (the arrays are padded)
+void ema_sweep_launch(cudaStream_t stream, const void* params, uint32_t n_padded, const __half* w_half, __half* w_ema) {
+	AdamParams P;
+	std::memcpy(&P, params, sizeof(P));
+	NGPB_STEP_KERNEL(ema_sweep_kernel);
+	ema_sweep_kernel<<<div_round_up(n_padded / 8, 256), 256, 0, stream>>>(P, n_padded / 8, w_half, w_ema);
+	NGPB_LAUNCH_CHECK();
 }
 size_t optimizer_params_bytes() { return sizeof(AdamParams); }
 // Sweeps parameters [first, first + count) (first and count multiples of 4 except for the last range).

@@ -20,6 +20,8 @@ void hash_encode_backward_launch(cudaStream_t stream, const ngpb_grid* g, const 
                                  uint32_t level_begin, uint32_t level_end);
 void optimizer_prepare(ngpb_optimizer* o, float loss_scale, void* params_out);
 size_t optimizer_params_bytes();
+void optimizer_disable_fused_ema(void* params);
+void ema_sweep_launch(cudaStream_t stream, const void* params, uint32_t n_padded, const __half* w_half, __half* w_ema);
 void optimizer_launch(cudaStream_t stream, const void* params, uint32_t first, uint32_t count, uint32_t n_matrix_params, float* grad, float* w_fp32, __half* w_half,
                       __half* w_ema, float* m1, float* m2, uint32_t* param_steps);
 void nerf_mlp_forward_launch(cudaStream_t stream, const __half* mlp, const __half* encoded, const float* coords, uint32_t n, const uint32_t* n_dev, __half* rgbsigma);
@@ -137,11 +139,7 @@ ngpb_testbed::ngpb_testbed(int device_) : device(device_) {
 ngpb_testbed::~ngpb_testbed() {
 	cudaSetDevice(device);
 	if (sampling_stream) cudaStreamSynchronize(sampling_stream);
-	if (comm_stream) cudaStreamSynchronize(comm_stream);
 	if (stream) cudaStreamSynchronize(stream);
-	for (auto& e : dp_scatter_done) if (e) cudaEventDestroy(e);
-	for (auto& e : dp_reduce_done) if (e) cudaEventDestroy(e);
-	if (comm_stream) cudaStreamDestroy(comm_stream);
 	if (nccl_comm) { try { NcclApi::get().CommDestroy(nccl_comm); } catch (...) {} }
 	if (prefetch_done) cudaEventDestroy(prefetch_done);
 	if (loss_ready) cudaEventDestroy(loss_ready);
@@ -256,19 +254,23 @@ void ngpb_testbed::reset_network(uint32_t seed_) {
 	if (new_n_params != n_params) {
 		dfree(w_fp32); dfree(w_half); dfree(w_ema); dfree(m1); dfree(m2); dfree(param_steps); dfree(grad);
 		n_params = new_n_params;
-		w_fp32 = (float*)dalloc(sizeof(float) * n_params);
-		w_half = (__half*)dalloc(sizeof(__half) * n_params);
-		w_ema = (__half*)dalloc(sizeof(__half) * n_params);
-		m1 = (float*)dalloc(sizeof(float) * n_params);
-		m2 = (float*)dalloc(sizeof(float) * n_params);
-		param_steps = (uint32_t*)dalloc(sizeof(uint32_t) * n_params);
-		grad = (float*)dalloc(sizeof(float) * n_params);
+		n_alloc = n_params + 4096; // slack: the sharded data-parallel optimizer works on world x ceil(n_params / world) padded ranges
+		w_fp32 = (float*)dalloc(sizeof(float) * n_alloc);
+		w_half = (__half*)dalloc(sizeof(__half) * n_alloc);
+		w_ema = (__half*)dalloc(sizeof(__half) * n_alloc);
+		m1 = (float*)dalloc(sizeof(float) * n_alloc);
+		m2 = (float*)dalloc(sizeof(float) * n_alloc);
+		param_steps = (uint32_t*)dalloc(sizeof(uint32_t) * n_alloc);
+		grad = (float*)dalloc(sizeof(float) * n_alloc);
 	}
-	NGPB_CUDA_CHECK(cudaMemsetAsync(w_ema, 0, sizeof(__half) * n_params, stream));
-	NGPB_CUDA_CHECK(cudaMemsetAsync(m1, 0, sizeof(float) * n_params, stream));
-	NGPB_CUDA_CHECK(cudaMemsetAsync(m2, 0, sizeof(float) * n_params, stream));
-	NGPB_CUDA_CHECK(cudaMemsetAsync(param_steps, 0, sizeof(uint32_t) * n_params, stream));
-	NGPB_CUDA_CHECK(cudaMemsetAsync(grad, 0, sizeof(float) * n_params, stream));
+	NGPB_CUDA_CHECK(cudaMemsetAsync(w_fp32, 0, sizeof(float) * n_alloc, stream));
+	NGPB_CUDA_CHECK(cudaMemsetAsync(w_half, 0, sizeof(__half) * n_alloc, stream));
+	NGPB_CUDA_CHECK(cudaMemsetAsync(w_ema, 0, sizeof(__half) * n_alloc, stream));
+	NGPB_CUDA_CHECK(cudaMemsetAsync(m1, 0, sizeof(float) * n_alloc, stream));
+	NGPB_CUDA_CHECK(cudaMemsetAsync(m2, 0, sizeof(float) * n_alloc, stream));
+	NGPB_CUDA_CHECK(cudaMemsetAsync(param_steps, 0, sizeof(uint32_t) * n_alloc, stream));
+	NGPB_CUDA_CHECK(cudaMemsetAsync(grad, 0, sizeof(float) * n_alloc, stream));
+	master_weights_sharded = false;
 
 	// Trainer ctor (tcnn trainer.h:53-99): pcg32 seeded from std::seed_seq{seed}; xavier-uniform MLP matrices drawn on the
 	// host in parameter order (gpu_matrix.h:291-305), grid drawn on the device (grid.h:1364-1369).
@@ -405,27 +407,10 @@ void ngpb_testbed::init_data_parallel(int rank, int world, const void* unique_id
 	NcclApi::UniqueId id;
 	std::memcpy(&id, unique_id128, sizeof(id));
 	nccl.check(nccl.CommInitRank(&nccl_comm, world, id, rank), "ncclCommInitRank");
-	if (!comm_stream) {
-		int prio_low = 0, prio_high = 0;
-		NGPB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
-		NGPB_CUDA_CHECK(cudaStreamCreateWithPriority(&comm_stream, cudaStreamNonBlocking, prio_high));
-		for (auto& e : dp_scatter_done) NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-		for (auto& e : dp_reduce_done) NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-	}
 }
 
-// Level boundaries of the DP_CHUNKS parameter ranges: roughly equal numbers of grid entries per range.
-void ngpb_testbed::dp_level_split(uint32_t* split) const {
-	const uint32_t total = grid.offsets[grid.n_levels];
-	split[0] = 0;
-	uint32_t level = 0;
-	for (uint32_t c = 1; c < DP_CHUNKS; ++c) {
-		const uint64_t target = (uint64_t)total * c / DP_CHUNKS;
-		while (level < grid.n_levels && grid.offsets[level + 1] <= target) ++level;
-		split[c] = std::max(level, split[c - 1]);
-	}
-	split[DP_CHUNKS] = grid.n_levels;
-}
+// Parameters per rank of the sharded optimizer: ceil(n_params / world), rounded up to the vector width of the optimizer kernels.
+uint32_t ngpb_testbed::dp_shard_count() const { return next_multiple(div_round_up(n_params, (uint32_t)dp_world), 8u); }
 
 // Launches K1 for the step described by `p` on stream `st`.
 void ngpb_testbed::launch_sampling(cudaStream_t st, const SamplingRequest& p) {
@@ -545,37 +530,39 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 		stage_end(NGPB_STAGE_OPTIMIZER, n_params, stream);
 	} else {
 		// Data parallel: the one exchange step of the path. The sum of the shards' gradients is the gradient of the global batch (the loss is
-		// normalised by the global ray count); fp32, in place, NCCL over NVLink / NVSwitch returns the same bits on every rank.
-		// Pipelined over DP_CHUNKS contiguous parameter ranges (MLP + levels 0-6 | 7-9 | 10-12 | 13-15 for the base config): the scatter-add of
-		// a level group runs on the training stream, its all-reduce on the communication stream as soon as the group is complete, and the
-		// optimizer sweep of a range as soon as its all-reduce is: scatter(g+1), all-reduce(g) and Adam(g-1) overlap.
+		// normalised by the global ray count); everything is fp32 and NCCL over NVLink / NVSwitch returns the same bits on every rank.
+		stage_begin(NGPB_STAGE_ENCODE_BACKWARD, stream);
+		hash_encode_backward_launch(stream, &grid, coords_compacted, COORD_FLOATS, batch, denc, grad + MLP_PARAMS, 0, grid.n_levels);
+		stage_end(NGPB_STAGE_ENCODE_BACKWARD, batch, stream);
 		NcclApi& nccl = NcclApi::get();
 		uint8_t opt_params[256];
 		optimizer_prepare(&opt, LOSS_SCALE, opt_params);
-		uint32_t level_split[DP_CHUNKS + 1];
-		dp_level_split(level_split);
-		stage_begin(NGPB_STAGE_ENCODE_BACKWARD, stream);
-		stage_begin(NGPB_STAGE_ALLREDUCE, comm_stream);
-		for (uint32_t c = 0; c < DP_CHUNKS; ++c) {
-			hash_encode_backward_launch(stream, &grid, coords_compacted, COORD_FLOATS, batch, denc, grad + MLP_PARAMS, level_split[c], level_split[c + 1]);
-			NGPB_CUDA_CHECK(cudaEventRecord(dp_scatter_done[c], stream));
-			const uint32_t first = c == 0 ? 0u : MLP_PARAMS + 2 * grid.offsets[level_split[c]];
-			const uint32_t last = MLP_PARAMS + 2 * grid.offsets[level_split[c + 1]];
-			NGPB_CUDA_CHECK(cudaStreamWaitEvent(comm_stream, dp_scatter_done[c], 0));
-			if (last > first) nccl.check(nccl.AllReduce(grad + first, grad + first, last - first, NcclApi::Float32, NcclApi::Sum, nccl_comm, comm_stream), "ncclAllReduce(gradients)");
-			NGPB_CUDA_CHECK(cudaEventRecord(dp_reduce_done[c], comm_stream));
+		if (dp_sharded_optimizer) {
+			// reduce-scatter the gradients, run Adam on this rank's 1/world of the parameters, all-gather the updated fp16 weights; the EMA
+			// copy follows from the gathered weights on every rank. Moves 3/4 of the all-reduce's bytes and divides the optimizer sweep by world.
+			const uint32_t count = dp_shard_count(), first = (uint32_t)dp_rank * count;
+			const uint32_t mine = first < n_params ? std::min(count, n_params - first) : 0u;
+			stage_begin(NGPB_STAGE_ALLREDUCE, stream);
+			nccl.check(nccl.ReduceScatter(grad, grad + first, count, NcclApi::Float32, NcclApi::Sum, nccl_comm, stream), "ncclReduceScatter(gradients)");
+			stage_end(NGPB_STAGE_ALLREDUCE, (uint64_t)n_params * 4, stream);
+			stage_begin(NGPB_STAGE_OPTIMIZER, stream);
+			optimizer_disable_fused_ema(opt_params);
+			optimizer_launch(stream, opt_params, first, mine, MLP_PARAMS, grad, w_fp32, w_half, w_ema, m1, m2, param_steps);
+			NGPB_CUDA_CHECK(cudaMemsetAsync(grad, 0, sizeof(float) * n_alloc, stream)); // the other ranks' ranges still hold this rank's partial sums
+			nccl.check(nccl.AllGather(w_half + first, w_half, count, NcclApi::Float16, nccl_comm, stream), "ncclAllGather(weights)");
+			ema_sweep_launch(stream, opt_params, next_multiple(n_params, 8), w_half, w_ema);
+			stage_end(NGPB_STAGE_OPTIMIZER, n_params, stream);
+			master_weights_sharded = true;
+			n_launches += 3;
+		} else {
+			stage_begin(NGPB_STAGE_ALLREDUCE, stream);
+			nccl.check(nccl.AllReduce(grad, grad, n_params, NcclApi::Float32, NcclApi::Sum, nccl_comm, stream), "ncclAllReduce(gradients)");
+			stage_end(NGPB_STAGE_ALLREDUCE, (uint64_t)n_params * 4, stream);
+			stage_begin(NGPB_STAGE_OPTIMIZER, stream);
+			optimizer_launch(stream, opt_params, 0, n_params, MLP_PARAMS, grad, w_fp32, w_half, w_ema, m1, m2, param_steps);
+			stage_end(NGPB_STAGE_OPTIMIZER, n_params, stream);
+			n_launches += 1;
 		}
-		stage_end(NGPB_STAGE_ENCODE_BACKWARD, batch, stream);
-		stage_end(NGPB_STAGE_ALLREDUCE, (uint64_t)n_params * 4, comm_stream);
-		stage_begin(NGPB_STAGE_OPTIMIZER, stream);
-		for (uint32_t c = 0; c < DP_CHUNKS; ++c) {
-			const uint32_t first = c == 0 ? 0u : MLP_PARAMS + 2 * grid.offsets[level_split[c]];
-			const uint32_t last = MLP_PARAMS + 2 * grid.offsets[level_split[c + 1]];
-			NGPB_CUDA_CHECK(cudaStreamWaitEvent(stream, dp_reduce_done[c], 0));
-			optimizer_launch(stream, opt_params, first, last - first, MLP_PARAMS, grad, w_fp32, w_half, w_ema, m1, m2, param_steps);
-		}
-		stage_end(NGPB_STAGE_OPTIMIZER, n_params, stream);
-		n_launches += 2 * (DP_CHUNKS - 1);
 	}
 	n_launches += 1 + 2 + 1 + 1;
 	// loss scalar every 16th step (:2885-2888): reduced on the device, read back without stalling the stream
@@ -639,6 +626,14 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 void ngpb_testbed::get_params(float* o_fp32, ngpb_half* o_half, ngpb_half* o_ema) {
 	NGPB_CUDA_CHECK(cudaSetDevice(device));
 	NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
+	if (o_fp32 && dp_world > 1 && master_weights_sharded) {
+		// the fp32 master copy is only current in each rank's own range: gather it (a collective -- call get_params on every rank)
+		NcclApi& nccl = NcclApi::get();
+		const uint32_t count = dp_shard_count();
+		nccl.check(nccl.AllGather(w_fp32 + (size_t)dp_rank * count, w_fp32, count, NcclApi::Float32, nccl_comm, stream), "ncclAllGather(master weights)");
+		NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
+		master_weights_sharded = false;
+	}
 	if (o_fp32) NGPB_CUDA_CHECK(cudaMemcpy(o_fp32, w_fp32, sizeof(float) * n_params, cudaMemcpyDeviceToHost));
 	if (o_half) NGPB_CUDA_CHECK(cudaMemcpy(o_half, w_half, sizeof(__half) * n_params, cudaMemcpyDeviceToHost));
 	if (o_ema) NGPB_CUDA_CHECK(cudaMemcpy(o_ema, w_ema, sizeof(__half) * n_params, cudaMemcpyDeviceToHost));
@@ -646,6 +641,7 @@ void ngpb_testbed::get_params(float* o_fp32, ngpb_half* o_half, ngpb_half* o_ema
 
 void ngpb_testbed::set_params(const float* i_fp32) {
 	NGPB_CUDA_CHECK(cudaSetDevice(device));
+	master_weights_sharded = false;
 	NGPB_CUDA_CHECK(cudaMemcpyAsync(w_fp32, i_fp32, sizeof(float) * n_params, cudaMemcpyHostToDevice, stream));
 	cast_params_kernel<<<div_round_up(n_params, 256), 256, 0, stream>>>(n_params, w_fp32, w_half);
 	NGPB_LAUNCH_CHECK();
@@ -757,6 +753,7 @@ extern "C" int ngpb_testbed_set_option(ngpb_testbed* t, const char* name, double
 	else if (k == "exposure") t->exposure = (float)v;
 	else if (k == "background_color_a") t->background_alpha = (float)v;
 	else if (k == "render_with_training_params") t->render_with_training_params = v != 0;
+	else if (k == "dp_sharded_optimizer") t->dp_sharded_optimizer = v != 0;
 	else if (k == "overlap_sampling") { t->drop_prefetch(); t->overlap_sampling = v != 0; }
 	else throw std::runtime_error("unknown option: " + k);
 	NGPB_API_END

@@ -41,10 +41,9 @@ struct ngpb_testbed {
 	// batch-size counters) are summed over NCCL before the optimizer, so the replicas stay bit-identical.
 	int dp_rank = 0, dp_world = 1;
 	void* nccl_comm = nullptr;
-	static constexpr uint32_t DP_CHUNKS = 4;
-	cudaStream_t comm_stream = nullptr;
-	cudaEvent_t dp_scatter_done[DP_CHUNKS] = {}, dp_reduce_done[DP_CHUNKS] = {};
-	void dp_level_split(uint32_t* split) const;
+	bool dp_sharded_optimizer = true;    // reduce-scatter + Adam on 1/world of the parameters + all-gather (false: all-reduce + full Adam)
+	bool master_weights_sharded = false; // the fp32 master copy is current only in this rank's range
+	uint32_t dp_shard_count() const;
 	void init_data_parallel(int rank, int world, const void* unique_id128);
 	uint32_t inference_budget(uint32_t measured_before_compaction) const;
 
@@ -68,7 +67,7 @@ struct ngpb_testbed {
 	// model + optimizer state: fp32 master, fp16 training copy, fp16 EMA (inference) copy, Adam moments
 	// (tcnn Trainer buffer trainer.h:80,:317-332). Flat order: density net, rgb net, grid levels.
 	ngpb_grid grid{};
-	uint32_t n_params = 0;
+	uint32_t n_params = 0, n_alloc = 0;
 	float* w_fp32 = nullptr; __half* w_half = nullptr; __half* w_ema = nullptr;
 	float* m1 = nullptr; float* m2 = nullptr; uint32_t* param_steps = nullptr; float* grad = nullptr;
 	ngpb_optimizer opt{};
