@@ -40,6 +40,12 @@ __global__ void __launch_bounds__(1024) sum_kernel(const float* __restrict__ v, 
 	if (threadIdx.x == 0) *out = (float)sm[0];
 }
 
+__global__ void __launch_bounds__(256) widen_params_kernel(const uint32_t n, const __half* __restrict__ w_half, float* __restrict__ w_fp32)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) w_fp32[i] = __half2float(w_half[i]);
+}
+
 __global__ void __launch_bounds__(256) cast_params_kernel(const uint32_t n, const float* __restrict__ w_fp32, __half* __restrict__ w_half)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -227,13 +233,19 @@ void ngpb_testbed::load_training_data(uint32_t n, const ngpb_host_image* host_im
 	NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
 	h2d_bytes += total + sizeof(ngpb_image) * n;
 
+	configure_scene_box();
+	training_data_available = true;
+	reset_network(seed);
+}
+
+// load_nerf_post (src/testbed_nerf.cu:2714-2730): scene box, cascade count and cone angle follow from aabb_scale
+void ngpb_testbed::configure_scene_box() {
 	const float half = 0.5f * std::min(1u << (NERF_CASCADES - 1), aabb_scale);
 	for (int c = 0; c < 3; ++c) { aabb[c] = 0.5f - half; aabb[3 + c] = 0.5f + half; }
 	max_cascade = 0;
 	while ((1u << max_cascade) < aabb_scale) ++max_cascade;
 	cone_angle_constant = aabb_scale <= 1 ? 0.0f : (1.0f / 256.0f);
-	training_data_available = true;
-	reset_network(seed);
+	scene_configured = true;
 }
 
 // Testbed::reset_network (src/testbed.cu:2249-2470) for configs/nerf/base.json
@@ -446,7 +458,7 @@ void ngpb_testbed::collect_loss_scalar() {
 // Steps that refresh the occupancy grid first are not prefetched. Results are identical to the serial schedule.
 void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 	NGPB_CUDA_CHECK(cudaSetDevice(device));
-	if (!training_data_available) throw std::runtime_error("train: no training data loaded");
+	if (!training_data_available) throw std::runtime_error("train: no training data loaded (a snapshot alone can be rendered, not trained)");
 	if (batch != ws_batch) drop_prefetch();
 	ensure_workspace(batch);
 	auto check = [](int st) { if (st != 0) throw std::runtime_error(ngpb_last_error()); };
@@ -667,7 +679,7 @@ extern "C" int ngpb_testbed_load_training_data(ngpb_testbed* t, uint32_t n_image
 }
 extern "C" int ngpb_testbed_reset_network(ngpb_testbed* t, uint32_t seed) {
 	NGPB_API_BEGIN
-	if (!t->training_data_available) throw std::runtime_error("reset_network: load training data first (the grid resolution depends on aabb_scale)");
+	if (!t->scene_configured) throw std::runtime_error("reset_network: load training data or a snapshot first (the grid resolution depends on aabb_scale)");
 	t->reset_network(seed);
 	NGPB_API_END
 }
@@ -711,6 +723,82 @@ extern "C" int ngpb_nccl_unique_id(void* out128) {
 }
 extern "C" int ngpb_testbed_init_data_parallel(ngpb_testbed* t, int rank, int world, const void* unique_id128) {
 	NGPB_API_BEGIN t->init_data_parallel(rank, world, unique_id128); NGPB_API_END
+}
+
+extern "C" int ngpb_testbed_configure(ngpb_testbed* t, uint32_t aabb_scale, uint32_t seed) {
+	NGPB_API_BEGIN
+	if (aabb_scale == 0 || (aabb_scale & (aabb_scale - 1)) != 0 || aabb_scale > (1u << (NERF_CASCADES - 1))) throw std::runtime_error("aabb_scale must be a power of two <= 128");
+	NGPB_CUDA_CHECK(cudaSetDevice(t->device));
+	t->drop_prefetch();
+	t->aabb_scale = aabb_scale;
+	t->configure_scene_box();
+	t->reset_network(seed);
+	NGPB_API_END
+}
+extern "C" int ngpb_testbed_set_params_half(ngpb_testbed* t, const ngpb_half* params, uint32_t n) {
+	NGPB_API_BEGIN
+	if (!params || n != t->n_params) throw std::runtime_error("set_params_half: parameter count does not match the network (" + std::to_string(t->n_params) + ")");
+	NGPB_CUDA_CHECK(cudaSetDevice(t->device));
+	t->drop_prefetch();
+	NGPB_CUDA_CHECK(cudaMemcpyAsync(t->w_half, params, sizeof(__half) * n, cudaMemcpyHostToDevice, t->stream));
+	NGPB_CUDA_CHECK(cudaMemcpyAsync(t->w_ema, t->w_half, sizeof(__half) * n, cudaMemcpyDeviceToDevice, t->stream));
+	widen_params_kernel<<<div_round_up(n, 256), 256, 0, t->stream>>>(n, t->w_half, t->w_fp32);
+	NGPB_LAUNCH_CHECK();
+	NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
+	t->master_weights_sharded = false;
+	NGPB_API_END
+}
+extern "C" int ngpb_testbed_set_density_grid(ngpb_testbed* t, const float* density_grid, uint32_t n_cells) {
+	NGPB_API_BEGIN
+	const uint32_t expect = NERF_GRID_CELLS * (t->max_cascade + 1);
+	if (!density_grid || n_cells != expect) throw std::runtime_error("Incompatible number of grid cascades."); // src/testbed.cu:3093
+	NGPB_CUDA_CHECK(cudaSetDevice(t->device));
+	t->drop_prefetch();
+	NGPB_CUDA_CHECK(cudaMemcpyAsync(t->density_grid, density_grid, sizeof(float) * n_cells, cudaMemcpyHostToDevice, t->stream));
+	if (ngpb_update_bitfield(t->stream, t->max_cascade + 1, t->density_grid, t->mean_density, t->bitfield) != 0) throw std::runtime_error(ngpb_last_error());
+	NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
+	NGPB_API_END
+}
+extern "C" int ngpb_testbed_get_training_state(ngpb_testbed* t, ngpb_training_state* o) {
+	NGPB_API_BEGIN
+	NGPB_CUDA_CHECK(cudaSetDevice(t->device));
+	t->collect_loss_scalar();
+	*o = ngpb_training_state{t->training_step, t->rays_per_batch, t->measured_batch_size, t->measured_batch_size_before_compaction, t->loss_scalar,
+		t->opt.step, t->opt.learning_rate, t->opt.lr_factor};
+	NGPB_API_END
+}
+extern "C" int ngpb_testbed_set_training_state(ngpb_testbed* t, const ngpb_training_state* in) {
+	NGPB_API_BEGIN
+	NGPB_CUDA_CHECK(cudaSetDevice(t->device));
+	t->drop_prefetch();
+	t->training_step = in->training_step; t->density_grid_ema_step = in->training_step;
+	t->rays_per_batch = in->rays_per_batch ? in->rays_per_batch : (1u << 12);
+	t->measured_batch_size = in->measured_batch_size; t->measured_batch_size_before_compaction = in->measured_batch_size_before_compaction;
+	t->loss_scalar = in->loss; t->loss_pending = false;
+	t->opt.step = in->optimizer_step;
+	if (in->learning_rate > 0.f) t->opt.learning_rate = in->learning_rate;
+	t->opt.lr_factor = in->learning_rate_factor > 0.f ? in->learning_rate_factor : 1.0f;
+	NGPB_API_END
+}
+extern "C" int ngpb_testbed_get_optimizer_state(ngpb_testbed* t, float* fm, float* sm, uint32_t* ps) {
+	NGPB_API_BEGIN
+	if (t->dp_world > 1 && t->dp_sharded_optimizer) throw std::runtime_error("optimizer state is sharded across the data-parallel ranks; save without it");
+	NGPB_CUDA_CHECK(cudaSetDevice(t->device));
+	NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
+	if (fm) NGPB_CUDA_CHECK(cudaMemcpy(fm, t->m1, sizeof(float) * t->n_params, cudaMemcpyDeviceToHost));
+	if (sm) NGPB_CUDA_CHECK(cudaMemcpy(sm, t->m2, sizeof(float) * t->n_params, cudaMemcpyDeviceToHost));
+	if (ps) NGPB_CUDA_CHECK(cudaMemcpy(ps, t->param_steps, sizeof(uint32_t) * t->n_params, cudaMemcpyDeviceToHost));
+	NGPB_API_END
+}
+extern "C" int ngpb_testbed_set_optimizer_state(ngpb_testbed* t, const float* fm, const float* sm, const uint32_t* ps) {
+	NGPB_API_BEGIN
+	NGPB_CUDA_CHECK(cudaSetDevice(t->device));
+	t->drop_prefetch();
+	NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
+	if (fm) NGPB_CUDA_CHECK(cudaMemcpy(t->m1, fm, sizeof(float) * t->n_params, cudaMemcpyHostToDevice));
+	if (sm) NGPB_CUDA_CHECK(cudaMemcpy(t->m2, sm, sizeof(float) * t->n_params, cudaMemcpyHostToDevice));
+	if (ps) NGPB_CUDA_CHECK(cudaMemcpy(t->param_steps, ps, sizeof(uint32_t) * t->n_params, cudaMemcpyHostToDevice));
+	NGPB_API_END
 }
 
 extern "C" void* ngpb_testbed_stream(ngpb_testbed* t) { return t ? (void*)t->stream : nullptr; }

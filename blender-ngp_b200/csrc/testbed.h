@@ -55,7 +55,8 @@ struct ngpb_testbed {
 	std::vector<void*> allocations;
 
 	// dataset (NerfDataset, nerf_loader.h:66-110)
-	bool training_data_available = false;
+	bool training_data_available = false, scene_configured = false;
+	void configure_scene_box();
 	std::vector<ngpb_image> images;
 	ngpb_image* images_dev = nullptr;
 	uint8_t* pixels = nullptr;

@@ -93,6 +93,80 @@ class RenderConfig(C.Structure):  # ngpb_render_config
                 ("color_space", C.c_int32), ("output_srgb", C.c_int32), ("exposure", C.c_float), ("background_color", C.c_float * 4)]
 
 
+class TrainingState(C.Structure):  # ngpb_training_state
+    _fields_ = [("training_step", C.c_uint32), ("rays_per_batch", C.c_uint32), ("measured_batch_size", C.c_uint32), ("measured_batch_size_before_compaction", C.c_uint32),
+                ("loss", C.c_float), ("optimizer_step", C.c_uint32), ("learning_rate", C.c_float), ("learning_rate_factor", C.c_float)]
+
+
+# ---- snapshot container (reference: Testbed::save_snapshot / load_snapshot, src/testbed.cu:3008-3106; tcnn Trainer::serialize, trainer.h:270-310;
+# Ema / ExponentialDecay / Adam ::serialize, ema.h:190, exponential_decay.h:136, adam.h:282). nlohmann::json::to_msgpack of the network config with a
+# "snapshot" object; binary blobs are msgpack bin. Pure functions, usable without a GPU. ----
+SNAPSHOT_FORMAT_VERSION = 1
+
+
+def build_snapshot(network_config, params_half, density_grid, aabb_scale, aabb, training_step, loss, rays_per_batch, measured_batch_size,
+                   measured_batch_size_before_compaction, optimizer=None):
+    """Returns the dict the reference serialises. params_half: fp16 inference (EMA) parameters in the reference's flat order; density_grid: float32."""
+    snap = {
+        "n_params": int(params_half.shape[0]), "params_type": "__half", "params_binary": np.ascontiguousarray(params_half, np.float16).tobytes(),
+        "version": SNAPSHOT_FORMAT_VERSION, "density_grid_size": 128,
+        "density_grid_binary": np.ascontiguousarray(density_grid, np.float32).astype(np.float16).tobytes(),
+        "nerf": {"aabb_scale": int(aabb_scale), "rgb": {"rays_per_batch": int(rays_per_batch), "measured_batch_size": int(measured_batch_size),
+                                                        "measured_batch_size_before_compaction": int(measured_batch_size_before_compaction)}},
+        "training_step": int(training_step), "loss": float(loss),
+        "aabb": {"min": [float(v) for v in aabb[:3]], "max": [float(v) for v in aabb[3:]]}, "bounding_radius": 1.0,
+    }
+    if optimizer is not None:
+        snap["optimizer"] = {  # Ema -> ExponentialDecay -> Adam
+            "weights_ema_binary": np.ascontiguousarray(params_half, np.float16).tobytes(),
+            "nested": {"learning_rate": float(optimizer["learning_rate"]), "learning_rate_factor": float(optimizer["learning_rate_factor"]),
+                       "nested": {"current_step": int(optimizer["current_step"]), "base_learning_rate": float(optimizer["learning_rate"]),
+                                  "first_moments_binary": np.ascontiguousarray(optimizer["first_moments"], np.float32).tobytes(),
+                                  "second_moments_binary": np.ascontiguousarray(optimizer["second_moments"], np.float32).tobytes(),
+                                  "param_steps_binary": np.ascontiguousarray(optimizer["param_steps"], np.uint32).tobytes()}}}
+    cfg = json.loads(json.dumps(network_config))
+    cfg["snapshot"] = snap
+    return cfg
+
+
+def _blob(v, dtype):
+    if isinstance(v, dict) and "bytes" in v:  # nlohmann's JSON rendering of a binary value
+        v = bytes(v["bytes"])
+    return np.frombuffer(bytes(v), dtype=dtype).copy()
+
+
+def parse_snapshot(cfg):
+    """Inverse of build_snapshot for files written by the reference or by this module. Raises like the reference on malformed files."""
+    if "snapshot" not in cfg:
+        raise RuntimeError("File does not contain a snapshot.")
+    snap = cfg["snapshot"]
+    if snap.get("version", 0) < SNAPSHOT_FORMAT_VERSION:
+        raise RuntimeError("Snapshot uses an old format.")
+    if snap.get("density_grid_size", 128) != 128:
+        raise RuntimeError("Incompatible grid size.")
+    ptype = snap.get("params_type", "__half")
+    if ptype == "__half":
+        params = _blob(snap["params_binary"], np.float16)
+    elif ptype == "float":
+        params = _blob(snap["params_binary"], np.float32).astype(np.float16)
+    else:
+        raise RuntimeError("Trainer: snapshot parameters must be of type float of __half")
+    out = dict(params_half=params, density_grid=_blob(snap.get("density_grid_binary", b""), np.float16).astype(np.float32),
+               aabb_scale=int(snap.get("nerf", {}).get("aabb_scale", 1)), training_step=int(snap.get("training_step", 0)), loss=float(snap.get("loss", 0.0)),
+               rgb=snap.get("nerf", {}).get("rgb", {}), aabb=snap.get("aabb"), optimizer=None,
+               network_config={k: v for k, v in cfg.items() if k != "snapshot"})
+    if "optimizer" in snap:
+        o = snap["optimizer"]
+        decay = o.get("nested", {})
+        adam = decay.get("nested", {})
+        if "first_moments_binary" in adam:
+            out["optimizer"] = dict(current_step=int(adam.get("current_step", 0)), learning_rate=float(decay.get("learning_rate", adam.get("base_learning_rate", 1e-2))),
+                                    learning_rate_factor=float(decay.get("learning_rate_factor", 1.0)),
+                                    first_moments=_blob(adam["first_moments_binary"], np.float32), second_moments=_blob(adam["second_moments_binary"], np.float32),
+                                    param_steps=_blob(adam["param_steps_binary"], np.uint32) if "param_steps_binary" in adam else None)
+    return out
+
+
 # every symbol include/ngpb.h declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = [
     "ngpb_last_error", "ngpb_version", "ngpb_check_device", "ngpb_grid_init", "ngpb_hash_encode_forward", "ngpb_hash_encode_backward",
@@ -102,7 +176,8 @@ EXPORTED_SYMBOLS = [
     "ngpb_testbed_create", "ngpb_testbed_destroy", "ngpb_testbed_load_training_data", "ngpb_testbed_reset_network", "ngpb_testbed_train",
     "ngpb_testbed_train_n", "ngpb_testbed_loss", "ngpb_testbed_training_step", "ngpb_testbed_stats", "ngpb_testbed_n_params",
     "ngpb_testbed_get_params", "ngpb_testbed_set_params", "ngpb_testbed_get_density_grid", "ngpb_testbed_set_option", "ngpb_testbed_get_option",
-    "ngpb_testbed_render", "ngpb_testbed_stream", "ngpb_testbed_stage_times", "ngpb_grid_device_scales", "ngpb_generate_training_samples_sharded", "ngpb_compute_loss_sharded", "ngpb_nccl_unique_id", "ngpb_testbed_init_data_parallel", "ngpb_render_workspace_bytes", "ngpb_render_nerf", "ngpb_testbed_last_render_ms", "ngpb_generate_training_samples_scratch_bytes", "ngpb_compute_loss_scratch_bytes",
+    "ngpb_testbed_render", "ngpb_testbed_stream", "ngpb_testbed_stage_times", "ngpb_grid_device_scales", "ngpb_testbed_configure", "ngpb_testbed_set_params_half", "ngpb_testbed_set_density_grid", "ngpb_testbed_get_training_state",
+    "ngpb_testbed_set_training_state", "ngpb_testbed_get_optimizer_state", "ngpb_testbed_set_optimizer_state", "ngpb_generate_training_samples_sharded", "ngpb_compute_loss_sharded", "ngpb_nccl_unique_id", "ngpb_testbed_init_data_parallel", "ngpb_render_workspace_bytes", "ngpb_render_nerf", "ngpb_testbed_last_render_ms", "ngpb_generate_training_samples_scratch_bytes", "ngpb_compute_loss_scratch_bytes",
 ]
 
 _lib = None
@@ -478,6 +553,60 @@ class Testbed:
     def stream(self):
         """cudaStream_t (as int) every kernel of this testbed runs on."""
         return int(lib().ngpb_testbed_stream(self._h) or 0)
+
+    # -- snapshots
+    def save_snapshot(self, path, include_optimizer_state=False):
+        """Testbed::save_snapshot (src/testbed.cu:3008): msgpack of the network config + snapshot object, readable by the reference."""
+        import msgpack
+        st = TrainingState()
+        check(lib().ngpb_testbed_get_training_state(self._h, C.byref(st)))
+        _, _, ema = self.get_params()
+        grid, _ = self.get_density_grid()
+        opt = None
+        if include_optimizer_state:
+            n = self.n_params
+            fm = np.empty(n, np.float32); sm = np.empty(n, np.float32); ps = np.empty(n, np.uint32)
+            check(lib().ngpb_testbed_get_optimizer_state(self._h, fm.ctypes.data_as(C.c_void_p), sm.ctypes.data_as(C.c_void_p), ps.ctypes.data_as(C.c_void_p)))
+            opt = dict(current_step=st.optimizer_step, learning_rate=st.learning_rate, learning_rate_factor=st.learning_rate_factor, first_moments=fm, second_moments=sm, param_steps=ps)
+        half = 0.5 * min(128, int(self._get("aabb_scale")))
+        aabb = [0.5 - half] * 3 + [0.5 + half] * 3
+        cfg = build_snapshot(self.network_config, ema, grid, int(self._get("aabb_scale")), aabb, st.training_step, st.loss, st.rays_per_batch,
+                             st.measured_batch_size, st.measured_batch_size_before_compaction, opt)
+        with open(path, "wb") as f:
+            f.write(msgpack.packb(cfg, use_bin_type=True))
+
+    def load_snapshot(self, path):
+        """Testbed::load_snapshot (src/testbed.cu:3044): restores network, occupancy grid and training counters; without a loaded dataset the
+        session can render but not train."""
+        import msgpack
+        with open(path, "rb") as f:
+            cfg = msgpack.unpackb(f.read(), raw=False, strict_map_key=False)
+        snap = parse_snapshot(cfg)
+        _validate_network_config(snap["network_config"])
+        self.network_config = snap["network_config"]
+        check(lib().ngpb_testbed_configure(self._h, snap["aabb_scale"], self._seed))
+        params = np.ascontiguousarray(snap["params_half"], np.float16)
+        check(lib().ngpb_testbed_set_params_half(self._h, params.ctypes.data_as(C.c_void_p), int(params.shape[0])))
+        if snap["density_grid"].size:
+            grid = np.ascontiguousarray(snap["density_grid"], np.float32)
+            check(lib().ngpb_testbed_set_density_grid(self._h, grid.ctypes.data_as(C.c_void_p), int(grid.shape[0])))
+        st = TrainingState()
+        st.training_step = snap["training_step"]; st.loss = snap["loss"]
+        st.rays_per_batch = int(snap["rgb"].get("rays_per_batch", 1 << 12))
+        st.measured_batch_size = int(snap["rgb"].get("measured_batch_size", 0))
+        st.measured_batch_size_before_compaction = int(snap["rgb"].get("measured_batch_size_before_compaction", 0))
+        opt = snap["optimizer"]
+        st.optimizer_step = opt["current_step"] if opt else snap["training_step"]
+        st.learning_rate = opt["learning_rate"] if opt else 0.0
+        st.learning_rate_factor = opt["learning_rate_factor"] if opt else 1.0
+        check(lib().ngpb_testbed_set_training_state(self._h, C.byref(st)))
+        if opt:
+            n = self.n_params
+            ps = opt["param_steps"] if opt["param_steps"] is not None else np.zeros(n, np.uint32)
+            fm, sm, ps = (np.ascontiguousarray(a) for a in (opt["first_moments"], opt["second_moments"], ps))
+            if not (fm.shape[0] == sm.shape[0] == ps.shape[0] == n):
+                raise RuntimeError("snapshot optimizer state does not match the parameter count")
+            check(lib().ngpb_testbed_set_optimizer_state(self._h, fm.ctypes.data_as(C.c_void_p), sm.ctypes.data_as(C.c_void_p), ps.ctypes.data_as(C.c_void_p)))
 
     # -- parameters / state
     def get_params(self):

@@ -243,6 +243,27 @@ enum { NGPB_STAGE_SAMPLING = 0,      /* K1  generate_training_samples           
        NGPB_N_STAGES };
 /* ms[NGPB_N_STAGES], calls[NGPB_N_STAGES], units[NGPB_N_STAGES]: accumulated since the last reset (reset != 0 clears). */
 int ngpb_testbed_stage_times(ngpb_testbed* t, double* ms, uint64_t* calls, uint64_t* units, int reset);
+/* ---- snapshot state (Testbed::save_snapshot / load_snapshot, src/testbed.cu:3008-3106; tcnn Trainer::serialize / deserialize, trainer.h:270-310).
+ * The .msgpack container itself is written / read by the host binding (pyngp.save_snapshot / load_snapshot); these calls move the state. ---- */
+/* Configures the scene box like load_nerf_post (src/testbed_nerf.cu:2714-2730) WITHOUT a dataset and resets the network: what load_snapshot does
+ * for a render-only session. */
+int ngpb_testbed_configure(ngpb_testbed* t, uint32_t aabb_scale, uint32_t seed);
+/* Trainer::deserialize for params_type "__half": the fp16 snapshot parameters become the training, inference (EMA) and fp32 master copies. */
+int ngpb_testbed_set_params_half(ngpb_testbed* t, const ngpb_half* params, uint32_t n_params);
+/* density_grid: float[128^3 * (max_cascade + 1)] (host). Uploads it and recomputes mean + bitfield (update_density_grid_mean_and_bitfield, :2844). */
+int ngpb_testbed_set_density_grid(ngpb_testbed* t, const float* density_grid, uint32_t n_cells);
+typedef struct {
+	uint32_t training_step, rays_per_batch, measured_batch_size, measured_batch_size_before_compaction;
+	float loss;
+	uint32_t optimizer_step;          /* Adam current_step (adam.h:284) */
+	float learning_rate, learning_rate_factor; /* ExponentialDecay state (exponential_decay.h:139-140) */
+} ngpb_training_state;
+int ngpb_testbed_get_training_state(ngpb_testbed* t, ngpb_training_state* out);
+int ngpb_testbed_set_training_state(ngpb_testbed* t, const ngpb_training_state* in);
+/* Adam moments and per-parameter step counters (host buffers of n_params elements each; any may be NULL). */
+int ngpb_testbed_get_optimizer_state(ngpb_testbed* t, float* first_moments, float* second_moments, uint32_t* param_steps);
+int ngpb_testbed_set_optimizer_state(ngpb_testbed* t, const float* first_moments, const float* second_moments, const uint32_t* param_steps);
+
 /* training options exposed as pyngp properties (python_api.cu:650-852) */
 int ngpb_testbed_set_option(ngpb_testbed* t, const char* name, double value);
 double ngpb_testbed_get_option(ngpb_testbed* t, const char* name);

@@ -60,3 +60,33 @@ def test_missing_gpu_fails_loudly():
         pytest.skip("a GPU is present")
     with pytest.raises(RuntimeError):
         pyngp.Testbed()
+
+
+def test_snapshot_container_round_trip():
+    """The .msgpack snapshot container (reference: src/testbed.cu:3008-3106) built and parsed without a GPU: binary blobs survive, the keys the
+    reference's loaders read (nerf/neural_radiance_field.cuh:163-298) are present, malformed files raise like the reference."""
+    import msgpack
+    import pytest
+    import pyngp
+    rs = np.random.RandomState(0)
+    n = 10240 + 64
+    params = rs.randn(n).astype(np.float16)
+    grid = (rs.rand(128 ** 3) * 0.02).astype(np.float32)
+    opt = dict(current_step=7, learning_rate=1e-2, learning_rate_factor=0.33, first_moments=rs.randn(n).astype(np.float32),
+               second_moments=rs.rand(n).astype(np.float32), param_steps=rs.randint(0, 9, n).astype(np.uint32))
+    cfg = pyngp.build_snapshot(pyngp.BASE_NETWORK_CONFIG, params, grid, 1, [0, 0, 0, 1, 1, 1], 123, 0.5, 4096, 1000, 2000, opt)
+    raw = msgpack.packb(cfg, use_bin_type=True)
+    back = msgpack.unpackb(raw, raw=False, strict_map_key=False)
+    for key in ("version", "density_grid_size", "density_grid_binary", "params_binary", "params_type", "n_params", "training_step", "loss", "aabb", "nerf"):
+        assert key in back["snapshot"]
+    assert back["snapshot"]["nerf"]["aabb_scale"] == 1 and back["encoding"]["otype"] == "HashGrid"
+    snap = pyngp.parse_snapshot(back)
+    assert np.array_equal(snap["params_half"].view(np.uint16), params.view(np.uint16))
+    assert np.array_equal(snap["density_grid"], grid.astype(np.float16).astype(np.float32))
+    assert snap["training_step"] == 123 and snap["rgb"]["rays_per_batch"] == 4096
+    assert np.array_equal(snap["optimizer"]["first_moments"], opt["first_moments"]) and snap["optimizer"]["learning_rate_factor"] == np.float32(0.33)
+    with pytest.raises(RuntimeError):
+        pyngp.parse_snapshot({"encoding": {}})
+    old = dict(back); old["snapshot"] = dict(back["snapshot"], version=0)
+    with pytest.raises(RuntimeError):
+        pyngp.parse_snapshot(old)
