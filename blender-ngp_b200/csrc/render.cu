@@ -16,6 +16,9 @@
 
 #include <algorithm>
 #include <cstring>
+#include <cmath>
+#include <stdexcept>
+#include <vector>
 
 namespace ngpb {
 
@@ -383,4 +386,422 @@ extern "C" int ngpb_render_nerf(void* stream_, const ngpb_render_config* cfg, co
 		cudaFreeHost(host_counter);
 		return 0;
 	} catch (const std::exception& e) { set_last_error(e.what()); return NGPB_ERR_RUNTIME; }
+}
+
+// =====================================================================================================================
+// K18: the Blender multi-NeRF renderer (the fork's addition). Replaces NerfRenderer::render (reference: src/nerf_renderer.cu:565-791):
+// init_global_rays_kernel :17-92, init_proxy_rays_kernel :94-146, compact_rays_kernel :240-270, march_active_rays :274-315,
+// cull_global_rays_and_set_proxy_rays_active_kernel :376-428, march_proxy_rays_and_generate_next_network_inputs :317-373,
+// composite_proxy_ray_colors_kernel :431-517, shade_buffer_with_rays_kernel :519-563, and Testbed::bl_render_frame (src/testbed.cu:2675).
+//
+// One global ray per (down-sampled) pixel and one proxy ray per NeRF in that NeRF's local frame. Every wave the nearest live proxy of a
+// ray becomes its active one, marches clamp(n_initial / n_alive, 1, 8) steps through its NeRF and is composited into the global ray's
+// colour with the NeRF's opacity. The image depends on that wave schedule, so the schedule is the reference's, including one live-ray
+// count read-back per wave; inside a wave the per-ray kernels are merged (init global+proxy, march+cull, compact+shade) and compaction
+// uses one atomic per warp. Each NeRF brings its own parameters, hash-grid geometry and occupancy bits (an ngpb_field).
+// Perspective camera; render masks and depth of field are not built.
+// =====================================================================================================================
+namespace ngpb {
+
+struct BlGlobalRay { float o[3]; uint32_t idx; float d[3]; uint32_t alive; float rgba[4]; };
+struct BlProxyRay { float o[3]; float t; float d[3]; uint32_t n_steps; uint32_t alive, active; uint32_t pad[2]; };
+struct BlNerfProps {
+	float transform[16], itransform[16]; // column-major
+	const uint8_t* bitfield;
+	Aabb render_aabb, train_aabb;
+	float cone_angle, opacity, min_transmittance;
+	int32_t rgb_activation, density_activation;
+};
+struct BlRequest {
+	int32_t width, height, skip, scaled_w, scaled_h, flip_y;
+	float cam[12], focal_length, near_distance, offset[2];
+};
+constexpr uint32_t BL_MAX_NERFS = 16;
+
+__device__ __forceinline__ float sum4(float a, float b, float c, float d) { return (a + b) + (c + d); }
+__device__ __forceinline__ V3 xform_point(const float* M, const V3& p) {
+	return {sum4(M[0] * p.x, M[4] * p.y, M[8] * p.z, M[12]), sum4(M[1] * p.x, M[5] * p.y, M[9] * p.z, M[13]), sum4(M[2] * p.x, M[6] * p.y, M[10] * p.z, M[14])};
+}
+__device__ __forceinline__ V3 xform_dir(const float* M, const V3& d) {
+	return {sum3(M[0] * d.x, M[4] * d.y, M[8] * d.z), sum3(M[1] * d.x, M[5] * d.y, M[9] * d.z), sum3(M[2] * d.x, M[6] * d.y, M[10] * d.z)};
+}
+__device__ __forceinline__ V3 normalized3(const V3& v) {
+	const float z = sum3(v.x * v.x, v.y * v.y, v.z * v.z);
+	if (z > 0.f) { const float n = sqrtf(z); return {v.x / n, v.y / n, v.z / n}; }
+	return v;
+}
+
+// hit_test_and_march (:149-211), no masks: advances t to the next sample position inside an occupied cell; false = left the NeRF's render box
+__device__ __forceinline__ bool hit_test_and_march(const V3& o, const V3& d, const V3& idir, float t_in, const BlNerfProps& P, float* t_out, float* dt_out) {
+	float t = t_in, dt = 0.0f, prev_t = t;
+	while (true) {
+		const V3 pos = V3{o.x + d.x * t, o.y + d.y * t, o.z + d.z * t};
+		if (!aabb_contains(P.render_aabb, pos)) { *t_out = prev_t; if (dt_out) *dt_out = dt; return false; }
+		dt = calc_dt(t, P.cone_angle);
+		const uint32_t mip = (uint32_t)max(0, mip_from_dt(dt, pos));
+		if (density_grid_occupied_at(pos, P.bitfield, mip)) break;
+		prev_t = t;
+		t = advance_to_next_voxel(t, P.cone_angle, pos, d, idir, NERF_GRIDSIZE >> mip);
+	}
+	*t_out = t; if (dt_out) *dt_out = dt;
+	return true;
+}
+
+// init_global_rays_kernel + init_proxy_rays_kernel: one thread per down-sampled pixel
+__global__ void __launch_bounds__(128) bl_init_rays_kernel(const BlRequest R, const uint32_t n_nerfs, const BlNerfProps* __restrict__ props, const uint32_t stride,
+                                                           BlGlobalRay* __restrict__ rays, BlProxyRay* __restrict__ proxies)
+{
+	const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= (uint32_t)R.scaled_w * (uint32_t)R.scaled_h) return;
+	const uint32_t x = (idx % (uint32_t)R.scaled_w) * R.skip, y = (idx / (uint32_t)R.scaled_w) * R.skip;
+	const float uvx = ((float)x + R.offset[0]) / (float)R.width, uvy = ((float)y + R.offset[1]) / (float)R.height;
+	const float dcam[3] = {(uvx - 0.5f) * (float)R.width / R.focal_length, (uvy - 0.5f) * (float)R.height / R.focal_length, 1.0f};
+	const float row0[3] = {R.cam[0], R.cam[3], R.cam[6]}, row1[3] = {R.cam[1], R.cam[4], R.cam[7]}, row2[3] = {R.cam[2], R.cam[5], R.cam[8]};
+	const V3 dw = {dot3(row0, dcam), dot3(row1, dcam), dot3(row2, dcam)};
+	const V3 go = {R.cam[9] + dw.x * R.near_distance, R.cam[10] + dw.y * R.near_distance, R.cam[11] + dw.z * R.near_distance};
+	const V3 gd = normalized3(dw);
+	BlGlobalRay g;
+	g.o[0] = go.x; g.o[1] = go.y; g.o[2] = go.z; g.d[0] = gd.x; g.d[1] = gd.y; g.d[2] = gd.z;
+	g.idx = idx; g.alive = 1u; g.rgba[0] = g.rgba[1] = g.rgba[2] = g.rgba[3] = 0.f;
+	rays[idx] = g;
+	for (uint32_t n = 0; n < n_nerfs; ++n) {
+		const BlNerfProps& P = props[n];
+		BlProxyRay p{};
+		const V3 o = xform_point(P.itransform, go);
+		const V3 d = normalized3(xform_dir(P.itransform, normalized3(gd)));
+		float tmin, tmax;
+		aabb_ray_intersect(P.render_aabb, o, d, &tmin, &tmax);
+		const float t = fmaxf(tmin, 0.0f) + 1e-5f;
+		p.d[0] = d.x; p.d[1] = d.y; p.d[2] = d.z;
+		if (aabb_contains(P.render_aabb, V3{o.x + d.x * t, o.y + d.y * t, o.z + d.z * t})) {
+			p.active = 1u; p.alive = 1u; p.t = 0.0f; p.n_steps = 0;
+			p.o[0] = o.x + t * d.x; p.o[1] = o.y + t * d.y; p.o[2] = o.z + t * d.z;
+		}
+		proxies[(size_t)n * stride + idx] = p;
+	}
+}
+
+// compact_rays_kernel + shade_buffer_with_rays_kernel: live rays (with their proxies) move to the next list, finished rays are shaded
+__global__ void __launch_bounds__(128) bl_compact_kernel(const BlRequest R, const uint32_t* __restrict__ n_in_dev, const uint32_t n_nerfs, const uint32_t stride,
+                                                         const BlGlobalRay* __restrict__ rays_in, const BlProxyRay* __restrict__ proxies_in,
+                                                         BlGlobalRay* __restrict__ rays_out, BlProxyRay* __restrict__ proxies_out, uint32_t* __restrict__ n_out_dev,
+                                                         float4* __restrict__ frame_buffer)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool in_range = i < *n_in_dev;
+	BlGlobalRay g{};
+	if (in_range) g = rays_in[i];
+	const bool alive = in_range && g.alive;
+	const uint32_t slot = warp_append(alive, n_out_dev);
+	if (alive) {
+		rays_out[slot] = g;
+		for (uint32_t n = 0; n < n_nerfs; ++n) proxies_out[(size_t)n * stride + slot] = proxies_in[(size_t)n * stride + i];
+	} else if (in_range && g.rgba[3] > 0.001f) {
+		const uint32_t x = R.skip * (g.idx % (uint32_t)R.scaled_w);
+		uint32_t y = R.skip * (g.idx / (uint32_t)R.scaled_w);
+		if (R.flip_y) y = R.height - y - 1;
+		const float4 tmp = make_float4(srgb_to_linear(g.rgba[0]), srgb_to_linear(g.rgba[1]), srgb_to_linear(g.rgba[2]), g.rgba[3]); // train_in_linear_colors = false (:599)
+		const uint32_t max_pixels = (uint32_t)R.width * (uint32_t)R.height;
+		for (int u = 0; u < R.skip; ++u) for (int v = 0; v < R.skip; ++v) {
+			const uint32_t pix = (x + u) + (y + v) * (uint32_t)R.width;
+			if (pix >= max_pixels) continue;
+			const float4 f = frame_buffer[pix];
+			const float k = 1.0f - tmp.w;
+			frame_buffer[pix] = make_float4(tmp.x + f.x * k, tmp.y + f.y * k, tmp.z + f.z * k, tmp.w + f.w * k);
+		}
+	}
+}
+
+// march_active_rays + cull_global_rays_and_set_proxy_rays_active_kernel
+__global__ void __launch_bounds__(128) bl_march_cull_kernel(const uint32_t n_alive, const uint32_t n_nerfs, const BlNerfProps* __restrict__ props, const uint32_t stride,
+                                                            const float cam_x, const float cam_y, const float cam_z, BlGlobalRay* __restrict__ rays, BlProxyRay* __restrict__ proxies)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_alive) return;
+	if (!rays[i].alive) return;
+	float min_d2 = 0.0f;
+	int active = -1;
+	uint32_t n_proxy_alive = 0;
+	for (uint32_t n = 0; n < n_nerfs; ++n) {
+		BlProxyRay& pr = proxies[(size_t)n * stride + i];
+		BlProxyRay p = pr;
+		if (p.alive && p.active) {
+			const V3 o = {p.o[0], p.o[1], p.o[2]}, d = {p.d[0], p.d[1], p.d[2]};
+			const V3 idir = {1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+			float t;
+			p.alive = hit_test_and_march(o, d, idir, p.t, props[n], &t, nullptr) ? 1u : 0u;
+			p.t = t;
+		}
+		if (p.alive) {
+			++n_proxy_alive;
+			const V3 q = xform_point(props[n].transform, V3{p.o[0] + p.d[0] * p.t, p.o[1] + p.d[1] * p.t, p.o[2] + p.d[2] * p.t});
+			const float dx = q.x - cam_x, dy = q.y - cam_y, dz = q.z - cam_z;
+			const float d2 = sum3(dx * dx, dy * dy, dz * dz);
+			if (d2 < min_d2 || active == -1) { min_d2 = d2; active = (int)n; }
+			p.active = 0u;
+		}
+		pr = p;
+	}
+	if (active >= 0) proxies[(size_t)active * stride + i].active = 1u;
+	if (n_proxy_alive == 0) rays[i].alive = 0u;
+}
+
+// march_proxy_rays_and_generate_next_network_inputs for one NeRF; ray-major slots [i * n_steps + j]
+__global__ void __launch_bounds__(128) bl_generate_inputs_kernel(const uint32_t n_alive, const uint32_t n_steps, const BlNerfProps* __restrict__ props_n,
+                                                                 const BlGlobalRay* __restrict__ rays, BlProxyRay* __restrict__ proxies_n, float* __restrict__ coords)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_alive) return;
+	float* c = coords + (size_t)i * n_steps * COORD_FLOATS;
+	BlProxyRay p = proxies_n[i];
+	uint32_t j = 0;
+	if (rays[i].alive && p.active) { // (the reference tests `active` only, :344-346)
+		const BlNerfProps& P = *props_n;
+		const V3 o = {p.o[0], p.o[1], p.o[2]}, d = {p.d[0], p.d[1], p.d[2]};
+		const V3 idir = {1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+		const V3 wd = {(d.x + 1.0f) * 0.5f, (d.y + 1.0f) * 0.5f, (d.z + 1.0f) * 0.5f};
+		float t = p.t, dt = calc_dt(t, P.cone_angle);
+		bool done = false;
+		for (; j < n_steps; ++j) {
+			const V3 wp = warp_position(V3{o.x + d.x * t, o.y + d.y * t, o.z + d.z * t}, P.train_aabb);
+			c[0] = wp.x; c[1] = wp.y; c[2] = wp.z; c[3] = warp_dt(dt); c[4] = wd.x; c[5] = wd.y; c[6] = wd.z;
+			c += COORD_FLOATS;
+			if (!hit_test_and_march(o, d, idir, t, P, &t, &dt)) { p.n_steps = j; done = true; ++j; break; }
+			t += dt;
+		}
+		if (!done) { p.t = t; p.n_steps = n_steps; }
+		proxies_n[i] = p;
+	}
+	for (; j < n_steps; ++j) { c[0] = c[1] = c[2] = 0.5f; c[3] = 0.f; c[4] = c[5] = c[6] = 0.5f; c += COORD_FLOATS; } // unused slots still go through the network
+}
+
+// composite_proxy_ray_colors_kernel for one NeRF
+__global__ void __launch_bounds__(128) bl_composite_kernel(const uint32_t n_alive, const uint32_t n_steps, const uint32_t current_step, const BlNerfProps* __restrict__ props_n,
+                                                           BlGlobalRay* __restrict__ rays, BlProxyRay* __restrict__ proxies_n, const float* __restrict__ coords,
+                                                           const __half* __restrict__ rgbsigma, unsigned long long* __restrict__ n_samples)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t done = 0;
+	if (i < n_alive && rays[i].alive) {
+		BlProxyRay p = proxies_n[i];
+		if (p.alive && p.active) {
+			const BlNerfProps& P = *props_n;
+			float4 local = make_float4(rays[i].rgba[0], rays[i].rgba[1], rays[i].rgba[2], rays[i].rgba[3]);
+			const float* c = coords + (size_t)i * n_steps * COORD_FLOATS;
+			const __half* out = rgbsigma + (size_t)i * n_steps * 4;
+			uint32_t j = 0;
+			for (; j < p.n_steps; ++j) {
+				const uint2 raw = *reinterpret_cast<const uint2*>(out + j * 4);
+				const __half2 h01 = *reinterpret_cast<const __half2*>(&raw.x), h23 = *reinterpret_cast<const __half2*>(&raw.y);
+				const float T = 1.f - local.w;
+				const float dt = unwarp_dt(c[j * COORD_FLOATS + 3]);
+				const float alpha = 1.f - __expf(-network_to_density(__high2float(h23), P.density_activation) * dt);
+				float weight = alpha * T;
+				weight *= P.opacity;
+				local.x += network_to_rgb(__low2float(h01), P.rgb_activation) * weight;
+				local.y += network_to_rgb(__high2float(h01), P.rgb_activation) * weight;
+				local.z += network_to_rgb(__low2float(h23), P.rgb_activation) * weight;
+				local.w += weight;
+				++done;
+				if (local.w > (1.0f - P.min_transmittance)) {
+					const float w = local.w;
+					local.x /= w; local.y /= w; local.z /= w; local.w /= w;
+					break;
+				}
+			}
+			if (j < n_steps) { p.alive = 0u; p.n_steps = j + current_step; proxies_n[i] = p; }
+			rays[i].rgba[0] = local.x; rays[i].rgba[1] = local.y; rays[i].rgba[2] = local.z; rays[i].rgba[3] = local.w;
+		}
+	}
+	#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) done += __shfl_xor_sync(0xffffffffu, done, o);
+	if ((threadIdx.x & 31) == 0 && done) atomicAdd(n_samples, (unsigned long long)done);
+}
+
+} // namespace ngpb
+
+// ---- a NeRF loaded from a snapshot, independent of any Testbed (NeuralRadianceField, nerf/neural_radiance_field.cuh) ----
+struct ngpb_field {
+	int device = 0;
+	uint32_t aabb_scale = 1, max_cascade = 0, n_params = 0;
+	ngpb_grid grid{};
+	__half* params = nullptr;
+	uint8_t* bitfield = nullptr;
+	float train_aabb[6] = {0, 0, 0, 1, 1, 1};
+	float cone_angle = 0.f;
+};
+
+extern "C" int ngpb_field_create(ngpb_field** out, int device, uint32_t aabb_scale, const ngpb_half* params_host, uint32_t n_params, const float* density_grid_host, uint32_t n_cells) {
+	ngpb_field* f = nullptr;
+	float *grid_dev = nullptr, *mean_dev = nullptr;
+	try {
+		if (!out || !params_host || aabb_scale == 0 || (aabb_scale & (aabb_scale - 1)) != 0 || aabb_scale > 128) { set_last_error("ngpb_field_create: invalid argument"); return NGPB_ERR_INVALID_ARGUMENT; }
+		if (ngpb_check_device(device) != 0) return NGPB_ERR_RUNTIME;
+		NGPB_CUDA_CHECK(cudaSetDevice(device));
+		f = new ngpb_field();
+		f->device = device; f->aabb_scale = aabb_scale;
+		while ((1u << f->max_cascade) < aabb_scale) ++f->max_cascade;
+		const float half = 0.5f * (float)aabb_scale;
+		for (int c = 0; c < 3; ++c) { f->train_aabb[c] = 0.5f - half; f->train_aabb[3 + c] = 0.5f + half; }
+		f->cone_angle = aabb_scale <= 1 ? 0.0f : (1.0f / 256.0f);
+		const float per_level_scale = std::exp(std::log(2048.0f * (float)aabb_scale / 16.0f) / 15.0f); // reset_network, src/testbed.cu:2313-2325
+		const uint32_t entries = ngpb_grid_init(&f->grid, 16, 19, 16, per_level_scale);
+		if (ngpb_grid_device_scales(nullptr, &f->grid) != 0) throw std::runtime_error(ngpb_last_error());
+		if (n_params != MLP_PARAMS + 2 * entries) throw std::runtime_error("snapshot parameter count does not match the base NeRF architecture for this aabb_scale");
+		f->n_params = n_params;
+		NGPB_CUDA_CHECK(cudaMalloc(&f->params, sizeof(__half) * n_params));
+		NGPB_CUDA_CHECK(cudaMemcpy(f->params, params_host, sizeof(__half) * n_params, cudaMemcpyHostToDevice));
+		const size_t bits_bytes = (size_t)NERF_GRID_CELLS * NERF_CASCADES / 8;
+		NGPB_CUDA_CHECK(cudaMalloc(&f->bitfield, bits_bytes));
+		NGPB_CUDA_CHECK(cudaMemset(f->bitfield, 0, bits_bytes));
+		if (n_cells) {
+			if (!density_grid_host || n_cells != NERF_GRID_CELLS * (f->max_cascade + 1)) throw std::runtime_error("Incompatible number of grid cascades.");
+			NGPB_CUDA_CHECK(cudaMalloc(&grid_dev, sizeof(float) * n_cells));
+			NGPB_CUDA_CHECK(cudaMalloc(&mean_dev, sizeof(float)));
+			NGPB_CUDA_CHECK(cudaMemcpy(grid_dev, density_grid_host, sizeof(float) * n_cells, cudaMemcpyHostToDevice));
+			if (ngpb_update_bitfield(nullptr, f->max_cascade + 1, grid_dev, mean_dev, f->bitfield) != 0) throw std::runtime_error(ngpb_last_error());
+			NGPB_CUDA_CHECK(cudaDeviceSynchronize());
+			cudaFree(grid_dev); cudaFree(mean_dev);
+		}
+		*out = f;
+		return 0;
+	} catch (const std::exception& e) {
+		if (grid_dev) cudaFree(grid_dev);
+		if (mean_dev) cudaFree(mean_dev);
+		if (f) { if (f->params) cudaFree(f->params); if (f->bitfield) cudaFree(f->bitfield); delete f; }
+		set_last_error(e.what());
+		return NGPB_ERR_RUNTIME;
+	}
+}
+extern "C" void ngpb_field_destroy(ngpb_field* f) {
+	if (!f) return;
+	cudaSetDevice(f->device);
+	if (f->params) cudaFree(f->params);
+	if (f->bitfield) cudaFree(f->bitfield);
+	delete f;
+}
+
+static bool invert4(const float* a, float* out) { // Gauss-Jordan with partial pivoting, column-major in and out (Eigen's Matrix4f::inverse in the reference)
+	double m[4][8];
+	for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) { m[r][c] = a[c * 4 + r]; m[r][4 + c] = r == c ? 1.0 : 0.0; }
+	for (int c = 0; c < 4; ++c) {
+		int piv = c;
+		for (int r = c + 1; r < 4; ++r) if (std::fabs(m[r][c]) > std::fabs(m[piv][c])) piv = r;
+		if (std::fabs(m[piv][c]) < 1e-30) return false;
+		if (piv != c) for (int k = 0; k < 8; ++k) std::swap(m[piv][k], m[c][k]);
+		const double d = m[c][c];
+		for (int k = 0; k < 8; ++k) m[c][k] /= d;
+		for (int r = 0; r < 4; ++r) if (r != c) { const double f = m[r][c]; for (int k = 0; k < 8; ++k) m[r][k] -= f * m[c][k]; }
+	}
+	for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) out[c * 4 + r] = (float)m[r][4 + c];
+	return true;
+}
+
+extern "C" int ngpb_blender_render(void* stream_, const ngpb_blender_request* rq, uint32_t n_nerfs, const ngpb_nerf_instance* nerfs, float* out_rgba_host,
+                                   uint64_t* n_samples_out, uint32_t* n_launches_out) {
+	uint8_t* ws = nullptr;
+	uint32_t* host_counter = nullptr;
+	try {
+		if (!rq || !out_rgba_host || rq->width <= 0 || rq->height <= 0 || rq->mip < 0 || rq->mip > 12 || n_nerfs > BL_MAX_NERFS || (n_nerfs && !nerfs)) {
+			set_last_error("ngpb_blender_render: invalid argument");
+			return NGPB_ERR_INVALID_ARGUMENT;
+		}
+		cudaStream_t stream = (cudaStream_t)stream_;
+		BlRequest R{};
+		R.width = rq->width; R.height = rq->height; R.skip = 1 << rq->mip; R.flip_y = rq->flip_y;
+		R.scaled_w = (rq->width + R.skip - 1) / R.skip; R.scaled_h = (rq->height + R.skip - 1) / R.skip;
+		for (int k = 0; k < 12; ++k) R.cam[k] = rq->camera[k];
+		R.focal_length = rq->focal_length; R.near_distance = rq->near_distance;
+		ld_random_pixel_offset(0u, R.offset); // sample index 0 ("todo: sample index", :624)
+		const uint32_t n_pixels = (uint32_t)rq->width * (uint32_t)rq->height, n_init = (uint32_t)R.scaled_w * (uint32_t)R.scaled_h;
+		const uint32_t max_steps = 8, nn = std::max(n_nerfs, 1u);
+		const size_t slots = (size_t)next_multiple(n_init, 128) * max_steps + 128;
+		// workspace (allocated per call: a Blender frame is milliseconds, the allocation microseconds)
+		size_t off = 0;
+		auto reserve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+		const size_t o_frame = reserve((size_t)n_pixels * 16), o_accum = reserve((size_t)n_pixels * 16), o_out = reserve((size_t)n_pixels * 16);
+		const size_t o_rays0 = reserve((size_t)n_init * sizeof(BlGlobalRay)), o_rays1 = reserve((size_t)n_init * sizeof(BlGlobalRay));
+		const size_t o_prox0 = reserve((size_t)n_init * nn * sizeof(BlProxyRay)), o_prox1 = reserve((size_t)n_init * nn * sizeof(BlProxyRay));
+		const size_t o_coords = reserve(slots * COORD_FLOATS * 4), o_enc = reserve(slots * N_ENC * 2), o_rgbs = reserve(slots * 8);
+		const size_t o_props = reserve(sizeof(BlNerfProps) * nn), o_cnt = reserve(64);
+		NGPB_CUDA_CHECK(cudaMalloc(&ws, off));
+		NGPB_CUDA_CHECK(cudaMallocHost(&host_counter, 16));
+		float4 *frame = (float4*)(ws + o_frame), *accum = (float4*)(ws + o_accum), *out = (float4*)(ws + o_out);
+		BlGlobalRay* rays[2] = {(BlGlobalRay*)(ws + o_rays0), (BlGlobalRay*)(ws + o_rays1)};
+		BlProxyRay* prox[2] = {(BlProxyRay*)(ws + o_prox0), (BlProxyRay*)(ws + o_prox1)};
+		float* coords = (float*)(ws + o_coords);
+		__half *encoded = (__half*)(ws + o_enc), *rgbsigma = (__half*)(ws + o_rgbs);
+		BlNerfProps* props_dev = (BlNerfProps*)(ws + o_props);
+		uint32_t* counters = (uint32_t*)(ws + o_cnt);
+		std::vector<BlNerfProps> props(nn);
+		for (uint32_t n = 0; n < n_nerfs; ++n) {
+			const ngpb_nerf_instance& in = nerfs[n];
+			if (!in.field) throw std::runtime_error("ngpb_blender_render: NeRF without a field");
+			BlNerfProps& P = props[n];
+			std::memcpy(P.transform, in.transform, 64);
+			if (!invert4(in.transform, P.itransform)) throw std::runtime_error("ngpb_blender_render: singular NeRF transform");
+			P.bitfield = in.field->bitfield;
+			P.render_aabb = make_aabb(in.aabb); P.train_aabb = make_aabb(in.field->train_aabb);
+			P.cone_angle = in.field->cone_angle; P.opacity = in.opacity; P.min_transmittance = 0.01f; // NeuralRadianceField::min_transmittance
+			P.rgb_activation = NGPB_ACT_LOGISTIC; P.density_activation = NGPB_ACT_EXPONENTIAL;           // NeuralRadianceField defaults
+		}
+		uint32_t launches = 0;
+		NGPB_CUDA_CHECK(cudaMemcpyAsync(props_dev, props.data(), sizeof(BlNerfProps) * nn, cudaMemcpyHostToDevice, stream));
+		NGPB_CUDA_CHECK(cudaMemsetAsync(frame, 0, (size_t)n_pixels * 16, stream)); // CudaRenderBuffer::clear_frame
+		NGPB_CUDA_CHECK(cudaMemsetAsync(accum, 0, (size_t)n_pixels * 16, stream));
+		NGPB_CUDA_CHECK(cudaMemsetAsync(counters, 0, 64, stream));
+		if (n_nerfs) { // "if (render_request.nerfs.size() == 0) return;" (:570): an empty request renders the background
+			bl_init_rays_kernel<<<div_round_up(n_init, 128), 128, 0, stream>>>(R, n_nerfs, props_dev, n_init, rays[0], prox[0]);
+			NGPB_LAUNCH_CHECK(); ++launches;
+			NGPB_CUDA_CHECK(cudaMemcpyAsync(counters + 0, &n_init, 4, cudaMemcpyHostToDevice, stream));
+			uint32_t cur = 0, n_in = n_init, step = 1;
+			while (step < 10000) {
+				NGPB_CUDA_CHECK(cudaMemsetAsync(counters + (cur ^ 1), 0, 4, stream));
+				bl_compact_kernel<<<div_round_up(n_in, 128), 128, 0, stream>>>(R, counters + cur, n_nerfs, n_init, rays[cur], prox[cur], rays[cur ^ 1], prox[cur ^ 1], counters + (cur ^ 1), frame);
+				NGPB_LAUNCH_CHECK(); ++launches;
+				cur ^= 1;
+				NGPB_CUDA_CHECK(cudaMemcpyAsync(host_counter, counters + cur, 4, cudaMemcpyDeviceToHost, stream));
+				NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
+				const uint32_t n_alive = host_counter[0];
+				n_in = n_alive;
+				if (n_alive == 0) break;
+				const uint32_t blocks = div_round_up(n_alive, 128);
+				bl_march_cull_kernel<<<blocks, 128, 0, stream>>>(n_alive, n_nerfs, props_dev, n_init, R.cam[9], R.cam[10], R.cam[11], rays[cur], prox[cur]);
+				NGPB_LAUNCH_CHECK(); ++launches;
+				const uint32_t n_steps = std::max(1u, std::min(max_steps, n_init / n_alive));
+				const uint32_t n_slots = next_multiple(n_alive * n_steps, 128);
+				for (uint32_t n = 0; n < n_nerfs; ++n) {
+					BlProxyRay* pn = prox[cur] + (size_t)n * n_init;
+					bl_generate_inputs_kernel<<<blocks, 128, 0, stream>>>(n_alive, n_steps, props_dev + n, rays[cur], pn, coords);
+					NGPB_LAUNCH_CHECK();
+					const ngpb_field* f = nerfs[n].field;
+					hash_encode_forward_launch(stream, &f->grid, f->params + MLP_PARAMS, coords, COORD_FLOATS, n_slots, nullptr, encoded);
+					nerf_mlp_forward_launch(stream, f->params, encoded, coords, n_slots, nullptr, rgbsigma);
+					bl_composite_kernel<<<blocks, 128, 0, stream>>>(n_alive, n_steps, step, props_dev + n, rays[cur], pn, coords, rgbsigma, reinterpret_cast<unsigned long long*>(counters + 2));
+					NGPB_LAUNCH_CHECK();
+					launches += 4;
+				}
+				step += n_steps;
+			}
+		}
+		// Testbed::bl_render_frame: accumulate (first sample) + tonemap, buffer and output colour space = the request's
+		render_accumulate_kernel<<<div_round_up(n_pixels, 256), 256, 0, stream>>>(n_pixels, frame, accum, 0.0f, rq->color_space);
+		render_tonemap_kernel<<<div_round_up(n_pixels, 256), 256, 0, stream>>>(n_pixels, powf(2.0f, rq->exposure),
+			make_float4(rq->background_color[0], rq->background_color[1], rq->background_color[2], rq->background_color[3]), accum, rq->color_space,
+			rq->color_space == NGPB_COLOR_SRGB ? 1 : 0, out);
+		NGPB_LAUNCH_CHECK(); launches += 2;
+		NGPB_CUDA_CHECK(cudaMemcpyAsync(out_rgba_host, out, (size_t)n_pixels * 16, cudaMemcpyDeviceToHost, stream));
+		NGPB_CUDA_CHECK(cudaMemcpyAsync(host_counter, counters + 2, 8, cudaMemcpyDeviceToHost, stream));
+		NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
+		if (n_samples_out) std::memcpy(n_samples_out, host_counter, 8);
+		if (n_launches_out) *n_launches_out = launches;
+		cudaFreeHost(host_counter);
+		cudaFree(ws);
+		return 0;
+	} catch (const std::exception& e) {
+		if (host_counter) cudaFreeHost(host_counter);
+		if (ws) cudaFree(ws);
+		set_last_error(e.what());
+		return NGPB_ERR_RUNTIME;
+	}
 }

@@ -53,6 +53,154 @@ class ColorSpace(enum.IntEnum):  # common.h:129-133
 NGPB_MAX_LEVELS = 32
 
 
+class TonemapCurve(enum.IntEnum):  # common.h ETonemapCurve; only Identity is built
+    Identity = 0
+    ACES = 1
+    Hable = 2
+    Reinhard = 3
+
+
+class CameraModel(enum.IntEnum):  # common.h ECameraModel; only Perspective is built
+    Perspective = 0
+    SphericalQuadrilateral = 1
+    QuadrilateralHexahedron = 2
+
+
+# ---- value types of the Blender render request (python_api.cu:409-538; nerf/render_request.cuh, nerf/nerf_descriptor.cuh, bounding_box.cuh) ----
+class BoundingBox:
+    def __init__(self, min=None, max=None):
+        self.min = np.full(3, np.inf, np.float32) if min is None else np.asarray(min, np.float32).reshape(3).copy()
+        self.max = np.full(3, -np.inf, np.float32) if max is None else np.asarray(max, np.float32).reshape(3).copy()
+
+    def center(self):
+        return 0.5 * (self.min + self.max)
+
+    def diag(self):
+        return self.max - self.min
+
+    def contains(self, p):
+        p = np.asarray(p, np.float32)
+        return bool(np.all(p >= self.min) and np.all(p <= self.max))
+
+    def enlarge(self, other):
+        if isinstance(other, BoundingBox):
+            self.min, self.max = np.minimum(self.min, other.min), np.maximum(self.max, other.max)
+        else:
+            p = np.asarray(other, np.float32)
+            self.min, self.max = np.minimum(self.min, p), np.maximum(self.max, p)
+
+    def inflate(self, amount):
+        self.min, self.max = self.min - np.float32(amount), self.max + np.float32(amount)
+
+    def intersection(self, other):
+        return BoundingBox(np.maximum(self.min, other.min), np.minimum(self.max, other.max))
+
+    def intersects(self, other):
+        return not bool(np.any(self.intersection(other).max < self.intersection(other).min))
+
+
+class DownsampleInfo:
+    """DownsampleInfo::MakeFromMip (common.h): every `skip`-th pixel is traced and replicated into a skip x skip block."""
+
+    def __init__(self, resolution, mip):
+        self.max_res = (int(resolution[0]), int(resolution[1]))
+        self.mip = int(mip)
+        self.skip = 1 << self.mip
+        self.scaled_res = tuple((r + self.skip - 1) // self.skip for r in self.max_res)
+
+    @staticmethod
+    def MakeFromMip(resolution, mip):
+        return DownsampleInfo(resolution, mip)
+
+
+class Mask3D:
+    """Render masks are outside the built scope: constructing one raises, so a request that needs them fails loudly rather than rendering unmasked."""
+
+    @staticmethod
+    def _unbuilt(*a, **k):
+        raise RuntimeError("render masks (Mask3D) are outside the built scope")
+
+    Box = Cylinder = Sphere = _unbuilt
+
+
+class RenderModifiers:
+    def __init__(self, masks=()):
+        if len(masks):
+            raise RuntimeError("render masks are outside the built scope")
+        self.masks = []
+
+
+class RenderOutputProperties:
+    def __init__(self, resolution, ds, spp, color_space, tonemap_curve, exposure, background_color, flip_y):
+        self.resolution, self.ds, self.spp = (int(resolution[0]), int(resolution[1])), ds, int(spp)
+        self.color_space, self.tonemap_curve, self.exposure = ColorSpace(color_space), TonemapCurve(tonemap_curve), float(exposure)
+        self.background_color, self.flip_y = [float(v) for v in background_color], bool(flip_y)
+
+
+class RenderCameraProperties:
+    def __init__(self, transform, model, focal_length, near_distance, aperture_size, focus_z, spherical_quadrilateral=None, quadrilateral_hexahedron=None):
+        self.transform = np.asarray(transform, np.float32).reshape(3, 4).copy()
+        self.model, self.focal_length, self.near_distance = CameraModel(model), float(focal_length), float(near_distance)
+        self.aperture_size, self.focus_z = float(aperture_size), float(focus_z)
+        self.spherical_quadrilateral, self.quadrilateral_hexahedron = spherical_quadrilateral, quadrilateral_hexahedron
+
+    def __eq__(self, o):
+        return (isinstance(o, RenderCameraProperties) and np.array_equal(self.transform, o.transform) and self.model == o.model
+                and (self.focal_length, self.near_distance, self.aperture_size, self.focus_z) == (o.focal_length, o.near_distance, o.aperture_size, o.focus_z))
+
+    __hash__ = None
+
+
+class NerfDescriptor:
+    def __init__(self, snapshot_path_str, aabb, transform, modifiers, opacity):
+        self.snapshot_path, self.aabb, self.modifiers, self.opacity = str(snapshot_path_str), aabb, modifiers, float(opacity)
+        self.transform = np.asarray(transform, np.float32).reshape(4, 4).copy()
+
+
+class RenderRequest:
+    def __init__(self, output, camera, modifiers, nerfs, aabb):
+        self.output, self.camera, self.modifiers, self.nerfs, self.aabb = output, camera, modifiers, list(nerfs), aabb
+
+
+class NerfInstance(C.Structure):  # ngpb_nerf_instance
+    _fields_ = [("field", C.c_void_p), ("aabb", C.c_float * 6), ("transform", C.c_float * 16), ("opacity", C.c_float)]
+
+
+class BlenderRequest(C.Structure):  # ngpb_blender_request
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("mip", C.c_int32), ("flip_y", C.c_int32), ("camera", C.c_float * 12),
+                ("focal_length", C.c_float), ("near_distance", C.c_float), ("color_space", C.c_int32), ("exposure", C.c_float), ("background_color", C.c_float * 4)]
+
+
+class Field:
+    """One NeRF loaded from a snapshot for the Blender renderer (NeuralRadianceField, nerf/neural_radiance_field.cuh:153-298)."""
+
+    def __init__(self, params_half, density_grid, aabb_scale, device=0):
+        params = np.ascontiguousarray(params_half, np.float16)
+        grid = np.ascontiguousarray(density_grid, np.float32)
+        h = C.c_void_p()
+        check(lib().ngpb_field_create(C.byref(h), int(device), int(aabb_scale), params.ctypes.data_as(C.c_void_p), int(params.shape[0]),
+                                      grid.ctypes.data_as(C.c_void_p) if grid.size else None, int(grid.size)))
+        self._h, self.aabb_scale = h, int(aabb_scale)
+
+    @staticmethod
+    def from_snapshot(path, device=0):
+        import msgpack
+        if not os.path.exists(path):
+            raise RuntimeError(f"Snapshot path {path} does not exist.")
+        with open(path, "rb") as f:
+            cfg = msgpack.unpackb(f.read(), raw=False, strict_map_key=False)
+        if "snapshot" not in cfg:
+            raise RuntimeError(f"File {path} does not contain a snapshot.")
+        snap = parse_snapshot(cfg)
+        _validate_network_config(snap["network_config"])
+        return Field(snap["params_half"], snap["density_grid"], snap["aabb_scale"], device)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().ngpb_field_destroy(self._h)
+            self._h = None
+
+
 class Grid(C.Structure):
     _fields_ = [("n_levels", C.c_uint32), ("base_resolution", C.c_uint32), ("log2_per_level_scale", C.c_float),
                 ("offsets", C.c_uint32 * (NGPB_MAX_LEVELS + 1)), ("scale", C.c_float * NGPB_MAX_LEVELS),
@@ -178,6 +326,7 @@ EXPORTED_SYMBOLS = [
     "ngpb_testbed_get_params", "ngpb_testbed_set_params", "ngpb_testbed_get_density_grid", "ngpb_testbed_set_option", "ngpb_testbed_get_option",
     "ngpb_testbed_render", "ngpb_testbed_stream", "ngpb_testbed_stage_times", "ngpb_grid_device_scales", "ngpb_testbed_configure", "ngpb_testbed_set_params_half", "ngpb_testbed_set_density_grid", "ngpb_testbed_get_training_state",
     "ngpb_testbed_set_training_state", "ngpb_testbed_get_optimizer_state", "ngpb_testbed_set_optimizer_state", "ngpb_generate_training_samples_sharded", "ngpb_compute_loss_sharded", "ngpb_nccl_unique_id", "ngpb_testbed_init_data_parallel", "ngpb_render_workspace_bytes", "ngpb_render_nerf", "ngpb_testbed_last_render_ms", "ngpb_generate_training_samples_scratch_bytes", "ngpb_compute_loss_scratch_bytes",
+    "ngpb_field_create", "ngpb_field_destroy", "ngpb_blender_render",
 ]
 
 _lib = None
@@ -207,6 +356,8 @@ def lib():
         l.ngpb_effective_xform.restype = None
         l.ngpb_optimizer_init.restype = None
         l.ngpb_testbed_destroy.restype = None
+        l.ngpb_field_destroy.restype = None
+        l.ngpb_field_destroy.argtypes = [C.c_void_p]
         l.ngpb_testbed_stream.restype = C.c_void_p
         l.ngpb_testbed_stream.argtypes = [C.c_void_p]
         _lib = l
@@ -420,6 +571,7 @@ class Testbed:
         self.training_batch_size = 1 << 18  # testbed.h:909
         self.network_config = json.loads(json.dumps(BASE_NETWORK_CONFIG))
         self._seed = 1337
+        self._device = int(device)
         self._keep = None
 
     def __del__(self):
@@ -645,6 +797,68 @@ class Testbed:
         self.last_render_samples = int(ns.value)
         self.last_render_ms = float(lib().ngpb_testbed_last_render_ms(self._h))
         return out
+
+    # -- the Blender multi-NeRF renderer (python_api.cu:214-262, :577-585)
+    def _fields_for(self, descriptors):
+        """RenderData::update_nerfs (nerf/render_data.cuh:44-80): fields are cached by snapshot path, dropped when no descriptor names them."""
+        cache = self.__dict__.setdefault("_bl_fields", {})
+        wanted = {d.snapshot_path for d in descriptors}
+        for k in [k for k in cache if k not in wanted]:
+            del cache[k]
+        for d in descriptors:
+            if d.snapshot_path not in cache:
+                cache[d.snapshot_path] = Field.from_snapshot(d.snapshot_path, self._device)
+        return [cache[d.snapshot_path] for d in descriptors]
+
+    def request_nerf_render_sync(self, render_request):
+        """Testbed::bl_request_nerf_render_sync (python_api.cu:233): float32 [H][W][4] of all the request's NeRFs composited front to back."""
+        out_p, cam_p = render_request.output, render_request.camera
+        w, h = out_p.resolution
+        result = np.zeros((h, w, 4), np.float32)
+        if self.__dict__.get("_currently_rendering", False):
+            return result
+        if cam_p.model != CameraModel.Perspective or cam_p.aperture_size != 0.0:
+            raise RuntimeError("only the perspective camera without depth of field is built for the Blender renderer")
+        if out_p.tonemap_curve != TonemapCurve.Identity:
+            raise RuntimeError("only TonemapCurve.Identity is built")
+        if render_request.modifiers is not None and len(render_request.modifiers.masks):
+            raise RuntimeError("render masks are outside the built scope")
+        self._currently_rendering = True
+        try:
+            fields = self._fields_for(render_request.nerfs)
+            rq = BlenderRequest()
+            rq.width, rq.height, rq.mip, rq.flip_y = w, h, out_p.ds.mip, int(out_p.flip_y)
+            cm = cam_p.transform.T.reshape(-1)
+            for k in range(12):
+                rq.camera[k] = float(cm[k])
+            rq.focal_length, rq.near_distance, rq.color_space, rq.exposure = cam_p.focal_length, cam_p.near_distance, int(out_p.color_space), out_p.exposure
+            for k in range(4):
+                rq.background_color[k] = out_p.background_color[k]
+            inst = (NerfInstance * max(1, len(fields)))()
+            for i, (d, f) in enumerate(zip(render_request.nerfs, fields)):
+                inst[i].field = f._h
+                for k in range(3):
+                    inst[i].aabb[k], inst[i].aabb[3 + k] = float(d.aabb.min[k]), float(d.aabb.max[k])
+                t = d.transform.T.reshape(-1)
+                for k in range(16):
+                    inst[i].transform[k] = float(t[k])
+                inst[i].opacity = d.opacity
+            ns, nl = C.c_uint64(0), C.c_uint32(0)
+            check(lib().ngpb_blender_render(C.c_void_p(self.stream or None), C.byref(rq), len(fields), inst, result.ctypes.data_as(C.c_void_p), C.byref(ns), C.byref(nl)))
+            self.last_render_samples, self.last_render_launches = int(ns.value), int(nl.value)
+        finally:
+            self._currently_rendering = False
+        return result
+
+    def request_nerf_render_async(self, render_request, render_callback):
+        """Testbed::bl_request_nerf_render_async (python_api.cu:214): renders on a detached thread and hands the image to the callback;
+        a request that arrives while one is in flight is dropped, as in the reference."""
+        import threading
+        if self.__dict__.get("_currently_rendering", False):
+            return
+        t = threading.Thread(target=lambda: render_callback(self.request_nerf_render_sync(render_request)), daemon=True)
+        t.start()
+        self._render_thread = t
 
     fov_axis = 1  # m_fov_axis (testbed.h:528)
     _relative_focal_length = (1.0, 1.0)  # m_relative_focal_length (testbed.h:527)

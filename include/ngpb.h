@@ -183,6 +183,32 @@ uint64_t ngpb_render_workspace_bytes(uint32_t n_pixels);
 int ngpb_render_nerf(void* stream, const ngpb_render_config* cfg, const ngpb_grid* g, const ngpb_half* params, const uint8_t* bitfield,
                      void* workspace, float* out_rgba_host, uint64_t* n_samples_out, uint32_t* n_launches_out);
 
+/* ---- K18: the Blender multi-NeRF renderer (NerfRenderer::render, src/nerf_renderer.cu:565-791; Testbed::bl_render_frame, src/testbed.cu:2675) ----
+ * A field is one NeRF loaded from a snapshot (NeuralRadianceField, nerf/neural_radiance_field.cuh:153-298): fp16 inference parameters in the
+ * reference's flat order, occupancy grid (float, 128^3 per cascade; n_cells may be 0 for an untrained model), aabb_scale. */
+typedef struct ngpb_field ngpb_field;
+int ngpb_field_create(ngpb_field** out, int device, uint32_t aabb_scale, const ngpb_half* params_host, uint32_t n_params, const float* density_grid_host, uint32_t n_cells);
+void ngpb_field_destroy(ngpb_field* f);
+typedef struct {            /* NerfDescriptor (nerf/nerf_descriptor.cuh) */
+	const ngpb_field* field;
+	float aabb[6];          /* render box in the NeRF's local frame */
+	float transform[16];    /* 4x4 local -> world, column-major */
+	float opacity;
+} ngpb_nerf_instance;
+typedef struct {            /* RenderRequest: RenderOutputProperties + RenderCameraProperties (nerf/render_request.cuh), perspective camera */
+	int32_t width, height;  /* output resolution */
+	int32_t mip;            /* DownsampleInfo::MakeFromMip(resolution, mip): every 2^mip-th pixel is traced and splatted */
+	int32_t flip_y;
+	float camera[12];       /* 3x4 camera-to-world, column-major */
+	float focal_length;     /* pixels */
+	float near_distance;
+	int32_t color_space;    /* NGPB_COLOR_* : accumulation and output space */
+	float exposure, background_color[4];
+} ngpb_blender_request;
+/* out_rgba_host: float [height][width][4]. Synchronises the stream once per wave (the reference's schedule, :704-705). */
+int ngpb_blender_render(void* stream, const ngpb_blender_request* rq, uint32_t n_nerfs, const ngpb_nerf_instance* nerfs, float* out_rgba_host,
+                        uint64_t* n_samples_out, uint32_t* n_launches_out);
+
 /* ---- development self-test of the tcgen05 building blocks (tests/test_umma_selftest.py) ---- */
 int ngpb_selftest_umma(void* stream, int variant, const ngpb_half* a, const ngpb_half* b, float* d);
 

@@ -1270,3 +1270,236 @@ extern "C" void orc_render_nerf(const orc_model* m, const orc_half* params, cons
 	}
 	if (n_samples_out) *n_samples_out = n_samples_total;
 }
+
+// =============================================================================================
+// Blender multi-NeRF renderer (the fork's addition): NerfRenderer::render, src/nerf_renderer.cu:565-791
+//   init_global_rays_kernel :17-92 (+ perspective_pixel_to_ray, camera_models.cuh:205-241), init_proxy_rays_kernel :94-146,
+//   compact_rays_kernel :240-270, hit_test_and_march :149-211 (helpers in src/nerf_utils.cu), march_active_rays :274-315,
+//   cull_global_rays_and_set_proxy_rays_active_kernel :376-428, march_proxy_rays_and_generate_next_network_inputs :317-373,
+//   composite_proxy_ray_colors_kernel :431-517, shade_buffer_with_rays_kernel :519-563, the wave loop :661-791,
+//   then Testbed::bl_render_frame (src/testbed.cu:2675-2693): accumulate + tonemap with the request's colour space.
+// Perspective camera, no masks, no depth of field. The result depends on the reference's wave schedule (the nearest live proxy ray is
+// re-selected once per wave of clamp(n_initial / n_alive, 1, 8) steps), so the waves are followed literally, all rays in lockstep.
+// =============================================================================================
+namespace {
+struct M4 { float m[16]; }; // column-major
+inline Vec3 xform_point(const M4& M, const Vec3& p) { // (M * p.homogeneous()).head<3>()
+	return {sum4(M.m[0] * p.x, M.m[4] * p.y, M.m[8] * p.z, M.m[12]), sum4(M.m[1] * p.x, M.m[5] * p.y, M.m[9] * p.z, M.m[13]), sum4(M.m[2] * p.x, M.m[6] * p.y, M.m[10] * p.z, M.m[14])};
+}
+inline Vec3 xform_dir(const M4& M, const Vec3& d) { // M.topLeftCorner<3,3>() * d
+	return {sum3(M.m[0] * d.x, M.m[4] * d.y, M.m[8] * d.z), sum3(M.m[1] * d.x, M.m[5] * d.y, M.m[9] * d.z), sum3(M.m[2] * d.x, M.m[6] * d.y, M.m[10] * d.z)};
+}
+inline Vec3 normalized(const Vec3& v) {
+	const float z = sum3(v.x * v.x, v.y * v.y, v.z * v.z);
+	if (z > 0.f) { const float n = std::sqrt(z); return {v.x / n, v.y / n, v.z / n}; }
+	return v;
+}
+inline bool invert4(const float* a, float* out) { // Gauss-Jordan with partial pivoting, column-major in and out
+	double m[4][8];
+	for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) { m[r][c] = a[c * 4 + r]; m[r][4 + c] = r == c ? 1.0 : 0.0; }
+	for (int c = 0; c < 4; ++c) {
+		int piv = c;
+		for (int r = c + 1; r < 4; ++r) if (std::fabs(m[r][c]) > std::fabs(m[piv][c])) piv = r;
+		if (std::fabs(m[piv][c]) < 1e-30) return false;
+		if (piv != c) for (int k = 0; k < 8; ++k) std::swap(m[piv][k], m[c][k]);
+		const double d = m[c][c];
+		for (int k = 0; k < 8; ++k) m[c][k] /= d;
+		for (int r = 0; r < 4; ++r) if (r != c) { const double f = m[r][c]; for (int k = 0; k < 8; ++k) m[r][k] -= f * m[c][k]; }
+	}
+	for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) out[c * 4 + r] = (float)m[r][4 + c];
+	return true;
+}
+struct ProxyRay { Vec3 o, d; float t; uint32_t n_steps; bool alive, active; };
+struct GlobalRay { Vec3 o, d; float rgba[4]; uint32_t idx; bool alive; };
+
+// hit_test_and_march (:149-211) with no masks: advances t to the next sample position in an occupied cell
+inline bool hit_test_and_march(const Vec3& o, const Vec3& d, const Vec3& idir, float t_in, const AABB& box, const uint8_t* bitfield, float cone_angle, float* t_out, float* dt_out) {
+	float t = t_in, dt = 0.0f, prev_t = t;
+	while (true) {
+		const Vec3 pos = {o.x + d.x * t, o.y + d.y * t, o.z + d.z * t};
+		if (!aabb_contains(box, pos)) { *t_out = prev_t; if (dt_out) *dt_out = dt; return false; }
+		dt = calc_dt(t, cone_angle);
+		const uint32_t mip = (uint32_t)std::max(0, mip_from_dt(dt, pos));
+		if (density_grid_occupied_at(pos, bitfield, mip)) break;
+		prev_t = t;
+		t = advance_to_next_voxel(t, cone_angle, pos, d, idir, NERF_GRIDSIZE >> mip);
+	}
+	*t_out = t; if (dt_out) *dt_out = dt;
+	return true;
+}
+} // namespace
+
+extern "C" void orc_blender_render(const orc_blender_request* rq, uint32_t n_nerfs, const orc_nerf_instance* nerfs, float* out_rgba, uint64_t* n_samples_out) {
+	const int W = rq->width, H = rq->height;
+	const int skip = 1 << rq->mip;
+	const int SW = (W + skip - 1) / skip, SH = (H + skip - 1) / skip; // DownsampleInfo::MakeFromMip (common.h:337-355)
+	const uint32_t n_init = (uint32_t)SW * SH;
+	std::vector<M4> T(n_nerfs), IT(n_nerfs);
+	std::vector<AABB> render_box(n_nerfs), train_box(n_nerfs);
+	std::vector<float> cone(n_nerfs);
+	for (uint32_t n = 0; n < n_nerfs; ++n) {
+		std::memcpy(T[n].m, nerfs[n].transform, 64);
+		if (!invert4(nerfs[n].transform, IT[n].m)) std::memset(IT[n].m, 0, 64);
+		render_box[n] = make_aabb(nerfs[n].render_aabb); train_box[n] = make_aabb(nerfs[n].train_aabb);
+		cone[n] = nerfs[n].aabb_scale <= 1 ? 0.0f : (1.0f / 256.0f);
+	}
+	// init_global_rays_kernel, sample_index 0
+	float offset[2];
+	ld_random_pixel_offset(0, offset);
+	std::vector<GlobalRay> rays(n_init);
+	std::vector<std::vector<ProxyRay>> proxies(n_nerfs, std::vector<ProxyRay>(n_init));
+	const float* cm = rq->camera;
+	for (uint32_t idx = 0; idx < n_init; ++idx) {
+		const uint32_t x = (idx % SW) * skip, y = (idx / SW) * skip;
+		const float uvx = ((float)x + offset[0]) / (float)W, uvy = ((float)y + offset[1]) / (float)H;
+		const float dcam[3] = {(uvx - 0.5f) * (float)W / rq->focal_length, (uvy - 0.5f) * (float)H / rq->focal_length, 1.0f};
+		const float row0[3] = {cm[0], cm[3], cm[6]}, row1[3] = {cm[1], cm[4], cm[7]}, row2[3] = {cm[2], cm[5], cm[8]};
+		const Vec3 d = {dot3(row0, dcam), dot3(row1, dcam), dot3(row2, dcam)};
+		GlobalRay& g = rays[idx];
+		g.o = {cm[9] + d.x * rq->near_distance, cm[10] + d.y * rq->near_distance, cm[11] + d.z * rq->near_distance};
+		g.d = normalized(d);
+		g.idx = idx; g.alive = true;
+		g.rgba[0] = g.rgba[1] = g.rgba[2] = g.rgba[3] = 0.f;
+		for (uint32_t n = 0; n < n_nerfs; ++n) { // init_proxy_rays_kernel
+			ProxyRay& p = proxies[n][idx];
+			p = ProxyRay{};
+			const Vec3 o = xform_point(IT[n], g.o);
+			p.d = normalized(xform_dir(IT[n], normalized(g.d)));
+			float tmin, tmax;
+			aabb_ray_intersect(render_box[n], o, p.d, &tmin, &tmax);
+			const float t = std::fmax(tmin, 0.0f) + 1e-5f;
+			if (!aabb_contains(render_box[n], Vec3{o.x + p.d.x * t, o.y + p.d.y * t, o.z + p.d.z * t})) { p.alive = false; continue; }
+			p.active = true; p.alive = true; p.t = 0.0f; p.n_steps = 0;
+			p.o = {o.x + t * p.d.x, o.y + t * p.d.y, o.z + t * p.d.z};
+		}
+	}
+	std::vector<float> frame((size_t)W * H * 4, 0.f);
+	const Vec3 cam_pos = {cm[9], cm[10], cm[11]};
+	uint64_t n_samples = 0;
+	std::vector<uint32_t> alive_list(n_init);
+	for (uint32_t i = 0; i < n_init; ++i) alive_list[i] = i;
+	uint32_t step = 1;
+	while (step < 10000) {
+		// compact_rays_kernel: live rays stay, finished rays with alpha > 0.001 are shaded at the end
+		std::vector<uint32_t> next;
+		next.reserve(alive_list.size());
+		for (uint32_t r : alive_list) if (rays[r].alive) next.push_back(r);
+		alive_list.swap(next);
+		const uint32_t n_alive = (uint32_t)alive_list.size();
+		if (n_alive == 0) break;
+		// march_active_rays + cull_global_rays_and_set_proxy_rays_active_kernel
+		#pragma omp parallel for schedule(dynamic, 64)
+		for (int64_t a = 0; a < (int64_t)n_alive; ++a) {
+			const uint32_t r = alive_list[a];
+			for (uint32_t n = 0; n < n_nerfs; ++n) {
+				ProxyRay& p = proxies[n][r];
+				if (!p.alive || !p.active) continue;
+				const Vec3 idir = {1.0f / p.d.x, 1.0f / p.d.y, 1.0f / p.d.z};
+				float t;
+				p.alive = hit_test_and_march(p.o, p.d, idir, p.t, render_box[n], nerfs[n].bitfield, cone[n], &t, nullptr);
+				p.t = t;
+			}
+			float min_d2 = 0.0f; int active = -1; uint32_t n_proxy_alive = 0;
+			for (uint32_t n = 0; n < n_nerfs; ++n) {
+				ProxyRay& p = proxies[n][r];
+				if (!p.alive) continue;
+				++n_proxy_alive;
+				const Vec3 q = xform_point(T[n], Vec3{p.o.x + p.d.x * p.t, p.o.y + p.d.y * p.t, p.o.z + p.d.z * p.t});
+				const float dx = q.x - cam_pos.x, dy = q.y - cam_pos.y, dz = q.z - cam_pos.z;
+				const float d2 = sum3(dx * dx, dy * dy, dz * dz);
+				if (d2 < min_d2 || active == -1) { min_d2 = d2; active = (int)n; }
+				p.active = false;
+			}
+			if (active >= 0) proxies[active][r].active = true;
+			if (n_proxy_alive == 0) rays[r].alive = false;
+		}
+		const uint32_t n_steps = std::max(1u, std::min(8u, n_init / n_alive));
+		for (uint32_t n = 0; n < n_nerfs; ++n) {
+			// march_proxy_rays_and_generate_next_network_inputs
+			std::vector<float> coords((size_t)n_alive * n_steps * 7, 0.f);
+			std::vector<uint8_t> takes(n_alive, 0);
+			#pragma omp parallel for schedule(dynamic, 64)
+			for (int64_t a = 0; a < (int64_t)n_alive; ++a) {
+				const uint32_t r = alive_list[a];
+				ProxyRay& p = proxies[n][r];
+				if (!rays[r].alive || !p.active) continue;
+				takes[a] = 1;
+				const Vec3 idir = {1.0f / p.d.x, 1.0f / p.d.y, 1.0f / p.d.z};
+				float t = p.t, dt = calc_dt(t, cone[n]);
+				bool done = false;
+				for (uint32_t j = 0; j < n_steps; ++j) {
+					const Vec3 pos = {p.o.x + p.d.x * t, p.o.y + p.d.y * t, p.o.z + p.d.z * t};
+					const Vec3 wp = warp_position(pos, train_box[n]);
+					float* c = &coords[((size_t)a * n_steps + j) * 7];
+					c[0] = wp.x; c[1] = wp.y; c[2] = wp.z; c[3] = warp_dt(dt); c[4] = (p.d.x + 1.0f) * 0.5f; c[5] = (p.d.y + 1.0f) * 0.5f; c[6] = (p.d.z + 1.0f) * 0.5f;
+					if (!hit_test_and_march(p.o, p.d, idir, t, render_box[n], nerfs[n].bitfield, cone[n], &t, &dt)) { p.n_steps = j; done = true; break; }
+					t += dt;
+				}
+				if (!done) { p.t = t; p.n_steps = n_steps; }
+			}
+			std::vector<orc_half> out((size_t)n_alive * n_steps * 4);
+			orc_nerf_inference(nerfs[n].model, nerfs[n].params, n_alive * n_steps, coords.data(), out.data());
+			// composite_proxy_ray_colors_kernel
+			for (uint32_t a = 0; a < n_alive; ++a) {
+				const uint32_t r = alive_list[a];
+				ProxyRay& p = proxies[n][r];
+				if (!rays[r].alive || !p.alive || !p.active) continue;
+				(void)takes;
+				float* rgba = rays[r].rgba;
+				uint32_t j = 0;
+				for (; j < p.n_steps; ++j) {
+					const size_t k = (size_t)a * n_steps + j;
+					const float T_ = 1.f - rgba[3];
+					const float dt = unwarp_dt(coords[k * 7 + 3]);
+					const float alpha = 1.f - std::exp(-network_to_density(h2f(out[k * 4 + 3]), nerfs[n].density_activation) * dt);
+					float weight = alpha * T_;
+					weight *= 1.f; // no masks
+					weight *= nerfs[n].opacity;
+					for (int c = 0; c < 3; ++c) rgba[c] += network_to_rgb(h2f(out[k * 4 + c]), nerfs[n].rgb_activation) * weight;
+					rgba[3] += weight;
+					++n_samples;
+					if (rgba[3] > (1.0f - nerfs[n].min_transmittance)) { const float w = rgba[3]; for (int c = 0; c < 4; ++c) rgba[c] /= w; break; }
+				}
+				if (j < n_steps) { p.alive = false; p.n_steps = j + step; }
+			}
+		}
+		step += n_steps;
+	}
+	// shade_buffer_with_rays_kernel (train_in_linear_colors = false)
+	for (uint32_t idx = 0; idx < n_init; ++idx) {
+		const GlobalRay& g = rays[idx];
+		if (g.alive || !(g.rgba[3] > 0.001f)) continue;
+		const uint32_t x = skip * (g.idx % (uint32_t)SW);
+		uint32_t y = skip * (g.idx / (uint32_t)SW);
+		if (rq->flip_y) y = H - y - 1;
+		float tmp[4] = {srgb_to_linear(g.rgba[0]), srgb_to_linear(g.rgba[1]), srgb_to_linear(g.rgba[2]), g.rgba[3]};
+		for (int u = 0; u < skip; ++u) for (int v = 0; v < skip; ++v) {
+			const uint64_t pix = (uint64_t)(x + u) + (uint64_t)(y + v) * W;
+			if (pix >= (uint64_t)W * H) continue; // (the reference tests only the linear index, :552-554)
+			float* f = &frame[pix * 4];
+			const float k = 1.0f - tmp[3];
+			for (int c = 0; c < 4; ++c) f[c] = tmp[c] + f[c] * k;
+		}
+	}
+	// accumulate (sample count 0) + tonemap, both in the request's colour space
+	float bg[4] = {rq->background_color[0], rq->background_color[1], rq->background_color[2], rq->background_color[3]};
+	if (rq->color_space != 1) for (int k = 0; k < 3; ++k) bg[k] = srgb_to_linear(bg[k]);
+	const float exposure_scale = std::pow(2.0f, rq->exposure);
+	for (size_t i = 0; i < (size_t)W * H; ++i) {
+		float color[4] = {frame[i * 4], frame[i * 4 + 1], frame[i * 4 + 2], frame[i * 4 + 3]};
+		if (rq->color_space == 1) for (int k = 0; k < 3; ++k) color[k] = linear_to_srgb(color[k]);
+		for (int k = 0; k < 4; ++k) color[k] = (0.f * 0.f + color[k]) / (0.f + 1);
+		const float weight = (1 - color[3]) * bg[3];
+		for (int k = 0; k < 3; ++k) color[k] += bg[k] * weight;
+		color[3] += weight;
+		for (int k = 0; k < 3; ++k) {
+			float v = color[k];
+			if (rq->color_space == 1) v = srgb_to_linear(v);
+			v *= exposure_scale;
+			if (rq->color_space == 1) v = linear_to_srgb(v); // bl_render_frame passes the same colour space as the output space (:2691)
+			color[k] = v;
+		}
+		for (int k = 0; k < 4; ++k) out_rgba[i * 4 + k] = color[k];
+	}
+	if (n_samples_out) *n_samples_out = n_samples;
+}

@@ -172,6 +172,24 @@ typedef struct {
 // out_rgba: float [height][width][4]. n_samples_out (nullable): network-evaluated samples.
 void orc_render_nerf(const orc_model* m, const orc_half* params, const uint8_t* bitfield, const orc_render_config* c, float* out_rgba, uint64_t* n_samples_out);
 
+// ---- Blender multi-NeRF render (NerfRenderer::render, src/nerf_renderer.cu:565-791): see ngp_oracle.cpp ----
+typedef struct {
+	const orc_model* model; const orc_half* params; const uint8_t* bitfield; // the NeRF's snapshot (inference parameters, occupancy bits)
+	float train_aabb[6]; uint32_t aabb_scale;
+	float render_aabb[6];      // NerfDescriptor::aabb, in the NeRF's local frame
+	float transform[16];       // NerfDescriptor::transform, 4x4 column-major (local -> world)
+	float opacity;
+	int32_t rgb_activation, density_activation;
+	float min_transmittance;
+} orc_nerf_instance;
+typedef struct {
+	int32_t width, height, mip, flip_y; // RenderOutputProperties: resolution, DownsampleInfo::MakeFromMip(resolution, mip), flip_y
+	float camera[12];                   // RenderCameraProperties::transform, 3x4 column-major
+	float focal_length, near_distance;  // pixels (same for x and y, :52)
+	int32_t color_space; float exposure, background_color[4];
+} orc_blender_request;
+void orc_blender_render(const orc_blender_request* rq, uint32_t n_nerfs, const orc_nerf_instance* nerfs, float* out_rgba, uint64_t* n_samples_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -312,6 +312,53 @@ def render_nerf(m, params_half, bitfield, cfg):
     return out, int(ns.value)
 
 
+class NerfInstance(C.Structure):
+    _fields_ = [("model", C.POINTER(Model)), ("params", C.c_void_p), ("bitfield", C.c_void_p), ("train_aabb", C.c_float * 6), ("aabb_scale", C.c_uint32),
+                ("render_aabb", C.c_float * 6), ("transform", C.c_float * 16), ("opacity", C.c_float),
+                ("rgb_activation", C.c_int32), ("density_activation", C.c_int32), ("min_transmittance", C.c_float)]
+
+
+class BlenderRequest(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("mip", C.c_int32), ("flip_y", C.c_int32), ("camera", C.c_float * 12),
+                ("focal_length", C.c_float), ("near_distance", C.c_float), ("color_space", C.c_int32), ("exposure", C.c_float), ("background_color", C.c_float * 4)]
+
+
+def blender_render(width, height, camera34, focal_length, nerfs, mip=0, flip_y=False, near_distance=0.0, color_space=1, exposure=0.0, background=(0, 0, 0, 0)):
+    """NerfRenderer::render on the CPU (src/nerf_renderer.cu:565-791). nerfs: list of dicts with model, params_half, bitfield, aabb_scale,
+    render_aabb (6), transform (4x4 row-major numpy, local -> world), opacity. Returns float32 [H][W][4] and the number of composited samples."""
+    rq = BlenderRequest()
+    rq.width, rq.height, rq.mip, rq.flip_y = width, height, mip, int(flip_y)
+    cm = np.asarray(camera34, dtype=np.float32).reshape(3, 4).T.reshape(-1)
+    for k in range(12):
+        rq.camera[k] = float(cm[k])
+    rq.focal_length, rq.near_distance, rq.color_space, rq.exposure = focal_length, near_distance, color_space, exposure
+    for k in range(4):
+        rq.background_color[k] = float(background[k])
+    arr = (NerfInstance * max(len(nerfs), 1))()
+    keep = []
+    for i, n in enumerate(nerfs):
+        params = np.ascontiguousarray(n["params_half"], dtype=np.float16)
+        bits = np.ascontiguousarray(n["bitfield"], dtype=np.uint8)
+        keep += [params, bits, n["model"]]
+        arr[i].model = C.pointer(n["model"])
+        arr[i].params, arr[i].bitfield = _p(params), _p(bits)
+        half = 0.5 * n["aabb_scale"]
+        arr[i].aabb_scale = n["aabb_scale"]
+        t = np.asarray(n.get("transform", np.eye(4)), dtype=np.float32).reshape(4, 4).T.reshape(-1)
+        for k in range(16):
+            arr[i].transform[k] = float(t[k])
+        ra = n.get("render_aabb", (0.5 - half,) * 3 + (0.5 + half,) * 3)
+        for k in range(6):
+            arr[i].train_aabb[k] = 0.5 - half if k < 3 else 0.5 + half
+            arr[i].render_aabb[k] = float(ra[k])
+        arr[i].opacity = n.get("opacity", 1.0)
+        arr[i].rgb_activation, arr[i].density_activation, arr[i].min_transmittance = 2, 3, 0.01
+    out = np.zeros((height, width, 4), np.float32)
+    ns = C.c_uint64(0)
+    lib().orc_blender_render(C.byref(rq), len(nerfs), arr, _p(out), C.byref(ns))
+    return out, int(ns.value)
+
+
 class Trainer:
     """Whole-iteration CPU restatement of Testbed::train for the NeRF mode (oracle/ngp_trainer.cpp)."""
 

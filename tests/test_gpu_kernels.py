@@ -593,3 +593,92 @@ def test_snapshot_save_load_render(small_scene, trained_testbed, tmp_path):
     assert np.array_equal(shot(tb3), img2)  # idempotent
     with pytest.raises(RuntimeError):
         tb2.train(1 << 14)
+
+
+# ------------------------------------------------------------------------------------------------------
+# K18: the Blender multi-NeRF renderer through pyngp.Testbed.request_nerf_render_sync vs the CPU oracle
+# ------------------------------------------------------------------------------------------------------
+def _blender_request(pyngp, small_scene, paths, transforms, opacities, res=(48, 40), mip=0, flip_y=False, color_space=None, cam=None, bg=(0.1, 0.2, 0.3, 0.0)):
+    color_space = pyngp.ColorSpace.SRGB if color_space is None else color_space
+    out = pyngp.RenderOutputProperties(res, pyngp.DownsampleInfo.MakeFromMip(res, mip), 1, color_space, pyngp.TonemapCurve.Identity, 0.0, bg, flip_y)
+    cam = small_scene["xforms"][3] if cam is None else cam
+    camera = pyngp.RenderCameraProperties(cam, pyngp.CameraModel.Perspective, small_scene["fx"] / 64.0 * res[0], 0.0, 0.0, 1.0, None, None)
+    box = pyngp.BoundingBox([0, 0, 0], [1, 1, 1])
+    nerfs = [pyngp.NerfDescriptor(p, box, t, pyngp.RenderModifiers([]), o) for p, t, o in zip(paths, transforms, opacities)]
+    return pyngp.RenderRequest(out, camera, pyngp.RenderModifiers([]), nerfs, pyngp.BoundingBox([-8, -8, -8], [8, 8, 8]))
+
+
+@pytest.mark.parametrize("case", ["single", "two_instances", "mip1_flip_linear"])
+def test_blender_render_matches_oracle(L, orc, small_scene, trained_testbed, tmp_path, case):
+    """request_nerf_render_sync (snapshot -> field -> wave renderer -> tone map) against oracle.blender_render on the same snapshot contents.
+    Floating-point path: PSNR >= 45 dB, mean |diff| <= 2e-3, >= 99 % of pixels within 1e-2, composited sample count within 1 %."""
+    import pyngp
+    import msgpack
+    tb = trained_testbed
+    path = str(tmp_path / "scene.msgpack")
+    tb.save_snapshot(path)
+    with open(path, "rb") as f:
+        snap = pyngp.parse_snapshot(msgpack.unpackb(f.read(), raw=False, strict_map_key=False))
+    m = orc.model()
+    g, _ = pyngp.grid_init(device_scales=True)
+    for l in range(16):
+        m.scales[l] = g.scale[l]
+    grid = snap["density_grid"]
+    bits = orc.bitfield(1, grid, orc.density_grid_mean(grid))
+    T0 = np.eye(4, dtype=np.float32)
+    T1 = np.eye(4, dtype=np.float32)
+    c, s = np.cos(0.6), np.sin(0.6)
+    T1[:3, :3] = np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]], np.float32) * 0.75
+    T1[:3, 3] = (0.55, 0.1, 0.35)
+    if case == "single":
+        transforms, opac, kw = [T0], [1.0], {}
+    elif case == "two_instances":
+        transforms, opac, kw = [T0, T1], [0.6, 1.0], {}
+    else:
+        transforms, opac, kw = [T0], [1.0], dict(mip=1, flip_y=True, color_space=pyngp.ColorSpace.Linear)
+    rq = _blender_request(pyngp, small_scene, [path] * len(transforms), transforms, opac, **kw)
+    got = tb.request_nerf_render_sync(rq)
+    W, H = rq.output.resolution
+    nerfs = [dict(model=m, params_half=snap["params_half"], bitfield=bits, aabb_scale=1, transform=t, opacity=o) for t, o in zip(transforms, opac)]
+    want, n_samples = orc.blender_render(W, H, rq.camera.transform, rq.camera.focal_length, nerfs, mip=rq.output.ds.mip, flip_y=rq.output.flip_y,
+                                         color_space=int(rq.output.color_space), background=rq.output.background_color)
+    assert got.shape == want.shape == (H, W, 4)
+    assert want[..., 3].max() > 0.9 and n_samples > 1000
+    diff = np.abs(got - want)
+    assert _psnr(got, want) >= 45.0, f"PSNR {_psnr(got, want):.1f} dB"
+    assert diff.mean() <= 2e-3
+    assert (diff.max(axis=-1) <= 1e-2).mean() >= 0.99
+    assert abs(tb.last_render_samples - n_samples) <= 0.01 * n_samples
+    assert tb.last_render_launches >= 6
+
+
+def test_blender_render_request_semantics(small_scene, trained_testbed, tmp_path):
+    """Empty request -> background; the field cache follows the request's snapshot paths; a missing snapshot and unbuilt options raise; the async
+    entry point delivers the same image to its callback."""
+    import pyngp
+    import threading
+    tb = trained_testbed
+    path = str(tmp_path / "scene.msgpack")
+    tb.save_snapshot(path)
+    rq0 = _blender_request(pyngp, small_scene, [], [], [], res=(16, 8), bg=(0.25, 0.5, 0.75, 1.0))
+    img = tb.request_nerf_render_sync(rq0)
+    np.testing.assert_allclose(img, np.broadcast_to(np.array([0.25, 0.5, 0.75, 1.0], np.float32), (8, 16, 4)), atol=3e-5)
+    rq = _blender_request(pyngp, small_scene, [path], [np.eye(4)], [1.0], res=(32, 32))
+    a = tb.request_nerf_render_sync(rq)
+    assert list(tb._bl_fields) == [path]
+    field = tb._bl_fields[path]
+    b = tb.request_nerf_render_sync(rq)
+    assert tb._bl_fields[path] is field and np.array_equal(a, b)  # cached field, deterministic render
+    got = []
+    done = threading.Event()
+    tb.request_nerf_render_async(rq, lambda im: (got.append(im), done.set()))
+    assert done.wait(60.0) and np.array_equal(got[0], a)
+    tb.request_nerf_render_sync(rq0)
+    assert not tb._bl_fields  # dropped when no descriptor names it
+    with pytest.raises(RuntimeError):
+        tb.request_nerf_render_sync(_blender_request(pyngp, small_scene, [str(tmp_path / "nope.msgpack")], [np.eye(4)], [1.0]))
+    with pytest.raises(RuntimeError):
+        pyngp.Mask3D.Box([1, 1, 1], np.eye(4), 0, 0.0, 1.0)
+    sing = np.zeros((4, 4), np.float32)
+    with pytest.raises(RuntimeError):
+        tb.request_nerf_render_sync(_blender_request(pyngp, small_scene, [path], [sing], [1.0]))

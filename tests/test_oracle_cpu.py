@@ -318,3 +318,53 @@ def test_render_oracle_invariants(orc):
 
 def orc_srgb_to_linear(v):
     return v / 12.92 if v <= 0.04045 else ((v + 0.055) / 1.055) ** 2.4
+
+
+def _blender_nerf(orc, rs, bits, **kw):
+    m = orc.model()
+    params = np.concatenate([(rs.rand(10240) - 0.5).astype(np.float16) * 0.3, (rs.randn(m.n_grid_params) * 0.1).astype(np.float16)])
+    return dict(model=m, params_half=params, bitfield=bits, aabb_scale=1, **kw)
+
+
+def test_blender_render_oracle_invariants(orc):
+    """Multi-NeRF render restatement (src/nerf_renderer.cu:565-791): empty request and empty occupancy give the background; opacity 0 contributes
+    nothing; moving NeRF and camera together leaves the image unchanged; flip_y mirrors rows; mip 1 replicates 2x2 blocks; a NeRF behind an opaque
+    one is never reached."""
+    rs = np.random.RandomState(1)
+    cam = np.array([[1, 0, 0, 0.5], [0, 1, 0, 0.5], [0, 0, 1, -1.5]], np.float32)
+    W, H, f = 16, 12, 20.0
+    bg = (0.5, 0.25, 1.0, 1.0)
+    img, n = orc.blender_render(W, H, cam, f, [], background=bg)
+    assert n == 0
+    np.testing.assert_allclose(img, np.broadcast_to(np.array(bg, np.float32), (H, W, 4)), atol=3e-5)  # sRGB buffer: background passes through the sRGB pair
+    empty = np.zeros(128 ** 3, np.uint8)
+    img, n = orc.blender_render(W, H, cam, f, [_blender_nerf(orc, rs, empty)], background=bg)
+    assert n == 0
+    np.testing.assert_allclose(img[..., :3], np.broadcast_to(np.array(bg[:3], np.float32), (H, W, 3)), atol=3e-5)
+    full = np.full(128 ** 3, 255, np.uint8)
+    nerf = _blender_nerf(orc, rs, full)
+    base, n_base = orc.blender_render(W, H, cam, f, [nerf])
+    assert n_base > W * H and 0.0 <= base[..., 3].min() and base[..., 3].max() <= 1.0 + 1e-6 and base[..., 3].max() > 0.5
+    # opacity 0: samples are taken but weigh nothing
+    img, n = orc.blender_render(W, H, cam, f, [dict(nerf, opacity=0.0)])
+    assert n > 0 and np.all(img == 0.0)
+    # rigid motion of NeRF + camera (translation by a power of two keeps the float arithmetic close)
+    T = np.eye(4, dtype=np.float32); T[:3, 3] = (2.0, -1.0, 4.0)
+    cam2 = cam.copy(); cam2[:, 3] += T[:3, 3]
+    moved, _ = orc.blender_render(W, H, cam2, f, [dict(nerf, transform=T)])
+    assert np.abs(moved - base).mean() < 2e-3
+    # flip_y mirrors the rows
+    flipped, _ = orc.blender_render(W, H, cam, f, [nerf], flip_y=True)
+    assert np.array_equal(flipped, base[::-1])
+    # mip 1: 2x2 blocks carry one traced pixel
+    low, n_low = orc.blender_render(W, H, cam, f, [nerf], mip=1)
+    assert n_low < n_base
+    blocks = low.reshape(H // 2, 2, W // 2, 2, 4)
+    assert np.array_equal(blocks, np.broadcast_to(blocks[:, :1, :, :1], blocks.shape))
+    # a second NeRF fully behind the first: rays that saturate in the first never sample it, and its presence leaves saturated pixels unchanged
+    Tb = np.eye(4, dtype=np.float32); Tb[2, 3] = 1.5
+    both, n_both = orc.blender_render(W, H, cam, f, [nerf, dict(_blender_nerf(orc, rs, full), transform=Tb)])
+    sat = base[..., 3] >= 0.999
+    if sat.any():
+        assert np.abs(both[sat] - base[sat]).max() < 1e-5
+    assert n_both >= n_base
