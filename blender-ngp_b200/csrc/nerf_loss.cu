@@ -264,7 +264,8 @@ __global__ void __launch_bounds__(1024) loss_gradient_kernel(
 	const LossParams P, const uint32_t* __restrict__ counters_in, const float* __restrict__ mean_density_ptr,
 	const __half* __restrict__ rgbsigma, const float* __restrict__ rays, uint32_t* __restrict__ numsteps_io, const float* __restrict__ coords_in,
 	const RayState* __restrict__ state, const uint32_t* __restrict__ compacted_counts, const uint32_t* __restrict__ local_bases, const uint32_t* __restrict__ block_prefix,
-	float* __restrict__ coords_out, __half* __restrict__ dloss_dout, float* __restrict__ loss_output)
+	float* __restrict__ coords_out, __half* __restrict__ dloss_dout, float* __restrict__ loss_output,
+	const uint4* __restrict__ rows_in, uint4* __restrict__ rows_out)
 {
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t i = blockIdx.x * LOSS_RAYS_PER_BLOCK + warp;
@@ -293,6 +294,12 @@ __global__ void __launch_bounds__(1024) loss_gradient_kernel(
 		const float* src = coords_in + (size_t)base * COORD_FLOATS;
 		float* dst = coords_out + (size_t)compacted_base * COORD_FLOATS;
 		for (uint32_t k = lane; k < cn * COORD_FLOATS; k += 32) dst[k] = src[k];
+		// ... and of their hash-grid features (64-byte rows), which the training pass would otherwise recompute from the same weights
+		if (rows_in) {
+			const uint4* rs = rows_in + (size_t)base * 4;
+			uint4* rd = rows_out + (size_t)compacted_base * 4;
+			for (uint32_t k = lane; k < cn * 4; k += 32) rd[k] = rs[k];
+		}
 	}
 
 	float T_in = 1.f;
@@ -343,7 +350,8 @@ __global__ void __launch_bounds__(1024) loss_gradient_kernel(
 
 // (D) roll-over padding of the compacted batch (tcnn common_device.h:517-537): element e >= n_valid copies
 // element e % n_valid; gradients of the padded copies are rescaled by n_valid / batch.
-__global__ void __launch_bounds__(256) rollover_kernel(const uint32_t batch, const uint32_t* __restrict__ counters_out, float* __restrict__ coords, __half* __restrict__ dloss_dout)
+__global__ void __launch_bounds__(256) rollover_kernel(const uint32_t batch, const uint32_t* __restrict__ counters_out, float* __restrict__ coords, __half* __restrict__ dloss_dout,
+                                                       uint4* __restrict__ rows)
 {
 	const uint32_t n_valid = min(counters_out[0], batch);
 	if (n_valid == 0 || n_valid >= batch) return;
@@ -357,6 +365,10 @@ __global__ void __launch_bounds__(256) rollover_kernel(const uint32_t batch, con
 	for (int k = 0; k < 4; ++k) {
 		const float v = __half2float(dloss_dout[(size_t)src * 4 + k]);
 		dloss_dout[(size_t)e * 4 + k] = __float2half_rn(v * n_valid / batch);
+	}
+	if (rows) {
+		#pragma unroll
+		for (int k = 0; k < 4; ++k) rows[(size_t)e * 4 + k] = rows[(size_t)src * 4 + k];
 	}
 }
 
@@ -378,11 +390,24 @@ extern "C" int ngpb_compute_loss(void* stream, uint32_t n_rays, const float* aab
 		mean_density_dev, coords_out, dloss_dout, loss_per_ray, counters_out, scratch);
 }
 
-extern "C" int ngpb_compute_loss_sharded(void* stream_, uint32_t n_rays, uint32_t n_rays_global, const float* aabb6, ngpb_rng rng_, uint32_t batch, const ngpb_loss_config* cfg,
+extern "C" int ngpb_compute_loss_sharded(void* stream, uint32_t n_rays, uint32_t n_rays_global, const float* aabb6, ngpb_rng rng, uint32_t batch, const ngpb_loss_config* cfg,
                                  uint32_t n_images, const ngpb_image* images_dev, const uint32_t* counters_in,
                                  const ngpb_half* rgbsigma, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords_in,
                                  const float* mean_density_dev, float* coords_out, ngpb_half* dloss_dout, float* loss_per_ray, uint32_t* counters_out, void* scratch) {
+	return ngpb_compute_loss_compact_features(stream, n_rays, n_rays_global, aabb6, rng, batch, cfg, n_images, images_dev, counters_in, rgbsigma, ray_indices, rays, numsteps, coords_in,
+		mean_density_dev, coords_out, dloss_dout, loss_per_ray, counters_out, scratch, nullptr, nullptr);
+}
+
+extern "C" int ngpb_compute_loss_compact_features(void* stream_, uint32_t n_rays, uint32_t n_rays_global, const float* aabb6, ngpb_rng rng_, uint32_t batch, const ngpb_loss_config* cfg,
+                                 uint32_t n_images, const ngpb_image* images_dev, const uint32_t* counters_in,
+                                 const ngpb_half* rgbsigma, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords_in,
+                                 const float* mean_density_dev, float* coords_out, ngpb_half* dloss_dout, float* loss_per_ray, uint32_t* counters_out, void* scratch,
+                                 const ngpb_half* encoded_in, ngpb_half* encoded_out) {
 	try {
+		if ((encoded_in == nullptr) != (encoded_out == nullptr) || (encoded_in && encoded_in == encoded_out)) {
+			set_last_error("ngpb_compute_loss: encoded_in and encoded_out must both be given, and differ");
+			return NGPB_ERR_INVALID_ARGUMENT;
+		}
 		if (!aabb6 || !cfg || !images_dev || !counters_in || !rgbsigma || !ray_indices || !rays || !numsteps || !coords_in || !mean_density_dev ||
 		    !coords_out || !dloss_dout || !counters_out || !scratch || n_images == 0 || batch == 0) {
 			set_last_error("ngpb_compute_loss: invalid argument");
@@ -410,9 +435,9 @@ extern "C" int ngpb_compute_loss_sharded(void* stream_, uint32_t n_rays, uint32_
 		loss_scan_kernel<<<1, 1024, 0, stream>>>(blocks, block_sums, counters_out);
 		NGPB_LAUNCH_CHECK();
 		loss_gradient_kernel<<<blocks, 1024, 0, stream>>>(P, counters_in, mean_density_dev, (const __half*)rgbsigma, rays, numsteps, coords_in, state, counts, local_bases, block_sums,
-			coords_out, (__half*)dloss_dout, loss_per_ray);
+			coords_out, (__half*)dloss_dout, loss_per_ray, reinterpret_cast<const uint4*>(encoded_in), reinterpret_cast<uint4*>(encoded_out));
 		NGPB_LAUNCH_CHECK();
-		rollover_kernel<<<div_round_up(batch, 256), 256, 0, stream>>>(batch, counters_out, coords_out, (__half*)dloss_dout);
+		rollover_kernel<<<div_round_up(batch, 256), 256, 0, stream>>>(batch, counters_out, coords_out, (__half*)dloss_dout, reinterpret_cast<uint4*>(encoded_out));
 		NGPB_LAUNCH_CHECK();
 		return 0;
 	} catch (const std::exception& e) { set_last_error(e.what()); return NGPB_ERR_RUNTIME; }

@@ -410,13 +410,32 @@ __global__ void __launch_bounds__(128, MODE == 2 ? 2 : 4) nerf_mlp_kernel(const 
 }
 
 // Fixed-order sum of the per-CTA partials (deterministic), overwrites mlp_grad.
+// Sums the per-CTA weight-gradient partials in a fixed order: 32 parameters x 8 groups per block, group g adds partials g, g+8, g+16, ... in
+// sequence (four independent chains in flight), then the 8 group sums are added in order 0..7. Same result on every run.
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partials, const uint32_t n_parts, float* __restrict__ mlp_grad)
 {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= MLP_PARAMS) return;
-	float s = 0.f;
-	for (uint32_t p = 0; p < n_parts; ++p) s += partials[(size_t)p * MLP_PARAMS + i];
-	mlp_grad[i] = s;
+	__shared__ float part[8][32];
+	const uint32_t col = threadIdx.x & 31, grp = threadIdx.x >> 5;
+	const uint32_t i = blockIdx.x * 32 + col;
+	float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+	if (i < MLP_PARAMS) {
+		uint32_t p = grp;
+		for (; p + 24 < n_parts; p += 32) {
+			s0 += partials[(size_t)p * MLP_PARAMS + i];
+			s1 += partials[(size_t)(p + 8) * MLP_PARAMS + i];
+			s2 += partials[(size_t)(p + 16) * MLP_PARAMS + i];
+			s3 += partials[(size_t)(p + 24) * MLP_PARAMS + i];
+		}
+		for (; p < n_parts; p += 8) s0 += partials[(size_t)p * MLP_PARAMS + i];
+	}
+	part[grp][col] = (s0 + s1) + (s2 + s3);
+	__syncthreads();
+	if (grp == 0 && i < MLP_PARAMS) {
+		float s = part[0][col];
+		#pragma unroll
+		for (int g = 1; g < 8; ++g) s += part[g][col];
+		mlp_grad[i] = s;
+	}
 }
 
 constexpr uint32_t SMEM_INFER = S_INFER_END + S_CTRL;
@@ -456,7 +475,7 @@ void nerf_mlp_forward_backward_launch(cudaStream_t stream, const __half* mlp, co
 	const uint32_t grid = std::min(tiles, TRAIN_GRID);
 	launch_mlp<MODE_TRAIN>(stream, a, grid, SMEM_TRAIN);
 	NGPB_STEP_KERNEL(reduce_partials_kernel);
-	reduce_partials_kernel<<<div_round_up(MLP_PARAMS, 256), 256, 0, stream>>>(partials, grid, mlp_grad);
+	reduce_partials_kernel<<<div_round_up(MLP_PARAMS, 32), 256, 0, stream>>>(partials, grid, mlp_grad);
 	NGPB_LAUNCH_CHECK();
 }
 

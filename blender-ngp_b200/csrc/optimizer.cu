@@ -10,6 +10,7 @@
 // part in the EMA, exactly as in the reference.
 #include "common.cuh"
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include "../../include/ngpb.h"
 
@@ -44,7 +45,8 @@ __device__ __forceinline__ void adam_ema_one(const AdamParams& P, bool is_matrix
 }
 
 // Four parameters per thread (128-bit accesses on the fp32 arrays, 64-bit on the fp16 ones); n4 = n / 4 full groups, the tail is scalar.
-__global__ void __launch_bounds__(256) adam_ema_kernel(const AdamParams P, float* __restrict__ grad, float* __restrict__ w_fp32, __half* __restrict__ w_half,
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(256, MIN_BLOCKS) adam_ema_kernel(const AdamParams P, float* __restrict__ grad, float* __restrict__ w_fp32, __half* __restrict__ w_half,
                                                        __half* __restrict__ w_ema, float* __restrict__ m1, float* __restrict__ m2, uint32_t* __restrict__ param_steps)
 {
 	const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -150,8 +152,13 @@ void optimizer_launch(cudaStream_t stream, const void* params, uint32_t first, u
 	std::memcpy(&P, params, sizeof(P));
 	P.n = count;
 	P.n_matrix = n_matrix_params > first ? n_matrix_params - first : 0u;
-	NGPB_STEP_KERNEL(adam_ema_kernel);
-	adam_ema_kernel<<<div_round_up(count / 4 + count % 4, 256), 256, 0, stream>>>(P, grad + first, w_fp32 + first, w_half + first, w_ema + first, m1 + first, m2 + first, param_steps + first);
+	// The sweep is a dependent pair of DRAM round trips per thread (gradient -> optimizer state), so bytes in flight = resident threads x 32 B:
+	// NGPB_ADAM_BLOCKS picks the occupancy target (registers per thread follow from it).
+	static const int min_blocks = [] { const char* e = std::getenv("NGPB_ADAM_BLOCKS"); return e ? std::atoi(e) : 6; }();
+	const uint32_t blocks = div_round_up(count / 4 + count % 4, 256);
+	if (min_blocks >= 8) adam_ema_kernel<8><<<blocks, 256, 0, stream>>>(P, grad + first, w_fp32 + first, w_half + first, w_ema + first, m1 + first, m2 + first, param_steps + first);
+	else if (min_blocks >= 6) adam_ema_kernel<6><<<blocks, 256, 0, stream>>>(P, grad + first, w_fp32 + first, w_half + first, w_ema + first, m1 + first, m2 + first, param_steps + first);
+	else adam_ema_kernel<4><<<blocks, 256, 0, stream>>>(P, grad + first, w_fp32 + first, w_half + first, w_ema + first, m1 + first, m2 + first, param_steps + first);
 	NGPB_LAUNCH_CHECK();
 }
 } // namespace ngpb

@@ -349,7 +349,7 @@ void ngpb_testbed::ensure_workspace(uint32_t batch) {
 	drop_prefetch();
 	NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
 	if (batch == 0 || batch % 128 != 0) throw std::runtime_error("training batch size must be a non-zero multiple of 128 (tcnn batch_size_granularity)");
-	dfree(ray_indices); dfree(rays); dfree(numsteps); dfree(coords); dfree(rgbsigma); dfree(encoded); dfree(coords_compacted);
+	dfree(ray_indices); dfree(rays); dfree(numsteps); dfree(coords); dfree(rgbsigma); dfree(encoded); dfree(encoded_compacted); dfree(coords_compacted);
 	dfree(dloss); dfree(denc); dfree(loss); dfree(scratch); dfree(counters); dfree(partials);
 	const size_t max_rays = 1u << 18;            // rays_per_batch cap (testbed_nerf.cu:2891)
 	const size_t max_samples = (size_t)batch * 16; // testbed_nerf.cu:3140
@@ -360,6 +360,7 @@ void ngpb_testbed::ensure_workspace(uint32_t batch) {
 	rgbsigma = (__half*)dalloc(sizeof(__half) * 4 * max_samples);
 	encoded = (__half*)dalloc(sizeof(__half) * N_ENC * max_samples);
 	coords_compacted = (float*)dalloc(sizeof(float) * COORD_FLOATS * batch);
+	encoded_compacted = (__half*)dalloc(sizeof(__half) * N_ENC * batch);
 	dloss = (__half*)dalloc(sizeof(__half) * 4 * batch);
 	denc = (__half*)dalloc(sizeof(__half) * N_ENC * batch);
 	loss = (float*)dalloc(sizeof(float) * max_rays);
@@ -370,6 +371,7 @@ void ngpb_testbed::ensure_workspace(uint32_t batch) {
 	NGPB_CUDA_CHECK(cudaMemsetAsync(coords, 0, sizeof(float) * COORD_FLOATS * max_samples, stream));
 	NGPB_CUDA_CHECK(cudaMemsetAsync(coords_compacted, 0, sizeof(float) * COORD_FLOATS * batch, stream));
 	NGPB_CUDA_CHECK(cudaMemsetAsync(dloss, 0, sizeof(__half) * 4 * batch, stream));
+	NGPB_CUDA_CHECK(cudaMemsetAsync(encoded_compacted, 0, sizeof(__half) * N_ENC * batch, stream));
 	NGPB_CUDA_CHECK(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * 16, stream));
 	ws_batch = batch;
 }
@@ -506,10 +508,11 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 	nerf_mlp_forward_launch(stream, w_half, encoded, coords, max_inference, counters, rgbsigma);
 	stage_end(NGPB_STAGE_MLP_INFERENCE, n_uncompacted_est, stream);
 	stage_begin(NGPB_STAGE_LOSS, stream);
-	check(ngpb_compute_loss_sharded(stream, R, (uint32_t)dp_world * R, aabb, r, batch, &loss_cfg, (uint32_t)images.size(), images_dev, counters, (const ngpb_half*)rgbsigma,
-		ray_indices, rays, numsteps, coords, mean_density, coords_compacted, (ngpb_half*)dloss, loss, counters + 2, scratch));
+	check(ngpb_compute_loss_compact_features(stream, R, (uint32_t)dp_world * R, aabb, r, batch, &loss_cfg, (uint32_t)images.size(), images_dev, counters, (const ngpb_half*)rgbsigma,
+		ray_indices, rays, numsteps, coords, mean_density, coords_compacted, (ngpb_half*)dloss, loss, counters + 2, scratch,
+		reuse_encoding ? (const ngpb_half*)encoded : nullptr, reuse_encoding ? (ngpb_half*)encoded_compacted : nullptr));
 	stage_end(NGPB_STAGE_LOSS, R, stream);
-	n_launches += 2 + 4;
+	n_launches += 2 + 5; // encode, mlp; loss target / composite / scan / gradient / rollover
 	if (dp_world > 1) {
 		// the controller needs the GLOBAL sample counts so that every rank derives the same next ray count: sum {uncompacted, kept rays,
 		// compacted} into counters[8..10] (the local values stay in [0..2] for the kernels of this step)
@@ -525,11 +528,16 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 
 	// ---- second half of the step, enqueued without waiting for the read-back (nothing in it depends on the host) ----
 	// forward + backward on the compacted, padded batch
-	stage_begin(NGPB_STAGE_ENCODE_TRAIN, stream);
-	hash_encode_forward_launch(stream, &grid, w_half + MLP_PARAMS, coords_compacted, COORD_FLOATS, batch, nullptr, encoded);
-	stage_end(NGPB_STAGE_ENCODE_TRAIN, batch, stream);
+	// The reference re-encodes the compacted samples (NerfNetwork::forward). Inference and training use the same fp16 weights within a step, so the
+	// features the inference pass produced for these very samples are bit-identical: the loss stage compacted them along with the coordinates.
+	if (!reuse_encoding) {
+		stage_begin(NGPB_STAGE_ENCODE_TRAIN, stream);
+		hash_encode_forward_launch(stream, &grid, w_half + MLP_PARAMS, coords_compacted, COORD_FLOATS, batch, nullptr, encoded_compacted);
+		stage_end(NGPB_STAGE_ENCODE_TRAIN, batch, stream);
+		++n_launches;
+	}
 	stage_begin(NGPB_STAGE_MLP_TRAIN, stream);
-	nerf_mlp_forward_backward_launch(stream, w_half, encoded, coords_compacted, dloss, batch, denc, grad, partials);
+	nerf_mlp_forward_backward_launch(stream, w_half, encoded_compacted, coords_compacted, dloss, batch, denc, grad, partials);
 	stage_end(NGPB_STAGE_MLP_TRAIN, batch, stream);
 	NGPB_CUDA_CHECK(cudaEventRecord(mlp_train_done, stream));
 	if (dp_world == 1) {
@@ -576,7 +584,7 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 			n_launches += 1;
 		}
 	}
-	n_launches += 1 + 2 + 1 + 1;
+	n_launches += 2 + 1 + 1; // mlp_train + reduce_partials, encode_backward, optimizer
 	// loss scalar every 16th step (:2885-2888): reduced on the device, read back without stalling the stream
 	if (get_loss_scalar) {
 		NGPB_STEP_KERNEL(sum_kernel);
@@ -843,6 +851,7 @@ extern "C" int ngpb_testbed_set_option(ngpb_testbed* t, const char* name, double
 	else if (k == "render_with_training_params") t->render_with_training_params = v != 0;
 	else if (k == "dp_sharded_optimizer") t->dp_sharded_optimizer = v != 0;
 	else if (k == "overlap_sampling") { t->drop_prefetch(); t->overlap_sampling = v != 0; }
+	else if (k == "reuse_encoding") t->reuse_encoding = v != 0;
 	else throw std::runtime_error("unknown option: " + k);
 	NGPB_API_END
 }

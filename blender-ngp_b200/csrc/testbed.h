@@ -34,6 +34,7 @@ struct ngpb_testbed {
 	cudaEvent_t prefetch_done = nullptr, loss_ready = nullptr, counters_ready = nullptr, mlp_train_done = nullptr;
 	SamplingRequest prefetch{};
 	bool prefetch_valid = false, overlap_sampling = true;
+	bool reuse_encoding = true; // the training pass starts from the inference pass's hash-grid features (compacted with the samples) instead of re-encoding
 	bool loss_pending = false;
 	float loss_pending_scale = 0.f;
 
@@ -82,7 +83,7 @@ struct ngpb_testbed {
 	// per-iteration workspace, sized by the batch (train_nerf_step scratch, testbed_nerf.cu:3145-3170)
 	uint32_t ws_batch = 0;
 	uint32_t* ray_indices = nullptr; float* rays = nullptr; uint32_t* numsteps = nullptr; float* coords = nullptr;
-	__half* rgbsigma = nullptr; __half* encoded = nullptr; float* coords_compacted = nullptr; __half* dloss = nullptr; __half* denc = nullptr;
+	__half* rgbsigma = nullptr; __half* encoded = nullptr; __half* encoded_compacted = nullptr; float* coords_compacted = nullptr; __half* dloss = nullptr; __half* denc = nullptr;
 	float* loss = nullptr; void* scratch = nullptr; uint32_t* counters = nullptr; float* partials = nullptr;
 	uint32_t* host_readback = nullptr;
 

@@ -326,7 +326,7 @@ EXPORTED_SYMBOLS = [
     "ngpb_testbed_get_params", "ngpb_testbed_set_params", "ngpb_testbed_get_density_grid", "ngpb_testbed_set_option", "ngpb_testbed_get_option",
     "ngpb_testbed_render", "ngpb_testbed_stream", "ngpb_testbed_stage_times", "ngpb_grid_device_scales", "ngpb_testbed_configure", "ngpb_testbed_set_params_half", "ngpb_testbed_set_density_grid", "ngpb_testbed_get_training_state",
     "ngpb_testbed_set_training_state", "ngpb_testbed_get_optimizer_state", "ngpb_testbed_set_optimizer_state", "ngpb_generate_training_samples_sharded", "ngpb_compute_loss_sharded", "ngpb_nccl_unique_id", "ngpb_testbed_init_data_parallel", "ngpb_render_workspace_bytes", "ngpb_render_nerf", "ngpb_testbed_last_render_ms", "ngpb_generate_training_samples_scratch_bytes", "ngpb_compute_loss_scratch_bytes",
-    "ngpb_field_create", "ngpb_field_destroy", "ngpb_blender_render",
+    "ngpb_field_create", "ngpb_field_destroy", "ngpb_blender_render", "ngpb_compute_loss_compact_features",
 ]
 
 _lib = None
@@ -491,6 +491,9 @@ def load_transforms(path):
     scale = meta.get("scale", 1.0)  # NERF_SCALE = 1.0 in this fork (nerf_loader.h:28)
     offset = meta.get("offset", [0.0, 0.0, 0.0])
     aabb_scale = int(meta.get("aabb_scale", 1))
+    # lens models (nerf_loader.cu:197-269) are outside the built scope: refuse rather than train on undistorted rays
+    if any(float(meta.get(k, 0.0)) != 0.0 for k in ("k1", "k2", "k3", "k4", "p1", "p2")) or meta.get("is_fisheye") or "ftheta_p0" in meta or "latlong" in meta:
+        raise RuntimeError("lens distortion / fisheye / f-theta camera models are outside the built scope")
     frames = sorted(meta["frames"], key=lambda fr: fr["file_path"])  # nerf_loader.cu:356-358
     images, xforms = [], []
     for fr in frames:

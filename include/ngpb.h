@@ -139,6 +139,14 @@ int ngpb_compute_loss_sharded(void* stream, uint32_t n_rays, uint32_t n_rays_glo
                               uint32_t n_images, const ngpb_image* images_dev, const uint32_t* counters_in,
                               const ngpb_half* rgbsigma, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords_in,
                               const float* mean_density_dev, float* coords_out, ngpb_half* dloss_dout, float* loss_per_ray, uint32_t* counters_out, void* scratch);
+/* Same, and additionally compacts the samples' hash-grid feature rows ([n][32] fp16, as written by ngpb_hash_encode_forward on coords_in with the
+ * weights of this step) into encoded_out[batch][32] with the same compaction and roll-over as coords_out. The training forward pass on coords_out
+ * (NerfNetwork::forward, nerf_network.h:143-185, re-encodes them in the reference) can then start from encoded_out: same function of the same inputs. */
+int ngpb_compute_loss_compact_features(void* stream, uint32_t n_rays, uint32_t n_rays_global, const float* aabb6, ngpb_rng rng, uint32_t batch, const ngpb_loss_config* cfg,
+                              uint32_t n_images, const ngpb_image* images_dev, const uint32_t* counters_in,
+                              const ngpb_half* rgbsigma, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords_in,
+                              const float* mean_density_dev, float* coords_out, ngpb_half* dloss_dout, float* loss_per_ray, uint32_t* counters_out, void* scratch,
+                                       const ngpb_half* encoded_in, ngpb_half* encoded_out);
 
 /* ---- K15: Ema(ExponentialDecay(Adam)) in one pass (tcnn adam.h:48-119, ema.h:63-76, exponential_decay.h:60-72) ---- */
 typedef struct {

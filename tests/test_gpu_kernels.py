@@ -359,6 +359,82 @@ def test_compute_loss(L, orc, small_scene, batch):
             assert np.array_equal(host(coords_out)[n_valid:], host(coords_out)[src])
 
 
+@pytest.mark.parametrize("batch", [1 << 16, 2048])
+def test_compute_loss_compacts_feature_rows(L, orc, small_scene, batch):
+    """ngpb_compute_loss_compact_features: feature rows follow exactly the compaction and roll-over of the coordinates (bit-exact gather), every
+    other output is bit-identical to ngpb_compute_loss, and mismatched arguments are refused."""
+    import pyngp
+    from conftest import scene_occupancy_bitfield
+    from gpu_util import dev, ptr, host, rng_struct
+    _, bits = scene_occupancy_bitfield(orc)
+    n_rays, max_samples = 2048, 1 << 16
+    rng = orc.pcg32(99)
+    rs = np.random.RandomState(4)
+    rgbsigma = np.zeros((max_samples, 4), np.float16)
+    rgbsigma[:, :3] = rs.randn(max_samples, 3).astype(np.float16)
+    rgbsigma[:, 3] = (rs.randn(max_samples) * 2.0 + 1.0).astype(np.float16)
+    rows = rs.randint(0, 1 << 15, size=(max_samples, 32)).astype(np.uint16).view(np.float16)  # arbitrary finite bit patterns
+    cfg = pyngp.LossConfig(128.0, (C.c_float * 3)(0, 0, 0), 1, 1, 0, 4, 2, 3, 1, 0.2)
+    aabb = np.array([0, 0, 0, 1, 1, 1], np.float32)
+    outs = []
+    for with_rows in (False, True):
+        g1 = _run_k1(L, small_scene, bits, n_rays, max_samples, rng)
+        d = g1["dev"]
+        numsteps_before = host(d["numsteps"]).view(np.uint32).copy()
+        d_rgbsigma, d_mean, d_rows = dev(rgbsigma), dev(np.array([0.005], np.float32)), dev(rows)
+        coords_out = torch.zeros((batch, 7), dtype=torch.float32, device="cuda")
+        dloss = torch.zeros((batch, 4), dtype=torch.float16, device="cuda")
+        rows_out = torch.zeros((batch, 32), dtype=torch.float16, device="cuda")
+        loss = torch.zeros(n_rays, dtype=torch.float32, device="cuda")
+        counters_out = torch.zeros(4, dtype=torch.int32, device="cuda")
+        scratch = torch.zeros(int(L.ngpb_compute_loss_scratch_bytes(n_rays)), dtype=torch.uint8, device="cuda")
+        args = [None, n_rays, n_rays, aabb.ctypes.data_as(C.c_void_p), rng_struct(rng), batch, C.byref(cfg), d["n_img"], ptr(d["meta"]), ptr(d["counters"]),
+                ptr(d_rgbsigma), ptr(d["ray_indices"]), ptr(d["rays"]), ptr(d["numsteps"]), ptr(d["coords"]), ptr(d_mean),
+                ptr(coords_out), ptr(dloss), ptr(loss), ptr(counters_out), ptr(scratch)]
+        if with_rows:
+            assert L.ngpb_compute_loss_compact_features(*args, ptr(d_rows), None) != 0
+            assert L.ngpb_compute_loss_compact_features(*args, ptr(d_rows), ptr(d_rows)) != 0
+            pyngp.check(L.ngpb_compute_loss_compact_features(*args, ptr(d_rows), ptr(rows_out)))
+        else:
+            pyngp.check(L.ngpb_compute_loss_sharded(*args))
+        outs.append(dict(coords=host(coords_out), dloss=host(dloss), loss=host(loss), total=int(host(counters_out).view(np.uint32)[0]),
+                         numsteps=host(d["numsteps"]).view(np.uint32).copy(), rows=host(rows_out), before=numsteps_before, n_kept=int(host(d["counters"]).view(np.uint32)[1])))
+    a, b = outs
+    for key in ("coords", "dloss", "loss", "numsteps"):
+        assert np.array_equal(a[key].view(np.uint8), b[key].view(np.uint8)), key
+    assert a["total"] == b["total"] > 0
+    # expected gather: ray i's first cn rows move from its uncompacted base to its compacted base; padding wraps modulo n_valid
+    n_valid = min(b["total"], batch)
+    src = np.zeros(batch, np.int64)
+    for i in range(b["n_kept"]):
+        cn, cbase = b["numsteps"][i]
+        base = b["before"][i, 1]
+        src[cbase:cbase + cn] = np.arange(base, base + cn)
+    src[n_valid:] = src[np.arange(n_valid, batch) % n_valid]
+    assert np.array_equal(b["rows"].view(np.uint16), rows.view(np.uint16)[src])
+    if batch == 2048:
+        assert b["total"] > batch  # the clipped case: the last kept ray is cut at the batch boundary
+    else:
+        assert n_valid < batch     # the roll-over case
+
+
+def test_training_step_reuses_inference_features(small_scene):
+    """The training pass started from the inference pass's compacted hash-grid features gives bit-identical parameters to re-encoding the compacted
+    samples (the reference's schedule): 20 steps each way from the same seed, occupancy-grid updates included."""
+    import pyngp
+    res = []
+    for reuse in (1.0, 0.0):
+        tb = pyngp.Testbed()
+        tb.load_training_images(small_scene["images"], small_scene["xforms"], small_scene["fx"], small_scene["fy"])
+        tb._set("reuse_encoding", reuse)
+        tb.train_n(20, 1 << 14)
+        w, h, e = tb.get_params()
+        res.append((w, h, e, tb.stats()))
+    assert np.array_equal(res[0][0].view(np.uint32), res[1][0].view(np.uint32))
+    assert np.array_equal(res[0][2].view(np.uint16), res[1][2].view(np.uint16))
+    assert res[0][3]["rays_per_batch"] == res[1][3]["rays_per_batch"]
+
+
 # ------------------------------------------------------------------------------------------------------
 # K15 optimizer
 # ------------------------------------------------------------------------------------------------------
