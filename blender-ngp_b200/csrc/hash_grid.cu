@@ -153,6 +153,43 @@ __global__ void __launch_bounds__(256) hash_encode_forward_kernel(
 	encoded[(size_t)i * L.n_levels + level] = r;
 }
 
+// Two-dimensional input (the neural-image model: N_POS_DIMS = 2 of kernel_grid, grid.h:220-349): four corners, x ^ y * 2654435761 when hashed.
+__global__ void __launch_bounds__(256) hash_encode_forward_2d_kernel(
+	const uint32_t n, const GridLevels L, const __half2* __restrict__ grid, const float* __restrict__ positions, const uint32_t pos_stride, __half2* __restrict__ encoded)
+{
+	__shared__ LevelConst lc[NGPB_MAX_LEVELS];
+	if (threadIdx.x < L.n_levels) lc[threadIdx.x] = LevelConst{L.scale[threadIdx.x], L.size[threadIdx.x], L.resolution[threadIdx.x], L.offset[threadIdx.x]};
+	__syncthreads();
+	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t level = tid % L.n_levels, i = tid / L.n_levels;
+	if (i >= n) return;
+	const LevelConst c = lc[level];
+	const __half2* __restrict__ g = grid + c.offset;
+	float pos[2];
+	uint32_t pg[2];
+	#pragma unroll
+	for (int d = 0; d < 2; ++d) { // pos_fract (tcnn common_device.h:434-445), see level_position
+		const float p = __fmaf_rn(positions[(size_t)i * pos_stride + d], c.scale, 0.5f);
+		const float fl = floorf(p);
+		pg[d] = (uint32_t)(int)fl;
+		pos[d] = p - fl;
+	}
+	// grid_index (grid.h:164-186): the stride loop stops once the stride exceeds the level size; hashed when the level is smaller than res^2
+	const bool x_only = c.resolution > c.size;                                   // stride after dim 0 already exceeds the table
+	const bool hashed = (uint64_t)c.size < (uint64_t)c.resolution * (x_only ? 1u : c.resolution);
+	__half2 r = __floats2half2_rn(0.f, 0.f);
+	#pragma unroll
+	for (uint32_t k = 0; k < 4; ++k) {
+		const uint32_t x = pg[0] + (k & 1), y = pg[1] + (k >> 1);
+		const uint32_t h = hashed ? (x ^ (y * 2654435761u)) : (x_only ? x : x + y * c.resolution);
+		const __half2 v = __ldg(g + h % c.size);
+		const float w = ((k & 1) ? pos[0] : 1.f - pos[0]) * ((k >> 1) ? pos[1] : 1.f - pos[1]);
+		const float2 f = __half22float2(v);
+		r = __hadd2(r, __floats2half2_rn(w * f.x, w * f.y));
+	}
+	encoded[(size_t)i * L.n_levels + level] = r;
+}
+
 // Backward: scatter-add weight * dL/dy into the fp32 gradient table. The reference uses atomicAdd(__half2) into an fp16 table
 // (grid.h:436-441); here the table is fp32 (one vectorised red.global.add.v2.f32 per corner), which removes the order-dependent fp16
 // rounding. Same thread mapping as the forward kernel; dL/dy enters through shared memory (coalesced read of the block's 2 KB).
@@ -239,6 +276,12 @@ void hash_encode_forward_launch(cudaStream_t stream, const ngpb_grid* g, const _
 	if (n == 0) return;
 	const GridLevels L = make_levels(g);
 	const uint64_t threads = (uint64_t)n * L.n_levels;
+	if (g->n_pos_dims == 2) {
+		if (n_dev) throw std::runtime_error("hash_encode_forward: a device-side count is not supported for 2-D grids");
+		hash_encode_forward_2d_kernel<<<(uint32_t)((threads + 255) / 256), 256, 0, stream>>>(n, L, (const __half2*)grid, positions, pos_stride, (__half2*)encoded);
+		NGPB_LAUNCH_CHECK();
+		return;
+	}
 	// no explicit shared-memory carve-out for this kernel: any non-default preference was measured 3x slower (L1 is what feeds the gathers)
 	hash_encode_forward_kernel<<<(uint32_t)((threads + 255) / 256), 256, 0, stream>>>(n, n_dev, L, (const __half2*)grid, positions, pos_stride, (__half2*)encoded);
 	NGPB_LAUNCH_CHECK();
@@ -257,8 +300,12 @@ void hash_encode_backward_launch(cudaStream_t stream, const ngpb_grid* g, const 
 using namespace ngpb;
 
 extern "C" uint32_t ngpb_grid_init(ngpb_grid* g, uint32_t n_levels, uint32_t log2_hashmap_size, uint32_t base_resolution, float per_level_scale) {
-	if (!g || n_levels == 0 || n_levels > NGPB_MAX_LEVELS) return 0;
+	return ngpb_grid_init_nd(g, 3, n_levels, log2_hashmap_size, base_resolution, per_level_scale);
+}
+extern "C" uint32_t ngpb_grid_init_nd(ngpb_grid* g, uint32_t n_pos_dims, uint32_t n_levels, uint32_t log2_hashmap_size, uint32_t base_resolution, float per_level_scale) {
+	if (!g || n_levels == 0 || n_levels > NGPB_MAX_LEVELS || (n_pos_dims != 2 && n_pos_dims != 3) || log2_hashmap_size > 30) return 0;
 	g->n_levels = n_levels;
+	g->n_pos_dims = n_pos_dims;
 	g->base_resolution = base_resolution;
 	g->log2_per_level_scale = std::log2(per_level_scale);
 	uint32_t offset = 0;
@@ -269,7 +316,7 @@ extern "C" uint32_t ngpb_grid_init(ngpb_grid* g, uint32_t n_levels, uint32_t log
 		g->scale[l] = scale;
 		g->resolution[l] = resolution;
 		const uint32_t max_params = 0xFFFFFFFFu / 2;
-		uint32_t params_in_level = powf((float)resolution, 3.f) > (float)max_params ? max_params : resolution * resolution * resolution;
+		uint32_t params_in_level = powf((float)resolution, (float)n_pos_dims) > (float)max_params ? max_params : (n_pos_dims == 2 ? resolution * resolution : resolution * resolution * resolution);
 		params_in_level = next_multiple(params_in_level, 8u);
 		params_in_level = params_in_level < (1u << log2_hashmap_size) ? params_in_level : (1u << log2_hashmap_size);
 		g->offsets[l] = offset;
@@ -306,7 +353,7 @@ extern "C" int ngpb_grid_device_scales(void* stream_, ngpb_grid* g) {
 extern "C" int ngpb_hash_encode_forward(void* stream, const ngpb_grid* g, const ngpb_half* grid, const float* positions, uint32_t pos_stride,
                                         uint32_t n, ngpb_half* encoded) {
 	try {
-		if (!g || !grid || !positions || !encoded || pos_stride < 3) { set_last_error("ngpb_hash_encode_forward: invalid argument"); return NGPB_ERR_INVALID_ARGUMENT; }
+		if (!g || !grid || !positions || !encoded || pos_stride < (g->n_pos_dims == 2 ? 2u : 3u)) { set_last_error("ngpb_hash_encode_forward: invalid argument"); return NGPB_ERR_INVALID_ARGUMENT; }
 		hash_encode_forward_launch((cudaStream_t)stream, g, (const __half*)grid, positions, pos_stride, n, nullptr, (__half*)encoded);
 		return 0;
 	} catch (const std::exception& e) { set_last_error(e.what()); return NGPB_ERR_RUNTIME; }
@@ -315,7 +362,7 @@ extern "C" int ngpb_hash_encode_forward(void* stream, const ngpb_grid* g, const 
 extern "C" int ngpb_hash_encode_backward(void* stream, const ngpb_grid* g, const float* positions, uint32_t pos_stride, uint32_t n,
                                          const ngpb_half* dL_dencoded, float* grid_grad) {
 	try {
-		if (!g || !positions || !dL_dencoded || !grid_grad || pos_stride < 3) { set_last_error("ngpb_hash_encode_backward: invalid argument"); return NGPB_ERR_INVALID_ARGUMENT; }
+		if (!g || !positions || !dL_dencoded || !grid_grad || pos_stride < 3 || g->n_pos_dims == 2) { set_last_error("ngpb_hash_encode_backward: invalid argument (3-D grids only)"); return NGPB_ERR_INVALID_ARGUMENT; }
 		hash_encode_backward_launch((cudaStream_t)stream, g, positions, pos_stride, n, (const __half*)dL_dencoded, grid_grad, 0, g->n_levels);
 		return 0;
 	} catch (const std::exception& e) { set_last_error(e.what()); return NGPB_ERR_RUNTIME; }

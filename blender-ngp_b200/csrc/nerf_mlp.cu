@@ -66,7 +66,7 @@ constexpr uint32_t TM_DW2R = 144;   // [64 x 64]   dW2r[o][i]
 constexpr uint32_t TM_DW3R = 208;   // [64 x 16]   dW3r^T[i][o]
 constexpr uint32_t TM_COLS_TRAIN = 256, TM_COLS_INFER = 64;
 
-enum MlpMode { MODE_DENSITY = 0, MODE_INFERENCE = 1, MODE_TRAIN = 2 };
+enum MlpMode { MODE_DENSITY = 0, MODE_INFERENCE = 1, MODE_TRAIN = 2, MODE_PLAIN = 3 }; // PLAIN: the 32 -> 64 -> 64 -> 16 network alone (neural image / SDF models)
 
 // ---- helpers ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void load_matrix_to_tile(uint8_t* smem, uint32_t dst, const __half* __restrict__ src, uint32_t rows, uint32_t cols) {
@@ -205,7 +205,13 @@ __global__ void __launch_bounds__(128, MODE == 2 ? 2 : 4) nerf_mlp_kernel(const 
 
 	if (warp == 0) tmem_alloc<TM_COLS>(tmem_slot);
 	if (tid == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
-	load_weights(smem, args.mlp);
+	if (MODE == MODE_PLAIN) { // FullyFusedMLP parameter order: first layer [64][32], hidden [64][64], last [16][64]
+		load_matrix_to_tile(smem, SW_W1R, args.mlp, 64, 32);
+		load_matrix_to_tile(smem, SW_W2R, args.mlp + 2048, 64, 64);
+		load_matrix_to_tile(smem, SW_W3R, args.mlp + 6144, 16, 64);
+	} else {
+		load_weights(smem, args.mlp);
+	}
 	tc_fence_before_sync();
 	__syncthreads();
 	tc_fence_after_sync();
@@ -238,11 +244,11 @@ __global__ void __launch_bounds__(128, MODE == 2 ? 2 : 4) nerf_mlp_kernel(const 
 			#pragma unroll
 			for (uint32_t k = 0; k < 4; ++k) {
 				const uint32_t q = tid + 128 * k;
-				*reinterpret_cast<uint4*>(smem + S_X + tile_offset(q >> 2, q & 3, 32)) = __ldg(src + q);
+				*reinterpret_cast<uint4*>(smem + (MODE == MODE_PLAIN ? S_RIN : S_X) + tile_offset(q >> 2, q & 3, 32)) = __ldg(src + q);
 			}
 		}
 		float dsigma = 0.f;
-		if (MODE != MODE_DENSITY) {
+		if (MODE == MODE_INFERENCE || MODE == MODE_TRAIN) {
 			const float* c = args.coords + row_g * COORD_FLOATS;
 			float sh[16];
 			sh4(c[4], c[5], c[6], sh);
@@ -264,13 +270,14 @@ __global__ void __launch_bounds__(128, MODE == 2 ? 2 : 4) nerf_mlp_kernel(const 
 			*reinterpret_cast<uint4*>(smem + S_DOR + tile_offset(tid, 1, 16)) = v1;
 		}
 
+		float sigma_logit = 0.f;
+		if (MODE != MODE_PLAIN) {
 		// ---- density net layer 1: H1 = relu(X W1d^T) ----
 		NGPB_MMA_BATCH(issue_forward(tmem_base + TM_ACC, sbase + S_X, 32, sbase + SW_W1D, 32, 64));
 		epilogue_store64<true>(t_row + TM_ACC, smem, S_H1, tid);
 
 		// ---- density net layer 2: Od = H1 W2d^T (16 outputs, no activation) ----
 		NGPB_MMA_BATCH(issue_forward(tmem_base + TM_ACC, sbase + S_H1, 64, sbase + SW_W2D, 64, 16));
-		float sigma_logit;
 		{
 			uint32_t r[16];
 			tmem_ld_x16(t_row + TM_ACC, r);
@@ -288,6 +295,7 @@ __global__ void __launch_bounds__(128, MODE == 2 ? 2 : 4) nerf_mlp_kernel(const 
 				}
 			}
 		}
+		}
 		if (MODE == MODE_DENSITY) { tc_fence_before_sync(); continue; }
 
 		constexpr uint32_t T_G1 = MODE == MODE_TRAIN ? S_G1 : S_H1;
@@ -300,6 +308,23 @@ __global__ void __launch_bounds__(128, MODE == 2 ? 2 : 4) nerf_mlp_kernel(const 
 		// ---- rgb net layer 2: G2 = relu(G1 W2r^T) ----
 		NGPB_MMA_BATCH(issue_forward(tmem_base + TM_ACC, sbase + T_G1, 64, sbase + SW_W2R, 64, 64));
 		epilogue_store64<true>(t_row + TM_ACC, smem, T_G2, tid);
+
+		if (MODE == MODE_PLAIN) {
+			// ---- output layer: all 16 padded outputs, no activation ([n][16] fp16, what FullyFusedMLP writes) ----
+			NGPB_MMA_BATCH(issue_forward(tmem_base + TM_ACC, sbase + T_G2, 64, sbase + SW_W3R, 64, 16));
+			uint32_t r[16];
+			tmem_ld_x16(t_row + TM_ACC, r);
+			tmem_ld_wait();
+			#pragma unroll
+			for (uint32_t h = 0; h < 2; ++h) {
+				uint4 v;
+				v.x = pack_half2(__uint_as_float(r[h * 8 + 0]), __uint_as_float(r[h * 8 + 1])); v.y = pack_half2(__uint_as_float(r[h * 8 + 2]), __uint_as_float(r[h * 8 + 3]));
+				v.z = pack_half2(__uint_as_float(r[h * 8 + 4]), __uint_as_float(r[h * 8 + 5])); v.w = pack_half2(__uint_as_float(r[h * 8 + 6]), __uint_as_float(r[h * 8 + 7]));
+				*reinterpret_cast<uint4*>(args.out + row_g * 16 + h * 8) = v;
+			}
+			tc_fence_before_sync();
+			continue;
+		}
 
 		if (MODE == MODE_INFERENCE) {
 			// ---- rgb net layer 3: 16 padded outputs, 3 used; output {r,g,b,sigma} (nerf_network.h:128-136) ----
@@ -463,6 +488,11 @@ void nerf_mlp_forward_launch(cudaStream_t stream, const __half* mlp, const __hal
 	const uint32_t tiles = n / TILE;
 	launch_mlp<MODE_INFERENCE>(stream, a, std::min(tiles, kNumSMs * INFER_CTAS_PER_SM), SMEM_INFER);
 }
+void plain_mlp_launch(cudaStream_t stream, const __half* weights, const __half* input, uint32_t n, __half* output) {
+	MlpArgs a{weights, input, nullptr, nullptr, output, nullptr, n, nullptr};
+	const uint32_t tiles = n / TILE;
+	launch_mlp<MODE_PLAIN>(stream, a, std::min(tiles, kNumSMs * INFER_CTAS_PER_SM), SMEM_INFER);
+}
 void nerf_density_mlp_launch(cudaStream_t stream, const __half* mlp, const __half* encoded, uint32_t n, __half* density) {
 	MlpArgs a{mlp, encoded, nullptr, nullptr, density, nullptr, n, nullptr};
 	const uint32_t tiles = n / TILE;
@@ -539,6 +569,14 @@ extern "C" int ngpb_nerf_mlp_forward(void* stream, const ngpb_half* mlp, const n
 		if (!mlp || !encoded || !coords || !rgbsigma || n % TILE != 0) { set_last_error("ngpb_nerf_mlp_forward: invalid argument (n must be a multiple of 128)"); return NGPB_ERR_INVALID_ARGUMENT; }
 		if (n == 0) return 0;
 		nerf_mlp_forward_launch((cudaStream_t)stream, (const __half*)mlp, (const __half*)encoded, coords, n, nullptr, (__half*)rgbsigma);
+		return 0;
+	} catch (const std::exception& e) { set_last_error(e.what()); return NGPB_ERR_RUNTIME; }
+}
+
+extern "C" int ngpb_mlp_forward(void* stream, const ngpb_half* weights, const ngpb_half* input, uint32_t n, ngpb_half* output) {
+	try {
+		if (!weights || !input || !output || n == 0 || n % TILE != 0) { set_last_error("ngpb_mlp_forward: null pointer or n not a non-zero multiple of 128"); return NGPB_ERR_INVALID_ARGUMENT; }
+		plain_mlp_launch((cudaStream_t)stream, (const __half*)weights, (const __half*)input, n, (__half*)output);
 		return 0;
 	} catch (const std::exception& e) { set_last_error(e.what()); return NGPB_ERR_RUNTIME; }
 }

@@ -204,7 +204,7 @@ class Field:
 class Grid(C.Structure):
     _fields_ = [("n_levels", C.c_uint32), ("base_resolution", C.c_uint32), ("log2_per_level_scale", C.c_float),
                 ("offsets", C.c_uint32 * (NGPB_MAX_LEVELS + 1)), ("scale", C.c_float * NGPB_MAX_LEVELS),
-                ("resolution", C.c_uint32 * NGPB_MAX_LEVELS)]
+                ("resolution", C.c_uint32 * NGPB_MAX_LEVELS), ("n_pos_dims", C.c_uint32)]
 
 
 class Image(C.Structure):
@@ -326,7 +326,7 @@ EXPORTED_SYMBOLS = [
     "ngpb_testbed_get_params", "ngpb_testbed_set_params", "ngpb_testbed_get_density_grid", "ngpb_testbed_set_option", "ngpb_testbed_get_option",
     "ngpb_testbed_render", "ngpb_testbed_stream", "ngpb_testbed_stage_times", "ngpb_grid_device_scales", "ngpb_testbed_configure", "ngpb_testbed_set_params_half", "ngpb_testbed_set_density_grid", "ngpb_testbed_get_training_state",
     "ngpb_testbed_set_training_state", "ngpb_testbed_get_optimizer_state", "ngpb_testbed_set_optimizer_state", "ngpb_generate_training_samples_sharded", "ngpb_compute_loss_sharded", "ngpb_nccl_unique_id", "ngpb_testbed_init_data_parallel", "ngpb_render_workspace_bytes", "ngpb_render_nerf", "ngpb_testbed_last_render_ms", "ngpb_generate_training_samples_scratch_bytes", "ngpb_compute_loss_scratch_bytes",
-    "ngpb_field_create", "ngpb_field_destroy", "ngpb_blender_render", "ngpb_compute_loss_compact_features",
+    "ngpb_field_create", "ngpb_field_destroy", "ngpb_blender_render", "ngpb_compute_loss_compact_features", "ngpb_grid_init_nd", "ngpb_mlp_forward",
 ]
 
 _lib = None
@@ -341,6 +341,7 @@ def lib():
         l = C.CDLL(_LIB_PATH)
         l.ngpb_last_error.restype = C.c_char_p
         l.ngpb_grid_init.restype = C.c_uint32
+        l.ngpb_grid_init_nd.restype = C.c_uint32
         l.ngpb_nerf_mlp_workspace_bytes.restype = C.c_uint64
         l.ngpb_generate_training_samples_scratch_bytes.restype = C.c_uint64
         l.ngpb_compute_loss_scratch_bytes.restype = C.c_uint64
@@ -369,12 +370,14 @@ def check(status):
         raise RuntimeError(lib().ngpb_last_error().decode() or f"ngpb error {status}")
 
 
-def grid_init(n_levels=16, log2_hashmap_size=19, base_resolution=16, per_level_scale=None, aabb_scale=1, device_scales=False):
-    """ngpb_grid for the given hash-grid config; device_scales=True replaces the level scales by the device-evaluated ones (needs a GPU)."""
+def grid_init(n_levels=16, log2_hashmap_size=19, base_resolution=16, per_level_scale=None, aabb_scale=1, device_scales=False, n_pos_dims=3, desired_resolution=2048.0):
+    """ngpb_grid for the given hash-grid config; device_scales=True replaces the level scales by the device-evaluated ones (needs a GPU).
+    desired_resolution: finest level over the unit cube (Testbed::reset_network, src/testbed.cu:2313-2325): 2048 for NeRF, max(image resolution) / 2 for
+    the neural-image model."""
     if per_level_scale is None:
-        per_level_scale = float(np.exp(np.log(np.float32(2048.0) * np.float32(aabb_scale) / np.float32(base_resolution)) / np.float32(n_levels - 1), dtype=np.float32))
+        per_level_scale = float(np.exp(np.log(np.float32(desired_resolution) * np.float32(aabb_scale) / np.float32(base_resolution)) / np.float32(n_levels - 1), dtype=np.float32))
     g = Grid()
-    entries = lib().ngpb_grid_init(C.byref(g), n_levels, log2_hashmap_size, base_resolution, C.c_float(per_level_scale))
+    entries = lib().ngpb_grid_init_nd(C.byref(g), n_pos_dims, n_levels, log2_hashmap_size, base_resolution, C.c_float(per_level_scale))
     if device_scales:
         check(lib().ngpb_grid_device_scales(None, C.byref(g)))
     return g, entries

@@ -49,10 +49,14 @@ typedef struct {
 	float scale[NGPB_MAX_LEVELS];          /* grid_scale(level) = exp2f(level*log2_pls)*base-1 (grid.h:194-199), host-evaluated by
 	                                          ngpb_grid_init; the reference evaluates it per thread with the device exp2f */
 	uint32_t resolution[NGPB_MAX_LEVELS];  /* grid_resolution(scale) = ceil(scale)+1 (grid.h:201-203) */
+	uint32_t n_pos_dims;                   /* 3 (NeRF, SDF) or 2 (neural image); 0 reads as 3 */
 } ngpb_grid;
 
 /* Host-only: fills `g` like the GridEncodingTemplated constructor (grid.h:959-1025). Returns total entries. */
 uint32_t ngpb_grid_init(ngpb_grid* g, uint32_t n_levels, uint32_t log2_hashmap_size, uint32_t base_resolution, float per_level_scale);
+/* Same for an N-dimensional input (N_POS_DIMS of GridEncodingTemplated): 2 = the neural-image model (configs/image/base.json), 3 = NeRF / SDF.
+ * Only ngpb_hash_encode_forward accepts 2-D grids. */
+uint32_t ngpb_grid_init_nd(ngpb_grid* g, uint32_t n_pos_dims, uint32_t n_levels, uint32_t log2_hashmap_size, uint32_t base_resolution, float per_level_scale);
 
 /* Replaces g->scale[] / g->resolution[] by the values the DEVICE's exp2f gives, which is what the reference's kernels use (they call
  * grid_scale per thread, grid.h:241); glibc's exp2f differs by one ulp on some levels. The level offsets stay host-derived, as in
@@ -67,6 +71,12 @@ int ngpb_hash_encode_forward(void* stream, const ngpb_grid* g, const ngpb_half* 
  * accumulated into with fp32 atomics (zero it first for EGradientMode::Overwrite, grid.h:1154). */
 int ngpb_hash_encode_backward(void* stream, const ngpb_grid* g, const float* positions, uint32_t pos_stride, uint32_t n,
                               const ngpb_half* dL_dencoded, float* grid_grad);
+
+/* The 32 -> 64 -> 64 -> 16 fully fused MLP alone (ReLU hidden, no output activation): the network of the neural-image and SDF models
+ * (configs/image/base.json, configs/sdf/base.json; tcnn FullyFusedMLP<__half,64>::inference_mixed_precision, fully_fused_mlp.cu:500-557,:661-729).
+ * weights: FullyFusedMLP's parameter order, row-major [out][in]: [64][32], [64][64], [16][64] (7168 halves). input [n][32], output [n][16]
+ * (the padded output width; an image model uses columns 0..2, an SDF column 0). n: multiple of 128. */
+int ngpb_mlp_forward(void* stream, const ngpb_half* weights, const ngpb_half* input, uint32_t n, ngpb_half* output);
 
 /* ---- NeRF MLPs (replaces NerfNetwork glue nerf_network.h:103-266 + tcnn FullyFusedMLP, fully_fused_mlp.cu) ----
  * mlp: half[10240] in the reference's flat order: density W1[64][32], W2[16][64]; rgb W1[64][32], W2[64][64], W3[16][64].

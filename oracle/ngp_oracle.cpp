@@ -1503,3 +1503,106 @@ extern "C" void orc_blender_render(const orc_blender_request* rq, uint32_t n_ner
 	}
 	if (n_samples_out) *n_samples_out = n_samples;
 }
+
+// =============================================================================================
+// The neural-image / SDF model family (BASELINE configs 1 and 5): N-dimensional hash grid + one FullyFusedMLP 32 -> 64 x n_hidden -> 16.
+// =============================================================================================
+// GridEncodingTemplated constructor for N_POS_DIMS in {2, 3} (grid.h:985-1018)
+extern "C" uint32_t orc_grid_offsets_nd(uint32_t n_dims, uint32_t n_levels, uint32_t log2_hashmap_size, uint32_t base_resolution, float per_level_scale, uint32_t* offsets) {
+	uint32_t offset = 0;
+	for (uint32_t i = 0; i < n_levels; ++i) {
+		const uint32_t resolution = grid_resolution(grid_scale(i, std::log2(per_level_scale), base_resolution));
+		uint32_t max_params = std::numeric_limits<uint32_t>::max() / 2;
+		uint32_t dense = 1;
+		for (uint32_t d = 0; d < n_dims; ++d) dense *= resolution;
+		uint32_t params_in_level = std::pow((float)resolution, (float)n_dims) > (float)max_params ? max_params : dense;
+		params_in_level = (params_in_level + 7u) / 8u * 8u;
+		params_in_level = std::min(params_in_level, 1u << log2_hashmap_size);
+		offsets[i] = offset;
+		offset += params_in_level;
+	}
+	offsets[n_levels] = offset;
+	return offset;
+}
+
+// kernel_grid for N_POS_DIMS = n_dims (grid.h:220-349): grid_index with the stride loop's early stop (:164-186), prime_hash over n_dims (:111-128)
+extern "C" void orc_grid_forward_nd(uint32_t n_dims, uint32_t n, uint32_t n_levels, const uint32_t* offsets, uint32_t base_resolution, float log2_per_level_scale,
+                                    const float* scales, const orc_half* grid, const float* positions, uint32_t pos_stride, orc_half* encoded) {
+	static const uint32_t primes[3] = {1u, 2654435761u, 805459861u};
+	#pragma omp parallel for schedule(static)
+	for (int64_t i = 0; i < (int64_t)n; ++i) {
+		for (uint32_t level = 0; level < n_levels; ++level) {
+			const orc_half* g = grid + (size_t)offsets[level] * 2;
+			const uint32_t hashmap_size = offsets[level + 1] - offsets[level];
+			const float scale = scales ? scales[level] : grid_scale(level, log2_per_level_scale, base_resolution);
+			const uint32_t resolution = grid_resolution(scale);
+			float pos[3]; uint32_t pg[3];
+			for (uint32_t d = 0; d < n_dims; ++d) pos_fract(positions[(size_t)i * pos_stride + d], &pos[d], &pg[d], scale);
+			orc_half result[2] = {0, 0};
+			for (uint32_t idx = 0; idx < (1u << n_dims); ++idx) {
+				float weight = 1; uint32_t pl[3];
+				for (uint32_t d = 0; d < n_dims; ++d) {
+					if ((idx & (1u << d)) == 0) { weight *= 1 - pos[d]; pl[d] = pg[d]; } else { weight *= pos[d]; pl[d] = pg[d] + 1; }
+				}
+				uint32_t stride = 1, index = 0;
+				for (uint32_t d = 0; d < n_dims && stride <= hashmap_size; ++d) { index += pl[d] * stride; stride *= resolution; }
+				if (hashmap_size < stride) { index = 0; for (uint32_t d = 0; d < n_dims; ++d) index ^= pl[d] * primes[d]; }
+				index = (index % hashmap_size) * 2;
+				for (int f = 0; f < 2; ++f) result[f] = hadd(result[f], f2h(weight * h2f(g[index + f])));
+			}
+			encoded[(size_t)i * (2 * n_levels) + level * 2 + 0] = result[0];
+			encoded[(size_t)i * (2 * n_levels) + level * 2 + 1] = result[1];
+		}
+	}
+}
+
+// FullyFusedMLP<__half, 64> with in = 32, ReLU hidden layers, no output activation, 16 padded outputs (fully_fused_mlp.cu:500-557 forward,
+// :151-314 backward, :805-847 weight gradients). weights: [64][32], (n_hidden - 1) x [64][64], [16][64], row-major [out][in].
+// Forward: out[n][16]. With dL_dout[n][16]: also dL_dinput[n][32] (nullable) and grad[n_params] (fp32, unscaled sum over the batch).
+// Activations round to fp16 at layer boundaries like the reference; accumulation is fp32 (the reference's wmma accumulates in fp16).
+extern "C" void orc_mlp_forward_backward(uint32_t n_hidden, uint32_t n, const orc_half* weights, const orc_half* input, orc_half* out,
+                                         const orc_half* dL_dout, orc_half* dL_dinput, float* grad) {
+	const uint32_t n_params = 64 * 32 + (n_hidden - 1) * 64 * 64 + 16 * 64;
+	std::vector<float> W(n_params);
+	for (uint32_t k = 0; k < n_params; ++k) W[k] = h2f(weights[k]);
+	const uint32_t w_last = 64 * 32 + (n_hidden - 1) * 64 * 64;
+	const int nt = omp_get_max_threads();
+	std::vector<std::vector<double>> partial(grad ? nt : 0, std::vector<double>(grad ? n_params : 0, 0.0));
+	#pragma omp parallel
+	{
+		double* G = grad ? partial[omp_get_thread_num()].data() : nullptr;
+		std::vector<float> acts((size_t)(n_hidden + 1) * 64), tmp(64), d(64), dprev(64);
+		#pragma omp for schedule(static)
+		for (int64_t i = 0; i < (int64_t)n; ++i) {
+			float* x = acts.data();
+			for (int k = 0; k < 32; ++k) x[k] = h2f(input[(size_t)i * 32 + k]);
+			const float* w = W.data();
+			int n_in = 32;
+			for (uint32_t l = 0; l < n_hidden; ++l) {
+				float* h = acts.data() + (size_t)(l + 1) * 64;
+				matvec(w, 64, n_in, acts.data() + (size_t)l * 64, tmp.data());
+				for (int k = 0; k < 64; ++k) h[k] = rh(tmp[k] > 0.f ? tmp[k] : 0.f);
+				w += 64 * n_in; n_in = 64;
+			}
+			const float* last = acts.data() + (size_t)n_hidden * 64;
+			matvec(W.data() + w_last, 16, 64, last, tmp.data());
+			if (out) for (int k = 0; k < 16; ++k) out[(size_t)i * 16 + k] = f2h(tmp[k]);
+			if (!dL_dout) continue;
+			float dout[16];
+			for (int k = 0; k < 16; ++k) dout[k] = h2f(dL_dout[(size_t)i * 16 + k]);
+			if (G) for (int o = 0; o < 16; ++o) for (int k = 0; k < 64; ++k) G[w_last + o * 64 + k] += (double)(dout[o] * last[k]);
+			matvec_t(W.data() + w_last, 16, 64, dout, d.data());
+			for (int k = 0; k < 64; ++k) d[k] = rh(last[k] > 0.f ? d[k] : 0.f); // backward through the ReLU, fp16 like the reference's fragments
+			for (int l = (int)n_hidden - 1; l >= 0; --l) {
+				const int in_w = l == 0 ? 32 : 64;
+				const uint32_t w_off = l == 0 ? 0u : 64u * 32u + (uint32_t)(l - 1) * 64u * 64u;
+				const float* a_in = acts.data() + (size_t)l * 64;
+				if (G) for (int o = 0; o < 64; ++o) for (int k = 0; k < in_w; ++k) G[w_off + o * in_w + k] += (double)(d[o] * a_in[k]);
+				matvec_t(W.data() + w_off, 64, in_w, d.data(), dprev.data());
+				if (l > 0) { for (int k = 0; k < 64; ++k) d[k] = rh(a_in[k] > 0.f ? dprev[k] : 0.f); }
+				else if (dL_dinput) { for (int k = 0; k < 32; ++k) dL_dinput[(size_t)i * 32 + k] = f2h(dprev[k]); }
+			}
+		}
+	}
+	if (grad) for (uint32_t k = 0; k < n_params; ++k) { double s = 0.0; for (int t = 0; t < nt; ++t) s += partial[t][k]; grad[k] = (float)s; }
+}

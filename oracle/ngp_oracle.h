@@ -190,6 +190,13 @@ typedef struct {
 } orc_blender_request;
 void orc_blender_render(const orc_blender_request* rq, uint32_t n_nerfs, const orc_nerf_instance* nerfs, float* out_rgba, uint64_t* n_samples_out);
 
+// ---- neural-image / SDF model family: N-dimensional hash grid (N in {2,3}) + FullyFusedMLP 32 -> 64 x n_hidden -> 16 (see ngp_oracle.cpp) ----
+uint32_t orc_grid_offsets_nd(uint32_t n_dims, uint32_t n_levels, uint32_t log2_hashmap_size, uint32_t base_resolution, float per_level_scale, uint32_t* offsets);
+void orc_grid_forward_nd(uint32_t n_dims, uint32_t n, uint32_t n_levels, const uint32_t* offsets, uint32_t base_resolution, float log2_per_level_scale,
+                         const float* scales, const orc_half* grid, const float* positions, uint32_t pos_stride, orc_half* encoded);
+void orc_mlp_forward_backward(uint32_t n_hidden, uint32_t n, const orc_half* weights, const orc_half* input, orc_half* out,
+                              const orc_half* dL_dout, orc_half* dL_dinput, float* grad);
+
 #ifdef __cplusplus
 }
 #endif

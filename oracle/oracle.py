@@ -312,6 +312,41 @@ def render_nerf(m, params_half, bitfield, cfg):
     return out, int(ns.value)
 
 
+def grid_offsets_nd(n_dims, n_levels=16, log2_hashmap_size=19, base_resolution=16, per_level_scale=2.0):
+    offsets = (C.c_uint32 * 33)()
+    lib().orc_grid_offsets_nd.restype = C.c_uint32
+    total = lib().orc_grid_offsets_nd(n_dims, n_levels, log2_hashmap_size, base_resolution, C.c_float(per_level_scale), offsets)
+    return np.array(offsets[:n_levels + 1], np.uint32), int(total)
+
+
+def grid_forward_nd(n_dims, offsets, grid_half, positions, per_level_scale, base_resolution=16, scales=None):
+    """Hash-grid forward for a 2-D or 3-D input: float16 [n][2 * n_levels]."""
+    positions = _f32(positions)
+    n, n_levels = positions.shape[0], len(offsets) - 1
+    out = np.zeros((n, 2 * n_levels), np.float16)
+    off = (C.c_uint32 * 33)(*[int(v) for v in offsets])
+    sc = _f32(scales) if scales is not None else None
+    lib().orc_grid_forward_nd(n_dims, n, n_levels, off, base_resolution, C.c_float(np.log2(np.float32(per_level_scale))), _p(sc),
+                              _p(np.ascontiguousarray(grid_half, np.float16)), _p(positions), positions.shape[1], _p(out))
+    return out
+
+
+def mlp_forward_backward(weights_half, input_half, n_hidden=2, dL_dout=None, want_input_grad=True):
+    """FullyFusedMLP 32 -> 64 x n_hidden -> 16 on the CPU: out [n][16]; with dL_dout also (dL_dinput [n][32], grad fp32 [n_params])."""
+    w = np.ascontiguousarray(weights_half, np.float16)
+    x = np.ascontiguousarray(input_half, np.float16)
+    n = x.shape[0]
+    out = np.zeros((n, 16), np.float16)
+    if dL_dout is None:
+        lib().orc_mlp_forward_backward(n_hidden, n, _p(w), _p(x), _p(out), None, None, None)
+        return out
+    dy = np.ascontiguousarray(dL_dout, np.float16)
+    din = np.zeros((n, 32), np.float16) if want_input_grad else None
+    grad = np.zeros(w.shape[0], np.float32)
+    lib().orc_mlp_forward_backward(n_hidden, n, _p(w), _p(x), _p(out), _p(dy), _p(din), _p(grad))
+    return out, din, grad
+
+
 class NerfInstance(C.Structure):
     _fields_ = [("model", C.POINTER(Model)), ("params", C.c_void_p), ("bitfield", C.c_void_p), ("train_aabb", C.c_float * 6), ("aabb_scale", C.c_uint32),
                 ("render_aabb", C.c_float * 6), ("transform", C.c_float * 16), ("opacity", C.c_float),

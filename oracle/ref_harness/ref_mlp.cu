@@ -13,6 +13,10 @@
 using namespace tcnn;
 using T = __half;
 
+// FullyFusedMLP::hyperparams() names its activations through tcnn::to_string(Activation), defined in tcnn's src/network.cu together with the whole
+// network factory (which would pull in every other network and CUTLASS instantiation). Nothing here calls hyperparams(): satisfy the linker.
+namespace tcnn { std::string to_string(Activation) { return "unused"; } }
+
 extern "C" {
 
 // params: half, reference order (first layer [64][in], hidden [64][64]..., last [16][64]), row-major [out][in].

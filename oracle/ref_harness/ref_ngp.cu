@@ -53,6 +53,39 @@ BoundingBox make_aabb(const float* aabb6) {
 
 extern "C" {
 
+// iters > 0: the launch (with its two counter memsets, as in train_nerf_step) is repeated `iters` times after one warm-up and *ms receives the mean
+// milliseconds per repetition (CUDA events on the NULL stream); the outputs are those of the last repetition.
+int ref_generate_training_samples_timed(
+	uint32_t n_rays, const float* aabb6, uint32_t max_samples, uint32_t n_rays_total,
+	uint64_t rng_state, uint64_t rng_inc,
+	uint32_t* ray_counter, uint32_t* numsteps_counter, uint32_t* ray_indices, float* rays /*6 floats*/, uint32_t* numsteps, float* coords /*7 floats*/,
+	uint32_t n_images, int w, int h, float fx, float fy, float cx, float cy, const uint8_t* pixels, const float* xforms_host,
+	const uint8_t* bitfield, int snap_to_pixel_centers, float cone_angle_constant, int iters, float* ms
+) {
+	DeviceDataset d = make_dataset(n_images, w, h, fx, fy, cx, cy, pixels, xforms_host);
+	default_rng_t rng; rng.state = rng_state; rng.inc = rng_inc;
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0); cudaEventCreate(&e1);
+	for (int it = 0; it <= iters; ++it) {
+		if (it == 1) cudaEventRecord(e0, nullptr);
+		cudaMemsetAsync(ray_counter, 0, 4, nullptr);
+		cudaMemsetAsync(numsteps_counter, 0, 4, nullptr);
+		linear_kernel(generate_training_samples_nerf, 0, 0,
+			n_rays, make_aabb(aabb6), max_samples, n_rays_total, rng,
+			ray_counter, numsteps_counter, ray_indices, (Ray*)rays, numsteps,
+			PitchedPtr<NerfCoordinate>((NerfCoordinate*)coords, 1, 0, 0),
+			n_images, d.metadata.data(), d.xforms.data(), bitfield,
+			false, (float*)nullptr, (bool)snap_to_pixel_centers, false, cone_angle_constant,
+			(const float*)nullptr, Vector2i{0, 0}, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, Vector2i{0, 0},
+			(const float*)nullptr, 0u);
+	}
+	cudaEventRecord(e1, nullptr);
+	cudaEventSynchronize(e1);
+	if (iters > 0 && ms) { cudaEventElapsedTime(ms, e0, e1); *ms /= (float)iters; }
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
+	return (int)cudaDeviceSynchronize();
+}
+
 int ref_generate_training_samples(
 	uint32_t n_rays, const float* aabb6, uint32_t max_samples, uint32_t n_rays_total,
 	uint64_t rng_state, uint64_t rng_inc,
@@ -103,6 +136,52 @@ int ref_compute_loss(
 		(float*)nullptr, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, Vector2i{0, 0}, Vector2i{0, 0},
 		(const float*)nullptr, Vector2i{0, 0}, (float*)nullptr, (float*)nullptr, mean_density_ptr,
 		(const Array3f*)exposure.data(), (Array3f*)nullptr, 0.0f, near_distance);
+	return (int)cudaDeviceSynchronize();
+}
+
+// Timing variant: see ref_generate_training_samples_timed.
+int ref_compute_loss_timed(
+	uint32_t n_rays, const float* aabb6, uint32_t n_rays_total, uint64_t rng_state, uint64_t rng_inc,
+	uint32_t max_samples_compacted, const uint32_t* rays_counter, float loss_scale, int padded_output_width,
+	const float* background_color3, int color_space, int random_bg, int linear_colors,
+	uint32_t n_images, int w, int h, float fx, float fy, float cx, float cy, const uint8_t* pixels, const float* xforms_host,
+	const void* network_output_half, uint32_t* numsteps_counter_compacted, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps,
+	const float* coords_in, float* coords_out, void* dloss_doutput_half, int loss_type, float* loss_output,
+	int rgb_activation, int density_activation, int snap_to_pixel_centers, const float* mean_density_ptr, float near_distance, int iters, float* ms
+) {
+	DeviceDataset d = make_dataset(n_images, w, h, fx, fy, cx, cy, pixels, xforms_host);
+	default_rng_t rng; rng.state = rng_state; rng.inc = rng_inc;
+	GPUMemory<Array3f> exposure(n_images);
+	exposure.memset(0);
+	GPUMemory<uint32_t> numsteps_backup((size_t)n_rays * 2);
+	cudaMemcpy(numsteps_backup.data(), numsteps, (size_t)n_rays * 8, cudaMemcpyDeviceToDevice);
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0); cudaEventCreate(&e1);
+	float total = 0.f;
+	for (int it = 0; it <= iters; ++it) {
+	cudaMemcpy(numsteps, numsteps_backup.data(), (size_t)n_rays * 8, cudaMemcpyDeviceToDevice); // the kernel rewrites numsteps in place: restore (untimed)
+	cudaEventRecord(e0, nullptr);
+	cudaMemsetAsync(numsteps_counter_compacted, 0, 4, nullptr);
+	linear_kernel(compute_loss_kernel_train_nerf, 0, 0,
+		n_rays, make_aabb(aabb6), n_rays_total, rng, max_samples_compacted, rays_counter, loss_scale, padded_output_width,
+		(const float*)nullptr, (float*)nullptr, Vector2i{0, 0}, ELossType::L2,
+		Array3f{background_color3[0], background_color3[1], background_color3[2]}, (EColorSpace)color_space, (bool)random_bg, (bool)linear_colors,
+		n_images, d.metadata.data(), (const network_precision_t*)network_output_half, numsteps_counter_compacted,
+		ray_indices, (const Ray*)rays, numsteps,
+		PitchedPtr<const NerfCoordinate>((NerfCoordinate*)coords_in, 1, 0, 0),
+		PitchedPtr<NerfCoordinate>((NerfCoordinate*)coords_out, 1, 0, 0),
+		(network_precision_t*)dloss_doutput_half, (ELossType)loss_type, ELossType::L1, loss_output,
+		false, (float*)nullptr, (ENerfActivation)rgb_activation, (ENerfActivation)density_activation, (bool)snap_to_pixel_centers,
+		(float*)nullptr, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, Vector2i{0, 0}, Vector2i{0, 0},
+		(const float*)nullptr, Vector2i{0, 0}, (float*)nullptr, (float*)nullptr, mean_density_ptr,
+		(const Array3f*)exposure.data(), (Array3f*)nullptr, 0.0f, near_distance);
+	cudaEventRecord(e1, nullptr);
+	cudaEventSynchronize(e1);
+	float t = 0.f; cudaEventElapsedTime(&t, e0, e1);
+	if (it > 0) total += t;
+	}
+	if (iters > 0 && ms) *ms = total / (float)iters;
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
 	return (int)cudaDeviceSynchronize();
 }
 

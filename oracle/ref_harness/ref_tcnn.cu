@@ -6,7 +6,7 @@
 // oracle/gen_golden.py to produce the golden vectors committed under tests/golden/.
 //
 // Kernels launched (reference file:line):
-//   kernel_grid<__half,3,2>            dependencies/tiny-cuda-nn/include/tiny-cuda-nn/encodings/grid.h:220
+//   kernel_grid<__half,3,2>, <__half,2,2>   dependencies/tiny-cuda-nn/include/tiny-cuda-nn/encodings/grid.h:220
 //   kernel_grid_backward<__half,__half,3,2,2>                                          grid.h:395
 //   kernel_sh<__half>                  .../encodings/spherical_harmonics.h:46
 //   adam_step<__half>                  .../optimizers/adam.h:48
@@ -39,6 +39,54 @@ int ref_grid_forward(uint32_t n, uint32_t n_levels, const uint32_t* offsets_host
 		n, n_levels * 2, t, base_resolution, log2_per_level_scale, 0.f, 1000.f, nullptr,
 		InterpolationType::Linear, GridType::Hash, HashType::CoherentPrime,
 		(const __half*)grid_half, MatrixView<const float>(positions, 1, pos_stride), (__half*)out_soa_half, nullptr);
+	return (int)cudaDeviceSynchronize();
+}
+
+// The same kernel instantiated for a two-dimensional input (the neural-image model, N_POS_DIMS = 2).
+int ref_grid_forward_2d(uint32_t n, uint32_t n_levels, const uint32_t* offsets_host, uint32_t base_resolution,
+                        float log2_per_level_scale, const void* grid_half, const float* positions, uint32_t pos_stride,
+                        void* out_soa_half) {
+	GridOffsetTable t = make_table(offsets_host, n_levels);
+	const dim3 blocks = { div_round_up(n, 512u), n_levels, 1 };
+	kernel_grid<__half, 2, 2><<<blocks, 512>>>(
+		n, n_levels * 2, t, base_resolution, log2_per_level_scale, 0.f, 1000.f, nullptr,
+		InterpolationType::Linear, GridType::Hash, HashType::CoherentPrime,
+		(const __half*)grid_half, MatrixView<const float>(positions, 1, pos_stride), (__half*)out_soa_half, nullptr);
+	return (int)cudaDeviceSynchronize();
+}
+
+// Timing: `iters` back-to-back launches of the reference's forward / backward grid kernels on the NULL stream, mean milliseconds per launch
+// (CUDA events), after one warm-up launch. The backward figure includes the gradient memset the reference issues before it (grid.h:1154).
+int ref_grid_time(uint32_t n, uint32_t n_levels, const uint32_t* offsets_host, uint32_t base_resolution, float log2_per_level_scale,
+                  const void* grid_half, void* grid_gradient_half, const float* positions, uint32_t pos_stride, void* out_soa_half,
+                  const void* dL_dy_soa_half, int iters, float* fwd_ms, float* bwd_ms) {
+	GridOffsetTable t = make_table(offsets_host, n_levels);
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0); cudaEventCreate(&e1);
+	const dim3 fb = { div_round_up(n, 512u), n_levels, 1 }, bb = { div_round_up(n * 2 / 2, 256u), n_levels, 1 };
+	for (int pass = 0; pass < 2; ++pass) {
+		const int reps = pass == 0 ? 1 : iters;
+		cudaEventRecord(e0, nullptr);
+		for (int it = 0; it < reps; ++it)
+			kernel_grid<__half, 3, 2><<<fb, 512>>>(n, n_levels * 2, t, base_resolution, log2_per_level_scale, 0.f, 1000.f, nullptr, InterpolationType::Linear, GridType::Hash,
+				HashType::CoherentPrime, (const __half*)grid_half, MatrixView<const float>(positions, 1, pos_stride), (__half*)out_soa_half, nullptr);
+		cudaEventRecord(e1, nullptr);
+		cudaEventSynchronize(e1);
+		if (pass) { cudaEventElapsedTime(fwd_ms, e0, e1); *fwd_ms /= (float)iters; }
+	}
+	for (int pass = 0; pass < 2; ++pass) {
+		const int reps = pass == 0 ? 1 : iters;
+		cudaEventRecord(e0, nullptr);
+		for (int it = 0; it < reps; ++it) {
+			cudaMemsetAsync(grid_gradient_half, 0, (size_t)offsets_host[n_levels] * 2 * sizeof(__half), nullptr);
+			kernel_grid_backward<__half, __half, 3, 2, 2><<<bb, 256>>>(n, n_levels * 2, t, base_resolution, log2_per_level_scale, 1000.f, nullptr, false, InterpolationType::Linear,
+				GridType::Hash, HashType::CoherentPrime, (__half*)grid_gradient_half, MatrixView<const float>(positions, 1, pos_stride), (const __half*)dL_dy_soa_half);
+		}
+		cudaEventRecord(e1, nullptr);
+		cudaEventSynchronize(e1);
+		if (pass) { cudaEventElapsedTime(bwd_ms, e0, e1); *bwd_ms /= (float)iters; }
+	}
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
 	return (int)cudaDeviceSynchronize();
 }
 

@@ -14,3 +14,37 @@ def grid_inputs(n_grid_params, seed=1234):
     dy = (rs.randn(32, N_GRID) * 0.01).astype(np.float16)   # [feature][sample], the reference's layout
     dirs = rs.rand(N_GRID, 3).astype(np.float32)
     return table, positions, dy, dirs
+
+
+N_MLP = 8192        # samples of the FullyFusedMLP golden
+
+
+def mlp_inputs(n_hidden, seed=77):
+    """Weights in FullyFusedMLP's parameter order ([64][32], (n_hidden-1) x [64][64], [16][64]), Xavier-like scale; inputs like hash-grid features /
+    SH coefficients (|x| <= 1); output gradients at the magnitude the loss kernel produces (loss scale 128 / rays)."""
+    rs = np.random.RandomState(seed + n_hidden)
+    n_params = 64 * 32 + (n_hidden - 1) * 64 * 64 + 16 * 64
+    w = (rs.uniform(-1, 1, n_params) * 0.25).astype(np.float16)
+    x = (rs.uniform(-1, 1, (N_MLP, 32)) * 0.5).astype(np.float16)
+    dy = np.zeros((N_MLP, 16), np.float16)
+    dy[:, :4] = (rs.randn(N_MLP, 4) * 0.02).astype(np.float16)
+    return w, x, dy
+
+
+IMAGE_RES = 512     # BASELINE config 1: neural image 512 x 512, configs/image/base.json
+
+
+def image_inputs(n_grid_params, seed=1337):
+    """Fixed random parameters of the neural-image model (network 7168 halves, then the 2-D grid), and all pixel centres ((x+0.5)/W, (y+0.5)/H)."""
+    rs = np.random.RandomState(seed)
+    net = (rs.uniform(-1, 1, 7168) * 0.3).astype(np.float16)
+    table = (rs.randn(n_grid_params) * 0.5).astype(np.float16)
+    ys, xs = np.meshgrid(np.arange(IMAGE_RES), np.arange(IMAGE_RES), indexing="ij")
+    uv = np.stack([(xs.reshape(-1) + 0.5) / IMAGE_RES, (ys.reshape(-1) + 0.5) / IMAGE_RES], axis=1).astype(np.float32)
+    return net, table, uv
+
+
+def image_grid_config():
+    """configs/image/base.json with Testbed::reset_network's per_level_scale for a 512 x 512 image (desired_resolution = 256)."""
+    pls = float(np.exp(np.log(np.float32(IMAGE_RES / 2.0) * np.float32(1) / np.float32(16)) / np.float32(15), dtype=np.float32))
+    return dict(n_levels=16, log2_hashmap_size=24, base_resolution=16, per_level_scale=pls)

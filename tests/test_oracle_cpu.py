@@ -368,3 +368,55 @@ def test_blender_render_oracle_invariants(orc):
     if sat.any():
         assert np.abs(both[sat] - base[sat]).max() < 1e-5
     assert n_both >= n_base
+
+
+# ------------------------------------------------------------------------------------------------------
+# neural-image / SDF model family (BASELINE configs 1 and 5): N-d hash grid + one fully fused MLP, pinned on the reference's own kernels
+# ------------------------------------------------------------------------------------------------------
+def test_grid_nd_restatement_agrees_with_3d(orc):
+    """The N-dimensional restatement at N = 3 is the 3-D one bit for bit, and its level table equals orc_grid_offsets."""
+    m = orc.model()
+    offsets, total = orc.grid_offsets_nd(3, 16, 19, 16, m.per_level_scale)
+    assert np.array_equal(offsets, np.array(m.offsets[:17], np.uint32)) and 2 * total == m.n_grid_params
+    rs = np.random.RandomState(5)
+    table = (rs.randn(m.n_grid_params) * 0.5).astype(np.float16)
+    pos = rs.rand(2000, 3).astype(np.float32)
+    a = orc.grid_forward(m, table, pos)
+    b = orc.grid_forward_nd(3, offsets, table, pos, m.per_level_scale)
+    assert np.array_equal(a.view(np.uint16), b.view(np.uint16))
+
+
+def test_golden_fully_fused_mlp(orc):
+    """Oracle vs the reference's FullyFusedMLP<__half,64> run on a B200 (tests/golden/ref_mlp.npz, oracle/gen_golden.py::gen_mlp), density-net shape
+    (1 hidden layer) and rgb / image / SDF shape (2). The reference accumulates in fp16 (wmma half accumulators) and rounds the weight gradients
+    of its split-K GEMMs to fp16; the oracle accumulates in fp32: outputs agree to one fp16 ulp, gradients to a few per cent of their range."""
+    from golden_inputs import mlp_inputs
+    g = np.load(os.path.join(GOLDEN, "ref_mlp.npz"))
+    for n_hidden in (1, 2):
+        w, x, dy = mlp_inputs(n_hidden)
+        out, din, grad = orc.mlp_forward_backward(w, x, n_hidden, dy)
+        ref_out = g[f"out_inference_{n_hidden}"].astype(np.float32)
+        assert np.array_equal(g[f"out_inference_{n_hidden}"], g[f"out_forward_{n_hidden}"])  # the reference's two code paths agree with each other
+        assert np.abs(out.astype(np.float32) - ref_out).max() <= 1e-3  # one fp16 ulp at 1.0
+        ref_din = g[f"dinput_{n_hidden}"].astype(np.float32)
+        err = np.abs(din.astype(np.float32) - ref_din) / np.abs(ref_din).max()
+        assert np.quantile(err, 0.999) <= 0.03 and err.max() <= 0.15  # ReLU-mask flips of activations that round to +-0 explain the tail
+        ref_grad = g[f"grad_{n_hidden}"].astype(np.float32)
+        assert np.abs(grad - ref_grad).max() <= 0.025 * np.abs(ref_grad).max()
+
+
+def test_golden_neural_image_forward(orc):
+    """BASELINE config 1 (neural image 512 x 512, configs/image/base.json, forward only): the reference's kernel_grid<__half,2,2> + FullyFusedMLP on all
+    pixel centres with fixed random parameters (tests/golden/ref_image.npz). Level table and encoded features bit-exact, RGB within one fp16 ulp."""
+    from golden_inputs import image_inputs, image_grid_config, IMAGE_RES
+    g = np.load(os.path.join(GOLDEN, "ref_image.npz"))
+    cfg = image_grid_config()
+    offsets, total = orc.grid_offsets_nd(2, cfg["n_levels"], cfg["log2_hashmap_size"], cfg["base_resolution"], cfg["per_level_scale"])
+    assert np.array_equal(offsets, g["offsets"]) and total == 213256  # every level is dense at this resolution (the 2^24 table is never reached)
+    net, table, uv = image_inputs(2 * total)
+    enc = orc.grid_forward_nd(2, offsets, table, uv, cfg["per_level_scale"], scales=g["device_scales"])
+    assert np.array_equal(enc[:4096].view(np.uint16), g["encoded_head"].view(np.uint16))
+    rgb = orc.mlp_forward_backward(net, enc, 2)[:, :3].astype(np.float32)
+    ref = g["rgb"].astype(np.float32)
+    assert rgb.shape == (IMAGE_RES * IMAGE_RES, 3)
+    assert np.abs(rgb - ref).max() <= 4e-3 and np.abs(rgb - ref).mean() <= 3e-4
