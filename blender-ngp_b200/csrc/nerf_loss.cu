@@ -11,6 +11,9 @@
 // Not built (out of scope for the lego/fox configs): envmap, exposure gradients,
 // depth supervision, error-map accumulation, max_level_rand_training.
 #include "nerf_device.cuh"
+#include <cstdio>
+#include <cstdlib>
+#include <utility>
 
 namespace ngpb {
 
@@ -97,26 +100,37 @@ __device__ __forceinline__ SampleEval eval_sample(const __half* __restrict__ rgb
 	return e;
 }
 
-// T before this lane's sample, given T before lane 0's sample; products taken in sample order.
+// A ray is walked by a GROUP of W adjacent lanes (W = 8, 16 or 32; 32 / W rays per warp): rays keep ~6 samples after compaction and ~15 before,
+// so a whole warp per ray leaves most lanes idle. All shuffles run warp-wide (every lane takes part), groups only select their own lanes.
+// T before this lane's sample, given T before the group's first sample; products taken in sample order.
+template <uint32_t W>
 __device__ __forceinline__ float sequential_prefix_product(float T_in, float one_minus_alpha, uint32_t lane) {
+	const uint32_t glane = lane & (W - 1), gbase = lane & ~(W - 1);
 	float T = T_in;
 	#pragma unroll
-	for (uint32_t k = 0; k < 31; ++k) {
-		const float v = __shfl_sync(0xffffffffu, one_minus_alpha, k);
-		if (k < lane) T *= v;
+	for (uint32_t k = 0; k < W - 1; ++k) {
+		const float v = __shfl_sync(0xffffffffu, one_minus_alpha, gbase + k);
+		if (k < glane) T *= v;
 	}
 	return T;
 }
-
-__device__ __forceinline__ float warp_sum(float v) {
+template <uint32_t W>
+__device__ __forceinline__ float group_sum(float v) {
 	#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
 	return v;
 }
-__device__ __forceinline__ float warp_inclusive_sum(float v, uint32_t lane) {
+template <uint32_t W>
+__device__ __forceinline__ float group_inclusive_sum(float v, uint32_t lane) {
+	const uint32_t glane = lane & (W - 1);
 	#pragma unroll
-	for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= (uint32_t)o) v += t; }
+	for (int o = 1; o < (int)W; o <<= 1) { const float t = __shfl_up_sync(0xffffffffu, v, o); if (glane >= (uint32_t)o) v += t; }
 	return v;
+}
+template <uint32_t W>
+__device__ __forceinline__ uint32_t group_ballot(bool pred, uint32_t lane) { // the group's W bits of a warp-wide ballot, group lane 0 = bit 0
+	const uint32_t b = __ballot_sync(0xffffffffu, pred);
+	return W == 32 ? b : (b >> (lane & ~(W - 1))) & ((1u << (W & 31)) - 1u);
 }
 
 // Block-wide exclusive scan of one value per warp (32 warps); returns the exclusive prefix for this warp and the block total.
@@ -186,7 +200,8 @@ __global__ void __launch_bounds__(128) loss_target_kernel(const LossParams P, co
 }
 
 // (A) forward compositing, :1341-1428. Writes the per-ray state, the ray's compacted step count, its exclusive prefix inside
-// the block (local_bases) and the block's total (block_sums).
+// the block (local_bases) and the block's total (block_sums). 1024 / W rays per block.
+template <uint32_t W>
 __global__ void __launch_bounds__(1024) loss_composite_kernel(
 	const LossParams P, const ngpb_image* __restrict__ images, const uint32_t* __restrict__ counters_in,
 	const __half* __restrict__ rgbsigma, const uint32_t* __restrict__ ray_indices, const uint32_t* __restrict__ numsteps_in,
@@ -194,31 +209,33 @@ __global__ void __launch_bounds__(1024) loss_composite_kernel(
 	uint32_t* __restrict__ block_sums)
 {
 	__shared__ uint32_t scan_smem[33];
-	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint32_t i = blockIdx.x * LOSS_RAYS_PER_BLOCK + warp;
+	constexpr uint32_t RAYS_PER_WARP = 32 / W, RAYS_PER_BLOCK = 1024 / W;
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, glane = lane & (W - 1);
+	const uint32_t i = blockIdx.x * RAYS_PER_BLOCK + warp * RAYS_PER_WARP + lane / W;
 	const bool active = i < P.n_rays && i < counters_in[1];
 	uint32_t cn = 0;
+	const uint32_t numsteps = active ? numsteps_in[i * 2 + 0] : 0u, base = active ? numsteps_in[i * 2 + 1] : 0u;
+	float T_in = 1.f;
+	float rgb_ray[3] = {0.f, 0.f, 0.f};
+	bool stopped = false;
+	for (uint32_t r0 = 0; __any_sync(0xffffffffu, r0 < numsteps && !stopped); r0 += W) {
+		const bool walking = r0 < numsteps && !stopped; // (uniform within the group)
+		const uint32_t j = r0 + glane;
+		const bool valid = walking && j < numsteps;
+		const SampleEval e = eval_sample(rgbsigma, coords_in, (size_t)base + j, P.cfg, valid);
+		const float T = sequential_prefix_product<W>(T_in, e.one_minus_alpha, lane);
+		// the serial loop tests `T < EPSILON` before it touches a sample (:1352): the walk ends at the first such sample
+		const uint32_t stop_mask = group_ballot<W>(valid && T < T_EPSILON, lane);
+		const uint32_t first_stop = stop_mask ? (uint32_t)__ffs(stop_mask) - 1 : 32u;
+		const bool counted = valid && glane < first_stop;
+		const float weight = counted ? e.alpha * T : 0.f;
+		#pragma unroll
+		for (int c = 0; c < 3; ++c) rgb_ray[c] += group_sum<W>(weight * e.rgb[c]);
+		cn += __popc(group_ballot<W>(counted, lane));
+		const float T_next = __shfl_sync(0xffffffffu, T * e.one_minus_alpha, (lane & ~(W - 1)) + W - 1);
+		if (walking) { stopped = stop_mask != 0; T_in = T_next; }
+	}
 	if (active) {
-		const uint32_t numsteps = numsteps_in[i * 2 + 0], base = numsteps_in[i * 2 + 1];
-		float T_in = 1.f;
-		float rgb_ray[3] = {0.f, 0.f, 0.f};
-		bool stopped = false;
-		for (uint32_t r0 = 0; r0 < numsteps && !stopped; r0 += 32) {
-			const uint32_t j = r0 + lane;
-			const bool valid = j < numsteps;
-			const SampleEval e = eval_sample(rgbsigma, coords_in, (size_t)base + j, P.cfg, valid);
-			const float T = sequential_prefix_product(T_in, e.one_minus_alpha, lane);
-			// the serial loop tests `T < EPSILON` before it touches a sample (:1352): the walk ends at the first such sample
-			const uint32_t stop_mask = __ballot_sync(0xffffffffu, valid && T < T_EPSILON);
-			const uint32_t first_stop = stop_mask ? (uint32_t)__ffs(stop_mask) - 1 : 32u;
-			const bool counted = valid && lane < first_stop;
-			const float weight = counted ? e.alpha * T : 0.f;
-			#pragma unroll
-			for (int c = 0; c < 3; ++c) rgb_ray[c] += warp_sum(weight * e.rgb[c]);
-			cn += __popc(__ballot_sync(0xffffffffu, counted));
-			stopped = stop_mask != 0;
-			T_in = __shfl_sync(0xffffffffu, T * e.one_minus_alpha, 31);
-		}
 		const RayState tgt = state[i]; // target colour and background, from loss_target_kernel
 		const float bg[3] = {tgt.bg[0], tgt.bg[1], tgt.bg[2]};
 		const float rgbtarget[3] = {tgt.rgbtarget[0], tgt.rgbtarget[1], tgt.rgbtarget[2]};
@@ -226,7 +243,7 @@ __global__ void __launch_bounds__(1024) loss_composite_kernel(
 			#pragma unroll
 			for (int c = 0; c < 3; ++c) rgb_ray[c] += T_in * bg[c];
 		}
-		if (lane == 0) {
+		if (glane == 0) {
 			RayState s;
 			#pragma unroll
 			for (int c = 0; c < 3; ++c) { s.rgb_ray[c] = rgb_ray[c]; s.rgbtarget[c] = rgbtarget[c]; }
@@ -237,9 +254,14 @@ __global__ void __launch_bounds__(1024) loss_composite_kernel(
 			state[i] = s;
 		}
 	}
+	// exclusive prefix of the rays' counts: across the groups of the warp (leaders carry the count), then across the warps of the block
+	uint32_t incl = glane == 0 ? cn : 0u;
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += t; }
+	const uint32_t warp_total = __shfl_sync(0xffffffffu, incl, 31);
 	uint32_t total;
-	const uint32_t local = block_scan_warps(cn, scan_smem, &total);
-	if (lane == 0 && i < P.n_rays) { compacted_counts[i] = cn; local_bases[i] = local; }
+	const uint32_t warp_base = block_scan_warps(warp_total, scan_smem, &total);
+	if (glane == 0 && i < P.n_rays) { compacted_counts[i] = cn; local_bases[i] = warp_base + incl - cn; }
 	if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
 }
 
@@ -259,62 +281,68 @@ __global__ void __launch_bounds__(1024) loss_scan_kernel(const uint32_t n_blocks
 	if (threadIdx.x == 0) counters_out[0] = carry;
 }
 
-// (C) gradient pass, :1436-1556: same walk over the first `cn` samples of the ray, now with the ray's colour known.
+// (C) gradient pass, :1436-1556: same walk over the first `cn` samples of the ray, now with the ray's colour known. W lanes per ray;
+// RB_C = rays per block of the composite kernel (the granularity of block_prefix).
+template <uint32_t W>
 __global__ void __launch_bounds__(1024) loss_gradient_kernel(
 	const LossParams P, const uint32_t* __restrict__ counters_in, const float* __restrict__ mean_density_ptr,
 	const __half* __restrict__ rgbsigma, const float* __restrict__ rays, uint32_t* __restrict__ numsteps_io, const float* __restrict__ coords_in,
 	const RayState* __restrict__ state, const uint32_t* __restrict__ compacted_counts, const uint32_t* __restrict__ local_bases, const uint32_t* __restrict__ block_prefix,
-	float* __restrict__ coords_out, __half* __restrict__ dloss_dout, float* __restrict__ loss_output,
+	const uint32_t RB_C, float* __restrict__ coords_out, __half* __restrict__ dloss_dout, float* __restrict__ loss_output,
 	const uint4* __restrict__ rows_in, uint4* __restrict__ rows_out)
 {
-	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint32_t i = blockIdx.x * LOSS_RAYS_PER_BLOCK + warp;
-	if (i >= P.n_rays) return;
-	if (i >= counters_in[1]) { if (loss_output && lane == 0) loss_output[i] = 0.f; return; }
-	const uint32_t base = numsteps_io[i * 2 + 1];
-	// clip to the batch (:1436-1437)
-	const uint32_t compacted_base = block_prefix[blockIdx.x] + local_bases[i];
-	const uint32_t cn = min(P.batch - min(P.batch, compacted_base), compacted_counts[i]);
+	constexpr uint32_t RAYS_PER_WARP = 32 / W, RAYS_PER_BLOCK = 1024 / W;
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, glane = lane & (W - 1);
+	const uint32_t i = blockIdx.x * RAYS_PER_BLOCK + warp * RAYS_PER_WARP + lane / W;
+	const bool in_range = i < P.n_rays;
+	const bool kept = in_range && i < counters_in[1];
+	uint32_t cn = 0, base = 0, compacted_base = 0;
+	if (kept) {
+		base = numsteps_io[i * 2 + 1];
+		// clip to the batch (:1436-1437)
+		compacted_base = block_prefix[i / RB_C] + local_bases[i];
+		cn = min(P.batch - min(P.batch, compacted_base), compacted_counts[i]);
+	}
 	__syncwarp();
-	if (lane == 0) { numsteps_io[i * 2 + 0] = cn; numsteps_io[i * 2 + 1] = compacted_base; }
-	if (cn == 0) { if (loss_output && lane == 0) loss_output[i] = 0.f; return; }
-	const RayState s = state[i];
-	const float ro[3] = {rays[(size_t)i * 6 + 0], rays[(size_t)i * 6 + 1], rays[(size_t)i * 6 + 2]};
-
-	const LossAndGradient lg = loss_and_gradient(s.rgbtarget, s.rgb_ray, P.cfg.loss_type);
-	const float mean_loss = sum3(lg.loss[0], lg.loss[1], lg.loss[2]) / 3.0f;
-	if (loss_output && lane == 0) loss_output[i] = mean_loss / (float)P.n_rays_global;
-
-	const float loss_scale = P.cfg.loss_scale / P.n_rays_global;
-	const float output_l2_reg = P.cfg.rgb_activation == NGPB_ACT_EXPONENTIAL ? 1e-4f : 0.0f;
-	const float output_l1_reg_density = *mean_density_ptr < NERF_MIN_OPTICAL_THICKNESS ? 1e-4f : 0.0f;
-
-	// compacted coordinates: a contiguous copy of the ray's first cn records, done by the whole warp
-	{
+	if (kept && glane == 0) { numsteps_io[i * 2 + 0] = cn; numsteps_io[i * 2 + 1] = compacted_base; }
+	if (in_range && cn == 0 && loss_output && glane == 0) loss_output[i] = 0.f;
+	RayState s{};
+	float ro[3] = {0.f, 0.f, 0.f};
+	LossAndGradient lg{};
+	if (cn > 0) {
+		s = state[i];
+		ro[0] = rays[(size_t)i * 6 + 0]; ro[1] = rays[(size_t)i * 6 + 1]; ro[2] = rays[(size_t)i * 6 + 2];
+		lg = loss_and_gradient(s.rgbtarget, s.rgb_ray, P.cfg.loss_type);
+		const float mean_loss = sum3(lg.loss[0], lg.loss[1], lg.loss[2]) / 3.0f;
+		if (loss_output && glane == 0) loss_output[i] = mean_loss / (float)P.n_rays_global;
+		// compacted coordinates: a contiguous copy of the ray's first cn records, done by the group
 		const float* src = coords_in + (size_t)base * COORD_FLOATS;
 		float* dst = coords_out + (size_t)compacted_base * COORD_FLOATS;
-		for (uint32_t k = lane; k < cn * COORD_FLOATS; k += 32) dst[k] = src[k];
+		for (uint32_t k = glane; k < cn * COORD_FLOATS; k += W) dst[k] = src[k];
 		// ... and of their hash-grid features (64-byte rows), which the training pass would otherwise recompute from the same weights
 		if (rows_in) {
 			const uint4* rs = rows_in + (size_t)base * 4;
 			uint4* rd = rows_out + (size_t)compacted_base * 4;
-			for (uint32_t k = lane; k < cn * 4; k += 32) rd[k] = rs[k];
+			for (uint32_t k = glane; k < cn * 4; k += W) rd[k] = rs[k];
 		}
 	}
+	const float loss_scale = P.cfg.loss_scale / P.n_rays_global;
+	const float output_l2_reg = P.cfg.rgb_activation == NGPB_ACT_EXPONENTIAL ? 1e-4f : 0.0f;
+	const float output_l1_reg_density = *mean_density_ptr < NERF_MIN_OPTICAL_THICKNESS ? 1e-4f : 0.0f;
 
 	float T_in = 1.f;
 	float prefix_rgb[3] = {0.f, 0.f, 0.f}; // rgb_ray2 after the previous round
-	for (uint32_t r0 = 0; r0 < cn; r0 += 32) {
-		const uint32_t j = r0 + lane;
+	for (uint32_t r0 = 0; __any_sync(0xffffffffu, r0 < cn); r0 += W) {
+		const uint32_t j = r0 + glane;
 		const bool valid = j < cn;
 		const size_t idx = (size_t)base + j;
 		const SampleEval e = eval_sample(rgbsigma, coords_in, idx, P.cfg, valid);
-		const float T_before = sequential_prefix_product(T_in, e.one_minus_alpha, lane);
+		const float T_before = sequential_prefix_product<W>(T_in, e.one_minus_alpha, lane);
 		const float weight = valid ? e.alpha * T_before : 0.f;
 		const float T = T_before * e.one_minus_alpha; // transmittance after this sample (:1520)
 		float rgb_ray2[3];
 		#pragma unroll
-		for (int c = 0; c < 3; ++c) rgb_ray2[c] = prefix_rgb[c] + warp_inclusive_sum(weight * e.rgb[c], lane);
+		for (int c = 0; c < 3; ++c) rgb_ray2[c] = prefix_rgb[c] + group_inclusive_sum<W>(weight * e.rgb[c], lane);
 		if (valid) {
 			const float* ci = coords_in + idx * COORD_FLOATS;
 			const float cpos[3] = {ci[0], ci[1], ci[2]};
@@ -342,9 +370,10 @@ __global__ void __launch_bounds__(1024) loss_gradient_kernel(
 			packed.y = *reinterpret_cast<const uint32_t*>(&h23);
 			*reinterpret_cast<uint2*>(dloss_dout + ((size_t)compacted_base + j) * 4) = packed;
 		}
+		const uint32_t last = (lane & ~(W - 1)) + W - 1;
 		#pragma unroll
-		for (int c = 0; c < 3; ++c) prefix_rgb[c] = __shfl_sync(0xffffffffu, rgb_ray2[c], 31);
-		T_in = __shfl_sync(0xffffffffu, T, 31);
+		for (int c = 0; c < 3; ++c) prefix_rgb[c] = __shfl_sync(0xffffffffu, rgb_ray2[c], last);
+		T_in = __shfl_sync(0xffffffffu, T, last);
 	}
 }
 
@@ -425,17 +454,27 @@ extern "C" int ngpb_compute_loss_compact_features(void* stream_, uint32_t n_rays
 		uint32_t* counts = reinterpret_cast<uint32_t*>(state + n_rays);
 		uint32_t* local_bases = counts + n_rays;
 		uint32_t* block_sums = local_bases + n_rays;
-		const uint32_t blocks = div_round_up(n_rays, LOSS_RAYS_PER_BLOCK);
-		NGPB_STEP_KERNEL(loss_composite_kernel); NGPB_STEP_KERNEL(loss_scan_kernel); NGPB_STEP_KERNEL(loss_gradient_kernel); NGPB_STEP_KERNEL(rollover_kernel);
-		NGPB_STEP_KERNEL(loss_target_kernel);
+		// lanes per ray for the composite / gradient pass. Measured on the Lego-shaped scene (loss stage, us): 32,32 -> 86; 16,16 -> 83; 16,8 -> 99; 8,8 -> 109:
+		// long rays dominate (a warp runs as many rounds as its longest ray), so narrow groups lose. NGPB_LOSS_LANES="c,g" overrides.
+		static const std::pair<int, int> lanes = [] {
+			int c = 16, g = 16;
+			if (const char* e = std::getenv("NGPB_LOSS_LANES")) std::sscanf(e, "%d,%d", &c, &g);
+			return std::make_pair(c, g);
+		}();
+		const uint32_t wc = lanes.first == 8 ? 8u : lanes.first == 32 ? 32u : 16u, wg = lanes.second == 16 ? 16u : lanes.second == 32 ? 32u : 8u;
+		const uint32_t rb_c = 1024 / wc, blocks_c = div_round_up(n_rays, rb_c), blocks_g = div_round_up(n_rays, 1024 / wg);
 		loss_target_kernel<<<div_round_up(n_rays, 128), 128, 0, stream>>>(P, images_dev, counters_in, ray_indices, state);
 		NGPB_LAUNCH_CHECK();
-		loss_composite_kernel<<<blocks, 1024, 0, stream>>>(P, images_dev, counters_in, (const __half*)rgbsigma, ray_indices, numsteps, coords_in, state, counts, local_bases, block_sums);
+		#define NGPB_COMPOSITE(W) loss_composite_kernel<W><<<blocks_c, 1024, 0, stream>>>(P, images_dev, counters_in, (const __half*)rgbsigma, ray_indices, numsteps, coords_in, state, counts, local_bases, block_sums)
+		if (wc == 8) NGPB_COMPOSITE(8); else if (wc == 16) NGPB_COMPOSITE(16); else NGPB_COMPOSITE(32);
+		#undef NGPB_COMPOSITE
 		NGPB_LAUNCH_CHECK();
-		loss_scan_kernel<<<1, 1024, 0, stream>>>(blocks, block_sums, counters_out);
+		loss_scan_kernel<<<1, 1024, 0, stream>>>(blocks_c, block_sums, counters_out);
 		NGPB_LAUNCH_CHECK();
-		loss_gradient_kernel<<<blocks, 1024, 0, stream>>>(P, counters_in, mean_density_dev, (const __half*)rgbsigma, rays, numsteps, coords_in, state, counts, local_bases, block_sums,
-			coords_out, (__half*)dloss_dout, loss_per_ray, reinterpret_cast<const uint4*>(encoded_in), reinterpret_cast<uint4*>(encoded_out));
+		#define NGPB_GRADIENT(W) loss_gradient_kernel<W><<<blocks_g, 1024, 0, stream>>>(P, counters_in, mean_density_dev, (const __half*)rgbsigma, rays, numsteps, coords_in, state, counts, local_bases, \
+			block_sums, rb_c, coords_out, (__half*)dloss_dout, loss_per_ray, reinterpret_cast<const uint4*>(encoded_in), reinterpret_cast<uint4*>(encoded_out))
+		if (wg == 8) NGPB_GRADIENT(8); else if (wg == 16) NGPB_GRADIENT(16); else NGPB_GRADIENT(32);
+		#undef NGPB_GRADIENT
 		NGPB_LAUNCH_CHECK();
 		rollover_kernel<<<div_round_up(batch, 256), 256, 0, stream>>>(batch, counters_out, coords_out, (__half*)dloss_dout, reinterpret_cast<uint4*>(encoded_out));
 		NGPB_LAUNCH_CHECK();

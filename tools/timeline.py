@@ -18,11 +18,21 @@ scene = synthetic.make_lego_scene(100, 800, device="cuda", as_numpy=True)
 tb = pyngp.Testbed()
 tb.load_training_images(list(scene["images"]), scene["xforms"], scene["fx"], scene["fy"])
 tb.train_n(530)
+if mode == "render":
+    import math
+    tb.camera_matrix = synthetic.nerf_matrix_to_ngp(synthetic.hemisphere_cameras(7, seed=3)[2])
+    tb.fov_axis = 0; tb.fov = math.degrees(synthetic.CAMERA_ANGLE_X)
+    tb.render(800, 800, 1, True)  # warm-up: workspace allocation
 torch.cuda.synchronize()
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     if mode == "train_n":
         tb.train_n(n_steps)
+    elif mode == "render":  # one classic 800 x 800 frame (K17)
+        import math
+        tb.camera_matrix = synthetic.nerf_matrix_to_ngp(synthetic.hemisphere_cameras(7, seed=3)[2])
+        tb.fov_axis = 0; tb.fov = math.degrees(synthetic.CAMERA_ANGLE_X)
+        tb.render(800, 800, 1, True)
     else:
         for _ in range(n_steps):
             tb.train(); _ = tb.loss
