@@ -111,20 +111,8 @@ __device__ __forceinline__ void corner_indices(const LevelConst& c, const uint32
 	}
 }
 
-__global__ void __launch_bounds__(256) hash_encode_forward_kernel(
-	const uint32_t n, const uint32_t* __restrict__ n_dev, const GridLevels L, const __half2* __restrict__ grid, const float* __restrict__ positions, const uint32_t pos_stride,
-	__half2* __restrict__ encoded)
-{
-	__shared__ LevelConst lc[NGPB_MAX_LEVELS];
-	if (threadIdx.x < L.n_levels) lc[threadIdx.x] = LevelConst{L.scale[threadIdx.x], L.size[threadIdx.x], L.resolution[threadIdx.x], L.offset[threadIdx.x]};
-	__syncthreads();
-	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-	uint32_t level, i;
-	if (L.n_levels == 16) { level = tid & 15u; i = tid >> 4; } else { level = tid % L.n_levels; i = tid / L.n_levels; }
-	if (i >= n) return;
-	if (n_dev && i >= *n_dev) return; // device-side sample count (no host round trip between K1 and the network)
-
-	const LevelConst c = lc[level];
+// Per-(sample, level) work shared by the forward kernels: position -> 8 gathers -> blended feature pair.
+__device__ __forceinline__ __half2 encode_one(const LevelConst& c, const __half2* __restrict__ grid, const float* __restrict__ positions, size_t i, uint32_t pos_stride) {
 	const __half2* __restrict__ g = grid + c.offset;
 	float pos[3];
 	uint32_t pg[3];
@@ -150,7 +138,45 @@ __global__ void __launch_bounds__(256) hash_encode_forward_kernel(
 		const float2 f = __half22float2(v[k]);
 		r = __hadd2(r, __floats2half2_rn(w * f.x, w * f.y));
 	}
-	encoded[(size_t)i * L.n_levels + level] = r;
+	return r;
+}
+
+// Generic level count: thread per (sample, level), level fastest.
+__global__ void __launch_bounds__(256) hash_encode_forward_kernel(
+	const uint32_t n, const uint32_t* __restrict__ n_dev, const GridLevels L, const __half2* __restrict__ grid, const float* __restrict__ positions, const uint32_t pos_stride,
+	__half2* __restrict__ encoded)
+{
+	__shared__ LevelConst lc[NGPB_MAX_LEVELS];
+	if (threadIdx.x < L.n_levels) lc[threadIdx.x] = LevelConst{L.scale[threadIdx.x], L.size[threadIdx.x], L.resolution[threadIdx.x], L.offset[threadIdx.x]};
+	__syncthreads();
+	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t level = tid % L.n_levels, i = tid / L.n_levels;
+	if (i >= n) return;
+	if (n_dev && i >= *n_dev) return; // device-side sample count (no host round trip between K1 and the network)
+	encoded[(size_t)i * L.n_levels + level] = encode_one(lc[level], grid, positions, i, pos_stride);
+}
+
+// 16 levels (every NeRF / SDF config of the reference): a block is 16 consecutive samples x 16 levels, as before, but a WARP is 16 samples x 2
+// levels. Dense and hashed levels index differently; with all 16 levels of a sample in one warp every warp executed both index computations
+// (ncu: 26 of 32 lanes active, 137 warp instructions per sample). Grouped by level, only the warp that holds the last dense and the first hashed
+// level diverges, and the 16 samples of a ray that share a coarse cell hit the same lines within one load. The block's working set -- what decides
+// the L1 hit rate -- is unchanged. Results go through a shared-memory tile so that the block still writes its 1 KB of `encoded` rows contiguously.
+__global__ void __launch_bounds__(256) hash_encode_forward16_kernel(
+	const uint32_t n, const uint32_t* __restrict__ n_dev, const GridLevels L, const __half2* __restrict__ grid, const float* __restrict__ positions, const uint32_t pos_stride,
+	__half2* __restrict__ encoded)
+{
+	__shared__ LevelConst lc[16];
+	__shared__ __half2 tile[16][17];
+	if (threadIdx.x < 16) lc[threadIdx.x] = LevelConst{L.scale[threadIdx.x], L.size[threadIdx.x], L.resolution[threadIdx.x], L.offset[threadIdx.x]};
+	__syncthreads();
+	const uint32_t level = threadIdx.x >> 4, s = threadIdx.x & 15u;
+	const uint32_t i0 = blockIdx.x * 16u, i = i0 + s;
+	const uint32_t n_eff = n_dev ? min(n, *n_dev) : n; // device-side sample count (no host round trip between K1 and the network)
+	if (i0 >= n_eff) return;
+	if (i < n_eff) tile[s][level] = encode_one(lc[level], grid, positions, i, pos_stride);
+	__syncthreads();
+	const uint32_t row = threadIdx.x >> 4, col = threadIdx.x & 15u; // (sample, level) of the element this thread writes out
+	if (i0 + row < n_eff) encoded[(size_t)i0 * 16u + threadIdx.x] = tile[row][col];
 }
 
 // Two-dimensional input (the neural-image model: N_POS_DIMS = 2 of kernel_grid, grid.h:220-349): four corners, x ^ y * 2654435761 when hashed.
@@ -283,7 +309,8 @@ void hash_encode_forward_launch(cudaStream_t stream, const ngpb_grid* g, const _
 		return;
 	}
 	// no explicit shared-memory carve-out for this kernel: any non-default preference was measured 3x slower (L1 is what feeds the gathers)
-	hash_encode_forward_kernel<<<(uint32_t)((threads + 255) / 256), 256, 0, stream>>>(n, n_dev, L, (const __half2*)grid, positions, pos_stride, (__half2*)encoded);
+	if (L.n_levels == 16) hash_encode_forward16_kernel<<<(uint32_t)((threads + 255) / 256), 256, 0, stream>>>(n, n_dev, L, (const __half2*)grid, positions, pos_stride, (__half2*)encoded);
+	else hash_encode_forward_kernel<<<(uint32_t)((threads + 255) / 256), 256, 0, stream>>>(n, n_dev, L, (const __half2*)grid, positions, pos_stride, (__half2*)encoded);
 	NGPB_LAUNCH_CHECK();
 }
 // [level_begin, level_end): the levels to scatter (all of them: 0, n_levels); the data-parallel pipeline launches level groups separately
