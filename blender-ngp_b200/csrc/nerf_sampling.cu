@@ -76,26 +76,32 @@ constexpr float TAU_NEXT = -INFINITY;
 
 __device__ __forceinline__ bool tau_is_end(float tau) { return tau != tau; }
 
+// With cone_angle == 0 (every aabb_scale-1 scene) calc_dt is the constant minimum step (t * 0 clamps to MIN_CONE_STEPSIZE) and mip_from_dt reduces to
+// mip_from_pos (dt * 256 < 1): the CONST_DT instantiations drop those per-candidate computations. Same values, fewer instructions.
+template <bool CONST_DT> __device__ __forceinline__ float chain_dt(float t, float cone_angle) { return CONST_DT ? MIN_CONE_STEPSIZE : calc_dt(t, cone_angle); }
+template <bool CONST_DT> __device__ __forceinline__ uint32_t chain_mip(float dt, const V3& pos) { return (uint32_t)(CONST_DT ? mip_from_pos(pos) : mip_from_dt(dt, pos)); }
+
 // Marches the 32 candidates of one word starting with candidate `entry` visited. t_word: chain value at candidate 0.
+template <bool CONST_DT>
 __device__ inline void march_word(const V3& o, const V3& d, const V3& idir, float cone_angle, const Aabb& aabb, const uint8_t* __restrict__ bitfield,
                                   float t_word, uint32_t entry, uint32_t* visited_out, uint32_t* emitted_out, float* tau_out) {
 	float t = t_word;
 	uint32_t c = 0, visited = 0, emitted = 0;
-	for (; c < entry; ++c) t += calc_dt(t, cone_angle);
+	for (; c < entry; ++c) t += chain_dt<CONST_DT>(t, cone_angle);
 	float tau = TAU_NEXT;
 	while (c < 32) {
 		const V3 pos = V3{o.x + t * d.x, o.y + t * d.y, o.z + t * d.z};
 		if (!aabb_contains(aabb, pos)) { tau = __uint_as_float(0x7FC00000u); break; }
 		visited |= 1u << c;
-		const float dt = calc_dt(t, cone_angle);
-		const uint32_t mip = mip_from_dt(dt, pos);
+		const float dt = chain_dt<CONST_DT>(t, cone_angle);
+		const uint32_t mip = chain_mip<CONST_DT>(dt, pos);
 		if (density_grid_occupied_at(pos, bitfield, mip)) {
 			emitted |= 1u << c;
 			t += dt;
 			++c;
 		} else {
 			const float t_target = t + distance_to_next_voxel(pos, d, idir, NERF_GRIDSIZE >> mip);
-			do { t += calc_dt(t, cone_angle); ++c; } while (t < t_target && c < 32); // advance_to_next_voxel, cut at the word's end
+			do { t += chain_dt<CONST_DT>(t, cone_angle); ++c; } while (t < t_target && c < 32); // advance_to_next_voxel, cut at the word's end
 			if (t < t_target) { tau = t_target; break; } // the jump continues in a later word
 		}
 	}
@@ -131,6 +137,7 @@ __device__ inline uint32_t march_serial(const TrainRay& r, const Aabb& aabb, con
 constexpr uint32_t K1_BLOCK = 128;
 
 // Pass 1: one thread per ray. Set-up and the t chain; appends one work item per word to `items`.
+template <bool CONST_DT>
 __global__ void __launch_bounds__(K1_BLOCK) chain_training_rays_kernel(
 	const uint32_t n_rays, const uint32_t ray_offset, const uint32_t n_rays_global, const Aabb aabb, const Pcg32 rng, const uint32_t n_images, const ngpb_image* __restrict__ images,
 	const bool snap, const float cone_angle_constant, RayRec* __restrict__ recs, MarchWord* __restrict__ words, uint32_t* __restrict__ items, uint32_t* __restrict__ n_items)
@@ -153,7 +160,7 @@ __global__ void __launch_bounds__(K1_BLOCK) chain_training_rays_kernel(
 				w[n_words++].t = t;
 				if (!(t <= t_end)) break;
 				#pragma unroll
-				for (int k = 0; k < 32; ++k) t += calc_dt(t, r.cone_angle);
+				for (int k = 0; k < 32; ++k) t += chain_dt<CONST_DT>(t, r.cone_angle);
 			}
 		}
 		RayRec rec;
@@ -176,6 +183,7 @@ __global__ void __launch_bounds__(K1_BLOCK) chain_training_rays_kernel(
 }
 
 // Pass 2: one thread per word: march the word's 32 candidates assuming candidate 0 is visited.
+template <bool CONST_DT>
 __global__ void __launch_bounds__(128) march_words_kernel(const uint32_t* __restrict__ n_items, const uint32_t* __restrict__ items, const Aabb aabb, const uint8_t* __restrict__ bitfield,
                                                           const RayRec* __restrict__ recs, MarchWord* __restrict__ words)
 {
@@ -187,11 +195,12 @@ __global__ void __launch_bounds__(128) march_words_kernel(const uint32_t* __rest
 	const V3 idir = {1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
 	MarchWord* mw = words + (size_t)i * MARCH_MAX_WORDS + w;
 	uint32_t visited, emitted; float tau;
-	march_word(o, d, idir, rec.cone_angle, aabb, bitfield, mw->t, 0, &visited, &emitted, &tau);
+	march_word<CONST_DT>(o, d, idir, rec.cone_angle, aabb, bitfield, mw->t, 0, &visited, &emitted, &tau);
 	mw->visited = visited; mw->emitted = emitted; mw->tau = tau;
 }
 
 // Pass 3: one thread per ray: resolve the words in order, then the block-local exclusive prefixes of (count, count > 0).
+template <bool CONST_DT>
 __global__ void __launch_bounds__(K1_BLOCK) resolve_training_rays_kernel(
 	const uint32_t n_rays, const uint32_t ray_offset, const uint32_t n_rays_global, const Aabb aabb, const Pcg32 rng, const uint32_t n_images, const ngpb_image* __restrict__ images,
 	const uint8_t* __restrict__ bitfield, const bool snap, const float cone_angle_constant, const RayRec* __restrict__ recs, MarchWord* __restrict__ words,
@@ -219,12 +228,12 @@ __global__ void __launch_bounds__(K1_BLOCK) resolve_training_rays_kernel(
 				uint32_t e = 0;
 				if (tau_in != TAU_NEXT) {
 					float t = mw.t;
-					while (e < 32 && t < tau_in) { t += calc_dt(t, rec.cone_angle); ++e; }
+					while (e < 32 && t < tau_in) { t += chain_dt<CONST_DT>(t, rec.cone_angle); ++e; }
 					if (e == 32) { rw[w].emitted = 0; continue; } // the jump passes over the whole word
 				}
 				uint32_t emitted; float tau_out;
 				if ((mw.visited >> e) & 1u) { emitted = mw.emitted & (0xFFFFFFFFu << e); tau_out = mw.tau; }
-				else { uint32_t v; march_word(o, d, idir, rec.cone_angle, aabb, bitfield, mw.t, e, &v, &emitted, &tau_out); }
+				else { uint32_t v; march_word<CONST_DT>(o, d, idir, rec.cone_angle, aabb, bitfield, mw.t, e, &v, &emitted, &tau_out); }
 				// the march stops once it holds NERF_STEPS samples (:1209)
 				const uint32_t n_here = __popc(emitted);
 				if (c + n_here >= NERF_STEPS) {
@@ -285,6 +294,7 @@ __global__ void __launch_bounds__(1024) scan_training_samples_kernel(const uint3
 // (:1221-1228); since bases grow with the ray index the kept rays are exactly the sample-bearing rays before the cut, so a kept
 // ray's slot is the number of sample-bearing rays before it.
 constexpr uint32_t WRITE_RAYS_PER_BLOCK = 8;
+template <bool CONST_DT>
 __global__ void __launch_bounds__(WRITE_RAYS_PER_BLOCK * 32) write_training_samples_kernel(
 	const uint32_t n_rays, const uint32_t ray_offset, const uint32_t n_rays_global, const uint32_t max_samples, const Aabb aabb, const Pcg32 rng, const uint32_t n_images, const ngpb_image* __restrict__ images,
 	const uint8_t* __restrict__ bitfield, const bool snap, const float cone_angle_constant,
@@ -357,8 +367,8 @@ __global__ void __launch_bounds__(WRITE_RAYS_PER_BLOCK * 32) write_training_samp
 			if (s < n_chunk) {
 				const uint32_t bit = __fns(mask, 0, (int)rank + 1); // position of the (rank+1)-th set bit
 				float t = t_word;
-				for (uint32_t k = 0; k < bit; ++k) t += calc_dt(t, rec.cone_angle);
-				const float dt = calc_dt(t, rec.cone_angle);
+				for (uint32_t k = 0; k < bit; ++k) t += chain_dt<CONST_DT>(t, rec.cone_angle);
+				const float dt = chain_dt<CONST_DT>(t, rec.cone_angle);
 				const V3 pos = V3{o.x + t * d.x, o.y + t * d.y, o.z + t * d.z};
 				const V3 wp = warp_position(pos, aabb);
 				float* c = out + (size_t)(carry + s) * COORD_FLOATS;
@@ -439,22 +449,25 @@ extern "C" int ngpb_generate_training_samples_sharded(void* stream_, uint32_t n_
 		const uint32_t blocks = div_round_up(n_rays, K1_BLOCK);
 		const bool snap = snap_to_pixel_centers != 0;
 		NGPB_CUDA_CHECK(cudaMemsetAsync(sc.n_items, 0, 4, stream));
-		chain_training_rays_kernel<<<blocks, K1_BLOCK, 0, stream>>>(n_rays, ray_offset, n_rays_global, aabb, rng, n_images, images_dev, snap, cone_angle_constant,
+		const bool const_dt = cone_angle_constant == 0.f;
+		#define NGPB_K1(kernel, grid, block, ...) do { if (const_dt) kernel<true><<<grid, block, 0, stream>>>(__VA_ARGS__); else kernel<false><<<grid, block, 0, stream>>>(__VA_ARGS__); } while (0)
+		NGPB_K1(chain_training_rays_kernel, blocks, K1_BLOCK, n_rays, ray_offset, n_rays_global, aabb, rng, n_images, images_dev, snap, cone_angle_constant,
 			sc.recs, words, sc.items, sc.n_items);
 		NGPB_LAUNCH_CHECK();
 		// one thread per word; the word count lives on the device, so the grid covers the worst case and surplus blocks exit at once.
 		// A ray of the unit cube has at most 33 words (1025 candidates); larger scenes up to MARCH_MAX_WORDS.
 		const uint64_t max_items = (uint64_t)n_rays * MARCH_MAX_WORDS;
-		march_words_kernel<<<(uint32_t)((max_items + 127) / 128), 128, 0, stream>>>(sc.n_items, sc.items, aabb, bitfield, sc.recs, words);
+		NGPB_K1(march_words_kernel, (uint32_t)((max_items + 127) / 128), 128, sc.n_items, sc.items, aabb, bitfield, sc.recs, words);
 		NGPB_LAUNCH_CHECK();
-		resolve_training_rays_kernel<<<blocks, K1_BLOCK, 0, stream>>>(n_rays, ray_offset, n_rays_global, aabb, rng, n_images, images_dev, bitfield, snap, cone_angle_constant,
+		NGPB_K1(resolve_training_rays_kernel, blocks, K1_BLOCK, n_rays, ray_offset, n_rays_global, aabb, rng, n_images, images_dev, bitfield, snap, cone_angle_constant,
 			sc.recs, words, counts, n_words, local_bases, local_slots, block_sums);
 		NGPB_LAUNCH_CHECK();
 		scan_training_samples_kernel<<<1, 1024, 0, stream>>>(blocks, block_sums, counters);
 		NGPB_LAUNCH_CHECK();
-		write_training_samples_kernel<<<div_round_up(n_rays, WRITE_RAYS_PER_BLOCK), WRITE_RAYS_PER_BLOCK * 32, 0, stream>>>(n_rays, ray_offset, n_rays_global, max_samples, aabb, rng, n_images, images_dev, bitfield,
+		NGPB_K1(write_training_samples_kernel, div_round_up(n_rays, WRITE_RAYS_PER_BLOCK), WRITE_RAYS_PER_BLOCK * 32, n_rays, ray_offset, n_rays_global, max_samples, aabb, rng, n_images, images_dev, bitfield,
 			snap_to_pixel_centers != 0, cone_angle_constant, counts, n_words, sc.recs, words, local_bases, local_slots, block_sums, counters, ray_indices, rays, numsteps, coords);
 		NGPB_LAUNCH_CHECK();
+		#undef NGPB_K1
 		return 0;
 	} catch (const std::exception& e) { set_last_error(e.what()); return NGPB_ERR_RUNTIME; }
 }

@@ -119,12 +119,14 @@ extern "C" void ngpb_effective_xform(const float* m12, float* out12) {
 // ---------------------------------------------------------------------------------------------------
 ngpb_testbed::ngpb_testbed(int device_) : device(device_) {
 	NGPB_CUDA_CHECK(cudaSetDevice(device));
-	NGPB_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-	// higher priority: when the sampling kernels are launched behind a kernel that fills the machine, their (few, long-running)
-	// blocks are placed as soon as the running kernel's blocks retire instead of after its whole grid
+	// Stream priorities (NGPB_STREAM_PRIORITY = "sampling" | "main" | "equal"): whichever stream has the higher priority gets its pending blocks placed
+	// first as resident blocks retire; the other stream's kernels fill what is left.
 	int prio_low = 0, prio_high = 0;
 	NGPB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
-	NGPB_CUDA_CHECK(cudaStreamCreateWithPriority(&sampling_stream, cudaStreamNonBlocking, prio_high));
+	const char* pe = std::getenv("NGPB_STREAM_PRIORITY");
+	const std::string pmode = pe ? pe : "sampling";
+	NGPB_CUDA_CHECK(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, pmode == "main" ? prio_high : prio_low));
+	NGPB_CUDA_CHECK(cudaStreamCreateWithPriority(&sampling_stream, cudaStreamNonBlocking, pmode == "sampling" ? prio_high : prio_low));
 	NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&prefetch_done, cudaEventDisableTiming));
 	NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&loss_ready, cudaEventDisableTiming));
 	NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&counters_ready, cudaEventDisableTiming));
