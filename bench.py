@@ -43,7 +43,10 @@ STAGE_ALGO = {  # stage -> (bound, per-unit quantity, unit of `achieved`)
     "encode_backward": ("hbm", HASH_BWD_BYTES, "GB/s"),
     "mlp_inference": ("tensor", MLP_FWD_FLOPS, "TFLOP/s"),
     "mlp_train": ("tensor", MLP_TRAIN_FLOPS, "TFLOP/s"),
-    "optimizer": ("hbm", 46, "GB/s"),  # per parameter: grad r+w 8, fp32 weight r+w 8, two moments r+w 16, step counter r+w 8, fp16 weight w 2, EMA r+w 4
+    # 10 B/param for every parameter (gradient read 4, fp16 weight read 2, EMA read + write 4) + 36 B for a parameter whose gradient is
+    # non-zero (gradient reset 4, fp32 weight / two moments / step counter r+w 32). The touched fraction is data dependent: the ncu capture of this
+    # workload measures 362 MB per launch = 49 % of the parameters touched, so 10 + 0.49 x 36 = 27.6 B/param is used as the per-unit figure.
+    "optimizer": ("hbm", 27.6, "GB/s"),
 }
 
 
@@ -283,7 +286,18 @@ def main():
     # dominant kernel = the stage with the largest share of the step among those with a roofline model
     dom = max((n for n in stage_report if "frac" in stage_report[n]), key=lambda n: stage_report[n]["share"])
     d = stage_report[dom]
-    roofline = dict(kernel=dom, bound=d["bound"], achieved=d["achieved"], peak=d["peak"], unit=d["unit"], frac=d["frac"], traffic=None,
+    # DRAM traffic per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` capture of this
+    # same command (profiles/r01_traffic.json, written by tools/ncu_summary.py traffic); null when the capture does not cover the stage
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            tj = json.load(f)
+        if dom in tj.get("stages", {}):
+            traffic, traffic_src = float(tj["stages"][dom]["dram_bytes_per_launch"]), tj.get("source")
+    except (OSError, ValueError, KeyError):
+        pass
+    roofline = dict(kernel=dom, bound=d["bound"], achieved=d["achieved"], peak=d["peak"], unit=d["unit"], frac=d["frac"], traffic=traffic, traffic_source=traffic_src,
+                    algorithmic_bytes_per_launch=(d["units_per_call"] * STAGE_ALGO[dom][1]) if d["bound"] == "hbm" else None,
                     peak_source=f"MEASURED_PEAKS.json ({pk['src']}; {'hbm_gbs' if d['bound'] == 'hbm' else 'bf16_tflops_sustained'})",
                     share_of_step=d["share"], per_stage=stage_report)
 
@@ -319,9 +333,10 @@ def main():
     s0 = tb.stats()
     barrier()
     t1 = time.perf_counter()
+    e2e_losses = []
     for _ in range(K):
         tb.train(args.batch)      # one optimizer step through the public call; syncs and reads the counters (+ loss every 16th step) back
-        _ = tb.loss               # host-side read of the step's result
+        e2e_losses.append(tb.loss)  # host-side read of the step's result
     torch.cuda.synchronize()
     t_steps = time.perf_counter() - t1
     s1 = tb.stats()
@@ -332,7 +347,7 @@ def main():
         e2e_s = float(t.item())
     e2e = dict(value=world * (args.batch / BATCH) * K / e2e_s, unit=UNIT,
                h2d_bytes_per_step=(dataset_bytes + 0.0) / K, d2h_bytes_per_step=(s1["d2h_bytes"] - s0["d2h_bytes"]) / K,
-               dataset_upload_ms=1e3 * t_load, ms_per_step_host=1e3 * t_steps / K)
+               dataset_upload_ms=1e3 * t_load, ms_per_step_host=1e3 * t_steps / K, mean_loss=float(np.mean(e2e_losses)) if e2e_losses else None)
     del tb
 
     cb = None

@@ -14,7 +14,7 @@ namespace ngpb {
 struct NcclApi {
 	typedef struct { char internal[128]; } UniqueId;
 	typedef void* Comm;
-	enum { Uint32 = 3, Float16 = 6, Float32 = 7 };
+	enum { Uint32 = 3, Float16 = 6, Float32 = 7, Bfloat16 = 9 }; // ncclDataType_t (nccl.h)
 	enum { Sum = 0 };
 
 	int (*GetUniqueId)(UniqueId*) = nullptr;

@@ -5,6 +5,7 @@
 // training_prep_nerf). All device memory is owned here and allocated once per (dataset, batch size):
 // nothing is allocated in the steady state, like the reference's per-stream arena.
 #include "testbed.h"
+#include <cuda_bf16.h>
 #include "nccl_dl.h"
 
 #include <algorithm>
@@ -116,6 +117,32 @@ extern "C" void ngpb_effective_xform(const float* m12, float* out12) {
 	out12[9] = m12[9]; out12[10] = m12[10]; out12[11] = m12[11];
 }
 
+// Data-parallel gradient exchange in fp16: cast the fp32 accumulation buffer (4 values per thread) and reset it in the same pass; widen the reduced slice.
+template <bool BF16>
+__global__ void __launch_bounds__(256) grads_to_16bit_and_reset_kernel(const uint32_t n4, float4* __restrict__ grad, uint2* __restrict__ out)
+{
+	const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= n4) return;
+	const float4 g = grad[q];
+	uint2 o;
+	if (BF16) {
+		const __nv_bfloat162 a = __floats2bfloat162_rn(g.x, g.y), b = __floats2bfloat162_rn(g.z, g.w);
+		o = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+	} else {
+		const __half2 a = __floats2half2_rn(g.x, g.y), b = __floats2half2_rn(g.z, g.w);
+		o = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+	}
+	out[q] = o;
+	grad[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+template <bool BF16>
+__global__ void __launch_bounds__(256) widen_16bit_kernel(const uint32_t n, const uint16_t* __restrict__ in, float* __restrict__ out)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	out[i] = BF16 ? __uint_as_float((uint32_t)in[i] << 16) : __half2float(__ushort_as_half(in[i]));
+}
+
 // ---------------------------------------------------------------------------------------------------
 ngpb_testbed::ngpb_testbed(int device_) : device(device_) {
 	NGPB_CUDA_CHECK(cudaSetDevice(device));
@@ -123,6 +150,7 @@ ngpb_testbed::ngpb_testbed(int device_) : device(device_) {
 	// first as resident blocks retire; the other stream's kernels fill what is left.
 	int prio_low = 0, prio_high = 0;
 	NGPB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
+	if (const char* ge = std::getenv("NGPB_DP_HALF_GRADIENTS")) dp_half_gradients = std::atoi(ge); // 0 fp32, 1 bf16 (default), 2 fp16
 	const char* pe = std::getenv("NGPB_STREAM_PRIORITY");
 	const std::string pmode = pe ? pe : "sampling";
 	NGPB_CUDA_CHECK(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, pmode == "main" ? prio_high : prio_low));
@@ -266,7 +294,7 @@ void ngpb_testbed::reset_network(uint32_t seed_) {
 	if (ngpb_grid_device_scales(stream, &grid) != 0) throw std::runtime_error(ngpb_last_error());
 	const uint32_t new_n_params = MLP_PARAMS + 2 * entries;
 	if (new_n_params != n_params) {
-		dfree(w_fp32); dfree(w_half); dfree(w_ema); dfree(m1); dfree(m2); dfree(param_steps); dfree(grad);
+		dfree(w_fp32); dfree(w_half); dfree(w_ema); dfree(m1); dfree(m2); dfree(param_steps); dfree(grad); dfree(grad_half); grad_half = nullptr;
 		n_params = new_n_params;
 		n_alloc = n_params + 4096; // slack: the sharded data-parallel optimizer works on world x ceil(n_params / world) padded ranges
 		w_fp32 = (float*)dalloc(sizeof(float) * n_alloc);
@@ -565,12 +593,36 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 			const uint32_t count = dp_shard_count(), first = (uint32_t)dp_rank * count;
 			const uint32_t mine = first < n_params ? std::min(count, n_params - first) : 0u;
 			stage_begin(NGPB_STAGE_ALLREDUCE, stream);
-			nccl.check(nccl.ReduceScatter(grad, grad + first, count, NcclApi::Float32, NcclApi::Sum, nccl_comm, stream), "ncclReduceScatter(gradients)");
-			stage_end(NGPB_STAGE_ALLREDUCE, (uint64_t)n_params * 4, stream);
+			if (dp_half_gradients) {
+				// Exchange the gradients in 16 bits, which halves the bytes on NVLink. The reference keeps its gradients in fp16 everywhere (tcnn
+				// accumulates them with atomicAdd(__half2) and hands fp16 to Adam); a rank's PARTIAL gradient is world x smaller than that, deep in
+				// fp16's subnormal range for sparsely hit grid entries, so the default is bf16 (fp32's range, 2^-9 relative rounding per partial sum;
+				// dp_half_gradients = 2 selects fp16). One pass casts the fp32 accumulation buffer and resets it; the reduced slice is widened again for
+				// the fp32 optimizer. Every rank receives the same bits, so replicas stay identical.
+				if (!grad_half) grad_half = (__half*)dalloc(sizeof(__half) * ((size_t)count * dp_world + count));
+				__half* shard_half = grad_half + (size_t)count * dp_world;
+				const uint32_t n_cast = count * (uint32_t)dp_world; // n_alloc >= n_params + 4096 covers the padding of the last slice
+				if (n_cast > n_alloc) throw std::runtime_error("data parallel: parameter padding too small for this world size");
+				const bool bf16 = dp_half_gradients == 1;
+				if (bf16) grads_to_16bit_and_reset_kernel<true><<<div_round_up(n_cast / 4, 256), 256, 0, stream>>>(n_cast / 4, reinterpret_cast<float4*>(grad), reinterpret_cast<uint2*>(grad_half));
+				else grads_to_16bit_and_reset_kernel<false><<<div_round_up(n_cast / 4, 256), 256, 0, stream>>>(n_cast / 4, reinterpret_cast<float4*>(grad), reinterpret_cast<uint2*>(grad_half));
+				NGPB_LAUNCH_CHECK();
+				nccl.check(nccl.ReduceScatter(grad_half, shard_half, count, bf16 ? NcclApi::Bfloat16 : NcclApi::Float16, NcclApi::Sum, nccl_comm, stream), "ncclReduceScatter(gradients, 16 bit)");
+				if (mine) {
+					if (bf16) widen_16bit_kernel<true><<<div_round_up(mine, 256), 256, 0, stream>>>(mine, reinterpret_cast<const uint16_t*>(shard_half), grad + first);
+					else widen_16bit_kernel<false><<<div_round_up(mine, 256), 256, 0, stream>>>(mine, reinterpret_cast<const uint16_t*>(shard_half), grad + first);
+					NGPB_LAUNCH_CHECK();
+				}
+				n_launches += 2;
+			} else {
+				nccl.check(nccl.ReduceScatter(grad, grad + first, count, NcclApi::Float32, NcclApi::Sum, nccl_comm, stream), "ncclReduceScatter(gradients)");
+			}
+			stage_end(NGPB_STAGE_ALLREDUCE, (uint64_t)n_params * (dp_half_gradients ? 2 : 4), stream);
 			stage_begin(NGPB_STAGE_OPTIMIZER, stream);
 			optimizer_disable_fused_ema(opt_params);
 			optimizer_launch(stream, opt_params, first, mine, MLP_PARAMS, grad, w_fp32, w_half, w_ema, m1, m2, param_steps);
-			NGPB_CUDA_CHECK(cudaMemsetAsync(grad, 0, sizeof(float) * n_alloc, stream)); // the other ranks' ranges still hold this rank's partial sums
+			// fp32 exchange: the other ranks' ranges still hold this rank's partial sums (the fp16 path reset the buffer while casting)
+			if (!dp_half_gradients) NGPB_CUDA_CHECK(cudaMemsetAsync(grad, 0, sizeof(float) * n_alloc, stream));
 			nccl.check(nccl.AllGather(w_half + first, w_half, count, NcclApi::Float16, nccl_comm, stream), "ncclAllGather(weights)");
 			ema_sweep_launch(stream, opt_params, next_multiple(n_params, 8), w_half, w_ema);
 			stage_end(NGPB_STAGE_OPTIMIZER, n_params, stream);
@@ -854,6 +906,7 @@ extern "C" int ngpb_testbed_set_option(ngpb_testbed* t, const char* name, double
 	else if (k == "dp_sharded_optimizer") t->dp_sharded_optimizer = v != 0;
 	else if (k == "overlap_sampling") { t->drop_prefetch(); t->overlap_sampling = v != 0; }
 	else if (k == "reuse_encoding") t->reuse_encoding = v != 0;
+	else if (k == "dp_half_gradients") t->dp_half_gradients = (int)v; // 0 fp32, 1 bf16, 2 fp16
 	else throw std::runtime_error("unknown option: " + k);
 	NGPB_API_END
 }

@@ -34,6 +34,8 @@ struct ngpb_testbed {
 	cudaEvent_t prefetch_done = nullptr, loss_ready = nullptr, counters_ready = nullptr, mlp_train_done = nullptr;
 	SamplingRequest prefetch{};
 	bool prefetch_valid = false, overlap_sampling = true;
+	int dp_half_gradients = 1; // data parallel gradient exchange: 0 fp32, 1 bf16, 2 fp16
+	__half* grad_half = nullptr;
 	bool reuse_encoding = true; // the training pass starts from the inference pass's hash-grid features (compacted with the samples) instead of re-encoding
 	bool loss_pending = false;
 	float loss_pending_scale = 0.f;

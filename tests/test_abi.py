@@ -4,6 +4,7 @@ import os
 import re
 
 import numpy as np
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -90,3 +91,30 @@ def test_snapshot_container_round_trip():
     old = dict(back); old["snapshot"] = dict(back["snapshot"], version=0)
     with pytest.raises(RuntimeError):
         pyngp.parse_snapshot(old)
+
+
+def test_transforms_json_loader_round_trip(tmp_path):
+    """pyngp.load_transforms (nerf_loader.cu:197-747 for a pinhole nerf_synthetic-style dataset): a scene written by synthetic.write_transforms_json comes
+    back with the same pixels, the same ngp-convention camera matrices (nerf_matrix_to_ngp with the file's scale / offset), the focal length from
+    camera_angle_x, frames sorted by path; lens-distortion keys are refused."""
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "blender-ngp_b200"))
+    import pyngp
+    import synthetic
+    scene = synthetic.make_lego_scene(3, 32, device="cpu", seed=1)
+    path = synthetic.write_transforms_json(scene, str(tmp_path))
+    got = pyngp.load_transforms(str(tmp_path))  # a directory: picks transforms_train.json
+    assert len(got["images"]) == 3 and got["aabb_scale"] == 1
+    order = sorted(range(3), key=lambda i: f"./train/r_{i}")
+    for k, i in enumerate(order):
+        assert np.array_equal(got["images"][k], np.asarray(scene["images"][i]))
+        np.testing.assert_allclose(got["xforms"][k], scene["xforms"][i], rtol=0, atol=1e-6)
+    assert abs(got["fx"] - scene["fx"]) < 1e-3 and abs(got["fy"] - scene["fy"]) < 1e-3 and got["cx"] == 0.5 and got["cy"] == 0.5
+    meta = json.load(open(path))
+    meta["k1"] = 0.1
+    bad = tmp_path / "distorted"
+    bad.mkdir()
+    json.dump(meta, open(bad / "transforms.json", "w"))
+    with pytest.raises(RuntimeError):
+        pyngp.load_transforms(str(bad / "transforms.json"))

@@ -1,6 +1,7 @@
 """Turns ncu outputs into the small text summaries committed under profiles/.
   python tools/ncu_summary.py launches <launch-list.csv>            -> per-kernel share of the step (gpu__time_duration.sum)
-  python tools/ncu_summary.py full <report.ncu-rep>                 -> key metrics per captured launch (needs ncu on PATH)"""
+  python tools/ncu_summary.py full <report.ncu-rep>                 -> key metrics per captured launch (needs ncu on PATH)
+  python tools/ncu_summary.py traffic <report.ncu-rep>              -> JSON: DRAM bytes per launch per bench stage (bench.py's roofline.traffic)"""
 import collections
 import csv
 import subprocess
@@ -46,5 +47,35 @@ def full(path):
                 print(f"  {k:78s} {r[idx[k]]:>18s} {units[idx[k]]}")
 
 
+# kernel-name prefix -> bench.py stage; the n-th launch of the hash forward kernel in a step decides inference (1st) vs training (2nd, when re-encoding)
+STAGE_OF = [("hash_encode_forward", "encode_inference"), ("void nerf_mlp_kernel<1>", "mlp_inference"), ("void nerf_mlp_kernel<(int)1>", "mlp_inference"),
+            ("void nerf_mlp_kernel<2>", "mlp_train"), ("void nerf_mlp_kernel<(int)2>", "mlp_train"), ("hash_encode_backward", "encode_backward"),
+            ("void adam_ema_kernel", "optimizer"), ("adam_ema_kernel", "optimizer")]
+
+
+def traffic(path):
+    import json
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+
+    def to_bytes(v, u):
+        v = float(v.replace(",", ""))
+        return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+    acc = collections.OrderedDict()
+    for r in rows[2:]:
+        name = r[idx["Kernel Name"]]
+        for prefix, stage in STAGE_OF:
+            if name.startswith(prefix):
+                b = to_bytes(r[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]]) + to_bytes(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
+                a = acc.setdefault(stage, [0, 0.0, name.split("(")[0]])
+                a[0] += 1; a[1] += b
+                break
+    out = {"source": "ncu --set full --clock-control none, " + path.split("/")[-1] + " (dram__bytes_read.sum + dram__bytes_write.sum, mean over the captured launches)",
+           "stages": {k: {"kernel": v[2], "launches": v[0], "dram_bytes_per_launch": v[1] / v[0]} for k, v in acc.items()}}
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])
