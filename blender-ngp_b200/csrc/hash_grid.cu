@@ -86,34 +86,52 @@ __device__ __forceinline__ void level_position(const float* __restrict__ positio
 // compiles to divergent constant-bank loads, which serialise in the address-divergence unit (ncu: ADU pipe at 88 % of peak).
 struct LevelConst { float scale; uint32_t size, resolution, offset; };
 
+// LevelConst.offset carries two flags in its top bits (entry offsets stay far below 2^30): the level is hashed (smaller than its dense grid), and
+// its size is a power of two. Both are per-level facts; evaluating them per corner cost a 64-bit product and a branch around every index.
+constexpr uint32_t LEVEL_HASHED = 0x80000000u, LEVEL_POW2 = 0x40000000u, LEVEL_OFFSET_MASK = 0x3FFFFFFFu;
+__device__ __forceinline__ LevelConst make_level_const(const GridLevels& L, uint32_t l) {
+	const uint32_t size = L.size[l], res = L.resolution[l];
+	const bool hashed = (uint64_t)size < (uint64_t)res * res * res, pow2 = (size & (size - 1)) == 0;
+	return LevelConst{L.scale[l], size, res, L.offset[l] | (hashed ? LEVEL_HASHED : 0u) | (pow2 ? LEVEL_POW2 : 0u)};
+}
+
 // The 8 corner entry indices of a cell (grid_index + prime_hash, grid.h:111-128,:164-186), with the per-axis products shared between corners.
 __device__ __forceinline__ void corner_indices(const LevelConst& c, const uint32_t pg[3], uint32_t idx[8]) {
-	const uint64_t dense = (uint64_t)c.resolution * c.resolution * c.resolution;
 	const uint32_t x[2] = {pg[0], pg[0] + 1};
-	if ((uint64_t)c.size < dense) { // hashed level: x ^ y * 2654435761 ^ z * 805459861
+	if (c.offset & LEVEL_HASHED) { // hashed level: x ^ y * 2654435761 ^ z * 805459861
 		const uint32_t y0 = pg[1] * 2654435761u, z0 = pg[2] * 805459861u;
 		const uint32_t y[2] = {y0, y0 + 2654435761u}, z[2] = {z0, z0 + 805459861u};
-		const bool pow2 = (c.size & (c.size - 1)) == 0;
 		#pragma unroll
-		for (uint32_t k = 0; k < 8; ++k) {
-			const uint32_t h = x[k & 1] ^ y[(k >> 1) & 1] ^ z[k >> 2];
-			idx[k] = pow2 ? (h & (c.size - 1)) : (h % c.size);
+		for (uint32_t k = 0; k < 8; ++k) idx[k] = x[k & 1] ^ y[(k >> 1) & 1] ^ z[k >> 2];
+		if (c.offset & LEVEL_POW2) {
+			const uint32_t mask = c.size - 1;
+			#pragma unroll
+			for (uint32_t k = 0; k < 8; ++k) idx[k] &= mask;
+		} else {
+			#pragma unroll
+			for (uint32_t k = 0; k < 8; ++k) idx[k] %= c.size;
 		}
 	} else { // dense level: x + y * res + z * res^2, wrapped into the level (the +0.5 offset can index `res`, common_device.h:404-408)
 		const uint32_t y0 = pg[1] * c.resolution, z0 = pg[2] * c.resolution * c.resolution;
 		const uint32_t y[2] = {y0, y0 + c.resolution}, z[2] = {z0, z0 + c.resolution * c.resolution};
+		bool far = false; // one subtraction wraps every index a position inside the unit cube can produce; anything beyond takes the modulo
 		#pragma unroll
 		for (uint32_t k = 0; k < 8; ++k) {
 			uint32_t h = x[k & 1] + y[(k >> 1) & 1] + z[k >> 2];
-			if (h >= c.size) { h -= c.size; if (h >= c.size) h %= c.size; }
+			h = h >= c.size ? h - c.size : h;
+			far |= h >= c.size;
 			idx[k] = h;
+		}
+		if (far) {
+			#pragma unroll
+			for (uint32_t k = 0; k < 8; ++k) idx[k] %= c.size;
 		}
 	}
 }
 
 // Per-(sample, level) work shared by the forward kernels: position -> 8 gathers -> blended feature pair.
 __device__ __forceinline__ __half2 encode_one(const LevelConst& c, const __half2* __restrict__ grid, const float* __restrict__ positions, size_t i, uint32_t pos_stride) {
-	const __half2* __restrict__ g = grid + c.offset;
+	const __half2* __restrict__ g = grid + (c.offset & LEVEL_OFFSET_MASK);
 	float pos[3];
 	uint32_t pg[3];
 	level_position(positions, i, pos_stride, c.scale, pos, pg);
@@ -147,7 +165,7 @@ __global__ void __launch_bounds__(256) hash_encode_forward_kernel(
 	__half2* __restrict__ encoded)
 {
 	__shared__ LevelConst lc[NGPB_MAX_LEVELS];
-	if (threadIdx.x < L.n_levels) lc[threadIdx.x] = LevelConst{L.scale[threadIdx.x], L.size[threadIdx.x], L.resolution[threadIdx.x], L.offset[threadIdx.x]};
+	if (threadIdx.x < L.n_levels) lc[threadIdx.x] = make_level_const(L, threadIdx.x);
 	__syncthreads();
 	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t level = tid % L.n_levels, i = tid / L.n_levels;
@@ -167,7 +185,7 @@ __global__ void __launch_bounds__(256) hash_encode_forward16_kernel(
 {
 	__shared__ LevelConst lc[16];
 	__shared__ __half2 tile[16][17];
-	if (threadIdx.x < 16) lc[threadIdx.x] = LevelConst{L.scale[threadIdx.x], L.size[threadIdx.x], L.resolution[threadIdx.x], L.offset[threadIdx.x]};
+	if (threadIdx.x < 16) lc[threadIdx.x] = make_level_const(L, threadIdx.x);
 	__syncthreads();
 	const uint32_t level = threadIdx.x >> 4, s = threadIdx.x & 15u;
 	const uint32_t i0 = blockIdx.x * 16u, i = i0 + s;
