@@ -319,6 +319,29 @@ def main():
                       note="network-evaluated samples of live rays / device time of Testbed.render (CUDA events around the whole call, incl. the frame's device-to-host copy)")
     except Exception as e:  # the render leg never invalidates the training number
         render = dict(error=str(e))
+    # Blender path (request_nerf_render_sync, K18): the same frame through a snapshot -> RenderRequest with one NeRF, host wall clock around the call
+    # (the call is synchronous and ends with the frame in host memory; the snapshot load is cached after the warm-up frame)
+    if world == 1 and isinstance(render, dict) and "error" not in render:  # (single process only: a snapshot of a data-parallel run is a collective)
+        try:
+            snap_path = os.path.join(tempfile.gettempdir(), f"ngpb_bench_{os.getpid()}.msgpack")
+            tb.save_snapshot(snap_path)
+            res2 = (args.res, args.res)
+            out_p = pyngp.RenderOutputProperties(res2, pyngp.DownsampleInfo.MakeFromMip(res2, 0), 1, pyngp.ColorSpace.SRGB, pyngp.TonemapCurve.Identity, 0.0, [0, 0, 0, 0], False)
+            cam_p = pyngp.RenderCameraProperties(cam, pyngp.CameraModel.Perspective, scene["fx"] / RES * args.res, 0.0, 0.0, 1.0, None, None)
+            box = pyngp.BoundingBox([0, 0, 0], [1, 1, 1])
+            rq = pyngp.RenderRequest(out_p, cam_p, pyngp.RenderModifiers([]), [pyngp.NerfDescriptor(snap_path, box, np.eye(4), pyngp.RenderModifiers([]), 1.0)], box)
+            tb.request_nerf_render_sync(rq)
+            ms_b, ns_b = [], []
+            for _ in range(5):
+                tb0 = time.perf_counter()
+                tb.request_nerf_render_sync(rq)
+                ms_b.append(1e3 * (time.perf_counter() - tb0)); ns_b.append(tb.last_render_samples)
+            render["blender"] = dict(metric="blender_render_msamples_per_sec", value=float(np.median(ns_b)) / (float(np.median(ms_b)) * 1e-3) / 1e6, unit="Msamples/s",
+                                     ms_per_frame=float(np.median(ms_b)), samples_per_frame=int(np.median(ns_b)), waves_launches=tb.last_render_launches,
+                                     note="Testbed.request_nerf_render_sync, one NeRF from a snapshot, host wall clock around the synchronous call")
+            os.remove(snap_path)
+        except Exception as e:
+            render["blender"] = dict(error=str(e))
 
     # ---- e2e arm: public pyngp surface, dataset starts in pinned host memory, loss read back every step ----
     # (same Testbed object: reloading a same-sized dataset re-uploads it and re-initialises the model without new allocations)

@@ -118,3 +118,31 @@ def test_transforms_json_loader_round_trip(tmp_path):
     json.dump(meta, open(bad / "transforms.json", "w"))
     with pytest.raises(RuntimeError):
         pyngp.load_transforms(str(bad / "transforms.json"))
+
+
+def test_render_request_value_types():
+    """The Blender request's value types (python_api.cu:409-538) behave like the reference's without a GPU: DownsampleInfo.MakeFromMip, BoundingBox
+    helpers, camera equality; what is outside the built scope raises instead of being ignored."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "blender-ngp_b200"))
+    import pyngp
+    ds = pyngp.DownsampleInfo.MakeFromMip((1920, 1080), 2)
+    assert ds.skip == 4 and ds.scaled_res == (480, 270) and ds.max_res == (1920, 1080)
+    assert pyngp.DownsampleInfo.MakeFromMip((5, 3), 1).scaled_res == (3, 2)  # rounds up
+    box = pyngp.BoundingBox([0, 0, 0], [1, 2, 3])
+    assert box.contains([0.5, 1.0, 2.9]) and not box.contains([1.5, 1.0, 1.0])
+    assert np.allclose(box.center(), [0.5, 1.0, 1.5]) and np.allclose(box.diag(), [1, 2, 3])
+    box.enlarge([2, 0, 0]); box.inflate(0.5)
+    assert np.allclose(box.min, [-0.5, -0.5, -0.5]) and np.allclose(box.max, [2.5, 2.5, 3.5])
+    assert box.intersects(pyngp.BoundingBox([2, 2, 3], [4, 4, 4])) and not box.intersects(pyngp.BoundingBox([3, 3, 4], [4, 4, 5]))
+    cam = lambda f: pyngp.RenderCameraProperties(np.eye(4)[:3], pyngp.CameraModel.Perspective, f, 0.0, 0.0, 1.0, None, None)
+    assert cam(100.0) == cam(100.0) and cam(100.0) != cam(101.0)
+    out = pyngp.RenderOutputProperties((8, 4), ds, 1, pyngp.ColorSpace.SRGB, pyngp.TonemapCurve.Identity, 0.0, [0, 0, 0, 0], True)
+    assert out.resolution == (8, 4) and out.flip_y is True
+    with pytest.raises(RuntimeError):
+        pyngp.Mask3D.Sphere(1.0, np.eye(4), 0, 0.0, 1.0)
+    with pytest.raises(RuntimeError):
+        pyngp.RenderModifiers([object()])
+    d = pyngp.NerfDescriptor("a.msgpack", box, np.eye(4), pyngp.RenderModifiers([]), 0.5)
+    rq = pyngp.RenderRequest(out, cam(50.0), pyngp.RenderModifiers([]), [d], box)
+    assert rq.nerfs[0].snapshot_path == "a.msgpack" and rq.nerfs[0].opacity == 0.5
