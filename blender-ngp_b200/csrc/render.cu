@@ -123,6 +123,18 @@ struct PinnedScratch {
 	}
 };
 static thread_local PinnedScratch g_pinned;
+// Device workspace of the Blender renderer, kept per host thread and device and grown on demand (cudaMalloc + cudaFree per frame cost more than the
+// frame's first waves).
+struct DeviceScratch {
+	uint8_t* p = nullptr; size_t bytes = 0; int device = -1;
+	uint8_t* get(size_t n) {
+		int dev = 0;
+		NGPB_CUDA_CHECK(cudaGetDevice(&dev));
+		if (n > bytes || dev != device) { if (p) cudaFree(p); p = nullptr; bytes = 0; NGPB_CUDA_CHECK(cudaMalloc(&p, n)); bytes = n; device = dev; }
+		return p;
+	}
+};
+static thread_local DeviceScratch g_blender_ws;
 
 static uint32_t render_max_hops() { static const uint32_t h = [] { const char* e = std::getenv("NGPB_RENDER_HOPS"); return e ? (uint32_t)std::atoi(e) : 24u; }(); return h; }
 static bool empty_space_blocks() { static const bool on = [] { const char* e = std::getenv("NGPB_RENDER_BLOCK_SKIP"); return !e || std::atoi(e) != 0; }(); return on; }
@@ -803,7 +815,7 @@ extern "C" int ngpb_blender_render(void* stream_, const ngpb_blender_request* rq
 		const size_t o_prox0 = reserve((size_t)n_init * nn * sizeof(BlProxyRay)), o_prox1 = reserve((size_t)n_init * nn * sizeof(BlProxyRay));
 		const size_t o_coords = reserve(slots * COORD_FLOATS * 4), o_enc = reserve(slots * N_ENC * 2), o_rgbs = reserve(slots * 8);
 		const size_t o_props = reserve(sizeof(BlNerfProps) * nn), o_cnt = reserve(64), o_coarse = reserve((size_t)COARSE_WORDS * 4 * nn);
-		NGPB_CUDA_CHECK(cudaMalloc(&ws, off));
+		ws = g_blender_ws.get(off);
 		uint8_t* pinned = g_pinned.get(256 + (size_t)rq->width * (size_t)rq->height * 16);
 		uint32_t* host_counter = reinterpret_cast<uint32_t*>(pinned);
 		float* host_frame = reinterpret_cast<float*>(pinned + 256);
@@ -883,10 +895,8 @@ extern "C" int ngpb_blender_render(void* stream_, const ngpb_blender_request* rq
 		std::memcpy(out_rgba_host, host_frame, (size_t)n_pixels * 16);
 		if (n_samples_out) std::memcpy(n_samples_out, host_counter, 8);
 		if (n_launches_out) *n_launches_out = launches;
-		cudaFree(ws);
 		return 0;
 	} catch (const std::exception& e) {
-		if (ws) cudaFree(ws);
 		set_last_error(e.what());
 		return NGPB_ERR_RUNTIME;
 	}

@@ -840,3 +840,56 @@ def test_sdf_model_forward(L, orc):
     want = orc.mlp_forward_backward(net, want_enc, 2).astype(np.float32)
     got = host(out).astype(np.float32)
     assert np.abs(got[:, 0] - want[:, 0]).max() <= 2.0 ** -8 * max(np.abs(want[:, 0]).max(), 1.0)
+
+
+# ------------------------------------------------------------------------------------------------------
+# degenerate inputs through the C ABI: empty batches are no-ops with defined outputs, malformed sizes are refused
+# ------------------------------------------------------------------------------------------------------
+def test_empty_and_malformed_inputs(L, orc, small_scene):
+    import pyngp
+    from gpu_util import dev, ptr, host, rng_struct
+    g, entries = pyngp.grid_init(device_scales=True)
+    table = torch.zeros(2 * entries, dtype=torch.float16, device="cuda")
+    coords = torch.zeros((128, 7), dtype=torch.float32, device="cuda")
+    enc = torch.full((128, 32), 7.0, dtype=torch.float16, device="cuda")
+    out = torch.full((128, 4), 7.0, dtype=torch.float16, device="cuda")
+    mlp = torch.zeros(10240, dtype=torch.float16, device="cuda")
+    # n = 0: nothing is written
+    pyngp.check(L.ngpb_hash_encode_forward(None, C.byref(g), ptr(table), ptr(coords), 7, 0, ptr(enc)))
+    pyngp.check(L.ngpb_nerf_mlp_forward(None, ptr(mlp), ptr(enc), ptr(coords), 0, ptr(out)))
+    grad = torch.zeros(2 * entries, dtype=torch.float32, device="cuda")
+    pyngp.check(L.ngpb_hash_encode_backward(None, C.byref(g), ptr(coords), 7, 0, ptr(enc), ptr(grad)))
+    assert float(host(enc).astype(np.float32).min()) == 7.0 and float(host(out).astype(np.float32).min()) == 7.0 and float(host(grad).max()) == 0.0
+    # ragged: 100 samples through the encoding (any n), but the tensor-core MLP insists on whole 128-sample tiles
+    pyngp.check(L.ngpb_hash_encode_forward(None, C.byref(g), ptr(table), ptr(coords), 7, 100, ptr(enc)))
+    got = host(enc).astype(np.float32)
+    assert np.all(got[:100] == 0.0) and np.all(got[100:] == 7.0)  # zero table -> zero features; rows past n untouched
+    assert L.ngpb_nerf_mlp_forward(None, ptr(mlp), ptr(enc), ptr(coords), 100, ptr(out)) != 0
+    assert b"128" in L.ngpb_last_error()
+    # K1 with an empty occupancy grid: no ray is kept, no sample is written; K6 on zero rays reports zero compacted samples
+    from conftest import scene_occupancy_bitfield
+    empty = np.zeros(128 ** 3, np.uint8)
+    k1 = _run_k1(L, small_scene, empty, 512, 1 << 14, orc.pcg32(5))
+    assert int(k1["counters"][0]) == 0 and int(k1["counters"][1]) == 0
+    aabb = np.array([0, 0, 0, 1, 1, 1], np.float32)
+    cfg = pyngp.LossConfig(128.0, (C.c_float * 3)(0, 0, 0), 1, 1, 0, 4, 2, 3, 1, 0.2)
+    d = k1["dev"]
+    counters_out = torch.full((4,), 9, dtype=torch.int32, device="cuda")
+    scratch = torch.zeros(int(L.ngpb_compute_loss_scratch_bytes(512)), dtype=torch.uint8, device="cuda")
+    coords_out = torch.zeros((2048, 7), dtype=torch.float32, device="cuda"); dloss = torch.zeros((2048, 4), dtype=torch.float16, device="cuda")
+    loss = torch.full((512,), 3.0, dtype=torch.float32, device="cuda")
+    rgbsigma = torch.zeros((1 << 14, 4), dtype=torch.float16, device="cuda")
+    mean = dev(np.array([0.005], np.float32))
+    pyngp.check(L.ngpb_compute_loss(None, 512, aabb.ctypes.data_as(C.c_void_p), rng_struct(orc.pcg32(5)), 2048, C.byref(cfg), d["n_img"], ptr(d["meta"]), ptr(d["counters"]),
+                                    ptr(rgbsigma), ptr(d["ray_indices"]), ptr(d["rays"]), ptr(d["numsteps"]), ptr(d["coords"]), ptr(mean), ptr(coords_out), ptr(dloss), ptr(loss),
+                                    ptr(counters_out), ptr(scratch)))
+    assert int(host(counters_out).view(np.uint32)[0]) == 0 and float(host(loss).max()) == 0.0
+    # a Testbed that has no data refuses to train and says why
+    tb = pyngp.Testbed()
+    with pytest.raises(RuntimeError):
+        tb.train(1 << 14)
+    tb.load_training_images(small_scene["images"], small_scene["xforms"], small_scene["fx"], small_scene["fy"])
+    with pytest.raises(RuntimeError):
+        tb.train(100)  # batch not a multiple of 128 (tcnn batch_size_granularity)
+    tb.train(1 << 14)
+    assert tb.training_step == 1
