@@ -22,11 +22,16 @@ struct AdamParams {
 	float log2_beta1, log2_beta2;
 	float ema_decay, ema_debias_old, ema_debias_new;
 	uint32_t do_ema; // 0: the EMA is swept separately (sharded data-parallel optimizer)
+	float inv_loss_scale; // 1 / loss_scale when loss_scale is a power of two (the division is then an exact scaling), else 0
 };
 
+// The debiased learning rate depends only on the parameter's step count; the two features of a grid entry -- usually all four parameters of a
+// thread's group -- share it, so it is computed once per distinct count (two exp2f, a square root and a division per parameter otherwise).
+struct LrCache { float step = -1.f, lr = 0.f; };
+
 // One parameter. Returns the fp16 value the EMA filters (the updated weight, or the unchanged one when Adam skips the entry).
-__device__ __forceinline__ void adam_ema_one(const AdamParams& P, bool is_matrix, float& grad, float& w, float& m1, float& m2, uint32_t& steps, __half& wh, __half& ema) {
-	float gradient = grad / P.loss_scale;
+__device__ __forceinline__ void adam_ema_one(const AdamParams& P, bool is_matrix, float& grad, float& w, float& m1, float& m2, uint32_t& steps, __half& wh, __half& ema, LrCache& cache) {
+	float gradient = P.inv_loss_scale != 0.f ? grad * P.inv_loss_scale : grad / P.loss_scale;
 	if (is_matrix || gradient != 0.f) { // hash-grid entries with a zero gradient are skipped (adam.h:76-79)
 		grad = 0.f;
 		if (is_matrix) gradient += P.l2_reg * w; // L2 only on matrix params (adam.h:88-91)
@@ -36,7 +41,8 @@ __device__ __forceinline__ void adam_ema_one(const AdamParams& P, bool is_matrix
 		const float step = (float)(++steps); // per-parameter debiasing (adam.h:104)
 		// beta^step as exp2(step * log2(beta)): the reference calls powf here; the two agree to ~1e-6 relative, far inside the fp32
 		// resolution of the resulting weight change, and powf was two thirds of this kernel's instructions
-		const float learning_rate = P.base_lr * sqrtf(1 - exp2f(step * P.log2_beta2)) / (1 - exp2f(step * P.log2_beta1));
+		if (step != cache.step) { cache.step = step; cache.lr = P.base_lr * sqrtf(1 - exp2f(step * P.log2_beta2)) / (1 - exp2f(step * P.log2_beta1)); }
+		const float learning_rate = cache.lr;
 		const float effective_learning_rate = fminf(fmaxf(learning_rate / (sqrtf(m2) + P.epsilon), 0.f), 3.402823466e+38f);
 		w = w - effective_learning_rate * m1; // weight decay terms are zero in nerf/base.json
 		wh = __float2half_rn(w);
@@ -67,8 +73,9 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) adam_ema_kernel(const AdamPar
 			uint4 st = reinterpret_cast<uint4*>(param_steps)[q];
 			float wv[4] = {w.x, w.y, w.z, w.w}, av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 			uint32_t sv[4] = {st.x, st.y, st.z, st.w};
+			LrCache cache;
 			#pragma unroll
-			for (int k = 0; k < 4; ++k) adam_ema_one(P, i0 + k < P.n_matrix, gv[k], wv[k], av[k], bv[k], sv[k], wh[k], em[k]);
+			for (int k = 0; k < 4; ++k) adam_ema_one(P, i0 + k < P.n_matrix, gv[k], wv[k], av[k], bv[k], sv[k], wh[k], em[k], cache);
 			reinterpret_cast<float4*>(grad)[q] = make_float4(gv[0], gv[1], gv[2], gv[3]);
 			reinterpret_cast<float4*>(w_fp32)[q] = make_float4(wv[0], wv[1], wv[2], wv[3]);
 			reinterpret_cast<float4*>(m1)[q] = make_float4(av[0], av[1], av[2], av[3]);
@@ -82,7 +89,8 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) adam_ema_kernel(const AdamPar
 		if (P.do_ema) reinterpret_cast<uint2*>(w_ema)[q] = *reinterpret_cast<uint2*>(em);
 	} else {
 		const uint32_t i = n4 * 4 + (q - n4);
-		if (i < P.n) adam_ema_one(P, i < P.n_matrix, grad[i], w_fp32[i], m1[i], m2[i], param_steps[i], w_half[i], w_ema[i]);
+		LrCache cache;
+		if (i < P.n) adam_ema_one(P, i < P.n_matrix, grad[i], w_fp32[i], m1[i], m2[i], param_steps[i], w_half[i], w_ema[i], cache);
 	}
 }
 
@@ -123,6 +131,7 @@ void optimizer_prepare(ngpb_optimizer* o, float loss_scale, void* params_out) {
 	if (o->step >= o->decay_start && o->decay_interval > 0 && (o->step - o->decay_start) % o->decay_interval == 0) o->lr_factor *= o->decay_base;
 	AdamParams P{};
 	P.loss_scale = loss_scale;
+	{ int e = 0; const float mant = std::frexp(loss_scale, &e); P.inv_loss_scale = (loss_scale > 0.f && mant == 0.5f) ? 1.0f / loss_scale : 0.f; }
 	P.base_lr = o->learning_rate * o->lr_factor;
 	P.beta1 = o->beta1; P.beta2 = o->beta2; P.epsilon = o->epsilon; P.l2_reg = o->l2_reg;
 	P.log2_beta1 = (float)std::log2((double)o->beta1); P.log2_beta2 = (float)std::log2((double)o->beta2);
