@@ -365,6 +365,12 @@ def lib():
     return _lib
 
 
+def free_temporary_memory():
+    """pyngp.free_temporary_memory (python_api.cu:309): tcnn's stream-ordered arena has no counterpart here -- workspaces are owned by their Testbed
+    and released with it -- so this only synchronises nothing and returns."""
+    return None
+
+
 def check(status):
     if status != 0:
         raise RuntimeError(lib().ngpb_last_error().decode() or f"ngpb error {status}")
@@ -564,6 +570,20 @@ class _Nerf:
     rgb_activation = property(lambda s: NerfActivation(int(s._tb._get("rgb_activation"))), lambda s, v: s._tb._set("rgb_activation", int(v)))
     density_activation = property(lambda s: NerfActivation(int(s._tb._get("density_activation"))), lambda s, v: s._tb._set("density_activation", int(v)))
 
+    # scripts/run.py sets these unconditionally (run.py:106,:145). Sharpening of the training images is not built: anything but 0 raises.
+    # render_with_lens_distortion is accepted: datasets with a lens model are refused at load time, so the render lens is always the pinhole.
+    @property
+    def sharpen(self):
+        return 0.0
+
+    @sharpen.setter
+    def sharpen(self, v):
+        if float(v) != 0.0:
+            raise RuntimeError("nerf.sharpen != 0 is outside the built scope")
+
+    render_with_lens_distortion = False
+    render_with_camera_distortion = False
+
 
 class Testbed:
     """pyngp.Testbed for ETestbedMode::Nerf (python_api.cu:540-732)."""
@@ -653,6 +673,19 @@ class Testbed:
         if self.shall_train:
             self.train(self.training_batch_size)
         return self.shall_train
+
+    def want_repl(self):
+        """Testbed::want_repl (python_api.cu): a GUI key binding; headless sessions never ask for one."""
+        return False
+
+    @property
+    def tonemap_curve(self):  # m_tonemap_curve (testbed.h): only the identity curve is built
+        return TonemapCurve.Identity
+
+    @tonemap_curve.setter
+    def tonemap_curve(self, v):
+        if TonemapCurve(int(v)) != TonemapCurve.Identity:
+            raise RuntimeError("only TonemapCurve.Identity is built")
 
     shall_train = property(lambda s: bool(s._get("shall_train")), lambda s, v: s._set("shall_train", 1.0 if v else 0.0))
     training_step = property(lambda s: int(lib().ngpb_testbed_training_step(s._h)))

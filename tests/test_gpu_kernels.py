@@ -893,3 +893,77 @@ def test_empty_and_malformed_inputs(L, orc, small_scene):
         tb.train(100)  # batch not a multiple of 128 (tcnn batch_size_granularity)
     tb.train(1 << 14)
     assert tb.training_step == 1
+
+
+# ------------------------------------------------------------------------------------------------------
+# the reference's own driver flow (scripts/run.py, headless NeRF mode) on the pyngp surface
+# ------------------------------------------------------------------------------------------------------
+def test_run_py_flow_on_a_transforms_dataset(tmp_path):
+    """Mirrors scripts/run.py:105-290 statement by statement on a generated nerf_synthetic-style dataset: load_training_data(dir), network config from a
+    json file with a `parent`, --nerf_compatibility settings, the `while testbed.frame()` loop, save_snapshot, then the PSNR evaluation over test frames
+    with set_nerf_camera_matrix / render -- and the same evaluation from the reloaded snapshot."""
+    import json
+    import pyngp as ngp
+    import synthetic
+    scene = synthetic.make_lego_scene(12, 64, device="cuda", seed=2)
+    synthetic.write_transforms_json(scene, str(tmp_path))
+    test_scene = synthetic.make_lego_scene(3, 64, device="cuda", seed=7)
+    test_path = synthetic.write_transforms_json(test_scene, str(tmp_path / "test"), name="transforms_test.json")
+    (tmp_path / "cfg").mkdir()
+    json.dump(ngp.BASE_NETWORK_CONFIG, open(tmp_path / "cfg" / "base.json", "w"))
+    with open(tmp_path / "cfg" / "child.json", "w") as f:
+        f.write('{\n  // a comment, as nlohmann::json accepts them\n  "parent": "base.json",\n  "optimizer": {"nested": {"nested": {"learning_rate": 1e-2}}}\n}\n')
+
+    testbed = ngp.Testbed(ngp.TestbedMode.Nerf)
+    testbed.nerf.sharpen = float(0.0)
+    testbed.exposure = 0.0
+    testbed.load_training_data(str(tmp_path))
+    testbed.reload_network_from_file(str(tmp_path / "cfg" / "child.json"))
+    testbed.shall_train = True
+    testbed.nerf.render_with_lens_distortion = True
+    testbed.nerf.training.near_distance = 0.2
+    testbed.color_space = ngp.ColorSpace.SRGB      # --nerf_compatibility
+    testbed.nerf.cone_angle_constant = 0
+    testbed.training_batch_size = 1 << 14
+    old_training_step, n_steps = 0, 400
+    while testbed.frame():
+        if testbed.want_repl():
+            break
+        if testbed.training_step >= n_steps:
+            break
+        assert testbed.training_step == old_training_step + 1
+        old_training_step = testbed.training_step
+    assert testbed.training_step == n_steps and np.isfinite(testbed.loss)
+    testbed.save_snapshot(str(tmp_path / "out.msgpack"), False)
+
+    def evaluate(tb, run_py_call):
+        with open(test_path) as f:
+            test_transforms = json.load(f)
+        tb.background_color = [0.0, 0.0, 0.0, 1.0]
+        tb.snap_to_pixel_centers = True
+        tb.nerf.render_min_transmittance = 1e-4
+        tb.fov_axis = 0
+        tb.fov = test_transforms["camera_angle_x"] * 180 / np.pi
+        tb.shall_train = False
+        psnrs = []
+        for k, frame in enumerate(test_transforms["frames"]):
+            ref = np.asarray(test_scene["images"][k]).astype(np.float32) / 255.0
+            ref_rgb = ref[..., :3] * ref[..., 3:4]  # sRGB over a black background (run.py:265-270 for colour space sRGB)
+            if run_py_call:  # run.py:276 -- the Testbed applies the loaded dataset's scale / offset
+                tb.set_nerf_camera_matrix(np.matrix(frame["transform_matrix"])[:-1, :])
+            else:            # a session restored from a snapshot has no dataset: hand over the ngp-convention matrix
+                tb.camera_matrix = ngp.nerf_matrix_to_ngp(frame["transform_matrix"], test_transforms["scale"], test_transforms["offset"])
+            image = tb.render(ref.shape[1], ref.shape[0], 2, True)
+            rgb = np.clip(np.where(image[..., :3] <= 0.0031308, 12.92 * image[..., :3], 1.055 * np.power(np.maximum(image[..., :3], 1e-9), 1 / 2.4) - 0.055), 0, 1)
+            psnrs.append(_psnr(rgb, ref_rgb))
+        return float(np.mean(psnrs))
+
+    p_trained = evaluate(testbed, True)
+    assert p_trained >= 22.0, f"PSNR {p_trained:.1f} dB after {n_steps} steps"
+    fresh = ngp.Testbed(ngp.TestbedMode.Nerf)
+    fresh.load_snapshot(str(tmp_path / "out.msgpack"))
+    fresh.color_space = ngp.ColorSpace.SRGB
+    p_loaded = evaluate(fresh, False)
+    assert abs(p_loaded - p_trained) <= 0.5
+    with pytest.raises(RuntimeError):
+        testbed.nerf.sharpen = 1.0
