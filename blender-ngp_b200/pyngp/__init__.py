@@ -253,7 +253,7 @@ SNAPSHOT_FORMAT_VERSION = 1
 
 
 def build_snapshot(network_config, params_half, density_grid, aabb_scale, aabb, training_step, loss, rays_per_batch, measured_batch_size,
-                   measured_batch_size_before_compaction, optimizer=None):
+                   measured_batch_size_before_compaction, optimizer=None, dataset_transform=None):
     """Returns the dict the reference serialises. params_half: fp16 inference (EMA) parameters in the reference's flat order; density_grid: float32."""
     snap = {
         "n_params": int(params_half.shape[0]), "params_type": "__half", "params_binary": np.ascontiguousarray(params_half, np.float16).tobytes(),
@@ -264,6 +264,10 @@ def build_snapshot(network_config, params_half, density_grid, aabb_scale, aabb, 
         "training_step": int(training_step), "loss": float(loss),
         "aabb": {"min": [float(v) for v in aabb[:3]], "max": [float(v) for v in aabb[3:]]}, "bounding_radius": 1.0,
     }
+    if dataset_transform is not None:
+        # The reference stores the whole NerfDataset under nerf.dataset (json_binding.h:120-160) and needs all of it when the key exists; this build keeps
+        # only what set_nerf_camera_matrix needs after load_snapshot, under a key of its own that the reference ignores.
+        snap["nerf"]["b200_dataset_transform"] = {"scale": float(dataset_transform[0]), "offset": [float(v) for v in dataset_transform[1]]}
     if optimizer is not None:
         snap["optimizer"] = {  # Ema -> ExponentialDecay -> Adam
             "weights_ema_binary": np.ascontiguousarray(params_half, np.float16).tobytes(),
@@ -301,8 +305,13 @@ def parse_snapshot(cfg):
         raise RuntimeError("Trainer: snapshot parameters must be of type float of __half")
     out = dict(params_half=params, density_grid=_blob(snap.get("density_grid_binary", b""), np.float16).astype(np.float32),
                aabb_scale=int(snap.get("nerf", {}).get("aabb_scale", 1)), training_step=int(snap.get("training_step", 0)), loss=float(snap.get("loss", 0.0)),
-               rgb=snap.get("nerf", {}).get("rgb", {}), aabb=snap.get("aabb"), optimizer=None,
+               rgb=snap.get("nerf", {}).get("rgb", {}), aabb=snap.get("aabb"), optimizer=None, dataset_transform=None,
                network_config={k: v for k, v in cfg.items() if k != "snapshot"})
+    nerf = snap.get("nerf", {})
+    for key in ("dataset", "b200_dataset_transform"):  # a reference snapshot carries its NerfDataset; ours the two numbers
+        if isinstance(nerf.get(key), dict) and "scale" in nerf[key] and "offset" in nerf[key]:
+            out["dataset_transform"] = (float(nerf[key]["scale"]), tuple(float(v) for v in nerf[key]["offset"]))
+            break
     if "optimizer" in snap:
         o = snap["optimizer"]
         decay = o.get("nested", {})
@@ -762,7 +771,7 @@ class Testbed:
         half = 0.5 * min(128, int(self._get("aabb_scale")))
         aabb = [0.5 - half] * 3 + [0.5 + half] * 3
         cfg = build_snapshot(self.network_config, ema, grid, int(self._get("aabb_scale")), aabb, st.training_step, st.loss, st.rays_per_batch,
-                             st.measured_batch_size, st.measured_batch_size_before_compaction, opt)
+                             st.measured_batch_size, st.measured_batch_size_before_compaction, opt, (self._dataset_scale, self._dataset_offset))
         with open(path, "wb") as f:
             f.write(msgpack.packb(cfg, use_bin_type=True))
 
@@ -775,6 +784,8 @@ class Testbed:
         snap = parse_snapshot(cfg)
         _validate_network_config(snap["network_config"])
         self.network_config = snap["network_config"]
+        if snap["dataset_transform"] is not None:
+            self._dataset_scale, self._dataset_offset = snap["dataset_transform"]
         check(lib().ngpb_testbed_configure(self._h, snap["aabb_scale"], self._seed))
         params = np.ascontiguousarray(snap["params_half"], np.float16)
         check(lib().ngpb_testbed_set_params_half(self._h, params.ctypes.data_as(C.c_void_p), int(params.shape[0])))

@@ -965,5 +965,6 @@ def test_run_py_flow_on_a_transforms_dataset(tmp_path):
     fresh.color_space = ngp.ColorSpace.SRGB
     p_loaded = evaluate(fresh, False)
     assert abs(p_loaded - p_trained) <= 0.5
+    assert abs(evaluate(fresh, True) - p_loaded) < 1e-6  # the snapshot carries the dataset's scale / offset: run.py's call works after load_snapshot
     with pytest.raises(RuntimeError):
         testbed.nerf.sharpen = 1.0
