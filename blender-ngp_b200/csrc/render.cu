@@ -262,6 +262,62 @@ __global__ void __launch_bounds__(128) render_march_kernel(const RenderParams P,
 }
 
 // composite_kernel_nerf (Shade) + compact_kernel_nerf + shade_kernel_nerf: composites this pass's samples; a ray that is still live is
+// The same pass with a WARP per ray: the 32 lanes test 32 consecutive members of the ray's t chain at once, the occupied ones (before the first one
+// outside the box) are the samples, in order. A ray's samples are exactly the chain members that fall into occupied cells -- the cell-to-cell hops of the
+// serial march only decide how empty space is crossed -- so this finds the same samples; positions agree to float rounding (lane l computes
+// t + l * dt where the serial march adds dt l times). The serial march is a chain of dependent occupancy loads with 3.5 of 32 lanes active on average;
+// here every load of a round is independent and rays inside the object finish a pass in one round. A ray scans at most `max_rounds` x 32 members per
+// pass (RAY_STEPS_RESUME otherwise).
+__global__ void __launch_bounds__(256) render_march_warp_kernel(const RenderParams P, const uint32_t* __restrict__ n_rays_dev, const uint32_t n_steps, const uint32_t max_rounds,
+                                                                const uint8_t* __restrict__ bitfield, RenderRay* __restrict__ rays, float* __restrict__ coords,
+                                                                uint32_t* __restrict__ ray_steps)
+{
+	const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	if (i >= *n_rays_dev) return;
+	const RenderRay r = rays[i];
+	const V3 o = {r.o[0], r.o[1], r.o[2]}, d = {r.d[0], r.d[1], r.d[2]};
+	const V3 wd = {(d.x + 1.0f) * 0.5f, (d.y + 1.0f) * 0.5f, (d.z + 1.0f) * 0.5f};
+	float* c = coords + (size_t)i * n_steps * COORD_FLOATS;
+	float t0 = r.t;
+	uint32_t j = 0, resume = RAY_STEPS_RESUME;
+	for (uint32_t round = 0; round < max_rounds; ++round) {
+		float t = t0;
+		if (P.cone_angle == 0.f) t = t0 + (float)lane * MIN_CONE_STEPSIZE;
+		else for (uint32_t k = 0; k < lane; ++k) t += calc_dt(t, P.cone_angle);
+		const float dt = calc_dt(t, P.cone_angle);
+		const V3 pos = V3{o.x + d.x * t, o.y + d.y * t, o.z + d.z * t};
+		const bool inside = aabb_contains(P.render_aabb, pos);
+		bool occ = false;
+		if (inside) occ = density_grid_occupied_at(pos, bitfield, (uint32_t)mip_from_dt(dt, pos));
+		const uint32_t out_mask = __ballot_sync(0xffffffffu, !inside);
+		const uint32_t before_exit = out_mask ? ((1u << (__ffs(out_mask) - 1)) - 1u) : 0xffffffffu; // lanes before the first member outside the box
+		const uint32_t occ_mask = __ballot_sync(0xffffffffu, occ) & before_exit;
+		const uint32_t need = n_steps - j;
+		const uint32_t rank = __popc(occ_mask & ((1u << lane) - 1u));
+		if (((occ_mask >> lane) & 1u) && rank < need) {
+			const V3 wp = warp_position(pos, P.train_aabb);
+			float* s = c + (size_t)(j + rank) * COORD_FLOATS;
+			s[0] = wp.x; s[1] = wp.y; s[2] = wp.z; s[3] = warp_dt(dt); s[4] = wd.x; s[5] = wd.y; s[6] = wd.z;
+		}
+		const uint32_t found = __popc(occ_mask);
+		if (found >= need) { // the pass is full: resume after the last sample taken
+			const uint32_t last = __fns(occ_mask, 0, (int)need);
+			t0 = __shfl_sync(0xffffffffu, t + dt, last);
+			j = n_steps;
+			resume = 0;
+			break;
+		}
+		j += found;
+		if (out_mask) { resume = 0; break; } // the ray left the box
+		t0 = __shfl_sync(0xffffffffu, t + dt, 31);
+	}
+	if (lane == 0) { ray_steps[i] = j | resume; rays[i].t = t0; }
+	for (uint32_t k = j * COORD_FLOATS + lane; k < n_steps * COORD_FLOATS; k += 32) { // unused slots still go through the network: keep them finite
+		const uint32_t f = k % COORD_FLOATS;
+		c[k] = f == 3 ? 0.f : 0.5f;
+	}
+}
+
 // appended to the next pass's list, a finished one with alpha > 0.001 is shaded into the frame buffer.
 __global__ void __launch_bounds__(128) render_composite_kernel(const RenderParams P, const uint32_t* __restrict__ n_rays_dev, const uint32_t n_steps,
                                                                const RenderRay* __restrict__ rays, const float4* __restrict__ rgba_in, const float* __restrict__ coords,
@@ -451,7 +507,10 @@ extern "C" int ngpb_render_nerf(void* stream_, const ngpb_render_config* cfg, co
 				const uint32_t n_slots = next_multiple(n_alive * n_steps, 128);
 				const uint32_t blocks = div_round_up(n_alive, 128);
 				NGPB_CUDA_CHECK(cudaMemsetAsync(counters + (cur ^ 1), 0, 4, stream));
-				render_march_kernel<<<blocks, 128, 0, stream>>>(P, counters + cur, n_steps, render_max_hops(), bitfield, coarse, rays[cur], coords, ray_steps);
+				static const bool warp_march = [] { const char* e = std::getenv("NGPB_RENDER_WARP_MARCH"); return !e || std::atoi(e) != 0; }();
+				static const uint32_t max_rounds = [] { const char* e = std::getenv("NGPB_RENDER_ROUNDS"); return e ? (uint32_t)std::atoi(e) : 16u; }();
+				if (warp_march) render_march_warp_kernel<<<div_round_up(n_alive, 8), 256, 0, stream>>>(P, counters + cur, n_steps, max_rounds, bitfield, rays[cur], coords, ray_steps);
+				else render_march_kernel<<<blocks, 128, 0, stream>>>(P, counters + cur, n_steps, render_max_hops(), bitfield, coarse, rays[cur], coords, ray_steps);
 				NGPB_LAUNCH_CHECK();
 				hash_encode_forward_launch(stream, g, (const __half*)params + MLP_PARAMS, coords, COORD_FLOATS, n_slots, nullptr, encoded);
 				nerf_mlp_forward_launch(stream, (const __half*)params, encoded, coords, n_slots, nullptr, rgbsigma);
