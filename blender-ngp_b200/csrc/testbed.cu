@@ -118,6 +118,93 @@ extern "C" void ngpb_effective_xform(const float* m12, float* out12) {
 }
 
 // Data-parallel gradient exchange in fp16: cast the fp32 accumulation buffer (4 values per thread) and reset it in the same pass; widen the reduced slice.
+// ---- peer-memory gradient / weight exchange (dp_exchange = 1) ------------------------------------------------------------------------------
+// One kernel per direction instead of cast + ncclReduceScatter + widen and ncclAllGather:
+//   scatter: every rank casts its fp32 partial gradients to bf16 and stores slice s straight into rank s's receive buffer over NVLink (and resets its
+//            accumulation buffer); the last block to finish publishes "step n delivered" in every peer's flag array (system-scope release).
+//   reduce : the owner waits for all world flags (system-scope acquire), sums the world slices of its range in rank order in fp32.
+//   gather : after Adam, every rank stores its updated fp16 weights into every peer's weight array and publishes a second flag; the next kernel that
+//            reads the weights is preceded by a wait on those flags.
+// Ordering across steps needs no double buffering: rank B only overwrites A's receive buffer in step n+1 after it has seen A's weights of step n, which A
+// sent after its reduce of step n had consumed the buffer.
+struct P2pTable { void* ptr[16][3]; }; // [rank] = {recv, flags, w_half}
+constexpr uint32_t P2P_SPIN_LIMIT = 1u << 26; // ~ seconds; on expiry the error word is set and the host raises at the next read-back
+
+__device__ __forceinline__ void p2p_publish(uint32_t* flag, uint32_t value) { asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(flag), "r"(value) : "memory"); }
+__device__ __forceinline__ uint32_t p2p_peek(const uint32_t* flag) { uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory"); return v; }
+__device__ __forceinline__ void p2p_wait_all(const uint32_t* flags, uint32_t world, uint32_t step, uint32_t* error_word) {
+	if (threadIdx.x < world) {
+		uint32_t spins = 0;
+		while ((int32_t)(p2p_peek(flags + threadIdx.x) - step) < 0) { if (++spins > P2P_SPIN_LIMIT) { *error_word = 0xDEADu; break; } __nanosleep(64); }
+	}
+	__syncthreads();
+}
+
+__global__ void __launch_bounds__(256) p2p_scatter_gradients_kernel(const uint32_t n8, const uint32_t count, const uint32_t rank, const uint32_t world, const uint32_t step,
+                                                                    float4* __restrict__ grad, const P2pTable T, uint32_t* __restrict__ my_flags)
+{
+	const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; // group of 8 parameters (count is a multiple of 8, so a group never straddles two slices)
+	if (q < n8) {
+		const float4 a = grad[2 * q], b = grad[2 * q + 1];
+		const __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w), h2 = __floats2bfloat162_rn(b.x, b.y), h3 = __floats2bfloat162_rn(b.z, b.w);
+		const uint32_t i = q * 8, s = i / count, off = i - s * count;
+		uint4 v = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1), *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+		uint16_t* dst = reinterpret_cast<uint16_t*>(T.ptr[s][0]) + (size_t)rank * count + off;
+		*reinterpret_cast<uint4*>(dst) = v;
+		grad[2 * q] = make_float4(0.f, 0.f, 0.f, 0.f); grad[2 * q + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+	}
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		const uint32_t done = atomicAdd(my_flags + 2 * world, 1u);
+		if (done == gridDim.x - 1) {
+			my_flags[2 * world] = 0u;
+			__threadfence_system();
+			for (uint32_t p = 0; p < world; ++p) p2p_publish(reinterpret_cast<uint32_t*>(T.ptr[p][1]) + rank, step);
+		}
+	}
+}
+
+__global__ void __launch_bounds__(256) p2p_reduce_gradients_kernel(const uint32_t mine, const uint32_t count, const uint32_t world, const uint32_t step,
+                                                                   const uint16_t* __restrict__ recv, uint32_t* __restrict__ my_flags, float* __restrict__ grad_shard)
+{
+	p2p_wait_all(my_flags, world, step, my_flags + 2 * world + 1);
+	const uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+	if (j >= mine) return;
+	float s0 = 0.f, s1 = 0.f;
+	for (uint32_t r = 0; r < world; ++r) { // fixed order: the same bits on every run
+		const uint32_t v = *reinterpret_cast<const volatile uint32_t*>(recv + (size_t)r * count + j);
+		s0 += __uint_as_float(v << 16); s1 += __uint_as_float(v & 0xFFFF0000u);
+	}
+	grad_shard[j] = s0;
+	if (j + 1 < mine) grad_shard[j + 1] = s1;
+}
+
+__global__ void __launch_bounds__(256) p2p_gather_weights_kernel(const uint32_t n8, const uint32_t first, const uint32_t rank, const uint32_t world, const uint32_t step,
+                                                                 const __half* __restrict__ w_half, const P2pTable T, uint32_t* __restrict__ my_flags)
+{
+	const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+	if (q < n8) {
+		const uint4 v = *reinterpret_cast<const uint4*>(w_half + first + (size_t)q * 8);
+		for (uint32_t p = 0; p < world; ++p) if (p != rank) *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(T.ptr[p][2]) + first + (size_t)q * 8) = v;
+	}
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		const uint32_t done = atomicAdd(my_flags + 2 * world, 1u);
+		if (done == gridDim.x - 1) {
+			my_flags[2 * world] = 0u;
+			__threadfence_system();
+			for (uint32_t p = 0; p < world; ++p) p2p_publish(reinterpret_cast<uint32_t*>(T.ptr[p][1]) + world + rank, step);
+		}
+	}
+}
+
+__global__ void __launch_bounds__(32) p2p_wait_weights_kernel(const uint32_t world, const uint32_t step, uint32_t* __restrict__ my_flags)
+{
+	p2p_wait_all(my_flags + world, world, step, my_flags + 2 * world + 1);
+}
+
 template <bool BF16>
 __global__ void __launch_bounds__(256) grads_to_16bit_and_reset_kernel(const uint32_t n4, float4* __restrict__ grad, uint2* __restrict__ out)
 {
@@ -151,6 +238,7 @@ ngpb_testbed::ngpb_testbed(int device_) : device(device_) {
 	int prio_low = 0, prio_high = 0;
 	NGPB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
 	if (const char* ge = std::getenv("NGPB_DP_HALF_GRADIENTS")) dp_half_gradients = std::atoi(ge); // 0 fp32, 1 bf16 (default), 2 fp16
+	if (const char* xe = std::getenv("NGPB_DP_EXCHANGE")) dp_exchange = std::atoi(xe);             // 0 NCCL (default), 1 peer memory
 	const char* pe = std::getenv("NGPB_STREAM_PRIORITY");
 	const std::string pmode = pe ? pe : "sampling";
 	NGPB_CUDA_CHECK(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, pmode == "main" ? prio_high : prio_low));
@@ -176,6 +264,7 @@ ngpb_testbed::~ngpb_testbed() {
 	cudaSetDevice(device);
 	if (sampling_stream) cudaStreamSynchronize(sampling_stream);
 	if (stream) cudaStreamSynchronize(stream);
+	p2p_teardown();
 	if (nccl_comm) { try { NcclApi::get().CommDestroy(nccl_comm); } catch (...) {} }
 	if (prefetch_done) cudaEventDestroy(prefetch_done);
 	if (loss_ready) cudaEventDestroy(loss_ready);
@@ -295,6 +384,7 @@ void ngpb_testbed::reset_network(uint32_t seed_) {
 	const uint32_t new_n_params = MLP_PARAMS + 2 * entries;
 	if (new_n_params != n_params) {
 		dfree(w_fp32); dfree(w_half); dfree(w_ema); dfree(m1); dfree(m2); dfree(param_steps); dfree(grad); dfree(grad_half); grad_half = nullptr;
+		p2p_teardown(); // the peers hold mappings of the old weight array
 		n_params = new_n_params;
 		n_alloc = n_params + 4096; // slack: the sharded data-parallel optimizer works on world x ceil(n_params / world) padded ranges
 		w_fp32 = (float*)dalloc(sizeof(float) * n_alloc);
@@ -369,7 +459,7 @@ void ngpb_testbed::reset_network(uint32_t seed_) {
 	measured_batch_size = measured_batch_size_before_compaction = 0;
 	n_rays_total = 0;
 	loss_scalar = 0.f;
-	if (!host_readback) NGPB_CUDA_CHECK(cudaMallocHost(&host_readback, 64));
+	if (!host_readback) { NGPB_CUDA_CHECK(cudaMallocHost(&host_readback, 64)); std::memset(host_readback, 0, 64); }
 	host_readback[8] = 0;
 	NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
 }
@@ -455,6 +545,54 @@ void ngpb_testbed::init_data_parallel(int rank, int world, const void* unique_id
 
 // Parameters per rank of the sharded optimizer: ceil(n_params / world), rounded up to the vector width of the optimizer kernels.
 uint32_t ngpb_testbed::dp_shard_count() const { return next_multiple(div_round_up(n_params, (uint32_t)dp_world), 8u); }
+
+// Allocates the receive buffer and flags, exchanges the CUDA IPC handles of {receive buffer, flags, fp16 weights} over the NCCL communicator and maps
+// every peer's buffers. Called by all ranks at the same point (first data-parallel step after the parameters were (re)allocated).
+void ngpb_testbed::p2p_setup() {
+	p2p_teardown();
+	if (dp_world > 16) throw std::runtime_error("peer-memory exchange supports up to 16 ranks");
+	const uint32_t count = dp_shard_count();
+	NGPB_CUDA_CHECK(cudaMalloc(&p2p_recv, sizeof(uint16_t) * (size_t)count * dp_world));
+	NGPB_CUDA_CHECK(cudaMalloc(&p2p_flags, sizeof(uint32_t) * (2 * dp_world + 2)));
+	NGPB_CUDA_CHECK(cudaMemset(p2p_flags, 0, sizeof(uint32_t) * (2 * dp_world + 2)));
+	cudaIpcMemHandle_t mine[3];
+	NGPB_CUDA_CHECK(cudaIpcGetMemHandle(&mine[0], p2p_recv));
+	NGPB_CUDA_CHECK(cudaIpcGetMemHandle(&mine[1], p2p_flags));
+	NGPB_CUDA_CHECK(cudaIpcGetMemHandle(&mine[2], w_half));
+	const size_t blob = sizeof(mine);
+	uint8_t* dev_blobs = nullptr;
+	NGPB_CUDA_CHECK(cudaMalloc(&dev_blobs, blob * dp_world));
+	NGPB_CUDA_CHECK(cudaMemcpy(dev_blobs + blob * dp_rank, mine, blob, cudaMemcpyHostToDevice));
+	NcclApi& nccl = NcclApi::get();
+	nccl.check(nccl.AllGather(dev_blobs + blob * dp_rank, dev_blobs, blob, 1 /* ncclUint8 */, nccl_comm, stream), "ncclAllGather(ipc handles)");
+	NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
+	std::vector<cudaIpcMemHandle_t> all((size_t)3 * dp_world);
+	NGPB_CUDA_CHECK(cudaMemcpy(all.data(), dev_blobs, blob * dp_world, cudaMemcpyDeviceToHost));
+	cudaFree(dev_blobs);
+	for (int r = 0; r < dp_world; ++r) {
+		if (r == dp_rank) { p2p_table[r][0] = p2p_recv; p2p_table[r][1] = p2p_flags; p2p_table[r][2] = w_half; continue; }
+		for (int k = 0; k < 3; ++k) {
+			void* p = nullptr;
+			NGPB_CUDA_CHECK(cudaIpcOpenMemHandle(&p, all[(size_t)3 * r + k], cudaIpcMemLazyEnablePeerAccess));
+			p2p_opened.push_back(p);
+			p2p_table[r][k] = p;
+		}
+	}
+	p2p_step = 0;
+	// nobody may publish into a peer's flags before that peer has zeroed them: a barrier through the communicator
+	nccl.check(nccl.AllReduce(p2p_flags + 2 * dp_world, p2p_flags + 2 * dp_world, 1, NcclApi::Uint32, NcclApi::Sum, nccl_comm, stream), "ncclAllReduce(barrier)");
+	NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
+	p2p_ready = true;
+}
+
+void ngpb_testbed::p2p_teardown() {
+	for (void* p : p2p_opened) cudaIpcCloseMemHandle(p);
+	p2p_opened.clear();
+	if (p2p_recv) cudaFree(p2p_recv);
+	if (p2p_flags) cudaFree(p2p_flags);
+	p2p_recv = nullptr; p2p_flags = nullptr;
+	p2p_ready = false;
+}
 
 // Launches K1 for the step described by `p` on stream `st`.
 void ngpb_testbed::launch_sampling(cudaStream_t st, const SamplingRequest& p) {
@@ -587,7 +725,35 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 		NcclApi& nccl = NcclApi::get();
 		uint8_t opt_params[256];
 		optimizer_prepare(&opt, LOSS_SCALE, opt_params);
-		if (dp_sharded_optimizer) {
+		if (dp_sharded_optimizer && dp_exchange == 1) {
+			if (!p2p_ready) p2p_setup();
+			const uint32_t count = dp_shard_count(), first = (uint32_t)dp_rank * count;
+			const uint32_t mine = first < n_params ? std::min(count, n_params - first) : 0u;
+			const uint32_t n_cast = count * (uint32_t)dp_world;
+			if (n_cast > n_alloc) throw std::runtime_error("data parallel: parameter padding too small for this world size");
+			P2pTable T;
+			static_assert(sizeof(T.ptr) == sizeof(p2p_table), "table layout");
+			std::memcpy(T.ptr, p2p_table, sizeof(p2p_table));
+			if (host_readback[12] == 0xDEADu) throw std::runtime_error("data parallel: a peer's gradients or weights did not arrive (peer-memory exchange timed out)");
+			const uint32_t step = ++p2p_step;
+			stage_begin(NGPB_STAGE_ALLREDUCE, stream);
+			p2p_scatter_gradients_kernel<<<div_round_up(n_cast / 8, 256), 256, 0, stream>>>(n_cast / 8, count, (uint32_t)dp_rank, (uint32_t)dp_world, step, reinterpret_cast<float4*>(grad), T, p2p_flags);
+			NGPB_LAUNCH_CHECK();
+			if (mine) { p2p_reduce_gradients_kernel<<<div_round_up(div_round_up(mine, 2u), 256), 256, 0, stream>>>(mine, count, (uint32_t)dp_world, step, p2p_recv, p2p_flags, grad + first); NGPB_LAUNCH_CHECK(); }
+			stage_end(NGPB_STAGE_ALLREDUCE, (uint64_t)n_params * 2, stream);
+			stage_begin(NGPB_STAGE_OPTIMIZER, stream);
+			optimizer_disable_fused_ema(opt_params);
+			optimizer_launch(stream, opt_params, first, mine, MLP_PARAMS, grad, w_fp32, w_half, w_ema, m1, m2, param_steps);
+			p2p_gather_weights_kernel<<<std::max(1u, div_round_up(count / 8, 256)), 256, 0, stream>>>(count / 8, first, (uint32_t)dp_rank, (uint32_t)dp_world, step, w_half, T, p2p_flags);
+			NGPB_LAUNCH_CHECK();
+			p2p_wait_weights_kernel<<<1, 32, 0, stream>>>((uint32_t)dp_world, step, p2p_flags);
+			NGPB_LAUNCH_CHECK();
+			ema_sweep_launch(stream, opt_params, next_multiple(n_params, 8), w_half, w_ema);
+			stage_end(NGPB_STAGE_OPTIMIZER, n_params, stream);
+			NGPB_CUDA_CHECK(cudaMemcpyAsync(host_readback + 12, p2p_flags + 2 * dp_world + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream)); // time-out word
+			master_weights_sharded = true;
+			n_launches += 5;
+		} else if (dp_sharded_optimizer) {
 			// reduce-scatter the gradients, run Adam on this rank's 1/world of the parameters, all-gather the updated fp16 weights; the EMA
 			// copy follows from the gathered weights on every rank. Moves 3/4 of the all-reduce's bytes and divides the optimizer sweep by world.
 			const uint32_t count = dp_shard_count(), first = (uint32_t)dp_rank * count;
@@ -907,6 +1073,7 @@ extern "C" int ngpb_testbed_set_option(ngpb_testbed* t, const char* name, double
 	else if (k == "overlap_sampling") { t->drop_prefetch(); t->overlap_sampling = v != 0; }
 	else if (k == "reuse_encoding") t->reuse_encoding = v != 0;
 	else if (k == "dp_half_gradients") t->dp_half_gradients = (int)v; // 0 fp32, 1 bf16, 2 fp16
+	else if (k == "dp_exchange") t->dp_exchange = (int)v;             // 0 NCCL collectives, 1 peer-memory kernels
 	else throw std::runtime_error("unknown option: " + k);
 	NGPB_API_END
 }

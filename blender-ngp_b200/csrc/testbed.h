@@ -44,6 +44,17 @@ struct ngpb_testbed {
 	// batch-size counters) are summed over NCCL before the optimizer, so the replicas stay bit-identical.
 	int dp_rank = 0, dp_world = 1;
 	void* nccl_comm = nullptr;
+	// Peer-memory exchange (dp_exchange = 1): gradients and weights move between the replicas' buffers with direct NVLink stores from this library's
+	// own kernels instead of NCCL collectives. Buffers are shared through CUDA IPC handles (exchanged once over the NCCL communicator).
+	int dp_exchange = 0;               // 0: NCCL reduce-scatter / all-gather, 1: peer-memory kernels
+	bool p2p_ready = false;
+	uint32_t p2p_step = 0;
+	uint16_t* p2p_recv = nullptr;      // [world][count] bf16: slice r holds rank r's partial gradients of THIS rank's parameter range
+	uint32_t* p2p_flags = nullptr;     // [2 * world + 2]: [r] = last step whose gradients rank r delivered, [world + r] = ... weights; [2w] block counter, [2w+1] error
+	void* p2p_table[16][3] = {};       // {recv, flags, w_half} of every rank as mapped into this process (own entries = local pointers)
+	std::vector<void*> p2p_opened;     // IPC mappings to close
+	void p2p_setup();
+	void p2p_teardown();
 	bool dp_sharded_optimizer = true;    // reduce-scatter + Adam on 1/world of the parameters + all-gather (false: all-reduce + full Adam)
 	bool master_weights_sharded = false; // the fp32 master copy is current only in this rank's range
 	uint32_t dp_shard_count() const;
