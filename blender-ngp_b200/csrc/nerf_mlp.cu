@@ -66,7 +66,9 @@ constexpr uint32_t TM_DW2R = 144;   // [64 x 64]   dW2r[o][i]
 constexpr uint32_t TM_DW3R = 208;   // [64 x 16]   dW3r^T[i][o]
 constexpr uint32_t TM_COLS_TRAIN = 256, TM_COLS_INFER = 64;
 
-enum MlpMode { MODE_DENSITY = 0, MODE_INFERENCE = 1, MODE_TRAIN = 2, MODE_PLAIN = 3 }; // PLAIN: the 32 -> 64 -> 64 -> 16 network alone (neural image / SDF models)
+// PLAIN / PLAIN_TRAIN: the 32 -> 64 -> 64 -> 16 network alone (neural image / SDF models), inference and forward + backward + weight gradients
+enum MlpMode { MODE_DENSITY = 0, MODE_INFERENCE = 1, MODE_TRAIN = 2, MODE_PLAIN = 3, MODE_PLAIN_TRAIN = 4 };
+constexpr uint32_t PLAIN_PARAMS = 64 * 32 + 64 * 64 + 16 * 64, PLAIN_W1 = 0, PLAIN_W2 = 2048, PLAIN_W3 = 6144;
 
 // ---- helpers ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void load_matrix_to_tile(uint8_t* smem, uint32_t dst, const __half* __restrict__ src, uint32_t rows, uint32_t cols) {
@@ -190,13 +192,14 @@ struct MlpArgs {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(128, MODE == 2 ? 2 : 4) nerf_mlp_kernel(const MlpArgs args)
+__global__ void __launch_bounds__(128, (MODE == 2 || MODE == 4) ? 2 : 4) nerf_mlp_kernel(const MlpArgs args)
 {
 	extern __shared__ __align__(128) uint8_t smem[];
-	constexpr uint32_t TILES_END = MODE == MODE_TRAIN ? S_TRAIN_END : S_INFER_END;
+	constexpr bool TRAINING = MODE == MODE_TRAIN || MODE == MODE_PLAIN_TRAIN, PLAIN_NET = MODE == MODE_PLAIN || MODE == MODE_PLAIN_TRAIN;
+	constexpr uint32_t TILES_END = TRAINING ? S_TRAIN_END : S_INFER_END;
 	uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + TILES_END);
 	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TILES_END + 16);
-	constexpr uint32_t TM_COLS = MODE == MODE_TRAIN ? TM_COLS_TRAIN : TM_COLS_INFER;
+	constexpr uint32_t TM_COLS = TRAINING ? TM_COLS_TRAIN : TM_COLS_INFER;
 
 	const uint32_t tid = threadIdx.x, warp = tid >> 5;
 	uint32_t n = args.n;
@@ -205,7 +208,7 @@ __global__ void __launch_bounds__(128, MODE == 2 ? 2 : 4) nerf_mlp_kernel(const 
 
 	if (warp == 0) tmem_alloc<TM_COLS>(tmem_slot);
 	if (tid == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
-	if (MODE == MODE_PLAIN) { // FullyFusedMLP parameter order: first layer [64][32], hidden [64][64], last [16][64]
+	if (PLAIN_NET) { // FullyFusedMLP parameter order: first layer [64][32], hidden [64][64], last [16][64]
 		load_matrix_to_tile(smem, SW_W1R, args.mlp, 64, 32);
 		load_matrix_to_tile(smem, SW_W2R, args.mlp + 2048, 64, 64);
 		load_matrix_to_tile(smem, SW_W3R, args.mlp + 6144, 16, 64);
@@ -244,7 +247,7 @@ __global__ void __launch_bounds__(128, MODE == 2 ? 2 : 4) nerf_mlp_kernel(const 
 			#pragma unroll
 			for (uint32_t k = 0; k < 4; ++k) {
 				const uint32_t q = tid + 128 * k;
-				*reinterpret_cast<uint4*>(smem + (MODE == MODE_PLAIN ? S_RIN : S_X) + tile_offset(q >> 2, q & 3, 32)) = __ldg(src + q);
+				*reinterpret_cast<uint4*>(smem + (PLAIN_NET ? S_RIN : S_X) + tile_offset(q >> 2, q & 3, 32)) = __ldg(src + q);
 			}
 		}
 		float dsigma = 0.f;
@@ -260,6 +263,11 @@ __global__ void __launch_bounds__(128, MODE == 2 ? 2 : 4) nerf_mlp_kernel(const 
 				*reinterpret_cast<uint4*>(smem + S_RIN + tile_offset(tid, 2 + h, 32)) = v;
 			}
 		}
+		if (MODE == MODE_PLAIN_TRAIN) { // dL/d(output), all 16 padded columns as the caller's loss kernel wrote them
+			const uint4* gsrc = reinterpret_cast<const uint4*>(args.dL_dout + row_g * 16);
+			*reinterpret_cast<uint4*>(smem + S_DOR + tile_offset(tid, 0, 16)) = __ldg(gsrc);
+			*reinterpret_cast<uint4*>(smem + S_DOR + tile_offset(tid, 1, 16)) = __ldg(gsrc + 1);
+		}
 		if (MODE == MODE_TRAIN) {
 			// dL/d(rgb out) = first three components, other 13 padded outputs get zero (nerf_network.h:202-206)
 			const uint2 g = *reinterpret_cast<const uint2*>(args.dL_dout + row_g * 4);
@@ -271,7 +279,7 @@ __global__ void __launch_bounds__(128, MODE == 2 ? 2 : 4) nerf_mlp_kernel(const 
 		}
 
 		float sigma_logit = 0.f;
-		if (MODE != MODE_PLAIN) {
+		if (!PLAIN_NET) {
 		// ---- density net layer 1: H1 = relu(X W1d^T) ----
 		NGPB_MMA_BATCH(issue_forward(tmem_base + TM_ACC, sbase + S_X, 32, sbase + SW_W1D, 32, 64));
 		epilogue_store64<true>(t_row + TM_ACC, smem, S_H1, tid);
@@ -298,8 +306,8 @@ __global__ void __launch_bounds__(128, MODE == 2 ? 2 : 4) nerf_mlp_kernel(const 
 		}
 		if (MODE == MODE_DENSITY) { tc_fence_before_sync(); continue; }
 
-		constexpr uint32_t T_G1 = MODE == MODE_TRAIN ? S_G1 : S_H1;
-		constexpr uint32_t T_G2 = MODE == MODE_TRAIN ? S_G2 : S_H1;
+		constexpr uint32_t T_G1 = TRAINING ? S_G1 : S_H1;
+		constexpr uint32_t T_G2 = TRAINING ? S_G2 : S_H1;
 
 		// ---- rgb net layer 1: G1 = relu(Rin W1r^T) ----
 		NGPB_MMA_BATCH(issue_forward(tmem_base + TM_ACC, sbase + S_RIN, 32, sbase + SW_W1R, 32, 64));
@@ -340,7 +348,7 @@ __global__ void __launch_bounds__(128, MODE == 2 ? 2 : 4) nerf_mlp_kernel(const 
 			continue;
 		}
 
-		if (MODE == MODE_TRAIN) {
+		if (TRAINING) {
 			const bool first = it == 0;
 			// ---- dG2 = (dOr W3r) . relu'(G2);  dW3r^T += G2^T dOr ----
 			NGPB_MMA_BATCH(
@@ -358,6 +366,21 @@ __global__ void __launch_bounds__(128, MODE == 2 ? 2 : 4) nerf_mlp_kernel(const 
 			NGPB_MMA_BATCH(
 				issue_dgrad(tmem_base + TM_ACC, sbase + S_DG1, 64, sbase + SW_W1R, 32, 64);
 				issue_wgrad(tmem_base + TM_DW1R, sbase + S_DG1, sbase + S_RIN, 32, 32, first));
+			if (MODE == MODE_PLAIN_TRAIN) { // dL/d(input), 32 columns, is this network's last product
+				uint32_t r[32];
+				tmem_ld_x32(t_row + TM_ACC, r);
+				tmem_ld_wait();
+				uint4* dst = reinterpret_cast<uint4*>(args.out + row_g * N_ENC);
+				#pragma unroll
+				for (uint32_t c = 0; c < 4; ++c) {
+					uint4 v;
+					v.x = pack_half2(__uint_as_float(r[c * 8 + 0]), __uint_as_float(r[c * 8 + 1])); v.y = pack_half2(__uint_as_float(r[c * 8 + 2]), __uint_as_float(r[c * 8 + 3]));
+					v.z = pack_half2(__uint_as_float(r[c * 8 + 4]), __uint_as_float(r[c * 8 + 5])); v.w = pack_half2(__uint_as_float(r[c * 8 + 6]), __uint_as_float(r[c * 8 + 7]));
+					dst[c] = v;
+				}
+				tc_fence_before_sync();
+				continue;
+			}
 			{
 				uint32_t r[16];
 				tmem_ld_x16(t_row + TM_ACC, r);
@@ -400,6 +423,22 @@ __global__ void __launch_bounds__(128, MODE == 2 ? 2 : 4) nerf_mlp_kernel(const 
 		}
 	}
 
+	if (MODE == MODE_PLAIN_TRAIN) { // same accumulator layout as below, FullyFusedMLP's parameter order
+		float* part = args.partials + (size_t)blockIdx.x * PLAIN_PARAMS;
+		const uint32_t lane = tid & 31, row = warp * 16 + lane;
+		const bool have = it > 0;
+		tc_fence_after_sync();
+		uint32_t r[32];
+		tmem_ld_x32(t_row + TM_DW1R, r); tmem_ld_wait();
+		if (lane < 16) { for (uint32_t i = 0; i < 32; ++i) part[PLAIN_W1 + row * 32 + i] = have ? __uint_as_float(r[i]) : 0.f; }
+		#pragma unroll
+		for (uint32_t h = 0; h < 2; ++h) {
+			tmem_ld_x32(t_row + TM_DW2R + h * 32, r); tmem_ld_wait();
+			if (lane < 16) { for (uint32_t i = 0; i < 32; ++i) part[PLAIN_W2 + row * 64 + h * 32 + i] = have ? __uint_as_float(r[i]) : 0.f; }
+		}
+		tmem_ld_x16(t_row + TM_DW3R, r); tmem_ld_wait();
+		if (lane < 16) { for (uint32_t o = 0; o < 16; ++o) part[PLAIN_W3 + o * 64 + row] = have ? __uint_as_float(r[o]) : 0.f; }
+	}
 	if (MODE == MODE_TRAIN) {
 		// ---- write this CTA's weight-gradient partial. M = 64 accumulators occupy lanes 0-15 of every
 		// 32-lane quadrant: warp w, lane l < 16 holds row 16*w + l. ----
@@ -437,25 +476,25 @@ __global__ void __launch_bounds__(128, MODE == 2 ? 2 : 4) nerf_mlp_kernel(const 
 // Fixed-order sum of the per-CTA partials (deterministic), overwrites mlp_grad.
 // Sums the per-CTA weight-gradient partials in a fixed order: 32 parameters x 8 groups per block, group g adds partials g, g+8, g+16, ... in
 // sequence (four independent chains in flight), then the 8 group sums are added in order 0..7. Same result on every run.
-__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partials, const uint32_t n_parts, float* __restrict__ mlp_grad)
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partials, const uint32_t n_parts, float* __restrict__ mlp_grad, const uint32_t n_weights)
 {
 	__shared__ float part[8][32];
 	const uint32_t col = threadIdx.x & 31, grp = threadIdx.x >> 5;
 	const uint32_t i = blockIdx.x * 32 + col;
 	float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-	if (i < MLP_PARAMS) {
+	if (i < n_weights) {
 		uint32_t p = grp;
 		for (; p + 24 < n_parts; p += 32) {
-			s0 += partials[(size_t)p * MLP_PARAMS + i];
-			s1 += partials[(size_t)(p + 8) * MLP_PARAMS + i];
-			s2 += partials[(size_t)(p + 16) * MLP_PARAMS + i];
-			s3 += partials[(size_t)(p + 24) * MLP_PARAMS + i];
+			s0 += partials[(size_t)p * n_weights + i];
+			s1 += partials[(size_t)(p + 8) * n_weights + i];
+			s2 += partials[(size_t)(p + 16) * n_weights + i];
+			s3 += partials[(size_t)(p + 24) * n_weights + i];
 		}
-		for (; p < n_parts; p += 8) s0 += partials[(size_t)p * MLP_PARAMS + i];
+		for (; p < n_parts; p += 8) s0 += partials[(size_t)p * n_weights + i];
 	}
 	part[grp][col] = (s0 + s1) + (s2 + s3);
 	__syncthreads();
-	if (grp == 0 && i < MLP_PARAMS) {
+	if (grp == 0 && i < n_weights) {
 		float s = part[0][col];
 		#pragma unroll
 		for (int g = 1; g < 8; ++g) s += part[g][col];
@@ -493,6 +532,15 @@ void plain_mlp_launch(cudaStream_t stream, const __half* weights, const __half* 
 	const uint32_t tiles = n / TILE;
 	launch_mlp<MODE_PLAIN>(stream, a, std::min(tiles, kNumSMs * INFER_CTAS_PER_SM), SMEM_INFER);
 }
+void plain_mlp_forward_backward_launch(cudaStream_t stream, const __half* weights, const __half* input, const __half* dL_dout16, uint32_t n, __half* dL_dinput, float* grad,
+                                       float* partials) {
+	MlpArgs a{weights, input, nullptr, dL_dout16, dL_dinput, partials, n, nullptr};
+	const uint32_t tiles = n / TILE;
+	const uint32_t grid = std::min(tiles, TRAIN_GRID);
+	launch_mlp<MODE_PLAIN_TRAIN>(stream, a, grid, SMEM_TRAIN);
+	reduce_partials_kernel<<<div_round_up(PLAIN_PARAMS, 32), 256, 0, stream>>>(partials, grid, grad, PLAIN_PARAMS);
+	NGPB_LAUNCH_CHECK();
+}
 void nerf_density_mlp_launch(cudaStream_t stream, const __half* mlp, const __half* encoded, uint32_t n, __half* density) {
 	MlpArgs a{mlp, encoded, nullptr, nullptr, density, nullptr, n, nullptr};
 	const uint32_t tiles = n / TILE;
@@ -505,7 +553,7 @@ void nerf_mlp_forward_backward_launch(cudaStream_t stream, const __half* mlp, co
 	const uint32_t grid = std::min(tiles, TRAIN_GRID);
 	launch_mlp<MODE_TRAIN>(stream, a, grid, SMEM_TRAIN);
 	NGPB_STEP_KERNEL(reduce_partials_kernel);
-	reduce_partials_kernel<<<div_round_up(MLP_PARAMS, 32), 256, 0, stream>>>(partials, grid, mlp_grad);
+	reduce_partials_kernel<<<div_round_up(MLP_PARAMS, 32), 256, 0, stream>>>(partials, grid, mlp_grad, MLP_PARAMS);
 	NGPB_LAUNCH_CHECK();
 }
 
@@ -577,6 +625,18 @@ extern "C" int ngpb_mlp_forward(void* stream, const ngpb_half* weights, const ng
 	try {
 		if (!weights || !input || !output || n == 0 || n % TILE != 0) { set_last_error("ngpb_mlp_forward: null pointer or n not a non-zero multiple of 128"); return NGPB_ERR_INVALID_ARGUMENT; }
 		plain_mlp_launch((cudaStream_t)stream, (const __half*)weights, (const __half*)input, n, (__half*)output);
+		return 0;
+	} catch (const std::exception& e) { set_last_error(e.what()); return NGPB_ERR_RUNTIME; }
+}
+
+extern "C" int ngpb_mlp_forward_backward(void* stream, const ngpb_half* weights, const ngpb_half* input, const ngpb_half* dL_dout, uint32_t n, ngpb_half* dL_dinput,
+                                         float* grad, void* workspace) {
+	try {
+		if (!weights || !input || !dL_dout || !dL_dinput || !grad || !workspace || n == 0 || n % TILE != 0) {
+			set_last_error("ngpb_mlp_forward_backward: null pointer or n not a non-zero multiple of 128");
+			return NGPB_ERR_INVALID_ARGUMENT;
+		}
+		plain_mlp_forward_backward_launch((cudaStream_t)stream, (const __half*)weights, (const __half*)input, (const __half*)dL_dout, n, (__half*)dL_dinput, grad, (float*)workspace);
 		return 0;
 	} catch (const std::exception& e) { set_last_error(e.what()); return NGPB_ERR_RUNTIME; }
 }

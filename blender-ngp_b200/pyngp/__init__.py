@@ -335,7 +335,7 @@ EXPORTED_SYMBOLS = [
     "ngpb_testbed_get_params", "ngpb_testbed_set_params", "ngpb_testbed_get_density_grid", "ngpb_testbed_set_option", "ngpb_testbed_get_option",
     "ngpb_testbed_render", "ngpb_testbed_stream", "ngpb_testbed_stage_times", "ngpb_grid_device_scales", "ngpb_testbed_configure", "ngpb_testbed_set_params_half", "ngpb_testbed_set_density_grid", "ngpb_testbed_get_training_state",
     "ngpb_testbed_set_training_state", "ngpb_testbed_get_optimizer_state", "ngpb_testbed_set_optimizer_state", "ngpb_generate_training_samples_sharded", "ngpb_compute_loss_sharded", "ngpb_nccl_unique_id", "ngpb_testbed_init_data_parallel", "ngpb_render_workspace_bytes", "ngpb_render_nerf", "ngpb_testbed_last_render_ms", "ngpb_generate_training_samples_scratch_bytes", "ngpb_compute_loss_scratch_bytes",
-    "ngpb_field_create", "ngpb_field_destroy", "ngpb_blender_render", "ngpb_compute_loss_compact_features", "ngpb_grid_init_nd", "ngpb_mlp_forward",
+    "ngpb_field_create", "ngpb_field_destroy", "ngpb_blender_render", "ngpb_compute_loss_compact_features", "ngpb_grid_init_nd", "ngpb_mlp_forward", "ngpb_mlp_forward_backward", "ngpb_loss",
 ]
 
 _lib = None

@@ -77,6 +77,18 @@ int ngpb_hash_encode_backward(void* stream, const ngpb_grid* g, const float* pos
  * weights: FullyFusedMLP's parameter order, row-major [out][in]: [64][32], [64][64], [16][64] (7168 halves). input [n][32], output [n][16]
  * (the padded output width; an image model uses columns 0..2, an SDF column 0). n: multiple of 128. */
 int ngpb_mlp_forward(void* stream, const ngpb_half* weights, const ngpb_half* input, uint32_t n, ngpb_half* output);
+/* Element-wise losses of the image / SDF models (tcnn losses/l2.h:40-80, losses/mape.h:40-80 through Trainer::training_step, trainer.h:121-159):
+ * predictions [n][16] fp16 (padded network output), targets [n][dims] fp32 -> values [n][16] fp32 (nullable; per-element loss / (n * dims)) and
+ * gradients [n][16] fp16 = loss_scale * dL/d(prediction) / (n * dims), padded columns zero. */
+#define NGPB_ELEMENT_LOSS_L2 0
+#define NGPB_ELEMENT_LOSS_MAPE 1
+int ngpb_loss(void* stream, int kind, uint32_t n, uint32_t dims, float loss_scale, const ngpb_half* predictions, const float* targets, float* values,
+              ngpb_half* gradients);
+/* Forward + backward of the same network in one kernel (FullyFusedMLP::forward + backward, fully_fused_mlp.cu:151-314,:759-850): recomputes the activations of
+ * `input`, then from dL_dout [n][16] (all padded columns, as the loss kernel wrote them) produces dL_dinput [n][32] (fp16, for the hash-grid backward) and the
+ * weight gradients grad[7168] (fp32, overwritten, summed over the batch, loss scale left in). workspace: ngpb_nerf_mlp_workspace_bytes() bytes. */
+int ngpb_mlp_forward_backward(void* stream, const ngpb_half* weights, const ngpb_half* input, const ngpb_half* dL_dout, uint32_t n, ngpb_half* dL_dinput,
+                              float* grad, void* workspace);
 
 /* ---- NeRF MLPs (replaces NerfNetwork glue nerf_network.h:103-266 + tcnn FullyFusedMLP, fully_fused_mlp.cu) ----
  * mlp: half[10240] in the reference's flat order: density W1[64][32], W2[16][64]; rgb W1[64][32], W2[64][64], W3[16][64].

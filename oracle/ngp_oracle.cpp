@@ -1606,3 +1606,26 @@ extern "C" void orc_mlp_forward_backward(uint32_t n_hidden, uint32_t n, const or
 	}
 	if (grad) for (uint32_t k = 0; k < n_params; ++k) { double s = 0.0; for (int t = 0; t < nt; ++t) s += partial[t][k]; grad[k] = (float)s; }
 }
+
+// tcnn l2_loss (losses/l2.h:40-80) / mape_loss (losses/mape.h:40-80), stride 16 (the network's padded output width), no data pdf. kind: 0 = L2, 1 = MAPE.
+extern "C" void orc_loss(int kind, uint32_t n, uint32_t dims, float loss_scale, const orc_half* predictions, const float* targets, float* values, orc_half* gradients) {
+	const uint32_t stride = 16, n_elements = n * stride, n_total = n_elements / stride * dims;
+	for (uint32_t i = 0; i < n_elements; ++i) {
+		const uint32_t intra = i % stride, inter = i / stride;
+		if (intra >= dims) { if (values) values[i] = 0.f; gradients[i] = f2h(0.f); continue; }
+		const float prediction = h2f(predictions[i]);
+		const float target = targets[inter * dims + intra];
+		const float difference = prediction - target;
+		float value, gradient;
+		if (kind == 1) {
+			const float scale = 1.0f / (std::fabs(target) + 1e-2f);
+			value = std::fabs(difference) * scale / n_total;
+			gradient = std::copysign(scale, difference);
+		} else {
+			value = difference * difference / n_total;
+			gradient = 2 * difference;
+		}
+		if (values) values[i] = value;
+		gradients[i] = f2h(loss_scale * gradient / n_total);
+	}
+}

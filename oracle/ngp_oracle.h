@@ -196,6 +196,7 @@ void orc_grid_forward_nd(uint32_t n_dims, uint32_t n, uint32_t n_levels, const u
                          const float* scales, const orc_half* grid, const float* positions, uint32_t pos_stride, orc_half* encoded);
 void orc_mlp_forward_backward(uint32_t n_hidden, uint32_t n, const orc_half* weights, const orc_half* input, orc_half* out,
                               const orc_half* dL_dout, orc_half* dL_dinput, float* grad);
+void orc_loss(int kind, uint32_t n, uint32_t dims, float loss_scale, const orc_half* predictions, const float* targets, float* values, orc_half* gradients);
 
 #ifdef __cplusplus
 }

@@ -347,6 +347,17 @@ def mlp_forward_backward(weights_half, input_half, n_hidden=2, dL_dout=None, wan
     return out, din, grad
 
 
+def loss(kind, predictions_half, targets, loss_scale=128.0):
+    """tcnn L2 (kind 0) / MAPE (kind 1) loss on the padded [n][16] fp16 network output: (values fp32 [n][16], gradients fp16 [n][16])."""
+    pred = np.ascontiguousarray(predictions_half, np.float16)
+    tgt = _f32(targets)
+    n, dims = pred.shape[0], tgt.shape[1]
+    values = np.zeros((n, 16), np.float32)
+    grads = np.zeros((n, 16), np.float16)
+    lib().orc_loss(kind, n, dims, C.c_float(loss_scale), _p(pred), _p(tgt), _p(values), _p(grads))
+    return values, grads
+
+
 class NerfInstance(C.Structure):
     _fields_ = [("model", C.POINTER(Model)), ("params", C.c_void_p), ("bitfield", C.c_void_p), ("train_aabb", C.c_float * 6), ("aabb_scale", C.c_uint32),
                 ("render_aabb", C.c_float * 6), ("transform", C.c_float * 16), ("opacity", C.c_float),
