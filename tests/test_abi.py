@@ -146,3 +146,17 @@ def test_render_request_value_types():
     d = pyngp.NerfDescriptor("a.msgpack", box, np.eye(4), pyngp.RenderModifiers([]), 0.5)
     rq = pyngp.RenderRequest(out, cam(50.0), pyngp.RenderModifiers([]), [d], box)
     assert rq.nerfs[0].snapshot_path == "a.msgpack" and rq.nerfs[0].opacity == 0.5
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/ngpb.h is the drop-in boundary: it must compile as C99 (no C++ or torch types in the signatures) with warnings as errors."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not on PATH")
+    src = tmp_path / "t.c"
+    src.write_text('#include "ngpb.h"\nint main(void) { ngpb_grid g; ngpb_blender_request r; (void)g; (void)r; return ngpb_version() ? 0 : 1; }\n')
+    res = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
