@@ -494,54 +494,123 @@ def nerf_matrix_to_ngp(c2w, scale, offset):
     return m[[1, 2, 0], :].copy()
 
 
+def _fov_to_focal_length(resolution, degrees):  # common_device.cuh:473
+    return 0.5 * resolution / math.tan(0.5 * degrees * math.pi / 180.0)
+
+
+def _read_focal_length(js, res, focal):
+    """read_focal_length (nerf_loader.cu:271-299): `<axis>_fov` (degrees) before `fl_<axis>` before `camera_angle_<axis>` (radians); x alone sets both
+    axes. Returns the updated (fx, fy) or None when `js` carries no focal information."""
+    def one(resolution, axis):
+        if axis + "_fov" in js:
+            return _fov_to_focal_length(resolution, float(js[axis + "_fov"]))
+        if "fl_" + axis in js:
+            return float(js["fl_" + axis])
+        if "camera_angle_" + axis in js:
+            return _fov_to_focal_length(resolution, float(js["camera_angle_" + axis]) * 180.0 / math.pi)
+        return 0.0
+    x_fl, y_fl = one(res[0], "x"), one(res[1], "y")
+    if x_fl != 0:
+        return (x_fl, y_fl if y_fl != 0 else x_fl)
+    if y_fl != 0:
+        return (y_fl, y_fl)
+    return None
+
+
+_UNBUILT_LENS_KEYS = ("k1", "k2", "k3", "k4", "p1", "p2")
+
+
+def _refuse_unbuilt_camera_models(js, where):
+    """read_lens (nerf_loader.cu:197-269) selects OpenCV / f-theta / lat-long lenses and a rolling shutter from these keys; none of them is built, and
+    training on undistorted rays instead would silently change the result."""
+    if any(float(js.get(k, 0.0)) != 0.0 for k in _UNBUILT_LENS_KEYS) or js.get("is_fisheye") or "ftheta_p0" in js or "latlong" in js:
+        raise RuntimeError(f"lens distortion / fisheye / f-theta / lat-long camera models are outside the built scope ({where})")
+    if "rolling_shutter" in js and any(float(v) != 0.0 for v in js["rolling_shutter"]):
+        raise RuntimeError(f"rolling-shutter cameras are outside the built scope ({where})")
+
+
 def load_transforms(path):
-    """Parses a transforms.json (or a directory holding transforms*.json) into decoded RGBA8 images + ngp camera matrices."""
+    """ngp::load_nerf for pinhole RGBA datasets (src/nerf_loader.cu:300-747, Testbed::load_nerf src/testbed_nerf.cu:2735-2758): a transforms json or a
+    directory, of which EVERY *.json is loaded (as the reference does: pass the file to train on one split). Frames sorted by file_path, `n_frames` and
+    sharpness culling, focal-length key precedence, per-frame focal / principal-point overrides, `scale` / `offset` / `aabb_scale` of the last json.
+    Returns decoded RGBA8 images, ngp-convention camera matrices and per-image intrinsics (`fx`, `fy`, `cx`, `cy` are scalars when all images agree)."""
     from PIL import Image as PILImage
     if os.path.isdir(path):
-        cands = sorted(p for p in os.listdir(path) if p.startswith("transforms") and p.endswith(".json"))
-        if not cands:
-            raise RuntimeError(f"no transforms*.json under {path}")
-        # the reference loads every json in the directory; train split first
-        path = os.path.join(path, "transforms_train.json" if "transforms_train.json" in cands else cands[0])
-    with open(path) as f:
-        meta = json.load(f)
-    base = os.path.dirname(path)
-    scale = meta.get("scale", 1.0)  # NERF_SCALE = 1.0 in this fork (nerf_loader.h:28)
-    offset = meta.get("offset", [0.0, 0.0, 0.0])
-    aabb_scale = int(meta.get("aabb_scale", 1))
-    # lens models (nerf_loader.cu:197-269) are outside the built scope: refuse rather than train on undistorted rays
-    if any(float(meta.get(k, 0.0)) != 0.0 for k in ("k1", "k2", "k3", "k4", "p1", "p2")) or meta.get("is_fisheye") or "ftheta_p0" in meta or "latlong" in meta:
-        raise RuntimeError("lens distortion / fisheye / f-theta camera models are outside the built scope")
-    frames = sorted(meta["frames"], key=lambda fr: fr["file_path"])  # nerf_loader.cu:356-358
-    images, xforms = [], []
-    for fr in frames:
-        p = os.path.join(base, fr["file_path"])
-        if not os.path.exists(p):
-            for ext in (".png", ".jpg", ".jpeg"):
-                if os.path.exists(p + ext):
-                    p = p + ext
-                    break
-        img = np.asarray(PILImage.open(p).convert("RGBA"), dtype=np.uint8)
-        images.append(np.ascontiguousarray(img))
-        xforms.append(nerf_matrix_to_ngp(fr["transform_matrix"], scale, offset))
-    h, w = images[0].shape[:2]
-    # focal-length key precedence, nerf_loader.cu:271-299
-    def focal(axis, res):
-        if ("fl_" + axis) in meta:
-            return float(meta["fl_" + axis])
-        if ("camera_angle_" + axis) in meta:
-            return 0.5 * res / math.tan(0.5 * float(meta["camera_angle_" + axis]))
-        return 0.0
-    fx, fy = focal("x", w), focal("y", h)
-    if fx == 0.0 and fy != 0.0:
-        fx = fy
-    if fy == 0.0 and fx != 0.0:
-        fy = fx
-    if fx == 0.0:
-        raise RuntimeError("Couldn't read fov.")
-    cx = float(meta.get("cx", 0.5 * w)) / w
-    cy = float(meta.get("cy", 0.5 * h)) / h
-    return dict(images=images, xforms=np.stack(xforms), fx=fx, fy=fy, cx=cx, cy=cy, aabb_scale=aabb_scale, scale=scale, offset=offset)
+        json_paths = sorted(os.path.join(path, p) for p in os.listdir(path) if p.lower().endswith(".json") and os.path.isfile(os.path.join(path, p)))
+    elif path.lower().endswith(".json"):
+        json_paths = [path]
+    else:
+        raise RuntimeError("NeRF data path must either be a json file or a directory containing json files.")
+    if not json_paths:
+        raise RuntimeError("Cannot load NeRF data from an empty set of paths.")
+    scale, offset, aabb_scale = 1.0, [0.0, 0.0, 0.0], 1  # NERF_SCALE = 1.0 and zero offset in this fork (nerf_loader.h:28, nerf_loader.cu:406-407)
+    images, xforms, fxs, fys, cxs, cys = [], [], [], [], [], []
+    per_json = []
+    for jp in json_paths:
+        with open(jp) as f:
+            meta = json.loads(_strip_json_comments(f.read()))
+        if not isinstance(meta.get("frames"), list):
+            continue  # "does not contain any frames. Skipping."
+        base = os.path.dirname(jp)
+        frames = sorted(meta["frames"], key=lambda fr: fr["file_path"])  # :356-358
+        if "n_frames" in meta:
+            frames = frames[:min(len(frames), int(meta["n_frames"]))]
+        if frames and "sharpness" in frames[0]:  # kill frames blurrier than their neighbours (:365-390)
+            threshold, kept = float(meta.get("sharpness_discard_threshold", 0.0)), []
+            for i, fr in enumerate(frames):
+                a, b = max(0, i - 3), min(i + 3, len(frames) - 1)
+                mean = sum(float(frames[k]["sharpness"]) for k in range(a, b)) / (b - a) if b > a else 0.0
+                fr = dict(fr, file_path=fr["file_path"].replace("\\", "/"))
+                if os.path.exists(os.path.join(base, fr["file_path"])) and float(fr["sharpness"]) > threshold * mean:
+                    kept.append(fr)
+            frames = kept
+        per_json.append((meta, base, frames))
+    if sum(len(fr) for _, _, fr in per_json) == 0:
+        raise RuntimeError("No training images were found for NeRF training!")
+    for meta, base, frames in per_json:
+        if "normal_mts_args" in meta:
+            raise RuntimeError("Mitsuba-convention datasets are outside the built scope")
+        scale = float(meta.get("scale", scale))
+        if "offset" in meta:
+            offset = [float(v) for v in meta["offset"]]
+        aabb_scale = int(meta.get("aabb_scale", aabb_scale))
+        _refuse_unbuilt_camera_models(meta, "dataset")
+        pp_json = [0.5, 0.5]
+        if "cx" in meta:
+            pp_json[0] = float(meta["cx"]) / float(meta["w"])
+        if "cy" in meta:
+            pp_json[1] = float(meta["cy"]) / float(meta["h"])
+        for fr in frames:
+            p = os.path.join(base, fr["file_path"])
+            if os.path.splitext(p)[1] == "":
+                if os.path.exists(p + ".png"):
+                    p = p + ".png"
+                elif os.path.exists(p + ".exr"):
+                    raise RuntimeError("EXR (HDR) training images are outside the built scope: " + p + ".exr")
+                else:
+                    raise RuntimeError("Could not find image file: " + p + ".png")
+            try:
+                img = np.asarray(PILImage.open(p).convert("RGBA"), dtype=np.uint8)
+            except OSError as e:
+                raise RuntimeError("Could not open image file: " + str(e))
+            h, w = img.shape[:2]
+            focal = _read_focal_length(meta, (w, h), None)
+            focal_frame = _read_focal_length(fr, (w, h), focal)
+            focal = focal_frame if focal_frame is not None else focal
+            if focal is None:
+                raise RuntimeError("Couldn't read fov.")
+            _refuse_unbuilt_camera_models(fr, fr["file_path"])
+            pp = list(pp_json)
+            if "cx" in fr:
+                pp[0] = float(fr["cx"]) / float(fr["w"])
+            if "cy" in fr:
+                pp[1] = float(fr["cy"]) / float(fr["h"])
+            images.append(np.ascontiguousarray(img))
+            xforms.append(nerf_matrix_to_ngp(fr["transform_matrix"], scale, offset))
+            fxs.append(float(focal[0])); fys.append(float(focal[1])); cxs.append(pp[0]); cys.append(pp[1])
+    uniform = lambda v: v[0] if all(x == v[0] for x in v) else list(v)
+    return dict(images=images, xforms=np.stack(xforms), fx=uniform(fxs), fy=uniform(fys), cx=uniform(cxs), cy=uniform(cys), aabb_scale=aabb_scale,
+                scale=scale, offset=offset)
 
 
 class _Training:
@@ -641,7 +710,8 @@ class Testbed:
             keep.append(px)
             arr[i].pixels = px.ctypes.data
             arr[i].h, arr[i].w = px.shape[0], px.shape[1]
-            arr[i].fx, arr[i].fy, arr[i].cx, arr[i].cy = fx, fy, cx, cy
+            pick = lambda v: float(v[i]) if isinstance(v, (list, tuple, np.ndarray)) else float(v)  # scalar = the same for every image
+            arr[i].fx, arr[i].fy, arr[i].cx, arr[i].cy = pick(fx), pick(fy), pick(cx), pick(cy)
             cm = np.asarray(xforms[i], dtype=np.float32).reshape(3, 4).T.reshape(-1)
             for k in range(12):
                 arr[i].xform[k] = float(cm[k])

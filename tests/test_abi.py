@@ -160,3 +160,45 @@ def test_header_is_plain_c(tmp_path):
     res = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
                          capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
+
+
+def test_transforms_json_loader_reference_rules(tmp_path):
+    """Rules of ngp::load_nerf the generated dataset does not exercise: every json of a directory is loaded, `<axis>_fov` (degrees) wins over `fl_<axis>`
+    over `camera_angle_<axis>`, per-frame focal length / principal point override the file's, `n_frames` culls after sorting, blurry frames are dropped
+    relative to their neighbourhood, a file without frames is skipped, an empty dataset raises."""
+    import json
+    import math
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "blender-ngp_b200"))
+    import pyngp
+    from PIL import Image
+    d = tmp_path / "scene"
+    d.mkdir()
+    eye = [[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 2], [0, 0, 0, 1]]
+    for k in range(6):
+        Image.fromarray(np.full((8, 16, 4), 40 * k, np.uint8)).save(d / f"im{k}.png")
+    a = {"x_fov": 90.0, "fl_x": 123.0, "camera_angle_x": 0.1, "cx": 4.0, "cy": 2.0, "w": 16, "h": 8, "aabb_scale": 4, "scale": 0.5, "offset": [0.5, 0.5, 0.5],
+         "frames": [{"file_path": "im1", "transform_matrix": eye}, {"file_path": "im0.png", "transform_matrix": eye, "fl_y": 50.0, "cx": 12.0, "w": 16}]}
+    b = {"fl_y": 20.0, "n_frames": 3, "sharpness_discard_threshold": 0.9,
+         "frames": [{"file_path": f"im{k}.png", "transform_matrix": eye, "sharpness": s} for k, s in ((5, 1.0), (2, 10.0), (3, 10.0), (4, 10.0))]}
+    json.dump(a, open(d / "a.json", "w")); json.dump(b, open(d / "b.json", "w")); json.dump({"note": "no frames here"}, open(d / "c.json", "w"))
+    got = pyngp.load_transforms(str(d))
+    # a.json: frames sorted by path -> im0.png, im1; b.json: sorted im2, im3, im4, im5 -> n_frames keeps im2..im4, all equally sharp -> kept
+    assert [int(im[0, 0, 0]) for im in got["images"]] == [0, 40, 80, 120, 160]
+    f90 = 0.5 * 16 / math.tan(math.radians(45.0))
+    assert got["fx"][0] == pytest.approx(50.0) and got["fy"][0] == pytest.approx(50.0)  # im0: the frame carries only fl_y, which then sets both axes (:292-293)
+    assert got["fx"][1] == pytest.approx(f90) and got["fy"][1] == pytest.approx(f90)    # im1: x_fov (degrees) wins over fl_x and camera_angle_x
+    assert got["cx"][0] == pytest.approx(12.0 / 16) and got["cx"][1] == pytest.approx(4.0 / 16) and got["cy"][1] == pytest.approx(2.0 / 8)
+    assert got["fx"][2] == pytest.approx(20.0) and got["fy"][2] == pytest.approx(20.0) and got["cx"][2] == 0.5
+    assert got["aabb_scale"] == 4 and got["scale"] == 0.5 and got["offset"] == [0.5, 0.5, 0.5]
+    np.testing.assert_allclose(got["xforms"][0][:, 3], [0.5, 1.5, 0.5])  # (0, 0, 2) * scale + offset, axes cycled (nerf_matrix_to_ngp)
+    # a single json can be named directly; a blurry frame between sharp neighbours is dropped
+    b["frames"][1]["sharpness"] = 1.0  # im2
+    del b["n_frames"]
+    json.dump(b, open(d / "b.json", "w"))
+    only_b = pyngp.load_transforms(str(d / "b.json"))
+    assert [int(im[0, 0, 0]) for im in only_b["images"]] == [120, 160]  # im2 (1.0) and im5 (1.0) fall below 0.9 x their neighbourhood mean
+    with pytest.raises(RuntimeError):
+        pyngp.load_transforms(str(d / "c.json"))
+    with pytest.raises(RuntimeError):
+        pyngp.load_transforms(str(d / "im0.png"))
