@@ -666,7 +666,10 @@ class _Nerf:
 class Testbed:
     """pyngp.Testbed for ETestbedMode::Nerf (python_api.cu:540-732)."""
 
-    def __init__(self, mode=TestbedMode.Nerf, device=0):
+    def __init__(self, mode=TestbedMode.Nerf, data_path=None, network_config=None, device=0):
+        """Testbed(mode), Testbed(mode, data_path, network_config_path) and Testbed(mode, data_path, network_config_json) (python_api.cu:542-544)."""
+        if isinstance(data_path, int) and network_config is None:  # Testbed(mode, device) of earlier drafts of this module
+            data_path, device = None, data_path
         if mode != TestbedMode.Nerf:
             raise RuntimeError("only TestbedMode.Nerf is implemented by this build (the NeRF train/render hot path)")
         self._h = C.c_void_p()
@@ -677,6 +680,12 @@ class Testbed:
         self._seed = 1337
         self._device = int(device)
         self._keep = None
+        if data_path is not None:
+            self.load_training_data(data_path)
+            if isinstance(network_config, dict):
+                self.reload_network_from_json(network_config)
+            elif network_config is not None:
+                self.reload_network_from_file(network_config)
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -693,7 +702,12 @@ class Testbed:
 
     # -- data
     def load_training_data(self, path):
-        """Testbed::load_training_data (src/testbed.cu:97): a transforms.json file or a directory holding one."""
+        """Testbed::load_training_data (src/testbed.cu:97) -> load_nerf (src/testbed_nerf.cu:2735-2758): a transforms json, a directory of them, or a
+        snapshot (.msgpack), which is loaded with training switched off."""
+        if str(path).lower().endswith(".msgpack"):
+            self.load_snapshot(path)
+            self.shall_train = False
+            return
         d = load_transforms(path)
         self._dataset_scale, self._dataset_offset = d["scale"], tuple(d["offset"])
         self.load_training_images(d["images"], d["xforms"], d["fx"], d["fy"], d["cx"], d["cy"], d["aabb_scale"])
