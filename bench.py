@@ -12,6 +12,11 @@ refresh at the reference's cadence. `value` is device-timed (CUDA events on the 
 resident in HBM; `e2e` goes through the public `pyngp.Testbed` calls with the dataset starting in pinned HOST memory
 (its upload is inside the timed region) and the loss read back to the host every step.
 
+Also in the line: `roofline` (dominant stage by share of the step: algorithmic bytes / event time against MEASURED_PEAKS.json, DRAM traffic per launch from the
+committed ncu capture profiles/r01_traffic.json, and the same for every stage under `per_stage`), `cpu_baseline` (the oracle's whole-iteration restatement on the
+host cores, bounded to --cpu-seconds), `render` (classic Testbed.render Msamples/s and, single GPU only, the Blender path request_nerf_render_sync from a snapshot),
+`clocks` (nvidia-smi sampled during the timed region), `gpu_launches`.
+
 Prints ONE JSON line (rank 0).
 """
 import argparse
