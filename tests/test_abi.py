@@ -16,6 +16,7 @@ def _declared_symbols():
 
 
 def test_library_exports_every_declared_symbol():
+    """Every function declared in include/ngpb.h is exported by libngpb200.so and listed in pyngp.EXPORTED_SYMBOLS (and vice versa); no compute call is made."""
     import pyngp
     lib = pyngp.lib()
     declared = _declared_symbols()

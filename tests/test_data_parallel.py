@@ -41,6 +41,7 @@ def _worker(rank, world, port, out_dir):
 
 
 def test_two_rank_shards_tile_the_global_batch(tmp_path):
+    """Two gloo ranks: the oracle's sharded K1 run on global ray ranges [0, R) and [R, 2R) reproduces, concatenated, the unsharded batch of 2R rays bit for bit."""
     import torch.multiprocessing as mp
     sys.path[:0] = [os.path.join(ROOT, "blender-ngp_b200"), os.path.join(ROOT, "oracle")]
     import oracle as orc
@@ -71,6 +72,7 @@ def test_two_rank_shards_tile_the_global_batch(tmp_path):
 
 
 def test_controller_matches_single_rank():
+    """Host logic of the data-parallel controller (pyngp.dp): with one rank it is the reference's update (testbed_nerf.cu:2890-2891, float arithmetic, multiple of 128, capped at 2^18); shard() maps a rank to its global ray range."""
     sys.path[:0] = [os.path.join(ROOT, "blender-ngp_b200")]
     from pyngp import dp
     # world = 1 reduces to the reference's update (testbed_nerf.cu:2890-2891)

@@ -69,6 +69,7 @@ def _grid_inputs(orc, n, seed, aabb_scale=1):
 
 @pytest.mark.parametrize("aabb_scale,n", [(1, 20000), (4, 4099)])
 def test_hash_encode_forward_bit_exact(L, orc, aabb_scale, n):
+    """K2 hash-grid forward through ngpb_hash_encode_forward against the oracle on the same table and positions (both position strides): bit-exact fp16 features, including the reference's corner order and fp16 accumulation (tcnn grid.h:220-349)."""
     import pyngp
     from gpu_util import dev, ptr, host
     m, g, table, pos = _grid_inputs(orc, n, 7, aabb_scale)
@@ -106,6 +107,7 @@ def test_hash_encode_matches_reference_golden(L, orc):
 
 
 def test_hash_encode_forward_empty_and_errors(L, orc):
+    """n = 0 is a no-op and null pointers are refused with a message (no launch)."""
     import pyngp
     from gpu_util import dev, ptr
     m, g, table, pos = _grid_inputs(orc, 16, 3)
@@ -175,6 +177,7 @@ def test_mlp_forward(L, orc):
 
 
 def test_mlp_forward_rejects_ragged(L):
+    """The tensor-core MLP works on whole 128-sample tiles (tcnn batch_size_granularity): any other n is refused."""
     import pyngp
     from gpu_util import dev, ptr
     w, enc, coords = _mlp_inputs(128, 1)
@@ -183,6 +186,7 @@ def test_mlp_forward_rejects_ragged(L):
 
 
 def test_density_mlp_forward(L, orc):
+    """K3 density network alone (NerfNetwork::density, nerf_network.h:268-300) against the oracle: <= 2^-8 of range."""
     import pyngp
     from gpu_util import dev, ptr, host
     n = 128 * 9
@@ -194,6 +198,7 @@ def test_density_mlp_forward(L, orc):
 
 
 def test_mlp_forward_backward(L, orc):
+    """K8-K11 in one tcgen05 kernel (forward, data gradients, five weight-gradient GEMMs) against the oracle: dL/dencoded 99.9 % within 2^-8 of range, every weight matrix within 2^-7; padded rgb outputs receive no gradient (nerf_network.h:202-206)."""
     import pyngp
     from gpu_util import dev, ptr, host
     n = 128 * 301  # more tiles than CTAs: exercises TMEM accumulation of the weight gradients across tiles
@@ -248,6 +253,7 @@ def _run_k1(L, scene, bitfield, n_rays, max_samples, rng, snap=True, ray_offset=
 
 @pytest.mark.parametrize("snap", [True, False])
 def test_generate_training_samples_bit_exact(L, orc, small_scene, snap):
+    """K1 (ray generation, occupancy marching, compaction) against the oracle for snapped and jittered pixel positions: counters, ray indices, rays, numsteps and every sample coordinate bit-exact (src/testbed_nerf.cu:1085-1260)."""
     from conftest import scene_occupancy_bitfield
     _, bits = scene_occupancy_bitfield(orc)
     n_rays, max_samples = 4096, 1 << 17
@@ -443,6 +449,7 @@ def test_training_step_reuses_inference_features(small_scene):
 # K15 optimizer
 # ------------------------------------------------------------------------------------------------------
 def test_optimizer_step(L, orc):
+    """K15 Ema(ExponentialDecay(Adam)) in one sweep against the oracle over four steps with sparse gradients: step counters exact, fp32 state to 1e-6 relative (device exp2f/sqrtf vs libm), gradients reset by the same pass (tcnn adam.h:48-119, ema.h:63-76)."""
     import pyngp
     from gpu_util import dev, ptr, host
     n, n_matrix = 10240 + 50000, 10240
@@ -472,6 +479,7 @@ def test_optimizer_step(L, orc):
 # K16 occupancy grid
 # ------------------------------------------------------------------------------------------------------
 def test_density_grid_kernels(L, orc, small_scene):
+    """K16 occupancy grid: marking of unseen cells, uniform / non-uniform sample generation and the bitfield with its mip pyramid bit-exact against the oracle; density splat + EMA to 1e-5 (src/testbed_nerf.cu:465-610,:2761-2859)."""
     import pyngp
     from gpu_util import dev, ptr, host, images_to_device, rng_struct
     meta, n_img, keep = images_to_device(small_scene)
@@ -872,6 +880,7 @@ def test_sdf_model_forward(L, orc):
 # degenerate inputs through the C ABI: empty batches are no-ops with defined outputs, malformed sizes are refused
 # ------------------------------------------------------------------------------------------------------
 def test_empty_and_malformed_inputs(L, orc, small_scene):
+    """Degenerate inputs through the C ABI: empty batches write nothing, ragged MLP batches are refused, an empty occupancy grid yields zero rays / samples and K6 reports zero compacted samples; a Testbed without data or with a batch that is not a multiple of 128 raises."""
     import pyngp
     from gpu_util import dev, ptr, host, rng_struct
     g, entries = pyngp.grid_init(device_scales=True)

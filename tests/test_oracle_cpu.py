@@ -9,6 +9,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def test_pcg32_known_answer(orc):
+    """PCG32 of the oracle against the published reference sequence of the generator (pcg32.h demo values) and advance() against stepping."""
     # pcg32 demo, pcg32_srandom(42, 54): the published first outputs of the minimal C implementation
     r = orc.pcg32(42, 54)
     assert [orc.pcg32_next_uint(r) for _ in range(6)] == [0xa15c02b7, 0x7b47f409, 0xba1d3330, 0x83d2f293, 0xbfa4784b, 0xcbed606e]
@@ -36,6 +37,7 @@ def test_level_table_matches_reference_derivation(orc):
 
 
 def test_grid_forward_is_interpolation_and_backward_is_its_adjoint(orc):
+    """Oracle hash grid: forward reproduces table values at cell corners and interpolates linearly in between; backward is the adjoint of forward (<dy, forward(table)> = <backward(dy), table>)."""
     m = orc.model()
     rs = np.random.RandomState(0)
     table = (rs.randn(m.n_grid_params) * 0.5).astype(np.float16)
@@ -58,6 +60,7 @@ def test_grid_forward_is_interpolation_and_backward_is_its_adjoint(orc):
 
 
 def test_mlp_backward_matches_finite_differences(orc):
+    """Oracle MLP backward against central finite differences of its own forward (fp16 rounding bounds the achievable agreement)."""
     rs = np.random.RandomState(1)
     shapes = [(64, 32), (16, 64), (64, 32), (64, 64), (16, 64)]
     w = np.concatenate([(rs.rand(o * i) * 2 - 1) * np.sqrt(6.0 / (o + i)) for o, i in shapes]).astype(np.float16)
@@ -88,6 +91,7 @@ def test_mlp_backward_matches_finite_differences(orc):
 
 
 def test_generate_training_samples_invariants(orc, small_scene):
+    """Oracle K1: kept rays have 1..1024 samples with exclusive-prefix bases in ray order and increasing ray indices, the counters add up, every sample lies inside the box in an occupied cell of cascade 0 with the constant-step dt code, and the run is deterministic."""
     from conftest import scene_occupancy_bitfield
     grid, bits = scene_occupancy_bitfield(orc)
     imgs = orc.make_images(small_scene["images"], small_scene["xforms"], small_scene["fx"], small_scene["fy"])
@@ -117,6 +121,7 @@ def test_generate_training_samples_invariants(orc, small_scene):
 
 
 def test_compute_loss_invariants(orc, small_scene):
+    """Oracle K6 on a dense medium: compacted counts never exceed the marched counts and terminated rays drop their tails, the compacted coordinates are each ray's sample prefix at its compacted base, gradients are finite and non-trivial, per-ray losses are non-negative."""
     from conftest import scene_occupancy_bitfield
     _, bits = scene_occupancy_bitfield(orc)
     imgs = orc.make_images(small_scene["images"], small_scene["xforms"], small_scene["fx"], small_scene["fy"])
