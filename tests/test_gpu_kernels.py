@@ -69,7 +69,7 @@ def _grid_inputs(orc, n, seed, aabb_scale=1):
 
 @pytest.mark.parametrize("aabb_scale,n", [(1, 20000), (4, 4099)])
 def test_hash_encode_forward_bit_exact(L, orc, aabb_scale, n):
-    """K2 hash-grid forward through ngpb_hash_encode_forward against the oracle on the same table and positions (both position strides): bit-exact fp16 features, including the reference's corner order and fp16 accumulation (tcnn grid.h:220-349)."""
+    """K2 hash-grid forward through ngpb_hash_encode_forward against the oracle on the same table and positions (aabb_scale 1 and 4, a sample count that is not a multiple of the block): bit-exact fp16 features, including the reference's corner order and fp16 accumulation (tcnn grid.h:220-349)."""
     import pyngp
     from gpu_util import dev, ptr, host
     m, g, table, pos = _grid_inputs(orc, n, 7, aabb_scale)
@@ -186,7 +186,7 @@ def test_mlp_forward_rejects_ragged(L):
 
 
 def test_density_mlp_forward(L, orc):
-    """K3 density network alone (NerfNetwork::density, nerf_network.h:268-300) against the oracle: <= 2^-8 of range."""
+    """K3 density network alone (NerfNetwork::density, nerf_network.h:268-300) against the oracle: <= 2^-9 of range."""
     import pyngp
     from gpu_util import dev, ptr, host
     n = 128 * 9
