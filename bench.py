@@ -393,7 +393,10 @@ def main():
                        "batch": args.batch, "rays_per_batch": st["rays_per_batch"], "samples_before_compaction": st["measured_batch_size_before_compaction"],
                        "samples_per_sec": value * BATCH, "pre_trained_steps": args.preroll + W, "final_loss": loss,
                        "parallelism": "single GPU" if world == 1 else f"dp{world}: ray-sharded replicas, NCCL gradient all-reduce",
-                       "l2": "no flush: the per-iteration working set (256 MB images + 293 MB parameter/optimizer state + ~150 MB sample buffers) exceeds the 126 MB L2"},
+                       "l2": "no flush: the per-iteration working set (256 MB images + 293 MB parameter/optimizer state + ~150 MB sample buffers) exceeds the 126 MB L2",
+                       "schedule": "every stage of the reference's iteration runs every step (K1, inference on all marched samples, K6, forward+backward on the compacted batch, "
+                                   "Adam/EMA, occupancy refresh at its cadence); the training pass reads the hash-grid features the inference pass computed for the same samples "
+                                   "with the same weights instead of re-encoding them (bit-identical, reuse_encoding=0 restores the second encode)"},
             "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roofline, "render": render,
         }
         if cb is not None:
