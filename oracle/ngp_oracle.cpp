@@ -1629,3 +1629,151 @@ extern "C" void orc_loss(int kind, uint32_t n, uint32_t dims, float loss_scale, 
 		gradients[i] = f2h(loss_scale * gradient / n_total);
 	}
 }
+
+// =============================================================================================
+// Input gradients (camera-extrinsics optimisation, K13/K14): PREPARATION FOR THE NEXT ROUND. PARITY UNPINNED -- no golden vector from the reference exists
+// for these yet; tests/test_oracle_cpu.py checks them against finite differences of the oracle's own forward paths. Nothing in the product uses them.
+// =============================================================================================
+
+// dL/dx of the hash-grid encoding: kernel_grid's dy_dx (grid.h:351-392: per level and feature, for each input dimension the difference of the two
+// neighbours along that dimension, blended linearly over the other dimensions, times the level scale) contracted with dL/dy as in
+// kernel_grid_backward_input (grid.h:546-575). positions [n][stride], dL_dy [n][2 * n_levels] fp16, dL_dx [n][3] fp32.
+extern "C" void orc_grid_input_gradient(uint32_t n, uint32_t n_levels, const uint32_t* offsets, uint32_t base_resolution, float log2_per_level_scale, const float* scales,
+                                        const orc_half* grid, const float* positions, uint32_t pos_stride, const orc_half* dL_dy, float* dL_dx) {
+	#pragma omp parallel for schedule(static)
+	for (int64_t i = 0; i < (int64_t)n; ++i) {
+		float result[3] = {0.f, 0.f, 0.f};
+		for (uint32_t level = 0; level < n_levels; ++level) {
+			const orc_half* g = grid + (size_t)offsets[level] * 2;
+			const uint32_t hashmap_size = offsets[level + 1] - offsets[level];
+			const float scale = scales ? scales[level] : grid_scale(level, log2_per_level_scale, base_resolution);
+			const uint32_t resolution = grid_resolution(scale);
+			float pos[3]; uint32_t pg[3];
+			for (int d = 0; d < 3; ++d) pos_fract(positions[(size_t)i * pos_stride + d], &pos[d], &pg[d], scale);
+			float grads[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+			for (uint32_t grad_dim = 0; grad_dim < 3; ++grad_dim) {
+				for (uint32_t idx = 0; idx < 4; ++idx) {
+					float weight = scale;
+					uint32_t pl[3];
+					for (uint32_t ng = 0; ng < 2; ++ng) {
+						const uint32_t dim = ng >= grad_dim ? ng + 1 : ng;
+						if ((idx & (1u << ng)) == 0) { weight *= 1 - pos[dim]; pl[dim] = pg[dim]; } else { weight *= pos[dim]; pl[dim] = pg[dim] + 1; }
+					}
+					pl[grad_dim] = pg[grad_dim];
+					const uint32_t left = grid_index(hashmap_size, resolution, pl) * 2;
+					pl[grad_dim] = pg[grad_dim] + 1;
+					const uint32_t right = grid_index(hashmap_size, resolution, pl) * 2;
+					for (int f = 0; f < 2; ++f) grads[f][grad_dim] += weight * (h2f(g[right + f]) - h2f(g[left + f])); // pos_derivative = 1 (linear interpolation)
+				}
+			}
+			for (int f = 0; f < 2; ++f) {
+				const float dl = h2f(dL_dy[(size_t)i * (2 * n_levels) + level * 2 + f]);
+				for (int d = 0; d < 3; ++d) result[d] += dl * grads[f][d];
+			}
+		}
+		for (int d = 0; d < 3; ++d) dL_dx[(size_t)i * 3 + d] = result[d];
+	}
+}
+
+// dL/d(direction input) of the degree-4 spherical harmonics (kernel_sh_backward, spherical_harmonics.h:154-390): the polynomials of sh4() above
+// differentiated term by term in x = 2 d - 1, times 2 for the [0,1] -> [-1,1] mapping. dirs [n][stride], dL_dy [n][16] fp16, dL_dx [n][3] fp32.
+extern "C" void orc_sh4_input_gradient(uint32_t n, const float* dirs, uint32_t stride, const orc_half* dL_dy, float* dL_dx) {
+	for (uint32_t i = 0; i < n; ++i) {
+		const float x = dirs[(size_t)i * stride + 0] * 2.f - 1.f, y = dirs[(size_t)i * stride + 1] * 2.f - 1.f, z = dirs[(size_t)i * stride + 2] * 2.f - 1.f;
+		const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+		float g[16];
+		for (int k = 0; k < 16; ++k) g[k] = h2f(dL_dy[(size_t)i * 16 + k]);
+		// Y1 = -c1 y, Y2 = c1 z, Y3 = -c1 x
+		const float c1 = 0.48860251190291987f, c4 = 1.0925484305920792f, c6 = 0.94617469575755997f, c8 = 0.54627421529603959f;
+		const float c9 = 0.59004358992664352f, c10 = 2.8906114426405538f, c11 = 0.45704579946446572f, c12 = 0.3731763325901154f, c14 = 1.4453057213202769f;
+		float dx = 0.f, dy = 0.f, dz = 0.f;
+		dy += g[1] * -c1; dz += g[2] * c1; dx += g[3] * -c1;
+		// Y4 = c4 xy, Y5 = -c4 yz, Y6 = c6 z2 - const, Y7 = -c4 xz, Y8 = c8 (x2 - y2)
+		dx += g[4] * (c4 * y); dy += g[4] * (c4 * x);
+		dy += g[5] * (-c4 * z); dz += g[5] * (-c4 * y);
+		dz += g[6] * (2.f * c6 * z);
+		dx += g[7] * (-c4 * z); dz += g[7] * (-c4 * x);
+		dx += g[8] * (2.f * c8 * x); dy += g[8] * (-2.f * c8 * y);
+		// Y9 = c9 y (y2 - 3 x2), Y10 = c10 xyz, Y11 = c11 y (1 - 5 z2), Y12 = c12 z (5 z2 - 3), Y13 = c11 x (1 - 5 z2), Y14 = c14 z (x2 - y2), Y15 = c9 x (3 y2 - x2)
+		dx += g[9] * (-6.f * c9 * xy); dy += g[9] * (3.f * c9 * (y2 - x2));
+		dx += g[10] * (c10 * yz); dy += g[10] * (c10 * xz); dz += g[10] * (c10 * xy);
+		dy += g[11] * (c11 * (1.f - 5.f * z2)); dz += g[11] * (-10.f * c11 * yz);
+		dz += g[12] * (c12 * (15.f * z2 - 3.f));
+		dx += g[13] * (c11 * (1.f - 5.f * z2)); dz += g[13] * (-10.f * c11 * xz);
+		dx += g[14] * (2.f * c14 * xz); dy += g[14] * (-2.f * c14 * yz); dz += g[14] * (c14 * (x2 - y2));
+		dx += g[15] * (3.f * c9 * (y2 - x2)); dy += g[15] * (6.f * c9 * xy);
+		dL_dx[(size_t)i * 3 + 0] = dx * 2.0f; dL_dx[(size_t)i * 3 + 1] = dy * 2.0f; dL_dx[(size_t)i * 3 + 2] = dz * 2.0f;
+	}
+}
+
+// dL/d(network input) of the NeRF model for a batch (NerfNetwork::backward with dL_dinput, nerf_network.h:187-266): position gradient through the density
+// network and the hash grid, direction gradient through the rgb network's SH inputs. dL_dcoords [n][7] fp32: {pos 3, dt (no gradient), dir 3}.
+extern "C" void orc_nerf_input_gradient(const orc_model* m, const orc_half* params, uint32_t n, const float* coords, const orc_half* dL_dout, float* dL_dcoords) {
+	std::vector<orc_half> enc((size_t)n * 32), denc((size_t)n * 32), dsh((size_t)n * 16);
+	const float l2 = std::log2(m->per_level_scale);
+	orc_grid_forward(n, m->n_levels, m->offsets, m->base_resolution, l2, m->scales, params + ORC_MLP_PARAMS, coords, 7, enc.data());
+	MlpWeightsF Wf(params);
+	const float* W = Wf.w.data();
+	#pragma omp parallel for schedule(static)
+	for (int64_t i = 0; i < (int64_t)n; ++i) { // the data-gradient half of orc_nerf_mlp_backward, keeping the SH part of the rgb network's input gradient
+		SampleActs a;
+		mlp_forward_one(W, enc.data() + (size_t)i * 32, coords + (size_t)i * 7, a);
+		float d_orgb[16] = {0}, tmp[64], d_g2[64], d_g1[64], d_rin[32], d_od[16], d_h1[64], d_x[32];
+		for (int c = 0; c < 3; ++c) d_orgb[c] = h2f(dL_dout[(size_t)i * 4 + c]);
+		matvec_t(W + W3R, 16, 64, d_orgb, tmp);
+		for (int k = 0; k < 64; ++k) d_g2[k] = rh(a.g2[k] > 0.f ? tmp[k] : 0.f);
+		matvec_t(W + W2R, 64, 64, d_g2, tmp);
+		for (int k = 0; k < 64; ++k) d_g1[k] = rh(a.g1[k] > 0.f ? tmp[k] : 0.f);
+		matvec_t(W + W1R, 64, 32, d_g1, tmp);
+		for (int k = 0; k < 32; ++k) d_rin[k] = rh(tmp[k]);
+		for (int k = 0; k < 16; ++k) { d_od[k] = d_rin[k]; dsh[(size_t)i * 16 + k] = f2h(d_rin[16 + k]); }
+		d_od[0] = rh(d_od[0] + h2f(dL_dout[(size_t)i * 4 + 3]));
+		matvec_t(W + W2D, 16, 64, d_od, tmp);
+		for (int k = 0; k < 64; ++k) d_h1[k] = rh(a.h1[k] > 0.f ? tmp[k] : 0.f);
+		matvec_t(W + W1D, 64, 32, d_h1, d_x);
+		for (int k = 0; k < 32; ++k) denc[(size_t)i * 32 + k] = f2h(d_x[k]);
+	}
+	std::vector<float> dpos((size_t)n * 3), ddir((size_t)n * 3);
+	orc_grid_input_gradient(n, m->n_levels, m->offsets, m->base_resolution, l2, m->scales, params + ORC_MLP_PARAMS, coords, 7, denc.data(), dpos.data());
+	orc_sh4_input_gradient(n, coords + 4, 7, dsh.data(), ddir.data());
+	for (uint32_t i = 0; i < n; ++i) {
+		float* o = dL_dcoords + (size_t)i * 7;
+		o[0] = dpos[(size_t)i * 3]; o[1] = dpos[(size_t)i * 3 + 1]; o[2] = dpos[(size_t)i * 3 + 2]; o[3] = 0.f;
+		o[4] = ddir[(size_t)i * 3]; o[5] = ddir[(size_t)i * 3 + 1]; o[6] = ddir[(size_t)i * 3 + 2];
+	}
+}
+
+// compute_cam_gradient_train_nerf (src/testbed_nerf.cu:1600-1707) without distortion / focal-length terms and with uniform pixel sampling (xy_pdf = 1):
+// per kept ray, the sum of its samples' position gradients is the gradient of the camera origin; the direction gradient (position gradients scaled by
+// the distance along the ray, plus the direction-input gradients) gives the rotation gradient as ray.d x ray_gradient.d. Sums per image (the kernel uses
+// atomicAdd; here doubles). rays_unnormalized [n][6]; cam_pos_gradient, cam_rot_gradient [n_images][3].
+extern "C" void orc_compute_cam_gradient(uint32_t n_kept, uint32_t n_rays_total, uint32_t n_images, const float* aabb6, const uint32_t* ray_indices,
+                                         const float* rays_unnormalized, const uint32_t* numsteps, const float* coords, const float* coords_gradient,
+                                         float* cam_pos_gradient, float* cam_rot_gradient) {
+	const AABB aabb = make_aabb(aabb6);
+	std::vector<double> pos_acc((size_t)n_images * 3, 0.0), rot_acc((size_t)n_images * 3, 0.0);
+	const Vec3 diag = {aabb.max.x - aabb.min.x, aabb.max.y - aabb.min.y, aabb.max.z - aabb.min.z};
+	for (uint32_t i = 0; i < n_kept; ++i) {
+		const uint32_t ns = numsteps[i * 2 + 0], base = numsteps[i * 2 + 1];
+		if (ns == 0) continue;
+		const uint32_t img = image_idx(ray_indices[i], n_rays_total, n_images);
+		const float* r = rays_unnormalized + (size_t)i * 6;
+		const Vec3 ro = {r[0], r[1], r[2]};
+		const Vec3 rd = normalized(Vec3{r[3], r[4], r[5]});
+		Vec3 go = {0.f, 0.f, 0.f}, gd = {0.f, 0.f, 0.f};
+		for (uint32_t j = 0; j < ns; ++j) {
+			const float* c = coords + (size_t)(base + j) * 7;
+			const float* gc = coords_gradient + (size_t)(base + j) * 7;
+			const Vec3 pg = {gc[0] * (1.0f / diag.x), gc[1] * (1.0f / diag.y), gc[2] * (1.0f / diag.z)}; // warp_position_derivative = 1 / aabb.diag()
+			go = {go.x + pg.x, go.y + pg.y, go.z + pg.z};
+			const Vec3 pos = unwarp_position(c, aabb);
+			const float dx = pos.x - ro.x, dy = pos.y - ro.y, dz = pos.z - ro.z;
+			const float t = std::sqrt(dx * dx + dy * dy + dz * dz);
+			gd = {gd.x + pg.x * t + gc[4] * 0.5f, gd.y + pg.y * t + gc[5] * 0.5f, gd.z + pg.z * t + gc[6] * 0.5f}; // warp_direction_derivative = 0.5
+		}
+		const Vec3 axis = {rd.y * gd.z - rd.z * gd.y, rd.z * gd.x - rd.x * gd.z, rd.x * gd.y - rd.y * gd.x};
+		pos_acc[(size_t)img * 3 + 0] += go.x; pos_acc[(size_t)img * 3 + 1] += go.y; pos_acc[(size_t)img * 3 + 2] += go.z;
+		rot_acc[(size_t)img * 3 + 0] += axis.x; rot_acc[(size_t)img * 3 + 1] += axis.y; rot_acc[(size_t)img * 3 + 2] += axis.z;
+	}
+	for (size_t k = 0; k < pos_acc.size(); ++k) { cam_pos_gradient[k] = (float)pos_acc[k]; cam_rot_gradient[k] = (float)rot_acc[k]; }
+}

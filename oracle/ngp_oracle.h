@@ -198,6 +198,15 @@ void orc_mlp_forward_backward(uint32_t n_hidden, uint32_t n, const orc_half* wei
                               const orc_half* dL_dout, orc_half* dL_dinput, float* grad);
 void orc_loss(int kind, uint32_t n, uint32_t dims, float loss_scale, const orc_half* predictions, const float* targets, float* values, orc_half* gradients);
 
+// ---- input gradients for camera-extrinsics optimisation (K13/K14): next round's oracle, PARITY UNPINNED (see ngp_oracle.cpp) ----
+void orc_grid_input_gradient(uint32_t n, uint32_t n_levels, const uint32_t* offsets, uint32_t base_resolution, float log2_per_level_scale, const float* scales,
+                             const orc_half* grid, const float* positions, uint32_t pos_stride, const orc_half* dL_dy, float* dL_dx);
+void orc_sh4_input_gradient(uint32_t n, const float* dirs, uint32_t stride, const orc_half* dL_dy, float* dL_dx);
+void orc_nerf_input_gradient(const orc_model* m, const orc_half* params, uint32_t n, const float* coords, const orc_half* dL_dout, float* dL_dcoords);
+void orc_compute_cam_gradient(uint32_t n_kept, uint32_t n_rays_total, uint32_t n_images, const float* aabb6, const uint32_t* ray_indices,
+                              const float* rays_unnormalized, const uint32_t* numsteps, const float* coords, const float* coords_gradient,
+                              float* cam_pos_gradient, float* cam_rot_gradient);
+
 #ifdef __cplusplus
 }
 #endif

@@ -358,6 +358,38 @@ def loss(kind, predictions_half, targets, loss_scale=128.0):
     return values, grads
 
 
+# ---- input gradients (camera-extrinsics optimisation; next round's oracle, parity unpinned) ----
+def grid_input_gradient(m, grid_half, positions, dL_dy, scales=None):
+    positions = _f32(positions)
+    n = positions.shape[0]
+    out = np.zeros((n, 3), np.float32)
+    sc = _f32(scales) if scales is not None else None
+    lib().orc_grid_input_gradient(n, m.n_levels, m.offsets, m.base_resolution, C.c_float(np.log2(np.float32(m.per_level_scale))), _p(sc),
+                                  _p(np.ascontiguousarray(grid_half, np.float16)), _p(positions), positions.shape[1], _p(np.ascontiguousarray(dL_dy, np.float16)), _p(out))
+    return out
+
+
+def sh4_input_gradient(dirs, dL_dy):
+    dirs = _f32(dirs)
+    out = np.zeros((dirs.shape[0], 3), np.float32)
+    lib().orc_sh4_input_gradient(dirs.shape[0], _p(dirs), dirs.shape[1], _p(np.ascontiguousarray(dL_dy, np.float16)), _p(out))
+    return out
+
+
+def nerf_input_gradient(m, params_half, coords, dL_dout):
+    coords = _f32(coords)
+    out = np.zeros((coords.shape[0], 7), np.float32)
+    lib().orc_nerf_input_gradient(C.byref(m), _p(np.ascontiguousarray(params_half, np.float16)), coords.shape[0], _p(coords), _p(np.ascontiguousarray(dL_dout, np.float16)), _p(out))
+    return out
+
+
+def compute_cam_gradient(n_kept, n_rays_total, n_images, aabb6, ray_indices, rays_unnormalized, numsteps, coords, coords_gradient):
+    pos = np.zeros((n_images, 3), np.float32); rot = np.zeros((n_images, 3), np.float32)
+    lib().orc_compute_cam_gradient(n_kept, n_rays_total, n_images, _p(_f32(aabb6)), _p(np.ascontiguousarray(ray_indices, np.uint32)), _p(_f32(rays_unnormalized)),
+                                   _p(np.ascontiguousarray(numsteps, np.uint32)), _p(_f32(coords)), _p(_f32(coords_gradient)), _p(pos), _p(rot))
+    return pos, rot
+
+
 class NerfInstance(C.Structure):
     _fields_ = [("model", C.POINTER(Model)), ("params", C.c_void_p), ("bitfield", C.c_void_p), ("train_aabb", C.c_float * 6), ("aabb_scale", C.c_uint32),
                 ("render_aabb", C.c_float * 6), ("transform", C.c_float * 16), ("opacity", C.c_float),

@@ -425,3 +425,95 @@ def test_golden_neural_image_forward(orc):
     ref = g["rgb"].astype(np.float32)
     assert rgb.shape == (IMAGE_RES * IMAGE_RES, 3)
     assert np.abs(rgb - ref).max() <= 4e-3 and np.abs(rgb - ref).mean() <= 3e-4
+
+
+# ------------------------------------------------------------------------------------------------------
+# input gradients (K13/K14 preparation): parity unpinned, checked against finite differences of the oracle's own forward paths
+# ------------------------------------------------------------------------------------------------------
+def _sh4_float64(d):
+    """The degree-4 basis of tcnn's kernel_sh (spherical_harmonics.h:62-101) in float64 for finite differences."""
+    x, y, z = (d * 2.0 - 1.0).T
+    xy, xz, yz, x2, y2, z2 = x * y, x * z, y * z, x * x, y * y, z * z
+    return np.stack([
+        np.full_like(x, 0.28209479177387814), -0.48860251190291987 * y, 0.48860251190291987 * z, -0.48860251190291987 * x,
+        1.0925484305920792 * xy, -1.0925484305920792 * yz, 0.94617469575755997 * z2 - 0.31539156525251999, -1.0925484305920792 * xz,
+        0.54627421529603959 * x2 - 0.54627421529603959 * y2, 0.59004358992664352 * y * (-3.0 * x2 + y2), 2.8906114426405538 * xy * z,
+        0.45704579946446572 * y * (1.0 - 5.0 * z2), 0.3731763325901154 * z * (5.0 * z2 - 3.0), 0.45704579946446572 * x * (1.0 - 5.0 * z2),
+        1.4453057213202769 * z * (x2 - y2), 0.59004358992664352 * x * (-x2 + 3.0 * y2)], axis=1)
+
+
+def test_sh4_input_gradient_matches_finite_differences(orc):
+    """dL/d(direction) of the degree-4 spherical harmonics (kernel_sh_backward, spherical_harmonics.h:154-390) against central differences of a float64
+    evaluation of the same basis; the forward oracle agrees with that float64 basis to fp16 rounding."""
+    rs = np.random.RandomState(3)
+    d = rs.rand(500, 3)
+    dy = rs.randn(500, 16).astype(np.float16)
+    got = orc.sh4_input_gradient(d.astype(np.float32), dy)
+    eps = 1e-5
+    fd = np.zeros((500, 3))
+    for k in range(3):
+        e = np.zeros(3); e[k] = eps
+        fd[:, k] = ((_sh4_float64(d + e) - _sh4_float64(d - e)) * dy.astype(np.float64)).sum(1) / (2 * eps)
+    assert np.abs(got - fd).max() <= 2e-4 * max(1.0, np.abs(fd).max())
+    assert np.abs(orc.sh4(d.astype(np.float32)).astype(np.float64) - _sh4_float64(d.astype(np.float32).astype(np.float64))).max() <= 2e-3
+
+
+def test_grid_input_gradient_matches_finite_differences(orc):
+    """dL/dx of the hash-grid encoding (kernel_grid's dy_dx + kernel_grid_backward_input, grid.h:351-392,:546-575) against central differences of a float64
+    interpolation built from the oracle's own corner indices and weights. The encoding is piecewise trilinear, so the two agree except where the
+    difference stencil straddles a cell boundary (a few per cent of the samples at this step size)."""
+    m = orc.model(n_levels=8, per_level_scale=1.3)
+    rs = np.random.RandomState(4)
+    table = (rs.randn(m.n_grid_params) * 0.5).astype(np.float16)
+    pos = (rs.rand(400, 3) * 0.9 + 0.05).astype(np.float32)
+    dy = rs.randn(400, 16).astype(np.float16)
+    got = orc.grid_input_gradient(m, table, pos, dy)
+
+    def objective(p):
+        total = np.zeros(p.shape[0])
+        for level in range(8):
+            idx, w = orc.grid_indices(m, level, p.astype(np.float32))
+            t = table[2 * m.offsets[level]: 2 * m.offsets[level + 1]].astype(np.float64).reshape(-1, 2)
+            val = (t[idx] * w.astype(np.float64)[..., None]).sum(1)
+            total += (val * dy[:, 2 * level: 2 * level + 2].astype(np.float64)).sum(1)
+        return total
+    eps = 2e-4
+    fd = np.zeros((400, 3))
+    for k in range(3):
+        e = np.zeros(3, np.float32); e[k] = eps
+        pp, pm = pos + e, pos - e
+        fd[:, k] = (objective(pp) - objective(pm)) / (pp[:, k].astype(np.float64) - pm[:, k].astype(np.float64))
+    err = np.abs(got - fd) / (np.abs(fd).max() + 1e-9)
+    assert np.quantile(err, 0.85) <= 2e-3, f"85th percentile {np.quantile(err, 0.85):.3e}"
+    assert np.median(err) <= 5e-4
+
+
+def test_input_gradient_composition_and_camera_gradient(orc):
+    """The model's input gradient is the grid gradient of the MLP's dL/dencoded plus the SH gradient of the rgb network's input gradient, dt gets none
+    (nerf_network.h:187-266); the camera gradient of compute_cam_gradient_train_nerf (src/testbed_nerf.cu:1600-1707) sums position gradients per image,
+    turns direction gradients into an angle-axis d x g, and ignores rays without samples."""
+    m = orc.model()
+    rs = np.random.RandomState(6)
+    params = np.concatenate([(rs.rand(10240) - 0.5).astype(np.float16) * 0.5, (rs.randn(m.n_grid_params) * 0.3).astype(np.float16)])
+    n = 256
+    coords = rs.rand(n, 7).astype(np.float32)
+    dout = (rs.randn(n, 4) * 0.1).astype(np.float16)
+    g = orc.nerf_input_gradient(m, params, coords, dout)
+    enc = orc.grid_forward(m, params[10240:], coords)
+    denc, _ = orc.mlp_backward(params[:10240], enc, coords, dout)
+    want_pos = orc.grid_input_gradient(m, params[10240:], coords, denc)
+    assert np.array_equal(g[:, :3], want_pos) and np.all(g[:, 3] == 0) and np.abs(g[:, 4:]).max() > 0
+    # camera gradient on a hand-made batch: two rays of image 0 (the second without samples), one ray of image 1
+    aabb = [0, 0, 0, 1, 1, 1]
+    rays = np.array([[0.5, 0.5, -1.0, 0, 0, 2.0], [0.5, 0.5, -1.0, 0, 1, 0], [0.2, 0.5, -1.0, 0, 0, 1.0]], np.float32)
+    numsteps = np.array([[2, 0], [0, 2], [1, 2]], np.uint32)
+    c = np.zeros((3, 7), np.float32); c[:, :3] = [[0.5, 0.5, 0.25], [0.5, 0.5, 0.75], [0.2, 0.5, 0.5]]; c[:, 4:] = 0.5
+    gc = np.zeros((3, 7), np.float32); gc[0, :3] = [1, 0, 0]; gc[1, :3] = [0, 2, 0]; gc[2, 4:] = [0.4, 0, 0]
+    ray_indices = np.array([0, 1, 5], np.uint32)  # image_idx(i, 6 rays, 2 images) = i * 2 // 6 -> images 0, 0, 1
+    pos_g, rot_g = orc.compute_cam_gradient(3, 6, 2, aabb, ray_indices, rays, numsteps, c, gc)
+    np.testing.assert_allclose(pos_g[0], [1, 2, 0], atol=1e-6)          # sum of the two samples' position gradients
+    np.testing.assert_allclose(pos_g[1], [0, 0, 0], atol=1e-6)
+    # ray 0: d = (0,0,1); g_d = (1,0,0) * 1.25 + (0,2,0) * 1.75 -> d x g_d = (-3.5, 1.25, 0)
+    np.testing.assert_allclose(rot_g[0], [-3.5, 1.25, 0], atol=1e-5)
+    # ray 2: only a direction gradient (0.4 * 0.5 along x) -> d x g = (0, 0.2, 0)
+    np.testing.assert_allclose(rot_g[1], [0, 0.2, 0], atol=1e-6)
