@@ -320,6 +320,7 @@ void hash_encode_forward_launch(cudaStream_t stream, const ngpb_grid* g, const _
 	if (n == 0) return;
 	const GridLevels L = make_levels(g);
 	const uint64_t threads = (uint64_t)n * L.n_levels;
+	if (threads > 0xFFFFFFFFull) throw std::runtime_error("hash_encode_forward: n * n_levels must fit 32 bits");
 	if (g->n_pos_dims == 2) {
 		if (n_dev) throw std::runtime_error("hash_encode_forward: a device-side count is not supported for 2-D grids");
 		hash_encode_forward_2d_kernel<<<(uint32_t)((threads + 255) / 256), 256, 0, stream>>>(n, L, (const __half2*)grid, positions, pos_stride, (__half2*)encoded);

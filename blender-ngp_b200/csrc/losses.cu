@@ -49,6 +49,7 @@ extern "C" int ngpb_loss(void* stream_, int kind, uint32_t n, uint32_t dims, flo
 			return NGPB_ERR_INVALID_ARGUMENT;
 		}
 		if (n == 0) return 0;
+		if (n > (0xFFFFFFFFu >> 4)) { set_last_error("ngpb_loss: batch too large (n * 16 must fit 32 bits)"); return NGPB_ERR_INVALID_ARGUMENT; }
 		cudaStream_t stream = (cudaStream_t)stream_;
 		const uint32_t n_elements = n * 16;
 		if (kind == NGPB_ELEMENT_LOSS_MAPE) loss_kernel<NGPB_ELEMENT_LOSS_MAPE><<<div_round_up(n_elements, 256), 256, 0, stream>>>(n_elements, dims, loss_scale, (const __half*)predictions, targets, values, (__half*)gradients);
