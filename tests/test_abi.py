@@ -203,3 +203,13 @@ def test_transforms_json_loader_reference_rules(tmp_path):
         pyngp.load_transforms(str(d / "c.json"))
     with pytest.raises(RuntimeError):
         pyngp.load_transforms(str(d / "im0.png"))
+
+
+def test_reference_arm_runs_on_rank_zero_only():
+    """bench.py --impl reference under torchrun: ranks other than 0 exit 0 without work or output (rank 0 alone times the CPU restatement)."""
+    import subprocess
+    import sys
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, env=env, timeout=120)
+    assert res.returncode == 0 and res.stdout.strip() == ""
