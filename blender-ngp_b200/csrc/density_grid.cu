@@ -169,19 +169,12 @@ extern "C" int ngpb_splat_and_ema(void* stream_, uint32_t n_samples, const uint3
 	} catch (const std::exception& e) { set_last_error(e.what()); return NGPB_ERR_RUNTIME; }
 }
 
-// scratch for the mean: 1024 doubles carved from the tail of the bitfield allocation is not possible
-// (the bitfield is exactly 2 MiB), so the partials live in a static device buffer per process.
-static double* mean_partials() {
-	static double* p = nullptr;
-	if (!p) NGPB_CUDA_CHECK(cudaMalloc(&p, 1024 * sizeof(double)));
-	return p;
-}
-
 extern "C" int ngpb_update_bitfield(void* stream_, uint32_t n_cascades_used, const float* grid, float* mean_dev, uint8_t* bitfield) {
 	try {
 		if (!grid || !mean_dev || !bitfield || n_cascades_used == 0 || n_cascades_used > NERF_CASCADES) { set_last_error("ngpb_update_bitfield: invalid argument"); return NGPB_ERR_INVALID_ARGUMENT; }
 		cudaStream_t stream = (cudaStream_t)stream_;
-		double* partials = mean_partials();
+		// per-owner scratch (no process-wide buffer: testbeds and fields live on different devices and streams): the 1024 block partials follow the mean
+		double* partials = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(mean_dev) + 8);
 		mean_partial_kernel<<<1024, 256, 0, stream>>>(grid, partials);
 		NGPB_LAUNCH_CHECK();
 		mean_final_kernel<<<1, 1024, 0, stream>>>(partials, mean_dev);

@@ -796,9 +796,14 @@ extern "C" int ngpb_field_create(ngpb_field** out, int device, uint32_t aabb_sca
 		for (int c = 0; c < 3; ++c) { f->train_aabb[c] = 0.5f - half; f->train_aabb[3 + c] = 0.5f + half; }
 		f->cone_angle = aabb_scale <= 1 ? 0.0f : (1.0f / 256.0f);
 		const float per_level_scale = std::exp(std::log(2048.0f * (float)aabb_scale / 16.0f) / 15.0f); // reset_network, src/testbed.cu:2313-2325
-		const uint32_t entries = ngpb_grid_init(&f->grid, 16, 19, 16, per_level_scale);
-		if (ngpb_grid_device_scales(nullptr, &f->grid) != 0) throw std::runtime_error(ngpb_last_error());
+		// encoding.log2_hashmap_size is the one architecture value a snapshot may vary (configs/nerf/*.json): it follows from the parameter count
+		uint32_t entries = 0;
+		for (uint32_t log2_t = 14; log2_t <= 24; ++log2_t) {
+			entries = ngpb_grid_init(&f->grid, 16, log2_t, 16, per_level_scale);
+			if (n_params == MLP_PARAMS + 2 * entries) break;
+		}
 		if (n_params != MLP_PARAMS + 2 * entries) throw std::runtime_error("snapshot parameter count does not match the base NeRF architecture for this aabb_scale");
+		if (ngpb_grid_device_scales(nullptr, &f->grid) != 0) throw std::runtime_error(ngpb_last_error());
 		f->n_params = n_params;
 		NGPB_CUDA_CHECK(cudaMalloc(&f->params, sizeof(__half) * n_params));
 		NGPB_CUDA_CHECK(cudaMemcpy(f->params, params_host, sizeof(__half) * n_params, cudaMemcpyHostToDevice));
@@ -808,7 +813,7 @@ extern "C" int ngpb_field_create(ngpb_field** out, int device, uint32_t aabb_sca
 		if (n_cells) {
 			if (!density_grid_host || n_cells != NERF_GRID_CELLS * (f->max_cascade + 1)) throw std::runtime_error("Incompatible number of grid cascades.");
 			NGPB_CUDA_CHECK(cudaMalloc(&grid_dev, sizeof(float) * n_cells));
-			NGPB_CUDA_CHECK(cudaMalloc(&mean_dev, sizeof(float)));
+			NGPB_CUDA_CHECK(cudaMalloc(&mean_dev, NGPB_MEAN_WORKSPACE_BYTES));
 			NGPB_CUDA_CHECK(cudaMemcpy(grid_dev, density_grid_host, sizeof(float) * n_cells, cudaMemcpyHostToDevice));
 			if (ngpb_update_bitfield(nullptr, f->max_cascade + 1, grid_dev, mean_dev, f->bitfield) != 0) throw std::runtime_error(ngpb_last_error());
 			NGPB_CUDA_CHECK(cudaDeviceSynchronize());

@@ -248,6 +248,7 @@ ngpb_testbed::ngpb_testbed(int device_) : device(device_) {
 	NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&counters_ready, cudaEventDisableTiming));
 	NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&mlp_train_done, cudaEventDisableTiming));
 	ngpb_optimizer_init(&opt);
+	ngpb_optimizer_init(&opt_hyper);
 	loss_cfg.loss_scale = LOSS_SCALE;
 	loss_cfg.background_color[0] = loss_cfg.background_color[1] = loss_cfg.background_color[2] = 0.f;
 	loss_cfg.color_space = NGPB_COLOR_LINEAR;     // m_color_space default, testbed.h:846
@@ -376,7 +377,7 @@ void ngpb_testbed::reset_network(uint32_t seed_) {
 	// m_rng = default_rng_t{m_seed}; density_grid_rng = default_rng_t{m_rng.next_uint()} (:2252,:2265)
 	rng.seed(seed);
 	density_grid_rng.seed(rng.next_uint());
-	const uint32_t n_levels = 16, log2_hashmap_size = 19, base_resolution = 16;
+	const uint32_t n_levels = 16, base_resolution = 16;
 	// per_level_scale = exp(ln(desired_resolution * aabb_scale / base) / (L-1)) (:2313-2325)
 	const float per_level_scale = std::exp(std::log(2048.0f * (float)aabb_scale / (float)base_resolution) / (n_levels - 1));
 	const uint32_t entries = ngpb_grid_init(&grid, n_levels, log2_hashmap_size, base_resolution, per_level_scale);
@@ -435,7 +436,7 @@ void ngpb_testbed::reset_network(uint32_t seed_) {
 		density_grid = (float*)dalloc(sizeof(float) * n_cells);
 		density_grid_tmp = (float*)dalloc(sizeof(float) * n_cells);
 		bitfield = (uint8_t*)dalloc((size_t)NERF_GRID_CELLS * NERF_CASCADES / 8);
-		mean_density = (float*)dalloc(sizeof(float));
+		mean_density = (float*)dalloc(NGPB_MEAN_WORKSPACE_BYTES);
 	}
 	NGPB_CUDA_CHECK(cudaMemsetAsync(density_grid, 0, sizeof(float) * n_cells, stream));
 	NGPB_CUDA_CHECK(cudaMemsetAsync(bitfield, 0, (size_t)NERF_GRID_CELLS * NERF_CASCADES / 8, stream));
@@ -452,7 +453,8 @@ void ngpb_testbed::reset_network(uint32_t seed_) {
 	}
 	NGPB_CUDA_CHECK(cudaMemsetAsync(dg_positions, 0, sizeof(float) * 3 * n_dg, stream));
 
-	ngpb_optimizer_init(&opt);
+	opt = opt_hyper; // fresh optimizer state with the configured hyper-parameters (Trainer ctor, tcnn trainer.h:53-99)
+	opt.step = 0; opt.lr_factor = 1.0f;
 	training_step = 0;
 	density_grid_ema_step = 0;
 	rays_per_batch = 1u << 12; // testbed.h:374
@@ -1062,7 +1064,20 @@ extern "C" int ngpb_testbed_set_option(ngpb_testbed* t, const char* name, double
 	else if (k == "density_grid_decay") t->density_grid_decay = (float)v;
 	else if (k == "shall_train") t->shall_train = v != 0;
 	else if (k == "render_min_transmittance") t->render_min_transmittance = (float)v;
-	else if (k == "learning_rate") t->opt.learning_rate = (float)v;
+	else if (k == "learning_rate") { t->opt.learning_rate = (float)v; t->opt_hyper.learning_rate = (float)v; }
+	// optimizer section of the network config (adam.h:121-160 update_hyperparams, exponential_decay.h:100-120, ema.h:150-170)
+	else if (k == "adam_beta1") { t->opt.beta1 = t->opt_hyper.beta1 = (float)v; }
+	else if (k == "adam_beta2") { t->opt.beta2 = t->opt_hyper.beta2 = (float)v; }
+	else if (k == "adam_epsilon") { t->opt.epsilon = t->opt_hyper.epsilon = (float)v; }
+	else if (k == "adam_l2_reg") { t->opt.l2_reg = t->opt_hyper.l2_reg = (float)v; }
+	else if (k == "ema_decay") { t->opt.ema_decay = t->opt_hyper.ema_decay = (float)v; }
+	else if (k == "decay_start") { t->opt.decay_start = t->opt_hyper.decay_start = (uint32_t)v; }
+	else if (k == "decay_interval") { t->opt.decay_interval = t->opt_hyper.decay_interval = (uint32_t)v; }
+	else if (k == "decay_base") { t->opt.decay_base = t->opt_hyper.decay_base = (float)v; }
+	else if (k == "log2_hashmap_size") {
+		if (v < 14 || v > 24) throw std::runtime_error("encoding.log2_hashmap_size must be in [14, 24]");
+		t->log2_hashmap_size = (uint32_t)v; // takes effect at the next reset_network
+	}
 	else if (k == "profile_stages") t->profile_stages = v != 0;
 	else if (k == "render_snap_to_pixel_centers") t->render_snap_to_pixel_centers = v != 0;
 	else if (k == "render_near_distance") t->render_near_distance = (float)v;
@@ -1092,6 +1107,15 @@ extern "C" double ngpb_testbed_get_option(ngpb_testbed* t, const char* name) {
 	if (k == "shall_train") return t->shall_train;
 	if (k == "render_min_transmittance") return t->render_min_transmittance;
 	if (k == "learning_rate") return t->opt.learning_rate;
+	if (k == "adam_beta1") return t->opt.beta1;
+	if (k == "adam_beta2") return t->opt.beta2;
+	if (k == "adam_epsilon") return t->opt.epsilon;
+	if (k == "adam_l2_reg") return t->opt.l2_reg;
+	if (k == "ema_decay") return t->opt.ema_decay;
+	if (k == "decay_start") return t->opt.decay_start;
+	if (k == "decay_interval") return t->opt.decay_interval;
+	if (k == "decay_base") return t->opt.decay_base;
+	if (k == "log2_hashmap_size") return t->log2_hashmap_size;
 	if (k == "render_snap_to_pixel_centers") return t->render_snap_to_pixel_centers;
 	if (k == "render_near_distance") return t->render_near_distance;
 	if (k == "exposure") return t->exposure;

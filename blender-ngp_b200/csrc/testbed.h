@@ -82,6 +82,8 @@ struct ngpb_testbed {
 	// model + optimizer state: fp32 master, fp16 training copy, fp16 EMA (inference) copy, Adam moments
 	// (tcnn Trainer buffer trainer.h:80,:317-332). Flat order: density net, rgb net, grid levels.
 	ngpb_grid grid{};
+	uint32_t log2_hashmap_size = 19; // encoding.log2_hashmap_size of the network config (configs/nerf/base.json:27); takes effect at reset_network
+	ngpb_optimizer opt_hyper{};      // hyper-parameters of the network config's optimizer section, re-applied by every reset_network
 	uint32_t n_params = 0, n_alloc = 0;
 	float* w_fp32 = nullptr; __half* w_half = nullptr; __half* w_ema = nullptr;
 	float* m1 = nullptr; float* m2 = nullptr; uint32_t* param_steps = nullptr; float* grad = nullptr;

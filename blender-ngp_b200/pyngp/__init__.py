@@ -471,7 +471,10 @@ def _validate_network_config(cfg):
         if not same:
             raise RuntimeError(f"unsupported network config: {section}.{key} = {got!r} (this build implements {value!r})")
     req("encoding", "otype", "HashGrid"); req("encoding", "n_levels", 16); req("encoding", "n_features_per_level", 2)
-    req("encoding", "log2_hashmap_size", 19); req("encoding", "base_resolution", 16)
+    req("encoding", "base_resolution", 16)
+    t = cfg.get("encoding", {}).get("log2_hashmap_size", 19)
+    if not (isinstance(t, int) and 14 <= t <= 24):
+        raise RuntimeError(f"unsupported network config: encoding.log2_hashmap_size = {t!r} (this build implements 14..24)")
     for s, hidden in (("network", 1), ("rgb_network", 2)):
         req(s, "otype", "FullyFusedMLP"); req(s, "activation", "ReLU"); req(s, "output_activation", "None")
         req(s, "n_neurons", 64); req(s, "n_hidden_layers", hidden)
@@ -736,13 +739,25 @@ class Testbed:
         cfg = load_network_config(path) if path else json.loads(json.dumps(BASE_NETWORK_CONFIG))
         self.reload_network_from_json(cfg)
 
+    def _apply_network_config(self, cfg):
+        """Pushes the config values the kernels read into the testbed: table size, and the hyper-parameters of Ema(ExponentialDecay(Adam))
+        (Optimizer::update_hyperparams: ema.h, exponential_decay.h, adam.h). Call before the network is (re)built."""
+        self._set("log2_hashmap_size", cfg.get("encoding", {}).get("log2_hashmap_size", 19))
+        ema = cfg.get("optimizer", {})
+        decay = ema.get("nested", {})
+        adam = decay.get("nested", {})
+        base = BASE_NETWORK_CONFIG["optimizer"]
+        self._set("ema_decay", ema.get("decay", base["decay"]))
+        for k in ("decay_start", "decay_interval", "decay_base"):
+            self._set(k, decay.get(k, base["nested"][k]))
+        for k, name in (("learning_rate", "learning_rate"), ("beta1", "adam_beta1"), ("beta2", "adam_beta2"), ("epsilon", "adam_epsilon"), ("l2_reg", "adam_l2_reg")):
+            self._set(name, adam.get(k, base["nested"]["nested"][k]))
+
     def reload_network_from_json(self, cfg, config_base_path=""):
         _validate_network_config(cfg)
         self.network_config = cfg
+        self._apply_network_config(cfg)
         check(lib().ngpb_testbed_reset_network(self._h, self._seed))
-        adam = cfg.get("optimizer", {}).get("nested", {}).get("nested", {})
-        if "learning_rate" in adam:
-            self._set("learning_rate", adam["learning_rate"])
         loss = str(cfg.get("loss", {}).get("otype", "Huber")).lower()
         names = {"l2": 0, "l1": 1, "mape": 2, "smape": 3, "huber": 4, "logl1": 5, "relativel2": 6}
         if loss not in names:
@@ -870,6 +885,7 @@ class Testbed:
         self.network_config = snap["network_config"]
         if snap["dataset_transform"] is not None:
             self._dataset_scale, self._dataset_offset = snap["dataset_transform"]
+        self._apply_network_config(self.network_config)
         check(lib().ngpb_testbed_configure(self._h, snap["aabb_scale"], self._seed))
         params = np.ascontiguousarray(snap["params_half"], np.float16)
         check(lib().ngpb_testbed_set_params_half(self._h, params.ctypes.data_as(C.c_void_p), int(params.shape[0])))
@@ -882,7 +898,8 @@ class Testbed:
         st.measured_batch_size = int(snap["rgb"].get("measured_batch_size", 0))
         st.measured_batch_size_before_compaction = int(snap["rgb"].get("measured_batch_size_before_compaction", 0))
         opt = snap["optimizer"]
-        st.optimizer_step = opt["current_step"] if opt else snap["training_step"]
+        # without an optimizer block the reference keeps the fresh optimizer reset_network built: step 0, factor 1 (Trainer::deserialize, trainer.h:290-310)
+        st.optimizer_step = opt["current_step"] if opt else 0
         st.learning_rate = opt["learning_rate"] if opt else 0.0
         st.learning_rate_factor = opt["learning_rate_factor"] if opt else 1.0
         check(lib().ngpb_testbed_set_training_state(self._h, C.byref(st)))

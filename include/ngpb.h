@@ -186,7 +186,10 @@ int ngpb_mark_untrained_density_grid(void* stream, uint32_t n_elements, float* g
 int ngpb_generate_grid_samples(void* stream, uint32_t n_elements, ngpb_rng rng, uint32_t step, const float* aabb6, const float* grid_in,
                                float* positions3, uint32_t* indices, uint32_t n_cascades, float thresh);
 int ngpb_splat_and_ema(void* stream, uint32_t n_samples, const uint32_t* indices, const ngpb_half* density, float* grid_tmp, uint32_t n_elements, float decay, float* grid);
-/* mean of max(v,0) over the first cascade -> *mean_dev, then bitfield + 7 max-pooled mips (2 MiB). */
+/* mean of max(v,0) over the first cascade -> mean_dev[0], then bitfield + 7 max-pooled mips (2 MiB).
+ * mean_dev: NGPB_MEAN_WORKSPACE_BYTES bytes of device memory, 8-byte aligned, owned by the caller (one per testbed / field / stream): the mean in
+ * the first float, the block partials of its fixed-order reduction behind it. */
+#define NGPB_MEAN_WORKSPACE_BYTES (8 + 1024 * 8)
 int ngpb_update_bitfield(void* stream, uint32_t n_cascades_used, const float* grid, float* mean_dev, uint8_t* bitfield);
 
 /* ---- K17: classic single-NeRF render (Testbed::render_nerf, src/testbed_nerf.cu:2354-2499; NerfTracer :2047-2267), ERenderMode::Shade,

@@ -1,0 +1,364 @@
+"""TEST INFRASTRUCTURE ONLY. Drives the UNMODIFIED reference `ngp::Testbed` (oracle/_ref/libref_full.so, compiled from /root/reference by
+oracle/Makefile.full) on a B200 and stores what it produces as fixtures:
+
+    gpurun -- 'python oracle/gen_golden_full.py gpurun_out/golden_full [small] [big]'
+
+  small  a reference-trained snapshot of a small scene written by the reference's own save_snapshot (configs/nerf/base.json with
+         log2_hashmap_size 15 so that the file stays small), frames rendered from it by the reference's render_frame (classic path,
+         K17 + accumulate + tonemap) and bl_render_frame (Blender path, K18: instances, opacity, masks, camera models, depth of field),
+         and the occupancy bitfield the reference derives from the snapshot's density grid.
+         -> ref_small.msgpack.gz + ref_full_small.npz; copy both to tests/golden/.
+  big    BASELINE config 2 at full size (100 x 800^2, batch 2^18): the reference's training speed on this GPU, its PSNR on held-out views,
+         and this repo's render of the REFERENCE's snapshot next to the reference's own render of it (PSNR / L1 between the two).
+         -> ref_full_big.json (numbers only; copy to profiles/).
+"""
+import ctypes as C
+import gzip
+import hashlib
+import json
+import math
+import os
+import shutil
+import sys
+import time
+import traceback
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, os.path.join(ROOT, "blender-ngp_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+class Mask(C.Structure):  # reff_mask
+    _fields_ = [("shape", C.c_int), ("mode", C.c_int), ("transform", C.c_float * 16), ("feather", C.c_float), ("opacity", C.c_float), ("dims", C.c_float * 3)]
+
+
+class Nerf(C.Structure):  # reff_nerf
+    _fields_ = [("snapshot_path", C.c_char_p), ("aabb", C.c_float * 6), ("transform", C.c_float * 16), ("opacity", C.c_float), ("n_masks", C.c_int), ("masks", C.POINTER(Mask))]
+
+
+class Request(C.Structure):  # reff_request
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("mip", C.c_int), ("flip_y", C.c_int), ("spp", C.c_int), ("color_space", C.c_int), ("tonemap_curve", C.c_int),
+                ("exposure", C.c_float), ("background_color", C.c_float * 4), ("camera", C.c_float * 12), ("camera_model", C.c_int), ("focal_length", C.c_float),
+                ("near_distance", C.c_float), ("aperture_size", C.c_float), ("focus_z", C.c_float), ("spherical_quadrilateral", C.c_float * 3),
+                ("quadrilateral_hexahedron", C.c_float * 24), ("aabb", C.c_float * 6), ("n_masks", C.c_int), ("masks", C.POINTER(Mask)), ("n_nerfs", C.c_int), ("nerfs", C.POINTER(Nerf))]
+
+
+class Ref:
+    """ctypes view of oracle/ref_harness/ref_full.cu"""
+
+    def __init__(self):
+        self.l = C.CDLL(os.path.join(HERE, "_ref", "libref_full.so"))
+        self.l.reff_last_error.restype = C.c_char_p
+        self.l.reff_training_step.restype = C.c_uint32
+        self.l.reff_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        self.h = C.c_void_p()
+        self.ck(self.l.reff_create(C.byref(self.h), 0))  # ETestbedMode::Nerf
+
+    def ck(self, st):
+        if st != 0:
+            raise RuntimeError("reference: " + self.l.reff_last_error().decode())
+
+    def set(self, **kw):
+        for k, v in kw.items():
+            self.ck(self.l.reff_set_option(self.h, k.encode(), float(v)))
+
+    def load(self, path):
+        self.ck(self.l.reff_load_training_data(self.h, path.encode()))
+
+    def network(self, cfg):
+        self.ck(self.l.reff_reload_network_from_json(self.h, json.dumps(cfg).encode()))
+
+    def train(self, batch, n):
+        loss = C.c_float(0)
+        self.ck(self.l.reff_train(self.h, batch, n, C.byref(loss)))
+        return loss.value
+
+    def stats(self):
+        s = (C.c_uint64 * 4)()
+        self.ck(self.l.reff_stats(self.h, s))
+        return dict(rays_per_batch=int(s[0]), measured_batch_size=int(s[1]), measured_batch_size_before_compaction=int(s[2]), n_params=int(s[3]))
+
+    def save(self, path, with_optimizer=False):
+        self.ck(self.l.reff_save_snapshot(self.h, path.encode(), int(with_optimizer)))
+
+    def load_snapshot(self, path):
+        self.ck(self.l.reff_load_snapshot(self.h, path.encode()))
+
+    def render(self, nerf_c2w, w, h, spp, linear):
+        """nerf_c2w: NeRF-convention camera-to-world (set_nerf_camera_matrix converts it with the dataset's scale / offset). Returns (frame, ngp camera 3x4)."""
+        out = np.zeros((h, w, 4), np.float32)
+        cam = np.ascontiguousarray(np.asarray(nerf_c2w, np.float32)[:3, :4].T.reshape(-1))
+        self.ck(self.l.reff_render(self.h, cam.ctypes.data_as(C.c_void_p), w, h, spp, int(linear), out.ctypes.data_as(C.c_void_p)))
+        ngp = np.zeros(12, np.float32)
+        self.ck(self.l.reff_get_camera(self.h, ngp.ctypes.data_as(C.c_void_p)))
+        return out, ngp.reshape(4, 3).T.copy()
+
+    def bl_render(self, rq):
+        out = np.zeros((rq.height, rq.width, 4), np.float32)
+        self.ck(self.l.reff_bl_render(self.h, C.byref(rq), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def density_grid(self, n_cascades):
+        g = np.zeros(128 ** 3 * n_cascades, np.float32); b = np.zeros(128 ** 3, np.uint8)
+        self.ck(self.l.reff_get_density_grid(self.h, g.ctypes.data_as(C.c_void_p), g.size, b.ctypes.data_as(C.c_void_p), b.size))
+        return g, b
+
+    def params(self, n):
+        w = np.zeros(n, np.float32); e = np.zeros(n, np.float16)
+        self.ck(self.l.reff_get_params(self.h, w.ctypes.data_as(C.c_void_p), e.ctypes.data_as(C.c_void_p), n))
+        return w, e
+
+
+def base_config(log2_hashmap_size=19):
+    import pyngp
+    cfg = json.loads(json.dumps(pyngp.BASE_NETWORK_CONFIG))
+    cfg["encoding"]["log2_hashmap_size"] = log2_hashmap_size
+    return cfg
+
+
+def fill(arr, values):
+    for i, v in enumerate(values):
+        arr[i] = float(v)
+
+
+def colmajor(m):
+    return np.asarray(m, np.float32).T.reshape(-1)
+
+
+def make_request(w, h, cam_ngp34, focal, nerfs, mip=0, flip_y=0, color_space=0, exposure=0.0, background=(0, 0, 0, 0), near=0.0, aperture=0.0, focus_z=1.0,
+                 model=0, sq=(0, 0, 0), qh=None, masks=()):
+    rq = Request()
+    rq.width, rq.height, rq.mip, rq.flip_y, rq.spp, rq.color_space, rq.tonemap_curve = w, h, mip, flip_y, 1, color_space, 0
+    rq.exposure = exposure
+    fill(rq.background_color, background)
+    fill(rq.camera, colmajor(cam_ngp34))
+    rq.camera_model, rq.focal_length, rq.near_distance, rq.aperture_size, rq.focus_z = model, focal, near, aperture, focus_z
+    fill(rq.spherical_quadrilateral, sq)
+    fill(rq.quadrilateral_hexahedron, np.zeros(24) if qh is None else np.asarray(qh).reshape(-1))
+    fill(rq.aabb, (-8, -8, -8, 8, 8, 8))
+    rq._keep = [nerfs, masks]
+    rq.n_masks = len(masks)
+    if masks:
+        arr = (Mask * len(masks))(*masks); rq._keep.append(arr); rq.masks = arr
+    arr = (Nerf * len(nerfs))(*nerfs); rq._keep.append(arr); rq.nerfs = arr; rq.n_nerfs = len(nerfs)
+    return rq
+
+
+def make_mask(shape, mode, transform, feather, opacity, dims):
+    m = Mask()
+    m.shape, m.mode, m.feather, m.opacity = shape, mode, feather, opacity
+    fill(m.transform, colmajor(transform)); fill(m.dims, list(dims) + [0.0] * (3 - len(dims)))
+    return m
+
+
+def make_nerf(path, transform44=None, opacity=1.0, aabb=(0, 0, 0, 1, 1, 1), masks=()):
+    n = Nerf()
+    n.snapshot_path = path.encode()
+    fill(n.aabb, aabb); fill(n.transform, colmajor(np.eye(4) if transform44 is None else transform44)); n.opacity = opacity
+    n.n_masks = len(masks)
+    if masks:
+        n._keep = (Mask * len(masks))(*masks); n.masks = n._keep
+    return n
+
+
+def translate(x, y, z, s=1.0):
+    m = np.eye(4, dtype=np.float32) * s; m[3, 3] = 1.0; m[:3, 3] = (x, y, z)
+    return m
+
+
+SMALL = dict(n_images=24, res=200, steps=1200, batch=1 << 16, log2_hashmap_size=15, frame=128)
+
+
+def blender_cases(snapshot_path, cam_ngp, focal):
+    """name -> kwargs of make_request; shared with the tests through the npz (every request parameter is stored next to the frame)."""
+    box_mask = dict(shape=0, mode=0, transform=translate(0.47, 0.40, 0.5), feather=0.0, opacity=1.0, dims=(0.30, 0.22, 0.30))
+    sphere_sub = dict(shape=2, mode=1, transform=translate(0.45, 0.40, 0.5), feather=0.06, opacity=1.0, dims=(0.10,))
+    cyl_add = dict(shape=1, mode=0, transform=translate(0.5, 0.42, 0.5), feather=0.04, opacity=0.8, dims=(0.16, 0.5))
+    qh = np.array([[-0.05, 0.05, 0.1], [0.05, 0.05, 0.1], [-0.05, -0.05, 0.1], [0.05, -0.05, 0.1],     # front tl tr bl br
+                   [-0.02, 0.02, 0.0], [0.02, 0.02, 0.0], [-0.02, -0.02, 0.0], [0.02, -0.02, 0.0]], np.float32)  # back
+    return {
+        "single": dict(nerfs=[dict()]),
+        "two_instances": dict(nerfs=[dict(), dict(transform=translate(0.25, 0.05, -0.1, 0.8), opacity=0.6)], background=(0.1, 0.2, 0.3, 1.0)),
+        "mip1_flip_srgb": dict(nerfs=[dict()], mip=1, flip_y=1, color_space=1, background=(0.3, 0.3, 0.3, 0.5), exposure=0.5),
+        "mask_box_add": dict(nerfs=[dict(masks=[box_mask])]),
+        "mask_sphere_subtract_global": dict(nerfs=[dict()], masks=[sphere_sub]),
+        "mask_cylinder_feather": dict(nerfs=[dict(masks=[cyl_add])], near=0.05),
+        "camera_spherical_quadrilateral": dict(nerfs=[dict()], model=2, sq=(0.35, 0.35, 0.12)),
+        "camera_quadrilateral_hexahedron": dict(nerfs=[dict()], model=1, qh=qh),
+        "depth_of_field": dict(nerfs=[dict()], aperture=0.02, focus_z=1.2),
+    }
+
+
+def build_request(case, snapshot_path, w, h, cam_ngp, focal):
+    kw = dict(case)
+    nerfs = [make_nerf(snapshot_path, n.get("transform"), n.get("opacity", 1.0), n.get("aabb", (0, 0, 0, 1, 1, 1)), [make_mask(**m) for m in n.get("masks", [])]) for n in kw.pop("nerfs")]
+    masks = [make_mask(**m) for m in kw.pop("masks", [])]
+    return make_request(w, h, cam_ngp, focal, nerfs, masks=masks, **kw)
+
+
+def gen_small(out_dir):
+    import synthetic
+    scratch = "/tmp/ngpb_ref_small"
+    shutil.rmtree(scratch, ignore_errors=True)
+    scene = synthetic.make_lego_scene(SMALL["n_images"], SMALL["res"], seed=0)
+    tj = synthetic.write_transforms_json(scene, scratch)
+    ref = Ref()
+    ref.load(tj)
+    ref.network(base_config(SMALL["log2_hashmap_size"]))
+    ref.set(shall_train=1)
+    loss = ref.train(SMALL["batch"], SMALL["steps"])
+    st = ref.stats()
+    print("reference trained the small scene:", SMALL["steps"], "steps, loss", loss, st)
+    snap = os.path.join(out_dir, "ref_small.msgpack")
+    ref.save(snap, False)
+    with open(snap, "rb") as f:
+        raw = f.read()
+    with gzip.open(snap + ".gz", "wb", compresslevel=9) as f:
+        f.write(raw)
+    out = dict(steps=SMALL["steps"], batch=SMALL["batch"], loss=np.float32(loss), n_params=st["n_params"], snapshot_sha256=np.frombuffer(hashlib.sha256(raw).digest(), np.uint8))
+
+    # occupancy: what the reference derives from the snapshot's (fp16) density grid after load_snapshot
+    ref2 = Ref()
+    ref2.load_snapshot(snap)
+    grid, bits = ref2.density_grid(1)
+    out["bitfield_packed"] = bits  # npz compression handles the sparsity
+    out["density_grid_sum"] = np.float64(grid.astype(np.float64).sum())
+    _, ema = ref2.params(st["n_params"])
+    out["params_sha256"] = np.frombuffer(hashlib.sha256(ema.tobytes()).digest(), np.uint8)
+
+    # classic renders (render_frame -> render_nerf -> accumulate + tonemap) from the loaded snapshot, held-out cameras
+    W = H = SMALL["frame"]
+    cams = synthetic.hemisphere_cameras(3, seed=7)
+    fov_deg = math.degrees(synthetic.CAMERA_ANGLE_X)
+    classic = [
+        dict(cam=0, spp=1, linear=1, snap=1, min_t=1e-4, bg=(0, 0, 0, 1), exposure=0.0),
+        dict(cam=1, spp=4, linear=0, snap=0, min_t=0.01, bg=(0.2, 0.4, 0.6, 1.0), exposure=0.0),
+        dict(cam=2, spp=2, linear=1, snap=1, min_t=0.01, bg=(1.0, 1.0, 1.0, 0.5), exposure=1.0),
+    ]
+    ngp_cams = []
+    for i, c in enumerate(classic):
+        ref2.set(fov_axis=0, fov=fov_deg, snap_to_pixel_centers=c["snap"], render_min_transmittance=c["min_t"], exposure=c["exposure"],
+                 background_color_r=c["bg"][0], background_color_g=c["bg"][1], background_color_b=c["bg"][2], background_color_a=c["bg"][3], dynamic_res=0)
+        frame, ngp = ref2.render(cams[c["cam"]], W, H, c["spp"], c["linear"])
+        out[f"classic_{i}"] = frame
+        out[f"classic_{i}_cfg"] = np.array([c["cam"], c["spp"], c["linear"], c["snap"], c["min_t"], *c["bg"], c["exposure"]], np.float64)
+        ngp_cams.append(ngp)
+        print(f"classic {i}: mean rgba {frame.reshape(-1, 4).mean(0)}")
+    out["nerf_cams"] = np.stack([np.asarray(c, np.float32) for c in cams]); out["ngp_cams"] = np.stack(ngp_cams); out["fov_deg"] = fov_deg
+
+    # Blender path
+    focal = 0.5 * W / math.tan(0.5 * synthetic.CAMERA_ANGLE_X)
+    out["bl_focal"] = np.float32(focal)
+    cases = blender_cases("SNAPSHOT", ngp_cams[0], focal)
+    out["bl_cases_json"] = np.frombuffer(json.dumps({k: json.loads(json.dumps(v, default=lambda a: np.asarray(a).tolist())) for k, v in cases.items()}).encode(), np.uint8)
+    for name, case in cases.items():
+        try:
+            rq = build_request(case, snap, W, H, ngp_cams[0], focal)
+            frame = ref2.bl_render(rq)
+            out[f"bl_{name}"] = frame
+            print(f"blender {name}: mean rgba {frame.reshape(-1, 4).mean(0)}")
+        except Exception:
+            traceback.print_exc()
+    # the other direction: this repo loads the reference's snapshot, writes it back with ITS OWN writer, and the reference loads that file
+    try:
+        import pyngp
+        tb = pyngp.Testbed()
+        tb.load_snapshot(snap)
+        ours_path = "/tmp/ngpb_ref_small/ours_resaved.msgpack"
+        tb.save_snapshot(ours_path)
+        ref3 = Ref()
+        ref3.load_snapshot(ours_path)
+        _, ema3 = ref3.params(st["n_params"])
+        c = classic[0]
+        ref3.set(fov_axis=0, fov=fov_deg, snap_to_pixel_centers=c["snap"], render_min_transmittance=c["min_t"], exposure=c["exposure"],
+                 background_color_r=c["bg"][0], background_color_g=c["bg"][1], background_color_b=c["bg"][2], background_color_a=c["bg"][3], dynamic_res=0)
+        # no nerf.dataset block in our file -> the reference's set_nerf_camera_matrix has no scale / offset: hand it the ngp matrix through m_camera instead
+        frame3 = ref3.bl_render(build_request(cases["single"], ours_path, W, H, ngp_cams[0], focal))
+        out["reference_reads_our_snapshot"] = np.array([float(np.array_equal(ema3, ema)), float(np.abs(frame3 - out["bl_single"]).max())], np.float64)
+        print("reference loaded the snapshot this repo wrote: params equal", np.array_equal(ema3, ema), "blender frame max abs diff", float(np.abs(frame3 - out["bl_single"]).max()))
+    except Exception:
+        traceback.print_exc()
+    np.savez_compressed(os.path.join(out_dir, "ref_full_small.npz"), **out)
+    print("small fixture written:", os.path.getsize(snap + ".gz"), "bytes of snapshot,", os.path.getsize(os.path.join(out_dir, "ref_full_small.npz")), "bytes of frames")
+
+
+def psnr(a, b):
+    mse = float(np.mean((np.asarray(a, np.float64) - np.asarray(b, np.float64)) ** 2))
+    return 10.0 * math.log10(1.0 / max(mse, 1e-12))
+
+
+def linear_to_srgb(x):
+    return np.where(x < 0.0031308, 12.92 * x, 1.055 * np.maximum(x, 1e-8) ** (1 / 2.4) - 0.055)
+
+
+def gen_big(out_dir, steps=2000, timed=300):
+    """BASELINE config 2 at full size, reference and this repo side by side on the same GPU."""
+    import torch
+    import synthetic
+    import pyngp
+    scratch = "/tmp/ngpb_ref_big"
+    shutil.rmtree(scratch, ignore_errors=True)
+    t0 = time.time()
+    scene = synthetic.make_lego_scene(100, 800, seed=0)
+    tj = synthetic.write_transforms_json(scene, scratch)
+    print(f"dataset written in {time.time() - t0:.1f} s")
+    report = dict(config="Lego-shaped synthetic scene, 100 x 800^2 RGBA8, configs/nerf/base.json, batch 2^18, seed 1337", steps=steps)
+    B = 1 << 18
+    ref = Ref()
+    t0 = time.time(); ref.load(tj); report["reference_load_s"] = time.time() - t0
+    ref.network(base_config(19))
+    ref.set(shall_train=1)
+    ref.train(B, steps - timed)
+    torch.cuda.synchronize()
+    t0 = time.time(); loss = ref.train(B, timed); dt = time.time() - t0  # reff_train ends with cudaDeviceSynchronize
+    report["reference"] = dict(it_per_s=timed / dt, ms_per_step=1e3 * dt / timed, loss=loss, timed_steps=timed, after_steps=steps - timed, stats=ref.stats(),
+                               how="wall clock around `timed` calls of ngp::Testbed::train(2^18) + cudaDeviceSynchronize, unmodified reference compiled for sm_100")
+    print("reference:", report["reference"])
+    snap = os.path.join(scratch, "ref_big.msgpack")
+    ref.save(snap, False)
+
+    # held-out views (scripts/run.py:216-303): 800^2, 8 spp, snap_to_pixel_centers, min transmittance 1e-4, black background, sRGB PSNR vs ground truth
+    cams = synthetic.hemisphere_cameras(4, seed=11)
+    fov_deg = math.degrees(synthetic.CAMERA_ANGLE_X)
+    fx = 0.5 * 800 / math.tan(0.5 * synthetic.CAMERA_ANGLE_X)
+    ref.set(fov_axis=0, fov=fov_deg, snap_to_pixel_centers=1, render_min_transmittance=1e-4, exposure=0.0, background_color_r=0, background_color_g=0, background_color_b=0, background_color_a=1, dynamic_res=0)
+    tb = pyngp.Testbed()
+    tb.load_snapshot(snap)  # THIS repo renders the REFERENCE's weights
+    tb.fov_axis = 0; tb.fov = fov_deg; tb.snap_to_pixel_centers = True; tb.nerf.render_min_transmittance = 1e-4; tb.background_color = [0, 0, 0, 1]
+    ours = pyngp.Testbed()
+    ours.load_training_data(tj)
+    ours.train_n(steps, B)
+    ours.fov_axis = 0; ours.fov = fov_deg; ours.snap_to_pixel_centers = True; ours.nerf.render_min_transmittance = 1e-4; ours.background_color = [0, 0, 0, 1]
+    rows = []
+    for i, c in enumerate(cams):
+        gt8 = synthetic.render_image(synthetic.nerf_matrix_to_ngp(c), 800, fx, fx, synthetic.lego_boxes(), device="cuda").cpu().numpy().astype(np.float32) / 255.0
+        gt = gt8[..., :3] * gt8[..., 3:4]  # composited on black, sRGB
+        fr, ngp = ref.render(c, 800, 800, 8, 0)
+        tb.set_nerf_camera_matrix(np.asarray(c)[:3]); fo = tb.render(800, 800, 8, linear=False)
+        ours.set_nerf_camera_matrix(np.asarray(c)[:3]); ft = ours.render(800, 800, 8, linear=False)
+        clip = lambda f: np.clip(f[..., :3], 0, 1)
+        rows.append(dict(view=i, psnr_reference_vs_gt=psnr(clip(fr), gt), psnr_ours_trained_vs_gt=psnr(clip(ft), gt), psnr_ours_on_reference_weights_vs_gt=psnr(clip(fo), gt),
+                         psnr_ours_vs_reference_same_weights=psnr(fo, fr), l1_ours_vs_reference_same_weights=float(np.abs(fo - fr).mean()),
+                         max_abs_ours_vs_reference_same_weights=float(np.abs(fo - fr).max())))
+        print(rows[-1])
+    report["held_out_views"] = rows
+    for k in rows[0]:
+        if k != "view":
+            report["mean_" + k] = float(np.mean([r[k] for r in rows]))
+    with open(os.path.join(out_dir, "ref_full_big.json"), "w") as f:
+        json.dump(report, f, indent=1)
+    print(json.dumps({k: v for k, v in report.items() if k.startswith("mean_")}))
+
+
+if __name__ == "__main__":
+    out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden_full")
+    os.makedirs(out, exist_ok=True)
+    jobs = sys.argv[2:] or ["small", "big"]
+    for j in jobs:
+        try:
+            dict(small=gen_small, big=gen_big)[j](out)
+        except Exception:
+            traceback.print_exc()

@@ -48,3 +48,30 @@ def image_grid_config():
     """configs/image/base.json with Testbed::reset_network's per_level_scale for a 512 x 512 image (desired_resolution = 256)."""
     pls = float(np.exp(np.log(np.float32(IMAGE_RES / 2.0) * np.float32(1) / np.float32(16)) / np.float32(15), dtype=np.float32))
     return dict(n_levels=16, log2_hashmap_size=24, base_resolution=16, per_level_scale=pls)
+
+
+# ---- occupancy grid (K16): two cascades, inputs regenerated from seeds; only the reference kernels' outputs are stored ----
+DG_CASCADES = 2
+DG_CELLS = 128 ** 3 * DG_CASCADES
+DG_SAMPLES = 16384
+DG_STEP = 3
+DG_AABB = np.array([-0.5, -0.5, -0.5, 1.5, 1.5, 1.5], np.float32)  # aabb_scale 2
+
+
+def density_grid_inputs(seed=2024):
+    """grid_in: 4 % of the cells above the occupancy threshold, 10 % marked untrained (-1), the rest small (the shape of a trained grid);
+    density: fp16 network outputs (logits) for the DG_SAMPLES sampled cells."""
+    rs = np.random.RandomState(seed)
+    u = rs.rand(DG_CELLS)
+    grid = (rs.rand(DG_CELLS) * 0.004).astype(np.float32)
+    grid[u < 0.04] = (0.01 + rs.rand(int((u < 0.04).sum())) * 0.5).astype(np.float32)
+    grid[u > 0.90] = -1.0
+    density = (rs.randn(DG_SAMPLES) * 3.0).astype(np.float16)
+    return np.ascontiguousarray(grid), density
+
+
+def density_grid_cameras():
+    """The 8-camera 64 x 64 synthetic scene of the other goldens (mark_untrained needs poses and intrinsics only)."""
+    import synthetic
+    scene = synthetic.make_lego_scene(8, 64, device="cpu", seed=0)
+    return scene
