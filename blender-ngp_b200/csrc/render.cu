@@ -134,7 +134,7 @@ struct DeviceScratch {
 		return p;
 	}
 };
-static thread_local DeviceScratch g_blender_ws;
+static thread_local DeviceScratch g_blender_ws, g_blender_masks;
 
 static uint32_t render_max_hops() { static const uint32_t h = [] { const char* e = std::getenv("NGPB_RENDER_HOPS"); return e ? (uint32_t)std::atoi(e) : 24u; }(); return h; }
 static bool empty_space_blocks() { static const bool on = [] { const char* e = std::getenv("NGPB_RENDER_BLOCK_SKIP"); return !e || std::atoi(e) != 0; }(); return on; }
@@ -391,9 +391,38 @@ __global__ void __launch_bounds__(256) render_accumulate_kernel(const uint32_t n
 	accumulate_buffer[i] = tmp;
 }
 
-// tonemap_kernel (render_buffer.cu:540-567) with ETonemapCurve::Identity, writing linear memory instead of a CUDA surface
+// tonemap(x, curve) (render_buffer.cu:272-329): identity, or a rational polynomial (ACES, Hable) / luminance (Reinhard) curve on the clamped colour
+__device__ __forceinline__ void tonemap_curve(float c[3], const int curve) {
+	if (curve == NGPB_TONEMAP_IDENTITY) return;
+	#pragma unroll
+	for (int k = 0; k < 3; ++k) c[k] = fmaxf(c[k], 0.f);
+	float k0, k1, k2, k3, k4, k5;
+	if (curve == NGPB_TONEMAP_ACES) {
+		k0 = 0.6f * 0.6f * 2.51f; k1 = 0.6f * 0.03f; k2 = 0.0f; k3 = 0.6f * 0.6f * 2.43f; k4 = 0.6f * 0.59f; k5 = 0.14f;
+	} else if (curve == NGPB_TONEMAP_HABLE) {
+		const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
+		k0 = A * F - A * E; k1 = C * B * F - B * E; k2 = 0.0f; k3 = A * F; k4 = B * F; k5 = D * F * F;
+		const float W = 11.2f;
+		const float nom = k0 * (W * W) + k1 * W + k2, denom = k3 * (W * W) + k4 * W + k5;
+		const float white_scale = denom / nom;
+		k0 = 4.0f * k0 * white_scale; k1 = 2.0f * k1 * white_scale; k2 = k2 * white_scale; k3 = 4.0f * k3; k4 = 2.0f * k4;
+	} else { // Reinhard
+		const float Y = sum3(0.2126f * c[0], 0.7152f * c[1], 0.0722f * c[2]);
+		const float s = 1.f / (Y + 1.0f);
+		#pragma unroll
+		for (int k = 0; k < 3; ++k) c[k] = c[k] * s;
+		return;
+	}
+	#pragma unroll
+	for (int k = 0; k < 3; ++k) {
+		const float sq = c[k] * c[k];
+		c[k] = (sq * k0 + k1 * c[k] + k2) / (k3 * sq + k4 * c[k] + k5);
+	}
+}
+
+// tonemap_kernel (render_buffer.cu:540-567), writing linear memory instead of a CUDA surface
 __global__ void __launch_bounds__(256) render_tonemap_kernel(const uint32_t n_pixels, const float exposure_scale, float4 background_color, const float4* __restrict__ accumulate_buffer,
-                                                             const int color_space, const int output_srgb, float4* __restrict__ out)
+                                                             const int color_space, const int output_srgb, const int curve, float4* __restrict__ out)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n_pixels) return;
@@ -406,12 +435,15 @@ __global__ void __launch_bounds__(256) render_tonemap_kernel(const uint32_t n_pi
 	color.w += weight;
 	float c[3] = {color.x, color.y, color.z};
 	#pragma unroll
-	for (int k = 0; k < 3; ++k) {
+	for (int k = 0; k < 3; ++k) { // 1. to linear, 2. exposure (render_buffer.cu:331-339)
 		float v = c[k];
 		if (color_space == NGPB_COLOR_SRGB) v = srgb_to_linear(v);
-		v *= exposure_scale;
-		if (output_srgb) v = linear_to_srgb(v);
-		c[k] = v;
+		c[k] = v * exposure_scale;
+	}
+	tonemap_curve(c, curve);      // 3. the curve, in linear space
+	if (output_srgb) {            // 4. to the output colour space
+		#pragma unroll
+		for (int k = 0; k < 3; ++k) c[k] = linear_to_srgb(c[k]);
 	}
 	out[i] = make_float4(c[0], c[1], c[2], color.w);
 }
@@ -525,7 +557,8 @@ extern "C" int ngpb_render_nerf(void* stream_, const ngpb_render_config* cfg, co
 			NGPB_LAUNCH_CHECK(); ++launches;
 		}
 		render_tonemap_kernel<<<div_round_up(n_pixels, 256), 256, 0, stream>>>(n_pixels, powf(2.0f, cfg->exposure),
-			make_float4(cfg->background_color[0], cfg->background_color[1], cfg->background_color[2], cfg->background_color[3]), accum, cfg->color_space, cfg->output_srgb, out);
+			make_float4(cfg->background_color[0], cfg->background_color[1], cfg->background_color[2], cfg->background_color[3]), accum, cfg->color_space, cfg->output_srgb,
+			cfg->tonemap_curve, out);
 		NGPB_LAUNCH_CHECK(); ++launches;
 		NGPB_CUDA_CHECK(cudaMemcpyAsync(host_frame, out, (size_t)n_pixels * 16, cudaMemcpyDeviceToHost, stream));
 		NGPB_CUDA_CHECK(cudaMemcpyAsync(host_counter, counters + 2, 8, cudaMemcpyDeviceToHost, stream));
@@ -554,8 +587,13 @@ namespace ngpb {
 
 struct BlGlobalRay { float o[3]; uint32_t idx; float d[3]; uint32_t alive; float rgba[4]; };
 struct BlProxyRay { float o[3]; float t; float d[3]; uint32_t n_steps; uint32_t alive, active; uint32_t pad[2]; };
+// Mask3D on the device (nerf/mask_3D.cuh:128-257): only the inverse transform is needed
+struct BlMask { int32_t shape, mode; float itransform[16]; float config[6]; float feather, opacity; };
+enum { MASK_BOX = 0, MASK_CYLINDER = 1, MASK_SPHERE = 2, MASK_ALL = 3, MASK_ADD = 0, MASK_SUBTRACT = 1 };
 struct BlNerfProps {
 	float transform[16], itransform[16]; // column-major
+	const BlMask* masks;                 // [All(opposite of the first mask's mode)] + the NeRF's own masks + the request's masks in local space (render_modifiers.cuh:28-62)
+	uint32_t n_masks, pad_;
 	const uint8_t* bitfield;
 	const uint32_t* coarse; // one bit per 8^3 block of occupancy cells (see hop_over_empty), or null
 	Aabb render_aabb, train_aabb;
@@ -565,6 +603,8 @@ struct BlNerfProps {
 struct BlRequest {
 	int32_t width, height, skip, scaled_w, scaled_h, flip_y;
 	float cam[12], focal_length, near_distance, offset[2];
+	int32_t camera_model;
+	float aperture_size, focus_z, sq[3], qh[24];
 };
 constexpr uint32_t BL_MAX_NERFS = 16;
 
@@ -579,6 +619,160 @@ __device__ __forceinline__ V3 normalized3(const V3& v) {
 	const float z = sum3(v.x * v.x, v.y * v.y, v.z * v.z);
 	if (z > 0.f) { const float n = sqrtf(z); return {v.x / n, v.y / n, v.z / n}; }
 	return v;
+}
+
+// ---- Mask3D (nerf/mask_3D.cuh) ----
+__device__ __forceinline__ float mask_signed_distance(const BlMask& m, const V3& p) { // signed_distance_to_point, :162-183
+	const V3 q = xform_point(m.itransform, p);
+	float d = 0.0f;
+	if (m.shape == MASK_BOX) { // sdf_box :31-34
+		const float dx = fabsf(q.x) - 0.5f * m.config[0], dy = fabsf(q.y) - 0.5f * m.config[1], dz = fabsf(q.z) - 0.5f * m.config[2];
+		const float ox = fmaxf(dx, 0.0f), oy = fmaxf(dy, 0.0f), oz = fmaxf(dz, 0.0f);
+		d = sqrtf(sum3(ox * ox, oy * oy, oz * oz)) + fminf(fmaxf(dx, fmaxf(dy, dz)), 0.0f);
+	} else if (m.shape == MASK_CYLINDER) { // sdf_cylinder :36-39: radial distance in xy, half height along z
+		const float dr = fabsf(sqrtf(q.y * q.y + q.x * q.x)) - m.config[0], dh = fabsf(q.z) - 0.5f * m.config[1];
+		const float orr = fmaxf(dr, 0.0f), oh = fmaxf(dh, 0.0f);
+		d = sqrtf(orr * orr + oh * oh) + fminf(fmaxf(dr, dh), 0.0f);
+	} else if (m.shape == MASK_SPHERE) {
+		d = sqrtf(sum3(q.x * q.x, q.y * q.y, q.z * q.z)) - m.config[0];
+	} else {
+		d = -1.0f;
+	}
+	return d * (m.mode == MASK_ADD ? 1.0f : -1.0f);
+}
+__device__ __forceinline__ float mask_sample(const BlMask& m, const V3& p) { // Mask3D::sample :194-213
+	const float k = m.mode == MASK_ADD ? 1.0f : -1.0f;
+	if (m.shape == MASK_ALL) return k;
+	const float d = mask_signed_distance(m, p);
+	const float alpha = m.feather == 0.0f ? (d < 0.0f ? 1.0f : 0.0f) : fminf(fmaxf(0.5f - d / m.feather, 0.0f), 1.0f);
+	return m.opacity * alpha * k;
+}
+__device__ __forceinline__ bool plane_hit(const V3& o, const V3& d, const float nz, const float pz, float* t) { // intersect_plane_ray :74-81 for n = (0, 0, nz), p = (0, 0, pz)
+	const float denom = nz * d.z;
+	if (denom > 1e-6f) { *t = ((pz - o.z) * nz) / denom; return *t >= 0.0f; }
+	return false;
+}
+__device__ __forceinline__ bool mask_intersects_ray(const BlMask& m, const V3& ro, const V3& rd) { // Mask3D::intersects_ray :215-247
+	if (m.mode == MASK_SUBTRACT) return true;
+	if (m.shape == MASK_ALL) return m.mode == MASK_ADD;
+	const V3 o = xform_point(m.itransform, ro);
+	const V3 d = normalized3(xform_dir(m.itransform, rd));
+	if (m.shape == MASK_BOX) { // ray_intersects_box :46-56 with box_dims + 0.5 * feather
+		float tmin_max = -INFINITY, tmax_min = INFINITY;
+		const float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+		#pragma unroll
+		for (int a = 0; a < 3; ++a) {
+			const float size = m.config[a] + 0.5f * m.feather, inv = 1.0f / dd[a];
+			const float t0 = (-0.5f * size - oo[a]) * inv, t1 = (0.5f * size - oo[a]) * inv;
+			tmin_max = fmaxf(tmin_max, fminf(t0, t1)); tmax_min = fminf(tmax_min, fmaxf(t0, t1));
+		}
+		return tmin_max <= tmax_min;
+	}
+	if (m.shape == MASK_SPHERE) { // ray_intersects_sphere :59-63
+		const float radius = m.config[0] + 0.5f * m.feather;
+		const float dot = sum3(d.x * o.x, d.y * o.y, d.z * o.z);
+		const float a = dot * dot, b = sum3(o.x * o.x, o.y * o.y, o.z * o.z) - radius * radius;
+		return !((a - b) < 0.0f);
+	}
+	// ray_intersects_cylinder :83-123
+	const float radius = m.config[0] + 0.5f * m.feather, height = m.config[1] + 0.5f * m.feather;
+	const float a = d.x * d.x + d.y * d.y, b = 2.0f * (d.x * o.x + d.y * o.y), c = (o.x * o.x + o.y * o.y) - radius * radius;
+	const float disc = b * b - 4.0f * a * c;
+	if (disc < 0.0f) return false;
+	const float sq = sqrtf(disc), a2 = 2.0f * a, h2 = 0.5f * height;
+	if (a2 > 1e-6f) {
+		const float t0 = (-b - sq) / a2, t1 = (-b + sq) / a2;
+		const float z0 = o.z + t0 * d.z, z1 = o.z + t1 * d.z;
+		if ((z0 >= -h2 && z0 <= h2) || (z1 >= -h2 && z1 <= h2)) return true;
+	}
+	float t = 0.0f;
+	if (plane_hit(o, d, 1.0f, h2, &t)) { const float px = o.x + t * d.x, py = o.y + t * d.y; if (px * px + py * py <= radius * radius) return true; }
+	if (plane_hit(o, d, -1.0f, -h2, &t)) { const float px = o.x + t * d.x, py = o.y + t * d.y; if (px * px + py * py <= radius * radius) return true; }
+	return false;
+}
+
+// ---- camera models (camera_models.cuh) ----
+__device__ __forceinline__ void ld_random_val_2d_dev(uint32_t index, uint32_t seed, float out[2]) { // random_val.cuh:261-268,:277-281
+	const float S = float(1.0 / (1ull << 32));
+	index = nested_uniform_scramble_base2(index, seed);
+	out[0] = (float)nested_uniform_scramble_base2(sobol_dim(index, 0), hash_combine(seed, 0u)) * S;
+	out[1] = (float)nested_uniform_scramble_base2(sobol_dim(index, 1), hash_combine(seed, 1u)) * S;
+}
+__device__ __forceinline__ void square2disk_shirley(const float a, const float b, float out[2]) { // random_val.cuh:109-125
+	const float PI = 3.14159265358979323846f;
+	float phi, r;
+	if (a * a > b * b) { r = a; phi = (PI / 4.0f) * (b / a); } else { r = b; phi = (PI / 2.0f) - (PI / 4.0f) * (a / b); }
+	float s, c;
+	sincosf(phi, &s, &c);
+	out[0] = r * c; out[1] = r * s;
+}
+// thin-lens blur shared by the three models (:99-104, :196-201, :232-237): sample index 0 ("todo: sample index", nerf_renderer.cu:624)
+__device__ __forceinline__ void apply_depth_of_field(const BlRequest& R, const uint32_t px, const uint32_t py, V3& origin, V3& dir) {
+	if (!(R.aperture_size > 0.0f)) return;
+	const V3 lookat = {origin.x + dir.x * R.focus_z, origin.y + dir.y * R.focus_z, origin.z + dir.z * R.focus_z};
+	float u[2], disk[2];
+	ld_random_val_2d_dev(0u, px * 19349663u + py * 96925573u, u);
+	square2disk_shirley(u[0] * 2.0f - 1.0f, u[1] * 2.0f - 1.0f, disk);
+	const float bx = R.aperture_size * disk[0], by = R.aperture_size * disk[1];
+	origin.x += R.cam[0] * bx + R.cam[3] * by; origin.y += R.cam[1] * bx + R.cam[4] * by; origin.z += R.cam[2] * bx + R.cam[5] * by;
+	dir = {(lookat.x - origin.x) / R.focus_z, (lookat.y - origin.y) / R.focus_z, (lookat.z - origin.z) / R.focus_z};
+}
+__device__ __forceinline__ V3 cam_rotate(const BlRequest& R, const V3& v) {
+	const float row0[3] = {R.cam[0], R.cam[3], R.cam[6]}, row1[3] = {R.cam[1], R.cam[4], R.cam[7]}, row2[3] = {R.cam[2], R.cam[5], R.cam[8]};
+	const float vv[3] = {v.x, v.y, v.z};
+	return {dot3(row0, vv), dot3(row1, vv), dot3(row2, vv)};
+}
+// pixel -> (origin, un-normalised direction) for the request's camera model (init_global_rays_kernel, nerf_renderer.cu:44-82)
+__device__ __forceinline__ void blender_pixel_to_ray(const BlRequest& R, const uint32_t x, const uint32_t y, V3& origin, V3& dir) {
+	const float W = (float)R.width, H = (float)R.height;
+	if (R.camera_model == NGPB_CAMERA_PERSPECTIVE) { // perspective_pixel_to_ray :205-241
+		const float uvx = ((float)x + R.offset[0]) / W, uvy = ((float)y + R.offset[1]) / H;
+		dir = cam_rotate(R, V3{(uvx - 0.5f) * W / R.focal_length, (uvy - 0.5f) * H / R.focal_length, 1.0f});
+		origin = {R.cam[9], R.cam[10], R.cam[11]};
+	} else if (R.camera_model == NGPB_CAMERA_QUADRILATERAL_HEXAHEDRON) { // quadrilateral_hexahedron_pixel_to_ray :82-110
+		const float ux = ((float)x + 0.5f) / W, uy = ((float)y + 0.5f) / H;
+		const float* q = R.qh;
+		float fp[3], bp[3];
+		#pragma unroll
+		for (int k = 0; k < 3; ++k) {
+			const float f_ab = q[0 + k] + ux * (q[3 + k] - q[0 + k]), f_dc = q[6 + k] + ux * (q[9 + k] - q[6 + k]);
+			fp[k] = f_ab + uy * (f_dc - f_ab);
+			const float b_ab = q[12 + k] + ux * (q[15 + k] - q[12 + k]), b_dc = q[18 + k] + ux * (q[21 + k] - q[18 + k]);
+			bp[k] = b_ab + uy * (b_dc - b_ab);
+		}
+		V3 d = {fp[0] - bp[0], fp[1] - bp[1], fp[2] - bp[2]};
+		d = {d.x / d.z, d.y / d.z, d.z / d.z};
+		const V3 o = cam_rotate(R, V3{bp[0], bp[1], bp[2]});
+		origin = {o.x + R.cam[9], o.y + R.cam[10], o.z + R.cam[11]};
+		dir = cam_rotate(R, d);
+	} else { // spherical_quadrilateral_pixel_to_ray :159-203
+		const float PI = 3.14159265358979323846f;
+		const float sw = R.sq[0], sh = R.sq[1], curvature = R.sq[2];
+		const float max_len = sqrtf(sw * sw + sh * sh);
+		const float ux = 2.0f * (((float)x + 0.5f) / W - 0.5f), uy = 2.0f * (((float)y + 0.5f) / H - 0.5f);
+		const float px = sw * ux, py = sh * uy;
+		const float az = atan2f(py, px), r = sqrtf(px * px + py * py);
+		// walk_along_sphere / walk_along_circle :137-157
+		float rz0 = 0.0f, rz1 = 0.0f;
+		const float arc_t = r / (2.0f * max_len);
+		if (!(arc_t == 0.0f || max_len == 0.0f)) {
+			if (curvature == 0.0f) { rz0 = max_len * arc_t; }
+			else { const float tpc = 2.0f * PI * curvature, s_tpc = max_len / tpc; rz0 = s_tpc * sinf(tpc * arc_t); rz1 = s_tpc * (1.0f - cosf(tpc * arc_t)); }
+		}
+		const V3 o_local = {rz0 * cosf(az), rz0 * sinf(az), rz1};
+		V3 d_local = {0.0f, 0.0f, 1.0f};
+		if (curvature != 0.0f) {
+			const V3 to_center = {0.0f - o_local.x, 0.0f - o_local.y, max_len / (2.0f * PI * curvature) - o_local.z};
+			const V3 n = normalized3(to_center);
+			const float k = curvature > 0.0f ? 1.0f : -1.0f;
+			d_local = {k * n.x, k * n.y, k * n.z};
+		}
+		const V3 o = cam_rotate(R, o_local);
+		origin = {o.x + R.cam[9], o.y + R.cam[10], o.z + R.cam[11]};
+		dir = cam_rotate(R, d_local);
+	}
+	apply_depth_of_field(R, x, y, origin, dir);
+	origin = {origin.x + dir.x * R.near_distance, origin.y + dir.y * R.near_distance, origin.z + dir.z * R.near_distance};
 }
 
 // hit_test_and_march (:149-211), no masks: advances t to the next sample position inside an occupied cell; false = left the NeRF's render box
@@ -605,11 +799,8 @@ __global__ void __launch_bounds__(128) bl_init_rays_kernel(const BlRequest R, co
 	const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
 	if (idx >= (uint32_t)R.scaled_w * (uint32_t)R.scaled_h) return;
 	const uint32_t x = (idx % (uint32_t)R.scaled_w) * R.skip, y = (idx / (uint32_t)R.scaled_w) * R.skip;
-	const float uvx = ((float)x + R.offset[0]) / (float)R.width, uvy = ((float)y + R.offset[1]) / (float)R.height;
-	const float dcam[3] = {(uvx - 0.5f) * (float)R.width / R.focal_length, (uvy - 0.5f) * (float)R.height / R.focal_length, 1.0f};
-	const float row0[3] = {R.cam[0], R.cam[3], R.cam[6]}, row1[3] = {R.cam[1], R.cam[4], R.cam[7]}, row2[3] = {R.cam[2], R.cam[5], R.cam[8]};
-	const V3 dw = {dot3(row0, dcam), dot3(row1, dcam), dot3(row2, dcam)};
-	const V3 go = {R.cam[9] + dw.x * R.near_distance, R.cam[10] + dw.y * R.near_distance, R.cam[11] + dw.z * R.near_distance};
+	V3 go, dw;
+	blender_pixel_to_ray(R, x, y, go, dw);
 	const V3 gd = normalized3(dw);
 	BlGlobalRay g;
 	g.o[0] = go.x; g.o[1] = go.y; g.o[2] = go.z; g.d[0] = gd.x; g.d[1] = gd.y; g.d[2] = gd.z;
@@ -625,7 +816,9 @@ __global__ void __launch_bounds__(128) bl_init_rays_kernel(const BlRequest R, co
 		const float t = fmaxf(tmin, 0.0f) + 1e-5f;
 		p.d[0] = d.x; p.d[1] = d.y; p.d[2] = d.z;
 		if (aabb_contains(P.render_aabb, V3{o.x + d.x * t, o.y + d.y * t, o.z + d.z * t})) {
-			p.active = 1u; p.alive = 1u; p.t = 0.0f; p.n_steps = 0;
+			bool hits_a_mask = P.n_masks == 0; // a NeRF with masks is only traced by rays that cross one of them (:127-140)
+			for (uint32_t k = 0; k < P.n_masks && !hits_a_mask; ++k) hits_a_mask = mask_intersects_ray(P.masks[k], o, d);
+			p.active = 1u; p.alive = hits_a_mask ? 1u : 0u; p.t = 0.0f; p.n_steps = 0;
 			p.o[0] = o.x + t * d.x; p.o[1] = o.y + t * d.y; p.o[2] = o.z + t * d.z;
 		}
 		proxies[(size_t)n * stride + idx] = p;
@@ -748,6 +941,12 @@ __global__ void __launch_bounds__(128) bl_composite_kernel(const uint32_t n_aliv
 				const float dt = unwarp_dt(c[j * COORD_FLOATS + 3]);
 				const float alpha = 1.f - __expf(-network_to_density(__high2float(h23), P.density_activation) * dt);
 				float weight = alpha * T;
+				if (P.n_masks) { // masks add / subtract visibility at the sample's position in the NeRF's frame (:490-496)
+					const V3 pos = unwarp_position(c + j * COORD_FLOATS, P.train_aabb);
+					float mask_weight = 1.f;
+					for (uint32_t k = 0; k < P.n_masks; ++k) mask_weight = fminf(fmaxf(mask_weight + mask_sample(P.masks[k], pos), 0.0f), 1.0f);
+					weight *= mask_weight;
+				}
 				weight *= P.opacity;
 				local.x += network_to_rgb(__low2float(h01), P.rgb_activation) * weight;
 				local.y += network_to_rgb(__high2float(h01), P.rgb_activation) * weight;
@@ -853,11 +1052,46 @@ static bool invert4(const float* a, float* out) { // Gauss-Jordan with partial p
 	return true;
 }
 
+static void mul4(const float* a, const float* b, float* out) { // column-major out = a * b
+	for (int c = 0; c < 4; ++c) for (int r = 0; r < 4; ++r) {
+		float v = 0.f;
+		for (int k = 0; k < 4; ++k) v += a[k * 4 + r] * b[c * 4 + k];
+		out[c * 4 + r] = v;
+	}
+}
+
+// The device mask list of one NeRF (RenderModifiers, nerf/render_modifiers.cuh:28-62): the NeRF's own masks, then the request's masks brought into the
+// NeRF's frame (Mask3D::transformed_by(itransform)), and in front of them an `All` mask of the opposite mode of the first one, so that a list starting
+// with an Add mask begins from "nothing visible" and one starting with a Subtract mask from "everything visible".
+static void build_mask_list(const ngpb_nerf_instance& in, const float* nerf_itransform, const ngpb_blender_request* rq, std::vector<BlMask>& out) {
+	auto push = [&](const ngpb_mask& m, const float* to_local) {
+		if (m.shape < MASK_BOX || m.shape > MASK_ALL || (m.mode != MASK_ADD && m.mode != MASK_SUBTRACT)) throw std::runtime_error("ngpb_blender_render: invalid mask shape or mode");
+		BlMask d{};
+		d.shape = m.shape; d.mode = m.mode; d.feather = m.feather; d.opacity = m.opacity;
+		std::memcpy(d.config, m.config, sizeof(d.config));
+		float t[16];
+		if (to_local) mul4(to_local, m.transform, t); else std::memcpy(t, m.transform, 64);
+		if (!invert4(t, d.itransform)) throw std::runtime_error("ngpb_blender_render: singular mask transform");
+		out.push_back(d);
+	};
+	const size_t first = out.size();
+	if (in.n_masks && !in.masks) throw std::runtime_error("ngpb_blender_render: mask count without masks");
+	for (uint32_t k = 0; k < in.n_masks; ++k) push(in.masks[k], nullptr);
+	for (uint32_t k = 0; k < rq->n_masks; ++k) push(rq->masks[k], nerf_itransform);
+	if (out.size() > first && out[first].shape != MASK_ALL) {
+		BlMask all{};
+		all.shape = MASK_ALL; all.mode = out[first].mode == MASK_ADD ? MASK_SUBTRACT : MASK_ADD; all.opacity = 1.0f;
+		for (int k = 0; k < 4; ++k) all.itransform[k * 5] = 1.0f;
+		out.insert(out.begin() + first, all);
+	}
+}
+
 extern "C" int ngpb_blender_render(void* stream_, const ngpb_blender_request* rq, uint32_t n_nerfs, const ngpb_nerf_instance* nerfs, float* out_rgba_host,
                                    uint64_t* n_samples_out, uint32_t* n_launches_out) {
 	uint8_t* ws = nullptr;
 	try {
-		if (!rq || !out_rgba_host || rq->width <= 0 || rq->height <= 0 || rq->mip < 0 || rq->mip > 12 || n_nerfs > BL_MAX_NERFS || (n_nerfs && !nerfs)) {
+		if (!rq || !out_rgba_host || rq->width <= 0 || rq->height <= 0 || rq->mip < 0 || rq->mip > 12 || n_nerfs > BL_MAX_NERFS || (n_nerfs && !nerfs) || (rq->n_masks && !rq->masks) ||
+			rq->camera_model < NGPB_CAMERA_PERSPECTIVE || rq->camera_model > NGPB_CAMERA_SPHERICAL_QUADRILATERAL || rq->tonemap_curve < NGPB_TONEMAP_IDENTITY || rq->tonemap_curve > NGPB_TONEMAP_REINHARD) {
 			set_last_error("ngpb_blender_render: invalid argument");
 			return NGPB_ERR_INVALID_ARGUMENT;
 		}
@@ -867,6 +1101,8 @@ extern "C" int ngpb_blender_render(void* stream_, const ngpb_blender_request* rq
 		R.scaled_w = (rq->width + R.skip - 1) / R.skip; R.scaled_h = (rq->height + R.skip - 1) / R.skip;
 		for (int k = 0; k < 12; ++k) R.cam[k] = rq->camera[k];
 		R.focal_length = rq->focal_length; R.near_distance = rq->near_distance;
+		R.camera_model = rq->camera_model; R.aperture_size = rq->aperture_size; R.focus_z = rq->focus_z;
+		std::memcpy(R.sq, rq->spherical_quadrilateral, sizeof(R.sq)); std::memcpy(R.qh, rq->quadrilateral_hexahedron, sizeof(R.qh));
 		ld_random_pixel_offset(0u, R.offset); // sample index 0 ("todo: sample index", :624)
 		const uint32_t n_pixels = (uint32_t)rq->width * (uint32_t)rq->height, n_init = (uint32_t)R.scaled_w * (uint32_t)R.scaled_h;
 		const uint32_t max_steps = 8, nn = std::max(n_nerfs, 1u);
@@ -891,12 +1127,23 @@ extern "C" int ngpb_blender_render(void* stream_, const ngpb_blender_request* rq
 		BlNerfProps* props_dev = (BlNerfProps*)(ws + o_props);
 		uint32_t* counters = (uint32_t*)(ws + o_cnt);
 		std::vector<BlNerfProps> props(nn);
+		std::vector<BlMask> masks_host;
+		std::vector<uint32_t> mask_first(nn + 1, 0u);
+		for (uint32_t n = 0; n < n_nerfs; ++n) {
+			float it[16];
+			if (!invert4(nerfs[n].transform, it)) throw std::runtime_error("ngpb_blender_render: singular NeRF transform");
+			build_mask_list(nerfs[n], it, rq, masks_host);
+			mask_first[n + 1] = (uint32_t)masks_host.size();
+		}
+		BlMask* masks_dev = reinterpret_cast<BlMask*>(g_blender_masks.get(std::max<size_t>(masks_host.size(), 1) * sizeof(BlMask)));
+		if (!masks_host.empty()) NGPB_CUDA_CHECK(cudaMemcpyAsync(masks_dev, masks_host.data(), masks_host.size() * sizeof(BlMask), cudaMemcpyHostToDevice, stream));
 		for (uint32_t n = 0; n < n_nerfs; ++n) {
 			const ngpb_nerf_instance& in = nerfs[n];
 			if (!in.field) throw std::runtime_error("ngpb_blender_render: NeRF without a field");
 			BlNerfProps& P = props[n];
 			std::memcpy(P.transform, in.transform, 64);
 			if (!invert4(in.transform, P.itransform)) throw std::runtime_error("ngpb_blender_render: singular NeRF transform");
+			P.masks = masks_dev + mask_first[n]; P.n_masks = mask_first[n + 1] - mask_first[n];
 			P.bitfield = in.field->bitfield;
 			P.coarse = nullptr;
 			if (empty_space_blocks()) {
@@ -951,7 +1198,7 @@ extern "C" int ngpb_blender_render(void* stream_, const ngpb_blender_request* rq
 		render_accumulate_kernel<<<div_round_up(n_pixels, 256), 256, 0, stream>>>(n_pixels, frame, accum, 0.0f, rq->color_space);
 		render_tonemap_kernel<<<div_round_up(n_pixels, 256), 256, 0, stream>>>(n_pixels, powf(2.0f, rq->exposure),
 			make_float4(rq->background_color[0], rq->background_color[1], rq->background_color[2], rq->background_color[3]), accum, rq->color_space,
-			rq->color_space == NGPB_COLOR_SRGB ? 1 : 0, out);
+			rq->color_space == NGPB_COLOR_SRGB ? 1 : 0, rq->tonemap_curve, out);
 		NGPB_LAUNCH_CHECK(); launches += 2;
 		NGPB_CUDA_CHECK(cudaMemcpyAsync(host_frame, out, (size_t)n_pixels * 16, cudaMemcpyDeviceToHost, stream));
 		NGPB_CUDA_CHECK(cudaMemcpyAsync(host_counter, counters + 2, 8, cudaMemcpyDeviceToHost, stream));

@@ -1082,6 +1082,7 @@ extern "C" int ngpb_testbed_set_option(ngpb_testbed* t, const char* name, double
 	else if (k == "render_snap_to_pixel_centers") t->render_snap_to_pixel_centers = v != 0;
 	else if (k == "render_near_distance") t->render_near_distance = (float)v;
 	else if (k == "exposure") t->exposure = (float)v;
+	else if (k == "tonemap_curve") { if (v < 0 || v > 3) throw std::runtime_error("tonemap_curve must be one of Identity, ACES, Hable, Reinhard"); t->tonemap_curve = (int)v; }
 	else if (k == "background_color_a") t->background_alpha = (float)v;
 	else if (k == "render_with_training_params") t->render_with_training_params = v != 0;
 	else if (k == "dp_sharded_optimizer") t->dp_sharded_optimizer = v != 0;
@@ -1119,6 +1120,7 @@ extern "C" double ngpb_testbed_get_option(ngpb_testbed* t, const char* name) {
 	if (k == "render_snap_to_pixel_centers") return t->render_snap_to_pixel_centers;
 	if (k == "render_near_distance") return t->render_near_distance;
 	if (k == "exposure") return t->exposure;
+	if (k == "tonemap_curve") return t->tonemap_curve;
 	if (k == "background_color_r") return t->loss_cfg.background_color[0];
 	if (k == "background_color_g") return t->loss_cfg.background_color[1];
 	if (k == "background_color_b") return t->loss_cfg.background_color[2];
@@ -1153,7 +1155,7 @@ void ngpb_testbed::render(const float* camera12, int w, int h, float fx, float f
 	c.cone_angle_constant = cone_angle_constant; c.min_transmittance = render_min_transmittance; c.near_distance = render_near_distance;
 	c.rgb_activation = loss_cfg.rgb_activation; c.density_activation = loss_cfg.density_activation; c.train_in_linear_colors = loss_cfg.linear_colors;
 	c.color_space = loss_cfg.color_space; c.output_srgb = linear ? 0 : 1;
-	c.exposure = exposure;
+	c.exposure = exposure; c.tonemap_curve = tonemap_curve;
 	for (int k = 0; k < 3; ++k) c.background_color[k] = loss_cfg.background_color[k];
 	c.background_color[3] = background_alpha;
 	// the prefetched sampling kernels of the next training step share no buffer with the render path; the main stream orders the rest

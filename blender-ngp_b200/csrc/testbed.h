@@ -115,6 +115,7 @@ struct ngpb_testbed {
 	// render state (testbed.h:547,:853,:875,:889)
 	int render_snap_to_pixel_centers = 0;
 	float render_near_distance = 0.f, exposure = 0.f, background_alpha = 1.0f;
+	int tonemap_curve = NGPB_TONEMAP_IDENTITY; // m_tonemap_curve, testbed.h:847
 	bool render_with_training_params = false;
 	void* render_ws = nullptr; size_t render_ws_bytes = 0;
 	double last_render_ms = 0.0;

@@ -53,17 +53,29 @@ class ColorSpace(enum.IntEnum):  # common.h:129-133
 NGPB_MAX_LEVELS = 32
 
 
-class TonemapCurve(enum.IntEnum):  # common.h ETonemapCurve; only Identity is built
+class TonemapCurve(enum.IntEnum):  # common.h:136-141 ETonemapCurve
     Identity = 0
     ACES = 1
     Hable = 2
     Reinhard = 3
 
 
-class CameraModel(enum.IntEnum):  # common.h ECameraModel; only Perspective is built
+class CameraModel(enum.IntEnum):  # camera_models.cuh:27-31 ECameraModel (integer values as declared there)
     Perspective = 0
-    SphericalQuadrilateral = 1
-    QuadrilateralHexahedron = 2
+    QuadrilateralHexahedron = 1
+    SphericalQuadrilateral = 2
+
+
+class MaskMode(enum.IntEnum):  # nerf/mask_3D.cuh:16-19
+    Add = 0
+    Subtract = 1
+
+
+class MaskShape(enum.IntEnum):  # nerf/mask_3D.cuh:21-26
+    Box = 0
+    Cylinder = 1
+    Sphere = 2
+    All = 3
 
 
 # ---- value types of the Blender render request (python_api.cu:409-538; nerf/render_request.cuh, nerf/nerf_descriptor.cuh, bounding_box.cuh) ----
@@ -114,20 +126,68 @@ class DownsampleInfo:
 
 
 class Mask3D:
-    """Render masks are outside the built scope: constructing one raises, so a request that needs them fails loudly rather than rendering unmasked."""
+    """Mask3D (nerf/mask_3D.cuh:128-257; python_api.cu:446-450): an SDF shape that adds or subtracts visibility inside a NeRF, with a feathered border.
+    `transform`: 4x4 shape -> NeRF-local frame (masks of a NerfDescriptor) or shape -> world (masks of a RenderRequest)."""
+
+    def __init__(self, shape, transform, mode, config, feather, opacity):
+        self.shape, self.mode = MaskShape(int(shape)), MaskMode(int(mode))
+        self.transform = np.asarray(transform, np.float32).reshape(4, 4).copy()
+        self.config = [float(v) for v in config] + [0.0] * (6 - len(config))
+        self.feather, self.opacity = float(feather), float(opacity)
 
     @staticmethod
-    def _unbuilt(*a, **k):
-        raise RuntimeError("render masks (Mask3D) are outside the built scope")
+    def Box(dims, transform, mode, feather, opacity):
+        d = np.asarray(dims, np.float32).reshape(3)
+        return Mask3D(MaskShape.Box, transform, mode, [d[0], d[1], d[2]], feather, opacity)
 
-    Box = Cylinder = Sphere = _unbuilt
+    @staticmethod
+    def Cylinder(radius, height, transform, mode, feather, opacity):
+        return Mask3D(MaskShape.Cylinder, transform, mode, [radius, height], feather, opacity)
+
+    @staticmethod
+    def Sphere(radius, transform, mode, feather, opacity):
+        return Mask3D(MaskShape.Sphere, transform, mode, [radius], feather, opacity)
 
 
-class RenderModifiers:
+class RenderModifiers:  # RenderModifiersDescriptor (nerf/render_modifiers_descriptor.cuh; python_api.cu:472-474)
     def __init__(self, masks=()):
-        if len(masks):
-            raise RuntimeError("render masks are outside the built scope")
-        self.masks = []
+        self.masks = list(masks)
+        for m in self.masks:
+            if not isinstance(m, Mask3D):
+                raise TypeError("RenderModifiers: masks must be Mask3D objects")
+
+
+class Quadrilateral3D:  # camera_models.cuh:33-58
+    def __init__(self, tl, tr, bl, br):
+        self.tl, self.tr, self.bl, self.br = (np.asarray(v, np.float32).reshape(3).copy() for v in (tl, tr, bl, br))
+
+    @staticmethod
+    def Zero():
+        return Quadrilateral3D(*([np.zeros(3, np.float32)] * 4))
+
+    def center(self):
+        return (self.tl + self.tr + self.bl + self.br) / np.float32(4.0)
+
+
+class QuadrilateralHexahedronConfig:  # QuadrilateralHexahedron, camera_models.cuh:60-80
+    def __init__(self, front, back):
+        self.front, self.back = front, back
+
+    @staticmethod
+    def Zero():
+        return QuadrilateralHexahedronConfig(Quadrilateral3D.Zero(), Quadrilateral3D.Zero())
+
+    def center(self):
+        return (self.front.center() + self.back.center()) / np.float32(2.0)
+
+
+class SphericalQuadrilateralConfig:  # SphericalQuadrilateral, camera_models.cuh:119-135
+    def __init__(self, width, height, curvature):
+        self.width, self.height, self.curvature = float(width), float(height), float(curvature)
+
+    @staticmethod
+    def Zero():
+        return SphericalQuadrilateralConfig(0.0, 0.0, 0.0)
 
 
 class RenderOutputProperties:
@@ -162,13 +222,34 @@ class RenderRequest:
         self.output, self.camera, self.modifiers, self.nerfs, self.aabb = output, camera, modifiers, list(nerfs), aabb
 
 
+class MaskStruct(C.Structure):  # ngpb_mask
+    _fields_ = [("shape", C.c_int32), ("mode", C.c_int32), ("transform", C.c_float * 16), ("config", C.c_float * 6), ("feather", C.c_float), ("opacity", C.c_float)]
+
+
 class NerfInstance(C.Structure):  # ngpb_nerf_instance
-    _fields_ = [("field", C.c_void_p), ("aabb", C.c_float * 6), ("transform", C.c_float * 16), ("opacity", C.c_float)]
+    _fields_ = [("field", C.c_void_p), ("aabb", C.c_float * 6), ("transform", C.c_float * 16), ("opacity", C.c_float), ("n_masks", C.c_uint32), ("masks", C.POINTER(MaskStruct))]
 
 
 class BlenderRequest(C.Structure):  # ngpb_blender_request
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("mip", C.c_int32), ("flip_y", C.c_int32), ("camera", C.c_float * 12),
-                ("focal_length", C.c_float), ("near_distance", C.c_float), ("color_space", C.c_int32), ("exposure", C.c_float), ("background_color", C.c_float * 4)]
+                ("focal_length", C.c_float), ("near_distance", C.c_float), ("color_space", C.c_int32), ("exposure", C.c_float), ("background_color", C.c_float * 4),
+                ("camera_model", C.c_int32), ("aperture_size", C.c_float), ("focus_z", C.c_float), ("spherical_quadrilateral", C.c_float * 3),
+                ("quadrilateral_hexahedron", C.c_float * 24), ("tonemap_curve", C.c_int32), ("n_masks", C.c_uint32), ("masks", C.POINTER(MaskStruct))]
+
+
+def _mask_array(masks):
+    """ctypes array of ngpb_mask for a list of Mask3D (None for an empty list)."""
+    if not masks:
+        return None
+    arr = (MaskStruct * len(masks))()
+    for a, m in zip(arr, masks):
+        a.shape, a.mode, a.feather, a.opacity = int(m.shape), int(m.mode), m.feather, m.opacity
+        t = m.transform.T.reshape(-1)
+        for k in range(16):
+            a.transform[k] = float(t[k])
+        for k in range(6):
+            a.config[k] = m.config[k]
+    return arr
 
 
 class Field:
@@ -238,7 +319,7 @@ class RenderConfig(C.Structure):  # ngpb_render_config
                 ("spp", C.c_int32), ("snap_to_pixel_centers", C.c_int32), ("aabb", C.c_float * 6), ("render_aabb", C.c_float * 6),
                 ("cone_angle_constant", C.c_float), ("min_transmittance", C.c_float), ("near_distance", C.c_float),
                 ("rgb_activation", C.c_int32), ("density_activation", C.c_int32), ("train_in_linear_colors", C.c_int32),
-                ("color_space", C.c_int32), ("output_srgb", C.c_int32), ("exposure", C.c_float), ("background_color", C.c_float * 4)]
+                ("color_space", C.c_int32), ("output_srgb", C.c_int32), ("exposure", C.c_float), ("background_color", C.c_float * 4), ("tonemap_curve", C.c_int32)]
 
 
 class TrainingState(C.Structure):  # ngpb_training_state
@@ -786,14 +867,7 @@ class Testbed:
         """Testbed::want_repl (python_api.cu): a GUI key binding; headless sessions never ask for one."""
         return False
 
-    @property
-    def tonemap_curve(self):  # m_tonemap_curve (testbed.h): only the identity curve is built
-        return TonemapCurve.Identity
-
-    @tonemap_curve.setter
-    def tonemap_curve(self, v):
-        if TonemapCurve(int(v)) != TonemapCurve.Identity:
-            raise RuntimeError("only TonemapCurve.Identity is built")
+    tonemap_curve = property(lambda s: TonemapCurve(int(s._get("tonemap_curve"))), lambda s, v: s._set("tonemap_curve", int(TonemapCurve(int(v)))))  # m_tonemap_curve (testbed.h:847)
 
     shall_train = property(lambda s: bool(s._get("shall_train")), lambda s, v: s._set("shall_train", 1.0 if v else 0.0))
     training_step = property(lambda s: int(lib().ngpb_testbed_training_step(s._h)))
@@ -968,12 +1042,6 @@ class Testbed:
         result = np.zeros((h, w, 4), np.float32)
         if self.__dict__.get("_currently_rendering", False):
             return result
-        if cam_p.model != CameraModel.Perspective or cam_p.aperture_size != 0.0:
-            raise RuntimeError("only the perspective camera without depth of field is built for the Blender renderer")
-        if out_p.tonemap_curve != TonemapCurve.Identity:
-            raise RuntimeError("only TonemapCurve.Identity is built")
-        if render_request.modifiers is not None and len(render_request.modifiers.masks):
-            raise RuntimeError("render masks are outside the built scope")
         self._currently_rendering = True
         try:
             fields = self._fields_for(render_request.nerfs)
@@ -985,6 +1053,17 @@ class Testbed:
             rq.focal_length, rq.near_distance, rq.color_space, rq.exposure = cam_p.focal_length, cam_p.near_distance, int(out_p.color_space), out_p.exposure
             for k in range(4):
                 rq.background_color[k] = out_p.background_color[k]
+            rq.camera_model, rq.aperture_size, rq.focus_z, rq.tonemap_curve = int(cam_p.model), cam_p.aperture_size, cam_p.focus_z, int(out_p.tonemap_curve)
+            sq, qh = cam_p.spherical_quadrilateral, cam_p.quadrilateral_hexahedron
+            if sq is not None:
+                rq.spherical_quadrilateral[0], rq.spherical_quadrilateral[1], rq.spherical_quadrilateral[2] = sq.width, sq.height, sq.curvature
+            if qh is not None:
+                flat = np.concatenate([q for quad in (qh.front, qh.back) for q in (quad.tl, quad.tr, quad.bl, quad.br)])
+                for k in range(24):
+                    rq.quadrilateral_hexahedron[k] = float(flat[k])
+            keep = [_mask_array(render_request.modifiers.masks if render_request.modifiers is not None else [])]
+            if keep[0] is not None:
+                rq.n_masks, rq.masks = len(keep[0]), keep[0]
             inst = (NerfInstance * max(1, len(fields)))()
             for i, (d, f) in enumerate(zip(render_request.nerfs, fields)):
                 inst[i].field = f._h
@@ -994,6 +1073,10 @@ class Testbed:
                 for k in range(16):
                     inst[i].transform[k] = float(t[k])
                 inst[i].opacity = d.opacity
+                arr = _mask_array(d.modifiers.masks if d.modifiers is not None else [])
+                if arr is not None:
+                    keep.append(arr)
+                    inst[i].n_masks, inst[i].masks = len(arr), arr
             ns, nl = C.c_uint64(0), C.c_uint32(0)
             check(lib().ngpb_blender_render(C.c_void_p(self.stream or None), C.byref(rq), len(fields), inst, result.ctypes.data_as(C.c_void_p), C.byref(ns), C.byref(nl)))
             self.last_render_samples, self.last_render_launches = int(ns.value), int(nl.value)

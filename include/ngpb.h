@@ -208,6 +208,7 @@ typedef struct {
 	int32_t color_space;        /* m_color_space: the space the accumulation buffer averages in */
 	int32_t output_srgb;        /* !linear argument of Testbed::render */
 	float exposure, background_color[4];
+	int32_t tonemap_curve;      /* NGPB_TONEMAP_* (m_tonemap_curve, testbed.h:847) */
 } ngpb_render_config;
 uint64_t ngpb_render_workspace_bytes(uint32_t n_pixels);
 /* params: half[10240 + grid] (inference = EMA weights for Testbed::render); bitfield: occupancy bits incl. mips; workspace: device memory of
@@ -222,12 +223,23 @@ int ngpb_render_nerf(void* stream, const ngpb_render_config* cfg, const ngpb_gri
 typedef struct ngpb_field ngpb_field;
 int ngpb_field_create(ngpb_field** out, int device, uint32_t aabb_scale, const ngpb_half* params_host, uint32_t n_params, const float* density_grid_host, uint32_t n_cells);
 void ngpb_field_destroy(ngpb_field* f);
+typedef struct {            /* Mask3D (nerf/mask_3D.cuh:128-257): an SDF shape that adds or subtracts visibility, with a feathered border */
+	int32_t shape;          /* EMaskShape: 0 Box (config = dims xyz), 1 Cylinder (radius, height), 2 Sphere (radius), 3 All */
+	int32_t mode;           /* EMaskMode: 0 Add, 1 Subtract */
+	float transform[16];    /* 4x4 shape -> NeRF-local (per-NeRF masks) or shape -> world (request masks), column-major */
+	float config[6];
+	float feather, opacity;
+} ngpb_mask;
 typedef struct {            /* NerfDescriptor (nerf/nerf_descriptor.cuh) */
 	const ngpb_field* field;
 	float aabb[6];          /* render box in the NeRF's local frame */
 	float transform[16];    /* 4x4 local -> world, column-major */
 	float opacity;
+	uint32_t n_masks;       /* NerfDescriptor::modifiers.masks, in the NeRF's local frame (host array) */
+	const ngpb_mask* masks;
 } ngpb_nerf_instance;
+enum { NGPB_CAMERA_PERSPECTIVE = 0, NGPB_CAMERA_QUADRILATERAL_HEXAHEDRON = 1, NGPB_CAMERA_SPHERICAL_QUADRILATERAL = 2 }; /* ECameraModel, camera_models.cuh:27-31 */
+enum { NGPB_TONEMAP_IDENTITY = 0, NGPB_TONEMAP_ACES = 1, NGPB_TONEMAP_HABLE = 2, NGPB_TONEMAP_REINHARD = 3 };                 /* ETonemapCurve, common.h:136-141 */
 typedef struct {            /* RenderRequest: RenderOutputProperties + RenderCameraProperties (nerf/render_request.cuh), perspective camera */
 	int32_t width, height;  /* output resolution */
 	int32_t mip;            /* DownsampleInfo::MakeFromMip(resolution, mip): every 2^mip-th pixel is traced and splatted */
@@ -237,6 +249,13 @@ typedef struct {            /* RenderRequest: RenderOutputProperties + RenderCam
 	float near_distance;
 	int32_t color_space;    /* NGPB_COLOR_* : accumulation and output space */
 	float exposure, background_color[4];
+	int32_t camera_model;   /* NGPB_CAMERA_* (RenderCameraProperties::model) */
+	float aperture_size, focus_z;            /* depth of field: thin-lens blur of the ray origin when aperture_size > 0 (camera_models.cuh:99-104,:196-201,:232-237) */
+	float spherical_quadrilateral[3];        /* width, height, curvature (camera_models.cuh:119-135) */
+	float quadrilateral_hexahedron[24];      /* front tl, tr, bl, br then back tl, tr, bl, br, xyz each (camera_models.cuh:33-80) */
+	int32_t tonemap_curve;  /* NGPB_TONEMAP_* (RenderOutputProperties::tonemap_curve) */
+	uint32_t n_masks;       /* RenderRequest::modifiers.masks, in world space (host array); applied to every NeRF */
+	const ngpb_mask* masks;
 } ngpb_blender_request;
 /* out_rgba_host: float [height][width][4]. Synchronises the stream once per wave (the reference's schedule, :704-705). */
 int ngpb_blender_render(void* stream, const ngpb_blender_request* rq, uint32_t n_nerfs, const ngpb_nerf_instance* nerfs, float* out_rgba_host,

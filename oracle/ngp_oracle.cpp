@@ -1147,6 +1147,27 @@ inline void ld_random_val_2d(uint32_t index, uint32_t seed, float* out) {
 	for (uint32_t i = 0; i < 2; ++i) out[i] = (float)nested_uniform_scramble_base2(sobol(index, i), hash_combine(seed, i)) * S;
 }
 inline float fractf(float x) { return x - std::floor(x); }
+// tonemap(x, curve), src/render_buffer.cu:272-329
+inline void tonemap_curve(float c[3], int curve) {
+	if (curve == 0) return; // Identity
+	for (int k = 0; k < 3; ++k) c[k] = std::fmax(c[k], 0.f);
+	float k0, k1, k2, k3, k4, k5;
+	if (curve == 1) { // ACES
+		k0 = 0.6f * 0.6f * 2.51f; k1 = 0.6f * 0.03f; k2 = 0.0f; k3 = 0.6f * 0.6f * 2.43f; k4 = 0.6f * 0.59f; k5 = 0.14f;
+	} else if (curve == 2) { // Hable
+		const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
+		k0 = A * F - A * E; k1 = C * B * F - B * E; k2 = 0.0f; k3 = A * F; k4 = B * F; k5 = D * F * F;
+		const float W = 11.2f;
+		const float nom = k0 * (W * W) + k1 * W + k2, denom = k3 * (W * W) + k4 * W + k5;
+		const float white_scale = denom / nom;
+		k0 = 4.0f * k0 * white_scale; k1 = 2.0f * k1 * white_scale; k2 = k2 * white_scale; k3 = 4.0f * k3; k4 = 2.0f * k4;
+	} else { // Reinhard
+		const float Y = sum3(0.2126f * c[0], 0.7152f * c[1], 0.0722f * c[2]);
+		for (int k = 0; k < 3; ++k) c[k] = c[k] * (1.f / (Y + 1.0f));
+		return;
+	}
+	for (int k = 0; k < 3; ++k) { const float sq = c[k] * c[k]; c[k] = (sq * k0 + k1 * c[k] + k2) / (k3 * sq + k4 * c[k] + k5); }
+}
 inline void ld_random_pixel_offset(uint32_t spp, float* out) {
 	float a[2], b[2];
 	ld_random_val_2d(0, 0xdeadbeef, a);
@@ -1262,10 +1283,10 @@ extern "C" void orc_render_nerf(const orc_model* m, const orc_half* params, cons
 		for (int k = 0; k < 3; ++k) {
 			float v = color[k];
 			if (c->color_space == 1) v = srgb_to_linear(v);
-			v *= exposure_scale;
-			if (c->output_srgb) v = linear_to_srgb(v);
-			color[k] = v;
+			color[k] = v * exposure_scale;
 		}
+		tonemap_curve(color, c->tonemap_curve);
+		if (c->output_srgb) for (int k = 0; k < 3; ++k) color[k] = linear_to_srgb(color[k]);
 		for (int k = 0; k < 4; ++k) out_rgba[i * 4 + k] = color[k];
 	}
 	if (n_samples_out) *n_samples_out = n_samples_total;
@@ -1278,7 +1299,8 @@ extern "C" void orc_render_nerf(const orc_model* m, const orc_half* params, cons
 //   cull_global_rays_and_set_proxy_rays_active_kernel :376-428, march_proxy_rays_and_generate_next_network_inputs :317-373,
 //   composite_proxy_ray_colors_kernel :431-517, shade_buffer_with_rays_kernel :519-563, the wave loop :661-791,
 //   then Testbed::bl_render_frame (src/testbed.cu:2675-2693): accumulate + tonemap with the request's colour space.
-// Perspective camera, no masks, no depth of field. The result depends on the reference's wave schedule (the nearest live proxy ray is
+// Camera models and depth of field: camera_models.cuh:82-241; masks: nerf/mask_3D.cuh, nerf/render_modifiers.cuh:28-62 (mask list of a NeRF),
+// :127-140 (ray/mask culling at init), :490-496 (mask weight while compositing). The result depends on the reference's wave schedule (the nearest live proxy ray is
 // re-selected once per wave of clamp(n_initial / n_alive, 1, 8) steps), so the waves are followed literally, all rays in lockstep.
 // =============================================================================================
 namespace {
@@ -1329,6 +1351,167 @@ inline bool hit_test_and_march(const Vec3& o, const Vec3& d, const Vec3& idir, f
 }
 } // namespace
 
+namespace {
+struct MaskL { int32_t shape, mode; M4 itransform; float config[6]; float feather, opacity; };
+inline float mask_signed_distance(const MaskL& m, const Vec3& p) { // Mask3D::signed_distance_to_point, mask_3D.cuh:162-183 (sdf_* :31-45)
+	const Vec3 q = xform_point(m.itransform, p);
+	float d = 0.0f;
+	if (m.shape == 0) {
+		const float dx = std::fabs(q.x) - 0.5f * m.config[0], dy = std::fabs(q.y) - 0.5f * m.config[1], dz = std::fabs(q.z) - 0.5f * m.config[2];
+		const float ox = std::fmax(dx, 0.0f), oy = std::fmax(dy, 0.0f), oz = std::fmax(dz, 0.0f);
+		d = std::sqrt(sum3(ox * ox, oy * oy, oz * oz)) + std::fmin(std::fmax(dx, std::fmax(dy, dz)), 0.0f);
+	} else if (m.shape == 1) {
+		const float dr = std::fabs(std::sqrt(q.y * q.y + q.x * q.x)) - m.config[0], dh = std::fabs(q.z) - 0.5f * m.config[1];
+		const float orr = std::fmax(dr, 0.0f), oh = std::fmax(dh, 0.0f);
+		d = std::sqrt(orr * orr + oh * oh) + std::fmin(std::fmax(dr, dh), 0.0f);
+	} else if (m.shape == 2) {
+		d = std::sqrt(sum3(q.x * q.x, q.y * q.y, q.z * q.z)) - m.config[0];
+	} else {
+		d = -1.0f;
+	}
+	return d * (m.mode == 0 ? 1.0f : -1.0f);
+}
+inline float mask_sample(const MaskL& m, const Vec3& p) { // Mask3D::sample, :194-213
+	const float k = m.mode == 0 ? 1.0f : -1.0f;
+	if (m.shape == 3) return k;
+	const float d = mask_signed_distance(m, p);
+	const float alpha = m.feather == 0.0f ? (d < 0.0f ? 1.0f : 0.0f) : std::fmin(std::fmax(0.5f - d / m.feather, 0.0f), 1.0f);
+	return m.opacity * alpha * k;
+}
+inline bool plane_hit(const Vec3& o, const Vec3& d, float nz, float pz, float* t) { // intersect_plane_ray :74-81, n = (0,0,nz), p = (0,0,pz)
+	const float denom = nz * d.z;
+	if (denom > 1e-6f) { *t = ((pz - o.z) * nz) / denom; return *t >= 0.0f; }
+	return false;
+}
+inline bool mask_intersects_ray(const MaskL& m, const Vec3& ro, const Vec3& rd) { // Mask3D::intersects_ray, :215-247
+	if (m.mode == 1) return true;
+	if (m.shape == 3) return m.mode == 0;
+	const Vec3 o = xform_point(m.itransform, ro);
+	const Vec3 d = normalized(xform_dir(m.itransform, rd));
+	if (m.shape == 0) { // ray_intersects_box :46-56
+		float lo = -INFINITY, hi = INFINITY;
+		const float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+		for (int a = 0; a < 3; ++a) {
+			const float size = m.config[a] + 0.5f * m.feather, inv = 1.0f / dd[a];
+			const float t0 = (-0.5f * size - oo[a]) * inv, t1 = (0.5f * size - oo[a]) * inv;
+			lo = std::fmax(lo, std::fmin(t0, t1)); hi = std::fmin(hi, std::fmax(t0, t1));
+		}
+		return lo <= hi;
+	}
+	if (m.shape == 2) { // ray_intersects_sphere :59-63
+		const float radius = m.config[0] + 0.5f * m.feather;
+		const float dot = sum3(d.x * o.x, d.y * o.y, d.z * o.z);
+		return !((dot * dot - (sum3(o.x * o.x, o.y * o.y, o.z * o.z) - radius * radius)) < 0.0f);
+	}
+	const float radius = m.config[0] + 0.5f * m.feather, height = m.config[1] + 0.5f * m.feather; // ray_intersects_cylinder :83-123
+	const float a = d.x * d.x + d.y * d.y, b = 2.0f * (d.x * o.x + d.y * o.y), c = (o.x * o.x + o.y * o.y) - radius * radius;
+	const float disc = b * b - 4.0f * a * c;
+	if (disc < 0.0f) return false;
+	const float sq = std::sqrt(disc), a2 = 2.0f * a, h2 = 0.5f * height;
+	if (a2 > 1e-6f) {
+		const float z0 = o.z + ((-b - sq) / a2) * d.z, z1 = o.z + ((-b + sq) / a2) * d.z;
+		if ((z0 >= -h2 && z0 <= h2) || (z1 >= -h2 && z1 <= h2)) return true;
+	}
+	float t = 0.0f;
+	if (plane_hit(o, d, 1.0f, h2, &t)) { const float px = o.x + t * d.x, py = o.y + t * d.y; if (px * px + py * py <= radius * radius) return true; }
+	if (plane_hit(o, d, -1.0f, -h2, &t)) { const float px = o.x + t * d.x, py = o.y + t * d.y; if (px * px + py * py <= radius * radius) return true; }
+	return false;
+}
+inline void mul4(const float* a, const float* b, float* out) {
+	for (int c = 0; c < 4; ++c) for (int r = 0; r < 4; ++r) { float v = 0.f; for (int k = 0; k < 4; ++k) v += a[k * 4 + r] * b[c * 4 + k]; out[c * 4 + r] = v; }
+}
+// RenderModifiers (render_modifiers.cuh:28-62): own masks, the request's masks moved into the NeRF's frame, and an `All` mask of the opposite mode in front
+inline std::vector<MaskL> build_mask_list(const orc_nerf_instance& in, const M4& nerf_itransform, const orc_blender_request* rq) {
+	std::vector<MaskL> out;
+	auto push = [&](const orc_mask& m, const float* to_local) {
+		MaskL d{};
+		d.shape = m.shape; d.mode = m.mode; d.feather = m.feather; d.opacity = m.opacity;
+		std::memcpy(d.config, m.config, sizeof(d.config));
+		float t[16];
+		if (to_local) mul4(to_local, m.transform, t); else std::memcpy(t, m.transform, 64);
+		if (!invert4(t, d.itransform.m)) std::memset(d.itransform.m, 0, 64);
+		out.push_back(d);
+	};
+	for (uint32_t k = 0; k < in.n_masks; ++k) push(in.masks[k], nullptr);
+	for (uint32_t k = 0; k < rq->n_masks; ++k) push(rq->masks[k], nerf_itransform.m);
+	if (!out.empty() && out[0].shape != 3) {
+		MaskL all{};
+		all.shape = 3; all.mode = out[0].mode == 0 ? 1 : 0; all.opacity = 1.0f;
+		for (int k = 0; k < 4; ++k) all.itransform.m[k * 5] = 1.0f;
+		out.insert(out.begin(), all);
+	}
+	return out;
+}
+inline void square2disk_shirley(float a, float b, float out[2]) { // random_val.cuh:109-125
+	const float PI = 3.14159265358979323846f;
+	float phi, r;
+	if (a * a > b * b) { r = a; phi = (PI / 4.0f) * (b / a); } else { r = b; phi = (PI / 2.0f) - (PI / 4.0f) * (a / b); }
+	out[0] = r * std::cos(phi); out[1] = r * std::sin(phi);
+}
+inline Vec3 cam_rotate(const float* cm, const Vec3& v) {
+	const float row0[3] = {cm[0], cm[3], cm[6]}, row1[3] = {cm[1], cm[4], cm[7]}, row2[3] = {cm[2], cm[5], cm[8]}, vv[3] = {v.x, v.y, v.z};
+	return {dot3(row0, vv), dot3(row1, vv), dot3(row2, vv)};
+}
+// init_global_rays_kernel's switch over the camera model (nerf_renderer.cu:44-82) with sample index 0
+inline void blender_pixel_to_ray(const orc_blender_request* rq, const float offset[2], uint32_t x, uint32_t y, Vec3& origin, Vec3& dir) {
+	const float W = (float)rq->width, H = (float)rq->height;
+	const float* cm = rq->camera;
+	if (rq->camera_model == 0) { // perspective_pixel_to_ray, camera_models.cuh:205-241
+		const float uvx = ((float)x + offset[0]) / W, uvy = ((float)y + offset[1]) / H;
+		dir = cam_rotate(cm, Vec3{(uvx - 0.5f) * W / rq->focal_length, (uvy - 0.5f) * H / rq->focal_length, 1.0f});
+		origin = {cm[9], cm[10], cm[11]};
+	} else if (rq->camera_model == 1) { // quadrilateral_hexahedron_pixel_to_ray, :82-110
+		const float ux = ((float)x + 0.5f) / W, uy = ((float)y + 0.5f) / H;
+		const float* q = rq->quadrilateral_hexahedron;
+		float fp[3], bp[3];
+		for (int k = 0; k < 3; ++k) {
+			const float f_ab = q[0 + k] + ux * (q[3 + k] - q[0 + k]), f_dc = q[6 + k] + ux * (q[9 + k] - q[6 + k]);
+			fp[k] = f_ab + uy * (f_dc - f_ab);
+			const float b_ab = q[12 + k] + ux * (q[15 + k] - q[12 + k]), b_dc = q[18 + k] + ux * (q[21 + k] - q[18 + k]);
+			bp[k] = b_ab + uy * (b_dc - b_ab);
+		}
+		Vec3 d = {fp[0] - bp[0], fp[1] - bp[1], fp[2] - bp[2]};
+		d = {d.x / d.z, d.y / d.z, d.z / d.z};
+		const Vec3 o = cam_rotate(cm, Vec3{bp[0], bp[1], bp[2]});
+		origin = {o.x + cm[9], o.y + cm[10], o.z + cm[11]};
+		dir = cam_rotate(cm, d);
+	} else { // spherical_quadrilateral_pixel_to_ray, :159-203 (walk_along_sphere / walk_along_circle :137-157)
+		const float PI = 3.14159265358979323846f;
+		const float sw = rq->spherical_quadrilateral[0], sh = rq->spherical_quadrilateral[1], curvature = rq->spherical_quadrilateral[2];
+		const float max_len = std::sqrt(sw * sw + sh * sh);
+		const float ux = 2.0f * (((float)x + 0.5f) / W - 0.5f), uy = 2.0f * (((float)y + 0.5f) / H - 0.5f);
+		const float px = sw * ux, py = sh * uy;
+		const float az = std::atan2(py, px), r = std::sqrt(px * px + py * py);
+		float rz0 = 0.0f, rz1 = 0.0f;
+		const float arc_t = r / (2.0f * max_len);
+		if (!(arc_t == 0.0f || max_len == 0.0f)) {
+			if (curvature == 0.0f) rz0 = max_len * arc_t;
+			else { const float tpc = 2.0f * PI * curvature, s_tpc = max_len / tpc; rz0 = s_tpc * std::sin(tpc * arc_t); rz1 = s_tpc * (1.0f - std::cos(tpc * arc_t)); }
+		}
+		const Vec3 o_local = {rz0 * std::cos(az), rz0 * std::sin(az), rz1};
+		Vec3 d_local = {0.0f, 0.0f, 1.0f};
+		if (curvature != 0.0f) {
+			const Vec3 n = normalized(Vec3{0.0f - o_local.x, 0.0f - o_local.y, max_len / (2.0f * PI * curvature) - o_local.z});
+			const float k = curvature > 0.0f ? 1.0f : -1.0f;
+			d_local = {k * n.x, k * n.y, k * n.z};
+		}
+		const Vec3 o = cam_rotate(cm, o_local);
+		origin = {o.x + cm[9], o.y + cm[10], o.z + cm[11]};
+		dir = cam_rotate(cm, d_local);
+	}
+	if (rq->aperture_size > 0.0f) { // thin-lens depth of field (:99-104, :196-201, :232-237)
+		const Vec3 lookat = {origin.x + dir.x * rq->focus_z, origin.y + dir.y * rq->focus_z, origin.z + dir.z * rq->focus_z};
+		float u[2], disk[2];
+		ld_random_val_2d(0u, x * 19349663u + y * 96925573u, u);
+		square2disk_shirley(u[0] * 2.0f - 1.0f, u[1] * 2.0f - 1.0f, disk);
+		const float bx = rq->aperture_size * disk[0], by = rq->aperture_size * disk[1];
+		origin.x += cm[0] * bx + cm[3] * by; origin.y += cm[1] * bx + cm[4] * by; origin.z += cm[2] * bx + cm[5] * by;
+		dir = {(lookat.x - origin.x) / rq->focus_z, (lookat.y - origin.y) / rq->focus_z, (lookat.z - origin.z) / rq->focus_z};
+	}
+	origin = {origin.x + dir.x * rq->near_distance, origin.y + dir.y * rq->near_distance, origin.z + dir.z * rq->near_distance};
+}
+} // namespace
+
 extern "C" void orc_blender_render(const orc_blender_request* rq, uint32_t n_nerfs, const orc_nerf_instance* nerfs, float* out_rgba, uint64_t* n_samples_out) {
 	const int W = rq->width, H = rq->height;
 	const int skip = 1 << rq->mip;
@@ -1337,11 +1520,13 @@ extern "C" void orc_blender_render(const orc_blender_request* rq, uint32_t n_ner
 	std::vector<M4> T(n_nerfs), IT(n_nerfs);
 	std::vector<AABB> render_box(n_nerfs), train_box(n_nerfs);
 	std::vector<float> cone(n_nerfs);
+	std::vector<std::vector<MaskL>> masks(n_nerfs);
 	for (uint32_t n = 0; n < n_nerfs; ++n) {
 		std::memcpy(T[n].m, nerfs[n].transform, 64);
 		if (!invert4(nerfs[n].transform, IT[n].m)) std::memset(IT[n].m, 0, 64);
 		render_box[n] = make_aabb(nerfs[n].render_aabb); train_box[n] = make_aabb(nerfs[n].train_aabb);
 		cone[n] = nerfs[n].aabb_scale <= 1 ? 0.0f : (1.0f / 256.0f);
+		masks[n] = build_mask_list(nerfs[n], IT[n], rq);
 	}
 	// init_global_rays_kernel, sample_index 0
 	float offset[2];
@@ -1351,12 +1536,9 @@ extern "C" void orc_blender_render(const orc_blender_request* rq, uint32_t n_ner
 	const float* cm = rq->camera;
 	for (uint32_t idx = 0; idx < n_init; ++idx) {
 		const uint32_t x = (idx % SW) * skip, y = (idx / SW) * skip;
-		const float uvx = ((float)x + offset[0]) / (float)W, uvy = ((float)y + offset[1]) / (float)H;
-		const float dcam[3] = {(uvx - 0.5f) * (float)W / rq->focal_length, (uvy - 0.5f) * (float)H / rq->focal_length, 1.0f};
-		const float row0[3] = {cm[0], cm[3], cm[6]}, row1[3] = {cm[1], cm[4], cm[7]}, row2[3] = {cm[2], cm[5], cm[8]};
-		const Vec3 d = {dot3(row0, dcam), dot3(row1, dcam), dot3(row2, dcam)};
 		GlobalRay& g = rays[idx];
-		g.o = {cm[9] + d.x * rq->near_distance, cm[10] + d.y * rq->near_distance, cm[11] + d.z * rq->near_distance};
+		Vec3 d;
+		blender_pixel_to_ray(rq, offset, x, y, g.o, d);
 		g.d = normalized(d);
 		g.idx = idx; g.alive = true;
 		g.rgba[0] = g.rgba[1] = g.rgba[2] = g.rgba[3] = 0.f;
@@ -1369,7 +1551,9 @@ extern "C" void orc_blender_render(const orc_blender_request* rq, uint32_t n_ner
 			aabb_ray_intersect(render_box[n], o, p.d, &tmin, &tmax);
 			const float t = std::fmax(tmin, 0.0f) + 1e-5f;
 			if (!aabb_contains(render_box[n], Vec3{o.x + p.d.x * t, o.y + p.d.y * t, o.z + p.d.z * t})) { p.alive = false; continue; }
-			p.active = true; p.alive = true; p.t = 0.0f; p.n_steps = 0;
+			bool hits_a_mask = masks[n].empty();
+			for (size_t k = 0; k < masks[n].size() && !hits_a_mask; ++k) hits_a_mask = mask_intersects_ray(masks[n][k], o, p.d);
+			p.active = true; p.alive = hits_a_mask; p.t = 0.0f; p.n_steps = 0;
 			p.o = {o.x + t * p.d.x, o.y + t * p.d.y, o.z + t * p.d.z};
 		}
 	}
@@ -1453,7 +1637,12 @@ extern "C" void orc_blender_render(const orc_blender_request* rq, uint32_t n_ner
 					const float dt = unwarp_dt(coords[k * 7 + 3]);
 					const float alpha = 1.f - std::exp(-network_to_density(h2f(out[k * 4 + 3]), nerfs[n].density_activation) * dt);
 					float weight = alpha * T_;
-					weight *= 1.f; // no masks
+					if (!masks[n].empty()) {
+						const Vec3 pos = unwarp_position(&coords[k * 7], train_box[n]);
+						float mask_weight = 1.f;
+						for (const MaskL& mk : masks[n]) mask_weight = std::fmin(std::fmax(mask_weight + mask_sample(mk, pos), 0.0f), 1.0f);
+						weight *= mask_weight;
+					}
 					weight *= nerfs[n].opacity;
 					for (int c = 0; c < 3; ++c) rgba[c] += network_to_rgb(h2f(out[k * 4 + c]), nerfs[n].rgb_activation) * weight;
 					rgba[3] += weight;
@@ -1495,10 +1684,10 @@ extern "C" void orc_blender_render(const orc_blender_request* rq, uint32_t n_ner
 		for (int k = 0; k < 3; ++k) {
 			float v = color[k];
 			if (rq->color_space == 1) v = srgb_to_linear(v);
-			v *= exposure_scale;
-			if (rq->color_space == 1) v = linear_to_srgb(v); // bl_render_frame passes the same colour space as the output space (:2691)
-			color[k] = v;
+			color[k] = v * exposure_scale;
 		}
+		tonemap_curve(color, rq->tonemap_curve);
+		if (rq->color_space == 1) for (int k = 0; k < 3; ++k) color[k] = linear_to_srgb(color[k]); // bl_render_frame passes the same colour space as the output space (:2691)
 		for (int k = 0; k < 4; ++k) out_rgba[i * 4 + k] = color[k];
 	}
 	if (n_samples_out) *n_samples_out = n_samples;

@@ -168,11 +168,18 @@ typedef struct {
 	int32_t color_space;        // m_color_space (0 linear, 1 sRGB): the space the accumulation buffer averages in
 	int32_t output_srgb;        // !linear argument of Testbed::render
 	float exposure, background_color[4];
+	int32_t tonemap_curve;      // ETonemapCurve
 } orc_render_config;
 // out_rgba: float [height][width][4]. n_samples_out (nullable): network-evaluated samples.
 void orc_render_nerf(const orc_model* m, const orc_half* params, const uint8_t* bitfield, const orc_render_config* c, float* out_rgba, uint64_t* n_samples_out);
 
 // ---- Blender multi-NeRF render (NerfRenderer::render, src/nerf_renderer.cu:565-791): see ngp_oracle.cpp ----
+typedef struct {               // Mask3D (nerf/mask_3D.cuh:128-257)
+	int32_t shape, mode;       // EMaskShape {Box, Cylinder, Sphere, All}, EMaskMode {Add, Subtract}
+	float transform[16];       // 4x4 column-major: shape -> NeRF-local (instance masks) or shape -> world (request masks)
+	float config[6];
+	float feather, opacity;
+} orc_mask;
 typedef struct {
 	const orc_model* model; const orc_half* params; const uint8_t* bitfield; // the NeRF's snapshot (inference parameters, occupancy bits)
 	float train_aabb[6]; uint32_t aabb_scale;
@@ -181,12 +188,19 @@ typedef struct {
 	float opacity;
 	int32_t rgb_activation, density_activation;
 	float min_transmittance;
+	uint32_t n_masks; const orc_mask* masks; // NerfDescriptor::modifiers.masks
 } orc_nerf_instance;
 typedef struct {
 	int32_t width, height, mip, flip_y; // RenderOutputProperties: resolution, DownsampleInfo::MakeFromMip(resolution, mip), flip_y
 	float camera[12];                   // RenderCameraProperties::transform, 3x4 column-major
 	float focal_length, near_distance;  // pixels (same for x and y, :52)
 	int32_t color_space; float exposure, background_color[4];
+	int32_t camera_model;               // ECameraModel {Perspective, QuadrilateralHexahedron, SphericalQuadrilateral} (camera_models.cuh:27-31)
+	float aperture_size, focus_z;
+	float spherical_quadrilateral[3];   // width, height, curvature
+	float quadrilateral_hexahedron[24]; // front tl, tr, bl, br; back tl, tr, bl, br
+	int32_t tonemap_curve;              // ETonemapCurve {Identity, ACES, Hable, Reinhard}
+	uint32_t n_masks; const orc_mask* masks; // RenderRequest::modifiers.masks (world space)
 } orc_blender_request;
 void orc_blender_render(const orc_blender_request* rq, uint32_t n_nerfs, const orc_nerf_instance* nerfs, float* out_rgba, uint64_t* n_samples_out);
 

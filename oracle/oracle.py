@@ -281,11 +281,11 @@ class RenderConfig(C.Structure):
                 ("spp", C.c_int32), ("snap_to_pixel_centers", C.c_int32), ("aabb", C.c_float * 6), ("render_aabb", C.c_float * 6),
                 ("cone_angle_constant", C.c_float), ("min_transmittance", C.c_float), ("near_distance", C.c_float),
                 ("rgb_activation", C.c_int32), ("density_activation", C.c_int32), ("train_in_linear_colors", C.c_int32),
-                ("color_space", C.c_int32), ("output_srgb", C.c_int32), ("exposure", C.c_float), ("background_color", C.c_float * 4)]
+                ("color_space", C.c_int32), ("output_srgb", C.c_int32), ("exposure", C.c_float), ("background_color", C.c_float * 4), ("tonemap_curve", C.c_int32)]
 
 
 def render_config(width, height, fx, fy, camera34, spp=1, snap=False, aabb=(0, 0, 0, 1, 1, 1), cone_angle=0.0, min_transmittance=0.01, near_distance=0.0,
-                  rgb_activation=2, density_activation=3, linear_colors=False, color_space=0, output_srgb=False, exposure=0.0, background=(0, 0, 0, 1)):
+                  rgb_activation=2, density_activation=3, linear_colors=False, color_space=0, output_srgb=False, exposure=0.0, background=(0, 0, 0, 1), tonemap_curve=0):
     """Defaults are the reference's Testbed defaults (testbed.h:547,:725,:846,:853,:875,:889)."""
     c = RenderConfig()
     c.width, c.height, c.fx, c.fy = width, height, fx, fy
@@ -298,7 +298,7 @@ def render_config(width, height, fx, fy, camera34, spp=1, snap=False, aabb=(0, 0
         c.aabb[k] = c.render_aabb[k] = float(aabb[k])
     c.cone_angle_constant, c.min_transmittance, c.near_distance = cone_angle, min_transmittance, near_distance
     c.rgb_activation, c.density_activation, c.train_in_linear_colors = rgb_activation, density_activation, int(linear_colors)
-    c.color_space, c.output_srgb, c.exposure = color_space, int(output_srgb), exposure
+    c.color_space, c.output_srgb, c.exposure, c.tonemap_curve = color_space, int(output_srgb), exposure, int(tonemap_curve)
     for k in range(4):
         c.background_color[k] = float(background[k])
     return c
@@ -390,21 +390,52 @@ def compute_cam_gradient(n_kept, n_rays_total, n_images, aabb6, ray_indices, ray
     return pos, rot
 
 
+class Mask(C.Structure):  # orc_mask
+    _fields_ = [("shape", C.c_int32), ("mode", C.c_int32), ("transform", C.c_float * 16), ("config", C.c_float * 6), ("feather", C.c_float), ("opacity", C.c_float)]
+
+
 class NerfInstance(C.Structure):
     _fields_ = [("model", C.POINTER(Model)), ("params", C.c_void_p), ("bitfield", C.c_void_p), ("train_aabb", C.c_float * 6), ("aabb_scale", C.c_uint32),
                 ("render_aabb", C.c_float * 6), ("transform", C.c_float * 16), ("opacity", C.c_float),
-                ("rgb_activation", C.c_int32), ("density_activation", C.c_int32), ("min_transmittance", C.c_float)]
+                ("rgb_activation", C.c_int32), ("density_activation", C.c_int32), ("min_transmittance", C.c_float), ("n_masks", C.c_uint32), ("masks", C.POINTER(Mask))]
 
 
 class BlenderRequest(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("mip", C.c_int32), ("flip_y", C.c_int32), ("camera", C.c_float * 12),
-                ("focal_length", C.c_float), ("near_distance", C.c_float), ("color_space", C.c_int32), ("exposure", C.c_float), ("background_color", C.c_float * 4)]
+                ("focal_length", C.c_float), ("near_distance", C.c_float), ("color_space", C.c_int32), ("exposure", C.c_float), ("background_color", C.c_float * 4),
+                ("camera_model", C.c_int32), ("aperture_size", C.c_float), ("focus_z", C.c_float), ("spherical_quadrilateral", C.c_float * 3),
+                ("quadrilateral_hexahedron", C.c_float * 24), ("tonemap_curve", C.c_int32), ("n_masks", C.c_uint32), ("masks", C.POINTER(Mask))]
 
 
-def blender_render(width, height, camera34, focal_length, nerfs, mip=0, flip_y=False, near_distance=0.0, color_space=1, exposure=0.0, background=(0, 0, 0, 0)):
+def mask_array(masks):
+    """masks: dicts with shape (0 box, 1 cylinder, 2 sphere), mode (0 add, 1 subtract), transform (4x4 row-major numpy), dims, feather, opacity."""
+    if not masks:
+        return None
+    arr = (Mask * len(masks))()
+    for a, m in zip(arr, masks):
+        a.shape, a.mode, a.feather, a.opacity = int(m["shape"]), int(m["mode"]), float(m["feather"]), float(m["opacity"])
+        t = np.asarray(m["transform"], dtype=np.float32).reshape(4, 4).T.reshape(-1)
+        for k in range(16):
+            a.transform[k] = float(t[k])
+        for k, v in enumerate(m["dims"]):
+            a.config[k] = float(v)
+    return arr
+
+
+def blender_render(width, height, camera34, focal_length, nerfs, mip=0, flip_y=False, near_distance=0.0, color_space=1, exposure=0.0, background=(0, 0, 0, 0),
+                   camera_model=0, aperture_size=0.0, focus_z=1.0, spherical_quadrilateral=(0, 0, 0), quadrilateral_hexahedron=None, tonemap_curve=0, masks=()):
     """NerfRenderer::render on the CPU (src/nerf_renderer.cu:565-791). nerfs: list of dicts with model, params_half, bitfield, aabb_scale,
-    render_aabb (6), transform (4x4 row-major numpy, local -> world), opacity. Returns float32 [H][W][4] and the number of composited samples."""
+    render_aabb (6), transform (4x4 row-major numpy, local -> world), opacity, masks. Returns float32 [H][W][4] and the number of composited samples."""
     rq = BlenderRequest()
+    rq.camera_model, rq.aperture_size, rq.focus_z, rq.tonemap_curve = int(camera_model), aperture_size, focus_z, int(tonemap_curve)
+    for k in range(3):
+        rq.spherical_quadrilateral[k] = float(spherical_quadrilateral[k])
+    if quadrilateral_hexahedron is not None:
+        for k, v in enumerate(np.asarray(quadrilateral_hexahedron, np.float32).reshape(-1)):
+            rq.quadrilateral_hexahedron[k] = float(v)
+    request_masks = mask_array(list(masks))
+    if request_masks is not None:
+        rq.n_masks, rq.masks = len(request_masks), request_masks
     rq.width, rq.height, rq.mip, rq.flip_y = width, height, mip, int(flip_y)
     cm = np.asarray(camera34, dtype=np.float32).reshape(3, 4).T.reshape(-1)
     for k in range(12):
@@ -431,6 +462,10 @@ def blender_render(width, height, camera34, focal_length, nerfs, mip=0, flip_y=F
             arr[i].render_aabb[k] = float(ra[k])
         arr[i].opacity = n.get("opacity", 1.0)
         arr[i].rgb_activation, arr[i].density_activation, arr[i].min_transmittance = 2, 3, 0.01
+        ma = mask_array(n.get("masks", []))
+        if ma is not None:
+            keep.append(ma)
+            arr[i].n_masks, arr[i].masks = len(ma), ma
     out = np.zeros((height, width, 4), np.float32)
     ns = C.c_uint64(0)
     lib().orc_blender_render(C.byref(rq), len(nerfs), arr, _p(out), C.byref(ns))

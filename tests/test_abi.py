@@ -140,11 +140,23 @@ def test_render_request_value_types():
     assert cam(100.0) == cam(100.0) and cam(100.0) != cam(101.0)
     out = pyngp.RenderOutputProperties((8, 4), ds, 1, pyngp.ColorSpace.SRGB, pyngp.TonemapCurve.Identity, 0.0, [0, 0, 0, 0], True)
     assert out.resolution == (8, 4) and out.flip_y is True
-    with pytest.raises(RuntimeError):
-        pyngp.Mask3D.Sphere(1.0, np.eye(4), 0, 0.0, 1.0)
-    with pytest.raises(RuntimeError):
+    # masks and the fork's camera models (python_api.cu:431-450): argument order and enum values of the reference
+    m = pyngp.Mask3D.Sphere(1.0, np.eye(4), pyngp.MaskMode.Subtract, 0.25, 0.5)
+    assert m.shape == pyngp.MaskShape.Sphere and m.mode == pyngp.MaskMode.Subtract and m.config[:2] == [1.0, 0.0] and (m.feather, m.opacity) == (0.25, 0.5)
+    b = pyngp.Mask3D.Box([1, 2, 3], np.eye(4), pyngp.MaskMode.Add, 0.0, 1.0)
+    c = pyngp.Mask3D.Cylinder(0.5, 2.0, np.eye(4), pyngp.MaskMode.Add, 0.0, 1.0)
+    assert b.config[:3] == [1.0, 2.0, 3.0] and c.config[:2] == [0.5, 2.0] and int(pyngp.MaskShape.All) == 3
+    arr = pyngp._mask_array([m, b])
+    assert len(arr) == 2 and arr[0].shape == 2 and arr[0].mode == 1 and arr[1].config[2] == 3.0 and pyngp._mask_array([]) is None
+    with pytest.raises(TypeError):
         pyngp.RenderModifiers([object()])
-    d = pyngp.NerfDescriptor("a.msgpack", box, np.eye(4), pyngp.RenderModifiers([]), 0.5)
+    assert (int(pyngp.CameraModel.Perspective), int(pyngp.CameraModel.QuadrilateralHexahedron), int(pyngp.CameraModel.SphericalQuadrilateral)) == (0, 1, 2)
+    quad = pyngp.Quadrilateral3D([0, 1, 0], [1, 1, 0], [0, 0, 0], [1, 0, 0])
+    qh = pyngp.QuadrilateralHexahedronConfig(quad, pyngp.Quadrilateral3D.Zero())
+    assert np.allclose(quad.center(), [0.5, 0.5, 0]) and np.allclose(qh.center(), [0.25, 0.25, 0])
+    sq = pyngp.SphericalQuadrilateralConfig(1.0, 2.0, 0.25)
+    assert (sq.width, sq.height, sq.curvature) == (1.0, 2.0, 0.25) and pyngp.SphericalQuadrilateralConfig.Zero().width == 0.0
+    d = pyngp.NerfDescriptor("a.msgpack", box, np.eye(4), pyngp.RenderModifiers([m]), 0.5)
     rq = pyngp.RenderRequest(out, cam(50.0), pyngp.RenderModifiers([]), [d], box)
     assert rq.nerfs[0].snapshot_path == "a.msgpack" and rq.nerfs[0].opacity == 0.5
 

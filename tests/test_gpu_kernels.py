@@ -385,14 +385,15 @@ def test_compute_loss(L, orc, small_scene, batch):
 
 
 def test_k1_k6_at_benchmark_scale(L, orc):
-    """BASELINE config 2 at the bench's own size: 100 cameras x 800^2, ~45 k rays, ~0.7 M uncompacted samples, batch 2^18. Covers what the 64^2
-    scene cannot: multi-block scans, 32-bit index ranges and the march-word overflow path of K1 (nerf_sampling.cu), multi-block compaction and the
+    """BASELINE config 2 at the bench's own size and beyond: 100 cameras x 800^2, 2^18 rays requested (the controller's cap) of which ~45 k hit the
+    occupied cells (the bench's steady-state ray count), ~3.6 M uncompacted samples against a 2^22 budget, batch 2^18. Covers what the 64^2 scene
+    cannot: multi-block scans, 32-bit index ranges and the march-word overflow path of K1 (nerf_sampling.cu), multi-block compaction and the
     roll-over of K6/K7. Same assertions as the small case: K1 bit-exact, K6 compaction exact."""
     import synthetic
     from conftest import scene_occupancy_bitfield
     scene = synthetic.make_lego_scene(100, 800, device="cuda", seed=0)
     _, bits = scene_occupancy_bitfield(orc)
-    r = _check_k1_k6(L, orc, scene, bits, 45056, 1 << 22, 1 << 18, 1337, 30000, 400000)
+    r = _check_k1_k6(L, orc, scene, bits, 1 << 18, 1 << 22, 1 << 18, 1337, 30000, 2000000)
     print("benchmark-scale K1/K6:", r)
 
 
@@ -797,8 +798,6 @@ def test_blender_render_request_semantics(small_scene, trained_testbed, tmp_path
     assert not tb._bl_fields  # dropped when no descriptor names it
     with pytest.raises(RuntimeError):
         tb.request_nerf_render_sync(_blender_request(pyngp, small_scene, [str(tmp_path / "nope.msgpack")], [np.eye(4)], [1.0]))
-    with pytest.raises(RuntimeError):
-        pyngp.Mask3D.Box([1, 1, 1], np.eye(4), 0, 0.0, 1.0)
     sing = np.zeros((4, 4), np.float32)
     with pytest.raises(RuntimeError):
         tb.request_nerf_render_sync(_blender_request(pyngp, small_scene, [path], [sing], [1.0]))
