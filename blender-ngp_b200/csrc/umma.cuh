@@ -27,6 +27,40 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 		"}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// Bounded wait for the warp-specialised pipelines: a protocol error must end in a trap (a sticky launch failure the host reports), never in a hung GPU.
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+	const uint32_t addr = smem_u32(bar);
+	uint32_t done = 0, spins = 0;
+	long long t0 = 0;
+	while (true) {
+		asm volatile(
+			"{\n"
+			".reg .pred p;\n"
+			"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+			"selp.u32 %0, 1, 0, p;\n"
+			"}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+		if (done) return;
+		if ((++spins & 1023u) == 0u) {
+			const long long now = clock64();
+			if (t0 == 0) t0 = now;
+			else if (now - t0 > 4000000000ll) asm volatile("trap;"); // ~2 s at 2 GHz
+		}
+	}
+}
+// arrive (count 1) with release semantics at CTA scope
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+	asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" :: "r"(smem_u32(bar)) : "memory");
+}
+// arrive (count 1) and announce `bytes` of asynchronous (bulk copy) traffic that will complete on this barrier
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+	asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared (1-D, `bytes` a multiple of 16, both addresses 16-byte aligned); completion is signalled on `bar` as transaction bytes
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		:: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 // ---- proxies and tcgen05 fences -------------------------------------------------------------------
 // Generic-proxy shared-memory writes must be fenced before the async proxy (tcgen05.mma) reads them.
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -118,6 +152,18 @@ __device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile_saddr, uint32_t co
 // MN-major view: MN starts at column chunk mn_chunk0, K (rows) starts at row k_row0 (multiple of 8).
 __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile_saddr, uint32_t cols, uint32_t mn_chunk0, uint32_t k_row0) {
 	return make_smem_desc(tile_saddr + (k_row0 >> 3) * (cols >> 3) * 128 + mn_chunk0 * 128, /*lbo*/(cols >> 3) * 128, /*sbo*/128);
+}
+
+// {lo = relu(a), hi = relu(b)} as fp16x2 in one conversion (cvt's first source goes to the upper half)
+__device__ __forceinline__ uint32_t pack_half2_relu(float a, float b) {
+	uint32_t r;
+	asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+	return r;
+}
+__device__ __forceinline__ uint32_t pack_half2_rn(float a, float b) {
+	uint32_t r;
+	asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+	return r;
 }
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {

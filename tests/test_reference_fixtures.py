@@ -10,7 +10,7 @@ oracle/gen_golden_full.py). The fixtures under tests/golden/ are what the refere
 
 CPU tests pin the ORACLE on them (so that the oracle used elsewhere as the checker is itself checked against the reference); GPU tests pin the product.
 Tolerances: the product accumulates the MLP in fp32 where the reference accumulates in fp16, and both use fast-math exponentials, so frames agree to
-PSNR >= 50 dB (measured 60-86 dB) rather than bit for bit; integer work (occupancy bits, sample indices, mask culling) is exact."""
+PSNR >= 70 dB for the CUDA path (measured 84-100 dB), >= 45 dB for the CPU oracle (libm instead of fast-math exponentials) rather than bit for bit; integer work (occupancy bits, sample indices, mask culling) is exact."""
 import gzip
 import hashlib
 import json
@@ -218,7 +218,7 @@ def test_product_classic_render_matches_reference(fx, loaded_testbed, i):
     tb.background_color = [r, g, b, a]
     tb.exposure = float(exposure)
     got = tb.render(want.shape[1], want.shape[0], int(spp), linear=bool(linear))
-    p = assert_frames_agree(got, want, 50.0, f"classic {i}")
+    p = assert_frames_agree(got, want, 70.0, f"classic {i}")
     print(f"classic {i}: PSNR vs reference {p:.1f} dB")
     tb.exposure = 0.0
 
@@ -261,7 +261,7 @@ def test_product_blender_render_matches_reference(fx, loaded_testbed, snapshot_p
     import pyngp
     rq = _pyngp_request(pyngp, fx, _blender_cases(fx)[name], snapshot_path)
     got = loaded_testbed.request_nerf_render_sync(rq)
-    p = assert_frames_agree(got, fx[f"bl_{name}"], 50.0, f"blender {name}")
+    p = assert_frames_agree(got, fx[f"bl_{name}"], 70.0, f"blender {name}")
     print(f"blender {name}: PSNR vs reference {p:.1f} dB")
 
 
