@@ -179,6 +179,10 @@ __global__ void __launch_bounds__(256) hash_encode_forward_kernel(
 // (ncu: 26 of 32 lanes active, 137 warp instructions per sample). Grouped by level, only the warp that holds the last dense and the first hashed
 // level diverges, and the 16 samples of a ray that share a coarse cell hit the same lines within one load. The block's working set -- what decides
 // the L1 hit rate -- is unchanged. Results go through a shared-memory tile so that the block still writes its 1 KB of `encoded` rows contiguously.
+// TILED: the block's 1 KB of output is written in the MLP kernels' UMMA core-matrix layout instead of row-major (umma.cuh tile_offset: per 128 samples an
+// 8 KB block, 8-row groups of 512 B, inside a group four 128-byte chunks of 4 levels x 8 rows). A block of 16 samples covers two whole row groups, i.e. the
+// SAME contiguous 1 KB as in the row-major layout, only permuted inside: the stores stay fully coalesced and the MLP kernel fetches a tile with one bulk copy.
+template <bool TILED>
 __global__ void __launch_bounds__(256) hash_encode_forward16_kernel(
 	const uint32_t n, const uint32_t* __restrict__ n_dev, const GridLevels L, const __half2* __restrict__ grid, const float* __restrict__ positions, const uint32_t pos_stride,
 	__half2* __restrict__ encoded)
@@ -193,7 +197,10 @@ __global__ void __launch_bounds__(256) hash_encode_forward16_kernel(
 	if (i0 >= n_eff) return;
 	if (i < n_eff) tile[s][level] = encode_one(lc[level], grid, positions, i, pos_stride);
 	__syncthreads();
-	const uint32_t row = threadIdx.x >> 4, col = threadIdx.x & 15u; // (sample, level) of the element this thread writes out
+	// (sample, level) of the element this thread writes out: thread k owns bytes [4k, 4k + 4) of the block's 1 KB
+	uint32_t row, col;
+	if (TILED) { row = ((threadIdx.x >> 7) << 3) | ((threadIdx.x >> 2) & 7u); col = (((threadIdx.x >> 5) & 3u) << 2) | (threadIdx.x & 3u); }
+	else { row = threadIdx.x >> 4; col = threadIdx.x & 15u; }
 	if (i0 + row < n_eff) encoded[(size_t)i0 * 16u + threadIdx.x] = tile[row][col];
 }
 
@@ -316,8 +323,9 @@ __global__ void __launch_bounds__(ENC_SAMPLES * ENC_WARPS) hash_encode_backward_
 
 // Internal launchers shared with the testbed host.
 void hash_encode_forward_launch(cudaStream_t stream, const ngpb_grid* g, const __half* grid, const float* positions, uint32_t pos_stride,
-                                uint32_t n, const uint32_t* n_dev, __half* encoded) {
+                                uint32_t n, const uint32_t* n_dev, __half* encoded, bool tiled) {
 	if (n == 0) return;
+	if (tiled && (g->n_levels != 16 || g->n_pos_dims == 2)) throw std::runtime_error("hash_encode_forward: the tiled feature layout needs a 3-D grid of 16 levels");
 	const GridLevels L = make_levels(g);
 	const uint64_t threads = (uint64_t)n * L.n_levels;
 	if (threads > 0xFFFFFFFFull) throw std::runtime_error("hash_encode_forward: n * n_levels must fit 32 bits");
@@ -328,7 +336,8 @@ void hash_encode_forward_launch(cudaStream_t stream, const ngpb_grid* g, const _
 		return;
 	}
 	// no explicit shared-memory carve-out for this kernel: any non-default preference was measured 3x slower (L1 is what feeds the gathers)
-	if (L.n_levels == 16) hash_encode_forward16_kernel<<<(uint32_t)((threads + 255) / 256), 256, 0, stream>>>(n, n_dev, L, (const __half2*)grid, positions, pos_stride, (__half2*)encoded);
+	if (L.n_levels == 16 && tiled) hash_encode_forward16_kernel<true><<<(uint32_t)((threads + 255) / 256), 256, 0, stream>>>(n, n_dev, L, (const __half2*)grid, positions, pos_stride, (__half2*)encoded);
+	else if (L.n_levels == 16) hash_encode_forward16_kernel<false><<<(uint32_t)((threads + 255) / 256), 256, 0, stream>>>(n, n_dev, L, (const __half2*)grid, positions, pos_stride, (__half2*)encoded);
 	else hash_encode_forward_kernel<<<(uint32_t)((threads + 255) / 256), 256, 0, stream>>>(n, n_dev, L, (const __half2*)grid, positions, pos_stride, (__half2*)encoded);
 	NGPB_LAUNCH_CHECK();
 }
@@ -400,7 +409,7 @@ extern "C" int ngpb_hash_encode_forward(void* stream, const ngpb_grid* g, const 
                                         uint32_t n, ngpb_half* encoded) {
 	try {
 		if (!g || !grid || !positions || !encoded || pos_stride < (g->n_pos_dims == 2 ? 2u : 3u)) { set_last_error("ngpb_hash_encode_forward: invalid argument"); return NGPB_ERR_INVALID_ARGUMENT; }
-		hash_encode_forward_launch((cudaStream_t)stream, g, (const __half*)grid, positions, pos_stride, n, nullptr, (__half*)encoded);
+		hash_encode_forward_launch((cudaStream_t)stream, g, (const __half*)grid, positions, pos_stride, n, nullptr, (__half*)encoded, false);
 		return 0;
 	} catch (const std::exception& e) { set_last_error(e.what()); return NGPB_ERR_RUNTIME; }
 }

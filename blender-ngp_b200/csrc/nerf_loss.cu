@@ -18,12 +18,18 @@
 namespace ngpb {
 
 struct LossParams {
+	uint32_t rows_tiled; // layout of the feature rows that are compacted along with the samples: 0 = [n][32] row-major (C ABI), 1 = UMMA tiles (hash_grid.cu)
 	uint32_t n_rays, batch, n_images;
 	uint32_t n_rays_global; // rays of the whole (all-shard) batch: pixel selection and loss normalisation use it (:1062-1083, :1493)
 	Aabb aabb;
 	Pcg32 rng;
 	ngpb_loss_config cfg;
 };
+
+// index (in 16-byte units) of chunk c of sample i's 64-byte feature row
+__device__ __forceinline__ size_t feature_chunk(uint32_t tiled, size_t i, uint32_t c) {
+	return tiled ? ((i >> 7) << 9) + (((i & 127u) >> 3) << 5) + (c << 3) + (i & 7u) : i * 4 + c;
+}
 
 struct LossAndGradient { float loss[3], gradient[3]; };
 
@@ -321,9 +327,7 @@ __global__ void __launch_bounds__(1024) loss_gradient_kernel(
 		for (uint32_t k = glane; k < cn * COORD_FLOATS; k += W) dst[k] = src[k];
 		// ... and of their hash-grid features (64-byte rows), which the training pass would otherwise recompute from the same weights
 		if (rows_in) {
-			const uint4* rs = rows_in + (size_t)base * 4;
-			uint4* rd = rows_out + (size_t)compacted_base * 4;
-			for (uint32_t k = glane; k < cn * 4; k += W) rd[k] = rs[k];
+			for (uint32_t k = glane; k < cn * 4; k += W) rows_out[feature_chunk(P.rows_tiled, (size_t)compacted_base + (k >> 2), k & 3u)] = rows_in[feature_chunk(P.rows_tiled, (size_t)base + (k >> 2), k & 3u)];
 		}
 	}
 	const float loss_scale = P.cfg.loss_scale / P.n_rays_global;
@@ -380,7 +384,7 @@ __global__ void __launch_bounds__(1024) loss_gradient_kernel(
 // (D) roll-over padding of the compacted batch (tcnn common_device.h:517-537): element e >= n_valid copies
 // element e % n_valid; gradients of the padded copies are rescaled by n_valid / batch.
 __global__ void __launch_bounds__(256) rollover_kernel(const uint32_t batch, const uint32_t* __restrict__ counters_out, float* __restrict__ coords, __half* __restrict__ dloss_dout,
-                                                       uint4* __restrict__ rows)
+                                                       uint4* __restrict__ rows, const uint32_t rows_tiled)
 {
 	const uint32_t n_valid = min(counters_out[0], batch);
 	if (n_valid == 0 || n_valid >= batch) return;
@@ -397,11 +401,16 @@ __global__ void __launch_bounds__(256) rollover_kernel(const uint32_t batch, con
 	}
 	if (rows) {
 		#pragma unroll
-		for (int k = 0; k < 4; ++k) rows[(size_t)e * 4 + k] = rows[(size_t)src * 4 + k];
+		for (int k = 0; k < 4; ++k) rows[feature_chunk(rows_tiled, e, k)] = rows[feature_chunk(rows_tiled, src, k)];
 	}
 }
 
 Aabb make_aabb(const float* a);
+int compute_loss_launch(void* stream_, uint32_t n_rays, uint32_t n_rays_global, const float* aabb6, ngpb_rng rng_, uint32_t batch, const ngpb_loss_config* cfg,
+                        uint32_t n_images, const ngpb_image* images_dev, const uint32_t* counters_in,
+                        const ngpb_half* rgbsigma, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords_in,
+                        const float* mean_density_dev, float* coords_out, ngpb_half* dloss_dout, float* loss_per_ray, uint32_t* counters_out, void* scratch,
+                        const ngpb_half* encoded_in, ngpb_half* encoded_out, bool rows_tiled);
 
 } // namespace ngpb
 
@@ -432,6 +441,16 @@ extern "C" int ngpb_compute_loss_compact_features(void* stream_, uint32_t n_rays
                                  const ngpb_half* rgbsigma, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords_in,
                                  const float* mean_density_dev, float* coords_out, ngpb_half* dloss_dout, float* loss_per_ray, uint32_t* counters_out, void* scratch,
                                  const ngpb_half* encoded_in, ngpb_half* encoded_out) {
+	return ngpb::compute_loss_launch(stream_, n_rays, n_rays_global, aabb6, rng_, batch, cfg, n_images, images_dev, counters_in, rgbsigma, ray_indices, rays, numsteps, coords_in,
+		mean_density_dev, coords_out, dloss_dout, loss_per_ray, counters_out, scratch, encoded_in, encoded_out, false);
+}
+
+// The implementation behind the C entry points; `rows_tiled` selects the layout of encoded_in / encoded_out (the testbed hands tiles from the hash-grid kernel to the MLP kernel).
+int ngpb::compute_loss_launch(void* stream_, uint32_t n_rays, uint32_t n_rays_global, const float* aabb6, ngpb_rng rng_, uint32_t batch, const ngpb_loss_config* cfg,
+                                 uint32_t n_images, const ngpb_image* images_dev, const uint32_t* counters_in,
+                                 const ngpb_half* rgbsigma, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords_in,
+                                 const float* mean_density_dev, float* coords_out, ngpb_half* dloss_dout, float* loss_per_ray, uint32_t* counters_out, void* scratch,
+                                 const ngpb_half* encoded_in, ngpb_half* encoded_out, bool rows_tiled) {
 	try {
 		if ((encoded_in == nullptr) != (encoded_out == nullptr) || (encoded_in && encoded_in == encoded_out)) {
 			set_last_error("ngpb_compute_loss: encoded_in and encoded_out must both be given, and differ");
@@ -445,6 +464,7 @@ extern "C" int ngpb_compute_loss_compact_features(void* stream_, uint32_t n_rays
 		cudaStream_t stream = (cudaStream_t)stream_;
 		if (n_rays == 0) { NGPB_CUDA_CHECK(cudaMemsetAsync(counters_out, 0, sizeof(uint32_t), stream)); return 0; }
 		LossParams P;
+		P.rows_tiled = rows_tiled ? 1u : 0u;
 		P.n_rays = n_rays; P.batch = batch; P.n_images = n_images; P.n_rays_global = n_rays_global;
 		P.aabb = make_aabb(aabb6);
 		P.rng.state = rng_.state; P.rng.inc = rng_.inc;
@@ -476,7 +496,7 @@ extern "C" int ngpb_compute_loss_compact_features(void* stream_, uint32_t n_rays
 		if (wg == 8) NGPB_GRADIENT(8); else if (wg == 16) NGPB_GRADIENT(16); else NGPB_GRADIENT(32);
 		#undef NGPB_GRADIENT
 		NGPB_LAUNCH_CHECK();
-		rollover_kernel<<<div_round_up(batch, 256), 256, 0, stream>>>(batch, counters_out, coords_out, (__half*)dloss_dout, reinterpret_cast<uint4*>(encoded_out));
+		rollover_kernel<<<div_round_up(batch, 256), 256, 0, stream>>>(batch, counters_out, coords_out, (__half*)dloss_dout, reinterpret_cast<uint4*>(encoded_out), P.rows_tiled);
 		NGPB_LAUNCH_CHECK();
 		return 0;
 	} catch (const std::exception& e) { set_last_error(e.what()); return NGPB_ERR_RUNTIME; }

@@ -449,8 +449,9 @@ __global__ void __launch_bounds__(256) render_tonemap_kernel(const uint32_t n_pi
 }
 
 Aabb make_aabb(const float* a);
-void hash_encode_forward_launch(cudaStream_t stream, const ngpb_grid* g, const __half* grid, const float* positions, uint32_t pos_stride, uint32_t n, const uint32_t* n_dev, __half* encoded);
-void nerf_mlp_forward_launch(cudaStream_t stream, const __half* mlp, const __half* encoded, const float* coords, uint32_t n, const uint32_t* n_dev, __half* rgbsigma);
+void hash_encode_forward_launch(cudaStream_t stream, const ngpb_grid* g, const __half* grid, const float* positions, uint32_t pos_stride, uint32_t n, const uint32_t* n_dev, __half* encoded, bool tiled);
+void nerf_mlp_forward_launch(cudaStream_t stream, const __half* mlp, const __half* encoded, bool tiled, const float* coords, uint32_t n, const uint32_t* n_dev, __half* rgbsigma);
+bool features_tiled();
 
 } // namespace ngpb
 
@@ -544,8 +545,8 @@ extern "C" int ngpb_render_nerf(void* stream_, const ngpb_render_config* cfg, co
 				if (warp_march) render_march_warp_kernel<<<div_round_up(n_alive, 8), 256, 0, stream>>>(P, counters + cur, n_steps, max_rounds, bitfield, rays[cur], coords, ray_steps);
 				else render_march_kernel<<<blocks, 128, 0, stream>>>(P, counters + cur, n_steps, render_max_hops(), bitfield, coarse, rays[cur], coords, ray_steps);
 				NGPB_LAUNCH_CHECK();
-				hash_encode_forward_launch(stream, g, (const __half*)params + MLP_PARAMS, coords, COORD_FLOATS, n_slots, nullptr, encoded);
-				nerf_mlp_forward_launch(stream, (const __half*)params, encoded, coords, n_slots, nullptr, rgbsigma);
+				hash_encode_forward_launch(stream, g, (const __half*)params + MLP_PARAMS, coords, COORD_FLOATS, n_slots, nullptr, encoded, features_tiled());
+				nerf_mlp_forward_launch(stream, (const __half*)params, encoded, features_tiled(), coords, n_slots, nullptr, rgbsigma);
 				render_composite_kernel<<<blocks, 128, 0, stream>>>(P, counters + cur, n_steps, rays[cur], rgba[cur], coords, rgbsigma, ray_steps,
 					rays[cur ^ 1], rgba[cur ^ 1], counters + (cur ^ 1), frame, reinterpret_cast<unsigned long long*>(counters + 2));
 				NGPB_LAUNCH_CHECK();
@@ -1185,8 +1186,8 @@ extern "C" int ngpb_blender_render(void* stream_, const ngpb_blender_request* rq
 					bl_generate_inputs_kernel<<<blocks, 128, 0, stream>>>(n_alive, n_steps, props_dev + n, rays[cur], pn, coords);
 					NGPB_LAUNCH_CHECK();
 					const ngpb_field* f = nerfs[n].field;
-					hash_encode_forward_launch(stream, &f->grid, f->params + MLP_PARAMS, coords, COORD_FLOATS, n_slots, nullptr, encoded);
-					nerf_mlp_forward_launch(stream, f->params, encoded, coords, n_slots, nullptr, rgbsigma);
+					hash_encode_forward_launch(stream, &f->grid, f->params + MLP_PARAMS, coords, COORD_FLOATS, n_slots, nullptr, encoded, features_tiled());
+					nerf_mlp_forward_launch(stream, f->params, encoded, features_tiled(), coords, n_slots, nullptr, rgbsigma);
 					bl_composite_kernel<<<blocks, 128, 0, stream>>>(n_alive, n_steps, step, props_dev + n, rays[cur], pn, coords, rgbsigma, reinterpret_cast<unsigned long long*>(counters + 2));
 					NGPB_LAUNCH_CHECK();
 					launches += 4;

@@ -16,7 +16,13 @@
 namespace ngpb {
 
 // launchers defined in the kernel translation units
-void hash_encode_forward_launch(cudaStream_t stream, const ngpb_grid* g, const __half* grid, const float* positions, uint32_t pos_stride, uint32_t n, const uint32_t* n_dev, __half* encoded);
+void hash_encode_forward_launch(cudaStream_t stream, const ngpb_grid* g, const __half* grid, const float* positions, uint32_t pos_stride, uint32_t n, const uint32_t* n_dev, __half* encoded, bool tiled);
+bool features_tiled();
+int compute_loss_launch(void* stream_, uint32_t n_rays, uint32_t n_rays_global, const float* aabb6, ngpb_rng rng_, uint32_t batch, const ngpb_loss_config* cfg,
+                        uint32_t n_images, const ngpb_image* images_dev, const uint32_t* counters_in,
+                        const ngpb_half* rgbsigma, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords_in,
+                        const float* mean_density_dev, float* coords_out, ngpb_half* dloss_dout, float* loss_per_ray, uint32_t* counters_out, void* scratch,
+                        const ngpb_half* encoded_in, ngpb_half* encoded_out, bool rows_tiled);
 void hash_encode_backward_launch(cudaStream_t stream, const ngpb_grid* g, const float* positions, uint32_t pos_stride, uint32_t n, const __half* dL_dencoded, float* grid_grad,
                                  uint32_t level_begin, uint32_t level_end);
 void optimizer_prepare(ngpb_optimizer* o, float loss_scale, void* params_out);
@@ -25,9 +31,9 @@ void optimizer_disable_fused_ema(void* params);
 void ema_sweep_launch(cudaStream_t stream, const void* params, uint32_t n_padded, const __half* w_half, __half* w_ema);
 void optimizer_launch(cudaStream_t stream, const void* params, uint32_t first, uint32_t count, uint32_t n_matrix_params, float* grad, float* w_fp32, __half* w_half,
                       __half* w_ema, float* m1, float* m2, uint32_t* param_steps);
-void nerf_mlp_forward_launch(cudaStream_t stream, const __half* mlp, const __half* encoded, const float* coords, uint32_t n, const uint32_t* n_dev, __half* rgbsigma);
-void nerf_density_mlp_launch(cudaStream_t stream, const __half* mlp, const __half* encoded, uint32_t n, __half* density);
-void nerf_mlp_forward_backward_launch(cudaStream_t stream, const __half* mlp, const __half* encoded, const float* coords, const __half* dL_dout, uint32_t n, __half* dL_dencoded, float* mlp_grad, float* partials);
+void nerf_mlp_forward_launch(cudaStream_t stream, const __half* mlp, const __half* encoded, bool tiled, const float* coords, uint32_t n, const uint32_t* n_dev, __half* rgbsigma);
+void nerf_density_mlp_launch(cudaStream_t stream, const __half* mlp, const __half* encoded, bool tiled, uint32_t n, __half* density);
+void nerf_mlp_forward_backward_launch(cudaStream_t stream, const __half* mlp, const __half* encoded, bool tiled, const float* coords, const __half* dL_dout, uint32_t n, __half* dL_dencoded, float* mlp_grad, float* partials);
 
 // sum of n floats in double, one block, fixed order (tcnn reduce_sum.h:54-118 is the reference's loss reduction)
 __global__ void __launch_bounds__(1024) sum_kernel(const float* __restrict__ v, const uint32_t n, float* __restrict__ out)
@@ -516,8 +522,8 @@ void ngpb_testbed::update_density_grid(uint32_t n_uniform, uint32_t n_nonuniform
 	density_grid_rng.advance();
 	// NerfNetwork::density with the training parameters (use_inference_params = false, :2833)
 	const uint32_t n_padded = next_multiple(n_samples, 128);
-	hash_encode_forward_launch(stream, &grid, w_half + MLP_PARAMS, dg_positions, 3, n_padded, nullptr, dg_encoded);
-	nerf_density_mlp_launch(stream, w_half, dg_encoded, n_padded, dg_density);
+	hash_encode_forward_launch(stream, &grid, w_half + MLP_PARAMS, dg_positions, 3, n_padded, nullptr, dg_encoded, features_tiled());
+	nerf_density_mlp_launch(stream, w_half, dg_encoded, features_tiled(), n_padded, dg_density);
 	check(ngpb_splat_and_ema(stream, n_samples, dg_indices, (const ngpb_half*)dg_density, density_grid_tmp, n_elements, density_grid_decay, density_grid));
 	++density_grid_ema_step;
 	check(ngpb_update_bitfield(stream, max_cascade + 1, density_grid, mean_density, bitfield));
@@ -672,15 +678,16 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 	}
 	// network inference on the uncompacted samples; the sample count stays on the device
 	stage_begin(NGPB_STAGE_ENCODE_INFERENCE, stream);
-	hash_encode_forward_launch(stream, &grid, w_half + MLP_PARAMS, coords, COORD_FLOATS, max_inference, counters, encoded);
+	const bool tiled = features_tiled();
+	hash_encode_forward_launch(stream, &grid, w_half + MLP_PARAMS, coords, COORD_FLOATS, max_inference, counters, encoded, tiled);
 	stage_end(NGPB_STAGE_ENCODE_INFERENCE, n_uncompacted_est, stream);
 	stage_begin(NGPB_STAGE_MLP_INFERENCE, stream);
-	nerf_mlp_forward_launch(stream, w_half, encoded, coords, max_inference, counters, rgbsigma);
+	nerf_mlp_forward_launch(stream, w_half, encoded, tiled, coords, max_inference, counters, rgbsigma);
 	stage_end(NGPB_STAGE_MLP_INFERENCE, n_uncompacted_est, stream);
 	stage_begin(NGPB_STAGE_LOSS, stream);
-	check(ngpb_compute_loss_compact_features(stream, R, (uint32_t)dp_world * R, aabb, r, batch, &loss_cfg, (uint32_t)images.size(), images_dev, counters, (const ngpb_half*)rgbsigma,
+	check(compute_loss_launch(stream, R, (uint32_t)dp_world * R, aabb, r, batch, &loss_cfg, (uint32_t)images.size(), images_dev, counters, (const ngpb_half*)rgbsigma,
 		ray_indices, rays, numsteps, coords, mean_density, coords_compacted, (ngpb_half*)dloss, loss, counters + 2, scratch,
-		reuse_encoding ? (const ngpb_half*)encoded : nullptr, reuse_encoding ? (ngpb_half*)encoded_compacted : nullptr));
+		reuse_encoding ? (const ngpb_half*)encoded : nullptr, reuse_encoding ? (ngpb_half*)encoded_compacted : nullptr, tiled));
 	stage_end(NGPB_STAGE_LOSS, R, stream);
 	n_launches += 2 + 5; // encode, mlp; loss target / composite / scan / gradient / rollover
 	if (dp_world > 1) {
@@ -702,12 +709,12 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 	// features the inference pass produced for these very samples are bit-identical: the loss stage compacted them along with the coordinates.
 	if (!reuse_encoding) {
 		stage_begin(NGPB_STAGE_ENCODE_TRAIN, stream);
-		hash_encode_forward_launch(stream, &grid, w_half + MLP_PARAMS, coords_compacted, COORD_FLOATS, batch, nullptr, encoded_compacted);
+		hash_encode_forward_launch(stream, &grid, w_half + MLP_PARAMS, coords_compacted, COORD_FLOATS, batch, nullptr, encoded_compacted, tiled);
 		stage_end(NGPB_STAGE_ENCODE_TRAIN, batch, stream);
 		++n_launches;
 	}
 	stage_begin(NGPB_STAGE_MLP_TRAIN, stream);
-	nerf_mlp_forward_backward_launch(stream, w_half, encoded_compacted, coords_compacted, dloss, batch, denc, grad, partials);
+	nerf_mlp_forward_backward_launch(stream, w_half, encoded_compacted, tiled, coords_compacted, dloss, batch, denc, grad, partials);
 	stage_end(NGPB_STAGE_MLP_TRAIN, batch, stream);
 	NGPB_CUDA_CHECK(cudaEventRecord(mlp_train_done, stream));
 	if (dp_world == 1) {
