@@ -9,19 +9,23 @@
 // the chain, each with its own activation tiles in shared memory and its own accumulator columns in TMEM:
 //
 //   warps 0 .. 4*SLOTS-1   SLOTS epilogue warpgroups; warpgroup s owns slot s (thread = one sample row = one TMEM lane)
-//   warp  4*SLOTS          MMA issuer: one thread walks (tile iteration, layer, slot) in that order, waits for the slot's operand tile,
-//                          issues the layer's tcgen05.mma batch and commits it to the slot's `mma_done` mbarrier
-//   warp  4*SLOTS + 1      producer: fetches the 8 KB feature tile of the slot's NEXT sample tile with ONE TMA bulk copy
+//   issuer warps           one thread each walks (tile iteration, layer) of ITS slots, waits for the slot's operand tile, issues the layer's
+//                          tcgen05.mma batch and commits it to the slot's `mma_done` mbarrier. Several issuers, because issuing is not free:
+//                          measured on B200 (tools/umma_probe.py) one tcgen05.mma + commit costs the issuing thread ~340 cycles even when
+//                          nothing waits on it, ~100 cycles per further MMA of the batch, independent of N -- for these small tiles (8-32
+//                          tensor-pipe cycles per instruction) a single issuer caps the tensor pipe at ~10 % (first version of this file).
+//   last warp              producer: fetches the 8 KB feature tile of the slot's NEXT sample tile with ONE TMA bulk copy
 //                          (cp.async.bulk, completion on the slot's `x_full` mbarrier) as soon as the current tile's last reader is done
 //
-// so while warpgroup s runs the epilogue of layer l, the tensor pipe executes layer l of slot s+1, s+2, ... The hash-grid kernels hand the
+// so while warpgroup s runs the epilogue of layer l, the tensor pipe executes layer l of the other slots. Epilogue -> issuer and epilogue ->
+// producer signals are shared-memory counters (ld.acquire polling, ~30 cycles) rather than mbarriers (try_wait on a completed barrier: ~170 cycles). The hash-grid kernels hand the
 // features over in the UMMA core-matrix layout (tile_offset in umma.cuh), 8 KB contiguous per 128 samples, which is what makes the bulk
 // copy a single instruction; the row-major layout of the public C ABI is converted by the producer warp with plain loads.
 //
-// Inference: 6 slots x (8 KB X/Rin + 16 KB hidden) + 20 KB weights = 164 KB, 6 x 64 TMEM columns, 832 threads, one CTA per SM.
+// Inference: 6 slots x (8 KB X/Rin + 16 KB hidden) + 20 KB weights = 164 KB, 6 x 64 TMEM columns, 24 epilogue + 3 issuer + 1 producer warps, one CTA per SM.
 // Training:  2 slots x 92 KB (all activations of the tile stay resident for the backward pass and the weight-gradient GEMMs, the feature
-//            tile is double-buffered) + 20 KB weights = 204 KB; accumulators 2 x 64 columns + 160 columns of weight gradients that both
-//            slots accumulate into across all tiles of the CTA; 320 threads, one CTA per SM.
+//            tile is double-buffered) + 20 KB weights = 204 KB; per slot a 64-column accumulator and 160 columns of weight gradients accumulated
+//            across all tiles of the slot; 8 epilogue + 2 issuer + 1 producer warps, one CTA per SM.
 #include "common.cuh"
 #include "umma.cuh"
 #include "nerf_mlp_shared.cuh"
@@ -32,17 +36,45 @@ using namespace umma;
 
 // ---- barriers of one slot ---------------------------------------------------------------------------------------------------------------
 struct SlotBars {
-	uint64_t x_full[2];   // producer -> MMA issuer: feature tile landed (TMA transaction bytes, or the producer warp's arrive)
-	uint64_t x_empty[2];  // epilogue -> producer: the last MMA reading the feature buffer has completed
-	uint64_t mma_done;    // MMA issuer (tcgen05.commit) -> epilogue warpgroup: this layer's accumulator is complete
-	uint64_t act_ready;   // epilogue warpgroup (4 warp arrivals) -> MMA issuer: next operand tile written, accumulator columns free
+	uint64_t x_full[2];   // mbarrier, producer -> MMA issuer: feature tile landed (TMA transaction bytes, or the producer warp's arrive)
+	uint64_t mma_done;    // mbarrier, MMA issuer (tcgen05.commit) -> epilogue warpgroup: this layer's accumulator is complete
+	uint32_t x_empty[2];  // counter, epilogue -> producer: +1 when the last MMA reading the feature buffer has completed
+	uint32_t act_ready;   // counter, epilogue -> MMA issuer: +4 (one per warp) per finished epilogue: next operand tile written, accumulator columns free
+	uint32_t pad_;
 };
 
-__device__ __forceinline__ void signal_act_ready(uint64_t* bar, uint32_t lane) {
+__device__ __forceinline__ void signal_act_ready(uint32_t* flag, uint32_t lane) {
 	tc_fence_before_sync();     // our tcgen05.ld of the accumulator are ordered before the MMA that overwrites it
 	fence_proxy_async_smem();   // our shared-memory writes are visible to the tensor core's (async proxy) reads
 	__syncwarp();
-	if (lane == 0) mbar_arrive(bar);
+	if (lane == 0) flag_signal(flag);
+}
+
+// ---- one layer's MMA batch, descriptors reduced to `address >> 4` + constants (see mma_f16_ss_fast) -------------------------------------
+// D[128 x N] = A[128 x K] * W[N x K]^T, both K-major; A lives in a tile of A_COLS columns. a16 / w16: shared-memory byte address >> 4.
+template <uint32_t A_COLS, uint32_t K, uint32_t N>
+__device__ __forceinline__ void issue_fwd(uint32_t acc, uint32_t a16, uint32_t w16) {
+	constexpr uint32_t ID = make_idesc_f16(128, N, false, false), LO = desc_lo_const(128), A_HI = desc_hi_const((A_COLS >> 3) * 128), W_HI = desc_hi_const((K >> 3) * 128);
+	mma_f16_ss_fast<A_HI, W_HI, ID, 0>(acc, a16 + LO, w16 + LO);
+	#pragma unroll
+	for (uint32_t k = 1; k < K / 16; ++k) mma_f16_ss_fast<A_HI, W_HI, ID, 1>(acc, a16 + LO + 16 * k, w16 + LO + 16 * k);
+}
+// dIn[128 x N_IN] = dOut[128 x N_OUT] * W[N_OUT x N_IN]: A K-major in a tile of G_COLS columns, B = the forward weight tile read MN-major
+template <uint32_t G_COLS, uint32_t N_IN, uint32_t N_OUT>
+__device__ __forceinline__ void issue_dg(uint32_t acc, uint32_t g16, uint32_t w16) {
+	constexpr uint32_t ID = make_idesc_f16(128, N_IN, false, true), A_LO = desc_lo_const(128), A_HI = desc_hi_const((G_COLS >> 3) * 128);
+	constexpr uint32_t B_LO = desc_lo_const((N_IN >> 3) * 128), B_HI = desc_hi_const(128), B_STEP = 16 * (N_IN >> 3);
+	mma_f16_ss_fast<A_HI, B_HI, ID, 0>(acc, g16 + A_LO, w16 + B_LO);
+	#pragma unroll
+	for (uint32_t k = 1; k < N_OUT / 16; ++k) mma_f16_ss_fast<A_HI, B_HI, ID, 1>(acc, g16 + A_LO + 16 * k, w16 + B_LO + B_STEP * k);
+}
+// D[64 x N] (+)= P[128 x 64]^T * Q[128 x N]: both tiles read MN-major, K = the 128 sample rows, M = 64
+template <uint32_t N, bool FIRST>
+__device__ __forceinline__ void issue_wg(uint32_t acc, uint32_t p16, uint32_t q16) {
+	constexpr uint32_t ID = make_idesc_f16(64, N, true, true), A_LO = desc_lo_const(8 * 128), B_LO = desc_lo_const((N >> 3) * 128), HI = desc_hi_const(128), B_STEP = 16 * (N >> 3);
+	mma_f16_ss_fast<HI, HI, ID, FIRST ? 0 : 1>(acc, p16 + A_LO, q16 + B_LO);
+	#pragma unroll
+	for (uint32_t k = 1; k < TILE / 16; ++k) mma_f16_ss_fast<HI, HI, ID, 1>(acc, p16 + A_LO + 128 * k, q16 + B_LO + B_STEP * k);
 }
 
 // accumulator row (64 fp32 columns) -> ReLU -> fp16 -> row `row` of a [128][64] tile
@@ -127,9 +159,9 @@ __device__ __forceinline__ void fetch_features(const __half* encoded, uint32_t t
 // =========================================================================================================================================
 // Inference: MODE_DENSITY (density network only), MODE_INFERENCE (density + SH + rgb network), MODE_PLAIN (32 -> 64 -> 64 -> 16 alone)
 // =========================================================================================================================================
-constexpr uint32_t PI_SLOTS = 6;
-constexpr uint32_t PI_THREADS = PI_SLOTS * 128 + 64;
-constexpr uint32_t PI_MMA_WARP = PI_SLOTS * 4, PI_PRODUCER_WARP = PI_SLOTS * 4 + 1;
+constexpr uint32_t PI_SLOTS = 6, PI_ISSUERS = 3, PI_SLOTS_PER_ISSUER = PI_SLOTS / PI_ISSUERS;
+constexpr uint32_t PI_ISSUER_WARP0 = PI_SLOTS * 4, PI_PRODUCER_WARP = PI_ISSUER_WARP0 + PI_ISSUERS;
+constexpr uint32_t PI_THREADS = (PI_PRODUCER_WARP + 1) * 32;
 constexpr uint32_t PI_XR = 0, PI_H = 8192, PI_SLOT_BYTES = 24576; // XR: features, later the rgb network's input [density out 16 | SH 16]
 constexpr uint32_t PI_SLOT0 = SW_END;
 constexpr uint32_t PI_CTRL = PI_SLOT0 + PI_SLOTS * PI_SLOT_BYTES;
@@ -155,11 +187,11 @@ __global__ void __launch_bounds__(PI_THREADS, 1) nerf_mlp_pipe_infer_kernel(cons
 	const uint32_t n_tiles = n / TILE;
 	const uint32_t n_my = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u; // tiles blockIdx.x, + gridDim.x, ...
 
-	if (warp == PI_MMA_WARP) tmem_alloc<PI_TMEM_COLS>(tmem_slot);
+	if (warp == PI_ISSUER_WARP0) tmem_alloc<PI_TMEM_COLS>(tmem_slot);
 	if (tid == 0) {
 		for (uint32_t s = 0; s < PI_SLOTS; ++s) {
-			mbar_init(&bars[s].x_full[0], 1); mbar_init(&bars[s].x_empty[0], 1); mbar_init(&bars[s].x_full[1], 1); mbar_init(&bars[s].x_empty[1], 1);
-			mbar_init(&bars[s].mma_done, 1); mbar_init(&bars[s].act_ready, 4);
+			mbar_init(&bars[s].x_full[0], 1); mbar_init(&bars[s].x_full[1], 1); mbar_init(&bars[s].mma_done, 1);
+			bars[s].x_empty[0] = bars[s].x_empty[1] = bars[s].act_ready = 0u;
 		}
 		fence_mbar_init();
 	}
@@ -194,7 +226,7 @@ __global__ void __launch_bounds__(PI_THREADS, 1) nerf_mlp_pipe_infer_kernel(cons
 			for (uint32_t step = 0; step < NSTEPS; ++step) {
 				mbar_wait_bounded(&B.mma_done, n_done & 1u); ++n_done;
 				tc_fence_after_sync();
-				if (step == X_FREE_STEP && wq == 0 && lane == 0) mbar_arrive(&B.x_empty[0]);
+				if (step == X_FREE_STEP && wq == 0 && lane == 0) flag_signal(&B.x_empty[0]);
 				const bool hidden = MODE == MODE_PLAIN ? step < 2 : (step == 0 || step == 2 || step == 3);
 				if (hidden) {
 					epi_relu64(t_acc, slot + PI_H, row);
@@ -228,34 +260,40 @@ __global__ void __launch_bounds__(PI_THREADS, 1) nerf_mlp_pipe_infer_kernel(cons
 				signal_act_ready(&B.act_ready, lane);
 			}
 		}
-	} else if (warp == PI_MMA_WARP) {
-		// ------------------------------------------------ MMA issuer ------------------------------------------------
-		if (lane == 0) {
+	} else if (warp < PI_PRODUCER_WARP) {
+		// ------------------------------------------------ MMA issuer of slots [s0, s0 + PI_SLOTS_PER_ISSUER) ------------------------------------------------
+		// (the whole warp walks the loop with warp-uniform values; tcgen05.mma / commit are issued by one elected lane, see mma_f16_ss_fast)
+		{
+			const uint32_t s0 = (warp - PI_ISSUER_WARP0) * PI_SLOTS_PER_ISSUER;
 			const uint32_t n_iters = (n_my + PI_SLOTS - 1) / PI_SLOTS;
+			const uint32_t w16 = sbase >> 4;
 			for (uint32_t it = 0; it < n_iters; ++it) {
 				#pragma unroll
 				for (uint32_t step = 0; step < NSTEPS; ++step) {
-					for (uint32_t s = 0; s < PI_SLOTS; ++s) {
-						if (it * PI_SLOTS + s >= n_my) break;
+					#pragma unroll
+					for (uint32_t q = 0; q < PI_SLOTS_PER_ISSUER; ++q) {
+						const uint32_t s = s0 + q;
+						if (it * PI_SLOTS + s >= n_my) continue;
 						SlotBars& B = bars[s];
 						if (step == 0) mbar_wait_bounded(&B.x_full[0], it & 1u);
-						const int32_t ready_idx = (int32_t)(it * NSTEPS + step) - 1; // the previous epilogue of this slot (the previous tile's last one for step 0)
-						if (ready_idx >= 0) mbar_wait_bounded(&B.act_ready, (uint32_t)ready_idx & 1u);
+						const uint32_t n_epilogues = it * NSTEPS + step; // epilogues of this slot that must have finished (the previous tile's last one for step 0)
+						if (n_epilogues > 0) flag_wait_bounded(&B.act_ready, 4u * n_epilogues);
+						__syncwarp();
 						tc_fence_after_sync();
 						const uint32_t acc = tmem_base + s * 64u;
-						const uint32_t xr = sbase + PI_SLOT0 + s * PI_SLOT_BYTES + PI_XR, hh = sbase + PI_SLOT0 + s * PI_SLOT_BYTES + PI_H;
+						const uint32_t xr = (sbase + PI_SLOT0 + s * PI_SLOT_BYTES + PI_XR) >> 4, hh = (sbase + PI_SLOT0 + s * PI_SLOT_BYTES + PI_H) >> 4;
 						if (MODE == MODE_PLAIN) {
-							if (step == 0) issue_forward(acc, xr, 32, sbase + SW_W1R, 32, 64);
-							else if (step == 1) issue_forward(acc, hh, 64, sbase + SW_W2R, 64, 64);
-							else issue_forward(acc, hh, 64, sbase + SW_W3R, 64, 16);
+							if (step == 0) issue_fwd<32, 32, 64>(acc, xr, w16 + (SW_W1R >> 4));
+							else if (step == 1) issue_fwd<64, 64, 64>(acc, hh, w16 + (SW_W2R >> 4));
+							else issue_fwd<64, 64, 16>(acc, hh, w16 + (SW_W3R >> 4));
 						} else {
-							if (step == 0) issue_forward(acc, xr, 32, sbase + SW_W1D, 32, 64);
-							else if (step == 1) issue_forward(acc, hh, 64, sbase + SW_W2D, 64, 16);
-							else if (step == 2) issue_forward(acc, xr, 32, sbase + SW_W1R, 32, 64);
-							else if (step == 3) issue_forward(acc, hh, 64, sbase + SW_W2R, 64, 64);
-							else issue_forward(acc, hh, 64, sbase + SW_W3R, 64, 16);
+							if (step == 0) issue_fwd<32, 32, 64>(acc, xr, w16 + (SW_W1D >> 4));
+							else if (step == 1) issue_fwd<64, 64, 16>(acc, hh, w16 + (SW_W2D >> 4));
+							else if (step == 2) issue_fwd<32, 32, 64>(acc, xr, w16 + (SW_W1R >> 4));
+							else if (step == 3) issue_fwd<64, 64, 64>(acc, hh, w16 + (SW_W2R >> 4));
+							else issue_fwd<64, 64, 16>(acc, hh, w16 + (SW_W3R >> 4));
 						}
-						mma_commit(&B.mma_done);
+						mma_commit_elect(&B.mma_done);
 					}
 				}
 			}
@@ -264,30 +302,31 @@ __global__ void __launch_bounds__(PI_THREADS, 1) nerf_mlp_pipe_infer_kernel(cons
 		// ------------------------------------------------ producer ------------------------------------------------
 		for (uint32_t k = 0; k < n_my; ++k) {
 			const uint32_t s = k % PI_SLOTS, it = k / PI_SLOTS;
-			if (it > 0) mbar_wait_bounded(&bars[s].x_empty[0], (it - 1) & 1u);
+			if (it > 0) flag_wait_bounded(&bars[s].x_empty[0], it);
 			fetch_features(args.encoded, args.tiled, blockIdx.x + k * gridDim.x, smem + PI_SLOT0 + s * PI_SLOT_BYTES + PI_XR, &bars[s].x_full[0], lane);
 		}
 	}
 
 	tc_fence_before_sync();
 	__syncthreads();
-	if (warp == PI_MMA_WARP) { __syncwarp(); tmem_dealloc<PI_TMEM_COLS>(tmem_base); }
+	if (warp == PI_ISSUER_WARP0) { __syncwarp(); tmem_dealloc<PI_TMEM_COLS>(tmem_base); }
 }
 
 // =========================================================================================================================================
 // Training: forward + data gradients + weight gradients in one pass. MODE_TRAIN (NeRF networks), MODE_PLAIN_TRAIN (32 -> 64 -> 64 -> 16)
 // =========================================================================================================================================
 constexpr uint32_t PT_SLOTS = 2;
-constexpr uint32_t PT_THREADS = PT_SLOTS * 128 + 64;
-constexpr uint32_t PT_MMA_WARP = PT_SLOTS * 4, PT_PRODUCER_WARP = PT_SLOTS * 4 + 1;
+constexpr uint32_t PT_ISSUER_WARP0 = PT_SLOTS * 4, PT_PRODUCER_WARP = PT_ISSUER_WARP0 + PT_SLOTS; // one issuer per slot
+constexpr uint32_t PT_THREADS = (PT_PRODUCER_WARP + 1) * 32;
 // per-slot tiles (bytes). dG1 is written after G2's last use, dH1 after dG2's, dOd after dOr's (see the step list below).
 constexpr uint32_t PT_X0 = 0, PT_X1 = 8192, PT_H1 = 16384, PT_RIN = 32768, PT_G1 = 40960, PT_G2 = 57344, PT_DG1 = PT_G2, PT_DO = 73728, PT_DG2 = 77824, PT_DH1 = PT_DG2;
 constexpr uint32_t PT_SLOT_BYTES = 94208;
 constexpr uint32_t PT_SLOT0 = SW_END;
 constexpr uint32_t PT_CTRL = PT_SLOT0 + PT_SLOTS * PT_SLOT_BYTES;
 constexpr uint32_t PT_SMEM = PT_CTRL + PT_SLOTS * (uint32_t)sizeof(SlotBars) + 32;
-// TMEM columns: one 64-column accumulator per slot, then the weight gradients (M = 64 accumulators, shared by the slots)
-constexpr uint32_t PT_ACC = 0, PT_DW1D = 128, PT_DW2D = 160, PT_DW1R = 176, PT_DW2R = 208, PT_DW3R = 272, PT_TMEM_COLS = 512;
+// TMEM columns: one 64-column accumulator per slot, then per slot 160 columns of weight gradients (M = 64 accumulators). Each slot has its own issuer
+// thread, and two threads must not accumulate into the same columns; the two partial sums are added by the fixed-order reduction kernel.
+constexpr uint32_t PT_ACC = 0, PT_DW = 128, PT_DW_COLS = 160, PT_DW1D = 0, PT_DW2D = 32, PT_DW1R = 48, PT_DW2R = 80, PT_DW3R = 144, PT_TMEM_COLS = 512;
 
 struct PipeTrainArgs {
 	const __half* mlp; const __half* encoded; const float* coords; const __half* dL_dout; __half* dL_dencoded; float* partials;
@@ -307,13 +346,13 @@ __global__ void __launch_bounds__(PT_THREADS, 1) nerf_mlp_pipe_train_kernel(cons
 	const uint32_t n_tiles = args.n / TILE;
 	const uint32_t n_my = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
 
-	if (warp == PT_MMA_WARP) tmem_alloc<PT_TMEM_COLS>(tmem_slot);
+	if (warp == PT_ISSUER_WARP0) tmem_alloc<PT_TMEM_COLS>(tmem_slot);
 	if (tid == 0) {
 		for (uint32_t s = 0; s < PT_SLOTS; ++s) {
-			mbar_init(&bars[s].x_full[0], 1); mbar_init(&bars[s].x_full[1], 1); mbar_init(&bars[s].x_empty[0], 1); mbar_init(&bars[s].x_empty[1], 1);
-			mbar_init(&bars[s].mma_done, 1); mbar_init(&bars[s].act_ready, 4);
+			mbar_init(&bars[s].x_full[0], 1); mbar_init(&bars[s].x_full[1], 1); mbar_init(&bars[s].mma_done, 1);
+			bars[s].x_empty[0] = bars[s].x_empty[1] = bars[s].act_ready = 0u;
 		}
-		mbar_init(final_bar, 1);
+		mbar_init(final_bar, PT_SLOTS);
 		fence_mbar_init();
 	}
 	if (PLAIN) {
@@ -351,7 +390,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) nerf_mlp_pipe_train_kernel(cons
 				wait_mma(); epi_dgrad64(t_acc, slot + PT_G2, slot + PT_DG2, row); signal_act_ready(&B.act_ready, lane);      // 2: dG2 = (dO W3) . relu'(G2)
 				wait_mma(); epi_dgrad64(t_acc, slot + PT_G1, slot + PT_DG1, row); signal_act_ready(&B.act_ready, lane);      // 3: dG1 = (dG2 W2) . relu'(G1)
 				wait_mma();                                                                                                   // 4: dX = dG1 W1 -> HBM
-				if (wq == 0 && lane == 0) mbar_arrive(&B.x_empty[it & 1u]);
+				if (wq == 0 && lane == 0) flag_signal(&B.x_empty[it & 1u]);
 				{
 					uint32_t r[32];
 					tmem_ld_x32(t_acc, r);
@@ -397,7 +436,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) nerf_mlp_pipe_train_kernel(cons
 			signal_act_ready(&B.act_ready, lane);
 			wait_mma(); epi_dgrad64(t_acc, slot + PT_H1, slot + PT_DH1, row); signal_act_ready(&B.act_ready, lane);           // 7: dH1 = (dOd W2d) . relu'(H1)
 			wait_mma();                                                                                                       // 8: dX = dH1 W1d -> dL/dencoded (HBM)
-			if (wq == 0 && lane == 0) mbar_arrive(&B.x_empty[it & 1u]);
+			if (wq == 0 && lane == 0) flag_signal(&B.x_empty[it & 1u]);
 			{
 				uint32_t r[32];
 				tmem_ld_x32(t_acc, r);
@@ -408,17 +447,17 @@ __global__ void __launch_bounds__(PT_THREADS, 1) nerf_mlp_pipe_train_kernel(cons
 			}
 			signal_act_ready(&B.act_ready, lane);
 		}
-		// ---- this CTA's weight-gradient partial, written by warpgroup 0 once every MMA of the CTA has completed. M = 64 accumulators occupy
-		// lanes 0-15 of every 32-lane quadrant: warp w, lane l < 16 holds row 16 w + l. ----
-		if (s == 0) {
+		// ---- this slot's weight-gradient partial (set 2 * blockIdx.x + s), written once every MMA of the CTA has completed. M = 64 accumulators
+		// occupy lanes 0-15 of every 32-lane quadrant: warp w, lane l < 16 holds row 16 w + l. ----
+		{
 			mbar_wait_bounded(final_bar, 0u);
 			tc_fence_after_sync();
-			const uint32_t t_row = tmem_base + ((wq * 32u) << 16);
+			const uint32_t t_row = tmem_base + ((wq * 32u) << 16) + PT_DW + s * PT_DW_COLS;
 			const uint32_t wrow = wq * 16 + lane;
-			const bool have = n_my > 0;
+			const bool have = n_my > s; // a slot that never got a tile contributes zeros
 			uint32_t r[32];
 			if (PLAIN) {
-				float* part = args.partials + (size_t)blockIdx.x * PLAIN_PARAMS;
+				float* part = args.partials + (size_t)(blockIdx.x * PT_SLOTS + s) * PLAIN_PARAMS;
 				tmem_ld_x32(t_row + PT_DW1R, r); tmem_ld_wait();
 				if (lane < 16) { for (uint32_t i = 0; i < 32; ++i) part[PLAIN_W1 + wrow * 32 + i] = have ? __uint_as_float(r[i]) : 0.f; }
 				#pragma unroll
@@ -429,7 +468,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) nerf_mlp_pipe_train_kernel(cons
 				tmem_ld_x16(t_row + PT_DW3R, r); tmem_ld_wait();
 				if (lane < 16) { for (uint32_t o = 0; o < 16; ++o) part[PLAIN_W3 + o * 64 + wrow] = have ? __uint_as_float(r[o]) : 0.f; }
 			} else {
-				float* part = args.partials + (size_t)blockIdx.x * MLP_PARAMS;
+				float* part = args.partials + (size_t)(blockIdx.x * PT_SLOTS + s) * MLP_PARAMS;
 				tmem_ld_x32(t_row + PT_DW1D, r); tmem_ld_wait();   // dW1d[o][i]
 				if (lane < 16) { for (uint32_t i = 0; i < 32; ++i) part[MLP_W1D + wrow * 32 + i] = have ? __uint_as_float(r[i]) : 0.f; }
 				tmem_ld_x16(t_row + PT_DW2D, r); tmem_ld_wait();   // dW2d^T[i][o]
@@ -445,62 +484,64 @@ __global__ void __launch_bounds__(PT_THREADS, 1) nerf_mlp_pipe_train_kernel(cons
 				if (lane < 16) { for (uint32_t o = 0; o < 16; ++o) part[MLP_W3R + o * 64 + wrow] = have ? __uint_as_float(r[o]) : 0.f; }
 			}
 		}
-	} else if (warp == PT_MMA_WARP) {
-		// ------------------------------------------------ MMA issuer ------------------------------------------------
-		if (lane == 0) {
-			const uint32_t n_iters = (n_my + PT_SLOTS - 1) / PT_SLOTS;
-			bool first = true; // the very first weight-gradient batch of the CTA overwrites its accumulators
-			for (uint32_t it = 0; it < n_iters; ++it) {
+	} else if (warp < PT_PRODUCER_WARP) {
+		// ------------------------------------------------ MMA issuer of slot s (whole warp, one elected lane issues) ------------------------------------------------
+		{
+			const uint32_t s = warp - PT_ISSUER_WARP0;
+			SlotBars& B = bars[s];
+			const uint32_t acc = tmem_base + PT_ACC + s * 64u, dw = tmem_base + PT_DW + s * PT_DW_COLS;
+			const uint32_t w16 = sbase >> 4, sl = (sbase + PT_SLOT0 + s * PT_SLOT_BYTES) >> 4;
+			const uint32_t W1D = w16 + (SW_W1D >> 4), W2D = w16 + (SW_W2D >> 4), W1R = w16 + (SW_W1R >> 4), W2R = w16 + (SW_W2R >> 4), W3R = w16 + (SW_W3R >> 4);
+			const uint32_t H1 = sl + (PT_H1 >> 4), RIN = sl + (PT_RIN >> 4), G1 = sl + (PT_G1 >> 4), G2 = sl + (PT_G2 >> 4), DG1 = sl + (PT_DG1 >> 4), DO = sl + (PT_DO >> 4),
+			               DG2 = sl + (PT_DG2 >> 4), DH1 = sl + (PT_DH1 >> 4);
+			uint32_t it = 0;
+			for (uint32_t k = s; k < n_my; k += PT_SLOTS, ++it) {
+				const uint32_t xb = it & 1u;
+				const uint32_t X = sl + ((xb ? PT_X1 : PT_X0) >> 4);
 				#pragma unroll
 				for (uint32_t step = 0; step < NSTEPS; ++step) {
-					for (uint32_t s = 0; s < PT_SLOTS; ++s) {
-						if (it * PT_SLOTS + s >= n_my) break;
-						SlotBars& B = bars[s];
-						const uint32_t xb = it & 1u;
-						if (step == 0) mbar_wait_bounded(&B.x_full[xb], (it >> 1) & 1u);
-						const int32_t ready_idx = (int32_t)(it * NSTEPS + step) - 1;
-						if (ready_idx >= 0) mbar_wait_bounded(&B.act_ready, (uint32_t)ready_idx & 1u);
-						tc_fence_after_sync();
-						const uint32_t acc = tmem_base + PT_ACC + s * 64u;
-						const uint32_t sl = sbase + PT_SLOT0 + s * PT_SLOT_BYTES;
-						const uint32_t X = sl + (xb ? PT_X1 : PT_X0);
-						const bool f = first && s == 0 && it == 0;
-						if (PLAIN) {
-							if (step == 0) issue_forward(acc, X, 32, sbase + SW_W1R, 32, 64);
-							else if (step == 1) issue_forward(acc, sl + PT_G1, 64, sbase + SW_W2R, 64, 64);
-							else if (step == 2) { issue_dgrad(acc, sl + PT_DO, 16, sbase + SW_W3R, 64, 16); issue_wgrad(tmem_base + PT_DW3R, sl + PT_G2, sl + PT_DO, 16, 16, f); }
-							else if (step == 3) { issue_dgrad(acc, sl + PT_DG2, 64, sbase + SW_W2R, 64, 64); issue_wgrad(tmem_base + PT_DW2R, sl + PT_DG2, sl + PT_G1, 64, 64, f); }
-							else { issue_dgrad(acc, sl + PT_DG1, 64, sbase + SW_W1R, 32, 64); issue_wgrad(tmem_base + PT_DW1R, sl + PT_DG1, X, 32, 32, f); }
-						} else {
-							if (step == 0) issue_forward(acc, X, 32, sbase + SW_W1D, 32, 64);
-							else if (step == 1) issue_forward(acc, sl + PT_H1, 64, sbase + SW_W2D, 64, 16);
-							else if (step == 2) issue_forward(acc, sl + PT_RIN, 32, sbase + SW_W1R, 32, 64);
-							else if (step == 3) issue_forward(acc, sl + PT_G1, 64, sbase + SW_W2R, 64, 64);
-							else if (step == 4) { issue_dgrad(acc, sl + PT_DO, 16, sbase + SW_W3R, 64, 16); issue_wgrad(tmem_base + PT_DW3R, sl + PT_G2, sl + PT_DO, 16, 16, f); }
-							else if (step == 5) { issue_dgrad(acc, sl + PT_DG2, 64, sbase + SW_W2R, 64, 64); issue_wgrad(tmem_base + PT_DW2R, sl + PT_DG2, sl + PT_G1, 64, 64, f); }
-							else if (step == 6) { issue_dgrad(acc, sl + PT_DG1, 64, sbase + SW_W1R, 32, 64); issue_wgrad(tmem_base + PT_DW1R, sl + PT_DG1, sl + PT_RIN, 32, 32, f); }
-							else if (step == 7) { issue_dgrad(acc, sl + PT_DO, 16, sbase + SW_W2D, 64, 16); issue_wgrad(tmem_base + PT_DW2D, sl + PT_H1, sl + PT_DO, 16, 16, f); }
-							else { issue_dgrad(acc, sl + PT_DH1, 64, sbase + SW_W1D, 32, 64); issue_wgrad(tmem_base + PT_DW1D, sl + PT_DH1, X, 32, 32, f); }
-						}
-						mma_commit(&B.mma_done);
+					if (step == 0) mbar_wait_bounded(&B.x_full[xb], (it >> 1) & 1u);
+					const uint32_t n_epilogues = it * NSTEPS + step;
+					if (n_epilogues > 0) flag_wait_bounded(&B.act_ready, 4u * n_epilogues);
+					__syncwarp();
+					tc_fence_after_sync();
+					// the first tile of the slot overwrites its weight-gradient accumulators, later tiles add to them
+					#define NGPB_WG(N, DST, P, Q) do { if (it == 0) issue_wg<N, true>(dw + DST, P, Q); else issue_wg<N, false>(dw + DST, P, Q); } while (0)
+					if (PLAIN) {
+						if (step == 0) issue_fwd<32, 32, 64>(acc, X, W1R);                                  // G1 = relu(X W1^T)
+						else if (step == 1) issue_fwd<64, 64, 64>(acc, G1, W2R);                            // G2 = relu(G1 W2^T)
+						else if (step == 2) { issue_dg<16, 64, 16>(acc, DO, W3R); NGPB_WG(16, PT_DW3R, G2, DO); }    // dG2; dW3^T += G2^T dO
+						else if (step == 3) { issue_dg<64, 64, 64>(acc, DG2, W2R); NGPB_WG(64, PT_DW2R, DG2, G1); }  // dG1; dW2 += dG2^T G1
+						else { issue_dg<64, 32, 64>(acc, DG1, W1R); NGPB_WG(32, PT_DW1R, DG1, X); }                  // dX;  dW1 += dG1^T X
+					} else {
+						if (step == 0) issue_fwd<32, 32, 64>(acc, X, W1D);                                  // H1 = relu(X W1d^T)
+						else if (step == 1) issue_fwd<64, 64, 16>(acc, H1, W2D);                            // Od = H1 W2d^T
+						else if (step == 2) issue_fwd<32, 32, 64>(acc, RIN, W1R);                           // G1 = relu(Rin W1r^T)
+						else if (step == 3) issue_fwd<64, 64, 64>(acc, G1, W2R);                            // G2 = relu(G1 W2r^T)
+						else if (step == 4) { issue_dg<16, 64, 16>(acc, DO, W3R); NGPB_WG(16, PT_DW3R, G2, DO); }    // dG2 = (dOr W3r) . relu'(G2);  dW3r^T += G2^T dOr
+						else if (step == 5) { issue_dg<64, 64, 64>(acc, DG2, W2R); NGPB_WG(64, PT_DW2R, DG2, G1); }  // dG1 = (dG2 W2r) . relu'(G1);  dW2r += dG2^T G1
+						else if (step == 6) { issue_dg<64, 32, 64>(acc, DG1, W1R); NGPB_WG(32, PT_DW1R, DG1, RIN); } // dRin = dG1 W1r;               dW1r += dG1^T Rin
+						else if (step == 7) { issue_dg<16, 64, 16>(acc, DO, W2D); NGPB_WG(16, PT_DW2D, H1, DO); }    // dH1 = (dOd W2d) . relu'(H1);  dW2d^T += H1^T dOd
+						else { issue_dg<64, 32, 64>(acc, DH1, W1D); NGPB_WG(32, PT_DW1D, DH1, X); }                  // dX = dH1 W1d;                 dW1d += dH1^T X
 					}
+					#undef NGPB_WG
+					mma_commit_elect(&B.mma_done);
 				}
-				first = false;
 			}
-			mma_commit(final_bar); // completes once every MMA issued above has: the weight-gradient accumulators are final
+			mma_commit_elect(final_bar); // arrives once every MMA this thread issued has completed: with both issuers' arrivals the weight gradients are final
 		}
 	} else {
 		// ------------------------------------------------ producer (feature tiles, one tile ahead per slot) ------------------------------------------------
 		for (uint32_t k = 0; k < n_my; ++k) {
 			const uint32_t s = k % PT_SLOTS, it = k / PT_SLOTS, xb = it & 1u;
-			if (it >= 2) mbar_wait_bounded(&bars[s].x_empty[xb], ((it >> 1) - 1u) & 1u);
+			if (it >= 2) flag_wait_bounded(&bars[s].x_empty[xb], it >> 1);
 			fetch_features(args.encoded, args.tiled, blockIdx.x + k * gridDim.x, smem + PT_SLOT0 + s * PT_SLOT_BYTES + (xb ? PT_X1 : PT_X0), &bars[s].x_full[xb], lane);
 		}
 	}
 
 	tc_fence_before_sync();
 	__syncthreads();
-	if (warp == PT_MMA_WARP) { __syncwarp(); tmem_dealloc<PT_TMEM_COLS>(tmem_base); }
+	if (warp == PT_ISSUER_WARP0) { __syncwarp(); tmem_dealloc<PT_TMEM_COLS>(tmem_base); }
 }
 
 // ---- launchers --------------------------------------------------------------------------------------------------------------------------
@@ -525,7 +566,7 @@ static uint32_t launch_pipe_train(cudaStream_t stream, const PipeTrainArgs& a) {
 	const uint32_t grid = std::min(a.n / TILE, kNumSMs);
 	nerf_mlp_pipe_train_kernel<MODE><<<grid, PT_THREADS, PT_SMEM, stream>>>(a);
 	NGPB_LAUNCH_CHECK();
-	return grid;
+	return grid * PT_SLOTS; // partial sets written (one per slot)
 }
 
 void pipe_nerf_forward(cudaStream_t stream, const __half* mlp, const __half* encoded, bool tiled, const float* coords, uint32_t n, const uint32_t* n_dev, __half* rgbsigma) {
