@@ -30,6 +30,8 @@
 #include "umma.cuh"
 #include "nerf_mlp_shared.cuh"
 #include "../../include/ngpb.h"
+#include <cstdio>
+#include <vector>
 
 namespace ngpb {
 using namespace umma;
@@ -171,7 +173,9 @@ constexpr uint32_t PI_TMEM_COLS = 512; // 6 x 64 used; allocations are powers of
 struct PipeInferArgs {
 	const __half* mlp; const __half* encoded; const float* coords; __half* out;
 	uint32_t n; const uint32_t* n_dev; uint32_t tiled;
+	long long* trace; // development aid (NGPB_PIPE_TRACE=path): CTA 0 records (role, slot, iteration, step, clock) events
 };
+#define NGPB_TRACE(role, slot_, it_, step_) do { if (args.trace && blockIdx.x == 0 && (it_) < 3) { args.trace[((((role) * 6 + (slot_)) * 3 + (it_)) * 8 + (step_))] = clock64(); } } while (0)
 
 template <int MODE>
 __global__ void __launch_bounds__(PI_THREADS, 1) nerf_mlp_pipe_infer_kernel(const PipeInferArgs args)
@@ -226,6 +230,7 @@ __global__ void __launch_bounds__(PI_THREADS, 1) nerf_mlp_pipe_infer_kernel(cons
 			for (uint32_t step = 0; step < NSTEPS; ++step) {
 				mbar_wait_bounded(&B.mma_done, n_done & 1u); ++n_done;
 				tc_fence_after_sync();
+				if (wq == 0 && lane == 0) NGPB_TRACE(0, s, k / PI_SLOTS, step);
 				if (step == X_FREE_STEP && wq == 0 && lane == 0) flag_signal(&B.x_empty[0]);
 				const bool hidden = MODE == MODE_PLAIN ? step < 2 : (step == 0 || step == 2 || step == 3);
 				if (hidden) {
@@ -258,6 +263,7 @@ __global__ void __launch_bounds__(PI_THREADS, 1) nerf_mlp_pipe_infer_kernel(cons
 					*reinterpret_cast<uint2*>(args.out + row_g * 4) = o;
 				}
 				signal_act_ready(&B.act_ready, lane);
+				if (wq == 0 && lane == 0) NGPB_TRACE(1, s, k / PI_SLOTS, step);
 			}
 		}
 	} else if (warp < PI_PRODUCER_WARP) {
@@ -280,6 +286,7 @@ __global__ void __launch_bounds__(PI_THREADS, 1) nerf_mlp_pipe_infer_kernel(cons
 						if (n_epilogues > 0) flag_wait_bounded(&B.act_ready, 4u * n_epilogues);
 						__syncwarp();
 						tc_fence_after_sync();
+						if (lane == 0) NGPB_TRACE(2, s, it, step);
 						const uint32_t acc = tmem_base + s * 64u;
 						const uint32_t xr = (sbase + PI_SLOT0 + s * PI_SLOT_BYTES + PI_XR) >> 4, hh = (sbase + PI_SLOT0 + s * PI_SLOT_BYTES + PI_H) >> 4;
 						if (MODE == MODE_PLAIN) {
@@ -294,6 +301,7 @@ __global__ void __launch_bounds__(PI_THREADS, 1) nerf_mlp_pipe_infer_kernel(cons
 							else issue_fwd<64, 64, 16>(acc, hh, w16 + (SW_W3R >> 4));
 						}
 						mma_commit_elect(&B.mma_done);
+						if (lane == 0) NGPB_TRACE(3, s, it, step);
 					}
 				}
 			}
@@ -377,6 +385,9 @@ __global__ void __launch_bounds__(PT_THREADS, 1) nerf_mlp_pipe_train_kernel(cons
 		const uint32_t t_acc = tmem_base + ((wq * 32u) << 16) + PT_ACC + s * 64u;
 		uint32_t n_done = 0, it = 0;
 		auto wait_mma = [&]() { mbar_wait_bounded(&B.mma_done, n_done & 1u); ++n_done; tc_fence_after_sync(); };
+		// The previous tile's feature buffer is last read by that tile's final weight-gradient batch, which is issued AFTER its step's commit; the first
+		// commit of this tile covers it, so the buffer goes back to the producer here (called right after wait_mma of step 0).
+		auto release_prev_x = [&]() { if (it > 0 && wq == 0 && lane == 0) flag_signal(&B.x_empty[(it - 1u) & 1u]); };
 		for (uint32_t k = s; k < n_my; k += PT_SLOTS, ++it) {
 			const uint32_t tile = blockIdx.x + k * gridDim.x;
 			const size_t row_g = (size_t)tile * TILE + row;
@@ -385,12 +396,11 @@ __global__ void __launch_bounds__(PT_THREADS, 1) nerf_mlp_pipe_train_kernel(cons
 				const uint4* g = reinterpret_cast<const uint4*>(args.dL_dout + row_g * 16);
 				*reinterpret_cast<uint4*>(slot + PT_DO + tile_offset(row, 0, 16)) = __ldg(g);
 				*reinterpret_cast<uint4*>(slot + PT_DO + tile_offset(row, 1, 16)) = __ldg(g + 1);
-				wait_mma(); epi_relu64(t_acc, slot + PT_G1, row); signal_act_ready(&B.act_ready, lane);                      // 0: G1 = relu(X W1^T)
+				wait_mma(); release_prev_x(); epi_relu64(t_acc, slot + PT_G1, row); signal_act_ready(&B.act_ready, lane);   // 0: G1 = relu(X W1^T)
 				wait_mma(); epi_relu64(t_acc, slot + PT_G2, row); signal_act_ready(&B.act_ready, lane);                      // 1: G2 = relu(G1 W2^T)
 				wait_mma(); epi_dgrad64(t_acc, slot + PT_G2, slot + PT_DG2, row); signal_act_ready(&B.act_ready, lane);      // 2: dG2 = (dO W3) . relu'(G2)
 				wait_mma(); epi_dgrad64(t_acc, slot + PT_G1, slot + PT_DG1, row); signal_act_ready(&B.act_ready, lane);      // 3: dG1 = (dG2 W2) . relu'(G1)
 				wait_mma();                                                                                                   // 4: dX = dG1 W1 -> HBM
-				if (wq == 0 && lane == 0) flag_signal(&B.x_empty[it & 1u]);
 				{
 					uint32_t r[32];
 					tmem_ld_x32(t_acc, r);
@@ -406,7 +416,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) nerf_mlp_pipe_train_kernel(cons
 			const float dx = cd[4], dy = cd[5], dz = cd[6];
 			const uint2 g = __ldg(reinterpret_cast<const uint2*>(args.dL_dout + row_g * 4));
 			const float dsigma = __high2float(*reinterpret_cast<const __half2*>(&g.y));
-			wait_mma(); epi_relu64(t_acc, slot + PT_H1, row); signal_act_ready(&B.act_ready, lane);                           // 0: H1 = relu(X W1d^T)
+			wait_mma(); release_prev_x(); epi_relu64(t_acc, slot + PT_H1, row); signal_act_ready(&B.act_ready, lane);        // 0: H1 = relu(X W1d^T)
 			wait_mma();                                                                                                       // 1: Od = H1 W2d^T -> Rin[:, :16]; SH -> Rin[:, 16:]; dOr
 			{
 				uint32_t r[16];
@@ -436,7 +446,6 @@ __global__ void __launch_bounds__(PT_THREADS, 1) nerf_mlp_pipe_train_kernel(cons
 			signal_act_ready(&B.act_ready, lane);
 			wait_mma(); epi_dgrad64(t_acc, slot + PT_H1, slot + PT_DH1, row); signal_act_ready(&B.act_ready, lane);           // 7: dH1 = (dOd W2d) . relu'(H1)
 			wait_mma();                                                                                                       // 8: dX = dH1 W1d -> dL/dencoded (HBM)
-			if (wq == 0 && lane == 0) flag_signal(&B.x_empty[it & 1u]);
 			{
 				uint32_t r[32];
 				tmem_ld_x32(t_acc, r);
@@ -505,8 +514,11 @@ __global__ void __launch_bounds__(PT_THREADS, 1) nerf_mlp_pipe_train_kernel(cons
 					if (n_epilogues > 0) flag_wait_bounded(&B.act_ready, 4u * n_epilogues);
 					__syncwarp();
 					tc_fence_after_sync();
-					// the first tile of the slot overwrites its weight-gradient accumulators, later tiles add to them
-					#define NGPB_WG(N, DST, P, Q) do { if (it == 0) issue_wg<N, true>(dw + DST, P, Q); else issue_wg<N, false>(dw + DST, P, Q); } while (0)
+					// The commit sits between the data-gradient batch and the weight-gradient batch: the epilogue only needs the former, and runs while the
+					// tensor pipe works through the eight dependent K-steps of the latter. The NEXT step's commit also covers this step's weight-gradient
+					// MMAs (a commit tracks everything its thread issued before), which is what the aliased tiles need before they are overwritten.
+					// The first tile of the slot overwrites its weight-gradient accumulators, later tiles add to them.
+					#define NGPB_WG(N, DST, P, Q) do { mma_commit_elect(&B.mma_done); if (it == 0) issue_wg<N, true>(dw + DST, P, Q); else issue_wg<N, false>(dw + DST, P, Q); } while (0)
 					if (PLAIN) {
 						if (step == 0) issue_fwd<32, 32, 64>(acc, X, W1R);                                  // G1 = relu(X W1^T)
 						else if (step == 1) issue_fwd<64, 64, 64>(acc, G1, W2R);                            // G2 = relu(G1 W2^T)
@@ -525,7 +537,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) nerf_mlp_pipe_train_kernel(cons
 						else { issue_dg<64, 32, 64>(acc, DH1, W1D); NGPB_WG(32, PT_DW1D, DH1, X); }                  // dX = dH1 W1d;                 dW1d += dH1^T X
 					}
 					#undef NGPB_WG
-					mma_commit_elect(&B.mma_done);
+					if (step < (PLAIN ? 2u : 4u)) mma_commit_elect(&B.mma_done); // forward steps: no weight-gradient batch, commit here
 				}
 			}
 			mma_commit_elect(final_bar); // arrives once every MMA this thread issued has completed: with both issuers' arrivals the weight gradients are final
@@ -569,14 +581,26 @@ static uint32_t launch_pipe_train(cudaStream_t stream, const PipeTrainArgs& a) {
 	return grid * PT_SLOTS; // partial sets written (one per slot)
 }
 
+static long long* g_trace_dev = nullptr;
 void pipe_nerf_forward(cudaStream_t stream, const __half* mlp, const __half* encoded, bool tiled, const float* coords, uint32_t n, const uint32_t* n_dev, __half* rgbsigma) {
-	launch_pipe_infer<MODE_INFERENCE>(stream, PipeInferArgs{mlp, encoded, coords, rgbsigma, n, n_dev, tiled ? 1u : 0u});
+	static const char* trace_path = getenv("NGPB_PIPE_TRACE");
+	static const bool force_tiled = getenv("NGPB_PIPE_FORCE_TILED") != nullptr; // timing experiments through the row-major C ABI: the layout does not change the arithmetic's cost
+	if (force_tiled) tiled = true;
+	if (trace_path && !g_trace_dev) { NGPB_CUDA_CHECK(cudaMalloc(&g_trace_dev, 4 * 6 * 3 * 8 * sizeof(long long))); }
+	if (g_trace_dev) NGPB_CUDA_CHECK(cudaMemsetAsync(g_trace_dev, 0, 4 * 6 * 3 * 8 * sizeof(long long), stream));
+	launch_pipe_infer<MODE_INFERENCE>(stream, PipeInferArgs{mlp, encoded, coords, rgbsigma, n, n_dev, tiled ? 1u : 0u, g_trace_dev});
+	if (g_trace_dev) {
+		std::vector<long long> h(4 * 6 * 3 * 8);
+		NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
+		NGPB_CUDA_CHECK(cudaMemcpy(h.data(), g_trace_dev, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+		if (FILE* f = fopen(trace_path, "w")) { for (size_t i = 0; i < h.size(); ++i) fprintf(f, "%lld\n", h[i]); fclose(f); }
+	}
 }
 void pipe_density_forward(cudaStream_t stream, const __half* mlp, const __half* encoded, bool tiled, uint32_t n, __half* density) {
-	launch_pipe_infer<MODE_DENSITY>(stream, PipeInferArgs{mlp, encoded, nullptr, density, n, nullptr, tiled ? 1u : 0u});
+	launch_pipe_infer<MODE_DENSITY>(stream, PipeInferArgs{mlp, encoded, nullptr, density, n, nullptr, tiled ? 1u : 0u, nullptr});
 }
 void pipe_plain_forward(cudaStream_t stream, const __half* weights, const __half* input, uint32_t n, __half* output) {
-	launch_pipe_infer<MODE_PLAIN>(stream, PipeInferArgs{weights, input, nullptr, output, n, nullptr, 0u});
+	launch_pipe_infer<MODE_PLAIN>(stream, PipeInferArgs{weights, input, nullptr, output, n, nullptr, 0u, nullptr});
 }
 uint32_t pipe_nerf_forward_backward(cudaStream_t stream, const __half* mlp, const __half* encoded, bool tiled, const float* coords, const __half* dL_dout, uint32_t n,
                                     __half* dL_dencoded, float* partials) {

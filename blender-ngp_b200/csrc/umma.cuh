@@ -71,16 +71,22 @@ __device__ __forceinline__ uint32_t flag_peek(const uint32_t* flag) {
 	asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(flag)) : "memory");
 	return v;
 }
+// Polls with relaxed loads (an acquire load per iteration carries a fence) and acquires once at the end.
 __device__ __forceinline__ void flag_wait_bounded(const uint32_t* flag, uint32_t target) {
+	const uint32_t addr = smem_u32(flag);
 	uint32_t spins = 0;
 	long long t0 = 0;
-	while ((int32_t)(flag_peek(flag) - target) < 0) {
+	while (true) {
+		uint32_t v;
+		asm volatile("ld.relaxed.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+		if ((int32_t)(v - target) >= 0) break;
 		if ((++spins & 4095u) == 0u) {
 			const long long now = clock64();
 			if (t0 == 0) t0 = now;
 			else if (now - t0 > 4000000000ll) asm volatile("trap;");
 		}
 	}
+	asm volatile("fence.acquire.cta;" ::: "memory");
 }
 
 // ---- proxies and tcgen05 fences -------------------------------------------------------------------

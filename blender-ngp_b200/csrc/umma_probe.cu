@@ -179,6 +179,34 @@ __global__ void __launch_bounds__(128) umma_probe_kernel(long long* __restrict__
 		if (acc == 0x12345678u) out[200] = 1;
 		record((t1 - t0) / 8);
 	}
+	// ---- F: tensor-pipe throughput with the warp-uniform issue path (mma_f16_ss_fast): W warps each issue 32 MMAs into their own accumulator, one commit each ----
+	slot = 30;
+	if (sections & 32u) {
+		for (uint32_t cfg = 0; cfg < 6; ++cfg) {
+			// cfg: 0: 1 warp N=64 K-major; 1: 4 warps N=64; 2: 1 warp N=16; 3: 4 warps N=16; 4: 1 warp wgrad-shaped (M=64, N=64, MN-major both); 5: 4 warps wgrad-shaped
+			const uint32_t n_warps = (cfg & 1u) ? 4u : 1u;
+			__syncthreads();
+			if (tid == 0) { for (uint32_t i = 0; i < 4; ++i) mbar_init(&bars[i], 1); fence_mbar_init(); }
+			__syncthreads();
+			const long long t0 = clock64();
+			if (warp < n_warps) {
+				const uint32_t acc = tmem_base + warp * 64u, a16 = (sbase + OFF_A) >> 4, w16 = (sbase + OFF_W) >> 4;
+				constexpr uint32_t LO = desc_lo_const(128), HI64 = desc_hi_const(8 * 128), MN_LO = desc_lo_const(8 * 128), MN_HI = desc_hi_const(128);
+				#pragma unroll
+				for (uint32_t j = 0; j < 32; ++j) {
+					if (cfg < 2) mma_f16_ss_fast<HI64, HI64, make_idesc_f16(128, 64, false, false), 1>(acc, a16 + LO + 16 * (j & 3), w16 + LO + 16 * (j & 3));
+					else if (cfg < 4) mma_f16_ss_fast<HI64, HI64, make_idesc_f16(128, 16, false, false), 1>(acc, a16 + LO + 16 * (j & 3), w16 + LO + 16 * (j & 3));
+					else mma_f16_ss_fast<MN_HI, MN_HI, make_idesc_f16(64, 64, true, true), 1>(acc, a16 + MN_LO + 128 * (j & 7), a16 + MN_LO + 128 * (j & 7));
+				}
+				mma_commit_elect(&bars[warp]);
+				__syncwarp();
+				mbar_wait_bounded(&bars[warp], 0);
+			}
+			__syncthreads();
+			const long long t1 = clock64();
+			record((t1 - t0) / 32);
+		}
+	}
 	tc_fence_before_sync();
 	__syncthreads();
 	if (warp == 0) tmem_dealloc<512>(tmem_base);
