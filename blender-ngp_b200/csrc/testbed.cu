@@ -663,6 +663,24 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 	}
 	if (training_step == 0) n_rays_total = 0;
 	n_rays_total += rays_per_batch;
+	// Development aid (NGPB_POISON = bit mask): overwrite per-step buffers with 0xFF (NaN patterns) before the step, so that any read of a value the
+	// step itself did not write shows up as NaN in the loss / parameters instead of hiding behind stale data of an earlier step or process.
+	static const uint32_t poison = getenv("NGPB_POISON") ? (uint32_t)strtoul(getenv("NGPB_POISON"), nullptr, 0) : 0u;
+	if (poison) {
+		drop_prefetch();
+		const size_t max_rays = 1u << 18;
+		if (poison & 1u) NGPB_CUDA_CHECK(cudaMemsetAsync(encoded, 0xFF, sizeof(__half) * N_ENC * max_samples, stream));
+		if (poison & 2u) NGPB_CUDA_CHECK(cudaMemsetAsync(rgbsigma, 0xFF, sizeof(__half) * 4 * max_samples, stream));
+		if (poison & 4u) NGPB_CUDA_CHECK(cudaMemsetAsync(coords, 0xFF, sizeof(float) * COORD_FLOATS * max_samples, stream));
+		if (poison & 8u) NGPB_CUDA_CHECK(cudaMemsetAsync(encoded_compacted, 0xFF, sizeof(__half) * N_ENC * batch, stream));
+		if (poison & 16u) NGPB_CUDA_CHECK(cudaMemsetAsync(coords_compacted, 0xFF, sizeof(float) * COORD_FLOATS * batch, stream));
+		if (poison & 32u) NGPB_CUDA_CHECK(cudaMemsetAsync(dloss, 0xFF, sizeof(__half) * 4 * batch, stream));
+		if (poison & 64u) NGPB_CUDA_CHECK(cudaMemsetAsync(denc, 0xFF, sizeof(__half) * N_ENC * batch, stream));
+		if (poison & 128u) NGPB_CUDA_CHECK(cudaMemsetAsync(partials, 0xFF, (size_t)ngpb_nerf_mlp_workspace_bytes(), stream));
+		if (poison & 256u) NGPB_CUDA_CHECK(cudaMemsetAsync(scratch, 0xFF, (size_t)std::max(ngpb_generate_training_samples_scratch_bytes((uint32_t)max_rays), ngpb_compute_loss_scratch_bytes((uint32_t)max_rays)), stream));
+		if (poison & 512u) NGPB_CUDA_CHECK(cudaMemsetAsync(loss, 0xFF, sizeof(float) * max_rays, stream));
+		if (poison & 1024u) { NGPB_CUDA_CHECK(cudaMemsetAsync(rays, 0xFF, sizeof(float) * 6 * max_rays, stream)); NGPB_CUDA_CHECK(cudaMemsetAsync(numsteps, 0xFF, sizeof(uint32_t) * 2 * max_rays, stream)); NGPB_CUDA_CHECK(cudaMemsetAsync(ray_indices, 0xFF, sizeof(uint32_t) * max_rays, stream)); }
+	}
 	const uint32_t R = rays_per_batch;
 	const SamplingRequest req{training_step, R, max_inference, ngpb_rng{rng.state, rng.inc}, loss_cfg.snap_to_pixel_centers, cone_angle_constant};
 	const ngpb_rng r = req.rng;
