@@ -20,6 +20,7 @@ host cores, bounded to --cpu-seconds), `render` (classic Testbed.render Msamples
 Prints ONE JSON line (rank 0).
 """
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -39,7 +40,8 @@ N_IMAGES, RES = 100, 800
 
 # Algorithmic bytes / flops per unit (restated in DESIGN.md s4)
 HASH_FWD_BYTES = 12 + 16 * 8 * 4 + 16 * 2 * 2      # 588 B/sample: position + 128 gathers x 4 B + 32 fp16 features out
-HASH_BWD_BYTES = 12 + 64 + 16 * 8 * 2 * 4           # 1100 B/sample: position + dL/dy + 128 x (2 x fp32) scatter-adds (counted once, before aggregation)
+HASH_BWD_BYTES = 12 + 64 + 16 * 8 * 4               # 588 B/sample: position + dL/dy + 128 scatter-adds of one fp16 pair each -- the REFERENCE's traffic
+HASH_BWD_BYTES_AS_EXECUTED = 12 + 64 + 16 * 8 * 2 * 4   # 1100 B/sample: this build accumulates fp32 pairs (8 B per scatter-add); reported next to the figure above, never instead of it
 MLP_FWD_FLOPS = 20480                               # padded widths as executed
 MLP_TRAIN_FLOPS = 61440
 STAGE_ALGO = {  # stage -> (bound, per-unit quantity, unit of `achieved`)
@@ -48,11 +50,24 @@ STAGE_ALGO = {  # stage -> (bound, per-unit quantity, unit of `achieved`)
     "encode_backward": ("hbm", HASH_BWD_BYTES, "GB/s"),
     "mlp_inference": ("tensor", MLP_FWD_FLOPS, "TFLOP/s"),
     "mlp_train": ("tensor", MLP_TRAIN_FLOPS, "TFLOP/s"),
-    # 10 B/param for every parameter (gradient read 4, fp16 weight read 2, EMA read + write 4) + 36 B for a parameter whose gradient is
-    # non-zero (gradient reset 4, fp32 weight / two moments / step counter r+w 32). The touched fraction is data dependent: the ncu capture of this
-    # workload measures 362 MB per launch = 49 % of the parameters touched, so 10 + 0.49 x 36 = 27.6 B/param is used as the per-unit figure.
-    "optimizer": ("hbm", 27.6, "GB/s"),
 }
+# Stages whose algorithmic bytes depend on more than one unit count; evaluated in stage_bytes() below:
+#   sampling (K1)   28 B per marched sample written + 36 B per ray
+#   loss (K6 + K7)  72 B per marched sample (8 B network output + 28 B coordinate in, 28 B coordinate + 8 B gradient out) + 56 B per ray
+#   optimizer (K15) 10 B per parameter (gradient memset 2 + Adam's gradient read 2 + EMA 6) + 34 B per parameter whose gradient is non-zero;
+#                   the touched count is MEASURED in the run (per-parameter step counters before / after one step), not fitted
+OPT_FIXED_BYTES, OPT_TOUCHED_BYTES = 10, 34
+L2_PEAK_BYTES_PER_CLK = 6300.0  # B300_MICROARCH.md "LTS throughput cap ~6300 B/cyc full-chip" (measured on B300; same L2 design): x the SM clock of the run
+
+
+def stage_bytes(name, rays, samples, batch, n_params, touched):
+    if name == "sampling":
+        return samples * 28 + rays * 36
+    if name == "loss":
+        return samples * 72 + rays * 56
+    if name == "optimizer":
+        return n_params * OPT_FIXED_BYTES + touched * OPT_TOUCHED_BYTES
+    return None
 
 
 def parse_args():
@@ -81,46 +96,55 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 50 ms during the timed region (B200_PROFILING.md's clocks line)."""
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock and throttle reasons polled through NVML every ~1 ms from a thread while the timed region runs (the timed call releases the GIL).
+    nvidia-smi's own polling (50 ms at best) is too coarse for a timed region of tens of milliseconds."""
 
     def __init__(self, index):
-        self.index = index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        import threading
+        self.index, self.samples, self.reasons, self.stop_flag, self.thread = index, [], set(), threading.Event(), None
+        self.max_mhz, self.power = None, []
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, n in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+                if len(self.samples) % 16 == 0:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1e3)
+            except Exception:
+                break
+            time.sleep(0.001)
 
     def start(self):
-        try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+        if self.nv is None:
+            return
+        import threading
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
-        if self.p is None:
+        out = dict(sm_mhz=None, sm_max_mhz=self.max_mhz, reasons=[])
+        if self.thread is None:
             return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.p.kill()
-        self.f.flush(); self.f.seek(0)
-        sm, smax, power, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.f.read().splitlines():
-            c = [x.strip() for x in line.split(",")]
-            if len(c) < 8:
-                continue
-            try:
-                sm.append(float(c[1])); smax.append(float(c[2])); power.append(float(c[3]))
-            except ValueError:
-                continue
-            for n, v in zip(names, c[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        os.unlink(self.f.name)
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), power_w_max=float(max(power)), samples=len(sm), reasons=sorted(reasons))
+        self.stop_flag.set()
+        self.thread.join(timeout=2)
+        if self.samples:
+            out.update(sm_mhz=float(np.median(self.samples)), sm_min_mhz=float(min(self.samples)), samples=len(self.samples), reasons=sorted(self.reasons),
+                       power_w_max=float(max(self.power)) if self.power else None, how="NVML polled every ~1 ms during the timed region")
         return out
 
 
@@ -139,6 +163,7 @@ def cpu_baseline(images_np, xforms, fx, fy, seconds, steps_cap=10 ** 9, warmup=1
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle as orc
     from conftest import scene_occupancy_bitfield
+    cores = orc.set_num_threads(os.cpu_count() or 1)  # all host threads, whatever OMP_NUM_THREADS says (torchrun exports 1)
     imgs = orc.make_images(images_np, xforms, fx, fy)
     grid, _ = scene_occupancy_bitfield(orc)
     t = orc.Trainer(imgs, aabb_scale=1, seed=1337)
@@ -156,7 +181,6 @@ def cpu_baseline(images_np, xforms, fx, fy, seconds, steps_cap=10 ** 9, warmup=1
             break
     dt = time.perf_counter() - t0
     it_s_cpu_batch = n / dt
-    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
     return dict(value=it_s_cpu_batch * batch_cpu / BATCH, unit=UNIT, cores=cores, kind="port",
                 sample=f"{n} training iterations at batch 2^{int(np.log2(batch_cpu))} ({it_s_cpu_batch:.2f} it/s), OpenMP over {cores} host threads, "
                        f"steady-state regime (step counter 257, occupancy grid from scene geometry); value = it/s x 2^{int(np.log2(batch_cpu))}/2^18",
@@ -276,35 +300,66 @@ def main():
     stages = tb.stage_times(reset=True)
     tb.profile_stages(False)
     pk = peaks()
+    # parameters whose gradient was non-zero in one step, measured: Adam advances a per-parameter step counter only for those (adam.h:76-79,:104)
+    n_params = tb.n_params
+    touched = None
+    if world == 1:
+        ps0 = np.empty(n_params, np.uint32); ps1 = np.empty(n_params, np.uint32)
+        pyngp.check(pyngp.lib().ngpb_testbed_get_optimizer_state(tb._h, None, None, ps0.ctypes.data_as(C.c_void_p)))
+        tb.train(args.batch)
+        pyngp.check(pyngp.lib().ngpb_testbed_get_optimizer_state(tb._h, None, None, ps1.ctypes.data_as(C.c_void_p)))
+        touched = int((ps0 != ps1).sum())
     stage_report = {}
     total_stage_ms = sum(v[0] for v in stages.values()) or 1.0
+    rays_per_call = stages["sampling"][2] / max(stages["sampling"][1], 1)
+    samples_per_call = stages["encode_inference"][2] / max(stages["encode_inference"][1], 1)
+    sm_hz = (clk.get("sm_mhz") or pk.get("sm_max_mhz", 1965.0)) * 1e6
     for name, (sms, calls, units) in stages.items():
         if calls == 0:
             continue
         rep = dict(ms_per_call=sms / calls, calls_per_step=calls / n_prof, share=sms / total_stage_ms, units_per_call=units / calls)
+        sec = sms * 1e-3 / calls
         if name in STAGE_ALGO and sms > 0:
             bound, per_unit, unit = STAGE_ALGO[name]
-            achieved = units * per_unit / (sms * 1e-3) / (1e9 if bound == "hbm" else 1e12)
+            achieved = (units / calls) * per_unit / sec / (1e9 if bound == "hbm" else 1e12)
             peak = pk["hbm"] if bound == "hbm" else pk["tensor_sustained"]
-            rep.update(bound=bound, achieved=achieved, peak=peak, unit=unit, frac=achieved / peak)
+            rep.update(bound=bound, achieved=achieved, peak=peak, unit=unit, frac=achieved / peak, algorithmic_per_unit=per_unit)
+            if name == "encode_backward":  # the fp32 scatter-adds this build executes, next to (never instead of) the reference's fp16 traffic model
+                rep.update(achieved_as_executed=(units / calls) * HASH_BWD_BYTES_AS_EXECUTED / sec / 1e9, frac_as_executed=(units / calls) * HASH_BWD_BYTES_AS_EXECUTED / sec / 1e9 / peak)
+            if name.startswith("encode"):  # the 24 MB table is L2-resident: the same bytes against the L2's measured ceiling (HBM is the wrong roof for this kernel)
+                l2_peak = L2_PEAK_BYTES_PER_CLK * sm_hz / 1e9
+                rep.update(l2=dict(achieved=achieved, peak=l2_peak, unit="GB/s", frac=achieved / l2_peak, peak_source="6300 B/clk (B300_MICROARCH.md LTS cap) x SM clock of this run"))
+        else:
+            nbytes = stage_bytes(name, rays_per_call, samples_per_call, args.batch, n_params, touched if touched is not None else 0)
+            if nbytes is not None and sms > 0 and not (name == "optimizer" and touched is None):
+                achieved = nbytes / sec / 1e9
+                rep.update(bound="hbm", achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"], algorithmic_bytes_per_launch=nbytes)
+                if name == "optimizer":
+                    rep.update(touched_params=touched, touched_fraction=touched / n_params, model="10 B x n_params + 34 B x touched (SURVEY.md s8d); touched measured from the per-parameter step counters")
         stage_report[name] = rep
     # dominant kernel = the stage with the largest share of the step among those with a roofline model
     dom = max((n for n in stage_report if "frac" in stage_report[n]), key=lambda n: stage_report[n]["share"])
     d = stage_report[dom]
-    # DRAM traffic per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` capture of this
-    # same command (profiles/r01_traffic.json, written by tools/ncu_summary.py traffic); null when the capture does not cover the stage
+    # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the stages' kernels from the committed `ncu --set full` capture of this same
+    # command (profiles/r02_traffic.json, written by tools/ncu_summary.py): a profiler number, read from the committed file because nothing timed may run under ncu
     traffic, traffic_src = None, None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            tj = json.load(f)
-        if dom in tj.get("stages", {}):
-            traffic, traffic_src = float(tj["stages"][dom]["dram_bytes_per_launch"]), tj.get("source")
-    except (OSError, ValueError, KeyError):
-        pass
+    for tf in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", tf)) as f:
+                tj = json.load(f)
+            for n2 in stage_report:
+                if n2 in tj.get("stages", {}):
+                    stage_report[n2].setdefault("traffic", float(tj["stages"][n2]["dram_bytes_per_launch"]))
+            if dom in tj.get("stages", {}) and traffic is None:
+                traffic, traffic_src = float(tj["stages"][dom]["dram_bytes_per_launch"]), f"profiles/{tf}: " + str(tj.get("source"))
+        except (OSError, ValueError, KeyError):
+            pass
     roofline = dict(kernel=dom, bound=d["bound"], achieved=d["achieved"], peak=d["peak"], unit=d["unit"], frac=d["frac"], traffic=traffic, traffic_source=traffic_src,
-                    algorithmic_bytes_per_launch=(d["units_per_call"] * STAGE_ALGO[dom][1]) if d["bound"] == "hbm" else None,
+                    algorithmic_bytes_per_launch=d.get("algorithmic_bytes_per_launch", (d["units_per_call"] * STAGE_ALGO[dom][1]) if dom in STAGE_ALGO and d["bound"] == "hbm" else None),
                     peak_source=f"MEASURED_PEAKS.json ({pk['src']}; {'hbm_gbs' if d['bound'] == 'hbm' else 'bf16_tflops_sustained'})",
                     share_of_step=d["share"], per_stage=stage_report)
+    if "l2" in d:
+        roofline["l2"] = d["l2"]
 
     # ---- render leg (second half of BASELINE.json's metric: "render Msamples/sec"): one 800x800 frame of the trained model, device-timed ----
     render = None
@@ -347,6 +402,52 @@ def main():
             os.remove(snap_path)
         except Exception as e:
             render["blender"] = dict(error=str(e))
+
+    # ---- PSNR leg (third part of BASELINE.json's metric: "PSNR vs ref"): the reference's own evaluation procedure (scripts/run.py:216-303) on held-out views of
+    # the model as trained so far: black background, snap_to_pixel_centers, 8 spp, render_min_transmittance 1e-4, linear render, PSNR of the sRGB-clipped images ----
+    psnr = None
+    try:
+        import math
+        def to_srgb(x):
+            return np.where(x < 0.0031308, 12.92 * x, 1.055 * np.maximum(x, 1e-8) ** (1 / 2.4) - 0.055)
+        def to_linear(x):
+            return np.where(x <= 0.04045, x / 12.92, ((x + 0.055) / 1.055) ** 2.4)
+        steps_trained = tb.training_step
+        tb.background_color = [0.0, 0.0, 0.0, 1.0]
+        tb.snap_to_pixel_centers = True
+        tb.nerf.render_min_transmittance = 1e-4
+        tb.fov_axis = 0
+        tb.fov = math.degrees(synthetic.CAMERA_ANGLE_X)
+        fx_eval = 0.5 * args.res / math.tan(0.5 * synthetic.CAMERA_ANGLE_X)
+        views, vals, mses = synthetic.hemisphere_cameras(4, seed=11), [], []
+        for c in views:
+            ngp_cam = synthetic.nerf_matrix_to_ngp(c)
+            gt8 = synthetic.render_image(ngp_cam, args.res, fx_eval, fx_eval, synthetic.lego_boxes(), device=f"cuda:{local_rank}").cpu().numpy().astype(np.float32) / 255.0
+            ref_lin = to_linear(gt8[..., :3]) * gt8[..., 3:4]  # scripts/common.py read_image: sRGB -> linear, premultiplied (black background)
+            tb.camera_matrix = ngp_cam
+            img = tb.render(args.res, args.res, 8, True)
+            A, R = np.clip(to_srgb(img[..., :3]), 0.0, 1.0), np.clip(to_srgb(ref_lin), 0.0, 1.0)
+            mse = float(np.mean((A - R) ** 2))
+            mses.append(mse); vals.append(10.0 * math.log10(1.0 / max(mse, 1e-12)))
+        psnr = dict(metric="psnr_db_held_out_views", value=float(np.mean(vals)), min=float(min(vals)), max=float(max(vals)), psnr_of_mean_mse=10.0 * math.log10(1.0 / max(float(np.mean(mses)), 1e-12)),
+                    views=len(vals), resolution=[args.res, args.res], spp=8, steps_trained=steps_trained,
+                    procedure="scripts/run.py:216-303 (black background, snap_to_pixel_centers, render_min_transmittance 1e-4, PSNR of sRGB-clipped frames) against the analytic ground truth of the synthetic scene")
+        tb.snap_to_pixel_centers = False
+        tb.nerf.render_min_transmittance = 0.01
+    except Exception as e:  # the PSNR leg never invalidates the training number
+        psnr = dict(error=str(e))
+    # the unmodified reference on the same GPU model, same scene and config (oracle/gen_golden_full.py `big`, committed numbers: a builder-run context figure, not a bench arm)
+    reference_on_b200 = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_reference_full.json")) as f:
+            rj = json.load(f)
+        reference_on_b200 = dict(it_per_s=rj["reference"]["it_per_s"], ms_per_step=rj["reference"]["ms_per_step"], after_steps=rj["steps"],
+                                 psnr_db_held_out_views=rj.get("mean_psnr_reference_vs_gt"), psnr_this_repo_same_run=rj.get("mean_psnr_ours_trained_vs_gt"),
+                                 psnr_this_repo_vs_reference_render_of_the_same_snapshot=rj.get("mean_psnr_ours_vs_reference_same_weights"),
+                                 l1_this_repo_vs_reference_render_of_the_same_snapshot=rj.get("mean_l1_ours_vs_reference_same_weights"),
+                                 source="profiles/r02_reference_full.json: ngp::Testbed compiled headless from /root/reference for sm_100 (oracle/Makefile.full), run on a B200 by oracle/gen_golden_full.py")
+    except (OSError, ValueError, KeyError):
+        pass
 
     # ---- e2e arm: public pyngp surface, dataset starts in pinned host memory, loss read back every step ----
     # (same Testbed object: reloading a same-sized dataset re-uploads it and re-initialises the model without new allocations)
@@ -397,8 +498,10 @@ def main():
                        "schedule": "every stage of the reference's iteration runs every step (K1, inference on all marched samples, K6, forward+backward on the compacted batch, "
                                    "Adam/EMA, occupancy refresh at its cadence); the training pass reads the hash-grid features the inference pass computed for the same samples "
                                    "with the same weights instead of re-encoding them (bit-identical, reuse_encoding=0 restores the second encode)"},
-            "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roofline, "render": render,
+            "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roofline, "render": render, "psnr": psnr,
         }
+        if reference_on_b200 is not None:
+            line["reference_on_b200"] = reference_on_b200
         if cb is not None:
             line["cpu_baseline"] = cb
         print(json.dumps(line))

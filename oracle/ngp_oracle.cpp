@@ -1966,3 +1966,6 @@ extern "C" void orc_compute_cam_gradient(uint32_t n_kept, uint32_t n_rays_total,
 	}
 	for (size_t k = 0; k < pos_acc.size(); ++k) { cam_pos_gradient[k] = (float)pos_acc[k]; cam_rot_gradient[k] = (float)rot_acc[k]; }
 }
+
+// Number of OpenMP threads the restatement uses (bench.py's CPU arm sets it to the host's core count: torchrun exports OMP_NUM_THREADS=1).
+extern "C" int orc_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); return omp_get_max_threads(); }

@@ -173,6 +173,8 @@ typedef struct {
 // out_rgba: float [height][width][4]. n_samples_out (nullable): network-evaluated samples.
 void orc_render_nerf(const orc_model* m, const orc_half* params, const uint8_t* bitfield, const orc_render_config* c, float* out_rgba, uint64_t* n_samples_out);
 
+int orc_set_num_threads(int n); // n <= 0: query only; returns omp_get_max_threads()
+
 // ---- Blender multi-NeRF render (NerfRenderer::render, src/nerf_renderer.cu:565-791): see ngp_oracle.cpp ----
 typedef struct {               // Mask3D (nerf/mask_3D.cuh:128-257)
 	int32_t shape, mode;       // EMaskShape {Box, Cylinder, Sphere, All}, EMaskMode {Add, Subtract}

@@ -70,6 +70,11 @@ def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
+def set_num_threads(n):
+    """OpenMP threads of the restatement (0: query). Returns the count in effect."""
+    return int(lib().orc_set_num_threads(int(n)))
+
+
 def pcg32(seed, seq=1):
     r = Pcg32()
     lib().orc_pcg32_seed(C.byref(r), C.c_uint64(seed), C.c_uint64(seq))
