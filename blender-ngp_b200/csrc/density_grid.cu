@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(128) mark_untrained_kernel(const uint32_t n_el
 	int count = 0;
 	for (uint32_t j = 0; j < n_images; ++j) {
 		const ngpb_image& im = images[j];
+		if (im.lens_mode == NGPB_LENS_FTHETA || im.lens_mode == NGPB_LENS_LATLONG) { count++; break; } // "not supported for now": such a camera sees every cell (:391-395)
 		const float half_resx = im.w * 0.5f, half_resy = im.h * 0.5f;
 		const float* xf = im.raw_xform;
 		const float ploc[3] = {pos[0] - xf[9], pos[1] - xf[10], pos[2] - xf[11]};

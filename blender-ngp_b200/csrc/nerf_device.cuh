@@ -181,6 +181,64 @@ __device__ __forceinline__ uint32_t image_idx(uint32_t base_idx, uint32_t n_rays
 	return ((base_idx * n_training_images) / n_rays) % n_training_images;
 }
 
+// ---- lens models of the training cameras (common_device.cuh:141-200,:236-258; used at testbed_nerf.cu:1166-1190) ----
+__device__ __forceinline__ void opencv_lens_distortion(const float* prm, float u, float v, float* du, float* dv) { // apply_opencv_lens_distortion :141-159
+	const float k1 = prm[0], k2 = prm[1], p1 = prm[2], p2 = prm[3];
+	const float u2 = u * u, uv = u * v, v2 = v * v, r2 = u2 + v2;
+	const float radial = k1 * r2 + k2 * r2 * r2;
+	*du = u * radial + 2.0f * p1 * uv + p2 * (r2 + 2.0f * u2);
+	*dv = v * radial + 2.0f * p2 * uv + p1 * (r2 + 2.0f * v2);
+}
+// iterative_opencv_lens_undistortion (:161-200): Newton iteration with central differences, at most 100 steps; operation order as written there
+// (Eigen's 2x2 inverse: adjugate times 1 / determinant)
+__device__ inline void opencv_lens_undistortion(const float* prm, float* u, float* v) {
+	const float x00 = *u, x01 = *v;
+	float x0 = *u, x1 = *v;
+	for (uint32_t i = 0; i < 100; ++i) {
+		const float step0 = fmaxf(1.1920928955078125e-07f, fabsf(1e-6f * x0)), step1 = fmaxf(1.1920928955078125e-07f, fabsf(1e-6f * x1));
+		float dx0, dx1, b00, b01, f00, f01, b10, b11, f10, f11;
+		opencv_lens_distortion(prm, x0, x1, &dx0, &dx1);
+		opencv_lens_distortion(prm, x0 - step0, x1, &b00, &b01);
+		opencv_lens_distortion(prm, x0 + step0, x1, &f00, &f01);
+		opencv_lens_distortion(prm, x0, x1 - step1, &b10, &b11);
+		opencv_lens_distortion(prm, x0, x1 + step1, &f10, &f11);
+		const float j00 = 1 + (f00 - b00) / (2 * step0), j01 = (f10 - b10) / (2 * step1), j10 = (f01 - b01) / (2 * step0), j11 = 1 + (f11 - b11) / (2 * step1);
+		const float invdet = 1.0f / (j00 * j11 - j10 * j01);
+		const float i00 = j11 * invdet, i10 = -j10 * invdet, i01 = -j01 * invdet, i11 = j00 * invdet;
+		const float r0 = (x0 + dx0) - x00, r1 = (x1 + dx1) - x01;
+		const float s0 = i00 * r0 + i01 * r1, s1 = i10 * r0 + i11 * r1;
+		x0 -= s0; x1 -= s1;
+		if (s0 * s0 + s1 * s1 < 1e-10f) break;
+	}
+	*u = x0; *v = x1;
+}
+__device__ inline V3 f_theta_undistortion(float u, float v, const float* prm, const V3& error_direction) { // :236-249
+	const float xpix = u * prm[5], ypix = v * prm[6];
+	const float norm = sqrtf(xpix * xpix + ypix * ypix);
+	const float alpha = prm[0] + norm * (prm[1] + norm * (prm[2] + norm * (prm[3] + norm * prm[4])));
+	float sin_alpha, cos_alpha;
+	sincosf(alpha, &sin_alpha, &cos_alpha);
+	if (cos_alpha <= 1.17549435e-38f || norm == 0.f) return error_direction;
+	sin_alpha *= 1.f / norm;
+	return {sin_alpha * xpix, sin_alpha * ypix, cos_alpha};
+}
+__device__ inline V3 latlong_to_dir(float u, float v) { // :251-258
+	const float PI = 3.14159265358979323846f;
+	const float theta = (v - 0.5f) * PI, phi = (u - 0.5f) * PI * 2.0f;
+	float sp, cp, st, ct;
+	sincosf(theta, &st, &ct);
+	sincosf(phi, &sp, &cp);
+	return {sp * ct, st, cp * ct};
+}
+// camera-space direction of pixel (x, y) in [0,1)^2 for the image's lens (testbed_nerf.cu:1166-1184), not normalised
+__device__ inline V3 training_ray_direction(const ngpb_image& im, float x, float y) {
+	if (im.lens_mode == NGPB_LENS_FTHETA) return f_theta_undistortion(x - im.cx, y - im.cy, im.lens_params, V3{0.f, 0.f, 1.f});
+	if (im.lens_mode == NGPB_LENS_LATLONG) return latlong_to_dir(x, y);
+	V3 d = {(x - im.cx) * (float)im.w / im.fx, (y - im.cy) * (float)im.h / im.fy, 1.0f};
+	if (im.lens_mode == NGPB_LENS_OPENCV) opencv_lens_undistortion(im.lens_params, &d.x, &d.y);
+	return d;
+}
+
 // nerf_random_image_pos_training without CDF: src/testbed_nerf.cu:1047-1060
 __device__ __forceinline__ void random_image_pos_training(Pcg32& rng, int w, int h, bool snap, float* x, float* y) {
 	float u = rng.next_float(), v = rng.next_float();

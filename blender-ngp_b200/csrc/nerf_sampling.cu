@@ -13,7 +13,7 @@ namespace ngpb {
 
 struct TrainRay { V3 o, d_unnorm, d; float startt, cone_angle, tmax; bool valid; };
 
-// Ray set-up: testbed_nerf.cu:1118-1202 (perspective lens, no rolling shutter, no distortion map,
+// Ray set-up: testbed_nerf.cu:1118-1202 (perspective / OpenCV / f-theta / lat-long lens, no rolling shutter, no distortion map,
 // uniform pixel sampling). RNG draws in the reference's order: xy(2), motion-blur time(1), start jitter(1).
 __device__ inline TrainRay setup_training_ray(uint32_t i, uint32_t n_rays, Pcg32 rng, uint32_t n_images, const ngpb_image* __restrict__ images,
                                               const Aabb& aabb, bool snap, float cone_angle_constant) {
@@ -29,7 +29,8 @@ __device__ inline TrainRay setup_training_ray(uint32_t i, uint32_t n_rays, Pcg32
 	(void)rng.next_float(); // motionblur_time (:1132); max_level_rand_training is off so no draw at :1130
 	const float* xf = im.xform;
 	r.o = {xf[9], xf[10], xf[11]};
-	const float dcam[3] = {(x - im.cx) * (float)im.w / im.fx, (y - im.cy) * (float)im.h / im.fy, 1.0f};
+	const V3 dc = training_ray_direction(im, x, y);
+	const float dcam[3] = {dc.x, dc.y, dc.z};
 	const float row0[3] = {xf[0], xf[3], xf[6]}, row1[3] = {xf[1], xf[4], xf[7]}, row2[3] = {xf[2], xf[5], xf[8]};
 	r.d_unnorm = {dot3(row0, dcam), dot3(row1, dcam), dot3(row2, dcam)};
 	const float z = sum3(r.d_unnorm.x * r.d_unnorm.x, r.d_unnorm.y * r.d_unnorm.y, r.d_unnorm.z * r.d_unnorm.z);

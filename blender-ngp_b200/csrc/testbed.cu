@@ -351,6 +351,8 @@ void ngpb_testbed::load_training_data(uint32_t n, const ngpb_host_image* host_im
 		ngpb_image& im = images[i];
 		im.pixels = pixels + off;
 		im.w = h.w; im.h = h.h; im.fx = h.fx; im.fy = h.fy; im.cx = h.cx; im.cy = h.cy;
+		if (h.lens_mode < NGPB_LENS_PERSPECTIVE || h.lens_mode > NGPB_LENS_LATLONG) throw std::runtime_error("load_training_data: unknown lens mode");
+		im.lens_mode = h.lens_mode; std::memcpy(im.lens_params, h.lens_params, sizeof(im.lens_params));
 		std::memcpy(im.raw_xform, h.xform, sizeof(float) * 12);
 		ngpb_effective_xform(h.xform, im.xform);
 		off += bytes;

@@ -288,14 +288,21 @@ class Grid(C.Structure):
                 ("resolution", C.c_uint32 * NGPB_MAX_LEVELS), ("n_pos_dims", C.c_uint32)]
 
 
+class LensMode(enum.IntEnum):  # common.h ELensMode (python_api.cu:385-390)
+    Perspective = 0
+    OpenCV = 1
+    FTheta = 2
+    LatLong = 3
+
+
 class Image(C.Structure):
     _fields_ = [("pixels", C.c_void_p), ("w", C.c_int32), ("h", C.c_int32), ("fx", C.c_float), ("fy", C.c_float),
-                ("cx", C.c_float), ("cy", C.c_float), ("xform", C.c_float * 12), ("raw_xform", C.c_float * 12)]
+                ("cx", C.c_float), ("cy", C.c_float), ("xform", C.c_float * 12), ("raw_xform", C.c_float * 12), ("lens_mode", C.c_int32), ("lens_params", C.c_float * 7)]
 
 
 class HostImage(C.Structure):
     _fields_ = [("pixels", C.c_void_p), ("w", C.c_int32), ("h", C.c_int32), ("fx", C.c_float), ("fy", C.c_float),
-                ("cx", C.c_float), ("cy", C.c_float), ("xform", C.c_float * 12)]
+                ("cx", C.c_float), ("cy", C.c_float), ("xform", C.c_float * 12), ("lens_mode", C.c_int32), ("lens_params", C.c_float * 7)]
 
 
 class Rng(C.Structure):
@@ -601,16 +608,30 @@ def _read_focal_length(js, res, focal):
     return None
 
 
-_UNBUILT_LENS_KEYS = ("k1", "k2", "k3", "k4", "p1", "p2")
-
-
-def _refuse_unbuilt_camera_models(js, where):
-    """read_lens (nerf_loader.cu:197-269) selects OpenCV / f-theta / lat-long lenses and a rolling shutter from these keys; none of them is built, and
-    training on undistorted rays instead would silently change the result."""
-    if any(float(js.get(k, 0.0)) != 0.0 for k in _UNBUILT_LENS_KEYS) or js.get("is_fisheye") or "ftheta_p0" in js or "latlong" in js:
-        raise RuntimeError(f"lens distortion / fisheye / f-theta / lat-long camera models are outside the built scope ({where})")
+def _read_lens(js, lens, pp):
+    """read_lens (nerf_loader.cu:197-269): OpenCV k1, k2, p1, p2 (any non-zero selects the model), f-theta polynomial, lat-long; `cx` / `cy` set the principal
+    point. `lens` = [mode, params(7)] and `pp` are updated in place; an inner (per-frame) block without lens keys keeps the outer (dataset) lens."""
+    mode = LensMode.Perspective
+    for k, key in enumerate(("k1", "k2", "p1", "p2")):
+        if key in js:
+            lens[1][k] = float(js[key])
+            if lens[1][k] != 0.0:
+                mode = LensMode.OpenCV
+    if "cx" in js:
+        pp[0] = float(js["cx"]) / float(js["w"])
+    if "cy" in js:
+        pp[1] = float(js["cy"]) / float(js["h"])
     if "rolling_shutter" in js and any(float(v) != 0.0 for v in js["rolling_shutter"]):
-        raise RuntimeError(f"rolling-shutter cameras are outside the built scope ({where})")
+        raise RuntimeError("rolling-shutter cameras are outside the built scope")
+    if "ftheta_p0" in js:
+        for k in range(5):
+            lens[1][k] = float(js[f"ftheta_p{k}"])
+        lens[1][5], lens[1][6] = float(js["w"]), float(js["h"])
+        mode = LensMode.FTheta
+    if "latlong" in js:
+        mode = LensMode.LatLong
+    if mode != LensMode.Perspective:
+        lens[0] = mode
 
 
 def load_transforms(path):
@@ -628,7 +649,7 @@ def load_transforms(path):
     if not json_paths:
         raise RuntimeError("Cannot load NeRF data from an empty set of paths.")
     scale, offset, aabb_scale = 1.0, [0.0, 0.0, 0.0], 1  # NERF_SCALE = 1.0 and zero offset in this fork (nerf_loader.h:28, nerf_loader.cu:406-407)
-    images, xforms, fxs, fys, cxs, cys = [], [], [], [], [], []
+    images, xforms, fxs, fys, cxs, cys, lenses = [], [], [], [], [], [], []
     per_json = []
     for jp in json_paths:
         with open(jp) as f:
@@ -658,12 +679,8 @@ def load_transforms(path):
         if "offset" in meta:
             offset = [float(v) for v in meta["offset"]]
         aabb_scale = int(meta.get("aabb_scale", aabb_scale))
-        _refuse_unbuilt_camera_models(meta, "dataset")
-        pp_json = [0.5, 0.5]
-        if "cx" in meta:
-            pp_json[0] = float(meta["cx"]) / float(meta["w"])
-        if "cy" in meta:
-            pp_json[1] = float(meta["cy"]) / float(meta["h"])
+        lens_json, pp_json = [LensMode.Perspective, [0.0] * 7], [0.5, 0.5]
+        _read_lens(meta, lens_json, pp_json)
         for fr in frames:
             p = os.path.join(base, fr["file_path"])
             if os.path.splitext(p)[1] == "":
@@ -683,18 +700,15 @@ def load_transforms(path):
             focal = focal_frame if focal_frame is not None else focal
             if focal is None:
                 raise RuntimeError("Couldn't read fov.")
-            _refuse_unbuilt_camera_models(fr, fr["file_path"])
-            pp = list(pp_json)
-            if "cx" in fr:
-                pp[0] = float(fr["cx"]) / float(fr["w"])
-            if "cy" in fr:
-                pp[1] = float(fr["cy"]) / float(fr["h"])
+            lens, pp = [lens_json[0], list(lens_json[1])], list(pp_json)
+            _read_lens(fr, lens, pp)  # per-frame lens / principal point override the dataset's (:640-643)
+            lenses.append((int(lens[0]), lens[1]))
             images.append(np.ascontiguousarray(img))
             xforms.append(nerf_matrix_to_ngp(fr["transform_matrix"], scale, offset))
             fxs.append(float(focal[0])); fys.append(float(focal[1])); cxs.append(pp[0]); cys.append(pp[1])
     uniform = lambda v: v[0] if all(x == v[0] for x in v) else list(v)
     return dict(images=images, xforms=np.stack(xforms), fx=uniform(fxs), fy=uniform(fys), cx=uniform(cxs), cy=uniform(cys), aabb_scale=aabb_scale,
-                scale=scale, offset=offset)
+                scale=scale, offset=offset, lenses=lenses)
 
 
 class _Training:
@@ -794,10 +808,10 @@ class Testbed:
             return
         d = load_transforms(path)
         self._dataset_scale, self._dataset_offset = d["scale"], tuple(d["offset"])
-        self.load_training_images(d["images"], d["xforms"], d["fx"], d["fy"], d["cx"], d["cy"], d["aabb_scale"])
+        self.load_training_images(d["images"], d["xforms"], d["fx"], d["fy"], d["cx"], d["cy"], d["aabb_scale"], d["lenses"])
 
-    def load_training_images(self, images, xforms, fx, fy, cx=0.5, cy=0.5, aabb_scale=1):
-        """Already-decoded data: images uint8 [n][h][w][4] (host), xforms float32 [n][3][4] in ngp convention."""
+    def load_training_images(self, images, xforms, fx, fy, cx=0.5, cy=0.5, aabb_scale=1, lenses=None):
+        """Already-decoded data: images uint8 [n][h][w][4] (host), xforms float32 [n][3][4] in ngp convention; lenses: per image (LensMode, 7 params) or None."""
         n = len(images)
         arr = (HostImage * n)()
         keep = []
@@ -810,6 +824,10 @@ class Testbed:
             arr[i].h, arr[i].w = px.shape[0], px.shape[1]
             pick = lambda v: float(v[i]) if isinstance(v, (list, tuple, np.ndarray)) else float(v)  # scalar = the same for every image
             arr[i].fx, arr[i].fy, arr[i].cx, arr[i].cy = pick(fx), pick(fy), pick(cx), pick(cy)
+            if lenses is not None:
+                arr[i].lens_mode = int(lenses[i][0])
+                for k in range(7):
+                    arr[i].lens_params[k] = float(lenses[i][1][k])
             cm = np.asarray(xforms[i], dtype=np.float32).reshape(3, 4).T.reshape(-1)
             for k in range(12):
                 arr[i].xform[k] = float(cm[k])

@@ -112,7 +112,10 @@ typedef struct {
 	float xform[12];       /* 3x4 camera-to-world, column-major, after the per-ray quaternion round trip of
 	                          get_xform_given_rolling_shutter (common_device.cuh:224-234); see ngpb_effective_xform */
 	float raw_xform[12];   /* the unmodified 3x4 (used by mark_untrained_density_grid, testbed_nerf.cu:398) */
+	int32_t lens_mode;     /* NGPB_LENS_* (ELensMode, common.h; nerf_loader.cu:197-269 read_lens) */
+	float lens_params[7];  /* OpenCV: k1, k2, p1, p2; FTheta: p0..p4, w, h (common_device.cuh:141-160,:236-249) */
 } ngpb_image;
+enum { NGPB_LENS_PERSPECTIVE = 0, NGPB_LENS_OPENCV = 1, NGPB_LENS_FTHETA = 2, NGPB_LENS_LATLONG = 3 };
 
 /* Host-only: the transform generate_training_samples_nerf effectively uses for a camera without rolling shutter. */
 void ngpb_effective_xform(const float* xform12, float* out12);
@@ -274,6 +277,8 @@ typedef struct {
 	int32_t w, h;
 	float fx, fy, cx, cy;
 	float xform[12];       /* 3x4 camera-to-world, column-major, ngp convention (after nerf_matrix_to_ngp, nerf_loader.h:113) */
+	int32_t lens_mode;     /* NGPB_LENS_* */
+	float lens_params[7];
 } ngpb_host_image;
 
 int ngpb_testbed_create(ngpb_testbed** out, int device);

@@ -675,6 +675,59 @@ extern "C" void orc_effective_xform(const float* m12, float* out12) {
 namespace {
 struct TrainRay { Vec3 o, d_unnorm, d; float startt; float cone_angle; bool valid; };
 
+// ---- lens models (include/neural-graphics-primitives/common_device.cuh:141-200, :236-258) ----
+inline void opencv_lens_distortion(const float* prm, float u, float v, float* du, float* dv) { // apply_opencv_lens_distortion
+	const float k1 = prm[0], k2 = prm[1], p1 = prm[2], p2 = prm[3];
+	const float u2 = u * u, uv = u * v, v2 = v * v, r2 = u2 + v2;
+	const float radial = k1 * r2 + k2 * r2 * r2;
+	*du = u * radial + 2.0f * p1 * uv + p2 * (r2 + 2.0f * u2);
+	*dv = v * radial + 2.0f * p2 * uv + p1 * (r2 + 2.0f * v2);
+}
+inline void opencv_lens_undistortion(const float* prm, float* u, float* v) { // iterative_opencv_lens_undistortion: Newton, central differences, <= 100 steps
+	const float x00 = *u, x01 = *v;
+	float x0 = *u, x1 = *v;
+	for (uint32_t i = 0; i < 100; ++i) {
+		const float step0 = std::max(std::numeric_limits<float>::epsilon(), std::abs(1e-6f * x0)), step1 = std::max(std::numeric_limits<float>::epsilon(), std::abs(1e-6f * x1));
+		float dx0, dx1, b00, b01, f00, f01, b10, b11, f10, f11;
+		opencv_lens_distortion(prm, x0, x1, &dx0, &dx1);
+		opencv_lens_distortion(prm, x0 - step0, x1, &b00, &b01);
+		opencv_lens_distortion(prm, x0 + step0, x1, &f00, &f01);
+		opencv_lens_distortion(prm, x0, x1 - step1, &b10, &b11);
+		opencv_lens_distortion(prm, x0, x1 + step1, &f10, &f11);
+		const float j00 = 1 + (f00 - b00) / (2 * step0), j01 = (f10 - b10) / (2 * step1), j10 = (f01 - b01) / (2 * step0), j11 = 1 + (f11 - b11) / (2 * step1);
+		const float invdet = 1.0f / (j00 * j11 - j10 * j01); // Eigen's 2x2 inverse: adjugate / determinant
+		const float i00 = j11 * invdet, i10 = -j10 * invdet, i01 = -j01 * invdet, i11 = j00 * invdet;
+		const float r0 = (x0 + dx0) - x00, r1 = (x1 + dx1) - x01;
+		const float s0 = i00 * r0 + i01 * r1, s1 = i10 * r0 + i11 * r1;
+		x0 -= s0; x1 -= s1;
+		if (s0 * s0 + s1 * s1 < 1e-10f) break;
+	}
+	*u = x0; *v = x1;
+}
+inline Vec3 f_theta_undistortion(float u, float v, const float* prm, const Vec3& error_direction) {
+	const float xpix = u * prm[5], ypix = v * prm[6];
+	const float norm = std::sqrt(xpix * xpix + ypix * ypix);
+	const float alpha = prm[0] + norm * (prm[1] + norm * (prm[2] + norm * (prm[3] + norm * prm[4])));
+	float sin_alpha = std::sin(alpha), cos_alpha = std::cos(alpha);
+	if (cos_alpha <= std::numeric_limits<float>::min() || norm == 0.f) return error_direction;
+	sin_alpha *= 1.f / norm;
+	return {sin_alpha * xpix, sin_alpha * ypix, cos_alpha};
+}
+inline Vec3 latlong_to_dir(float u, float v) {
+	const float PI = 3.14159265358979323846f;
+	const float theta = (v - 0.5f) * PI, phi = (u - 0.5f) * PI * 2.0f;
+	const float st = std::sin(theta), ct = std::cos(theta), sp = std::sin(phi), cp = std::cos(phi);
+	return {sp * ct, st, cp * ct};
+}
+// camera-space direction of pixel (x, y) for the image's lens (testbed_nerf.cu:1166-1184), not normalised
+inline Vec3 training_ray_direction(const orc_image& im, float x, float y) {
+	if (im.lens_mode == 2) return f_theta_undistortion(x - im.cx, y - im.cy, im.lens_params, Vec3{0.f, 0.f, 1.f});
+	if (im.lens_mode == 3) return latlong_to_dir(x, y);
+	Vec3 d = {(x - im.cx) * (float)im.w / im.fx, (y - im.cy) * (float)im.h / im.fy, 1.0f};
+	if (im.lens_mode == 1) opencv_lens_undistortion(im.lens_params, &d.x, &d.y);
+	return d;
+}
+
 // ray set-up shared by K1 and nothing else (K6 only re-derives the pixel). testbed_nerf.cu:1118-1202
 inline TrainRay setup_training_ray(uint32_t i, uint32_t n_rays, orc_pcg32 rng, uint32_t n_images, const orc_image* images,
                                    const float* eff_xforms, const AABB& aabb, bool snap, float cone_angle_constant) {
@@ -691,7 +744,8 @@ inline TrainRay setup_training_ray(uint32_t i, uint32_t n_rays, orc_pcg32 rng, u
 	float motionblur_time = orc_pcg32_next_float(&rng); (void)motionblur_time;
 	const float* xf = eff_xforms + (size_t)img * 12;
 	r.o = {xf[9], xf[10], xf[11]};
-	float dcam[3] = {(x - im.cx) * (float)im.w / im.fx, (y - im.cy) * (float)im.h / im.fy, 1.0f};
+	const Vec3 dc = training_ray_direction(im, x, y);
+	float dcam[3] = {dc.x, dc.y, dc.z};
 	// xform.block<3,3>(0,0) * d: row r = sum3 over columns (column-major storage)
 	float row0[3] = {xf[0], xf[3], xf[6]}, row1[3] = {xf[1], xf[4], xf[7]}, row2[3] = {xf[2], xf[5], xf[8]};
 	r.d_unnorm = {dot3(row0, dcam), dot3(row1, dcam), dot3(row2, dcam)};
@@ -1010,6 +1064,7 @@ extern "C" void orc_mark_untrained_density_grid(uint32_t n_elements, float* grid
 		int count = 0;
 		for (uint32_t j = 0; j < n_images; ++j) {
 			const orc_image& im = images[j];
+			if (im.lens_mode == 2 || im.lens_mode == 3) { count++; break; } // f-theta / lat-long: "not supported for now", every cell counts as visible (:391-395)
 			float half_resx = im.w * 0.5f, half_resy = im.h * 0.5f;
 			const float* xf = im.xform;
 			float ploc[3] = {pos[0] - xf[9], pos[1] - xf[10], pos[2] - xf[11]};

@@ -80,6 +80,8 @@ typedef struct {
 	int32_t w, h;
 	float fx, fy, cx, cy;  // focal length in pixels, principal point as a fraction (nerf_loader.h:41-42)
 	float xform[12];       // 3x4 camera-to-world, column-major, ngp convention (nerf_loader.h:113-132)
+	int32_t lens_mode;     // ELensMode {Perspective, OpenCV, FTheta, LatLong} (common.h)
+	float lens_params[7];  // OpenCV: k1, k2, p1, p2; FTheta: p0..p4, w, h
 } orc_image;
 
 // effective per-image transform the reference derives per ray through a quaternion round trip

@@ -28,7 +28,7 @@ class Model(C.Structure):
 
 class Image(C.Structure):
     _fields_ = [("pixels", C.c_void_p), ("w", C.c_int32), ("h", C.c_int32), ("fx", C.c_float), ("fy", C.c_float),
-                ("cx", C.c_float), ("cy", C.c_float), ("xform", C.c_float * 12)]
+                ("cx", C.c_float), ("cy", C.c_float), ("xform", C.c_float * 12), ("lens_mode", C.c_int32), ("lens_params", C.c_float * 7)]
 
 
 class Optimizer(C.Structure):
@@ -102,8 +102,8 @@ def model(n_levels=16, log2_hashmap_size=19, base_resolution=16, per_level_scale
     return m
 
 
-def make_images(pixels_list, xforms, fx, fy, cx=0.5, cy=0.5):
-    """pixels_list: list/array of uint8 [h,w,4]; xforms: [n,3,4] ngp camera matrices. Keeps references alive."""
+def make_images(pixels_list, xforms, fx, fy, cx=0.5, cy=0.5, lens=None):
+    """pixels_list: list/array of uint8 [h,w,4]; xforms: [n,3,4] ngp camera matrices; lens: (mode, 7 params) applied to every image. Keeps references alive."""
     n = len(pixels_list)
     arr = (Image * n)()
     keep = []
@@ -113,6 +113,10 @@ def make_images(pixels_list, xforms, fx, fy, cx=0.5, cy=0.5):
         arr[i].pixels = px.ctypes.data
         arr[i].h, arr[i].w = px.shape[0], px.shape[1]
         arr[i].fx, arr[i].fy, arr[i].cx, arr[i].cy = fx, fy, cx, cy
+        if lens is not None:
+            arr[i].lens_mode = int(lens[0])
+            for k in range(7):
+                arr[i].lens_params[k] = float(lens[1][k])
         xf = np.asarray(xforms[i], dtype=np.float32).reshape(3, 4)
         col_major = xf.T.reshape(-1)  # column-major 3x4
         for k in range(12):

@@ -25,6 +25,9 @@ struct DeviceDataset {
 
 // Builds the per-image metadata array the reference kernels read (nerf_loader.h:30-46).
 // pixels: one device buffer holding n_images RGBA8 images of w*h pixels back to back.
+// lens applied to every image of the next make_dataset call (set by ref_set_lens; mode 0 = perspective)
+static Lens g_lens{};
+
 DeviceDataset make_dataset(uint32_t n_images, int w, int h, float fx, float fy, float cx, float cy, const uint8_t* pixels, const float* xforms_3x4_colmajor_host) {
 	std::vector<TrainingImageMetadata> md(n_images);
 	std::vector<TrainingXForm> xf(n_images);
@@ -34,6 +37,7 @@ DeviceDataset make_dataset(uint32_t n_images, int w, int h, float fx, float fy, 
 		md[i].resolution = {w, h};
 		md[i].focal_length = {fx, fy};
 		md[i].principal_point = {cx, cy};
+		md[i].lens = g_lens;
 		Matrix<float, 3, 4> m;
 		for (int k = 0; k < 12; ++k) m.data()[k] = xforms_3x4_colmajor_host[i * 12 + k];
 		xf[i].start = m;
@@ -52,6 +56,9 @@ BoundingBox make_aabb(const float* aabb6) {
 }
 
 extern "C" {
+
+// ELensMode + the 7 lens parameters used by the datasets the following calls build (generate_training_samples, mark_untrained_density_grid)
+void ref_set_lens(int mode, const float* params7) { g_lens.mode = (ELensMode)mode; for (int k = 0; k < 7; ++k) g_lens.params[k] = params7 ? params7[k] : 0.f; }
 
 // iters > 0: the launch (with its two counter memsets, as in train_nerf_step) is repeated `iters` times after one warm-up and *ms receives the mean
 // milliseconds per repetition (CUDA events on the NULL stream); the outputs are those of the last repetition.

@@ -75,3 +75,12 @@ def density_grid_cameras():
     import synthetic
     scene = synthetic.make_lego_scene(8, 64, device="cpu", seed=0)
     return scene
+
+
+# ---- K1 with the non-pinhole lens models (testbed_nerf.cu:1166-1190): (ELensMode, 7 parameters, principal point) applied to every camera of the 8 x 64^2 scene ----
+LENS_CASES = {
+    "opencv": (1, [0.0578421, -0.0805099, -0.000980296, 0.00015575, 0.0, 0.0, 0.0], (0.5135, 0.5027)),   # data/nerf/fox/transforms.json k1, k2, p1, p2, cx/w, cy/h
+    "ftheta": (2, [0.0, 0.02, 1e-5, 0.0, 0.0, 64.0, 64.0], (0.5, 0.5)),                                     # alpha = 0.02 rad/px + 1e-5 rad/px^2 over a 64 x 64 sensor
+    "latlong": (3, [0.0] * 7, (0.5, 0.5)),
+}
+LENS_N_RAYS, LENS_MAX_SAMPLES = 2048, 1 << 17

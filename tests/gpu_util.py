@@ -33,7 +33,7 @@ def host(t):
     return t.cpu().numpy()
 
 
-def images_to_device(scene):
+def images_to_device(scene, lens=None):
     """Uploads the scene; returns (device Image array tensor, n, keepalive)."""
     imgs = scene["images"]
     n = len(imgs)
@@ -44,6 +44,11 @@ def images_to_device(scene):
         arr[i].pixels = pix.data_ptr() + i * per
         arr[i].h, arr[i].w = imgs[i].shape[0], imgs[i].shape[1]
         arr[i].fx, arr[i].fy, arr[i].cx, arr[i].cy = scene["fx"], scene["fy"], scene["cx"], scene["cy"]
+        if lens is not None:  # (ELensMode, 7 parameters, principal point) for every image
+            arr[i].lens_mode = int(lens[0])
+            for k in range(7):
+                arr[i].lens_params[k] = float(lens[1][k])
+            arr[i].cx, arr[i].cy = lens[2]
         cm = np.asarray(scene["xforms"][i], dtype=np.float32).reshape(3, 4).T.reshape(-1).copy()
         eff = np.empty(12, np.float32)
         pyngp.lib().ngpb_effective_xform(cm.ctypes.data_as(C.c_void_p), eff.ctypes.data_as(C.c_void_p))

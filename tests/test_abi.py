@@ -97,7 +97,7 @@ def test_snapshot_container_round_trip():
 def test_transforms_json_loader_round_trip(tmp_path):
     """pyngp.load_transforms (nerf_loader.cu:197-747 for a pinhole nerf_synthetic-style dataset): a scene written by synthetic.write_transforms_json comes
     back with the same pixels, the same ngp-convention camera matrices (nerf_matrix_to_ngp with the file's scale / offset), the focal length from
-    camera_angle_x, frames sorted by path; lens-distortion keys are refused."""
+    camera_angle_x, frames sorted by path (lens keys: test_transforms_json_lens_models)."""
     import json
     import sys
     sys.path.insert(0, os.path.join(ROOT, "blender-ngp_b200"))
@@ -112,13 +112,12 @@ def test_transforms_json_loader_round_trip(tmp_path):
         assert np.array_equal(got["images"][k], np.asarray(scene["images"][i]))
         np.testing.assert_allclose(got["xforms"][k], scene["xforms"][i], rtol=0, atol=1e-6)
     assert abs(got["fx"] - scene["fx"]) < 1e-3 and abs(got["fy"] - scene["fy"]) < 1e-3 and got["cx"] == 0.5 and got["cy"] == 0.5
-    meta = json.load(open(path))
-    meta["k1"] = 0.1
-    bad = tmp_path / "distorted"
+    assert all(l[0] == int(pyngp.LensMode.Perspective) for l in got["lenses"])
+    bad = tmp_path / "no_images"
     bad.mkdir()
-    json.dump(meta, open(bad / "transforms.json", "w"))
+    json.dump(json.load(open(path)), open(bad / "transforms.json", "w"))
     with pytest.raises(RuntimeError):
-        pyngp.load_transforms(str(bad / "transforms.json"))
+        pyngp.load_transforms(str(bad / "transforms.json"))  # the json names images that do not exist
 
 
 def test_render_request_value_types():
@@ -225,3 +224,42 @@ def test_reference_arm_runs_on_rank_zero_only():
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, env=env, timeout=120)
     assert res.returncode == 0 and res.stdout.strip() == ""
+
+
+def test_transforms_json_lens_models(tmp_path):
+    """read_lens (src/nerf_loader.cu:197-269): OpenCV k1 k2 p1 p2 (any non-zero coefficient selects the model), the f-theta polynomial and lat-long, at dataset
+    level with per-frame overrides; cx / cy become the principal point as a fraction of w / h. And, where the reference tree is mounted, its bundled real-capture
+    dataset data/nerf/fox (BASELINE config 3: 50 photographs 1080 x 1920, OpenCV lens, aabb_scale 4), which round 1's loader refused."""
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "blender-ngp_b200"))
+    import pyngp
+    from PIL import Image
+    d = tmp_path / "scene"
+    d.mkdir()
+    eye = [[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 2], [0, 0, 0, 1]]
+    for k in range(3):
+        Image.fromarray(np.full((8, 16, 3), 40 * k, np.uint8)).save(d / f"im{k}.jpg")  # JPEG: no alpha channel -> opaque RGBA
+    meta = {"fl_x": 20.0, "k1": 0.05, "k2": -0.08, "p1": -0.001, "p2": 0.0002, "cx": 7.0, "cy": 5.0, "w": 16.0, "h": 8.0, "aabb_scale": 4,
+            "frames": [{"file_path": "im0.jpg", "transform_matrix": eye},
+                       {"file_path": "im1.jpg", "transform_matrix": eye, "ftheta_p0": 0.0, "ftheta_p1": 0.02, "ftheta_p2": 1e-5, "ftheta_p3": 0.0, "ftheta_p4": 0.0, "w": 16.0, "h": 8.0},
+                       {"file_path": "im2.jpg", "transform_matrix": eye, "latlong": True}]}
+    json.dump(meta, open(d / "transforms.json", "w"))
+    got = pyngp.load_transforms(str(d))
+    assert [l[0] for l in got["lenses"]] == [int(pyngp.LensMode.OpenCV), int(pyngp.LensMode.FTheta), int(pyngp.LensMode.LatLong)]
+    assert got["lenses"][0][1][:4] == pytest.approx([0.05, -0.08, -0.001, 0.0002])
+    assert got["lenses"][1][1] == pytest.approx([0.0, 0.02, 1e-5, 0.0, 0.0, 16.0, 8.0])
+    assert got["cx"] == pytest.approx(7.0 / 16) and got["cy"] == pytest.approx(5.0 / 8) and got["images"][0].shape == (8, 16, 4) and int(got["images"][0][0, 0, 3]) == 255
+    with pytest.raises(RuntimeError):
+        json.dump(dict(meta, rolling_shutter=[0.0, 0.0, 1.0, 0.0]), open(d / "transforms.json", "w"))
+        pyngp.load_transforms(str(d))
+    fox = "/root/reference/data/nerf/fox"
+    if os.path.isdir(fox):
+        got = pyngp.load_transforms(fox)
+        with open(os.path.join(fox, "transforms.json")) as f:
+            js = json.load(f)
+        present = [fr for fr in js["frames"] if os.path.exists(os.path.join(fox, fr["file_path"]))]  # the json lists 67 frames, 50 photographs ship: missing ones are culled (:365-390)
+        assert len(got["images"]) == len(present) == 50 and got["images"][0].shape == (1920, 1080, 4) and got["aabb_scale"] == 4
+        assert all(l[0] == int(pyngp.LensMode.OpenCV) and l[1][:4] == pytest.approx([js["k1"], js["k2"], js["p1"], js["p2"]]) for l in got["lenses"])
+        assert got["fx"] == pytest.approx(js["fl_x"]) and got["fy"] == pytest.approx(js["fl_y"]) and got["cx"] == pytest.approx(js["cx"] / js["w"])
+        assert got["scale"] == 1.0 and got["offset"] == [0.0, 0.0, 0.0]  # this fork's loader defaults (nerf_loader.h:28, nerf_loader.cu:406-407)

@@ -227,10 +227,10 @@ def test_mlp_forward_backward(L, orc):
 # ------------------------------------------------------------------------------------------------------
 # K1: ray generation + marching, bit-exact
 # ------------------------------------------------------------------------------------------------------
-def _run_k1(L, scene, bitfield, n_rays, max_samples, rng, snap=True, ray_offset=0, n_rays_global=None):
+def _run_k1(L, scene, bitfield, n_rays, max_samples, rng, snap=True, ray_offset=0, n_rays_global=None, lens=None):
     import pyngp
     from gpu_util import dev, ptr, host, images_to_device, rng_struct
-    meta, n_img, keep = images_to_device(scene)
+    meta, n_img, keep = images_to_device(scene, lens)
     aabb = np.array([0, 0, 0, 1, 1, 1], np.float32)
     d_bits = dev(bitfield)
     counters = torch.zeros(8, dtype=torch.int32, device="cuda")
@@ -269,6 +269,30 @@ def test_generate_training_samples_bit_exact(L, orc, small_scene, snap):
     assert np.array_equal(got["rays"][:k].view(np.uint32), want["rays"][:k].view(np.uint32))
     n_s = int(want["counters"][0])
     assert np.array_equal(got["coords"][:n_s].view(np.uint32), want["coords"][:n_s].view(np.uint32))
+
+
+@pytest.mark.parametrize("name", ["opencv", "ftheta", "latlong"])
+def test_generate_training_samples_lens_models(L, small_scene, orc, name):
+    """K1 with the reference's other lens models (testbed_nerf.cu:1166-1190: OpenCV k1 k2 p1 p2 with its 100-step Newton undistortion, the f-theta polynomial,
+    lat-long) and an off-centre principal point, against the REFERENCE's own kernel (tests/golden/ref_k1_lens.npz, built -fmad=false; stored in ray-index
+    order, which is this kernel's order): counters, kept rays, unnormalised directions, per-ray counts and every sample record bit for bit (device sincosf on
+    both sides). The OpenCV parameters are those of the bundled data/nerf/fox dataset."""
+    import hashlib
+    from conftest import scene_occupancy_bitfield
+    from golden_inputs import LENS_CASES, LENS_N_RAYS, LENS_MAX_SAMPLES
+    g = np.load(os.path.join(GOLDEN_DIR, "ref_k1_lens.npz"))
+    mode, params, pp = LENS_CASES[name]
+    _, bits = scene_occupancy_bitfield(orc)
+    rng = orc.pcg32(1337)
+    got = _run_k1(L, small_scene, bits, LENS_N_RAYS, LENS_MAX_SAMPLES, rng, lens=(mode, params, pp))
+    n_s, k = (int(v) for v in g[f"{name}_counters"])
+    assert k > 5 and n_s > 500
+    assert got["counters"][:2].tolist() == [n_s, k]
+    assert np.array_equal(got["ray_indices"][:k], g[f"{name}_ray_indices"]) and np.array_equal(got["numsteps"][:k, 0], g[f"{name}_counts"])
+    assert np.array_equal(got["rays"][:k].view(np.uint32), g[f"{name}_rays"].view(np.uint32))
+    coords = np.ascontiguousarray(got["coords"][:n_s])
+    assert np.array_equal(coords[:4096].view(np.uint32), g[f"{name}_coords_head"].view(np.uint32))
+    assert np.array_equal(np.frombuffer(hashlib.sha256(coords.tobytes()).digest(), np.uint8), g[f"{name}_coords_sha256"])
 
 
 def test_generate_training_samples_overflow_and_empty(L, orc, small_scene):

@@ -231,6 +231,40 @@ def test_golden_training_samples(orc):
         assert np.array_equal(g["coords"][b_ref: b_ref + n].view(np.uint32), out["coords"][b: b + n].view(np.uint32))
 
 
+@pytest.mark.parametrize("name", ["opencv", "ftheta", "latlong"])
+def test_golden_training_samples_lens_models(orc, name):
+    """K1 with OpenCV / f-theta / lat-long lenses against the reference's own generate_training_samples_nerf (built -fmad=false, tests/golden/ref_k1_lens.npz;
+    the reference allocates slots with atomics, so the golden is stored in ray-index order, which is the oracle's order): kept rays, per-ray sample counts,
+    unnormalised ray directions and every sample record."""
+    import hashlib
+    import synthetic
+    from conftest import scene_occupancy_bitfield
+    from golden_inputs import LENS_CASES, LENS_N_RAYS, LENS_MAX_SAMPLES
+    g = np.load(os.path.join(GOLDEN, "ref_k1_lens.npz"))
+    mode, params, pp = LENS_CASES[name]
+    scene = synthetic.make_lego_scene(8, 64, device="cpu", seed=0)
+    _, bits = scene_occupancy_bitfield(orc)
+    rng = orc.pcg32(1337)
+    assert int(g["rng_state"]) == rng.state
+    imgs = orc.make_images(scene["images"], scene["xforms"], scene["fx"], scene["fy"], cx=pp[0], cy=pp[1], lens=(mode, params))
+    out = orc.generate_training_samples(LENS_N_RAYS, [0, 0, 0, 1, 1, 1], LENS_MAX_SAMPLES, rng, imgs, bits)
+    k, n_s = out["n_kept"], int(out["counters"][0])
+    if name == "opencv":  # polynomial + Newton iteration in plain float arithmetic: bit for bit
+        assert [n_s, k] == g[f"{name}_counters"].tolist()
+        assert np.array_equal(out["ray_indices"][:k], g[f"{name}_ray_indices"]) and np.array_equal(out["numsteps"][:k, 0], g[f"{name}_counts"])
+        assert np.array_equal(out["rays"][:k].view(np.uint32), g[f"{name}_rays"].view(np.uint32))
+        coords = np.ascontiguousarray(out["coords"][:n_s])
+        assert np.array_equal(coords[:4096].view(np.uint32), g[f"{name}_coords_head"].view(np.uint32))
+        assert np.array_equal(np.frombuffer(hashlib.sha256(coords.tobytes()).digest(), np.uint8), g[f"{name}_coords_sha256"])
+    else:  # sincosf: the device's and glibc's differ in the last bit, which moves a ray direction by an ulp and, rarely, a sample across a cell boundary
+        gk, gn = int(g[f"{name}_counters"][1]), int(g[f"{name}_counters"][0])
+        assert abs(k - gk) <= 1 and abs(n_s - gn) <= max(4, gn // 500)
+        common, ia, ib = np.intersect1d(out["ray_indices"][:k], g[f"{name}_ray_indices"], return_indices=True)
+        assert len(common) >= max(k, gk) - 1
+        np.testing.assert_allclose(out["rays"][:k][ia], g[f"{name}_rays"][ib], rtol=2e-6, atol=2e-7)
+        assert (out["numsteps"][:k, 0][ia] != g[f"{name}_counts"][ib]).sum() <= max(2, len(common) // 50)
+
+
 def test_golden_optimizer(orc):
     """Reference adam_step<__half> + ema_step_half_precision (tcnn adam.h:48, ema.h:63) for three steps on a B200. The reference build
     contracts a*b+c into FMAs, the oracle rounds every operation: fp32 state within 2e-6 relative (+2e-8 absolute for the weights), fp16 copies within one ulp."""
