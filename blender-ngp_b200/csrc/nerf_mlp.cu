@@ -425,7 +425,7 @@ void pipe_nerf_forward(cudaStream_t stream, const __half* mlp, const __half* enc
 void pipe_density_forward(cudaStream_t stream, const __half* mlp, const __half* encoded, bool tiled, uint32_t n, __half* density);
 void pipe_plain_forward(cudaStream_t stream, const __half* weights, const __half* input, uint32_t n, __half* output);
 uint32_t pipe_nerf_forward_backward(cudaStream_t stream, const __half* mlp, const __half* encoded, bool tiled, const float* coords, const __half* dL_dout, uint32_t n,
-                                    __half* dL_dencoded, float* partials);
+                                    __half* dL_dencoded, float* partials, __half* dL_dsh);
 uint32_t pipe_plain_forward_backward(cudaStream_t stream, const __half* weights, const __half* input, const __half* dL_dout16, uint32_t n, __half* dL_dinput, float* partials);
 
 bool mlp_legacy() { static const bool v = getenv("NGPB_MLP_LEGACY") && atoi(getenv("NGPB_MLP_LEGACY")) != 0; return v; }
@@ -468,12 +468,12 @@ void nerf_density_mlp_launch(cudaStream_t stream, const __half* mlp, const __hal
 	launch_mlp<MODE_DENSITY>(stream, a, std::min(tiles, kNumSMs * INFER_CTAS_PER_SM), SMEM_INFER);
 }
 void nerf_mlp_forward_backward_launch(cudaStream_t stream, const __half* mlp, const __half* encoded, bool tiled, const float* coords, const __half* dL_dout, uint32_t n,
-                                      __half* dL_dencoded, float* mlp_grad, float* partials) {
+                                      __half* dL_dencoded, float* mlp_grad, float* partials, __half* dL_dsh) {
 	uint32_t grid;
 	if (!mlp_legacy()) {
-		grid = pipe_nerf_forward_backward(stream, mlp, encoded, tiled, coords, dL_dout, n, dL_dencoded, partials);
+		grid = pipe_nerf_forward_backward(stream, mlp, encoded, tiled, coords, dL_dout, n, dL_dencoded, partials, dL_dsh);
 	} else {
-		if (tiled) throw std::runtime_error("NGPB_MLP_LEGACY kernels read row-major features");
+		if (tiled || dL_dsh) throw std::runtime_error("NGPB_MLP_LEGACY kernels read row-major features and do not return the direction gradient");
 		MlpArgs a{mlp, encoded, coords, dL_dout, dL_dencoded, partials, n, nullptr};
 		grid = std::min(n / TILE, TRAIN_GRID);
 		launch_mlp<MODE_TRAIN>(stream, a, grid, SMEM_TRAIN);
@@ -586,7 +586,21 @@ extern "C" int ngpb_nerf_mlp_forward_backward(void* stream, const ngpb_half* mlp
 			return NGPB_ERR_INVALID_ARGUMENT;
 		}
 		nerf_mlp_forward_backward_launch((cudaStream_t)stream, (const __half*)mlp, (const __half*)encoded, false, coords, (const __half*)dL_dout, n,
-			(__half*)dL_dencoded, mlp_grad, (float*)workspace);
+			(__half*)dL_dencoded, mlp_grad, (float*)workspace, nullptr);
+		return 0;
+	} catch (const std::exception& e) { set_last_error(e.what()); return NGPB_ERR_RUNTIME; }
+}
+
+// The same pass, also returning dL/d(SH inputs of the rgb network) [n][16] half: the direction half of the input gradient (camera_optimizer.cu)
+extern "C" int ngpb_nerf_mlp_forward_backward_sh(void* stream, const ngpb_half* mlp, const ngpb_half* encoded, const float* coords, const ngpb_half* dL_dout,
+                                                 uint32_t n, ngpb_half* dL_dencoded, float* mlp_grad, void* workspace, ngpb_half* dL_dsh) {
+	try {
+		if (!mlp || !encoded || !coords || !dL_dout || !dL_dencoded || !mlp_grad || !workspace || !dL_dsh || n == 0 || n % TILE != 0) {
+			set_last_error("ngpb_nerf_mlp_forward_backward_sh: invalid argument (n must be a non-zero multiple of 128)");
+			return NGPB_ERR_INVALID_ARGUMENT;
+		}
+		nerf_mlp_forward_backward_launch((cudaStream_t)stream, (const __half*)mlp, (const __half*)encoded, false, coords, (const __half*)dL_dout, n,
+			(__half*)dL_dencoded, mlp_grad, (float*)workspace, (__half*)dL_dsh);
 		return 0;
 	} catch (const std::exception& e) { set_last_error(e.what()); return NGPB_ERR_RUNTIME; }
 }

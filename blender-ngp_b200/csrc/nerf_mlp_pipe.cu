@@ -339,6 +339,7 @@ constexpr uint32_t PT_ACC = 0, PT_DW = 128, PT_DW_COLS = 160, PT_DW1D = 0, PT_DW
 struct PipeTrainArgs {
 	const __half* mlp; const __half* encoded; const float* coords; const __half* dL_dout; __half* dL_dencoded; float* partials;
 	uint32_t n; uint32_t tiled;
+	__half* dL_dsh; // optional [n][16]: gradient of the loss with respect to the rgb network's 16 SH inputs (camera-extrinsics optimisation needs dL/d(direction))
 };
 
 template <int MODE>
@@ -435,6 +436,13 @@ __global__ void __launch_bounds__(PT_THREADS, 1) nerf_mlp_pipe_train_kernel(cons
 			wait_mma(); epi_dgrad64(t_acc, slot + PT_G2, slot + PT_DG2, row); signal_act_ready(&B.act_ready, lane);           // 4: dG2 = (dOr W3r) . relu'(G2)
 			wait_mma(); epi_dgrad64(t_acc, slot + PT_G1, slot + PT_DG1, row); signal_act_ready(&B.act_ready, lane);           // 5: dG1 = (dG2 W2r) . relu'(G1)
 			wait_mma();                                                                                                       // 6: dRin = dG1 W1r; dOd = dRin[:, :16] (+ dL/dsigma on column 0, nerf_network.h:232-239)
+			if (args.dL_dsh) { // columns 16..31 of dRin: dL/d(SH coefficients), kept for kernel_sh_backward's counterpart (camera_optimizer.cu)
+				uint32_t r[16];
+				tmem_ld_x16(t_acc + 16, r);
+				tmem_ld_wait();
+				*reinterpret_cast<uint4*>(args.dL_dsh + row_g * 16) = pack8(r);
+				*reinterpret_cast<uint4*>(args.dL_dsh + row_g * 16 + 8) = pack8(r + 8);
+			}
 			{
 				uint32_t r[16];
 				tmem_ld_x16(t_acc, r);
@@ -603,11 +611,11 @@ void pipe_plain_forward(cudaStream_t stream, const __half* weights, const __half
 	launch_pipe_infer<MODE_PLAIN>(stream, PipeInferArgs{weights, input, nullptr, output, n, nullptr, 0u, nullptr});
 }
 uint32_t pipe_nerf_forward_backward(cudaStream_t stream, const __half* mlp, const __half* encoded, bool tiled, const float* coords, const __half* dL_dout, uint32_t n,
-                                    __half* dL_dencoded, float* partials) {
-	return launch_pipe_train<MODE_TRAIN>(stream, PipeTrainArgs{mlp, encoded, coords, dL_dout, dL_dencoded, partials, n, tiled ? 1u : 0u});
+                                    __half* dL_dencoded, float* partials, __half* dL_dsh) {
+	return launch_pipe_train<MODE_TRAIN>(stream, PipeTrainArgs{mlp, encoded, coords, dL_dout, dL_dencoded, partials, n, tiled ? 1u : 0u, dL_dsh});
 }
 uint32_t pipe_plain_forward_backward(cudaStream_t stream, const __half* weights, const __half* input, const __half* dL_dout16, uint32_t n, __half* dL_dinput, float* partials) {
-	return launch_pipe_train<MODE_PLAIN_TRAIN>(stream, PipeTrainArgs{weights, input, nullptr, dL_dout16, dL_dinput, partials, n, 0u});
+	return launch_pipe_train<MODE_PLAIN_TRAIN>(stream, PipeTrainArgs{weights, input, nullptr, dL_dout16, dL_dinput, partials, n, 0u, nullptr});
 }
 
 } // namespace ngpb

@@ -33,7 +33,10 @@ void optimizer_launch(cudaStream_t stream, const void* params, uint32_t first, u
                       __half* w_ema, float* m1, float* m2, uint32_t* param_steps);
 void nerf_mlp_forward_launch(cudaStream_t stream, const __half* mlp, const __half* encoded, bool tiled, const float* coords, uint32_t n, const uint32_t* n_dev, __half* rgbsigma);
 void nerf_density_mlp_launch(cudaStream_t stream, const __half* mlp, const __half* encoded, bool tiled, uint32_t n, __half* density);
-void nerf_mlp_forward_backward_launch(cudaStream_t stream, const __half* mlp, const __half* encoded, bool tiled, const float* coords, const __half* dL_dout, uint32_t n, __half* dL_dencoded, float* mlp_grad, float* partials);
+void nerf_mlp_forward_backward_launch(cudaStream_t stream, const __half* mlp, const __half* encoded, bool tiled, const float* coords, const __half* dL_dout, uint32_t n, __half* dL_dencoded, float* mlp_grad, float* partials, __half* dL_dsh);
+void nerf_input_gradient_launch(cudaStream_t stream, const ngpb_grid* g, const __half* grid, const float* coords, uint32_t n, const __half* dL_dencoded, const __half* dL_dsh, float* coords_gradient);
+void cam_gradient_launch(cudaStream_t stream, uint32_t max_rays, uint32_t n_rays_global, const float* aabb6, const uint32_t* rays_counter, uint32_t n_images, const uint32_t* ray_indices,
+                         const float* rays, const uint32_t* numsteps, const float* coords, const float* coords_gradient, float* cam_pos_gradient, float* cam_rot_gradient);
 
 // sum of n floats in double, one block, fixed order (tcnn reduce_sum.h:54-118 is the reference's loss reduction)
 __global__ void __launch_bounds__(1024) sum_kernel(const float* __restrict__ v, const uint32_t n, float* __restrict__ out)
@@ -343,9 +346,17 @@ void ngpb_testbed::load_training_data(uint32_t n, const ngpb_host_image* host_im
 		pixels_bytes = total;
 	}
 	images.resize(n);
+	dataset_xforms.assign((size_t)n * 12, 0.f);
+	dfree(cam_gradients);
+	cam_gradients = (float*)dalloc(sizeof(float) * 6 * n);
+	NGPB_CUDA_CHECK(cudaMemsetAsync(cam_gradients, 0, sizeof(float) * 6 * n, stream));
+	cam_gradients_host.assign((size_t)n * 6, 0.f);
+	cam_pos_state.assign((size_t)n * 10, 0.f); cam_rot_state.assign((size_t)n * 10, 0.f);
+	n_steps_since_cam_update = 0;
 	size_t off = 0;
 	for (uint32_t i = 0; i < n; ++i) {
 		const ngpb_host_image& h = host_images[i];
+		std::memcpy(&dataset_xforms[(size_t)i * 12], h.xform, sizeof(float) * 12);
 		const size_t bytes = (size_t)h.w * h.h * 4;
 		NGPB_CUDA_CHECK(cudaMemcpyAsync(pixels + off, h.pixels, bytes, cudaMemcpyHostToDevice, stream));
 		ngpb_image& im = images[i];
@@ -385,6 +396,14 @@ void ngpb_testbed::reset_network(uint32_t seed_) {
 	// m_rng = default_rng_t{m_seed}; density_grid_rng = default_rng_t{m_rng.next_uint()} (:2252,:2265)
 	rng.seed(seed);
 	density_grid_rng.seed(rng.next_uint());
+	// m_nerf.training.reset_camera_extrinsics() (src/testbed.cu:2267); the training transforms follow at once (the reference leaves them until the next update)
+	if (!images.empty()) {
+		bool moved = false;
+		for (size_t i = 0; i < images.size() && !moved; ++i) for (int c = 7; c < 10; ++c) moved |= cam_pos_state[i * 10 + c] != 0.f || cam_rot_state[i * 10 + c] != 0.f;
+		reset_camera_extrinsics();
+		if (moved) update_transforms();
+	}
+	n_steps_since_cam_update = 0;
 	const uint32_t n_levels = 16, base_resolution = 16;
 	// per_level_scale = exp(ln(desired_resolution * aabb_scale / base) / (L-1)) (:2313-2325)
 	const float per_level_scale = std::exp(std::log(2048.0f * (float)aabb_scale / (float)base_resolution) / (n_levels - 1));
@@ -481,6 +500,7 @@ void ngpb_testbed::ensure_workspace(uint32_t batch) {
 	if (batch == 0 || batch % 128 != 0) throw std::runtime_error("training batch size must be a non-zero multiple of 128 (tcnn batch_size_granularity)");
 	dfree(ray_indices); dfree(rays); dfree(numsteps); dfree(coords); dfree(rgbsigma); dfree(encoded); dfree(encoded_compacted); dfree(coords_compacted);
 	dfree(dloss); dfree(denc); dfree(loss); dfree(scratch); dfree(counters); dfree(partials);
+	dfree(dL_dsh); dfree(coords_gradient); dL_dsh = nullptr; coords_gradient = nullptr;
 	const size_t max_rays = 1u << 18;            // rays_per_batch cap (testbed_nerf.cu:2891)
 	const size_t max_samples = (size_t)batch * 16; // testbed_nerf.cu:3140
 	ray_indices = (uint32_t*)dalloc(sizeof(uint32_t) * max_rays);
@@ -683,6 +703,7 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 		if (poison & 512u) NGPB_CUDA_CHECK(cudaMemsetAsync(loss, 0xFF, sizeof(float) * max_rays, stream));
 		if (poison & 1024u) { NGPB_CUDA_CHECK(cudaMemsetAsync(rays, 0xFF, sizeof(float) * 6 * max_rays, stream)); NGPB_CUDA_CHECK(cudaMemsetAsync(numsteps, 0xFF, sizeof(uint32_t) * 2 * max_rays, stream)); NGPB_CUDA_CHECK(cudaMemsetAsync(ray_indices, 0xFF, sizeof(uint32_t) * max_rays, stream)); }
 	}
+	if (n_steps_since_cam_update == 0) NGPB_CUDA_CHECK(cudaMemsetAsync(cam_gradients, 0, sizeof(float) * 6 * images.size(), stream)); // :2916-2919
 	const uint32_t R = rays_per_batch;
 	const SamplingRequest req{training_step, R, max_inference, ngpb_rng{rng.state, rng.inc}, loss_cfg.snap_to_pixel_centers, cone_angle_constant};
 	const ngpb_rng r = req.rng;
@@ -734,9 +755,24 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 		++n_launches;
 	}
 	stage_begin(NGPB_STAGE_MLP_TRAIN, stream);
-	nerf_mlp_forward_backward_launch(stream, w_half, encoded_compacted, tiled, coords_compacted, dloss, batch, denc, grad, partials);
+	if (optimize_extrinsics && !dL_dsh) {
+		dL_dsh = (__half*)dalloc(sizeof(__half) * 16 * batch);
+		coords_gradient = (float*)dalloc(sizeof(float) * COORD_FLOATS * batch);
+	}
+	nerf_mlp_forward_backward_launch(stream, w_half, encoded_compacted, tiled, coords_compacted, dloss, batch, denc, grad, partials, optimize_extrinsics ? dL_dsh : nullptr);
 	stage_end(NGPB_STAGE_MLP_TRAIN, batch, stream);
-	NGPB_CUDA_CHECK(cudaEventRecord(mlp_train_done, stream));
+	if (!optimize_extrinsics) NGPB_CUDA_CHECK(cudaEventRecord(mlp_train_done, stream));
+	if (optimize_extrinsics) {
+		// K13 / K14 (train_nerf_step :3324-3372): gradients w.r.t. the network inputs of the compacted batch, reduced per camera. The reference runs the
+		// input gradient over the padded batch too; padding samples carry a zero loss gradient and belong to no ray.
+		nerf_input_gradient_launch(stream, &grid, w_half + MLP_PARAMS, coords_compacted, batch, denc, dL_dsh, coords_gradient);
+		cam_gradient_launch(stream, R, (uint32_t)dp_world * R, aabb, counters + 1, (uint32_t)images.size(), ray_indices, rays, numsteps, coords_compacted, coords_gradient,
+			cam_gradients, cam_gradients + 3 * images.size());
+		n_launches += 2;
+		// the camera-gradient kernel is the last reader of this step's rays / numsteps / ray counter: the prefetched sampling of the next step, which
+		// rewrites them on the sampling stream, has to wait for it
+		NGPB_CUDA_CHECK(cudaEventRecord(mlp_train_done, stream));
+	}
 	if (dp_world == 1) {
 		stage_begin(NGPB_STAGE_ENCODE_BACKWARD, stream);
 		hash_encode_backward_launch(stream, &grid, coords_compacted, COORD_FLOATS, batch, denc, grad + MLP_PARAMS, 0, grid.n_levels);
@@ -850,6 +886,8 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 	}
 	++training_step;
 	rng.advance(); // m_rng.advance() (:3380)
+	++n_steps_since_cam_update; // (:3026)
+	if (optimize_extrinsics && n_steps_since_cam_update >= n_steps_between_cam_updates) camera_update_step();
 
 	// ---- batch-size controller (:2870-2894) ----
 	NGPB_CUDA_CHECK(cudaEventSynchronize(counters_ready));
@@ -879,7 +917,7 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 			prefetch = SamplingRequest{training_step, rays_per_batch, next_multiple(std::min(inference_budget(measured_batch_size_before_compaction), max_samples), 128),
 				ngpb_rng{rng.state, rng.inc}, loss_cfg.snap_to_pixel_centers, cone_angle_constant};
 			static const bool after_mlp = getenv("NGPB_K1_AFTER_MLP") && atoi(getenv("NGPB_K1_AFTER_MLP")) != 0;
-			if (after_mlp) NGPB_CUDA_CHECK(cudaStreamWaitEvent(sampling_stream, mlp_train_done, 0));
+			if (after_mlp || optimize_extrinsics) NGPB_CUDA_CHECK(cudaStreamWaitEvent(sampling_stream, mlp_train_done, 0));
 			launch_sampling(sampling_stream, prefetch);
 			NGPB_CUDA_CHECK(cudaEventRecord(prefetch_done, sampling_stream));
 			prefetch_valid = true;
@@ -890,6 +928,56 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 		collect_loss_scalar();
 		if (profile_stages) stage_collect();
 	}
+}
+
+// Host half of the camera optimisation (train_nerf :3056-3083, :3134): read the accumulated gradients, one Adam step per camera and offset, new transforms.
+// Synchronises the stream (as the reference does); nothing that reads the image table is in flight afterwards -- the prefetch of the next step's sampling is
+// launched after this returns.
+void ngpb_testbed::camera_update_step() {
+	const size_t n = images.size();
+	if (dp_world > 1) {
+		NcclApi& nccl = NcclApi::get();
+		nccl.check(nccl.AllReduce(cam_gradients, cam_gradients, 6 * n, NcclApi::Float32, NcclApi::Sum, nccl_comm, stream), "ncclAllReduce(camera gradients)");
+	}
+	NGPB_CUDA_CHECK(cudaMemcpyAsync(cam_gradients_host.data(), cam_gradients, sizeof(float) * 6 * n, cudaMemcpyDeviceToHost, stream));
+	NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
+	d2h_bytes += sizeof(float) * 6 * n;
+	const float per_camera_loss_scale = (float)n / LOSS_SCALE / (float)n_steps_between_cam_updates;
+	const float lr_floor = opt.learning_rate * opt.lr_factor / 1000.0f; // m_optimizer->learning_rate() / 1000
+	for (size_t i = 0; i < n; ++i) {
+		float* ps = &cam_pos_state[i * 10]; float* rs = &cam_rot_state[i * 10];
+		float pg[3], rg[3];
+		for (int c = 0; c < 3; ++c) {
+			pg[c] = cam_gradients_host[i * 3 + c] * per_camera_loss_scale + ps[7 + c] * extrinsic_l2_reg;
+			rg[c] = cam_gradients_host[(n + i) * 3 + c] * per_camera_loss_scale + rs[7 + c] * extrinsic_l2_reg;
+		}
+		const float lr_p = std::max(extrinsic_learning_rate * std::pow(0.33f, (float)((uint32_t)ps[0] / 128u)), lr_floor);
+		const float lr_r = std::max(extrinsic_learning_rate * std::pow(0.33f, (float)((uint32_t)rs[0] / 128u)), lr_floor);
+		ngpb_camera_adam_step(ps, pg, lr_p, 0);
+		ngpb_camera_adam_step(rs, rg, lr_r, 1);
+	}
+	update_transforms();
+	n_steps_since_cam_update = 0;
+}
+
+// Training::update_transforms (:2597-2633): training transform = dataset transform with the camera's offsets applied; re-upload the image table.
+void ngpb_testbed::update_transforms() {
+	const size_t n = images.size();
+	if (n == 0) return;
+	drop_prefetch();
+	NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
+	for (size_t i = 0; i < n; ++i) {
+		ngpb_apply_camera_offsets(&dataset_xforms[i * 12], &cam_pos_state[i * 10 + 7], &cam_rot_state[i * 10 + 7], images[i].raw_xform);
+		ngpb_effective_xform(images[i].raw_xform, images[i].xform);
+	}
+	NGPB_CUDA_CHECK(cudaMemcpyAsync(images_dev, images.data(), sizeof(ngpb_image) * n, cudaMemcpyHostToDevice, stream));
+	NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
+	h2d_bytes += sizeof(ngpb_image) * n;
+}
+
+void ngpb_testbed::reset_camera_extrinsics() { // Training::reset_camera_extrinsics (:2543-2555)
+	std::fill(cam_pos_state.begin(), cam_pos_state.end(), 0.f);
+	std::fill(cam_rot_state.begin(), cam_rot_state.end(), 0.f);
 }
 
 void ngpb_testbed::get_params(float* o_fp32, ngpb_half* o_half, ngpb_half* o_ema) {
@@ -1058,6 +1146,29 @@ extern "C" int ngpb_testbed_set_optimizer_state(ngpb_testbed* t, const float* fm
 	NGPB_API_END
 }
 
+// nerf.training.get_camera_extrinsics / set_camera_extrinsics / reset_camera_extrinsics (:2518-2555, :2590-2595), in the library's (ngp) coordinates
+extern "C" int ngpb_testbed_get_camera_extrinsics(ngpb_testbed* t, uint32_t frame_idx, float* xform12, float* pos_offset3, float* rot_offset3) {
+	NGPB_API_BEGIN
+	if (frame_idx >= t->images.size()) throw std::runtime_error("get_camera_extrinsics: frame index out of range");
+	if (xform12) std::memcpy(xform12, t->images[frame_idx].raw_xform, sizeof(float) * 12);
+	if (pos_offset3) std::memcpy(pos_offset3, &t->cam_pos_state[(size_t)frame_idx * 10 + 7], sizeof(float) * 3);
+	if (rot_offset3) std::memcpy(rot_offset3, &t->cam_rot_state[(size_t)frame_idx * 10 + 7], sizeof(float) * 3);
+	NGPB_API_END
+}
+extern "C" int ngpb_testbed_set_camera_extrinsics(ngpb_testbed* t, uint32_t frame_idx, const float* xform12) {
+	NGPB_API_BEGIN
+	if (frame_idx >= t->images.size() || !xform12) throw std::runtime_error("set_camera_extrinsics: invalid argument");
+	std::memcpy(&t->dataset_xforms[(size_t)frame_idx * 12], xform12, sizeof(float) * 12);
+	t->update_transforms();
+	NGPB_API_END
+}
+extern "C" int ngpb_testbed_reset_camera_extrinsics(ngpb_testbed* t) {
+	NGPB_API_BEGIN
+	t->reset_camera_extrinsics();
+	t->update_transforms();
+	NGPB_API_END
+}
+
 extern "C" void* ngpb_testbed_stream(ngpb_testbed* t) { return t ? (void*)t->stream : nullptr; }
 extern "C" int ngpb_testbed_stage_times(ngpb_testbed* t, double* ms, uint64_t* calls, uint64_t* units, int reset) {
 	NGPB_API_BEGIN
@@ -1105,6 +1216,10 @@ extern "C" int ngpb_testbed_set_option(ngpb_testbed* t, const char* name, double
 		if (v < 14 || v > 24) throw std::runtime_error("encoding.log2_hashmap_size must be in [14, 24]");
 		t->log2_hashmap_size = (uint32_t)v; // takes effect at the next reset_network
 	}
+	else if (k == "optimize_extrinsics") t->optimize_extrinsics = v != 0;
+	else if (k == "extrinsic_learning_rate") t->extrinsic_learning_rate = (float)v;
+	else if (k == "extrinsic_l2_reg") t->extrinsic_l2_reg = (float)v;
+	else if (k == "n_steps_between_cam_updates") { if (v < 1) throw std::runtime_error("n_steps_between_cam_updates must be >= 1"); t->n_steps_between_cam_updates = (uint32_t)v; }
 	else if (k == "profile_stages") t->profile_stages = v != 0;
 	else if (k == "render_snap_to_pixel_centers") t->render_snap_to_pixel_centers = v != 0;
 	else if (k == "render_near_distance") t->render_near_distance = (float)v;
@@ -1144,6 +1259,11 @@ extern "C" double ngpb_testbed_get_option(ngpb_testbed* t, const char* name) {
 	if (k == "decay_interval") return t->opt.decay_interval;
 	if (k == "decay_base") return t->opt.decay_base;
 	if (k == "log2_hashmap_size") return t->log2_hashmap_size;
+	if (k == "optimize_extrinsics") return t->optimize_extrinsics;
+	if (k == "extrinsic_learning_rate") return t->extrinsic_learning_rate;
+	if (k == "extrinsic_l2_reg") return t->extrinsic_l2_reg;
+	if (k == "n_steps_between_cam_updates") return t->n_steps_between_cam_updates;
+	if (k == "n_steps_since_cam_update") return t->n_steps_since_cam_update;
 	if (k == "render_snap_to_pixel_centers") return t->render_snap_to_pixel_centers;
 	if (k == "render_near_distance") return t->render_near_distance;
 	if (k == "exposure") return t->exposure;

@@ -79,6 +79,20 @@ struct ngpb_testbed {
 	float aabb[6] = {0, 0, 0, 1, 1, 1};
 	float cone_angle_constant = 0.f;
 
+	// camera-extrinsics optimisation (Testbed::Nerf::Training, testbed.h:620-650; train_nerf :3056-3083): per-camera position / rotation offsets moved by a
+	// host-side Adam every n_steps_between_cam_updates steps from gradients accumulated on the device (camera_optimizer.cu)
+	bool optimize_extrinsics = false;
+	float extrinsic_learning_rate = 1e-3f, extrinsic_l2_reg = 1e-4f;
+	uint32_t n_steps_since_cam_update = 0, n_steps_between_cam_updates = 16;
+	std::vector<float> dataset_xforms;                // [n_images][12]: the transforms as loaded (dataset.xforms); images[i].raw_xform = these + offsets
+	std::vector<float> cam_pos_state, cam_rot_state;  // [n_images][10]: {iter, m1[3], m2[3], variable[3]} of ngpb_camera_adam_step
+	std::vector<float> cam_gradients_host;            // [2][n_images][3]
+	float* cam_gradients = nullptr;                   // device, [2][n_images][3]: position then rotation
+	float* coords_gradient = nullptr; __half* dL_dsh = nullptr; // workspace, sized by the batch (allocated on first use)
+	void reset_camera_extrinsics();
+	void update_transforms();
+	void camera_update_step();
+
 	// model + optimizer state: fp32 master, fp16 training copy, fp16 EMA (inference) copy, Adam moments
 	// (tcnn Trainer buffer trainer.h:80,:317-332). Flat order: density net, rgb net, grid levels.
 	ngpb_grid grid{};

@@ -424,6 +424,8 @@ EXPORTED_SYMBOLS = [
     "ngpb_testbed_render", "ngpb_testbed_stream", "ngpb_testbed_stage_times", "ngpb_grid_device_scales", "ngpb_testbed_configure", "ngpb_testbed_set_params_half", "ngpb_testbed_set_density_grid", "ngpb_testbed_get_training_state",
     "ngpb_testbed_set_training_state", "ngpb_testbed_get_optimizer_state", "ngpb_testbed_set_optimizer_state", "ngpb_generate_training_samples_sharded", "ngpb_compute_loss_sharded", "ngpb_nccl_unique_id", "ngpb_testbed_init_data_parallel", "ngpb_render_workspace_bytes", "ngpb_render_nerf", "ngpb_testbed_last_render_ms", "ngpb_generate_training_samples_scratch_bytes", "ngpb_compute_loss_scratch_bytes",
     "ngpb_field_create", "ngpb_field_destroy", "ngpb_blender_render", "ngpb_compute_loss_compact_features", "ngpb_grid_init_nd", "ngpb_mlp_forward", "ngpb_mlp_forward_backward", "ngpb_loss",
+    "ngpb_nerf_mlp_forward_backward_sh", "ngpb_nerf_input_gradient", "ngpb_compute_cam_gradient", "ngpb_camera_adam_step", "ngpb_apply_camera_offsets",
+    "ngpb_testbed_get_camera_extrinsics", "ngpb_testbed_set_camera_extrinsics", "ngpb_testbed_reset_camera_extrinsics", "ngpb_probe_umma",
 ]
 
 _lib = None
@@ -458,6 +460,13 @@ def lib():
         l.ngpb_field_destroy.argtypes = [C.c_void_p]
         l.ngpb_testbed_stream.restype = C.c_void_p
         l.ngpb_testbed_stream.argtypes = [C.c_void_p]
+        l.ngpb_camera_adam_step.restype = None
+        l.ngpb_camera_adam_step.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_int]
+        l.ngpb_apply_camera_offsets.restype = None
+        l.ngpb_apply_camera_offsets.argtypes = [C.c_void_p] * 4
+        l.ngpb_testbed_get_camera_extrinsics.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.ngpb_testbed_set_camera_extrinsics.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        l.ngpb_testbed_reset_camera_extrinsics.argtypes = [C.c_void_p]
         _lib = l
     return _lib
 
@@ -583,6 +592,16 @@ def nerf_matrix_to_ngp(c2w, scale, offset):
     m[:, 2] *= -1
     m[:, 3] = m[:, 3] * np.float32(scale) + np.asarray(offset, dtype=np.float32)
     return m[[1, 2, 0], :].copy()
+
+
+def ngp_matrix_to_nerf(m, scale, offset):
+    """nerf_loader.h:134-151 (from_mitsuba = false, scale_columns = false): the inverse of nerf_matrix_to_ngp."""
+    m = np.array(m, dtype=np.float32)[:3, :4]
+    r = m[[2, 0, 1], :].copy()  # cycle axes xyz -> yzx back
+    r[:, 1] *= -1
+    r[:, 2] *= -1
+    r[:, 3] = (r[:, 3] - np.asarray(offset, dtype=np.float32)) / np.float32(scale)
+    return r
 
 
 def _fov_to_focal_length(resolution, degrees):  # common_device.cuh:473
@@ -726,14 +745,39 @@ class _Training:
     near_distance = property(lambda s: s._tb._get("near_distance"), lambda s, v: s._tb._set("near_distance", float(v)))
     density_grid_decay = property(lambda s: s._tb._get("density_grid_decay"), lambda s, v: s._tb._set("density_grid_decay", float(v)))
 
-    @property
-    def optimize_extrinsics(self):
-        return False
+    # camera-extrinsics optimisation (python_api.cu:811-844; K13 / K14)
+    optimize_extrinsics = _bool_prop("optimize_extrinsics")
+    extrinsic_l2_reg = property(lambda s: s._tb._get("extrinsic_l2_reg"), lambda s, v: s._tb._set("extrinsic_l2_reg", float(v)))
+    extrinsic_learning_rate = property(lambda s: s._tb._get("extrinsic_learning_rate"), lambda s, v: s._tb._set("extrinsic_learning_rate", float(v)))
+    n_steps_between_cam_updates = property(lambda s: int(s._tb._get("n_steps_between_cam_updates")), lambda s, v: s._tb._set("n_steps_between_cam_updates", int(v)))
+    n_steps_since_cam_update = property(lambda s: int(s._tb._get("n_steps_since_cam_update")))
 
-    @optimize_extrinsics.setter
-    def optimize_extrinsics(self, v):
-        if v:
-            raise RuntimeError("optimize_extrinsics is outside the built scope (SURVEY.md s8: K13/K14)")
+    def get_camera_extrinsics(self, frame_idx):
+        """Training::get_camera_extrinsics (src/testbed_nerf.cu:2590-2595): the frame's CURRENT training transform (dataset transform + learned offsets),
+        as a NeRF-convention 3x4 camera-to-world matrix. Out-of-range indices return the identity, as the reference does."""
+        tb = self._tb
+        out = np.zeros(12, np.float32)
+        if lib().ngpb_testbed_get_camera_extrinsics(tb._h, int(frame_idx) & 0xFFFFFFFF, out.ctypes.data, None, None) != 0:
+            return np.eye(4, dtype=np.float32)[:3]
+        return ngp_matrix_to_nerf(out.reshape(4, 3).T, tb._dataset_scale, tb._dataset_offset)
+
+    def get_camera_offsets(self, frame_idx):
+        """(position offset, rotation offset as angle-axis) of a frame: cam_pos_offset[i].variable() / cam_rot_offset[i].variable() (testbed.h:637-640)."""
+        pos, rot = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        check(lib().ngpb_testbed_get_camera_extrinsics(self._tb._h, int(frame_idx), None, pos.ctypes.data, rot.ctypes.data))
+        return pos, rot
+
+    def set_camera_extrinsics(self, frame_idx, camera_to_world, convert_to_ngp=True):
+        """Training::set_camera_extrinsics (:2539): replaces the dataset transform of a training frame."""
+        tb = self._tb
+        m = np.asarray(camera_to_world, dtype=np.float32)[:3, :4]
+        if convert_to_ngp:
+            m = nerf_matrix_to_ngp(m, tb._dataset_scale, tb._dataset_offset)
+        flat = np.ascontiguousarray(m.T, np.float32).reshape(-1)  # 3x4 column-major
+        check(lib().ngpb_testbed_set_camera_extrinsics(tb._h, int(frame_idx), flat.ctypes.data))
+
+    def reset_camera_extrinsics(self):
+        check(lib().ngpb_testbed_reset_camera_extrinsics(self._tb._h))
 
 
 class _Nerf:

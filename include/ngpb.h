@@ -100,6 +100,10 @@ int ngpb_nerf_mlp_forward(void* stream, const ngpb_half* mlp, const ngpb_half* e
 uint64_t ngpb_nerf_mlp_workspace_bytes(void);
 int ngpb_nerf_mlp_forward_backward(void* stream, const ngpb_half* mlp, const ngpb_half* encoded, const float* coords, const ngpb_half* dL_dout,
                                    uint32_t n, ngpb_half* dL_dencoded, float* mlp_grad, void* workspace);
+/* As above, and dL_dsh [n][16] half: the gradient with respect to the rgb network's spherical-harmonics inputs (columns 16..31 of its input), which
+ * camera-extrinsics optimisation carries on to dL/d(direction) (NerfNetwork::backward_impl with dL_dinput, nerf_network.h:286-400). */
+int ngpb_nerf_mlp_forward_backward_sh(void* stream, const ngpb_half* mlp, const ngpb_half* encoded, const float* coords, const ngpb_half* dL_dout,
+                                      uint32_t n, ngpb_half* dL_dencoded, float* mlp_grad, void* workspace, ngpb_half* dL_dsh);
 /* density network only (NerfNetwork::density, nerf_network.h:268-284): encoded [n][32] -> density logit half[n]. */
 int ngpb_nerf_density_mlp_forward(void* stream, const ngpb_half* mlp, const ngpb_half* encoded, uint32_t n, ngpb_half* density);
 
@@ -308,6 +312,38 @@ int ngpb_testbed_get_density_grid(ngpb_testbed* t, float* grid, uint8_t* bitfiel
  * every rank. NCCL is resolved with dlopen("libnccl.so.2") at the first call. */
 int ngpb_nccl_unique_id(void* out128);
 int ngpb_testbed_init_data_parallel(ngpb_testbed* t, int rank, int world, const void* unique_id128);
+
+/* ---- camera-extrinsics optimisation (K13 / K14; nerf.training.optimize_extrinsics, python_api.cu:806) ----
+ * Gradient of the loss with respect to the network inputs of n samples: coords_gradient [n][7] float = {dL/dpos[3], 0, dL/ddir[3]} in the
+ * coordinates' own [0,1] units. Position part: kernel_grid's dy_dx + kernel_grid_backward_input (tcnn encodings/grid.h:351-392,:551-575) from
+ * dL_dencoded [n][32] half and the grid; direction part: kernel_sh_backward (encodings/spherical_harmonics.h:154-390) from dL_dsh [n][16] half
+ * (NULL: zero). grid: half2 table of all levels (the parameters after the 10240 MLP weights). */
+int ngpb_nerf_input_gradient(void* stream, const ngpb_grid* g, const ngpb_half* grid, const float* coords, uint32_t n, const ngpb_half* dL_dencoded,
+                             const ngpb_half* dL_dsh, float* coords_gradient);
+/* compute_cam_gradient_train_nerf (src/testbed_nerf.cu:1600-1707), uniform pixel sampling: per kept ray, sums the sample gradients into a ray
+ * origin / direction gradient and accumulates (atomicAdd) into cam_pos_gradient / cam_rot_gradient [n_images][3] (either may be NULL). numsteps
+ * [max_rays][2] = {compacted sample count, compacted base} as ngpb_compute_loss leaves it; coords / coords_gradient: the compacted batch. */
+int ngpb_compute_cam_gradient(void* stream, uint32_t max_rays, uint32_t n_rays_global, const float* aabb6, const uint32_t* rays_counter_dev, uint32_t n_images,
+                              const uint32_t* ray_indices, const float* rays, const uint32_t* numsteps, const float* coords, const float* coords_gradient,
+                              float* cam_pos_gradient, float* cam_rot_gradient);
+/* Host-side: one step of AdamOptimizer<Vector3f> (rotation = 0) or RotationAdamOptimizer (rotation = 1; the variable is an angle-axis vector and the
+ * update is composed as a rotation) (include/neural-graphics-primitives/adam_optimizer.h:20-159; beta1 .9, beta2 .99, eps 1e-8).
+ * state10 = {iter, first_moment[3], second_moment[3], variable[3]}. */
+void ngpb_camera_adam_step(float* state10, const float* gradient3, float learning_rate, int rotation);
+/* Host-side: Training::update_transforms for one camera (src/testbed_nerf.cu:2597-2633): out = dataset transform (3x4 column-major) with the rotation
+ * offset (angle-axis) applied on the left of its 3x3 block and the position offset added to its translation. */
+void ngpb_apply_camera_offsets(const float* xform12, const float* pos_offset3, const float* rot_offset3, float* out12);
+/* Options "optimize_extrinsics", "extrinsic_learning_rate", "extrinsic_l2_reg", "n_steps_between_cam_updates" (ngpb_testbed_set_option) switch the
+ * per-camera optimisation on inside ngpb_testbed_train. The current training transform of a frame (dataset transform + learned offsets, ngp coordinates),
+ * and the offsets themselves (any pointer may be NULL): */
+int ngpb_testbed_get_camera_extrinsics(ngpb_testbed* t, uint32_t frame_idx, float* xform12, float* pos_offset3, float* rot_offset3);
+/* Training::set_camera_extrinsics (:2539): replaces the dataset transform of a frame (ngp coordinates); reset_camera_extrinsics (:2543) zeroes every
+ * camera's offsets and Adam state. */
+int ngpb_testbed_set_camera_extrinsics(ngpb_testbed* t, uint32_t frame_idx, const float* xform12);
+int ngpb_testbed_reset_camera_extrinsics(ngpb_testbed* t);
+
+/* Development aid (tools/umma_probe.py): cycle counts of tcgen05 issue / commit / wait sequences on this GPU; sections is a bit mask. */
+int ngpb_probe_umma(void* stream, long long* cycles_host, uint32_t n, uint32_t sections);
 
 /* The stream every testbed kernel is launched on (Testbed::m_stream, testbed.h:895), as a cudaStream_t. */
 void* ngpb_testbed_stream(ngpb_testbed* t);

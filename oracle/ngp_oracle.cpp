@@ -1875,8 +1875,9 @@ extern "C" void orc_loss(int kind, uint32_t n, uint32_t dims, float loss_scale, 
 }
 
 // =============================================================================================
-// Input gradients (camera-extrinsics optimisation, K13/K14): PREPARATION FOR THE NEXT ROUND. PARITY UNPINNED -- no golden vector from the reference exists
-// for these yet; tests/test_oracle_cpu.py checks them against finite differences of the oracle's own forward paths. Nothing in the product uses them.
+// Input gradients (camera-extrinsics optimisation, K13/K14). Pinned on the reference's own kernels (kernel_grid dy_dx + kernel_grid_backward_input,
+// kernel_sh_backward, compute_cam_gradient_train_nerf run on a B200: tests/golden/ref_camera.npz, tests/test_camera_optimizer.py); tests/test_oracle_cpu.py
+// additionally checks them against finite differences of the oracle's own forward paths.
 // =============================================================================================
 
 // dL/dx of the hash-grid encoding: kernel_grid's dy_dx (grid.h:351-392: per level and feature, for each input dimension the difference of the two

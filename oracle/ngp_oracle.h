@@ -216,7 +216,7 @@ void orc_mlp_forward_backward(uint32_t n_hidden, uint32_t n, const orc_half* wei
                               const orc_half* dL_dout, orc_half* dL_dinput, float* grad);
 void orc_loss(int kind, uint32_t n, uint32_t dims, float loss_scale, const orc_half* predictions, const float* targets, float* values, orc_half* gradients);
 
-// ---- input gradients for camera-extrinsics optimisation (K13/K14): next round's oracle, PARITY UNPINNED (see ngp_oracle.cpp) ----
+// ---- input gradients for camera-extrinsics optimisation (K13/K14); pinned on tests/golden/ref_camera.npz (see ngp_oracle.cpp) ----
 void orc_grid_input_gradient(uint32_t n, uint32_t n_levels, const uint32_t* offsets, uint32_t base_resolution, float log2_per_level_scale, const float* scales,
                              const orc_half* grid, const float* positions, uint32_t pos_stride, const orc_half* dL_dy, float* dL_dx);
 void orc_sh4_input_gradient(uint32_t n, const float* dirs, uint32_t stride, const orc_half* dL_dy, float* dL_dx);

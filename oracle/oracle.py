@@ -367,7 +367,7 @@ def loss(kind, predictions_half, targets, loss_scale=128.0):
     return values, grads
 
 
-# ---- input gradients (camera-extrinsics optimisation; next round's oracle, parity unpinned) ----
+# ---- input gradients (camera-extrinsics optimisation, K13 / K14; pinned on tests/golden/ref_camera.npz) ----
 def grid_input_gradient(m, grid_half, positions, dL_dy, scales=None):
     positions = _f32(positions)
     n = positions.shape[0]

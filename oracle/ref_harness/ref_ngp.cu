@@ -221,4 +221,28 @@ int ref_bitfield(uint32_t n_cascades_used, const float* grid, uint8_t* bitfield,
 	return (int)cudaDeviceSynchronize();
 }
 
+
+// compute_cam_gradient_train_nerf (src/testbed_nerf.cu:1598-1707) with uniform pixel sampling, no distortion map, no focal-length gradient.
+// cam_pos_gradient / cam_rot_gradient: device float[n_images][3], zeroed here first. All other pointers are device buffers.
+int ref_compute_cam_gradient(
+	uint32_t n_rays, uint32_t n_rays_total, const float* aabb6, const uint32_t* rays_counter,
+	uint32_t n_images, int w, int h, float fx, float fy, float cx, float cy, const uint8_t* pixels, const float* xforms_host,
+	const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords, const float* coords_gradient,
+	float* cam_pos_gradient, float* cam_rot_gradient
+) {
+	DeviceDataset d = make_dataset(n_images, w, h, fx, fy, cx, cy, pixels, xforms_host);
+	default_rng_t rng;
+	cudaMemset(cam_pos_gradient, 0, sizeof(float) * 3 * n_images);
+	cudaMemset(cam_rot_gradient, 0, sizeof(float) * 3 * n_images);
+	linear_kernel(compute_cam_gradient_train_nerf, 0, 0,
+		n_rays, n_rays_total, rng, make_aabb(aabb6), rays_counter, d.xforms.data(), false,
+		(Vector3f*)cam_pos_gradient, (Vector3f*)cam_rot_gradient, n_images, d.metadata.data(),
+		ray_indices, (const Ray*)rays, numsteps,
+		PitchedPtr<NerfCoordinate>((NerfCoordinate*)coords, 1, 0, 0),
+		PitchedPtr<NerfCoordinate>((NerfCoordinate*)coords_gradient, 1, 0, 0),
+		(float*)nullptr, (float*)nullptr, Vector2i{0, 0}, (Vector2f*)nullptr,
+		(const float*)nullptr, (const float*)nullptr, (const float*)nullptr, Vector2i{0, 0});
+	return (int)cudaDeviceSynchronize();
+}
+
 }

@@ -9,9 +9,12 @@
 //   kernel_grid<__half,3,2>, <__half,2,2>   dependencies/tiny-cuda-nn/include/tiny-cuda-nn/encodings/grid.h:220
 //   kernel_grid_backward<__half,__half,3,2,2>                                          grid.h:395
 //   kernel_sh<__half>                  .../encodings/spherical_harmonics.h:46
+//   kernel_grid (dy_dx) + kernel_grid_backward_input<__half,3>                          grid.h:351,:551
+//   kernel_sh_backward<__half>         .../encodings/spherical_harmonics.h:154
 //   adam_step<__half>                  .../optimizers/adam.h:48
 //   ema_step_half_precision<__half>    .../optimizers/ema.h:63
 #include <tiny-cuda-nn/common.h>
+#include <tiny-cuda-nn/gpu_memory.h>
 #include <tiny-cuda-nn/encodings/grid.h>
 #include <tiny-cuda-nn/encodings/spherical_harmonics.h>
 #include <tiny-cuda-nn/optimizers/adam.h>
@@ -119,6 +122,30 @@ int ref_adam_step(uint32_t n, uint32_t n_matrix, float loss_scale, float lr, flo
 
 int ref_ema_step(uint32_t n, float decay, float debias_old, float debias_new, const void* w_half, void* w_ema_half) {
 	linear_kernel(ema_step_half_precision<__half>, 0, 0, n, decay, debias_old, debias_new, (const __half*)w_half, (__half*)w_ema_half);
+	return (int)cudaDeviceSynchronize();
+}
+
+
+// Input gradient of the grid encoding: kernel_grid with dy_dx (grid.h:351-392) followed by kernel_grid_backward_input (grid.h:551-575), as
+// GridEncoding::forward_impl(prepare_input_gradients) + backward_impl do. dL_dy: SoA half [n_features][n]. dL_dx: AoS float, dx_stride floats per sample.
+int ref_grid_input_gradient(uint32_t n, uint32_t n_levels, const uint32_t* offsets_host, uint32_t base_resolution, float log2_per_level_scale,
+                            const void* grid_half, const float* positions, uint32_t pos_stride, const void* dL_dy_soa_half, float* dL_dx, uint32_t dx_stride) {
+	GridOffsetTable t = make_table(offsets_host, n_levels);
+	GPUMemory<float> dy_dx((size_t)n * n_levels * 2 * 3);
+	GPUMemory<__half> encoded((size_t)n * n_levels * 2);
+	const dim3 blocks = { div_round_up(n, 512u), n_levels, 1 };
+	kernel_grid<__half, 3, 2><<<blocks, 512>>>(
+		n, n_levels * 2, t, base_resolution, log2_per_level_scale, 0.f, 1000.f, nullptr,
+		InterpolationType::Linear, GridType::Hash, HashType::CoherentPrime,
+		(const __half*)grid_half, MatrixView<const float>(positions, 1, pos_stride), encoded.data(), dy_dx.data());
+	linear_kernel(kernel_grid_backward_input<__half, 3>, 0, 0, n, n_levels * 2, (const __half*)dL_dy_soa_half, dy_dx.data(), MatrixView<float>(dL_dx, 1, dx_stride));
+	return (int)cudaDeviceSynchronize();
+}
+
+// kernel_sh_backward (spherical_harmonics.h:154-390), degree 4. dL_dy: AoS half, dy_stride halfs per sample; dirs / dL_dx: AoS float.
+int ref_sh4_backward(uint32_t n, const void* dL_dy_half, uint32_t dy_stride, const float* dirs, uint32_t dir_stride, float* dL_dx, uint32_t dx_stride) {
+	linear_kernel(kernel_sh_backward<__half>, 0, 0, n, 4u, 0u, MatrixView<const __half>((const __half*)dL_dy_half, 1, dy_stride),
+		MatrixView<const float>(dirs, 1, dir_stride), MatrixView<float>(dL_dx, 1, dx_stride));
 	return (int)cudaDeviceSynchronize();
 }
 

@@ -84,3 +84,39 @@ LENS_CASES = {
     "latlong": (3, [0.0] * 7, (0.5, 0.5)),
 }
 LENS_N_RAYS, LENS_MAX_SAMPLES = 2048, 1 << 17
+
+
+# ---- camera-extrinsics optimisation (K13 / K14) ----
+N_CAM_SAMPLES = 4096
+CAM_N_IMAGES, CAM_N_RAYS, CAM_N_KEPT = 8, 1024, 1000
+CAM_AABB = np.array([-0.5, -0.5, -0.5, 1.5, 1.5, 1.5], np.float32)
+CAM_ADAM_STEPS = 400
+
+
+def camera_inputs(seed=4242):
+    """Inputs of tests/golden/ref_camera.npz. Samples: positions / directions in [0,1], loss gradients at the hash features [n][32] and SH inputs [n][16].
+    Rays: CAM_N_KEPT kept rays of CAM_N_RAYS with 0..12 compacted samples each; coords / coords_gradient [total][7]."""
+    rs = np.random.RandomState(seed)
+    n = N_CAM_SAMPLES
+    d = dict(positions=rs.rand(n, 3).astype(np.float32), dirs=rs.rand(n, 3).astype(np.float32),
+             dL_dencoded=(rs.randn(n, 32) * 0.01).astype(np.float16), dL_dsh=(rs.randn(n, 16) * 0.01).astype(np.float16))
+    d["positions"][0] = 0.0; d["positions"][1] = 1.0; d["positions"][2] = [0.5, 0.25, 0.75]
+    counts = rs.randint(0, 13, CAM_N_RAYS).astype(np.uint32)
+    bases = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.uint32)
+    total = int(counts.sum())
+    d["numsteps"] = np.stack([counts, bases], 1).astype(np.uint32)
+    d["ray_indices"] = rs.randint(0, CAM_N_RAYS, CAM_N_RAYS).astype(np.uint32)
+    rays = np.concatenate([rs.rand(CAM_N_RAYS, 3) * 2 - 0.5, rs.randn(CAM_N_RAYS, 3) * 3], 1).astype(np.float32)
+    d["rays"] = rays
+    coords = rs.rand(total, 7).astype(np.float32)
+    d["coords"] = coords
+    d["coords_gradient"] = (rs.randn(total, 7) * 0.05).astype(np.float32)
+    # per-camera Adam: gradients spanning the magnitudes seen in training, the reference's learning-rate schedule (x200 for the rotation case so that the
+    # composed rotations leave the small-angle regime)
+    d["adam_gradients"] = (rs.randn(CAM_ADAM_STEPS, 3) * rs.choice([1e-3, 1.0, 30.0], size=(CAM_ADAM_STEPS, 1))).astype(np.float32)
+    d["adam_lr"] = (1e-3 * 0.33 ** (np.arange(CAM_ADAM_STEPS) // 128)).astype(np.float32)
+    d["offsets_xforms"] = rs.randn(6, 12).astype(np.float32)
+    d["offsets_pos"] = (rs.randn(6, 3) * 0.1).astype(np.float32)
+    d["offsets_rot"] = (rs.randn(6, 3) * 0.3).astype(np.float32)
+    d["offsets_rot"][0] = 0.0
+    return d
