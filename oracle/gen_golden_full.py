@@ -353,12 +353,109 @@ def gen_big(out_dir, steps=2000, timed=300):
     print(json.dumps({k: v for k, v in report.items() if k.startswith("mean_")}))
 
 
+def _pose_errors(get, truth):
+    pos, ang = [], []
+    for i, t in enumerate(truth):
+        m = np.asarray(get(i), np.float64)
+        pos.append(np.linalg.norm(m[:, 3] - t[:, 3]))
+        r = m[:, :3] @ np.asarray(t, np.float64)[:, :3].T
+        ang.append(np.degrees(np.arccos(np.clip((np.trace(r) - 1) / 2, -1, 1))))
+    return dict(mean_position_error=float(np.mean(pos)), mean_rotation_error_deg=float(np.mean(ang)))
+
+
+def gen_config3(out_dir, steps=3000):
+    """BASELINE config 3 (occupancy-grid update + camera-extrinsics optimisation), reference and this repo side by side on the same GPU.
+      A. the synthetic scene with every training camera perturbed (1.7 degrees, 0.03 units): pose error against the true cameras before / after training with
+         nerf.training.optimize_extrinsics, for both implementations (same protocol, same dataset files);
+      B. the reference's bundled fox capture (50 images 1080 x 1920, OpenCV lens, aabb_scale 4), when a copy lies under oracle/_ref/fox (git-ignored; it
+         travels to the GPU box): training speed and loss with the option on, both implementations.
+    -> ref_config3.json (numbers only; copy to profiles/)."""
+    import torch
+    import synthetic
+    import pyngp
+    report = dict(steps=steps)
+    # ---- A ----
+    scratch = "/tmp/ngpb_ref_c3"
+    shutil.rmtree(scratch, ignore_errors=True)
+    n_cam, res, B = 50, 400, 1 << 16
+    scene = synthetic.make_lego_scene(n_cam, res, seed=0)
+    truth = [np.asarray(c, np.float32)[:3] for c in scene["nerf_c2w"]]
+    rs = np.random.RandomState(11)
+    perturbed = []
+    for t in truth:
+        axis = rs.randn(3); axis /= np.linalg.norm(axis)
+        ang = np.radians(1.7)
+        K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+        R = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+        p = np.eye(4, dtype=np.float32)
+        p[:3, :3] = (R @ t[:, :3]).astype(np.float32)
+        p[:3, 3] = t[:, 3] + (rs.randn(3) * 0.03).astype(np.float32)
+        perturbed.append(p)
+    scene_p = dict(scene); scene_p["nerf_c2w"] = [p.tolist() for p in perturbed]
+    tj = synthetic.write_transforms_json(scene_p, scratch)
+    # both loaders sort the frames by file_path (nerf_loader.cu:356-358): frame index i of the testbed = i-th name in lexicographic order
+    order = sorted(range(n_cam), key=lambda i: f"./train/r_{i}")
+    truth = [truth[i] for i in order]
+    A = dict(config=f"Lego-shaped synthetic scene, {n_cam} x {res}^2, cameras perturbed by 1.7 deg / sigma 0.03, batch 2^16, {steps} steps, optimize_extrinsics")
+    ref = Ref()
+    ref.l.reff_get_camera_extrinsics.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    def ref_get(i):
+        o = np.zeros(12, np.float32)
+        ref.ck(ref.l.reff_get_camera_extrinsics(ref.h, i, o.ctypes.data))
+        return o.reshape(4, 3).T
+    ref.load(tj); ref.network(base_config(19)); ref.set(shall_train=1, optimize_extrinsics=1)
+    A["before"] = _pose_errors(ref_get, truth)
+    t0 = time.time(); loss = ref.train(B, steps); dt = time.time() - t0
+    A["reference"] = dict(_pose_errors(ref_get, truth), loss=loss, it_per_s=steps / dt)
+    ours = pyngp.Testbed()
+    ours.load_training_data(tj)
+    ours.nerf.training.optimize_extrinsics = True
+    A["before_ours"] = _pose_errors(ours.nerf.training.get_camera_extrinsics, truth)
+    torch.cuda.synchronize(); t0 = time.time(); ours.train_n(steps, B); dt = time.time() - t0
+    A["ours"] = dict(_pose_errors(ours.nerf.training.get_camera_extrinsics, truth), loss=ours.loss, it_per_s=steps / dt)
+    print("config 3 / A:", json.dumps(A))
+    report["perturbed_synthetic"] = A
+    del ref, ours
+    # ---- B ----
+    fox = os.path.join(HERE, "_ref", "fox", "transforms.json")
+    if os.path.exists(fox):
+        Bf, n_steps, timed = 1 << 18, 2000, 300
+        Bd = dict(config="data/nerf/fox of the reference (50 x 1080 x 1920 JPEG, OpenCV lens, aabb_scale 4), configs/nerf/base.json, batch 2^18, optimize_extrinsics, 2000 steps")
+        ref = Ref()
+        ref.l.reff_get_camera_extrinsics.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        ref.load(fox); ref.network(base_config(19)); ref.set(shall_train=1, optimize_extrinsics=1)
+        start = []
+        for i in range(50):
+            o = np.zeros(12, np.float32); ref.ck(ref.l.reff_get_camera_extrinsics(ref.h, i, o.ctypes.data)); start.append(o.reshape(4, 3).T.copy())
+        ref.train(Bf, n_steps - timed)
+        t0 = time.time(); loss = ref.train(Bf, timed); dt = time.time() - t0
+        moved = []
+        for i in range(50):
+            o = np.zeros(12, np.float32); ref.ck(ref.l.reff_get_camera_extrinsics(ref.h, i, o.ctypes.data)); moved.append(o.reshape(4, 3).T.copy())
+        Bd["reference"] = dict(it_per_s=timed / dt, ms_per_step=1e3 * dt / timed, loss=loss, stats=ref.stats(), camera_motion=_pose_errors(lambda i: moved[i], start))
+        del ref
+        ours = pyngp.Testbed()
+        ours.load_training_data(fox)
+        ours.nerf.training.optimize_extrinsics = True
+        start = [ours.nerf.training.get_camera_extrinsics(i) for i in range(50)]
+        ours.train_n(n_steps - timed, Bf)
+        torch.cuda.synchronize(); t0 = time.time(); ours.train_n(timed, Bf); dt = time.time() - t0
+        Bd["ours"] = dict(it_per_s=timed / dt, ms_per_step=1e3 * dt / timed, loss=ours.loss, stats=ours.stats(),
+                          camera_motion=_pose_errors(ours.nerf.training.get_camera_extrinsics, start))
+        print("config 3 / B:", json.dumps(Bd))
+        report["fox"] = Bd
+    else:
+        report["fox"] = "oracle/_ref/fox absent"
+    with open(os.path.join(out_dir, "ref_config3.json"), "w") as f:
+        json.dump(report, f, indent=1)
+
+
 if __name__ == "__main__":
     out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden_full")
     os.makedirs(out, exist_ok=True)
     jobs = sys.argv[2:] or ["small", "big"]
     for j in jobs:
         try:
-            dict(small=gen_small, big=gen_big)[j](out)
+            dict(small=gen_small, big=gen_big, config3=gen_config3)[j](out)
         except Exception:
             traceback.print_exc()
