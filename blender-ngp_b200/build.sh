@@ -6,7 +6,7 @@ NVCC=${NVCC:-nvcc}
 FLAGS="-std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false -Xcompiler -fPIC -Xcompiler -O2"
 mkdir -p build
 pids=()
-for f in common hash_grid nerf_mlp nerf_mlp_pipe umma_probe camera_optimizer nerf_sampling nerf_loss losses optimizer density_grid render testbed; do
+for f in common hash_grid nerf_mlp nerf_mlp_pipe umma_probe camera_optimizer model nerf_sampling nerf_loss losses optimizer density_grid render testbed; do
 	if [ -f csrc/$f.cu ]; then
 		( $NVCC $FLAGS -c csrc/$f.cu -o build/$f.o ) &
 		pids+=($!)

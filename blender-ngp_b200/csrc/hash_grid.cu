@@ -275,7 +275,8 @@ __global__ void __launch_bounds__(ENC_SAMPLES * ENC_WARPS) hash_encode_backward_
 			// Coarse level (warp-uniform branch): consecutive samples of a ray sit in the same cell, so most of the warp's 32 x 8 updates go
 			// to a handful of entries -- and the whole batch hammers a few thousand addresses. Sum the contributions of each run of lanes
 			// with equal cell over the run (segmented warp scan) and let the run's last lane issue the 8 atomics.
-			const uint32_t key = contributes ? (pg[0] | (pg[1] << 8) | (pg[2] << 16)) : (0xFF000000u | lane);
+			// (a cell coordinate that does not fit a byte -- positions outside [0,1] -- keeps its lane as a run of its own)
+			const uint32_t key = contributes && (pg[0] | pg[1] | pg[2]) < 256u ? (pg[0] | (pg[1] << 8) | (pg[2] << 16)) : (0xFF000000u | lane);
 			const uint32_t key_prev = __shfl_up_sync(0xffffffffu, key, 1), key_next = __shfl_down_sync(0xffffffffu, key, 1);
 			const bool head = lane == 0 || key != key_prev, last = lane == 31 || key != key_next;
 			uint32_t head_lane = head ? lane : 0u; // inclusive max-scan: the lane at which this lane's run starts
@@ -321,6 +322,41 @@ __global__ void __launch_bounds__(ENC_SAMPLES * ENC_WARPS) hash_encode_backward_
 	}
 }
 
+// Two-dimensional input (kernel_grid_backward with N_POS_DIMS = 2, grid.h:395-518): one thread per (sample, level), four corners.
+__global__ void __launch_bounds__(256) hash_encode_backward_2d_kernel(
+	const uint32_t n, const GridLevels L, const float* __restrict__ positions, const uint32_t pos_stride, const __half2* __restrict__ dL_dencoded, float2* __restrict__ grid_grad)
+{
+	__shared__ LevelConst lc[NGPB_MAX_LEVELS];
+	if (threadIdx.x < L.n_levels) lc[threadIdx.x] = LevelConst{L.scale[threadIdx.x], L.size[threadIdx.x], L.resolution[threadIdx.x], L.offset[threadIdx.x]};
+	__syncthreads();
+	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t level = tid % L.n_levels, i = tid / L.n_levels;
+	if (i >= n) return;
+	const float2 g = __half22float2(dL_dencoded[(size_t)i * L.n_levels + level]);
+	if (g.x == 0.f && g.y == 0.f) return;
+	const LevelConst c = lc[level];
+	float2* __restrict__ gg = grid_grad + c.offset;
+	float pos[2];
+	uint32_t pg[2];
+	#pragma unroll
+	for (int d = 0; d < 2; ++d) {
+		const float p = __fmaf_rn(positions[(size_t)i * pos_stride + d], c.scale, 0.5f);
+		const float fl = floorf(p);
+		pg[d] = (uint32_t)(int)fl;
+		pos[d] = p - fl;
+	}
+	const bool x_only = c.resolution > c.size;
+	const bool hashed = (uint64_t)c.size < (uint64_t)c.resolution * (x_only ? 1u : c.resolution);
+	#pragma unroll
+	for (uint32_t k = 0; k < 4; ++k) {
+		const uint32_t x = pg[0] + (k & 1), y = pg[1] + (k >> 1);
+		const uint32_t h = hashed ? (x ^ (y * 2654435761u)) : (x_only ? x : x + y * c.resolution);
+		const float w = ((k & 1) ? pos[0] : 1.f - pos[0]) * ((k >> 1) ? pos[1] : 1.f - pos[1]);
+		float* addr = reinterpret_cast<float*>(gg + h % c.size);
+		asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" :: "l"(addr), "f"(g.x * w), "f"(g.y * w) : "memory");
+	}
+}
+
 // Internal launchers shared with the testbed host.
 void hash_encode_forward_launch(cudaStream_t stream, const ngpb_grid* g, const __half* grid, const float* positions, uint32_t pos_stride,
                                 uint32_t n, const uint32_t* n_dev, __half* encoded, bool tiled) {
@@ -346,6 +382,14 @@ void hash_encode_backward_launch(cudaStream_t stream, const ngpb_grid* g, const 
                                  const __half* dL_dencoded, float* grid_grad, uint32_t level_begin, uint32_t level_end) {
 	if (n == 0 || level_begin >= level_end) return;
 	const GridLevels L = make_levels(g);
+	if (g->n_pos_dims == 2) {
+		const uint64_t threads = (uint64_t)n * L.n_levels;
+		if (threads > 0xFFFFFFFFull) throw std::runtime_error("hash_encode_backward: n * n_levels must fit 32 bits");
+		if (level_begin != 0 || level_end != L.n_levels) throw std::runtime_error("hash_encode_backward: level groups are not supported for 2-D grids");
+		hash_encode_backward_2d_kernel<<<(uint32_t)((threads + 255) / 256), 256, 0, stream>>>(n, L, positions, pos_stride, (const __half2*)dL_dencoded, (float2*)grid_grad);
+		NGPB_LAUNCH_CHECK();
+		return;
+	}
 	hash_encode_backward_kernel<<<div_round_up(n, ENC_SAMPLES), ENC_SAMPLES * ENC_WARPS, 0, stream>>>(n, L, positions, pos_stride, (const __half2*)dL_dencoded, (float2*)grid_grad, level_begin, level_end);
 	NGPB_LAUNCH_CHECK();
 }
@@ -417,7 +461,7 @@ extern "C" int ngpb_hash_encode_forward(void* stream, const ngpb_grid* g, const 
 extern "C" int ngpb_hash_encode_backward(void* stream, const ngpb_grid* g, const float* positions, uint32_t pos_stride, uint32_t n,
                                          const ngpb_half* dL_dencoded, float* grid_grad) {
 	try {
-		if (!g || !positions || !dL_dencoded || !grid_grad || pos_stride < 3 || g->n_pos_dims == 2) { set_last_error("ngpb_hash_encode_backward: invalid argument (3-D grids only)"); return NGPB_ERR_INVALID_ARGUMENT; }
+		if (!g || !positions || !dL_dencoded || !grid_grad || pos_stride < (g->n_pos_dims == 2 ? 2u : 3u)) { set_last_error("ngpb_hash_encode_backward: invalid argument"); return NGPB_ERR_INVALID_ARGUMENT; }
 		hash_encode_backward_launch((cudaStream_t)stream, g, positions, pos_stride, n, (const __half*)dL_dencoded, grid_grad, 0, g->n_levels);
 		return 0;
 	} catch (const std::exception& e) { set_last_error(e.what()); return NGPB_ERR_RUNTIME; }

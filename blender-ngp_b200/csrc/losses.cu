@@ -1,5 +1,5 @@
 // Element-wise training losses of the neural-image and SDF models. Replaces tcnn's l2_loss (dependencies/tiny-cuda-nn/include/tiny-cuda-nn/losses/l2.h:40-80,
-// configs/image/base.json) and mape_loss (losses/mape.h:40-80, configs/sdf/base.json) as called by Trainer::training_step (trainer.h:121-159): from the
+// configs/image/base.json), relative_l2_loss (losses/relative_l2.h:40-77) and mape_loss (losses/mape.h:40-80, configs/sdf/base.json) as called by Trainer::training_step (trainer.h:121-159): from the
 // network's padded fp16 output [n][16] and the fp32 targets [n][dims] it writes the per-element loss values and dL/d(output) (fp16, loss scale applied,
 // padded columns zero) that ngpb_mlp_forward_backward consumes.
 #include "common.cuh"
@@ -29,6 +29,10 @@ __global__ void __launch_bounds__(256) loss_kernel(const uint32_t n_elements, co
 		const float scale = 1.0f / (fabsf(target) + 1e-2f);
 		value = fabsf(difference) * scale / n_total;
 		gradient = copysignf(scale, difference);
+	} else if (KIND == NGPB_ELEMENT_LOSS_RELATIVE_L2) { // losses/relative_l2.h:40-77
+		const float prediction_sq_plus_epsilon = prediction * prediction + 0.01f;
+		value = difference * difference / prediction_sq_plus_epsilon / 1.0f / n_total;
+		gradient = 2 * difference / prediction_sq_plus_epsilon / 1.0f;
 	} else {
 		value = difference * difference / n_total;
 		gradient = 2 * difference;
@@ -44,7 +48,7 @@ using namespace ngpb;
 extern "C" int ngpb_loss(void* stream_, int kind, uint32_t n, uint32_t dims, float loss_scale, const ngpb_half* predictions, const float* targets, float* values,
                          ngpb_half* gradients) {
 	try {
-		if (!predictions || !targets || !gradients || dims == 0 || dims > 16 || (kind != NGPB_ELEMENT_LOSS_L2 && kind != NGPB_ELEMENT_LOSS_MAPE)) {
+		if (!predictions || !targets || !gradients || dims == 0 || dims > 16 || (kind != NGPB_ELEMENT_LOSS_L2 && kind != NGPB_ELEMENT_LOSS_MAPE && kind != NGPB_ELEMENT_LOSS_RELATIVE_L2)) {
 			set_last_error("ngpb_loss: invalid argument");
 			return NGPB_ERR_INVALID_ARGUMENT;
 		}
@@ -53,6 +57,7 @@ extern "C" int ngpb_loss(void* stream_, int kind, uint32_t n, uint32_t dims, flo
 		cudaStream_t stream = (cudaStream_t)stream_;
 		const uint32_t n_elements = n * 16;
 		if (kind == NGPB_ELEMENT_LOSS_MAPE) loss_kernel<NGPB_ELEMENT_LOSS_MAPE><<<div_round_up(n_elements, 256), 256, 0, stream>>>(n_elements, dims, loss_scale, (const __half*)predictions, targets, values, (__half*)gradients);
+		else if (kind == NGPB_ELEMENT_LOSS_RELATIVE_L2) loss_kernel<NGPB_ELEMENT_LOSS_RELATIVE_L2><<<div_round_up(n_elements, 256), 256, 0, stream>>>(n_elements, dims, loss_scale, (const __half*)predictions, targets, values, (__half*)gradients);
 		else loss_kernel<NGPB_ELEMENT_LOSS_L2><<<div_round_up(n_elements, 256), 256, 0, stream>>>(n_elements, dims, loss_scale, (const __half*)predictions, targets, values, (__half*)gradients);
 		NGPB_LAUNCH_CHECK();
 		return 0;

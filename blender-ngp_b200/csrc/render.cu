@@ -449,6 +449,18 @@ __global__ void __launch_bounds__(256) render_tonemap_kernel(const uint32_t n_pi
 }
 
 Aabb make_aabb(const float* a);
+// the frame's way out of render_frame, shared with the neural-image mode (model.cu)
+void render_accumulate_launch(cudaStream_t stream, uint32_t n_pixels, const float* frame_rgba, float* accumulate_rgba, float sample_count, int color_space) {
+	render_accumulate_kernel<<<div_round_up(n_pixels, 256u), 256, 0, stream>>>(n_pixels, (const float4*)frame_rgba, (float4*)accumulate_rgba, sample_count, color_space);
+	NGPB_LAUNCH_CHECK();
+}
+void render_tonemap_launch(cudaStream_t stream, uint32_t n_pixels, float exposure, const float* background4, const float* accumulate_rgba, int color_space, int output_srgb, int curve, float* out_rgba) {
+	render_tonemap_kernel<<<div_round_up(n_pixels, 256u), 256, 0, stream>>>(n_pixels, powf(2.0f, exposure), make_float4(background4[0], background4[1], background4[2], background4[3]),
+		(const float4*)accumulate_rgba, color_space, output_srgb, curve, (float4*)out_rgba);
+	NGPB_LAUNCH_CHECK();
+}
+void ld_random_pixel_offset_host(uint32_t spp, float* out2) { ld_random_pixel_offset(spp, out2); }
+
 void hash_encode_forward_launch(cudaStream_t stream, const ngpb_grid* g, const __half* grid, const float* positions, uint32_t pos_stride, uint32_t n, const uint32_t* n_dev, __half* encoded, bool tiled);
 void nerf_mlp_forward_launch(cudaStream_t stream, const __half* mlp, const __half* encoded, bool tiled, const float* coords, uint32_t n, const uint32_t* n_dev, __half* rgbsigma);
 bool features_tiled();
@@ -1019,6 +1031,7 @@ extern "C" int ngpb_field_create(ngpb_field** out, int device, uint32_t aabb_sca
 			NGPB_CUDA_CHECK(cudaDeviceSynchronize());
 			cudaFree(grid_dev); cudaFree(mean_dev);
 		}
+		NGPB_CUDA_CHECK(cudaDeviceSynchronize()); // a cudaMemcpy from pageable memory may return before its DMA has landed; renders run on the caller's streams
 		*out = f;
 		return 0;
 	} catch (const std::exception& e) {

@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(128) init_grid_kernel(const uint64_t n_element
 	for (uint64_t j = 0; j < 4; ++j) {
 		const uint64_t idx = i + n_threads * j;
 		if (idx >= n_elements) return;
-		out[idx] = rng.next_float() * (1e-4f - -1e-4f) + -1e-4f;
+		out[idx] = __fmaf_rn(rng.next_float(), 1e-4f - -1e-4f, -1e-4f); // the reference's lambda (val * (upper - lower) + lower) is compiled with FMA contraction
 	}
 }
 
@@ -593,6 +593,7 @@ void ngpb_testbed::p2p_setup() {
 	uint8_t* dev_blobs = nullptr;
 	NGPB_CUDA_CHECK(cudaMalloc(&dev_blobs, blob * dp_world));
 	NGPB_CUDA_CHECK(cudaMemcpy(dev_blobs + blob * dp_rank, mine, blob, cudaMemcpyHostToDevice));
+	NGPB_CUDA_CHECK(cudaDeviceSynchronize()); // (the copy's DMA may still be in flight when cudaMemcpy returns; `stream` does not wait for the default stream)
 	NcclApi& nccl = NcclApi::get();
 	nccl.check(nccl.AllGather(dev_blobs + blob * dp_rank, dev_blobs, blob, 1 /* ncclUint8 */, nccl_comm, stream), "ncclAllGather(ipc handles)");
 	NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -1143,6 +1144,7 @@ extern "C" int ngpb_testbed_set_optimizer_state(ngpb_testbed* t, const float* fm
 	if (fm) NGPB_CUDA_CHECK(cudaMemcpy(t->m1, fm, sizeof(float) * t->n_params, cudaMemcpyHostToDevice));
 	if (sm) NGPB_CUDA_CHECK(cudaMemcpy(t->m2, sm, sizeof(float) * t->n_params, cudaMemcpyHostToDevice));
 	if (ps) NGPB_CUDA_CHECK(cudaMemcpy(t->param_steps, ps, sizeof(uint32_t) * t->n_params, cudaMemcpyHostToDevice));
+	NGPB_CUDA_CHECK(cudaDeviceSynchronize()); // (see p2p_setup: pageable copies may outlive the call)
 	NGPB_API_END
 }
 

@@ -321,6 +321,11 @@ class Optimizer(C.Structure):
                 ("decay_base", C.c_float), ("step", C.c_uint32), ("lr_factor", C.c_float)]
 
 
+class ModelConfig(C.Structure):  # ngpb_model_config
+    _fields_ = [("n_pos_dims", C.c_uint32), ("n_output_dims", C.c_uint32), ("n_levels", C.c_uint32), ("log2_hashmap_size", C.c_uint32), ("base_resolution", C.c_uint32),
+                ("per_level_scale", C.c_float), ("desired_resolution", C.c_float), ("loss", C.c_int32), ("use_ema", C.c_int32), ("optimizer", Optimizer), ("seed", C.c_uint32)]
+
+
 class RenderConfig(C.Structure):  # ngpb_render_config
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("fx", C.c_float), ("fy", C.c_float), ("screen_center", C.c_float * 2), ("camera", C.c_float * 12),
                 ("spp", C.c_int32), ("snap_to_pixel_centers", C.c_int32), ("aabb", C.c_float * 6), ("render_aabb", C.c_float * 6),
@@ -426,6 +431,10 @@ EXPORTED_SYMBOLS = [
     "ngpb_field_create", "ngpb_field_destroy", "ngpb_blender_render", "ngpb_compute_loss_compact_features", "ngpb_grid_init_nd", "ngpb_mlp_forward", "ngpb_mlp_forward_backward", "ngpb_loss",
     "ngpb_nerf_mlp_forward_backward_sh", "ngpb_nerf_input_gradient", "ngpb_compute_cam_gradient", "ngpb_camera_adam_step", "ngpb_apply_camera_offsets",
     "ngpb_testbed_get_camera_extrinsics", "ngpb_testbed_set_camera_extrinsics", "ngpb_testbed_reset_camera_extrinsics", "ngpb_probe_umma",
+    "ngpb_model_create", "ngpb_model_destroy", "ngpb_model_reset", "ngpb_model_n_params", "ngpb_model_training_step", "ngpb_model_loss", "ngpb_model_launches", "ngpb_model_stream",
+    "ngpb_model_set_option", "ngpb_model_get_params", "ngpb_model_set_params_half", "ngpb_model_set_training_step", "ngpb_model_train", "ngpb_model_inference",
+    "ngpb_model_set_image", "ngpb_model_set_image_rgba8", "ngpb_model_train_image", "ngpb_model_image_mse", "ngpb_model_render_image", "ngpb_model_set_sdf_data",
+    "ngpb_model_train_sdf", "ngpb_model_get_training_batch",
 ]
 
 _lib = None
@@ -460,6 +469,26 @@ def lib():
         l.ngpb_field_destroy.argtypes = [C.c_void_p]
         l.ngpb_testbed_stream.restype = C.c_void_p
         l.ngpb_testbed_stream.argtypes = [C.c_void_p]
+        l.ngpb_model_destroy.restype = None
+        l.ngpb_model_destroy.argtypes = [C.c_void_p]
+        l.ngpb_model_n_params.restype = C.c_uint32
+        l.ngpb_model_training_step.restype = C.c_uint32
+        l.ngpb_model_loss.restype = C.c_float
+        l.ngpb_model_launches.restype = C.c_uint64
+        l.ngpb_model_stream.restype = C.c_void_p
+        for fn in (l.ngpb_model_n_params, l.ngpb_model_training_step, l.ngpb_model_loss, l.ngpb_model_launches, l.ngpb_model_stream):
+            fn.argtypes = [C.c_void_p]
+        l.ngpb_model_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        l.ngpb_model_train.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int]
+        l.ngpb_model_inference.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int]
+        l.ngpb_model_get_training_batch.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        l.ngpb_model_set_sdf_data.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        l.ngpb_model_set_image.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        l.ngpb_model_set_image_rgba8.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        l.ngpb_model_train_image.argtypes = [C.c_void_p, C.c_uint32, C.c_int]
+        l.ngpb_model_train_sdf.argtypes = [C.c_void_p, C.c_uint32, C.c_int]
+        l.ngpb_model_set_params_half.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        l.ngpb_model_get_params.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         l.ngpb_camera_adam_step.restype = None
         l.ngpb_camera_adam_step.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_int]
         l.ngpb_apply_camera_offsets.restype = None
@@ -806,14 +835,24 @@ class _Nerf:
 
 
 class Testbed:
-    """pyngp.Testbed for ETestbedMode::Nerf (python_api.cu:540-732)."""
+    """pyngp.Testbed (python_api.cu:540-732). ETestbedMode::Nerf is this class; Image and Sdf return the classes of pyngp/modes.py (same constructor
+    arguments); Volume is not built."""
+
+    def __new__(cls, mode=TestbedMode.Nerf, *args, **kwargs):
+        if cls is Testbed and mode in (TestbedMode.Image, TestbedMode.Sdf):
+            from . import modes
+            obj = object.__new__(modes.ImageTestbed if mode == TestbedMode.Image else modes.SdfTestbed)
+            obj.__init__(mode, *args, **kwargs)  # (not a Testbed subclass, so Python does not call it)
+            return obj
+        return object.__new__(cls)
 
     def __init__(self, mode=TestbedMode.Nerf, data_path=None, network_config=None, device=0):
         """Testbed(mode), Testbed(mode, data_path, network_config_path) and Testbed(mode, data_path, network_config_json) (python_api.cu:542-544)."""
         if isinstance(data_path, int) and network_config is None:  # Testbed(mode, device) of earlier drafts of this module
             data_path, device = None, data_path
         if mode != TestbedMode.Nerf:
-            raise RuntimeError("only TestbedMode.Nerf is implemented by this build (the NeRF train/render hot path)")
+            raise RuntimeError("TestbedMode.Volume is not implemented by this build (Nerf, Image and Sdf are)")
+        self.mode = mode
         self._h = C.c_void_p()
         check(lib().ngpb_testbed_create(C.byref(self._h), int(device)))
         self.nerf = _Nerf(self)

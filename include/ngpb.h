@@ -55,7 +55,7 @@ typedef struct {
 /* Host-only: fills `g` like the GridEncodingTemplated constructor (grid.h:959-1025). Returns total entries. */
 uint32_t ngpb_grid_init(ngpb_grid* g, uint32_t n_levels, uint32_t log2_hashmap_size, uint32_t base_resolution, float per_level_scale);
 /* Same for an N-dimensional input (N_POS_DIMS of GridEncodingTemplated): 2 = the neural-image model (configs/image/base.json), 3 = NeRF / SDF.
- * Only ngpb_hash_encode_forward accepts 2-D grids. */
+ * The testbed / render entry points are 3-D only; ngpb_hash_encode_forward / _backward and ngpb_model accept 2-D grids. */
 uint32_t ngpb_grid_init_nd(ngpb_grid* g, uint32_t n_pos_dims, uint32_t n_levels, uint32_t log2_hashmap_size, uint32_t base_resolution, float per_level_scale);
 
 /* Replaces g->scale[] / g->resolution[] by the values the DEVICE's exp2f gives, which is what the reference's kernels use (they call
@@ -82,6 +82,7 @@ int ngpb_mlp_forward(void* stream, const ngpb_half* weights, const ngpb_half* in
  * gradients [n][16] fp16 = loss_scale * dL/d(prediction) / (n * dims), padded columns zero. */
 #define NGPB_ELEMENT_LOSS_L2 0
 #define NGPB_ELEMENT_LOSS_MAPE 1
+#define NGPB_ELEMENT_LOSS_RELATIVE_L2 2 /* losses/relative_l2.h:40-77 */
 int ngpb_loss(void* stream, int kind, uint32_t n, uint32_t dims, float loss_scale, const ngpb_half* predictions, const float* targets, float* values,
               ngpb_half* gradients);
 /* Forward + backward of the same network in one kernel (FullyFusedMLP::forward + backward, fully_fused_mlp.cu:151-314,:759-850): recomputes the activations of
@@ -341,6 +342,52 @@ int ngpb_testbed_get_camera_extrinsics(ngpb_testbed* t, uint32_t frame_idx, floa
  * camera's offsets and Adam state. */
 int ngpb_testbed_set_camera_extrinsics(ngpb_testbed* t, uint32_t frame_idx, const float* xform12);
 int ngpb_testbed_reset_camera_extrinsics(ngpb_testbed* t);
+
+/* ---- neural-image and SDF modes (ETestbedMode::Image / Sdf): NetworkWithInputEncoding + Trainer around the same kernels ----
+ * Replaces Testbed::reset_network for these modes (src/testbed.cu:2244-2470), tcnn Trainer::training_step / optimizer_step (trainer.h:108-190),
+ * Testbed::train_image / render_image / compute_image_mse (src/testbed_image.cu:220-523) and Testbed::train_sdf (src/testbed_sdf.cu:1229-1252) on
+ * supplied (position, distance) pairs. Parameters in NetworkWithInputEncoding's flat order: network (7168), then the grid levels. */
+typedef struct ngpb_model ngpb_model;
+typedef struct {
+	uint32_t n_pos_dims;        /* 2 neural image, 3 SDF */
+	uint32_t n_output_dims;     /* 3 / 1 */
+	uint32_t n_levels, log2_hashmap_size, base_resolution; /* encoding section */
+	float per_level_scale;      /* > 0: taken as is; otherwise derived like reset_network does (src/testbed.cu:2318-2322) from ... */
+	float desired_resolution;   /* ... the finest level's target resolution: 2048 (SDF), half the image's larger side (image) */
+	int32_t loss;               /* NGPB_ELEMENT_LOSS_* */
+	int32_t use_ema;            /* optimizer is Ema(...) (configs/sdf/base.json) or not (configs/image/base.json) */
+	ngpb_optimizer optimizer;   /* hyper-parameters; step / lr_factor ignored */
+	uint32_t seed;              /* m_seed (1337) */
+} ngpb_model_config;
+int ngpb_model_create(ngpb_model** out, int device, const ngpb_model_config* cfg);
+void ngpb_model_destroy(ngpb_model* m);
+int ngpb_model_reset(ngpb_model* m, uint32_t seed);                 /* reset_network: fresh parameters, optimizer and RNG */
+uint32_t ngpb_model_n_params(const ngpb_model* m);
+uint32_t ngpb_model_training_step(const ngpb_model* m);
+float ngpb_model_loss(const ngpb_model* m);                         /* the last step trained with get_loss != 0: Trainer::loss = sum of the per-element values */
+uint64_t ngpb_model_launches(const ngpb_model* m);
+void* ngpb_model_stream(ngpb_model* m);
+int ngpb_model_set_option(ngpb_model* m, const char* name, double value); /* "snap_to_pixel_centers", "linear_colors" (m_image.training.*), "learning_rate" */
+int ngpb_model_get_params(ngpb_model* m, float* w_fp32, ngpb_half* w_half, ngpb_half* w_inference);
+int ngpb_model_set_params_half(ngpb_model* m, const ngpb_half* params, uint32_t n);
+int ngpb_model_set_training_step(ngpb_model* m, uint32_t step);
+/* One Trainer::training_step on a caller-supplied device batch (positions [n][n_pos_dims], targets [n][n_output_dims], n a multiple of 128). */
+int ngpb_model_train(ngpb_model* m, const float* positions_dev, const float* targets_dev, uint32_t n, int run_optimizer, int get_loss);
+/* Network::inference: positions [n][n_pos_dims] -> out [n][n_output_dims] fp32 (device pointers, any n). */
+int ngpb_model_inference(ngpb_model* m, const float* positions_dev, uint32_t n, float* out_dev, int use_inference_params);
+/* Neural image. pixels: RGBA float (is_half 0) or RGBA half (1), linear, row-major, host. */
+int ngpb_model_set_image(ngpb_model* m, const void* pixels_host, int width, int height, int is_half);
+int ngpb_model_set_image_rgba8(ngpb_model* m, const uint8_t* pixels_host, int width, int height); /* an 8-bit file: sRGB -> linear, premultiplied, on the device (from_rgba32) */
+int ngpb_model_train_image(ngpb_model* m, uint32_t batch, int get_loss);
+int ngpb_model_image_mse(ngpb_model* m, int quantize_to_byte, float* mse_out);
+/* view5 = {m_scale, m_image.pos x, y, m_screen_center x, y} (defaults 1, 0, 0, 0.5, 0.5); out: width x height RGBA float, host. */
+int ngpb_model_render_image(ngpb_model* m, int width, int height, int spp, const float* view5, int render_snap_to_pixel_centers, int color_space, int output_srgb,
+                            float exposure, const float* background4, int tonemap_curve, float* out_rgba_host);
+/* SDF on supplied pairs (positions already in the unit cube, distances in its units): the pool, and one train_sdf step drawn from it. */
+int ngpb_model_set_sdf_data(ngpb_model* m, const float* positions_host, const float* distances_host, uint32_t n);
+int ngpb_model_train_sdf(ngpb_model* m, uint32_t batch, int get_loss);
+/* The batch the last training step used (device -> host), for parity tests. */
+int ngpb_model_get_training_batch(ngpb_model* m, uint32_t n, float* positions_host, float* targets_host);
 
 /* Development aid (tools/umma_probe.py): cycle counts of tcgen05 issue / commit / wait sequences on this GPU; sections is a bit mask. */
 int ngpb_probe_umma(void* stream, long long* cycles_host, uint32_t n, uint32_t sections);

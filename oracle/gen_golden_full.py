@@ -450,12 +450,108 @@ def gen_config3(out_dir, steps=3000):
         json.dump(report, f, indent=1)
 
 
+def _sha(a):
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), np.uint8)
+
+
+def gen_modes(out_dir):
+    """ETestbedMode::Image and ::Sdf of the unmodified reference on the inputs of tests/golden_inputs.py (procedural_image, sdf_pool):
+    initial parameters, the training batches of the first steps, the loss every 16th step, and for the image model the trained parameters with the
+    reference's own inference, compute_image_mse and render of them. -> ref_modes.npz (copy to tests/golden/)."""
+    from PIL import Image as PILImage
+    from golden_inputs import procedural_image, sdf_pool, MODE_IMAGE_RES, MODE_IMAGE_BATCH, MODE_SDF_BATCH
+    scratch = "/tmp/ngpb_ref_modes"
+    shutil.rmtree(scratch, ignore_errors=True); os.makedirs(scratch)
+    out = {}
+
+    def mode_ref(mode):
+        r = Ref.__new__(Ref)
+        r.l = C.CDLL(os.path.join(HERE, "_ref", "libref_full.so"))
+        r.l.reff_last_error.restype = C.c_char_p
+        r.l.reff_training_step.restype = C.c_uint32
+        r.l.reff_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        r.h = C.c_void_p()
+        r.ck(r.l.reff_create(C.byref(r.h), mode))
+        return r
+
+    def params(r):
+        n = r.stats()["n_params"]
+        fp = np.zeros(n, np.float32); hf = np.zeros(n, np.float16)
+        r.ck(r.l.reff_get_params(r.h, fp.ctypes.data_as(C.c_void_p), hf.ctypes.data_as(C.c_void_p), n))
+        return fp, hf
+
+    # ---- image ----
+    w, h = MODE_IMAGE_RES
+    png = os.path.join(scratch, "image.png")
+    PILImage.fromarray(procedural_image()).save(png)
+    from pyngp.modes import IMAGE_NETWORK_CONFIG, SDF_NETWORK_CONFIG
+    r = mode_ref(2)
+    r.load(png); r.network(IMAGE_NETWORK_CONFIG); r.set(shall_train=1)
+    wh = (C.c_int * 2)(); r.ck(r.l.reff_image_resolution(r.h, wh)); assert (wh[0], wh[1]) == (w, h)
+    data = np.zeros((h, w, 4), np.float32); r.ck(r.l.reff_image_data(r.h, data.ctypes.data_as(C.c_void_p)))
+    out["image_data_sha"] = _sha(data); out["image_data_head"] = data.reshape(-1, 4)[:4096].copy()
+    fp, _ = params(r)
+    out["image_n_params"] = np.uint32(fp.shape[0]); out["image_init_sha"] = _sha(fp); out["image_init_head"] = fp[:8192].copy(); out["image_init_grid_head"] = fp[7168:7168 + 4096].copy()
+    B = MODE_IMAGE_BATCH
+    losses = []
+    for step in range(3):
+        losses.append(r.train(B, 1))
+        pos = np.zeros((B, 2), np.float32); tgt = np.zeros((B, 3), np.float32)
+        r.ck(r.l.reff_image_training_batch(r.h, B, pos.ctypes.data_as(C.c_void_p), tgt.ctypes.data_as(C.c_void_p)))
+        out[f"image_batch{step}_pos_sha"] = _sha(pos); out[f"image_batch{step}_tgt_sha"] = _sha(tgt)
+        out[f"image_batch{step}_pos_head"] = pos[:2048].copy(); out[f"image_batch{step}_tgt_head"] = tgt[:2048].copy()
+    # reff_train returns m_loss_scalar.val(): the loss of the last step whose index was a multiple of 16 (the reference reads the scalar on those steps only)
+    curve = [losses[0]]
+    for k in range(1, 63):
+        curve.append(r.train(B, 16 if k > 1 else 14))  # up to and including step 16 k
+    out["image_loss_curve"] = np.array(curve, np.float32); out["image_steps"] = np.uint32(r.l.reff_training_step(r.h))
+    _, hf = params(r)
+    out["image_trained_params"] = hf
+    mse = C.c_float()
+    r.ck(r.l.reff_image_mse(r.h, 0, C.byref(mse))); out["image_mse"] = np.float32(mse.value)
+    r.ck(r.l.reff_image_mse(r.h, 1, C.byref(mse))); out["image_mse_quantized"] = np.float32(mse.value)
+    ys, xs = np.meshgrid(np.arange(64), np.arange(64), indexing="ij")
+    q = np.stack([(xs.reshape(-1) * 8 + 0.5) / w, (ys.reshape(-1) * 6 + 0.5) / h], 1).astype(np.float32)
+    o = np.zeros((4096, 3), np.float32)
+    r.ck(r.l.reff_inference(r.h, q.ctypes.data_as(C.c_void_p), 4096, 2, 3, o.ctypes.data_as(C.c_void_p)))
+    out["image_query"] = q; out["image_inference"] = o
+    r.set(snap_to_pixel_centers=1, dynamic_res=0, background_color_r=0.2, background_color_g=0.3, background_color_b=0.4, background_color_a=1.0, exposure=0.0)
+    for name, (rw, rh, spp, linear) in dict(a=(256, 192, 1, 0), b=(200, 120, 2, 1)).items():
+        fr = np.zeros((rh, rw, 4), np.float32)
+        r.ck(r.l.reff_render(r.h, None, rw, rh, spp, linear, fr.ctypes.data_as(C.c_void_p)))
+        out[f"image_render_{name}"] = fr.astype(np.float16); out[f"image_render_{name}_cfg"] = np.array([rw, rh, spp, linear], np.int32)
+    print("image: loss", curve[0], "->", curve[-1], "mse", out["image_mse"], "steps", out["image_steps"])
+    del r
+
+    # ---- sdf ----
+    bunny = os.path.join(HERE, "_ref", "bunny.obj")
+    r = mode_ref(1)
+    r.load(bunny); r.network(SDF_NETWORK_CONFIG); r.set(shall_train=1)
+    info = np.zeros(7, np.float32); r.ck(r.l.reff_sdf_mesh_info(r.h, info.ctypes.data_as(C.c_void_p))); out["sdf_bunny_mesh_info"] = info
+    fp, _ = params(r)
+    out["sdf_n_params"] = np.uint32(fp.shape[0]); out["sdf_init_sha"] = _sha(fp); out["sdf_init_head"] = fp[:8192].copy()
+    pos, dist = sdf_pool()
+    r.ck(r.l.reff_sdf_override_training_data(r.h, pos.ctypes.data_as(C.c_void_p), dist.ctypes.data_as(C.c_void_p), pos.shape[0]))
+    B = MODE_SDF_BATCH
+    curve = []
+    for step in range(3):
+        curve.append(r.train(B, 1))
+        bp = np.zeros((B, 3), np.float32); bd = np.zeros(B, np.float32)
+        r.ck(r.l.reff_sdf_training_batch(r.h, B, bp.ctypes.data_as(C.c_void_p), bd.ctypes.data_as(C.c_void_p)))
+        out[f"sdf_batch{step}_pos_sha"] = _sha(bp); out[f"sdf_batch{step}_dist_sha"] = _sha(bd); out[f"sdf_batch{step}_dist_head"] = bd[:1024].copy()
+    for k in range(1, 63):
+        curve.append(r.train(B, 16 if k > 1 else 14))
+    out["sdf_loss_curve"] = np.array(curve[0:1] + curve[3:], np.float32); out["sdf_steps"] = np.uint32(r.l.reff_training_step(r.h))
+    print("sdf: loss", curve[0], "->", curve[-1], "steps", out["sdf_steps"], "bunny", info)
+    np.savez_compressed(os.path.join(out_dir, "ref_modes.npz"), **out)
+
+
 if __name__ == "__main__":
     out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden_full")
     os.makedirs(out, exist_ok=True)
     jobs = sys.argv[2:] or ["small", "big"]
     for j in jobs:
         try:
-            dict(small=gen_small, big=gen_big, config3=gen_config3)[j](out)
+            dict(small=gen_small, big=gen_big, config3=gen_config3, modes=gen_modes)[j](out)
         except Exception:
             traceback.print_exc()

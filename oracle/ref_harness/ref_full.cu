@@ -200,4 +200,78 @@ int reff_get_camera_extrinsics(void* tp, int frame, float* out12) {
 	REFF_END
 }
 
+
+// ---- neural-image and SDF modes (reff_create with mode 2 / 1): what the parity tests need beyond load / train / render / snapshots ----
+// the batch Testbed::train_image just trained on (m_image.training.positions / targets, src/testbed_image.cu:228-272)
+int reff_image_training_batch(void* tp, uint32_t n, float* positions2, float* targets3) {
+	REFF_BEGIN
+	Testbed* t = (Testbed*)tp;
+	CUDA_CHECK_THROW(cudaDeviceSynchronize());
+	if (n > t->m_image.training.positions.size()) throw std::runtime_error("reff_image_training_batch: larger than the last batch");
+	CUDA_CHECK_THROW(cudaMemcpy(positions2, t->m_image.training.positions.data(), sizeof(float) * 2 * n, cudaMemcpyDeviceToHost));
+	CUDA_CHECK_THROW(cudaMemcpy(targets3, t->m_image.training.targets.data(), sizeof(float) * 3 * n, cudaMemcpyDeviceToHost));
+	REFF_END
+}
+int reff_image_resolution(void* tp, int* wh) { REFF_BEGIN Testbed* t = (Testbed*)tp; wh[0] = t->m_image.resolution.x(); wh[1] = t->m_image.resolution.y(); REFF_END }
+// the loaded image as the training kernels see it (RGBA float, linear)
+int reff_image_data(void* tp, float* rgba) {
+	REFF_BEGIN
+	Testbed* t = (Testbed*)tp;
+	if (t->m_image.type != Testbed::EDataType::Float) throw std::runtime_error("reff_image_data: half-precision image");
+	CUDA_CHECK_THROW(cudaMemcpy(rgba, t->m_image.data.data(), sizeof(float) * 4 * (size_t)t->m_image.resolution.prod(), cudaMemcpyDeviceToHost));
+	REFF_END
+}
+int reff_image_mse(void* tp, int quantize_to_byte, float* out) { REFF_BEGIN *out = ((Testbed*)tp)->compute_image_mse(quantize_to_byte != 0); REFF_END }
+// m_network->inference on host positions [n][dims_in] -> [n][dims_out] (n a multiple of 128)
+int reff_inference(void* tp, const float* positions, uint32_t n, uint32_t dims_in, uint32_t dims_out, float* out) {
+	REFF_BEGIN
+	Testbed* t = (Testbed*)tp;
+	tcnn::GPUMemory<float> in(n * dims_in), o(n * dims_out);
+	in.copy_from_host(positions);
+	tcnn::GPUMatrix<float> im(in.data(), dims_in, n), om(o.data(), dims_out, n);
+	t->m_network->inference(t->m_stream.get(), im, om);
+	CUDA_CHECK_THROW(cudaDeviceSynchronize());
+	o.copy_to_host(out);
+	REFF_END
+}
+// the last assignments of Testbed::override_sdf_training_data (src/python_api.cu:96-103) for pairs that already are in the unit cube
+int reff_sdf_override_training_data(void* tp, const float* points3, const float* distances, uint32_t n) {
+	REFF_BEGIN
+	Testbed* t = (Testbed*)tp;
+	auto& tr = t->m_sdf.training;
+	tr.positions.enlarge(n); tr.positions_shuffled.enlarge(n); tr.distances.enlarge(n); tr.distances_shuffled.enlarge(n);
+	CUDA_CHECK_THROW(cudaMemcpy(tr.positions.data(), points3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice));
+	CUDA_CHECK_THROW(cudaMemcpy(tr.distances.data(), distances, sizeof(float) * n, cudaMemcpyHostToDevice));
+	tr.size = n; tr.idx = 0; tr.max_size = n; tr.generate_sdf_data_online = false;
+	REFF_END
+}
+// the batch Testbed::train_sdf just trained on (positions_shuffled / distances_shuffled, src/testbed_sdf.cu:1237-1243)
+int reff_sdf_training_batch(void* tp, uint32_t n, float* positions3, float* distances) {
+	REFF_BEGIN
+	Testbed* t = (Testbed*)tp;
+	CUDA_CHECK_THROW(cudaDeviceSynchronize());
+	CUDA_CHECK_THROW(cudaMemcpy(positions3, t->m_sdf.training.positions_shuffled.data(), sizeof(float) * 3 * n, cudaMemcpyDeviceToHost));
+	CUDA_CHECK_THROW(cudaMemcpy(distances, t->m_sdf.training.distances_shuffled.data(), sizeof(float) * n, cudaMemcpyDeviceToHost));
+	REFF_END
+}
+// Testbed::load_mesh's bounding box and scale (src/testbed_sdf.cu:1026-1036): {raw_aabb.min[3], raw_aabb.max[3], mesh_scale}
+int reff_sdf_mesh_info(void* tp, float* out7) {
+	REFF_BEGIN
+	Testbed* t = (Testbed*)tp;
+	for (int k = 0; k < 3; ++k) { out7[k] = t->m_raw_aabb.min[k]; out7[3 + k] = t->m_raw_aabb.max[k]; }
+	out7[6] = t->m_sdf.mesh_scale;
+	REFF_END
+}
+// (position, distance) pairs as the reference samples them from the loaded mesh (generate_training_samples_sdf, src/testbed_sdf.cu:1108-1178): the SDF workload
+int reff_sdf_generate(void* tp, uint32_t n, float* positions3, float* distances) {
+	REFF_BEGIN
+	Testbed* t = (Testbed*)tp;
+	tcnn::GPUMemory<Eigen::Vector3f> p(n); tcnn::GPUMemory<float> d(n);
+	t->generate_training_samples_sdf(p.data(), d.data(), n, t->m_stream.get(), false);
+	CUDA_CHECK_THROW(cudaDeviceSynchronize());
+	CUDA_CHECK_THROW(cudaMemcpy(positions3, p.data(), sizeof(float) * 3 * n, cudaMemcpyDeviceToHost));
+	d.copy_to_host(distances);
+	REFF_END
+}
+
 } // extern "C"

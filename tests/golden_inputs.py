@@ -120,3 +120,42 @@ def camera_inputs(seed=4242):
     d["offsets_rot"] = (rs.randn(6, 3) * 0.3).astype(np.float32)
     d["offsets_rot"][0] = 0.0
     return d
+
+
+# ---- neural-image and SDF modes ----
+MODE_IMAGE_RES = (512, 384)     # width, height: not square, so that the aspect handling of render_image is exercised
+MODE_IMAGE_BATCH = 1 << 16
+MODE_SDF_POOL = 1 << 16
+MODE_SDF_BATCH = 1 << 14
+
+
+def procedural_image(seed=5):
+    """RGBA8 [h][w][4]: oriented sinusoids plus soft discs, opaque except for one transparent corner patch (exercises the alpha premultiplication)."""
+    w, h = MODE_IMAGE_RES
+    rs = np.random.RandomState(seed)
+    ys, xs = np.meshgrid(np.arange(h, dtype=np.float32) / h, np.arange(w, dtype=np.float32) / w, indexing="ij")
+    img = np.zeros((h, w, 3), np.float32)
+    for c in range(3):
+        for _ in range(4):
+            fx, fy, ph = rs.uniform(2, 24), rs.uniform(2, 24), rs.uniform(0, 6.28)
+            img[..., c] += 0.12 * np.sin(6.2831853 * (fx * xs + fy * ys) + ph)
+    for _ in range(12):
+        cx, cy, r = rs.rand(), rs.rand(), rs.uniform(0.03, 0.15)
+        col = rs.rand(3)
+        m = np.clip(1.0 - np.hypot(xs - cx, ys - cy) / r, 0, 1)[..., None]
+        img = img * (1 - m) + col * m
+    img = np.clip(img + 0.5, 0, 1)
+    alpha = np.ones((h, w, 1), np.float32)
+    alpha[: h // 8, : w // 8] = 0.5
+    return np.round(np.concatenate([img, alpha], -1) * 255.0).astype(np.uint8)
+
+
+def sdf_pool(seed=9):
+    """(positions [n][3] in the unit cube, distances [n]): the exact distance to the union of a sphere and a box (exact outside, a bound inside), uniform positions."""
+    rs = np.random.RandomState(seed)
+    n = MODE_SDF_POOL
+    pos = rs.rand(n, 3).astype(np.float32)
+    d_sphere = np.linalg.norm(pos - np.array([0.4, 0.5, 0.5], np.float32), axis=1) - 0.25
+    q = np.abs(pos - np.array([0.65, 0.5, 0.5], np.float32)) - np.array([0.15, 0.2, 0.1], np.float32)
+    d_box = np.linalg.norm(np.maximum(q, 0), axis=1) + np.minimum(q.max(1), 0)
+    return pos, np.minimum(d_sphere, d_box).astype(np.float32)

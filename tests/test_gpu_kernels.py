@@ -904,9 +904,17 @@ def test_neural_image_forward(L, orc):
     ref = gold["rgb"].astype(np.float32)
     assert rgb.shape == (IMAGE_RES * IMAGE_RES, 3)
     assert np.abs(rgb - ref).max() <= 4e-3 and np.abs(rgb - ref).mean() <= 3e-4
-    # the backward entry point is 3-D only and says so
+    # 2-D backward (kernel_grid_backward<.., 2, ..>): the four bilinear weights of a sample sum to one, so every level's gradient table sums to that level's
+    # dL/dy summed over the batch (tests/test_modes.py follows the reference's image training curve through this kernel)
     grad = torch.zeros(2 * entries, dtype=torch.float32, device="cuda")
-    assert L.ngpb_hash_encode_backward(None, C.byref(g), ptr(dev(uv)), 2, n, ptr(enc), ptr(grad)) != 0
+    rs = np.random.RandomState(3)
+    dy = (rs.randn(n, 32) * 0.01).astype(np.float16)
+    pyngp.check(L.ngpb_hash_encode_backward(None, C.byref(g), ptr(dev(uv)), 2, n, ptr(dev(dy)), ptr(grad)))
+    gg = host(grad).astype(np.float64).reshape(-1, 2)
+    for l in range(16):
+        want = dy[:, 2 * l:2 * l + 2].astype(np.float64).sum(0)
+        got = gg[g.offsets[l]:g.offsets[l + 1]].sum(0)
+        assert np.abs(got - want).max() <= 1e-4 * np.abs(dy[:, 2 * l:2 * l + 2].astype(np.float64)).sum(), (l, got, want)
 
 
 def test_sdf_model_forward(L, orc):
