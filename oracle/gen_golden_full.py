@@ -546,12 +546,64 @@ def gen_modes(out_dir):
     np.savez_compressed(os.path.join(out_dir, "ref_modes.npz"), **out)
 
 
+def gen_modes_speed(out_dir, steps=600, timed=400):
+    """BASELINE configs 1 and 5 as training throughput, reference and this repo side by side on the same GPU: neural image 512 x 512 (procedural), SDF on a
+    supplied pool of 2^20 analytic pairs; batch 2^18 (the Testbed default), wall clock around `timed` steps after a warm-up. -> ref_modes_speed.json"""
+    import torch
+    import pyngp
+    from PIL import Image as PILImage
+    from pyngp.modes import IMAGE_NETWORK_CONFIG, SDF_NETWORK_CONFIG
+    import golden_inputs as gi
+    scratch = "/tmp/ngpb_ref_modes_speed"
+    shutil.rmtree(scratch, ignore_errors=True); os.makedirs(scratch)
+    B = 1 << 18
+    report = dict(batch=B, steps=steps, timed=timed, how="wall clock around `timed` calls of Testbed::train(2^18) ending in a device synchronisation")
+    gi.MODE_IMAGE_RES = (512, 512)
+    img = gi.procedural_image()
+    png = os.path.join(scratch, "image.png"); PILImage.fromarray(img).save(png)
+    rs = np.random.RandomState(1)
+    pool = rs.rand(1 << 20, 3).astype(np.float32)
+    dist = (np.linalg.norm(pool - 0.5, axis=1) - 0.3).astype(np.float32)
+
+    def ref_of(mode):
+        r = Ref.__new__(Ref)
+        r.l = C.CDLL(os.path.join(HERE, "_ref", "libref_full.so")); r.l.reff_last_error.restype = C.c_char_p
+        r.l.reff_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        r.h = C.c_void_p(); r.ck(r.l.reff_create(C.byref(r.h), mode))
+        return r
+    for name, mode in (("image", 2), ("sdf", 1)):
+        r = ref_of(mode)
+        if name == "image":
+            r.load(png); r.network(IMAGE_NETWORK_CONFIG)
+        else:
+            r.load(os.path.join(HERE, "_ref", "bunny.obj")); r.network(SDF_NETWORK_CONFIG)
+            r.ck(r.l.reff_sdf_override_training_data(r.h, pool.ctypes.data_as(C.c_void_p), dist.ctypes.data_as(C.c_void_p), pool.shape[0]))
+        r.set(shall_train=1)
+        r.train(B, steps - timed)
+        t0 = time.time(); loss = r.train(B, timed); dt = time.time() - t0
+        ref_row = dict(it_per_s=timed / dt, ms_per_step=1e3 * dt / timed, loss=loss)
+        del r
+        tb = pyngp.Testbed(pyngp.TestbedMode.Image if name == "image" else pyngp.TestbedMode.Sdf)
+        if name == "image":
+            tb.load_image_data(img)
+        else:
+            tb.set_unit_cube_pairs(pool, dist)
+        tb.train_n(steps - timed, B)
+        torch.cuda.synchronize(); tb.training_batch(0)
+        t0 = time.time(); tb.train_n(timed, B); tb.training_batch(0); dt = time.time() - t0
+        ours = dict(it_per_s=timed / dt, ms_per_step=1e3 * dt / timed, loss=tb.loss)
+        report[name] = dict(reference=ref_row, ours=ours, speedup=ours["it_per_s"] / ref_row["it_per_s"])
+        print(name, json.dumps(report[name]))
+    with open(os.path.join(out_dir, "ref_modes_speed.json"), "w") as f:
+        json.dump(report, f, indent=1)
+
+
 if __name__ == "__main__":
     out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden_full")
     os.makedirs(out, exist_ok=True)
     jobs = sys.argv[2:] or ["small", "big"]
     for j in jobs:
         try:
-            dict(small=gen_small, big=gen_big, config3=gen_config3, modes=gen_modes)[j](out)
+            dict(small=gen_small, big=gen_big, config3=gen_config3, modes=gen_modes, modes_speed=gen_modes_speed)[j](out)
         except Exception:
             traceback.print_exc()
