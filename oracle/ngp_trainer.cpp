@@ -68,7 +68,7 @@ static void init_params(orc_trainer* t, uint32_t seed) {
 		for (size_t j = 0; j < 4; ++j) {
 			size_t idx = (size_t)i + n_threads * j;
 			if (idx >= n) break;
-			out[idx] = orc_pcg32_next_float(&r) * (1e-4f - -1e-4f) + -1e-4f;
+			out[idx] = std::fmaf(orc_pcg32_next_float(&r), 1e-4f - -1e-4f, -1e-4f); // the reference's device lambda is compiled with FMA contraction (pinned by tests/golden/ref_modes.npz)
 		}
 	}
 	for (size_t i = 0; i < t->n_params; ++i) t->w_half[i] = f2h(t->w_fp32[i]);
@@ -127,6 +127,18 @@ extern "C" void orc_trainer_set_state(orc_trainer* t, uint32_t training_step, ui
 		t->mean_density = orc_density_grid_mean(t->density_grid.data());
 		orc_bitfield(t->max_cascade + 1, t->density_grid.data(), t->mean_density, t->bitfield.data());
 	}
+}
+
+// Teacher forcing for the whole-iteration parity test: the state another implementation reached (Adam moments and step counters, the decay state, the
+// batch-size controller's memory) replaces this trainer's, so that the next step starts from identical inputs.
+extern "C" void orc_trainer_set_optimizer_state(orc_trainer* t, const float* m1, const float* m2, const uint32_t* param_steps, uint32_t optimizer_step, float lr_factor,
+                                                uint32_t measured_batch_size_before_compaction, uint32_t n_rays_total) {
+	std::memcpy(t->m1.data(), m1, t->n_params * 4);
+	std::memcpy(t->m2.data(), m2, t->n_params * 4);
+	std::memcpy(t->param_steps.data(), param_steps, t->n_params * 4);
+	t->opt.step = optimizer_step; t->opt.lr_factor = lr_factor;
+	t->measured_batch_size_before_compaction = measured_batch_size_before_compaction;
+	t->n_rays_total = n_rays_total;
 }
 
 // update_density_grid_nerf + update_density_grid_mean_and_bitfield: src/testbed_nerf.cu:2761-2859

@@ -510,6 +510,11 @@ class Trainer:
         g = _f32(density_grid) if density_grid is not None else None
         lib().orc_trainer_set_state(self._h, int(training_step), int(rays_per_batch), _p(g))
 
+    def set_optimizer_state(self, m1, m2, param_steps, optimizer_step, lr_factor, measured_batch_size_before_compaction, n_rays_total):
+        """Teacher forcing (tests/test_gpu_kernels.py::test_training_iteration_teacher_forced)."""
+        lib().orc_trainer_set_optimizer_state(self._h, _p(_f32(m1)), _p(_f32(m2)), _p(np.ascontiguousarray(param_steps, np.uint32)), int(optimizer_step), C.c_float(lr_factor),
+                                              int(measured_batch_size_before_compaction), int(n_rays_total))
+
     def params(self):
         w = np.empty(self.n_params, np.float32); h = np.empty(self.n_params, np.float16); e = np.empty(self.n_params, np.float16)
         lib().orc_trainer_get_params(self._h, _p(w), _p(h), _p(e))

@@ -333,6 +333,90 @@ def test_sharded_sampling_tiles_the_batch(L, orc, small_scene):
     assert L.ngpb_generate_training_samples_sharded(None, 2048, 3000, 4096, None, 0, None, 0, None, None, 0, C.c_float(0), None, None, None, None, None, None) != 0
 
 
+def test_sharded_loss_and_gradient_sum(L, orc, small_scene):
+    """Data parallelism through the product's own kernels (the exchange itself is tests/test_data_parallel.py + tools/dp_check.py): two ray
+    shards against the unsharded batch. (1) K6 on each shard (ngpb_compute_loss_sharded, loss normalised by the GLOBAL ray count) yields, sample for sample
+    and bit for bit, the compacted coordinates and loss gradients of the unsharded batch. (2) The backward pass is additive over the batch: MLP + hash-grid
+    gradients of the two shards' samples sum to the gradients of all samples to 1e-4 of the largest entry (fp32 accumulation order). (3) The default 16-bit
+    exchange: summing the shards' partial gradients in bf16 deviates from the fp32 sum by at most 2^-7 of |a| + |b| per entry."""
+    import pyngp
+    from conftest import scene_occupancy_bitfield
+    from gpu_util import dev, ptr, host, rng_struct
+    _, bits = scene_occupancy_bitfield(orc)
+    rng = orc.pcg32(977)
+    R, max_samples, batch = 4096, 1 << 18, 1 << 16
+    aabb = np.array([0, 0, 0, 1, 1, 1], np.float32)
+    cfg = pyngp.LossConfig(128.0, (C.c_float * 3)(0, 0, 0), 1, 1, 0, 4, 2, 3, 1, 0.2)
+    d_mean = dev(np.array([0.005], np.float32))
+
+    def k6(k1, rgbsigma, n_rays, n_rays_global):
+        d = k1["dev"]
+        coords_out = torch.zeros((batch, 7), dtype=torch.float32, device="cuda"); dloss = torch.zeros((batch, 4), dtype=torch.float16, device="cuda")
+        loss = torch.zeros(n_rays, dtype=torch.float32, device="cuda"); counters_out = torch.zeros(4, dtype=torch.int32, device="cuda")
+        scratch = torch.zeros(int(L.ngpb_compute_loss_scratch_bytes(n_rays)), dtype=torch.uint8, device="cuda")
+        pyngp.check(L.ngpb_compute_loss_sharded(None, n_rays, n_rays_global, aabb.ctypes.data_as(C.c_void_p), rng_struct(rng), batch, C.byref(cfg), d["n_img"], ptr(d["meta"]),
+                                                ptr(d["counters"]), ptr(dev(rgbsigma)), ptr(d["ray_indices"]), ptr(d["rays"]), ptr(d["numsteps"]), ptr(d["coords"]), ptr(d_mean),
+                                                ptr(coords_out), ptr(dloss), ptr(loss), ptr(counters_out), ptr(scratch)))
+        n_c = int(host(counters_out).view(np.uint32)[0])
+        assert 0 < n_c < batch
+        return host(coords_out)[:n_c].copy(), host(dloss)[:n_c].copy(), float(host(loss).astype(np.float64).sum())
+
+    full = _run_k1(L, small_scene, bits, R, max_samples, rng)
+    n_s = int(full["counters"][0])
+    rs = np.random.RandomState(4)
+    rgbsigma = np.zeros((max_samples, 4), np.float16)
+    rgbsigma[:n_s, :3] = rs.randn(n_s, 3).astype(np.float16)
+    rgbsigma[:n_s, 3] = (rs.randn(n_s) * 2.0 + 1.0).astype(np.float16)
+    coords_full, dloss_full, loss_full = k6(full, rgbsigma, R, R)
+    parts, pos, loss_sum = [], 0, 0.0
+    for r in range(2):
+        sh = _run_k1(L, small_scene, bits, R // 2, max_samples, rng, ray_offset=r * (R // 2), n_rays_global=R)
+        ks, n = int(sh["counters"][1]), int(sh["counters"][0])
+        b0 = int(full["numsteps"][pos, 1])  # the shard's samples are this slice of the unsharded sample array (test_sharded_sampling_tiles_the_batch)
+        rgbsigma_s = np.zeros((max_samples, 4), np.float16); rgbsigma_s[:n] = rgbsigma[b0:b0 + n]
+        c, g, l = k6(sh, rgbsigma_s, R // 2, R)
+        parts.append((c, g)); loss_sum += l; pos += ks
+    # (1) the shards' compacted samples and loss gradients, concatenated, ARE the unsharded batch's
+    assert np.array_equal(np.concatenate([p[0] for p in parts]).view(np.uint32), coords_full.view(np.uint32))
+    assert np.array_equal(np.concatenate([p[1] for p in parts]).view(np.uint16), dloss_full.view(np.uint16))
+    assert abs(loss_sum - loss_full) <= 1e-6 * abs(loss_full)
+    assert np.count_nonzero(dloss_full) > 1000
+
+    # (2) gradients are additive over the batch
+    m = orc.model(aabb_scale=1)
+    g, entries = pyngp.grid_init(aabb_scale=1, device_scales=True)
+    n_params = 10240 + 2 * entries
+    params = np.concatenate([(rs.uniform(-1, 1, 10240) * 0.25).astype(np.float16), (rs.randn(2 * entries) * 0.3).astype(np.float16)])
+    d_params = dev(params)
+    ws = torch.zeros(int(L.ngpb_nerf_mlp_workspace_bytes()) // 4, dtype=torch.float32, device="cuda")
+
+    def gradients(coords, dloss):
+        n = (coords.shape[0] + 127) // 128 * 128
+        c = np.zeros((n, 7), np.float32); c[:coords.shape[0]] = coords; c[coords.shape[0]:] = coords[0]
+        dl = np.zeros((n, 4), np.float16); dl[:dloss.shape[0]] = dloss  # padding rows carry no gradient
+        d_c = dev(c)
+        enc = torch.zeros((n, 32), dtype=torch.float16, device="cuda"); denc = torch.zeros((n, 32), dtype=torch.float16, device="cuda")
+        grad = torch.zeros(n_params, dtype=torch.float32, device="cuda")
+        pyngp.check(L.ngpb_hash_encode_forward(None, C.byref(g), C.c_void_p(d_params.data_ptr() + 20480), ptr(d_c), 7, n, ptr(enc)))
+        pyngp.check(L.ngpb_nerf_mlp_forward_backward(None, ptr(d_params), ptr(enc), ptr(d_c), ptr(dev(dl)), n, ptr(denc), ptr(grad), ptr(ws)))
+        pyngp.check(L.ngpb_hash_encode_backward(None, C.byref(g), ptr(d_c), 7, n, ptr(denc), C.c_void_p(grad.data_ptr() + 40960)))
+        return host(grad).astype(np.float64)
+
+    G = gradients(coords_full, dloss_full)
+    G0, G1 = gradients(*parts[0]), gradients(*parts[1])
+    scale_mlp, scale_grid = np.abs(G[:10240]).max(), np.abs(G[10240:]).max()
+    assert scale_mlp > 0 and scale_grid > 0
+    assert np.abs(G0[:10240] + G1[:10240] - G[:10240]).max() <= 1e-4 * scale_mlp
+    assert np.abs(G0[10240:] + G1[10240:] - G[10240:]).max() <= 1e-4 * scale_grid
+
+    # (3) what the bf16 exchange costs: bf16(bf16(a) + bf16(b)) against a + b
+    a, b = torch.from_numpy(G0.astype(np.float32)), torch.from_numpy(G1.astype(np.float32))
+    exchanged = (a.to(torch.bfloat16).float() + b.to(torch.bfloat16).float()).to(torch.bfloat16).float().numpy().astype(np.float64)
+    err = np.abs(exchanged - (G0 + G1))
+    bound = 2.0 ** -7 * (np.abs(G0) + np.abs(G1)) + 1e-30
+    assert np.all(err <= bound), float((err / bound).max())
+
+
 # ------------------------------------------------------------------------------------------------------
 # K6 + K7: compositing, loss, gradients, compaction, roll-over
 # ------------------------------------------------------------------------------------------------------
@@ -710,6 +794,66 @@ def test_training_iteration_matches_oracle(L, orc, small_scene, aabb_scale):
     flips = int(np.unpackbits(bits_gpu[: n_bits // 8] ^ bits_cpu[: n_bits // 8]).sum())
     occupied = int(np.unpackbits(bits_cpu[: n_bits // 8]).sum())
     assert occupied > 1000 and flips <= 0.05 * occupied, f"{flips} of {occupied} occupancy bits differ"
+
+
+def test_training_iteration_teacher_forced(L, orc, small_scene):
+    """Whole training iterations with teacher forcing: before every step the oracle trainer receives the GPU's complete state (fp32 parameters, Adam moments
+    and per-parameter step counters, decay state, occupancy grid, ray-batch size and the controller's memory), so each step starts from identical inputs and
+    its outputs can be compared tightly instead of statistically -- sample counters to 0.5 % (occupancy cells on the threshold still flip through the fp16
+    network), the loss to 2 %, the Adam update of the MLP matrices by direction (cosine >= 0.995; measured 1.0000) and size, the set of grid entries touched (Jaccard >= 0.99; measured 1.0000)
+    and the update of the entries both touched. A wrong regulariser, loss scale, learning-rate schedule or gradient normalisation moves every one of these."""
+    import pyngp
+    tb = pyngp.Testbed()
+    tb.load_training_images(small_scene["images"], small_scene["xforms"], small_scene["fx"], small_scene["fy"])
+    imgs = orc.make_images(small_scene["images"], small_scene["xforms"], small_scene["fx"], small_scene["fy"])
+    ot = orc.Trainer(imgs, aabb_scale=1, seed=1337)
+    g, _ = pyngp.grid_init(aabb_scale=1, device_scales=True)
+    ot.set_level_scales(np.array(g.scale[:16], np.float32))
+    n = tb.n_params
+    batch = 1 << 14
+    n_rays_total = 0
+
+    def gpu_state():
+        st = pyngp.TrainingState()
+        pyngp.check(L.ngpb_testbed_get_training_state(tb._h, C.byref(st)))
+        fm = np.empty(n, np.float32); sm = np.empty(n, np.float32); ps = np.empty(n, np.uint32)
+        pyngp.check(L.ngpb_testbed_get_optimizer_state(tb._h, fm.ctypes.data_as(C.c_void_p), sm.ctypes.data_as(C.c_void_p), ps.ctypes.data_as(C.c_void_p)))
+        return st, fm, sm, ps
+
+    for k in range(4):
+        w0, _, _ = tb.get_params()
+        st, fm, sm, ps = gpu_state()
+        if k > 0:
+            grid, _ = tb.get_density_grid()
+            ot.set_params(w0)
+            ot.set_optimizer_state(fm, sm, ps, st.optimizer_step, st.learning_rate_factor, st.measured_batch_size_before_compaction, n_rays_total)
+            ot.set_state(k, st.rays_per_batch, grid)
+        rays = tb.stats()["rays_per_batch"]
+        n_rays_total += rays
+        cpu = ot.train(batch)
+        tb.train(batch)
+        s = tb.stats()
+        assert cpu["rays_per_batch"] == rays
+        for got, want, what in ((s["measured_batch_size_before_compaction"], cpu["measured_batch_size_before_compaction"], "samples before compaction"),
+                                (s["measured_batch_size"], cpu["measured_batch_size"], "compacted samples")):
+            assert abs(got - want) <= 0.005 * want + 32, f"step {k}: {what} {got} vs {want}"
+        if k == 0:
+            assert abs(tb.loss - cpu["loss"]) <= 0.02 * cpu["loss"], (tb.loss, cpu["loss"])
+        w1, _, _ = tb.get_params()
+        c1, _, _ = ot.params()
+        c0 = w0  # forced (identical initialisation at k = 0)
+        d_gpu, d_cpu = (w1 - w0).astype(np.float64), (c1 - c0).astype(np.float64)
+        m_gpu, m_cpu = d_gpu[:10240], d_cpu[:10240]
+        cos = float(m_gpu @ m_cpu / (np.linalg.norm(m_gpu) * np.linalg.norm(m_cpu)))
+        size = float(np.linalg.norm(m_gpu) / np.linalg.norm(m_cpu))
+        t_gpu, t_cpu = d_gpu[10240:] != 0, d_cpu[10240:] != 0
+        both = t_gpu & t_cpu
+        jac = float(both.sum() / max((t_gpu | t_cpu).sum(), 1))
+        gg, gc = d_gpu[10240:][both], d_cpu[10240:][both]
+        gcos = float(gg @ gc / (np.linalg.norm(gg) * np.linalg.norm(gc)))
+        print(f"step {k}: rays {rays}, MLP update cos {cos:.4f} size ratio {size:.4f}; grid entries touched {int(t_cpu.sum())}, Jaccard {jac:.4f}, update cos {gcos:.4f}")
+        assert cos >= 0.995 and 0.98 <= size <= 1.02
+        assert jac >= 0.99 and gcos >= 0.995 and int(t_cpu.sum()) > 10000
 
 
 def test_snapshot_save_load_render(small_scene, trained_testbed, tmp_path):
