@@ -451,7 +451,10 @@ extern "C" int ngpb_generate_training_samples_sharded(void* stream_, uint32_t n_
 		const bool snap = snap_to_pixel_centers != 0;
 		NGPB_CUDA_CHECK(cudaMemsetAsync(sc.n_items, 0, 4, stream));
 		const bool const_dt = cone_angle_constant == 0.f;
-		#define NGPB_K1(kernel, grid, block, ...) do { if (const_dt) kernel<true><<<grid, block, 0, stream>>>(__VA_ARGS__); else kernel<false><<<grid, block, 0, stream>>>(__VA_ARGS__); } while (0)
+		// Development aid: NGPB_K1_SMEM = bytes of (unused) dynamic shared memory per block, which caps the resident blocks per SM of the K1 kernels so that
+		// kernels of the training stream can co-reside while K1 runs on the sampling stream.
+		static const uint32_t k1_smem = [] { const char* e = std::getenv("NGPB_K1_SMEM"); return e ? (uint32_t)std::atoi(e) : 0u; }();
+		#define NGPB_K1(kernel, grid, block, ...) do { if (const_dt) kernel<true><<<grid, block, k1_smem, stream>>>(__VA_ARGS__); else kernel<false><<<grid, block, k1_smem, stream>>>(__VA_ARGS__); } while (0)
 		NGPB_K1(chain_training_rays_kernel, blocks, K1_BLOCK, n_rays, ray_offset, n_rays_global, aabb, rng, n_images, images_dev, snap, cone_angle_constant,
 			sc.recs, words, sc.items, sc.n_items);
 		NGPB_LAUNCH_CHECK();
