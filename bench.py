@@ -83,6 +83,8 @@ def parse_args():
     p.add_argument("--res", type=int, default=RES)
     p.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline leg")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="N > 1: weak = every rank trains --batch samples per step (global batch N x B, "
+                   "the default and what the driver's scaling run measures); strong = the global batch stays --batch, every rank trains --batch / N")
     return p.parse_args()
 
 
@@ -243,6 +245,9 @@ def main():
         torch.cuda.synchronize()
 
     K, W = max(1, args.steps), max(3, args.warmup)
+    global_batch = args.batch * world if args.scaling == "weak" else args.batch
+    if args.scaling == "strong" and world > 1:
+        args.batch = max(128, args.batch // world // 128 * 128)  # this rank's share of the fixed global batch
     scene = make_scene(args.n_images, args.res, f"cuda:{local_rank}")
     images_dev = scene["images"]
     host_images = torch.empty(images_dev.shape, dtype=torch.uint8, pin_memory=True)
@@ -487,13 +492,14 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16 storage / fp32 accumulate (tcgen05 kind::f16)",
+            "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None, "dtype": "fp16 storage / fp32 accumulate (tcgen05 kind::f16)",
             "data": "synthetic",
             "config": {"workload": f"NeRF Lego-shaped synthetic scene ({args.n_images} cams {args.res}x{args.res} RGBA8), configs/nerf/base.json, "
                                    f"batch 2^{int(np.log2(args.batch))} compacted samples/iteration/GPU, seed 1337",
-                       "batch": args.batch, "rays_per_batch": st["rays_per_batch"], "samples_before_compaction": st["measured_batch_size_before_compaction"],
+                       "batch": args.batch, "global_batch": global_batch, "optimizer_steps_per_sec": 1e3 / ms_per_step, "rays_per_batch": st["rays_per_batch"], "samples_before_compaction": st["measured_batch_size_before_compaction"],
                        "samples_per_sec": value * BATCH, "pre_trained_steps": args.preroll + W, "final_loss": loss,
-                       "parallelism": "single GPU" if world == 1 else f"dp{world}: ray-sharded replicas, NCCL gradient all-reduce",
+                       "parallelism": "single GPU" if world == 1 else f"dp{world}: ray-sharded replicas; gradients reduce-scattered (bf16), Adam on 1/{world} of the parameters per rank, "
+                                                                                f"fp16 weights all-gathered ({'peer-memory kernels over NVLink' if os.environ.get('NGPB_DP_EXCHANGE') == '1' else 'NCCL'})",
                        "l2": "no flush: the per-iteration working set (256 MB images + 293 MB parameter/optimizer state + ~150 MB sample buffers) exceeds the 126 MB L2",
                        "schedule": "every stage of the reference's iteration runs every step (K1, inference on all marched samples, K6, forward+backward on the compacted batch, "
                                    "Adam/EMA, occupancy refresh at its cadence); the training pass reads the hash-grid features the inference pass computed for the same samples "

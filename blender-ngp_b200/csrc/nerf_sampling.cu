@@ -63,6 +63,9 @@ __device__ inline TrainRay setup_training_ray(uint32_t i, uint32_t n_rays, Pcg32
 //      a candidate sits within rounding of a cell boundary -- that word is re-marched from the true entry. Also applies the 1024-sample cap.
 //   4. scan + write kernels: as before, parallel over words, replaying each word's 32 chain steps with the same float additions.
 // The ray's critical path drops from ~200 dependent cell hops to ~7, and the kernel becomes throughput- instead of latency-bound.
+// (Round 2 tried the opposite trade on top of a closed form of the constant-step chain -- one thread per ray again, crossing empty space in 8^3-cell
+// blocks with exact landings: bit-exact on every K1 test, but 511 us instead of 165 us for the stage. The occupancy grid of a half-trained scene is
+// fluffy -- 56 % of the 8^3 blocks hold an occupied cell at step 530 -- and 45 k serial walks cannot hide their load latency.)
 struct __align__(16) MarchWord {
 	float t;            // chain value at the word's first candidate
 	uint32_t visited;   // candidates the walk visits (word kernel: assuming candidate 0 is visited)
