@@ -36,6 +36,46 @@ __device__ __forceinline__ float advance_to_next_voxel(float t, float cone_angle
 	return t;
 }
 
+// The constant-step t chain in closed form: t_{k+1} = fl(t_k + dt) with dt = MIN_CONE_STEPSIZE (cone_angle == 0), advanced by n steps with the SAME bits as n
+// additions. While t stays inside one binade every t_k is a multiple of u = ulp(t) and dt = q u + r, so every addition rounds the same way and moves the
+// mantissa by the same integer (q, or q + 1 when r > u / 2): k steps are one multiply-add on the mantissa, and only a step that leaves the binade is a
+// real addition. A tie (r == u / 2) would round by parity; for this dt it only occurs for t in [2^-9, 2^-8), which is stepped one addition at a time.
+// Checked against step-by-step addition for 200 000 random (t, n).
+__device__ __forceinline__ float chain_advance(float t, uint32_t n) {
+	const uint32_t dt_bits = __float_as_uint(MIN_CONE_STEPSIZE);
+	const uint32_t e_dt = dt_bits >> 23, m_dt = (dt_bits & 0x7FFFFFu) | 0x800000u;
+	while (n) {
+		const uint32_t tb = __float_as_uint(t);
+		const uint32_t e_t = tb >> 23; // t >= 0
+		const uint32_t s = e_t - e_dt;
+		bool fast = e_t >= e_dt && s <= 23u;
+		uint32_t inc = 0;
+		if (fast) {
+			if (s == 0) inc = m_dt;
+			else { const uint32_t rb = m_dt & ((1u << s) - 1u), half = 1u << (s - 1); fast = rb != half; inc = (m_dt >> s) + (rb > half ? 1u : 0u); }
+		}
+		if (!fast) { t += MIN_CONE_STEPSIZE; --n; continue; }
+		const uint32_t m = (tb & 0x7FFFFFu) | 0x800000u;
+		const uint32_t room = 0xFFFFFFu - m;
+		uint32_t k = n;
+		if ((uint64_t)n * inc > room) k = room / inc;
+		t = __uint_as_float((e_t << 23) | ((m + k * inc) & 0x7FFFFFu));
+		n -= k;
+		if (n) { t += MIN_CONE_STEPSIZE; --n; } // the step that leaves the binade
+	}
+	return t;
+}
+// do { t += dt; } while (t < t_target) for the constant step: the first chain member (at least one step on) at or past t_target, same bits
+__device__ __forceinline__ float chain_advance_to(float t, float t_target) {
+	const float est = (t_target - t) * (1.0f / MIN_CONE_STEPSIZE);
+	uint32_t n = est < 1.0f ? 1u : (est < 1.0e6f ? (uint32_t)ceilf(est) : 1000000u);
+	float ta = n > 1 ? chain_advance(t, n - 1) : t;
+	while (n > 1 && ta >= t_target) { --n; ta = n > 1 ? chain_advance(t, n - 1) : t; }
+	float tb = ta + MIN_CONE_STEPSIZE;
+	for (int k = 0; k < 64 && tb < t_target; ++k) tb += MIN_CONE_STEPSIZE; // (the estimate is off by a step at most; the bound only guards non-finite targets)
+	return tb;
+}
+
 // frexpf exponent of a non-negative finite float, as used by mip_from_pos / mip_from_dt: v = m * 2^e with m in [0.5, 1);
 // frexpf(0) reports exponent 0. Read from the bit pattern instead of calling the library routine. Subnormal inputs (|v| < 2^-126)
 // report -126 instead of their true, smaller exponent: every caller clamps the result from below at 0, so it is indistinguishable.
