@@ -309,8 +309,11 @@ int ngpb_testbed_get_density_grid(ngpb_testbed* t, float* grid, uint8_t* bitfiel
  *   rank 0: ngpb_nccl_unique_id(id); broadcast the 128 bytes to all ranks by any means (bench.py uses torch.distributed);
  *   all:    ngpb_testbed_init_data_parallel(t, rank, world, id).
  * Afterwards each ngpb_testbed_train step marches this rank's shard of a global batch of world x rays_per_batch rays to `batch_size`
- * compacted samples, all-reduces (sum) the fp32 gradients and the batch-size counters over NCCL, and applies the same optimizer step on
- * every rank. NCCL is resolved with dlopen("libnccl.so.2") at the first call. */
+ * compacted samples, sums the batch-size counters and exchanges the gradients over NCCL: by default the partial gradients are rounded to bf16 and
+ * reduce-scattered, every rank runs Adam on its 1/world slice of the parameters and the fp16 weights are all-gathered (options "dp_half_gradients"
+ * 0 = fp32 exchange / 1 = bf16 / 2 = fp16, "dp_sharded_optimizer" 0 = plain fp32 all-reduce + full Adam on every rank, "dp_exchange" 1 = the
+ * library's own peer-memory kernels instead of NCCL collectives). Every rank ends a step with identical weights. With "optimize_extrinsics" the
+ * per-camera gradients are all-reduced before the host-side Adam. NCCL is resolved with dlopen("libnccl.so.2") at the first call. */
 int ngpb_nccl_unique_id(void* out128);
 int ngpb_testbed_init_data_parallel(ngpb_testbed* t, int rank, int world, const void* unique_id128);
 
