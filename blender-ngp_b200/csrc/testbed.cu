@@ -910,8 +910,7 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 	measured_batch_size_before_compaction = counter_cpu / (uint32_t)dp_world;
 	measured_batch_size = std::max(1u, compacted_counter_cpu / (uint32_t)dp_world);
 	if (get_loss_scalar) { loss_pending = true; loss_pending_scale = (float)measured_batch_size / (float)batch; }
-	rays_per_batch = (uint32_t)((float)rays_per_batch * (float)batch / (float)measured_batch_size);
-	rays_per_batch = std::min(next_multiple(rays_per_batch, 128u), 1u << 18);
+	rays_per_batch = ngpb_next_rays_per_batch(rays_per_batch, batch, compacted_counter_cpu, (uint32_t)dp_world);
 
 	// ---- K1 of the next step, on the sampling stream, unless that step starts with an occupancy-grid refresh ----
 	{
@@ -931,6 +930,19 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 		collect_loss_scalar();
 		if (profile_stages) stage_collect();
 	}
+}
+
+// The batch-size controller's arithmetic and the ray shard of a rank, host only (used by train() above; tests/test_data_parallel.py runs them under gloo).
+// NerfCounters::update_after_training (:2890-2891) on the per-rank average of the summed compacted count, in float like the reference.
+extern "C" uint32_t ngpb_next_rays_per_batch(uint32_t rays_per_batch, uint32_t batch, uint32_t global_compacted, uint32_t world) {
+	const uint32_t measured = std::max(1u, global_compacted / std::max(world, 1u));
+	const uint32_t r = (uint32_t)((float)rays_per_batch * (float)batch / (float)measured);
+	return std::min(next_multiple(r, 128u), 1u << 18);
+}
+// every rank marches rays [rank * rays_per_batch, (rank + 1) * rays_per_batch) of a global batch of world * rays_per_batch
+extern "C" void ngpb_ray_shard(uint32_t rank, uint32_t world, uint32_t rays_per_batch, uint32_t* ray_offset, uint32_t* n_rays_global) {
+	if (ray_offset) *ray_offset = rank * rays_per_batch;
+	if (n_rays_global) *n_rays_global = world * rays_per_batch;
 }
 
 // Host half of the camera optimisation (train_nerf :3056-3083, :3134): read the accumulated gradients, one Adam step per camera and offset, new transforms.

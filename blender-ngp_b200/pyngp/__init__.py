@@ -434,7 +434,7 @@ EXPORTED_SYMBOLS = [
     "ngpb_model_create", "ngpb_model_destroy", "ngpb_model_reset", "ngpb_model_n_params", "ngpb_model_training_step", "ngpb_model_loss", "ngpb_model_launches", "ngpb_model_stream",
     "ngpb_model_set_option", "ngpb_model_get_params", "ngpb_model_set_params_half", "ngpb_model_set_training_step", "ngpb_model_train", "ngpb_model_inference",
     "ngpb_model_set_image", "ngpb_model_set_image_rgba8", "ngpb_model_train_image", "ngpb_model_image_mse", "ngpb_model_render_image", "ngpb_model_set_sdf_data",
-    "ngpb_model_train_sdf", "ngpb_model_get_training_batch",
+    "ngpb_model_train_sdf", "ngpb_model_get_training_batch", "ngpb_next_rays_per_batch", "ngpb_ray_shard",
 ]
 
 _lib = None
@@ -489,6 +489,10 @@ def lib():
         l.ngpb_model_train_sdf.argtypes = [C.c_void_p, C.c_uint32, C.c_int]
         l.ngpb_model_set_params_half.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         l.ngpb_model_get_params.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.ngpb_next_rays_per_batch.restype = C.c_uint32
+        l.ngpb_next_rays_per_batch.argtypes = [C.c_uint32] * 4
+        l.ngpb_ray_shard.restype = None
+        l.ngpb_ray_shard.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         l.ngpb_camera_adam_step.restype = None
         l.ngpb_camera_adam_step.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_int]
         l.ngpb_apply_camera_offsets.restype = None

@@ -314,6 +314,10 @@ int ngpb_testbed_get_density_grid(ngpb_testbed* t, float* grid, uint8_t* bitfiel
  * 0 = fp32 exchange / 1 = bf16 / 2 = fp16, "dp_sharded_optimizer" 0 = plain fp32 all-reduce + full Adam on every rank, "dp_exchange" 1 = the
  * library's own peer-memory kernels instead of NCCL collectives). Every rank ends a step with identical weights. With "optimize_extrinsics" the
  * per-camera gradients are all-reduced before the host-side Adam. NCCL is resolved with dlopen("libnccl.so.2") at the first call. */
+/* Host-only arithmetic of the sharded batch (what train() uses): the next ray count from the SUMMED compacted-sample count (every rank derives the
+ * same value; NerfCounters::update_after_training, src/testbed_nerf.cu:2890-2891), and a rank's slice of the global ray batch. */
+uint32_t ngpb_next_rays_per_batch(uint32_t rays_per_batch, uint32_t batch, uint32_t global_compacted, uint32_t world);
+void ngpb_ray_shard(uint32_t rank, uint32_t world, uint32_t rays_per_batch, uint32_t* ray_offset, uint32_t* n_rays_global);
 int ngpb_nccl_unique_id(void* out128);
 int ngpb_testbed_init_data_parallel(ngpb_testbed* t, int rank, int world, const void* unique_id128);
 
