@@ -289,15 +289,17 @@ __global__ void __launch_bounds__(1024) loss_scan_kernel(const uint32_t n_blocks
 
 // (C) gradient pass, :1436-1556: same walk over the first `cn` samples of the ray, now with the ray's colour known. W lanes per ray;
 // RB_C = rays per block of the composite kernel (the granularity of block_prefix).
+// (256-thread blocks: the kernel needs 62 registers, so a 1024-thread block filled an SM alone and held it until its longest ray finished)
+constexpr uint32_t GRAD_BLOCK = 256;
 template <uint32_t W>
-__global__ void __launch_bounds__(1024) loss_gradient_kernel(
+__global__ void __launch_bounds__(GRAD_BLOCK) loss_gradient_kernel(
 	const LossParams P, const uint32_t* __restrict__ counters_in, const float* __restrict__ mean_density_ptr,
 	const __half* __restrict__ rgbsigma, const float* __restrict__ rays, uint32_t* __restrict__ numsteps_io, const float* __restrict__ coords_in,
 	const RayState* __restrict__ state, const uint32_t* __restrict__ compacted_counts, const uint32_t* __restrict__ local_bases, const uint32_t* __restrict__ block_prefix,
 	const uint32_t RB_C, float* __restrict__ coords_out, __half* __restrict__ dloss_dout, float* __restrict__ loss_output,
 	const uint4* __restrict__ rows_in, uint4* __restrict__ rows_out)
 {
-	constexpr uint32_t RAYS_PER_WARP = 32 / W, RAYS_PER_BLOCK = 1024 / W;
+	constexpr uint32_t RAYS_PER_WARP = 32 / W, RAYS_PER_BLOCK = GRAD_BLOCK / W;
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, glane = lane & (W - 1);
 	const uint32_t i = blockIdx.x * RAYS_PER_BLOCK + warp * RAYS_PER_WARP + lane / W;
 	const bool in_range = i < P.n_rays;
@@ -482,7 +484,7 @@ int ngpb::compute_loss_launch(void* stream_, uint32_t n_rays, uint32_t n_rays_gl
 			return std::make_pair(c, g);
 		}();
 		const uint32_t wc = lanes.first == 8 ? 8u : lanes.first == 32 ? 32u : 16u, wg = lanes.second == 16 ? 16u : lanes.second == 32 ? 32u : 8u;
-		const uint32_t rb_c = 1024 / wc, blocks_c = div_round_up(n_rays, rb_c), blocks_g = div_round_up(n_rays, 1024 / wg);
+		const uint32_t rb_c = 1024 / wc, blocks_c = div_round_up(n_rays, rb_c), blocks_g = div_round_up(n_rays, GRAD_BLOCK / wg);
 		loss_target_kernel<<<div_round_up(n_rays, 128), 128, 0, stream>>>(P, images_dev, counters_in, ray_indices, state);
 		NGPB_LAUNCH_CHECK();
 		#define NGPB_COMPOSITE(W) loss_composite_kernel<W><<<blocks_c, 1024, 0, stream>>>(P, images_dev, counters_in, (const __half*)rgbsigma, ray_indices, numsteps, coords_in, state, counts, local_bases, block_sums)
@@ -491,7 +493,7 @@ int ngpb::compute_loss_launch(void* stream_, uint32_t n_rays, uint32_t n_rays_gl
 		NGPB_LAUNCH_CHECK();
 		loss_scan_kernel<<<1, 1024, 0, stream>>>(blocks_c, block_sums, counters_out);
 		NGPB_LAUNCH_CHECK();
-		#define NGPB_GRADIENT(W) loss_gradient_kernel<W><<<blocks_g, 1024, 0, stream>>>(P, counters_in, mean_density_dev, (const __half*)rgbsigma, rays, numsteps, coords_in, state, counts, local_bases, \
+		#define NGPB_GRADIENT(W) loss_gradient_kernel<W><<<blocks_g, GRAD_BLOCK, 0, stream>>>(P, counters_in, mean_density_dev, (const __half*)rgbsigma, rays, numsteps, coords_in, state, counts, local_bases, \
 			block_sums, rb_c, coords_out, (__half*)dloss_dout, loss_per_ray, reinterpret_cast<const uint4*>(encoded_in), reinterpret_cast<uint4*>(encoded_out))
 		if (wg == 8) NGPB_GRADIENT(8); else if (wg == 16) NGPB_GRADIENT(16); else NGPB_GRADIENT(32);
 		#undef NGPB_GRADIENT

@@ -48,9 +48,10 @@ def full(path):
 
 
 # kernel-name prefix -> bench.py stage; the n-th launch of the hash forward kernel in a step decides inference (1st) vs training (2nd, when re-encoding)
-STAGE_OF = [("hash_encode_forward", "encode_inference"), ("void nerf_mlp_kernel<1>", "mlp_inference"), ("void nerf_mlp_kernel<(int)1>", "mlp_inference"),
-            ("void nerf_mlp_kernel<2>", "mlp_train"), ("void nerf_mlp_kernel<(int)2>", "mlp_train"), ("hash_encode_backward", "encode_backward"),
-            ("void adam_ema_kernel", "optimizer"), ("adam_ema_kernel", "optimizer")]
+STAGE_OF = [("hash_encode_forward", "encode_inference"), ("nerf_mlp_pipe_infer_kernel<1>", "mlp_inference"), ("nerf_mlp_pipe_infer_kernel<(int)1>", "mlp_inference"),
+            ("nerf_mlp_pipe_train_kernel<2>", "mlp_train"), ("nerf_mlp_pipe_train_kernel<(int)2>", "mlp_train"), ("nerf_mlp_kernel<1>", "mlp_inference"),
+            ("nerf_mlp_kernel<2>", "mlp_train"), ("hash_encode_backward", "encode_backward"), ("adam_ema_kernel", "optimizer"),
+            ("march_words_kernel", "sampling"), ("loss_gradient_kernel", "loss")]
 
 
 def traffic(path):
@@ -67,7 +68,7 @@ def traffic(path):
     for r in rows[2:]:
         name = r[idx["Kernel Name"]]
         for prefix, stage in STAGE_OF:
-            if name.startswith(prefix):
+            if prefix in name.split("(")[0]:
                 b = to_bytes(r[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]]) + to_bytes(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
                 a = acc.setdefault(stage, [0, 0.0, name.split("(")[0]])
                 a[0] += 1; a[1] += b
