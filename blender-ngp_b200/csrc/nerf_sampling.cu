@@ -65,7 +65,9 @@ __device__ inline TrainRay setup_training_ray(uint32_t i, uint32_t n_rays, Pcg32
 // The ray's critical path drops from ~200 dependent cell hops to ~7, and the kernel becomes throughput- instead of latency-bound.
 // (Round 2 tried the opposite trade on top of a closed form of the constant-step chain -- one thread per ray again, crossing empty space in 8^3-cell
 // blocks with exact landings: bit-exact on every K1 test, but 511 us instead of 165 us for the stage. The occupancy grid of a half-trained scene is
-// fluffy -- 56 % of the 8^3 blocks hold an occupied cell at step 530 -- and 45 k serial walks cannot hide their load latency.)
+// fluffy -- 56 % of the 8^3 blocks hold an occupied cell at step 530 -- and 45 k serial walks cannot hide their load latency. The same exact block hops
+// (8^3 and 4^3) inside march_word, keeping the word-parallel structure: bit-exact again, stage 261 us -- deciding that a hop is unambiguous costs more
+// instructions than the four cell-sized hops it replaces.)
 struct __align__(16) MarchWord {
 	float t;            // chain value at the word's first candidate
 	uint32_t visited;   // candidates the walk visits (word kernel: assuming candidate 0 is visited)
