@@ -18,6 +18,18 @@ scene = synthetic.make_lego_scene(100, 800, device="cuda", as_numpy=True)
 tb = pyngp.Testbed()
 tb.load_training_images(list(scene["images"]), scene["xforms"], scene["fx"], scene["fy"])
 tb.train_n(530)
+rq = None
+if mode == "blender":  # one 800 x 800 frame through request_nerf_render_sync (K18), one NeRF from a snapshot
+    import math
+    import numpy as np
+    snap = "/tmp/ngpb_timeline.msgpack"
+    tb.save_snapshot(snap)
+    cam = synthetic.nerf_matrix_to_ngp(synthetic.hemisphere_cameras(7, seed=3)[2])
+    out_p = pyngp.RenderOutputProperties((800, 800), pyngp.DownsampleInfo.MakeFromMip((800, 800), 0), 1, pyngp.ColorSpace.SRGB, pyngp.TonemapCurve.Identity, 0.0, [0, 0, 0, 0], False)
+    cam_p = pyngp.RenderCameraProperties(cam, pyngp.CameraModel.Perspective, scene["fx"], 0.0, 0.0, 1.0, None, None)
+    box = pyngp.BoundingBox([0, 0, 0], [1, 1, 1])
+    rq = pyngp.RenderRequest(out_p, cam_p, pyngp.RenderModifiers([]), [pyngp.NerfDescriptor(snap, box, np.eye(4), pyngp.RenderModifiers([]), 1.0)], box)
+    tb.request_nerf_render_sync(rq)
 if mode == "render":
     import math
     tb.camera_matrix = synthetic.nerf_matrix_to_ngp(synthetic.hemisphere_cameras(7, seed=3)[2])
@@ -28,6 +40,8 @@ from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     if mode == "train_n":
         tb.train_n(n_steps)
+    elif mode == "blender":
+        tb.request_nerf_render_sync(rq)
     elif mode == "render":  # one classic 800 x 800 frame (K17)
         import math
         tb.camera_matrix = synthetic.nerf_matrix_to_ngp(synthetic.hemisphere_cameras(7, seed=3)[2])
