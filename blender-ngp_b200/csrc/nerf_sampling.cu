@@ -165,8 +165,11 @@ __global__ void __launch_bounds__(K1_BLOCK) chain_training_rays_kernel(
 				if (n_words == MARCH_MAX_WORDS) { overflow = true; break; }
 				w[n_words++].t = t;
 				if (!(t <= t_end)) break;
-				#pragma unroll
-				for (int k = 0; k < 32; ++k) t += chain_dt<CONST_DT>(t, r.cone_angle);
+				if (CONST_DT) t = chain_advance(t, 32); // the same 32 additions in closed form (nerf_device.cuh): no dependent chain of FADDs
+				else {
+					#pragma unroll
+					for (int k = 0; k < 32; ++k) t += chain_dt<CONST_DT>(t, r.cone_angle);
+				}
 			}
 		}
 		RayRec rec;
@@ -373,7 +376,8 @@ __global__ void __launch_bounds__(WRITE_RAYS_PER_BLOCK * 32) write_training_samp
 			if (s < n_chunk) {
 				const uint32_t bit = __fns(mask, 0, (int)rank + 1); // position of the (rank+1)-th set bit
 				float t = t_word;
-				for (uint32_t k = 0; k < bit; ++k) t += chain_dt<CONST_DT>(t, rec.cone_angle);
+				if (CONST_DT) t = chain_advance(t, bit);
+				else for (uint32_t k = 0; k < bit; ++k) t += chain_dt<CONST_DT>(t, rec.cone_angle);
 				const float dt = chain_dt<CONST_DT>(t, rec.cone_angle);
 				const V3 pos = V3{o.x + t * d.x, o.y + t * d.y, o.z + t * d.z};
 				const V3 wp = warp_position(pos, aabb);
