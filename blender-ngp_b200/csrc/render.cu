@@ -141,7 +141,14 @@ struct DeviceScratch {
 	uint8_t* get(size_t n) {
 		int dev = 0;
 		NGPB_CUDA_CHECK(cudaGetDevice(&dev));
-		if (n > bytes || dev != device) { if (p) cudaFree(p); p = nullptr; bytes = 0; NGPB_CUDA_CHECK(cudaMalloc(&p, n)); bytes = n; device = dev; }
+		if (n > bytes || dev != device) {
+			if (p) cudaFree(p);
+			p = nullptr; bytes = 0;
+			NGPB_CUDA_CHECK(cudaMalloc(&p, n));
+			NGPB_CUDA_CHECK(cudaMemset(p, 0, n)); // the network passes run over whole 128-sample tiles: the slots past a wave's last sample are read (and ignored), never left undefined
+			NGPB_CUDA_CHECK(cudaDeviceSynchronize());
+			bytes = n; device = dev;
+		}
 		return p;
 	}
 };

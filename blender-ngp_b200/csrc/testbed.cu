@@ -1307,6 +1307,7 @@ void ngpb_testbed::render(const float* camera12, int w, int h, float fx, float f
 		dfree(render_ws);
 		render_ws = dalloc(need);
 		render_ws_bytes = need;
+		NGPB_CUDA_CHECK(cudaMemsetAsync(render_ws, 0, need, stream)); // (the network passes run over whole 128-sample tiles: slots past a wave's last sample are read and ignored)
 	}
 	ngpb_render_config c{};
 	c.width = w; c.height = h; c.fx = fx; c.fy = fy;

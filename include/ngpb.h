@@ -220,7 +220,8 @@ typedef struct {
 } ngpb_render_config;
 uint64_t ngpb_render_workspace_bytes(uint32_t n_pixels);
 /* params: half[10240 + grid] (inference = EMA weights for Testbed::render); bitfield: occupancy bits incl. mips; workspace: device memory of
- * ngpb_render_workspace_bytes(width*height). out_rgba_host: float [height][width][4] (host). n_samples_out: samples that went through the
+ * ngpb_render_workspace_bytes(width*height), zero-filled once by the caller (the network passes run over whole 128-sample tiles and read the slots past a
+ * wave's last sample). out_rgba_host: float [height][width][4] (host). n_samples_out: samples that went through the
  * network for live rays; n_launches_out: kernels launched. Synchronises the stream (the live-ray count is read back once per pass). */
 int ngpb_render_nerf(void* stream, const ngpb_render_config* cfg, const ngpb_grid* g, const ngpb_half* params, const uint8_t* bitfield,
                      void* workspace, float* out_rgba_host, uint64_t* n_samples_out, uint32_t* n_launches_out);
