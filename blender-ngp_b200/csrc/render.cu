@@ -19,6 +19,7 @@
 #include <cstring>
 #include <cmath>
 #include <stdexcept>
+#include <thread>
 #include <vector>
 
 namespace ngpb {
@@ -134,6 +135,28 @@ struct PinnedScratch {
 	}
 };
 static thread_local PinnedScratch g_pinned;
+// The finished frame's way to the caller: straight into the caller's buffer when that is page-locked memory (pyngp hands out such buffers), otherwise through the
+// page-locked staging buffer and a host copy split over a few threads (a single-threaded copy into freshly allocated pageable memory runs at ~10 GB/s, longer
+// than the PCIe transfer of an 800 x 800 frame).
+static bool host_pointer_is_pinned(const void* p) {
+	cudaPointerAttributes attr{};
+	if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return false; }
+	return attr.type == cudaMemoryTypeHost;
+}
+static void parallel_host_copy(void* dst, const void* src, size_t bytes) {
+	constexpr size_t MIN_PER_THREAD = 1u << 20;
+	const unsigned n_threads = (unsigned)std::min<size_t>(4, bytes / MIN_PER_THREAD);
+	if (n_threads <= 1) { std::memcpy(dst, src, bytes); return; }
+	std::vector<std::thread> th;
+	const size_t chunk = (bytes / n_threads + 4095) & ~(size_t)4095;
+	for (unsigned k = 1; k < n_threads; ++k) {
+		const size_t off = k * chunk;
+		if (off >= bytes) break;
+		th.emplace_back([=] { std::memcpy((uint8_t*)dst + off, (const uint8_t*)src + off, std::min(chunk, bytes - off)); });
+	}
+	std::memcpy(dst, src, std::min(chunk, bytes));
+	for (auto& t : th) t.join();
+}
 // Device workspace of the Blender renderer, kept per host thread and device and grown on demand (cudaMalloc + cudaFree per frame cost more than the
 // frame's first waves).
 struct DeviceScratch {
@@ -596,10 +619,11 @@ extern "C" int ngpb_render_nerf(void* stream_, const ngpb_render_config* cfg, co
 			make_float4(cfg->background_color[0], cfg->background_color[1], cfg->background_color[2], cfg->background_color[3]), accum, cfg->color_space, cfg->output_srgb,
 			cfg->tonemap_curve, out);
 		NGPB_LAUNCH_CHECK(); ++launches;
-		NGPB_CUDA_CHECK(cudaMemcpyAsync(host_frame, out, (size_t)n_pixels * 16, cudaMemcpyDeviceToHost, stream));
+		const bool direct = host_pointer_is_pinned(out_rgba_host);
+		NGPB_CUDA_CHECK(cudaMemcpyAsync(direct ? out_rgba_host : host_frame, out, (size_t)n_pixels * 16, cudaMemcpyDeviceToHost, stream));
 		NGPB_CUDA_CHECK(cudaMemcpyAsync(host_counter, counters + 2, 8, cudaMemcpyDeviceToHost, stream));
 		NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
-		std::memcpy(out_rgba_host, host_frame, (size_t)n_pixels * 16);
+		if (!direct) parallel_host_copy(out_rgba_host, host_frame, (size_t)n_pixels * 16);
 		if (n_samples_out) std::memcpy(n_samples_out, host_counter, 8);
 		if (n_launches_out) *n_launches_out = launches;
 		return 0;
@@ -892,12 +916,27 @@ __global__ void __launch_bounds__(128) bl_compact_kernel(const BlRequest R, cons
 	}
 }
 
+// The wave schedule on the device. The reference reads the live-ray count back after every compaction and derives the wave's step count from it on the
+// host (nerf_renderer.cu:650-700); here the count stays on the device: a one-thread kernel derives n_steps = clamp(n_initial / n_alive, 1, max_steps), the
+// sample-slot count and the running step index from it, and the wave's kernels read them from there. The host only needs an UPPER BOUND of the live count
+// to size its launches -- the previous wave's count, whose read-back has long completed by the time it is needed -- so it never waits for the GPU.
+struct BlWave { uint32_t n_steps, n_slots, current_step, next_step; };
+__global__ void bl_wave_setup_kernel(const uint32_t* __restrict__ n_alive_dev, const uint32_t n_initial, const uint32_t max_steps, BlWave* __restrict__ wave)
+{
+	const uint32_t n_alive = *n_alive_dev;
+	const uint32_t n_steps = n_alive ? max(1u, min(max_steps, n_initial / n_alive)) : 1u;
+	wave->n_steps = n_steps;
+	wave->n_slots = n_alive * n_steps;
+	wave->current_step = wave->next_step;
+	wave->next_step += n_steps;
+}
+
 // march_active_rays + cull_global_rays_and_set_proxy_rays_active_kernel
-__global__ void __launch_bounds__(128) bl_march_cull_kernel(const uint32_t n_alive, const uint32_t n_nerfs, const BlNerfProps* __restrict__ props, const uint32_t stride,
+__global__ void __launch_bounds__(128) bl_march_cull_kernel(const uint32_t* __restrict__ n_alive_dev, const uint32_t n_nerfs, const BlNerfProps* __restrict__ props, const uint32_t stride,
                                                             const float cam_x, const float cam_y, const float cam_z, BlGlobalRay* __restrict__ rays, BlProxyRay* __restrict__ proxies)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n_alive) return;
+	if (i >= *n_alive_dev) return;
 	if (!rays[i].alive) return;
 	float min_d2 = 0.0f;
 	int active = -1;
@@ -927,11 +966,12 @@ __global__ void __launch_bounds__(128) bl_march_cull_kernel(const uint32_t n_ali
 }
 
 // march_proxy_rays_and_generate_next_network_inputs for one NeRF; ray-major slots [i * n_steps + j]
-__global__ void __launch_bounds__(128) bl_generate_inputs_kernel(const uint32_t n_alive, const uint32_t n_steps, const BlNerfProps* __restrict__ props_n,
+__global__ void __launch_bounds__(128) bl_generate_inputs_kernel(const uint32_t* __restrict__ n_alive_dev, const BlWave* __restrict__ wave, const BlNerfProps* __restrict__ props_n,
                                                                  const BlGlobalRay* __restrict__ rays, BlProxyRay* __restrict__ proxies_n, float* __restrict__ coords)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n_alive) return;
+	if (i >= *n_alive_dev) return;
+	const uint32_t n_steps = wave->n_steps;
 	float* c = coords + (size_t)i * n_steps * COORD_FLOATS;
 	BlProxyRay p = proxies_n[i];
 	uint32_t j = 0;
@@ -982,11 +1022,12 @@ __device__ __forceinline__ bool warp_first_occupied(const V3& o, const V3& d, co
 	return false;
 }
 
-__global__ void __launch_bounds__(256) bl_generate_inputs_warp_kernel(const uint32_t n_alive, const uint32_t n_steps, const BlNerfProps* __restrict__ props_n,
+__global__ void __launch_bounds__(256) bl_generate_inputs_warp_kernel(const uint32_t* __restrict__ n_alive_dev, const BlWave* __restrict__ wave, const BlNerfProps* __restrict__ props_n,
                                                                       const BlGlobalRay* __restrict__ rays, BlProxyRay* __restrict__ proxies_n, float* __restrict__ coords)
 {
 	const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-	if (i >= n_alive) return;
+	if (i >= *n_alive_dev) return;
+	const uint32_t n_steps = wave->n_steps;
 	float* c = coords + (size_t)i * n_steps * COORD_FLOATS;
 	BlProxyRay p = proxies_n[i];
 	uint32_t w = 0; // sample slots written
@@ -1038,11 +1079,12 @@ __global__ void __launch_bounds__(256) bl_generate_inputs_warp_kernel(const uint
 }
 
 // composite_proxy_ray_colors_kernel for one NeRF
-__global__ void __launch_bounds__(128) bl_composite_kernel(const uint32_t n_alive, const uint32_t n_steps, const uint32_t current_step, const BlNerfProps* __restrict__ props_n,
+__global__ void __launch_bounds__(128) bl_composite_kernel(const uint32_t* __restrict__ n_alive_dev, const BlWave* __restrict__ wave, const BlNerfProps* __restrict__ props_n,
                                                            BlGlobalRay* __restrict__ rays, BlProxyRay* __restrict__ proxies_n, const float* __restrict__ coords,
                                                            const __half* __restrict__ rgbsigma, unsigned long long* __restrict__ n_samples)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t n_alive = *n_alive_dev, n_steps = wave->n_steps, current_step = wave->current_step;
 	uint32_t done = 0;
 	if (i < n_alive && rays[i].alive) {
 		BlProxyRay p = proxies_n[i];
@@ -1283,41 +1325,49 @@ extern "C" int ngpb_blender_render(void* stream_, const ngpb_blender_request* rq
 			bl_init_rays_kernel<<<div_round_up(n_init, 128), 128, 0, stream>>>(R, n_nerfs, props_dev, n_init, rays[0], prox[0]);
 			NGPB_LAUNCH_CHECK(); ++launches;
 			NGPB_CUDA_CHECK(cudaMemcpyAsync(counters + 0, &n_init, 4, cudaMemcpyHostToDevice, stream));
-			uint32_t cur = 0, n_in = n_init, step = 1;
+			uint32_t cur = 0, bound = n_init; // bound >= the live-ray count of the wave being launched
 			// warp-per-ray march kernels when every NeRF of the request steps with the constant dt (NGPB_BLENDER_WARP_MARCH=0: the serial kernels)
 			static const bool warp_march_enabled = [] { const char* e = std::getenv("NGPB_BLENDER_WARP_MARCH"); return !e || std::atoi(e) != 0; }();
 			bool warp_march = warp_march_enabled;
 			for (uint32_t n = 0; n < n_nerfs; ++n) warp_march = warp_march && props[n].cone_angle == 0.f;
-			while (step < 10000) {
+			BlWave* wave = reinterpret_cast<BlWave*>(counters + 8);
+			const BlWave wave0{1u, 0u, 1u, 1u}; // the reference's `n_steps_total = 1` before the first wave
+			NGPB_CUDA_CHECK(cudaMemcpyAsync(wave, &wave0, sizeof(BlWave), cudaMemcpyHostToDevice, stream));
+			static thread_local cudaEvent_t count_ready[2] = {nullptr, nullptr};
+			for (auto& e : count_ready) if (!e) NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+			for (uint32_t k = 0; k < 10000; ++k) {
 				NGPB_CUDA_CHECK(cudaMemsetAsync(counters + (cur ^ 1), 0, 4, stream));
-				bl_compact_kernel<<<div_round_up(n_in, 128), 128, 0, stream>>>(R, counters + cur, n_nerfs, n_init, rays[cur], prox[cur], rays[cur ^ 1], prox[cur ^ 1], counters + (cur ^ 1), frame);
+				bl_compact_kernel<<<div_round_up(bound, 128), 128, 0, stream>>>(R, counters + cur, n_nerfs, n_init, rays[cur], prox[cur], rays[cur ^ 1], prox[cur ^ 1], counters + (cur ^ 1), frame);
 				NGPB_LAUNCH_CHECK(); ++launches;
 				cur ^= 1;
-				NGPB_CUDA_CHECK(cudaMemcpyAsync(host_counter, counters + cur, 4, cudaMemcpyDeviceToHost, stream));
-				NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
-				const uint32_t n_alive = host_counter[0];
-				n_in = n_alive;
-				if (n_alive == 0) break;
-				const uint32_t blocks = div_round_up(n_alive, 128);
-				// (a warp-per-ray form of this kernel was measured: 2.5 ms instead of 1.1 ms per frame -- before the first hit a ray crosses the empty part of the box,
-				// where the serial walk's block hops beat testing every chain member)
-				bl_march_cull_kernel<<<blocks, 128, 0, stream>>>(n_alive, n_nerfs, props_dev, n_init, R.cam[9], R.cam[10], R.cam[11], rays[cur], prox[cur]);
+				// this wave's live count travels to the host without anybody waiting for it ...
+				NGPB_CUDA_CHECK(cudaMemcpyAsync(host_counter + 4 + (k & 1), counters + cur, 4, cudaMemcpyDeviceToHost, stream));
+				NGPB_CUDA_CHECK(cudaEventRecord(count_ready[k & 1], stream));
+				// ... the launches below only need a bound: the PREVIOUS wave's count (rays only die), whose copy finished while that wave's kernels were queued
+				if (k > 0) {
+					NGPB_CUDA_CHECK(cudaEventSynchronize(count_ready[(k - 1) & 1]));
+					bound = std::min(bound, host_counter[4 + ((k - 1) & 1)]);
+					if (bound == 0) break; // the previous wave already ran on no rays: the frame is complete (this wave's compaction was a no-op)
+				}
+				const uint32_t blocks = div_round_up(bound, 128);
+				bl_wave_setup_kernel<<<1, 1, 0, stream>>>(counters + cur, n_init, max_steps, wave);
 				NGPB_LAUNCH_CHECK(); ++launches;
-				const uint32_t n_steps = std::max(1u, std::min(max_steps, n_init / n_alive));
-				const uint32_t n_slots = next_multiple(n_alive * n_steps, 128);
+				bl_march_cull_kernel<<<blocks, 128, 0, stream>>>(counters + cur, n_nerfs, props_dev, n_init, R.cam[9], R.cam[10], R.cam[11], rays[cur], prox[cur]);
+				NGPB_LAUNCH_CHECK(); ++launches;
+				// n_alive * n_steps <= max(n_initial, ...) by construction of n_steps; with the bound: min(n_initial, bound * max_steps) slots at most
+				const uint32_t slot_bound = next_multiple((uint32_t)std::min<uint64_t>((uint64_t)bound * max_steps, std::max<uint64_t>(n_init, bound)), 128);
 				for (uint32_t n = 0; n < n_nerfs; ++n) {
 					BlProxyRay* pn = prox[cur] + (size_t)n * n_init;
-					if (warp_march) bl_generate_inputs_warp_kernel<<<div_round_up(n_alive, 8u), 256, 0, stream>>>(n_alive, n_steps, props_dev + n, rays[cur], pn, coords);
-					else bl_generate_inputs_kernel<<<blocks, 128, 0, stream>>>(n_alive, n_steps, props_dev + n, rays[cur], pn, coords);
+					if (warp_march) bl_generate_inputs_warp_kernel<<<div_round_up(bound, 8u), 256, 0, stream>>>(counters + cur, wave, props_dev + n, rays[cur], pn, coords);
+					else bl_generate_inputs_kernel<<<blocks, 128, 0, stream>>>(counters + cur, wave, props_dev + n, rays[cur], pn, coords);
 					NGPB_LAUNCH_CHECK();
 					const ngpb_field* f = nerfs[n].field;
-					hash_encode_forward_launch(stream, &f->grid, f->params + MLP_PARAMS, coords, COORD_FLOATS, n_slots, nullptr, encoded, features_tiled());
-					nerf_mlp_forward_launch(stream, f->params, encoded, features_tiled(), coords, n_slots, nullptr, rgbsigma);
-					bl_composite_kernel<<<blocks, 128, 0, stream>>>(n_alive, n_steps, step, props_dev + n, rays[cur], pn, coords, rgbsigma, reinterpret_cast<unsigned long long*>(counters + 2));
+					hash_encode_forward_launch(stream, &f->grid, f->params + MLP_PARAMS, coords, COORD_FLOATS, slot_bound, &wave->n_slots, encoded, features_tiled());
+					nerf_mlp_forward_launch(stream, f->params, encoded, features_tiled(), coords, slot_bound, &wave->n_slots, rgbsigma);
+					bl_composite_kernel<<<blocks, 128, 0, stream>>>(counters + cur, wave, props_dev + n, rays[cur], pn, coords, rgbsigma, reinterpret_cast<unsigned long long*>(counters + 2));
 					NGPB_LAUNCH_CHECK();
 					launches += 4;
 				}
-				step += n_steps;
 			}
 		}
 		// Testbed::bl_render_frame: accumulate (first sample) + tonemap, buffer and output colour space = the request's
@@ -1326,10 +1376,11 @@ extern "C" int ngpb_blender_render(void* stream_, const ngpb_blender_request* rq
 			make_float4(rq->background_color[0], rq->background_color[1], rq->background_color[2], rq->background_color[3]), accum, rq->color_space,
 			rq->color_space == NGPB_COLOR_SRGB ? 1 : 0, rq->tonemap_curve, out);
 		NGPB_LAUNCH_CHECK(); launches += 2;
-		NGPB_CUDA_CHECK(cudaMemcpyAsync(host_frame, out, (size_t)n_pixels * 16, cudaMemcpyDeviceToHost, stream));
+		const bool direct = host_pointer_is_pinned(out_rgba_host);
+		NGPB_CUDA_CHECK(cudaMemcpyAsync(direct ? out_rgba_host : host_frame, out, (size_t)n_pixels * 16, cudaMemcpyDeviceToHost, stream));
 		NGPB_CUDA_CHECK(cudaMemcpyAsync(host_counter, counters + 2, 8, cudaMemcpyDeviceToHost, stream));
 		NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
-		std::memcpy(out_rgba_host, host_frame, (size_t)n_pixels * 16);
+		if (!direct) parallel_host_copy(out_rgba_host, host_frame, (size_t)n_pixels * 16);
 		if (n_samples_out) std::memcpy(n_samples_out, host_counter, 8);
 		if (n_launches_out) *n_launches_out = launches;
 		return 0;

@@ -838,6 +838,16 @@ class _Nerf:
     render_with_camera_distortion = False
 
 
+def frame_buffer(height, width):
+    """A float32 [height][width][4] array for a rendered frame. Page-locked when torch is importable (its caching host allocator hands the pages out without a
+    page fault per 4 KB, and the library then copies the frame from the device straight into it); plain numpy memory otherwise."""
+    try:
+        import torch
+        return torch.empty((int(height), int(width), 4), dtype=torch.float32, pin_memory=True).numpy()
+    except Exception:
+        return np.empty((int(height), int(width), 4), np.float32)
+
+
 class Testbed:
     """pyngp.Testbed (python_api.cu:540-732). ETestbedMode::Nerf is this class; Image and Sdf return the classes of pyngp/modes.py (same constructor
     arguments); Volume is not built."""
@@ -1120,7 +1130,7 @@ class Testbed:
         rel = self._relative_focal_length
         res_axis = (width, height)[self.fov_axis]
         fx, fy = rel[0] * res_axis, rel[1] * res_axis
-        out = np.empty((height, width, 4), np.float32)
+        out = frame_buffer(height, width)
         ns = C.c_uint64(0)
         check(lib().ngpb_testbed_render(self._h, cam.ctypes.data_as(C.c_void_p), int(width), int(height), C.c_float(fx), C.c_float(fy), int(spp), int(bool(linear)),
                                         out.ctypes.data_as(C.c_void_p), C.byref(ns)))
@@ -1144,8 +1154,9 @@ class Testbed:
         """Testbed::bl_request_nerf_render_sync (python_api.cu:233): float32 [H][W][4] of all the request's NeRFs composited front to back."""
         out_p, cam_p = render_request.output, render_request.camera
         w, h = out_p.resolution
-        result = np.zeros((h, w, 4), np.float32)
+        result = frame_buffer(h, w)
         if self.__dict__.get("_currently_rendering", False):
+            result.fill(0.0)
             return result
         self._currently_rendering = True
         try:
