@@ -238,6 +238,9 @@ __device__ __forceinline__ uint32_t warp_append(bool pred, uint32_t* __restrict_
 	return base + __popc(mask & ((1u << lane) - 1u));
 }
 
+// live rays x steps of the pass, for the network kernels' device-side sample count
+__global__ void render_slot_count_kernel(const uint32_t* __restrict__ n_rays_dev, const uint32_t n_steps, uint32_t* __restrict__ n_slots_dev) { *n_slots_dev = *n_rays_dev * n_steps; }
+
 // init_rays_with_payload_kernel_nerf + advance_pos_nerf: one thread per pixel; live rays are appended to `rays`.
 __global__ void __launch_bounds__(128) render_init_kernel(const RenderParams P, const uint8_t* __restrict__ bitfield, const uint32_t* __restrict__ coarse,
                                                           RenderRay* __restrict__ rays, float4* __restrict__ rgba, uint32_t* __restrict__ counter)
@@ -586,29 +589,40 @@ extern "C" int ngpb_render_nerf(void* stream_, const ngpb_render_config* cfg, co
 			NGPB_CUDA_CHECK(cudaMemsetAsync(counters, 0, 8, stream));
 			render_init_kernel<<<div_round_up(n_pixels, 128), 128, 0, stream>>>(P, bitfield, coarse, rays[0], rgba[0], counters + 0);
 			NGPB_LAUNCH_CHECK(); ++launches;
-			uint32_t cur = 0, n_alive = 0, n_alive0 = 0;
-			for (uint32_t pass = 0;; ++pass) {
-				NGPB_CUDA_CHECK(cudaMemcpyAsync(host_counter, counters + cur, 4, cudaMemcpyDeviceToHost, stream));
-				NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
-				n_alive = host_counter[0];
-				if (n_alive == 0) break;
-				if (pass == 0) n_alive0 = n_alive;
+			// Passes without a blocking read-back: a pass's launches are sized by (and its step count derived from) the PREVIOUS pass's live-ray count, whose
+			// copy to the host completed while that pass's kernels were queued; the kernels read the current count from the device. The image does not depend
+			// on the pass schedule (unlike the Blender path's), so a step count derived from the slightly larger previous count is as good as the exact one.
+			uint32_t cur = 0, bound = n_pixels, n_alive0 = 0;
+			static thread_local cudaEvent_t count_ready[2] = {nullptr, nullptr};
+			for (auto& e : count_ready) if (!e) NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+			for (uint32_t pass = 0; pass < 100000; ++pass) {
+				NGPB_CUDA_CHECK(cudaMemcpyAsync(host_counter + 4 + (pass & 1), counters + cur, 4, cudaMemcpyDeviceToHost, stream));
+				NGPB_CUDA_CHECK(cudaEventRecord(count_ready[pass & 1], stream));
+				if (pass > 0) {
+					NGPB_CUDA_CHECK(cudaEventSynchronize(count_ready[(pass - 1) & 1]));
+					const uint32_t prev = host_counter[4 + ((pass - 1) & 1)];
+					if (prev == 0) break; // the previous pass already ran on no rays
+					bound = std::min(bound, prev);
+					if (pass == 1) n_alive0 = prev;
+				}
 				// steps this pass: grows as rays die, bounded so that the slot count never exceeds the first pass's
-				uint32_t n_steps = std::min<uint64_t>(NGPB_RENDER_MAX_PASS_STEPS, std::max<uint64_t>(NGPB_RENDER_FIRST_PASS_STEPS, (uint64_t)n_alive0 * NGPB_RENDER_FIRST_PASS_STEPS / n_alive));
-				const uint32_t n_slots = next_multiple(n_alive * n_steps, 128);
-				const uint32_t blocks = div_round_up(n_alive, 128);
+				const uint32_t n_steps = pass == 0 ? NGPB_RENDER_FIRST_PASS_STEPS
+					: (uint32_t)std::min<uint64_t>(NGPB_RENDER_MAX_PASS_STEPS, std::max<uint64_t>(NGPB_RENDER_FIRST_PASS_STEPS, (uint64_t)n_alive0 * NGPB_RENDER_FIRST_PASS_STEPS / bound));
+				const uint32_t n_slots = next_multiple(bound * n_steps, 128);
+				const uint32_t blocks = div_round_up(bound, 128);
 				NGPB_CUDA_CHECK(cudaMemsetAsync(counters + (cur ^ 1), 0, 4, stream));
+				render_slot_count_kernel<<<1, 1, 0, stream>>>(counters + cur, n_steps, counters + 8);
 				static const bool warp_march = [] { const char* e = std::getenv("NGPB_RENDER_WARP_MARCH"); return !e || std::atoi(e) != 0; }();
 				static const uint32_t max_rounds = [] { const char* e = std::getenv("NGPB_RENDER_ROUNDS"); return e ? (uint32_t)std::atoi(e) : 16u; }();
-				if (warp_march) render_march_warp_kernel<<<div_round_up(n_alive, 8), 256, 0, stream>>>(P, counters + cur, n_steps, max_rounds, bitfield, rays[cur], coords, ray_steps);
+				if (warp_march) render_march_warp_kernel<<<div_round_up(bound, 8), 256, 0, stream>>>(P, counters + cur, n_steps, max_rounds, bitfield, rays[cur], coords, ray_steps);
 				else render_march_kernel<<<blocks, 128, 0, stream>>>(P, counters + cur, n_steps, render_max_hops(), bitfield, coarse, rays[cur], coords, ray_steps);
 				NGPB_LAUNCH_CHECK();
-				hash_encode_forward_launch(stream, g, (const __half*)params + MLP_PARAMS, coords, COORD_FLOATS, n_slots, nullptr, encoded, features_tiled());
-				nerf_mlp_forward_launch(stream, (const __half*)params, encoded, features_tiled(), coords, n_slots, nullptr, rgbsigma);
+				hash_encode_forward_launch(stream, g, (const __half*)params + MLP_PARAMS, coords, COORD_FLOATS, n_slots, counters + 8, encoded, features_tiled());
+				nerf_mlp_forward_launch(stream, (const __half*)params, encoded, features_tiled(), coords, n_slots, counters + 8, rgbsigma);
 				render_composite_kernel<<<blocks, 128, 0, stream>>>(P, counters + cur, n_steps, rays[cur], rgba[cur], coords, rgbsigma, ray_steps,
 					rays[cur ^ 1], rgba[cur ^ 1], counters + (cur ^ 1), frame, reinterpret_cast<unsigned long long*>(counters + 2));
 				NGPB_LAUNCH_CHECK();
-				launches += 4;
+				launches += 5;
 				cur ^= 1;
 			}
 			if (s == 0) NGPB_CUDA_CHECK(cudaMemsetAsync(accum, 0, (size_t)n_pixels * 16, stream));
