@@ -252,6 +252,9 @@ ngpb_testbed::ngpb_testbed(int device_) : device(device_) {
 	const std::string pmode = pe ? pe : "sampling";
 	NGPB_CUDA_CHECK(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, pmode == "main" ? prio_high : prio_low));
 	NGPB_CUDA_CHECK(cudaStreamCreateWithPriority(&sampling_stream, cudaStreamNonBlocking, pmode == "sampling" ? prio_high : prio_low));
+	NGPB_CUDA_CHECK(cudaStreamCreateWithPriority(&ema_stream, cudaStreamNonBlocking, prio_low));
+	NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&weights_gathered, cudaEventDisableTiming));
+	NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&ema_done, cudaEventDisableTiming));
 	NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&prefetch_done, cudaEventDisableTiming));
 	NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&loss_ready, cudaEventDisableTiming));
 	NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&counters_ready, cudaEventDisableTiming));
@@ -276,6 +279,9 @@ ngpb_testbed::~ngpb_testbed() {
 	if (stream) cudaStreamSynchronize(stream);
 	p2p_teardown();
 	if (nccl_comm) { try { NcclApi::get().CommDestroy(nccl_comm); } catch (...) {} }
+	if (ema_stream) { cudaStreamSynchronize(ema_stream); cudaStreamDestroy(ema_stream); }
+	if (weights_gathered) cudaEventDestroy(weights_gathered);
+	if (ema_done) cudaEventDestroy(ema_done);
 	if (prefetch_done) cudaEventDestroy(prefetch_done);
 	if (loss_ready) cudaEventDestroy(loss_ready);
 	if (counters_ready) cudaEventDestroy(counters_ready);
@@ -636,6 +642,7 @@ void ngpb_testbed::launch_sampling(cudaStream_t st, const SamplingRequest& p) {
 }
 
 void ngpb_testbed::drop_prefetch() {
+	join_ema(); // (every caller is about to touch state the side streams may still use)
 	if (!prefetch_valid) return;
 	NGPB_CUDA_CHECK(cudaStreamSynchronize(sampling_stream)); // its outputs are about to be overwritten or freed
 	prefetch_valid = false;
@@ -811,12 +818,13 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 			stage_end(NGPB_STAGE_ALLREDUCE, (uint64_t)n_params * 2, stream);
 			stage_begin(NGPB_STAGE_OPTIMIZER, stream);
 			optimizer_disable_fused_ema(opt_params);
+			join_ema(); // the previous step's EMA sweep still reads the fp16 weights this launch overwrites
 			optimizer_launch(stream, opt_params, first, mine, MLP_PARAMS, grad, w_fp32, w_half, w_ema, m1, m2, param_steps);
 			p2p_gather_weights_kernel<<<std::max(1u, div_round_up(count / 8, 256)), 256, 0, stream>>>(count / 8, first, (uint32_t)dp_rank, (uint32_t)dp_world, step, w_half, T, p2p_flags);
 			NGPB_LAUNCH_CHECK();
 			p2p_wait_weights_kernel<<<1, 32, 0, stream>>>((uint32_t)dp_world, step, p2p_flags);
 			NGPB_LAUNCH_CHECK();
-			ema_sweep_launch(stream, opt_params, next_multiple(n_params, 8), w_half, w_ema);
+			launch_ema_sweep_async(opt_params); // (on its own stream: only renders and snapshots read the EMA copy)
 			stage_end(NGPB_STAGE_OPTIMIZER, n_params, stream);
 			NGPB_CUDA_CHECK(cudaMemcpyAsync(host_readback + 12, p2p_flags + 2 * dp_world + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream)); // time-out word
 			master_weights_sharded = true;
@@ -854,11 +862,12 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 			stage_end(NGPB_STAGE_ALLREDUCE, (uint64_t)n_params * (dp_half_gradients ? 2 : 4), stream);
 			stage_begin(NGPB_STAGE_OPTIMIZER, stream);
 			optimizer_disable_fused_ema(opt_params);
+			join_ema(); // the previous step's EMA sweep still reads the fp16 weights this launch overwrites
 			optimizer_launch(stream, opt_params, first, mine, MLP_PARAMS, grad, w_fp32, w_half, w_ema, m1, m2, param_steps);
 			// fp32 exchange: the other ranks' ranges still hold this rank's partial sums (the fp16 path reset the buffer while casting)
 			if (!dp_half_gradients) NGPB_CUDA_CHECK(cudaMemsetAsync(grad, 0, sizeof(float) * n_alloc, stream));
 			nccl.check(nccl.AllGather(w_half + first, w_half, count, NcclApi::Float16, nccl_comm, stream), "ncclAllGather(weights)");
-			ema_sweep_launch(stream, opt_params, next_multiple(n_params, 8), w_half, w_ema);
+			launch_ema_sweep_async(opt_params); // (on its own stream: only renders and snapshots read the EMA copy)
 			stage_end(NGPB_STAGE_OPTIMIZER, n_params, stream);
 			master_weights_sharded = true;
 			n_launches += 3;
@@ -867,6 +876,7 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 			nccl.check(nccl.AllReduce(grad, grad, n_params, NcclApi::Float32, NcclApi::Sum, nccl_comm, stream), "ncclAllReduce(gradients)");
 			stage_end(NGPB_STAGE_ALLREDUCE, (uint64_t)n_params * 4, stream);
 			stage_begin(NGPB_STAGE_OPTIMIZER, stream);
+			join_ema();
 			optimizer_launch(stream, opt_params, 0, n_params, MLP_PARAMS, grad, w_fp32, w_half, w_ema, m1, m2, param_steps);
 			stage_end(NGPB_STAGE_OPTIMIZER, n_params, stream);
 			n_launches += 1;
@@ -945,6 +955,20 @@ extern "C" void ngpb_ray_shard(uint32_t rank, uint32_t world, uint32_t rays_per_
 	if (n_rays_global) *n_rays_global = world * rays_per_batch;
 }
 
+// The sharded optimizer's EMA sweep (a function of the gathered fp16 weights only), off the training stream: it runs under the next step's first half.
+void ngpb_testbed::launch_ema_sweep_async(const void* opt_params) {
+	NGPB_CUDA_CHECK(cudaEventRecord(weights_gathered, stream));
+	NGPB_CUDA_CHECK(cudaStreamWaitEvent(ema_stream, weights_gathered, 0));
+	ema_sweep_launch(ema_stream, opt_params, next_multiple(n_params, 8), w_half, w_ema);
+	NGPB_CUDA_CHECK(cudaEventRecord(ema_done, ema_stream));
+	ema_pending = true;
+}
+void ngpb_testbed::join_ema() {
+	if (!ema_pending) return;
+	NGPB_CUDA_CHECK(cudaStreamWaitEvent(stream, ema_done, 0));
+	ema_pending = false;
+}
+
 // Host half of the camera optimisation (train_nerf :3056-3083, :3134): read the accumulated gradients, one Adam step per camera and offset, new transforms.
 // Synchronises the stream (as the reference does); nothing that reads the image table is in flight afterwards -- the prefetch of the next step's sampling is
 // launched after this returns.
@@ -997,6 +1021,7 @@ void ngpb_testbed::reset_camera_extrinsics() { // Training::reset_camera_extrins
 
 void ngpb_testbed::get_params(float* o_fp32, ngpb_half* o_half, ngpb_half* o_ema) {
 	NGPB_CUDA_CHECK(cudaSetDevice(device));
+	join_ema();
 	NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
 	if (o_fp32 && dp_world > 1 && master_weights_sharded) {
 		// the fp32 master copy is only current in each rank's own range: gather it (a collective -- call get_params on every rank)
@@ -1298,6 +1323,7 @@ extern "C" double ngpb_testbed_get_option(ngpb_testbed* t, const char* name) {
 // Testbed::render_to_cpu (src/python_api.cu:132-190) -> render_frame (src/testbed.cu:2695) -> render_nerf (src/testbed_nerf.cu:2354) for a static camera.
 void ngpb_testbed::render(const float* camera12, int w, int h, float fx, float fy, int spp, bool linear, float* out_rgba, uint64_t* n_samples_out) {
 	NGPB_CUDA_CHECK(cudaSetDevice(device));
+	join_ema();
 	if (!camera12 || !out_rgba || w <= 0 || h <= 0 || spp <= 0) throw std::runtime_error("render: invalid argument");
 	if (n_params == 0) throw std::runtime_error("render: no network (load training data or a snapshot first)");
 	const uint32_t n_pixels = (uint32_t)w * (uint32_t)h;

@@ -55,6 +55,12 @@ struct ngpb_testbed {
 	std::vector<void*> p2p_opened;     // IPC mappings to close
 	void p2p_setup();
 	void p2p_teardown();
+	// the EMA sweep of the sharded optimizer runs on its own stream, under the next step's first half (only renders / snapshots read the EMA copy)
+	cudaStream_t ema_stream = nullptr;
+	cudaEvent_t weights_gathered = nullptr, ema_done = nullptr;
+	bool ema_pending = false;
+	void launch_ema_sweep_async(const void* opt_params);
+	void join_ema(); // makes `stream` wait for a pending EMA sweep (before anything that overwrites the fp16 weights or reads the EMA copy)
 	bool dp_sharded_optimizer = true;    // reduce-scatter + Adam on 1/world of the parameters + all-gather (false: all-reduce + full Adam)
 	bool master_weights_sharded = false; // the fp32 master copy is current only in this rank's range
 	uint32_t dp_shard_count() const;
