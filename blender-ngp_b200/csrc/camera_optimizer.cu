@@ -232,6 +232,22 @@ extern "C" void ngpb_camera_adam_step(float* state10, const float* gradient3, fl
 	angle_axis_from_matrix(M, var);
 }
 
+// The exposure block of Testbed::train_nerf (src/testbed_nerf.cu:3105-3131), host only: one AdamOptimizer<Array3f> step per image on
+// gradient * per_camera_loss_scale + l2_reg * exposure, then all exposures are re-centred on a zero mean (the renormalisation writes through to the
+// optimizers' variables). states: [n_images][10] as ngpb_camera_adam_step; gradients: [n_images][3].
+extern "C" void ngpb_exposure_update(uint32_t n_images, float* states, const float* gradients, float per_camera_loss_scale, float l2_reg, float learning_rate) {
+	float mean[3] = {0.f, 0.f, 0.f};
+	for (uint32_t i = 0; i < n_images; ++i) {
+		float* st = states + (size_t)i * 10;
+		float g[3];
+		for (int c = 0; c < 3; ++c) g[c] = gradients[(size_t)i * 3 + c] * per_camera_loss_scale + st[7 + c] * l2_reg;
+		ngpb_camera_adam_step(st, g, learning_rate, 0);
+		for (int c = 0; c < 3; ++c) mean[c] += st[7 + c];
+	}
+	for (int c = 0; c < 3; ++c) mean[c] /= (float)n_images;
+	for (uint32_t i = 0; i < n_images; ++i) for (int c = 0; c < 3; ++c) states[(size_t)i * 10 + 7 + c] -= mean[c];
+}
+
 // Training::update_transforms (:2597-2633): the camera's transform = dataset transform with the rotation offset applied on the left of its 3x3 block and the
 // position offset added to its translation. xform12 in / out: 3x4 column-major.
 extern "C" void ngpb_apply_camera_offsets(const float* xform12, const float* pos_offset3, const float* rot_offset3, float* out12) {

@@ -157,6 +157,10 @@ __device__ __forceinline__ float srgb_to_linear(float srgb) {
 	if (srgb <= 0.04045f) return srgb / 12.92f;
 	return powf((srgb + 0.055f) / 1.055f, 2.4f);
 }
+__device__ __forceinline__ float srgb_to_linear_derivative(float srgb) {
+	if (srgb <= 0.04045f) return 1.0f / 12.92f;
+	return 2.4f / 1.055f * powf((srgb + 0.055f) / 1.055f, 1.4f);
+}
 __device__ __forceinline__ float linear_to_srgb(float linear) {
 	if (linear < 0.0031308f) return 12.92f * linear;
 	return 1.055f * powf(linear, 0.41666f) - 0.055f;

@@ -160,7 +160,7 @@ __device__ __forceinline__ uint32_t block_scan_warps(uint32_t v_warp, uint32_t* 
 // (A0) target colour and background of every ray, one THREAD per ray (:1378-1420): the pixel is recovered from the same RNG stream as K1, the
 // random background comes from the next three draws. Kept out of the warp-per-ray kernels, where all 32 lanes would repeat it.
 __global__ void __launch_bounds__(128) loss_target_kernel(const LossParams P, const ngpb_image* __restrict__ images, const uint32_t* __restrict__ counters_in,
-                                                          const uint32_t* __restrict__ ray_indices, RayState* __restrict__ state)
+                                                          const uint32_t* __restrict__ ray_indices, RayState* __restrict__ state, const float* __restrict__ exposure)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= P.n_rays || i >= counters_in[1]) return;
@@ -180,9 +180,15 @@ __global__ void __launch_bounds__(128) loss_target_kernel(const LossParams P, co
 		float texsamp[4];
 		read_rgba(x, y, im, texsamp);
 		float rgbtarget[3];
+		// exposure_scale = exp(ln 2 * exposure) per channel of the image (:1403); exactly 1 for a zero exposure
+		float es[3] = {1.0f, 1.0f, 1.0f};
+		if (exposure) {
+			#pragma unroll
+			for (int c = 0; c < 3; ++c) es[c] = expf(0.6931471805599453f * exposure[(size_t)img * 3 + c]);
+		}
 		if (P.cfg.linear_colors || P.cfg.color_space == NGPB_COLOR_LINEAR) {
 			#pragma unroll
-			for (int c = 0; c < 3; ++c) rgbtarget[c] = 1.0f * texsamp[c] + (1.0f - texsamp[3]) * bg[c];
+			for (int c = 0; c < 3; ++c) rgbtarget[c] = es[c] * texsamp[c] + (1.0f - texsamp[3]) * bg[c];
 			if (!P.cfg.linear_colors) {
 				#pragma unroll
 				for (int c = 0; c < 3; ++c) { rgbtarget[c] = linear_to_srgb(rgbtarget[c]); bg[c] = linear_to_srgb(bg[c]); }
@@ -192,7 +198,7 @@ __global__ void __launch_bounds__(128) loss_target_kernel(const LossParams P, co
 			for (int c = 0; c < 3; ++c) bg[c] = linear_to_srgb(bg[c]);
 			if (texsamp[3] > 0) {
 				#pragma unroll
-				for (int c = 0; c < 3; ++c) rgbtarget[c] = linear_to_srgb(1.0f * texsamp[c] / texsamp[3]) * texsamp[3] + (1.0f - texsamp[3]) * bg[c];
+				for (int c = 0; c < 3; ++c) rgbtarget[c] = linear_to_srgb(es[c] * texsamp[c] / texsamp[3]) * texsamp[3] + (1.0f - texsamp[3]) * bg[c];
 			} else {
 				#pragma unroll
 				for (int c = 0; c < 3; ++c) rgbtarget[c] = bg[c];
@@ -383,6 +389,28 @@ __global__ void __launch_bounds__(GRAD_BLOCK) loss_gradient_kernel(
 	}
 }
 
+// (C') gradient of the loss w.r.t. each image's exposure (:1558-1571), one thread per ray, only launched while exposures are being optimised. The loss
+// is symmetric in (prediction, target), so d loss / d target = -d loss / d prediction; training in sRGB adds the derivative of the transfer function.
+__global__ void __launch_bounds__(128) exposure_gradient_kernel(const LossParams P, const uint32_t* __restrict__ counters_in, const uint32_t* __restrict__ ray_indices,
+                                                                const uint32_t* __restrict__ numsteps, const RayState* __restrict__ state,
+                                                                const float* __restrict__ exposure, float* __restrict__ exposure_gradient)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= P.n_rays || i >= counters_in[1]) return;
+	if (numsteps[i * 2 + 0] == 0) return; // rays without a compacted sample leave the kernel before this point (:1438)
+	const RayState s = state[i];
+	const uint32_t img = image_idx(ray_indices[i], P.n_rays_global, P.n_images);
+	const LossAndGradient lg = loss_and_gradient(s.rgbtarget, s.rgb_ray, P.cfg.loss_type);
+	const float loss_scale = P.cfg.loss_scale / P.n_rays_global;
+	#pragma unroll
+	for (int c = 0; c < 3; ++c) {
+		float dloss_by_dgt = -lg.gradient[c];
+		if (!P.cfg.linear_colors) dloss_by_dgt /= srgb_to_linear_derivative(s.rgbtarget[c]);
+		const float es = expf(0.6931471805599453f * exposure[(size_t)img * 3 + c]);
+		atomicAdd(&exposure_gradient[(size_t)img * 3 + c], loss_scale * dloss_by_dgt * es * 0.6931471805599453f);
+	}
+}
+
 // (D) roll-over padding of the compacted batch (tcnn common_device.h:517-537): element e >= n_valid copies
 // element e % n_valid; gradients of the padded copies are rescaled by n_valid / batch.
 __global__ void __launch_bounds__(256) rollover_kernel(const uint32_t batch, const uint32_t* __restrict__ counters_out, float* __restrict__ coords, __half* __restrict__ dloss_dout,
@@ -412,7 +440,7 @@ int compute_loss_launch(void* stream_, uint32_t n_rays, uint32_t n_rays_global, 
                         uint32_t n_images, const ngpb_image* images_dev, const uint32_t* counters_in,
                         const ngpb_half* rgbsigma, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords_in,
                         const float* mean_density_dev, float* coords_out, ngpb_half* dloss_dout, float* loss_per_ray, uint32_t* counters_out, void* scratch,
-                        const ngpb_half* encoded_in, ngpb_half* encoded_out, bool rows_tiled);
+                        const ngpb_half* encoded_in, ngpb_half* encoded_out, bool rows_tiled, const float* exposure, float* exposure_gradient);
 
 } // namespace ngpb
 
@@ -444,7 +472,16 @@ extern "C" int ngpb_compute_loss_compact_features(void* stream_, uint32_t n_rays
                                  const float* mean_density_dev, float* coords_out, ngpb_half* dloss_dout, float* loss_per_ray, uint32_t* counters_out, void* scratch,
                                  const ngpb_half* encoded_in, ngpb_half* encoded_out) {
 	return ngpb::compute_loss_launch(stream_, n_rays, n_rays_global, aabb6, rng_, batch, cfg, n_images, images_dev, counters_in, rgbsigma, ray_indices, rays, numsteps, coords_in,
-		mean_density_dev, coords_out, dloss_dout, loss_per_ray, counters_out, scratch, encoded_in, encoded_out, false);
+		mean_density_dev, coords_out, dloss_dout, loss_per_ray, counters_out, scratch, encoded_in, encoded_out, false, nullptr, nullptr);
+}
+
+extern "C" int ngpb_compute_loss_exposure(void* stream_, uint32_t n_rays, uint32_t n_rays_global, const float* aabb6, ngpb_rng rng_, uint32_t batch, const ngpb_loss_config* cfg,
+                                 uint32_t n_images, const ngpb_image* images_dev, const uint32_t* counters_in,
+                                 const ngpb_half* rgbsigma, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords_in,
+                                 const float* mean_density_dev, float* coords_out, ngpb_half* dloss_dout, float* loss_per_ray, uint32_t* counters_out, void* scratch,
+                                 const float* exposure_dev, float* exposure_gradient_dev) {
+	return ngpb::compute_loss_launch(stream_, n_rays, n_rays_global, aabb6, rng_, batch, cfg, n_images, images_dev, counters_in, rgbsigma, ray_indices, rays, numsteps, coords_in,
+		mean_density_dev, coords_out, dloss_dout, loss_per_ray, counters_out, scratch, nullptr, nullptr, false, exposure_dev, exposure_gradient_dev);
 }
 
 // The implementation behind the C entry points; `rows_tiled` selects the layout of encoded_in / encoded_out (the testbed hands tiles from the hash-grid kernel to the MLP kernel).
@@ -452,8 +489,9 @@ int ngpb::compute_loss_launch(void* stream_, uint32_t n_rays, uint32_t n_rays_gl
                                  uint32_t n_images, const ngpb_image* images_dev, const uint32_t* counters_in,
                                  const ngpb_half* rgbsigma, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords_in,
                                  const float* mean_density_dev, float* coords_out, ngpb_half* dloss_dout, float* loss_per_ray, uint32_t* counters_out, void* scratch,
-                                 const ngpb_half* encoded_in, ngpb_half* encoded_out, bool rows_tiled) {
+                                 const ngpb_half* encoded_in, ngpb_half* encoded_out, bool rows_tiled, const float* exposure, float* exposure_gradient) {
 	try {
+		if (exposure_gradient && !exposure) { set_last_error("ngpb_compute_loss: an exposure gradient needs the exposures"); return NGPB_ERR_INVALID_ARGUMENT; }
 		if ((encoded_in == nullptr) != (encoded_out == nullptr) || (encoded_in && encoded_in == encoded_out)) {
 			set_last_error("ngpb_compute_loss: encoded_in and encoded_out must both be given, and differ");
 			return NGPB_ERR_INVALID_ARGUMENT;
@@ -485,7 +523,7 @@ int ngpb::compute_loss_launch(void* stream_, uint32_t n_rays, uint32_t n_rays_gl
 		}();
 		const uint32_t wc = lanes.first == 8 ? 8u : lanes.first == 32 ? 32u : 16u, wg = lanes.second == 16 ? 16u : lanes.second == 32 ? 32u : 8u;
 		const uint32_t rb_c = 1024 / wc, blocks_c = div_round_up(n_rays, rb_c), blocks_g = div_round_up(n_rays, GRAD_BLOCK / wg);
-		loss_target_kernel<<<div_round_up(n_rays, 128), 128, 0, stream>>>(P, images_dev, counters_in, ray_indices, state);
+		loss_target_kernel<<<div_round_up(n_rays, 128), 128, 0, stream>>>(P, images_dev, counters_in, ray_indices, state, exposure);
 		NGPB_LAUNCH_CHECK();
 		#define NGPB_COMPOSITE(W) loss_composite_kernel<W><<<blocks_c, 1024, 0, stream>>>(P, images_dev, counters_in, (const __half*)rgbsigma, ray_indices, numsteps, coords_in, state, counts, local_bases, block_sums)
 		if (wc == 8) NGPB_COMPOSITE(8); else if (wc == 16) NGPB_COMPOSITE(16); else NGPB_COMPOSITE(32);
@@ -498,6 +536,10 @@ int ngpb::compute_loss_launch(void* stream_, uint32_t n_rays, uint32_t n_rays_gl
 		if (wg == 8) NGPB_GRADIENT(8); else if (wg == 16) NGPB_GRADIENT(16); else NGPB_GRADIENT(32);
 		#undef NGPB_GRADIENT
 		NGPB_LAUNCH_CHECK();
+		if (exposure_gradient) {
+			exposure_gradient_kernel<<<div_round_up(n_rays, 128), 128, 0, stream>>>(P, counters_in, ray_indices, numsteps, state, exposure, exposure_gradient);
+			NGPB_LAUNCH_CHECK();
+		}
 		rollover_kernel<<<div_round_up(batch, 256), 256, 0, stream>>>(batch, counters_out, coords_out, (__half*)dloss_dout, reinterpret_cast<uint4*>(encoded_out), P.rows_tiled);
 		NGPB_LAUNCH_CHECK();
 		return 0;

@@ -22,7 +22,7 @@ int compute_loss_launch(void* stream_, uint32_t n_rays, uint32_t n_rays_global, 
                         uint32_t n_images, const ngpb_image* images_dev, const uint32_t* counters_in,
                         const ngpb_half* rgbsigma, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords_in,
                         const float* mean_density_dev, float* coords_out, ngpb_half* dloss_dout, float* loss_per_ray, uint32_t* counters_out, void* scratch,
-                        const ngpb_half* encoded_in, ngpb_half* encoded_out, bool rows_tiled);
+                        const ngpb_half* encoded_in, ngpb_half* encoded_out, bool rows_tiled, const float* exposure, float* exposure_gradient);
 void hash_encode_backward_launch(cudaStream_t stream, const ngpb_grid* g, const float* positions, uint32_t pos_stride, uint32_t n, const __half* dL_dencoded, float* grid_grad,
                                  uint32_t level_begin, uint32_t level_end);
 void optimizer_prepare(ngpb_optimizer* o, float loss_scale, void* params_out);
@@ -353,11 +353,14 @@ void ngpb_testbed::load_training_data(uint32_t n, const ngpb_host_image* host_im
 	}
 	images.resize(n);
 	dataset_xforms.assign((size_t)n * 12, 0.f);
-	dfree(cam_gradients);
-	cam_gradients = (float*)dalloc(sizeof(float) * 6 * n);
-	NGPB_CUDA_CHECK(cudaMemsetAsync(cam_gradients, 0, sizeof(float) * 6 * n, stream));
-	cam_gradients_host.assign((size_t)n * 6, 0.f);
-	cam_pos_state.assign((size_t)n * 10, 0.f); cam_rot_state.assign((size_t)n * 10, 0.f);
+	dfree(cam_gradients); dfree(cam_exposure);
+	cam_gradients = (float*)dalloc(sizeof(float) * 9 * n);
+	cam_exposure = (float*)dalloc(sizeof(float) * 3 * n);
+	NGPB_CUDA_CHECK(cudaMemsetAsync(cam_gradients, 0, sizeof(float) * 9 * n, stream));
+	NGPB_CUDA_CHECK(cudaMemsetAsync(cam_exposure, 0, sizeof(float) * 3 * n, stream));
+	cam_gradients_host.assign((size_t)n * 9, 0.f);
+	cam_pos_state.assign((size_t)n * 10, 0.f); cam_rot_state.assign((size_t)n * 10, 0.f); cam_exposure_state.assign((size_t)n * 10, 0.f);
+	exposure_active = false;
 	n_steps_since_cam_update = 0;
 	size_t off = 0;
 	for (uint32_t i = 0; i < n; ++i) {
@@ -408,6 +411,7 @@ void ngpb_testbed::reset_network(uint32_t seed_) {
 		for (size_t i = 0; i < images.size() && !moved; ++i) for (int c = 7; c < 10; ++c) moved |= cam_pos_state[i * 10 + c] != 0.f || cam_rot_state[i * 10 + c] != 0.f;
 		reset_camera_extrinsics();
 		if (moved) update_transforms();
+		if (exposure_active) upload_exposures();
 	}
 	n_steps_since_cam_update = 0;
 	const uint32_t n_levels = 16, base_resolution = 16;
@@ -711,7 +715,8 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 		if (poison & 512u) NGPB_CUDA_CHECK(cudaMemsetAsync(loss, 0xFF, sizeof(float) * max_rays, stream));
 		if (poison & 1024u) { NGPB_CUDA_CHECK(cudaMemsetAsync(rays, 0xFF, sizeof(float) * 6 * max_rays, stream)); NGPB_CUDA_CHECK(cudaMemsetAsync(numsteps, 0xFF, sizeof(uint32_t) * 2 * max_rays, stream)); NGPB_CUDA_CHECK(cudaMemsetAsync(ray_indices, 0xFF, sizeof(uint32_t) * max_rays, stream)); }
 	}
-	if (n_steps_since_cam_update == 0) NGPB_CUDA_CHECK(cudaMemsetAsync(cam_gradients, 0, sizeof(float) * 6 * images.size(), stream)); // :2916-2919
+	if (n_steps_since_cam_update == 0) NGPB_CUDA_CHECK(cudaMemsetAsync(cam_gradients, 0, sizeof(float) * 9 * images.size(), stream)); // :2916-2919
+	if (optimize_exposure) exposure_active = true;
 	const uint32_t R = rays_per_batch;
 	const SamplingRequest req{training_step, R, max_inference, ngpb_rng{rng.state, rng.inc}, loss_cfg.snap_to_pixel_centers, cone_angle_constant};
 	const ngpb_rng r = req.rng;
@@ -736,9 +741,10 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 	stage_begin(NGPB_STAGE_LOSS, stream);
 	check(compute_loss_launch(stream, R, (uint32_t)dp_world * R, aabb, r, batch, &loss_cfg, (uint32_t)images.size(), images_dev, counters, (const ngpb_half*)rgbsigma,
 		ray_indices, rays, numsteps, coords, mean_density, coords_compacted, (ngpb_half*)dloss, loss, counters + 2, scratch,
-		reuse_encoding ? (const ngpb_half*)encoded : nullptr, reuse_encoding ? (ngpb_half*)encoded_compacted : nullptr, tiled));
+		reuse_encoding ? (const ngpb_half*)encoded : nullptr, reuse_encoding ? (ngpb_half*)encoded_compacted : nullptr, tiled,
+		exposure_active ? cam_exposure : nullptr, optimize_exposure ? cam_gradients + 6 * images.size() : nullptr));
 	stage_end(NGPB_STAGE_LOSS, R, stream);
-	n_launches += 2 + 5; // encode, mlp; loss target / composite / scan / gradient / rollover
+	n_launches += 2 + 5 + (optimize_exposure ? 1 : 0); // encode, mlp; loss target / composite / scan / gradient / rollover (+ exposure gradient)
 	if (dp_world > 1) {
 		// the controller needs the GLOBAL sample counts so that every rank derives the same next ray count: sum {uncompacted, kept rays,
 		// compacted} into counters[8..10] (the local values stay in [0..2] for the kernels of this step)
@@ -900,7 +906,7 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 	++training_step;
 	rng.advance(); // m_rng.advance() (:3380)
 	++n_steps_since_cam_update; // (:3026)
-	if (optimize_extrinsics && n_steps_since_cam_update >= n_steps_between_cam_updates) camera_update_step();
+	if ((optimize_extrinsics || optimize_exposure) && n_steps_since_cam_update >= n_steps_between_cam_updates) camera_update_step();
 
 	// ---- batch-size controller (:2870-2894) ----
 	NGPB_CUDA_CHECK(cudaEventSynchronize(counters_ready));
@@ -976,14 +982,18 @@ void ngpb_testbed::camera_update_step() {
 	const size_t n = images.size();
 	if (dp_world > 1) {
 		NcclApi& nccl = NcclApi::get();
-		nccl.check(nccl.AllReduce(cam_gradients, cam_gradients, 6 * n, NcclApi::Float32, NcclApi::Sum, nccl_comm, stream), "ncclAllReduce(camera gradients)");
+		nccl.check(nccl.AllReduce(cam_gradients, cam_gradients, 9 * n, NcclApi::Float32, NcclApi::Sum, nccl_comm, stream), "ncclAllReduce(camera gradients)");
 	}
-	NGPB_CUDA_CHECK(cudaMemcpyAsync(cam_gradients_host.data(), cam_gradients, sizeof(float) * 6 * n, cudaMemcpyDeviceToHost, stream));
+	NGPB_CUDA_CHECK(cudaMemcpyAsync(cam_gradients_host.data(), cam_gradients, sizeof(float) * 9 * n, cudaMemcpyDeviceToHost, stream));
 	NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
-	d2h_bytes += sizeof(float) * 6 * n;
+	d2h_bytes += sizeof(float) * 9 * n;
 	const float per_camera_loss_scale = (float)n / LOSS_SCALE / (float)n_steps_between_cam_updates;
 	const float lr_floor = opt.learning_rate * opt.lr_factor / 1000.0f; // m_optimizer->learning_rate() / 1000
-	for (size_t i = 0; i < n; ++i) {
+	if (optimize_exposure) { // (:3105-3131)
+		ngpb_exposure_update((uint32_t)n, cam_exposure_state.data(), &cam_gradients_host[6 * n], per_camera_loss_scale, exposure_l2_reg, opt.learning_rate * opt.lr_factor);
+		upload_exposures();
+	}
+	for (size_t i = 0; optimize_extrinsics && i < n; ++i) {
 		float* ps = &cam_pos_state[i * 10]; float* rs = &cam_rot_state[i * 10];
 		float pg[3], rg[3];
 		for (int c = 0; c < 3; ++c) {
@@ -995,8 +1005,17 @@ void ngpb_testbed::camera_update_step() {
 		ngpb_camera_adam_step(ps, pg, lr_p, 0);
 		ngpb_camera_adam_step(rs, rg, lr_r, 1);
 	}
-	update_transforms();
+	if (optimize_extrinsics) update_transforms();
 	n_steps_since_cam_update = 0;
+}
+
+void ngpb_testbed::upload_exposures() {
+	const size_t n = images.size();
+	std::vector<float> e(n * 3);
+	for (size_t i = 0; i < n; ++i) for (int c = 0; c < 3; ++c) e[i * 3 + c] = cam_exposure_state[i * 10 + 7 + c];
+	NGPB_CUDA_CHECK(cudaMemcpyAsync(cam_exposure, e.data(), sizeof(float) * 3 * n, cudaMemcpyHostToDevice, stream));
+	NGPB_CUDA_CHECK(cudaStreamSynchronize(stream)); // (the staging vector is about to go away)
+	h2d_bytes += sizeof(float) * 3 * n;
 }
 
 // Training::update_transforms (:2597-2633): training transform = dataset transform with the camera's offsets applied; re-upload the image table.
@@ -1017,6 +1036,7 @@ void ngpb_testbed::update_transforms() {
 void ngpb_testbed::reset_camera_extrinsics() { // Training::reset_camera_extrinsics (:2543-2555)
 	std::fill(cam_pos_state.begin(), cam_pos_state.end(), 0.f);
 	std::fill(cam_rot_state.begin(), cam_rot_state.end(), 0.f);
+	std::fill(cam_exposure_state.begin(), cam_exposure_state.end(), 0.f);
 }
 
 void ngpb_testbed::get_params(float* o_fp32, ngpb_half* o_half, ngpb_half* o_ema) {
@@ -1207,6 +1227,24 @@ extern "C" int ngpb_testbed_reset_camera_extrinsics(ngpb_testbed* t) {
 	NGPB_API_BEGIN
 	t->reset_camera_extrinsics();
 	t->update_transforms();
+	if (t->exposure_active) t->upload_exposures();
+	NGPB_API_END
+}
+// Per-image exposures (Training::cam_exposure, testbed.h:632): exposures3[n_images][3], in stops (the loss sees colours x 2^exposure).
+extern "C" int ngpb_testbed_get_camera_exposures(ngpb_testbed* t, float* exposures3) {
+	NGPB_API_BEGIN
+	if (!exposures3) throw std::runtime_error("get_camera_exposures: invalid argument");
+	for (size_t i = 0; i < t->images.size(); ++i) for (int c = 0; c < 3; ++c) exposures3[i * 3 + c] = t->cam_exposure_state[i * 10 + 7 + c];
+	NGPB_API_END
+}
+extern "C" int ngpb_testbed_set_camera_exposures(ngpb_testbed* t, const float* exposures3) {
+	NGPB_API_BEGIN
+	if (!exposures3 || t->images.empty()) throw std::runtime_error("set_camera_exposures: invalid argument");
+	NGPB_CUDA_CHECK(cudaSetDevice(t->device));
+	std::fill(t->cam_exposure_state.begin(), t->cam_exposure_state.end(), 0.f); // (fresh optimizer state, as Training::set_camera_extrinsics does for a frame)
+	for (size_t i = 0; i < t->images.size(); ++i) for (int c = 0; c < 3; ++c) t->cam_exposure_state[i * 10 + 7 + c] = exposures3[i * 3 + c];
+	t->exposure_active = true;
+	t->upload_exposures();
 	NGPB_API_END
 }
 
@@ -1258,6 +1296,8 @@ extern "C" int ngpb_testbed_set_option(ngpb_testbed* t, const char* name, double
 		t->log2_hashmap_size = (uint32_t)v; // takes effect at the next reset_network
 	}
 	else if (k == "optimize_extrinsics") t->optimize_extrinsics = v != 0;
+	else if (k == "optimize_exposure") t->optimize_exposure = v != 0;
+	else if (k == "exposure_l2_reg") t->exposure_l2_reg = (float)v;
 	else if (k == "extrinsic_learning_rate") t->extrinsic_learning_rate = (float)v;
 	else if (k == "extrinsic_l2_reg") t->extrinsic_l2_reg = (float)v;
 	else if (k == "n_steps_between_cam_updates") { if (v < 1) throw std::runtime_error("n_steps_between_cam_updates must be >= 1"); t->n_steps_between_cam_updates = (uint32_t)v; }
@@ -1301,6 +1341,9 @@ extern "C" double ngpb_testbed_get_option(ngpb_testbed* t, const char* name) {
 	if (k == "decay_base") return t->opt.decay_base;
 	if (k == "log2_hashmap_size") return t->log2_hashmap_size;
 	if (k == "optimize_extrinsics") return t->optimize_extrinsics;
+	if (k == "optimize_exposure") return t->optimize_exposure;
+	if (k == "n_images") return (double)t->images.size();
+	if (k == "exposure_l2_reg") return t->exposure_l2_reg;
 	if (k == "extrinsic_learning_rate") return t->extrinsic_learning_rate;
 	if (k == "extrinsic_l2_reg") return t->extrinsic_l2_reg;
 	if (k == "n_steps_between_cam_updates") return t->n_steps_between_cam_updates;

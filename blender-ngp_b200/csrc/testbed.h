@@ -92,8 +92,16 @@ struct ngpb_testbed {
 	uint32_t n_steps_since_cam_update = 0, n_steps_between_cam_updates = 16;
 	std::vector<float> dataset_xforms;                // [n_images][12]: the transforms as loaded (dataset.xforms); images[i].raw_xform = these + offsets
 	std::vector<float> cam_pos_state, cam_rot_state;  // [n_images][10]: {iter, m1[3], m2[3], variable[3]} of ngpb_camera_adam_step
-	std::vector<float> cam_gradients_host;            // [2][n_images][3]
-	float* cam_gradients = nullptr;                   // device, [2][n_images][3]: position then rotation
+	std::vector<float> cam_gradients_host;            // [3][n_images][3]
+	float* cam_gradients = nullptr;                   // device, [3][n_images][3]: position, rotation, exposure
+	// per-image exposure optimisation (train_nerf :3105-3131): 2^exposure scales the image's colours in the loss (K6 :1403); the gradient accumulates in
+	// cam_gradients[2] and a host Adam (learning rate of the network optimizer) moves the exposures, which are then re-centred on a zero mean
+	bool optimize_exposure = false;
+	float exposure_l2_reg = 0.0f;
+	bool exposure_active = false;                     // the loss kernels read cam_exposure (set once exposures are optimised or set)
+	std::vector<float> cam_exposure_state;            // [n_images][10], as cam_pos_state
+	float* cam_exposure = nullptr;                    // device, [n_images][3]
+	void upload_exposures();
 	float* coords_gradient = nullptr; __half* dL_dsh = nullptr; // workspace, sized by the batch (allocated on first use)
 	void reset_camera_extrinsics();
 	void update_transforms();

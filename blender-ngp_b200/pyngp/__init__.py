@@ -431,6 +431,7 @@ EXPORTED_SYMBOLS = [
     "ngpb_field_create", "ngpb_field_destroy", "ngpb_blender_render", "ngpb_compute_loss_compact_features", "ngpb_grid_init_nd", "ngpb_mlp_forward", "ngpb_mlp_forward_backward", "ngpb_loss",
     "ngpb_nerf_mlp_forward_backward_sh", "ngpb_nerf_input_gradient", "ngpb_compute_cam_gradient", "ngpb_camera_adam_step", "ngpb_apply_camera_offsets",
     "ngpb_testbed_get_camera_extrinsics", "ngpb_testbed_set_camera_extrinsics", "ngpb_testbed_reset_camera_extrinsics", "ngpb_probe_umma",
+    "ngpb_exposure_update", "ngpb_compute_loss_exposure", "ngpb_testbed_get_camera_exposures", "ngpb_testbed_set_camera_exposures",
     "ngpb_model_create", "ngpb_model_destroy", "ngpb_model_reset", "ngpb_model_n_params", "ngpb_model_training_step", "ngpb_model_loss", "ngpb_model_launches", "ngpb_model_stream",
     "ngpb_model_set_option", "ngpb_model_get_params", "ngpb_model_set_params_half", "ngpb_model_set_training_step", "ngpb_model_train", "ngpb_model_inference",
     "ngpb_model_set_image", "ngpb_model_set_image_rgba8", "ngpb_model_train_image", "ngpb_model_image_mse", "ngpb_model_render_image", "ngpb_model_set_sdf_data",
@@ -500,6 +501,10 @@ def lib():
         l.ngpb_testbed_get_camera_extrinsics.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         l.ngpb_testbed_set_camera_extrinsics.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         l.ngpb_testbed_reset_camera_extrinsics.argtypes = [C.c_void_p]
+        l.ngpb_exposure_update.restype = None
+        l.ngpb_exposure_update.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float]
+        l.ngpb_testbed_get_camera_exposures.argtypes = [C.c_void_p, C.c_void_p]
+        l.ngpb_testbed_set_camera_exposures.argtypes = [C.c_void_p, C.c_void_p]
         _lib = l
     return _lib
 
@@ -811,6 +816,22 @@ class _Training:
 
     def reset_camera_extrinsics(self):
         check(lib().ngpb_testbed_reset_camera_extrinsics(self._tb._h))
+
+    # per-image exposure optimisation (python_api.cu:813,:827; train_nerf :3105-3131)
+    optimize_exposure = _bool_prop("optimize_exposure")
+    exposure_l2_reg = property(lambda s: s._tb._get("exposure_l2_reg"), lambda s, v: s._tb._set("exposure_l2_reg", float(v)))
+
+    def get_camera_exposures(self):
+        """The learned per-image exposures in stops, [n_images, 3] (cam_exposure[i].variable(), testbed.h:632). The reference only plots these in
+        its GUI (src/testbed.cu:879-885); this accessor is an addition."""
+        out = np.zeros((int(self._tb._get("n_images")), 3), np.float32)
+        check(lib().ngpb_testbed_get_camera_exposures(self._tb._h, out.ctypes.data))
+        return out
+
+    def set_camera_exposures(self, exposures):
+        """Replaces the per-image exposures (and resets their optimizer state). An addition, like get_camera_exposures."""
+        e = np.ascontiguousarray(np.asarray(exposures, np.float32).reshape(int(self._tb._get("n_images")), 3))
+        check(lib().ngpb_testbed_set_camera_exposures(self._tb._h, e.ctypes.data))
 
 
 class _Nerf:

@@ -342,6 +342,23 @@ void ngpb_camera_adam_step(float* state10, const float* gradient3, float learnin
 /* Host-side: Training::update_transforms for one camera (src/testbed_nerf.cu:2597-2633): out = dataset transform (3x4 column-major) with the rotation
  * offset (angle-axis) applied on the left of its 3x3 block and the position offset added to its translation. */
 void ngpb_apply_camera_offsets(const float* xform12, const float* pos_offset3, const float* rot_offset3, float* out12);
+/* Host-side: the exposure block of Testbed::train_nerf (src/testbed_nerf.cu:3105-3131): one AdamOptimizer<Array3f> step per image on
+ * gradient * per_camera_loss_scale + l2_reg * exposure, then the exposures are re-centred on a zero mean. states [n_images][10] as
+ * ngpb_camera_adam_step, gradients [n_images][3] (what K6 accumulated over the last n_steps_between_cam_updates steps). */
+void ngpb_exposure_update(uint32_t n_images, float* states, const float* gradients, float per_camera_loss_scale, float l2_reg, float learning_rate);
+/* K6 with per-image exposures (src/testbed_nerf.cu:1326-1327,:1403,:1558-1571): exposure_dev [n_images][3] (in stops; the target colour of a ray
+ * is its image's colour x 2^exposure) and, when exposure_gradient_dev [n_images][3] is given, the gradient of the loss w.r.t. the exposures is
+ * accumulated into it (atomicAdd, scaled by loss_scale / n_rays_global like the network gradients). Otherwise as ngpb_compute_loss_sharded. */
+int ngpb_compute_loss_exposure(void* stream, uint32_t n_rays, uint32_t n_rays_global, const float* aabb6, ngpb_rng rng, uint32_t batch, const ngpb_loss_config* cfg,
+                               uint32_t n_images, const ngpb_image* images_dev, const uint32_t* counters_in,
+                               const ngpb_half* rgbsigma, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords_in,
+                               const float* mean_density_dev, float* coords_out, ngpb_half* dloss_dout, float* loss_per_ray, uint32_t* counters_out, void* scratch,
+                               const float* exposure_dev, float* exposure_gradient_dev);
+/* Options "optimize_exposure" and "exposure_l2_reg" (ngpb_testbed_set_option) switch the per-image exposure optimisation on inside ngpb_testbed_train
+ * (same 16-step cadence as the extrinsics; Adam at the network optimizer's learning rate). The reference shows the exposures only in its GUI; these two
+ * calls read / replace them: exposures3 [n_images][3]. Setting exposures resets their optimizer state. */
+int ngpb_testbed_get_camera_exposures(ngpb_testbed* t, float* exposures3);
+int ngpb_testbed_set_camera_exposures(ngpb_testbed* t, const float* exposures3);
 /* Options "optimize_extrinsics", "extrinsic_learning_rate", "extrinsic_l2_reg", "n_steps_between_cam_updates" (ngpb_testbed_set_option) switch the
  * per-camera optimisation on inside ngpb_testbed_train. The current training transform of a frame (dataset transform + learned offsets, ngp coordinates),
  * and the offsets themselves (any pointer may be NULL): */

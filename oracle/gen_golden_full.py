@@ -598,12 +598,48 @@ def gen_modes_speed(out_dir, steps=600, timed=400):
         json.dump(report, f, indent=1)
 
 
+def gen_exposure(out_dir):
+    """Per-image exposure optimisation (nerf.training.optimize_exposure) of the REFERENCE on the small synthetic scene whose images carry the exposure
+    errors of tests/golden_inputs.py:exposure_scene_offsets -> ref_exposure_train.npz: the learned exposures every 500 steps (frame order = the loaders'
+    file_path order) and the loss. This repo's run of the same protocol is printed next to it."""
+    import synthetic
+    import pyngp
+    from golden_inputs import EXPOSURE_SCENE, exposure_scene_offsets, apply_image_exposures
+    n, res, B, steps = EXPOSURE_SCENE["n_images"], EXPOSURE_SCENE["res"], EXPOSURE_SCENE["batch"], EXPOSURE_SCENE["steps"]
+    scratch = "/tmp/ngpb_ref_exposure"
+    shutil.rmtree(scratch, ignore_errors=True)
+    scene = synthetic.make_lego_scene(n, res, seed=0)
+    e = exposure_scene_offsets(n)
+    scene = dict(scene); scene["images"] = apply_image_exposures(np.asarray(scene["images"]), e)
+    tj = synthetic.write_transforms_json(scene, scratch)
+    order = sorted(range(n), key=lambda i: f"./train/r_{i}")
+    ref = Ref()
+    ref.load(tj)
+    ref.network(base_config())
+    ref.set(shall_train=1, optimize_exposure=1)
+    learned, losses = [], []
+    for _ in range(steps // 500):
+        losses.append(ref.train(B, 500))
+        o = np.zeros((n, 3), np.float32); ref.ck(ref.l.reff_get_exposures(ref.h, o.ctypes.data_as(C.c_void_p))); learned.append(o)
+    want = -(e[order] - e[order].mean(0))
+    print("reference: loss", losses, "rms(learned - expected)", float(np.sqrt(np.mean((learned[-1] - want) ** 2))), "rms(expected)", float(np.sqrt(np.mean(want ** 2))))
+    np.savez_compressed(os.path.join(out_dir, "ref_exposure_train.npz"), offsets=e, order=np.array(order, np.int32), learned=np.stack(learned), losses=np.array(losses, np.float32))
+    tb = pyngp.Testbed()
+    tb.load_training_data(tj)
+    tb.nerf.training.optimize_exposure = True
+    for k in range(steps // 500):
+        tb.train_n(500, B)
+        o = tb.nerf.training.get_camera_exposures()
+        print(f"ours after {tb.training_step}: loss {tb.loss:.6f} rms(ours - reference) {float(np.sqrt(np.mean((o - learned[k]) ** 2))):.4f} rms(ours - expected) {float(np.sqrt(np.mean((o - want) ** 2))):.4f}"
+              f" corr {float(np.corrcoef(o.ravel(), learned[k].ravel())[0, 1]):.4f}")
+
+
 if __name__ == "__main__":
     out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden_full")
     os.makedirs(out, exist_ok=True)
     jobs = sys.argv[2:] or ["small", "big"]
     for j in jobs:
         try:
-            dict(small=gen_small, big=gen_big, config3=gen_config3, modes=gen_modes, modes_speed=gen_modes_speed)[j](out)
+            dict(small=gen_small, big=gen_big, config3=gen_config3, modes=gen_modes, modes_speed=gen_modes_speed, exposure=gen_exposure)[j](out)
         except Exception:
             traceback.print_exc()

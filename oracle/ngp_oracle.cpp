@@ -74,6 +74,10 @@ inline float srgb_to_linear(float srgb) {
 	if (srgb <= 0.04045f) return srgb / 12.92f;
 	return std::pow((srgb + 0.055f) / 1.055f, 2.4f);
 }
+inline float srgb_to_linear_derivative(float srgb) { // common_device.cuh:43-49
+	if (srgb <= 0.04045f) return 1.0f / 12.92f;
+	return 2.4f / 1.055f * std::pow((srgb + 0.055f) / 1.055f, 1.4f);
+}
 inline float linear_to_srgb(float linear) {
 	if (linear < 0.0031308f) return 12.92f * linear;
 	return 1.055f * std::pow(linear, 0.41666f) - 0.055f;
@@ -847,17 +851,20 @@ extern "C" uint32_t orc_generate_training_samples_sharded(
 // =============================================================================================
 // K6: compute_loss_kernel_train_nerf, src/testbed_nerf.cu:1280-1597
 // =============================================================================================
-extern "C" uint32_t orc_compute_loss(
+// `exposure` (3 floats per image, null = all zero) scales the target colour by 2^exposure (:1403); `exposure_gradient` (3 floats per image, null = off)
+// accumulates d loss / d exposure per image (:1558-1571).
+extern "C" uint32_t orc_compute_loss_exposure(
 	uint32_t n_rays_kept, uint32_t n_rays, const float* aabb6, uint32_t n_rays_total, orc_pcg32 rng, uint32_t max_samples_compacted,
 	float loss_scale_in, const float* background_color3, int color_space, int random_bg, int linear_colors,
 	uint32_t n_images, const orc_image* images, const orc_half* rgbsigma, const uint32_t* ray_indices, const float* rays,
 	uint32_t* numsteps_io, const float* coords_in_all, float* coords_out_all, orc_half* dloss_dout_all, int loss_type, float* loss_output,
-	int rgb_activation, int density_activation, int snap_to_pixel_centers, float mean_density, float near_distance) {
+	int rgb_activation, int density_activation, int snap_to_pixel_centers, float mean_density, float near_distance,
+	const float* exposure, float* exposure_gradient) {
 	(void)n_rays_total;
 	const AABB aabb = make_aabb(aabb6);
 	const float EPSILON = 1e-4f;
 
-	struct PerRay { float rgb_ray[3]; float depth_ray; uint32_t compacted; float rgbtarget[3]; };
+	struct PerRay { float rgb_ray[3]; float depth_ray; uint32_t compacted; float rgbtarget[3]; float exposure_scale[3]; uint32_t img; };
 	std::vector<PerRay> pr(n_rays_kept);
 
 	// phase 1 (parallel): forward compositing + target colour (:1341-1428)
@@ -898,22 +905,23 @@ extern "C" uint32_t orc_compute_loss(
 		float texsamp[4];
 		read_rgba(x, y, im, texsamp);
 		float rgbtarget[3];
-		// exposure is zero: exposure_scale = exp(0.693..*0) = 1 (:1403)
+		float es[3] = {1.0f, 1.0f, 1.0f}; // exposure_scale = exp(0.693.. * exposure) (:1403); exp(0) = 1
+		if (exposure) { for (int c = 0; c < 3; ++c) es[c] = std::exp(0.6931471805599453f * exposure[(size_t)img * 3 + c]); }
 		if (linear_colors || color_space == 0) {
-			for (int c = 0; c < 3; ++c) rgbtarget[c] = 1.0f * texsamp[c] + (1.0f - texsamp[3]) * bg[c];
+			for (int c = 0; c < 3; ++c) rgbtarget[c] = es[c] * texsamp[c] + (1.0f - texsamp[3]) * bg[c];
 			if (!linear_colors) { for (int c = 0; c < 3; ++c) { rgbtarget[c] = linear_to_srgb(rgbtarget[c]); bg[c] = linear_to_srgb(bg[c]); } }
 		} else {
 			for (int c = 0; c < 3; ++c) bg[c] = linear_to_srgb(bg[c]);
 			if (texsamp[3] > 0) {
-				for (int c = 0; c < 3; ++c) rgbtarget[c] = linear_to_srgb(1.0f * texsamp[c] / texsamp[3]) * texsamp[3] + (1.0f - texsamp[3]) * bg[c];
+				for (int c = 0; c < 3; ++c) rgbtarget[c] = linear_to_srgb(es[c] * texsamp[c] / texsamp[3]) * texsamp[3] + (1.0f - texsamp[3]) * bg[c];
 			} else {
 				for (int c = 0; c < 3; ++c) rgbtarget[c] = bg[c];
 			}
 		}
 		if (cn == numsteps) { for (int c = 0; c < 3; ++c) rgb_ray[c] += T * bg[c]; }
 		PerRay& p = pr[i];
-		for (int c = 0; c < 3; ++c) { p.rgb_ray[c] = rgb_ray[c]; p.rgbtarget[c] = rgbtarget[c]; }
-		p.depth_ray = depth_ray; p.compacted = cn;
+		for (int c = 0; c < 3; ++c) { p.rgb_ray[c] = rgb_ray[c]; p.rgbtarget[c] = rgbtarget[c]; p.exposure_scale[c] = es[c]; }
+		p.depth_ray = depth_ray; p.compacted = cn; p.img = img;
 	}
 
 	// compaction in ray-slot order (one valid serialisation of the atomicAdd at :1434)
@@ -987,8 +995,28 @@ extern "C" uint32_t orc_compute_loss(
 				(o3 > -10.0f && depth < near_distance ? 1e-4f : 0.0f));
 			no += 4;
 		}
+		if (exposure_gradient) { // :1558-1571 (xy_pdf = 1 without an error map)
+			for (int c = 0; c < 3; ++c) {
+				float dloss_by_dgt = -lg.gradient[c];
+				if (!linear_colors) dloss_by_dgt /= srgb_to_linear_derivative(p.rgbtarget[c]);
+				const float g = loss_scale * dloss_by_dgt * p.exposure_scale[c] * 0.6931471805599453f;
+				#pragma omp atomic
+				exposure_gradient[(size_t)p.img * 3 + c] += g;
+			}
+		}
 	}
 	return counter;
+}
+
+extern "C" uint32_t orc_compute_loss(
+	uint32_t n_rays_kept, uint32_t n_rays, const float* aabb6, uint32_t n_rays_total, orc_pcg32 rng, uint32_t max_samples_compacted,
+	float loss_scale_in, const float* background_color3, int color_space, int random_bg, int linear_colors,
+	uint32_t n_images, const orc_image* images, const orc_half* rgbsigma, const uint32_t* ray_indices, const float* rays,
+	uint32_t* numsteps_io, const float* coords_in_all, float* coords_out_all, orc_half* dloss_dout_all, int loss_type, float* loss_output,
+	int rgb_activation, int density_activation, int snap_to_pixel_centers, float mean_density, float near_distance) {
+	return orc_compute_loss_exposure(n_rays_kept, n_rays, aabb6, n_rays_total, rng, max_samples_compacted, loss_scale_in, background_color3, color_space, random_bg, linear_colors,
+		n_images, images, rgbsigma, ray_indices, rays, numsteps_io, coords_in_all, coords_out_all, dloss_dout_all, loss_type, loss_output,
+		rgb_activation, density_activation, snap_to_pixel_centers, mean_density, near_distance, nullptr, nullptr);
 }
 
 // K7: fill_rollover / fill_rollover_and_rescale, tcnn common_device.h:517-537

@@ -110,6 +110,15 @@ uint32_t orc_compute_loss(
 	uint32_t n_images, const orc_image* images, const orc_half* rgbsigma /*[.][4]*/, const uint32_t* ray_indices, const float* rays,
 	uint32_t* numsteps, const float* coords_in, float* coords_out, orc_half* dloss_dout /*[.][4]*/, int loss_type, float* loss_output,
 	int rgb_activation, int density_activation, int snap_to_pixel_centers, float mean_density, float near_distance);
+// The same with per-image exposures (3 floats per image, null = zero; :1403) and, when `exposure_gradient` is given, the accumulated
+// d loss / d exposure per image (:1558-1571) that Testbed::train_nerf hands to the per-image Adam optimisers (:3105-3131).
+uint32_t orc_compute_loss_exposure(
+	uint32_t n_rays_kept, uint32_t n_rays, const float* aabb6, uint32_t n_rays_total, orc_pcg32 rng, uint32_t max_samples_compacted,
+	float loss_scale, const float* background_color3, int color_space, int random_bg, int linear_colors,
+	uint32_t n_images, const orc_image* images, const orc_half* rgbsigma /*[.][4]*/, const uint32_t* ray_indices, const float* rays,
+	uint32_t* numsteps, const float* coords_in, float* coords_out, orc_half* dloss_dout /*[.][4]*/, int loss_type, float* loss_output,
+	int rgb_activation, int density_activation, int snap_to_pixel_centers, float mean_density, float near_distance,
+	const float* exposure, float* exposure_gradient);
 // K7: tcnn common_device.h:517-537
 void orc_fill_rollover(uint32_t n_target, uint32_t n_valid, float* coords /*[.][7]*/, orc_half* dloss_dout /*[.][4]*/);
 

@@ -53,6 +53,7 @@ def lib():
         _LIB.orc_grid_offsets.restype = C.c_uint32
         _LIB.orc_generate_training_samples.restype = C.c_uint32
         _LIB.orc_compute_loss.restype = C.c_uint32
+        _LIB.orc_compute_loss_exposure.restype = C.c_uint32
         _LIB.orc_density_grid_mean.restype = C.c_float
         _LIB.orc_trainer_create.restype = C.c_void_p
         _LIB.orc_trainer_n_params.restype = C.c_uint32
@@ -235,16 +236,19 @@ def generate_training_samples(n_rays, aabb6, max_samples, rng, images, bitfield,
 
 def compute_loss(n_kept, n_rays, aabb6, rng, batch, images, rgbsigma, ray_indices, rays, numsteps, coords_in, mean_density,
                  loss_scale=128.0, background=(0, 0, 0), color_space=1, random_bg=True, linear_colors=False, loss_type=4,
-                 rgb_activation=2, density_activation=3, snap=True, near_distance=0.2):
+                 rgb_activation=2, density_activation=3, snap=True, near_distance=0.2, exposure=None, want_exposure_gradient=False):
     aabb6 = _f32(aabb6)
     numsteps = np.array(numsteps, dtype=np.uint32, copy=True)
     coords_out = np.zeros((batch, 7), np.float32); dloss = np.zeros((batch, 4), np.float16); loss = np.zeros(n_rays, np.float32)
     bg = _f32(background)
-    total = lib().orc_compute_loss(n_kept, n_rays, _p(aabb6), 0, rng, batch, C.c_float(loss_scale), _p(bg), color_space, int(random_bg), int(linear_colors),
+    exposure = None if exposure is None else _f32(exposure).reshape(len(images), 3)
+    exposure_gradient = np.zeros((len(images), 3), np.float32) if want_exposure_gradient else None
+    total = lib().orc_compute_loss_exposure(n_kept, n_rays, _p(aabb6), 0, rng, batch, C.c_float(loss_scale), _p(bg), color_space, int(random_bg), int(linear_colors),
                                    len(images), images, _p(np.ascontiguousarray(rgbsigma, dtype=np.float16)), _p(np.ascontiguousarray(ray_indices, dtype=np.uint32)),
                                    _p(_f32(rays)), _p(numsteps), _p(_f32(coords_in)), _p(coords_out), _p(dloss), loss_type, _p(loss),
-                                   rgb_activation, density_activation, int(snap), C.c_float(mean_density), C.c_float(near_distance))
-    return dict(compacted=total, numsteps=numsteps, coords_out=coords_out, dloss=dloss, loss=loss)
+                                   rgb_activation, density_activation, int(snap), C.c_float(mean_density), C.c_float(near_distance),
+                                   None if exposure is None else _p(exposure), None if exposure_gradient is None else _p(exposure_gradient))
+    return dict(compacted=total, numsteps=numsteps, coords_out=coords_out, dloss=dloss, loss=loss, exposure_gradient=exposure_gradient)
 
 
 def fill_rollover(batch, n_valid, coords, dloss):

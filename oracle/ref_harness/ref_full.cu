@@ -200,6 +200,16 @@ int reff_get_camera_extrinsics(void* tp, int frame, float* out12) {
 	REFF_END
 }
 
+// learned per-image exposures (m_nerf.training.cam_exposure[i].variable(), testbed.h:632): out[n_images][3]
+int reff_get_exposures(void* tp, float* out) {
+	REFF_BEGIN
+	Testbed* t = (Testbed*)tp;
+	for (size_t i = 0; i < t->m_nerf.training.cam_exposure.size(); ++i) {
+		auto v = t->m_nerf.training.cam_exposure[i].variable();
+		for (int c = 0; c < 3; ++c) out[i * 3 + c] = v[c];
+	}
+	REFF_END
+}
 
 // ---- neural-image and SDF modes (reff_create with mode 2 / 1): what the parity tests need beyond load / train / render / snapshots ----
 // the batch Testbed::train_image just trained on (m_image.training.positions / targets, src/testbed_image.cu:228-272)

@@ -146,6 +146,42 @@ int ref_compute_loss(
 	return (int)cudaDeviceSynchronize();
 }
 
+// The same kernel with per-image exposures (host float[n_images*3]) and the accumulated exposure gradient (host float[n_images*3], out):
+// src/testbed_nerf.cu:1403,:1558-1571.
+int ref_compute_loss_exposure(
+	uint32_t n_rays, const float* aabb6, uint32_t n_rays_total, uint64_t rng_state, uint64_t rng_inc,
+	uint32_t max_samples_compacted, const uint32_t* rays_counter, float loss_scale, int padded_output_width,
+	const float* background_color3, int color_space, int random_bg, int linear_colors,
+	uint32_t n_images, int w, int h, float fx, float fy, float cx, float cy, const uint8_t* pixels, const float* xforms_host,
+	const void* network_output_half, uint32_t* numsteps_counter_compacted, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps,
+	const float* coords_in, float* coords_out, void* dloss_doutput_half, int loss_type, float* loss_output,
+	int rgb_activation, int density_activation, int snap_to_pixel_centers, const float* mean_density_ptr, float near_distance,
+	const float* exposure_host, float* exposure_gradient_host
+) {
+	DeviceDataset d = make_dataset(n_images, w, h, fx, fy, cx, cy, pixels, xforms_host);
+	default_rng_t rng; rng.state = rng_state; rng.inc = rng_inc;
+	GPUMemory<Array3f> exposure(n_images), exposure_gradient(n_images);
+	cudaMemcpy(exposure.data(), exposure_host, (size_t)n_images * 12, cudaMemcpyHostToDevice);
+	exposure_gradient.memset(0);
+	cudaMemset(numsteps_counter_compacted, 0, 4);
+	linear_kernel(compute_loss_kernel_train_nerf, 0, 0,
+		n_rays, make_aabb(aabb6), n_rays_total, rng, max_samples_compacted, rays_counter, loss_scale, padded_output_width,
+		(const float*)nullptr, (float*)nullptr, Vector2i{0, 0}, ELossType::L2,
+		Array3f{background_color3[0], background_color3[1], background_color3[2]}, (EColorSpace)color_space, (bool)random_bg, (bool)linear_colors,
+		n_images, d.metadata.data(), (const network_precision_t*)network_output_half, numsteps_counter_compacted,
+		ray_indices, (const Ray*)rays, numsteps,
+		PitchedPtr<const NerfCoordinate>((NerfCoordinate*)coords_in, 1, 0, 0),
+		PitchedPtr<NerfCoordinate>((NerfCoordinate*)coords_out, 1, 0, 0),
+		(network_precision_t*)dloss_doutput_half, (ELossType)loss_type, ELossType::L1, loss_output,
+		false, (float*)nullptr, (ENerfActivation)rgb_activation, (ENerfActivation)density_activation, (bool)snap_to_pixel_centers,
+		(float*)nullptr, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, Vector2i{0, 0}, Vector2i{0, 0},
+		(const float*)nullptr, Vector2i{0, 0}, (float*)nullptr, (float*)nullptr, mean_density_ptr,
+		(const Array3f*)exposure.data(), exposure_gradient.data(), 0.0f, near_distance);
+	int st = (int)cudaDeviceSynchronize();
+	cudaMemcpy(exposure_gradient_host, exposure_gradient.data(), (size_t)n_images * 12, cudaMemcpyDeviceToHost);
+	return st;
+}
+
 // Timing variant: see ref_generate_training_samples_timed.
 int ref_compute_loss_timed(
 	uint32_t n_rays, const float* aabb6, uint32_t n_rays_total, uint64_t rng_state, uint64_t rng_inc,

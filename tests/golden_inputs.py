@@ -159,3 +159,40 @@ def sdf_pool(seed=9):
     q = np.abs(pos - np.array([0.65, 0.5, 0.5], np.float32)) - np.array([0.15, 0.2, 0.1], np.float32)
     d_box = np.linalg.norm(np.maximum(q, 0), axis=1) + np.minimum(q.max(1), 0)
     return pos, np.minimum(d_sphere, d_box).astype(np.float32)
+
+
+# ---- per-image exposures (K6 exposure term + the host-side exposure optimizer; src/testbed_nerf.cu:1403,:1558-1571,:3105-3131) ----
+EXPOSURE_UPDATES = 200          # camera-update rounds of the host-side golden
+EXPOSURE_N_IMAGES = 8
+EXPOSURE_L2_REG = 1e-3
+EXPOSURE_PER_CAMERA_LOSS_SCALE = 8.0 / 128.0 / 16.0  # n_images / LOSS_SCALE / n_steps_between_cam_updates
+
+
+def exposure_inputs(n_images=EXPOSURE_N_IMAGES, seed=11):
+    """exposures [n_images][3] in stops for the K6 golden; gradients [EXPOSURE_UPDATES][n_images][3] and learning rates for the optimizer golden."""
+    rs = np.random.RandomState(seed)
+    exposures = rs.uniform(-1.0, 1.0, (n_images, 3)).astype(np.float32)
+    gradients = (rs.randn(EXPOSURE_UPDATES, n_images, 3) * np.exp(rs.uniform(-3, 3, (EXPOSURE_UPDATES, n_images, 1)))).astype(np.float32)
+    learning_rates = np.where(np.arange(EXPOSURE_UPDATES) < 120, 1e-2, 3.3e-3).astype(np.float32)
+    return dict(exposures=exposures, gradients=gradients, learning_rates=learning_rates)
+
+
+# ---- end-to-end exposure optimisation (tests/golden/ref_exposure_train.npz: the reference's learned exposures on this dataset) ----
+EXPOSURE_SCENE = dict(n_images=24, res=96, batch=1 << 16, steps=2000)
+
+
+def exposure_scene_offsets(n_images=EXPOSURE_SCENE["n_images"], seed=21):
+    """The per-image, per-channel exposure error (stops) the dataset is given: one offset per image plus a small per-channel part."""
+    rs = np.random.RandomState(seed)
+    return (rs.uniform(-0.6, 0.6, (n_images, 1)) + 0.1 * rs.uniform(-1, 1, (n_images, 3))).astype(np.float32)
+
+
+def apply_image_exposures(images_u8, e):
+    """images_u8 [n][h][w][4] sRGB straight-alpha; multiplies the LINEAR colours of image i by 2^e[i] and re-encodes (clipped) to 8-bit sRGB."""
+    x = images_u8[..., :3].astype(np.float64) / 255.0
+    lin = np.where(x <= 0.04045, x / 12.92, ((x + 0.055) / 1.055) ** 2.4)
+    lin = np.clip(lin * (2.0 ** e.astype(np.float64))[:, None, None, :], 0.0, 1.0)
+    srgb = np.where(lin < 0.0031308, 12.92 * lin, 1.055 * lin ** (1 / 2.4) - 0.055)
+    out = images_u8.copy()
+    out[..., :3] = np.clip(np.rint(srgb * 255.0), 0, 255).astype(np.uint8)
+    return out
