@@ -101,19 +101,20 @@ __global__ void __launch_bounds__(256) nerf_input_gradient_kernel(const uint32_t
 	out[4] = dx; out[5] = dy; out[6] = dz;
 }
 
-// compute_cam_gradient_train_nerf (:1600-1707), uniform pixel sampling (xy_pdf = 1), no distortion map / focal length: one thread per kept ray.
+// compute_cam_gradient_train_nerf (:1600-1707), no distortion map / focal length: one thread per kept ray. cdf_img (may be null): the image CDF the batch's
+// rays were drawn from (K19), so that a ray finds its image again.
 // numsteps holds, per kept ray, {compacted sample count, compacted base} as left by the loss stage; coords / coords_gradient are the compacted batch.
 __global__ void __launch_bounds__(128) cam_gradient_kernel(const uint32_t n_rays_global, const Aabb aabb, const uint32_t* __restrict__ rays_counter, const uint32_t n_images,
                                                            const uint32_t* __restrict__ ray_indices, const float* __restrict__ rays_unnormalized, const uint32_t* __restrict__ numsteps,
                                                            const float* __restrict__ coords, const float* __restrict__ coords_gradient,
-                                                           float* __restrict__ cam_pos_gradient, float* __restrict__ cam_rot_gradient)
+                                                           float* __restrict__ cam_pos_gradient, float* __restrict__ cam_rot_gradient, const float* __restrict__ cdf_img)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= *rays_counter) return;
 	const uint32_t ns = numsteps[i * 2 + 0];
 	if (ns == 0) return;
 	const uint32_t base = numsteps[i * 2 + 1];
-	const uint32_t img = image_idx(ray_indices[i], n_rays_global, n_images);
+	const uint32_t img = image_idx(ray_indices[i], n_rays_global, n_images, cdf_img);
 	const float* r = rays_unnormalized + (size_t)i * 6;
 	const V3 ro = {r[0], r[1], r[2]};
 	V3 rd = {r[3], r[4], r[5]};
@@ -156,10 +157,11 @@ void nerf_input_gradient_launch(cudaStream_t stream, const ngpb_grid* g, const _
 }
 
 void cam_gradient_launch(cudaStream_t stream, uint32_t max_rays, uint32_t n_rays_global, const float* aabb6, const uint32_t* rays_counter, uint32_t n_images, const uint32_t* ray_indices,
-                         const float* rays, const uint32_t* numsteps, const float* coords, const float* coords_gradient, float* cam_pos_gradient, float* cam_rot_gradient) {
+                         const float* rays, const uint32_t* numsteps, const float* coords, const float* coords_gradient, float* cam_pos_gradient, float* cam_rot_gradient,
+                         const float* cdf_img) {
 	if (max_rays == 0) return;
 	cam_gradient_kernel<<<div_round_up(max_rays, 128), 128, 0, stream>>>(n_rays_global, make_aabb(aabb6), rays_counter, n_images, ray_indices, rays, numsteps, coords, coords_gradient,
-		cam_pos_gradient, cam_rot_gradient);
+		cam_pos_gradient, cam_rot_gradient, cdf_img);
 	NGPB_LAUNCH_CHECK();
 }
 
@@ -276,7 +278,7 @@ extern "C" int ngpb_compute_cam_gradient(void* stream, uint32_t max_rays, uint32
                                          float* cam_pos_gradient, float* cam_rot_gradient) {
 	try {
 		if (!aabb6 || !rays_counter_dev || !ray_indices || !rays || !numsteps || !coords || !coords_gradient || n_images == 0) { set_last_error("ngpb_compute_cam_gradient: invalid argument"); return NGPB_ERR_INVALID_ARGUMENT; }
-		cam_gradient_launch((cudaStream_t)stream, max_rays, n_rays_global, aabb6, rays_counter_dev, n_images, ray_indices, rays, numsteps, coords, coords_gradient, cam_pos_gradient, cam_rot_gradient);
+		cam_gradient_launch((cudaStream_t)stream, max_rays, n_rays_global, aabb6, rays_counter_dev, n_images, ray_indices, rays, numsteps, coords, coords_gradient, cam_pos_gradient, cam_rot_gradient, nullptr);
 		return 0;
 	} catch (const std::exception& e) { set_last_error(e.what()); return NGPB_ERR_RUNTIME; }
 }

@@ -63,6 +63,15 @@ constexpr uint32_t MLP_W1D = 0, MLP_W2D = 2048, MLP_W1R = 3072, MLP_W2R = 5120, 
 constexpr uint32_t COORD_FLOATS = 7; // NerfCoordinate {pos[3], dt, dir[3]}, nerf.h:81-107
 
 // ---- PCG32 (tcnn/dependencies/pcg32/pcg32.h), device + host ----------------------------------
+// K19: the error-map CDFs the training kernels draw pixels / images from (see nerf_device.cuh); null members = uniform.
+struct ErrorCdf {
+	const float* x_cond_y; // [n_images][res_y][res_x]: per row, the CDF over the columns
+	const float* y;        // [n_images][res_y]: CDF over the rows
+	const float* img;      // [n_images]: CDF over the images
+	int res_x, res_y;
+};
+__host__ __device__ inline ErrorCdf no_error_cdf() { return ErrorCdf{nullptr, nullptr, nullptr, 0, 0}; }
+
 struct Pcg32 {
 	uint64_t state, inc;
 	__host__ __device__ uint32_t next_uint() {

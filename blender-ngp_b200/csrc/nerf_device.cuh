@@ -220,9 +220,73 @@ __device__ inline bool read_rgba(float x, float y, const ngpb_image& im, float o
 	return true;
 }
 
-// image_idx without error-map CDF: src/testbed_nerf.cu:1076-1082
-__device__ __forceinline__ uint32_t image_idx(uint32_t base_idx, uint32_t n_rays, uint32_t n_training_images) {
+// ---- scrambled Sobol building blocks: include/neural-graphics-primitives/random_val.cuh:159-258 (dimension 0 of the sequence is a bit reversal) ----
+__host__ __device__ inline uint32_t hash_combine(uint32_t seed, uint32_t v) { return seed ^ (v + (seed << 6) + (seed >> 2)); }
+__host__ __device__ inline uint32_t reverse_bits(uint32_t x) {
+	x = (((x & 0xaaaaaaaa) >> 1) | ((x & 0x55555555) << 1));
+	x = (((x & 0xcccccccc) >> 2) | ((x & 0x33333333) << 2));
+	x = (((x & 0xf0f0f0f0) >> 4) | ((x & 0x0f0f0f0f) << 4));
+	x = (((x & 0xff00ff00) >> 8) | ((x & 0x00ff00ff) << 8));
+	return ((x >> 16) | (x << 16));
+}
+__host__ __device__ inline uint32_t laine_karras_permutation(uint32_t x, uint32_t seed) {
+	x += seed; x ^= x * 0x6c50b47cu; x ^= x * 0xb82f1e52u; x ^= x * 0xc7afe638u; x ^= x * 0x8d22f6e6u;
+	return x;
+}
+__host__ __device__ inline uint32_t nested_uniform_scramble_base2(uint32_t x, uint32_t seed) { return reverse_bits(laine_karras_permutation(reverse_bits(x), seed)); }
+// ld_random_val(index, seed, dim = 0) (random_val.cuh:261-268)
+__host__ __device__ inline float ld_random_val_dim0(uint32_t index, uint32_t seed) {
+	const float S = float(1.0 / (1ull << 32));
+	index = nested_uniform_scramble_base2(index, seed);
+	return (float)nested_uniform_scramble_base2(reverse_bits(index), hash_combine(seed, 0u)) * S;
+}
+
+// ---- K19: importance sampling of training pixels / images by accumulated error (Testbed::Nerf::Training::ErrorMap, testbed.h:600-615) ----
+// The CDFs K1, K6 and the camera-gradient kernel draw from; a null pointer switches the respective importance sampling off (uniform pixels,
+// round-robin images), which is the reference's behaviour unless nerf.training.sample_*_proportional_to_error is set.
+__host__ inline ErrorCdf make_error_cdf(const ngpb_error_cdf* c) { return c ? ErrorCdf{c->cdf_x_cond_y, c->cdf_y, c->cdf_img, c->res_x, c->res_y} : no_error_cdf(); }
+
+// binary_search: include/neural-graphics-primitives/common.h:201-223 (first element not below val, clamped to the last)
+__device__ __forceinline__ uint32_t binary_search(float val, const float* __restrict__ data, uint32_t length) {
+	if (length == 0) return 0;
+	uint32_t it, count = length, step, first = 0;
+	while (count > 0) {
+		it = first; step = count / 2; it += step;
+		if (data[it] < val) { first = ++it; count -= step + 1; } else count = step;
+	}
+	return min(first, length - 1);
+}
+
+// image_idx: src/testbed_nerf.cu:1062-1083. pdf (optional) receives the image's sampling density relative to uniform.
+__device__ __forceinline__ uint32_t image_idx(uint32_t base_idx, uint32_t n_rays, uint32_t n_training_images, const float* __restrict__ cdf_img = nullptr, float* pdf = nullptr) {
+	if (cdf_img) {
+		const float sample = ld_random_val_dim0(base_idx, 0xdeadbeefu);
+		const uint32_t img = binary_search(sample, cdf_img, n_training_images);
+		if (pdf) { const float prev = img > 0 ? cdf_img[img - 1] : 0.0f; *pdf = (cdf_img[img] - prev) * (float)n_training_images; }
+		return img;
+	}
+	if (pdf) *pdf = 1.0f;
 	return ((base_idx * n_training_images) / n_rays) % n_training_images;
+}
+
+// sample_cdf_2d: src/testbed_nerf.cu:991-1022. Half of the samples stay uniform (UNIFORM_SAMPLING_FRACTION; their pdf is left untouched, i.e. the
+// caller's initial 1); the others pick a row from cdf_y, then a column from that row's CDF, and are placed inside the chosen error-map texel.
+__device__ inline void sample_cdf_2d(float* sx, float* sy, uint32_t img, const ErrorCdf& cdf, float* pdf) {
+	if (*sx < 0.5f) { *sx /= 0.5f; return; }
+	*sx = (*sx - 0.5f) / (1.0f - 0.5f);
+	const float* cdf_y = cdf.y + (size_t)img * cdf.res_y;
+	const uint32_t y = binary_search(*sy, cdf_y, (uint32_t)cdf.res_y);
+	float prev = y > 0 ? cdf_y[y - 1] : 0.0f;
+	const float pmf_y = cdf_y[y] - prev;
+	*sy = (*sy - prev) / pmf_y;
+	const float* cdf_x = cdf.x_cond_y + ((size_t)img * cdf.res_y + y) * cdf.res_x;
+	const uint32_t x = binary_search(*sx, cdf_x, (uint32_t)cdf.res_x);
+	prev = x > 0 ? cdf_x[x - 1] : 0.0f;
+	const float pmf_x = cdf_x[x] - prev;
+	*sx = (*sx - prev) / pmf_x;
+	if (pdf) *pdf = pmf_x * pmf_y * (float)(cdf.res_x * cdf.res_y);
+	*sx = ((float)x + *sx) / (float)cdf.res_x;
+	*sy = ((float)y + *sy) / (float)cdf.res_y;
 }
 
 // ---- lens models of the training cameras (common_device.cuh:141-200,:236-258; used at testbed_nerf.cu:1166-1190) ----
@@ -283,9 +347,12 @@ __device__ inline V3 training_ray_direction(const ngpb_image& im, float x, float
 	return d;
 }
 
-// nerf_random_image_pos_training without CDF: src/testbed_nerf.cu:1047-1060
-__device__ __forceinline__ void random_image_pos_training(Pcg32& rng, int w, int h, bool snap, float* x, float* y) {
+// nerf_random_image_pos_training: src/testbed_nerf.cu:1047-1060
+__device__ __forceinline__ void random_image_pos_training(Pcg32& rng, int w, int h, bool snap, float* x, float* y,
+                                                          const ErrorCdf& cdf = ErrorCdf{nullptr, nullptr, nullptr, 0, 0}, uint32_t img = 0, float* pdf = nullptr) {
 	float u = rng.next_float(), v = rng.next_float();
+	if (pdf) *pdf = 1.0f;
+	if (cdf.x_cond_y) sample_cdf_2d(&u, &v, img, cdf, pdf);
 	if (snap) {
 		u = ((float)min(max((int)(u * (float)w), 0), w - 1) + 0.5f) / (float)w;
 		v = ((float)min(max((int)(v * (float)h), 0), h - 1) + 0.5f) / (float)h;

@@ -24,6 +24,7 @@ struct LossParams {
 	Aabb aabb;
 	Pcg32 rng;
 	ngpb_loss_config cfg;
+	ErrorCdf cdf; // K19: the CDFs K1 drew this batch's pixels / images from (null members: uniform)
 };
 
 // index (in 16-byte units) of chunk c of sample i's 64-byte feature row
@@ -71,7 +72,8 @@ __device__ inline LossAndGradient loss_and_gradient(const float* target, const f
 	return r;
 }
 
-struct __align__(16) RayState { float rgb_ray[3]; float pad; float rgbtarget[3]; uint32_t compacted; float bg[3]; float pad2; };
+// pdf = img_pdf * xy_pdf: density (relative to uniform) the ray's pixel was drawn with, xy_pdf its pixel factor; both exactly 1 without error-map sampling
+struct __align__(16) RayState { float rgb_ray[3]; float pdf; float rgbtarget[3]; uint32_t compacted; float bg[3]; float xy_pdf; };
 
 __device__ __forceinline__ void load_rgbsigma(const __half* p, float o[4]) {
 	const uint2 raw = *reinterpret_cast<const uint2*>(p);
@@ -169,10 +171,11 @@ __global__ void __launch_bounds__(128) loss_target_kernel(const LossParams P, co
 		const uint32_t ray_idx = ray_indices[i];
 		Pcg32 rng = P.rng;
 		rng.advance((int64_t)ray_idx * N_MAX_RANDOM_SAMPLES_PER_RAY);
-		const uint32_t img = image_idx(ray_idx, P.n_rays_global, P.n_images);
+		float img_pdf = 1.0f, xy_pdf = 1.0f;
+		const uint32_t img = image_idx(ray_idx, P.n_rays_global, P.n_images, P.cdf.img, &img_pdf);
 		const ngpb_image& im = images[img];
 		float x, y;
-		random_image_pos_training(rng, im.w, im.h, P.cfg.snap_to_pixel_centers != 0, &x, &y);
+		random_image_pos_training(rng, im.w, im.h, P.cfg.snap_to_pixel_centers != 0, &x, &y, P.cdf, img, &xy_pdf);
 		float bg[3] = {P.cfg.background_color[0], P.cfg.background_color[1], P.cfg.background_color[2]};
 		if (P.cfg.random_bg_color) { bg[0] = rng.next_float(); bg[1] = rng.next_float(); bg[2] = rng.next_float(); }
 		#pragma unroll
@@ -207,6 +210,7 @@ __global__ void __launch_bounds__(128) loss_target_kernel(const LossParams P, co
 		RayState s{};
 		#pragma unroll
 		for (int c = 0; c < 3; ++c) { s.rgbtarget[c] = rgbtarget[c]; s.bg[c] = bg[c]; }
+		s.pdf = img_pdf * xy_pdf; s.xy_pdf = xy_pdf;
 		state[i] = s;
 	}
 }
@@ -259,7 +263,7 @@ __global__ void __launch_bounds__(1024) loss_composite_kernel(
 			RayState s;
 			#pragma unroll
 			for (int c = 0; c < 3; ++c) { s.rgb_ray[c] = rgb_ray[c]; s.rgbtarget[c] = rgbtarget[c]; }
-			s.pad = 0.f; s.pad2 = 0.f;
+			s.pdf = tgt.pdf; s.xy_pdf = tgt.xy_pdf;
 			#pragma unroll
 			for (int c = 0; c < 3; ++c) s.bg[c] = bg[c];
 			s.compacted = cn;
@@ -327,6 +331,9 @@ __global__ void __launch_bounds__(GRAD_BLOCK) loss_gradient_kernel(
 		s = state[i];
 		ro[0] = rays[(size_t)i * 6 + 0]; ro[1] = rays[(size_t)i * 6 + 1]; ro[2] = rays[(size_t)i * 6 + 2];
 		lg = loss_and_gradient(s.rgbtarget, s.rgb_ray, P.cfg.loss_type);
+		// the loss -- not its gradient -- is divided by the density the pixel was sampled with (:1448, :1454-1458; a division by exactly 1 without K19)
+		#pragma unroll
+		for (int c = 0; c < 3; ++c) lg.loss[c] /= s.pdf;
 		const float mean_loss = sum3(lg.loss[0], lg.loss[1], lg.loss[2]) / 3.0f;
 		if (loss_output && glane == 0) loss_output[i] = mean_loss / (float)P.n_rays_global;
 		// compacted coordinates: a contiguous copy of the ray's first cn records, done by the group
@@ -399,15 +406,91 @@ __global__ void __launch_bounds__(128) exposure_gradient_kernel(const LossParams
 	if (i >= P.n_rays || i >= counters_in[1]) return;
 	if (numsteps[i * 2 + 0] == 0) return; // rays without a compacted sample leave the kernel before this point (:1438)
 	const RayState s = state[i];
-	const uint32_t img = image_idx(ray_indices[i], P.n_rays_global, P.n_images);
+	const uint32_t img = image_idx(ray_indices[i], P.n_rays_global, P.n_images, P.cdf.img);
 	const LossAndGradient lg = loss_and_gradient(s.rgbtarget, s.rgb_ray, P.cfg.loss_type);
 	const float loss_scale = P.cfg.loss_scale / P.n_rays_global;
 	#pragma unroll
 	for (int c = 0; c < 3; ++c) {
-		float dloss_by_dgt = -lg.gradient[c];
+		float dloss_by_dgt = -lg.gradient[c] / s.xy_pdf;
 		if (!P.cfg.linear_colors) dloss_by_dgt /= srgb_to_linear_derivative(s.rgbtarget[c]);
 		const float es = expf(0.6931471805599453f * exposure[(size_t)img * 3 + c]);
 		atomicAdd(&exposure_gradient[(size_t)img * 3 + c], loss_scale * dloss_by_dgt * es * 0.6931471805599453f);
+	}
+}
+
+// (C'') K19: every ray with a compacted sample deposits its loss (after the division by its sampling density) bilinearly into its image's error map
+// (:1465-1491; no sharpness weighting). One thread per ray, only launched while an error map is accumulated; the pixel is recovered from the ray's RNG
+// stream like in loss_target_kernel. The texel index is clamped against the IMAGE resolution, as the reference does.
+__global__ void __launch_bounds__(128) error_map_deposit_kernel(const LossParams P, const ngpb_image* __restrict__ images, const uint32_t* __restrict__ counters_in,
+                                                                const uint32_t* __restrict__ ray_indices, const uint32_t* __restrict__ numsteps, const RayState* __restrict__ state,
+                                                                float* __restrict__ error_map, const int res_x, const int res_y)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= P.n_rays || i >= counters_in[1]) return;
+	if (numsteps[i * 2 + 0] == 0) return; // (:1438)
+	const RayState s = state[i];
+	const uint32_t ray_idx = ray_indices[i];
+	Pcg32 rng = P.rng;
+	rng.advance((int64_t)ray_idx * N_MAX_RANDOM_SAMPLES_PER_RAY);
+	const uint32_t img = image_idx(ray_idx, P.n_rays_global, P.n_images, P.cdf.img);
+	const ngpb_image& im = images[img];
+	float x, y;
+	random_image_pos_training(rng, im.w, im.h, P.cfg.snap_to_pixel_centers != 0, &x, &y, P.cdf, img);
+	LossAndGradient lg = loss_and_gradient(s.rgbtarget, s.rgb_ray, P.cfg.loss_type);
+	#pragma unroll
+	for (int c = 0; c < 3; ++c) lg.loss[c] /= s.pdf;
+	const float mean_loss = sum3(lg.loss[0], lg.loss[1], lg.loss[2]) / 3.0f;
+	const float px = fminf(fmaxf(x * (float)res_x - 0.5f, 0.0f), (float)res_x - (1.0f + 1e-4f));
+	const float py = fminf(fmaxf(y * (float)res_y - 0.5f, 0.0f), (float)res_y - (1.0f + 1e-4f));
+	const int ix = (int)px, iy = (int)py;
+	const float wx = px - (float)ix, wy = py - (float)iy;
+	const int jx = max(min(ix, im.w - 2), 0), jy = max(min(iy, im.h - 2), 0);
+	float* em = error_map + (size_t)img * res_x * res_y;
+	atomicAdd(&em[(size_t)jy * res_x + jx], (1 - wx) * (1 - wy) * mean_loss);
+	atomicAdd(&em[(size_t)jy * res_x + jx + 1], wx * (1 - wy) * mean_loss);
+	atomicAdd(&em[(size_t)(jy + 1) * res_x + jx], (1 - wx) * wy * mean_loss);
+	atomicAdd(&em[(size_t)(jy + 1) * res_x + jx + 1], wx * wy * mean_loss);
+}
+
+// construct_cdf_2d (:1984-2012): one thread per (row, image) runs the row's cumulative sum serially -- the rounding of the running sum is part of the
+// result -- and normalises it with a correctly rounded reciprocal, blended with MIN_PDF = 1 % uniform.
+__global__ void __launch_bounds__(128) construct_cdf_2d_kernel(const uint32_t n_images, const uint32_t height, const uint32_t width, const float* __restrict__ data,
+                                                               float* __restrict__ cdf_x_cond_y, float* __restrict__ cdf_y)
+{
+	const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x; // = img * height + y
+	if (row >= n_images * height) return;
+	const size_t off = (size_t)row * width;
+	float cum = 0;
+	for (uint32_t x = 0; x < width; ++x) { cum += data[off + x] + 1e-10f; cdf_x_cond_y[off + x] = cum; }
+	cdf_y[row] = cum;
+	const float norm = __frcp_rn(cum);
+	for (uint32_t x = 0; x < width; ++x) cdf_x_cond_y[off + x] = (1.0f - 0.01f) * cdf_x_cond_y[off + x] * norm + 0.01f * (float)(x + 1) / (float)width;
+}
+// construct_cdf_1d (:2014-2037) per image over its row sums, then -- one thread, as on the reference's host (:3000-3015) -- the CDF over the image sums
+// with MIN_PMF = 10 % uniform.
+__global__ void __launch_bounds__(128) construct_cdf_1d_kernel(const uint32_t n_images, const uint32_t height, float* __restrict__ cdf_y, float* __restrict__ cdf_img)
+{
+	const uint32_t img = blockIdx.x * blockDim.x + threadIdx.x;
+	if (img >= n_images) return;
+	float* cy = cdf_y + (size_t)img * height;
+	float cum = 0;
+	for (uint32_t y = 0; y < height; ++y) { cum += cy[y]; cy[y] = cum; }
+	cdf_img[img] = cum;
+	const float norm = __frcp_rn(cum);
+	for (uint32_t y = 0; y < height; ++y) cy[y] = (1.0f - 0.01f) * cy[y] * norm + 0.01f * (float)(y + 1) / (float)height;
+}
+__global__ void normalize_image_cdf_kernel(const uint32_t n_images, float* __restrict__ cdf_img, float* __restrict__ pmf_img)
+{
+	if (blockIdx.x != 0 || threadIdx.x != 0) return;
+	float total = 0;
+	for (uint32_t i = 0; i < n_images; ++i) total += cdf_img[i];
+	const float norm = 1.0f / total;
+	float cum = 0;
+	for (uint32_t i = 0; i < n_images; ++i) {
+		const float sum = cdf_img[i];
+		cum += sum;
+		if (pmf_img) pmf_img[i] = (1.0f - 0.1f) * sum * norm + 0.1f / (float)n_images;
+		cdf_img[i] = (1.0f - 0.1f) * cum * norm + 0.1f * (float)(i + 1) / (float)n_images;
 	}
 }
 
@@ -440,7 +523,8 @@ int compute_loss_launch(void* stream_, uint32_t n_rays, uint32_t n_rays_global, 
                         uint32_t n_images, const ngpb_image* images_dev, const uint32_t* counters_in,
                         const ngpb_half* rgbsigma, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords_in,
                         const float* mean_density_dev, float* coords_out, ngpb_half* dloss_dout, float* loss_per_ray, uint32_t* counters_out, void* scratch,
-                        const ngpb_half* encoded_in, ngpb_half* encoded_out, bool rows_tiled, const float* exposure, float* exposure_gradient);
+                        const ngpb_half* encoded_in, ngpb_half* encoded_out, bool rows_tiled, const float* exposure, float* exposure_gradient,
+                        const ErrorCdf& cdf, float* error_map, int error_map_res_x, int error_map_res_y);
 
 } // namespace ngpb
 
@@ -472,7 +556,7 @@ extern "C" int ngpb_compute_loss_compact_features(void* stream_, uint32_t n_rays
                                  const float* mean_density_dev, float* coords_out, ngpb_half* dloss_dout, float* loss_per_ray, uint32_t* counters_out, void* scratch,
                                  const ngpb_half* encoded_in, ngpb_half* encoded_out) {
 	return ngpb::compute_loss_launch(stream_, n_rays, n_rays_global, aabb6, rng_, batch, cfg, n_images, images_dev, counters_in, rgbsigma, ray_indices, rays, numsteps, coords_in,
-		mean_density_dev, coords_out, dloss_dout, loss_per_ray, counters_out, scratch, encoded_in, encoded_out, false, nullptr, nullptr);
+		mean_density_dev, coords_out, dloss_dout, loss_per_ray, counters_out, scratch, encoded_in, encoded_out, false, nullptr, nullptr, no_error_cdf(), nullptr, 0, 0);
 }
 
 extern "C" int ngpb_compute_loss_exposure(void* stream_, uint32_t n_rays, uint32_t n_rays_global, const float* aabb6, ngpb_rng rng_, uint32_t batch, const ngpb_loss_config* cfg,
@@ -481,7 +565,36 @@ extern "C" int ngpb_compute_loss_exposure(void* stream_, uint32_t n_rays, uint32
                                  const float* mean_density_dev, float* coords_out, ngpb_half* dloss_dout, float* loss_per_ray, uint32_t* counters_out, void* scratch,
                                  const float* exposure_dev, float* exposure_gradient_dev) {
 	return ngpb::compute_loss_launch(stream_, n_rays, n_rays_global, aabb6, rng_, batch, cfg, n_images, images_dev, counters_in, rgbsigma, ray_indices, rays, numsteps, coords_in,
-		mean_density_dev, coords_out, dloss_dout, loss_per_ray, counters_out, scratch, nullptr, nullptr, false, exposure_dev, exposure_gradient_dev);
+		mean_density_dev, coords_out, dloss_dout, loss_per_ray, counters_out, scratch, nullptr, nullptr, false, exposure_dev, exposure_gradient_dev, no_error_cdf(), nullptr, 0, 0);
+}
+
+extern "C" int ngpb_compute_loss_error_map(void* stream_, uint32_t n_rays, uint32_t n_rays_global, const float* aabb6, ngpb_rng rng_, uint32_t batch, const ngpb_loss_config* cfg,
+                                 uint32_t n_images, const ngpb_image* images_dev, const uint32_t* counters_in,
+                                 const ngpb_half* rgbsigma, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords_in,
+                                 const float* mean_density_dev, float* coords_out, ngpb_half* dloss_dout, float* loss_per_ray, uint32_t* counters_out, void* scratch,
+                                 const float* exposure_dev, float* exposure_gradient_dev,
+                                 const ngpb_error_cdf* error_cdf, float* error_map_dev, int32_t error_map_res_x, int32_t error_map_res_y) {
+	return ngpb::compute_loss_launch(stream_, n_rays, n_rays_global, aabb6, rng_, batch, cfg, n_images, images_dev, counters_in, rgbsigma, ray_indices, rays, numsteps, coords_in,
+		mean_density_dev, coords_out, dloss_dout, loss_per_ray, counters_out, scratch, nullptr, nullptr, false, exposure_dev, exposure_gradient_dev,
+		make_error_cdf(error_cdf), error_map_dev, error_map_res_x, error_map_res_y);
+}
+
+extern "C" int ngpb_construct_error_cdfs(void* stream_, uint32_t n_images, uint32_t res_y, uint32_t res_x, const float* error_map_dev,
+                                         float* cdf_x_cond_y, float* cdf_y, float* cdf_img, float* pmf_img) {
+	try {
+		if (!error_map_dev || !cdf_x_cond_y || !cdf_y || !cdf_img || n_images == 0 || res_x == 0 || res_y == 0) {
+			set_last_error("ngpb_construct_error_cdfs: invalid argument");
+			return NGPB_ERR_INVALID_ARGUMENT;
+		}
+		cudaStream_t stream = (cudaStream_t)stream_;
+		construct_cdf_2d_kernel<<<div_round_up(n_images * res_y, 128), 128, 0, stream>>>(n_images, res_y, res_x, error_map_dev, cdf_x_cond_y, cdf_y);
+		NGPB_LAUNCH_CHECK();
+		construct_cdf_1d_kernel<<<div_round_up(n_images, 128), 128, 0, stream>>>(n_images, res_y, cdf_y, cdf_img);
+		NGPB_LAUNCH_CHECK();
+		normalize_image_cdf_kernel<<<1, 32, 0, stream>>>(n_images, cdf_img, pmf_img);
+		NGPB_LAUNCH_CHECK();
+		return 0;
+	} catch (const std::exception& e) { set_last_error(e.what()); return NGPB_ERR_RUNTIME; }
 }
 
 // The implementation behind the C entry points; `rows_tiled` selects the layout of encoded_in / encoded_out (the testbed hands tiles from the hash-grid kernel to the MLP kernel).
@@ -489,8 +602,11 @@ int ngpb::compute_loss_launch(void* stream_, uint32_t n_rays, uint32_t n_rays_gl
                                  uint32_t n_images, const ngpb_image* images_dev, const uint32_t* counters_in,
                                  const ngpb_half* rgbsigma, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords_in,
                                  const float* mean_density_dev, float* coords_out, ngpb_half* dloss_dout, float* loss_per_ray, uint32_t* counters_out, void* scratch,
-                                 const ngpb_half* encoded_in, ngpb_half* encoded_out, bool rows_tiled, const float* exposure, float* exposure_gradient) {
+                                 const ngpb_half* encoded_in, ngpb_half* encoded_out, bool rows_tiled, const float* exposure, float* exposure_gradient,
+                                 const ErrorCdf& cdf, float* error_map, int error_map_res_x, int error_map_res_y) {
 	try {
+		if (cdf.x_cond_y && (!cdf.y || cdf.res_x <= 0 || cdf.res_y <= 0)) { set_last_error("ngpb_compute_loss: cdf_x_cond_y needs cdf_y and a resolution"); return NGPB_ERR_INVALID_ARGUMENT; }
+		if (error_map && (error_map_res_x < 2 || error_map_res_y < 2)) { set_last_error("ngpb_compute_loss: the error map needs at least 2 x 2 texels"); return NGPB_ERR_INVALID_ARGUMENT; }
 		if (exposure_gradient && !exposure) { set_last_error("ngpb_compute_loss: an exposure gradient needs the exposures"); return NGPB_ERR_INVALID_ARGUMENT; }
 		if ((encoded_in == nullptr) != (encoded_out == nullptr) || (encoded_in && encoded_in == encoded_out)) {
 			set_last_error("ngpb_compute_loss: encoded_in and encoded_out must both be given, and differ");
@@ -509,6 +625,7 @@ int ngpb::compute_loss_launch(void* stream_, uint32_t n_rays, uint32_t n_rays_gl
 		P.aabb = make_aabb(aabb6);
 		P.rng.state = rng_.state; P.rng.inc = rng_.inc;
 		P.cfg = *cfg;
+		P.cdf = cdf;
 		// scratch layout: RayState[n_rays] (32 B each) | uint32 counts[n_rays] | uint32 local_bases[n_rays] | uint32 block_sums[n_blocks]
 		RayState* state = reinterpret_cast<RayState*>(scratch);
 		uint32_t* counts = reinterpret_cast<uint32_t*>(state + n_rays);
@@ -538,6 +655,10 @@ int ngpb::compute_loss_launch(void* stream_, uint32_t n_rays, uint32_t n_rays_gl
 		NGPB_LAUNCH_CHECK();
 		if (exposure_gradient) {
 			exposure_gradient_kernel<<<div_round_up(n_rays, 128), 128, 0, stream>>>(P, counters_in, ray_indices, numsteps, state, exposure, exposure_gradient);
+			NGPB_LAUNCH_CHECK();
+		}
+		if (error_map) {
+			error_map_deposit_kernel<<<div_round_up(n_rays, 128), 128, 0, stream>>>(P, images_dev, counters_in, ray_indices, numsteps, state, error_map, error_map_res_x, error_map_res_y);
 			NGPB_LAUNCH_CHECK();
 		}
 		rollover_kernel<<<div_round_up(batch, 256), 256, 0, stream>>>(batch, counters_out, coords_out, (__half*)dloss_dout, reinterpret_cast<uint4*>(encoded_out), P.rows_tiled);

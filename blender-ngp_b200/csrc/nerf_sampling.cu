@@ -14,16 +14,16 @@ namespace ngpb {
 struct TrainRay { V3 o, d_unnorm, d; float startt, cone_angle, tmax; bool valid; };
 
 // Ray set-up: testbed_nerf.cu:1118-1202 (perspective / OpenCV / f-theta / lat-long lens, no rolling shutter, no distortion map,
-// uniform pixel sampling). RNG draws in the reference's order: xy(2), motion-blur time(1), start jitter(1).
+// pixels / images uniform or drawn from the error-map CDFs). RNG draws in the reference's order: xy(2), motion-blur time(1), start jitter(1).
 __device__ inline TrainRay setup_training_ray(uint32_t i, uint32_t n_rays, Pcg32 rng, uint32_t n_images, const ngpb_image* __restrict__ images,
-                                              const Aabb& aabb, bool snap, float cone_angle_constant) {
+                                              const Aabb& aabb, bool snap, float cone_angle_constant, const ErrorCdf& cdf) {
 	TrainRay r;
 	r.valid = false;
-	const uint32_t img = image_idx(i, n_rays, n_images);
+	const uint32_t img = image_idx(i, n_rays, n_images, cdf.img);
 	const ngpb_image& im = images[img];
 	rng.advance((int64_t)i * N_MAX_RANDOM_SAMPLES_PER_RAY);
 	float x, y;
-	random_image_pos_training(rng, im.w, im.h, snap, &x, &y);
+	random_image_pos_training(rng, im.w, im.h, snap, &x, &y, cdf, img);
 	float px[4];
 	if (!read_rgba(x, y, im, px)) return r; // masked-away pixel (:1126)
 	(void)rng.next_float(); // motionblur_time (:1132); max_level_rand_training is off so no draw at :1130
@@ -146,7 +146,7 @@ constexpr uint32_t K1_BLOCK = 128;
 template <bool CONST_DT>
 __global__ void __launch_bounds__(K1_BLOCK) chain_training_rays_kernel(
 	const uint32_t n_rays, const uint32_t ray_offset, const uint32_t n_rays_global, const Aabb aabb, const Pcg32 rng, const uint32_t n_images, const ngpb_image* __restrict__ images,
-	const bool snap, const float cone_angle_constant, RayRec* __restrict__ recs, MarchWord* __restrict__ words, uint32_t* __restrict__ items, uint32_t* __restrict__ n_items)
+	const bool snap, const float cone_angle_constant, const ErrorCdf cdf, RayRec* __restrict__ recs, MarchWord* __restrict__ words, uint32_t* __restrict__ items, uint32_t* __restrict__ n_items)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t lane = threadIdx.x & 31;
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(K1_BLOCK) chain_training_rays_kernel(
 	bool overflow = false;
 	if (i < n_rays) {
 		// everything about a ray derives from its GLOBAL index (:1118-1121, :1062-1083): a shard reproduces its slice of the full batch
-		const TrainRay r = setup_training_ray(ray_offset + i, n_rays_global, rng, n_images, images, aabb, snap, cone_angle_constant);
+		const TrainRay r = setup_training_ray(ray_offset + i, n_rays_global, rng, n_images, images, aabb, snap, cone_angle_constant, cdf);
 		if (r.valid && r.tmax < 3.0e38f) {
 			MarchWord* w = words + (size_t)i * MARCH_MAX_WORDS;
 			// every candidate beyond t_end is outside the box by a margin far above the rounding of o + t * d, so no visited candidate of the
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(128) march_words_kernel(const uint32_t* __rest
 template <bool CONST_DT>
 __global__ void __launch_bounds__(K1_BLOCK) resolve_training_rays_kernel(
 	const uint32_t n_rays, const uint32_t ray_offset, const uint32_t n_rays_global, const Aabb aabb, const Pcg32 rng, const uint32_t n_images, const ngpb_image* __restrict__ images,
-	const uint8_t* __restrict__ bitfield, const bool snap, const float cone_angle_constant, const RayRec* __restrict__ recs, MarchWord* __restrict__ words,
+	const uint8_t* __restrict__ bitfield, const bool snap, const float cone_angle_constant, const ErrorCdf cdf, const RayRec* __restrict__ recs, MarchWord* __restrict__ words,
 	uint32_t* __restrict__ counts, uint32_t* __restrict__ n_words_out, uint32_t* __restrict__ local_bases, uint32_t* __restrict__ local_slots, uint2* __restrict__ block_sums)
 {
 	__shared__ uint32_t warp_sums[2][K1_BLOCK / 32];
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(K1_BLOCK) resolve_training_rays_kernel(
 		const RayRec rec = recs[i];
 		uint32_t nw = rec.n_words;
 		if (nw == MARCH_OVERFLOW) {
-			const TrainRay r = setup_training_ray(ray_offset + i, n_rays_global, rng, n_images, images, aabb, snap, cone_angle_constant);
+			const TrainRay r = setup_training_ray(ray_offset + i, n_rays_global, rng, n_images, images, aabb, snap, cone_angle_constant, cdf);
 			c = march_serial<false>(r, aabb, bitfield, NERF_STEPS, nullptr);
 		} else if (nw) {
 			const V3 o = {rec.o[0], rec.o[1], rec.o[2]}, d = {rec.d[0], rec.d[1], rec.d[2]};
@@ -306,7 +306,7 @@ constexpr uint32_t WRITE_RAYS_PER_BLOCK = 8;
 template <bool CONST_DT>
 __global__ void __launch_bounds__(WRITE_RAYS_PER_BLOCK * 32) write_training_samples_kernel(
 	const uint32_t n_rays, const uint32_t ray_offset, const uint32_t n_rays_global, const uint32_t max_samples, const Aabb aabb, const Pcg32 rng, const uint32_t n_images, const ngpb_image* __restrict__ images,
-	const uint8_t* __restrict__ bitfield, const bool snap, const float cone_angle_constant,
+	const uint8_t* __restrict__ bitfield, const bool snap, const float cone_angle_constant, const ErrorCdf cdf,
 	const uint32_t* __restrict__ counts, const uint32_t* __restrict__ n_words, const RayRec* __restrict__ recs, const MarchWord* __restrict__ words,
 	const uint32_t* __restrict__ local_bases, const uint32_t* __restrict__ local_slots, const uint2* __restrict__ block_prefix,
 	uint32_t* __restrict__ counters, uint32_t* __restrict__ ray_indices, float* __restrict__ rays, uint32_t* __restrict__ numsteps, float* __restrict__ coords)
@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(WRITE_RAYS_PER_BLOCK * 32) write_training_samp
 	const uint32_t nw = n_words[i];
 	if (nw & MARCH_OVERFLOW) {
 		if (lane == 0) {
-			const TrainRay r = setup_training_ray(ray_offset + i, n_rays_global, rng, n_images, images, aabb, snap, cone_angle_constant);
+			const TrainRay r = setup_training_ray(ray_offset + i, n_rays_global, rng, n_images, images, aabb, snap, cone_angle_constant, cdf);
 			march_serial<true>(r, aabb, bitfield, count, out);
 		}
 		return;
@@ -437,12 +437,27 @@ extern "C" int ngpb_generate_training_samples(void* stream, uint32_t n_rays, con
 		counters, ray_indices, rays, numsteps, coords, scratch);
 }
 
-extern "C" int ngpb_generate_training_samples_sharded(void* stream_, uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, const float* aabb6, uint32_t max_samples, ngpb_rng rng_,
+extern "C" int ngpb_generate_training_samples_sharded(void* stream, uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, const float* aabb6, uint32_t max_samples, ngpb_rng rng,
                                               uint32_t n_images, const ngpb_image* images_dev, const uint8_t* bitfield,
                                               int snap_to_pixel_centers, float cone_angle_constant,
-                                              uint32_t* counters, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, void* scratch_) {
+                                              uint32_t* counters, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, void* scratch) {
+	return ngpb_generate_training_samples_cdf(stream, n_rays, ray_offset, n_rays_global, aabb6, max_samples, rng, n_images, images_dev, bitfield, snap_to_pixel_centers, cone_angle_constant,
+		counters, ray_indices, rays, numsteps, coords, scratch, nullptr);
+}
+
+// K1 with the error-map CDFs (K19): pixels and / or images drawn proportionally to the accumulated training error (:991-1083). error_cdf == NULL or
+// null members: the uniform choices above.
+extern "C" int ngpb_generate_training_samples_cdf(void* stream_, uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, const float* aabb6, uint32_t max_samples, ngpb_rng rng_,
+                                              uint32_t n_images, const ngpb_image* images_dev, const uint8_t* bitfield,
+                                              int snap_to_pixel_centers, float cone_angle_constant,
+                                              uint32_t* counters, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, void* scratch_, const ngpb_error_cdf* error_cdf) {
 	try {
 		void* scratch = scratch_;
+		const ErrorCdf cdf = make_error_cdf(error_cdf);
+		if (cdf.x_cond_y && (!cdf.y || cdf.res_x <= 0 || cdf.res_y <= 0)) {
+			set_last_error("ngpb_generate_training_samples: cdf_x_cond_y needs cdf_y and a resolution");
+			return NGPB_ERR_INVALID_ARGUMENT;
+		}
 		if (!aabb6 || !images_dev || !bitfield || !counters || !ray_indices || !rays || !numsteps || !coords || !scratch || n_images == 0 ||
 		    (uint64_t)ray_offset + n_rays > n_rays_global) {
 			set_last_error("ngpb_generate_training_samples: invalid argument");
@@ -464,7 +479,7 @@ extern "C" int ngpb_generate_training_samples_sharded(void* stream_, uint32_t n_
 		// kernels of the training stream can co-reside while K1 runs on the sampling stream.
 		static const uint32_t k1_smem = [] { const char* e = std::getenv("NGPB_K1_SMEM"); return e ? (uint32_t)std::atoi(e) : 0u; }();
 		#define NGPB_K1(kernel, grid, block, ...) do { if (const_dt) kernel<true><<<grid, block, k1_smem, stream>>>(__VA_ARGS__); else kernel<false><<<grid, block, k1_smem, stream>>>(__VA_ARGS__); } while (0)
-		NGPB_K1(chain_training_rays_kernel, blocks, K1_BLOCK, n_rays, ray_offset, n_rays_global, aabb, rng, n_images, images_dev, snap, cone_angle_constant,
+		NGPB_K1(chain_training_rays_kernel, blocks, K1_BLOCK, n_rays, ray_offset, n_rays_global, aabb, rng, n_images, images_dev, snap, cone_angle_constant, cdf,
 			sc.recs, words, sc.items, sc.n_items);
 		NGPB_LAUNCH_CHECK();
 		// one thread per word; the word count lives on the device, so the grid covers the worst case and surplus blocks exit at once.
@@ -472,13 +487,13 @@ extern "C" int ngpb_generate_training_samples_sharded(void* stream_, uint32_t n_
 		const uint64_t max_items = (uint64_t)n_rays * MARCH_MAX_WORDS;
 		NGPB_K1(march_words_kernel, (uint32_t)((max_items + 127) / 128), 128, sc.n_items, sc.items, aabb, bitfield, sc.recs, words);
 		NGPB_LAUNCH_CHECK();
-		NGPB_K1(resolve_training_rays_kernel, blocks, K1_BLOCK, n_rays, ray_offset, n_rays_global, aabb, rng, n_images, images_dev, bitfield, snap, cone_angle_constant,
+		NGPB_K1(resolve_training_rays_kernel, blocks, K1_BLOCK, n_rays, ray_offset, n_rays_global, aabb, rng, n_images, images_dev, bitfield, snap, cone_angle_constant, cdf,
 			sc.recs, words, counts, n_words, local_bases, local_slots, block_sums);
 		NGPB_LAUNCH_CHECK();
 		scan_training_samples_kernel<<<1, 1024, 0, stream>>>(blocks, block_sums, counters);
 		NGPB_LAUNCH_CHECK();
 		NGPB_K1(write_training_samples_kernel, div_round_up(n_rays, WRITE_RAYS_PER_BLOCK), WRITE_RAYS_PER_BLOCK * 32, n_rays, ray_offset, n_rays_global, max_samples, aabb, rng, n_images, images_dev, bitfield,
-			snap_to_pixel_centers != 0, cone_angle_constant, counts, n_words, sc.recs, words, local_bases, local_slots, block_sums, counters, ray_indices, rays, numsteps, coords);
+			snap_to_pixel_centers != 0, cone_angle_constant, cdf, counts, n_words, sc.recs, words, local_bases, local_slots, block_sums, counters, ray_indices, rays, numsteps, coords);
 		NGPB_LAUNCH_CHECK();
 		#undef NGPB_K1
 		return 0;

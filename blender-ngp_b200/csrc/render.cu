@@ -50,19 +50,7 @@ __host__ __device__ inline uint32_t sobol_dim(uint32_t index, uint32_t dim) {
 #endif
 	return X;
 }
-__host__ __device__ inline uint32_t hash_combine(uint32_t seed, uint32_t v) { return seed ^ (v + (seed << 6) + (seed >> 2)); }
-__host__ __device__ inline uint32_t reverse_bits(uint32_t x) {
-	x = (((x & 0xaaaaaaaa) >> 1) | ((x & 0x55555555) << 1));
-	x = (((x & 0xcccccccc) >> 2) | ((x & 0x33333333) << 2));
-	x = (((x & 0xf0f0f0f0) >> 4) | ((x & 0x0f0f0f0f) << 4));
-	x = (((x & 0xff00ff00) >> 8) | ((x & 0x00ff00ff) << 8));
-	return ((x >> 16) | (x << 16));
-}
-__host__ __device__ inline uint32_t laine_karras_permutation(uint32_t x, uint32_t seed) {
-	x += seed; x ^= x * 0x6c50b47cu; x ^= x * 0xb82f1e52u; x ^= x * 0xc7afe638u; x ^= x * 0x8d22f6e6u;
-	return x;
-}
-__host__ __device__ inline uint32_t nested_uniform_scramble_base2(uint32_t x, uint32_t seed) { return reverse_bits(laine_karras_permutation(reverse_bits(x), seed)); }
+// (hash_combine, reverse_bits, laine_karras_permutation, nested_uniform_scramble_base2: nerf_device.cuh, shared with the error-map image sampling)
 __host__ __device__ inline float ld_random_val(uint32_t index, uint32_t seed, uint32_t dim = 0) {
 	const float S = float(1.0 / (1ull << 32));
 	index = nested_uniform_scramble_base2(index, seed);

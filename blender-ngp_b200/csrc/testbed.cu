@@ -22,7 +22,8 @@ int compute_loss_launch(void* stream_, uint32_t n_rays, uint32_t n_rays_global, 
                         uint32_t n_images, const ngpb_image* images_dev, const uint32_t* counters_in,
                         const ngpb_half* rgbsigma, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords_in,
                         const float* mean_density_dev, float* coords_out, ngpb_half* dloss_dout, float* loss_per_ray, uint32_t* counters_out, void* scratch,
-                        const ngpb_half* encoded_in, ngpb_half* encoded_out, bool rows_tiled, const float* exposure, float* exposure_gradient);
+                        const ngpb_half* encoded_in, ngpb_half* encoded_out, bool rows_tiled, const float* exposure, float* exposure_gradient,
+                        const ErrorCdf& cdf, float* error_map, int error_map_res_x, int error_map_res_y);
 void hash_encode_backward_launch(cudaStream_t stream, const ngpb_grid* g, const float* positions, uint32_t pos_stride, uint32_t n, const __half* dL_dencoded, float* grid_grad,
                                  uint32_t level_begin, uint32_t level_end);
 void optimizer_prepare(ngpb_optimizer* o, float loss_scale, void* params_out);
@@ -36,7 +37,8 @@ void nerf_density_mlp_launch(cudaStream_t stream, const __half* mlp, const __hal
 void nerf_mlp_forward_backward_launch(cudaStream_t stream, const __half* mlp, const __half* encoded, bool tiled, const float* coords, const __half* dL_dout, uint32_t n, __half* dL_dencoded, float* mlp_grad, float* partials, __half* dL_dsh);
 void nerf_input_gradient_launch(cudaStream_t stream, const ngpb_grid* g, const __half* grid, const float* coords, uint32_t n, const __half* dL_dencoded, const __half* dL_dsh, float* coords_gradient);
 void cam_gradient_launch(cudaStream_t stream, uint32_t max_rays, uint32_t n_rays_global, const float* aabb6, const uint32_t* rays_counter, uint32_t n_images, const uint32_t* ray_indices,
-                         const float* rays, const uint32_t* numsteps, const float* coords, const float* coords_gradient, float* cam_pos_gradient, float* cam_rot_gradient);
+                         const float* rays, const uint32_t* numsteps, const float* coords, const float* coords_gradient, float* cam_pos_gradient, float* cam_rot_gradient,
+                         const float* cdf_img);
 
 // sum of n floats in double, one block, fixed order (tcnn reduce_sum.h:54-118 is the reference's loss reduction)
 __global__ void __launch_bounds__(1024) sum_kernel(const float* __restrict__ v, const uint32_t n, float* __restrict__ out)
@@ -259,6 +261,7 @@ ngpb_testbed::ngpb_testbed(int device_) : device(device_) {
 	NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&loss_ready, cudaEventDisableTiming));
 	NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&counters_ready, cudaEventDisableTiming));
 	NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&mlp_train_done, cudaEventDisableTiming));
+	NGPB_CUDA_CHECK(cudaEventCreateWithFlags(&error_cdf_built, cudaEventDisableTiming));
 	ngpb_optimizer_init(&opt);
 	ngpb_optimizer_init(&opt_hyper);
 	loss_cfg.loss_scale = LOSS_SCALE;
@@ -286,6 +289,7 @@ ngpb_testbed::~ngpb_testbed() {
 	if (loss_ready) cudaEventDestroy(loss_ready);
 	if (counters_ready) cudaEventDestroy(counters_ready);
 	if (mlp_train_done) cudaEventDestroy(mlp_train_done);
+	if (error_cdf_built) cudaEventDestroy(error_cdf_built);
 	if (sampling_stream) cudaStreamDestroy(sampling_stream);
 	for (void* p : allocations) cudaFree(p);
 	for (auto& e : stage_ev) { if (e[0]) cudaEventDestroy(e[0]); if (e[1]) cudaEventDestroy(e[1]); }
@@ -354,6 +358,11 @@ void ngpb_testbed::load_training_data(uint32_t n, const ngpb_host_image* host_im
 	images.resize(n);
 	dataset_xforms.assign((size_t)n * 12, 0.f);
 	dfree(cam_gradients); dfree(cam_exposure);
+	// error-map buffers are sized by the image count: start over
+	dfree(error_map); dfree(error_cdf_x_cond_y); dfree(error_cdf_y); dfree(error_cdf_img); dfree(error_pmf_img);
+	error_map = error_cdf_x_cond_y = error_cdf_y = error_cdf_img = error_pmf_img = nullptr;
+	error_map_capacity = error_cdf_capacity = 0;
+	error_cdf_valid = error_map_live = error_cdf_used = false;
 	cam_gradients = (float*)dalloc(sizeof(float) * 9 * n);
 	cam_exposure = (float*)dalloc(sizeof(float) * 3 * n);
 	NGPB_CUDA_CHECK(cudaMemsetAsync(cam_gradients, 0, sizeof(float) * 9 * n, stream));
@@ -414,6 +423,11 @@ void ngpb_testbed::reset_network(uint32_t seed_) {
 		if (exposure_active) upload_exposures();
 	}
 	n_steps_since_cam_update = 0;
+	// (src/testbed.cu:2261-2264)
+	n_steps_since_error_map_update = 0;
+	n_steps_between_error_map_updates = 128;
+	error_cdf_valid = false;
+	error_map_live = false;
 	const uint32_t n_levels = 16, base_resolution = 16;
 	// per_level_scale = exp(ln(desired_resolution * aabb_scale / base) / (L-1)) (:2313-2325)
 	const float per_level_scale = std::exp(std::log(2048.0f * (float)aabb_scale / (float)base_resolution) / (n_levels - 1));
@@ -639,8 +653,9 @@ void ngpb_testbed::p2p_teardown() {
 void ngpb_testbed::launch_sampling(cudaStream_t st, const SamplingRequest& p) {
 	stage_begin(NGPB_STAGE_SAMPLING, st);
 	// this rank's shard: local rays [rank * n_rays, (rank + 1) * n_rays) of a global batch of world * n_rays rays
-	if (ngpb_generate_training_samples_sharded(st, p.n_rays, (uint32_t)dp_rank * p.n_rays, (uint32_t)dp_world * p.n_rays, aabb, p.max_inference, p.rng,
-		(uint32_t)images.size(), images_dev, bitfield, p.snap, p.cone_angle, counters, ray_indices, rays, numsteps, coords, scratch) != 0) throw std::runtime_error(ngpb_last_error());
+	if (ngpb_generate_training_samples_cdf(st, p.n_rays, (uint32_t)dp_rank * p.n_rays, (uint32_t)dp_world * p.n_rays, aabb, p.max_inference, p.rng,
+		(uint32_t)images.size(), images_dev, bitfield, p.snap, p.cone_angle, counters, ray_indices, rays, numsteps, coords, scratch, &p.cdf) != 0) throw std::runtime_error(ngpb_last_error());
+	if (p.cdf.cdf_x_cond_y || p.cdf.cdf_img) error_cdf_used = true;
 	stage_end(NGPB_STAGE_SAMPLING, p.n_rays, st);
 	n_launches += 5;
 }
@@ -717,8 +732,10 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 	}
 	if (n_steps_since_cam_update == 0) NGPB_CUDA_CHECK(cudaMemsetAsync(cam_gradients, 0, sizeof(float) * 9 * images.size(), stream)); // :2916-2919
 	if (optimize_exposure) exposure_active = true;
+	if (n_steps_since_error_map_update == 0) begin_error_map_window(); // (:2933-2939)
 	const uint32_t R = rays_per_batch;
-	const SamplingRequest req{training_step, R, max_inference, ngpb_rng{rng.state, rng.inc}, loss_cfg.snap_to_pixel_centers, cone_angle_constant};
+	const ngpb_error_cdf step_cdf = sampling_cdf();
+	const SamplingRequest req{training_step, R, max_inference, ngpb_rng{rng.state, rng.inc}, loss_cfg.snap_to_pixel_centers, cone_angle_constant, step_cdf};
 	const ngpb_rng r = req.rng;
 
 	// the uncompacted sample count of this step stays on the device; for the per-stage accounting the previous step's is used
@@ -742,9 +759,10 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 	check(compute_loss_launch(stream, R, (uint32_t)dp_world * R, aabb, r, batch, &loss_cfg, (uint32_t)images.size(), images_dev, counters, (const ngpb_half*)rgbsigma,
 		ray_indices, rays, numsteps, coords, mean_density, coords_compacted, (ngpb_half*)dloss, loss, counters + 2, scratch,
 		reuse_encoding ? (const ngpb_half*)encoded : nullptr, reuse_encoding ? (ngpb_half*)encoded_compacted : nullptr, tiled,
-		exposure_active ? cam_exposure : nullptr, optimize_exposure ? cam_gradients + 6 * images.size() : nullptr));
+		exposure_active ? cam_exposure : nullptr, optimize_exposure ? cam_gradients + 6 * images.size() : nullptr,
+		ErrorCdf{step_cdf.cdf_x_cond_y, step_cdf.cdf_y, step_cdf.cdf_img, step_cdf.res_x, step_cdf.res_y}, error_map_live ? error_map : nullptr, error_map_res[0], error_map_res[1]));
 	stage_end(NGPB_STAGE_LOSS, R, stream);
-	n_launches += 2 + 5 + (optimize_exposure ? 1 : 0); // encode, mlp; loss target / composite / scan / gradient / rollover (+ exposure gradient)
+	n_launches += 2 + 5 + (optimize_exposure ? 1 : 0) + (error_map_live ? 1 : 0); // encode, mlp; loss target / composite / scan / gradient / rollover (+ exposure gradient, + error-map deposit)
 	if (dp_world > 1) {
 		// the controller needs the GLOBAL sample counts so that every rank derives the same next ray count: sum {uncompacted, kept rays,
 		// compacted} into counters[8..10] (the local values stay in [0..2] for the kernels of this step)
@@ -781,7 +799,7 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 		// input gradient over the padded batch too; padding samples carry a zero loss gradient and belong to no ray.
 		nerf_input_gradient_launch(stream, &grid, w_half + MLP_PARAMS, coords_compacted, batch, denc, dL_dsh, coords_gradient);
 		cam_gradient_launch(stream, R, (uint32_t)dp_world * R, aabb, counters + 1, (uint32_t)images.size(), ray_indices, rays, numsteps, coords_compacted, coords_gradient,
-			cam_gradients, cam_gradients + 3 * images.size());
+			cam_gradients, cam_gradients + 3 * images.size(), step_cdf.cdf_img);
 		n_launches += 2;
 		// the camera-gradient kernel is the last reader of this step's rays / numsteps / ray counter: the prefetched sampling of the next step, which
 		// rewrites them on the sampling stream, has to wait for it
@@ -907,6 +925,10 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 	rng.advance(); // m_rng.advance() (:3380)
 	++n_steps_since_cam_update; // (:3026)
 	if ((optimize_extrinsics || optimize_exposure) && n_steps_since_cam_update >= n_steps_between_cam_updates) camera_update_step();
+	// CDFs from the error map (:2970-3023); enqueued on the training stream, after this step's loss kernels and before the next step's sampling
+	++n_steps_since_error_map_update;
+	bool cdf_rebuilt = false;
+	if (n_steps_since_error_map_update >= n_steps_between_error_map_updates) { cdf_rebuilt = error_map_live; finish_error_map_window(); }
 
 	// ---- batch-size controller (:2870-2894) ----
 	NGPB_CUDA_CHECK(cudaEventSynchronize(counters_ready));
@@ -933,9 +955,10 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 		const uint32_t next_skip = std::max(1u, std::min(training_step / 16u, 16u));
 		if (overlap_sampling && training_step % next_skip != 0) {
 			prefetch = SamplingRequest{training_step, rays_per_batch, next_multiple(std::min(inference_budget(measured_batch_size_before_compaction), max_samples), 128),
-				ngpb_rng{rng.state, rng.inc}, loss_cfg.snap_to_pixel_centers, cone_angle_constant};
+				ngpb_rng{rng.state, rng.inc}, loss_cfg.snap_to_pixel_centers, cone_angle_constant, sampling_cdf()};
 			static const bool after_mlp = getenv("NGPB_K1_AFTER_MLP") && atoi(getenv("NGPB_K1_AFTER_MLP")) != 0;
 			if (after_mlp || optimize_extrinsics) NGPB_CUDA_CHECK(cudaStreamWaitEvent(sampling_stream, mlp_train_done, 0));
+			if (cdf_rebuilt) NGPB_CUDA_CHECK(cudaStreamWaitEvent(sampling_stream, error_cdf_built, 0)); // the next step draws from the CDFs just enqueued
 			launch_sampling(sampling_stream, prefetch);
 			NGPB_CUDA_CHECK(cudaEventRecord(prefetch_done, sampling_stream));
 			prefetch_valid = true;
@@ -959,6 +982,70 @@ extern "C" uint32_t ngpb_next_rays_per_batch(uint32_t rays_per_batch, uint32_t b
 extern "C" void ngpb_ray_shard(uint32_t rank, uint32_t world, uint32_t rays_per_batch, uint32_t* ray_offset, uint32_t* n_rays_global) {
 	if (ray_offset) *ray_offset = rank * rays_per_batch;
 	if (n_rays_global) *n_rays_global = world * rays_per_batch;
+}
+
+// ---- K19: error-map windows (train_nerf :2933-2939, :2970-3023) ----
+ngpb_error_cdf ngpb_testbed::sampling_cdf() const {
+	ngpb_error_cdf c{nullptr, nullptr, nullptr, 0, 0};
+	if (!error_cdf_valid) return c; // (:3211-3212)
+	if (sample_focal_plane_proportional_to_error) { c.cdf_x_cond_y = error_cdf_x_cond_y; c.cdf_y = error_cdf_y; c.res_x = error_cdf_res[0]; c.res_y = error_cdf_res[1]; }
+	if (sample_image_proportional_to_error) c.cdf_img = error_cdf_img;
+	return c;
+}
+
+// Start of a window: the map's resolution follows the number of rays an image will receive during the window, capped by the first image's resolution; the
+// map is cleared. Without one of the two switches nothing would read the map, and nothing is accumulated.
+void ngpb_testbed::begin_error_map_window() {
+	error_map_live = false;
+	if (!(sample_focal_plane_proportional_to_error || sample_image_proportional_to_error) || images.empty()) return;
+	const uint32_t n_images = (uint32_t)images.size();
+	const uint32_t n_samples_per_image = (n_steps_between_error_map_updates * rays_per_batch) / n_images; // (32-bit like the reference)
+	const int side = (int)(std::sqrt(std::sqrt((float)n_samples_per_image)) * 3.5f);
+	const int rx = std::min(side, images[0].w), ry = std::min(side, images[0].h);
+	if (rx < 2 || ry < 2) return; // (the bilinear deposit touches texel + 1)
+	const size_t n = (size_t)n_images * rx * ry;
+	if (n > error_map_capacity) {
+		NGPB_CUDA_CHECK(cudaStreamSynchronize(stream)); // the previous window's deposits
+		dfree(error_map);
+		error_map = (float*)dalloc(sizeof(float) * n);
+		error_map_capacity = n;
+	}
+	error_map_res[0] = rx; error_map_res[1] = ry;
+	NGPB_CUDA_CHECK(cudaMemsetAsync(error_map, 0, sizeof(float) * n, stream));
+	error_map_live = true;
+}
+
+// End of a window: CDFs from the accumulated map (device kernels, incl. the image normalisation the reference runs on the host), counters reset, and the
+// next window is 1.5x longer. Data parallel: every rank deposited its shard's rays; the maps are summed first, so all ranks build the same CDFs.
+void ngpb_testbed::finish_error_map_window() {
+	if (error_map_live) {
+		const uint32_t n_images = (uint32_t)images.size();
+		const size_t n = (size_t)n_images * error_map_res[0] * error_map_res[1];
+		if (n > error_cdf_capacity) {
+			if (error_cdf_used) { drop_prefetch(); NGPB_CUDA_CHECK(cudaStreamSynchronize(stream)); } // kernels that still read the old CDFs
+			dfree(error_cdf_x_cond_y); dfree(error_cdf_y);
+			error_cdf_x_cond_y = (float*)dalloc(sizeof(float) * n);
+			error_cdf_y = (float*)dalloc(sizeof(float) * n); // (rows only; sized like the map so that any later aspect fits)
+			error_cdf_capacity = n;
+		}
+		if (!error_cdf_img) { error_cdf_img = (float*)dalloc(sizeof(float) * n_images); error_pmf_img = (float*)dalloc(sizeof(float) * n_images); }
+		if (dp_world > 1) {
+			NcclApi& nccl = NcclApi::get();
+			nccl.check(nccl.AllReduce(error_map, error_map, n, NcclApi::Float32, NcclApi::Sum, nccl_comm, stream), "ncclAllReduce(error map)");
+		}
+		// The sampling stream may still run the prefetched K1 of a step that reads the CDFs about to be overwritten: it is always consumed (waited for by
+		// `stream`) before this point, because this runs after the step's own loss kernels.
+		error_cdf_res[0] = error_map_res[0]; error_cdf_res[1] = error_map_res[1];
+		if (ngpb_construct_error_cdfs(stream, n_images, (uint32_t)error_cdf_res[1], (uint32_t)error_cdf_res[0], error_map, error_cdf_x_cond_y, error_cdf_y, error_cdf_img, error_pmf_img) != 0)
+			throw std::runtime_error(ngpb_last_error());
+		NGPB_CUDA_CHECK(cudaEventRecord(error_cdf_built, stream));
+		n_launches += 3;
+		error_cdf_valid = true;
+		error_cdf_used = false;
+	}
+	n_steps_since_error_map_update = 0;
+	n_steps_between_error_map_updates = (uint32_t)((float)n_steps_between_error_map_updates * 1.5f);
+	error_map_live = false;
 }
 
 // The sharded optimizer's EMA sweep (a function of the gathered fp16 weights only), off the training stream: it runs under the next step's first half.
@@ -1237,6 +1324,19 @@ extern "C" int ngpb_testbed_get_camera_exposures(ngpb_testbed* t, float* exposur
 	for (size_t i = 0; i < t->images.size(); ++i) for (int c = 0; c < 3; ++c) exposures3[i * 3 + c] = t->cam_exposure_state[i * 10 + 7 + c];
 	NGPB_API_END
 }
+// Sampling probabilities of the images after the last CDF update (ErrorMap::pmf_img_cpu); uniform before the first.
+extern "C" int ngpb_testbed_get_error_map_pmf(ngpb_testbed* t, float* pmf_img) {
+	NGPB_API_BEGIN
+	if (!pmf_img) throw std::runtime_error("get_error_map_pmf: invalid argument");
+	const size_t n = t->images.size();
+	if (!t->error_cdf_valid) { for (size_t i = 0; i < n; ++i) pmf_img[i] = 1.0f / (float)n; }
+	else {
+		NGPB_CUDA_CHECK(cudaSetDevice(t->device));
+		NGPB_CUDA_CHECK(cudaMemcpyAsync(pmf_img, t->error_pmf_img, sizeof(float) * n, cudaMemcpyDeviceToHost, t->stream));
+		NGPB_CUDA_CHECK(cudaStreamSynchronize(t->stream));
+	}
+	NGPB_API_END
+}
 extern "C" int ngpb_testbed_set_camera_exposures(ngpb_testbed* t, const float* exposures3) {
 	NGPB_API_BEGIN
 	if (!exposures3 || t->images.empty()) throw std::runtime_error("set_camera_exposures: invalid argument");
@@ -1297,6 +1397,8 @@ extern "C" int ngpb_testbed_set_option(ngpb_testbed* t, const char* name, double
 	}
 	else if (k == "optimize_extrinsics") t->optimize_extrinsics = v != 0;
 	else if (k == "optimize_exposure") t->optimize_exposure = v != 0;
+	else if (k == "sample_focal_plane_proportional_to_error") t->sample_focal_plane_proportional_to_error = v != 0;
+	else if (k == "sample_image_proportional_to_error") t->sample_image_proportional_to_error = v != 0;
 	else if (k == "exposure_l2_reg") t->exposure_l2_reg = (float)v;
 	else if (k == "extrinsic_learning_rate") t->extrinsic_learning_rate = (float)v;
 	else if (k == "extrinsic_l2_reg") t->extrinsic_l2_reg = (float)v;
@@ -1342,6 +1444,12 @@ extern "C" double ngpb_testbed_get_option(ngpb_testbed* t, const char* name) {
 	if (k == "log2_hashmap_size") return t->log2_hashmap_size;
 	if (k == "optimize_extrinsics") return t->optimize_extrinsics;
 	if (k == "optimize_exposure") return t->optimize_exposure;
+	if (k == "sample_focal_plane_proportional_to_error") return t->sample_focal_plane_proportional_to_error;
+	if (k == "sample_image_proportional_to_error") return t->sample_image_proportional_to_error;
+	if (k == "error_map_res") return t->error_cdf_valid ? t->error_cdf_res[0] : 0;
+	if (k == "error_cdf_valid") return t->error_cdf_valid;
+	if (k == "n_steps_between_error_map_updates") return t->n_steps_between_error_map_updates;
+	if (k == "n_steps_since_error_map_update") return t->n_steps_since_error_map_update;
 	if (k == "n_images") return (double)t->images.size();
 	if (k == "exposure_l2_reg") return t->exposure_l2_reg;
 	if (k == "extrinsic_learning_rate") return t->extrinsic_learning_rate;

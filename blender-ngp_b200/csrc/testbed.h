@@ -23,8 +23,9 @@ struct ngpb_testbed {
 	// K1 of the next step, prefetched on a second stream (see train())
 	struct SamplingRequest {
 		uint32_t step, n_rays, max_inference; ngpb_rng rng; int snap; float cone_angle;
+		ngpb_error_cdf cdf; // K19: the CDFs the pixels / images are drawn from (null members: uniform)
 		bool operator==(const SamplingRequest& o) const {
-			return step == o.step && n_rays == o.n_rays && max_inference == o.max_inference && rng.state == o.rng.state && rng.inc == o.rng.inc && snap == o.snap && cone_angle == o.cone_angle;
+			return cdf.cdf_x_cond_y == o.cdf.cdf_x_cond_y && cdf.cdf_y == o.cdf.cdf_y && cdf.cdf_img == o.cdf.cdf_img && cdf.res_x == o.cdf.res_x && cdf.res_y == o.cdf.res_y && step == o.step && n_rays == o.n_rays && max_inference == o.max_inference && rng.state == o.rng.state && rng.inc == o.rng.inc && snap == o.snap && cone_angle == o.cone_angle;
 		}
 	};
 	void launch_sampling(cudaStream_t st, const SamplingRequest& p);
@@ -102,6 +103,22 @@ struct ngpb_testbed {
 	std::vector<float> cam_exposure_state;            // [n_images][10], as cam_pos_state
 	float* cam_exposure = nullptr;                    // device, [n_images][3]
 	void upload_exposures();
+	// K19, error-map importance sampling (Testbed::Nerf::Training::ErrorMap testbed.h:600-615, train_nerf :2933-2939 and :2971-3023): every ray's loss is
+	// deposited into a low-resolution map per image; every n_steps_between_error_map_updates steps the map becomes a set of CDFs the next windows draw their
+	// pixels / images from. The counters always follow the reference's cadence; the map is only accumulated while one of the two switches is on (the
+	// reference always accumulates, for its GUI -- without the switches nothing reads the result).
+	bool sample_focal_plane_proportional_to_error = false, sample_image_proportional_to_error = false;
+	uint32_t n_steps_between_error_map_updates = 128, n_steps_since_error_map_update = 0;
+	bool error_map_live = false;   // the map was cleared at the start of the current window and receives every step's losses
+	bool error_cdf_valid = false;  // is_cdf_valid
+	bool error_cdf_used = false;   // the CDFs have been handed to a kernel since they were built (their buffers may not be re-sized without a sync)
+	int error_map_res[2] = {0, 0}, error_cdf_res[2] = {0, 0};
+	float *error_map = nullptr, *error_cdf_x_cond_y = nullptr, *error_cdf_y = nullptr, *error_cdf_img = nullptr, *error_pmf_img = nullptr;
+	size_t error_map_capacity = 0, error_cdf_capacity = 0; // floats
+	cudaEvent_t error_cdf_built = nullptr;
+	ngpb_error_cdf sampling_cdf() const; // what K1 / K6 / the camera gradient receive this step (null members unless valid and switched on)
+	void begin_error_map_window();
+	void finish_error_map_window();
 	float* coords_gradient = nullptr; __half* dL_dsh = nullptr; // workspace, sized by the batch (allocated on first use)
 	void reset_camera_extrinsics();
 	void update_transforms();

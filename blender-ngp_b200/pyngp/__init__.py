@@ -309,6 +309,11 @@ class Rng(C.Structure):
     _fields_ = [("state", C.c_uint64), ("inc", C.c_uint64)]
 
 
+class ErrorCdf(C.Structure):
+    """ngpb_error_cdf (include/ngpb.h): device pointers of the error-map CDFs; null members = uniform sampling."""
+    _fields_ = [("cdf_x_cond_y", C.c_void_p), ("cdf_y", C.c_void_p), ("cdf_img", C.c_void_p), ("res_x", C.c_int32), ("res_y", C.c_int32)]
+
+
 class LossConfig(C.Structure):
     _fields_ = [("loss_scale", C.c_float), ("background_color", C.c_float * 3), ("color_space", C.c_int32), ("random_bg_color", C.c_int32),
                 ("linear_colors", C.c_int32), ("loss_type", C.c_int32), ("rgb_activation", C.c_int32), ("density_activation", C.c_int32),
@@ -432,6 +437,7 @@ EXPORTED_SYMBOLS = [
     "ngpb_nerf_mlp_forward_backward_sh", "ngpb_nerf_input_gradient", "ngpb_compute_cam_gradient", "ngpb_camera_adam_step", "ngpb_apply_camera_offsets",
     "ngpb_testbed_get_camera_extrinsics", "ngpb_testbed_set_camera_extrinsics", "ngpb_testbed_reset_camera_extrinsics", "ngpb_probe_umma",
     "ngpb_exposure_update", "ngpb_compute_loss_exposure", "ngpb_testbed_get_camera_exposures", "ngpb_testbed_set_camera_exposures",
+    "ngpb_generate_training_samples_cdf", "ngpb_compute_loss_error_map", "ngpb_construct_error_cdfs", "ngpb_testbed_get_error_map_pmf",
     "ngpb_model_create", "ngpb_model_destroy", "ngpb_model_reset", "ngpb_model_n_params", "ngpb_model_training_step", "ngpb_model_loss", "ngpb_model_launches", "ngpb_model_stream",
     "ngpb_model_set_option", "ngpb_model_get_params", "ngpb_model_set_params_half", "ngpb_model_set_training_step", "ngpb_model_train", "ngpb_model_inference",
     "ngpb_model_set_image", "ngpb_model_set_image_rgba8", "ngpb_model_train_image", "ngpb_model_image_mse", "ngpb_model_render_image", "ngpb_model_set_sdf_data",
@@ -504,6 +510,8 @@ def lib():
         l.ngpb_exposure_update.restype = None
         l.ngpb_exposure_update.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float]
         l.ngpb_testbed_get_camera_exposures.argtypes = [C.c_void_p, C.c_void_p]
+        l.ngpb_testbed_get_error_map_pmf.argtypes = [C.c_void_p, C.c_void_p]
+        l.ngpb_construct_error_cdfs.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32] + [C.c_void_p] * 5
         l.ngpb_testbed_set_camera_exposures.argtypes = [C.c_void_p, C.c_void_p]
         _lib = l
     return _lib
@@ -832,6 +840,20 @@ class _Training:
         """Replaces the per-image exposures (and resets their optimizer state). An addition, like get_camera_exposures."""
         e = np.ascontiguousarray(np.asarray(exposures, np.float32).reshape(int(self._tb._get("n_images")), 3))
         check(lib().ngpb_testbed_set_camera_exposures(self._tb._h, e.ctypes.data))
+
+
+    # K19: importance sampling by accumulated training error (python_api.cu:817-818; train_nerf :2933-2939, :2971-3023)
+    sample_focal_plane_proportional_to_error = _bool_prop("sample_focal_plane_proportional_to_error")
+    sample_image_proportional_to_error = _bool_prop("sample_image_proportional_to_error")
+    n_steps_between_error_map_updates = property(lambda s: int(s._tb._get("n_steps_between_error_map_updates")))
+    n_steps_since_error_map_update = property(lambda s: int(s._tb._get("n_steps_since_error_map_update")))
+
+    def get_error_map_pmf(self):
+        """Sampling probabilities of the training images after the last CDF update (ErrorMap::pmf_img_cpu, testbed.h:611; the reference shows them in
+        its GUI); uniform before the first update. An addition, like get_camera_exposures."""
+        out = np.zeros(int(self._tb._get("n_images")), np.float32)
+        check(lib().ngpb_testbed_get_error_map_pmf(self._tb._h, out.ctypes.data))
+        return out
 
 
 class _Nerf:

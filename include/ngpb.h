@@ -354,6 +354,43 @@ int ngpb_compute_loss_exposure(void* stream, uint32_t n_rays, uint32_t n_rays_gl
                                const ngpb_half* rgbsigma, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords_in,
                                const float* mean_density_dev, float* coords_out, ngpb_half* dloss_dout, float* loss_per_ray, uint32_t* counters_out, void* scratch,
                                const float* exposure_dev, float* exposure_gradient_dev);
+/* ---- K19: importance sampling of training pixels / images by accumulated error (Testbed::Nerf::Training::ErrorMap, testbed.h:600-615;
+ * nerf.training.sample_focal_plane_proportional_to_error / sample_image_proportional_to_error, python_api.cu:817-818) ----
+ * The CDFs (device pointers): cdf_x_cond_y [n_images][res_y][res_x] + cdf_y [n_images][res_y] choose a texel of the image's error map for half of
+ * the rays (sample_cdf_2d, src/testbed_nerf.cu:991-1022), cdf_img [n_images] chooses the image (image_idx, :1062-1083). Null members switch the
+ * respective choice back to uniform pixels / round-robin images. */
+typedef struct {
+	const float* cdf_x_cond_y;
+	const float* cdf_y;
+	const float* cdf_img;
+	int32_t res_x, res_y;
+} ngpb_error_cdf;
+/* K1 drawing its pixels / images from the CDFs; otherwise ngpb_generate_training_samples_sharded (error_cdf may be NULL). */
+int ngpb_generate_training_samples_cdf(void* stream, uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, const float* aabb6, uint32_t max_samples, ngpb_rng rng,
+                                       uint32_t n_images, const ngpb_image* images_dev, const uint8_t* density_grid_bitfield,
+                                       int snap_to_pixel_centers, float cone_angle_constant,
+                                       uint32_t* counters, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, void* scratch,
+                                       const ngpb_error_cdf* error_cdf);
+/* K6 recovering its pixels from the same CDFs (error_cdf, may be NULL): the per-ray loss -- not its gradient -- is divided by the sampling density
+ * (:1448-1458) and the exposure gradient by the pixel density (:1560). error_map_dev (may be NULL) [n_images][error_map_res_y][error_map_res_x]: every
+ * ray with a compacted sample deposits its loss bilinearly (atomicAdd, :1465-1491; no sharpness weighting). Otherwise ngpb_compute_loss_exposure. */
+int ngpb_compute_loss_error_map(void* stream, uint32_t n_rays, uint32_t n_rays_global, const float* aabb6, ngpb_rng rng, uint32_t batch, const ngpb_loss_config* cfg,
+                                uint32_t n_images, const ngpb_image* images_dev, const uint32_t* counters_in,
+                                const ngpb_half* rgbsigma, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords_in,
+                                const float* mean_density_dev, float* coords_out, ngpb_half* dloss_dout, float* loss_per_ray, uint32_t* counters_out, void* scratch,
+                                const float* exposure_dev, float* exposure_gradient_dev,
+                                const ngpb_error_cdf* error_cdf, float* error_map_dev, int32_t error_map_res_x, int32_t error_map_res_y);
+/* construct_cdf_2d + construct_cdf_1d (:1984-2037) and the image normalisation the reference does on the host (:3000-3015), all on the device:
+ * per row the running sum of error + 1e-10, normalised and blended with 1 % uniform; the same over the row sums per image; then over the image sums
+ * with 10 % uniform. cdf_x_cond_y [n_images][res_y][res_x], cdf_y [n_images][res_y], cdf_img [n_images], pmf_img [n_images] (may be NULL: the
+ * per-image sampling probabilities, pmf_img_cpu). The sums run serially in the reference's order (bit-exact CDFs); one thread per row / image. */
+int ngpb_construct_error_cdfs(void* stream, uint32_t n_images, uint32_t res_y, uint32_t res_x, const float* error_map_dev,
+                              float* cdf_x_cond_y, float* cdf_y, float* cdf_img, float* pmf_img);
+/* Options "sample_focal_plane_proportional_to_error" and "sample_image_proportional_to_error" (ngpb_testbed_set_option) switch the error map on inside
+ * ngpb_testbed_train with the reference's cadence (:2933-2939, :2971-3023: map re-sized and cleared at the start of a window, CDFs rebuilt after
+ * n_steps_between_error_map_updates steps, which then grows by 1.5x from 128); read-only options "error_map_res", "error_cdf_valid",
+ * "n_steps_between_error_map_updates". pmf_img [n_images]: sampling probabilities of the images after the last CDF update. */
+int ngpb_testbed_get_error_map_pmf(ngpb_testbed* t, float* pmf_img);
 /* Options "optimize_exposure" and "exposure_l2_reg" (ngpb_testbed_set_option) switch the per-image exposure optimisation on inside ngpb_testbed_train
  * (same 16-step cadence as the extrinsics; Adam at the network optimizer's learning rate). The reference shows the exposures only in its GUI; these two
  * calls read / replace them: exposures3 [n_images][3]. Setting exposures resets their optimizer state. */

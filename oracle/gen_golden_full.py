@@ -634,12 +634,51 @@ def gen_exposure(out_dir):
               f" corr {float(np.corrcoef(o.ravel(), learned[k].ravel())[0, 1]):.4f}")
 
 
+def gen_error_map(out_dir):
+    """K19 through the REFERENCE's own Testbed: the small scene with one damaged image (tests/golden_inputs.py:error_scene_images), trained with
+    sample_focal_plane_proportional_to_error + sample_image_proportional_to_error over three error-map windows (128, 192, 288 steps) ->
+    ref_error_map_train.npz: after each window the error-map resolution, the window length, is_cdf_valid, the image probabilities (pmf_img_cpu) and the
+    loss. This repo's run of the same protocol is printed next to it."""
+    import synthetic
+    import pyngp
+    from golden_inputs import ERROR_SCENE, error_scene_images
+    n, res, B = ERROR_SCENE["n_images"], ERROR_SCENE["res"], ERROR_SCENE["batch"]
+    scratch = "/tmp/ngpb_ref_error_map"
+    shutil.rmtree(scratch, ignore_errors=True)
+    scene = dict(synthetic.make_lego_scene(n, res, seed=0))
+    scene["images"] = error_scene_images(np.asarray(scene["images"]))
+    tj = synthetic.write_transforms_json(scene, scratch)
+    ref = Ref()
+    ref.load(tj)
+    ref.network(base_config())
+    ref.set(shall_train=1, sample_focal_plane_proportional_to_error=1, sample_image_proportional_to_error=1)
+    states, pmfs, losses, rpb = [], [], [], []
+    for w in ERROR_SCENE["windows"]:
+        losses.append(ref.train(B, w))
+        st = (C.c_int * 5)(); pmf = np.zeros(n, np.float32)
+        ref.ck(ref.l.reff_error_map_state(ref.h, st, pmf.ctypes.data_as(C.c_void_p)))
+        states.append(list(st)); pmfs.append(pmf); rpb.append(ref.stats()["rays_per_batch"])
+        print("reference after", sum(ERROR_SCENE["windows"][:len(states)]), "steps: state", list(st), "pmf", np.round(pmf, 4), "loss", losses[-1], "rays/batch", rpb[-1])
+    np.savez_compressed(os.path.join(out_dir, "ref_error_map_train.npz"), states=np.array(states, np.int32), pmf=np.stack(pmfs), losses=np.array(losses, np.float32),
+                        rays_per_batch=np.array(rpb, np.int32))
+    tb = pyngp.Testbed()
+    tb.load_training_data(tj)
+    tr = tb.nerf.training
+    tr.sample_focal_plane_proportional_to_error = True
+    tr.sample_image_proportional_to_error = True
+    for k, w in enumerate(ERROR_SCENE["windows"]):
+        tb.train_n(w, B)
+        pmf = tr.get_error_map_pmf()
+        print(f"ours after {tb.training_step}: res {int(tb._get('error_map_res'))} between {tr.n_steps_between_error_map_updates} since {tr.n_steps_since_error_map_update} pmf {np.round(pmf, 4)}"
+              f" loss {tb.loss:.6f} max |pmf - reference| {float(np.abs(pmf - pmfs[k]).max()):.4f}")
+
+
 if __name__ == "__main__":
     out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden_full")
     os.makedirs(out, exist_ok=True)
     jobs = sys.argv[2:] or ["small", "big"]
     for j in jobs:
         try:
-            dict(small=gen_small, big=gen_big, config3=gen_config3, modes=gen_modes, modes_speed=gen_modes_speed, exposure=gen_exposure)[j](out)
+            dict(small=gen_small, big=gen_big, config3=gen_config3, modes=gen_modes, modes_speed=gen_modes_speed, exposure=gen_exposure, error_map=gen_error_map)[j](out)
         except Exception:
             traceback.print_exc()

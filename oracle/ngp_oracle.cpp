@@ -224,8 +224,36 @@ inline void read_rgba(float x, float y, const orc_image& img, float out[4]) {
 	out[3] = alpha;
 }
 
-// image_idx: src/testbed_nerf.cu:1062-1083 (no error-map CDF). uint32 wrap-around multiply as in the reference.
-inline uint32_t image_idx(uint32_t base_idx, uint32_t n_rays, uint32_t n_training_images) {
+// ---- K19: importance sampling by accumulated error (Testbed::Nerf::Training::ErrorMap, testbed.h:600-615) ----
+// The CDFs / error map the K1, K6 restatements below use; set through orc_set_error_cdf / orc_set_error_map (all null = uniform sampling, no accumulation,
+// which is the reference's behaviour until its sample_*_proportional_to_error switches are on).
+struct ErrorCdf { const float* x_cond_y; const float* y; const float* img; int res_x, res_y; };
+static ErrorCdf g_cdf = {nullptr, nullptr, nullptr, 0, 0};
+static float* g_error_map = nullptr;
+static int g_error_map_res[2] = {0, 0};
+
+inline float ld_random_val(uint32_t index, uint32_t seed, uint32_t dim); // (defined with the render restatement below)
+
+// binary_search: include/neural-graphics-primitives/common.h:201-223
+inline uint32_t binary_search(float val, const float* data, uint32_t length) {
+	if (length == 0) return 0;
+	uint32_t it, count = length, step, first = 0;
+	while (count > 0) {
+		it = first; step = count / 2; it += step;
+		if (data[it] < val) { first = ++it; count -= step + 1; } else count = step;
+	}
+	return std::min(first, length - 1);
+}
+
+// image_idx: src/testbed_nerf.cu:1062-1083. uint32 wrap-around multiply as in the reference.
+inline uint32_t image_idx(uint32_t base_idx, uint32_t n_rays, uint32_t n_training_images, float* pdf = nullptr) {
+	if (g_cdf.img) {
+		const float sample = ld_random_val(base_idx, 0xdeadbeefu, 0);
+		const uint32_t img = binary_search(sample, g_cdf.img, n_training_images);
+		if (pdf) { const float prev = img > 0 ? g_cdf.img[img - 1] : 0.0f; *pdf = (g_cdf.img[img] - prev) * n_training_images; }
+		return img;
+	}
+	if (pdf) *pdf = 1.0f;
 	return ((base_idx * n_training_images) / n_rays) % n_training_images;
 }
 
@@ -271,9 +299,31 @@ inline LossAndGradient loss_and_gradient(const float* target, const float* predi
 
 inline orc_pcg32 rng_advanced(orc_pcg32 rng, int64_t delta) { orc_pcg32_advance(&rng, delta); return rng; }
 
-// nerf_random_image_pos_training: src/testbed_nerf.cu:1047-1060 (no CDF)
-inline void random_image_pos_training(orc_pcg32& rng, int w, int h, bool snap, float* x, float* y) {
+// sample_cdf_2d: src/testbed_nerf.cu:991-1022 (UNIFORM_SAMPLING_FRACTION = 0.5: half of the samples stay uniform)
+inline void sample_cdf_2d(float* sx, float* sy, uint32_t img, float* pdf) {
+	const int rx = g_cdf.res_x, ry = g_cdf.res_y;
+	if (*sx < 0.5f) { *sx /= 0.5f; return; }
+	*sx = (*sx - 0.5f) / (1.0f - 0.5f);
+	const float* cdf_y = g_cdf.y + (size_t)img * ry;
+	const uint32_t y = binary_search(*sy, cdf_y, (uint32_t)ry);
+	float prev = y > 0 ? cdf_y[y - 1] : 0.0f;
+	const float pmf_y = cdf_y[y] - prev;
+	*sy = (*sy - prev) / pmf_y;
+	const float* cdf_x = g_cdf.x_cond_y + (size_t)img * ry * rx + (size_t)y * rx;
+	const uint32_t x = binary_search(*sx, cdf_x, (uint32_t)rx);
+	prev = x > 0 ? cdf_x[x - 1] : 0.0f;
+	const float pmf_x = cdf_x[x] - prev;
+	*sx = (*sx - prev) / pmf_x;
+	if (pdf) *pdf = pmf_x * pmf_y * (float)(rx * ry);
+	*sx = ((float)x + *sx) / (float)rx;
+	*sy = ((float)y + *sy) / (float)ry;
+}
+
+// nerf_random_image_pos_training: src/testbed_nerf.cu:1047-1060
+inline void random_image_pos_training(orc_pcg32& rng, int w, int h, bool snap, float* x, float* y, uint32_t img = 0, float* pdf = nullptr) {
 	float u = orc_pcg32_next_float(&rng), v = orc_pcg32_next_float(&rng);
+	if (pdf) *pdf = 1.0f; // (the uniform half of sample_cdf_2d leaves the caller's initial value, 1, :1378-1386)
+	if (g_cdf.x_cond_y) sample_cdf_2d(&u, &v, img, pdf);
 	if (snap) {
 		u = ((float)std::min(std::max((int)(u * (float)w), 0), w - 1) + 0.5f) / (float)w;
 		v = ((float)std::min(std::max((int)(v * (float)h), 0), h - 1) + 0.5f) / (float)h;
@@ -740,7 +790,7 @@ inline TrainRay setup_training_ray(uint32_t i, uint32_t n_rays, orc_pcg32 rng, u
 	const orc_image& im = images[img];
 	orc_pcg32_advance(&rng, (int64_t)i * N_MAX_RANDOM_SAMPLES_PER_RAY);
 	float x, y;
-	random_image_pos_training(rng, im.w, im.h, snap, &x, &y);
+	random_image_pos_training(rng, im.w, im.h, snap, &x, &y, img);
 	float px[4];
 	read_rgba(x, y, im, px);
 	if (px[0] < 0.0f) { r.valid = false; return r; }
@@ -864,7 +914,7 @@ extern "C" uint32_t orc_compute_loss_exposure(
 	const AABB aabb = make_aabb(aabb6);
 	const float EPSILON = 1e-4f;
 
-	struct PerRay { float rgb_ray[3]; float depth_ray; uint32_t compacted; float rgbtarget[3]; float exposure_scale[3]; uint32_t img; };
+	struct PerRay { float rgb_ray[3]; float depth_ray; uint32_t compacted; float rgbtarget[3]; float exposure_scale[3]; uint32_t img; float img_pdf, xy_pdf, x, y; int w, h; };
 	std::vector<PerRay> pr(n_rays_kept);
 
 	// phase 1 (parallel): forward compositing + target colour (:1341-1428)
@@ -895,10 +945,11 @@ extern "C" uint32_t orc_compute_loss_exposure(
 		}
 		uint32_t ray_idx = ray_indices[i];
 		orc_pcg32 r = rng_advanced(rng, (int64_t)ray_idx * N_MAX_RANDOM_SAMPLES_PER_RAY);
-		uint32_t img = image_idx(ray_idx, n_rays, n_images);
+		float img_pdf = 1.0f, xy_pdf = 1.0f;
+		uint32_t img = image_idx(ray_idx, n_rays, n_images, &img_pdf);
 		const orc_image& im = images[img];
 		float x, y;
-		random_image_pos_training(r, im.w, im.h, snap_to_pixel_centers != 0, &x, &y);
+		random_image_pos_training(r, im.w, im.h, snap_to_pixel_centers != 0, &x, &y, img, &xy_pdf);
 		float bg[3] = {background_color3[0], background_color3[1], background_color3[2]};
 		if (random_bg) { bg[0] = orc_pcg32_next_float(&r); bg[1] = orc_pcg32_next_float(&r); bg[2] = orc_pcg32_next_float(&r); }
 		for (int c = 0; c < 3; ++c) bg[c] = srgb_to_linear(bg[c]);
@@ -921,7 +972,7 @@ extern "C" uint32_t orc_compute_loss_exposure(
 		if (cn == numsteps) { for (int c = 0; c < 3; ++c) rgb_ray[c] += T * bg[c]; }
 		PerRay& p = pr[i];
 		for (int c = 0; c < 3; ++c) { p.rgb_ray[c] = rgb_ray[c]; p.rgbtarget[c] = rgbtarget[c]; p.exposure_scale[c] = es[c]; }
-		p.depth_ray = depth_ray; p.compacted = cn; p.img = img;
+		p.depth_ray = depth_ray; p.compacted = cn; p.img = img; p.img_pdf = img_pdf; p.xy_pdf = xy_pdf; p.x = x; p.y = y; p.w = im.w; p.h = im.h;
 	}
 
 	// compaction in ray-slot order (one valid serialisation of the atomicAdd at :1434)
@@ -955,8 +1006,24 @@ extern "C" uint32_t orc_compute_loss_exposure(
 		const float* ro = rays + (size_t)i * 6;
 
 		LossAndGradient lg = loss_and_gradient(p.rgbtarget, p.rgb_ray, loss_type);
+		{ const float pdf = p.img_pdf * p.xy_pdf; for (int c = 0; c < 3; ++c) lg.loss[c] /= pdf; } // the loss, not its gradient, is divided by the sampling pdf (:1448, :1454-1458)
 		float mean_loss = sum3(lg.loss[0], lg.loss[1], lg.loss[2]) / 3.0f; // Eigen mean(): redux sum / size
 		if (loss_output) loss_output[i] = mean_loss / (float)n_rays;
+		if (g_error_map) { // bilinear deposit of the ray's loss into the image's error map (:1465-1491; no sharpness weighting)
+			const int rx = g_error_map_res[0], ry = g_error_map_res[1];
+			const float px = std::min(std::max(p.x * (float)rx - 0.5f, 0.0f), (float)rx - (1.0f + 1e-4f));
+			const float py = std::min(std::max(p.y * (float)ry - 0.5f, 0.0f), (float)ry - (1.0f + 1e-4f));
+			const int ix = (int)px, iy = (int)py;
+			const float wx = px - (float)ix, wy = py - (float)iy;
+			const int jx = std::max(std::min(ix, p.w - 2), 0), jy = std::max(std::min(iy, p.h - 2), 0); // (clamped against the IMAGE resolution, as the reference does)
+			float* em = g_error_map + (size_t)p.img * rx * ry;
+			const float vals[4] = {(1 - wx) * (1 - wy) * mean_loss, wx * (1 - wy) * mean_loss, (1 - wx) * wy * mean_loss, wx * wy * mean_loss};
+			const size_t at[4] = {(size_t)jy * rx + jx, (size_t)jy * rx + jx + 1, (size_t)(jy + 1) * rx + jx, (size_t)(jy + 1) * rx + jx + 1};
+			for (int k = 0; k < 4; ++k) {
+				#pragma omp atomic
+				em[at[k]] += vals[k];
+			}
+		}
 
 		float rgb_ray2[3] = {0, 0, 0};
 		float depth_ray2 = 0.f;
@@ -997,7 +1064,7 @@ extern "C" uint32_t orc_compute_loss_exposure(
 		}
 		if (exposure_gradient) { // :1558-1571 (xy_pdf = 1 without an error map)
 			for (int c = 0; c < 3; ++c) {
-				float dloss_by_dgt = -lg.gradient[c];
+				float dloss_by_dgt = -lg.gradient[c] / p.xy_pdf;
 				if (!linear_colors) dloss_by_dgt /= srgb_to_linear_derivative(p.rgbtarget[c]);
 				const float g = loss_scale * dloss_by_dgt * p.exposure_scale[c] * 0.6931471805599453f;
 				#pragma omp atomic
@@ -1017,6 +1084,44 @@ extern "C" uint32_t orc_compute_loss(
 	return orc_compute_loss_exposure(n_rays_kept, n_rays, aabb6, n_rays_total, rng, max_samples_compacted, loss_scale_in, background_color3, color_space, random_bg, linear_colors,
 		n_images, images, rgbsigma, ray_indices, rays, numsteps_io, coords_in_all, coords_out_all, dloss_dout_all, loss_type, loss_output,
 		rgb_activation, density_activation, snap_to_pixel_centers, mean_density, near_distance, nullptr, nullptr);
+}
+
+// ---- K19 state and CDF construction ----
+extern "C" void orc_set_error_cdf(const float* cdf_x_cond_y, const float* cdf_y, const float* cdf_img, int res_x, int res_y) { g_cdf = {cdf_x_cond_y, cdf_y, cdf_img, res_x, res_y}; }
+extern "C" void orc_set_error_map(float* error_map, int res_x, int res_y) { g_error_map = error_map; g_error_map_res[0] = res_x; g_error_map_res[1] = res_y; }
+
+// construct_cdf_2d + construct_cdf_1d (src/testbed_nerf.cu:1982-2037): per row the running sum of error + 1e-10, normalised by a correctly rounded
+// reciprocal and blended with 1 % uniform; then the same over the row sums per image. cdf_img receives the un-normalised image sums.
+extern "C" void orc_construct_cdfs(uint32_t n_images, uint32_t height, uint32_t width, const float* error_map, float* cdf_x_cond_y, float* cdf_y, float* cdf_img) {
+	const float MIN_PDF = 0.01f;
+	for (uint32_t img = 0; img < n_images; ++img) {
+		for (uint32_t y = 0; y < height; ++y) {
+			const size_t off = ((size_t)img * height + y) * width;
+			float cum = 0;
+			for (uint32_t x = 0; x < width; ++x) { cum += error_map[off + x] + 1e-10f; cdf_x_cond_y[off + x] = cum; }
+			cdf_y[(size_t)img * height + y] = cum;
+			const float norm = 1.0f / cum; // __frcp_rn: IEEE round-to-nearest reciprocal
+			for (uint32_t x = 0; x < width; ++x) cdf_x_cond_y[off + x] = (1.0f - MIN_PDF) * cdf_x_cond_y[off + x] * norm + MIN_PDF * (float)(x + 1) / (float)width;
+		}
+		float* cy = cdf_y + (size_t)img * height;
+		float cum = 0;
+		for (uint32_t y = 0; y < height; ++y) { cum += cy[y]; cy[y] = cum; }
+		cdf_img[img] = cum;
+		const float norm = 1.0f / cum;
+		for (uint32_t y = 0; y < height; ++y) cy[y] = (1.0f - MIN_PDF) * cy[y] * norm + MIN_PDF * (float)(y + 1) / (float)height;
+	}
+}
+
+// The host part of the CDF update (:3000-3015): image sums -> per-image sampling probabilities (10 % uniform) and their CDF.
+extern "C" void orc_normalize_image_cdf(uint32_t n_images, const float* image_sums, float* pmf_img, float* cdf_img) {
+	float cum = 0;
+	for (uint32_t i = 0; i < n_images; ++i) { cum += image_sums[i]; cdf_img[i] = cum; }
+	const float norm = 1.0f / cum;
+	const float MIN_PMF = 0.1f;
+	for (uint32_t i = 0; i < n_images; ++i) {
+		pmf_img[i] = (1.0f - MIN_PMF) * image_sums[i] * norm + MIN_PMF / (float)n_images;
+		cdf_img[i] = (1.0f - MIN_PMF) * cdf_img[i] * norm + MIN_PMF * (float)(i + 1) / (float)n_images;
+	}
 }
 
 // K7: fill_rollover / fill_rollover_and_rescale, tcnn common_device.h:517-537

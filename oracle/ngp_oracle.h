@@ -119,6 +119,14 @@ uint32_t orc_compute_loss_exposure(
 	uint32_t* numsteps, const float* coords_in, float* coords_out, orc_half* dloss_dout /*[.][4]*/, int loss_type, float* loss_output,
 	int rgb_activation, int density_activation, int snap_to_pixel_centers, float mean_density, float near_distance,
 	const float* exposure, float* exposure_gradient);
+// ---- K19: error-map importance sampling (src/testbed_nerf.cu:991-1083, :1465-1491, :1982-2037, :2933-3023) ----
+// The CDFs K1 / K6 sample pixels (x_cond_y [n_images][res_y][res_x], y [n_images][res_y]) and images (img [n_images]) from; null pointers switch
+// the respective importance sampling off. Global state of the restatement: set, call orc_generate_training_samples* / orc_compute_loss*, clear.
+void orc_set_error_cdf(const float* cdf_x_cond_y, const float* cdf_y, const float* cdf_img, int res_x, int res_y);
+// The error map K6 deposits every ray's loss into ([n_images][res_y][res_x], added to); null = no accumulation.
+void orc_set_error_map(float* error_map, int res_x, int res_y);
+void orc_construct_cdfs(uint32_t n_images, uint32_t height, uint32_t width, const float* error_map, float* cdf_x_cond_y, float* cdf_y, float* cdf_img_sums);
+void orc_normalize_image_cdf(uint32_t n_images, const float* image_sums, float* pmf_img, float* cdf_img);
 // K7: tcnn common_device.h:517-537
 void orc_fill_rollover(uint32_t n_target, uint32_t n_valid, float* coords /*[.][7]*/, orc_half* dloss_dout /*[.][4]*/);
 

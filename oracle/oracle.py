@@ -251,6 +251,45 @@ def compute_loss(n_kept, n_rays, aabb6, rng, batch, images, rgbsigma, ray_indice
     return dict(compacted=total, numsteps=numsteps, coords_out=coords_out, dloss=dloss, loss=loss, exposure_gradient=exposure_gradient)
 
 
+# ---- K19: error-map importance sampling (global state of the restatement: set, call generate_training_samples / compute_loss, clear) ----
+import contextlib
+
+
+@contextlib.contextmanager
+def error_sampling(cdf_x_cond_y=None, cdf_y=None, cdf_img=None, error_map=None):
+    """Inside the block generate_training_samples / compute_loss / compute_cam_gradient draw pixels from cdf_x_cond_y [n_img, ry, rx] + cdf_y [n_img, ry]
+    and images from cdf_img [n_img] (either may be None), and compute_loss deposits every ray's loss into error_map [n_img, ry, rx] (float32, in place)."""
+    keep = []
+    rx = ry = 0
+    if cdf_x_cond_y is not None:
+        cdf_x_cond_y = _f32(cdf_x_cond_y); cdf_y = _f32(cdf_y)
+        ry, rx = cdf_x_cond_y.shape[1:]
+        keep += [cdf_x_cond_y, cdf_y]
+    if cdf_img is not None:
+        cdf_img = _f32(cdf_img); keep.append(cdf_img)
+    lib().orc_set_error_cdf(None if cdf_x_cond_y is None else _p(cdf_x_cond_y), None if cdf_x_cond_y is None else _p(cdf_y),
+                            None if cdf_img is None else _p(cdf_img), int(rx), int(ry))
+    if error_map is not None:
+        assert error_map.dtype == np.float32 and error_map.flags.c_contiguous and error_map.ndim == 3
+        lib().orc_set_error_map(_p(error_map), int(error_map.shape[2]), int(error_map.shape[1]))
+    try:
+        yield
+    finally:
+        lib().orc_set_error_cdf(None, None, None, 0, 0)
+        lib().orc_set_error_map(None, 0, 0)
+
+
+def construct_cdfs(error_map):
+    """construct_cdf_2d + construct_cdf_1d + the host normalisation: error_map [n_img, ry, rx] -> dict(cdf_x_cond_y, cdf_y, image_sums, pmf_img, cdf_img)."""
+    em = _f32(error_map)
+    n, ry, rx = em.shape
+    x = np.zeros_like(em); y = np.zeros((n, ry), np.float32); sums = np.zeros(n, np.float32)
+    lib().orc_construct_cdfs(n, ry, rx, _p(em), _p(x), _p(y), _p(sums))
+    pmf = np.zeros(n, np.float32); cdf = np.zeros(n, np.float32)
+    lib().orc_normalize_image_cdf(n, _p(sums), _p(pmf), _p(cdf))
+    return dict(cdf_x_cond_y=x, cdf_y=y, image_sums=sums, pmf_img=pmf, cdf_img=cdf)
+
+
 def fill_rollover(batch, n_valid, coords, dloss):
     lib().orc_fill_rollover(batch, n_valid, _p(coords), _p(dloss))
 

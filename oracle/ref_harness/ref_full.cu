@@ -75,6 +75,8 @@ int reff_set_option(void* tp, const char* name, double v) {
 	else if (k == "snap_to_pixel_centers") t->m_snap_to_pixel_centers = v != 0;
 	else if (k == "optimize_extrinsics") t->m_nerf.training.optimize_extrinsics = v != 0;
 	else if (k == "optimize_exposure") t->m_nerf.training.optimize_exposure = v != 0;
+	else if (k == "sample_focal_plane_proportional_to_error") t->m_nerf.training.sample_focal_plane_proportional_to_error = v != 0;
+	else if (k == "sample_image_proportional_to_error") t->m_nerf.training.sample_image_proportional_to_error = v != 0;
 	else if (k == "optimize_distortion") t->m_nerf.training.optimize_distortion = v != 0;
 	else if (k == "optimize_focal_length") t->m_nerf.training.optimize_focal_length = v != 0;
 	else if (k == "near_distance") t->m_nerf.training.near_distance = (float)v;
@@ -208,6 +210,17 @@ int reff_get_exposures(void* tp, float* out) {
 		auto v = t->m_nerf.training.cam_exposure[i].variable();
 		for (int c = 0; c < 3; ++c) out[i * 3 + c] = v[c];
 	}
+	REFF_END
+}
+// error-map state (Testbed::Nerf::Training::ErrorMap, testbed.h:600-615): state5 = {error-map res x, y, n_steps_between_error_map_updates, is_cdf_valid,
+// n_steps_since_error_map_update}; pmf_img (may be null) receives the per-image sampling probabilities of the last CDF update (pmf_img_cpu).
+int reff_error_map_state(void* tp, int* state5, float* pmf_img) {
+	REFF_BEGIN
+	Testbed* t = (Testbed*)tp;
+	auto& tr = t->m_nerf.training;
+	state5[0] = tr.error_map.resolution.x(); state5[1] = tr.error_map.resolution.y(); state5[2] = (int)tr.n_steps_between_error_map_updates;
+	state5[3] = tr.error_map.is_cdf_valid ? 1 : 0; state5[4] = (int)tr.n_steps_since_error_map_update;
+	if (pmf_img) for (size_t i = 0; i < tr.error_map.pmf_img_cpu.size(); ++i) pmf_img[i] = tr.error_map.pmf_img_cpu[i];
 	REFF_END
 }
 

@@ -182,6 +182,74 @@ int ref_compute_loss_exposure(
 	return st;
 }
 
+// ---- K19: error-map importance sampling (src/testbed_nerf.cu:991-1083, :1465-1491, :1984-2039) ----
+// K1 with the error-map CDFs (device pointers; cdf_img may be null): pixels and images are drawn proportionally to the accumulated error.
+int ref_generate_training_samples_cdf(
+	uint32_t n_rays, const float* aabb6, uint32_t max_samples, uint32_t n_rays_total,
+	uint64_t rng_state, uint64_t rng_inc,
+	uint32_t* ray_counter, uint32_t* numsteps_counter, uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords,
+	uint32_t n_images, int w, int h, float fx, float fy, float cx, float cy, const uint8_t* pixels, const float* xforms_host,
+	const uint8_t* bitfield, int snap_to_pixel_centers, float cone_angle_constant,
+	const float* cdf_x_cond_y, const float* cdf_y, const float* cdf_img, int cdf_res_x, int cdf_res_y
+) {
+	DeviceDataset d = make_dataset(n_images, w, h, fx, fy, cx, cy, pixels, xforms_host);
+	default_rng_t rng; rng.state = rng_state; rng.inc = rng_inc;
+	cudaMemset(ray_counter, 0, 4);
+	cudaMemset(numsteps_counter, 0, 4);
+	linear_kernel(generate_training_samples_nerf, 0, 0,
+		n_rays, make_aabb(aabb6), max_samples, n_rays_total, rng,
+		ray_counter, numsteps_counter, ray_indices, (Ray*)rays, numsteps,
+		PitchedPtr<NerfCoordinate>((NerfCoordinate*)coords, 1, 0, 0),
+		n_images, d.metadata.data(), d.xforms.data(), bitfield,
+		false, (float*)nullptr, (bool)snap_to_pixel_centers, false, cone_angle_constant,
+		(const float*)nullptr, Vector2i{0, 0}, cdf_x_cond_y, cdf_y, cdf_img, Vector2i{cdf_res_x, cdf_res_y},
+		(const float*)nullptr, 0u);
+	return (int)cudaDeviceSynchronize();
+}
+
+// K6 with the CDFs (the loss is divided by the sampling pdf) and the error-map accumulation (error_map: device float[n_images * res_y * res_x], added to).
+int ref_compute_loss_error_map(
+	uint32_t n_rays, const float* aabb6, uint32_t n_rays_total, uint64_t rng_state, uint64_t rng_inc,
+	uint32_t max_samples_compacted, const uint32_t* rays_counter, float loss_scale, int padded_output_width,
+	const float* background_color3, int color_space, int random_bg, int linear_colors,
+	uint32_t n_images, int w, int h, float fx, float fy, float cx, float cy, const uint8_t* pixels, const float* xforms_host,
+	const void* network_output_half, uint32_t* numsteps_counter_compacted, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps,
+	const float* coords_in, float* coords_out, void* dloss_doutput_half, int loss_type, float* loss_output,
+	int rgb_activation, int density_activation, int snap_to_pixel_centers, const float* mean_density_ptr, float near_distance,
+	float* error_map, int error_map_res_x, int error_map_res_y,
+	const float* cdf_x_cond_y, const float* cdf_y, const float* cdf_img, int cdf_res_x, int cdf_res_y
+) {
+	DeviceDataset d = make_dataset(n_images, w, h, fx, fy, cx, cy, pixels, xforms_host);
+	default_rng_t rng; rng.state = rng_state; rng.inc = rng_inc;
+	GPUMemory<Array3f> exposure(n_images);
+	exposure.memset(0);
+	cudaMemset(numsteps_counter_compacted, 0, 4);
+	linear_kernel(compute_loss_kernel_train_nerf, 0, 0,
+		n_rays, make_aabb(aabb6), n_rays_total, rng, max_samples_compacted, rays_counter, loss_scale, padded_output_width,
+		(const float*)nullptr, (float*)nullptr, Vector2i{0, 0}, ELossType::L2,
+		Array3f{background_color3[0], background_color3[1], background_color3[2]}, (EColorSpace)color_space, (bool)random_bg, (bool)linear_colors,
+		n_images, d.metadata.data(), (const network_precision_t*)network_output_half, numsteps_counter_compacted,
+		ray_indices, (const Ray*)rays, numsteps,
+		PitchedPtr<const NerfCoordinate>((NerfCoordinate*)coords_in, 1, 0, 0),
+		PitchedPtr<NerfCoordinate>((NerfCoordinate*)coords_out, 1, 0, 0),
+		(network_precision_t*)dloss_doutput_half, (ELossType)loss_type, ELossType::L1, loss_output,
+		false, (float*)nullptr, (ENerfActivation)rgb_activation, (ENerfActivation)density_activation, (bool)snap_to_pixel_centers,
+		error_map, cdf_x_cond_y, cdf_y, cdf_img, Vector2i{error_map_res_x, error_map_res_y}, Vector2i{cdf_res_x, cdf_res_y},
+		(const float*)nullptr, Vector2i{0, 0}, (float*)nullptr, (float*)nullptr, mean_density_ptr,
+		(const Array3f*)exposure.data(), (Array3f*)nullptr, 0.0f, near_distance);
+	return (int)cudaDeviceSynchronize();
+}
+
+// construct_cdf_2d + construct_cdf_1d with the launch shapes of Testbed::train_nerf (:2985-2998). All pointers on the device; cdf_img receives the
+// un-normalised per-image sums (the reference normalises them on the host, :3000-3015).
+int ref_construct_cdfs(uint32_t n_images, uint32_t height, uint32_t width, const float* error_map, float* cdf_x_cond_y, float* cdf_y, float* cdf_img) {
+	const dim3 threads = { 16, 8, 1 };
+	const dim3 blocks = { div_round_up(height, threads.x), div_round_up(n_images, threads.y), 1 };
+	construct_cdf_2d<<<blocks, threads, 0, nullptr>>>(n_images, height, width, error_map, cdf_x_cond_y, cdf_y);
+	linear_kernel(construct_cdf_1d, 0, nullptr, n_images, height, cdf_y, cdf_img);
+	return (int)cudaDeviceSynchronize();
+}
+
 // Timing variant: see ref_generate_training_samples_timed.
 int ref_compute_loss_timed(
 	uint32_t n_rays, const float* aabb6, uint32_t n_rays_total, uint64_t rng_state, uint64_t rng_inc,

@@ -196,3 +196,33 @@ def apply_image_exposures(images_u8, e):
     out = images_u8.copy()
     out[..., :3] = np.clip(np.rint(srgb * 255.0), 0, 255).astype(np.uint8)
     return out
+
+
+# ---- K19: error-map importance sampling (tests/golden/ref_error_map.npz) ----
+ERROR_CDF_RES = (12, 10)   # (res_x, res_y) of the error map the CDFs are built from
+ERROR_MAP_RES = (9, 11)    # (res_x, res_y) of the map K6 deposits into (the reference allows the two to differ: the map is re-sized at the start of a window)
+
+
+def error_map_inputs(n_images, seed=31):
+    """An accumulated error map [n_images][res_y][res_x] like a training window leaves it: per-ray losses ~1e-4 .. 1e-2 concentrated on a few texels, one
+    row and one whole image without any error (the 1e-10 floor and the uniform blend keep those samplable), one image with ten times the error."""
+    rx, ry = ERROR_CDF_RES
+    rs = np.random.RandomState(seed)
+    em = (rs.rand(n_images, ry, rx) ** 4 * 1e-2).astype(np.float32)
+    em[:, 3, :] = 0.0
+    em[1 % n_images] = 0.0
+    em[2 % n_images] *= 10.0
+    return em
+
+
+# ---- end-to-end error-map sampling (tests/golden/ref_error_map_train.npz: the reference's window state and image probabilities on this dataset) ----
+ERROR_SCENE = dict(n_images=8, res=64, batch=1 << 14, damaged=5, windows=(128, 192, 288))
+
+
+def error_scene_images(images_u8):
+    """The small scene with one image replaced by opaque mid-grey: no radiance field explains it together with the others, so its error stays high and the
+    image CDF must favour it."""
+    out = np.array(images_u8, copy=True)
+    out[ERROR_SCENE["damaged"], ..., :3] = 128
+    out[ERROR_SCENE["damaged"], ..., 3] = 255
+    return out
