@@ -12,7 +12,7 @@ refresh at the reference's cadence. `value` is device-timed (CUDA events on the 
 resident in HBM; `e2e` goes through the public `pyngp.Testbed` calls with the dataset starting in pinned HOST memory
 (its upload is inside the timed region) and the loss read back to the host every step.
 
-Also in the line: `roofline` (dominant stage by share of the step: algorithmic bytes / event time against MEASURED_PEAKS.json, DRAM traffic per launch from the
+Also in the line: `roofline` (dominant kernel by share of the step in the committed ncu launch list: algorithmic bytes / event time against MEASURED_PEAKS.json, DRAM traffic per launch from the
 committed ncu capture profiles/r01_traffic.json, and the same for every stage under `per_stage`), `cpu_baseline` (the oracle's whole-iteration restatement on the
 host cores, bounded to --cpu-seconds), `render` (classic Testbed.render Msamples/s and, single GPU only, the Blender path request_nerf_render_sync from a snapshot),
 `clocks` (nvidia-smi sampled during the timed region), `gpu_launches`.
@@ -51,6 +51,11 @@ STAGE_ALGO = {  # stage -> (bound, per-unit quantity, unit of `achieved`)
     "mlp_inference": ("tensor", MLP_FWD_FLOPS, "TFLOP/s"),
     "mlp_train": ("tensor", MLP_TRAIN_FLOPS, "TFLOP/s"),
 }
+# kernel-name fragment -> stage (to place the top line of the committed ncu launch list, profiles/r02_launches_summary.txt)
+KERNEL_STAGE = [("hash_encode_forward", "encode_inference"), ("hash_encode_backward", "encode_backward"), ("adam_ema", "optimizer"),
+                ("nerf_mlp_pipe_train", "mlp_train"), ("reduce_partials", "mlp_train"), ("nerf_mlp_pipe_infer", "mlp_inference"),
+                ("march_words", "sampling"), ("training_samples", "sampling"), ("training_rays", "sampling"),
+                ("loss_", "loss"), ("rollover", "loss")]
 # Stages whose algorithmic bytes depend on more than one unit count; evaluated in stage_bytes() below:
 #   sampling (K1)   28 B per marched sample written + 36 B per ray
 #   loss (K6 + K7)  72 B per marched sample (8 B network output + 28 B coordinate in, 28 B coordinate + 8 B gradient out) + 56 B per ray
@@ -342,8 +347,26 @@ def main():
                 if name == "optimizer":
                     rep.update(touched_params=touched, touched_fraction=touched / n_params, model="10 B x n_params + 34 B x touched (SURVEY.md s8d); touched measured from the per-parameter step counters")
         stage_report[name] = rep
-    # dominant kernel = the stage with the largest share of the step among those with a roofline model
-    dom = max((n for n in stage_report if "frac" in stage_report[n]), key=lambda n: stage_report[n]["share"])
+    # Dominant KERNEL of the step: the first line of the committed ncu launch list of this same command (profiles/r02_launches_summary.txt, shares of the
+    # serialised kernel time), mapped to the stage it belongs to -- a stage such as `sampling` is five kernels, none of which is the step's largest. The
+    # stage's live event time in THIS run then gives `achieved`; every stage, `sampling` included, keeps its own entry in per_stage. Without the file: the
+    # single-kernel stage with the largest share of this run.
+    dom, dom_kernel, dom_share_ncu = None, None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_launches_summary.txt")) as f:
+            for line in f:
+                parts = line.split()
+                if len(parts) >= 4 and parts[0].endswith("%"):
+                    kname = " ".join(parts[3:]).replace("void ", "")
+                    stage = next((s_ for pat, s_ in KERNEL_STAGE if pat in kname), None)
+                    if stage in stage_report and "frac" in stage_report[stage]:
+                        dom, dom_kernel, dom_share_ncu = stage, kname, float(parts[0].rstrip("%")) / 100.0
+                    break
+    except (OSError, ValueError):
+        pass
+    if dom is None:
+        single = [n for n in stage_report if "frac" in stage_report[n] and n in ("encode_inference", "encode_backward", "optimizer", "mlp_inference")]
+        dom = max(single or [n for n in stage_report if "frac" in stage_report[n]], key=lambda n: stage_report[n]["share"])
     d = stage_report[dom]
     # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the stages' kernels from the committed `ncu --set full` capture of this same
     # command (profiles/r02_traffic.json, written by tools/ncu_summary.py): a profiler number, read from the committed file because nothing timed may run under ncu
@@ -359,7 +382,8 @@ def main():
                 traffic, traffic_src = float(tj["stages"][dom]["dram_bytes_per_launch"]), f"profiles/{tf}: " + str(tj.get("source"))
         except (OSError, ValueError, KeyError):
             pass
-    roofline = dict(kernel=dom, bound=d["bound"], achieved=d["achieved"], peak=d["peak"], unit=d["unit"], frac=d["frac"], traffic=traffic, traffic_source=traffic_src,
+    roofline = dict(kernel=dom if dom_kernel is None else f"{dom_kernel} (stage {dom})", kernel_share_ncu=dom_share_ncu,
+                    largest_stage=max((n for n in stage_report if "frac" in stage_report[n]), key=lambda n: stage_report[n]["share"]), bound=d["bound"], achieved=d["achieved"], peak=d["peak"], unit=d["unit"], frac=d["frac"], traffic=traffic, traffic_source=traffic_src,
                     algorithmic_bytes_per_launch=d.get("algorithmic_bytes_per_launch", (d["units_per_call"] * STAGE_ALGO[dom][1]) if dom in STAGE_ALGO and d["bound"] == "hbm" else None),
                     peak_source=f"MEASURED_PEAKS.json ({pk['src']}; {'hbm_gbs' if d['bound'] == 'hbm' else 'bf16_tflops_sustained'})",
                     share_of_step=d["share"], per_stage=stage_report)

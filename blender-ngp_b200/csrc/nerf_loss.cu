@@ -282,7 +282,12 @@ __global__ void __launch_bounds__(1024) loss_composite_kernel(
 }
 
 // (B) one block: exclusive scan of the per-block totals (one valid serialisation of the atomicAdd at :1434).
-__global__ void __launch_bounds__(1024) loss_scan_kernel(const uint32_t n_blocks, uint32_t* __restrict__ block_sums, uint32_t* __restrict__ counters_out)
+// Compaction order. Ray-slot order while the batch holds every sample. When it overflows, the rays served last are clipped (:1436-1437): in slot order
+// those would always be the rays of the LAST training images (slots follow the ray index, the ray index selects the image), whereas the reference's
+// atomics clip whichever rays its blocks happen to process last. So the order then starts at a ray drawn from the step's RNG (past the rays' own
+// sub-streams) and wraps around: rot[0] = that ray's slot, rot[1] = its base in slot order; the gradient kernel rotates every base by it.
+__global__ void __launch_bounds__(1024) loss_scan_kernel(const LossParams P, const uint32_t* __restrict__ counters_in, const uint32_t n_blocks, uint32_t* __restrict__ block_sums,
+                                                         const uint32_t* __restrict__ local_bases, const uint32_t RB_C, uint32_t* __restrict__ counters_out, uint32_t* __restrict__ rot)
 {
 	__shared__ uint32_t smem[33];
 	uint32_t carry = 0;
@@ -294,7 +299,19 @@ __global__ void __launch_bounds__(1024) loss_scan_kernel(const uint32_t n_blocks
 		if (b < n_blocks) block_sums[b] = carry + excl;
 		carry += total;
 	}
-	if (threadIdx.x == 0) counters_out[0] = carry;
+	__syncthreads(); // (thread 0 reads prefixes written by other threads)
+	if (threadIdx.x == 0) {
+		counters_out[0] = carry;
+		uint32_t first = 0, start = 0;
+		const uint32_t kept = min(P.n_rays, counters_in[1]);
+		if (carry > P.batch && kept > 0) {
+			Pcg32 r = P.rng;
+			r.advance((int64_t)P.n_rays_global * N_MAX_RANDOM_SAMPLES_PER_RAY);
+			first = r.next_uint() % kept;
+			start = block_sums[first / RB_C] + local_bases[first];
+		}
+		rot[0] = first; rot[1] = start;
+	}
 }
 
 // (C) gradient pass, :1436-1556: same walk over the first `cn` samples of the ray, now with the ray's colour known. W lanes per ray;
@@ -306,7 +323,7 @@ __global__ void __launch_bounds__(GRAD_BLOCK) loss_gradient_kernel(
 	const LossParams P, const uint32_t* __restrict__ counters_in, const float* __restrict__ mean_density_ptr,
 	const __half* __restrict__ rgbsigma, const float* __restrict__ rays, uint32_t* __restrict__ numsteps_io, const float* __restrict__ coords_in,
 	const RayState* __restrict__ state, const uint32_t* __restrict__ compacted_counts, const uint32_t* __restrict__ local_bases, const uint32_t* __restrict__ block_prefix,
-	const uint32_t RB_C, float* __restrict__ coords_out, __half* __restrict__ dloss_dout, float* __restrict__ loss_output,
+	const uint32_t* __restrict__ rot, const uint32_t* __restrict__ compacted_total, const uint32_t RB_C, float* __restrict__ coords_out, __half* __restrict__ dloss_dout, float* __restrict__ loss_output,
 	const uint4* __restrict__ rows_in, uint4* __restrict__ rows_out)
 {
 	constexpr uint32_t RAYS_PER_WARP = 32 / W, RAYS_PER_BLOCK = GRAD_BLOCK / W;
@@ -319,6 +336,11 @@ __global__ void __launch_bounds__(GRAD_BLOCK) loss_gradient_kernel(
 		base = numsteps_io[i * 2 + 1];
 		// clip to the batch (:1436-1437)
 		compacted_base = block_prefix[i / RB_C] + local_bases[i];
+		const uint32_t total = *compacted_total;
+		if (total > P.batch) { // overflow: the order starts at slot rot[0] and wraps around (see loss_scan_kernel)
+			const uint32_t first = rot[0], start = rot[1];
+			compacted_base = i >= first ? compacted_base - start : compacted_base + (total - start);
+		}
 		cn = min(P.batch - min(P.batch, compacted_base), compacted_counts[i]);
 	}
 	__syncwarp();
@@ -646,10 +668,11 @@ int ngpb::compute_loss_launch(void* stream_, uint32_t n_rays, uint32_t n_rays_gl
 		if (wc == 8) NGPB_COMPOSITE(8); else if (wc == 16) NGPB_COMPOSITE(16); else NGPB_COMPOSITE(32);
 		#undef NGPB_COMPOSITE
 		NGPB_LAUNCH_CHECK();
-		loss_scan_kernel<<<1, 1024, 0, stream>>>(blocks_c, block_sums, counters_out);
+		uint32_t* rot = block_sums + blocks_c; // (two words inside the scratch's slack, see ngpb_compute_loss_scratch_bytes)
+		loss_scan_kernel<<<1, 1024, 0, stream>>>(P, counters_in, blocks_c, block_sums, local_bases, rb_c, counters_out, rot);
 		NGPB_LAUNCH_CHECK();
 		#define NGPB_GRADIENT(W) loss_gradient_kernel<W><<<blocks_g, GRAD_BLOCK, 0, stream>>>(P, counters_in, mean_density_dev, (const __half*)rgbsigma, rays, numsteps, coords_in, state, counts, local_bases, \
-			block_sums, rb_c, coords_out, (__half*)dloss_dout, loss_per_ray, reinterpret_cast<const uint4*>(encoded_in), reinterpret_cast<uint4*>(encoded_out))
+			block_sums, rot, counters_out, rb_c, coords_out, (__half*)dloss_dout, loss_per_ray, reinterpret_cast<const uint4*>(encoded_in), reinterpret_cast<uint4*>(encoded_out))
 		if (wg == 8) NGPB_GRADIENT(8); else if (wg == 16) NGPB_GRADIENT(16); else NGPB_GRADIENT(32);
 		#undef NGPB_GRADIENT
 		NGPB_LAUNCH_CHECK();

@@ -975,10 +975,23 @@ extern "C" uint32_t orc_compute_loss_exposure(
 		p.depth_ray = depth_ray; p.compacted = cn; p.img = img; p.img_pdf = img_pdf; p.xy_pdf = xy_pdf; p.x = x; p.y = y; p.w = im.w; p.h = im.h;
 	}
 
-	// compaction in ray-slot order (one valid serialisation of the atomicAdd at :1434)
+	// Compaction order: one valid serialisation of the atomicAdd at :1434. Ray-slot order while the batch holds every sample. When it overflows, the rays
+	// served last are clipped (:1436-1437) -- in slot order those would always be the rays of the LAST training images (slots follow the ray index, the
+	// ray index selects the image), whereas the reference's atomics clip whichever rays its blocks happen to process last. So the order then starts at a
+	// ray drawn from the step's RNG (past the rays' own sub-streams) and wraps around.
+	uint32_t first = 0;
+	{
+		uint64_t total = 0;
+		for (uint32_t i = 0; i < n_rays_kept; ++i) total += pr[i].compacted;
+		if (total > max_samples_compacted && n_rays_kept > 0) {
+			orc_pcg32 r = rng_advanced(rng, (int64_t)n_rays * N_MAX_RANDOM_SAMPLES_PER_RAY);
+			first = orc_pcg32_next_uint(&r) % n_rays_kept;
+		}
+	}
 	uint32_t counter = 0;
 	std::vector<uint32_t> cbase(n_rays_kept);
-	for (uint32_t i = 0; i < n_rays_kept; ++i) {
+	for (uint32_t k = 0; k < n_rays_kept; ++k) {
+		const uint32_t i = first + k < n_rays_kept ? first + k : first + k - n_rays_kept;
 		uint32_t compacted_base = counter;
 		counter += pr[i].compacted;
 		uint32_t cn = std::min(max_samples_compacted - std::min(max_samples_compacted, compacted_base), pr[i].compacted);

@@ -148,6 +148,47 @@ def test_compute_loss_invariants(orc, small_scene):
     assert np.all(out["loss"] >= 0) and out["loss"].sum() > 0
 
 
+def test_compute_loss_overflow_order_is_unbiased(orc, small_scene):
+    """Which rays an overflowing batch clips (src/testbed_nerf.cu:1434-1437 serves rays in the order of an atomicAdd): while everything fits, compaction is
+    in ray-slot order (exclusive prefix of the counts); on overflow the order starts at a ray drawn from the step's RNG and wraps around, so that the
+    clipped rays are not always those of the last training images. Either way the compacted ranges tile the batch exactly once."""
+    from conftest import scene_occupancy_bitfield
+    _, bits = scene_occupancy_bitfield(orc)
+    imgs = orc.make_images(small_scene["images"], small_scene["xforms"], small_scene["fx"], small_scene["fy"])
+    n_rays = 1024
+    rs = np.random.RandomState(0)
+    starts, last_kept = [], 0
+    for seed in range(6):
+        rng = orc.pcg32(100 + seed)
+        k1 = orc.generate_training_samples(n_rays, [0, 0, 0, 1, 1, 1], 1 << 16, rng, imgs, bits)
+        n_s, k = int(k1["counters"][0]), k1["n_kept"]
+        rgbsigma = np.zeros((1 << 16, 4), np.float16)
+        rgbsigma[:n_s] = rs.randn(n_s, 4).astype(np.float16)
+        fits = orc.compute_loss(k, n_rays, [0, 0, 0, 1, 1, 1], rng, 1 << 16, imgs, rgbsigma, k1["ray_indices"], k1["rays"], k1["numsteps"], k1["coords"], 0.005)
+        counts = fits["numsteps"][:k, 0].astype(np.int64)
+        assert fits["compacted"] == counts.sum() < (1 << 16)
+        assert np.array_equal(fits["numsteps"][:k, 1], np.concatenate([[0], np.cumsum(counts)[:-1]]))  # slot order
+        batch = int(counts.sum()) // 3
+        out = orc.compute_loss(k, n_rays, [0, 0, 0, 1, 1, 1], rng, batch, imgs, rgbsigma, k1["ray_indices"], k1["rays"], k1["numsteps"], k1["coords"], 0.005)
+        assert out["compacted"] == fits["compacted"]  # the counter is the unclipped total
+        cn, base = out["numsteps"][:k, 0].astype(np.int64), out["numsteps"][:k, 1].astype(np.int64)
+        assert cn.sum() == batch and np.all(cn <= counts)
+        covered = np.zeros(batch, np.int32)
+        for i in np.nonzero(cn)[0]:
+            covered[base[i]: base[i] + cn[i]] += 1
+        assert np.all(covered == 1)
+        first = int(np.nonzero((base == 0) & (cn > 0))[0][0])
+        # circular order: the rays served are a contiguous (wrapping) run of slots starting at `first`
+        served = np.nonzero(cn)[0]
+        run = (served - first) % k
+        assert run.max() < k and np.array_equal(np.sort(run), np.arange(run.max() + 1)[np.isin(np.arange(run.max() + 1), run)])
+        assert np.all(counts[(first + np.arange(run.max() + 1)) % k][cn[(first + np.arange(run.max() + 1)) % k] == 0] == 0)
+        starts.append(first)
+        last_kept += int(cn[k - 1] > 0)
+    assert len(set(starts)) >= 4 and any(s > 0 for s in starts)  # the start moves with the step's RNG
+    assert 0 < last_kept  # the last slots (the last images' rays) are not always the clipped ones
+
+
 def test_trainer_loss_decreases(orc, small_scene):
     """Whole-iteration restatement: a few steps at a small batch reduce the loss and adapt rays_per_batch (testbed_nerf.cu:2890)."""
     imgs = orc.make_images(small_scene["images"], small_scene["xforms"], small_scene["fx"], small_scene["fy"])
