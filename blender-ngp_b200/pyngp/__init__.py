@@ -784,6 +784,18 @@ class _Training:
     def _bool_prop(name):
         return property(lambda s: bool(s._tb._get(name)), lambda s, v: s._tb._set(name, 1.0 if v else 0.0))
 
+    def _unbuilt_prop(name, default):
+        """Reference options (python_api.cu:806-827) this path does not build: they read as the reference's default and refuse any other value."""
+        def setter(s, v):
+            if v != default:
+                raise RuntimeError(f"nerf.training.{name} = {v!r}: not built in this library (only the default {default!r})")
+        return property(lambda s: default, setter)
+
+    optimize_distortion = _unbuilt_prop("optimize_distortion", False)
+    optimize_focal_length = _unbuilt_prop("optimize_focal_length", False)
+    optimize_extra_dims = _unbuilt_prop("optimize_extra_dims", False)
+    include_sharpness_in_error = _unbuilt_prop("include_sharpness_in_error", False)
+    depth_supervision_lambda = _unbuilt_prop("depth_supervision_lambda", 0.0)
     random_bg_color = _bool_prop("random_bg_color")
     linear_colors = _bool_prop("linear_colors")
     snap_to_pixel_centers = _bool_prop("snap_to_pixel_centers")

@@ -263,3 +263,16 @@ def test_transforms_json_lens_models(tmp_path):
         assert all(l[0] == int(pyngp.LensMode.OpenCV) and l[1][:4] == pytest.approx([js["k1"], js["k2"], js["p1"], js["p2"]]) for l in got["lenses"])
         assert got["fx"] == pytest.approx(js["fl_x"]) and got["fy"] == pytest.approx(js["fl_y"]) and got["cx"] == pytest.approx(js["cx"] / js["w"])
         assert got["scale"] == 1.0 and got["offset"] == [0.0, 0.0, 0.0]  # this fork's loader defaults (nerf_loader.h:28, nerf_loader.cu:406-407)
+
+
+def test_unbuilt_training_options_refuse():
+    """Reference training options outside this path (python_api.cu:806-827: distortion / focal-length / extra-dims optimisation, sharpness-weighted error,
+    depth supervision) read as the reference's defaults and raise on any other value instead of being silently ignored."""
+    import pyngp
+    tr = pyngp._Training(None)
+    for name, default in (("optimize_distortion", False), ("optimize_focal_length", False), ("optimize_extra_dims", False), ("include_sharpness_in_error", False),
+                          ("depth_supervision_lambda", 0.0)):
+        assert getattr(tr, name) == default
+        setattr(tr, name, default)
+        with pytest.raises(RuntimeError, match="not built"):
+            setattr(tr, name, True if default is False else 1.0)
