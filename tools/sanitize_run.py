@@ -1,5 +1,6 @@
 """Short run of every mode for compute-sanitizer (memcheck / initcheck): NeRF training with the camera optimisation, a classic and a Blender frame with
-masks, the image and SDF modes.  compute-sanitizer --tool memcheck python tools/sanitize_run.py"""
+masks, the image and SDF modes.  compute-sanitizer --tool memcheck python tools/sanitize_run.py
+`python tools/sanitize_run.py k19`: the error-map importance sampling and exposure paths only."""
 import os
 import sys
 
@@ -12,6 +13,16 @@ import synthetic
 from golden_inputs import procedural_image, sdf_pool
 
 scene = synthetic.make_lego_scene(8, 64, device="cpu", seed=0)
+if "k19" in sys.argv[1:]:
+    # error-map importance sampling + exposure optimisation only: two windows, so that CDFs are built, drawn from (K1, K6, camera gradient) and rebuilt
+    tb = pyngp.Testbed()
+    tb.load_training_images(scene["images"], scene["xforms"], scene["fx"], scene["fy"])
+    tr = tb.nerf.training
+    tr.sample_focal_plane_proportional_to_error = tr.sample_image_proportional_to_error = True
+    tr.optimize_exposure = tr.optimize_extrinsics = True
+    tb.train_n(128 + 192 + 3, 1 << 12)
+    print("k19 loss", tb.loss, "pmf", tr.get_error_map_pmf(), "window", tr.n_steps_between_error_map_updates)
+    sys.exit(0)
 tb = pyngp.Testbed()
 tb.load_training_images(scene["images"], scene["xforms"], scene["fx"], scene["fy"])
 tb.nerf.training.optimize_extrinsics = True
