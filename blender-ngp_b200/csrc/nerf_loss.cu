@@ -307,6 +307,7 @@ __global__ void __launch_bounds__(1024) loss_scan_kernel(const LossParams P, con
 		if (carry > P.batch && kept > 0) {
 			Pcg32 r = P.rng;
 			r.advance((int64_t)P.n_rays_global * N_MAX_RANDOM_SAMPLES_PER_RAY);
+			(void)r.next_uint(); // (the first draw of this stream rotates K1's allocation order)
 			first = r.next_uint() % kept;
 			start = block_sums[first / RB_C] + local_bases[first];
 		}

@@ -283,7 +283,13 @@ __global__ void __launch_bounds__(K1_BLOCK) resolve_training_rays_kernel(
 
 // Pass 4: one block. Exclusive scan of the per-block totals: sample bases (the reference's numsteps_counter atomicAdd, :1225)
 // and ray slots (the ray_counter atomicAdd, :1232). counters[0] = samples requested; counters[1] is zeroed and counted by pass 5.
-__global__ void __launch_bounds__(1024) scan_training_samples_kernel(const uint32_t n_blocks, uint2* __restrict__ block_sums, uint32_t* __restrict__ counters)
+// Allocation order. Ray order while every sample fits max_samples. When the demand exceeds it, the rays served last are dropped (:1226): in ray order
+// those would always be the rays of the LAST training images (the ray index selects the image, :1076-1082), whereas the reference's atomics drop
+// whichever rays its blocks process last. So the order then starts at a ray drawn from the step's RNG (past the rays' own sub-streams) and wraps
+// around: rot = {that ray, its sample base and its slot in ray order, number of sample-bearing rays}; pass 5 rotates bases and slots by it.
+__global__ void __launch_bounds__(1024) scan_training_samples_kernel(const uint32_t n_blocks, uint2* __restrict__ block_sums, uint32_t* __restrict__ counters,
+                                                                     const uint32_t n_rays, const uint32_t n_rays_global, const uint32_t max_samples, const Pcg32 rng,
+                                                                     const uint32_t* __restrict__ local_bases, const uint32_t* __restrict__ local_slots, uint32_t* __restrict__ rot)
 {
 	__shared__ uint32_t smem[33];
 	uint32_t carry_c = 0, carry_z = 0;
@@ -296,7 +302,19 @@ __global__ void __launch_bounds__(1024) scan_training_samples_kernel(const uint3
 		if (b < n_blocks) block_sums[b] = make_uint2(carry_c + ex_c, carry_z + ex_z);
 		carry_c += tot_c; carry_z += tot_z;
 	}
-	if (threadIdx.x == 0) { counters[0] = carry_c; counters[1] = 0; }
+	__syncthreads(); // (thread 0 reads prefixes written by other threads)
+	if (threadIdx.x == 0) {
+		counters[0] = carry_c; counters[1] = 0;
+		uint32_t first = 0, start_c = 0, start_z = 0;
+		if (carry_c > max_samples && n_rays > 0) {
+			Pcg32 r = rng;
+			r.advance((int64_t)n_rays_global * N_MAX_RANDOM_SAMPLES_PER_RAY);
+			first = r.next_uint() % n_rays;
+			const uint2 bp = block_sums[first / K1_BLOCK];
+			start_c = bp.x + local_bases[first]; start_z = bp.y + local_slots[first];
+		}
+		rot[0] = first; rot[1] = start_c; rot[2] = start_z; rot[3] = carry_z;
+	}
 }
 
 // Pass 5: one warp per ray, one lane per march word. A ray is kept iff it has samples and base + count <= max_samples
@@ -308,7 +326,7 @@ __global__ void __launch_bounds__(WRITE_RAYS_PER_BLOCK * 32) write_training_samp
 	const uint32_t n_rays, const uint32_t ray_offset, const uint32_t n_rays_global, const uint32_t max_samples, const Aabb aabb, const Pcg32 rng, const uint32_t n_images, const ngpb_image* __restrict__ images,
 	const uint8_t* __restrict__ bitfield, const bool snap, const float cone_angle_constant, const ErrorCdf cdf,
 	const uint32_t* __restrict__ counts, const uint32_t* __restrict__ n_words, const RayRec* __restrict__ recs, const MarchWord* __restrict__ words,
-	const uint32_t* __restrict__ local_bases, const uint32_t* __restrict__ local_slots, const uint2* __restrict__ block_prefix,
+	const uint32_t* __restrict__ local_bases, const uint32_t* __restrict__ local_slots, const uint2* __restrict__ block_prefix, const uint32_t* __restrict__ rot,
 	uint32_t* __restrict__ counters, uint32_t* __restrict__ ray_indices, float* __restrict__ rays, uint32_t* __restrict__ numsteps, float* __restrict__ coords)
 {
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -320,6 +338,11 @@ __global__ void __launch_bounds__(WRITE_RAYS_PER_BLOCK * 32) write_training_samp
 		const uint2 bp = block_prefix[i / K1_BLOCK];
 		base = bp.x + local_bases[i];
 		slot = bp.y + local_slots[i];
+		const uint32_t total = counters[0];
+		if (total > max_samples) { // the demand exceeds the budget: allocation starts at ray rot[0] and wraps around (see pass 4)
+			const uint32_t first = rot[0], start_c = rot[1], start_z = rot[2], total_z = rot[3];
+			if (i >= first) { base -= start_c; slot -= start_z; } else { base += total - start_c; slot += total_z - start_z; }
+		}
 		kept = count > 0 && base + count <= max_samples;
 	}
 	const uint32_t n_kept_block = __syncthreads_count(kept && lane == 0);
@@ -490,10 +513,11 @@ extern "C" int ngpb_generate_training_samples_cdf(void* stream_, uint32_t n_rays
 		NGPB_K1(resolve_training_rays_kernel, blocks, K1_BLOCK, n_rays, ray_offset, n_rays_global, aabb, rng, n_images, images_dev, bitfield, snap, cone_angle_constant, cdf,
 			sc.recs, words, counts, n_words, local_bases, local_slots, block_sums);
 		NGPB_LAUNCH_CHECK();
-		scan_training_samples_kernel<<<1, 1024, 0, stream>>>(blocks, block_sums, counters);
+		uint32_t* rot = sc.n_items + 4; // (four words of the 256-byte slot that holds the item counter)
+		scan_training_samples_kernel<<<1, 1024, 0, stream>>>(blocks, block_sums, counters, n_rays, n_rays_global, max_samples, rng, local_bases, local_slots, rot);
 		NGPB_LAUNCH_CHECK();
 		NGPB_K1(write_training_samples_kernel, div_round_up(n_rays, WRITE_RAYS_PER_BLOCK), WRITE_RAYS_PER_BLOCK * 32, n_rays, ray_offset, n_rays_global, max_samples, aabb, rng, n_images, images_dev, bitfield,
-			snap_to_pixel_centers != 0, cone_angle_constant, cdf, counts, n_words, sc.recs, words, local_bases, local_slots, block_sums, counters, ray_indices, rays, numsteps, coords);
+			snap_to_pixel_centers != 0, cone_angle_constant, cdf, counts, n_words, sc.recs, words, local_bases, local_slots, block_sums, rot, counters, ray_indices, rays, numsteps, coords);
 		NGPB_LAUNCH_CHECK();
 		#undef NGPB_K1
 		return 0;

@@ -865,10 +865,23 @@ extern "C" uint32_t orc_generate_training_samples_sharded(
 		tr[i] = setup_training_ray(ray_offset + (uint32_t)i, n_rays_global, rng, n_images, images, eff.data(), aabb, snap_to_pixel_centers != 0, cone_angle_constant);
 		if (tr[i].valid) counts[i] = march_training_ray(tr[i], aabb, bitfield, NERF_STEPS, [](uint32_t, const Vec3&, float) {});
 	}
-	// allocation in ray order: one valid serialisation of the reference's atomicAdd (:1225,:1232)
+	// Allocation order: one valid serialisation of the reference's atomicAdd (:1225,:1232). Ray order while every sample fits max_samples. When the demand
+	// exceeds it, the rays served last are dropped (:1226) -- in ray order always those of the LAST training images (the ray index selects the image),
+	// whereas the reference's atomics drop whichever rays its blocks process last. So the order then starts at a ray drawn from the step's RNG (first draw
+	// past the rays' own sub-streams; K6 takes the second) and wraps around.
+	uint32_t first = 0;
+	{
+		uint64_t total = 0;
+		for (uint32_t i = 0; i < n_rays; ++i) total += counts[i];
+		if (total > max_samples && n_rays > 0) {
+			orc_pcg32 r = rng_advanced(rng, (int64_t)n_rays_global * N_MAX_RANDOM_SAMPLES_PER_RAY);
+			first = orc_pcg32_next_uint(&r) % n_rays;
+		}
+	}
 	uint32_t numsteps_counter = 0, ray_counter = 0;
 	std::vector<uint32_t> base_of(n_rays, 0xFFFFFFFFu), slot_of(n_rays, 0);
-	for (uint32_t i = 0; i < n_rays; ++i) {
+	for (uint32_t k = 0; k < n_rays; ++k) {
+		const uint32_t i = first + k < n_rays ? first + k : first + k - n_rays;
 		if (!tr[i].valid || counts[i] == 0) continue;
 		uint32_t base = numsteps_counter;
 		numsteps_counter += counts[i];
@@ -985,6 +998,7 @@ extern "C" uint32_t orc_compute_loss_exposure(
 		for (uint32_t i = 0; i < n_rays_kept; ++i) total += pr[i].compacted;
 		if (total > max_samples_compacted && n_rays_kept > 0) {
 			orc_pcg32 r = rng_advanced(rng, (int64_t)n_rays * N_MAX_RANDOM_SAMPLES_PER_RAY);
+			(void)orc_pcg32_next_uint(&r); // (the first draw of this stream rotates K1's allocation order)
 			first = orc_pcg32_next_uint(&r) % n_rays_kept;
 		}
 	}
