@@ -206,11 +206,23 @@ __device__ __forceinline__ void image_pos(float x, float y, int w, int h, int* p
 	*px = max(min((int)(x * (float)w), w - 1), 0);
 	*py = max(min((int)(y * (float)h), h - 1), 0);
 }
-// returns false for masked-away pixels (0x00FF00FF, read_rgba returns -1)
+// returns false for masked-away pixels (Byte: 0x00FF00FF, for which read_rgba returns -1; Half / Float: a negative red channel -- K1 tests `.x() < 0`, :1126)
 __device__ inline bool read_rgba(float x, float y, const ngpb_image& im, float out[4]) {
 	int px, py;
 	image_pos(x, y, im.w, im.h, &px, &py);
-	const uint32_t packed = reinterpret_cast<const uint32_t*>(im.pixels)[(size_t)px + (size_t)py * im.w];
+	const size_t idx = (size_t)px + (size_t)py * im.w;
+	if (im.image_type == NGPB_IMAGE_FLOAT) { // linear, premultiplied alpha, as stored
+		const float4 v = reinterpret_cast<const float4*>(im.pixels)[idx];
+		out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+		return v.x >= 0.0f;
+	}
+	if (im.image_type == NGPB_IMAGE_HALF) {
+		const uint2 raw = reinterpret_cast<const uint2*>(im.pixels)[idx];
+		const __half2 a = *reinterpret_cast<const __half2*>(&raw.x), b = *reinterpret_cast<const __half2*>(&raw.y);
+		out[0] = __low2float(a); out[1] = __high2float(a); out[2] = __low2float(b); out[3] = __high2float(b);
+		return out[0] >= 0.0f;
+	}
+	const uint32_t packed = reinterpret_cast<const uint32_t*>(im.pixels)[idx];
 	if (packed == 0x00FF00FFu) { out[0] = out[1] = out[2] = out[3] = -1.0f; return false; }
 	const float alpha = (float)(packed >> 24) * (1.0f / 255.0f);
 	out[0] = srgb_to_linear((float)(packed & 0xFF) * (1.0f / 255.0f)) * alpha;

@@ -335,7 +335,14 @@ void ngpb_testbed::dfree(void* p) {
 }
 
 // Testbed::load_training_data -> load_nerf -> load_nerf_post (src/testbed_nerf.cu:2643-2733)
-void ngpb_testbed::load_training_data(uint32_t n, const ngpb_host_image* host_images, uint32_t aabb_scale_) {
+static size_t image_bytes_per_pixel(int32_t image_type) {
+	if (image_type == NGPB_IMAGE_BYTE) return 4;
+	if (image_type == NGPB_IMAGE_HALF) return 8;
+	if (image_type == NGPB_IMAGE_FLOAT) return 16;
+	throw std::runtime_error("training image: unknown image_type");
+}
+
+void ngpb_testbed::load_training_data(uint32_t n, const ngpb_host_image* host_images, uint32_t aabb_scale_, bool allow_empty) {
 	NGPB_CUDA_CHECK(cudaSetDevice(device));
 	if (n == 0 || !host_images) throw std::runtime_error("load_training_data: no images");
 	if (aabb_scale_ == 0 || (aabb_scale_ & (aabb_scale_ - 1)) != 0) throw std::runtime_error("NeRF dataset's `aabb_scale` must be a power of two");
@@ -343,12 +350,15 @@ void ngpb_testbed::load_training_data(uint32_t n, const ngpb_host_image* host_im
 	aabb_scale = aabb_scale_;
 	size_t total = 0;
 	for (uint32_t i = 0; i < n; ++i) {
-		if (!host_images[i].pixels || host_images[i].w <= 0 || host_images[i].h <= 0) throw std::runtime_error("load_training_data: invalid image");
-		total += (size_t)host_images[i].w * host_images[i].h * 4;
+		const bool empty = !host_images[i].pixels && host_images[i].w == 0 && host_images[i].h == 0;
+		if (!(allow_empty && empty) && (!host_images[i].pixels || host_images[i].w <= 0 || host_images[i].h <= 0)) throw std::runtime_error("load_training_data: invalid image");
+		total += next_multiple((size_t)host_images[i].w * host_images[i].h * image_bytes_per_pixel(host_images[i].image_type), (size_t)16); // (float pixels are read as 16-byte vectors)
 	}
 	drop_prefetch();
 	NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
 	// a reload of a same-sized dataset reuses the device buffers (no allocation in the steady state, like the reference's arena)
+	for (void* p : own_pixels) dfree(p);
+	own_pixels.assign(n, nullptr);
 	if (total != pixels_bytes || n != images.size()) {
 		dfree(pixels); dfree(images_dev);
 		pixels = (uint8_t*)dalloc(total);
@@ -375,17 +385,19 @@ void ngpb_testbed::load_training_data(uint32_t n, const ngpb_host_image* host_im
 	for (uint32_t i = 0; i < n; ++i) {
 		const ngpb_host_image& h = host_images[i];
 		std::memcpy(&dataset_xforms[(size_t)i * 12], h.xform, sizeof(float) * 12);
-		const size_t bytes = (size_t)h.w * h.h * 4;
-		NGPB_CUDA_CHECK(cudaMemcpyAsync(pixels + off, h.pixels, bytes, cudaMemcpyHostToDevice, stream));
+		const size_t bytes = (size_t)h.w * h.h * image_bytes_per_pixel(h.image_type);
+		if (bytes) NGPB_CUDA_CHECK(cudaMemcpyAsync(pixels + off, h.pixels, bytes, cudaMemcpyHostToDevice, stream));
 		ngpb_image& im = images[i];
 		im.pixels = pixels + off;
+		im.image_type = h.image_type;
 		im.w = h.w; im.h = h.h; im.fx = h.fx; im.fy = h.fy; im.cx = h.cx; im.cy = h.cy;
 		if (h.lens_mode < NGPB_LENS_PERSPECTIVE || h.lens_mode > NGPB_LENS_LATLONG) throw std::runtime_error("load_training_data: unknown lens mode");
 		im.lens_mode = h.lens_mode; std::memcpy(im.lens_params, h.lens_params, sizeof(im.lens_params));
 		std::memcpy(im.raw_xform, h.xform, sizeof(float) * 12);
 		ngpb_effective_xform(h.xform, im.xform);
-		off += bytes;
+		off += next_multiple(bytes, (size_t)16);
 	}
+	n_images_for_training = n_images_for_training_prev = n; // load_nerf_post (:2646)
 	NGPB_CUDA_CHECK(cudaMemcpyAsync(images_dev, images.data(), sizeof(ngpb_image) * n, cudaMemcpyHostToDevice, stream));
 	NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
 	h2d_bytes += total + sizeof(ngpb_image) * n;
@@ -555,9 +567,10 @@ void ngpb_testbed::update_density_grid(uint32_t n_uniform, uint32_t n_nonuniform
 	const uint32_t n_elements = NERF_GRID_CELLS * (max_cascade + 1);
 	const uint32_t n_samples = n_uniform + n_nonuniform;
 	auto check = [](int st) { if (st != 0) throw std::runtime_error(ngpb_last_error()); };
-	if (training_step == 0) {
-		density_grid_ema_step = 0;
-		check(ngpb_mark_untrained_density_grid(stream, n_elements, density_grid, (uint32_t)images.size(), images_dev, 1));
+	if (training_step == 0 || n_images_for_training != n_images_for_training_prev) { // (:2783-2799)
+		n_images_for_training_prev = n_images_for_training;
+		if (training_step == 0) density_grid_ema_step = 0;
+		check(ngpb_mark_untrained_density_grid(stream, n_elements, density_grid, n_images_for_training, images_dev, training_step == 0 ? 1 : 0));
 		n_launches += 1;
 	}
 	ngpb_rng r{density_grid_rng.state, density_grid_rng.inc};
@@ -654,7 +667,7 @@ void ngpb_testbed::launch_sampling(cudaStream_t st, const SamplingRequest& p) {
 	stage_begin(NGPB_STAGE_SAMPLING, st);
 	// this rank's shard: local rays [rank * n_rays, (rank + 1) * n_rays) of a global batch of world * n_rays rays
 	if (ngpb_generate_training_samples_cdf(st, p.n_rays, (uint32_t)dp_rank * p.n_rays, (uint32_t)dp_world * p.n_rays, aabb, p.max_inference, p.rng,
-		(uint32_t)images.size(), images_dev, bitfield, p.snap, p.cone_angle, counters, ray_indices, rays, numsteps, coords, scratch, &p.cdf) != 0) throw std::runtime_error(ngpb_last_error());
+		n_images_for_training, images_dev, bitfield, p.snap, p.cone_angle, counters, ray_indices, rays, numsteps, coords, scratch, &p.cdf) != 0) throw std::runtime_error(ngpb_last_error());
 	if (p.cdf.cdf_x_cond_y || p.cdf.cdf_img) error_cdf_used = true;
 	stage_end(NGPB_STAGE_SAMPLING, p.n_rays, st);
 	n_launches += 5;
@@ -686,6 +699,9 @@ void ngpb_testbed::collect_loss_scalar() {
 void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 	NGPB_CUDA_CHECK(cudaSetDevice(device));
 	if (!training_data_available) throw std::runtime_error("train: no training data loaded (a snapshot alone can be rendered, not trained)");
+	if (n_images_for_training == 0) return; // (train_nerf :2897, training_prep_nerf :3389: an empty dataset trains nothing)
+	for (uint32_t i = 0; i < n_images_for_training; ++i)
+		if (images[i].w <= 0 || images[i].h <= 0) throw std::runtime_error("train: a training image among the first n_images_for_training has not been set");
 	if (batch != ws_batch) drop_prefetch();
 	ensure_workspace(batch);
 	auto check = [](int st) { if (st != 0) throw std::runtime_error(ngpb_last_error()); };
@@ -756,7 +772,7 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 	nerf_mlp_forward_launch(stream, w_half, encoded, tiled, coords, max_inference, counters, rgbsigma);
 	stage_end(NGPB_STAGE_MLP_INFERENCE, n_uncompacted_est, stream);
 	stage_begin(NGPB_STAGE_LOSS, stream);
-	check(compute_loss_launch(stream, R, (uint32_t)dp_world * R, aabb, r, batch, &loss_cfg, (uint32_t)images.size(), images_dev, counters, (const ngpb_half*)rgbsigma,
+	check(compute_loss_launch(stream, R, (uint32_t)dp_world * R, aabb, r, batch, &loss_cfg, n_images_for_training, images_dev, counters, (const ngpb_half*)rgbsigma,
 		ray_indices, rays, numsteps, coords, mean_density, coords_compacted, (ngpb_half*)dloss, loss, counters + 2, scratch,
 		reuse_encoding ? (const ngpb_half*)encoded : nullptr, reuse_encoding ? (ngpb_half*)encoded_compacted : nullptr, tiled,
 		exposure_active ? cam_exposure : nullptr, optimize_exposure ? cam_gradients + 6 * images.size() : nullptr,
@@ -798,7 +814,7 @@ void ngpb_testbed::train(uint32_t batch, bool sync_at_end) {
 		// K13 / K14 (train_nerf_step :3324-3372): gradients w.r.t. the network inputs of the compacted batch, reduced per camera. The reference runs the
 		// input gradient over the padded batch too; padding samples carry a zero loss gradient and belong to no ray.
 		nerf_input_gradient_launch(stream, &grid, w_half + MLP_PARAMS, coords_compacted, batch, denc, dL_dsh, coords_gradient);
-		cam_gradient_launch(stream, R, (uint32_t)dp_world * R, aabb, counters + 1, (uint32_t)images.size(), ray_indices, rays, numsteps, coords_compacted, coords_gradient,
+		cam_gradient_launch(stream, R, (uint32_t)dp_world * R, aabb, counters + 1, n_images_for_training, ray_indices, rays, numsteps, coords_compacted, coords_gradient,
 			cam_gradients, cam_gradients + 3 * images.size(), step_cdf.cdf_img);
 		n_launches += 2;
 		// the camera-gradient kernel is the last reader of this step's rays / numsteps / ray counter: the prefetched sampling of the next step, which
@@ -1074,13 +1090,14 @@ void ngpb_testbed::camera_update_step() {
 	NGPB_CUDA_CHECK(cudaMemcpyAsync(cam_gradients_host.data(), cam_gradients, sizeof(float) * 9 * n, cudaMemcpyDeviceToHost, stream));
 	NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
 	d2h_bytes += sizeof(float) * 9 * n;
-	const float per_camera_loss_scale = (float)n / LOSS_SCALE / (float)n_steps_between_cam_updates;
+	const size_t n_train = n_images_for_training; // (:3058, :3067, :3111: scale and loops run over the images in training)
+	const float per_camera_loss_scale = (float)n_train / LOSS_SCALE / (float)n_steps_between_cam_updates;
 	const float lr_floor = opt.learning_rate * opt.lr_factor / 1000.0f; // m_optimizer->learning_rate() / 1000
 	if (optimize_exposure) { // (:3105-3131)
-		ngpb_exposure_update((uint32_t)n, cam_exposure_state.data(), &cam_gradients_host[6 * n], per_camera_loss_scale, exposure_l2_reg, opt.learning_rate * opt.lr_factor);
+		ngpb_exposure_update((uint32_t)n_train, cam_exposure_state.data(), &cam_gradients_host[6 * n], per_camera_loss_scale, exposure_l2_reg, opt.learning_rate * opt.lr_factor);
 		upload_exposures();
 	}
-	for (size_t i = 0; optimize_extrinsics && i < n; ++i) {
+	for (size_t i = 0; optimize_extrinsics && i < n_train; ++i) {
 		float* ps = &cam_pos_state[i * 10]; float* rs = &cam_rot_state[i * 10];
 		float pg[3], rg[3];
 		for (int c = 0; c < 3; ++c) {
@@ -1115,9 +1132,66 @@ void ngpb_testbed::update_transforms() {
 		ngpb_apply_camera_offsets(&dataset_xforms[i * 12], &cam_pos_state[i * 10 + 7], &cam_rot_state[i * 10 + 7], images[i].raw_xform);
 		ngpb_effective_xform(images[i].raw_xform, images[i].xform);
 	}
+	upload_image_table();
+}
+
+void ngpb_testbed::upload_image_table() {
+	const size_t n = images.size();
 	NGPB_CUDA_CHECK(cudaMemcpyAsync(images_dev, images.data(), sizeof(ngpb_image) * n, cudaMemcpyHostToDevice, stream));
 	NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
 	h2d_bytes += sizeof(ngpb_image) * n;
+}
+
+// Testbed::create_empty_nerf_dataset (src/testbed_nerf.cu:2635-2641): n empty slots at identity poses, nothing in training yet
+void ngpb_testbed::create_empty_dataset(uint32_t n, uint32_t aabb_scale_) {
+	if (n == 0) throw std::runtime_error("create_empty_nerf_dataset: n_images must be positive");
+	std::vector<ngpb_host_image> empty(n);
+	for (auto& h : empty) {
+		h = ngpb_host_image{};
+		h.fx = h.fy = 1000.0f; h.cx = h.cy = 0.5f; // (nerf_loader.cu create_empty_nerf_dataset: metadata defaults)
+		h.xform[0] = h.xform[4] = h.xform[8] = 1.0f;
+	}
+	load_training_data(n, empty.data(), aabb_scale_, true);
+	n_images_for_training = n_images_for_training_prev = 0;
+}
+
+// nerf.training.set_image -> NerfDataset::set_training_image (python_api.cu:56-76): one slot's pixels, at any resolution and data type
+void ngpb_testbed::set_training_image(uint32_t frame_idx, const ngpb_host_image& h) {
+	NGPB_CUDA_CHECK(cudaSetDevice(device));
+	if (frame_idx >= images.size()) throw std::runtime_error("Invalid frame index");
+	if (!h.pixels || h.w <= 0 || h.h <= 0) throw std::runtime_error("set_image: image should be (H,W,C) where C=4");
+	const size_t bytes = (size_t)h.w * h.h * image_bytes_per_pixel(h.image_type);
+	drop_prefetch();
+	NGPB_CUDA_CHECK(cudaStreamSynchronize(stream)); // kernels of earlier steps may still read the slot
+	ngpb_image& im = images[frame_idx];
+	const size_t old_bytes = (size_t)im.w * im.h * image_bytes_per_pixel(im.image_type);
+	if (bytes != old_bytes || !im.pixels) { // a slot of another size gets its own allocation (slots loaded in bulk live in `pixels`)
+		dfree(own_pixels[frame_idx]);
+		own_pixels[frame_idx] = dalloc(bytes);
+		im.pixels = (const uint8_t*)own_pixels[frame_idx];
+	}
+	NGPB_CUDA_CHECK(cudaMemcpyAsync(const_cast<uint8_t*>(im.pixels), h.pixels, bytes, cudaMemcpyHostToDevice, stream));
+	im.w = h.w; im.h = h.h; im.image_type = h.image_type;
+	h2d_bytes += bytes;
+	upload_image_table();
+}
+
+// Training::set_camera_intrinsics (src/testbed_nerf.cu:2502-2516)
+void ngpb_testbed::set_camera_intrinsics(uint32_t frame_idx, float fx, float fy, float cx, float cy, float k1, float k2, float p1, float p2) {
+	NGPB_CUDA_CHECK(cudaSetDevice(device));
+	if (frame_idx >= images.size()) return; // (the reference ignores out-of-range frames)
+	if (fx <= 0.f) fx = fy;
+	if (fy <= 0.f) fy = fx;
+	ngpb_image& im = images[frame_idx];
+	if (cx < 0.f) cx = -cx; else cx = cx / (float)im.w;
+	if (cy < 0.f) cy = -cy; else cy = cy / (float)im.h;
+	im.lens_mode = (k1 != 0.f || k2 != 0.f || p1 != 0.f || p2 != 0.f) ? NGPB_LENS_OPENCV : NGPB_LENS_PERSPECTIVE;
+	std::memset(im.lens_params, 0, sizeof(im.lens_params));
+	im.lens_params[0] = k1; im.lens_params[1] = k2; im.lens_params[2] = p1; im.lens_params[3] = p2;
+	im.cx = cx; im.cy = cy; im.fx = fx; im.fy = fy;
+	drop_prefetch();
+	NGPB_CUDA_CHECK(cudaStreamSynchronize(stream));
+	upload_image_table();
 }
 
 void ngpb_testbed::reset_camera_extrinsics() { // Training::reset_camera_extrinsics (:2543-2555)
@@ -1294,6 +1368,22 @@ extern "C" int ngpb_testbed_set_optimizer_state(ngpb_testbed* t, const float* fm
 	NGPB_API_END
 }
 
+extern "C" int ngpb_testbed_create_empty_dataset(ngpb_testbed* t, uint32_t n_images, uint32_t aabb_scale) {
+	NGPB_API_BEGIN
+	t->create_empty_dataset(n_images, aabb_scale);
+	NGPB_API_END
+}
+extern "C" int ngpb_testbed_set_training_image(ngpb_testbed* t, uint32_t frame_idx, const ngpb_host_image* image) {
+	NGPB_API_BEGIN
+	if (!image) throw std::runtime_error("set_training_image: invalid argument");
+	t->set_training_image(frame_idx, *image);
+	NGPB_API_END
+}
+extern "C" int ngpb_testbed_set_camera_intrinsics(ngpb_testbed* t, uint32_t frame_idx, float fx, float fy, float cx, float cy, float k1, float k2, float p1, float p2) {
+	NGPB_API_BEGIN
+	t->set_camera_intrinsics(frame_idx, fx, fy, cx, cy, k1, k2, p1, p2);
+	NGPB_API_END
+}
 // nerf.training.get_camera_extrinsics / set_camera_extrinsics / reset_camera_extrinsics (:2518-2555, :2590-2595), in the library's (ngp) coordinates
 extern "C" int ngpb_testbed_get_camera_extrinsics(ngpb_testbed* t, uint32_t frame_idx, float* xform12, float* pos_offset3, float* rot_offset3) {
 	NGPB_API_BEGIN
@@ -1399,6 +1489,11 @@ extern "C" int ngpb_testbed_set_option(ngpb_testbed* t, const char* name, double
 	else if (k == "optimize_exposure") t->optimize_exposure = v != 0;
 	else if (k == "sample_focal_plane_proportional_to_error") t->sample_focal_plane_proportional_to_error = v != 0;
 	else if (k == "sample_image_proportional_to_error") t->sample_image_proportional_to_error = v != 0;
+	else if (k == "n_images_for_training") {
+		if (v < 0 || v > (double)t->images.size()) throw std::runtime_error("n_images_for_training must be in [0, n_images]");
+		t->drop_prefetch(); // (a prefetched K1 drew its images from the previous count)
+		t->n_images_for_training = (uint32_t)v;
+	}
 	else if (k == "exposure_l2_reg") t->exposure_l2_reg = (float)v;
 	else if (k == "extrinsic_learning_rate") t->extrinsic_learning_rate = (float)v;
 	else if (k == "extrinsic_l2_reg") t->extrinsic_l2_reg = (float)v;
@@ -1451,6 +1546,7 @@ extern "C" double ngpb_testbed_get_option(ngpb_testbed* t, const char* name) {
 	if (k == "n_steps_between_error_map_updates") return t->n_steps_between_error_map_updates;
 	if (k == "n_steps_since_error_map_update") return t->n_steps_since_error_map_update;
 	if (k == "n_images") return (double)t->images.size();
+	if (k == "n_images_for_training") return (double)t->n_images_for_training;
 	if (k == "exposure_l2_reg") return t->exposure_l2_reg;
 	if (k == "extrinsic_learning_rate") return t->extrinsic_learning_rate;
 	if (k == "extrinsic_l2_reg") return t->extrinsic_l2_reg;

@@ -11,7 +11,14 @@ struct ngpb_testbed {
 	ngpb_testbed(const ngpb_testbed&) = delete;
 	ngpb_testbed& operator=(const ngpb_testbed&) = delete;
 
-	void load_training_data(uint32_t n, const ngpb_host_image* host_images, uint32_t aabb_scale);
+	void load_training_data(uint32_t n, const ngpb_host_image* host_images, uint32_t aabb_scale, bool allow_empty = false);
+	// datasets filled while training runs (Testbed::create_empty_nerf_dataset, nerf.training.set_image / set_camera_intrinsics / n_images_for_training)
+	void create_empty_dataset(uint32_t n, uint32_t aabb_scale);
+	void set_training_image(uint32_t frame_idx, const ngpb_host_image& image);
+	void set_camera_intrinsics(uint32_t frame_idx, float fx, float fy, float cx, float cy, float k1, float k2, float p1, float p2);
+	void upload_image_table();
+	uint32_t n_images_for_training = 0, n_images_for_training_prev = 0; // the first n images take part in training (testbed.h:660)
+	std::vector<void*> own_pixels;                                        // per-image allocations made by set_training_image (null: the image lives in `pixels`)
 	void reset_network(uint32_t seed);
 	void train(uint32_t batch, bool sync_at_end = true);
 	void update_density_grid(uint32_t n_uniform, uint32_t n_nonuniform);

@@ -297,12 +297,31 @@ class LensMode(enum.IntEnum):  # common.h ELensMode (python_api.cu:385-390)
 
 class Image(C.Structure):
     _fields_ = [("pixels", C.c_void_p), ("w", C.c_int32), ("h", C.c_int32), ("fx", C.c_float), ("fy", C.c_float),
-                ("cx", C.c_float), ("cy", C.c_float), ("xform", C.c_float * 12), ("raw_xform", C.c_float * 12), ("lens_mode", C.c_int32), ("lens_params", C.c_float * 7)]
+                ("cx", C.c_float), ("cy", C.c_float), ("xform", C.c_float * 12), ("raw_xform", C.c_float * 12), ("lens_mode", C.c_int32), ("lens_params", C.c_float * 7),
+                ("image_type", C.c_int32)]
 
 
 class HostImage(C.Structure):
     _fields_ = [("pixels", C.c_void_p), ("w", C.c_int32), ("h", C.c_int32), ("fx", C.c_float), ("fy", C.c_float),
-                ("cx", C.c_float), ("cy", C.c_float), ("xform", C.c_float * 12), ("lens_mode", C.c_int32), ("lens_params", C.c_float * 7)]
+                ("cx", C.c_float), ("cy", C.c_float), ("xform", C.c_float * 12), ("lens_mode", C.c_int32), ("lens_params", C.c_float * 7), ("image_type", C.c_int32)]
+
+
+IMAGE_BYTE, IMAGE_HALF, IMAGE_FLOAT = 0, 1, 2  # NGPB_IMAGE_* (EImageDataType)
+
+
+def _image_array(img):
+    """A training image as the C ABI takes it: (contiguous [h][w][4] array, NGPB_IMAGE_*). float32 / float16 arrays keep their type, anything else is RGBA8."""
+    px = np.asarray(img)
+    if px.dtype == np.float32:
+        itype = IMAGE_FLOAT
+    elif px.dtype == np.float16:
+        itype = IMAGE_HALF
+    else:
+        px, itype = px.astype(np.uint8, copy=False), IMAGE_BYTE
+    px = np.ascontiguousarray(px)
+    if px.ndim != 3 or px.shape[2] != 4:
+        raise RuntimeError("image should be (H,W,C) where C=4")
+    return px, itype
 
 
 class Rng(C.Structure):
@@ -438,6 +457,7 @@ EXPORTED_SYMBOLS = [
     "ngpb_testbed_get_camera_extrinsics", "ngpb_testbed_set_camera_extrinsics", "ngpb_testbed_reset_camera_extrinsics", "ngpb_probe_umma",
     "ngpb_exposure_update", "ngpb_compute_loss_exposure", "ngpb_testbed_get_camera_exposures", "ngpb_testbed_set_camera_exposures",
     "ngpb_generate_training_samples_cdf", "ngpb_compute_loss_error_map", "ngpb_construct_error_cdfs", "ngpb_testbed_get_error_map_pmf",
+    "ngpb_testbed_create_empty_dataset", "ngpb_testbed_set_training_image", "ngpb_testbed_set_camera_intrinsics",
     "ngpb_model_create", "ngpb_model_destroy", "ngpb_model_reset", "ngpb_model_n_params", "ngpb_model_training_step", "ngpb_model_loss", "ngpb_model_launches", "ngpb_model_stream",
     "ngpb_model_set_option", "ngpb_model_get_params", "ngpb_model_set_params_half", "ngpb_model_set_training_step", "ngpb_model_train", "ngpb_model_inference",
     "ngpb_model_set_image", "ngpb_model_set_image_rgba8", "ngpb_model_train_image", "ngpb_model_image_mse", "ngpb_model_render_image", "ngpb_model_set_sdf_data",
@@ -511,6 +531,9 @@ def lib():
         l.ngpb_exposure_update.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float]
         l.ngpb_testbed_get_camera_exposures.argtypes = [C.c_void_p, C.c_void_p]
         l.ngpb_testbed_get_error_map_pmf.argtypes = [C.c_void_p, C.c_void_p]
+        l.ngpb_testbed_create_empty_dataset.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+        l.ngpb_testbed_set_training_image.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        l.ngpb_testbed_set_camera_intrinsics.argtypes = [C.c_void_p, C.c_uint32] + [C.c_float] * 8
         l.ngpb_construct_error_cdfs.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32] + [C.c_void_p] * 5
         l.ngpb_testbed_set_camera_exposures.argtypes = [C.c_void_p, C.c_void_p]
         _lib = l
@@ -854,6 +877,22 @@ class _Training:
         check(lib().ngpb_testbed_set_camera_exposures(self._tb._h, e.ctypes.data))
 
 
+    # datasets filled from arrays while training runs (python_api.cu:806, :830-851; with Testbed.create_empty_nerf_dataset)
+    n_images_for_training = property(lambda s: int(s._tb._get("n_images_for_training")), lambda s, v: s._tb._set("n_images_for_training", int(v)))
+
+    def set_image(self, frame_idx, img, depth_img=None, depth_scale=1.0):
+        """Training::set_image (python_api.cu:56-76): replaces one training image. img: (H, W, 4) float32 (or float16) linear colours with premultiplied
+        alpha, as in the reference; a uint8 array is taken as sRGB RGBA8 (an addition). depth_img is accepted and unused: depth supervision is not built."""
+        px, itype = _image_array(img)
+        h = HostImage()
+        h.pixels, h.w, h.h, h.image_type = px.ctypes.data, px.shape[1], px.shape[0], itype
+        check(lib().ngpb_testbed_set_training_image(self._tb._h, int(frame_idx) & 0xFFFFFFFF, C.byref(h)))
+
+    def set_camera_intrinsics(self, frame_idx, fx=0.0, fy=0.0, cx=-0.5, cy=-0.5, k1=0.0, k2=0.0, p1=0.0, p2=0.0):
+        """Training::set_camera_intrinsics (src/testbed_nerf.cu:2502-2516): focal lengths in pixels (a non-positive one is copied from the other), principal
+        point in pixels (negative: minus the fraction of the resolution), OpenCV distortion if any coefficient is non-zero."""
+        check(lib().ngpb_testbed_set_camera_intrinsics(self._tb._h, int(frame_idx) & 0xFFFFFFFF, float(fx), float(fy), float(cx), float(cy), float(k1), float(k2), float(p1), float(p2)))
+
     # K19: importance sampling by accumulated training error (python_api.cu:817-818; train_nerf :2933-2939, :2971-3023)
     sample_focal_plane_proportional_to_error = _bool_prop("sample_focal_plane_proportional_to_error")
     sample_image_proportional_to_error = _bool_prop("sample_image_proportional_to_error")
@@ -962,17 +1001,24 @@ class Testbed:
         self._dataset_scale, self._dataset_offset = d["scale"], tuple(d["offset"])
         self.load_training_images(d["images"], d["xforms"], d["fx"], d["fy"], d["cx"], d["cy"], d["aabb_scale"], d["lenses"])
 
+    def create_empty_nerf_dataset(self, n_images, aabb_scale=1, is_hdr=False):
+        """Testbed::create_empty_nerf_dataset (python_api.cu:545, src/testbed_nerf.cu:2635-2641): n_images empty slots to be filled with
+        nerf.training.set_image / set_camera_intrinsics / set_camera_extrinsics; nerf.training.n_images_for_training starts at 0 (train() is then a no-op)."""
+        self._dataset_scale, self._dataset_offset = 0.33, (0.5, 0.5, 0.5)  # NerfDataset defaults (nerf_loader.h:107-108)
+        check(lib().ngpb_testbed_create_empty_dataset(self._h, int(n_images), int(aabb_scale)))
+        self._set("rgb_activation", int(NerfActivation.Exponential if is_hdr else NerfActivation.Logistic))  # load_nerf_post (:2644)
+
     def load_training_images(self, images, xforms, fx, fy, cx=0.5, cy=0.5, aabb_scale=1, lenses=None):
-        """Already-decoded data: images uint8 [n][h][w][4] (host), xforms float32 [n][3][4] in ngp convention; lenses: per image (LensMode, 7 params) or None."""
+        """Already-decoded data: images [n][h][w][4] (host) -- uint8 sRGB with straight alpha, or float16 / float32 linear colours with premultiplied alpha
+        (EImageDataType Byte / Half / Float) --, xforms float32 [n][3][4] in ngp convention; lenses: per image (LensMode, 7 params) or None."""
         n = len(images)
         arr = (HostImage * n)()
         keep = []
         for i in range(n):
-            px = np.ascontiguousarray(images[i], dtype=np.uint8)
-            if px.ndim != 3 or px.shape[2] != 4:
-                raise RuntimeError("training images must be RGBA8 [h][w][4]")
+            px, itype = _image_array(images[i])
             keep.append(px)
             arr[i].pixels = px.ctypes.data
+            arr[i].image_type = itype
             arr[i].h, arr[i].w = px.shape[0], px.shape[1]
             pick = lambda v: float(v[i]) if isinstance(v, (list, tuple, np.ndarray)) else float(v)  # scalar = the same for every image
             arr[i].fx, arr[i].fy, arr[i].cx, arr[i].cy = pick(fx), pick(fy), pick(cx), pick(cy)

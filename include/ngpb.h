@@ -110,7 +110,7 @@ int ngpb_nerf_density_mlp_forward(void* stream, const ngpb_half* mlp, const ngpb
 
 /* ---- training images ---- */
 typedef struct {
-	const uint8_t* pixels; /* device pointer, RGBA8 (EImageDataType::Byte) */
+	const uint8_t* pixels; /* device pointer; layout by image_type below (16-byte aligned for the float type, 8 for half) */
 	int32_t w, h;
 	float fx, fy;          /* focal length in pixels (nerf_loader.h:42) */
 	float cx, cy;          /* principal point as a fraction of the resolution (nerf_loader.h:41) */
@@ -119,7 +119,11 @@ typedef struct {
 	float raw_xform[12];   /* the unmodified 3x4 (used by mark_untrained_density_grid, testbed_nerf.cu:398) */
 	int32_t lens_mode;     /* NGPB_LENS_* (ELensMode, common.h; nerf_loader.cu:197-269 read_lens) */
 	float lens_params[7];  /* OpenCV: k1, k2, p1, p2; FTheta: p0..p4, w, h (common_device.cuh:141-160,:236-249) */
+	int32_t image_type;    /* NGPB_IMAGE_* (EImageDataType; read_rgba, common_device.cuh:677-705) */
 } ngpb_image;
+/* Byte: RGBA8 sRGB with straight alpha (0x00FF00FF = masked-away pixel); Half / Float: 4 x fp16 / fp32 linear colours with premultiplied alpha, as the
+ * reference keeps EXR files and the arrays handed to nerf.training.set_image (a negative red channel = masked away). */
+enum { NGPB_IMAGE_BYTE = 0, NGPB_IMAGE_HALF = 1, NGPB_IMAGE_FLOAT = 2 };
 enum { NGPB_LENS_PERSPECTIVE = 0, NGPB_LENS_OPENCV = 1, NGPB_LENS_FTHETA = 2, NGPB_LENS_LATLONG = 3 };
 
 /* Host-only: the transform generate_training_samples_nerf effectively uses for a camera without rolling shutter. */
@@ -279,18 +283,28 @@ int ngpb_selftest_umma(void* stream, int variant, const ngpb_half* a, const ngpb
 typedef struct ngpb_testbed ngpb_testbed;
 
 typedef struct {
-	const uint8_t* pixels; /* host pointer, RGBA8, w*h*4 bytes */
+	const uint8_t* pixels; /* host pointer, w*h*{4, 8, 16} bytes by image_type */
 	int32_t w, h;
 	float fx, fy, cx, cy;
 	float xform[12];       /* 3x4 camera-to-world, column-major, ngp convention (after nerf_matrix_to_ngp, nerf_loader.h:113) */
 	int32_t lens_mode;     /* NGPB_LENS_* */
 	float lens_params[7];
+	int32_t image_type;    /* NGPB_IMAGE_* */
 } ngpb_host_image;
 
 int ngpb_testbed_create(ngpb_testbed** out, int device);
 void ngpb_testbed_destroy(ngpb_testbed* t);
 /* Testbed::load_training_data (src/testbed.cu:97) for already-decoded images; aabb_scale as in transforms.json. */
 int ngpb_testbed_load_training_data(ngpb_testbed* t, uint32_t n_images, const ngpb_host_image* images, uint32_t aabb_scale);
+/* Datasets filled from the caller's arrays while training runs (python_api.cu:545, :56-76; src/testbed_nerf.cu:2502-2516, :2635-2641):
+ * Testbed::create_empty_nerf_dataset allocates n_images empty slots and sets n_images_for_training = 0 (train() then returns without a step, :2897);
+ * nerf.training.set_image replaces one slot's pixels (any resolution / NGPB_IMAGE_* type; only pixels, w, h, image_type of `image` are read);
+ * set_camera_intrinsics follows the reference's conventions (fx or fy <= 0: copied from the other; cx, cy >= 0 in pixels, negative = minus the fraction;
+ * any of k1 k2 p1 p2 non-zero selects the OpenCV lens). Option "n_images_for_training" (ngpb_testbed_set_option): the first n slots take part in training;
+ * the occupancy grid is re-marked when it changes (:2783-2799). Extrinsics: ngpb_testbed_set_camera_extrinsics. */
+int ngpb_testbed_create_empty_dataset(ngpb_testbed* t, uint32_t n_images, uint32_t aabb_scale);
+int ngpb_testbed_set_training_image(ngpb_testbed* t, uint32_t frame_idx, const ngpb_host_image* image);
+int ngpb_testbed_set_camera_intrinsics(ngpb_testbed* t, uint32_t frame_idx, float fx, float fy, float cx, float cy, float k1, float k2, float p1, float p2);
 /* Testbed::reset_network (src/testbed.cu:2249) with configs/nerf/base.json and the given seed (m_seed, testbed.h:567). */
 int ngpb_testbed_reset_network(ngpb_testbed* t, uint32_t seed);
 /* Testbed::train(batch_size) (src/testbed.cu:2527): exactly one optimizer step. */

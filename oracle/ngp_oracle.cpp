@@ -213,6 +213,13 @@ inline void image_pos(float x, float y, int w, int h, int* px, int* py) {
 inline void read_rgba(float x, float y, const orc_image& img, float out[4]) {
 	int px, py;
 	image_pos(x, y, img.w, img.h, &px, &py);
+	if (img.image_type == 2) { std::memcpy(out, img.pixels + 16 * ((size_t)px + (size_t)py * img.w), 16); return; } // Float: as stored (:702-703)
+	if (img.image_type == 1) { // Half (:697-700)
+		orc_half v[4];
+		std::memcpy(v, img.pixels + 8 * ((size_t)px + (size_t)py * img.w), 8);
+		for (int c = 0; c < 4; ++c) out[c] = h2f(v[c]);
+		return;
+	}
 	uint8_t val[4];
 	std::memcpy(val, img.pixels + 4 * ((size_t)px + (size_t)py * img.w), 4);
 	uint32_t packed; std::memcpy(&packed, val, 4);

@@ -76,12 +76,13 @@ void orc_nerf_forward_backward(const orc_model* m, const orc_half* params, uint3
 
 // ---- dataset ---------------------------------------------------------------------------------
 typedef struct {
-	const uint8_t* pixels; // RGBA8, row-major, w*h*4 bytes (EImageDataType::Byte)
+	const uint8_t* pixels; // row-major, w*h*{4, 8, 16} bytes by image_type
 	int32_t w, h;
 	float fx, fy, cx, cy;  // focal length in pixels, principal point as a fraction (nerf_loader.h:41-42)
 	float xform[12];       // 3x4 camera-to-world, column-major, ngp convention (nerf_loader.h:113-132)
 	int32_t lens_mode;     // ELensMode {Perspective, OpenCV, FTheta, LatLong} (common.h)
 	float lens_params[7];  // OpenCV: k1, k2, p1, p2; FTheta: p0..p4, w, h
+	int32_t image_type;    // EImageDataType {0 Byte, 1 Half, 2 Float} (read_rgba, common_device.cuh:677-705); Half / Float: linear, premultiplied alpha
 } orc_image;
 
 // effective per-image transform the reference derives per ray through a quaternion round trip

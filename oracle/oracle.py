@@ -28,7 +28,7 @@ class Model(C.Structure):
 
 class Image(C.Structure):
     _fields_ = [("pixels", C.c_void_p), ("w", C.c_int32), ("h", C.c_int32), ("fx", C.c_float), ("fy", C.c_float),
-                ("cx", C.c_float), ("cy", C.c_float), ("xform", C.c_float * 12), ("lens_mode", C.c_int32), ("lens_params", C.c_float * 7)]
+                ("cx", C.c_float), ("cy", C.c_float), ("xform", C.c_float * 12), ("lens_mode", C.c_int32), ("lens_params", C.c_float * 7), ("image_type", C.c_int32)]
 
 
 class Optimizer(C.Structure):
@@ -104,14 +104,17 @@ def model(n_levels=16, log2_hashmap_size=19, base_resolution=16, per_level_scale
 
 
 def make_images(pixels_list, xforms, fx, fy, cx=0.5, cy=0.5, lens=None):
-    """pixels_list: list/array of uint8 [h,w,4]; xforms: [n,3,4] ngp camera matrices; lens: (mode, 7 params) applied to every image. Keeps references alive."""
+    """pixels_list: list/array of uint8 (or float16 / float32) [h,w,4]; xforms: [n,3,4] ngp camera matrices; lens: (mode, 7 params) applied to every image. Keeps references alive."""
     n = len(pixels_list)
     arr = (Image * n)()
     keep = []
     for i in range(n):
-        px = np.ascontiguousarray(pixels_list[i], dtype=np.uint8)
+        px = np.ascontiguousarray(pixels_list[i])
+        if px.dtype not in (np.float16, np.float32):  # (float16 / float32 arrays: EImageDataType Half / Float, linear premultiplied colours)
+            px = np.ascontiguousarray(px, dtype=np.uint8)
         keep.append(px)
         arr[i].pixels = px.ctypes.data
+        arr[i].image_type = 2 if px.dtype == np.float32 else 1 if px.dtype == np.float16 else 0
         arr[i].h, arr[i].w = px.shape[0], px.shape[1]
         arr[i].fx, arr[i].fy, arr[i].cx, arr[i].cy = fx, fy, cx, cy
         if lens is not None:

@@ -9,7 +9,8 @@ FILES = (("tests/test_gpu_kernels.py", "GPU parity tests (`pytest -m gpu`)"), ("
          ("tests/test_camera_optimizer.py", "K13 / K14 camera-extrinsics optimisation against the reference's kernels and its host optimizers"),
          ("tests/test_modes.py", "Image and SDF Testbed modes against the reference's own modes"),
          ("tests/test_exposure.py", "Per-image exposure optimisation against the reference's kernel, its host optimizer and its Testbed"),
-         ("tests/test_error_map.py", "K19 error-map importance sampling against the reference's kernels and its Testbed"))
+         ("tests/test_error_map.py", "K19 error-map importance sampling against the reference's kernels and its Testbed"),
+         ("tests/test_online_dataset.py", "Datasets filled from arrays while training runs; Half / Float training images"))
 out = ["# PARITY — what each test pins, against what, at which tolerance\n",
        "Generated from the test docstrings (`python tools/make_parity_ledger.py`). `gpu` tests call the CUDA path through the C ABI (`libngpb200.so`) and compare it with the",
        "CPU oracle (`oracle/`) and with golden vectors produced by the reference's own kernels on a B200 (`tests/golden/`, `oracle/gen_golden.py`); the other tests run",
