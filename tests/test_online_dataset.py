@@ -162,9 +162,9 @@ def test_dataset_filled_from_arrays_while_training():
     print(f"online dataset (float images): loss {tb.loss:.6f} after 60 + 240 steps; bulk 8-bit load: {ref.loss:.6f} after 300")
     assert np.isfinite(tb.loss) and tb.loss < 10.0 * ref.loss + 1e-3  # (measured 2.2e-4 vs 1.1e-4: the first 60 steps saw half of the images)
     # both render the scene: the held-in view agrees
-    cam = np.asarray(scene["nerf_c2w"][0])[:3]
-    tb.set_nerf_camera_matrix(cam); ref.set_nerf_camera_matrix(cam)
+    cam = np.asarray(scene["xforms"][0], np.float32).reshape(3, 4)  # (the training transform itself: the two sessions hold different NeRF -> ngp conversions)
+    tb.camera_matrix = cam; ref.camera_matrix = cam
     a, b = tb.render(res, res, 1, True), ref.render(res, res, 1, True)
     mse = float(np.mean((a[..., :3] - b[..., :3]) ** 2))
     print(f"PSNR between the two models' renders of training view 0: {-10 * np.log10(mse + 1e-12):.1f} dB")
-    assert -10 * np.log10(mse + 1e-12) > 16.0  # (two 300-step models of an 8-image scene, each ~22 dB from the ground truth; measured 19.7 dB)
+    assert -10 * np.log10(mse + 1e-12) > 22.0  # (two independently trained 300-step models of an 8-image scene; measured 29.9 dB)
