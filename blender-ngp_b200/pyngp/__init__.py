@@ -799,6 +799,23 @@ def load_transforms(path):
                 scale=scale, offset=offset, lenses=lenses)
 
 
+class _CountInt(int):
+    """A count the reference exposes as a method (`testbed.n_params()`, python_api.cu:612-613) and earlier versions of this module as a property: both
+    spellings work."""
+
+    def __call__(self):
+        return int(self)
+
+
+def _unbuilt(owner, name, default):
+    """A reference option this path does not build: it reads as the reference's default and refuses any other value instead of being silently ignored."""
+    def setter(s, v):
+        same = (list(v) == list(default)) if isinstance(default, (list, tuple)) else (v == default)
+        if not same:
+            raise RuntimeError(f"{owner}.{name} = {v!r}: not built in this library (only the default {default!r})")
+    return property(lambda s: default, setter)
+
+
 class _Training:
     """`testbed.nerf.training.*` (python_api.cu:744-852): the properties this path reads."""
     def __init__(self, tb):
@@ -914,6 +931,7 @@ class _Nerf:
 
     cone_angle_constant = property(lambda s: s._tb._get("cone_angle_constant"), lambda s, v: s._tb._set("cone_angle_constant", float(v)))
     render_min_transmittance = property(lambda s: s._tb._get("render_min_transmittance"), lambda s, v: s._tb._set("render_min_transmittance", float(v)))
+    rendering_min_transmittance = render_min_transmittance  # (both names are bound, python_api.cu:755-756)
     rgb_activation = property(lambda s: NerfActivation(int(s._tb._get("rgb_activation"))), lambda s, v: s._tb._set("rgb_activation", int(v)))
     density_activation = property(lambda s: NerfActivation(int(s._tb._get("density_activation"))), lambda s, v: s._tb._set("density_activation", int(v)))
 
@@ -1006,6 +1024,7 @@ class Testbed:
         nerf.training.set_image / set_camera_intrinsics / set_camera_extrinsics; nerf.training.n_images_for_training starts at 0 (train() is then a no-op)."""
         self._dataset_scale, self._dataset_offset = 0.33, (0.5, 0.5, 0.5)  # NerfDataset defaults (nerf_loader.h:107-108)
         check(lib().ngpb_testbed_create_empty_dataset(self._h, int(n_images), int(aabb_scale)))
+        self._intrinsics = None
         self._set("rgb_activation", int(NerfActivation.Exponential if is_hdr else NerfActivation.Logistic))  # load_nerf_post (:2644)
 
     def load_training_images(self, images, xforms, fx, fy, cx=0.5, cy=0.5, aabb_scale=1, lenses=None):
@@ -1013,7 +1032,7 @@ class Testbed:
         (EImageDataType Byte / Half / Float) --, xforms float32 [n][3][4] in ngp convention; lenses: per image (LensMode, 7 params) or None."""
         n = len(images)
         arr = (HostImage * n)()
-        keep = []
+        keep, intrinsics = [], []
         for i in range(n):
             px, itype = _image_array(images[i])
             keep.append(px)
@@ -1022,6 +1041,7 @@ class Testbed:
             arr[i].h, arr[i].w = px.shape[0], px.shape[1]
             pick = lambda v: float(v[i]) if isinstance(v, (list, tuple, np.ndarray)) else float(v)  # scalar = the same for every image
             arr[i].fx, arr[i].fy, arr[i].cx, arr[i].cy = pick(fx), pick(fy), pick(cx), pick(cy)
+            intrinsics.append((pick(fx), pick(fy), px.shape[1], px.shape[0]))
             if lenses is not None:
                 arr[i].lens_mode = int(lenses[i][0])
                 for k in range(7):
@@ -1030,6 +1050,7 @@ class Testbed:
             for k in range(12):
                 arr[i].xform[k] = float(cm[k])
         check(lib().ngpb_testbed_load_training_data(self._h, n, arr, int(aabb_scale)))
+        self._intrinsics = intrinsics  # (for set_camera_to_training_view)
 
     def reload_network_from_file(self, path=None):
         """Testbed::reload_network_from_file (src/testbed.cu:147). Only the base NeRF architecture is built; optimizer values are honoured."""
@@ -1088,7 +1109,33 @@ class Testbed:
     shall_train = property(lambda s: bool(s._get("shall_train")), lambda s, v: s._set("shall_train", 1.0 if v else 0.0))
     training_step = property(lambda s: int(lib().ngpb_testbed_training_step(s._h)))
     loss = property(lambda s: float(lib().ngpb_testbed_loss(s._h)))
-    n_params = property(lambda s: int(lib().ngpb_testbed_n_params(s._h)))
+    n_params = property(lambda s: _CountInt(lib().ngpb_testbed_n_params(s._h)))  # Testbed::n_params() (python_api.cu:612)
+    n_encoding_params = property(lambda s: _CountInt(max(int(lib().ngpb_testbed_n_params(s._h)) - 10240, 0)))  # Testbed::n_encoding_params() (:613): the hash-grid entries
+    # options of the reference's Testbed outside this path (python_api.cu:656-694): defaults only
+    shall_train_encoding = _unbuilt("testbed", "shall_train_encoding", True)
+    shall_train_network = _unbuilt("testbed", "shall_train_network", True)
+    max_level_rand_training = _unbuilt("testbed", "max_level_rand_training", False)
+    render_with_rolling_shutter = _unbuilt("testbed", "render_with_rolling_shutter", False)
+    dlss = _unbuilt("testbed", "dlss", False)
+    dynamic_res = _unbuilt("testbed", "dynamic_res", False)
+    # the fork's mask / camera-model members act on the Blender path through RenderRequest (request_nerf_render_sync); Testbed.render is the classic path
+    render_masks = _unbuilt("testbed", "render_masks", [])
+
+    def first_training_view(self):
+        """Testbed::first_training_view (src/testbed_nerf.cu): the camera moves to training image 0."""
+        self.set_camera_to_training_view(0)
+
+    def set_camera_to_training_view(self, trainview):
+        """Testbed::set_camera_to_training_view: camera = the image's current training transform, focal length = the image's (relative to the
+        resolution along fov_axis). The classic render keeps the principal point at the centre (an off-centre one is not built)."""
+        out = np.zeros(12, np.float32)
+        check(lib().ngpb_testbed_get_camera_extrinsics(self._h, int(trainview), out.ctypes.data, None, None))
+        self.camera_matrix = out.reshape(4, 3).T.copy()
+        intr = self.__dict__.get("_intrinsics")
+        if intr is not None and 0 <= int(trainview) < len(intr):
+            fx, fy, w, h = intr[int(trainview)]
+            res = (w, h)[self.fov_axis]
+            self._relative_focal_length = (fx / res, fy / res)
 
     @property
     def background_color(self):  # m_background_color, RGBA (testbed.h:875)

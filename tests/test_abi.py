@@ -276,3 +276,24 @@ def test_unbuilt_training_options_refuse():
         setattr(tr, name, default)
         with pytest.raises(RuntimeError, match="not built"):
             setattr(tr, name, True if default is False else 1.0)
+
+
+def test_reference_spellings_and_unbuilt_testbed_options():
+    """Names of the reference's bindings that need no kernel: n_params() / n_encoding_params() are methods there and attributes in earlier versions of this
+    module (both work), nerf.rendering_min_transmittance is an alias (python_api.cu:755-756), and Testbed options outside this path refuse non-default
+    values (python_api.cu:656-694)."""
+    import pyngp
+    n = pyngp._CountInt(12206480)
+    assert n == 12206480 and n() == 12206480 and isinstance(n(), int) and np.empty(pyngp._CountInt(3), np.uint32).shape == (3,)
+    assert pyngp._Nerf.rendering_min_transmittance is pyngp._Nerf.render_min_transmittance
+    tb = object.__new__(pyngp.Testbed)  # (no device behind it: only the pure-Python members are touched)
+    for name, default, other in (("shall_train_encoding", True, False), ("shall_train_network", True, False), ("max_level_rand_training", False, True),
+                                 ("render_with_rolling_shutter", False, True), ("dlss", False, True), ("dynamic_res", False, True), ("render_masks", [], [object()])):
+        assert getattr(tb, name) == default
+        setattr(tb, name, default)
+        with pytest.raises(RuntimeError, match="not built"):
+            setattr(tb, name, other)
+    for name in ("n_params", "n_encoding_params", "first_training_view", "set_camera_to_training_view", "create_empty_nerf_dataset"):
+        assert hasattr(pyngp.Testbed, name)
+    for name in ("set_image", "set_camera_intrinsics", "n_images_for_training", "sample_image_proportional_to_error", "get_error_map_pmf"):
+        assert hasattr(pyngp._Training, name)
