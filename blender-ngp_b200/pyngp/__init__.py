@@ -384,7 +384,8 @@ def build_snapshot(network_config, params_half, density_grid, aabb_scale, aabb, 
     if dataset_transform is not None:
         # The reference stores the whole NerfDataset under nerf.dataset (json_binding.h:120-160) and needs all of it when the key exists; this build keeps
         # only what set_nerf_camera_matrix needs after load_snapshot, under a key of its own that the reference ignores.
-        snap["nerf"]["b200_dataset_transform"] = {"scale": float(dataset_transform[0]), "offset": [float(v) for v in dataset_transform[1]]}
+        snap["nerf"]["b200_dataset_transform"] = {"scale": float(dataset_transform[0]), "offset": [float(v) for v in dataset_transform[1]],
+                                                  "from_mitsuba": bool(dataset_transform[2]) if len(dataset_transform) > 2 else False}
     if optimizer is not None:
         snap["optimizer"] = {  # Ema -> ExponentialDecay -> Adam
             "weights_ema_binary": np.ascontiguousarray(params_half, np.float16).tobytes(),
@@ -428,6 +429,7 @@ def parse_snapshot(cfg):
     for key in ("dataset", "b200_dataset_transform"):  # a reference snapshot carries its NerfDataset; ours the two numbers
         if isinstance(nerf.get(key), dict) and "scale" in nerf[key] and "offset" in nerf[key]:
             out["dataset_transform"] = (float(nerf[key]["scale"]), tuple(float(v) for v in nerf[key]["offset"]))
+            out["dataset_from_mitsuba"] = bool(nerf[key].get("from_mitsuba", False))
             break
     if "optimizer" in snap:
         o = snap["optimizer"]
@@ -654,19 +656,29 @@ def _validate_network_config(cfg):
 
 
 # ---- transforms.json loader (reference: src/nerf_loader.cu:197-747), host side ------------------------
-def nerf_matrix_to_ngp(c2w, scale, offset):
-    """nerf_loader.h:113-132 (from_mitsuba = false)."""
+def nerf_matrix_to_ngp(c2w, scale, offset, from_mitsuba=False):
+    """NerfDataset::nerf_matrix_to_ngp (nerf_loader.h:113-132, scale_columns = false). Mitsuba-convention datasets flip columns 0 and 2 instead of cycling
+    the axes."""
     m = np.array(c2w, dtype=np.float32)[:3, :4].copy()
     m[:, 1] *= -1
     m[:, 2] *= -1
     m[:, 3] = m[:, 3] * np.float32(scale) + np.asarray(offset, dtype=np.float32)
+    if from_mitsuba:
+        m[:, 0] *= -1
+        m[:, 2] *= -1
+        return m
     return m[[1, 2, 0], :].copy()
 
 
-def ngp_matrix_to_nerf(m, scale, offset):
-    """nerf_loader.h:134-151 (from_mitsuba = false, scale_columns = false): the inverse of nerf_matrix_to_ngp."""
+def ngp_matrix_to_nerf(m, scale, offset, from_mitsuba=False):
+    """NerfDataset::ngp_matrix_to_nerf (nerf_loader.h:134-151, scale_columns = false): the inverse of nerf_matrix_to_ngp."""
     m = np.array(m, dtype=np.float32)[:3, :4]
-    r = m[[2, 0, 1], :].copy()  # cycle axes xyz -> yzx back
+    if from_mitsuba:
+        r = m.copy()
+        r[:, 0] *= -1
+        r[:, 2] *= -1
+    else:
+        r = m[[2, 0, 1], :].copy()  # cycle axes xyz -> yzx back
     r[:, 1] *= -1
     r[:, 2] *= -1
     r[:, 3] = (r[:, 3] - np.asarray(offset, dtype=np.float32)) / np.float32(scale)
@@ -760,9 +772,13 @@ def load_transforms(path):
         per_json.append((meta, base, frames))
     if sum(len(fr) for _, _, fr in per_json) == 0:
         raise RuntimeError("No training images were found for NeRF training!")
+    # a file with "normal_mts_args" makes the whole dataset Mitsuba-convention (nerf_loader.cu:442-453): other default scale / offset, which the file's own
+    # "scale" / "offset" still override, and no axis cycling in the camera matrices
+    from_mitsuba = any("normal_mts_args" in meta for meta, _, _ in per_json)
     for meta, base, frames in per_json:
         if "normal_mts_args" in meta:
-            raise RuntimeError("Mitsuba-convention datasets are outside the built scope")
+            scale = float(np.float32(0.66))
+            offset = [float(np.float32(0.25) * np.float32(0.66))] * 3
         scale = float(meta.get("scale", scale))
         if "offset" in meta:
             offset = [float(v) for v in meta["offset"]]
@@ -792,11 +808,11 @@ def load_transforms(path):
             _read_lens(fr, lens, pp)  # per-frame lens / principal point override the dataset's (:640-643)
             lenses.append((int(lens[0]), lens[1]))
             images.append(np.ascontiguousarray(img))
-            xforms.append(nerf_matrix_to_ngp(fr["transform_matrix"], scale, offset))
+            xforms.append(nerf_matrix_to_ngp(fr["transform_matrix"], scale, offset, from_mitsuba))
             fxs.append(float(focal[0])); fys.append(float(focal[1])); cxs.append(pp[0]); cys.append(pp[1])
     uniform = lambda v: v[0] if all(x == v[0] for x in v) else list(v)
     return dict(images=images, xforms=np.stack(xforms), fx=uniform(fxs), fy=uniform(fys), cx=uniform(cxs), cy=uniform(cys), aabb_scale=aabb_scale,
-                scale=scale, offset=offset, lenses=lenses)
+                scale=scale, offset=offset, lenses=lenses, from_mitsuba=from_mitsuba)
 
 
 class _CountInt(int):
@@ -857,7 +873,7 @@ class _Training:
         out = np.zeros(12, np.float32)
         if lib().ngpb_testbed_get_camera_extrinsics(tb._h, int(frame_idx) & 0xFFFFFFFF, out.ctypes.data, None, None) != 0:
             return np.eye(4, dtype=np.float32)[:3]
-        return ngp_matrix_to_nerf(out.reshape(4, 3).T, tb._dataset_scale, tb._dataset_offset)
+        return ngp_matrix_to_nerf(out.reshape(4, 3).T, tb._dataset_scale, tb._dataset_offset, tb._from_mitsuba)
 
     def get_camera_offsets(self, frame_idx):
         """(position offset, rotation offset as angle-axis) of a frame: cam_pos_offset[i].variable() / cam_rot_offset[i].variable() (testbed.h:637-640)."""
@@ -870,7 +886,7 @@ class _Training:
         tb = self._tb
         m = np.asarray(camera_to_world, dtype=np.float32)[:3, :4]
         if convert_to_ngp:
-            m = nerf_matrix_to_ngp(m, tb._dataset_scale, tb._dataset_offset)
+            m = nerf_matrix_to_ngp(m, tb._dataset_scale, tb._dataset_offset, tb._from_mitsuba)
         flat = np.ascontiguousarray(m.T, np.float32).reshape(-1)  # 3x4 column-major
         check(lib().ngpb_testbed_set_camera_extrinsics(tb._h, int(frame_idx), flat.ctypes.data))
 
@@ -1017,12 +1033,14 @@ class Testbed:
             return
         d = load_transforms(path)
         self._dataset_scale, self._dataset_offset = d["scale"], tuple(d["offset"])
+        self._from_mitsuba = bool(d.get("from_mitsuba", False))
         self.load_training_images(d["images"], d["xforms"], d["fx"], d["fy"], d["cx"], d["cy"], d["aabb_scale"], d["lenses"])
 
     def create_empty_nerf_dataset(self, n_images, aabb_scale=1, is_hdr=False):
         """Testbed::create_empty_nerf_dataset (python_api.cu:545, src/testbed_nerf.cu:2635-2641): n_images empty slots to be filled with
         nerf.training.set_image / set_camera_intrinsics / set_camera_extrinsics; nerf.training.n_images_for_training starts at 0 (train() is then a no-op)."""
         self._dataset_scale, self._dataset_offset = 0.33, (0.5, 0.5, 0.5)  # NerfDataset defaults (nerf_loader.h:107-108)
+        self._from_mitsuba = False
         check(lib().ngpb_testbed_create_empty_dataset(self._h, int(n_images), int(aabb_scale)))
         self._intrinsics = None
         self._set("rgb_activation", int(NerfActivation.Exponential if is_hdr else NerfActivation.Logistic))  # load_nerf_post (:2644)
@@ -1207,7 +1225,7 @@ class Testbed:
         half = 0.5 * min(128, int(self._get("aabb_scale")))
         aabb = [0.5 - half] * 3 + [0.5 + half] * 3
         cfg = build_snapshot(self.network_config, ema, grid, int(self._get("aabb_scale")), aabb, st.training_step, st.loss, st.rays_per_batch,
-                             st.measured_batch_size, st.measured_batch_size_before_compaction, opt, (self._dataset_scale, self._dataset_offset))
+                             st.measured_batch_size, st.measured_batch_size_before_compaction, opt, (self._dataset_scale, self._dataset_offset, self._from_mitsuba))
         with open(path, "wb") as f:
             f.write(msgpack.packb(cfg, use_bin_type=True))
 
@@ -1222,6 +1240,7 @@ class Testbed:
         self.network_config = snap["network_config"]
         if snap["dataset_transform"] is not None:
             self._dataset_scale, self._dataset_offset = snap["dataset_transform"]
+            self._from_mitsuba = bool(snap.get("dataset_from_mitsuba", False))
         self._apply_network_config(self.network_config)
         check(lib().ngpb_testbed_configure(self._h, snap["aabb_scale"], self._seed))
         params = np.ascontiguousarray(snap["params_half"], np.float16)
@@ -1362,6 +1381,7 @@ class Testbed:
     _relative_focal_length = (1.0, 1.0)  # m_relative_focal_length (testbed.h:527)
     camera_matrix = np.eye(4, dtype=np.float32)[:3]  # m_camera, 3x4, ngp convention
     _dataset_scale, _dataset_offset = 1.0, (0.0, 0.0, 0.0)
+    _from_mitsuba = False  # NerfDataset::from_mitsuba (nerf_loader.h:99): set by a transforms.json with "normal_mts_args"
 
     @property
     def fov(self):  # degrees along fov_axis (Testbed::fov, src/testbed.cu:2153)
@@ -1379,4 +1399,4 @@ class Testbed:
     def set_nerf_camera_matrix(self, m):
         """python_api.cu:681 -> Testbed::set_nerf_camera_matrix: a NeRF-convention camera-to-world matrix, converted with the dataset's
         scale / offset (NerfDataset::nerf_matrix_to_ngp, nerf_loader.h:113-132)."""
-        self.camera_matrix = nerf_matrix_to_ngp(np.asarray(m, dtype=np.float32), self._dataset_scale, self._dataset_offset)
+        self.camera_matrix = nerf_matrix_to_ngp(np.asarray(m, dtype=np.float32), self._dataset_scale, self._dataset_offset, self._from_mitsuba)

@@ -216,6 +216,43 @@ def test_transforms_json_loader_reference_rules(tmp_path):
         pyngp.load_transforms(str(d / "im0.png"))
 
 
+def test_mitsuba_convention_dataset(tmp_path):
+    """A transforms.json with "normal_mts_args" is a Mitsuba-convention dataset (nerf_loader.cu:442-453, nerf_loader.h:113-151): default scale 0.66 and offset
+    0.25 x 0.66 (still overridden by the file's own keys), and camera matrices whose columns 0 and 2 are flipped instead of the axes being cycled; the
+    conversion and its inverse round-trip, and the flag travels through this library's snapshots."""
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "blender-ngp_b200"))
+    import pyngp
+    from PIL import Image
+    d = tmp_path / "mts"
+    d.mkdir()
+    Image.fromarray(np.full((8, 8, 4), 200, np.uint8)).save(d / "im0.png")
+    m = [[0.0, -1.0, 0.0, 1.0], [1.0, 0.0, 0.0, 2.0], [0.0, 0.0, 1.0, 3.0], [0, 0, 0, 1]]
+    js = {"normal_mts_args": {"anything": 1}, "camera_angle_x": 0.8, "frames": [{"file_path": "im0", "transform_matrix": m}]}
+    json.dump(js, open(d / "transforms.json", "w"))
+    got = pyngp.load_transforms(str(d / "transforms.json"))
+    s = float(np.float32(0.66)); o = float(np.float32(0.25) * np.float32(0.66))
+    assert got["from_mitsuba"] is True and got["scale"] == pytest.approx(s) and got["offset"] == pytest.approx([o, o, o])
+    # by hand: negate columns 1, 2; translation * scale + offset; then negate columns 0 and 2 -> columns (-c0, -c1, +c2), no row cycling
+    want = np.array(m, np.float32)[:3].copy()
+    want[:, 0] *= -1; want[:, 1] *= -1
+    want[:, 3] = np.array(m, np.float32)[:3, 3] * np.float32(s) + np.float32(o)
+    np.testing.assert_allclose(got["xforms"][0], want, rtol=0, atol=1e-7)
+    back = pyngp.ngp_matrix_to_nerf(got["xforms"][0], got["scale"], got["offset"], True)
+    np.testing.assert_allclose(back, np.array(m, np.float32)[:3], rtol=0, atol=1e-6)
+    assert not np.allclose(pyngp.nerf_matrix_to_ngp(m, s, [o] * 3, False), want)
+    # the file's own scale / offset win over the Mitsuba defaults
+    js.update(scale=0.5, offset=[0.1, 0.2, 0.3])
+    json.dump(js, open(d / "transforms.json", "w"))
+    got = pyngp.load_transforms(str(d / "transforms.json"))
+    assert got["scale"] == 0.5 and got["offset"] == [0.1, 0.2, 0.3] and got["from_mitsuba"] is True
+    # snapshots keep the flag next to scale / offset
+    cfg = pyngp.build_snapshot(pyngp.BASE_NETWORK_CONFIG, np.zeros(16, np.float16), np.zeros(128 ** 3, np.float32), 1, [0, 0, 0, 1, 1, 1], 0, 0.0, 4096, 0, 0, None, (0.5, (0.1, 0.2, 0.3), True))
+    assert cfg["snapshot"]["nerf"]["b200_dataset_transform"]["from_mitsuba"] is True
+    assert pyngp.parse_snapshot(cfg)["dataset_from_mitsuba"] is True and pyngp.parse_snapshot(cfg)["dataset_transform"][0] == 0.5
+
+
 def test_reference_arm_runs_on_rank_zero_only():
     """bench.py --impl reference under torchrun: ranks other than 0 exit 0 without work or output (rank 0 alone times the CPU restatement)."""
     import subprocess
