@@ -685,6 +685,35 @@ def ngp_matrix_to_nerf(m, scale, offset, from_mitsuba=False):
     return r
 
 
+def load_exr_float(path):
+    """load_exr (src/tinyexr_wrapper.cu:121-135, tinyexr's LoadEXR): an EXR file as [h][w][4] float32 R, G, B, A (A = 1 when the file has none). Decoded with
+    OpenCV (the reference uses tinyexr); a single-channel file is taken as grey."""
+    os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")  # (OpenCV ships its EXR codec switched off)
+    try:
+        import cv2
+    except ImportError as e:
+        raise RuntimeError("EXR images need OpenCV's EXR codec: " + str(e))
+    img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    if img is None:
+        raise RuntimeError("Failed to load EXR image: " + path)
+    img = np.asarray(img, dtype=np.float32)
+    if img.ndim == 2:
+        img = np.repeat(img[..., None], 3, axis=2)
+    out = np.empty(img.shape[:2] + (4,), np.float32)
+    out[..., :3] = img[..., 2::-1] if img.shape[2] >= 3 else np.repeat(img[..., :1], 3, axis=2)  # OpenCV hands out B, G, R
+    out[..., 3] = img[..., 3] if img.shape[2] >= 4 else 1.0
+    return out
+
+
+def _load_exr_half(path, fix_premult):
+    """load_exr_to_gpu + interleave_and_cast_kernel (src/tinyexr_wrapper.cu:41-55,:137-227): an EXR frame as [h][w][4] halfs -- R, G, B as stored (times alpha
+    when the dataset says "fix_premult"), A or 1 -- i.e. EImageDataType::Half."""
+    img = load_exr_float(path)
+    if fix_premult:
+        img[..., :3] *= img[..., 3:4]
+    return img.astype(np.float16)
+
+
 def _fov_to_focal_length(resolution, degrees):  # common_device.cuh:473
     return 0.5 * resolution / math.tan(0.5 * degrees * math.pi / 180.0)
 
@@ -775,7 +804,10 @@ def load_transforms(path):
     # a file with "normal_mts_args" makes the whole dataset Mitsuba-convention (nerf_loader.cu:442-453): other default scale / offset, which the file's own
     # "scale" / "offset" still override, and no axis cycling in the camera matrices
     from_mitsuba = any("normal_mts_args" in meta for meta, _, _ in per_json)
+    fix_premult, is_hdr = False, False
     for meta, base, frames in per_json:
+        if "fix_premult" in meta:  # (:446-448)
+            fix_premult = bool(meta["fix_premult"])
         if "normal_mts_args" in meta:
             scale = float(np.float32(0.66))
             offset = [float(np.float32(0.25) * np.float32(0.66))] * 3
@@ -791,13 +823,17 @@ def load_transforms(path):
                 if os.path.exists(p + ".png"):
                     p = p + ".png"
                 elif os.path.exists(p + ".exr"):
-                    raise RuntimeError("EXR (HDR) training images are outside the built scope: " + p + ".exr")
+                    p = p + ".exr"
                 else:
-                    raise RuntimeError("Could not find image file: " + p + ".png")
-            try:
-                img = np.asarray(PILImage.open(p).convert("RGBA"), dtype=np.uint8)
-            except OSError as e:
-                raise RuntimeError("Could not open image file: " + str(e))
+                    raise RuntimeError("Could not find image file: " + p + ".exr")
+            if p.lower().endswith(".exr"):  # HDR frames are kept as halfs, linear (nerf_loader.cu:573-577)
+                img = _load_exr_half(p, fix_premult)
+                is_hdr = True
+            else:
+                try:
+                    img = np.asarray(PILImage.open(p).convert("RGBA"), dtype=np.uint8)
+                except OSError as e:
+                    raise RuntimeError("Could not open image file: " + str(e))
             h, w = img.shape[:2]
             focal = _read_focal_length(meta, (w, h), None)
             focal_frame = _read_focal_length(fr, (w, h), focal)
@@ -812,7 +848,7 @@ def load_transforms(path):
             fxs.append(float(focal[0])); fys.append(float(focal[1])); cxs.append(pp[0]); cys.append(pp[1])
     uniform = lambda v: v[0] if all(x == v[0] for x in v) else list(v)
     return dict(images=images, xforms=np.stack(xforms), fx=uniform(fxs), fy=uniform(fys), cx=uniform(cxs), cy=uniform(cys), aabb_scale=aabb_scale,
-                scale=scale, offset=offset, lenses=lenses, from_mitsuba=from_mitsuba)
+                scale=scale, offset=offset, lenses=lenses, from_mitsuba=from_mitsuba, is_hdr=is_hdr)
 
 
 class _CountInt(int):
@@ -1035,6 +1071,8 @@ class Testbed:
         self._dataset_scale, self._dataset_offset = d["scale"], tuple(d["offset"])
         self._from_mitsuba = bool(d.get("from_mitsuba", False))
         self.load_training_images(d["images"], d["xforms"], d["fx"], d["fy"], d["cx"], d["cy"], d["aabb_scale"], d["lenses"])
+        if d.get("is_hdr"):  # load_nerf_post (src/testbed_nerf.cu:2644): HDR datasets train an exponential colour activation
+            self._set("rgb_activation", int(NerfActivation.Exponential))
 
     def create_empty_nerf_dataset(self, n_images, aabb_scale=1, is_hdr=False):
         """Testbed::create_empty_nerf_dataset (python_api.cu:545, src/testbed_nerf.cu:2635-2641): n_images empty slots to be filled with

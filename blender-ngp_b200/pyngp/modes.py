@@ -267,15 +267,15 @@ class ImageTestbed(ModelTestbedBase):
         return max(self._res) / 2.0  # m_image.resolution.maxCoeff() / 2 (src/testbed.cu:2311)
 
     def load_training_data(self, path):
-        """Testbed::load_image (src/testbed_image.cu:349-432): `.bin` = {int32 height, int32 width, RGBA half pixels}; `.exr` is not built; anything else is an
+        """Testbed::load_image (src/testbed_image.cu:349-432): `.bin` = {int32 height, int32 width, RGBA half pixels}; `.exr` = float RGBA as stored; anything else is an
         8-bit file decoded to RGBA8 and converted like load_stbi (sRGB -> linear, premultiplied by alpha)."""
         path = str(path)
         if not os.path.exists(path):
             raise RuntimeError(f"{path} does not exist.")
         ext = os.path.splitext(path)[1].lower()
-        if ext == ".exr":
-            raise RuntimeError("EXR images are outside the built scope (no decoder in this build); convert to .bin (RGBA half) or an 8-bit format")
-        if ext == ".bin":
+        if ext == ".exr":  # load_exr_image (src/testbed_image.cu:385-398): the file's floats as they are (EDataType::Float)
+            self.load_image_data(_pyngp().load_exr_float(path))
+        elif ext == ".bin":
             with open(path, "rb") as f:
                 h, w = np.frombuffer(f.read(8), np.int32)
                 px = np.frombuffer(f.read(int(h) * int(w) * 8), np.float16).reshape(int(h), int(w), 4)

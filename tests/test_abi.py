@@ -253,6 +253,58 @@ def test_mitsuba_convention_dataset(tmp_path):
     assert pyngp.parse_snapshot(cfg)["dataset_from_mitsuba"] is True and pyngp.parse_snapshot(cfg)["dataset_transform"][0] == 0.5
 
 
+def test_exr_frames_load_as_half_images(tmp_path):
+    """HDR datasets (nerf_loader.cu:562-577, tinyexr_wrapper.cu:41-55): a frame without extension resolves to .png, then .exr; EXR frames are kept as
+    [h][w][4] halfs -- R, G, B as stored, times alpha under "fix_premult", A or 1 -- and flag the dataset HDR; 8-bit and EXR frames mix in one dataset. The
+    oracle then trains on them through the Half branch of read_rgba."""
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "blender-ngp_b200"))
+    os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")
+    cv2 = pytest.importorskip("cv2")
+    import pyngp
+    from PIL import Image
+    d = tmp_path / "hdr"
+    d.mkdir()
+    rs = np.random.RandomState(0)
+    rgba = rs.rand(6, 8, 4).astype(np.float32) * np.array([4.0, 2.0, 1.0, 1.0], np.float32)  # values above 1: HDR
+    assert cv2.imwrite(str(d / "f0.exr"), np.ascontiguousarray(rgba[..., [2, 1, 0, 3]]))  # OpenCV stores B, G, R, A
+    assert cv2.imwrite(str(d / "f1.exr"), np.ascontiguousarray(rgba[..., [2, 1, 0]]))     # no alpha channel
+    Image.fromarray(np.full((6, 8, 4), 128, np.uint8)).save(d / "f2.png")
+    eye = [[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 2], [0, 0, 0, 1]]
+    js = {"camera_angle_x": 0.8, "frames": [{"file_path": f"f{k}", "transform_matrix": eye} for k in range(3)]}
+    json.dump(js, open(d / "transforms.json", "w"))
+    got = pyngp.load_transforms(str(d / "transforms.json"))
+    assert got["is_hdr"] is True and [im.dtype for im in got["images"]] == [np.float16, np.float16, np.uint8]
+    assert np.array_equal(got["images"][0], rgba.astype(np.float16))
+    assert np.array_equal(got["images"][1][..., :3], rgba[..., :3].astype(np.float16)) and np.all(got["images"][1][..., 3] == 1)
+    js["fix_premult"] = True
+    json.dump(js, open(d / "transforms.json", "w"))
+    fixed = pyngp.load_transforms(str(d / "transforms.json"))
+    assert np.array_equal(fixed["images"][0][..., :3], (rgba[..., :3] * rgba[..., 3:4]).astype(np.float16)) and np.array_equal(fixed["images"][0][..., 3], rgba[..., 3].astype(np.float16))
+    px, itype = pyngp._image_array(got["images"][0])
+    assert itype == pyngp.IMAGE_HALF and px.dtype == np.float16
+    only_png = dict(js, frames=js["frames"][2:])
+    json.dump(only_png, open(d / "transforms.json", "w"))
+    assert pyngp.load_transforms(str(d / "transforms.json"))["is_hdr"] is False
+
+
+def test_exr_decoder_on_the_reference_image():
+    """pyngp.load_exr_float (what Testbed(TestbedMode.Image, "albert.exr") and HDR NeRF frames go through) on the reference's own data/image/albert.exr, where
+    the reference tree is mounted: 1024 x 1024 float RGBA, grey (R = G = B), opaque, values in (0, 1)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "blender-ngp_b200"))
+    p = "/root/reference/data/image/albert.exr"
+    if not os.path.exists(p):
+        pytest.skip("the reference tree is not mounted here")
+    pytest.importorskip("cv2")
+    import pyngp
+    a = pyngp.load_exr_float(p)
+    assert a.shape == (1024, 1024, 4) and a.dtype == np.float32
+    assert np.array_equal(a[..., 0], a[..., 1]) and np.array_equal(a[..., 1], a[..., 2]) and np.all(a[..., 3] == 1.0)
+    assert 0.0 < float(a[..., 0].min()) < float(a[..., 0].max()) < 1.0 and float(a[..., 0].std()) > 0.05
+
+
 def test_reference_arm_runs_on_rank_zero_only():
     """bench.py --impl reference under torchrun: ranks other than 0 exit 0 without work or output (rank 0 alone times the CPU restatement)."""
     import subprocess
