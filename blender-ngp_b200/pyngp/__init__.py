@@ -685,6 +685,39 @@ def ngp_matrix_to_nerf(m, scale, offset, from_mitsuba=False):
     return r
 
 
+def _apply_byte_image_rules(img, base, file_path, path, white_transparent, black_transparent):
+    """What ngp::load_nerf does to an 8-bit frame besides decoding it (nerf_loader.cu:584-620 and convert_rgba32, :58-81): a separate alpha image
+    `<file_path>.alpha.<ext>` (its red channel, sRGB -> linear, replaces the alpha channel), a `dynamic_mask_<name>.png` next to the frame (pixels where its
+    red channel is non-zero become 0x00FF00FF, which the training kernels skip), and the dataset's "white_transparent" / "black_transparent" switches."""
+    from PIL import Image as PILImage
+    ext = os.path.splitext(path)[1][1:]
+    alpha_path = os.path.join(base, f"{file_path}.alpha.{ext}")
+    if os.path.exists(alpha_path):
+        try:
+            a = np.asarray(PILImage.open(alpha_path).convert("RGBA"), dtype=np.uint8)
+        except OSError:
+            raise RuntimeError("Could not load alpha image " + alpha_path)
+        if a.shape[:2] != img.shape[:2]:
+            raise RuntimeError(f"Alpha image {alpha_path} has wrong resolution.")
+        x = a[..., 0].astype(np.float32) * np.float32(1.0 / 255.0)
+        lin = np.where(x <= np.float32(0.04045), x / np.float32(12.92), np.power((x + np.float32(0.055)) / np.float32(1.055), np.float32(2.4)))
+        img[..., 3] = (np.float32(255.0) * lin.astype(np.float32)).astype(np.uint8)  # (truncating cast, as the reference's (uint8_t))
+    mask_path = os.path.join(os.path.dirname(path), f"dynamic_mask_{os.path.splitext(os.path.basename(path))[0]}.png")
+    if os.path.exists(mask_path):
+        try:
+            m = np.asarray(PILImage.open(mask_path).convert("RGBA"), dtype=np.uint8)
+        except OSError:
+            raise RuntimeError(f"Dynamic mask {mask_path} could not be loaded.")
+        if m.shape[:2] != img.shape[:2]:
+            raise RuntimeError(f"Dynamic mask {mask_path} has wrong resolution.")
+        img[m[..., 0] != 0] = np.array([0xFF, 0x00, 0xFF, 0x00], np.uint8)  # 0x00FF00FF, "hot pink"
+    if white_transparent:  # (the NSVF datasets' "white = transparent")
+        img[np.all(img[..., :3] == 255, axis=-1), 3] = 0
+    if black_transparent:
+        img[np.all(img[..., :3] == 0, axis=-1), 3] = 0
+    return img
+
+
 def load_exr_float(path):
     """load_exr (src/tinyexr_wrapper.cu:121-135, tinyexr's LoadEXR): an EXR file as [h][w][4] float32 R, G, B, A (A = 1 when the file has none). Decoded with
     OpenCV (the reference uses tinyexr); a single-channel file is taken as grey."""
@@ -812,9 +845,16 @@ def load_transforms(path):
             scale = float(np.float32(0.66))
             offset = [float(np.float32(0.25) * np.float32(0.66))] * 3
         scale = float(meta.get("scale", scale))
-        if "offset" in meta:
-            offset = [float(v) for v in meta["offset"]]
         aabb_scale = int(meta.get("aabb_scale", aabb_scale))
+        if "offset" in meta:  # an array, or one number for all three axes (:499-504)
+            offset = [float(v) for v in meta["offset"]] if isinstance(meta["offset"], (list, tuple)) else [float(meta["offset"])] * 3
+        if "aabb" in meta:  # [[min], [max]]: isotropic scale + translation that fit the box into the unit cube, centred (:506-511)
+            lo, hi = np.asarray(meta["aabb"][0], np.float32), np.asarray(meta["aabb"][1], np.float32)
+            length = max(np.float32(0.000001), np.abs(hi - lo).max())
+            scale_f = np.float32(1.0) / np.float32(length)
+            scale = float(scale_f)
+            offset = [float(v) for v in ((hi + lo) * np.float32(0.5)) * -scale_f + np.float32(0.5)]
+        white_transparent, black_transparent = bool(meta.get("white_transparent", False)), bool(meta.get("black_transparent", False))  # (:464-470)
         lens_json, pp_json = [LensMode.Perspective, [0.0] * 7], [0.5, 0.5]
         _read_lens(meta, lens_json, pp_json)
         for fr in frames:
@@ -831,9 +871,10 @@ def load_transforms(path):
                 is_hdr = True
             else:
                 try:
-                    img = np.asarray(PILImage.open(p).convert("RGBA"), dtype=np.uint8)
+                    img = np.array(PILImage.open(p).convert("RGBA"), dtype=np.uint8)
                 except OSError as e:
                     raise RuntimeError("Could not open image file: " + str(e))
+                img = _apply_byte_image_rules(img, base, fr["file_path"], p, white_transparent, black_transparent)
             h, w = img.shape[:2]
             focal = _read_focal_length(meta, (w, h), None)
             focal_frame = _read_focal_length(fr, (w, h), focal)
@@ -1077,7 +1118,7 @@ class Testbed:
     def create_empty_nerf_dataset(self, n_images, aabb_scale=1, is_hdr=False):
         """Testbed::create_empty_nerf_dataset (python_api.cu:545, src/testbed_nerf.cu:2635-2641): n_images empty slots to be filled with
         nerf.training.set_image / set_camera_intrinsics / set_camera_extrinsics; nerf.training.n_images_for_training starts at 0 (train() is then a no-op)."""
-        self._dataset_scale, self._dataset_offset = 0.33, (0.5, 0.5, 0.5)  # NerfDataset defaults (nerf_loader.h:107-108)
+        self._dataset_scale, self._dataset_offset = 1.0, (0.0, 0.0, 0.0)  # create_empty_nerf_dataset: NERF_SCALE (1.0 in this fork) and a zero offset (nerf_loader.cu:185-186)
         self._from_mitsuba = False
         check(lib().ngpb_testbed_create_empty_dataset(self._h, int(n_images), int(aabb_scale)))
         self._intrinsics = None

@@ -289,6 +289,45 @@ def test_exr_frames_load_as_half_images(tmp_path):
     assert pyngp.load_transforms(str(d / "transforms.json"))["is_hdr"] is False
 
 
+def test_loader_alpha_files_masks_transparency_and_aabb(tmp_path):
+    """More rules of ngp::load_nerf (nerf_loader.cu:464-511, :584-620, convert_rgba32 :58-81): `<file_path>.alpha.<ext>` replaces the alpha channel (red channel,
+    sRGB -> linear, truncated), `dynamic_mask_<name>.png` turns its non-zero pixels into 0x00FF00FF (which K1 skips), "white_transparent" / "black_transparent"
+    zero the alpha of pure white / black pixels, a scalar "offset" applies to all axes, and an "aabb" key derives scale and offset."""
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "blender-ngp_b200"))
+    import pyngp
+    from PIL import Image
+    d = tmp_path / "rules"
+    (d / "img").mkdir(parents=True)
+    base = np.zeros((4, 6, 4), np.uint8)
+    base[..., :3] = 100; base[..., 3] = 255
+    base[0, 0, :3] = 255; base[0, 1, :3] = 0
+    Image.fromarray(base).save(d / "img" / "a.png")
+    alpha = np.zeros((4, 6, 4), np.uint8); alpha[..., 0] = 128; alpha[..., 3] = 255; alpha[1, :, 0] = 255; alpha[2, :, 0] = 0
+    Image.fromarray(alpha).save(d / "img" / "a.alpha.png")
+    mask = np.zeros((4, 6, 4), np.uint8); mask[..., 3] = 255; mask[3, 2:4, 0] = 255
+    Image.fromarray(mask).save(d / "img" / "dynamic_mask_a.png")
+    eye = [[1, 0, 0, 1.0], [0, 1, 0, 2.0], [0, 0, 1, 3.0], [0, 0, 0, 1]]
+    js = {"camera_angle_x": 0.8, "white_transparent": True, "black_transparent": True, "offset": 0.25, "frames": [{"file_path": "img/a", "transform_matrix": eye}]}
+    json.dump(js, open(d / "transforms.json", "w"))
+    got = pyngp.load_transforms(str(d / "transforms.json"))
+    im = got["images"][0]
+    lin128 = ((128 / 255 + 0.055) / 1.055) ** 2.4
+    assert im[0, 2, 3] == int(255 * lin128) and im[1, 2, 3] == 255 and im[2, 2, 3] == 0  # alpha file: sRGB -> linear, truncated
+    assert im[0, 0, 3] == 0 and im[0, 1, 3] == 0 and tuple(im[0, 0, :3]) == (255, 255, 255)   # white / black pixels made transparent
+    assert np.all(im[3, 2:4] == np.array([255, 0, 255, 0], np.uint8)) and im[3, 1, 3] == int(255 * lin128)  # masked pixels: 0x00FF00FF
+    assert im.view(np.uint32)[3, 2, 0] == 0x00FF00FF
+    assert got["offset"] == [0.25, 0.25, 0.25] and got["scale"] == 1.0  # (NERF_SCALE is 1.0 in this fork, nerf_loader.h:28)
+    js["aabb"] = [[-1.0, -2.0, 0.0], [3.0, 0.0, 1.0]]  # longest side 4 -> scale 1/4, centre (1, -1, 0.5) -> offset 0.5 - centre / 4
+    json.dump(js, open(d / "transforms.json", "w"))
+    got = pyngp.load_transforms(str(d / "transforms.json"))
+    assert got["scale"] == pytest.approx(0.25) and got["offset"] == pytest.approx([0.25, 0.75, 0.375])
+    Image.fromarray(np.zeros((2, 2, 4), np.uint8)).save(d / "img" / "dynamic_mask_a.png")
+    with pytest.raises(RuntimeError, match="wrong resolution"):
+        pyngp.load_transforms(str(d / "transforms.json"))
+
+
 def test_exr_decoder_on_the_reference_image():
     """pyngp.load_exr_float (what Testbed(TestbedMode.Image, "albert.exr") and HDR NeRF frames go through) on the reference's own data/image/albert.exr, where
     the reference tree is mounted: 1024 x 1024 float RGBA, grey (R = G = B), opaque, values in (0, 1)."""
