@@ -425,3 +425,27 @@ def test_reference_spellings_and_unbuilt_testbed_options():
         assert hasattr(pyngp.Testbed, name)
     for name in ("set_image", "set_camera_intrinsics", "n_images_for_training", "sample_image_proportional_to_error", "get_error_map_pmf"):
         assert hasattr(pyngp._Training, name)
+
+
+def test_bench_maps_every_profiled_training_kernel_to_a_stage():
+    """bench.py names the roofline's kernel from the committed ncu launch list (profiles/r02_launches_summary.txt): every kernel of the training step listed
+    there must map to one of the stages the bench times, and the top line -- the dominant kernel -- to a stage with an algorithmic-byte model."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    rows = []
+    with open(os.path.join(ROOT, "profiles", "r02_launches_summary.txt")) as f:
+        for line in f:
+            parts = line.split()
+            if len(parts) >= 4 and parts[0].endswith("%"):
+                rows.append((float(parts[0].rstrip("%")), " ".join(parts[3:]).replace("void ", "")))
+    assert len(rows) >= 15 and rows == sorted(rows, key=lambda r: -r[0])
+    stage_of = lambda k: next((s for pat, s in bench.KERNEL_STAGE if pat in k), None)
+    assert stage_of(rows[0][1]) in bench.STAGE_ALGO  # the dominant kernel has a roofline model
+    density_grid = ("generate_grid_samples", "bitfield_max_pool", "ema_kernel", "splat_kernel", "sum_kernel", "grid_to_bitfield", "mean_partial", "mean_final", "infer_kernel<0>")
+    for share, k in rows:
+        if any(d in k for d in density_grid):
+            continue  # the occupancy-grid refresh is reported as one stage without a byte model
+        assert stage_of(k) is not None, k
+    assert sum(share for share, k in rows if stage_of(k) is not None) > 90.0
