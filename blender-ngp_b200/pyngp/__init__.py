@@ -796,11 +796,42 @@ def _read_lens(js, lens, pp):
         lens[0] = mode
 
 
-def load_transforms(path):
+def byte_image_to_half(img):
+    """from_rgba32<__half> (common_device.cuh:563-590): RGBA8 sRGB with straight alpha -> halfs, linear colours times alpha; a masked pixel (0x00FF00FF) becomes
+    -1 in all four channels. (What the loader keeps when the training images are sharpened.)"""
+    img = np.ascontiguousarray(img, np.uint8)
+    x = img.astype(np.float32) * np.float32(1.0 / 255.0)
+    lin = np.where(x[..., :3] <= np.float32(0.04045), x[..., :3] / np.float32(12.92), np.power((x[..., :3] + np.float32(0.055)) / np.float32(1.055), np.float32(2.4))).astype(np.float32)
+    out = np.empty(img.shape, np.float16)
+    out[..., :3] = (lin * x[..., 3:4]).astype(np.float16)
+    out[..., 3] = x[..., 3].astype(np.float16)
+    out[img.view(np.uint32)[..., 0] == 0x00FF00FF] = np.float16(-1.0)
+    return out
+
+
+def sharpen_image(img, amount):
+    """The `sharpen` kernel of NerfDataset::set_training_image (nerf_loader.cu:102-125, :805-826) on a Half / Float image [h][w][4]: centre weight
+    4 + 1 / amount minus the four neighbours (by flat index i - 1, i - w, i + 1, i + w; below zero clamps to pixel 0, past the end wraps around), divided by
+    1 / amount, clamped at zero -- all four channels, alpha included."""
+    px = np.ascontiguousarray(img)
+    h, w = px.shape[:2]
+    n = h * w
+    flat = px.reshape(n, 4).astype(np.float32)
+    center_w = np.float32(4.0) + np.float32(1.0) / np.float32(amount)
+    inv_totalw = np.float32(1.0) / (center_w - np.float32(4.0))
+    i = np.arange(n, dtype=np.int64)
+    acc = flat * center_w
+    for j in (np.maximum(i - 1, 0), np.maximum(i - w, 0), np.where(i + 1 >= n, i + 1 - n, i + 1), np.where(i + w >= n, i + w - n, i + w)):
+        acc = acc - flat[j]
+    return np.maximum(np.float32(0.0), acc * inv_totalw).astype(px.dtype).reshape(h, w, 4)
+
+
+def load_transforms(path, sharpen_amount=0.0):
     """ngp::load_nerf for pinhole RGBA datasets (src/nerf_loader.cu:300-747, Testbed::load_nerf src/testbed_nerf.cu:2735-2758): a transforms json or a
     directory, of which EVERY *.json is loaded (as the reference does: pass the file to train on one split). Frames sorted by file_path, `n_frames` and
     sharpness culling, focal-length key precedence, per-frame focal / principal-point overrides, `scale` / `offset` / `aabb_scale` of the last json.
-    Returns decoded RGBA8 images, ngp-convention camera matrices and per-image intrinsics (`fx`, `fy`, `cx`, `cy` are scalars when all images agree)."""
+    Returns decoded images (RGBA8; halfs for EXR frames and for every frame when `sharpen_amount` -- nerf.sharpen, or the dataset's "sharpen" key -- is
+    positive), ngp-convention camera matrices and per-image intrinsics (`fx`, `fy`, `cx`, `cy` are scalars when all images agree)."""
     from PIL import Image as PILImage
     if os.path.isdir(path):
         json_paths = sorted(os.path.join(path, p) for p in os.listdir(path) if p.lower().endswith(".json") and os.path.isfile(os.path.join(path, p)))
@@ -841,6 +872,8 @@ def load_transforms(path):
     for meta, base, frames in per_json:
         if "fix_premult" in meta:  # (:446-448)
             fix_premult = bool(meta["fix_premult"])
+        if "sharpen" in meta:  # (:460-462)
+            sharpen_amount = float(meta["sharpen"])
         if "normal_mts_args" in meta:
             scale = float(np.float32(0.66))
             offset = [float(np.float32(0.25) * np.float32(0.66))] * 3
@@ -887,6 +920,8 @@ def load_transforms(path):
             images.append(np.ascontiguousarray(img))
             xforms.append(nerf_matrix_to_ngp(fr["transform_matrix"], scale, offset, from_mitsuba))
             fxs.append(float(focal[0])); fys.append(float(focal[1])); cxs.append(pp[0]); cys.append(pp[1])
+    if sharpen_amount > 0.0:  # applied to every image once all files are read (:732, :805-826); 8-bit frames become halfs first
+        images = [sharpen_image(byte_image_to_half(im) if im.dtype == np.uint8 else im, sharpen_amount) for im in images]
     uniform = lambda v: v[0] if all(x == v[0] for x in v) else list(v)
     return dict(images=images, xforms=np.stack(xforms), fx=uniform(fxs), fy=uniform(fys), cx=uniform(cxs), cy=uniform(cys), aabb_scale=aabb_scale,
                 scale=scale, offset=offset, lenses=lenses, from_mitsuba=from_mitsuba, is_hdr=is_hdr)
@@ -1028,16 +1063,9 @@ class _Nerf:
     rgb_activation = property(lambda s: NerfActivation(int(s._tb._get("rgb_activation"))), lambda s, v: s._tb._set("rgb_activation", int(v)))
     density_activation = property(lambda s: NerfActivation(int(s._tb._get("density_activation"))), lambda s, v: s._tb._set("density_activation", int(v)))
 
-    # scripts/run.py sets these unconditionally (run.py:106,:145). Sharpening of the training images is not built: anything but 0 raises.
-    # render_with_lens_distortion is accepted: datasets with a lens model are refused at load time, so the render lens is always the pinhole.
-    @property
-    def sharpen(self):
-        return 0.0
-
-    @sharpen.setter
-    def sharpen(self, v):
-        if float(v) != 0.0:
-            raise RuntimeError("nerf.sharpen != 0 is outside the built scope")
+    # scripts/run.py sets these unconditionally (run.py:106,:145). nerf.sharpen (python_api.cu:749) is the amount of sharpening the NEXT load_training_data
+    # applies to the training images (Testbed::load_nerf hands it to ngp::load_nerf, src/testbed_nerf.cu:2754).
+    sharpen = 0.0
 
     render_with_lens_distortion = False
     render_with_camera_distortion = False
@@ -1108,7 +1136,7 @@ class Testbed:
             self.load_snapshot(path)
             self.shall_train = False
             return
-        d = load_transforms(path)
+        d = load_transforms(path, float(self.nerf.sharpen))
         self._dataset_scale, self._dataset_offset = d["scale"], tuple(d["offset"])
         self._from_mitsuba = bool(d.get("from_mitsuba", False))
         self.load_training_images(d["images"], d["xforms"], d["fx"], d["fy"], d["cx"], d["cy"], d["aabb_scale"], d["lenses"])

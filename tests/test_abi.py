@@ -328,6 +328,52 @@ def test_loader_alpha_files_masks_transparency_and_aabb(tmp_path):
         pyngp.load_transforms(str(d / "transforms.json"))
 
 
+def test_sharpened_training_images(tmp_path):
+    """nerf.sharpen / the dataset's "sharpen" key (python_api.cu:749, nerf_loader.cu:460-462, :805-826): every frame is converted to halfs (from_rgba32:
+    linear x alpha, masked pixels -1) and run through the reference's 5-tap kernel over the flat pixel index. Checked against a per-pixel restatement of
+    that kernel; a flat image stays flat, an edge overshoots."""
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "blender-ngp_b200"))
+    import pyngp
+    from PIL import Image
+    rs = np.random.RandomState(3)
+    img = rs.randint(0, 256, size=(5, 7, 4)).astype(np.uint8)
+    img[2, 3] = [255, 0, 255, 0]  # a masked pixel
+    half = pyngp.byte_image_to_half(img)
+    x = img.astype(np.float64) / 255.0
+    lin = np.where(x[..., :3] <= 0.04045, x[..., :3] / 12.92, ((x[..., :3] + 0.055) / 1.055) ** 2.4) * x[..., 3:4]
+    ok = np.ones((5, 7), bool); ok[2, 3] = False
+    assert np.abs(half[..., :3].astype(np.float64) - lin)[ok].max() < 1e-3 and np.all(half[2, 3] == -1)
+    amount = 0.5
+    got = pyngp.sharpen_image(half, amount)
+    flat = half.reshape(-1, 4).astype(np.float32)
+    n, w = flat.shape[0], 7
+    cw = np.float32(4.0 + 1.0 / amount); inv = np.float32(1.0) / (cw - np.float32(4.0))
+    want = np.zeros_like(flat)
+    for i in range(n):
+        acc = flat[i] * cw
+        for j in (max(i - 1, 0), max(i - w, 0), i + 1 - n if i + 1 >= n else i + 1, i + w - n if i + w >= n else i + w):
+            acc = acc - flat[j]
+        want[i] = np.maximum(np.float32(0), acc * inv)
+    assert got.dtype == np.float16 and np.array_equal(got.reshape(-1, 4), want.astype(np.float16))
+    const = np.full((4, 4, 4), 0.25, np.float32)
+    assert np.allclose(pyngp.sharpen_image(const, 1.0), 0.25)  # weights sum to one
+    # through the loader: the json's key wins over the argument; 0 leaves the 8-bit frames alone
+    d = tmp_path / "sharp"
+    d.mkdir()
+    Image.fromarray(img).save(d / "a.png")
+    eye = [[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 2], [0, 0, 0, 1]]
+    js = {"camera_angle_x": 0.8, "frames": [{"file_path": "a", "transform_matrix": eye}]}
+    json.dump(js, open(d / "transforms.json", "w"))
+    assert pyngp.load_transforms(str(d / "transforms.json"))["images"][0].dtype == np.uint8
+    assert np.array_equal(pyngp.load_transforms(str(d / "transforms.json"), 0.5)["images"][0], got)
+    js["sharpen"] = 1.0
+    json.dump(js, open(d / "transforms.json", "w"))
+    assert np.array_equal(pyngp.load_transforms(str(d / "transforms.json"), 0.5)["images"][0], pyngp.sharpen_image(half, 1.0))
+    assert pyngp._Nerf.sharpen == 0.0
+
+
 def test_exr_decoder_on_the_reference_image():
     """pyngp.load_exr_float (what Testbed(TestbedMode.Image, "albert.exr") and HDR NeRF frames go through) on the reference's own data/image/albert.exr, where
     the reference tree is mounted: 1024 x 1024 float RGBA, grey (R = G = B), opaque, values in (0, 1)."""
