@@ -918,7 +918,14 @@ def load_transforms(path, sharpen_amount=0.0):
             _read_lens(fr, lens, pp)  # per-frame lens / principal point override the dataset's (:640-643)
             lenses.append((int(lens[0]), lens[1]))
             images.append(np.ascontiguousarray(img))
-            xforms.append(nerf_matrix_to_ngp(fr["transform_matrix"], scale, offset, from_mitsuba))
+            # transform_matrix_start / _end (nerf_loader.cu:517-518, :690-700): a camera that moves while the frame is exposed needs K1's per-pixel transform
+            # interpolation, which is not built; a start matrix alone (end defaults to it) is an ordinary frame
+            m_start = fr["transform_matrix_start"] if "transform_matrix_start" in fr else fr.get("transform_matrix")
+            if m_start is None:
+                raise RuntimeError(f"frame {fr.get('file_path')!r} has no transform_matrix")
+            if "transform_matrix_end" in fr and not np.array_equal(np.asarray(fr["transform_matrix_end"], np.float64), np.asarray(m_start, np.float64)):
+                raise RuntimeError("frames with different transform_matrix_start / transform_matrix_end (rolling shutter, motion blur) are outside the built scope")
+            xforms.append(nerf_matrix_to_ngp(m_start, scale, offset, from_mitsuba))
             fxs.append(float(focal[0])); fys.append(float(focal[1])); cxs.append(pp[0]); cys.append(pp[1])
     if sharpen_amount > 0.0:  # applied to every image once all files are read (:732, :805-826); 8-bit frames become halfs first
         images = [sharpen_image(byte_image_to_half(im) if im.dtype == np.uint8 else im, sharpen_amount) for im in images]

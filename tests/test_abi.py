@@ -326,6 +326,16 @@ def test_loader_alpha_files_masks_transparency_and_aabb(tmp_path):
     Image.fromarray(np.zeros((2, 2, 4), np.uint8)).save(d / "img" / "dynamic_mask_a.png")
     with pytest.raises(RuntimeError, match="wrong resolution"):
         pyngp.load_transforms(str(d / "transforms.json"))
+    os.remove(d / "img" / "dynamic_mask_a.png")
+    # transform_matrix_start alone is an ordinary frame; a different end matrix (a camera moving during the exposure) is refused, not silently ignored
+    js["frames"][0] = {"file_path": "img/a", "transform_matrix_start": eye}
+    json.dump(js, open(d / "transforms.json", "w"))
+    assert pyngp.load_transforms(str(d / "transforms.json"))["xforms"].shape == (1, 3, 4)
+    moved = [row[:] for row in eye]; moved[0][3] = 1.5
+    js["frames"][0]["transform_matrix_end"] = moved
+    json.dump(js, open(d / "transforms.json", "w"))
+    with pytest.raises(RuntimeError, match="outside the built scope"):
+        pyngp.load_transforms(str(d / "transforms.json"))
 
 
 def test_sharpened_training_images(tmp_path):
